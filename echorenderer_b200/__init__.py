@@ -1,0 +1,12 @@
+"""echo-b200: a B200-native path-tracing core behind Echo's evaluator/aggregator interface.
+
+The package holds only what the hot path needs: csrc/ (hand-written CUDA for sm_100a + the C ABI, and the host-side
+scene preparation in C++), the ctypes binding, and the host-side mirror of the reference interface for this path.
+"""
+from . import structs  # noqa: F401
+from .host import PreparedArrays, SceneDescription, prepare  # noqa: F401
+from .scene import (EvaluationOperation, EvaluationProfile, PathTracedEvaluator, PreparedScene, RenderTexture,  # noqa: F401
+                    shard_tiles)
+from ._native import EchoNativeError  # noqa: F401
+
+__version__ = "0.1.0"

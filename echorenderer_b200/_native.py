@@ -1,0 +1,99 @@
+"""ctypes binding of libecho_b200.so — the C ABI a C# host would bind with [DllImport("echo_b200")].
+
+The library is mandatory: there is no CPU fallback. A missing .so or a missing CUDA device raises EchoNativeError.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIBRARY_PATH = os.path.join(_HERE, "libecho_b200.so")
+
+OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_UNSUPPORTED = range(5)
+
+
+class EchoNativeError(RuntimeError):
+    """Raised like OidnDenoise.ThrowOnNativeError does (Processes/Composition/OidnDenoise.cs:201-206): the status code
+    of the failed call plus the message pulled from echo_b200_last_error()."""
+
+    def __init__(self, status, message):
+        super().__init__(f"libecho_b200 error {status}: {message}")
+        self.status = status
+
+
+_lib = None
+
+# every symbol include/echo_b200.h and include/echo_b200_debug.h declare
+EXPORTS = [
+    "echo_b200_device_count", "echo_b200_scene_create", "echo_b200_scene_set_qbvh", "echo_b200_scene_set_triangles",
+    "echo_b200_scene_set_spheres", "echo_b200_scene_set_materials", "echo_b200_scene_set_light_tree", "echo_b200_scene_set_infinite",
+    "echo_b200_scene_set_camera", "echo_b200_scene_commit", "echo_b200_scene_destroy", "echo_b200_trace_batch", "echo_b200_occlude_batch",
+    "echo_b200_trace_batch_device", "echo_b200_occlude_batch_device", "echo_b200_render_tiles", "echo_b200_render_frame_device",
+    "echo_b200_frame_resolve_device", "echo_b200_last_error", "echo_b200_version",
+    "echo_b200_trace_batch_device_counted", "echo_b200_occlude_batch_device_counted", "echo_b200_debug_bxdf_batch", "echo_b200_debug_math",
+    "echo_b200_debug_evaluate_samples",
+]
+
+
+def library():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIBRARY_PATH):
+        raise EchoNativeError(-1, f"{LIBRARY_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`")
+
+    lib = ctypes.CDLL(LIBRARY_PATH)
+    p, u32, u64, i32, f32 = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_int32, ctypes.c_float
+
+    signatures = {
+        "echo_b200_device_count": [ctypes.POINTER(i32)],
+        "echo_b200_scene_create": [ctypes.POINTER(p), i32],
+        "echo_b200_scene_set_qbvh": [p, p, u32, u32],
+        "echo_b200_scene_set_triangles": [p, p, u32],
+        "echo_b200_scene_set_spheres": [p, p, u32],
+        "echo_b200_scene_set_materials": [p, p, u32],
+        "echo_b200_scene_set_light_tree": [p, p, u32, p, p, u32, p, u32],
+        "echo_b200_scene_set_infinite": [p, p, u32, f32, f32],
+        "echo_b200_scene_set_camera": [p, p],
+        "echo_b200_scene_commit": [p],
+        "echo_b200_scene_destroy": [p],
+        "echo_b200_trace_batch": [p, p, u64, p],
+        "echo_b200_occlude_batch": [p, p, u64, p],
+        "echo_b200_trace_batch_device": [p, p, u64, p, p],
+        "echo_b200_occlude_batch_device": [p, p, u64, p, p],
+        "echo_b200_render_tiles": [p, p, p, u32, p, p],
+        "echo_b200_render_frame_device": [p, p, p, u32, p, p, p],
+        "echo_b200_frame_resolve_device": [p, p, i32, i32, p],
+        "echo_b200_trace_batch_device_counted": [p, p, u64, p, p, p],
+        "echo_b200_occlude_batch_device_counted": [p, p, u64, p, p, p],
+        "echo_b200_debug_bxdf_batch": [i32, i32, p, p, p, u64, p, p, p],
+        "echo_b200_debug_math": [i32, i32, p, p, p, u64, p],
+        "echo_b200_debug_evaluate_samples": [p, p, p, p, u64, p],
+    }
+
+    for name, argtypes in signatures.items():
+        function = getattr(lib, name)
+        function.argtypes = argtypes
+        function.restype = i32
+
+    lib.echo_b200_last_error.restype = ctypes.c_char_p
+    lib.echo_b200_version.restype = ctypes.c_char_p
+    _lib = lib
+    return lib
+
+
+def check(status):
+    if status != OK:
+        raise EchoNativeError(status, library().echo_b200_last_error().decode("utf-8", "replace"))
+
+
+def pointer(array):
+    """Raw address of a numpy array (or None / empty -> NULL)."""
+    if array is None or array.size == 0:
+        return ctypes.c_void_p(0)
+    return ctypes.c_void_p(array.ctypes.data)
+
+
+def device_count():
+    count = ctypes.c_int32()
+    check(library().echo_b200_device_count(ctypes.byref(count)))
+    return count.value

@@ -1,0 +1,573 @@
+// api.cu — the C ABI of libecho_b200.so (include/echo_b200.h, include/echo_b200_debug.h): scene upload and layout
+// conversion, the batched trace/occlude entry points with pipelined host<->device copies, and the tile renderer.
+// There is no CPU fallback anywhere in this library: without a CUDA device every compute call fails.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
+#include "../../include/echo_b200_debug.h"
+#include "echo_internal.h"
+
+namespace echo
+{
+
+static thread_local std::string lastError;
+
+void set_error(const std::string& message) { lastError = message; }
+
+bool check_cuda(cudaError_t status, const char* what)
+{
+	if (status == cudaSuccess) return true;
+	lastError = std::string(what) + ": " + cudaGetErrorString(status);
+	return false;
+}
+
+bool evaluate_sample_list(RenderState* state, const DeviceScene& scene, const EchoRenderParams& params, const int32_t* pixelXYHost, const uint32_t* sampleIndexHost,
+                          uint64_t n, float* outRGBHost, cudaStream_t stream);
+
+} // namespace echo
+
+using namespace echo;
+
+namespace
+{
+
+struct DeviceGuard
+{
+	int previous = -1;
+	bool ok = false;
+
+	explicit DeviceGuard(int device)
+	{
+		if (cudaGetDevice(&previous) != cudaSuccess) previous = -1;
+		ok = check_cuda(cudaSetDevice(device), "cudaSetDevice");
+	}
+
+	~DeviceGuard()
+	{
+		if (previous >= 0) cudaSetDevice(previous);
+	}
+};
+
+template<class T>
+bool upload(EchoScene* scene, const std::vector<T>& host, const T*& device)
+{
+	void* p = nullptr;
+	size_t bytes = sizeof(T) * std::max<size_t>(host.size(), 1);
+	if (!check_cuda(cudaMalloc(&p, bytes), "cudaMalloc(scene)")) return false;
+	scene->allocations.push_back(p);
+	if (!host.empty() && !check_cuda(cudaMemcpy(p, host.data(), sizeof(T) * host.size(), cudaMemcpyHostToDevice), "cudaMemcpy(scene)")) return false;
+	device = (const T*)p;
+	return true;
+}
+
+void free_device(EchoScene* scene)
+{
+	for (void* p : scene->allocations) cudaFree(p);
+	scene->allocations.clear();
+	scene->committed = false;
+}
+
+int32_t fail(int32_t code, const char* message)
+{
+	set_error(message);
+	return code;
+}
+
+bool require_committed(EchoScene* scene)
+{
+	if (!scene) { set_error("scene is null"); return false; }
+	if (!scene->committed) { set_error("scene is not committed"); return false; }
+	return true;
+}
+
+constexpr uint64_t kChunkRays = 1ull << 21; // 2 M rays per pipelined chunk: 64 MB in, 32 MB out
+
+bool ensure_scratch(EchoScene* scene, uint64_t rays)
+{
+	if (scene->scratchCapacity >= rays) return true;
+
+	for (int i = 0; i < 2; i++)
+	{
+		if (scene->scratchRays[i]) cudaFree(scene->scratchRays[i]);
+		if (scene->scratchOut[i]) cudaFree(scene->scratchOut[i]);
+		scene->scratchRays[i] = scene->scratchOut[i] = nullptr;
+	}
+
+	scene->scratchCapacity = 0;
+
+	for (int i = 0; i < 2; i++)
+	{
+		if (!check_cuda(cudaMalloc(&scene->scratchRays[i], sizeof(EchoRay) * rays), "cudaMalloc(scratch rays)")) return false;
+		if (!check_cuda(cudaMalloc(&scene->scratchOut[i], sizeof(EchoHit) * rays), "cudaMalloc(scratch out)")) return false;
+		if (!scene->copyStreams[i] && !check_cuda(cudaStreamCreateWithFlags(&scene->copyStreams[i], cudaStreamNonBlocking), "cudaStreamCreate")) return false;
+		if (!scene->chunkDone[i] && !check_cuda(cudaEventCreateWithFlags(&scene->chunkDone[i], cudaEventDisableTiming), "cudaEventCreate")) return false;
+	}
+
+	scene->scratchCapacity = rays;
+	return true;
+}
+
+// Host-buffer batch: chunks alternate between two streams so that chunk k's upload overlaps chunk k-1's kernel and
+// download (H2D, compute and D2H engines run concurrently). With pinned host buffers the copies are truly asynchronous.
+template<class Out, class Launch>
+int32_t batch_host(EchoScene* scene, const EchoRay* rays, uint64_t n, Out* out, Launch launch)
+{
+	if (!require_committed(scene)) return ECHO_B200_ERR_INVALID;
+	if (n == 0) return ECHO_B200_OK;
+	if (!rays || !out) return fail(ECHO_B200_ERR_INVALID, "null buffer");
+
+	DeviceGuard guard(scene->device);
+	if (!guard.ok) return ECHO_B200_ERR_NO_DEVICE;
+
+	uint64_t chunk = std::min<uint64_t>(kChunkRays, n);
+	if (!ensure_scratch(scene, chunk)) return ECHO_B200_ERR_CUDA;
+
+	int slot = 0;
+
+	for (uint64_t first = 0; first < n; first += chunk, slot ^= 1)
+	{
+		uint64_t count = std::min<uint64_t>(chunk, n - first);
+		cudaStream_t stream = scene->copyStreams[slot];
+
+		if (!check_cuda(cudaMemcpyAsync(scene->scratchRays[slot], rays + first, sizeof(EchoRay) * count, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync(rays)")) return ECHO_B200_ERR_CUDA;
+		if (!launch((const EchoRay*)scene->scratchRays[slot], count, (Out*)scene->scratchOut[slot], stream)) return ECHO_B200_ERR_CUDA;
+		if (!check_cuda(cudaMemcpyAsync(out + first, scene->scratchOut[slot], sizeof(Out) * count, cudaMemcpyDeviceToHost, stream), "cudaMemcpyAsync(out)")) return ECHO_B200_ERR_CUDA;
+	}
+
+	for (int i = 0; i < 2; i++)
+		if (!check_cuda(cudaStreamSynchronize(scene->copyStreams[i]), "batch")) return ECHO_B200_ERR_CUDA;
+
+	return ECHO_B200_OK;
+}
+
+} // namespace
+
+extern "C"
+{
+
+const char* echo_b200_last_error(void) { return lastError.c_str(); }
+const char* echo_b200_version(void) { return "echo-b200 0.1 (sm_100a)"; }
+
+int32_t echo_b200_device_count(int32_t* out)
+{
+	if (!out) return fail(ECHO_B200_ERR_INVALID, "out is null");
+	int count = 0;
+	cudaError_t status = cudaGetDeviceCount(&count);
+
+	if (status != cudaSuccess || count == 0)
+	{
+		*out = 0;
+		cudaGetLastError();
+		return fail(ECHO_B200_ERR_NO_DEVICE, "no usable CUDA device");
+	}
+
+	*out = count;
+	return ECHO_B200_OK;
+}
+
+int32_t echo_b200_scene_create(EchoScene** out, int32_t device)
+{
+	if (!out) return fail(ECHO_B200_ERR_INVALID, "out is null");
+	*out = nullptr;
+
+	int32_t count = 0;
+	int32_t status = echo_b200_device_count(&count);
+	if (status != ECHO_B200_OK) return status;
+	if (device < 0 || device >= count) return fail(ECHO_B200_ERR_INVALID, "device index out of range");
+
+	EchoScene* scene = new EchoScene();
+	scene->device = device;
+
+	DeviceGuard guard(device);
+
+	if (!guard.ok || !check_cuda(cudaStreamCreateWithFlags(&scene->stream, cudaStreamNonBlocking), "cudaStreamCreate"))
+	{
+		delete scene;
+		return ECHO_B200_ERR_CUDA;
+	}
+
+	scene->render = render_state_create();
+	*out = scene;
+	return ECHO_B200_OK;
+}
+
+int32_t echo_b200_scene_destroy(EchoScene* scene)
+{
+	if (!scene) return ECHO_B200_OK;
+	DeviceGuard guard(scene->device);
+	free_device(scene);
+	render_state_destroy(scene->render);
+
+	for (int i = 0; i < 2; i++)
+	{
+		if (scene->scratchRays[i]) cudaFree(scene->scratchRays[i]);
+		if (scene->scratchOut[i]) cudaFree(scene->scratchOut[i]);
+		if (scene->copyStreams[i]) cudaStreamDestroy(scene->copyStreams[i]);
+		if (scene->chunkDone[i]) cudaEventDestroy(scene->chunkDone[i]);
+	}
+
+	if (scene->stream) cudaStreamDestroy(scene->stream);
+	delete scene;
+	return ECHO_B200_OK;
+}
+
+int32_t echo_b200_scene_set_qbvh(EchoScene* scene, const EchoQbvhNode* nodes, uint32_t count, uint32_t maxDepth)
+{
+	if (!scene || (!nodes && count)) return fail(ECHO_B200_ERR_INVALID, "null argument");
+	if (count == 0) return fail(ECHO_B200_ERR_INVALID, "a QBVH needs at least one node");
+	if (stack_class(maxDepth) < 0) return fail(ECHO_B200_ERR_UNSUPPORTED, "QBVH deeper than 63 quad levels is not supported");
+	scene->nodes.assign(nodes, nodes + count);
+	scene->maxDepth = maxDepth;
+	scene->committed = false;
+	return ECHO_B200_OK;
+}
+
+int32_t echo_b200_scene_set_triangles(EchoScene* scene, const EchoTriangle* triangles, uint32_t count)
+{
+	if (!scene || (!triangles && count)) return fail(ECHO_B200_ERR_INVALID, "null argument");
+	scene->triangles.assign(triangles, triangles + count);
+	scene->committed = false;
+	return ECHO_B200_OK;
+}
+
+int32_t echo_b200_scene_set_spheres(EchoScene* scene, const EchoSphere* spheres, uint32_t count)
+{
+	if (!scene || (!spheres && count)) return fail(ECHO_B200_ERR_INVALID, "null argument");
+	scene->spheres.assign(spheres, spheres + count);
+	scene->committed = false;
+	return ECHO_B200_OK;
+}
+
+int32_t echo_b200_scene_set_materials(EchoScene* scene, const EchoMaterial* materials, uint32_t count)
+{
+	if (!scene || (!materials && count)) return fail(ECHO_B200_ERR_INVALID, "null argument");
+
+	for (uint32_t i = 0; i < count; i++)
+	{
+		if (materials[i].type > ECHO_MATERIAL_INVISIBLE) return fail(ECHO_B200_ERR_UNSUPPORTED, "material type outside the hot path");
+		if (materials[i].type == ECHO_MATERIAL_ONESIDED && materials[i].base >= count) return fail(ECHO_B200_ERR_INVALID, "OneSided base index out of range");
+	}
+
+	scene->materials.assign(materials, materials + count);
+	scene->committed = false;
+	return ECHO_B200_OK;
+}
+
+int32_t echo_b200_scene_set_light_tree(EchoScene* scene, const EchoLightNode* nodes, uint32_t nodeCount, const uint32_t* tokens, const uint64_t* paths,
+                                       uint32_t emitterCount, const EchoPointLight* points, uint32_t pointCount)
+{
+	if (!scene || (!nodes && nodeCount) || ((!tokens || !paths) && emitterCount) || (!points && pointCount)) return fail(ECHO_B200_ERR_INVALID, "null argument");
+	scene->lightNodes.assign(nodes, nodes + nodeCount);
+
+	// LightTree.map as a sorted array (binary-searched on the device)
+	std::vector<uint32_t> order(emitterCount);
+	std::iota(order.begin(), order.end(), 0u);
+	std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return tokens[a] < tokens[b]; });
+	scene->emitterTokens.resize(emitterCount);
+	scene->emitterPaths.resize(emitterCount);
+
+	for (uint32_t i = 0; i < emitterCount; i++)
+	{
+		scene->emitterTokens[i] = tokens[order[i]];
+		scene->emitterPaths[i] = paths[order[i]];
+	}
+
+	scene->pointLights.assign(points, points + pointCount);
+	scene->committed = false;
+	return ECHO_B200_OK;
+}
+
+int32_t echo_b200_scene_set_infinite(EchoScene* scene, const EchoInfiniteLight* lights, uint32_t count, float threshold, float pdf)
+{
+	if (!scene || (!lights && count)) return fail(ECHO_B200_ERR_INVALID, "null argument");
+	scene->infiniteLights.assign(lights, lights + count);
+	scene->infiniteThreshold = threshold;
+	scene->infinitePdf = pdf;
+	scene->committed = false;
+	return ECHO_B200_OK;
+}
+
+int32_t echo_b200_scene_set_camera(EchoScene* scene, const EchoCamera* camera)
+{
+	if (!scene || !camera) return fail(ECHO_B200_ERR_INVALID, "null argument");
+	scene->camera = *camera;
+	if (scene->committed) scene->d.camera = *camera; // the camera travels by value with every launch
+	return ECHO_B200_OK;
+}
+
+int32_t echo_b200_scene_commit(EchoScene* scene)
+{
+	if (!scene) return fail(ECHO_B200_ERR_INVALID, "scene is null");
+	if (scene->nodes.empty()) return fail(ECHO_B200_ERR_INVALID, "no QBVH was set");
+
+	// every token in the node array must point at an uploaded primitive
+	for (const EchoQbvhNode& node : scene->nodes)
+	{
+		for (uint32_t token : node.token4)
+		{
+			if (token == ECHO_TOKEN_EMPTY) continue;
+			uint32_t type = token >> ECHO_TOKEN_INDEX_BITS, index = token & ((1u << ECHO_TOKEN_INDEX_BITS) - 1u);
+			bool ok = (type == ECHO_TOKEN_TYPE_NODE && index < scene->nodes.size()) || (type == ECHO_TOKEN_TYPE_TRIANGLE && index < scene->triangles.size())
+				|| (type == ECHO_TOKEN_TYPE_SPHERE && index < scene->spheres.size());
+			if (type == ECHO_TOKEN_TYPE_INSTANCE) return fail(ECHO_B200_ERR_UNSUPPORTED, "instanced tokens are outside the hot path");
+			if (!ok) return fail(ECHO_B200_ERR_INVALID, "QBVH token out of range");
+		}
+	}
+
+	for (const EchoTriangle& t : scene->triangles)
+		if (t.material >= scene->materials.size() && !scene->materials.empty()) return fail(ECHO_B200_ERR_INVALID, "triangle material index out of range");
+	for (const EchoSphere& s : scene->spheres)
+		if (s.material >= scene->materials.size() && !scene->materials.empty()) return fail(ECHO_B200_ERR_INVALID, "sphere material index out of range");
+
+	DeviceGuard guard(scene->device);
+	if (!guard.ok) return ECHO_B200_ERR_NO_DEVICE;
+	free_device(scene);
+
+	DeviceScene& d = scene->d;
+	d = DeviceScene{};
+
+	// layout conversion (DESIGN.md "Data layout in HBM")
+	std::vector<float4> triHot(scene->triangles.size() * 3), triShade(scene->triangles.size() * 3);
+
+	for (size_t i = 0; i < scene->triangles.size(); i++)
+	{
+		const EchoTriangle& t = scene->triangles[i];
+		float materialBits;
+		std::memcpy(&materialBits, &t.material, 4);
+		triHot[i * 3 + 0] = make_float4(t.vertex0[0], t.vertex0[1], t.vertex0[2], 0.0f);
+		triHot[i * 3 + 1] = make_float4(t.edge1[0], t.edge1[1], t.edge1[2], 0.0f);
+		triHot[i * 3 + 2] = make_float4(t.edge2[0], t.edge2[1], t.edge2[2], 0.0f);
+		triShade[i * 3 + 0] = make_float4(t.normal0[0], t.normal0[1], t.normal0[2], materialBits);
+		triShade[i * 3 + 1] = make_float4(t.normal1[0], t.normal1[1], t.normal1[2], 0.0f);
+		triShade[i * 3 + 2] = make_float4(t.normal2[0], t.normal2[1], t.normal2[2], 0.0f);
+	}
+
+	std::vector<float4> spheres(scene->spheres.size());
+	std::vector<uint32_t> sphereMaterial(scene->spheres.size());
+
+	for (size_t i = 0; i < scene->spheres.size(); i++)
+	{
+		const EchoSphere& s = scene->spheres[i];
+		spheres[i] = make_float4(s.position[0], s.position[1], s.position[2], s.radius);
+		sphereMaterial[i] = s.material;
+	}
+
+	std::vector<float4> pointLights(scene->pointLights.size() * 2), infiniteLights(scene->infiniteLights.size());
+
+	for (size_t i = 0; i < scene->pointLights.size(); i++)
+	{
+		const EchoPointLight& p = scene->pointLights[i];
+		pointLights[i * 2] = make_float4(p.intensity[0], p.intensity[1], p.intensity[2], 0.0f);
+		pointLights[i * 2 + 1] = make_float4(p.position[0], p.position[1], p.position[2], 0.0f);
+	}
+
+	for (size_t i = 0; i < scene->infiniteLights.size(); i++)
+	{
+		const EchoInfiniteLight& l = scene->infiniteLights[i];
+		float visibleBits;
+		std::memcpy(&visibleBits, &l.directlyVisible, 4);
+		infiniteLights[i] = make_float4(l.radiance[0], l.radiance[1], l.radiance[2], visibleBits);
+	}
+
+	static_assert(sizeof(EchoQbvhNode) == 128 && sizeof(EchoMaterial) == 64 && sizeof(EchoLightNode) == 64, "POD layout");
+	static_assert(sizeof(EchoTriangle) == 100 && sizeof(EchoSphere) == 20 && sizeof(EchoRay) == 32 && sizeof(EchoHit) == 16, "POD layout");
+
+	const EchoQbvhNode* nodes = nullptr;
+	const EchoMaterial* materials = nullptr;
+	const EchoLightNode* lightNodes = nullptr;
+
+	bool ok = upload(scene, scene->nodes, nodes) && upload(scene, triHot, d.triHot) && upload(scene, triShade, d.triShade)
+		&& upload(scene, spheres, d.spheres) && upload(scene, sphereMaterial, d.sphereMaterial) && upload(scene, scene->materials, materials)
+		&& upload(scene, scene->lightNodes, lightNodes) && upload(scene, scene->emitterTokens, d.emitterTokens)
+		&& upload(scene, scene->emitterPaths, d.emitterPaths) && upload(scene, pointLights, d.pointLights) && upload(scene, infiniteLights, d.infiniteLights);
+
+	if (!ok)
+	{
+		free_device(scene);
+		return ECHO_B200_ERR_CUDA;
+	}
+
+	d.nodes = reinterpret_cast<const float4*>(nodes);
+	d.materials = reinterpret_cast<const float4*>(materials);
+	d.lightNodes = reinterpret_cast<const float4*>(lightNodes);
+	d.nodeCount = (uint32_t)scene->nodes.size();
+	d.triangleCount = (uint32_t)scene->triangles.size();
+	d.sphereCount = (uint32_t)scene->spheres.size();
+	d.materialCount = (uint32_t)scene->materials.size();
+	d.lightNodeCount = (uint32_t)scene->lightNodes.size();
+	d.emitterCount = (uint32_t)scene->emitterTokens.size();
+	d.pointLightCount = (uint32_t)scene->pointLights.size();
+	d.infiniteLightCount = (uint32_t)scene->infiniteLights.size();
+	d.maxDepth = scene->maxDepth;
+	d.infiniteThreshold = scene->infiniteThreshold;
+	d.infinitePdf = scene->infinitePdf;
+	d.camera = scene->camera;
+
+	scene->committed = true;
+	return ECHO_B200_OK;
+}
+
+int32_t echo_b200_trace_batch(EchoScene* scene, const EchoRay* rays, uint64_t n, EchoHit* hits)
+{
+	return batch_host<EchoHit>(scene, rays, n, hits, [&](const EchoRay* in, uint64_t count, EchoHit* out, cudaStream_t stream)
+	{
+		return launch_trace(scene->d, in, count, out, nullptr, stream);
+	});
+}
+
+int32_t echo_b200_occlude_batch(EchoScene* scene, const EchoRay* rays, uint64_t n, uint8_t* occluded)
+{
+	return batch_host<uint8_t>(scene, rays, n, occluded, [&](const EchoRay* in, uint64_t count, uint8_t* out, cudaStream_t stream)
+	{
+		return launch_occlude(scene->d, in, count, out, nullptr, stream);
+	});
+}
+
+int32_t echo_b200_trace_batch_device(EchoScene* scene, const EchoRay* rays, uint64_t n, EchoHit* hits, void* stream)
+{
+	if (!require_committed(scene)) return ECHO_B200_ERR_INVALID;
+	DeviceGuard guard(scene->device);
+	if (!guard.ok) return ECHO_B200_ERR_NO_DEVICE;
+	return launch_trace(scene->d, rays, n, hits, nullptr, (cudaStream_t)stream) ? ECHO_B200_OK : ECHO_B200_ERR_CUDA;
+}
+
+int32_t echo_b200_occlude_batch_device(EchoScene* scene, const EchoRay* rays, uint64_t n, uint8_t* occluded, void* stream)
+{
+	if (!require_committed(scene)) return ECHO_B200_ERR_INVALID;
+	DeviceGuard guard(scene->device);
+	if (!guard.ok) return ECHO_B200_ERR_NO_DEVICE;
+	return launch_occlude(scene->d, rays, n, occluded, nullptr, (cudaStream_t)stream) ? ECHO_B200_OK : ECHO_B200_ERR_CUDA;
+}
+
+int32_t echo_b200_trace_batch_device_counted(EchoScene* scene, const EchoRay* rays, uint64_t n, EchoHit* hits, uint64_t* counts, void* stream)
+{
+	if (!require_committed(scene)) return ECHO_B200_ERR_INVALID;
+	if (!counts) return fail(ECHO_B200_ERR_INVALID, "d_counts3 is null");
+	DeviceGuard guard(scene->device);
+	if (!guard.ok) return ECHO_B200_ERR_NO_DEVICE;
+	return launch_trace(scene->d, rays, n, hits, (unsigned long long*)counts, (cudaStream_t)stream) ? ECHO_B200_OK : ECHO_B200_ERR_CUDA;
+}
+
+int32_t echo_b200_occlude_batch_device_counted(EchoScene* scene, const EchoRay* rays, uint64_t n, uint8_t* occluded, uint64_t* counts, void* stream)
+{
+	if (!require_committed(scene)) return ECHO_B200_ERR_INVALID;
+	if (!counts) return fail(ECHO_B200_ERR_INVALID, "d_counts3 is null");
+	DeviceGuard guard(scene->device);
+	if (!guard.ok) return ECHO_B200_ERR_NO_DEVICE;
+	return launch_occlude(scene->d, rays, n, occluded, (unsigned long long*)counts, (cudaStream_t)stream) ? ECHO_B200_OK : ECHO_B200_ERR_CUDA;
+}
+
+int32_t echo_b200_render_tiles(EchoScene* scene, const EchoRenderParams* params, const int32_t* tileXY, uint32_t tileCount, float* outRGBA, EchoStats* stats)
+{
+	if (!require_committed(scene)) return ECHO_B200_ERR_INVALID;
+	if (!params || (!tileXY && tileCount) || (!outRGBA && tileCount)) return fail(ECHO_B200_ERR_INVALID, "null argument");
+	if (stats) *stats = EchoStats{};
+	if (tileCount == 0) return ECHO_B200_OK;
+
+	DeviceGuard guard(scene->device);
+	if (!guard.ok) return ECHO_B200_ERR_NO_DEVICE;
+
+	uint64_t pixels = (uint64_t)tileCount * params->tileSize * params->tileSize;
+	float4* deviceOut = nullptr;
+	if (!check_cuda(cudaMalloc((void**)&deviceOut, sizeof(float4) * pixels), "cudaMalloc(tiles)")) return ECHO_B200_ERR_CUDA;
+
+	bool ok = render_tiles(scene->render, scene->d, *params, tileXY, tileCount, deviceOut, nullptr, stats, scene->stream);
+	ok = ok && check_cuda(cudaMemcpyAsync(outRGBA, deviceOut, sizeof(float4) * pixels, cudaMemcpyDeviceToHost, scene->stream), "cudaMemcpyAsync(tiles)");
+	ok = ok && check_cuda(cudaStreamSynchronize(scene->stream), "render_tiles");
+	cudaFree(deviceOut);
+	return ok ? ECHO_B200_OK : ECHO_B200_ERR_CUDA;
+}
+
+int32_t echo_b200_render_frame_device(EchoScene* scene, const EchoRenderParams* params, const int32_t* tileXY, uint32_t tileCount, float* frame, EchoStats* stats, void* stream)
+{
+	if (!require_committed(scene)) return ECHO_B200_ERR_INVALID;
+	if (!params || (!tileXY && tileCount) || !frame) return fail(ECHO_B200_ERR_INVALID, "null argument");
+	if (stats) *stats = EchoStats{};
+	if (tileCount == 0) return ECHO_B200_OK;
+
+	DeviceGuard guard(scene->device);
+	if (!guard.ok) return ECHO_B200_ERR_NO_DEVICE;
+
+	cudaStream_t s = stream ? (cudaStream_t)stream : scene->stream;
+	return render_tiles(scene->render, scene->d, *params, tileXY, tileCount, nullptr, (float4*)frame, stats, s) ? ECHO_B200_OK : ECHO_B200_ERR_CUDA;
+}
+
+int32_t echo_b200_frame_resolve_device(EchoScene* scene, float* frame, int32_t width, int32_t height, void* stream)
+{
+	if (!scene || !frame || width <= 0 || height <= 0) return fail(ECHO_B200_ERR_INVALID, "invalid argument");
+	DeviceGuard guard(scene->device);
+	if (!guard.ok) return ECHO_B200_ERR_NO_DEVICE;
+	cudaStream_t s = stream ? (cudaStream_t)stream : scene->stream;
+	return launch_frame_resolve((float4*)frame, width, height, s) ? ECHO_B200_OK : ECHO_B200_ERR_CUDA;
+}
+
+int32_t echo_b200_debug_evaluate_samples(EchoScene* scene, const EchoRenderParams* params, const int32_t* pixelXY, const uint32_t* sampleIndex, uint64_t n, float* outRGB)
+{
+	if (!require_committed(scene)) return ECHO_B200_ERR_INVALID;
+	if (!params || !pixelXY || !sampleIndex || !outRGB) return fail(ECHO_B200_ERR_INVALID, "null argument");
+	DeviceGuard guard(scene->device);
+	if (!guard.ok) return ECHO_B200_ERR_NO_DEVICE;
+	return evaluate_sample_list(scene->render, scene->d, *params, pixelXY, sampleIndex, n, outRGB, scene->stream) ? ECHO_B200_OK : ECHO_B200_ERR_CUDA;
+}
+
+static int32_t debug_device(int32_t device)
+{
+	int32_t count = 0;
+	int32_t status = echo_b200_device_count(&count);
+	if (status != ECHO_B200_OK) return status;
+	if (device < 0 || device >= count) return fail(ECHO_B200_ERR_INVALID, "device index out of range");
+	return ECHO_B200_OK;
+}
+
+int32_t echo_b200_debug_bxdf_batch(int32_t device, int32_t kind, const float* params, const float* outgoing, const float* samples, uint64_t n,
+                                   float* sampled8, float* evaluated4, float* inverse4)
+{
+	int32_t status = debug_device(device);
+	if (status != ECHO_B200_OK) return status;
+	DeviceGuard guard(device);
+	if (!guard.ok) return ECHO_B200_ERR_NO_DEVICE;
+
+	float *dParams = nullptr, *dOutgoing = nullptr, *dSamples = nullptr, *dSampled = nullptr, *dEvaluated = nullptr, *dInverse = nullptr;
+	bool ok = check_cuda(cudaMalloc((void**)&dParams, sizeof(float) * 11), "cudaMalloc") && check_cuda(cudaMalloc((void**)&dOutgoing, sizeof(float) * 3 * n), "cudaMalloc")
+		&& check_cuda(cudaMalloc((void**)&dSamples, sizeof(float) * 2 * n), "cudaMalloc") && check_cuda(cudaMalloc((void**)&dSampled, sizeof(float) * 8 * n), "cudaMalloc")
+		&& check_cuda(cudaMalloc((void**)&dEvaluated, sizeof(float) * 4 * n), "cudaMalloc") && check_cuda(cudaMalloc((void**)&dInverse, sizeof(float) * 4 * n), "cudaMalloc");
+
+	ok = ok && check_cuda(cudaMemcpy(dParams, params, sizeof(float) * 11, cudaMemcpyHostToDevice), "cudaMemcpy")
+		&& check_cuda(cudaMemcpy(dOutgoing, outgoing, sizeof(float) * 3 * n, cudaMemcpyHostToDevice), "cudaMemcpy")
+		&& check_cuda(cudaMemcpy(dSamples, samples, sizeof(float) * 2 * n, cudaMemcpyHostToDevice), "cudaMemcpy");
+
+	ok = ok && launch_debug_bxdf(kind, dParams, dOutgoing, dSamples, n, dSampled, dEvaluated, dInverse, nullptr);
+	ok = ok && check_cuda(cudaDeviceSynchronize(), "debug_bxdf");
+	ok = ok && check_cuda(cudaMemcpy(sampled8, dSampled, sizeof(float) * 8 * n, cudaMemcpyDeviceToHost), "cudaMemcpy")
+		&& check_cuda(cudaMemcpy(evaluated4, dEvaluated, sizeof(float) * 4 * n, cudaMemcpyDeviceToHost), "cudaMemcpy")
+		&& check_cuda(cudaMemcpy(inverse4, dInverse, sizeof(float) * 4 * n, cudaMemcpyDeviceToHost), "cudaMemcpy");
+
+	for (float* p : { dParams, dOutgoing, dSamples, dSampled, dEvaluated, dInverse }) if (p) cudaFree(p);
+	return ok ? ECHO_B200_OK : ECHO_B200_ERR_CUDA;
+}
+
+int32_t echo_b200_debug_math(int32_t device, int32_t op, const float* a, const float* b, const float* c, uint64_t n, float* out)
+{
+	int32_t status = debug_device(device);
+	if (status != ECHO_B200_OK) return status;
+	DeviceGuard guard(device);
+	if (!guard.ok) return ECHO_B200_ERR_NO_DEVICE;
+
+	float* buffers[4] = { nullptr, nullptr, nullptr, nullptr };
+	const float* hosts[3] = { a, b, c };
+	bool ok = true;
+
+	for (int i = 0; i < 4 && ok; i++) ok = check_cuda(cudaMalloc((void**)&buffers[i], sizeof(float) * std::max<uint64_t>(n, 1)), "cudaMalloc");
+	for (int i = 0; i < 3 && ok; i++) ok = check_cuda(cudaMemcpy(buffers[i], hosts[i], sizeof(float) * n, cudaMemcpyHostToDevice), "cudaMemcpy");
+
+	ok = ok && launch_debug_math(op, buffers[0], buffers[1], buffers[2], n, buffers[3], nullptr);
+	ok = ok && check_cuda(cudaDeviceSynchronize(), "debug_math");
+	ok = ok && check_cuda(cudaMemcpy(out, buffers[3], sizeof(float) * n, cudaMemcpyDeviceToHost), "cudaMemcpy");
+
+	for (float* p : buffers) if (p) cudaFree(p);
+	return ok ? ECHO_B200_OK : ECHO_B200_ERR_CUDA;
+}
+
+} // extern "C"

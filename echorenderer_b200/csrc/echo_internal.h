@@ -1,0 +1,77 @@
+// echo_internal.h — host-side state behind the opaque EchoScene handle and the kernel launch entry points.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "echo_scene.cuh"
+
+namespace echo
+{
+
+void set_error(const std::string& message);
+bool check_cuda(cudaError_t status, const char* what);
+
+// smallest compiled traversal stack that holds the reference's `maxDepth * 3 + 1` entries (QuadBoundingVolumeHierarchy.cs:34)
+int stack_class(uint32_t maxDepth); // 0: 48, 1: 96, 2: 192 entries, -1: unsupported
+
+// ---- trace.cu ----
+// all launches are asynchronous on `stream`; counts (optional) receives 3 x uint64 totals {nodes, triangles, spheres}
+bool launch_trace(const DeviceScene& scene, const EchoRay* rays, uint64_t n, EchoHit* hits, unsigned long long* counts, cudaStream_t stream);
+bool launch_occlude(const DeviceScene& scene, const EchoRay* rays, uint64_t n, uint8_t* occluded, unsigned long long* counts, cudaStream_t stream);
+
+// ---- render.cu ----
+struct RenderState; // wavefront buffers, owned per scene
+
+RenderState* render_state_create();
+void render_state_destroy(RenderState* state);
+
+// Renders `tileCount` tiles. When `frame` is non-null the per-pixel means are ADDED into the full-frame device buffer
+// (xyz = mean * epochs rendered, w += epochs) for multi-device sample/tile sharding; when `tilesOut` is non-null the
+// tile-major Float4 means are written there (device pointer). Synchronises `stream` internally between wavefront steps.
+bool render_tiles(RenderState* state, const DeviceScene& scene, const EchoRenderParams& params, const int32_t* tileXY, uint32_t tileCount,
+                  float4* tilesOut, float4* frame, EchoStats* stats, cudaStream_t stream);
+
+bool launch_frame_resolve(float4* frame, int32_t width, int32_t height, cudaStream_t stream);
+
+// ---- debug.cu: device mirrors of the oracle's known-answer hooks ----
+bool launch_debug_bxdf(int32_t kind, const float* params, const float* outgoing, const float* samples, uint64_t n,
+                       float* sampled8, float* evaluated4, float* inverse4, cudaStream_t stream);
+bool launch_debug_math(int32_t op, const float* a, const float* b, const float* c, uint64_t n, float* out, cudaStream_t stream);
+
+} // namespace echo
+
+struct EchoScene
+{
+	int device = 0;
+	bool committed = false;
+	cudaStream_t stream = nullptr;
+
+	// host staging until commit
+	std::vector<EchoQbvhNode> nodes;
+	uint32_t maxDepth = 0;
+	std::vector<EchoTriangle> triangles;
+	std::vector<EchoSphere> spheres;
+	std::vector<EchoMaterial> materials;
+	std::vector<EchoLightNode> lightNodes;
+	std::vector<uint32_t> emitterTokens;
+	std::vector<uint64_t> emitterPaths;
+	std::vector<EchoPointLight> pointLights;
+	std::vector<EchoInfiniteLight> infiniteLights;
+	float infiniteThreshold = 0.0f, infinitePdf = 0.0f;
+	EchoCamera camera = {};
+
+	// device
+	echo::DeviceScene d = {};
+	std::vector<void*> allocations;
+
+	// scratch for the host-buffer batch calls (grown on demand)
+	void* scratchRays[2] = { nullptr, nullptr };
+	void* scratchOut[2] = { nullptr, nullptr };
+	uint64_t scratchCapacity = 0; // rays per chunk buffer
+	cudaStream_t copyStreams[2] = { nullptr, nullptr };
+	cudaEvent_t chunkDone[2] = { nullptr, nullptr };
+
+	echo::RenderState* render = nullptr;
+};

@@ -1,0 +1,1392 @@
+// render.cu — the wavefront path tracer behind echo_b200_render_tiles: one EvaluationOperation worth of tiles
+// (Processes/Evaluation/EvaluationOperation.cs:83-148) evaluated by PathTracedEvaluator.Evaluate
+// (Evaluation/Evaluators/PathTracedEvaluator.cs:43-207) re-organised as kernels over SoA path state:
+//
+//   raygen  ->  [ extend (QBVH closest hit, classifies the hit by material into per-class queues)
+//                 shade<class> (emission + MIS bookkeeping, BSDF sample, light pick/sample, shadow-ray emit, RR)
+//                 shadow (QBVH occlusion, adds the pending NEE contribution) ]*  ->  accumulate (Kahan-Welford per pixel)
+//
+// Every path keeps the reference's draw order of random numbers and its order of floating-point accumulation, so a
+// sample's radiance is bit-identical to the oracle's. Queue management uses warp-aggregated atomics (ballot + popc).
+#include <algorithm>
+
+#include "echo_internal.h"
+#include "echo_shading.cuh"
+
+namespace echo
+{
+
+constexpr int kBlock = 128;
+
+enum PathMode : uint32_t { MODE_FIRST = 0, MODE_NO_MIS = 1, MODE_MIS = 2 };
+enum ShadeClass : int { CLASS_MISS = 0, CLASS_DIFFUSE = 1, CLASS_DIELECTRIC = 2, CLASS_CONDUCTOR = 3, CLASS_TERMINAL = 4, CLASS_COUNT = 5 };
+
+// counter slots in RenderState::counters
+enum : int { COUNTER_NEXT = 0, COUNTER_SHADOW = 1, COUNTER_CLASS = 2, COUNTER_PIXELS = COUNTER_CLASS + CLASS_COUNT, COUNTER_TOTAL = COUNTER_PIXELS + 1 };
+
+struct PathBuffers
+{
+	float4* rayOrigin;    // xyz
+	float4* rayDirection; // xyz, w = ignore token bits
+	float4* hit;          // token bits, distance, uv
+	float4* energy;       // rgb, w = scatterPdf of the bounce that spawned the current ray (MIS)
+	float4* result;       // rgb, w = bits: bounces done | mode << 16
+	float4* oldPosition;  // MIS: GeometryPoint oldPoint
+	float4* oldNormal;
+	uint32_t* key;        // sample_key(seed, pixel, sample)
+
+	float4* shadowOrigin;    // xyz, w = travel
+	float4* shadowDirection; // xyz, w = ignore token bits
+	float4* shadowValue;     // pending energy * radiant, w = path id bits
+
+	uint32_t* queue[2];
+	uint32_t* classQueue[CLASS_COUNT];
+	uint32_t* counters;
+	unsigned long long* stats; // EchoStats layout
+};
+
+struct RenderState
+{
+	uint64_t capacity = 0;
+	PathBuffers paths = {};
+	std::vector<void*> allocations;
+
+	int2* pixelXY = nullptr;        // per path slot
+	uint32_t* sampleIndex = nullptr;
+	float4* sampleOut = nullptr;    // per path slot radiance
+
+	// per-pixel accumulators of the current tile batch
+	uint64_t pixelCapacity = 0;
+	float4* accumulator = nullptr;  // 4 x float4 per pixel: average total/error, squared total/error
+	uint32_t* sampleCount = nullptr;
+	uint32_t* activePixels[2] = { nullptr, nullptr };
+	int2* batchPixelXY = nullptr;
+	int32_t* tileXYDevice = nullptr;
+	uint64_t tileCapacity = 0;
+
+	uint32_t* hostCounters = nullptr; // pinned
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------------------------------------------
+
+// warp-aggregated append: one atomic per warp (ballot + popc + shuffle)
+ECHO_DEVICE uint32_t queue_slot(uint32_t* counter, bool predicate)
+{
+	uint32_t mask = __ballot_sync(0xFFFFFFFFu, predicate);
+	if (mask == 0u) return 0u;
+
+	uint32_t lane = threadIdx.x & 31u;
+	int leader = __ffs(mask) - 1;
+	uint32_t base = 0u;
+	if ((int)lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
+	base = __shfl_sync(0xFFFFFFFFu, base, leader);
+	return base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+}
+
+ECHO_DEVICE void stat_add(unsigned long long* stats, int slot, bool predicate)
+{
+	uint32_t mask = __ballot_sync(0xFFFFFFFFu, predicate);
+	if (mask != 0u && (threadIdx.x & 31u) == (uint32_t)(__ffs(mask) - 1)) atomicAdd(stats + slot, (unsigned long long)__popc(mask));
+}
+
+// EchoStats slots
+enum : int
+{
+	STAT_SAMPLE_EVALUATED = 0, STAT_SAMPLE_REJECTED, STAT_PIXEL_EVALUATED, STAT_BOUNCE_CREATED, STAT_BOUNCE_SPECULAR, STAT_BOUNCE_MIS,
+	STAT_LIGHT_SAMPLED, STAT_LIGHT_OCCLUSION_CHECKED, STAT_LIGHT_OCCLUSION_PASSED, STAT_LIGHT_EVALUATED_INFINITE,
+	STAT_TRACE_QUERIES, STAT_OCCLUDE_QUERIES, STAT_KERNEL_LAUNCHES, STAT_COUNT = 16
+};
+
+ECHO_DEVICE vec3 xyz(float4 v) { return { v.x, v.y, v.z }; }
+ECHO_DEVICE rgb as_rgb(float4 v) { return { v.x, v.y, v.z }; }
+ECHO_DEVICE float4 make4(vec3 v, float w) { return make_float4(v.x, v.y, v.z, w); }
+ECHO_DEVICE float4 make4(rgb v, float w) { return make_float4(v.r, v.g, v.b, w); }
+
+ECHO_DEVICE uint32_t token_light_type(uint32_t token) { return token_index(token) >> ECHO_LIGHT_INDEX_BITS; }
+ECHO_DEVICE uint32_t token_light_index(uint32_t token) { return token & ((1u << ECHO_LIGHT_INDEX_BITS) - 1u); }
+ECHO_DEVICE bool token_is_raw_geometry(uint32_t token) { uint32_t t = token_type(token); return t == ECHO_TOKEN_TYPE_TRIANGLE || t == ECHO_TOKEN_TYPE_SPHERE; }
+
+ECHO_DEVICE bool token_is_infinite_light(uint32_t token) // EntityToken.cs:194-202
+{
+	if (token_type(token) != ECHO_TOKEN_TYPE_LIGHT) return false;
+	return token_light_type(token) <= ECHO_LIGHT_TYPE_INFINITE_DELTA;
+}
+
+ECHO_DEVICE bool token_is_area_light(uint32_t token) // EntityToken.cs:187-192
+{
+	if (token_is_raw_geometry(token)) return true;
+	if (token_type(token) != ECHO_TOKEN_TYPE_LIGHT) return false;
+	return token_light_type(token) == ECHO_LIGHT_TYPE_INFINITE;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// geometry records
+// ---------------------------------------------------------------------------------------------------------------------
+
+struct TriangleData
+{
+	vec3 vertex0, edge1, edge2, normal0, normal1, normal2;
+	uint32_t material;
+};
+
+ECHO_DEVICE TriangleData load_triangle(const DeviceScene& scene, uint32_t index)
+{
+	const float4* hot = scene.triHot + (size_t)index * 3;
+	const float4* shade = scene.triShade + (size_t)index * 3;
+	float4 a = __ldg(hot), b = __ldg(hot + 1), c = __ldg(hot + 2);
+	float4 d = __ldg(shade), e = __ldg(shade + 1), f = __ldg(shade + 2);
+	return { xyz(a), xyz(b), xyz(c), xyz(d), xyz(e), xyz(f), __float_as_uint(d.w) };
+}
+
+ECHO_DEVICE vec3 triangle_normal(const TriangleData& t) { return normalized(cross(t.edge1, t.edge2)); }           // TriangleEntity.cs:136
+ECHO_DEVICE float triangle_area(const TriangleData& t) { return div(magnitude(cross(t.edge1, t.edge2)), 2.0f); }  // TriangleEntity.cs:148
+
+ECHO_DEVICE vec3 triangle_shading_normal(const TriangleData& t, vec2 uv) // TriangleEntity.cs:187
+{
+	return normalized((1.0f - uv.x - uv.y) * t.normal0 + uv.x * t.normal1 + uv.y * t.normal2);
+}
+
+ECHO_DEVICE vec3 triangle_point(const TriangleData& t, vec2 uv) { return t.vertex0 + uv.x * t.edge1 + uv.y * t.edge2; } // TriangleEntity.cs:265
+
+ECHO_DEVICE vec3 sphere_normal(vec2 uv) // SphereEntity.cs:229-234,252-266
+{
+	float sinT = uv.x, sinP = uv.y, sign = 1.0f;
+
+	if (sinT > 1.5f)
+	{
+		sinT -= 3.0f;
+		sign = -1.0f;
+	}
+
+	float cosT = identity(sinT) * sign;
+	float cosP = identity(sinP);
+	return normalized(vec3{ sinT * cosP, sinP, cosT * cosP });
+}
+
+ECHO_DEVICE float sphere_area(float radius) { return 4.0f * kPi * radius * radius; } // SphereEntity.cs:72
+
+struct SurfacePoint // GeometryPoint
+{
+	vec3 position, normal;
+};
+
+ECHO_DEVICE float geometry_point_pdf(const SurfacePoint& point, vec3 origin, float area) // GeometryPoint.cs:28-39
+{
+	vec3 delta = point.position - origin;
+	float length2 = squared_magnitude(delta);
+	float length = sqrt0(length2);
+
+	float d = abs_bits(dot(point.normal, delta));
+	if (!positive(d)) return 0.0f;
+	return div(length2 * length, d * area);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// light tree (Aggregation/Selection/LightTree.cs, Aggregation/Bounds/LightBound.cs)
+// ---------------------------------------------------------------------------------------------------------------------
+
+struct LightNode
+{
+	vec3 boxMin, boxMax, coneAxis;
+	float cosOffset, cosExtend, power;
+	uint32_t child0, child1;
+};
+
+ECHO_DEVICE LightNode load_light_node(const DeviceScene& scene, uint32_t index)
+{
+	const float4* p = scene.lightNodes + (size_t)index * 4;
+	float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
+	LightNode n;
+	n.boxMin = { a.x, a.y, a.z };
+	n.boxMax = { a.w, b.x, b.y };
+	n.coneAxis = { b.z, b.w, c.x };
+	n.cosOffset = c.y;
+	n.cosExtend = c.z;
+	n.power = c.w;
+	n.child0 = __float_as_uint(d.x);
+	n.child1 = __float_as_uint(d.y);
+	return n;
+}
+
+ECHO_DEVICE float clamp_subtract_cos(float sin0, float cos0, float sin1, float cos1) { return cos0 > cos1 ? 1.0f : cos0 * cos1 + sin0 * sin1; } // LightBound.cs:79
+ECHO_DEVICE float clamp_subtract_sin(float sin0, float cos0, float sin1, float cos1) { return cos0 > cos1 ? 0.0f : sin0 * cos1 - cos0 * sin1; } // LightBound.cs:80
+
+ECHO_DEVICE float light_importance(const LightNode& bound, const SurfacePoint& origin) // LightBound.cs:30-60
+{
+	vec3 center = (bound.boxMax + bound.boxMin) / 2.0f;
+	vec3 incident = origin.position - center;
+
+	float length2 = squared_magnitude(incident);
+
+	if (almost_zero(length2)) incident = { 0.0f, 0.0f, 0.0f };
+	else incident = incident * sqrt_r0(length2);
+
+	float cosAxis = dot(bound.coneAxis, incident);
+	float sinAxis = identity(cosAxis);
+
+	float cosOffset = bound.cosOffset;
+	float sinOffset = identity(cosOffset);
+
+	float sinRadius, cosRadius; // FindSubtendedAngles, :62-77
+	vec3 size = bound.boxMax - bound.boxMin;
+	float radius2 = div(squared_magnitude(size), 4.0f);
+
+	if (length2 < radius2)
+	{
+		sinRadius = 0.0f;
+		cosRadius = -1.0f;
+	}
+	else
+	{
+		float sinRadius2 = div(radius2, length2);
+		sinRadius = sqrt0(sinRadius2);
+		cosRadius = sqrt0(1.0f - sinRadius2);
+	}
+
+	float cosRemain = clamp_subtract_cos(sinAxis, cosAxis, sinOffset, cosOffset);
+	float sinRemain = clamp_subtract_sin(sinAxis, cosAxis, sinOffset, cosOffset);
+	float cosFinal = clamp_subtract_cos(sinRemain, cosRemain, sinRadius, cosRadius);
+	if (cosFinal <= bound.cosExtend) return 0.0f;
+
+	float cosIncident = abs_bits(dot(origin.normal, incident));
+	float sinIncident = identity(cosIncident);
+	float cosReflect = clamp_subtract_cos(sinIncident, cosIncident, sinRadius, cosRadius);
+
+	length2 = max_net(length2, div(magnitude(size), 2.0f));
+	return max0(div(bound.power, length2) * cosFinal * cosReflect);
+}
+
+// LightTree.Pick, LightTree.cs:115-134 (tail recursion as a loop). Returns the token; pdf == 0 means impossible.
+ECHO_DEVICE uint32_t light_tree_pick(const DeviceScene& scene, const SurfacePoint& origin, float sample, float& outPdf)
+{
+	outPdf = 0.0f;
+	if (scene.lightNodeCount == 0u) return ECHO_TOKEN_EMPTY;
+
+	LightNode node = load_light_node(scene, 0u);
+	float pdf = 1.0f;
+
+	while (true)
+	{
+		if (node.child0 == ECHO_TOKEN_EMPTY)
+		{
+			outPdf = pdf;
+			return node.child1;
+		}
+
+		LightNode left = load_light_node(scene, node.child0);
+		LightNode right = load_light_node(scene, node.child1);
+		float importance0 = light_importance(left, origin);
+		float importance1 = light_importance(right, origin);
+
+		if (!positive(importance0) && !positive(importance1)) return ECHO_TOKEN_EMPTY;
+
+		float split = div(importance0, importance0 + importance1);
+
+		if (sample < split)
+		{
+			sample = sample_stretch(sample, 0.0f, split);
+			node = left;
+			pdf = pdf * split;
+		}
+		else
+		{
+			sample = sample_stretch(sample, split, 1.0f);
+			node = right;
+			pdf = pdf * (1.0f - split);
+		}
+	}
+}
+
+// LightTree.ProbabilityMass, LightTree.cs:53-57,136-154: the recursion multiplies split factors from the leaf upward,
+// so the factors of the root-to-leaf walk are kept and folded right to left.
+ECHO_DEVICE float light_tree_mass(const DeviceScene& scene, uint32_t token, const SurfacePoint& origin)
+{
+	// map.TryGetValue: binary search over the sorted emitter tokens
+	int low = 0, high = (int)scene.emitterCount - 1, found = -1;
+
+	while (low <= high)
+	{
+		int middle = (low + high) >> 1;
+		uint32_t value = __ldg(scene.emitterTokens + middle);
+		if (value == token) { found = middle; break; }
+		if (value < token) low = middle + 1;
+		else high = middle - 1;
+	}
+
+	if (found < 0) return 0.0f;
+	unsigned long long branches = __ldg(scene.emitterPaths + found);
+
+	float factors[64];
+	int depth = 0;
+	LightNode node = load_light_node(scene, 0u);
+
+	while (node.child0 != ECHO_TOKEN_EMPTY && depth < 64)
+	{
+		LightNode left = load_light_node(scene, node.child0);
+		LightNode right = load_light_node(scene, node.child1);
+		float importance0 = light_importance(left, origin);
+		float importance1 = light_importance(right, origin);
+		float split = div(importance0, importance0 + importance1);
+
+		if ((branches & 1ull) == 0ull)
+		{
+			factors[depth++] = split;
+			node = left;
+		}
+		else
+		{
+			factors[depth++] = 1.0f - split;
+			node = right;
+		}
+
+		branches >>= 1;
+	}
+
+	float mass = 1.0f;
+	for (int i = depth - 1; i >= 0; i--) mass = factors[i] * mass;
+	return mass;
+}
+
+// PreparedScene.Pick, PreparedScene.cs:113-150
+ECHO_DEVICE uint32_t scene_pick(const DeviceScene& scene, const SurfacePoint& origin, float sample, float& outPdf)
+{
+	if (sample < scene.infiniteThreshold)
+	{
+		sample = sample_stretch(sample, 0.0f, scene.infiniteThreshold);
+		int index = sample_range(sample, (int)scene.infiniteLightCount);
+		outPdf = scene.infinitePdf;
+		return ECHO_LIGHT_TOKEN_MAKE(ECHO_LIGHT_TYPE_INFINITE, (uint32_t)index);
+	}
+
+	sample = sample_stretch(sample, scene.infiniteThreshold, 1.0f);
+	float pdf = 1.0f - scene.infiniteThreshold;
+
+	float tokenPdf;
+	uint32_t token = light_tree_pick(scene, origin, sample, tokenPdf);
+
+	if (almost_zero(tokenPdf))
+	{
+		outPdf = 0.0f;
+		return ECHO_TOKEN_EMPTY;
+	}
+
+	outPdf = pdf * tokenPdf;
+	return token;
+}
+
+// PreparedScene.ProbabilityMass, PreparedScene.cs:158-179
+ECHO_DEVICE float scene_probability_mass(const DeviceScene& scene, uint32_t light, const SurfacePoint& origin)
+{
+	if (token_is_infinite_light(light)) return scene.infinitePdf;
+	float pdf = 1.0f - scene.infiniteThreshold;
+	return pdf * light_tree_mass(scene, light, origin);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// light sampling (Aggregation/Preparation/LightCollection.cs, TriangleEntity.cs:166-185, SphereEntity.cs:151-225)
+// ---------------------------------------------------------------------------------------------------------------------
+
+ECHO_DEVICE uint32_t geometry_material(const DeviceScene& scene, uint32_t token)
+{
+	if (token_type(token) == ECHO_TOKEN_TYPE_TRIANGLE) return __float_as_uint(__ldg(scene.triShade + (size_t)token_index(token) * 3).w);
+	return __ldg(scene.sphereMaterial + token_index(token));
+}
+
+ECHO_DEVICE bool geometry_sample(const DeviceScene& scene, uint32_t token, vec3 origin, vec2 sample, SurfacePoint& point, float& pdf)
+{
+	if (token_type(token) == ECHO_TOKEN_TYPE_TRIANGLE)
+	{
+		TriangleData triangle = load_triangle(scene, token_index(token));
+		vec2 uv = uniform_triangle(sample);
+		point.position = triangle_point(triangle, uv);
+		point.normal = triangle_shading_normal(triangle, uv);
+		pdf = geometry_point_pdf(point, origin, triangle_area(triangle));
+		return true;
+	}
+
+	float4 sphere = __ldg(scene.spheres + token_index(token));
+	vec3 position = { sphere.x, sphere.y, sphere.z };
+	float radius = sphere.w;
+
+	vec3 offset = origin - position;
+	float radius2 = radius * radius;
+	float length2 = squared_magnitude(offset);
+
+	if (length2 < radius2)
+	{
+		vec3 normal = uniform_sphere(sample);
+		point = { normal * radius + position, normal }; // GetPoint, SphereEntity.cs:227
+		pdf = geometry_point_pdf(point, origin, sphere_area(radius));
+		return true;
+	}
+
+	float sinMaxT2 = div(radius2, length2);
+	float cosMaxT = sqrt0(1.0f - sinMaxT2);
+
+	if (almost_zero(1.0f - cosMaxT))
+	{
+		pdf = 0.0f;
+		return false;
+	}
+
+	float cosT = fma_f(cosMaxT - 1.0f, sample.x, 1.0f);
+	float sinT = identity(cosT);
+	float phi = sample.y * kTau;
+
+	float length = sqrt0(length2);
+	float project = length * cosT - sqrt0(radius2 - length2 * sinT * sinT);
+	float cosA = div(length2 + radius2 - project * project, 2.0f * length * radius);
+	float sinA = identity(cosA);
+
+	float sinP, cosP;
+	sincos_det(phi, sinP, cosP);
+	vec3 normal = normalized(vec3{ sinA * cosP, sinA * sinP, cosA });
+	pdf = uniform_cone_pdf(cosMaxT);
+
+	frame transform = make_frame(offset / length);
+	vec3 world = apply_forward(transform, normal);
+	point = { world * radius + position, world };
+	return true;
+}
+
+ECHO_DEVICE float geometry_pdf(const DeviceScene& scene, uint32_t token, vec3 origin, vec3 incident)
+{
+	if (token_type(token) == ECHO_TOKEN_TYPE_TRIANGLE)
+	{
+		TriangleData triangle = load_triangle(scene, token_index(token));
+		vec2 uv = { 0.0f, 0.0f };
+		float distance = triangle_intersect(triangle.vertex0, triangle.edge1, triangle.edge2, origin, incident, uv);
+		if (distance == kInfinity) return 0.0f;
+		return div(distance * distance, abs_bits(dot(triangle_shading_normal(triangle, uv), incident) * triangle_area(triangle)));
+	}
+
+	float4 sphere = __ldg(scene.spheres + token_index(token));
+	float radius = sphere.w;
+	vec3 offset = origin - vec3{ sphere.x, sphere.y, sphere.z };
+	float radius2 = radius * radius;
+	float length2 = squared_magnitude(offset);
+
+	if (length2 <= radius2)
+	{
+		float projected = dot(offset, incident);
+		float extend2 = fma_f(projected, projected, radius2 - length2);
+
+		float distance = sqrt0(extend2) - projected;
+		vec3 normal = offset + incident * distance;
+
+		float cosWeight = dot(incident, normal) * radius;
+		if (almost_zero(cosWeight)) return 0.0f;
+
+		return div(distance * distance, abs_bits(cosWeight)) * kUniformSpherePdf;
+	}
+
+	float sinMaxT2 = div(radius2, length2);
+	float cosMaxT = sqrt0(1.0f - sinMaxT2);
+	return almost_zero(1.0f - cosMaxT) ? 0.0f : uniform_cone_pdf(cosMaxT);
+}
+
+// PreparedScene.Sample, PreparedScene.cs:182-204 -> LightCollection.Sample (:141-193) / PointLight.cs:48-66 / AmbientLight.cs:60-67
+ECHO_DEVICE Sampled scene_sample_light(const DeviceScene& scene, uint32_t light, const SurfacePoint& origin, vec2 sample, vec3& incident, float& travel)
+{
+	incident = { 0.0f, 0.0f, 0.0f };
+	travel = 0.0f;
+
+	if (token_is_infinite_light(light))
+	{
+		float4 infinite = __ldg(scene.infiniteLights + token_light_index(light));
+		incident = uniform_sphere(sample); // IDirectionalTexture.Sample default, Textures/Directional/IDirectionalTexture.cs
+		travel = kInfinity;
+		return { as_rgb(infinite), kUniformSpherePdf };
+	}
+
+	if (token_type(light) == ECHO_TOKEN_TYPE_LIGHT)
+	{
+		const float4* p = scene.pointLights + (size_t)token_light_index(light) * 2;
+		float4 intensity = __ldg(p), position = __ldg(p + 1);
+		vec3 offset = xyz(position) - origin.position;
+		float travel2 = squared_magnitude(offset);
+
+		if (!positive(travel2)) return impossible();
+
+		travel = sqrt0(travel2);
+		float travelR = rcp(travel);
+		incident = offset * travelR;
+		return { as_rgb(intensity) * travelR * travelR, 1.0f };
+	}
+
+	MaterialRecord material = load_material(scene, geometry_material(scene, light));
+	if (material.type != ECHO_MATERIAL_EMISSIVE) return impossible();
+
+	SurfacePoint point;
+	float pdf;
+	if (!geometry_sample(scene, light, origin.position, sample, point, pdf)) return impossible();
+	if (!positive(pdf)) return impossible();
+
+	vec3 delta = point.position - origin.position;
+	float travel2 = squared_magnitude(delta);
+	if (!positive(travel2)) return impossible();
+
+	travel = sqrt0(travel2);
+	incident = delta * rcp(travel);
+	travel *= 1.0f - 2E-5f; // TravelMultiplier, LightCollection.cs:89
+
+	rgb emitted = dot(-incident, point.normal) > 0.0f ? material_emission(material) : make_rgb(0.0f); // Emissive.Emit, Emissive.cs:64
+	return { emitted, pdf };
+}
+
+// PreparedScene.ProbabilityDensity, PreparedScene.cs:207-225
+ECHO_DEVICE float scene_light_pdf(const DeviceScene& scene, uint32_t light, const SurfacePoint& origin, vec3 incident)
+{
+	if (token_is_infinite_light(light)) return kUniformSpherePdf;
+	if (token_type(light) == ECHO_TOKEN_TYPE_LIGHT) return 1.0f;
+	vec3 direction = normalized(identity_multiply_direction(incident));
+	return geometry_pdf(scene, light, origin.position, direction);
+}
+
+ECHO_DEVICE rgb evaluate_infinite(const DeviceScene& scene, bool direct) // PreparedScene.cs:233-253
+{
+	rgb total = make_rgb(0.0f);
+
+	for (uint32_t i = 0; i < scene.infiniteLightCount; i++)
+	{
+		float4 light = __ldg(scene.infiniteLights + i);
+		if (direct && __float_as_uint(light.w) == 0u) continue;
+		total = total + as_rgb(light);
+	}
+
+	return total;
+}
+
+ECHO_DEVICE float power_heuristic(float pdf0, float pdf1) // PathTracedEvaluator.cs:213-217
+{
+	float squared = pdf0 * pdf0;
+	return div(squared, squared + pdf1 * pdf1);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// camera (Scenic/Cameras/PerspectiveCamera.cs:51-98, RaySpawner.cs:19-46)
+// ---------------------------------------------------------------------------------------------------------------------
+
+ECHO_DEVICE vec3 camera_direction(const EchoCamera& c, vec3 d)
+{
+	const float* m = c.transform;
+	return { m[0] * d.x + m[1] * d.y + m[2] * d.z, m[4] * d.x + m[5] * d.y + m[6] * d.z, m[8] * d.x + m[9] * d.y + m[10] * d.z };
+}
+
+ECHO_DEVICE vec3 camera_point(const EchoCamera& c, vec3 p)
+{
+	const float* m = c.transform;
+	return { m[0] * p.x + m[1] * p.y + m[2] * p.z + m[3], m[4] * p.x + m[5] * p.y + m[6] * p.z + m[7], m[8] * p.x + m[9] * p.y + m[10] * p.z + m[11] };
+}
+
+ECHO_DEVICE void camera_spawn(const EchoCamera& camera, int width, int height, int px, int py, vec2 shift, vec2 lens, vec3& origin, vec3& direction)
+{
+	float sizeRX = rcp((float)width);                       // TextureGrid.cs:22
+	float offsetY = div(div((float)height, (float)width), -2.0f); // aspects.Y / -2, RaySpawner.cs:22
+	float sx = shift.x + (float)px, sy = shift.y + (float)py;
+	vec2 uv = { fma_f(sx, sizeRX, 1.0f / -2.0f), fma_f(sy, sizeRX, offsetY) }; // SpawnX, RaySpawner.cs:37-46
+
+	bool hasDepthOfField = positive(camera.lensRadius) && positive(camera.focalDistance);
+
+	if (!hasDepthOfField)
+	{
+		origin = { camera.transform[3], camera.transform[7], camera.transform[11] };
+		direction = normalized(camera_direction(camera, vec3{ uv.x, uv.y, camera.forwardLength }));
+		return;
+	}
+
+	float focusScale = div(camera.focalDistance, camera.forwardLength);
+	vec2 disk = concentric_disk(lens);
+	vec3 lensPoint = { disk.x * camera.lensRadius, disk.y * camera.lensRadius, 0.0f };
+	vec3 focus = { uv.x * focusScale, uv.y * focusScale, camera.focalDistance };
+
+	origin = camera_point(camera, lensPoint);
+	direction = normalized(camera_direction(camera, focus - lensPoint));
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(kBlock) raygen_kernel(DeviceScene scene, EchoRenderParams params, uint32_t count, const int2* __restrict__ pixelXY,
+                                                       const uint32_t* __restrict__ sampleIndex, PathBuffers paths)
+{
+	uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+	if (i >= count) return;
+
+	int2 pixel = pixelXY[i];
+	uint32_t key = sample_key(params.seed, (uint32_t)pixel.y * (uint32_t)params.width + (uint32_t)pixel.x, sampleIndex[i]);
+
+	vec2 shift = { sample_value(key, 0u), sample_value(key, 1u) }; // CameraSample.Create, CameraSample.cs:19-23
+	vec2 lens = { sample_value(key, 2u), sample_value(key, 3u) };
+
+	vec3 origin, direction;
+	camera_spawn(scene.camera, params.width, params.height, pixel.x, pixel.y, shift, lens, origin, direction);
+
+	paths.rayOrigin[i] = make4(origin, 0.0f);
+	paths.rayDirection[i] = make4(direction, __uint_as_float(ECHO_TOKEN_EMPTY));
+	paths.energy[i] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+	paths.result[i] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(MODE_FIRST << 16));
+	paths.key[i] = key;
+	paths.queue[0][i] = i;
+}
+
+ECHO_DEVICE int classify_material(const DeviceScene& scene, uint32_t materialIndex)
+{
+	const float4* p = scene.materials + (size_t)materialIndex * 4;
+	uint32_t type = __float_as_uint(__ldg(p).x);
+
+	for (int level = 0; level < 4 && type == ECHO_MATERIAL_ONESIDED; level++)
+	{
+		uint32_t base = __float_as_uint(__ldg(p + 3).w);
+		p = scene.materials + (size_t)base * 4;
+		type = __float_as_uint(__ldg(p).x);
+	}
+
+	switch (type)
+	{
+		case ECHO_MATERIAL_DIFFUSE: return CLASS_DIFFUSE;
+		case ECHO_MATERIAL_DIELECTRIC: return CLASS_DIELECTRIC;
+		case ECHO_MATERIAL_CONDUCTOR: return CLASS_CONDUCTOR;
+		default: return CLASS_TERMINAL;
+	}
+}
+
+// Path.Advance's scene.Trace (PathTracedEvaluator.cs:261-271 -> PreparedScene.cs:66-75), then the material-class sort
+template<int STACK>
+__global__ void __launch_bounds__(kBlock) extend_kernel(DeviceScene scene, const uint32_t* __restrict__ queue, const uint32_t* __restrict__ queueCount, PathBuffers paths)
+{
+	uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+	bool active = i < *queueCount;
+	int shadeClass = -1;
+	uint32_t id = 0u;
+
+	if (active)
+	{
+		id = queue[i];
+		float4 o = paths.rayOrigin[id], d = paths.rayDirection[id];
+
+		float distance = kInfinity;
+		uint32_t token = ECHO_TOKEN_EMPTY;
+		vec2 uv = { 0.0f, 0.0f };
+
+		bool hit = scene_trace<STACK, false>(scene, xyz(o), xyz(d), __float_as_uint(d.w), distance, token, uv, nullptr);
+		paths.hit[id] = make_float4(__uint_as_float(hit ? token : ECHO_TOKEN_EMPTY), distance, uv.x, uv.y);
+
+		shadeClass = hit ? classify_material(scene, geometry_material(scene, token)) : CLASS_MISS;
+	}
+
+	stat_add(paths.stats, STAT_TRACE_QUERIES, active);
+
+#pragma unroll
+	for (int c = 0; c < CLASS_COUNT; c++)
+	{
+		bool mine = shadeClass == c;
+		uint32_t slot = queue_slot(paths.counters + COUNTER_CLASS + c, mine);
+		if (mine) paths.classQueue[c][slot] = id;
+	}
+}
+
+// One loop body of PathTracedEvaluator.Evaluate for every path in a material-class queue.
+template<int CLASS, uint32_t KINDS>
+__global__ void __launch_bounds__(kBlock) shade_kernel(DeviceScene scene, EchoRenderParams params, const uint32_t* __restrict__ queue,
+                                                      const uint32_t* __restrict__ queueCount, PathBuffers paths, uint32_t* __restrict__ nextQueue)
+{
+	uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+	bool active = i < *queueCount;
+
+	bool statInfinite = false, statBounce = false, statSpecular = false, statMis = false;
+	bool statSampled = false, statChecked = false;
+	bool survive = false, shadow = false;
+	uint32_t id = 0u;
+
+	float4 nextOrigin = make_float4(0, 0, 0, 0), nextDirection = make_float4(0, 0, 0, 0), nextEnergy = make_float4(0, 0, 0, 0);
+	float4 shadowOrigin = make_float4(0, 0, 0, 0), shadowDirection = make_float4(0, 0, 0, 0), shadowValue = make_float4(0, 0, 0, 0);
+
+	if (active)
+	{
+		id = queue[i];
+
+		float4 rayD = paths.rayDirection[id];
+		float4 energy4 = paths.energy[id];
+		float4 result4 = paths.result[id];
+
+		vec3 direction = xyz(rayD);
+		rgb energy = as_rgb(energy4);
+		rgb result = as_rgb(result4);
+		float scatterPdfPrevious = energy4.w;
+		uint32_t state = __float_as_uint(result4.w);
+		uint32_t bounces = state & 0xFFFFu, mode = state >> 16;
+
+		if (CLASS == CLASS_MISS)
+		{
+			// no intersection: PathTracedEvaluator.cs:48-52 (first), :112-130 (MIS), :137-143 (fallback)
+			statInfinite = true;
+
+			if (mode == MODE_FIRST) result = evaluate_infinite(scene, true);
+			else if (mode == MODE_NO_MIS) result = result + energy * evaluate_infinite(scene, false);
+			else
+			{
+				SurfacePoint oldPoint = { xyz(paths.oldPosition[id]), xyz(paths.oldNormal[id]) };
+				(void)oldPoint;
+
+				for (uint32_t light = 0; light < scene.infiniteLightCount; light++)
+				{
+					float pdf = scene.infinitePdf * kUniformSpherePdf; // ProbabilityMass * light.ProbabilityDensity, :122-123
+					if (!positive(pdf)) continue;
+					float weight = power_heuristic(scatterPdfPrevious, pdf);
+					result = result + energy * (as_rgb(__ldg(scene.infiniteLights + light)) * weight);
+				}
+			}
+
+			paths.result[id] = make4(result, result4.w);
+		}
+		else
+		{
+			// ---- PreparedScene.Interact, PreparedScene.cs:95-105 + GeometryCollection.GetContactInfo (:200-232) ----
+			float4 hit4 = paths.hit[id];
+			uint32_t token = __float_as_uint(hit4.x);
+			float distance = hit4.y;
+			vec2 uv = { hit4.z, hit4.w };
+			vec3 rayOrigin = xyz(paths.rayOrigin[id]);
+
+			vec3 infoNormal, infoShading;
+			uint32_t materialIndex;
+
+			if (token_type(token) == ECHO_TOKEN_TYPE_TRIANGLE)
+			{
+				TriangleData triangle = load_triangle(scene, token_index(token));
+				materialIndex = triangle.material;
+				infoNormal = triangle_normal(triangle);
+				infoShading = triangle_shading_normal(triangle, uv);
+			}
+			else
+			{
+				materialIndex = __ldg(scene.sphereMaterial + token_index(token));
+				infoNormal = infoShading = sphere_normal(uv);
+			}
+
+			SurfacePoint point;
+			point.position = direction * max_net(distance, kEpsilon) + rayOrigin; // TraceQuery.Position, TraceQuery.cs:76-82
+			point.normal = normalized(identity_multiply_direction(infoNormal));
+			vec3 shadeNormal = normalized(identity_multiply_direction(infoShading));
+			vec3 outgoing = -direction;
+
+			MaterialRecord material = load_material(scene, materialIndex);
+			Bsdf bsdf;
+			material_scatter(scene, material, outgoing, point.normal, shadeNormal, bsdf);
+
+			// ---- emission of the new vertex: ContributeEmissive (:305-311), MIS-weighted after a MIS bounce (:96-109) ----
+			if (CLASS == CLASS_TERMINAL && material.type == ECHO_MATERIAL_EMISSIVE && positive(emissive_power(material)))
+			{
+				float weight = 1.0f;
+				bool contribute = true;
+
+				if (mode == MODE_MIS)
+				{
+					SurfacePoint oldPoint = { xyz(paths.oldPosition[id]), xyz(paths.oldNormal[id]) };
+					float pmf = scene_probability_mass(scene, token, oldPoint);
+					contribute = positive(pmf);
+
+					if (contribute)
+					{
+						float pdf = scene_light_pdf(scene, token, oldPoint, direction);
+						contribute = positive(pdf);
+						if (contribute) weight = power_heuristic(scatterPdfPrevious, pmf * pdf);
+					}
+				}
+
+				if (contribute)
+				{
+					rgb emitted = dot(outgoing, point.normal) > 0.0f ? material_emission(material) : make_rgb(0.0f);
+					result = result + energy * (emitted * weight);
+				}
+			}
+
+			// ---- the loop body: `for (int depth = 0; depth < BounceLimit; depth++)`, :57 ----
+			if (bounces < (uint32_t)params.bounceLimit)
+			{
+				uint32_t key = paths.key[id];
+				uint32_t dimension = 4u + 6u * bounces;
+				vec2 bounceSample = { sample_value(key, dimension), sample_value(key, dimension + 1u) };
+				float survivalSample = sample_value(key, dimension + 2u);
+				float lightSample = sample_value(key, dimension + 3u);
+				vec2 radiantSample = { sample_value(key, dimension + 4u), sample_value(key, dimension + 5u) };
+
+				// Bounce, :326-354
+				vec3 incident;
+				int selectedType;
+				Sampled bounced = bsdf_sample<KINDS>(bsdf, outgoing, bounceSample, incident, selectedType);
+				rgb scatter = bounced.content * abs_bits(dot(incident, shadeNormal));
+				float scatterPdf = bounced.pdf;
+				statBounce = true;
+
+				bool mis = false;
+
+				if (!positive(scatterPdf) || (selectedType & FT_SPECULAR)) statSpecular = true;
+				else
+				{
+					// ---- ImportanceSampleRadiant, :162-207 ----
+					float lightPdf;
+					uint32_t light = scene_pick(scene, point, lightSample, lightPdf);
+
+					if (positive(lightPdf))
+					{
+						vec3 lightIncident;
+						float travel;
+						Sampled radiantSampled = scene_sample_light(scene, light, point, radiantSample, lightIncident, travel);
+						rgb radiant = radiantSampled.content;
+
+						float pdf = lightPdf * radiantSampled.pdf;
+						mis = token_is_area_light(light);
+
+						if (positive(pdf) && !is_zero(radiant))
+						{
+							statSampled = true;
+
+							rgb lightScatter = bsdf_evaluate<KINDS>(bsdf, outgoing, lightIncident);
+							lightScatter = lightScatter * abs_bits(dot(lightIncident, shadeNormal));
+
+							if (!is_zero(lightScatter))
+							{
+								statChecked = true;
+
+								radiant = radiant * (lightScatter / pdf);
+								if (mis) radiant = radiant * power_heuristic(pdf, bsdf_pdf<KINDS>(bsdf, outgoing, lightIncident));
+
+								shadow = true;
+								shadowOrigin = make4(point.position, travel);
+								shadowDirection = make4(lightIncident, __uint_as_float(token));
+								shadowValue = make4(energy * radiant, __uint_as_float(id));
+							}
+						}
+					}
+				}
+
+				// ---- Path.Continue, :282-293 ----
+				if (positive(scatterPdf))
+				{
+					energy = energy * (scatter / scatterPdf);
+
+					float rate = clamp01(params.survivability * luminance(energy)); // RussianRoulette, :313-320
+
+					if (!(survivalSample >= rate))
+					{
+						energy = energy / rate;
+						survive = true;
+
+						if (mis && !statSpecular)
+						{
+							statMis = true;
+							paths.oldPosition[id] = make4(point.position, 0.0f);
+							paths.oldNormal[id] = make4(point.normal, 0.0f);
+						}
+
+						uint32_t nextMode = (mis && !statSpecular) ? MODE_MIS : MODE_NO_MIS;
+						nextOrigin = make4(point.position, 0.0f);
+						nextDirection = make4(incident, __uint_as_float(token)); // SpawnTrace: ignore = hit token, TraceQuery.cs:88
+						nextEnergy = make4(energy, scatterPdf);
+						result4.w = __uint_as_float((bounces + 1u) | (nextMode << 16));
+					}
+				}
+			}
+
+			paths.result[id] = make4(result, result4.w);
+
+			if (survive)
+			{
+				paths.rayOrigin[id] = nextOrigin;
+				paths.rayDirection[id] = nextDirection;
+				paths.energy[id] = nextEnergy;
+			}
+		}
+	}
+
+	uint32_t nextSlot = queue_slot(paths.counters + COUNTER_NEXT, survive);
+	if (survive) nextQueue[nextSlot] = id;
+
+	uint32_t shadowSlot = queue_slot(paths.counters + COUNTER_SHADOW, shadow);
+
+	if (shadow)
+	{
+		paths.shadowOrigin[shadowSlot] = shadowOrigin;
+		paths.shadowDirection[shadowSlot] = shadowDirection;
+		paths.shadowValue[shadowSlot] = shadowValue;
+	}
+
+	stat_add(paths.stats, STAT_LIGHT_EVALUATED_INFINITE, statInfinite);
+	stat_add(paths.stats, STAT_BOUNCE_CREATED, statBounce);
+	stat_add(paths.stats, STAT_BOUNCE_SPECULAR, statSpecular);
+	stat_add(paths.stats, STAT_BOUNCE_MIS, statMis);
+	stat_add(paths.stats, STAT_LIGHT_SAMPLED, statSampled);
+	stat_add(paths.stats, STAT_LIGHT_OCCLUSION_CHECKED, statChecked);
+}
+
+// scene.Occlude of ImportanceSampleRadiant (:196-197); unoccluded pending contributions go into Path.Result (:80-84)
+template<int STACK>
+__global__ void __launch_bounds__(kBlock) shadow_kernel(DeviceScene scene, const uint32_t* __restrict__ shadowCount, PathBuffers paths)
+{
+	uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+	bool active = i < *shadowCount;
+	bool passed = false;
+
+	if (active)
+	{
+		float4 o = paths.shadowOrigin[i], d = paths.shadowDirection[i];
+		bool occluded = scene_occlude<STACK, false>(scene, xyz(o), xyz(d), __float_as_uint(d.w), o.w, nullptr);
+		passed = !occluded;
+
+		if (passed)
+		{
+			float4 value = paths.shadowValue[i];
+			uint32_t id = __float_as_uint(value.w);
+			float4 result = paths.result[id];
+			result.x += value.x;
+			result.y += value.y;
+			result.z += value.z;
+			paths.result[id] = result;
+		}
+	}
+
+	stat_add(paths.stats, STAT_OCCLUDE_QUERIES, active);
+	stat_add(paths.stats, STAT_LIGHT_OCCLUSION_PASSED, passed);
+}
+
+__global__ void __launch_bounds__(kBlock) finish_kernel(uint32_t count, PathBuffers paths, float4* __restrict__ out)
+{
+	uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+	if (i >= count) return;
+	float4 result = paths.result[i];
+	out[i] = make_float4(result.x, result.y, result.z, 0.0f);
+}
+
+// iteration bookkeeping: the next-queue count becomes the active count, per-iteration counters are cleared
+__global__ void rotate_counters_kernel(uint32_t* counters, uint32_t* activeCount, uint32_t* hostMirror)
+{
+	*activeCount = counters[COUNTER_NEXT];
+	*hostMirror = counters[COUNTER_NEXT];
+	counters[COUNTER_NEXT] = 0u;
+	counters[COUNTER_SHADOW] = 0u;
+	for (int c = 0; c < CLASS_COUNT; c++) counters[COUNTER_CLASS + c] = 0u;
+}
+
+// ---- Kahan summation + Welford accumulation, Summation.cs:8-58 + Accumulator.cs:11-71 ----
+struct Sum4
+{
+	float4 total, error;
+};
+
+ECHO_DEVICE float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+ECHO_DEVICE float4 sub4(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+ECHO_DEVICE float4 mul4(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+ECHO_DEVICE float4 neg4(float4 a) { return make_float4(-a.x, -a.y, -a.z, -a.w); }
+
+ECHO_DEVICE Sum4 sum_add(Sum4 s, float4 value) // Summation.cs:31-38
+{
+	float4 delta = sub4(value, s.error);
+	float4 total = add4(s.total, delta);
+	float4 error = sub4(sub4(total, s.total), delta);
+	return { total, error };
+}
+
+ECHO_DEVICE Sum4 sum_add(Sum4 s, Sum4 value) // Summation.cs:42-51
+{
+	float4 error = add4(s.error, value.error);
+	float4 delta = sub4(value.total, error);
+	float4 total = add4(s.total, delta);
+	error = sub4(sub4(total, s.total), delta);
+	return { total, error };
+}
+
+ECHO_DEVICE Sum4 sum_scale(Sum4 s, float4 value) { return { mul4(s.total, value), mul4(s.error, value) }; } // Summation.cs:40
+ECHO_DEVICE Sum4 sum_negate(Sum4 s) { return { neg4(s.total), neg4(s.error) }; }
+
+// one thread per pixel walks its `extend` samples of this epoch in sample order (EvaluationOperation.cs:117-135)
+__global__ void __launch_bounds__(kBlock) accumulate_kernel(EchoRenderParams params, uint32_t pixelCount, const uint32_t* __restrict__ activePixels,
+                                                           const float4* __restrict__ samples, float4* __restrict__ accumulator, uint32_t* __restrict__ sampleCount,
+                                                           uint32_t epoch, uint32_t* __restrict__ nextActive, uint32_t* __restrict__ counters, unsigned long long* __restrict__ stats)
+{
+	uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+	bool valid = i < pixelCount;
+	bool again = false;
+	uint32_t rejected = 0u;
+	uint32_t pixel = 0u;
+
+	if (valid)
+	{
+		pixel = activePixels[i];
+		Sum4 average = { accumulator[pixel * 4u], accumulator[pixel * 4u + 1u] };
+		Sum4 squared = { accumulator[pixel * 4u + 2u], accumulator[pixel * 4u + 3u] };
+		uint32_t count = sampleCount[pixel];
+
+		for (int s = 0; s < params.extend; s++)
+		{
+			float4 sample = samples[(size_t)i * params.extend + s];
+			float sum = (sample.x + sample.y) + (sample.z + sample.w); // Float4.Sum
+
+			if (!isfinite(sum)) // Accumulator.Add gate, Accumulator.cs:57
+			{
+				++rejected;
+				continue;
+			}
+
+			++count;
+
+			Sum4 delta = sum_add(average, neg4(sample));                       // average - sample
+			float countR = rcp((float)count);
+			average = sum_add(average, sum_negate(sum_scale(delta, make_float4(countR, countR, countR, countR)))); // average -= delta / count
+			Sum4 after = sum_add(average, neg4(sample));
+			squared = sum_add(squared, sum_scale(delta, after.total));         // squared += delta * (average - sample).Result
+		}
+
+		accumulator[pixel * 4u] = average.total;
+		accumulator[pixel * 4u + 1u] = average.error;
+		accumulator[pixel * 4u + 2u] = squared.total;
+		accumulator[pixel * 4u + 3u] = squared.error;
+		sampleCount[pixel] = count;
+
+		// epoch loop condition, EvaluationOperation.cs:137; Accumulator.Noise (:28-51) with exact 1/x and 1/sqrt
+		if (epoch < (uint32_t)params.maxEpoch)
+		{
+			if (epoch < (uint32_t)params.minEpoch) again = true;
+			else if (count >= 2u)
+			{
+				float oneLess = (float)(count - 1u);
+				oneLess *= oneLess * oneLess;
+
+				float mean[4] = { average.total.x, average.total.y, average.total.z, average.total.w };
+				float m2[4] = { squared.total.x, squared.total.y, squared.total.z, squared.total.w };
+				float noiseMax = 0.0f;
+
+				for (int c = 0; c < 4; c++)
+				{
+					float numerator = mean[c] * mean[c] * oneLess;
+					float denominator = rcp(m2[c]);
+					float noise = numerator != 0.0f ? rcp(__fsqrt_rn(numerator * denominator)) : 0.0f;
+					if (c == 0 || noise > noiseMax) noiseMax = noise;
+				}
+
+				again = noiseMax > params.noiseThreshold;
+			}
+		}
+	}
+
+	uint32_t slot = queue_slot(counters + COUNTER_PIXELS, again);
+	if (again) nextActive[slot] = pixel;
+
+	if (valid)
+	{
+		atomicAdd(stats + STAT_SAMPLE_EVALUATED, (unsigned long long)params.extend);
+		if (rejected) atomicAdd(stats + STAT_SAMPLE_REJECTED, (unsigned long long)rejected);
+	}
+}
+
+// fills the per-slot (pixel, sample index) descriptors of one epoch from the active pixel list
+__global__ void __launch_bounds__(kBlock) epoch_slots_kernel(EchoRenderParams params, uint32_t pixelCount, const uint32_t* __restrict__ activePixels,
+                                                            const int2* __restrict__ batchPixelXY, uint32_t epoch, int2* __restrict__ pixelXY, uint32_t* __restrict__ sampleIndex)
+{
+	uint64_t i = (uint64_t)blockIdx.x * kBlock + threadIdx.x;
+	uint64_t total = (uint64_t)pixelCount * params.extend;
+	if (i >= total) return;
+
+	uint32_t p = (uint32_t)(i / params.extend), s = (uint32_t)(i % params.extend);
+	pixelXY[i] = batchPixelXY[activePixels[p]];
+	sampleIndex[i] = (uint32_t)(params.epochOffset + (int)epoch - 1) * (uint32_t)params.extend + s;
+}
+
+// lays out the pixels of a batch of tiles; pixels outside the image are not listed
+__global__ void __launch_bounds__(kBlock) batch_pixels_kernel(EchoRenderParams params, const int32_t* __restrict__ tileXY, uint32_t tileCount,
+                                                             int2* __restrict__ batchPixelXY, uint32_t* __restrict__ activePixels, uint32_t* __restrict__ counters,
+                                                             float4* __restrict__ accumulator, uint32_t* __restrict__ sampleCount)
+{
+	uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+	uint32_t perTile = (uint32_t)(params.tileSize * params.tileSize);
+	bool inside = false;
+
+	if (i < tileCount * perTile)
+	{
+		uint32_t tile = i / perTile, local = i % perTile;
+		int px = tileXY[tile * 2u] * params.tileSize + (int)(local % (uint32_t)params.tileSize);
+		int py = tileXY[tile * 2u + 1u] * params.tileSize + (int)(local / (uint32_t)params.tileSize);
+		inside = px < params.width && py < params.height;
+
+		batchPixelXY[i] = make_int2(px, py);
+		accumulator[i * 4u] = accumulator[i * 4u + 1u] = accumulator[i * 4u + 2u] = accumulator[i * 4u + 3u] = make_float4(0, 0, 0, 0);
+		sampleCount[i] = 0u;
+	}
+
+	uint32_t slot = queue_slot(counters + COUNTER_PIXELS, inside);
+	if (inside) activePixels[slot] = i;
+}
+
+__global__ void __launch_bounds__(kBlock) resolve_tiles_kernel(EchoRenderParams params, uint32_t pixelTotal, const int2* __restrict__ batchPixelXY,
+                                                              const float4* __restrict__ accumulator, float4* __restrict__ tilesOut, float4* __restrict__ frame,
+                                                              unsigned long long* __restrict__ stats)
+{
+	uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+	if (i >= pixelTotal) return;
+
+	int2 pixel = batchPixelXY[i];
+	bool inside = pixel.x < params.width && pixel.y < params.height;
+	float4 value = inside ? accumulator[i * 4u] : make_float4(0, 0, 0, 0); // Accumulator.Value = average.Result
+
+	if (tilesOut) tilesOut[i] = value;
+	if (frame && inside) frame[(size_t)pixel.y * params.width + pixel.x] = make_float4(value.x, value.y, value.z, 1.0f);
+	if (inside) atomicAdd(stats + STAT_PIXEL_EVALUATED, 1ull);
+}
+
+__global__ void __launch_bounds__(kBlock) frame_resolve_kernel(float4* frame, uint32_t count)
+{
+	uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+	if (i >= count) return;
+	float4 value = frame[i];
+	if (value.w > 0.0f) frame[i] = make_float4(div(value.x, value.w), div(value.y, value.w), div(value.z, value.w), 0.0f);
+	else frame[i] = make_float4(0, 0, 0, 0);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------------
+
+RenderState* render_state_create() { return new RenderState(); }
+
+static void release(RenderState* state)
+{
+	for (void* p : state->allocations) cudaFree(p);
+	state->allocations.clear();
+	state->capacity = 0;
+	state->pixelCapacity = 0;
+	state->tileCapacity = 0;
+}
+
+void render_state_destroy(RenderState* state)
+{
+	if (!state) return;
+	release(state);
+	if (state->hostCounters) cudaFreeHost(state->hostCounters);
+	delete state;
+}
+
+template<class T>
+static bool allocate(RenderState* state, T*& pointer, uint64_t count)
+{
+	void* p = nullptr;
+	if (!check_cuda(cudaMalloc(&p, sizeof(T) * std::max<uint64_t>(count, 1)), "cudaMalloc(render state)")) return false;
+	state->allocations.push_back(p);
+	pointer = (T*)p;
+	return true;
+}
+
+static bool ensure_capacity(RenderState* state, uint64_t paths, uint64_t pixels, uint64_t tiles)
+{
+	if (!state->hostCounters && !check_cuda(cudaMallocHost((void**)&state->hostCounters, sizeof(uint32_t) * 64), "cudaMallocHost")) return false;
+	if (paths <= state->capacity && pixels <= state->pixelCapacity && tiles <= state->tileCapacity) return true;
+
+	paths = std::max(paths, state->capacity);
+	pixels = std::max(pixels, state->pixelCapacity);
+	tiles = std::max(tiles, state->tileCapacity);
+	release(state);
+
+	PathBuffers& b = state->paths;
+	bool ok = allocate(state, b.rayOrigin, paths) && allocate(state, b.rayDirection, paths) && allocate(state, b.hit, paths)
+		&& allocate(state, b.energy, paths) && allocate(state, b.result, paths) && allocate(state, b.oldPosition, paths)
+		&& allocate(state, b.oldNormal, paths) && allocate(state, b.key, paths) && allocate(state, b.shadowOrigin, paths)
+		&& allocate(state, b.shadowDirection, paths) && allocate(state, b.shadowValue, paths) && allocate(state, b.queue[0], paths)
+		&& allocate(state, b.queue[1], paths) && allocate(state, b.counters, 64) && allocate(state, b.stats, STAT_COUNT)
+		&& allocate(state, state->pixelXY, paths) && allocate(state, state->sampleIndex, paths) && allocate(state, state->sampleOut, paths)
+		&& allocate(state, state->accumulator, pixels * 4) && allocate(state, state->sampleCount, pixels)
+		&& allocate(state, state->activePixels[0], pixels) && allocate(state, state->activePixels[1], pixels)
+		&& allocate(state, state->batchPixelXY, pixels) && allocate(state, state->tileXYDevice, tiles * 2);
+
+	for (int c = 0; ok && c < CLASS_COUNT; c++) ok = allocate(state, b.classQueue[c], paths);
+	if (!ok) return false;
+
+	state->capacity = paths;
+	state->pixelCapacity = pixels;
+	state->tileCapacity = tiles;
+	return true;
+}
+
+static unsigned int blocks_for(uint64_t count) { return (unsigned int)std::max<uint64_t>((count + kBlock - 1) / kBlock, 1); }
+
+// Evaluates `count` path slots already described in state->pixelXY / sampleIndex; radiance lands in state->sampleOut.
+template<int STACK>
+static bool evaluate_paths(RenderState* state, const DeviceScene& scene, const EchoRenderParams& params, uint32_t count, uint64_t& launches, cudaStream_t stream)
+{
+	PathBuffers& paths = state->paths;
+	uint32_t* counters = paths.counters;
+	uint32_t* activeCount = counters + 32; // separate slot read by the kernels of one iteration
+
+	if (!check_cuda(cudaMemsetAsync(counters, 0, sizeof(uint32_t) * 64, stream), "cudaMemsetAsync(counters)")) return false;
+
+	raygen_kernel<<<blocks_for(count), kBlock, 0, stream>>>(scene, params, count, state->pixelXY, state->sampleIndex, paths);
+	if (!check_cuda(cudaMemcpyAsync(activeCount, &count, sizeof(uint32_t), cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync(count)")) return false;
+	++launches;
+
+	uint32_t active = count;
+	int current = 0;
+
+	while (active > 0)
+	{
+		unsigned int blocks = blocks_for(active);
+
+		extend_kernel<STACK><<<blocks, kBlock, 0, stream>>>(scene, paths.queue[current], activeCount, paths);
+
+		uint32_t* next = paths.queue[current ^ 1];
+		shade_kernel<CLASS_MISS, 0u><<<blocks, kBlock, 0, stream>>>(scene, params, paths.classQueue[CLASS_MISS], counters + COUNTER_CLASS + CLASS_MISS, paths, next);
+		shade_kernel<CLASS_DIFFUSE, KINDS_DIFFUSE><<<blocks, kBlock, 0, stream>>>(scene, params, paths.classQueue[CLASS_DIFFUSE], counters + COUNTER_CLASS + CLASS_DIFFUSE, paths, next);
+		shade_kernel<CLASS_DIELECTRIC, KINDS_DIELECTRIC><<<blocks, kBlock, 0, stream>>>(scene, params, paths.classQueue[CLASS_DIELECTRIC], counters + COUNTER_CLASS + CLASS_DIELECTRIC, paths, next);
+		shade_kernel<CLASS_CONDUCTOR, KINDS_CONDUCTOR><<<blocks, kBlock, 0, stream>>>(scene, params, paths.classQueue[CLASS_CONDUCTOR], counters + COUNTER_CLASS + CLASS_CONDUCTOR, paths, next);
+		shade_kernel<CLASS_TERMINAL, KINDS_TERMINAL><<<blocks, kBlock, 0, stream>>>(scene, params, paths.classQueue[CLASS_TERMINAL], counters + COUNTER_CLASS + CLASS_TERMINAL, paths, next);
+
+		shadow_kernel<STACK><<<blocks, kBlock, 0, stream>>>(scene, counters + COUNTER_SHADOW, paths);
+		rotate_counters_kernel<<<1, 1, 0, stream>>>(counters, activeCount, state->hostCounters);
+		launches += 8;
+
+		if (!check_cuda(cudaGetLastError(), "wavefront launch")) return false;
+		if (!check_cuda(cudaStreamSynchronize(stream), "wavefront iteration")) return false;
+
+		active = state->hostCounters[0];
+		current ^= 1;
+	}
+
+	finish_kernel<<<blocks_for(count), kBlock, 0, stream>>>(count, paths, state->sampleOut);
+	++launches;
+	return check_cuda(cudaGetLastError(), "finish_kernel launch");
+}
+
+static bool evaluate_paths_dispatch(RenderState* state, const DeviceScene& scene, const EchoRenderParams& params, uint32_t count, uint64_t& launches, cudaStream_t stream)
+{
+	switch (stack_class(scene.maxDepth))
+	{
+		case 0: return evaluate_paths<48>(state, scene, params, count, launches, stream);
+		case 1: return evaluate_paths<96>(state, scene, params, count, launches, stream);
+		case 2: return evaluate_paths<192>(state, scene, params, count, launches, stream);
+		default: set_error("QBVH deeper than 63 quad levels is not supported"); return false;
+	}
+}
+
+static void collect_stats(RenderState* state, EchoStats* stats, uint64_t launches, cudaStream_t stream)
+{
+	if (!stats) return;
+	unsigned long long host[STAT_COUNT];
+	cudaMemcpyAsync(host, state->paths.stats, sizeof(host), cudaMemcpyDeviceToHost, stream);
+	cudaStreamSynchronize(stream);
+	uint64_t* out = reinterpret_cast<uint64_t*>(stats);
+	for (int i = 0; i < STAT_COUNT; i++) out[i] += host[i];
+	stats->kernelLaunches += launches;
+}
+
+constexpr uint64_t kPathsPerBatch = 1ull << 22; // ~4 M paths in flight (about 0.8 GB of wavefront state)
+
+bool render_tiles(RenderState* state, const DeviceScene& scene, const EchoRenderParams& params, const int32_t* tileXY, uint32_t tileCount,
+                  float4* tilesOut, float4* frame, EchoStats* stats, cudaStream_t stream)
+{
+	if (params.width <= 0 || params.height <= 0 || params.tileSize <= 0 || params.extend <= 0 || params.maxEpoch < 1 || params.minEpoch > params.maxEpoch)
+	{
+		set_error("invalid EchoRenderParams");
+		return false;
+	}
+
+	uint64_t perTile = (uint64_t)params.tileSize * params.tileSize;
+	uint64_t tilesPerBatch = std::max<uint64_t>(1, kPathsPerBatch / (perTile * params.extend));
+	tilesPerBatch = std::min<uint64_t>(tilesPerBatch, tileCount);
+
+	if (!ensure_capacity(state, tilesPerBatch * perTile * params.extend, tilesPerBatch * perTile, tilesPerBatch)) return false;
+
+	uint64_t launches = 0;
+	if (!check_cuda(cudaMemsetAsync(state->paths.stats, 0, sizeof(unsigned long long) * STAT_COUNT, stream), "cudaMemsetAsync(stats)")) return false;
+
+	for (uint64_t first = 0; first < tileCount; first += tilesPerBatch)
+	{
+		uint32_t tiles = (uint32_t)std::min<uint64_t>(tilesPerBatch, tileCount - first);
+		uint32_t pixelTotal = (uint32_t)(tiles * perTile);
+
+		if (!check_cuda(cudaMemcpyAsync(state->tileXYDevice, tileXY + first * 2, sizeof(int32_t) * 2 * tiles, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync(tiles)")) return false;
+		if (!check_cuda(cudaMemsetAsync(state->paths.counters, 0, sizeof(uint32_t) * 64, stream), "cudaMemsetAsync(counters)")) return false;
+
+		batch_pixels_kernel<<<blocks_for(pixelTotal), kBlock, 0, stream>>>(params, state->tileXYDevice, tiles, state->batchPixelXY, state->activePixels[0],
+		                                                                 state->paths.counters, state->accumulator, state->sampleCount);
+		++launches;
+
+		if (!check_cuda(cudaMemcpyAsync(state->hostCounters + 8, state->paths.counters + COUNTER_PIXELS, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream), "cudaMemcpyAsync(pixels)")) return false;
+		if (!check_cuda(cudaStreamSynchronize(stream), "batch setup")) return false;
+
+		uint32_t activePixels = state->hostCounters[8];
+		int list = 0;
+
+		for (uint32_t epoch = 1; activePixels > 0 && epoch <= (uint32_t)params.maxEpoch; epoch++)
+		{
+			uint32_t slots = activePixels * (uint32_t)params.extend;
+
+			epoch_slots_kernel<<<blocks_for(slots), kBlock, 0, stream>>>(params, activePixels, state->activePixels[list], state->batchPixelXY, epoch, state->pixelXY, state->sampleIndex);
+			++launches;
+
+			if (!evaluate_paths_dispatch(state, scene, params, slots, launches, stream)) return false;
+
+			if (!check_cuda(cudaMemsetAsync(state->paths.counters + COUNTER_PIXELS, 0, sizeof(uint32_t), stream), "cudaMemsetAsync(pixel counter)")) return false;
+
+			accumulate_kernel<<<blocks_for(activePixels), kBlock, 0, stream>>>(params, activePixels, state->activePixels[list], state->sampleOut, state->accumulator,
+			                                                                 state->sampleCount, epoch, state->activePixels[list ^ 1], state->paths.counters, state->paths.stats);
+			++launches;
+
+			if (!check_cuda(cudaMemcpyAsync(state->hostCounters + 8, state->paths.counters + COUNTER_PIXELS, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream), "cudaMemcpyAsync(pixels)")) return false;
+			if (!check_cuda(cudaStreamSynchronize(stream), "epoch")) return false;
+
+			activePixels = state->hostCounters[8];
+			list ^= 1;
+		}
+
+		resolve_tiles_kernel<<<blocks_for(pixelTotal), kBlock, 0, stream>>>(params, pixelTotal, state->batchPixelXY, state->accumulator,
+		                                                                  tilesOut ? tilesOut + first * perTile : nullptr, frame, state->paths.stats);
+		++launches;
+		if (!check_cuda(cudaGetLastError(), "resolve_tiles_kernel launch")) return false;
+	}
+
+	collect_stats(state, stats, launches, stream);
+	return check_cuda(cudaStreamSynchronize(stream), "render_tiles");
+}
+
+// debug: explicit (pixel, sample) lists -> per-sample radiance (device pointers in, device pointer out)
+bool evaluate_sample_list(RenderState* state, const DeviceScene& scene, const EchoRenderParams& params, const int32_t* pixelXYHost, const uint32_t* sampleIndexHost,
+                          uint64_t n, float* outRGBHost, cudaStream_t stream)
+{
+	std::vector<float4> staging;
+
+	for (uint64_t first = 0; first < n; first += kPathsPerBatch)
+	{
+		uint32_t count = (uint32_t)std::min<uint64_t>(kPathsPerBatch, n - first);
+		if (!ensure_capacity(state, count, 1, 1)) return false;
+
+		if (!check_cuda(cudaMemcpyAsync(state->pixelXY, pixelXYHost + first * 2, sizeof(int2) * count, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync(pixels)")) return false;
+		if (!check_cuda(cudaMemcpyAsync(state->sampleIndex, sampleIndexHost + first, sizeof(uint32_t) * count, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync(samples)")) return false;
+		if (!check_cuda(cudaMemsetAsync(state->paths.stats, 0, sizeof(unsigned long long) * STAT_COUNT, stream), "cudaMemsetAsync(stats)")) return false;
+
+		uint64_t launches = 0;
+		if (!evaluate_paths_dispatch(state, scene, params, count, launches, stream)) return false;
+
+		staging.resize(count);
+		if (!check_cuda(cudaMemcpyAsync(staging.data(), state->sampleOut, sizeof(float4) * count, cudaMemcpyDeviceToHost, stream), "cudaMemcpyAsync(out)")) return false;
+		if (!check_cuda(cudaStreamSynchronize(stream), "evaluate_sample_list")) return false;
+
+		for (uint32_t i = 0; i < count; i++)
+		{
+			outRGBHost[(first + i) * 3 + 0] = staging[i].x;
+			outRGBHost[(first + i) * 3 + 1] = staging[i].y;
+			outRGBHost[(first + i) * 3 + 2] = staging[i].z;
+		}
+	}
+
+	return true;
+}
+
+bool launch_frame_resolve(float4* frame, int32_t width, int32_t height, cudaStream_t stream)
+{
+	uint32_t count = (uint32_t)width * (uint32_t)height;
+	frame_resolve_kernel<<<blocks_for(count), kBlock, 0, stream>>>(frame, count);
+	return check_cuda(cudaGetLastError(), "frame_resolve_kernel launch");
+}
+
+} // namespace echo

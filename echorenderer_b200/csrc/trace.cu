@@ -1,0 +1,155 @@
+// trace.cu — batched Accelerator.Trace / Accelerator.Occlude: one thread per query over AoS EchoRay input read with
+// two 128-bit loads, EchoHit output written with one 128-bit store. These are the kernels behind
+// echo_b200_trace_batch / echo_b200_occlude_batch (BASELINE config C2) and the batched analogue of the benchmark loops in
+// the reference's src/Echo.Experimental/Benchmarks/Accelerators.cs:131-157.
+#include "echo_internal.h"
+
+namespace echo
+{
+
+constexpr int kTraceBlock = 128;
+
+template<int STACK, bool COUNT>
+__global__ void __launch_bounds__(kTraceBlock) trace_batch_kernel(DeviceScene scene, const float4* __restrict__ rays, uint64_t n,
+                                                                  float4* __restrict__ hits, unsigned long long* __restrict__ counts)
+{
+	uint64_t i = (uint64_t)blockIdx.x * kTraceBlock + threadIdx.x;
+	VisitCounts local = { 0u, 0u, 0u };
+
+	if (i < n)
+	{
+		float4 a = __ldg(rays + i * 2);     // origin.xyz, direction.x
+		float4 b = __ldg(rays + i * 2 + 1); // direction.yz, distance, ignore
+
+		vec3 origin = { a.x, a.y, a.z };
+		vec3 direction = { a.w, b.x, b.y };
+		float limit = b.z;
+		uint32_t ignore = __float_as_uint(b.w);
+
+		float distance = limit;
+		uint32_t token = ECHO_TOKEN_EMPTY;
+		vec2 uv = { 0.0f, 0.0f };
+
+		bool hit = scene_trace<STACK, COUNT>(scene, origin, direction, ignore, distance, token, uv, &local);
+
+		float4 out;
+		out.x = __uint_as_float(hit ? token : ECHO_TOKEN_EMPTY);
+		out.y = hit ? distance : limit;
+		out.z = hit ? uv.x : 0.0f;
+		out.w = hit ? uv.y : 0.0f;
+		hits[i] = out;
+	}
+
+	if (COUNT)
+	{
+		// warp-level reduction, then one atomic per warp per counter
+		for (int offset = 16; offset > 0; offset >>= 1)
+		{
+			local.nodes += __shfl_down_sync(0xFFFFFFFFu, local.nodes, offset);
+			local.triangles += __shfl_down_sync(0xFFFFFFFFu, local.triangles, offset);
+			local.spheres += __shfl_down_sync(0xFFFFFFFFu, local.spheres, offset);
+		}
+
+		if ((threadIdx.x & 31) == 0)
+		{
+			atomicAdd(counts + 0, (unsigned long long)local.nodes);
+			atomicAdd(counts + 1, (unsigned long long)local.triangles);
+			atomicAdd(counts + 2, (unsigned long long)local.spheres);
+		}
+	}
+}
+
+template<int STACK, bool COUNT>
+__global__ void __launch_bounds__(kTraceBlock) occlude_batch_kernel(DeviceScene scene, const float4* __restrict__ rays, uint64_t n,
+                                                                    uint8_t* __restrict__ occluded, unsigned long long* __restrict__ counts)
+{
+	uint64_t i = (uint64_t)blockIdx.x * kTraceBlock + threadIdx.x;
+	VisitCounts local = { 0u, 0u, 0u };
+
+	if (i < n)
+	{
+		float4 a = __ldg(rays + i * 2);
+		float4 b = __ldg(rays + i * 2 + 1);
+
+		vec3 origin = { a.x, a.y, a.z };
+		vec3 direction = { a.w, b.x, b.y };
+
+		bool result = scene_occlude<STACK, COUNT>(scene, origin, direction, __float_as_uint(b.w), b.z, &local);
+		occluded[i] = result ? 1 : 0;
+	}
+
+	if (COUNT)
+	{
+		for (int offset = 16; offset > 0; offset >>= 1)
+		{
+			local.nodes += __shfl_down_sync(0xFFFFFFFFu, local.nodes, offset);
+			local.triangles += __shfl_down_sync(0xFFFFFFFFu, local.triangles, offset);
+			local.spheres += __shfl_down_sync(0xFFFFFFFFu, local.spheres, offset);
+		}
+
+		if ((threadIdx.x & 31) == 0)
+		{
+			atomicAdd(counts + 0, (unsigned long long)local.nodes);
+			atomicAdd(counts + 1, (unsigned long long)local.triangles);
+			atomicAdd(counts + 2, (unsigned long long)local.spheres);
+		}
+	}
+}
+
+int stack_class(uint32_t maxDepth)
+{
+	uint32_t size = maxDepth * 3 + 1;
+	if (size <= 48) return 0;
+	if (size <= 96) return 1;
+	if (size <= 192) return 2;
+	return -1;
+}
+
+template<bool COUNT>
+static bool launch_trace_impl(const DeviceScene& scene, const EchoRay* rays, uint64_t n, EchoHit* hits, unsigned long long* counts, cudaStream_t stream)
+{
+	if (n == 0) return true;
+	unsigned int blocks = (unsigned int)((n + kTraceBlock - 1) / kTraceBlock);
+	const float4* in = reinterpret_cast<const float4*>(rays);
+	float4* out = reinterpret_cast<float4*>(hits);
+
+	switch (stack_class(scene.maxDepth))
+	{
+		case 0: trace_batch_kernel<48, COUNT><<<blocks, kTraceBlock, 0, stream>>>(scene, in, n, out, counts); break;
+		case 1: trace_batch_kernel<96, COUNT><<<blocks, kTraceBlock, 0, stream>>>(scene, in, n, out, counts); break;
+		case 2: trace_batch_kernel<192, COUNT><<<blocks, kTraceBlock, 0, stream>>>(scene, in, n, out, counts); break;
+		default: set_error("QBVH deeper than 63 quad levels is not supported"); return false;
+	}
+
+	return check_cuda(cudaGetLastError(), "trace_batch_kernel launch");
+}
+
+template<bool COUNT>
+static bool launch_occlude_impl(const DeviceScene& scene, const EchoRay* rays, uint64_t n, uint8_t* occluded, unsigned long long* counts, cudaStream_t stream)
+{
+	if (n == 0) return true;
+	unsigned int blocks = (unsigned int)((n + kTraceBlock - 1) / kTraceBlock);
+	const float4* in = reinterpret_cast<const float4*>(rays);
+
+	switch (stack_class(scene.maxDepth))
+	{
+		case 0: occlude_batch_kernel<48, COUNT><<<blocks, kTraceBlock, 0, stream>>>(scene, in, n, occluded, counts); break;
+		case 1: occlude_batch_kernel<96, COUNT><<<blocks, kTraceBlock, 0, stream>>>(scene, in, n, occluded, counts); break;
+		case 2: occlude_batch_kernel<192, COUNT><<<blocks, kTraceBlock, 0, stream>>>(scene, in, n, occluded, counts); break;
+		default: set_error("QBVH deeper than 63 quad levels is not supported"); return false;
+	}
+
+	return check_cuda(cudaGetLastError(), "occlude_batch_kernel launch");
+}
+
+bool launch_trace(const DeviceScene& scene, const EchoRay* rays, uint64_t n, EchoHit* hits, unsigned long long* counts, cudaStream_t stream)
+{
+	return counts ? launch_trace_impl<true>(scene, rays, n, hits, counts, stream) : launch_trace_impl<false>(scene, rays, n, hits, nullptr, stream);
+}
+
+bool launch_occlude(const DeviceScene& scene, const EchoRay* rays, uint64_t n, uint8_t* occluded, unsigned long long* counts, cudaStream_t stream)
+{
+	return counts ? launch_occlude_impl<true>(scene, rays, n, occluded, counts, stream) : launch_occlude_impl<false>(scene, rays, n, occluded, nullptr, stream);
+}
+
+} // namespace echo

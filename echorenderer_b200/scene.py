@@ -1,0 +1,230 @@
+"""Host-side mirror of the reference interface for the hot path, on top of the C ABI.
+
+  PreparedScene          Aggregation/Preparation/PreparedScene.cs — Trace / Occlude (batched) and the scene payload
+  PathTracedEvaluator    Evaluation/Evaluators/PathTracedEvaluator.cs:33,40 — BounceLimit, Survivability
+  EvaluationProfile      Processes/Evaluation/EvaluationProfile.cs:13-75 — Evaluator, Distribution.Extend, Min/MaxEpoch, NoiseThreshold
+  RenderTexture          Textures/Evaluation/RenderTexture.cs — tile-based destination (CreateTile / Apply semantics)
+  EvaluationOperation    Processes/Evaluation/EvaluationOperation.cs:21-177 — tilePositions, destination, profile, TotalSamples, Execute
+
+Names, argument meaning and error behaviour follow the reference (validation errors raise like EvaluationProfile.Validate,
+native failures raise EchoNativeError with the pulled error string). The compute always runs in libecho_b200.so.
+"""
+import ctypes
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _native, structs
+from .host import PreparedArrays
+
+
+class PreparedScene:
+    """The flattened scene resident on one B200; the device twin of Echo's PreparedScene."""
+
+    def __init__(self, prepared: PreparedArrays, device: int = 0):
+        lib = _native.library()
+        self._lib = lib
+        self.prepared = prepared
+        self.device = device
+        self._handle = ctypes.c_void_p()
+        _native.check(lib.echo_b200_scene_create(ctypes.byref(self._handle), device))
+
+        try:
+            d = prepared.description
+            ptr = _native.pointer
+            _native.check(lib.echo_b200_scene_set_qbvh(self._handle, ptr(prepared.nodes), len(prepared.nodes), prepared.max_depth))
+            _native.check(lib.echo_b200_scene_set_triangles(self._handle, ptr(d.triangles), len(d.triangles)))
+            _native.check(lib.echo_b200_scene_set_spheres(self._handle, ptr(d.spheres), len(d.spheres)))
+            _native.check(lib.echo_b200_scene_set_materials(self._handle, ptr(d.materials), len(d.materials)))
+            _native.check(lib.echo_b200_scene_set_light_tree(self._handle, ptr(prepared.light_nodes), len(prepared.light_nodes),
+                                                             ptr(prepared.emitter_tokens), ptr(prepared.emitter_bitpaths), len(prepared.emitter_tokens),
+                                                             ptr(d.point_lights), len(d.point_lights)))
+            _native.check(lib.echo_b200_scene_set_infinite(self._handle, ptr(d.infinite_lights), len(d.infinite_lights),
+                                                           prepared.infinite_threshold, prepared.infinite_pdf))
+            _native.check(lib.echo_b200_scene_set_camera(self._handle, ptr(d.camera)))
+            _native.check(lib.echo_b200_scene_commit(self._handle))
+        except Exception:
+            self.close()
+            raise
+
+    def close(self):
+        if getattr(self, "_handle", None) is not None and self._handle.value:
+            self._lib.echo_b200_scene_destroy(self._handle)
+            self._handle = ctypes.c_void_p()
+
+    def __del__(self):
+        self.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *_):
+        self.close()
+
+    @property
+    def handle(self):
+        return self._handle
+
+    # ---- PreparedScene.Trace / Occlude, batched (PreparedScene.cs:66-86); host numpy buffers ----
+    def trace(self, rays, out=None):
+        """Closest hit for every TraceQuery in `rays` (structs.RAY). Returns structs.HIT records: on a miss token is
+        TOKEN_EMPTY and distance keeps the query's input distance."""
+        rays = np.ascontiguousarray(rays, dtype=structs.RAY)
+        hits = out if out is not None else np.empty(len(rays), dtype=structs.HIT)
+        _native.check(self._lib.echo_b200_trace_batch(self._handle, _native.pointer(rays), len(rays), _native.pointer(hits)))
+        return hits
+
+    def occlude(self, rays, out=None):
+        """Any hit within `distance` (the OccludeQuery travel) for every query; returns uint8 0/1."""
+        rays = np.ascontiguousarray(rays, dtype=structs.RAY)
+        occluded = out if out is not None else np.empty(len(rays), dtype=np.uint8)
+        _native.check(self._lib.echo_b200_occlude_batch(self._handle, _native.pointer(rays), len(rays), _native.pointer(occluded)))
+        return occluded
+
+    # ---- raw-pointer variants for pinned host memory / device memory owned by the caller (torch tensors) ----
+    def trace_pointers(self, rays_pointer, count, hits_pointer):
+        _native.check(self._lib.echo_b200_trace_batch(self._handle, ctypes.c_void_p(rays_pointer), count, ctypes.c_void_p(hits_pointer)))
+
+    def occlude_pointers(self, rays_pointer, count, occluded_pointer):
+        _native.check(self._lib.echo_b200_occlude_batch(self._handle, ctypes.c_void_p(rays_pointer), count, ctypes.c_void_p(occluded_pointer)))
+
+    def trace_device(self, rays_pointer, count, hits_pointer, stream=0, counts_pointer=None):
+        """Asynchronous launch on `stream` (a cudaStream_t value) over device-resident buffers."""
+        if counts_pointer is None:
+            _native.check(self._lib.echo_b200_trace_batch_device(self._handle, ctypes.c_void_p(rays_pointer), count, ctypes.c_void_p(hits_pointer), ctypes.c_void_p(stream)))
+        else:
+            _native.check(self._lib.echo_b200_trace_batch_device_counted(self._handle, ctypes.c_void_p(rays_pointer), count, ctypes.c_void_p(hits_pointer),
+                                                                       ctypes.c_void_p(counts_pointer), ctypes.c_void_p(stream)))
+
+    def occlude_device(self, rays_pointer, count, occluded_pointer, stream=0, counts_pointer=None):
+        if counts_pointer is None:
+            _native.check(self._lib.echo_b200_occlude_batch_device(self._handle, ctypes.c_void_p(rays_pointer), count, ctypes.c_void_p(occluded_pointer), ctypes.c_void_p(stream)))
+        else:
+            _native.check(self._lib.echo_b200_occlude_batch_device_counted(self._handle, ctypes.c_void_p(rays_pointer), count, ctypes.c_void_p(occluded_pointer),
+                                                                         ctypes.c_void_p(counts_pointer), ctypes.c_void_p(stream)))
+
+    # ---- tile rendering ----
+    def render_tiles(self, params, tile_xy):
+        """One EvaluationOperation worth of tiles -> (tiles[n, tileSize, tileSize, 4] float32, stats record)."""
+        tile_xy = np.ascontiguousarray(tile_xy, dtype=np.int32).reshape(-1, 2)
+        tile_size = int(params["tileSize"][0])
+        out = np.zeros((len(tile_xy), tile_size, tile_size, 4), dtype=np.float32)
+        stats = np.zeros(1, dtype=structs.STATS)
+        _native.check(self._lib.echo_b200_render_tiles(self._handle, _native.pointer(params), _native.pointer(tile_xy), len(tile_xy),
+                                                       _native.pointer(out), _native.pointer(stats)))
+        return out, stats
+
+    def render_frame_device(self, params, tile_xy, frame_pointer, stream=0):
+        """Renders tiles into a device-resident full frame (width*height Float4; xyz = mean, w = 1 where rendered)."""
+        tile_xy = np.ascontiguousarray(tile_xy, dtype=np.int32).reshape(-1, 2)
+        stats = np.zeros(1, dtype=structs.STATS)
+        _native.check(self._lib.echo_b200_render_frame_device(self._handle, _native.pointer(params), _native.pointer(tile_xy), len(tile_xy),
+                                                              ctypes.c_void_p(frame_pointer), _native.pointer(stats), ctypes.c_void_p(stream)))
+        return stats
+
+    def frame_resolve_device(self, frame_pointer, width, height, stream=0):
+        _native.check(self._lib.echo_b200_frame_resolve_device(self._handle, ctypes.c_void_p(frame_pointer), width, height, ctypes.c_void_p(stream)))
+
+    def evaluate_samples(self, params, pixel_xy, sample_index):
+        """Diagnostic: one Evaluator.Evaluate per (pixel, sample index) -> radiance[n, 3]."""
+        pixel_xy = np.ascontiguousarray(pixel_xy, dtype=np.int32).reshape(-1, 2)
+        sample_index = np.ascontiguousarray(sample_index, dtype=np.uint32)
+        out = np.zeros((len(sample_index), 3), dtype=np.float32)
+        _native.check(self._lib.echo_b200_debug_evaluate_samples(self._handle, _native.pointer(params), _native.pointer(pixel_xy),
+                                                                 _native.pointer(sample_index), len(sample_index), _native.pointer(out)))
+        return out
+
+
+@dataclass(frozen=True)
+class PathTracedEvaluator:
+    """Evaluation/Evaluators/PathTracedEvaluator.cs:33,40."""
+    bounce_limit: int = 128
+    survivability: float = 2.5
+
+
+@dataclass(frozen=True)
+class EvaluationProfile:
+    """Processes/Evaluation/EvaluationProfile.cs:13-75 (Distribution reduced to its Extend and seed)."""
+    evaluator: PathTracedEvaluator = field(default_factory=PathTracedEvaluator)
+    extend: int = 16                # ContinuousDistribution.Extend, ContinuousDistribution.cs:25
+    min_epoch: int = 1
+    max_epoch: int = 20
+    noise_threshold: float = 0.045
+    seed: int = 1
+
+    def validate(self):
+        """EvaluationProfile.Validate, EvaluationProfile.cs:65-75."""
+        if self.evaluator is None:
+            raise ValueError("Evaluator is null")
+        if self.extend <= 0:
+            raise ValueError("Distribution.Extend out of bounds")
+        if self.min_epoch <= 0 or self.max_epoch < self.min_epoch:
+            raise ValueError("MinEpoch / MaxEpoch out of bounds")
+        if self.noise_threshold < 0:
+            raise ValueError("NoiseThreshold out of bounds")
+
+
+class RenderTexture:
+    """Tile-based destination, rows growing upward (Textures/Evaluation/RenderTexture.cs, EvaluationLayer.cs:16-52)."""
+
+    def __init__(self, width, height, tile_size=16):
+        if width <= 0 or height <= 0 or tile_size <= 0:
+            raise ValueError("size out of bounds")
+        self.width, self.height, self.tile_size = width, height, tile_size
+        self.pixels = np.zeros((height, width, 4), dtype=np.float32)
+
+    @property
+    def tile_positions(self):
+        tiles_x = (self.width + self.tile_size - 1) // self.tile_size
+        tiles_y = (self.height + self.tile_size - 1) // self.tile_size
+        ty, tx = np.meshgrid(np.arange(tiles_y), np.arange(tiles_x), indexing="ij")
+        return np.stack([tx.reshape(-1), ty.reshape(-1)], axis=-1).astype(np.int32)
+
+    def apply(self, tile_position, tile):
+        """IEvaluationLayer.Apply for one finished tile (EvaluationLayer.cs:111-121): tiles are immutable once applied."""
+        x0, y0 = int(tile_position[0]) * self.tile_size, int(tile_position[1]) * self.tile_size
+        w, h = min(self.tile_size, self.width - x0), min(self.tile_size, self.height - y0)
+        self.pixels[y0:y0 + h, x0:x0 + w] = tile[:h, :w]
+
+
+def shard_tiles(tile_positions, rank, world_size):
+    """Tile sharding across devices: tile i -> rank (i mod world_size), the static analogue of Operation.Execute's shared
+    procedure counter (Common/Compute/Operation.cs:164-177). Round-robin over the scan order balances load."""
+    tile_positions = np.asarray(tile_positions, dtype=np.int32).reshape(-1, 2)
+    return np.ascontiguousarray(tile_positions[rank::world_size])
+
+
+class EvaluationOperation:
+    """Processes/Evaluation/EvaluationOperation.cs:21-177 on the GPU: same public surface (tile_positions, destination,
+    profile, total_samples, statistics), Execute renders every tile through libecho_b200 and applies it to the destination."""
+
+    def __init__(self, scene: PreparedScene, profile: EvaluationProfile, destination: RenderTexture, tile_positions=None):
+        profile.validate()
+        self.scene = scene
+        self.profile = profile
+        self.destination = destination
+        self.tile_positions = destination.tile_positions if tile_positions is None else np.asarray(tile_positions, dtype=np.int32).reshape(-1, 2)
+        self.statistics = np.zeros(1, dtype=structs.STATS)
+
+    @property
+    def params(self):
+        p = self.profile
+        return structs.render_params(self.destination.width, self.destination.height, self.destination.tile_size, p.extend, p.min_epoch,
+                                     p.max_epoch, p.noise_threshold, p.evaluator.bounce_limit, p.evaluator.survivability, p.seed)
+
+    @property
+    def total_samples(self):
+        """EvaluationOperation.TotalSamples (:73-81): the "Sample/Evaluated" counter."""
+        return int(self.statistics["sampleEvaluated"][0])
+
+    def execute(self):
+        tiles, stats = self.scene.render_tiles(self.params, self.tile_positions)
+        for position, tile in zip(self.tile_positions, tiles):
+            self.destination.apply(position, tile)
+        for name in structs.STATS_FIELDS:
+            self.statistics[name] += stats[name]
+        return self.destination
+
+    def statistics_report(self):
+        """label -> count, the labels EvaluatorStatistics.Report uses on this path."""
+        return {label: int(self.statistics[name][0]) for label, name in zip(structs.STATS_LABELS, structs.STATS_FIELDS)}

@@ -1,0 +1,245 @@
+/*
+ * echo_b200.h — C ABI of libecho_b200.so, the B200-native path-tracing core behind Echo's
+ * evaluator/aggregator interface.
+ *
+ * Echo (GaryHuan9/EchoRenderer) has no FFI on this path: it is in-process C# virtual calls. The seams this
+ * library sits behind (all paths relative to the reference's src/Echo.Core/):
+ *   - Accelerator.Trace(ref TraceQuery) / Accelerator.Occlude(ref OccludeQuery)
+ *       Aggregation/Acceleration/Accelerator.cs:90,96   -> echo_b200_trace_batch / echo_b200_occlude_batch
+ *   - EvaluationOperation.Execute (pixel -> epoch -> sample loop, Accumulator, tile write)
+ *       Processes/Evaluation/EvaluationOperation.cs:83-148 -> echo_b200_render_tiles
+ *   - the prepared, flattened scene those calls read:
+ *       QuadBoundingVolumeHierarchy.Node  Aggregation/Acceleration/QuadBoundingVolumeHierarchy.cs:406-469
+ *       PreparedTriangle                  Scenic/Geometries/TriangleEntity.cs:57-129
+ *       PreparedSphere                    Scenic/Geometries/SphereEntity.cs:48-63
+ *       PreparedSwatch materials          Scenic/Preparation/PreparedSwatch.cs:20
+ *       LightTree                         Aggregation/Selection/LightTree.cs:19-171
+ *       PreparedScene infinite lights     Aggregation/Preparation/PreparedScene.cs:34-39
+ *       PerspectiveCamera                 Scenic/Cameras/PerspectiveCamera.cs:41-98
+ * P/Invoke conventions follow Echo's one native precedent, Processes/Composition/OidnDenoise.cs:48-300:
+ * opaque handle, raw pinned pointers that the library never retains, errors pulled with a *_last_error call.
+ *
+ * Every function returns 0 on success and a non-zero ECHO_B200_ERR_* code otherwise. The library copies host
+ * data on upload and owns device memory until echo_b200_scene_destroy. There is no CPU fallback: without a
+ * CUDA device every compute entry point fails with ECHO_B200_ERR_NO_DEVICE.
+ */
+#ifndef ECHO_B200_H
+#define ECHO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ECHO_B200_OK 0
+#define ECHO_B200_ERR_INVALID 1     /* bad argument / scene not committed */
+#define ECHO_B200_ERR_NO_DEVICE 2   /* no usable CUDA device */
+#define ECHO_B200_ERR_CUDA 3        /* CUDA runtime failure; see echo_b200_last_error() */
+#define ECHO_B200_ERR_UNSUPPORTED 4 /* feature outside the hot path (e.g. instanced tokens) */
+
+/* ---- tokens: Aggregation/Primitives/EntityToken.cs:22-73, TokenType.cs:12-38 ---- */
+#define ECHO_TOKEN_TYPE_NODE 0u
+#define ECHO_TOKEN_TYPE_TRIANGLE 1u
+#define ECHO_TOKEN_TYPE_SPHERE 2u
+#define ECHO_TOKEN_TYPE_INSTANCE 3u
+#define ECHO_TOKEN_TYPE_LIGHT 4u
+#define ECHO_TOKEN_EMPTY 0xFFFFFFFFu
+#define ECHO_TOKEN_INDEX_BITS 28
+#define ECHO_TOKEN_MAKE(type, index) ((((uint32_t)(type)) << ECHO_TOKEN_INDEX_BITS) | (uint32_t)(index))
+/* light tokens: 6-bit LightType above a 22-bit index (EntityToken.cs:29,68-71; Scenic/Lights/LightType.cs) */
+#define ECHO_LIGHT_TYPE_INFINITE 0u
+#define ECHO_LIGHT_TYPE_INFINITE_DELTA 1u
+#define ECHO_LIGHT_TYPE_POINT 2u
+#define ECHO_LIGHT_INDEX_BITS 22
+#define ECHO_LIGHT_TOKEN_MAKE(ltype, index) \
+	ECHO_TOKEN_MAKE(ECHO_TOKEN_TYPE_LIGHT, (((uint32_t)(ltype)) << ECHO_LIGHT_INDEX_BITS) | (uint32_t)(index))
+
+/* ---- QuadBoundingVolumeHierarchy.Node, 128 B explicit layout (QuadBoundingVolumeHierarchy.cs:406-469) ---- */
+typedef struct EchoQbvhNode
+{
+	float minX[4], minY[4], minZ[4]; /* BoxBound4 @0 (Aggregation/Bounds/BoxBound4.cs:32-38) */
+	float maxX[4], maxY[4], maxZ[4];
+	int32_t axisMajor;  /* @96  0..2 */
+	int32_t axisMinor0; /* @100 0..2, or 3 = [leaf, empty] pair */
+	int32_t axisMinor1; /* @104 */
+	uint32_t token4[4]; /* @108 child tokens; ECHO_TOKEN_EMPTY for none */
+	uint32_t pad;       /* @124 */
+} EchoQbvhNode;
+
+/* ---- PreparedTriangle, 100 B sequential layout (TriangleEntity.cs:118-139) ---- */
+typedef struct EchoTriangle
+{
+	float vertex0[3], edge1[3], edge2[3];
+	float normal0[3], normal1[3], normal2[3]; /* unit shading normals */
+	float texcoord0[2], texcoord1[2], texcoord2[2];
+	uint32_t material; /* MaterialIndex */
+} EchoTriangle;
+
+/* ---- PreparedSphere, 20 B (SphereEntity.cs:59-63) ---- */
+typedef struct EchoSphere
+{
+	float position[3];
+	float radius;
+	uint32_t material;
+} EchoSphere;
+
+/* ---- one query: Ray + TraceQuery/OccludeQuery inputs (Ray.cs:17-28, TraceQuery.cs:16-40, OccludeQuery.cs:10-30).
+ * `direction` must be unit length; `distance` is TraceQuery.distance / OccludeQuery.travel (may be +inf);
+ * `ignore` is the top token of the TokenHierarchy to skip (ECHO_TOKEN_EMPTY for none). ---- */
+typedef struct EchoRay
+{
+	float origin[3];
+	float direction[3];
+	float distance;
+	uint32_t ignore;
+} EchoRay;
+
+/* ---- TraceQuery outputs (TraceQuery.cs:42-58). token == ECHO_TOKEN_EMPTY and distance == input distance on a miss. ---- */
+typedef struct EchoHit
+{
+	uint32_t token;
+	float distance;
+	float uv[2];
+} EchoHit;
+
+/* ---- materials with constant (Pure) textures flattened (Evaluation/Materials/) ---- */
+#define ECHO_MATERIAL_DIFFUSE 0u    /* Diffuse.cs:33-47 */
+#define ECHO_MATERIAL_DIELECTRIC 1u /* Dielectric.cs:29-47 */
+#define ECHO_MATERIAL_CONDUCTOR 2u  /* Conductor.cs:72-124 */
+#define ECHO_MATERIAL_EMISSIVE 3u   /* Emissive.cs:30-64 */
+#define ECHO_MATERIAL_ONESIDED 4u   /* OneSided.cs:50-58 */
+#define ECHO_MATERIAL_INVISIBLE 5u  /* Invisible.cs:22-26 */
+#define ECHO_MATERIAL_FLAG_TRANSMISSIVE 1u /* Diffuse.Transmissive */
+#define ECHO_MATERIAL_FLAG_ARTISTIC 2u     /* Conductor.Artistic */
+#define ECHO_MATERIAL_FLAG_BACKFACE 4u     /* OneSided.Backface */
+
+typedef struct EchoMaterial
+{
+	uint32_t type;
+	uint32_t flags;
+	float albedo[4];    /* RGBA; alpha < 0.5 makes the surface Invisible (Material.cs:63-75). Emissive: emission RGB */
+	float roughness[2]; /* R and G of the Roughness texture */
+	float ior;          /* Dielectric.RefractiveIndex */
+	float paramA[3];    /* Conductor: MainColor (artistic) or RefractiveIndex (physical) */
+	float paramB[3];    /* Conductor: EdgeColor (artistic) or Extinction (physical) */
+	uint32_t base;      /* OneSided.Base material index */
+} EchoMaterial; /* 64 B */
+
+/* ---- flattened LightTree node (LightTree.cs:156-171, LightBound.cs:10-20, ConeBound.cs:20-24). Node 0 = root.
+ * Branch: child0/child1 are node indices. Leaf: child0 == ECHO_TOKEN_EMPTY and child1 holds the light's token. ---- */
+typedef struct EchoLightNode
+{
+	float boxMin[3], boxMax[3];
+	float coneAxis[3];
+	float cosOffset, cosExtend;
+	float power;
+	uint32_t child0, child1;
+	uint32_t pad[2];
+} EchoLightNode; /* 64 B */
+
+/* ---- PreparedPointLight (Scenic/Lights/PointLight.cs:20-33) ---- */
+typedef struct EchoPointLight
+{
+	float intensity[3];
+	float position[3];
+} EchoPointLight;
+
+/* ---- infinite lights with constant textures: AmbientLight over a Pure texture (Scenic/Lights/AmbientLight.cs). ---- */
+typedef struct EchoInfiniteLight
+{
+	float radiance[3];        /* Intensity * Texture colour */
+	uint32_t directlyVisible; /* InfiniteLight.DirectlyVisible */
+} EchoInfiniteLight;
+
+/* ---- PerspectiveCamera + RaySpawner inputs (PerspectiveCamera.cs:41-98, RaySpawner.cs:11-64) ---- */
+typedef struct EchoCamera
+{
+	float transform[12]; /* rows 0..2 of Entity.InverseTransform (entity -> world), row-major f00..f23 */
+	float forwardLength; /* 0.5 / tan(fov / 2) */
+	float lensRadius;
+	float focalDistance; /* depth of field is on iff lensRadius and focalDistance are both >= 8e-7 */
+	float pad;
+} EchoCamera;
+
+/* ---- EvaluationProfile + PathTracedEvaluator knobs (EvaluationProfile.cs:42-60, PathTracedEvaluator.cs:33,40) ---- */
+typedef struct EchoRenderParams
+{
+	int32_t width, height;  /* RenderTexture size */
+	int32_t tileSize;       /* square tiles (RenderProfile.cs:45) */
+	int32_t extend;         /* samples per epoch (ContinuousDistribution.Extend) */
+	int32_t minEpoch, maxEpoch;
+	float noiseThreshold;
+	int32_t bounceLimit;    /* PathTracedEvaluator.BounceLimit */
+	float survivability;    /* PathTracedEvaluator.Survivability */
+	uint32_t seed;          /* counter-based sample sequence seed */
+	int32_t epochOffset;    /* first epoch index this call renders (sample sharding across devices) */
+	int32_t reserved;
+} EchoRenderParams;
+
+/* ---- EvaluatorStatistics rows on the hot path, same labels/order as the reference reports them
+ * (EvaluationOperation.cs:130-140; PathTracedEvaluator.cs:50-199) ---- */
+typedef struct EchoStats
+{
+	uint64_t sampleEvaluated;        /* "Sample/Evaluated" */
+	uint64_t sampleRejected;         /* "Sample/Rejected" */
+	uint64_t pixelEvaluated;         /* "Pixel/Evaluated" */
+	uint64_t bounceCreated;          /* "Bounce/Created" */
+	uint64_t bounceSpecular;         /* "Bounce/Specular" */
+	uint64_t bounceMis;              /* "Bounce/Multiple Importance" */
+	uint64_t lightSampled;           /* "Light/Sampled" */
+	uint64_t lightOcclusionChecked;  /* "Light/Occlusion Checked" */
+	uint64_t lightOcclusionPassed;   /* "Light/Occlusion Passed" */
+	uint64_t lightEvaluatedInfinite; /* "Light/Evaluated Infinite" */
+	uint64_t traceQueries;           /* closest-hit queries issued */
+	uint64_t occludeQueries;         /* occlusion queries issued */
+	uint64_t kernelLaunches;         /* CUDA kernels launched by this call */
+	uint64_t reserved[3];
+} EchoStats;
+
+typedef struct EchoScene EchoScene;
+
+int32_t echo_b200_device_count(int32_t* out);
+int32_t echo_b200_scene_create(EchoScene** out, int32_t device);
+
+/* scene upload; pointers are only read during the call */
+int32_t echo_b200_scene_set_qbvh(EchoScene*, const EchoQbvhNode* nodes, uint32_t node_count, uint32_t max_depth);
+int32_t echo_b200_scene_set_triangles(EchoScene*, const EchoTriangle* triangles, uint32_t count);
+int32_t echo_b200_scene_set_spheres(EchoScene*, const EchoSphere* spheres, uint32_t count);
+int32_t echo_b200_scene_set_materials(EchoScene*, const EchoMaterial* materials, uint32_t count);
+int32_t echo_b200_scene_set_light_tree(EchoScene*, const EchoLightNode* nodes, uint32_t node_count,
+                                       const uint32_t* emitter_tokens, const uint64_t* emitter_bitpaths, uint32_t emitter_count,
+                                       const EchoPointLight* points, uint32_t point_count);
+int32_t echo_b200_scene_set_infinite(EchoScene*, const EchoInfiniteLight* lights, uint32_t count, float threshold, float pdf);
+int32_t echo_b200_scene_set_camera(EchoScene*, const EchoCamera* camera);
+int32_t echo_b200_scene_commit(EchoScene*);
+int32_t echo_b200_scene_destroy(EchoScene*);
+
+/* batched Accelerator.Trace / Accelerator.Occlude through PreparedScene's guards (PreparedScene.cs:66-86). Host buffers. */
+int32_t echo_b200_trace_batch(EchoScene*, const EchoRay* rays, uint64_t n, EchoHit* hits);
+int32_t echo_b200_occlude_batch(EchoScene*, const EchoRay* rays, uint64_t n, uint8_t* occluded);
+
+/* same, device-resident buffers on `stream` (a cudaStream_t passed as void*; NULL = default stream). Asynchronous. */
+int32_t echo_b200_trace_batch_device(EchoScene*, const EchoRay* d_rays, uint64_t n, EchoHit* d_hits, void* stream);
+int32_t echo_b200_occlude_batch_device(EchoScene*, const EchoRay* d_rays, uint64_t n, uint8_t* d_occluded, void* stream);
+
+/* one EvaluationOperation worth of tiles. tile_xy holds tile_count (x, y) tile positions (in tiles, not pixels).
+ * out_rgba is tile-major: tile i occupies tileSize*tileSize Float4s, row-major inside the tile, rows growing upward
+ * like Echo's textures; pixels of a partial tile outside the image are left zero. Host buffer. */
+int32_t echo_b200_render_tiles(EchoScene*, const EchoRenderParams*, const int32_t* tile_xy, uint32_t tile_count,
+                               float* out_rgba, EchoStats* stats);
+
+/* device-resident accumulation into a full-frame buffer (width*height Float4: RGB sum of sample means weight, W = epochs
+ * rendered). Used for multi-GPU sharding: each device renders its tiles/epochs into its own frame, frames are summed
+ * with one NCCL all-reduce, then echo_b200_frame_resolve divides by W. Asynchronous on `stream`. */
+int32_t echo_b200_render_frame_device(EchoScene*, const EchoRenderParams*, const int32_t* tile_xy, uint32_t tile_count,
+                                      float* d_frame_rgba, EchoStats* stats, void* stream);
+int32_t echo_b200_frame_resolve_device(EchoScene*, float* d_frame_rgba, int32_t width, int32_t height, void* stream);
+
+const char* echo_b200_last_error(void);
+const char* echo_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

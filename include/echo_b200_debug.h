@@ -1,0 +1,35 @@
+/*
+ * echo_b200_debug.h — diagnostic entry points of libecho_b200.so. Not part of the drop-in surface: they exist so the
+ * parity tests can drive individual device routines (BxDFs, FastMath shims, per-sample radiance) against the oracle,
+ * and so bench.py can read the traversal visit counters that give the algorithmic bytes of a batch
+ * (the device counterpart of Accelerator.TraceCost, Aggregation/Acceleration/QuadBoundingVolumeHierarchy.cs:317-361).
+ */
+#ifndef ECHO_B200_DEBUG_H
+#define ECHO_B200_DEBUG_H
+
+#include "echo_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* like echo_b200_trace_batch_device / occlude, additionally accumulating {node, triangle, sphere} visit totals into
+ * d_counts3 (3 x uint64 on the device, added to, not reset). */
+int32_t echo_b200_trace_batch_device_counted(EchoScene*, const EchoRay* d_rays, uint64_t n, EchoHit* d_hits, uint64_t* d_counts3, void* stream);
+int32_t echo_b200_occlude_batch_device_counted(EchoScene*, const EchoRay* d_rays, uint64_t n, uint8_t* d_occluded, uint64_t* d_counts3, void* stream);
+
+/* BxDF known-answer hook, same kinds / parameter packing / outputs as oracle_bxdf_batch (oracle/oracle.h). Host buffers. */
+int32_t echo_b200_debug_bxdf_batch(int32_t device, int32_t kind, const float* params11, const float* outgoing3, const float* samples2,
+                                   uint64_t n, float* sampled8, float* evaluated4, float* inverse4);
+
+/* FastMath / sincos shims, same op codes as oracle_fastmath (op 100: sin, 101: cos of the deterministic sincos). Host buffers. */
+int32_t echo_b200_debug_math(int32_t device, int32_t op, const float* a, const float* b, const float* c, uint64_t n, float* out);
+
+/* One Evaluator.Evaluate per listed (pixel, sample index): out_rgb receives n x 3 floats. Host buffers. */
+int32_t echo_b200_debug_evaluate_samples(EchoScene*, const EchoRenderParams*, const int32_t* pixel_xy, const uint32_t* sample_index,
+                                         uint64_t n, float* out_rgb);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

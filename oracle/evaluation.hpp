@@ -1,0 +1,655 @@
+// oracle/evaluation.hpp — TEST INFRASTRUCTURE ONLY. CPU restatement of the per-sample integrator and its driver:
+// PreparedScene.Interact / Sample / ProbabilityDensity / EvaluateInfinite, LightCollection, PathTracedEvaluator,
+// PerspectiveCamera.SpawnRay, Accumulator and the EvaluationOperation pixel/epoch/sample loop.
+// Citations are relative to /root/reference/src/Echo.Core/.
+#pragma once
+#include "scattering.hpp"
+
+namespace oracle
+{
+
+// ---- Evaluation/Materials/Emissive.cs:52-53,64 ----
+inline RGB material_emission(const EchoMaterial& m) { return { m.albedo[0], m.albedo[1], m.albedo[2] }; }
+inline float emissive_power(const EchoMaterial& m) { return luminance(material_emission(m)) * kPi; }
+
+inline RGB emissive_emit(const EchoMaterial& m, const GeometryPoint& point, Float3 outgoing)
+{
+	return dot(outgoing, point.normal) > 0.0f ? material_emission(m) : kBlack;
+}
+
+// ---- PreparedScene.Interact (PreparedScene.cs:95-105) + GeometryCollection.GetContactInfo (:200-232) + Material.Scatter ----
+inline void interact(const Scene& scene, const TraceQuery& query, Contact& contact)
+{
+	Float3 infoNormal, infoShading;
+	uint32_t material;
+
+	if (token_type(query.token) == ECHO_TOKEN_TYPE_TRIANGLE)
+	{
+		const EchoTriangle& triangle = scene.triangles[token_index(query.token)];
+		material = triangle.material;
+		infoNormal = triangle_normal(triangle);
+		infoShading = triangle_shading_normal(triangle, query.uv);
+	}
+	else
+	{
+		material = scene.spheres[token_index(query.token)].material;
+		infoNormal = infoShading = sphere_normal(query.uv);
+	}
+
+	// root instance: inverseTransform is the identity, but MultiplyDirection + Normalized still run (:100-101)
+	contact.token = query.token;
+	contact.outgoing = -query.ray.direction;                                    // Contact.cs:39
+	contact.point.position = query.position();                                  // Contact.cs:25
+	contact.point.normal = normalized(identity_multiply_direction(infoNormal));
+	contact.shadeNormal = normalized(identity_multiply_direction(infoShading)); // constant Pure.normal: no normal mapping (Material.cs:61,84-86)
+	contact.material = material;
+
+	scatter_material(scene, material, contact);
+}
+
+// ---- PreparedTriangle.Sample (TriangleEntity.cs:166-174) / PreparedSphere.Sample (SphereEntity.cs:151-191) ----
+inline bool geometry_sample(const Scene& scene, uint32_t token, Float3 origin, Float2 sample, GeometryPoint& point, float& pdf)
+{
+	if (token_type(token) == ECHO_TOKEN_TYPE_TRIANGLE)
+	{
+		const EchoTriangle& triangle = scene.triangles[token_index(token)];
+		Float2 uv = uniform_triangle(sample);
+		point.position = triangle_point(triangle, uv);
+		point.normal = triangle_shading_normal(triangle, uv);
+		pdf = geometry_point_pdf(point, origin, triangle_area(triangle));
+		return true;
+	}
+
+	const EchoSphere& sphere = scene.spheres[token_index(token)];
+	Float3 position = f3(sphere.position);
+	float radius = sphere.radius;
+
+	auto get_point = [&](Float3 normal) { return GeometryPoint{ normal * radius + position, normal }; }; // SphereEntity.cs:227
+
+	Float3 offset = origin - position;
+	float radius2 = radius * radius;
+	float length2 = squared_magnitude(offset);
+
+	if (length2 < radius2)
+	{
+		point = get_point(uniform_sphere(sample));
+		pdf = geometry_point_pdf(point, origin, sphere_area(sphere));
+		return true;
+	}
+
+	float sinMaxT2 = radius2 / length2;
+	float cosMaxT = sqrt0(1.0f - sinMaxT2);
+
+	if (almost_zero(1.0f - cosMaxT))
+	{
+		pdf = 0.0f; // Probable.Impossible
+		return false;
+	}
+
+	float cosT = fma_f(cosMaxT - 1.0f, sample.x, 1.0f);
+	float sinT = identity(cosT);
+	float phi = sample.y * kTau;
+
+	float length = sqrt0(length2);
+	float project = length * cosT - sqrt0(radius2 - length2 * sinT * sinT);
+	float cosA = (length2 + radius2 - project * project) / (2.0f * length * radius);
+	float sinA = identity(cosA);
+
+	float sinP, cosP;
+	sincos_det(phi, sinP, cosP);
+	Float3 normal = normalized(Float3{ sinA * cosP, sinA * sinP, cosA });
+	pdf = uniform_cone_pdf(cosMaxT);
+
+	OrthonormalTransform transform(offset / length);
+	point = get_point(transform.apply_forward(normal));
+	return true;
+}
+
+// ---- PreparedTriangle.ProbabilityDensity (TriangleEntity.cs:177-185) / PreparedSphere.ProbabilityDensity (SphereEntity.cs:194-225) ----
+inline float geometry_pdf(const Scene& scene, uint32_t token, Float3 origin, Float3 incident)
+{
+	if (token_type(token) == ECHO_TOKEN_TYPE_TRIANGLE)
+	{
+		const EchoTriangle& triangle = scene.triangles[token_index(token)];
+		Float2 uv = { 0.0f, 0.0f };
+		float distance = triangle_intersect(triangle, origin, incident, uv);
+		if (distance == kInfinity) return 0.0f;
+		return distance * distance / fabs_bits(dot(triangle_shading_normal(triangle, uv), incident) * triangle_area(triangle));
+	}
+
+	const EchoSphere& sphere = scene.spheres[token_index(token)];
+	float radius = sphere.radius;
+	Float3 offset = origin - f3(sphere.position);
+	float radius2 = radius * radius;
+	float length2 = squared_magnitude(offset);
+
+	if (length2 <= radius2)
+	{
+		float projected = dot(offset, incident);
+		float extend2 = fma_f(projected, projected, radius2 - length2);
+
+		float distance = sqrt0(extend2) - projected;
+		Float3 normal = offset + incident * distance;
+
+		float cosWeight = dot(incident, normal) * radius;
+		if (almost_zero(cosWeight)) return 0.0f;
+
+		return distance * distance / fabs_bits(cosWeight) * kUniformSpherePdf;
+	}
+
+	float sinMaxT2 = radius2 / length2;
+	float cosMaxT = sqrt0(1.0f - sinMaxT2);
+	return almost_zero(1.0f - cosMaxT) ? 0.0f : uniform_cone_pdf(cosMaxT);
+}
+
+// ---- PreparedScene.Sample (PreparedScene.cs:182-204) -> LightCollection.Sample (LightCollection.cs:141-193),
+//      PreparedPointLight.Sample (Scenic/Lights/PointLight.cs:48-66), AmbientLight.Sample over a Pure texture ----
+inline ProbableRGB scene_sample_light(const Scene& scene, uint32_t light, const GeometryPoint& origin, Float2 sample, Float3& incident, float& travel)
+{
+	incident = { 0.0f, 0.0f, 0.0f };
+	travel = 0.0f;
+
+	if (token_is_infinite_light(light))
+	{
+		// AmbientLight.cs:60-67 with Pure as IDirectionalTexture: the default interface Sample draws a uniform sphere
+		// direction with pdf 1/(4 pi) (Textures/Directional/IDirectionalTexture.cs); rotation is the identity in scope.
+		const EchoInfiniteLight& infinite = scene.infiniteLights[token_light_index(light)];
+		incident = uniform_sphere(sample);
+		travel = kInfinity;
+		return { RGB{ infinite.radiance[0], infinite.radiance[1], infinite.radiance[2] }, kUniformSpherePdf };
+	}
+
+	if (token_type(light) == ECHO_TOKEN_TYPE_LIGHT) // point light
+	{
+		const EchoPointLight& point = scene.pointLights[token_light_index(light)];
+		Float3 offset = f3(point.position) - origin.position;
+		float travel2 = squared_magnitude(offset);
+
+		if (!positive(travel2)) return {};
+
+		travel = sqrt0(travel2);
+		float travelR = 1.0f / travel;
+		incident = offset * travelR;
+
+		RGB intensity = { point.intensity[0], point.intensity[1], point.intensity[2] };
+		return { intensity * travelR * travelR, 1.0f };
+	}
+
+	// emissive geometry: LightCollection.HandleGeometry, LightCollection.cs:166-183
+	uint32_t materialIndex = scene.geometry_material(light);
+	const EchoMaterial& material = scene.materials[materialIndex];
+	if (material.type != ECHO_MATERIAL_EMISSIVE) return {};
+
+	GeometryPoint point;
+	float pdf;
+	if (!geometry_sample(scene, light, origin.position, sample, point, pdf)) return {};
+	if (!positive(pdf)) return {};
+
+	Float3 delta = point.position - origin.position;
+	float travel2 = squared_magnitude(delta);
+	if (!positive(travel2)) return {};
+
+	travel = sqrt0(travel2);
+	incident = delta * (1.0f / travel);
+
+	travel *= 1.0f - 2E-5f; // TravelMultiplier, LightCollection.cs:89
+	return { emissive_emit(material, point, -incident), pdf };
+}
+
+// ---- PreparedScene.ProbabilityDensity (PreparedScene.cs:207-225) -> LightCollection.ProbabilityDensity (:196-219) ----
+inline float scene_light_pdf(const Scene& scene, uint32_t light, const GeometryPoint& origin, Float3 incident)
+{
+	if (token_is_infinite_light(light)) return kUniformSpherePdf;
+	if (token_type(light) == ECHO_TOKEN_TYPE_LIGHT) return 1.0f; // LightCollection.cs:206 (point)
+
+	// identity forwardTransform: MultiplyDirection(incident).Normalized still runs (:221-224)
+	Float3 direction = normalized(identity_multiply_direction(incident));
+	return geometry_pdf(scene, light, origin.position, direction);
+}
+
+// ---- PreparedScene.EvaluateInfinite (PreparedScene.cs:233-253) ----
+inline RGB evaluate_infinite(const Scene& scene, Float3 /*direction*/, bool direct)
+{
+	RGB total = kBlack;
+
+	for (const EchoInfiniteLight& light : scene.infiniteLights)
+	{
+		if (direct && !light.directlyVisible) continue;
+		total = total + RGB{ light.radiance[0], light.radiance[1], light.radiance[2] };
+	}
+
+	return total;
+}
+
+// per-sample random numbers in the reference's draw order (CameraSample.cs:19-23; PathTracedEvaluator.cs:60-66)
+struct SampleStream
+{
+	uint32_t key;
+	uint32_t dimension = 0;
+
+	float next1d() { return sample_value(key, dimension++); }
+
+	Float2 next2d()
+	{
+		float x = next1d();
+		float y = next1d();
+		return { x, y };
+	}
+};
+
+struct EvaluatorStats // the labels of EvaluatorStatistics used on this path, echo_b200.h EchoStats order
+{
+	uint64_t bounceCreated = 0, bounceSpecular = 0, bounceMis = 0;
+	uint64_t lightSampled = 0, lightOcclusionChecked = 0, lightOcclusionPassed = 0, lightEvaluatedInfinite = 0;
+	uint64_t traceQueries = 0, occludeQueries = 0;
+
+	void add(const EvaluatorStats& o)
+	{
+		bounceCreated += o.bounceCreated; bounceSpecular += o.bounceSpecular; bounceMis += o.bounceMis;
+		lightSampled += o.lightSampled; lightOcclusionChecked += o.lightOcclusionChecked;
+		lightOcclusionPassed += o.lightOcclusionPassed; lightEvaluatedInfinite += o.lightEvaluatedInfinite;
+		traceQueries += o.traceQueries; occludeQueries += o.occludeQueries;
+	}
+};
+
+// ---- Evaluation/Evaluators/PathTracedEvaluator.cs ----
+struct PathTracedEvaluator
+{
+	int bounceLimit = 128;      // :33
+	float survivability = 2.5f; // :40
+
+	static float power_heuristic(float pdf0, float pdf1) // :213-217
+	{
+		float squared = pdf0 * pdf0;
+		return squared / (squared + pdf1 * pdf1);
+	}
+
+	struct Path // :223-321
+	{
+		RGB result = kBlack;
+		RGB energy = kWhite;
+		Contact contact;
+		TraceQuery query;
+
+		Float3 current_direction() const { return query.ray.direction; }
+
+		bool advance(const Scene& scene, EvaluatorStats& stats)
+		{
+			++stats.traceQueries;
+			if (!scene.trace(query)) return false;
+			interact(scene, query, contact);
+			return true;
+		}
+
+		void contribute(RGB value) { result = result + energy * value; }
+
+		void contribute_emissive(const Scene& scene, float weight = 1.0f)
+		{
+			const EchoMaterial& material = scene.materials[contact.material];
+			if (material.type != ECHO_MATERIAL_EMISSIVE) return;
+			if (!positive(emissive_power(material))) return;
+			contribute(emissive_emit(material, contact.point, contact.outgoing) * weight);
+		}
+
+		bool russian_roulette(float survivability, float sample) // :313-320
+		{
+			float rate = clamp01(survivability * luminance(energy));
+			if (sample >= rate) return false;
+			energy = energy / rate;
+			return true;
+		}
+
+		bool proceed(RGB scatter, float scatterPdf, Float3 incident, float survivability, float sample) // Continue, :282-293
+		{
+			if (!positive(scatterPdf)) return false;
+
+			energy = energy * (scatter / scatterPdf);
+
+			bool survived = russian_roulette(survivability, sample);
+
+			if (survived)
+			{
+				// TraceQuery.SpawnTrace, TraceQuery.cs:88 — new origin is the hit position, ignore = hit token
+				TraceQuery spawned;
+				spawned.ray = Ray(query.position(), incident);
+				spawned.ignore = query.token;
+				query = spawned;
+			}
+
+			return survived;
+		}
+	};
+
+	// :162-207
+	RGB importance_sample_radiant(const Scene& scene, const Contact& contact, EvaluatorStats& stats, float lightSample, Float2 radiantSample, bool& mis) const
+	{
+		float lightPdf;
+		uint32_t light = scene.pick(contact.point, lightSample, lightPdf);
+
+		if (!positive(lightPdf))
+		{
+			mis = false;
+			return kBlack;
+		}
+
+		Float3 incident;
+		float travel;
+		ProbableRGB radiantSampled = scene_sample_light(scene, light, contact.point, radiantSample, incident, travel);
+		RGB radiant = radiantSampled.content;
+
+		float pdf = lightPdf * radiantSampled.pdf;
+		mis = token_is_area_light(light);
+
+		if (!positive(pdf) || is_zero(radiant)) return kBlack;
+		++stats.lightSampled;
+
+		RGB scatter = contact.bsdf.evaluate(contact.outgoing, incident);
+		scatter = scatter * contact.normal_dot(incident);
+
+		if (is_zero(scatter)) return kBlack;
+		++stats.lightOcclusionChecked;
+
+		OccludeQuery query; // Contact.SpawnOcclude, Contact.cs:86
+		query.ray = Ray(contact.point.position, incident);
+		query.travel = travel;
+		query.ignore = contact.token;
+		++stats.occludeQueries;
+		if (scene.occlude(query)) return kBlack;
+
+		++stats.lightOcclusionPassed;
+
+		radiant = radiant * (scatter / pdf);
+		if (!mis) return radiant;
+
+		float scatterPdf = contact.bsdf.probability_density(contact.outgoing, incident);
+		return radiant * power_heuristic(pdf, scatterPdf);
+	}
+
+	// :43-150
+	RGB evaluate(const Scene& scene, const Ray& ray, SampleStream& distribution, EvaluatorStats& stats) const
+	{
+		Path path;
+		path.query.ray = ray;
+
+		if (!path.advance(scene, stats))
+		{
+			++stats.lightEvaluatedInfinite;
+			return evaluate_infinite(scene, path.current_direction(), true);
+		}
+
+		path.contribute_emissive(scene);
+
+		for (int depth = 0; depth < bounceLimit; depth++)
+		{
+			// Bounce, :326-354
+			Float3 bounceIncident;
+			const BxDF* function;
+			ProbableRGB bounced = path.contact.bsdf.sample(path.contact.outgoing, distribution.next2d(), bounceIncident, function);
+			RGB bounceScatter = bounced.content * path.contact.normal_dot(bounceIncident);
+			float bounceScatterPdf = bounced.pdf;
+			++stats.bounceCreated;
+
+			float survivalSample = distribution.next1d();
+			float lightSample = distribution.next1d();
+			Float2 radiantSample = distribution.next2d();
+
+			if (!positive(bounceScatterPdf) || type_any(function->type, Specular))
+			{
+				++stats.bounceSpecular;
+				if (!path.proceed(bounceScatter, bounceScatterPdf, bounceIncident, survivability, survivalSample)) break;
+			}
+			else
+			{
+				bool mis;
+				path.contribute(importance_sample_radiant(scene, path.contact, stats, lightSample, radiantSample, mis));
+
+				if (!path.proceed(bounceScatter, bounceScatterPdf, bounceIncident, survivability, survivalSample)) break;
+
+				if (mis)
+				{
+					GeometryPoint oldPoint = path.contact.point;
+					++stats.bounceMis;
+
+					if (path.advance(scene, stats))
+					{
+						uint32_t light = path.contact.token;
+						float pmf = scene.probability_mass(light, oldPoint);
+						if (!positive(pmf)) continue;
+
+						float pdf = scene_light_pdf(scene, light, oldPoint, path.current_direction());
+						if (!positive(pdf)) continue;
+
+						path.contribute_emissive(scene, power_heuristic(bounceScatterPdf, pmf * pdf));
+						continue;
+					}
+
+					Float3 direction = path.current_direction();
+
+					for (size_t i = 0; i < scene.infiniteLights.size(); i++)
+					{
+						uint32_t token = ECHO_LIGHT_TOKEN_MAKE(ECHO_LIGHT_TYPE_INFINITE, (uint32_t)i);
+						float pdf = scene.probability_mass(token, oldPoint) * scene_light_pdf(scene, token, oldPoint, direction);
+						if (!positive(pdf)) continue;
+
+						float weight = power_heuristic(bounceScatterPdf, pdf);
+						const EchoInfiniteLight& light = scene.infiniteLights[i];
+						path.contribute(RGB{ light.radiance[0], light.radiance[1], light.radiance[2] } * weight);
+					}
+
+					++stats.lightEvaluatedInfinite;
+					break;
+				}
+			}
+
+			if (!path.advance(scene, stats))
+			{
+				++stats.lightEvaluatedInfinite;
+				path.contribute(evaluate_infinite(scene, path.current_direction(), false));
+				break;
+			}
+
+			path.contribute_emissive(scene);
+		}
+
+		return path.result;
+	}
+};
+
+// ---- Scenic/Cameras/RaySpawner.cs:19-46 + PerspectiveCamera.cs:51-98 ----
+struct CameraSpawner
+{
+	float sizeRX, offsetY;
+
+	CameraSpawner(int width, int height)
+	{
+		sizeRX = 1.0f / (float)width;                        // TextureGrid.cs:22
+		float aspectY = (float)height / (float)width;        // TextureGrid.cs:25-29
+		offsetY = aspectY / -2.0f;                           // RaySpawner.cs:22
+	}
+
+	Float2 spawn_x(int px, int py, Float2 shift) const // RaySpawner.cs:37-46
+	{
+		float sx = shift.x + (float)px;
+		float sy = shift.y + (float)py;
+		return { fma_f(sx, sizeRX, 1.0f / -2.0f), fma_f(sy, sizeRX, offsetY) };
+	}
+};
+
+inline Float3 camera_multiply_direction(const EchoCamera& c, Float3 d) // Float4x4.cs:267-272
+{
+	const float* m = c.transform;
+	return {
+		m[0] * d.x + m[1] * d.y + m[2] * d.z,
+		m[4] * d.x + m[5] * d.y + m[6] * d.z,
+		m[8] * d.x + m[9] * d.y + m[10] * d.z
+	};
+}
+
+inline Float3 camera_multiply_point(const EchoCamera& c, Float3 p) // Float4x4.cs:260-265
+{
+	const float* m = c.transform;
+	return {
+		m[0] * p.x + m[1] * p.y + m[2] * p.z + m[3],
+		m[4] * p.x + m[5] * p.y + m[6] * p.z + m[7],
+		m[8] * p.x + m[9] * p.y + m[10] * p.z + m[11]
+	};
+}
+
+inline Ray camera_spawn_ray(const EchoCamera& camera, const CameraSpawner& spawner, int px, int py, Float2 shift, Float2 lens)
+{
+	bool hasDepthOfField = positive(camera.lensRadius) && positive(camera.focalDistance); // PerspectiveCamera.cs:46
+
+	if (!hasDepthOfField) // :93-98
+	{
+		Float2 uv = spawner.spawn_x(px, py, shift);
+		Float3 direction = camera_multiply_direction(camera, Float3{ uv.x, uv.y, camera.forwardLength });
+		Float3 position = { camera.transform[3], camera.transform[7], camera.transform[11] }; // RootedPosition
+		return Ray(position, normalized(direction));
+	}
+
+	// :55-68
+	float focusScale = camera.focalDistance / camera.forwardLength;
+	Float2 disk = concentric_disk(lens);
+	Float2 lensPoint = { disk.x * camera.lensRadius, disk.y * camera.lensRadius };
+	Float2 uv = spawner.spawn_x(px, py, shift);
+	Float3 focus = { uv.x * focusScale, uv.y * focusScale, camera.focalDistance };
+
+	Float3 origin = { lensPoint.x, lensPoint.y, 0.0f };
+	Float3 direction = focus - origin;
+
+	return Ray(camera_multiply_point(camera, origin), normalized(camera_multiply_direction(camera, direction)));
+}
+
+// ---- Common/Mathematics/Primitives/Summation.cs (Kahan) on one Float4 lane-set; W lane carried like the reference ----
+struct Float4
+{
+	float v[4];
+};
+
+inline Float4 f4_op(Float4 a, Float4 b, char op)
+{
+	Float4 r;
+	for (int i = 0; i < 4; i++) r.v[i] = op == '+' ? a.v[i] + b.v[i] : (op == '-' ? a.v[i] - b.v[i] : a.v[i] * b.v[i]);
+	return r;
+}
+
+struct Summation
+{
+	Float4 total = { { 0, 0, 0, 0 } }, error = { { 0, 0, 0, 0 } };
+
+	Summation add(Float4 value) const // Summation.cs:31-38
+	{
+		Float4 delta = f4_op(value, error, '-');
+		Float4 newTotal = f4_op(total, delta, '+');
+		Float4 newError = f4_op(f4_op(newTotal, total, '-'), delta, '-');
+		return { newTotal, newError };
+	}
+
+	Summation add(const Summation& value) const // Summation.cs:42-51
+	{
+		Float4 newError = f4_op(error, value.error, '+');
+		Float4 delta = f4_op(value.total, newError, '-');
+		Float4 newTotal = f4_op(total, delta, '+');
+		newError = f4_op(f4_op(newTotal, total, '-'), delta, '-');
+		return { newTotal, newError };
+	}
+
+	Summation scale(Float4 value) const { return { f4_op(total, value, '*'), f4_op(error, value, '*') }; } // Summation.cs:40
+
+	Summation negated() const
+	{
+		Summation r;
+		for (int i = 0; i < 4; i++) { r.total.v[i] = -total.v[i]; r.error.v[i] = -error.v[i]; }
+		return r;
+	}
+};
+
+// ---- Processes/Evaluation/Accumulator.cs:11-71 ----
+struct Accumulator
+{
+	Summation average, squared;
+	uint32_t count = 0;
+
+	bool add(Float4 sample)
+	{
+		float sum = (sample.v[0] + sample.v[1]) + (sample.v[2] + sample.v[3]); // Float4.Sum, Float4.cs:73-81
+		if (!std::isfinite(sum)) return false;
+
+		++count;
+
+		Float4 negative = { { -sample.v[0], -sample.v[1], -sample.v[2], -sample.v[3] } };
+		Summation delta = average.add(negative); // average - sample
+
+		float countR = 1.0f / (float)count;      // Summation operator / : multiply by 1f / value
+		Float4 countRV = { { countR, countR, countR, countR } };
+		average = average.add(delta.scale(countRV).negated()); // average -= delta / count
+
+		Summation after = average.add(negative);                // (average - sample)
+		squared = squared.add(delta.scale(after.total));        // squared += delta * (average - sample).Result
+		return true;
+	}
+
+	Float4 value() const { return average.total; }
+
+	// Accumulator.Noise (:28-51) with exact 1/x and 1/sqrt(x) in place of rcpps/rsqrtps (12-bit hardware
+	// approximations whose bits differ between CPU vendors); only the adaptive-epoch stop test reads it.
+	float noise_max() const
+	{
+		if (count < 2) return 0.0f;
+
+		float oneLess = (float)(count - 1u);
+		oneLess *= oneLess * oneLess;
+
+		float result = 0.0f;
+
+		for (int i = 0; i < 4; i++)
+		{
+			float mean = average.total.v[i];
+			float numerator = mean * mean * oneLess;
+			float denominator = 1.0f / squared.total.v[i];
+			float noise = numerator != 0.0f ? 1.0f / std::sqrt(numerator * denominator) : 0.0f;
+			if (i == 0 || noise > result) result = noise; // Float4.MaxComponent over the masked lanes
+		}
+
+		return result;
+	}
+};
+
+// ---- Processes/Evaluation/EvaluationOperation.cs:100-141, one pixel ----
+inline Float4 evaluate_pixel(const Scene& scene, const EchoRenderParams& params, int px, int py, EvaluatorStats& stats, uint64_t& samples, uint64_t& rejected)
+{
+	PathTracedEvaluator evaluator;
+	evaluator.bounceLimit = params.bounceLimit;
+	evaluator.survivability = params.survivability;
+
+	CameraSpawner spawner(params.width, params.height);
+	Accumulator accumulator;
+	uint32_t pixel = (uint32_t)py * (uint32_t)params.width + (uint32_t)px;
+
+	int epoch = 0;
+
+	do
+	{
+		++epoch;
+
+		for (int i = 0; i < params.extend; i++)
+		{
+			uint32_t sampleIndex = (uint32_t)(params.epochOffset + epoch - 1) * (uint32_t)params.extend + (uint32_t)i;
+			SampleStream distribution{ sample_key(params.seed, pixel, sampleIndex) };
+
+			Float2 shift = distribution.next2d(); // CameraSample.Create, CameraSample.cs:19-23
+			Float2 lens = distribution.next2d();
+			Ray ray = camera_spawn_ray(scene.camera, spawner, px, py, shift, lens);
+
+			RGB evaluated = evaluator.evaluate(scene, ray, distribution, stats);
+			++samples;
+
+			if (!accumulator.add(Float4{ { evaluated.r, evaluated.g, evaluated.b, 0.0f } })) ++rejected;
+		}
+	}
+	while (epoch < params.maxEpoch && (epoch < params.minEpoch || accumulator.noise_max() > params.noiseThreshold));
+
+	return accumulator.value();
+}
+
+} // namespace oracle

@@ -1,0 +1,46 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _native_libraries():
+    """The oracle and the host library are built on demand so a fresh checkout can run the CPU suite directly."""
+    import subprocess
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
+    host = os.path.join(ROOT, "echorenderer_b200", "libecho_host.so")
+    if not os.path.exists(host):
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "echorenderer_b200", "csrc"), "../libecho_host.so"], check=True)
+
+
+@pytest.fixture(scope="session")
+def cornell():
+    from echorenderer_b200 import host, scenes
+    return host.prepare(scenes.cornell_box())
+
+
+@pytest.fixture(scope="session")
+def terrain_small():
+    from echorenderer_b200 import host, scenes
+    return host.prepare(scenes.terrain_scene(96, 48, 400))
+
+
+@pytest.fixture(scope="session")
+def mixed_small():
+    from echorenderer_b200 import host, scenes
+    return host.prepare(scenes.mixed_material_scene(rings=24, segments=24))
+
+
+@pytest.fixture(scope="session")
+def lights_small():
+    from echorenderer_b200 import host, scenes
+    return host.prepare(scenes.many_lights_scene(light_count=300, rings=16, segments=16))
