@@ -1,0 +1,106 @@
+"""Parity of the wavefront path tracer with the oracle's per-sample PathTracedEvaluator, through the C ABI.
+
+Device and oracle share the sample sequence and a deterministic sincos, and every other operation is an IEEE-rounded
++, -, *, /, sqrt or fma in the same order, so a sample's radiance is expected to be bit-identical. The tests allow a
+tiny budget of differing samples (none observed so far) and bound the image error far below the north-star tolerance
+(relative RMSE <= 1e-3 at matched spp)."""
+import numpy as np
+import pytest
+
+from echorenderer_b200 import EvaluationOperation, EvaluationProfile, PathTracedEvaluator, PreparedScene, RenderTexture, scenes, structs
+from tests import oracle_lib
+
+pytestmark = pytest.mark.gpu
+
+
+def sample_grid(width, height, spp, stride=1):
+    ys, xs = np.meshgrid(np.arange(0, height, stride), np.arange(0, width, stride), indexing="ij")
+    pixels = np.stack([xs.reshape(-1), ys.reshape(-1)], axis=-1).astype(np.int32)
+    pixel_xy = np.repeat(pixels, spp, axis=0)
+    sample_index = np.tile(np.arange(spp, dtype=np.uint32), len(pixels))
+    return pixel_xy, sample_index
+
+
+def relative_rmse(actual, expected):
+    return float(np.sqrt(np.mean((actual - expected) ** 2)) / max(np.sqrt(np.mean(expected ** 2)), 1e-12))
+
+
+@pytest.mark.parametrize("fixture,bounce_limit", [("cornell", 128), ("mixed_small", 8), ("lights_small", 128), ("terrain_small", 16)])
+def test_samples_match_oracle(fixture, bounce_limit, request):
+    prepared = request.getfixturevalue(fixture)
+    oracle = oracle_lib.OracleScene(prepared)
+    width, height = 96, 64
+    params = structs.render_params(width, height, 16, extend=4, bounce_limit=bounce_limit, seed=7)
+    pixel_xy, sample_index = sample_grid(width, height, 4)
+
+    with PreparedScene(prepared) as scene:
+        actual = scene.evaluate_samples(params, pixel_xy, sample_index)
+
+    expected = oracle.evaluate_samples(params, pixel_xy, sample_index)
+    assert np.isfinite(actual).all()
+    assert expected.max() > 0
+
+    different = np.any(actual.view(np.uint32) != expected.view(np.uint32), axis=1)
+    assert different.mean() <= 1e-4, f"{different.sum()} of {len(different)} samples are not bit-identical"
+    assert relative_rmse(actual, expected) <= 1e-4
+
+
+@pytest.mark.parametrize("fixture", ["cornell", "mixed_small"])
+def test_render_tiles_match_oracle(fixture, request):
+    prepared = request.getfixturevalue(fixture)
+    oracle = oracle_lib.OracleScene(prepared)
+    width, height = 80, 48  # ragged: partial tiles on both edges
+    params = structs.render_params(width, height, 32, extend=8, min_epoch=2, max_epoch=2, bounce_limit=16, seed=3)
+    tiles = scenes.tile_grid(width, height, 32)
+
+    with PreparedScene(prepared) as scene:
+        actual, stats = scene.render_tiles(params, tiles)
+
+    expected, expected_stats = oracle.render_tiles(params, tiles)
+    assert relative_rmse(actual, expected) <= 1e-4
+
+    # the statistics rows of EvaluatorStatistics agree exactly when every sample takes the same decisions
+    for name in structs.STATS_FIELDS[:12]:
+        assert abs(int(stats[name][0]) - int(expected_stats[name][0])) <= 1e-4 * max(1, int(expected_stats[name][0])), name
+    assert int(stats["sampleEvaluated"][0]) == width * height * 16
+    assert int(stats["kernelLaunches"][0]) > 0
+
+
+def test_adaptive_epochs_match_oracle(cornell):
+    """MinEpoch < MaxEpoch: the noise-driven epoch loop (EvaluationOperation.cs:137) stops per pixel like the oracle's."""
+    oracle = oracle_lib.OracleScene(cornell)
+    width = height = 32
+    params = structs.render_params(width, height, 16, extend=8, min_epoch=1, max_epoch=6, noise_threshold=0.3, seed=5)
+    tiles = scenes.tile_grid(width, height, 16)
+
+    with PreparedScene(cornell) as scene:
+        actual, stats = scene.render_tiles(params, tiles)
+
+    expected, expected_stats = oracle.render_tiles(params, tiles)
+    assert int(stats["sampleEvaluated"][0]) == int(expected_stats["sampleEvaluated"][0])
+    assert width * height * 8 < int(stats["sampleEvaluated"][0]) < width * height * 48
+    assert relative_rmse(actual, expected) <= 1e-4
+
+
+def test_evaluation_operation_interface(cornell):
+    """The host-side mirror of EvaluationOperation: profile validation, tile application, TotalSamples, statistics labels."""
+    with pytest.raises(ValueError):
+        EvaluationProfile(extend=0).validate()
+    with pytest.raises(ValueError):
+        EvaluationProfile(min_epoch=3, max_epoch=2).validate()
+
+    with PreparedScene(cornell) as scene:
+        destination = RenderTexture(64, 64, 16)
+        profile = EvaluationProfile(evaluator=PathTracedEvaluator(), extend=4, min_epoch=1, max_epoch=1)
+        operation = EvaluationOperation(scene, profile, destination)
+        operation.execute()
+
+        assert operation.total_samples == 64 * 64 * 4
+        report = operation.statistics_report()
+        assert report["Pixel/Evaluated"] == 64 * 64
+        assert report["Bounce/Created"] > 0
+        image = destination.pixels
+        assert np.isfinite(image).all() and image[..., :3].mean() > 0.01
+        # the red wall is on the left, the green wall on the right (CornellBox.cs:44-45)
+        assert image[24:40, 2:8, 0].mean() > 2 * image[24:40, 2:8, 1].mean()
+        assert image[24:40, -8:-2, 1].mean() > 2 * image[24:40, -8:-2, 0].mean()
