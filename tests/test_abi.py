@@ -1,0 +1,109 @@
+"""The C-ABI boundary without a GPU: the library loads, exports every symbol include/*.h declares, keeps the POD layouts of
+the reference's structs, and refuses compute without a device (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from echorenderer_b200 import _native, structs
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions(header):
+    text = open(os.path.join(ROOT, "include", header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return set(re.findall(r"\b(echo_(?:b200|host)_\w+)\s*\(", text))
+
+
+def have_gpu():
+    try:
+        return _native.device_count() > 0
+    except _native.EchoNativeError:
+        return False
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _native.library()
+    declared = declared_functions("echo_b200.h") | declared_functions("echo_b200_debug.h")
+    assert declared == set(_native.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert b"sm_100a" in lib.echo_b200_version()
+
+
+def test_host_library_exports_every_declared_symbol():
+    from echorenderer_b200 import host
+    lib = host._library()
+    for name in declared_functions("echo_host.h"):
+        assert hasattr(lib, name), name
+
+
+def test_pod_layouts_match_the_header():
+    """sizeof / offsetof of the C structs, recomputed by compiling the header (gcc), equal the numpy mirrors."""
+    import subprocess
+    import tempfile
+    fields = {
+        "EchoQbvhNode": ("QBVH_NODE", ["minX", "maxZ", "axisMajor", "axisMinor1", "token4", "pad"]),
+        "EchoTriangle": ("TRIANGLE", ["vertex0", "edge2", "normal0", "texcoord0", "material"]),
+        "EchoSphere": ("SPHERE", ["position", "radius", "material"]),
+        "EchoRay": ("RAY", ["origin", "direction", "distance", "ignore"]),
+        "EchoHit": ("HIT", ["token", "distance", "uv"]),
+        "EchoMaterial": ("MATERIAL", ["type", "albedo", "roughness", "ior", "paramA", "paramB", "base"]),
+        "EchoLightNode": ("LIGHT_NODE", ["boxMin", "coneAxis", "cosOffset", "power", "child0", "child1"]),
+        "EchoCamera": ("CAMERA", ["transform", "forwardLength", "focalDistance"]),
+        "EchoRenderParams": ("RENDER_PARAMS", ["width", "extend", "noiseThreshold", "seed", "epochOffset"]),
+        "EchoStats": ("STATS", ["sampleEvaluated", "lightEvaluatedInfinite", "kernelLaunches"]),
+    }
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "echo_b200.h"', "int main(void) {"]
+    for c_name, (_, names) in fields.items():
+        lines.append(f'printf("{c_name} %zu\\n", sizeof({c_name}));')
+        for name in names:
+            lines.append(f'printf("{c_name}.{name} %zu\\n", offsetof({c_name}, {name}));')
+    lines.append("return 0; }")
+
+    with tempfile.TemporaryDirectory() as directory:
+        source, binary = os.path.join(directory, "layout.c"), os.path.join(directory, "layout")
+        open(source, "w").write("\n".join(lines))
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), source, "-o", binary], check=True)
+        output = subprocess.run([binary], check=True, capture_output=True, text=True).stdout
+
+    for line in output.splitlines():
+        key, value = line.split()
+        c_name, _, member = key.partition(".")
+        dtype = getattr(structs, fields[c_name][0])
+        assert int(value) == (dtype.fields[member][1] if member else dtype.itemsize), line
+
+    # the sizes the reference's structs have (a1, a9, a10)
+    assert structs.QBVH_NODE.itemsize == 128 and structs.TRIANGLE.itemsize == 100 and structs.SPHERE.itemsize == 20
+
+
+@pytest.mark.skipif(have_gpu(), reason="checks the no-device behaviour")
+def test_no_cpu_fallback_without_a_device(cornell):
+    """Every compute entry point fails loudly (ECHO_B200_ERR_NO_DEVICE) instead of falling back to the CPU."""
+    from echorenderer_b200 import PreparedScene
+    lib = _native.library()
+    count = ctypes.c_int32(-1)
+    assert lib.echo_b200_device_count(ctypes.byref(count)) == _native.ERR_NO_DEVICE and count.value == 0
+    assert b"CUDA" in lib.echo_b200_last_error()
+
+    handle = ctypes.c_void_p()
+    assert lib.echo_b200_scene_create(ctypes.byref(handle), 0) == _native.ERR_NO_DEVICE and not handle.value
+
+    with pytest.raises(_native.EchoNativeError) as error:
+        PreparedScene(cornell)
+    assert error.value.status == _native.ERR_NO_DEVICE
+
+    out = np.zeros(8, dtype=np.float32)
+    zeros = np.zeros(8, dtype=np.float32)
+    assert lib.echo_b200_debug_math(0, 0, _native.pointer(zeros), _native.pointer(zeros), _native.pointer(zeros), 8, _native.pointer(out)) == _native.ERR_NO_DEVICE
+
+
+def test_null_scene_is_rejected():
+    lib = _native.library()
+    assert lib.echo_b200_scene_commit(None) == _native.ERR_INVALID
+    assert lib.echo_b200_trace_batch(None, None, 0, None) == _native.ERR_INVALID
+    assert lib.echo_b200_render_tiles(None, None, None, 0, None, None) == _native.ERR_INVALID
+    assert lib.echo_b200_scene_destroy(None) == _native.OK
