@@ -21,6 +21,9 @@ int stack_class(uint32_t maxDepth); // 0: 48, 1: 96, 2: 192 entries, -1: unsuppo
 bool launch_trace(const DeviceScene& scene, const EchoRay* rays, uint64_t n, EchoHit* hits, unsigned long long* counts, cudaStream_t stream);
 bool launch_occlude(const DeviceScene& scene, const EchoRay* rays, uint64_t n, uint8_t* occluded, unsigned long long* counts, cudaStream_t stream);
 
+unsigned long long* next_ray_counter(cudaStream_t stream); // zeroed work counter for one persistent launch
+int persistent_grid(const void* kernel);                  // resident CTAs of a persistent kernel on the current device
+
 // ---- render.cu ----
 struct RenderState; // wavefront buffers, owned per scene
 

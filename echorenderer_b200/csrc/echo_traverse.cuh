@@ -1,0 +1,302 @@
+// echo_traverse.cuh — the persistent, work-replacing QBVH traversal core used by every closest-hit / occlusion kernel.
+//
+// Why not one thread per ray: in an incoherent batch most rays leave the tree after 1-3 nodes while a few need 30+, so a
+// warp that walks 32 fixed rays runs at ~5 active lanes (measured: profiles/r1a, 4.88 threads per instruction). Here a
+// grid of resident warps pulls rays from a global counter: each warp reserves a pool of kPool consecutive rays with one
+// global atomic, lanes take the next ray from the pool with a shared-memory atomic the moment their ray ends (work
+// replacement), and primitive tests are postponed until several lanes have one pending (while-while with a vote), so the
+// expensive fp64-cross Möller–Trumbore code is issued for many lanes at once.
+//
+// Per ray, the sequence of operations is exactly the reference's (QuadBoundingVolumeHierarchy.cs:123-315,
+// GeometryCollection.cs:85-171): same visit order, same culling comparisons, leaves intersected in push order. Only the
+// interleaving ACROSS rays changes, so results stay bit-identical to the one-thread-per-ray kernels and to the oracle.
+#pragma once
+#include "echo_scene.cuh"
+
+namespace echo
+{
+
+constexpr int kTraverseBlock = 128;              // 4 warps per CTA
+constexpr int kTraverseWarps = kTraverseBlock / 32;
+constexpr unsigned long long kPool = 256;         // rays reserved per global atomic
+constexpr int kLeafVote = 8;                      // run the primitive tests once this many lanes have one pending
+
+struct WarpPool
+{
+	unsigned long long next, end;
+};
+
+// BoxBound4.Intersect for one lane with hardware min/max. Bit-identical to slab() whenever no operand is NaN, which holds
+// when the three reciprocal direction components and the origin are finite (a NaN needs 0 * inf or inf - inf); the sign
+// of a zero result may differ, which no comparison downstream can observe.
+ECHO_DEVICE float slab_finite(float minX, float minY, float minZ, float maxX, float maxY, float maxZ, vec3 origin, vec3 directionR)
+{
+	float x0 = (minX - origin.x) * directionR.x, x1 = (maxX - origin.x) * directionR.x;
+	float y0 = (minY - origin.y) * directionR.y, y1 = (maxY - origin.y) * directionR.y;
+	float z0 = (minZ - origin.z) * directionR.z, z1 = (maxZ - origin.z) * directionR.z;
+
+	float far = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1));
+	float near = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fminf(z0, z1));
+
+	far *= 1.00000024f;
+	return ((far >= near) & (far >= 0.0f)) ? near : kInfinity;
+}
+
+ECHO_DEVICE bool finite_bits(float v) { return (__float_as_uint(v) & 0x7F800000u) != 0x7F800000u; }
+
+// IO concept:
+//   void load(unsigned long long index, vec3& origin, vec3& direction, float& limit, uint32_t& ignore)
+//   void store_closest(unsigned long long index, bool hit, uint32_t token, float distance, vec2 uv, float limit)
+//   void store_any(unsigned long long index, bool occluded)
+//
+// Control flow is "if-if": one warp-wide loop whose body is a fixed sequence of predicated stages, so all 32 lanes
+// reconverge at every stage (a per-lane while loop with continue/break leaves the lanes of a warp scattered over the
+// loop body: measured 5.2 active threads per instruction, profiles/r1b). Stages per iteration:
+//   B  node visit      lanes whose current node has no slots left pop the next un-culled node and run the 4 slab tests
+//   C  slot scan       the Push calls of that node in reference order, up to the first primitive (which becomes pending)
+//   D  primitive test  only when enough lanes have a primitive pending (or nobody can do anything else), then C again
+//   E  finish + fetch  lanes whose stack ran empty store their result and take the next ray of the warp's pool
+template<int STACK, bool ANY, class IO>
+ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, unsigned long long count, unsigned long long* __restrict__ nextRay, WarpPool* pools)
+{
+	const unsigned int lane = threadIdx.x & 31u;
+	const unsigned int lanesBelow = (1u << lane) - 1u;
+	(void)pools;
+
+	// warp-uniform pool of reserved ray indices [poolNext, poolEnd)
+	unsigned long long poolNext = 0ull, poolEnd = 0ull;
+	bool exhausted = false;
+
+	// per-lane ray state
+	bool haveRay = false;
+	unsigned long long rayIndex = 0ull;
+	vec3 origin = { 0, 0, 0 }, direction = { 0, 0, 0 }, directionR = { 0, 0, 0 };
+	uint32_t orders = 0u, ignore = ECHO_TOKEN_EMPTY, bestToken = ECHO_TOKEN_EMPTY;
+	float limit = 0.0f, best = 0.0f; // best: TraceQuery.distance (closest) / OccludeQuery.travel (any)
+	vec2 bestUV = { 0.0f, 0.0f };
+	bool finite = true;
+
+	// per-lane node state
+	float t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+	uint32_t token0 = 0, token1 = 0, token2 = 0, token3 = 0, order = 0u;
+	int slotsLeft = 0, next = 0;
+	uint32_t leaf = ECHO_TOKEN_EMPTY;
+
+	uint32_t stackToken[STACK];
+	float stackHit[ANY ? 1 : STACK];
+
+	// the Push calls of the current node, in order, up to the first primitive (:200-216 / :296-312)
+	auto scan_slots = [&]()
+	{
+		while (slotsLeft > 0)
+		{
+			int slot = order & 3u;
+			order >>= 2;
+			--slotsLeft;
+
+			float hit = select4(slot, t0, t1, t2, t3);
+			if (hit >= best) continue;
+
+			uint32_t child = select4(slot, token0, token1, token2, token3);
+
+			if (token_type(child) == ECHO_TOKEN_TYPE_NODE)
+			{
+				stackToken[next] = child;
+				if (!ANY) stackHit[next] = hit;
+				++next;
+			}
+			else if (!(token_type(child) == ECHO_TOKEN_TYPE_TRIANGLE && child == ignore)) // GeometryCollection.cs:93-94
+			{
+				leaf = child;
+				break;
+			}
+		}
+	};
+
+	while (true)
+	{
+		// ---- E: finish rays whose traversal ran out of work, then hand the idle lanes new rays ----
+		if (haveRay && leaf == ECHO_TOKEN_EMPTY && slotsLeft == 0 && next == 0)
+		{
+			if (ANY) io.store_any(rayIndex, false);
+			else io.store_closest(rayIndex, best < limit, bestToken, best, bestUV, limit);
+			haveRay = false;
+		}
+
+		unsigned int idle = __ballot_sync(0xFFFFFFFFu, !haveRay);
+
+		if (idle != 0u && !(exhausted && poolNext >= poolEnd))
+		{
+			unsigned int wanted = (unsigned int)__popc(idle);
+			unsigned int rank = (unsigned int)__popc(idle & lanesBelow);
+			unsigned long long available = poolEnd - poolNext;
+			unsigned long long index = poolNext + rank;
+			bool got = !haveRay && rank < available;
+
+			if (available < wanted && !exhausted)
+			{
+				// the pool cannot serve everyone: reserve the next kPool rays with one global atomic
+				unsigned long long base = 0ull;
+				if (lane == 0u) base = atomicAdd(nextRay, kPool);
+				base = __shfl_sync(0xFFFFFFFFu, base, 0);
+				exhausted = base >= count;
+
+				unsigned long long end = exhausted ? base : (base + kPool < count ? base + kPool : count);
+
+				if (!haveRay && !got)
+				{
+					index = base + (rank - available);
+					got = index < end;
+				}
+
+				poolNext = base + (wanted - available);
+				if (poolNext > end) poolNext = end;
+				poolEnd = end;
+			}
+			else poolNext += wanted < available ? wanted : available;
+
+			if (got)
+			{
+				rayIndex = index;
+				io.load(index, origin, direction, limit, ignore);
+				best = limit;
+				bestToken = ECHO_TOKEN_EMPTY;
+
+				if (!positive(limit)) // PreparedScene.Trace / Occlude guard, PreparedScene.cs:69,84
+				{
+					if (ANY) io.store_any(index, false);
+					else io.store_closest(index, false, ECHO_TOKEN_EMPTY, limit, bestUV, limit);
+				}
+				else
+				{
+					directionR = { rcp(direction.x), rcp(direction.y), rcp(direction.z) }; // Ray.cs:23
+					orders = (directionR.x > 0.0f ? 1u : 0u) | (directionR.y > 0.0f ? 2u : 0u) | (directionR.z > 0.0f ? 4u : 0u) | 8u;
+					finite = finite_bits(directionR.x) && finite_bits(directionR.y) && finite_bits(directionR.z)
+						&& finite_bits(origin.x) && finite_bits(origin.y) && finite_bits(origin.z);
+
+					haveRay = true;
+					stackToken[0] = 0u; // NewNodeToken(0)
+					if (!ANY) stackHit[0] = 0.0f;
+					next = 1;
+					slotsLeft = 0;
+				}
+			}
+		}
+
+		if (__ballot_sync(0xFFFFFFFFu, haveRay) == 0u && exhausted && poolNext >= poolEnd) break;
+
+		// ---- B: node visit ----
+		bool visit = false;
+		uint32_t nodeToken = 0u;
+
+		if (haveRay && leaf == ECHO_TOKEN_EMPTY && slotsLeft == 0)
+		{
+			while (next > 0) // pop; skip entries the closest hit has already passed (:144-146)
+			{
+				--next;
+				if (ANY || !(stackHit[next] >= best))
+				{
+					nodeToken = stackToken[next];
+					visit = true;
+					break;
+				}
+			}
+		}
+
+		if (visit)
+		{
+			const float4* base = scene.nodes + (size_t)token_index(nodeToken) * 8;
+			float4 minX = __ldg(base + 0), minY = __ldg(base + 1), minZ = __ldg(base + 2);
+			float4 maxX = __ldg(base + 3), maxY = __ldg(base + 4), maxZ = __ldg(base + 5);
+			float4 a = __ldg(base + 6), b = __ldg(base + 7);
+
+			if (finite)
+			{
+				t0 = slab_finite(minX.x, minY.x, minZ.x, maxX.x, maxY.x, maxZ.x, origin, directionR);
+				t1 = slab_finite(minX.y, minY.y, minZ.y, maxX.y, maxY.y, maxZ.y, origin, directionR);
+				t2 = slab_finite(minX.z, minY.z, minZ.z, maxX.z, maxY.z, maxZ.z, origin, directionR);
+				t3 = slab_finite(minX.w, minY.w, minZ.w, maxX.w, maxY.w, maxZ.w, origin, directionR);
+			}
+			else
+			{
+				t0 = slab(minX.x, minY.x, minZ.x, maxX.x, maxY.x, maxZ.x, origin, directionR);
+				t1 = slab(minX.y, minY.y, minZ.y, maxX.y, maxY.y, maxZ.y, origin, directionR);
+				t2 = slab(minX.z, minY.z, minZ.z, maxX.z, maxY.z, maxZ.z, origin, directionR);
+				t3 = slab(minX.w, minY.w, minZ.w, maxX.w, maxY.w, maxZ.w, origin, directionR);
+			}
+
+			token0 = __float_as_uint(a.w);
+			token1 = __float_as_uint(b.x);
+			token2 = __float_as_uint(b.y);
+			token3 = __float_as_uint(b.z);
+			order = visit_order(orders, __float_as_int(a.x), __float_as_int(a.y), __float_as_int(a.z));
+			slotsLeft = 4;
+		}
+
+		// ---- C: slot scan ----
+		if (haveRay && leaf == ECHO_TOKEN_EMPTY) scan_slots();
+
+		// ---- D: primitive tests, once enough lanes wait for one (or no lane could use another node visit instead) ----
+		unsigned int pending = __ballot_sync(0xFFFFFFFFu, leaf != ECHO_TOKEN_EMPTY);
+		unsigned int working = __ballot_sync(0xFFFFFFFFu, haveRay);
+
+		if (pending != 0u && (__popc(pending) >= kLeafVote || pending == working))
+		{
+			if (leaf != ECHO_TOKEN_EMPTY)
+			{
+				bool occluded = false;
+
+				if (token_type(leaf) == ECHO_TOKEN_TYPE_TRIANGLE)
+				{
+					const float4* data = scene.triHot + (size_t)token_index(leaf) * 3;
+					float4 a = __ldg(data), b = __ldg(data + 1), c = __ldg(data + 2);
+
+					if (ANY) occluded = triangle_occlude({ a.x, a.y, a.z }, { b.x, b.y, b.z }, { c.x, c.y, c.z }, origin, direction, best);
+					else
+					{
+						vec2 uv;
+						float d = triangle_intersect({ a.x, a.y, a.z }, { b.x, b.y, b.z }, { c.x, c.y, c.z }, origin, direction, uv);
+
+						if (!(d >= best)) // GeometryCollection.cs:99
+						{
+							best = d;
+							bestToken = leaf;
+							bestUV = uv;
+						}
+					}
+				}
+				else
+				{
+					float4 sphere = __ldg(scene.spheres + token_index(leaf));
+
+					if (ANY) occluded = sphere_occlude(sphere, origin, direction, best, leaf == ignore);
+					else
+					{
+						vec2 uv;
+						float d = sphere_intersect(sphere, origin, direction, uv, leaf == ignore);
+
+						if (!(d >= best)) // GeometryCollection.cs:115
+						{
+							best = d;
+							bestToken = leaf;
+							bestUV = uv;
+						}
+					}
+				}
+
+				leaf = ECHO_TOKEN_EMPTY;
+
+				if (ANY && occluded)
+				{
+					io.store_any(rayIndex, true);
+					haveRay = false;
+					slotsLeft = 0;
+					next = 0;
+				}
+				else scan_slots(); // the rest of this node's Push calls
+			}
+		}
+	}
+}
+
+} // namespace echo

@@ -2,7 +2,11 @@
 // two 128-bit loads, EchoHit output written with one 128-bit store. These are the kernels behind
 // echo_b200_trace_batch / echo_b200_occlude_batch (BASELINE config C2) and the batched analogue of the benchmark loops in
 // the reference's src/Echo.Experimental/Benchmarks/Accelerators.cs:131-157.
+#include <cstdlib>
+#include <mutex>
+
 #include "echo_internal.h"
+#include "echo_traverse.cuh"
 
 namespace echo
 {
@@ -96,6 +100,93 @@ __global__ void __launch_bounds__(kTraceBlock) occlude_batch_kernel(DeviceScene 
 	}
 }
 
+// AoS EchoRay in (two 128-bit loads), EchoHit out (one 128-bit store) / one byte per occlusion query
+struct BatchIO
+{
+	const float4* __restrict__ rays;
+	float4* __restrict__ hits;
+	uint8_t* __restrict__ occluded;
+
+	ECHO_DEVICE void load(unsigned long long index, vec3& origin, vec3& direction, float& limit, uint32_t& ignore) const
+	{
+		float4 a = __ldg(rays + index * 2), b = __ldg(rays + index * 2 + 1);
+		origin = { a.x, a.y, a.z };
+		direction = { a.w, b.x, b.y };
+		limit = b.z;
+		ignore = __float_as_uint(b.w);
+	}
+
+	ECHO_DEVICE void store_closest(unsigned long long index, bool hit, uint32_t token, float distance, vec2 uv, float limit) const
+	{
+		hits[index] = make_float4(__uint_as_float(hit ? token : ECHO_TOKEN_EMPTY), hit ? distance : limit, hit ? uv.x : 0.0f, hit ? uv.y : 0.0f);
+	}
+
+	ECHO_DEVICE void store_any(unsigned long long index, bool result) const { occluded[index] = result ? 1 : 0; }
+};
+
+template<int STACK, bool ANY>
+__global__ void __launch_bounds__(kTraverseBlock) persistent_batch_kernel(DeviceScene scene, BatchIO io, unsigned long long n, unsigned long long* __restrict__ nextRay)
+{
+	__shared__ WarpPool pools[kTraverseWarps];
+	persistent_traverse<STACK, ANY>(scene, io, n, nextRay, pools);
+}
+
+// Every persistent launch needs its own zeroed ray counter (launches on different streams may overlap): a per-device ring.
+constexpr unsigned int kCounterRing = 256;
+
+unsigned long long* next_ray_counter(cudaStream_t stream)
+{
+	static std::mutex guard;
+	static unsigned long long* rings[64] = {};
+	static unsigned int cursors[64] = {};
+
+	int device = 0;
+	cudaGetDevice(&device);
+	device &= 63;
+
+	std::lock_guard<std::mutex> lock(guard);
+	if (!rings[device] && !check_cuda(cudaMalloc((void**)&rings[device], sizeof(unsigned long long) * kCounterRing), "cudaMalloc(ray counters)")) return nullptr;
+
+	unsigned long long* counter = rings[device] + (cursors[device]++ % kCounterRing);
+	if (!check_cuda(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream), "cudaMemsetAsync(ray counter)")) return nullptr;
+	return counter;
+}
+
+int persistent_grid(const void* kernel)
+{
+	int device = 0, sms = 0, perSM = 0;
+	cudaGetDevice(&device);
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, kTraverseBlock, 0);
+	return sms * (perSM > 0 ? perSM : 1); // one resident wave: 148 SMs x resident CTAs per SM
+}
+
+template<int STACK, bool ANY>
+static bool launch_persistent(const DeviceScene& scene, const EchoRay* rays, uint64_t n, EchoHit* hits, uint8_t* occluded, cudaStream_t stream)
+{
+	unsigned long long* counter = next_ray_counter(stream);
+	if (!counter) return false;
+
+	BatchIO io = { reinterpret_cast<const float4*>(rays), reinterpret_cast<float4*>(hits), occluded };
+	static int grid = persistent_grid((const void*)persistent_batch_kernel<STACK, ANY>);
+
+	uint64_t needed = (n + kTraverseBlock - 1) / kTraverseBlock;
+	unsigned int blocks = (unsigned int)(needed < (uint64_t)grid ? needed : (uint64_t)grid);
+	persistent_batch_kernel<STACK, ANY><<<blocks, kTraverseBlock, 0, stream>>>(scene, io, n, counter);
+	return check_cuda(cudaGetLastError(), "persistent_batch_kernel launch");
+}
+
+static bool use_simple_kernels()
+{
+	static int cached = -1;
+	if (cached < 0)
+	{
+		const char* value = std::getenv("ECHO_B200_SIMPLE_TRACE"); // A/B switch: one thread per ray, no work replacement
+		cached = value && value[0] == '1' ? 1 : 0;
+	}
+	return cached == 1;
+}
+
 int stack_class(uint32_t maxDepth)
 {
 	uint32_t size = maxDepth * 3 + 1;
@@ -144,11 +235,37 @@ static bool launch_occlude_impl(const DeviceScene& scene, const EchoRay* rays, u
 
 bool launch_trace(const DeviceScene& scene, const EchoRay* rays, uint64_t n, EchoHit* hits, unsigned long long* counts, cudaStream_t stream)
 {
+	if (n == 0) return true;
+
+	if (!counts && !use_simple_kernels())
+	{
+		switch (stack_class(scene.maxDepth))
+		{
+			case 0: return launch_persistent<48, false>(scene, rays, n, hits, nullptr, stream);
+			case 1: return launch_persistent<96, false>(scene, rays, n, hits, nullptr, stream);
+			case 2: return launch_persistent<192, false>(scene, rays, n, hits, nullptr, stream);
+			default: set_error("QBVH deeper than 63 quad levels is not supported"); return false;
+		}
+	}
+
 	return counts ? launch_trace_impl<true>(scene, rays, n, hits, counts, stream) : launch_trace_impl<false>(scene, rays, n, hits, nullptr, stream);
 }
 
 bool launch_occlude(const DeviceScene& scene, const EchoRay* rays, uint64_t n, uint8_t* occluded, unsigned long long* counts, cudaStream_t stream)
 {
+	if (n == 0) return true;
+
+	if (!counts && !use_simple_kernels())
+	{
+		switch (stack_class(scene.maxDepth))
+		{
+			case 0: return launch_persistent<48, true>(scene, rays, n, nullptr, occluded, stream);
+			case 1: return launch_persistent<96, true>(scene, rays, n, nullptr, occluded, stream);
+			case 2: return launch_persistent<192, true>(scene, rays, n, nullptr, occluded, stream);
+			default: set_error("QBVH deeper than 63 quad levels is not supported"); return false;
+		}
+	}
+
 	return counts ? launch_occlude_impl<true>(scene, rays, n, occluded, counts, stream) : launch_occlude_impl<false>(scene, rays, n, occluded, nullptr, stream);
 }
 
