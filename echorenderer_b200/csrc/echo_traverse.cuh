@@ -42,6 +42,21 @@ ECHO_DEVICE float slab_finite(float minX, float minY, float minZ, float maxX, fl
 	return ((far >= near) & (far >= 0.0f)) ? near : kInfinity;
 }
 
+// one 32-byte sector per lane per instruction (LDG.E.256, sm_100+): a 128-byte node costs 4 sector reads instead of the 8
+// half-sector reads of LDG.128 — the L1 data pipe was the busiest unit of the first persistent kernel (78 %, profiles/r1c).
+struct __align__(32) float8
+{
+	float v[8];
+};
+
+ECHO_DEVICE float8 ldg256(const void* pointer)
+{
+	float8 r;
+	asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+		: "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7]) : "l"(pointer));
+	return r;
+}
+
 ECHO_DEVICE bool finite_bits(float v) { return (__float_as_uint(v) & 0x7F800000u) != 0x7F800000u; }
 
 // IO concept:
@@ -76,47 +91,46 @@ ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, unsigned 
 	vec2 bestUV = { 0.0f, 0.0f };
 	bool finite = true;
 
-	// per-lane node state
-	float t0 = 0, t1 = 0, t2 = 0, t3 = 0;
-	uint32_t token0 = 0, token1 = 0, token2 = 0, token3 = 0, order = 0u;
-	int slotsLeft = 0, next = 0;
+	// per-lane node state: entry distances and tokens of the current node's children IN VISIT ORDER, scan position 0..4
+	float hit0 = 0, hit1 = 0, hit2 = 0, hit3 = 0;
+	uint32_t child0 = 0, child1 = 0, child2 = 0, child3 = 0;
+	int position = 4, next = 0;
 	uint32_t leaf = ECHO_TOKEN_EMPTY;
 
-	uint32_t stackToken[STACK];
-	float stackHit[ANY ? 1 : STACK];
+	uint2 stack[STACK]; // {token, entry distance bits}: one 64-bit local store per push
 
-	// the Push calls of the current node, in order, up to the first primitive (:200-216 / :296-312)
+	// the Push calls of the current node, in order, up to the first primitive (:200-216 / :296-312). `best` only changes in
+	// a primitive test, so one pass over the (up to four) remaining slots with predication replaces the reference's loop.
 	auto scan_slots = [&]()
 	{
-		while (slotsLeft > 0)
-		{
-			int slot = order & 3u;
-			order >>= 2;
-			--slotsLeft;
-
-			float hit = select4(slot, t0, t1, t2, t3);
-			if (hit >= best) continue;
-
-			uint32_t child = select4(slot, token0, token1, token2, token3);
-
-			if (token_type(child) == ECHO_TOKEN_TYPE_NODE)
-			{
-				stackToken[next] = child;
-				if (!ANY) stackHit[next] = hit;
-				++next;
-			}
-			else if (!(token_type(child) == ECHO_TOKEN_TYPE_TRIANGLE && child == ignore)) // GeometryCollection.cs:93-94
-			{
-				leaf = child;
-				break;
-			}
+#define ECHO_SLOT(k, hitK, childK)                                                                                     \
+		if (position <= (k) && leaf == ECHO_TOKEN_EMPTY && !((hitK) >= best))                                          \
+		{                                                                                                              \
+			if (token_type(childK) == ECHO_TOKEN_TYPE_NODE)                                                            \
+			{                                                                                                          \
+				stack[next] = make_uint2((childK), __float_as_uint(hitK));                                             \
+				++next;                                                                                                \
+			}                                                                                                          \
+			else if (!(token_type(childK) == ECHO_TOKEN_TYPE_TRIANGLE && (childK) == ignore)) /* GeometryCollection.cs:93-94 */ \
+			{                                                                                                          \
+				leaf = (childK);                                                                                       \
+				position = (k) + 1;                                                                                    \
+			}                                                                                                          \
 		}
+
+		ECHO_SLOT(0, hit0, child0)
+		ECHO_SLOT(1, hit1, child1)
+		ECHO_SLOT(2, hit2, child2)
+		ECHO_SLOT(3, hit3, child3)
+#undef ECHO_SLOT
+
+		if (leaf == ECHO_TOKEN_EMPTY) position = 4;
 	};
 
 	while (true)
 	{
 		// ---- E: finish rays whose traversal ran out of work, then hand the idle lanes new rays ----
-		if (haveRay && leaf == ECHO_TOKEN_EMPTY && slotsLeft == 0 && next == 0)
+		if (haveRay && leaf == ECHO_TOKEN_EMPTY && position == 4 && next == 0)
 		{
 			if (ANY) io.store_any(rayIndex, false);
 			else io.store_closest(rayIndex, best < limit, bestToken, best, bestUV, limit);
@@ -175,10 +189,9 @@ ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, unsigned 
 						&& finite_bits(origin.x) && finite_bits(origin.y) && finite_bits(origin.z);
 
 					haveRay = true;
-					stackToken[0] = 0u; // NewNodeToken(0)
-					if (!ANY) stackHit[0] = 0.0f;
+					stack[0] = make_uint2(0u, 0u); // NewNodeToken(0), entry distance 0
 					next = 1;
-					slotsLeft = 0;
+					position = 4;
 				}
 			}
 		}
@@ -189,14 +202,16 @@ ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, unsigned 
 		bool visit = false;
 		uint32_t nodeToken = 0u;
 
-		if (haveRay && leaf == ECHO_TOKEN_EMPTY && slotsLeft == 0)
+		if (haveRay && leaf == ECHO_TOKEN_EMPTY && position == 4)
 		{
 			while (next > 0) // pop; skip entries the closest hit has already passed (:144-146)
 			{
 				--next;
-				if (ANY || !(stackHit[next] >= best))
+				uint2 entry = stack[next];
+
+				if (ANY || !(__uint_as_float(entry.y) >= best))
 				{
-					nodeToken = stackToken[next];
+					nodeToken = entry.x;
 					visit = true;
 					break;
 				}
@@ -206,31 +221,35 @@ ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, unsigned 
 		if (visit)
 		{
 			const float4* base = scene.nodes + (size_t)token_index(nodeToken) * 8;
-			float4 minX = __ldg(base + 0), minY = __ldg(base + 1), minZ = __ldg(base + 2);
-			float4 maxX = __ldg(base + 3), maxY = __ldg(base + 4), maxZ = __ldg(base + 5);
-			float4 a = __ldg(base + 6), b = __ldg(base + 7);
+			float8 q0 = ldg256(base + 0), q1 = ldg256(base + 2), q2 = ldg256(base + 4), q3 = ldg256(base + 6);
+			// q0 = minX[4] minY[4], q1 = minZ[4] maxX[4], q2 = maxY[4] maxZ[4], q3 = axisMajor axisMinor0 axisMinor1 token4[4] pad
+
+			float t0, t1, t2, t3;
 
 			if (finite)
 			{
-				t0 = slab_finite(minX.x, minY.x, minZ.x, maxX.x, maxY.x, maxZ.x, origin, directionR);
-				t1 = slab_finite(minX.y, minY.y, minZ.y, maxX.y, maxY.y, maxZ.y, origin, directionR);
-				t2 = slab_finite(minX.z, minY.z, minZ.z, maxX.z, maxY.z, maxZ.z, origin, directionR);
-				t3 = slab_finite(minX.w, minY.w, minZ.w, maxX.w, maxY.w, maxZ.w, origin, directionR);
+				t0 = slab_finite(q0.v[0], q0.v[4], q1.v[0], q1.v[4], q2.v[0], q2.v[4], origin, directionR);
+				t1 = slab_finite(q0.v[1], q0.v[5], q1.v[1], q1.v[5], q2.v[1], q2.v[5], origin, directionR);
+				t2 = slab_finite(q0.v[2], q0.v[6], q1.v[2], q1.v[6], q2.v[2], q2.v[6], origin, directionR);
+				t3 = slab_finite(q0.v[3], q0.v[7], q1.v[3], q1.v[7], q2.v[3], q2.v[7], origin, directionR);
 			}
 			else
 			{
-				t0 = slab(minX.x, minY.x, minZ.x, maxX.x, maxY.x, maxZ.x, origin, directionR);
-				t1 = slab(minX.y, minY.y, minZ.y, maxX.y, maxY.y, maxZ.y, origin, directionR);
-				t2 = slab(minX.z, minY.z, minZ.z, maxX.z, maxY.z, maxZ.z, origin, directionR);
-				t3 = slab(minX.w, minY.w, minZ.w, maxX.w, maxY.w, maxZ.w, origin, directionR);
+				t0 = slab(q0.v[0], q0.v[4], q1.v[0], q1.v[4], q2.v[0], q2.v[4], origin, directionR);
+				t1 = slab(q0.v[1], q0.v[5], q1.v[1], q1.v[5], q2.v[1], q2.v[5], origin, directionR);
+				t2 = slab(q0.v[2], q0.v[6], q1.v[2], q1.v[6], q2.v[2], q2.v[6], origin, directionR);
+				t3 = slab(q0.v[3], q0.v[7], q1.v[3], q1.v[7], q2.v[3], q2.v[7], origin, directionR);
 			}
 
-			token0 = __float_as_uint(a.w);
-			token1 = __float_as_uint(b.x);
-			token2 = __float_as_uint(b.y);
-			token3 = __float_as_uint(b.z);
-			order = visit_order(orders, __float_as_int(a.x), __float_as_int(a.y), __float_as_int(a.z));
-			slotsLeft = 4;
+			uint32_t token0 = __float_as_uint(q3.v[3]), token1 = __float_as_uint(q3.v[4]), token2 = __float_as_uint(q3.v[5]), token3 = __float_as_uint(q3.v[6]);
+			uint32_t order = visit_order(orders, __float_as_int(q3.v[0]), __float_as_int(q3.v[1]), __float_as_int(q3.v[2]));
+
+			int s0 = order & 3u, s1 = (order >> 2) & 3u, s2 = (order >> 4) & 3u, s3 = (order >> 6) & 3u;
+			hit0 = select4(s0, t0, t1, t2, t3); child0 = select4(s0, token0, token1, token2, token3);
+			hit1 = select4(s1, t0, t1, t2, t3); child1 = select4(s1, token0, token1, token2, token3);
+			hit2 = select4(s2, t0, t1, t2, t3); child2 = select4(s2, token0, token1, token2, token3);
+			hit3 = select4(s3, t0, t1, t2, t3); child3 = select4(s3, token0, token1, token2, token3);
+			position = 0;
 		}
 
 		// ---- C: slot scan ----
@@ -290,7 +309,7 @@ ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, unsigned 
 				{
 					io.store_any(rayIndex, true);
 					haveRay = false;
-					slotsLeft = 0;
+					position = 4;
 					next = 0;
 				}
 				else scan_slots(); // the rest of this node's Push calls
