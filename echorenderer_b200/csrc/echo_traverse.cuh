@@ -60,31 +60,35 @@ ECHO_DEVICE float8 ldg256(const void* pointer)
 ECHO_DEVICE bool finite_bits(float v) { return (__float_as_uint(v) & 0x7F800000u) != 0x7F800000u; }
 
 // IO concept:
-//   void load(unsigned long long index, vec3& origin, vec3& direction, float& limit, uint32_t& ignore)
-//   void store_closest(unsigned long long index, bool hit, uint32_t token, float distance, vec2 uv, float limit)
-//   void store_any(unsigned long long index, bool occluded)
+//   const float4* ray_pointer(uint32_t index)   -> 32 contiguous bytes: origin.xyz direction.x | direction.yz limit ignore
+//   void store_closest(uint32_t index, bool hit, uint32_t token, float distance, vec2 uv, float limit)
+//   void store_any(uint32_t index, bool occluded)
 //
 // Control flow is "if-if": one warp-wide loop whose body is a fixed sequence of predicated stages, so all 32 lanes
 // reconverge at every stage (a per-lane while loop with continue/break leaves the lanes of a warp scattered over the
 // loop body: measured 5.2 active threads per instruction, profiles/r1b). Stages per iteration:
+//   E  finish + fetch  lanes whose stack ran empty store their result, take the ray staged for them in shared memory and
+//                      stage the next ray of the warp's pool with cp.async (global -> shared, L1 bypassed), so the DRAM
+//                      latency of the ray stream never stalls the warp
 //   B  node visit      lanes whose current node has no slots left pop the next un-culled node and run the 4 slab tests
 //   C  slot scan       the Push calls of that node in reference order, up to the first primitive (which becomes pending)
 //   D  primitive test  only when enough lanes have a primitive pending (or nobody can do anything else), then C again
-//   E  finish + fetch  lanes whose stack ran empty store their result and take the next ray of the warp's pool
 template<int STACK, bool ANY, class IO>
-ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, unsigned long long count, unsigned long long* __restrict__ nextRay, WarpPool* pools)
+ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, uint32_t count, unsigned long long* __restrict__ nextRay, float4* stagedRays)
 {
 	const unsigned int lane = threadIdx.x & 31u;
 	const unsigned int lanesBelow = (1u << lane) - 1u;
-	(void)pools;
+
+	float4* stagedSlot = stagedRays + threadIdx.x * 2;
+	const uint32_t stagedAddress = (uint32_t)__cvta_generic_to_shared(stagedSlot);
 
 	// warp-uniform pool of reserved ray indices [poolNext, poolEnd)
-	unsigned long long poolNext = 0ull, poolEnd = 0ull;
+	uint32_t poolNext = 0u, poolEnd = 0u;
 	bool exhausted = false;
 
 	// per-lane ray state
-	bool haveRay = false;
-	unsigned long long rayIndex = 0ull;
+	bool haveRay = false, staged = false;
+	uint32_t rayIndex = 0u, stagedIndex = 0u;
 	vec3 origin = { 0, 0, 0 }, direction = { 0, 0, 0 }, directionR = { 0, 0, 0 };
 	uint32_t orders = 0u, ignore = ECHO_TOKEN_EMPTY, bestToken = ECHO_TOKEN_EMPTY;
 	float limit = 0.0f, best = 0.0f; // best: TraceQuery.distance (closest) / OccludeQuery.travel (any)
@@ -97,67 +101,115 @@ ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, unsigned 
 	int position = 4, next = 0;
 	uint32_t leaf = ECHO_TOKEN_EMPTY;
 
-	uint2 stack[STACK]; // {token, entry distance bits}: one 64-bit local store per push
+	// Traversal stack {token, entry distance bits}. The newest entry lives in registers (`top`): the nearest child pushed by
+	// a node visit is popped by the very next one, so most pushes and pops never touch local memory (per-thread local
+	// arrays are interleaved at 4-byte granularity: every 8-byte entry costs two 32-byte sectors in the L1 data pipe).
+	uint2 stack[STACK];
+	uint2 top = make_uint2(0u, 0u);
+	bool haveTop = false;
 
-	// the Push calls of the current node, in order, up to the first primitive (:200-216 / :296-312). `best` only changes in
-	// a primitive test, so one pass over the (up to four) remaining slots with predication replaces the reference's loop.
+	// The Push calls of the current node, in order, up to the first primitive (:200-216 / :296-312). `best` only changes in
+	// a primitive test, so the remaining slots are classified at once: bit k of `valid` = slot k passes the distance test,
+	// `nodes` = it is a branch, `leaves` = it is a primitive that is not the ignored triangle (GeometryCollection.cs:93-94).
 	auto scan_slots = [&]()
 	{
-#define ECHO_SLOT(k, hitK, childK)                                                                                     \
-		if (position <= (k) && leaf == ECHO_TOKEN_EMPTY && !((hitK) >= best))                                          \
-		{                                                                                                              \
-			if (token_type(childK) == ECHO_TOKEN_TYPE_NODE)                                                            \
-			{                                                                                                          \
-				stack[next] = make_uint2((childK), __float_as_uint(hitK));                                             \
-				++next;                                                                                                \
-			}                                                                                                          \
-			else if (!(token_type(childK) == ECHO_TOKEN_TYPE_TRIANGLE && (childK) == ignore)) /* GeometryCollection.cs:93-94 */ \
-			{                                                                                                          \
-				leaf = (childK);                                                                                       \
-				position = (k) + 1;                                                                                    \
-			}                                                                                                          \
+		uint32_t pending = 0xFu << position & 0xFu;
+		uint32_t valid = ((!(hit0 >= best)) ? 1u : 0u) | ((!(hit1 >= best)) ? 2u : 0u) | ((!(hit2 >= best)) ? 4u : 0u) | ((!(hit3 >= best)) ? 8u : 0u);
+		uint32_t nodes = (token_type(child0) == 0u ? 1u : 0u) | (token_type(child1) == 0u ? 2u : 0u) | (token_type(child2) == 0u ? 4u : 0u) | (token_type(child3) == 0u ? 8u : 0u);
+		uint32_t ignored = (child0 == ignore && token_type(child0) == ECHO_TOKEN_TYPE_TRIANGLE ? 1u : 0u) | (child1 == ignore && token_type(child1) == ECHO_TOKEN_TYPE_TRIANGLE ? 2u : 0u)
+			| (child2 == ignore && token_type(child2) == ECHO_TOKEN_TYPE_TRIANGLE ? 4u : 0u) | (child3 == ignore && token_type(child3) == ECHO_TOKEN_TYPE_TRIANGLE ? 8u : 0u);
+
+		valid &= pending;
+		uint32_t leaves = valid & ~nodes & ~ignored;
+		uint32_t first = leaves ? (uint32_t)(__ffs(leaves) - 1) : 4u; // first primitive to test, in visit order
+		uint32_t pushes = valid & nodes & ((1u << first) - 1u);            // branches pushed before it
+
+#define ECHO_PUSH(bit, childK, hitK)                                   \
+		if (pushes & (bit))                                            \
+		{                                                              \
+			if (haveTop) stack[next++] = top;                          \
+			top = make_uint2((childK), __float_as_uint(hitK));         \
+			haveTop = true;                                            \
 		}
 
-		ECHO_SLOT(0, hit0, child0)
-		ECHO_SLOT(1, hit1, child1)
-		ECHO_SLOT(2, hit2, child2)
-		ECHO_SLOT(3, hit3, child3)
-#undef ECHO_SLOT
+		ECHO_PUSH(1u, child0, hit0)
+		ECHO_PUSH(2u, child1, hit1)
+		ECHO_PUSH(4u, child2, hit2)
+		ECHO_PUSH(8u, child3, hit3)
+#undef ECHO_PUSH
 
-		if (leaf == ECHO_TOKEN_EMPTY) position = 4;
+		if (first < 4u) leaf = first == 0u ? child0 : (first == 1u ? child1 : (first == 2u ? child2 : child3));
+		position = first < 4u ? (int)first + 1 : 4;
 	};
 
 	while (true)
 	{
-		// ---- E: finish rays whose traversal ran out of work, then hand the idle lanes new rays ----
-		if (haveRay && leaf == ECHO_TOKEN_EMPTY && position == 4 && next == 0)
+		// ---- E: finish rays whose traversal ran out of work ----
+		if (haveRay && leaf == ECHO_TOKEN_EMPTY && position == 4 && next == 0 && !haveTop)
 		{
 			if (ANY) io.store_any(rayIndex, false);
 			else io.store_closest(rayIndex, best < limit, bestToken, best, bestUV, limit);
 			haveRay = false;
 		}
 
-		unsigned int idle = __ballot_sync(0xFFFFFFFFu, !haveRay);
-
-		if (idle != 0u && !(exhausted && poolNext >= poolEnd))
+		// ---- E: idle lanes take their staged ray (already in shared memory) ----
+		if (!haveRay && staged)
 		{
-			unsigned int wanted = (unsigned int)__popc(idle);
-			unsigned int rank = (unsigned int)__popc(idle & lanesBelow);
-			unsigned long long available = poolEnd - poolNext;
-			unsigned long long index = poolNext + rank;
-			bool got = !haveRay && rank < available;
+			asm volatile("cp.async.wait_all;" ::: "memory");
+			float4 a = stagedSlot[0], b = stagedSlot[1];
+			staged = false;
+
+			rayIndex = stagedIndex;
+			origin = { a.x, a.y, a.z };
+			direction = { a.w, b.x, b.y };
+			limit = b.z;
+			ignore = __float_as_uint(b.w);
+			best = limit;
+			bestToken = ECHO_TOKEN_EMPTY;
+
+			if (!positive(limit)) // PreparedScene.Trace / Occlude guard, PreparedScene.cs:69,84
+			{
+				if (ANY) io.store_any(rayIndex, false);
+				else io.store_closest(rayIndex, false, ECHO_TOKEN_EMPTY, limit, bestUV, limit);
+			}
+			else
+			{
+				directionR = { rcp(direction.x), rcp(direction.y), rcp(direction.z) }; // Ray.cs:23
+				orders = (directionR.x > 0.0f ? 1u : 0u) | (directionR.y > 0.0f ? 2u : 0u) | (directionR.z > 0.0f ? 4u : 0u) | 8u;
+				finite = finite_bits(directionR.x) && finite_bits(directionR.y) && finite_bits(directionR.z)
+					&& finite_bits(origin.x) && finite_bits(origin.y) && finite_bits(origin.z);
+
+				haveRay = true;
+				top = make_uint2(0u, 0u); // NewNodeToken(0), entry distance 0
+				haveTop = true;
+				next = 0;
+				position = 4;
+			}
+		}
+
+		// ---- E: lanes with an empty staging slot reserve the next ray of the pool and start its copy ----
+		unsigned int empty = __ballot_sync(0xFFFFFFFFu, !staged);
+
+		if (empty != 0u && !(exhausted && poolNext >= poolEnd))
+		{
+			uint32_t wanted = (uint32_t)__popc(empty);
+			uint32_t rank = (uint32_t)__popc(empty & lanesBelow);
+			uint32_t available = poolEnd - poolNext;
+			uint32_t index = poolNext + rank;
+			bool got = !staged && rank < available;
 
 			if (available < wanted && !exhausted)
 			{
 				// the pool cannot serve everyone: reserve the next kPool rays with one global atomic
-				unsigned long long base = 0ull;
-				if (lane == 0u) base = atomicAdd(nextRay, kPool);
-				base = __shfl_sync(0xFFFFFFFFu, base, 0);
-				exhausted = base >= count;
+				unsigned long long base64 = 0ull;
+				if (lane == 0u) base64 = atomicAdd(nextRay, kPool);
+				base64 = __shfl_sync(0xFFFFFFFFu, base64, 0);
+				exhausted = base64 >= (unsigned long long)count;
 
-				unsigned long long end = exhausted ? base : (base + kPool < count ? base + kPool : count);
+				uint32_t base = exhausted ? count : (uint32_t)base64;
+				uint32_t end = (unsigned long long)base + kPool < (unsigned long long)count ? base + (uint32_t)kPool : count;
 
-				if (!haveRay && !got)
+				if (!staged && !got)
 				{
 					index = base + (rank - available);
 					got = index < end;
@@ -171,32 +223,16 @@ ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, unsigned 
 
 			if (got)
 			{
-				rayIndex = index;
-				io.load(index, origin, direction, limit, ignore);
-				best = limit;
-				bestToken = ECHO_TOKEN_EMPTY;
-
-				if (!positive(limit)) // PreparedScene.Trace / Occlude guard, PreparedScene.cs:69,84
-				{
-					if (ANY) io.store_any(index, false);
-					else io.store_closest(index, false, ECHO_TOKEN_EMPTY, limit, bestUV, limit);
-				}
-				else
-				{
-					directionR = { rcp(direction.x), rcp(direction.y), rcp(direction.z) }; // Ray.cs:23
-					orders = (directionR.x > 0.0f ? 1u : 0u) | (directionR.y > 0.0f ? 2u : 0u) | (directionR.z > 0.0f ? 4u : 0u) | 8u;
-					finite = finite_bits(directionR.x) && finite_bits(directionR.y) && finite_bits(directionR.z)
-						&& finite_bits(origin.x) && finite_bits(origin.y) && finite_bits(origin.z);
-
-					haveRay = true;
-					stack[0] = make_uint2(0u, 0u); // NewNodeToken(0), entry distance 0
-					next = 1;
-					position = 4;
-				}
+				const float4* source = io.ray_pointer(index);
+				asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(stagedAddress), "l"(source) : "memory");
+				asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(stagedAddress + 16u), "l"(source + 1) : "memory");
+				asm volatile("cp.async.commit_group;" ::: "memory");
+				stagedIndex = index;
+				staged = true;
 			}
 		}
 
-		if (__ballot_sync(0xFFFFFFFFu, haveRay) == 0u && exhausted && poolNext >= poolEnd) break;
+		if (__ballot_sync(0xFFFFFFFFu, haveRay || staged) == 0u) break; // `staged` is only false for good once the pool ran dry
 
 		// ---- B: node visit ----
 		bool visit = false;
@@ -204,10 +240,11 @@ ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, unsigned 
 
 		if (haveRay && leaf == ECHO_TOKEN_EMPTY && position == 4)
 		{
-			while (next > 0) // pop; skip entries the closest hit has already passed (:144-146)
+			while (haveTop || next > 0) // pop; skip entries the closest hit has already passed (:144-146)
 			{
-				--next;
-				uint2 entry = stack[next];
+				uint2 entry = top;
+				if (haveTop) haveTop = false;
+				else entry = stack[--next];
 
 				if (ANY || !(__uint_as_float(entry.y) >= best))
 				{
@@ -242,18 +279,23 @@ ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, unsigned 
 			}
 
 			uint32_t token0 = __float_as_uint(q3.v[3]), token1 = __float_as_uint(q3.v[4]), token2 = __float_as_uint(q3.v[5]), token3 = __float_as_uint(q3.v[6]);
-			uint32_t order = visit_order(orders, __float_as_int(q3.v[0]), __float_as_int(q3.v[1]), __float_as_int(q3.v[2]));
 
-			int s0 = order & 3u, s1 = (order >> 2) & 3u, s2 = (order >> 4) & 3u, s3 = (order >> 6) & 3u;
-			hit0 = select4(s0, t0, t1, t2, t3); child0 = select4(s0, token0, token1, token2, token3);
-			hit1 = select4(s1, t0, t1, t2, t3); child1 = select4(s1, token0, token1, token2, token3);
-			hit2 = select4(s2, t0, t1, t2, t3); child2 = select4(s2, token0, token1, token2, token3);
-			hit3 = select4(s3, t0, t1, t2, t3); child3 = select4(s3, token0, token1, token2, token3);
+			// Visit order (QuadBoundingVolumeHierarchy.cs:151-198) as three conditional swaps: inside the first pair when
+			// orders[axisMinor0], inside the second pair when orders[axisMinor1], and the pairs themselves when orders[axisMajor].
+			bool swap0 = (orders >> __float_as_int(q3.v[1])) & 1u;
+			bool swap1 = (orders >> __float_as_int(q3.v[2])) & 1u;
+			bool swapPairs = (orders >> __float_as_int(q3.v[0])) & 1u;
+
+			float a0 = swap0 ? t1 : t0, a1 = swap0 ? t0 : t1, b0 = swap1 ? t3 : t2, b1 = swap1 ? t2 : t3;
+			uint32_t c0 = swap0 ? token1 : token0, c1 = swap0 ? token0 : token1, d0 = swap1 ? token3 : token2, d1 = swap1 ? token2 : token3;
+
+			hit0 = swapPairs ? b0 : a0; hit1 = swapPairs ? b1 : a1; hit2 = swapPairs ? a0 : b0; hit3 = swapPairs ? a1 : b1;
+			child0 = swapPairs ? d0 : c0; child1 = swapPairs ? d1 : c1; child2 = swapPairs ? c0 : d0; child3 = swapPairs ? c1 : d1;
 			position = 0;
 		}
 
 		// ---- C: slot scan ----
-		if (haveRay && leaf == ECHO_TOKEN_EMPTY) scan_slots();
+		if (haveRay && leaf == ECHO_TOKEN_EMPTY && position < 4) scan_slots();
 
 		// ---- D: primitive tests, once enough lanes wait for one (or no lane could use another node visit instead) ----
 		unsigned int pending = __ballot_sync(0xFFFFFFFFu, leaf != ECHO_TOKEN_EMPTY);
@@ -309,10 +351,11 @@ ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, unsigned 
 				{
 					io.store_any(rayIndex, true);
 					haveRay = false;
+					haveTop = false;
 					position = 4;
 					next = 0;
 				}
-				else scan_slots(); // the rest of this node's Push calls
+				else if (position < 4) scan_slots(); // the rest of this node's Push calls
 			}
 		}
 	}

@@ -107,28 +107,21 @@ struct BatchIO
 	float4* __restrict__ hits;
 	uint8_t* __restrict__ occluded;
 
-	ECHO_DEVICE void load(unsigned long long index, vec3& origin, vec3& direction, float& limit, uint32_t& ignore) const
+	ECHO_DEVICE const float4* ray_pointer(uint32_t index) const { return rays + (size_t)index * 2; }
+
+	ECHO_DEVICE void store_closest(uint32_t index, bool hit, uint32_t token, float distance, vec2 uv, float limit) const
 	{
-		float4 a = __ldg(rays + index * 2), b = __ldg(rays + index * 2 + 1);
-		origin = { a.x, a.y, a.z };
-		direction = { a.w, b.x, b.y };
-		limit = b.z;
-		ignore = __float_as_uint(b.w);
+		__stcs(hits + index, make_float4(__uint_as_float(hit ? token : ECHO_TOKEN_EMPTY), hit ? distance : limit, hit ? uv.x : 0.0f, hit ? uv.y : 0.0f));
 	}
 
-	ECHO_DEVICE void store_closest(unsigned long long index, bool hit, uint32_t token, float distance, vec2 uv, float limit) const
-	{
-		hits[index] = make_float4(__uint_as_float(hit ? token : ECHO_TOKEN_EMPTY), hit ? distance : limit, hit ? uv.x : 0.0f, hit ? uv.y : 0.0f);
-	}
-
-	ECHO_DEVICE void store_any(unsigned long long index, bool result) const { occluded[index] = result ? 1 : 0; }
+	ECHO_DEVICE void store_any(uint32_t index, bool result) const { occluded[index] = result ? 1 : 0; }
 };
 
 template<int STACK, bool ANY>
-__global__ void __launch_bounds__(kTraverseBlock) persistent_batch_kernel(DeviceScene scene, BatchIO io, unsigned long long n, unsigned long long* __restrict__ nextRay)
+__global__ void __launch_bounds__(kTraverseBlock) persistent_batch_kernel(DeviceScene scene, BatchIO io, uint32_t n, unsigned long long* __restrict__ nextRay)
 {
-	__shared__ WarpPool pools[kTraverseWarps];
-	persistent_traverse<STACK, ANY>(scene, io, n, nextRay, pools);
+	__shared__ float4 stagedRays[kTraverseBlock * 2];
+	persistent_traverse<STACK, ANY>(scene, io, n, nextRay, stagedRays);
 }
 
 // Every persistent launch needs its own zeroed ray counter (launches on different streams may overlap): a per-device ring.
@@ -164,16 +157,23 @@ int persistent_grid(const void* kernel)
 template<int STACK, bool ANY>
 static bool launch_persistent(const DeviceScene& scene, const EchoRay* rays, uint64_t n, EchoHit* hits, uint8_t* occluded, cudaStream_t stream)
 {
-	unsigned long long* counter = next_ray_counter(stream);
-	if (!counter) return false;
-
-	BatchIO io = { reinterpret_cast<const float4*>(rays), reinterpret_cast<float4*>(hits), occluded };
 	static int grid = persistent_grid((const void*)persistent_batch_kernel<STACK, ANY>);
+	constexpr uint64_t kLaunchLimit = 1ull << 31; // ray indices are 32-bit inside the kernel
 
-	uint64_t needed = (n + kTraverseBlock - 1) / kTraverseBlock;
-	unsigned int blocks = (unsigned int)(needed < (uint64_t)grid ? needed : (uint64_t)grid);
-	persistent_batch_kernel<STACK, ANY><<<blocks, kTraverseBlock, 0, stream>>>(scene, io, n, counter);
-	return check_cuda(cudaGetLastError(), "persistent_batch_kernel launch");
+	for (uint64_t first = 0; first < n; first += kLaunchLimit)
+	{
+		uint64_t count = n - first < kLaunchLimit ? n - first : kLaunchLimit;
+		unsigned long long* counter = next_ray_counter(stream);
+		if (!counter) return false;
+
+		BatchIO io = { reinterpret_cast<const float4*>(rays + first), hits ? reinterpret_cast<float4*>(hits + first) : nullptr, occluded ? occluded + first : nullptr };
+		uint64_t needed = (count + kTraverseBlock - 1) / kTraverseBlock;
+		unsigned int blocks = (unsigned int)(needed < (uint64_t)grid ? needed : (uint64_t)grid);
+		persistent_batch_kernel<STACK, ANY><<<blocks, kTraverseBlock, 0, stream>>>(scene, io, (uint32_t)count, counter);
+		if (!check_cuda(cudaGetLastError(), "persistent_batch_kernel launch")) return false;
+	}
+
+	return true;
 }
 
 static bool use_simple_kernels()
