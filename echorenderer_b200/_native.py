@@ -6,7 +6,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIBRARY_PATH = os.path.join(_HERE, "libecho_b200.so")
+LIBRARY_PATH = os.environ.get("ECHO_B200_LIBRARY", os.path.join(_HERE, "libecho_b200.so"))  # override: A/B builds of the same ABI
 
 OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_UNSUPPORTED = range(5)
 

@@ -19,7 +19,13 @@ namespace echo
 constexpr int kTraverseBlock = 128;              // 4 warps per CTA
 constexpr int kTraverseWarps = kTraverseBlock / 32;
 constexpr unsigned long long kPool = 256;         // rays reserved per global atomic
-constexpr int kLeafVote = 8;                      // run the primitive tests once this many lanes have one pending
+#ifndef ECHO_LEAF_VOTE
+#define ECHO_LEAF_VOTE 8
+#endif
+#ifndef ECHO_MIN_BLOCKS
+#define ECHO_MIN_BLOCKS 1
+#endif
+constexpr int kLeafVote = ECHO_LEAF_VOTE;                      // run the primitive tests once this many lanes have one pending
 
 struct WarpPool
 {
@@ -82,9 +88,13 @@ ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, uint32_t 
 	float4* stagedSlot = stagedRays + threadIdx.x * 2;
 	const uint32_t stagedAddress = (uint32_t)__cvta_generic_to_shared(stagedSlot);
 
-	// warp-uniform pool of reserved ray indices [poolNext, poolEnd)
+	// warp-uniform pool of reserved ray indices [poolNext, poolEnd). Pool size: kPool for big batches; for small ones (late
+	// wavefront bounces) just enough that every resident warp gets a share, never less than one ray per lane.
 	uint32_t poolNext = 0u, poolEnd = 0u;
 	bool exhausted = false;
+	const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+	uint32_t poolSize = (count / (warps * 4u) + 31u) & ~31u;
+	poolSize = poolSize < 32u ? 32u : (poolSize > (uint32_t)kPool ? (uint32_t)kPool : poolSize);
 
 	// per-lane ray state
 	bool haveRay = false, staged = false;
@@ -202,12 +212,12 @@ ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, uint32_t 
 			{
 				// the pool cannot serve everyone: reserve the next kPool rays with one global atomic
 				unsigned long long base64 = 0ull;
-				if (lane == 0u) base64 = atomicAdd(nextRay, kPool);
+				if (lane == 0u) base64 = atomicAdd(nextRay, (unsigned long long)poolSize);
 				base64 = __shfl_sync(0xFFFFFFFFu, base64, 0);
 				exhausted = base64 >= (unsigned long long)count;
 
 				uint32_t base = exhausted ? count : (uint32_t)base64;
-				uint32_t end = (unsigned long long)base + kPool < (unsigned long long)count ? base + (uint32_t)kPool : count;
+				uint32_t end = (unsigned long long)base + poolSize < (unsigned long long)count ? base + poolSize : count;
 
 				if (!staged && !got)
 				{

@@ -9,9 +9,12 @@
 // Every path keeps the reference's draw order of random numbers and its order of floating-point accumulation, so a
 // sample's radiance is bit-identical to the oracle's. Queue management uses warp-aggregated atomics (ballot + popc).
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 
 #include "echo_internal.h"
 #include "echo_shading.cuh"
+#include "echo_traverse.cuh"
 
 namespace echo
 {
@@ -26,21 +29,24 @@ enum : int { COUNTER_NEXT = 0, COUNTER_SHADOW = 1, COUNTER_CLASS = 2, COUNTER_PI
 
 struct PathBuffers
 {
-	float4* rayOrigin;    // xyz
-	float4* rayDirection; // xyz, w = ignore token bits
-	float4* hit;          // token bits, distance, uv
+	// rays in flight, compacted: slot i of rayQueue[q] holds 32 bytes {origin.xyz, direction.x | direction.yz, limit, ignore}
+	// (the EchoRay layout, so the persistent traversal core streams it exactly like a batch) and rayPath[q][i] its path id
+	float4* rayQueue[2];
+	uint32_t* rayPath[2];
+	float4* hitQueue;     // per ray slot: token bits, distance, uv
+
+	// per path id
 	float4* energy;       // rgb, w = scatterPdf of the bounce that spawned the current ray (MIS)
 	float4* result;       // rgb, w = bits: bounces done | mode << 16
 	float4* oldPosition;  // MIS: GeometryPoint oldPoint
 	float4* oldNormal;
 	uint32_t* key;        // sample_key(seed, pixel, sample)
 
-	float4* shadowOrigin;    // xyz, w = travel
-	float4* shadowDirection; // xyz, w = ignore token bits
-	float4* shadowValue;     // pending energy * radiant, w = path id bits
+	// shadow rays of the current bounce, compacted: {origin.xyz, direction.x | direction.yz, travel, ignore} + pending value
+	float4* shadowQueue;
+	float4* shadowValue;  // pending energy * radiant, w = path id bits
 
-	uint32_t* queue[2];
-	uint32_t* classQueue[CLASS_COUNT];
+	uint32_t* classQueue[CLASS_COUNT]; // ray slots sorted by the material class of what they hit
 	uint32_t* counters;
 	unsigned long long* stats; // EchoStats layout
 };
@@ -625,12 +631,12 @@ __global__ void __launch_bounds__(kBlock) raygen_kernel(DeviceScene scene, EchoR
 	vec3 origin, direction;
 	camera_spawn(scene.camera, params.width, params.height, pixel.x, pixel.y, shift, lens, origin, direction);
 
-	paths.rayOrigin[i] = make4(origin, 0.0f);
-	paths.rayDirection[i] = make4(direction, __uint_as_float(ECHO_TOKEN_EMPTY));
+	paths.rayQueue[0][i * 2u] = make_float4(origin.x, origin.y, origin.z, direction.x);
+	paths.rayQueue[0][i * 2u + 1u] = make_float4(direction.y, direction.z, kInfinity, __uint_as_float(ECHO_TOKEN_EMPTY));
+	paths.rayPath[0][i] = i;
 	paths.energy[i] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
 	paths.result[i] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(MODE_FIRST << 16));
 	paths.key[i] = key;
-	paths.queue[0][i] = i;
 }
 
 ECHO_DEVICE int classify_material(const DeviceScene& scene, uint32_t materialIndex)
@@ -654,28 +660,40 @@ ECHO_DEVICE int classify_material(const DeviceScene& scene, uint32_t materialInd
 	}
 }
 
-// Path.Advance's scene.Trace (PathTracedEvaluator.cs:261-271 -> PreparedScene.cs:66-75), then the material-class sort
+// Path.Advance's scene.Trace (PathTracedEvaluator.cs:261-271 -> PreparedScene.cs:66-75) over the compacted ray queue
+struct ExtendIO
+{
+	const float4* __restrict__ rays;
+	float4* __restrict__ hits;
+
+	ECHO_DEVICE const float4* ray_pointer(uint32_t index) const { return rays + (size_t)index * 2; }
+
+	ECHO_DEVICE void store_closest(uint32_t index, bool hit, uint32_t token, float distance, vec2 uv, float limit) const
+	{
+		hits[index] = make_float4(__uint_as_float(hit ? token : ECHO_TOKEN_EMPTY), hit ? distance : limit, uv.x, uv.y);
+	}
+
+	ECHO_DEVICE void store_any(uint32_t, bool) const {}
+};
+
 template<int STACK>
-__global__ void __launch_bounds__(kBlock) extend_kernel(DeviceScene scene, const uint32_t* __restrict__ queue, const uint32_t* __restrict__ queueCount, PathBuffers paths)
+__global__ void __launch_bounds__(kTraverseBlock) extend_kernel(DeviceScene scene, ExtendIO io, const uint32_t* __restrict__ queueCount, unsigned long long* __restrict__ nextRay)
+{
+	__shared__ float4 stagedRays[kTraverseBlock * 2];
+	persistent_traverse<STACK, false>(scene, io, *queueCount, nextRay, stagedRays);
+}
+
+// the material-class sort: one thread per traced ray appends its slot to the queue of the class it hit
+__global__ void __launch_bounds__(kBlock) classify_kernel(DeviceScene scene, const uint32_t* __restrict__ queueCount, PathBuffers paths)
 {
 	uint32_t i = blockIdx.x * kBlock + threadIdx.x;
 	bool active = i < *queueCount;
 	int shadeClass = -1;
-	uint32_t id = 0u;
 
 	if (active)
 	{
-		id = queue[i];
-		float4 o = paths.rayOrigin[id], d = paths.rayDirection[id];
-
-		float distance = kInfinity;
-		uint32_t token = ECHO_TOKEN_EMPTY;
-		vec2 uv = { 0.0f, 0.0f };
-
-		bool hit = scene_trace<STACK, false>(scene, xyz(o), xyz(d), __float_as_uint(d.w), distance, token, uv, nullptr);
-		paths.hit[id] = make_float4(__uint_as_float(hit ? token : ECHO_TOKEN_EMPTY), distance, uv.x, uv.y);
-
-		shadeClass = hit ? classify_material(scene, geometry_material(scene, token)) : CLASS_MISS;
+		uint32_t token = __float_as_uint(paths.hitQueue[i].x);
+		shadeClass = token != ECHO_TOKEN_EMPTY ? classify_material(scene, geometry_material(scene, token)) : CLASS_MISS;
 	}
 
 	stat_add(paths.stats, STAT_TRACE_QUERIES, active);
@@ -685,14 +703,14 @@ __global__ void __launch_bounds__(kBlock) extend_kernel(DeviceScene scene, const
 	{
 		bool mine = shadeClass == c;
 		uint32_t slot = queue_slot(paths.counters + COUNTER_CLASS + c, mine);
-		if (mine) paths.classQueue[c][slot] = id;
+		if (mine) paths.classQueue[c][slot] = i;
 	}
 }
 
 // One loop body of PathTracedEvaluator.Evaluate for every path in a material-class queue.
 template<int CLASS, uint32_t KINDS>
 __global__ void __launch_bounds__(kBlock) shade_kernel(DeviceScene scene, EchoRenderParams params, const uint32_t* __restrict__ queue,
-                                                      const uint32_t* __restrict__ queueCount, PathBuffers paths, uint32_t* __restrict__ nextQueue)
+                                                      const uint32_t* __restrict__ queueCount, PathBuffers paths, int current)
 {
 	uint32_t i = blockIdx.x * kBlock + threadIdx.x;
 	bool active = i < *queueCount;
@@ -707,13 +725,14 @@ __global__ void __launch_bounds__(kBlock) shade_kernel(DeviceScene scene, EchoRe
 
 	if (active)
 	{
-		id = queue[i];
+		uint32_t raySlot = queue[i];
+		id = paths.rayPath[current][raySlot];
 
-		float4 rayD = paths.rayDirection[id];
+		float4 rayA = paths.rayQueue[current][raySlot * 2u], rayB = paths.rayQueue[current][raySlot * 2u + 1u];
 		float4 energy4 = paths.energy[id];
 		float4 result4 = paths.result[id];
 
-		vec3 direction = xyz(rayD);
+		vec3 direction = { rayA.w, rayB.x, rayB.y };
 		rgb energy = as_rgb(energy4);
 		rgb result = as_rgb(result4);
 		float scatterPdfPrevious = energy4.w;
@@ -746,11 +765,11 @@ __global__ void __launch_bounds__(kBlock) shade_kernel(DeviceScene scene, EchoRe
 		else
 		{
 			// ---- PreparedScene.Interact, PreparedScene.cs:95-105 + GeometryCollection.GetContactInfo (:200-232) ----
-			float4 hit4 = paths.hit[id];
+			float4 hit4 = paths.hitQueue[raySlot];
 			uint32_t token = __float_as_uint(hit4.x);
 			float distance = hit4.y;
 			vec2 uv = { hit4.z, hit4.w };
-			vec3 rayOrigin = xyz(paths.rayOrigin[id]);
+			vec3 rayOrigin = xyz(rayA);
 
 			vec3 infoNormal, infoShading;
 			uint32_t materialIndex;
@@ -857,8 +876,8 @@ __global__ void __launch_bounds__(kBlock) shade_kernel(DeviceScene scene, EchoRe
 								if (mis) radiant = radiant * power_heuristic(pdf, bsdf_pdf<KINDS>(bsdf, outgoing, lightIncident));
 
 								shadow = true;
-								shadowOrigin = make4(point.position, travel);
-								shadowDirection = make4(lightIncident, __uint_as_float(token));
+								shadowOrigin = make_float4(point.position.x, point.position.y, point.position.z, lightIncident.x);
+								shadowDirection = make_float4(lightIncident.y, lightIncident.z, travel, __uint_as_float(token)); // SpawnOcclude: ignore = hit token
 								shadowValue = make4(energy * radiant, __uint_as_float(id));
 							}
 						}
@@ -885,8 +904,8 @@ __global__ void __launch_bounds__(kBlock) shade_kernel(DeviceScene scene, EchoRe
 						}
 
 						uint32_t nextMode = (mis && !statSpecular) ? MODE_MIS : MODE_NO_MIS;
-						nextOrigin = make4(point.position, 0.0f);
-						nextDirection = make4(incident, __uint_as_float(token)); // SpawnTrace: ignore = hit token, TraceQuery.cs:88
+						nextOrigin = make_float4(point.position.x, point.position.y, point.position.z, incident.x);
+						nextDirection = make_float4(incident.y, incident.z, kInfinity, __uint_as_float(token)); // SpawnTrace: ignore = hit token, TraceQuery.cs:88
 						nextEnergy = make4(energy, scatterPdf);
 						result4.w = __uint_as_float((bounces + 1u) | (nextMode << 16));
 					}
@@ -894,25 +913,25 @@ __global__ void __launch_bounds__(kBlock) shade_kernel(DeviceScene scene, EchoRe
 			}
 
 			paths.result[id] = make4(result, result4.w);
-
-			if (survive)
-			{
-				paths.rayOrigin[id] = nextOrigin;
-				paths.rayDirection[id] = nextDirection;
-				paths.energy[id] = nextEnergy;
-			}
+			if (survive) paths.energy[id] = nextEnergy;
 		}
 	}
 
 	uint32_t nextSlot = queue_slot(paths.counters + COUNTER_NEXT, survive);
-	if (survive) nextQueue[nextSlot] = id;
+
+	if (survive)
+	{
+		paths.rayQueue[current ^ 1][nextSlot * 2u] = nextOrigin;
+		paths.rayQueue[current ^ 1][nextSlot * 2u + 1u] = nextDirection;
+		paths.rayPath[current ^ 1][nextSlot] = id;
+	}
 
 	uint32_t shadowSlot = queue_slot(paths.counters + COUNTER_SHADOW, shadow);
 
 	if (shadow)
 	{
-		paths.shadowOrigin[shadowSlot] = shadowOrigin;
-		paths.shadowDirection[shadowSlot] = shadowDirection;
+		paths.shadowQueue[shadowSlot * 2u] = shadowOrigin;
+		paths.shadowQueue[shadowSlot * 2u + 1u] = shadowDirection;
 		paths.shadowValue[shadowSlot] = shadowValue;
 	}
 
@@ -924,34 +943,44 @@ __global__ void __launch_bounds__(kBlock) shade_kernel(DeviceScene scene, EchoRe
 	stat_add(paths.stats, STAT_LIGHT_OCCLUSION_CHECKED, statChecked);
 }
 
-// scene.Occlude of ImportanceSampleRadiant (:196-197); unoccluded pending contributions go into Path.Result (:80-84)
-template<int STACK>
-__global__ void __launch_bounds__(kBlock) shadow_kernel(DeviceScene scene, const uint32_t* __restrict__ shadowCount, PathBuffers paths)
+// scene.Occlude of ImportanceSampleRadiant (:196-197); unoccluded pending contributions go into Path.Result (:80-84).
+// A path has at most one shadow ray per bounce, so the read-modify-write of its result needs no atomic.
+struct ShadowIO
 {
-	uint32_t i = blockIdx.x * kBlock + threadIdx.x;
-	bool active = i < *shadowCount;
-	bool passed = false;
+	const float4* __restrict__ rays;
+	const float4* __restrict__ values;
+	float4* __restrict__ result;
+	uint32_t passed;
 
-	if (active)
+	ECHO_DEVICE const float4* ray_pointer(uint32_t index) const { return rays + (size_t)index * 2; }
+	ECHO_DEVICE void store_closest(uint32_t, bool, uint32_t, float, vec2, float) const {}
+
+	ECHO_DEVICE void store_any(uint32_t index, bool occluded)
 	{
-		float4 o = paths.shadowOrigin[i], d = paths.shadowDirection[i];
-		bool occluded = scene_occlude<STACK, false>(scene, xyz(o), xyz(d), __float_as_uint(d.w), o.w, nullptr);
-		passed = !occluded;
-
-		if (passed)
-		{
-			float4 value = paths.shadowValue[i];
-			uint32_t id = __float_as_uint(value.w);
-			float4 result = paths.result[id];
-			result.x += value.x;
-			result.y += value.y;
-			result.z += value.z;
-			paths.result[id] = result;
-		}
+		if (occluded) return;
+		float4 value = values[index];
+		uint32_t id = __float_as_uint(value.w);
+		float4 total = result[id];
+		total.x += value.x;
+		total.y += value.y;
+		total.z += value.z;
+		result[id] = total;
+		++passed;
 	}
+};
 
-	stat_add(paths.stats, STAT_OCCLUDE_QUERIES, active);
-	stat_add(paths.stats, STAT_LIGHT_OCCLUSION_PASSED, passed);
+template<int STACK>
+__global__ void __launch_bounds__(kTraverseBlock) shadow_kernel(DeviceScene scene, ShadowIO io, const uint32_t* __restrict__ shadowCount, unsigned long long* __restrict__ nextRay,
+                                                              unsigned long long* __restrict__ stats)
+{
+	__shared__ float4 stagedRays[kTraverseBlock * 2];
+	io.passed = 0u;
+	persistent_traverse<STACK, true>(scene, io, *shadowCount, nextRay, stagedRays);
+
+	uint32_t passed = io.passed;
+	for (int offset = 16; offset > 0; offset >>= 1) passed += __shfl_down_sync(0xFFFFFFFFu, passed, offset);
+	if ((threadIdx.x & 31u) == 0u && passed) atomicAdd(stats + STAT_LIGHT_OCCLUSION_PASSED, (unsigned long long)passed);
+	if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(stats + STAT_OCCLUDE_QUERIES, (unsigned long long)*shadowCount);
 }
 
 __global__ void __launch_bounds__(kBlock) finish_kernel(uint32_t count, PathBuffers paths, float4* __restrict__ out)
@@ -1190,11 +1219,11 @@ static bool ensure_capacity(RenderState* state, uint64_t paths, uint64_t pixels,
 	release(state);
 
 	PathBuffers& b = state->paths;
-	bool ok = allocate(state, b.rayOrigin, paths) && allocate(state, b.rayDirection, paths) && allocate(state, b.hit, paths)
+	bool ok = allocate(state, b.rayQueue[0], paths * 2) && allocate(state, b.rayQueue[1], paths * 2) && allocate(state, b.rayPath[0], paths)
+		&& allocate(state, b.rayPath[1], paths) && allocate(state, b.hitQueue, paths)
 		&& allocate(state, b.energy, paths) && allocate(state, b.result, paths) && allocate(state, b.oldPosition, paths)
-		&& allocate(state, b.oldNormal, paths) && allocate(state, b.key, paths) && allocate(state, b.shadowOrigin, paths)
-		&& allocate(state, b.shadowDirection, paths) && allocate(state, b.shadowValue, paths) && allocate(state, b.queue[0], paths)
-		&& allocate(state, b.queue[1], paths) && allocate(state, b.counters, 64) && allocate(state, b.stats, STAT_COUNT)
+		&& allocate(state, b.oldNormal, paths) && allocate(state, b.key, paths) && allocate(state, b.shadowQueue, paths * 2)
+		&& allocate(state, b.shadowValue, paths) && allocate(state, b.counters, 64) && allocate(state, b.stats, STAT_COUNT)
 		&& allocate(state, state->pixelXY, paths) && allocate(state, state->sampleIndex, paths) && allocate(state, state->sampleOut, paths)
 		&& allocate(state, state->accumulator, pixels * 4) && allocate(state, state->sampleCount, pixels)
 		&& allocate(state, state->activePixels[0], pixels) && allocate(state, state->activePixels[1], pixels)
@@ -1209,6 +1238,54 @@ static bool ensure_capacity(RenderState* state, uint64_t paths, uint64_t pixels,
 	return true;
 }
 
+// ECHO_B200_PROFILE=1: per-kernel device time of the wavefront (CUDA events around every launch, synchronised; the
+// numbers printed by a run with this switch on are diagnostics, never bench values).
+struct KernelTimer
+{
+	enum { RAYGEN, EXTEND, SHADE_MISS, SHADE_DIFFUSE, SHADE_DIELECTRIC, SHADE_CONDUCTOR, SHADE_TERMINAL, SHADOW, ROTATE, FINISH, ACCUMULATE, OTHER, COUNT };
+	bool enabled = false;
+	double milliseconds[COUNT] = {};
+	uint64_t launches[COUNT] = {};
+	cudaEvent_t begin = nullptr, end = nullptr;
+
+	KernelTimer()
+	{
+		const char* value = std::getenv("ECHO_B200_PROFILE");
+		enabled = value && value[0] == '1';
+		if (enabled) { cudaEventCreate(&begin); cudaEventCreate(&end); }
+	}
+
+	void start(cudaStream_t stream) { if (enabled) cudaEventRecord(begin, stream); }
+
+	float last = 0.0f;
+
+	void stop(int slot, cudaStream_t stream)
+	{
+		if (!enabled) return;
+		cudaEventRecord(end, stream);
+		cudaEventSynchronize(end);
+		float ms = 0.0f;
+		cudaEventElapsedTime(&ms, begin, end);
+		milliseconds[slot] += ms;
+		++launches[slot];
+		last = ms;
+	}
+
+	void report()
+	{
+		if (!enabled) return;
+		static const char* names[COUNT] = { "raygen", "extend", "shade<miss>", "shade<diffuse>", "shade<dielectric>", "shade<conductor>", "shade<terminal>", "shadow", "rotate", "finish", "accumulate", "other" };
+		double total = 0.0;
+		for (double ms : milliseconds) total += ms;
+		for (int i = 0; i < COUNT; i++)
+			if (launches[i]) std::fprintf(stderr, "[echo_b200 profile] %-18s %8llu launches %10.3f ms %5.1f %%\n", names[i], (unsigned long long)launches[i], milliseconds[i], 100.0 * milliseconds[i] / total);
+		std::fprintf(stderr, "[echo_b200 profile] total %.3f ms\n", total);
+		for (int i = 0; i < COUNT; i++) { milliseconds[i] = 0.0; launches[i] = 0; }
+	}
+};
+
+static KernelTimer gTimer;
+
 static unsigned int blocks_for(uint64_t count) { return (unsigned int)std::max<uint64_t>((count + kBlock - 1) / kBlock, 1); }
 
 // Evaluates `count` path slots already described in state->pixelXY / sampleIndex; radiance lands in state->sampleOut.
@@ -1221,7 +1298,9 @@ static bool evaluate_paths(RenderState* state, const DeviceScene& scene, const E
 
 	if (!check_cuda(cudaMemsetAsync(counters, 0, sizeof(uint32_t) * 64, stream), "cudaMemsetAsync(counters)")) return false;
 
+	gTimer.start(stream);
 	raygen_kernel<<<blocks_for(count), kBlock, 0, stream>>>(scene, params, count, state->pixelXY, state->sampleIndex, paths);
+	gTimer.stop(KernelTimer::RAYGEN, stream);
 	if (!check_cuda(cudaMemcpyAsync(activeCount, &count, sizeof(uint32_t), cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync(count)")) return false;
 	++launches;
 
@@ -1232,18 +1311,53 @@ static bool evaluate_paths(RenderState* state, const DeviceScene& scene, const E
 	{
 		unsigned int blocks = blocks_for(active);
 
-		extend_kernel<STACK><<<blocks, kBlock, 0, stream>>>(scene, paths.queue[current], activeCount, paths);
+		static int extendGrid = persistent_grid((const void*)extend_kernel<STACK>);
+		static int shadowGrid = persistent_grid((const void*)shadow_kernel<STACK>);
+		unsigned long long* extendCounter = next_ray_counter(stream);
+		unsigned long long* shadowCounter = next_ray_counter(stream);
+		if (!extendCounter || !shadowCounter) return false;
 
-		uint32_t* next = paths.queue[current ^ 1];
-		shade_kernel<CLASS_MISS, 0u><<<blocks, kBlock, 0, stream>>>(scene, params, paths.classQueue[CLASS_MISS], counters + COUNTER_CLASS + CLASS_MISS, paths, next);
-		shade_kernel<CLASS_DIFFUSE, KINDS_DIFFUSE><<<blocks, kBlock, 0, stream>>>(scene, params, paths.classQueue[CLASS_DIFFUSE], counters + COUNTER_CLASS + CLASS_DIFFUSE, paths, next);
-		shade_kernel<CLASS_DIELECTRIC, KINDS_DIELECTRIC><<<blocks, kBlock, 0, stream>>>(scene, params, paths.classQueue[CLASS_DIELECTRIC], counters + COUNTER_CLASS + CLASS_DIELECTRIC, paths, next);
-		shade_kernel<CLASS_CONDUCTOR, KINDS_CONDUCTOR><<<blocks, kBlock, 0, stream>>>(scene, params, paths.classQueue[CLASS_CONDUCTOR], counters + COUNTER_CLASS + CLASS_CONDUCTOR, paths, next);
-		shade_kernel<CLASS_TERMINAL, KINDS_TERMINAL><<<blocks, kBlock, 0, stream>>>(scene, params, paths.classQueue[CLASS_TERMINAL], counters + COUNTER_CLASS + CLASS_TERMINAL, paths, next);
+		gTimer.start(stream);
+		ExtendIO extendIO = { paths.rayQueue[current], paths.hitQueue };
+		extend_kernel<STACK><<<std::min<unsigned int>(blocks, (unsigned int)extendGrid), kTraverseBlock, 0, stream>>>(scene, extendIO, activeCount, extendCounter);
+		gTimer.stop(KernelTimer::EXTEND, stream);
+		float extendMs = gTimer.last;
 
-		shadow_kernel<STACK><<<blocks, kBlock, 0, stream>>>(scene, counters + COUNTER_SHADOW, paths);
+		gTimer.start(stream);
+		classify_kernel<<<blocks, kBlock, 0, stream>>>(scene, activeCount, paths);
+		gTimer.stop(KernelTimer::OTHER, stream);
+
+		gTimer.start(stream);
+		shade_kernel<CLASS_MISS, 0u><<<blocks, kBlock, 0, stream>>>(scene, params, paths.classQueue[CLASS_MISS], counters + COUNTER_CLASS + CLASS_MISS, paths, current);
+		gTimer.stop(KernelTimer::SHADE_MISS, stream);
+		gTimer.start(stream);
+		shade_kernel<CLASS_DIFFUSE, KINDS_DIFFUSE><<<blocks, kBlock, 0, stream>>>(scene, params, paths.classQueue[CLASS_DIFFUSE], counters + COUNTER_CLASS + CLASS_DIFFUSE, paths, current);
+		gTimer.stop(KernelTimer::SHADE_DIFFUSE, stream);
+		gTimer.start(stream);
+		shade_kernel<CLASS_DIELECTRIC, KINDS_DIELECTRIC><<<blocks, kBlock, 0, stream>>>(scene, params, paths.classQueue[CLASS_DIELECTRIC], counters + COUNTER_CLASS + CLASS_DIELECTRIC, paths, current);
+		gTimer.stop(KernelTimer::SHADE_DIELECTRIC, stream);
+		gTimer.start(stream);
+		shade_kernel<CLASS_CONDUCTOR, KINDS_CONDUCTOR><<<blocks, kBlock, 0, stream>>>(scene, params, paths.classQueue[CLASS_CONDUCTOR], counters + COUNTER_CLASS + CLASS_CONDUCTOR, paths, current);
+		gTimer.stop(KernelTimer::SHADE_CONDUCTOR, stream);
+		gTimer.start(stream);
+		shade_kernel<CLASS_TERMINAL, KINDS_TERMINAL><<<blocks, kBlock, 0, stream>>>(scene, params, paths.classQueue[CLASS_TERMINAL], counters + COUNTER_CLASS + CLASS_TERMINAL, paths, current);
+		gTimer.stop(KernelTimer::SHADE_TERMINAL, stream);
+
+		gTimer.start(stream);
+		ShadowIO shadowIO = { paths.shadowQueue, paths.shadowValue, paths.result, 0u };
+		shadow_kernel<STACK><<<std::min<unsigned int>(blocks, (unsigned int)shadowGrid), kTraverseBlock, 0, stream>>>(scene, shadowIO, counters + COUNTER_SHADOW, shadowCounter, paths.stats);
+		gTimer.stop(KernelTimer::SHADOW, stream);
+		if (gTimer.enabled && std::getenv("ECHO_B200_PROFILE_ITERATIONS"))
+		{
+			uint32_t shadowRays = 0;
+			cudaMemcpy(&shadowRays, counters + COUNTER_SHADOW, sizeof(uint32_t), cudaMemcpyDeviceToHost);
+			std::fprintf(stderr, "[echo_b200 iteration] rays %9u extend %7.3f ms (%6.0f Mrays/s)  shadow rays %9u %7.3f ms (%6.0f Mrays/s)\n", active, extendMs,
+			             active / (extendMs * 1e3), shadowRays, gTimer.last, shadowRays / (gTimer.last * 1e3));
+		}
+		gTimer.start(stream);
 		rotate_counters_kernel<<<1, 1, 0, stream>>>(counters, activeCount, state->hostCounters);
-		launches += 8;
+		gTimer.stop(KernelTimer::ROTATE, stream);
+		launches += 9;
 
 		if (!check_cuda(cudaGetLastError(), "wavefront launch")) return false;
 		if (!check_cuda(cudaStreamSynchronize(stream), "wavefront iteration")) return false;
@@ -1252,7 +1366,9 @@ static bool evaluate_paths(RenderState* state, const DeviceScene& scene, const E
 		current ^= 1;
 	}
 
+	gTimer.start(stream);
 	finish_kernel<<<blocks_for(count), kBlock, 0, stream>>>(count, paths, state->sampleOut);
+	gTimer.stop(KernelTimer::FINISH, stream);
 	++launches;
 	return check_cuda(cudaGetLastError(), "finish_kernel launch");
 }
@@ -1279,7 +1395,7 @@ static void collect_stats(RenderState* state, EchoStats* stats, uint64_t launche
 	stats->kernelLaunches += launches;
 }
 
-constexpr uint64_t kPathsPerBatch = 1ull << 22; // ~4 M paths in flight (about 0.8 GB of wavefront state)
+constexpr uint64_t kPathsPerBatch = 1ull << 24; // 16 Mi paths in flight (about 4 GB of wavefront state): long tails of late bounces stay wide
 
 bool render_tiles(RenderState* state, const DeviceScene& scene, const EchoRenderParams& params, const int32_t* tileXY, uint32_t tileCount,
                   float4* tilesOut, float4* frame, EchoStats* stats, cudaStream_t stream)
@@ -1328,8 +1444,10 @@ bool render_tiles(RenderState* state, const DeviceScene& scene, const EchoRender
 
 			if (!check_cuda(cudaMemsetAsync(state->paths.counters + COUNTER_PIXELS, 0, sizeof(uint32_t), stream), "cudaMemsetAsync(pixel counter)")) return false;
 
+			gTimer.start(stream);
 			accumulate_kernel<<<blocks_for(activePixels), kBlock, 0, stream>>>(params, activePixels, state->activePixels[list], state->sampleOut, state->accumulator,
 			                                                                 state->sampleCount, epoch, state->activePixels[list ^ 1], state->paths.counters, state->paths.stats);
+			gTimer.stop(KernelTimer::ACCUMULATE, stream);
 			++launches;
 
 			if (!check_cuda(cudaMemcpyAsync(state->hostCounters + 8, state->paths.counters + COUNTER_PIXELS, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream), "cudaMemcpyAsync(pixels)")) return false;
@@ -1346,6 +1464,7 @@ bool render_tiles(RenderState* state, const DeviceScene& scene, const EchoRender
 	}
 
 	collect_stats(state, stats, launches, stream);
+	gTimer.report();
 	return check_cuda(cudaStreamSynchronize(stream), "render_tiles");
 }
 

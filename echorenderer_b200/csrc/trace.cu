@@ -118,7 +118,7 @@ struct BatchIO
 };
 
 template<int STACK, bool ANY>
-__global__ void __launch_bounds__(kTraverseBlock) persistent_batch_kernel(DeviceScene scene, BatchIO io, uint32_t n, unsigned long long* __restrict__ nextRay)
+__global__ void __launch_bounds__(kTraverseBlock, ECHO_MIN_BLOCKS) persistent_batch_kernel(DeviceScene scene, BatchIO io, uint32_t n, unsigned long long* __restrict__ nextRay)
 {
 	__shared__ float4 stagedRays[kTraverseBlock * 2];
 	persistent_traverse<STACK, ANY>(scene, io, n, nextRay, stagedRays);
