@@ -55,6 +55,16 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed `ncu --set full` capture of this
+    command (profiles/ncu_traffic.json); null when no capture has been recorded."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(path):
+        with open(path) as file:
+            return json.load(file).get(key)
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe). nvidia-smi needs a moment to
     start, so the sampler is started before the warm-up and `mark()`s delimit the timed region; samples are stamped on arrival."""
@@ -206,8 +216,9 @@ def render_config(args):
 
 
 def base_line(args, unit, value, ms_per_step, config, dtype):
+    # trace: every rank traces its own batch (weak); render: one fixed frame sharded by tiles (strong)
     return {"metric": "Mrays/s" if unit == "Mrays/s" else "samples/sec", "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if unit == "Mrays/s" else "strong", "vs_baseline": None,
             "dtype": dtype, "data": "synthetic", "config": config}
 
 
@@ -321,11 +332,11 @@ def main():
 
         line = base_line(args, "Mrays/s", value, total_ms / args.steps, trace_config(args, n), "f32")
         achieved = bytes_trace * n / (trace_ms * 1e-3) / 1e9
-        line["roofline"] = {"bound": "hbm", "kernel": "trace_batch_kernel (closest hit)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                            "traffic": None, "peak_source": peak_source, "algorithmic_bytes_per_query": bytes_trace, "ms_per_launch": trace_ms,
+        line["roofline"] = {"bound": "hbm", "kernel": "persistent_batch_kernel<48, false> (closest hit)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                            "traffic": ncu_traffic("closest_hit_dram_bytes_per_launch"), "peak_source": peak_source, "algorithmic_bytes_per_query": bytes_trace, "ms_per_launch": trace_ms,
                             "mrays_per_s": n / (trace_ms * 1e-3) / MRAYS,
                             "visits_per_query": {"nodes": counts[0], "triangles": counts[1], "spheres": counts[2]},
-                            "occlusion": {"kernel": "occlude_batch_kernel", "achieved": bytes_occlude * n / (occlude_ms * 1e-3) / 1e9, "algorithmic_bytes_per_query": bytes_occlude,
+                            "occlusion": {"kernel": "persistent_batch_kernel<48, true>", "traffic": ncu_traffic("occlusion_dram_bytes_per_launch"), "achieved": bytes_occlude * n / (occlude_ms * 1e-3) / 1e9, "algorithmic_bytes_per_query": bytes_occlude,
                                           "ms_per_launch": occlude_ms, "mrays_per_s": n / (occlude_ms * 1e-3) / MRAYS,
                                           "visits_per_query": {"nodes": counts[3], "triangles": counts[4], "spheres": counts[5]}}}
         line["e2e"] = {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 2 * n * 32, "d2h_bytes_per_step": n * 16 + n, "ms_per_step": e2e_ms / args.steps}
