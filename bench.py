@@ -43,6 +43,8 @@ def parse():
     parser.add_argument("--width", type=int, default=1920)
     parser.add_argument("--height", type=int, default=1080)
     parser.add_argument("--spp", type=int, default=16, help="render workload: samples per pixel per step (one epoch)")
+    parser.add_argument("--scene", default="mixed", choices=["cornell", "mixed", "lights", "large"], help="render workload scene: C1 / C3 / C4 / C5")
+    parser.add_argument("--bounce-limit", type=int, default=8, help="render workload: PathTracedEvaluator.BounceLimit (C3: 8; reference default 128)")
     parser.add_argument("--no-cpu-baseline", action="store_true")
     return parser.parse_args()
 
@@ -175,12 +177,12 @@ def reference_arm(args):
         sample = f"{len(rays)} closest-hit + {len(rays)} occlusion queries per step (bounded sample of the 16 Mi-ray batch)"
         line = base_line(args, "Mrays/s", value, seconds / args.steps * 1e3, trace_config(args, len(rays)), "f32")
     else:
-        prepared = host.prepare(scenes.mixed_material_scene())
+        prepared = host.prepare(RENDER_SCENES[args.scene][1]())
         from tests import oracle_lib
         oracle = oracle_lib.OracleScene(prepared)
         cores = os.cpu_count() or 1
         width, height = 256, 144  # bounded sample: a 256 x 144 crop of the frame's tile grid at the same spp
-        params = structs.render_params(args.width, args.height, 16, extend=args.spp, min_epoch=1, max_epoch=1, bounce_limit=8)
+        params = structs.render_params(args.width, args.height, 16, extend=args.spp, min_epoch=1, max_epoch=1, bounce_limit=args.bounce_limit)
         tiles = scenes.tile_grid(args.width, args.height, 16)
         tiles_x = (args.width + 15) // 16
         crop = tiles.reshape(-1, tiles_x, 2)[(args.height // 32) - 4:(args.height // 32) + 5, (tiles_x // 2) - 8:(tiles_x // 2) + 8].reshape(-1, 2)
@@ -209,10 +211,18 @@ def trace_config(args, rays):
             "l2": "inputs larger than L2 (ray batch 512 MiB + hit buffer 256 MiB per pass vs 126 MB L2)"}
 
 
+RENDER_SCENES = {
+    "cornell": ("C1 Cornell box (CornellBox.cs / cornell.echo)", scenes.cornell_box),
+    "mixed": ("C3 mixed-material scene (Dielectric, Conductor GGX, Oren-Nayar)", scenes.mixed_material_scene),
+    "lights": ("C4 many-lights scene (10 k emissive triangles, light-tree NEE)", scenes.many_lights_scene),
+    "large": ("C5 ~10 M-triangle terrain with the C3 material mix", scenes.large_scene),
+}
+
+
 def render_config(args):
-    return {"workload": "C3 mixed-material scene (Dielectric, Conductor GGX, Oren-Nayar), path tracer depth 8", "width": args.width,
+    return {"workload": f"{RENDER_SCENES[args.scene][0]}, path tracer bounce limit {args.bounce_limit}", "width": args.width,
             "height": args.height, "spp_per_step": args.spp, "parallelism": f"tile-sharded x{args.gpus} + NCCL all-reduce of the frame",
-            "l2": "wavefront state (~0.8 GB) larger than L2"}
+            "l2": "wavefront state (up to ~4 GB) larger than L2"}
 
 
 def base_line(args, unit, value, ms_per_step, config, dtype):
@@ -347,7 +357,7 @@ def main():
             cpu_value, cores, seconds, sample = cpu_baseline_trace(prepared, rays, shadow, args.cpu_sample)
             line["cpu_baseline"] = {"value": cpu_value, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample, "seconds": seconds}
     else:
-        prepared = host.prepare(scenes.mixed_material_scene())
+        prepared = host.prepare(RENDER_SCENES[args.scene][1]())
         scene = PreparedScene(prepared, device=local_rank)
         width, height, tile = args.width, args.height, 16
         all_tiles = scenes.tile_grid(width, height, tile)
@@ -361,7 +371,7 @@ def main():
 
         def step(index):
             nonlocal launches, samples
-            params = structs.render_params(width, height, tile, extend=args.spp, min_epoch=1, max_epoch=1, bounce_limit=8, seed=1, epoch_offset=index)
+            params = structs.render_params(width, height, tile, extend=args.spp, min_epoch=1, max_epoch=1, bounce_limit=args.bounce_limit, seed=1, epoch_offset=index)
             frame.zero_()
             stats = scene.render_frame_device(params, tiles, frame.data_ptr(), stream)
             if distributed:

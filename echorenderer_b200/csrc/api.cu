@@ -15,6 +15,7 @@ namespace echo
 static thread_local std::string lastError;
 
 void set_error(const std::string& message) { lastError = message; }
+std::string last_error_string() { return lastError; }
 
 bool check_cuda(cudaError_t status, const char* what)
 {

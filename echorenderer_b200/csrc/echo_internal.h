@@ -11,6 +11,7 @@ namespace echo
 {
 
 void set_error(const std::string& message);
+std::string last_error_string(); // the calling thread's last error (worker threads hand theirs to the caller)
 bool check_cuda(cudaError_t status, const char* what);
 
 // smallest compiled traversal stack that holds the reference's `maxDepth * 3 + 1` entries (QuadBoundingVolumeHierarchy.cs:34)

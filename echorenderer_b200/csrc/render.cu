@@ -9,6 +9,9 @@
 // Every path keeps the reference's draw order of random numbers and its order of floating-point accumulation, so a
 // sample's radiance is bit-identical to the oracle's. Queue management uses warp-aggregated atomics (ballot + popc).
 #include <algorithm>
+#include <atomic>
+#include <string>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 
@@ -51,8 +54,9 @@ struct PathBuffers
 	unsigned long long* stats; // EchoStats layout
 };
 
-struct RenderState
+struct WorkerState
 {
+	cudaStream_t stream = nullptr;
 	uint64_t capacity = 0;
 	PathBuffers paths = {};
 	std::vector<void*> allocations;
@@ -71,6 +75,15 @@ struct RenderState
 	uint64_t tileCapacity = 0;
 
 	uint32_t* hostCounters = nullptr; // pinned
+};
+
+// Tile batches are rendered by up to kWorkers concurrent pipelines (host thread + stream + wavefront buffers each): the
+// long, narrow tail of one batch's late bounces overlaps the wide first bounces of another, keeping the SMs busy.
+constexpr int kWorkers = 4;
+
+struct RenderState
+{
+	std::vector<WorkerState*> workers;
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1181,7 +1194,7 @@ __global__ void __launch_bounds__(kBlock) frame_resolve_kernel(float4* frame, ui
 
 RenderState* render_state_create() { return new RenderState(); }
 
-static void release(RenderState* state)
+static void release(WorkerState* state)
 {
 	for (void* p : state->allocations) cudaFree(p);
 	state->allocations.clear();
@@ -1193,13 +1206,38 @@ static void release(RenderState* state)
 void render_state_destroy(RenderState* state)
 {
 	if (!state) return;
-	release(state);
-	if (state->hostCounters) cudaFreeHost(state->hostCounters);
+
+	for (WorkerState* worker : state->workers)
+	{
+		release(worker);
+		if (worker->hostCounters) cudaFreeHost(worker->hostCounters);
+		if (worker->stream) cudaStreamDestroy(worker->stream);
+		delete worker;
+	}
+
 	delete state;
 }
 
+static WorkerState* get_worker(RenderState* state, size_t index)
+{
+	while (state->workers.size() <= index)
+	{
+		WorkerState* worker = new WorkerState();
+
+		if (!check_cuda(cudaStreamCreateWithFlags(&worker->stream, cudaStreamNonBlocking), "cudaStreamCreate(render worker)"))
+		{
+			delete worker;
+			return nullptr;
+		}
+
+		state->workers.push_back(worker);
+	}
+
+	return state->workers[index];
+}
+
 template<class T>
-static bool allocate(RenderState* state, T*& pointer, uint64_t count)
+static bool allocate(WorkerState* state, T*& pointer, uint64_t count)
 {
 	void* p = nullptr;
 	if (!check_cuda(cudaMalloc(&p, sizeof(T) * std::max<uint64_t>(count, 1)), "cudaMalloc(render state)")) return false;
@@ -1208,7 +1246,7 @@ static bool allocate(RenderState* state, T*& pointer, uint64_t count)
 	return true;
 }
 
-static bool ensure_capacity(RenderState* state, uint64_t paths, uint64_t pixels, uint64_t tiles)
+static bool ensure_capacity(WorkerState* state, uint64_t paths, uint64_t pixels, uint64_t tiles)
 {
 	if (!state->hostCounters && !check_cuda(cudaMallocHost((void**)&state->hostCounters, sizeof(uint32_t) * 64), "cudaMallocHost")) return false;
 	if (paths <= state->capacity && pixels <= state->pixelCapacity && tiles <= state->tileCapacity) return true;
@@ -1290,7 +1328,7 @@ static unsigned int blocks_for(uint64_t count) { return (unsigned int)std::max<u
 
 // Evaluates `count` path slots already described in state->pixelXY / sampleIndex; radiance lands in state->sampleOut.
 template<int STACK>
-static bool evaluate_paths(RenderState* state, const DeviceScene& scene, const EchoRenderParams& params, uint32_t count, uint64_t& launches, cudaStream_t stream)
+static bool evaluate_paths(WorkerState* state, const DeviceScene& scene, const EchoRenderParams& params, uint32_t count, uint64_t& launches, cudaStream_t stream)
 {
 	PathBuffers& paths = state->paths;
 	uint32_t* counters = paths.counters;
@@ -1373,7 +1411,7 @@ static bool evaluate_paths(RenderState* state, const DeviceScene& scene, const E
 	return check_cuda(cudaGetLastError(), "finish_kernel launch");
 }
 
-static bool evaluate_paths_dispatch(RenderState* state, const DeviceScene& scene, const EchoRenderParams& params, uint32_t count, uint64_t& launches, cudaStream_t stream)
+static bool evaluate_paths_dispatch(WorkerState* state, const DeviceScene& scene, const EchoRenderParams& params, uint32_t count, uint64_t& launches, cudaStream_t stream)
 {
 	switch (stack_class(scene.maxDepth))
 	{
@@ -1384,7 +1422,7 @@ static bool evaluate_paths_dispatch(RenderState* state, const DeviceScene& scene
 	}
 }
 
-static void collect_stats(RenderState* state, EchoStats* stats, uint64_t launches, cudaStream_t stream)
+static void collect_stats(WorkerState* state, EchoStats* stats, uint64_t launches, cudaStream_t stream)
 {
 	if (!stats) return;
 	unsigned long long host[STAT_COUNT];
@@ -1395,7 +1433,58 @@ static void collect_stats(RenderState* state, EchoStats* stats, uint64_t launche
 	stats->kernelLaunches += launches;
 }
 
-constexpr uint64_t kPathsPerBatch = 1ull << 24; // 16 Mi paths in flight (about 4 GB of wavefront state): long tails of late bounces stay wide
+constexpr uint64_t kPathsPerBatch = 1ull << 22; // 4 Mi paths per batch and pipeline (about 1 GB of wavefront state each)
+
+// one batch of tiles: pixel loop -> epoch loop -> sample loop of EvaluationOperation.Execute (EvaluationOperation.cs:100-141)
+static bool render_batch(WorkerState* state, const DeviceScene& scene, const EchoRenderParams& params, const int32_t* tileXY, uint32_t tiles,
+                         float4* tilesOut, float4* frame, uint64_t& launches)
+{
+	cudaStream_t stream = state->stream;
+	uint64_t perTile = (uint64_t)params.tileSize * params.tileSize;
+	uint32_t pixelTotal = (uint32_t)(tiles * perTile);
+
+	if (!ensure_capacity(state, (uint64_t)pixelTotal * params.extend, pixelTotal, tiles)) return false;
+	if (!check_cuda(cudaMemcpyAsync(state->tileXYDevice, tileXY, sizeof(int32_t) * 2 * tiles, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync(tiles)")) return false;
+	if (!check_cuda(cudaMemsetAsync(state->paths.counters, 0, sizeof(uint32_t) * 64, stream), "cudaMemsetAsync(counters)")) return false;
+
+	batch_pixels_kernel<<<blocks_for(pixelTotal), kBlock, 0, stream>>>(params, state->tileXYDevice, tiles, state->batchPixelXY, state->activePixels[0],
+	                                                                 state->paths.counters, state->accumulator, state->sampleCount);
+	++launches;
+
+	if (!check_cuda(cudaMemcpyAsync(state->hostCounters + 8, state->paths.counters + COUNTER_PIXELS, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream), "cudaMemcpyAsync(pixels)")) return false;
+	if (!check_cuda(cudaStreamSynchronize(stream), "batch setup")) return false;
+
+	uint32_t activePixels = state->hostCounters[8];
+	int list = 0;
+
+	for (uint32_t epoch = 1; activePixels > 0 && epoch <= (uint32_t)params.maxEpoch; epoch++)
+	{
+		uint32_t slots = activePixels * (uint32_t)params.extend;
+
+		epoch_slots_kernel<<<blocks_for(slots), kBlock, 0, stream>>>(params, activePixels, state->activePixels[list], state->batchPixelXY, epoch, state->pixelXY, state->sampleIndex);
+		++launches;
+
+		if (!evaluate_paths_dispatch(state, scene, params, slots, launches, stream)) return false;
+
+		if (!check_cuda(cudaMemsetAsync(state->paths.counters + COUNTER_PIXELS, 0, sizeof(uint32_t), stream), "cudaMemsetAsync(pixel counter)")) return false;
+
+		gTimer.start(stream);
+		accumulate_kernel<<<blocks_for(activePixels), kBlock, 0, stream>>>(params, activePixels, state->activePixels[list], state->sampleOut, state->accumulator,
+		                                                                 state->sampleCount, epoch, state->activePixels[list ^ 1], state->paths.counters, state->paths.stats);
+		gTimer.stop(KernelTimer::ACCUMULATE, stream);
+		++launches;
+
+		if (!check_cuda(cudaMemcpyAsync(state->hostCounters + 8, state->paths.counters + COUNTER_PIXELS, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream), "cudaMemcpyAsync(pixels)")) return false;
+		if (!check_cuda(cudaStreamSynchronize(stream), "epoch")) return false;
+
+		activePixels = state->hostCounters[8];
+		list ^= 1;
+	}
+
+	resolve_tiles_kernel<<<blocks_for(pixelTotal), kBlock, 0, stream>>>(params, pixelTotal, state->batchPixelXY, state->accumulator, tilesOut, frame, state->paths.stats);
+	++launches;
+	return check_cuda(cudaGetLastError(), "resolve_tiles_kernel launch");
+}
 
 bool render_tiles(RenderState* state, const DeviceScene& scene, const EchoRenderParams& params, const int32_t* tileXY, uint32_t tileCount,
                   float4* tilesOut, float4* frame, EchoStats* stats, cudaStream_t stream)
@@ -1406,72 +1495,81 @@ bool render_tiles(RenderState* state, const DeviceScene& scene, const EchoRender
 		return false;
 	}
 
+	// work submitted earlier on the caller's stream (e.g. clearing the frame) must be visible to the worker streams
+	if (!check_cuda(cudaStreamSynchronize(stream), "render_tiles entry")) return false;
+
 	uint64_t perTile = (uint64_t)params.tileSize * params.tileSize;
 	uint64_t tilesPerBatch = std::max<uint64_t>(1, kPathsPerBatch / (perTile * params.extend));
 	tilesPerBatch = std::min<uint64_t>(tilesPerBatch, tileCount);
+	uint64_t batchCount = (tileCount + tilesPerBatch - 1) / tilesPerBatch;
 
-	if (!ensure_capacity(state, tilesPerBatch * perTile * params.extend, tilesPerBatch * perTile, tilesPerBatch)) return false;
+	int workerCount = (int)std::min<uint64_t>(gTimer.enabled ? 1 : kWorkers, batchCount);
+	for (int i = 0; i < workerCount; i++)
+		if (!get_worker(state, i)) return false;
 
-	uint64_t launches = 0;
-	if (!check_cuda(cudaMemsetAsync(state->paths.stats, 0, sizeof(unsigned long long) * STAT_COUNT, stream), "cudaMemsetAsync(stats)")) return false;
+	int device = 0;
+	cudaGetDevice(&device);
 
-	for (uint64_t first = 0; first < tileCount; first += tilesPerBatch)
+	std::atomic<uint64_t> nextBatch{ 0 };
+	std::atomic<bool> failed{ false };
+	std::vector<uint64_t> launches(workerCount, 0);
+	std::vector<std::string> errors(workerCount);
+
+	auto work = [&](int index)
 	{
-		uint32_t tiles = (uint32_t)std::min<uint64_t>(tilesPerBatch, tileCount - first);
-		uint32_t pixelTotal = (uint32_t)(tiles * perTile);
+		WorkerState* worker = state->workers[index];
+		bool ok = check_cuda(cudaSetDevice(device), "cudaSetDevice(render worker)");
 
-		if (!check_cuda(cudaMemcpyAsync(state->tileXYDevice, tileXY + first * 2, sizeof(int32_t) * 2 * tiles, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync(tiles)")) return false;
-		if (!check_cuda(cudaMemsetAsync(state->paths.counters, 0, sizeof(uint32_t) * 64, stream), "cudaMemsetAsync(counters)")) return false;
+		// the statistics buffer is allocated with the wavefront state: size the worker for a full batch up front
+		ok = ok && ensure_capacity(worker, tilesPerBatch * perTile * params.extend, tilesPerBatch * perTile, tilesPerBatch);
+		ok = ok && check_cuda(cudaMemsetAsync(worker->paths.stats, 0, sizeof(unsigned long long) * STAT_COUNT, worker->stream), "cudaMemsetAsync(stats)");
 
-		batch_pixels_kernel<<<blocks_for(pixelTotal), kBlock, 0, stream>>>(params, state->tileXYDevice, tiles, state->batchPixelXY, state->activePixels[0],
-		                                                                 state->paths.counters, state->accumulator, state->sampleCount);
-		++launches;
-
-		if (!check_cuda(cudaMemcpyAsync(state->hostCounters + 8, state->paths.counters + COUNTER_PIXELS, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream), "cudaMemcpyAsync(pixels)")) return false;
-		if (!check_cuda(cudaStreamSynchronize(stream), "batch setup")) return false;
-
-		uint32_t activePixels = state->hostCounters[8];
-		int list = 0;
-
-		for (uint32_t epoch = 1; activePixels > 0 && epoch <= (uint32_t)params.maxEpoch; epoch++)
+		while (ok && !failed.load())
 		{
-			uint32_t slots = activePixels * (uint32_t)params.extend;
+			uint64_t batch = nextBatch.fetch_add(1);
+			if (batch >= batchCount) break;
 
-			epoch_slots_kernel<<<blocks_for(slots), kBlock, 0, stream>>>(params, activePixels, state->activePixels[list], state->batchPixelXY, epoch, state->pixelXY, state->sampleIndex);
-			++launches;
-
-			if (!evaluate_paths_dispatch(state, scene, params, slots, launches, stream)) return false;
-
-			if (!check_cuda(cudaMemsetAsync(state->paths.counters + COUNTER_PIXELS, 0, sizeof(uint32_t), stream), "cudaMemsetAsync(pixel counter)")) return false;
-
-			gTimer.start(stream);
-			accumulate_kernel<<<blocks_for(activePixels), kBlock, 0, stream>>>(params, activePixels, state->activePixels[list], state->sampleOut, state->accumulator,
-			                                                                 state->sampleCount, epoch, state->activePixels[list ^ 1], state->paths.counters, state->paths.stats);
-			gTimer.stop(KernelTimer::ACCUMULATE, stream);
-			++launches;
-
-			if (!check_cuda(cudaMemcpyAsync(state->hostCounters + 8, state->paths.counters + COUNTER_PIXELS, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream), "cudaMemcpyAsync(pixels)")) return false;
-			if (!check_cuda(cudaStreamSynchronize(stream), "epoch")) return false;
-
-			activePixels = state->hostCounters[8];
-			list ^= 1;
+			uint64_t first = batch * tilesPerBatch;
+			uint32_t tiles = (uint32_t)std::min<uint64_t>(tilesPerBatch, tileCount - first);
+			ok = render_batch(worker, scene, params, tileXY + first * 2, tiles, tilesOut ? tilesOut + first * perTile : nullptr, frame, launches[index]);
 		}
 
-		resolve_tiles_kernel<<<blocks_for(pixelTotal), kBlock, 0, stream>>>(params, pixelTotal, state->batchPixelXY, state->accumulator,
-		                                                                  tilesOut ? tilesOut + first * perTile : nullptr, frame, state->paths.stats);
-		++launches;
-		if (!check_cuda(cudaGetLastError(), "resolve_tiles_kernel launch")) return false;
+		ok = ok && check_cuda(cudaStreamSynchronize(worker->stream), "render worker");
+
+		if (!ok)
+		{
+			failed.store(true);
+			errors[index] = last_error_string();
+		}
+	};
+
+	if (workerCount == 1) work(0);
+	else
+	{
+		std::vector<std::thread> threads;
+		for (int i = 0; i < workerCount; i++) threads.emplace_back(work, i);
+		for (std::thread& thread : threads) thread.join();
 	}
 
-	collect_stats(state, stats, launches, stream);
+	if (failed.load())
+	{
+		for (const std::string& error : errors)
+			if (!error.empty()) set_error(error);
+		return false;
+	}
+
+	for (int i = 0; i < workerCount; i++) collect_stats(state->workers[i], stats, launches[i], state->workers[i]->stream);
 	gTimer.report();
-	return check_cuda(cudaStreamSynchronize(stream), "render_tiles");
+	return true;
 }
 
 // debug: explicit (pixel, sample) lists -> per-sample radiance (device pointers in, device pointer out)
-bool evaluate_sample_list(RenderState* state, const DeviceScene& scene, const EchoRenderParams& params, const int32_t* pixelXYHost, const uint32_t* sampleIndexHost,
-                          uint64_t n, float* outRGBHost, cudaStream_t stream)
+bool evaluate_sample_list(RenderState* renderState, const DeviceScene& scene, const EchoRenderParams& params, const int32_t* pixelXYHost, const uint32_t* sampleIndexHost,
+                          uint64_t n, float* outRGBHost, cudaStream_t)
 {
+	WorkerState* state = get_worker(renderState, 0);
+	if (!state) return false;
+	cudaStream_t stream = state->stream;
 	std::vector<float4> staging;
 
 	for (uint64_t first = 0; first < n; first += kPathsPerBatch)
