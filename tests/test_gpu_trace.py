@@ -90,3 +90,93 @@ def test_cornell_ties(cornell):
 
     with PreparedScene(cornell) as scene:
         assert_hits_equal(scene.trace(rays), oracle.trace(rays))
+
+
+def chain_scene(depth):
+    """A hand-built, maximally unbalanced QBVH: node i = [triangle i, empty, node i + 1, empty] (axisMinor = 3 marks the
+    [leaf, empty] pairs, QuadBoundingVolumeHierarchy.cs:531-533). Quad depth = `depth`, stack size = 3 * depth + 1 (:34)."""
+    from echorenderer_b200 import host as host_module
+    count = depth  # triangles; the last node holds the last two
+    x = np.arange(count, dtype=np.float64) * 2.0
+    v0 = np.stack([x, np.zeros(count), -np.ones(count)], axis=-1)
+    v1 = np.stack([x + 1.0, np.zeros(count), -np.ones(count)], axis=-1)
+    v2 = np.stack([x + 0.5, np.ones(count), np.ones(count)], axis=-1)
+    triangles = scenes.make_triangles(v0, v1, v2, 0)
+    low = np.minimum(np.minimum(v0, v1), v2).astype(np.float32)
+    high = np.maximum(np.maximum(v0, v1), v2).astype(np.float32)
+
+    nodes = np.zeros(count - 1, dtype=structs.QBVH_NODE)
+    for key in ("minX", "minY", "minZ", "maxX", "maxY", "maxZ"):
+        nodes[key] = np.inf
+    nodes["token4"] = structs.TOKEN_EMPTY
+    nodes["axisMajor"], nodes["axisMinor0"], nodes["axisMinor1"] = 0, 3, 3
+
+    for i in range(count - 1):
+        last = i == count - 2
+        rest_low, rest_high = low[i + 1:].min(axis=0), high[i + 1:].max(axis=0)
+        for slot, (lo, hi, token) in ((0, (low[i], high[i], structs.make_token(1, i))),
+                                      (2, (rest_low, rest_high, structs.make_token(1, i + 1) if last else structs.make_token(0, i + 1)))):
+            nodes["minX"][i, slot], nodes["minY"][i, slot], nodes["minZ"][i, slot] = lo
+            nodes["maxX"][i, slot], nodes["maxY"][i, slot], nodes["maxZ"][i, slot] = hi
+            nodes["token4"][i, slot] = token
+
+    description = host_module.SceneDescription(triangles=triangles, materials=scenes.material(structs.MATERIAL_DIFFUSE),
+                                               camera=scenes.perspective_camera((0, 5, -5)))
+    empty_u32, empty_u64 = np.zeros(0, np.uint32), np.zeros(0, np.uint64)
+    return host_module.PreparedArrays(description, nodes, count, np.zeros(0, structs.LIGHT_NODE), empty_u32, empty_u64, 0.0, 0.0, 0.0)
+
+
+@pytest.mark.parametrize("depth", [12, 20, 40])
+def test_deep_trees_use_the_larger_stack_classes(depth):
+    """maxDepth 12 / 20 / 40 -> 37 / 61 / 121 stack entries -> the 48 / 96 / 192-entry kernels."""
+    prepared = chain_scene(depth)
+    oracle = oracle_lib.OracleScene(prepared)
+    rays = scenes.random_rays(prepared.bounds, 50_000, seed=23)
+    rays["direction"][::2] = np.array([1.0, 0.0, 0.0], dtype=np.float32) * np.where(np.arange(25_000) % 2, 1, -1)[:, None]  # rays along the chain
+    rays["origin"][::2, 1] = 0.3
+    rays["origin"][::2, 2] = 0.0
+    shadow = rays.copy()
+    shadow["distance"] = 7.0
+
+    with PreparedScene(prepared) as scene:
+        expected = oracle.trace(rays)
+        assert (expected["token"] != structs.TOKEN_EMPTY).mean() > 0.2
+        assert_hits_equal(scene.trace(rays), expected)
+        assert np.array_equal(scene.occlude(shadow), oracle.occlude(shadow))
+
+
+def test_too_deep_tree_is_rejected():
+    from echorenderer_b200 import EchoNativeError
+    with pytest.raises(EchoNativeError) as error:
+        PreparedScene(chain_scene(70))
+    assert error.value.status == 4  # ECHO_B200_ERR_UNSUPPORTED
+
+
+def test_spheres_only_and_tiny_scenes():
+    """A scene of spheres only (no triangle array at all) and the smallest legal hierarchy (2 primitives)."""
+    from echorenderer_b200 import host as host_module
+    rng = np.random.default_rng(5)
+    spheres = np.zeros(700, dtype=structs.SPHERE)
+    spheres["position"] = rng.uniform(-10, 10, size=(700, 3)).astype(np.float32)
+    spheres["radius"] = rng.uniform(0.1, 1.0, size=700).astype(np.float32)
+    description = host_module.SceneDescription(spheres=spheres, materials=scenes.material(structs.MATERIAL_DIFFUSE), camera=scenes.perspective_camera((0, 0, -30)))
+    prepared = host_module.prepare(description)
+    oracle = oracle_lib.OracleScene(prepared)
+    rays = scenes.random_rays(prepared.bounds, 100_000, seed=31)
+
+    with PreparedScene(prepared) as scene:
+        expected = oracle.trace(rays)
+        assert_hits_equal(scene.trace(rays), expected)
+        inside = scenes.secondary_rays(prepared, rays, expected)   # leave the sphere surfaces: findFar path (SphereEntity.cs:106-109)
+        assert_hits_equal(scene.trace(inside), oracle.trace(inside))
+        inside["distance"] = 3.0
+        assert np.array_equal(scene.occlude(inside), oracle.occlude(inside))
+
+    description = host_module.SceneDescription(triangles=scenes.plane(0, (2, 2)), materials=scenes.material(structs.MATERIAL_DIFFUSE), camera=scenes.perspective_camera((0, 3, -3)))
+    prepared = host_module.prepare(description)
+    assert len(prepared.nodes) == 1
+    oracle = oracle_lib.OracleScene(prepared)
+    rays = scenes.random_rays((np.array([-1, -1, -1.0]), np.array([1, 1, 1.0])), 20_000, seed=33)
+
+    with PreparedScene(prepared) as scene:
+        assert_hits_equal(scene.trace(rays), oracle.trace(rays))
