@@ -23,7 +23,10 @@ constexpr unsigned long long kPool = 256;         // rays reserved per global at
 #define ECHO_LEAF_VOTE 8
 #endif
 #ifndef ECHO_MIN_BLOCKS
-#define ECHO_MIN_BLOCKS 1
+#define ECHO_MIN_BLOCKS 7
+#endif
+#ifndef ECHO_LEAF_MAX_WAIT
+#define ECHO_LEAF_MAX_WAIT 2 // a lane waits at most two iterations for its primitive test (A/B on C2/C3/C4: +1-2 %)
 #endif
 constexpr int kLeafVote = ECHO_LEAF_VOTE;                      // run the primitive tests once this many lanes have one pending
 
@@ -151,6 +154,8 @@ ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, uint32_t 
 		if (first < 4u) leaf = first == 0u ? child0 : (first == 1u ? child1 : (first == 2u ? child2 : child3));
 		position = first < 4u ? (int)first + 1 : 4;
 	};
+
+	int waited = 0; // warp-uniform: iterations some lane has been waiting for its primitive test
 
 	while (true)
 	{
@@ -311,8 +316,12 @@ ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, uint32_t 
 		unsigned int pending = __ballot_sync(0xFFFFFFFFu, leaf != ECHO_TOKEN_EMPTY);
 		unsigned int working = __ballot_sync(0xFFFFFFFFu, haveRay);
 
-		if (pending != 0u && (__popc(pending) >= kLeafVote || pending == working))
+		waited = pending != 0u ? waited + 1 : 0;
+
+		if (pending != 0u && (__popc(pending) >= kLeafVote || pending == working || waited > ECHO_LEAF_MAX_WAIT))
 		{
+			waited = 0;
+
 			if (leaf != ECHO_TOKEN_EMPTY)
 			{
 				bool occluded = false;

@@ -79,7 +79,7 @@ struct WorkerState
 
 // Tile batches are rendered by up to kWorkers concurrent pipelines (host thread + stream + wavefront buffers each): the
 // long, narrow tail of one batch's late bounces overlaps the wide first bounces of another, keeping the SMs busy.
-constexpr int kWorkers = 4;
+constexpr int kWorkers = 8; // A/B on C3/C4/C5: 1 -> 134, 2 -> 207, 4 -> 280, 8 -> 329, 12 -> 330 M samples/s on C5 (profiles/README.md)
 
 struct RenderState
 {
@@ -690,7 +690,7 @@ struct ExtendIO
 };
 
 template<int STACK>
-__global__ void __launch_bounds__(kTraverseBlock) extend_kernel(DeviceScene scene, ExtendIO io, const uint32_t* __restrict__ queueCount, unsigned long long* __restrict__ nextRay)
+__global__ void __launch_bounds__(kTraverseBlock, ECHO_MIN_BLOCKS) extend_kernel(DeviceScene scene, ExtendIO io, const uint32_t* __restrict__ queueCount, unsigned long long* __restrict__ nextRay)
 {
 	__shared__ float4 stagedRays[kTraverseBlock * 2];
 	persistent_traverse<STACK, false>(scene, io, *queueCount, nextRay, stagedRays);
@@ -983,7 +983,7 @@ struct ShadowIO
 };
 
 template<int STACK>
-__global__ void __launch_bounds__(kTraverseBlock) shadow_kernel(DeviceScene scene, ShadowIO io, const uint32_t* __restrict__ shadowCount, unsigned long long* __restrict__ nextRay,
+__global__ void __launch_bounds__(kTraverseBlock, ECHO_MIN_BLOCKS) shadow_kernel(DeviceScene scene, ShadowIO io, const uint32_t* __restrict__ shadowCount, unsigned long long* __restrict__ nextRay,
                                                               unsigned long long* __restrict__ stats)
 {
 	__shared__ float4 stagedRays[kTraverseBlock * 2];
@@ -1503,7 +1503,14 @@ bool render_tiles(RenderState* state, const DeviceScene& scene, const EchoRender
 	tilesPerBatch = std::min<uint64_t>(tilesPerBatch, tileCount);
 	uint64_t batchCount = (tileCount + tilesPerBatch - 1) / tilesPerBatch;
 
-	int workerCount = (int)std::min<uint64_t>(gTimer.enabled ? 1 : kWorkers, batchCount);
+	static const int configuredWorkers = []
+	{
+		const char* value = std::getenv("ECHO_B200_RENDER_WORKERS");
+		int workers = value ? std::atoi(value) : kWorkers;
+		return workers < 1 ? 1 : (workers > 16 ? 16 : workers);
+	}();
+
+	int workerCount = (int)std::min<uint64_t>(gTimer.enabled ? 1 : configuredWorkers, batchCount);
 	for (int i = 0; i < workerCount; i++)
 		if (!get_worker(state, i)) return false;
 

@@ -132,9 +132,11 @@ def test_deep_trees_use_the_larger_stack_classes(depth):
     prepared = chain_scene(depth)
     oracle = oracle_lib.OracleScene(prepared)
     rays = scenes.random_rays(prepared.bounds, 50_000, seed=23)
-    rays["direction"][::2] = np.array([1.0, 0.0, 0.0], dtype=np.float32) * np.where(np.arange(25_000) % 2, 1, -1)[:, None]  # rays along the chain
-    rays["origin"][::2, 1] = 0.3
-    rays["origin"][::2, 2] = 0.0
+    # every other ray is aimed at the centroid of some triangle of the chain, so it crosses many of the nested boxes
+    target = prepared.triangles[np.arange(25_000) % len(prepared.triangles)]
+    centroid = target["vertex0"] + (target["edge1"] + target["edge2"]) / np.float32(3)
+    aim = (centroid - rays["origin"][::2]).astype(np.float64)
+    rays["direction"][::2] = (aim / np.linalg.norm(aim, axis=1, keepdims=True)).astype(np.float32)
     shadow = rays.copy()
     shadow["distance"] = 7.0
 
