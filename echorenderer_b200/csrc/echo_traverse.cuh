@@ -1,11 +1,11 @@
 // echo_traverse.cuh — the persistent, work-replacing QBVH traversal core used by every closest-hit / occlusion kernel.
 //
 // Why not one thread per ray: in an incoherent batch most rays leave the tree after 1-3 nodes while a few need 30+, so a
-// warp that walks 32 fixed rays runs at ~5 active lanes (measured: profiles/r1a, 4.88 threads per instruction). Here a
-// grid of resident warps pulls rays from a global counter: each warp reserves a pool of kPool consecutive rays with one
-// global atomic, lanes take the next ray from the pool with a shared-memory atomic the moment their ray ends (work
-// replacement), and primitive tests are postponed until several lanes have one pending (while-while with a vote), so the
-// expensive fp64-cross Möller–Trumbore code is issued for many lanes at once.
+// warp that walks 32 fixed rays runs at ~5 active lanes (measured: profiles/r1a, 4.88 threads per instruction). Here one
+// resident wave of warps pulls rays from a global counter: each warp reserves a pool of consecutive rays with one global
+// atomic, a lane whose ray ended takes the next ray of the pool (work replacement), rays are staged global -> shared
+// with cp.async one ray ahead of their use, and primitive tests are postponed until several lanes have one pending, so
+// the expensive fp64-cross Möller–Trumbore code is issued for many lanes at once.
 //
 // Per ray, the sequence of operations is exactly the reference's (QuadBoundingVolumeHierarchy.cs:123-315,
 // GeometryCollection.cs:85-171): same visit order, same culling comparisons, leaves intersected in push order. Only the
@@ -17,7 +17,6 @@ namespace echo
 {
 
 constexpr int kTraverseBlock = 128;              // 4 warps per CTA
-constexpr int kTraverseWarps = kTraverseBlock / 32;
 constexpr unsigned long long kPool = 256;         // rays reserved per global atomic
 #ifndef ECHO_LEAF_VOTE
 #define ECHO_LEAF_VOTE 8
@@ -29,11 +28,6 @@ constexpr unsigned long long kPool = 256;         // rays reserved per global at
 #define ECHO_LEAF_MAX_WAIT 2 // a lane waits at most two iterations for its primitive test (A/B on C2/C3/C4: +1-2 %)
 #endif
 constexpr int kLeafVote = ECHO_LEAF_VOTE;                      // run the primitive tests once this many lanes have one pending
-
-struct WarpPool
-{
-	unsigned long long next, end;
-};
 
 // BoxBound4.Intersect for one lane with hardware min/max. Bit-identical to slab() whenever no operand is NaN, which holds
 // when the three reciprocal direction components and the origin are finite (a NaN needs 0 * inf or inf - inf); the sign

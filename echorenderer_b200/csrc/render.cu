@@ -79,6 +79,7 @@ struct WorkerState
 
 // Tile batches are rendered by up to kWorkers concurrent pipelines (host thread + stream + wavefront buffers each): the
 // long, narrow tail of one batch's late bounces overlaps the wide first bounces of another, keeping the SMs busy.
+constexpr uint32_t kNarrowLimit = 262144; // below this many rays a bounce uses the one-thread-per-ray kernels
 constexpr int kWorkers = 8; // A/B on C3/C4/C5: 1 -> 134, 2 -> 207, 4 -> 280, 8 -> 329, 12 -> 330 M samples/s on C5 (profiles/README.md)
 
 struct RenderState
@@ -696,6 +697,23 @@ __global__ void __launch_bounds__(kTraverseBlock, ECHO_MIN_BLOCKS) extend_kernel
 	persistent_traverse<STACK, false>(scene, io, *queueCount, nextRay, stagedRays);
 }
 
+// Narrow wavefronts (late bounces) have fewer rays than resident lanes: work replacement has nothing to replace with and
+// the launch is bound by the latency of its longest ray, so the leaner one-thread-per-ray loop is used instead.
+template<int STACK>
+__global__ void __launch_bounds__(kBlock) extend_narrow_kernel(DeviceScene scene, ExtendIO io, const uint32_t* __restrict__ queueCount)
+{
+	uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+	if (i >= *queueCount) return;
+
+	float4 a = io.rays[i * 2u], b = io.rays[i * 2u + 1u];
+	float distance = b.z;
+	uint32_t token = ECHO_TOKEN_EMPTY;
+	vec2 uv = { 0.0f, 0.0f };
+
+	bool hit = scene_trace<STACK, false>(scene, { a.x, a.y, a.z }, { a.w, b.x, b.y }, __float_as_uint(b.w), distance, token, uv, nullptr);
+	io.store_closest(i, hit, token, distance, uv, b.z);
+}
+
 // the material-class sort: one thread per traced ray appends its slot to the queue of the class it hit
 __global__ void __launch_bounds__(kBlock) classify_kernel(DeviceScene scene, const uint32_t* __restrict__ queueCount, PathBuffers paths)
 {
@@ -994,6 +1012,24 @@ __global__ void __launch_bounds__(kTraverseBlock, ECHO_MIN_BLOCKS) shadow_kernel
 	for (int offset = 16; offset > 0; offset >>= 1) passed += __shfl_down_sync(0xFFFFFFFFu, passed, offset);
 	if ((threadIdx.x & 31u) == 0u && passed) atomicAdd(stats + STAT_LIGHT_OCCLUSION_PASSED, (unsigned long long)passed);
 	if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(stats + STAT_OCCLUDE_QUERIES, (unsigned long long)*shadowCount);
+}
+
+template<int STACK>
+__global__ void __launch_bounds__(kBlock) shadow_narrow_kernel(DeviceScene scene, ShadowIO io, const uint32_t* __restrict__ shadowCount, unsigned long long* __restrict__ stats)
+{
+	uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+	bool active = i < *shadowCount;
+	io.passed = 0u;
+
+	if (active)
+	{
+		float4 a = io.rays[i * 2u], b = io.rays[i * 2u + 1u];
+		bool occluded = scene_occlude<STACK, false>(scene, { a.x, a.y, a.z }, { a.w, b.x, b.y }, __float_as_uint(b.w), b.z, nullptr);
+		io.store_any(i, occluded);
+	}
+
+	stat_add(stats, STAT_OCCLUDE_QUERIES, active);
+	stat_add(stats, STAT_LIGHT_OCCLUSION_PASSED, io.passed != 0u);
 }
 
 __global__ void __launch_bounds__(kBlock) finish_kernel(uint32_t count, PathBuffers paths, float4* __restrict__ out)
@@ -1355,9 +1391,16 @@ static bool evaluate_paths(WorkerState* state, const DeviceScene& scene, const E
 		unsigned long long* shadowCounter = next_ray_counter(stream);
 		if (!extendCounter || !shadowCounter) return false;
 
+		static const uint32_t narrowLimit = []
+		{
+			const char* value = std::getenv("ECHO_B200_NARROW_LIMIT");
+			return value ? (uint32_t)std::atoll(value) : kNarrowLimit;
+		}();
+
 		gTimer.start(stream);
 		ExtendIO extendIO = { paths.rayQueue[current], paths.hitQueue };
-		extend_kernel<STACK><<<std::min<unsigned int>(blocks, (unsigned int)extendGrid), kTraverseBlock, 0, stream>>>(scene, extendIO, activeCount, extendCounter);
+		if (active < narrowLimit) extend_narrow_kernel<STACK><<<blocks, kBlock, 0, stream>>>(scene, extendIO, activeCount);
+		else extend_kernel<STACK><<<std::min<unsigned int>(blocks, (unsigned int)extendGrid), kTraverseBlock, 0, stream>>>(scene, extendIO, activeCount, extendCounter);
 		gTimer.stop(KernelTimer::EXTEND, stream);
 		float extendMs = gTimer.last;
 
@@ -1383,7 +1426,8 @@ static bool evaluate_paths(WorkerState* state, const DeviceScene& scene, const E
 
 		gTimer.start(stream);
 		ShadowIO shadowIO = { paths.shadowQueue, paths.shadowValue, paths.result, 0u };
-		shadow_kernel<STACK><<<std::min<unsigned int>(blocks, (unsigned int)shadowGrid), kTraverseBlock, 0, stream>>>(scene, shadowIO, counters + COUNTER_SHADOW, shadowCounter, paths.stats);
+		if (active < narrowLimit) shadow_narrow_kernel<STACK><<<blocks, kBlock, 0, stream>>>(scene, shadowIO, counters + COUNTER_SHADOW, paths.stats);
+		else shadow_kernel<STACK><<<std::min<unsigned int>(blocks, (unsigned int)shadowGrid), kTraverseBlock, 0, stream>>>(scene, shadowIO, counters + COUNTER_SHADOW, shadowCounter, paths.stats);
 		gTimer.stop(KernelTimer::SHADOW, stream);
 		if (gTimer.enabled && std::getenv("ECHO_B200_PROFILE_ITERATIONS"))
 		{
@@ -1498,17 +1542,23 @@ bool render_tiles(RenderState* state, const DeviceScene& scene, const EchoRender
 	// work submitted earlier on the caller's stream (e.g. clearing the frame) must be visible to the worker streams
 	if (!check_cuda(cudaStreamSynchronize(stream), "render_tiles entry")) return false;
 
-	uint64_t perTile = (uint64_t)params.tileSize * params.tileSize;
-	uint64_t tilesPerBatch = std::max<uint64_t>(1, kPathsPerBatch / (perTile * params.extend));
-	tilesPerBatch = std::min<uint64_t>(tilesPerBatch, tileCount);
-	uint64_t batchCount = (tileCount + tilesPerBatch - 1) / tilesPerBatch;
-
 	static const int configuredWorkers = []
 	{
 		const char* value = std::getenv("ECHO_B200_RENDER_WORKERS");
 		int workers = value ? std::atoi(value) : kWorkers;
 		return workers < 1 ? 1 : (workers > 16 ? 16 : workers);
 	}();
+
+	// batch size: at most kPathsPerBatch paths, but small jobs are still split so that every pipeline gets a share
+	// (never below 256 Ki paths per batch: smaller wavefronts are launch- and latency-bound from the first bounce)
+	uint64_t perTile = (uint64_t)params.tileSize * params.tileSize;
+	uint64_t pathsPerTile = perTile * params.extend;
+	uint64_t maxTiles = std::max<uint64_t>(1, kPathsPerBatch / pathsPerTile);
+	uint64_t minTiles = std::max<uint64_t>(1, (1ull << 18) / pathsPerTile);
+	uint64_t share = (tileCount + configuredWorkers - 1) / configuredWorkers;
+	uint64_t tilesPerBatch = std::min<uint64_t>(std::max<uint64_t>(share, minTiles), maxTiles);
+	tilesPerBatch = std::min<uint64_t>(tilesPerBatch, tileCount);
+	uint64_t batchCount = (tileCount + tilesPerBatch - 1) / tilesPerBatch;
 
 	int workerCount = (int)std::min<uint64_t>(gTimer.enabled ? 1 : configuredWorkers, batchCount);
 	for (int i = 0; i < workerCount; i++)
