@@ -247,7 +247,7 @@ int32_t echo_b200_scene_set_materials(EchoScene* scene, const EchoMaterial* mate
 
 	for (uint32_t i = 0; i < count; i++)
 	{
-		if (materials[i].type > ECHO_MATERIAL_INVISIBLE) return fail(ECHO_B200_ERR_UNSUPPORTED, "material type outside the hot path");
+		if (materials[i].type > ECHO_MATERIAL_COATED_DIFFUSE) return fail(ECHO_B200_ERR_UNSUPPORTED, "material type outside the hot path");
 		if (materials[i].type == ECHO_MATERIAL_ONESIDED && materials[i].base >= count) return fail(ECHO_B200_ERR_INVALID, "OneSided base index out of range");
 	}
 

@@ -11,7 +11,7 @@ namespace echo
 enum : int
 {
 	DBG_LAMBERTIAN_REFLECTION = 0, DBG_LAMBERTIAN, DBG_OREN_NAYAR, DBG_SPECULAR_REFLECTION_REAL, DBG_SPECULAR_REFLECTION_COMPLEX,
-	DBG_SPECULAR_TRANSMISSION, DBG_SPECULAR_FRESNEL, DBG_GLOSSY_REFLECTION_REAL, DBG_GLOSSY_REFLECTION_COMPLEX, DBG_GLOSSY_TRANSMISSION
+	DBG_SPECULAR_TRANSMISSION, DBG_SPECULAR_FRESNEL, DBG_GLOSSY_REFLECTION_REAL, DBG_GLOSSY_REFLECTION_COMPLEX, DBG_GLOSSY_TRANSMISSION, DBG_COATED_LAMBERTIAN
 };
 
 ECHO_DEVICE int debug_type(int kind)
@@ -19,6 +19,7 @@ ECHO_DEVICE int debug_type(int kind)
 	switch (kind)
 	{
 		case DBG_LAMBERTIAN_REFLECTION:
+		case DBG_COATED_LAMBERTIAN:
 		case DBG_OREN_NAYAR: return FT_REFLECTIVE | FT_DIFFUSE;
 		case DBG_LAMBERTIAN: return FT_DIFFUSE | FT_REFLECTIVE | FT_TRANSMISSIVE;
 		case DBG_SPECULAR_REFLECTION_REAL:
@@ -44,6 +45,7 @@ ECHO_DEVICE Sampled debug_sample(int kind, const Bsdf& b, vec2 sample, vec3 outg
 		case DBG_SPECULAR_FRESNEL: return specular_fresnel_sample(b, sample, outgoing, incident);
 		case DBG_GLOSSY_REFLECTION_REAL: return glossy_reflection_sample<true>(b, sample, outgoing, incident);
 		case DBG_GLOSSY_REFLECTION_COMPLEX: return glossy_reflection_sample<false>(b, sample, outgoing, incident);
+		case DBG_COATED_LAMBERTIAN: return coated_lambert_sample(b, sample, outgoing, incident);
 		default: return glossy_transmission_sample(b, sample, outgoing, incident);
 	}
 }
@@ -58,6 +60,7 @@ ECHO_DEVICE rgb debug_evaluate(int kind, const Bsdf& b, vec3 outgoing, vec3 inci
 		case DBG_GLOSSY_REFLECTION_REAL: return glossy_reflection_evaluate<true>(b, outgoing, incident);
 		case DBG_GLOSSY_REFLECTION_COMPLEX: return glossy_reflection_evaluate<false>(b, outgoing, incident);
 		case DBG_GLOSSY_TRANSMISSION: return glossy_transmission_evaluate(b, outgoing, incident);
+		case DBG_COATED_LAMBERTIAN: return coated_lambert_evaluate(b, outgoing, incident);
 		default: return make_rgb(0.0f);
 	}
 }
@@ -67,6 +70,7 @@ ECHO_DEVICE float debug_pdf(int kind, const Bsdf& b, vec3 outgoing, vec3 inciden
 	switch (kind)
 	{
 		case DBG_LAMBERTIAN_REFLECTION:
+		case DBG_COATED_LAMBERTIAN:
 		case DBG_OREN_NAYAR: return lambert_reflection_pdf(outgoing, incident);
 		case DBG_LAMBERTIAN: return abs_bits(cosine_p(incident)) * kTauR;
 		case DBG_GLOSSY_REFLECTION_REAL: return glossy_reflection_pdf<true>(b, outgoing, incident);
@@ -90,6 +94,8 @@ __global__ void debug_bxdf_kernel(int kind, const float* __restrict__ params, co
 
 	if (kind == DBG_SPECULAR_REFLECTION_COMPLEX || kind == DBG_GLOSSY_REFLECTION_COMPLEX)
 		complex_fresnel_setup({ params[2], params[3], params[4] }, { params[5], params[6], params[7] }, { params[8], params[9], params[10] }, b.eta2, b.etaK2);
+
+	if (kind == DBG_COATED_LAMBERTIAN) coated_lambert_setup(b, { params[5], params[6], params[7] }, params[4]);
 
 	if (kind == DBG_OREN_NAYAR)
 	{
@@ -152,7 +158,7 @@ __global__ void debug_math_kernel(int op, const float* __restrict__ a, const flo
 bool launch_debug_bxdf(int32_t kind, const float* params, const float* outgoing, const float* samples, uint64_t n,
                        float* sampled8, float* evaluated4, float* inverse4, cudaStream_t stream)
 {
-	if (kind < 0 || kind > DBG_GLOSSY_TRANSMISSION) { set_error("unknown BxDF kind"); return false; }
+	if (kind < 0 || kind > DBG_COATED_LAMBERTIAN) { set_error("unknown BxDF kind"); return false; }
 	if (n == 0) return true;
 	debug_bxdf_kernel<<<(unsigned int)((n + 127) / 128), 128, 0, stream>>>(kind, params, outgoing, samples, n, sampled8, evaluated4, inverse4);
 	return check_cuda(cudaGetLastError(), "debug_bxdf_kernel launch");

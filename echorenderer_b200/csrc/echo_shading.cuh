@@ -23,12 +23,13 @@ enum BsdfKind : int
 	BSDF_CONDUCTOR_GLOSSY = 6,     // GlossyReflection<TR, ComplexFresnel> (Materials/Conductor.cs:117-119)
 	BSDF_CONDUCTOR_SPECULAR = 7,   // SpecularReflection<ComplexFresnel> (Materials/Conductor.cs:121)
 	BSDF_INVISIBLE = 8,            // SpecularTransmission(1 / 1) (Materials/Invisible.cs:22-26)
+	BSDF_COATED_DIFFUSE = 9,       // CoatedLambertianReflection + GlossyReflection<TR, RealFresnel> (Materials/CoatedDiffuse.cs:37-55)
 };
 
 #define kind_bit(kind) (1u << (kind))
-constexpr uint32_t KINDS_ALL = 0x1FFu;
+constexpr uint32_t KINDS_ALL = 0x3FFu;
 constexpr uint32_t KINDS_DIFFUSE = kind_bit(BSDF_LAMBERT_REFLECTION) | kind_bit(BSDF_LAMBERT_TWO_SIDED) | kind_bit(BSDF_OREN_NAYAR) | kind_bit(BSDF_INVISIBLE);
-constexpr uint32_t KINDS_DIELECTRIC = kind_bit(BSDF_DIELECTRIC_GLOSSY) | kind_bit(BSDF_DIELECTRIC_SPECULAR) | kind_bit(BSDF_INVISIBLE);
+constexpr uint32_t KINDS_DIELECTRIC = kind_bit(BSDF_DIELECTRIC_GLOSSY) | kind_bit(BSDF_DIELECTRIC_SPECULAR) | kind_bit(BSDF_COATED_DIFFUSE) | kind_bit(BSDF_INVISIBLE);
 constexpr uint32_t KINDS_CONDUCTOR = kind_bit(BSDF_CONDUCTOR_GLOSSY) | kind_bit(BSDF_CONDUCTOR_SPECULAR) | kind_bit(BSDF_INVISIBLE);
 constexpr uint32_t KINDS_TERMINAL = kind_bit(BSDF_EMPTY) | kind_bit(BSDF_INVISIBLE);
 
@@ -43,6 +44,7 @@ struct Bsdf
 	float etaAbove, etaBelow;     // RealFresnel
 	rgb eta2, etaK2;              // ComplexFresnel
 	float orenA, orenB;           // OrenNayar a, b
+	rgb coatedMultiplier;         // CoatedLambertianReflection.multiplier
 };
 
 struct Sampled // Probable<RGB128>
@@ -426,6 +428,33 @@ ECHO_DEVICE Sampled lambert_reflection_sample(const Bsdf& b, vec2 sample, vec3 o
 	return { lambert_reflection_evaluate<OREN>(b, outgoing, incident), pdf };
 }
 
+// CoatedLambertianReflection.Evaluate, Lambertian.cs:152-161 (pdf and sampling are LambertianReflection's)
+ECHO_DEVICE rgb coated_lambert_evaluate(const Bsdf& b, vec3 outgoing, vec3 incident)
+{
+	if (flat_or_opposite_hemisphere(outgoing, incident)) return make_rgb(0.0f);
+
+	float evaluatedOutgoing = real_fresnel(b.etaAbove, b.etaBelow, abs_bits(cosine_p(outgoing)));
+	float evaluatedIncident = real_fresnel(b.etaAbove, b.etaBelow, abs_bits(cosine_p(incident)));
+
+	return b.coatedMultiplier * (1.0f - evaluatedOutgoing) * (1.0f - evaluatedIncident);
+}
+
+ECHO_DEVICE Sampled coated_lambert_sample(const Bsdf& b, vec2 sample, vec3 outgoing, vec3& incident)
+{
+	incident = cosine_hemisphere(sample);
+	float pdf = cosine_p(incident) * kPiR;
+
+	if (outgoing.z < 0.0f) incident = negate_z(incident);
+	return { coated_lambert_evaluate(b, outgoing, incident), pdf };
+}
+
+ECHO_DEVICE void coated_lambert_setup(Bsdf& b, rgb albedo, float reflectance) // CoatedLambertianReflection.Reset, Lambertian.cs:139-147
+{
+	float eta = div(b.etaAbove, b.etaBelow);
+	float numerator = eta * eta * kPiR;
+	b.coatedMultiplier = { div(numerator, 1.0f - albedo.r * reflectance), div(numerator, 1.0f - albedo.g * reflectance), div(numerator, 1.0f - albedo.b * reflectance) };
+}
+
 // Lambertian.cs:74-98
 ECHO_DEVICE Sampled lambert_two_sided_sample(vec2 sample, vec3 outgoing, vec3& incident)
 {
@@ -491,7 +520,7 @@ ECHO_DEVICE Sampled specular_fresnel_sample(const Bsdf& b, vec2 sample, vec3 out
 // the BSDF container (Scattering/BSDF.cs)
 // =====================================================================================================================
 
-ECHO_DEVICE int bsdf_lobe_count(int kind) { return kind == BSDF_EMPTY ? 0 : (kind == BSDF_DIELECTRIC_GLOSSY ? 2 : 1); }
+ECHO_DEVICE int bsdf_lobe_count(int kind) { return kind == BSDF_EMPTY ? 0 : ((kind == BSDF_DIELECTRIC_GLOSSY || kind == BSDF_COATED_DIFFUSE) ? 2 : 1); }
 
 // FunctionType of lobe `index`
 ECHO_DEVICE int bsdf_lobe_type(int kind, int index)
@@ -506,6 +535,7 @@ ECHO_DEVICE int bsdf_lobe_type(int kind, int index)
 		case BSDF_CONDUCTOR_GLOSSY: return FT_GLOSSY | FT_REFLECTIVE;
 		case BSDF_CONDUCTOR_SPECULAR: return FT_SPECULAR | FT_REFLECTIVE;
 		case BSDF_INVISIBLE: return FT_SPECULAR | FT_TRANSMISSIVE;
+		case BSDF_COATED_DIFFUSE: return index == 0 ? (FT_REFLECTIVE | FT_DIFFUSE) : (FT_GLOSSY | FT_REFLECTIVE);
 		default: return 0;
 	}
 }
@@ -527,6 +557,7 @@ ECHO_DEVICE rgb lobe_evaluate(const Bsdf& b, int index, vec3 outgoing, vec3 inci
 	if (ECHO_HAS(BSDF_LAMBERT_TWO_SIDED)) return make_rgb(kTauR); // Lambertian.cs:78
 	if (ECHO_HAS(BSDF_DIELECTRIC_GLOSSY)) return index == 0 ? glossy_reflection_evaluate<true>(b, outgoing, incident) : glossy_transmission_evaluate(b, outgoing, incident);
 	if (ECHO_HAS(BSDF_CONDUCTOR_GLOSSY)) return glossy_reflection_evaluate<false>(b, outgoing, incident);
+	if (ECHO_HAS(BSDF_COATED_DIFFUSE)) return index == 0 ? coated_lambert_evaluate(b, outgoing, incident) : glossy_reflection_evaluate<true>(b, outgoing, incident);
 	return make_rgb(0.0f); // specular lobes evaluate to black (Specular.cs:17,41,70)
 }
 
@@ -537,6 +568,7 @@ ECHO_DEVICE float lobe_pdf(const Bsdf& b, int index, vec3 outgoing, vec3 inciden
 	if (ECHO_HAS(BSDF_LAMBERT_TWO_SIDED)) return abs_bits(cosine_p(incident)) * kTauR; // Lambertian.cs:80
 	if (ECHO_HAS(BSDF_DIELECTRIC_GLOSSY)) return index == 0 ? glossy_reflection_pdf<true>(b, outgoing, incident) : glossy_transmission_pdf(b, outgoing, incident);
 	if (ECHO_HAS(BSDF_CONDUCTOR_GLOSSY)) return glossy_reflection_pdf<false>(b, outgoing, incident);
+	if (ECHO_HAS(BSDF_COATED_DIFFUSE)) return index == 0 ? lambert_reflection_pdf(outgoing, incident) : glossy_reflection_pdf<true>(b, outgoing, incident);
 	return 0.0f;
 }
 
@@ -551,6 +583,7 @@ ECHO_DEVICE Sampled lobe_sample(const Bsdf& b, int index, vec2 sample, vec3 outg
 	if (ECHO_HAS(BSDF_CONDUCTOR_GLOSSY)) return glossy_reflection_sample<false>(b, sample, outgoing, incident);
 	if (ECHO_HAS(BSDF_CONDUCTOR_SPECULAR)) return specular_reflection_sample<false>(b, outgoing, incident);
 	if (ECHO_HAS(BSDF_INVISIBLE)) return specular_transmission_sample(1.0f, 1.0f, outgoing, incident);
+	if (ECHO_HAS(BSDF_COATED_DIFFUSE)) return index == 0 ? coated_lambert_sample(b, sample, outgoing, incident) : glossy_reflection_sample<true>(b, sample, outgoing, incident);
 	incident = { 0.0f, 0.0f, 0.0f };
 	return impossible();
 }
@@ -693,6 +726,7 @@ ECHO_DEVICE void material_scatter(const DeviceScene& scene, const MaterialRecord
 	b.etaAbove = b.etaBelow = 1.0f;
 	b.eta2 = b.etaK2 = make_rgb(0.0f);
 	b.orenA = b.orenB = 0.0f;
+	b.coatedMultiplier = make_rgb(0.0f);
 
 	MaterialRecord m = top;
 	bool invisible = false;
@@ -747,6 +781,15 @@ ECHO_DEVICE void material_scatter(const DeviceScene& scene, const MaterialRecord
 	b.alphaX = microfacet_alpha(m.roughness[0], specularX);
 	b.alphaY = microfacet_alpha(m.roughness[1], specularY);
 	bool glossy = !specularX || !specularY;
+
+	if (m.type == ECHO_MATERIAL_COATED_DIFFUSE) // CoatedDiffuse.cs:37-55: always glossy, whatever the roughness
+	{
+		b.etaAbove = 1.0f;
+		b.etaBelow = m.ior;
+		coated_lambert_setup(b, b.tint, m.paramA[0]);
+		b.kind = BSDF_COATED_DIFFUSE;
+		return;
+	}
 
 	if (m.type == ECHO_MATERIAL_DIELECTRIC) // Dielectric.cs:29-47
 	{

@@ -784,6 +784,54 @@ float echo_host_ambient_power(const float radiance[3], const EchoQbvhNode* root)
 	return kPi * radius * radius * luminance(radiance);
 }
 
+static float entrance_reflectance(float eta) // Lambertian.cs:175-199
+{
+	float eta2 = eta * eta;
+	float eta4 = eta2 * eta2;
+
+	float eta1a1 = eta + 1.0f, eta2a1 = eta2 + 1.0f, eta4a1 = eta4 + 1.0f;
+	float eta1s1 = eta - 1.0f, eta2s1 = eta2 - 1.0f, eta4s1 = eta4 - 1.0f;
+
+	float quotient0 = eta1s1 * std::fma(3.0f, eta, 1.0f) / (6.0f * eta1a1 * eta1a1);
+	float quotient1 = eta2 * eta2s1 * eta2s1 / (eta2a1 * eta2a1 * eta2a1);
+	float quotient2 = -2.0f * eta2 * eta * (eta2 + eta + eta1s1) / (eta2a1 * eta4s1);
+	float quotient3 = 8.0f * eta4 * eta4a1 / (eta2a1 * eta4s1 * eta4s1);
+
+	float fma0 = std::fma(std::log(eta1s1 / eta1a1), quotient1, quotient0);
+	float fma1 = std::fma(std::log(eta), quotient3, quotient2);
+
+	return 0.5f + fma0 + fma1;
+}
+
+float echo_host_fresnel_diffuse_reflectance(float eta) // Lambertian.cs:168-173
+{
+	// eta.AlmostEquals(1f), Scalars.cs:153-169
+	float difference = std::fabs(eta - 1.0f);
+	if (eta == 1.0f || difference < 1E-5f * std::fmin(std::fabs(eta) + 1.0f, std::numeric_limits<float>::max())) return 0.0f;
+	if (eta >= 1.0f) return entrance_reflectance(eta);
+	float reflectance = entrance_reflectance(1.0f / eta);
+	return 1.0f - eta * eta * (1.0f - reflectance);
+}
+
+float echo_host_fresnel_diffuse_reflectance_fast(float eta) // Lambertian.cs:202-230
+{
+	auto entrance = [](float etaR)
+	{
+		float etaR2 = etaR * etaR, etaR3 = etaR2 * etaR, etaR4 = etaR2 * etaR2, etaR5 = etaR4 * etaR;
+		float sum = +0.91932f;
+		sum = std::fma(-3.47930f, etaR, sum);
+		sum = std::fma(+6.75335f, etaR2, sum);
+		sum = std::fma(-7.80989f, etaR3, sum);
+		sum = std::fma(+4.98554f, etaR4, sum);
+		sum = std::fma(-1.36881f, etaR5, sum);
+		return sum;
+	};
+
+	if (eta >= 1.0f) return entrance(1.0f / eta);
+	float reflectance = entrance(eta);
+	return 1.0f - eta * eta * (1.0f - reflectance);
+}
+
 void echo_host_free(void* pointer) { std::free(pointer); }
 
 } // extern "C"

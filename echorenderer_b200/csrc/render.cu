@@ -668,7 +668,8 @@ ECHO_DEVICE int classify_material(const DeviceScene& scene, uint32_t materialInd
 	switch (type)
 	{
 		case ECHO_MATERIAL_DIFFUSE: return CLASS_DIFFUSE;
-		case ECHO_MATERIAL_DIELECTRIC: return CLASS_DIELECTRIC;
+		case ECHO_MATERIAL_DIELECTRIC:
+		case ECHO_MATERIAL_COATED_DIFFUSE: return CLASS_DIELECTRIC; // shares the GlossyReflection<TR, RealFresnel> code
 		case ECHO_MATERIAL_CONDUCTOR: return CLASS_CONDUCTOR;
 		default: return CLASS_TERMINAL;
 	}

@@ -39,6 +39,10 @@ def _library():
     lib.echo_host_ambient_power.restype = ctypes.c_float
     lib.echo_host_emissive_power.argtypes = [p]
     lib.echo_host_emissive_power.restype = ctypes.c_float
+    lib.echo_host_fresnel_diffuse_reflectance.argtypes = [ctypes.c_float]
+    lib.echo_host_fresnel_diffuse_reflectance.restype = ctypes.c_float
+    lib.echo_host_fresnel_diffuse_reflectance_fast.argtypes = [ctypes.c_float]
+    lib.echo_host_fresnel_diffuse_reflectance_fast.restype = ctypes.c_float
     lib.echo_host_free.argtypes = [p]
     lib.echo_host_free.restype = None
     _lib = lib
@@ -107,6 +111,12 @@ class PreparedArrays:
         low = np.array([root[k][valid].min() for k in ("minX", "minY", "minZ")], dtype=np.float32)
         high = np.array([root[k][valid].max() for k in ("maxX", "maxY", "maxZ")], dtype=np.float32)
         return low, high
+
+
+def fresnel_diffuse_reflectance(eta, fast=False):
+    """CoatedLambertianReflection.FresnelDiffuseReflectance[Fast] (Evaluation/Scattering/Lambertian.cs:168-230)."""
+    lib = _library()
+    return float((lib.echo_host_fresnel_diffuse_reflectance_fast if fast else lib.echo_host_fresnel_diffuse_reflectance)(float(eta)))
 
 
 def build_qbvh(triangles, spheres, threads=0):

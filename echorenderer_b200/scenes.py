@@ -117,6 +117,13 @@ def material(kind, albedo=(1, 1, 1), alpha=1.0, roughness=(0, 0), ior=1.5, param
     return m
 
 
+def coated_diffuse(albedo=(1, 1, 1), roughness=(0, 0), ior=1.5):
+    """CoatedDiffuse (Evaluation/Materials/CoatedDiffuse.cs:13-55) with the reflectance its Prepare() caches."""
+    from .host import fresnel_diffuse_reflectance
+    reflectance = fresnel_diffuse_reflectance(np.float32(1.0) / np.float32(ior))
+    return material(structs.MATERIAL_COATED_DIFFUSE, albedo, roughness=roughness, ior=ior, param_a=(reflectance, 0, 0))
+
+
 def hex_color(value):
     """RGBA128.Parse("0xRRGGBB"): byte / 255, linear, no sRGB decode (Textures/Colors/RGBA128.Parser.cs:293-316)."""
     return tuple(np.float32(((value >> shift) & 0xFF) / 255.0) for shift in (16, 8, 0))

@@ -23,6 +23,7 @@ MATERIAL_CONDUCTOR = 2
 MATERIAL_EMISSIVE = 3
 MATERIAL_ONESIDED = 4
 MATERIAL_INVISIBLE = 5
+MATERIAL_COATED_DIFFUSE = 6
 MATERIAL_FLAG_TRANSMISSIVE = 1
 MATERIAL_FLAG_ARTISTIC = 2
 MATERIAL_FLAG_BACKFACE = 4

@@ -110,6 +110,7 @@ typedef struct EchoHit
 #define ECHO_MATERIAL_EMISSIVE 3u   /* Emissive.cs:30-64 */
 #define ECHO_MATERIAL_ONESIDED 4u   /* OneSided.cs:50-58 */
 #define ECHO_MATERIAL_INVISIBLE 5u  /* Invisible.cs:22-26 */
+#define ECHO_MATERIAL_COATED_DIFFUSE 6u /* CoatedDiffuse.cs:37-55 */
 #define ECHO_MATERIAL_FLAG_TRANSMISSIVE 1u /* Diffuse.Transmissive */
 #define ECHO_MATERIAL_FLAG_ARTISTIC 2u     /* Conductor.Artistic */
 #define ECHO_MATERIAL_FLAG_BACKFACE 4u     /* OneSided.Backface */
@@ -120,8 +121,9 @@ typedef struct EchoMaterial
 	uint32_t flags;
 	float albedo[4];    /* RGBA; alpha < 0.5 makes the surface Invisible (Material.cs:63-75). Emissive: emission RGB */
 	float roughness[2]; /* R and G of the Roughness texture */
-	float ior;          /* Dielectric.RefractiveIndex */
-	float paramA[3];    /* Conductor: MainColor (artistic) or RefractiveIndex (physical) */
+	float ior;          /* Dielectric.RefractiveIndex / CoatedDiffuse.RefractiveIndex */
+	float paramA[3];    /* Conductor: MainColor (artistic) or RefractiveIndex (physical); CoatedDiffuse: [0] = the reflectance cached by
+	                       CoatedDiffuse.Prepare = FresnelDiffuseReflectance(1 / RefractiveIndex) (echo_host_fresnel_diffuse_reflectance) */
 	float paramB[3];    /* Conductor: EdgeColor (artistic) or Extinction (physical) */
 	uint32_t base;      /* OneSided.Base material index */
 } EchoMaterial; /* 64 B */

@@ -46,6 +46,10 @@ float echo_host_ambient_power(const float radiance[3], const EchoQbvhNode* root)
 /* Emissive.Power for a constant emission colour (Emissive.cs:52-53). */
 float echo_host_emissive_power(const float emission[3]);
 
+/* CoatedLambertianReflection.FresnelDiffuseReflectance / ...Fast (Lambertian.cs:168-230): what CoatedDiffuse.Prepare caches. */
+float echo_host_fresnel_diffuse_reflectance(float eta);
+float echo_host_fresnel_diffuse_reflectance_fast(float eta);
+
 void echo_host_free(void* pointer);
 
 #ifdef __cplusplus

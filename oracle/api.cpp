@@ -408,6 +408,7 @@ struct BxDFBox
 	GlossyReflection<RealFresnel> glossyReflectionReal;
 	GlossyReflection<ComplexFresnel> glossyReflectionComplex;
 	GlossyTransmission glossyTransmission;
+	CoatedLambertianReflection coatedLambertianReflection;
 
 	const BxDF* configure(int32_t kind, const float* p)
 	{
@@ -434,6 +435,9 @@ struct BxDFBox
 				glossyTransmission.microfacet = TrowbridgeReitz{ p[0], p[1] };
 				glossyTransmission.fresnel = RealFresnel{ p[2], p[3] };
 				return &glossyTransmission;
+			case ORACLE_BXDF_COATED_LAMBERTIAN:
+				coatedLambertianReflection.reset(rgb(5), RealFresnel{ p[2], p[3] }, p[4]);
+				return &coatedLambertianReflection;
 			default: return nullptr;
 		}
 	}

@@ -23,6 +23,7 @@ typedef struct OracleScene OracleScene;
 #define ORACLE_BXDF_GLOSSY_REFLECTION_REAL 7
 #define ORACLE_BXDF_GLOSSY_REFLECTION_COMPLEX 8
 #define ORACLE_BXDF_GLOSSY_TRANSMISSION 9
+#define ORACLE_BXDF_COATED_LAMBERTIAN 10 /* RealFresnel in [2..3], [4] = reflectance, [5..7] = albedo RGB */
 
 #ifdef __cplusplus
 }

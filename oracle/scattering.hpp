@@ -245,6 +245,33 @@ struct ComplexFresnel
 	}
 };
 
+// ---- Lambertian.cs:131-161 (CoatedDiffuse) ----
+struct CoatedLambertianReflection : LambertianReflection
+{
+	void reset(RGB albedo, RealFresnel newFresnel, float reflectance)
+	{
+		fresnel = newFresnel;
+
+		float eta = newFresnel.etaAbove / newFresnel.etaBelow;
+		RGB denominator = { 1.0f - albedo.r * reflectance, 1.0f - albedo.g * reflectance, 1.0f - albedo.b * reflectance }; // RGB128.White - albedo * reflectance
+		float numerator = eta * eta * kPiR;
+		multiplier = { numerator / denominator.r, numerator / denominator.g, numerator / denominator.b };
+	}
+
+	RealFresnel fresnel;
+	RGB multiplier = kBlack;
+
+	RGB evaluate(Float3 outgoing, Float3 incident) const override
+	{
+		if (flat_or_opposite_hemisphere(outgoing, incident)) return kBlack;
+
+		float evaluatedOutgoing = fresnel.evaluate_scalar(fabs_bits(cosine_p(outgoing)));
+		float evaluatedIncident = fresnel.evaluate_scalar(fabs_bits(cosine_p(incident)));
+
+		return multiplier * (1.0f - evaluatedOutgoing) * (1.0f - evaluatedIncident);
+	}
+};
+
 // ---- Evaluation/Scattering/IMicrofacet.cs:43-51 ----
 inline float microfacet_alpha(float roughness, bool& specular)
 {
@@ -563,6 +590,7 @@ struct BSDF
 	LambertianReflection lambertianReflection;
 	Lambertian lambertian;
 	OrenNayar orenNayar;
+	CoatedLambertianReflection coatedLambertianReflection;
 	GlossyReflection<RealFresnel> glossyReflectionReal;
 	GlossyReflection<ComplexFresnel> glossyReflectionComplex;
 	GlossyTransmission glossyTransmission;
@@ -773,6 +801,22 @@ inline void scatter_material(const Scene& scene, uint32_t materialIndex, Contact
 				bsdf.add(&bsdf.specularFresnel);
 			}
 
+			break;
+		}
+		case ECHO_MATERIAL_COATED_DIFFUSE: // CoatedDiffuse.cs:37-55
+		{
+			RealFresnel fresnel{ 1.0f, material.ior };
+
+			bool unused;
+			float alphaX = microfacet_alpha(material.roughness[0], unused);
+			float alphaY = microfacet_alpha(material.roughness[1], unused);
+
+			bsdf.coatedLambertianReflection.reset(albedo, fresnel, material.paramA[0]);
+			bsdf.add(&bsdf.coatedLambertianReflection);
+
+			bsdf.glossyReflectionReal.microfacet = TrowbridgeReitz{ alphaX, alphaY };
+			bsdf.glossyReflectionReal.fresnel = fresnel;
+			bsdf.add(&bsdf.glossyReflectionReal);
 			break;
 		}
 		case ECHO_MATERIAL_CONDUCTOR: // Conductor.cs:72-124

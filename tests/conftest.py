@@ -44,3 +44,17 @@ def mixed_small():
 def lights_small():
     from echorenderer_b200 import host, scenes
     return host.prepare(scenes.many_lights_scene(light_count=300, rings=16, segments=16))
+
+
+@pytest.fixture(scope="session")
+def coated_small():
+    """The small mixed scene with CoatedDiffuse (Evaluation/Materials/CoatedDiffuse.cs) on the ground and on one blob."""
+    import numpy as np
+    from echorenderer_b200 import host, scenes
+    description = scenes.mixed_material_scene(rings=24, segments=24)
+    coated = np.concatenate([scenes.coated_diffuse((0.8, 0.5, 0.3), roughness=(0.3, 0.3), ior=1.5), scenes.coated_diffuse((0.9, 0.9, 0.9), roughness=(0.0, 0.6), ior=1.7)])
+    first = len(description.materials)
+    description.materials = np.concatenate([description.materials, coated])
+    description.triangles["material"][description.triangles["material"] == 0] = first       # ground
+    description.triangles["material"][description.triangles["material"] == 4] = first + 1   # the Lambertian blobs
+    return host.prepare(description)

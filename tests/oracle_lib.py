@@ -14,7 +14,7 @@ _lib = None
 
 BXDF_LAMBERTIAN_REFLECTION, BXDF_LAMBERTIAN, BXDF_OREN_NAYAR, BXDF_SPECULAR_REFLECTION_REAL, BXDF_SPECULAR_REFLECTION_COMPLEX, \
     BXDF_SPECULAR_TRANSMISSION, BXDF_SPECULAR_FRESNEL, BXDF_GLOSSY_REFLECTION_REAL, BXDF_GLOSSY_REFLECTION_COMPLEX, \
-    BXDF_GLOSSY_TRANSMISSION = range(10)
+    BXDF_GLOSSY_TRANSMISSION, BXDF_COATED_LAMBERTIAN = range(11)
 
 FM_MAX0, FM_CLAMP01, FM_CLAMP11, FM_CLAMP_EPSILON, FM_ABS, FM_SQRT0, FM_SQRTR0, FM_ONE_MINUS2, FM_IDENTITY, FM_FMA, \
     FM_POSITIVE, FM_ALMOST_ZERO, FM_MIN, FM_MAX = range(14)
@@ -185,7 +185,8 @@ def sincos(radians):
     return np.float32(s.value), np.float32(c.value)
 
 
-def bxdf_params(alpha=(1.0, 1.0), real=None, complex_=None, roughness=None):
+def bxdf_params(alpha=(1.0, 1.0), real=None, complex_=None, roughness=None, coated=None):
+    """coated = (albedo rgb, reflectance) for CoatedLambertianReflection (together with real=)."""
     params = np.zeros(11, dtype=np.float32)
     params[0:2] = alpha
     if roughness is not None:
@@ -194,6 +195,9 @@ def bxdf_params(alpha=(1.0, 1.0), real=None, complex_=None, roughness=None):
         params[2:4] = real
     if complex_ is not None:
         params[2:11] = np.asarray(complex_, dtype=np.float32).reshape(-1)
+    if coated is not None:
+        params[5:8] = coated[0]
+        params[4] = coated[1]
     return params
 
 

@@ -307,7 +307,12 @@ TITANIUM = [[1.3, 1.0, 0.8], [2.74070, 2.54180, 2.26700], [3.81430, 3.43450, 3.0
 EPS_RGB = [8e-7 / 0.212671, 8e-7 / 0.715160, 8e-7 / 0.072169]
 PERFECT = [[1, 1, 1], EPS_RGB, [0, 0, 0]]
 
-# Evaluation/BxDFTests.cs:49-83, minus LambertianTransmission / CoatedLambertianReflection (materials outside the hot path)
+def fdr(eta, fast=False):
+    from echorenderer_b200 import host
+    return host.fresnel_diffuse_reflectance(np.float32(eta), fast)
+
+
+# Evaluation/BxDFTests.cs:49-83, minus LambertianTransmission (no in-scope material creates that lobe)
 BXDF_TABLE = [
     ("everything", ol.BXDF_LAMBERTIAN_REFLECTION, ol.bxdf_params()),
     ("everything", ol.BXDF_LAMBERTIAN, ol.bxdf_params()),
@@ -336,6 +341,11 @@ BXDF_TABLE = [
     ("oneDirection", ol.BXDF_GLOSSY_REFLECTION_COMPLEX, ol.bxdf_params((0.7, 0.4), complex_=TITANIUM)),
     ("oneDirection", ol.BXDF_GLOSSY_REFLECTION_COMPLEX, ol.bxdf_params((1.0, 1.0), complex_=PERFECT)),
     ("oneDirection", ol.BXDF_GLOSSY_REFLECTION_COMPLEX, ol.bxdf_params((1e-4, 1e-4), complex_=[[1, 1, 1], [2, 2, 2], [3, 3, 3]])),
+    # CoatedLambertianReflection (BxDFTests.cs:79-82): exact reflectance twice, then the Reset overload that uses the fast fit
+    ("oneDirection", ol.BXDF_COATED_LAMBERTIAN, ol.bxdf_params(real=(1.1, 1.7), coated=((1, 1, 1), fdr(np.float32(1.1) / np.float32(1.7))))),
+    ("oneDirection", ol.BXDF_COATED_LAMBERTIAN, ol.bxdf_params(real=(1.7, 1.1), coated=((0.3, 0.3, 0.3), fdr(np.float32(1.7) / np.float32(1.1))))),
+    ("oneDirection", ol.BXDF_COATED_LAMBERTIAN, ol.bxdf_params(real=(1.1, 1.7), coated=((0.3, 0.3, 0.3), fdr(np.float32(1.1) / np.float32(1.7), fast=True)))),
+    ("everything", ol.BXDF_COATED_LAMBERTIAN, ol.bxdf_params(real=(1.0, 1.0), coated=((1, 1, 1), fdr(1.0, fast=True)))),
 ]
 
 SPECULAR = 16
@@ -410,6 +420,37 @@ def run_bxdf_checks(batch, check_type, kind, params):
 def test_bxdf_table(check_type, kind, params):
     good = run_bxdf_checks(ol.bxdf_batch, check_type, kind, params)
     assert good > 0
+
+
+def converged_reflectance(eta):
+    """FresnelDiffuseReflectanceConverge (Lambertian.cs:232-251) by quadrature instead of 1e6 samples: the mean of
+    RealFresnel(eta, 1).Evaluate(cos) over cosine-weighted directions = integral of F(mu) 2 mu dmu."""
+    mu = (np.arange(200_000) + 0.5) / 200_000
+    # outgoing = -CosineHemisphere has a negative cosine: the packet swaps to etaOutgoing = 1 (below), etaIncident = eta (Fresnel.cs:37-40)
+    sin_i2 = (1 - mu * mu) / (eta * eta)
+    cos_i = np.sqrt(np.maximum(0.0, 1 - sin_i2))
+    para = (eta * mu - cos_i) / (eta * mu + cos_i)
+    perp = (mu - eta * cos_i) / (mu + eta * cos_i)
+    fresnel = np.where(sin_i2 >= 1, 1.0, (para * para + perp * perp) / 2)
+    return float(np.mean(fresnel * 2 * mu))
+
+
+def reflectance_inputs():
+    """CoatedLambertianReflectionTests.cs:13-29: literal etas, then 50 random ones in [0.6, 2.2), all inverted."""
+    rng = np.random.default_rng(42)
+    values = [1.0, 1.001, 0.999, 1.5, 1.7, 2.0, 1 / 1.2, 1 / 1.5] + list(rng.uniform(0.6, 2.2, 50))
+    return [float(np.float32(1.0) / np.float32(v)) for v in values]
+
+
+@pytest.mark.parametrize("eta", reflectance_inputs())
+def test_coated_reflectance(eta):
+    """CoatedLambertianReflectionTests.ReflectanceExact / ReflectanceFast (:33-58)."""
+    converged = converged_reflectance(eta)
+    exact, fast = fdr(eta), fdr(eta, fast=True)
+    assert exact >= 0 and converged >= 0
+    epsilon = 1e-4 if abs(eta - 1) < 1e-2 else 1e-6
+    assert (exact - converged) ** 2 < epsilon
+    assert (fast - converged) ** 2 < 1e-6
 
 
 def test_accumulator_matches_welford():
