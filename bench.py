@@ -46,6 +46,7 @@ def parse():
     parser.add_argument("--scene", default="mixed", choices=["cornell", "mixed", "lights", "large"], help="render workload scene: C1 / C3 / C4 / C5")
     parser.add_argument("--bounce-limit", type=int, default=8, help="render workload: PathTracedEvaluator.BounceLimit (C3: 8; reference default 128)")
     parser.add_argument("--no-cpu-baseline", action="store_true")
+    parser.add_argument("--no-secondary", action="store_true", help="skip the secondary-ray batch reported beside the headline (SURVEY.md 8d)")
     return parser.parse_args()
 
 
@@ -137,6 +138,61 @@ def build_trace_inputs(args, rank):
     diagonal = float(np.linalg.norm(np.asarray(high, np.float64) - np.asarray(low, np.float64)))
     shadow["distance"] = scenes.uniform(17 + 1000 * rank, np.arange(args.rays, dtype=np.uint64)) * np.float32(diagonal)
     return prepared, rays, shadow
+
+
+def secondary_batch(scene, prepared, rays, d_hits, device, stream, args, max_over_ranks):
+    """The second batch SURVEY.md §8(d) asks to report beside the headline: rays leaving the surfaces the first batch hit
+    (cosine-hemisphere directions, ignore = hit token, as TraceQuery.SpawnTrace does), tiled up to the size of the first batch.
+    Reported separately; it is not part of `value`."""
+    import torch
+    hits = d_hits.cpu().numpy().view(structs.HIT)
+    spawned = scenes.secondary_rays(prepared, rays, hits)
+    if len(spawned) == 0:
+        return None
+    unique = len(spawned)
+    spawned = np.tile(spawned, (len(rays) + unique - 1) // unique)[:len(rays)]
+    n = len(spawned)
+    shadow = spawned.copy()
+    low, high = prepared.bounds
+    diagonal = float(np.linalg.norm(np.asarray(high, np.float64) - np.asarray(low, np.float64)))
+    shadow["distance"] = scenes.uniform(29, np.arange(n, dtype=np.uint64)) * np.float32(diagonal)
+
+    d_rays = torch.from_numpy(spawned.view(np.uint8).reshape(-1)).to(device)
+    d_shadow = torch.from_numpy(shadow.view(np.uint8).reshape(-1)).to(device)
+    d_out = torch.empty(n * 16, dtype=torch.uint8, device=device)
+    d_flags = torch.empty(n, dtype=torch.uint8, device=device)
+    d_counts = torch.zeros(6, dtype=torch.int64, device=device)
+    scene.trace_device(d_rays.data_ptr(), n, d_out.data_ptr(), stream, d_counts.data_ptr())
+    scene.occlude_device(d_shadow.data_ptr(), n, d_flags.data_ptr(), stream, d_counts.data_ptr() + 24)
+    torch.cuda.synchronize()
+    counts = d_counts.cpu().numpy().astype(np.float64) / n
+    hit_rate = float(np.mean(d_out.cpu().numpy().view(structs.HIT)["token"] != structs.TOKEN_EMPTY))
+
+    for _ in range(args.warmup):
+        scene.trace_device(d_rays.data_ptr(), n, d_out.data_ptr(), stream)
+        scene.occlude_device(d_shadow.data_ptr(), n, d_flags.data_ptr(), stream)
+    events = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    trace_ms = occlude_ms = 0.0
+    torch.cuda.synchronize()
+    for _ in range(args.steps):
+        events[0].record()
+        scene.trace_device(d_rays.data_ptr(), n, d_out.data_ptr(), stream)
+        events[1].record()
+        scene.occlude_device(d_shadow.data_ptr(), n, d_flags.data_ptr(), stream)
+        events[2].record()
+        torch.cuda.synchronize()
+        trace_ms += events[0].elapsed_time(events[1]) / args.steps
+        occlude_ms += events[1].elapsed_time(events[2]) / args.steps
+    trace_ms, occlude_ms = max_over_ranks(trace_ms), max_over_ranks(occlude_ms)
+    bytes_trace = 32 + 16 + 128 * counts[0] + 36 * counts[1] + 16 * counts[2]
+    bytes_occlude = 32 + 1 + 128 * counts[3] + 36 * counts[4] + 16 * counts[5]
+    return {"rays_per_pass_per_gpu": n, "distinct_rays": unique, "hit_rate": hit_rate,
+            "closest_hit": {"mrays_per_s": n / (trace_ms * 1e-3) / MRAYS, "ms_per_launch": trace_ms, "algorithmic_bytes_per_query": bytes_trace,
+                            "achieved_gbs": bytes_trace * n / (trace_ms * 1e-3) / 1e9,
+                            "visits_per_query": {"nodes": counts[0], "triangles": counts[1], "spheres": counts[2]}},
+            "occlusion": {"mrays_per_s": n / (occlude_ms * 1e-3) / MRAYS, "ms_per_launch": occlude_ms, "algorithmic_bytes_per_query": bytes_occlude,
+                          "achieved_gbs": bytes_occlude * n / (occlude_ms * 1e-3) / 1e9,
+                          "visits_per_query": {"nodes": counts[3], "triangles": counts[4], "spheres": counts[5]}}}
 
 
 def cpu_baseline_trace(prepared, rays, shadow, sample, threads=0):
@@ -352,6 +408,9 @@ def main():
         line["e2e"] = {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 2 * n * 32, "d2h_bytes_per_step": n * 16 + n, "ms_per_step": e2e_ms / args.steps}
         line["gpu_launches"] = 2 * args.steps
         line["clocks"] = clocks.summary()
+
+        if not args.no_secondary:
+            line["secondary"] = secondary_batch(scene, prepared, rays, d_hits, device, stream, args, max_over_ranks)
 
         if rank == 0 and not args.no_cpu_baseline:
             cpu_value, cores, seconds, sample = cpu_baseline_trace(prepared, rays, shadow, args.cpu_sample)

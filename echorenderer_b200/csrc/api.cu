@@ -3,6 +3,7 @@
 // There is no CPU fallback anywhere in this library: without a CUDA device every compute call fails.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 
@@ -83,13 +84,25 @@ bool require_committed(EchoScene* scene)
 	return true;
 }
 
-constexpr uint64_t kChunkRays = 1ull << 21; // 2 M rays per pipelined chunk: 64 MB in, 32 MB out
+// rays per pipelined chunk of the host-buffer batch (1 Mi: 32 MB in, 16 MB out); the last chunk's kernel and download are
+// the only work the PCIe upload cannot hide, so chunks are kept small, but large enough to fill one resident wave
+uint64_t chunk_rays()
+{
+	static const uint64_t value = []
+	{
+		const char* text = getenv("ECHO_B200_CHUNK_RAYS");
+		long long parsed = text ? atoll(text) : 0;
+		return parsed >= 4096 ? (uint64_t)parsed : 1ull << 20;
+	}();
+
+	return value;
+}
 
 bool ensure_scratch(EchoScene* scene, uint64_t rays)
 {
 	if (scene->scratchCapacity >= rays) return true;
 
-	for (int i = 0; i < 2; i++)
+	for (int i = 0; i < EchoScene::kSlots; i++)
 	{
 		if (scene->scratchRays[i]) cudaFree(scene->scratchRays[i]);
 		if (scene->scratchOut[i]) cudaFree(scene->scratchOut[i]);
@@ -98,7 +111,7 @@ bool ensure_scratch(EchoScene* scene, uint64_t rays)
 
 	scene->scratchCapacity = 0;
 
-	for (int i = 0; i < 2; i++)
+	for (int i = 0; i < EchoScene::kSlots; i++)
 	{
 		if (!check_cuda(cudaMalloc(&scene->scratchRays[i], sizeof(EchoRay) * rays), "cudaMalloc(scratch rays)")) return false;
 		if (!check_cuda(cudaMalloc(&scene->scratchOut[i], sizeof(EchoHit) * rays), "cudaMalloc(scratch out)")) return false;
@@ -110,8 +123,8 @@ bool ensure_scratch(EchoScene* scene, uint64_t rays)
 	return true;
 }
 
-// Host-buffer batch: chunks alternate between two streams so that chunk k's upload overlaps chunk k-1's kernel and
-// download (H2D, compute and D2H engines run concurrently). With pinned host buffers the copies are truly asynchronous.
+// Host-buffer batch: chunks rotate over kSlots streams so that chunk k's upload overlaps the kernels and downloads of the
+// chunks before it (H2D, compute and D2H engines run concurrently). With pinned host buffers the copies are truly asynchronous.
 template<class Out, class Launch>
 int32_t batch_host(EchoScene* scene, const EchoRay* rays, uint64_t n, Out* out, Launch launch)
 {
@@ -122,12 +135,12 @@ int32_t batch_host(EchoScene* scene, const EchoRay* rays, uint64_t n, Out* out, 
 	DeviceGuard guard(scene->device);
 	if (!guard.ok) return ECHO_B200_ERR_NO_DEVICE;
 
-	uint64_t chunk = std::min<uint64_t>(kChunkRays, n);
+	uint64_t chunk = std::min<uint64_t>(chunk_rays(), n);
 	if (!ensure_scratch(scene, chunk)) return ECHO_B200_ERR_CUDA;
 
 	int slot = 0;
 
-	for (uint64_t first = 0; first < n; first += chunk, slot ^= 1)
+	for (uint64_t first = 0; first < n; first += chunk, slot = (slot + 1) % EchoScene::kSlots)
 	{
 		uint64_t count = std::min<uint64_t>(chunk, n - first);
 		cudaStream_t stream = scene->copyStreams[slot];
@@ -137,7 +150,7 @@ int32_t batch_host(EchoScene* scene, const EchoRay* rays, uint64_t n, Out* out, 
 		if (!check_cuda(cudaMemcpyAsync(out + first, scene->scratchOut[slot], sizeof(Out) * count, cudaMemcpyDeviceToHost, stream), "cudaMemcpyAsync(out)")) return ECHO_B200_ERR_CUDA;
 	}
 
-	for (int i = 0; i < 2; i++)
+	for (int i = 0; i < EchoScene::kSlots; i++)
 		if (!check_cuda(cudaStreamSynchronize(scene->copyStreams[i]), "batch")) return ECHO_B200_ERR_CUDA;
 
 	return ECHO_B200_OK;
@@ -201,7 +214,7 @@ int32_t echo_b200_scene_destroy(EchoScene* scene)
 	free_device(scene);
 	render_state_destroy(scene->render);
 
-	for (int i = 0; i < 2; i++)
+	for (int i = 0; i < EchoScene::kSlots; i++)
 	{
 		if (scene->scratchRays[i]) cudaFree(scene->scratchRays[i]);
 		if (scene->scratchOut[i]) cudaFree(scene->scratchOut[i]);

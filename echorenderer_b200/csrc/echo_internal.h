@@ -71,11 +71,12 @@ struct EchoScene
 	std::vector<void*> allocations;
 
 	// scratch for the host-buffer batch calls (grown on demand)
-	void* scratchRays[2] = { nullptr, nullptr };
-	void* scratchOut[2] = { nullptr, nullptr };
+	static constexpr int kSlots = 4; // chunk buffers of the host-buffer batch pipeline
+	void* scratchRays[kSlots] = {};
+	void* scratchOut[kSlots] = {};
 	uint64_t scratchCapacity = 0; // rays per chunk buffer
-	cudaStream_t copyStreams[2] = { nullptr, nullptr };
-	cudaEvent_t chunkDone[2] = { nullptr, nullptr };
+	cudaStream_t copyStreams[kSlots] = {};
+	cudaEvent_t chunkDone[kSlots] = {};
 
 	echo::RenderState* render = nullptr;
 };
