@@ -311,23 +311,88 @@ int32_t echo_b200_scene_set_camera(EchoScene* scene, const EchoCamera* camera)
 	return ECHO_B200_OK;
 }
 
+int32_t echo_b200_scene_set_packs(EchoScene* scene, const EchoPack* packs, uint32_t packCount, const EchoInstance* instances, uint32_t instanceCount)
+{
+	if (!scene || (!packs && packCount) || (!instances && instanceCount)) return fail(ECHO_B200_ERR_INVALID, "null argument");
+	scene->packs.assign(packs, packs + packCount);
+	scene->instances.assign(instances, instances + instanceCount);
+	scene->committed = false;
+	return ECHO_B200_OK;
+}
+
+namespace
+{
+
+// Traversal stack entries the deepest chain of packs needs below `pack`: the reference stackallocs maxDepth * 3 + 1 per
+// recursion (QuadBoundingVolumeHierarchy.cs:34,125); the device keeps all layers in one stack. 0 = invalid (cycle / too deep).
+uint32_t chain_stack(const EchoScene* scene, uint32_t pack, uint32_t layer)
+{
+	if (layer > ECHO_MAX_INSTANCE_LAYERS) return 0u;
+	const EchoPack& p = scene->packs[pack];
+	uint32_t deepest = 0u;
+
+	for (uint32_t i = 0; i < p.instanceCount; i++)
+	{
+		uint32_t below = chain_stack(scene, scene->instances[p.instanceOffset + i].pack, layer + 1u);
+		if (below == 0u) return 0u;
+		deepest = std::max(deepest, below);
+	}
+
+	return p.maxDepth * 3u + 1u + deepest;
+}
+
+} // namespace
+
 int32_t echo_b200_scene_commit(EchoScene* scene)
 {
 	if (!scene) return fail(ECHO_B200_ERR_INVALID, "scene is null");
 	if (scene->nodes.empty()) return fail(ECHO_B200_ERR_INVALID, "no QBVH was set");
 
-	// every token in the node array must point at an uploaded primitive
-	for (const EchoQbvhNode& node : scene->nodes)
+	// the packs the arrays are divided into; a scene without set_packs is one pack
+	std::vector<EchoPack> packs = scene->packs;
+
+	if (packs.empty())
 	{
-		for (uint32_t token : node.token4)
+		if (!scene->instances.empty()) return fail(ECHO_B200_ERR_INVALID, "instances without packs");
+		EchoPack whole = {};
+		whole.nodeCount = (uint32_t)scene->nodes.size();
+		whole.maxDepth = scene->maxDepth;
+		whole.triangleCount = (uint32_t)scene->triangles.size();
+		whole.sphereCount = (uint32_t)scene->spheres.size();
+		packs.push_back(whole);
+	}
+
+	for (const EchoPack& pack : packs)
+	{
+		if (pack.nodeCount == 0 || (uint64_t)pack.nodeOffset + pack.nodeCount > scene->nodes.size() || (uint64_t)pack.triangleOffset + pack.triangleCount > scene->triangles.size()
+			|| (uint64_t)pack.sphereOffset + pack.sphereCount > scene->spheres.size() || (uint64_t)pack.instanceOffset + pack.instanceCount > scene->instances.size())
+			return fail(ECHO_B200_ERR_INVALID, "pack range out of bounds");
+
+		// every token in the pack's nodes must point at one of the pack's own primitives
+		for (uint32_t n = 0; n < pack.nodeCount; n++)
 		{
-			if (token == ECHO_TOKEN_EMPTY) continue;
-			uint32_t type = token >> ECHO_TOKEN_INDEX_BITS, index = token & ((1u << ECHO_TOKEN_INDEX_BITS) - 1u);
-			bool ok = (type == ECHO_TOKEN_TYPE_NODE && index < scene->nodes.size()) || (type == ECHO_TOKEN_TYPE_TRIANGLE && index < scene->triangles.size())
-				|| (type == ECHO_TOKEN_TYPE_SPHERE && index < scene->spheres.size());
-			if (type == ECHO_TOKEN_TYPE_INSTANCE) return fail(ECHO_B200_ERR_UNSUPPORTED, "instanced tokens are outside the hot path");
-			if (!ok) return fail(ECHO_B200_ERR_INVALID, "QBVH token out of range");
+			for (uint32_t token : scene->nodes[pack.nodeOffset + n].token4)
+			{
+				if (token == ECHO_TOKEN_EMPTY) continue;
+				uint32_t type = token >> ECHO_TOKEN_INDEX_BITS, index = token & ((1u << ECHO_TOKEN_INDEX_BITS) - 1u);
+				bool ok = (type == ECHO_TOKEN_TYPE_NODE && index < pack.nodeCount) || (type == ECHO_TOKEN_TYPE_TRIANGLE && index < pack.triangleCount)
+					|| (type == ECHO_TOKEN_TYPE_SPHERE && index < pack.sphereCount) || (type == ECHO_TOKEN_TYPE_INSTANCE && index < pack.instanceCount);
+				if (!ok) return fail(ECHO_B200_ERR_INVALID, "QBVH token out of range");
+			}
 		}
+	}
+
+	for (const EchoInstance& instance : scene->instances)
+		if (instance.pack >= packs.size() || instance.pack == 0u) return fail(ECHO_B200_ERR_INVALID, "instance refers to a pack that does not exist (pack 0 is the scene)");
+
+	uint32_t stackDepth = scene->maxDepth;
+
+	if (!scene->packs.empty())
+	{
+		uint32_t entries = chain_stack(scene, 0u, 0u);
+		if (entries == 0u) return fail(ECHO_B200_ERR_INVALID, "instancing deeper than TokenHierarchy.MaxLayer (5) or cyclic");
+		stackDepth = (entries + 1u) / 3u; // smallest depth with depth * 3 + 1 >= entries
+		if (stack_class(stackDepth) < 0) return fail(ECHO_B200_ERR_UNSUPPORTED, "the deepest chain of instanced packs needs more than 192 stack entries");
 	}
 
 	for (const EchoTriangle& t : scene->triangles)
@@ -391,8 +456,11 @@ int32_t echo_b200_scene_commit(EchoScene* scene)
 	const EchoQbvhNode* nodes = nullptr;
 	const EchoMaterial* materials = nullptr;
 	const EchoLightNode* lightNodes = nullptr;
+	const EchoPack* devicePacks = nullptr;
+	const EchoInstance* deviceInstances = nullptr;
+	static_assert(sizeof(EchoPack) == 64 && sizeof(EchoInstance) == 128 && sizeof(EchoTokenHierarchy) == 24, "POD layout");
 
-	bool ok = upload(scene, scene->nodes, nodes) && upload(scene, triHot, d.triHot) && upload(scene, triShade, d.triShade)
+	bool ok = upload(scene, scene->packs, devicePacks) && upload(scene, scene->instances, deviceInstances) && upload(scene, scene->nodes, nodes) && upload(scene, triHot, d.triHot) && upload(scene, triShade, d.triShade)
 		&& upload(scene, spheres, d.spheres) && upload(scene, sphereMaterial, d.sphereMaterial) && upload(scene, scene->materials, materials)
 		&& upload(scene, scene->lightNodes, lightNodes) && upload(scene, scene->emitterTokens, d.emitterTokens)
 		&& upload(scene, scene->emitterPaths, d.emitterPaths) && upload(scene, pointLights, d.pointLights) && upload(scene, infiniteLights, d.infiniteLights);
@@ -414,7 +482,11 @@ int32_t echo_b200_scene_commit(EchoScene* scene)
 	d.emitterCount = (uint32_t)scene->emitterTokens.size();
 	d.pointLightCount = (uint32_t)scene->pointLights.size();
 	d.infiniteLightCount = (uint32_t)scene->infiniteLights.size();
-	d.maxDepth = scene->maxDepth;
+	d.maxDepth = stackDepth;
+	d.packs = reinterpret_cast<const uint4*>(devicePacks);
+	d.instances = reinterpret_cast<const float4*>(deviceInstances);
+	d.packCount = (uint32_t)scene->packs.size();
+	d.instanceCount = (uint32_t)scene->instances.size();
 	d.infiniteThreshold = scene->infiniteThreshold;
 	d.infinitePdf = scene->infinitePdf;
 	d.camera = scene->camera;
@@ -437,6 +509,61 @@ int32_t echo_b200_occlude_batch(EchoScene* scene, const EchoRay* rays, uint64_t 
 	{
 		return launch_occlude(scene->d, in, count, out, nullptr, stream);
 	});
+}
+
+namespace
+{
+
+// Host-buffer hierarchy batch: one upload, one launch, one download (the instanced path is not the bandwidth-tuned one).
+int32_t hierarchy_host(EchoScene* scene, const EchoRay* rays, const EchoTokenHierarchy* ignore, uint64_t n, EchoHit* hits, EchoTokenHierarchy* hitLayers, uint8_t* occluded)
+{
+	if (!require_committed(scene)) return ECHO_B200_ERR_INVALID;
+	if (n == 0) return ECHO_B200_OK;
+	if (!rays || (!hits && !occluded)) return fail(ECHO_B200_ERR_INVALID, "null buffer");
+	if (scene->d.packCount == 0u) return fail(ECHO_B200_ERR_INVALID, "the scene has no packs: use the plain batch calls");
+
+	DeviceGuard guard(scene->device);
+	if (!guard.ok) return ECHO_B200_ERR_NO_DEVICE;
+
+	void *dRays = nullptr, *dIgnore = nullptr, *dOut = nullptr, *dLayers = nullptr;
+	size_t outBytes = hits ? sizeof(EchoHit) * n : n;
+	cudaStream_t stream = scene->stream;
+
+	bool ok = check_cuda(cudaMalloc(&dRays, sizeof(EchoRay) * n), "cudaMalloc(rays)") && check_cuda(cudaMalloc(&dOut, outBytes), "cudaMalloc(out)")
+		&& (!ignore || check_cuda(cudaMalloc(&dIgnore, sizeof(EchoTokenHierarchy) * n), "cudaMalloc(ignore)"))
+		&& (!hitLayers || check_cuda(cudaMalloc(&dLayers, sizeof(EchoTokenHierarchy) * n), "cudaMalloc(layers)"))
+		&& check_cuda(cudaMemcpyAsync(dRays, rays, sizeof(EchoRay) * n, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync(rays)")
+		&& (!ignore || check_cuda(cudaMemcpyAsync(dIgnore, ignore, sizeof(EchoTokenHierarchy) * n, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync(ignore)"));
+
+	if (ok)
+	{
+		ok = hits ? launch_trace_instanced(scene->d, (const EchoRay*)dRays, (const EchoTokenHierarchy*)dIgnore, n, (EchoHit*)dOut, (EchoTokenHierarchy*)dLayers, nullptr, stream)
+		          : launch_occlude_instanced(scene->d, (const EchoRay*)dRays, (const EchoTokenHierarchy*)dIgnore, n, (uint8_t*)dOut, nullptr, stream);
+	}
+
+	ok = ok && check_cuda(cudaMemcpyAsync(hits ? (void*)hits : (void*)occluded, dOut, outBytes, cudaMemcpyDeviceToHost, stream), "cudaMemcpyAsync(out)")
+		&& (!hitLayers || check_cuda(cudaMemcpyAsync(hitLayers, dLayers, sizeof(EchoTokenHierarchy) * n, cudaMemcpyDeviceToHost, stream), "cudaMemcpyAsync(layers)"))
+		&& check_cuda(cudaStreamSynchronize(stream), "hierarchy batch");
+
+	cudaFree(dRays);
+	cudaFree(dIgnore);
+	cudaFree(dOut);
+	cudaFree(dLayers);
+	return ok ? ECHO_B200_OK : ECHO_B200_ERR_CUDA;
+}
+
+} // namespace
+
+int32_t echo_b200_trace_batch_hierarchy(EchoScene* scene, const EchoRay* rays, const EchoTokenHierarchy* ignore, uint64_t n, EchoHit* hits, EchoTokenHierarchy* hitLayers)
+{
+	if (!hits && n != 0) return fail(ECHO_B200_ERR_INVALID, "null buffer");
+	return hierarchy_host(scene, rays, ignore, n, hits, hitLayers, nullptr);
+}
+
+int32_t echo_b200_occlude_batch_hierarchy(EchoScene* scene, const EchoRay* rays, const EchoTokenHierarchy* ignore, uint64_t n, uint8_t* occluded)
+{
+	if (!occluded && n != 0) return fail(ECHO_B200_ERR_INVALID, "null buffer");
+	return hierarchy_host(scene, rays, ignore, n, nullptr, nullptr, occluded);
 }
 
 int32_t echo_b200_trace_batch_device(EchoScene* scene, const EchoRay* rays, uint64_t n, EchoHit* hits, void* stream)

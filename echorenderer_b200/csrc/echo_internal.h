@@ -22,6 +22,12 @@ int stack_class(uint32_t maxDepth); // 0: 48, 1: 96, 2: 192 entries, -1: unsuppo
 bool launch_trace(const DeviceScene& scene, const EchoRay* rays, uint64_t n, EchoHit* hits, unsigned long long* counts, cudaStream_t stream);
 bool launch_occlude(const DeviceScene& scene, const EchoRay* rays, uint64_t n, uint8_t* occluded, unsigned long long* counts, cudaStream_t stream);
 
+// ---- instanced.cu: the same queries through instanced packs, with TokenHierarchy layers in and out (either may be null) ----
+bool launch_trace_instanced(const DeviceScene& scene, const EchoRay* rays, const EchoTokenHierarchy* ignore, uint64_t n, EchoHit* hits,
+                            EchoTokenHierarchy* hitLayers, unsigned long long* counts, cudaStream_t stream);
+bool launch_occlude_instanced(const DeviceScene& scene, const EchoRay* rays, const EchoTokenHierarchy* ignore, uint64_t n, uint8_t* occluded,
+                              unsigned long long* counts, cudaStream_t stream);
+
 unsigned long long* next_ray_counter(cudaStream_t stream); // zeroed work counter for one persistent launch
 int persistent_grid(const void* kernel);                  // resident CTAs of a persistent kernel on the current device
 
@@ -65,6 +71,8 @@ struct EchoScene
 	std::vector<EchoInfiniteLight> infiniteLights;
 	float infiniteThreshold = 0.0f, infinitePdf = 0.0f;
 	EchoCamera camera = {};
+	std::vector<EchoPack> packs; // empty: the arrays are one pack
+	std::vector<EchoInstance> instances;
 
 	// device
 	echo::DeviceScene d = {};

@@ -29,10 +29,13 @@ struct DeviceScene
 	const uint64_t* emitterPaths;  // LightTree.map values, parallel to emitterTokens
 	const float4* pointLights;     // 2 x float4: {intensity, 0}, {position, 0}
 	const float4* infiniteLights;  // {radiance, directlyVisible bits}
+	const uint4* packs;            // 4 x uint4 per EchoPack; null when the scene is a single pack
+	const float4* instances;       // 8 x float4 per EchoInstance
 
 	uint32_t nodeCount, triangleCount, sphereCount, materialCount;
 	uint32_t lightNodeCount, emitterCount, pointLightCount, infiniteLightCount;
-	uint32_t maxDepth;
+	uint32_t maxDepth;             // quad depth whose 3 * maxDepth + 1 stack entries serve the deepest chain of packs
+	uint32_t packCount, instanceCount;
 	float infiniteThreshold, infinitePdf;
 
 	EchoCamera camera;

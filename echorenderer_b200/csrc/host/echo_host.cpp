@@ -655,16 +655,26 @@ Box sphere_box(const EchoSphere& s) // PreparedSphere.BoxBound, SphereEntity.cs:
 extern "C"
 {
 
-int32_t echo_host_build_qbvh(const EchoTriangle* triangles, uint32_t triangleCount, const EchoSphere* spheres, uint32_t sphereCount,
-                             int32_t threads, EchoQbvhNode** outNodes, uint32_t* outNodeCount, uint32_t* outMaxDepth)
+int32_t echo_host_build_qbvh_instanced(const EchoTriangle* triangles, uint32_t triangleCount, const EchoSphere* spheres, uint32_t sphereCount,
+                                       const float* instanceBounds, uint32_t instanceCount, int32_t threads,
+                                       EchoQbvhNode** outNodes, uint32_t* outNodeCount, uint32_t* outMaxDepth)
 {
-	uint64_t total = (uint64_t)triangleCount + sphereCount;
+	uint64_t total = (uint64_t)triangleCount + sphereCount + instanceCount;
 	if (total < 2 || total >= (1u << ECHO_TOKEN_INDEX_BITS) || !outNodes || !outNodeCount || !outMaxDepth) return ECHO_B200_ERR_INVALID;
 
-	// GeometryCollection.CreateBounds, GeometryCollection.cs:52-81: triangles then spheres
+	// GeometryCollection.CreateBounds, GeometryCollection.cs:52-81: triangles, spheres, then instances
 	std::vector<Tokenized> bounds(total);
 	for (uint32_t i = 0; i < triangleCount; i++) bounds[i] = { ECHO_TOKEN_MAKE(ECHO_TOKEN_TYPE_TRIANGLE, i), triangle_box(triangles[i]) };
 	for (uint32_t i = 0; i < sphereCount; i++) bounds[triangleCount + i] = { ECHO_TOKEN_MAKE(ECHO_TOKEN_TYPE_SPHERE, i), sphere_box(spheres[i]) };
+
+	for (uint32_t i = 0; i < instanceCount; i++)
+	{
+		const float* b = instanceBounds + (size_t)i * 6; // PreparedInstance.BoxBound: min xyz, max xyz
+		Box box;
+		box.min = { b[0], b[1], b[2] };
+		box.max = { b[3], b[4], b[5] };
+		bounds[(size_t)triangleCount + sphereCount + i] = { ECHO_TOKEN_MAKE(ECHO_TOKEN_TYPE_INSTANCE, i), box };
+	}
 
 	gMaxBuilders = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
 	if (gMaxBuilders < 1) gMaxBuilders = 1;
@@ -686,6 +696,12 @@ int32_t echo_host_build_qbvh(const EchoTriangle* triangles, uint32_t triangleCou
 	*outNodeCount = (uint32_t)quad.nodes.size();
 	*outMaxDepth = (uint32_t)depth;
 	return *outNodes ? ECHO_B200_OK : ECHO_B200_ERR_INVALID;
+}
+
+int32_t echo_host_build_qbvh(const EchoTriangle* triangles, uint32_t triangleCount, const EchoSphere* spheres, uint32_t sphereCount,
+                             int32_t threads, EchoQbvhNode** outNodes, uint32_t* outNodeCount, uint32_t* outMaxDepth)
+{
+	return echo_host_build_qbvh_instanced(triangles, triangleCount, spheres, sphereCount, nullptr, 0, threads, outNodes, outNodeCount, outMaxDepth);
 }
 
 float echo_host_emissive_power(const float emission[3]) { return luminance(emission) * kPi; } // Emissive.cs:52-53

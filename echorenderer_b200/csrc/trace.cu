@@ -236,6 +236,7 @@ static bool launch_occlude_impl(const DeviceScene& scene, const EchoRay* rays, u
 bool launch_trace(const DeviceScene& scene, const EchoRay* rays, uint64_t n, EchoHit* hits, unsigned long long* counts, cudaStream_t stream)
 {
 	if (n == 0) return true;
+	if (scene.packCount != 0u) return launch_trace_instanced(scene, rays, nullptr, n, hits, nullptr, counts, stream);
 
 	if (!counts && !use_simple_kernels())
 	{
@@ -254,6 +255,7 @@ bool launch_trace(const DeviceScene& scene, const EchoRay* rays, uint64_t n, Ech
 bool launch_occlude(const DeviceScene& scene, const EchoRay* rays, uint64_t n, uint8_t* occluded, unsigned long long* counts, cudaStream_t stream)
 {
 	if (n == 0) return true;
+	if (scene.packCount != 0u) return launch_occlude_instanced(scene, rays, nullptr, n, occluded, counts, stream);
 
 	if (!counts && !use_simple_kernels())
 	{

@@ -30,6 +30,8 @@ def _library():
     u32 = ctypes.c_uint32
     lib.echo_host_build_qbvh.argtypes = [p, u32, p, u32, ctypes.c_int32, ctypes.POINTER(p), ctypes.POINTER(u32), ctypes.POINTER(u32)]
     lib.echo_host_build_qbvh.restype = ctypes.c_int32
+    lib.echo_host_build_qbvh_instanced.argtypes = [p, u32, p, u32, p, u32, ctypes.c_int32, ctypes.POINTER(p), ctypes.POINTER(u32), ctypes.POINTER(u32)]
+    lib.echo_host_build_qbvh_instanced.restype = ctypes.c_int32
     lib.echo_host_build_light_tree.argtypes = [p, u32, p, u32, p, u32, p, u32, ctypes.POINTER(p), ctypes.POINTER(u32),
                                                ctypes.POINTER(p), ctypes.POINTER(p), ctypes.POINTER(u32), ctypes.POINTER(ctypes.c_float)]
     lib.echo_host_build_light_tree.restype = ctypes.c_int32
@@ -67,11 +69,33 @@ def _take(pointer, count, dtype):
 
 
 @dataclass
+class InstanceDescription:
+    """Scenic/Hierarchies/PackInstance.cs: one placement of an EntityPack. `pack` indexes SceneDescription.packs (0-based);
+    rotation is Euler degrees, scale is uniform; `materials` optionally replaces the pack's swatch for this placement."""
+    pack: int
+    position: tuple = (0.0, 0.0, 0.0)
+    rotation: tuple = (0.0, 0.0, 0.0)
+    scale: float = 1.0
+    materials: np.ndarray = None
+
+
+@dataclass
+class PackDescription:
+    """Scenic/Hierarchies/EntityPack.cs: geometry that is prepared once (PreparedPack) and instanced any number of times."""
+    triangles: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=structs.TRIANGLE))
+    spheres: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=structs.SPHERE))
+    materials: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=structs.MATERIAL))
+    instances: list = field(default_factory=list)
+
+
+@dataclass
 class SceneDescription:
     """What Echo's Scene + ScenePreparer hand to PreparedScene, with constant (Pure) textures flattened."""
     triangles: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=structs.TRIANGLE))
     spheres: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=structs.SPHERE))
     materials: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=structs.MATERIAL))
+    instances: list = field(default_factory=list)  # InstanceDescription placed directly in the scene
+    packs: list = field(default_factory=list)      # PackDescription referred to by instances
     point_lights: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=structs.POINT_LIGHT))
     infinite_lights: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=structs.INFINITE_LIGHT))
     camera: np.ndarray = field(default_factory=lambda: np.zeros(1, dtype=structs.CAMERA))
@@ -90,18 +114,24 @@ class PreparedArrays:
     infinite_threshold: float
     infinite_pdf: float
     scene_power: float
+    # instanced scenes: every pack's arrays back to back (include/echo_b200.h EchoPack); None for a single pack
+    packs: np.ndarray = None
+    instances: np.ndarray = None
+    all_triangles: np.ndarray = None
+    all_spheres: np.ndarray = None
+    all_materials: np.ndarray = None
 
     @property
     def triangles(self):
-        return self.description.triangles
+        return self.description.triangles if self.all_triangles is None else self.all_triangles
 
     @property
     def spheres(self):
-        return self.description.spheres
+        return self.description.spheres if self.all_spheres is None else self.all_spheres
 
     @property
     def materials(self):
-        return self.description.materials
+        return self.description.materials if self.all_materials is None else self.all_materials
 
     @property
     def bounds(self):
@@ -119,17 +149,76 @@ def fresnel_diffuse_reflectance(eta, fast=False):
     return float((lib.echo_host_fresnel_diffuse_reflectance_fast if fast else lib.echo_host_fresnel_diffuse_reflectance)(float(eta)))
 
 
-def build_qbvh(triangles, spheres, threads=0):
-    """SweepBuilder + QuadBoundingVolumeHierarchy constructor (SweepBuilder.cs:24-36, QuadBoundingVolumeHierarchy.cs:24-36)."""
+def build_qbvh(triangles, spheres, threads=0, instance_bounds=None):
+    """SweepBuilder + QuadBoundingVolumeHierarchy constructor (SweepBuilder.cs:24-36, QuadBoundingVolumeHierarchy.cs:24-36).
+    instance_bounds: [n, 6] float32 boxes (min xyz, max xyz) of the pack's instances, tokenized after the spheres."""
     lib = _library()
     triangles = np.ascontiguousarray(triangles, dtype=structs.TRIANGLE)
     spheres = np.ascontiguousarray(spheres, dtype=structs.SPHERE)
+    boxes = np.zeros((0, 6), dtype=np.float32) if instance_bounds is None else np.ascontiguousarray(instance_bounds, dtype=np.float32).reshape(-1, 6)
     nodes, count, depth = ctypes.c_void_p(), ctypes.c_uint32(), ctypes.c_uint32()
-    status = lib.echo_host_build_qbvh(_pointer(triangles), len(triangles), _pointer(spheres), len(spheres), threads,
-                                      ctypes.byref(nodes), ctypes.byref(count), ctypes.byref(depth))
+    status = lib.echo_host_build_qbvh_instanced(_pointer(triangles), len(triangles), _pointer(spheres), len(spheres), _pointer(boxes), len(boxes),
+                                                threads, ctypes.byref(nodes), ctypes.byref(count), ctypes.byref(depth))
     if status != 0:
         raise ValueError(f"echo_host_build_qbvh failed with status {status} (needs 2..2^28-1 primitives)")
     return _take(nodes, count.value, structs.QBVH_NODE), int(depth.value)
+
+
+def fill_bounds(nodes, depth=6):
+    """QuadBoundingVolumeHierarchy.FillBounds (QuadBoundingVolumeHierarchy.cs:62-118): the child boxes found `depth // 2`
+    quad levels below the root (leaves met earlier are kept), as [n, 6] min/max rows."""
+    iteration = depth // 2 - 1
+    boxes, stack = [], [0]
+
+    def bound(node, j):
+        return [node["minX"][j], node["minY"][j], node["minZ"][j], node["maxX"][j], node["maxY"][j], node["maxZ"][j]]
+
+    for _ in range(iteration):
+        following = []
+        while stack:
+            node = nodes[stack.pop()]
+            for j in range(4):
+                child = int(node["token4"][j])
+                if child == structs.TOKEN_EMPTY:
+                    continue
+                if structs.token_type(child) == structs.TOKEN_TYPE_NODE:
+                    following.append(structs.token_index(child))
+                else:
+                    boxes.append(bound(node, j))
+        stack = following
+
+    while stack:
+        node = nodes[stack.pop()]
+        for j in range(4):
+            if int(node["token4"][j]) != structs.TOKEN_EMPTY:
+                boxes.append(bound(node, j))
+
+    return np.asarray(boxes, dtype=np.float32).reshape(-1, 6)
+
+
+def transformed_bound(boxes, matrix):
+    """BoxBound(ReadOnlySpan<BoxBound>, Float4x4) (BoxBound.cs:39-57): centre/extent transform of every box, then the union."""
+    matrix = np.asarray(matrix, dtype=np.float32).reshape(3, 4)
+    center = (boxes[:, 3:] + boxes[:, :3]) / np.float32(2)
+    extend = (boxes[:, 3:] - boxes[:, :3]) / np.float32(2)
+    center = (center @ matrix[:, :3].T + matrix[:, 3]).astype(np.float32)
+    extend = (extend @ np.abs(matrix[:, :3]).T).astype(np.float32)
+    return np.concatenate([(center - extend).min(axis=0), (center + extend).max(axis=0)]).astype(np.float32)
+
+
+def instance_matrices(instance):
+    """PreparedInstance constructor (PreparedInstance.cs:15-27) from a PackInstance's position / rotation / uniform scale:
+    inverseTransform = Float4x4.Transformation (local -> parent), forwardTransform = its inverse, and the two scale multipliers."""
+    from .scenes import rotation_matrix
+    rotation = np.asarray(rotation_matrix(*instance.rotation), dtype=np.float64)
+    inverse = np.eye(4)
+    inverse[:3, :3] = rotation * float(instance.scale)
+    inverse[:3, 3] = instance.position
+    inverse = inverse.astype(np.float32)
+    forward = np.linalg.inv(inverse.astype(np.float64)).astype(np.float32)
+    inverse_scale = np.float32(np.sqrt(np.sum(inverse[0, :3].astype(np.float64) ** 2)))
+    forward_scale = np.float32(1) / inverse_scale
+    return forward[:3].reshape(-1), inverse[:3].reshape(-1), forward_scale, inverse_scale
 
 
 def build_light_tree(description):
@@ -148,8 +237,87 @@ def build_light_tree(description):
             _take(paths, emitter_count.value, np.uint64), float(power.value))
 
 
+def _prepare_packs(description, threads):
+    """ScenePreparer: every EntityPack becomes one PreparedPack (children before parents), then all arrays are laid back to
+    back with an EchoPack record per pack (pack 0 = the scene) and an EchoInstance record per placement."""
+    sources = [description] + list(description.packs)  # pack k+1 = description.packs[k]
+    built = {}
+
+    def build(index, trail=()):
+        if index in built:
+            return built[index]
+        if index in trail or len(trail) > structs.MAX_INSTANCE_LAYERS:
+            raise ValueError("instancing is cyclic or deeper than TokenHierarchy.MaxLayer")
+        source = sources[index]
+        boxes, records = [], []
+        for instance in source.instances:
+            child = instance.pack + 1
+            child_nodes, _ = build(child, trail + (index,))
+            forward, inverse, forward_scale, inverse_scale = instance_matrices(instance)
+            boxes.append(transformed_bound(fill_bounds(child_nodes), inverse))  # PreparedInstance.BoxBound
+            records.append((forward, inverse, forward_scale, inverse_scale, child, instance))
+        nodes, depth = build_qbvh(source.triangles, source.spheres, threads, np.asarray(boxes, dtype=np.float32) if boxes else None)
+        built[index] = (nodes, depth)
+        source._records = records
+        return built[index]
+
+    build(0)
+    used = sorted(built)  # packs nothing refers to are dropped
+    remap = {old: new for new, old in enumerate(used)}
+    packs = np.zeros(len(used), dtype=structs.PACK)
+    all_nodes, all_triangles, all_spheres, all_materials, all_instances = [], [], [], [], []
+    counts = dict(node=0, triangle=0, sphere=0, material=0, instance=0)
+    overrides = []
+
+    for new, old in enumerate(used):
+        source, (nodes, depth) = sources[old], built[old]
+        triangles = np.ascontiguousarray(source.triangles, dtype=structs.TRIANGLE)
+        spheres = np.ascontiguousarray(source.spheres, dtype=structs.SPHERE)
+        materials = np.ascontiguousarray(source.materials, dtype=structs.MATERIAL)
+        record = packs[new]
+        record["nodeOffset"], record["nodeCount"], record["maxDepth"] = counts["node"], len(nodes), depth
+        record["triangleOffset"], record["triangleCount"] = counts["triangle"], len(triangles)
+        record["sphereOffset"], record["sphereCount"] = counts["sphere"], len(spheres)
+        record["instanceOffset"], record["instanceCount"] = counts["instance"], len(source.instances)
+        record["materialOffset"] = counts["material"]
+        all_nodes.append(nodes), all_triangles.append(triangles), all_spheres.append(spheres), all_materials.append(materials)
+        counts["node"] += len(nodes)
+        counts["triangle"] += len(triangles)
+        counts["sphere"] += len(spheres)
+        counts["material"] += len(materials)
+        counts["instance"] += len(source.instances)
+        all_instances.extend((new, r) for r in getattr(source, "_records", []))
+
+    instances = np.zeros(len(all_instances), dtype=structs.INSTANCE)
+
+    for i, (_, (forward, inverse, forward_scale, inverse_scale, child, instance)) in enumerate(all_instances):
+        record = instances[i]
+        record["forward"], record["inverse"] = forward, inverse
+        record["forwardScale"], record["inverseScale"] = forward_scale, inverse_scale
+        record["pack"] = remap[child]
+        if instance.materials is None:
+            record["materialOffset"] = packs[remap[child]]["materialOffset"]  # PackInstance without a swatch: the pack's own
+        else:
+            record["materialOffset"] = counts["material"]
+            override = np.ascontiguousarray(instance.materials, dtype=structs.MATERIAL)
+            overrides.append(override)
+            counts["material"] += len(override)
+
+    # OneSided.base indexes the swatch it lives in: make it absolute
+    blocks = all_materials + overrides
+    materials = np.concatenate(blocks) if blocks else np.zeros(0, dtype=structs.MATERIAL)
+    offset = 0
+    for block in blocks:
+        view = materials[offset:offset + len(block)]
+        view["base"][view["type"] == structs.MATERIAL_ONESIDED] += offset
+        offset += len(block)
+
+    return (packs, instances, np.concatenate(all_nodes), np.concatenate(all_triangles), np.concatenate(all_spheres), materials,
+            max(int(p["maxDepth"]) for p in packs))
+
+
 def prepare(description, threads=0):
-    """ScenePreparer.Prepare -> PreparedScene constructor (PreparedScene.cs:26-40) for a scene without instances."""
+    """ScenePreparer.Prepare -> PreparedScene constructor (PreparedScene.cs:26-40)."""
     lib = _library()
     d = description
     d.triangles = np.ascontiguousarray(d.triangles, dtype=structs.TRIANGLE)
@@ -158,8 +326,12 @@ def prepare(description, threads=0):
     d.point_lights = np.ascontiguousarray(d.point_lights, dtype=structs.POINT_LIGHT)
     d.infinite_lights = np.ascontiguousarray(d.infinite_lights, dtype=structs.INFINITE_LIGHT)
 
-    nodes, max_depth = build_qbvh(d.triangles, d.spheres, threads)
-    light_nodes, tokens, paths, scene_power = build_light_tree(d)
+    instanced = bool(d.instances)
+    if instanced:
+        packs, instances, nodes, all_triangles, all_spheres, all_materials, max_depth = _prepare_packs(d, threads)
+    else:
+        nodes, max_depth = build_qbvh(d.triangles, d.spheres, threads)
+    light_nodes, tokens, paths, scene_power = build_light_tree(d)  # lights inside instanced packs: not sampled yet
 
     # FilterLights / SumInfiniteLightsPower / CalculateThreshold (PreparedScene.cs:279-325)
     infinite_power = np.float32(0)
@@ -183,4 +355,8 @@ def prepare(description, threads=0):
     if count == 0:
         pdf = 0.0  # never read: Pick only takes the infinite branch when sample < threshold == 0
 
-    return PreparedArrays(d, nodes, max_depth, light_nodes, tokens, paths, threshold, pdf, scene_power)
+    result = PreparedArrays(d, nodes, max_depth, light_nodes, tokens, paths, threshold, pdf, scene_power)
+    if instanced:
+        result.packs, result.instances = packs, instances
+        result.all_triangles, result.all_spheres, result.all_materials = all_triangles, all_spheres, all_materials
+    return result

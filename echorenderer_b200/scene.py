@@ -33,9 +33,12 @@ class PreparedScene:
             d = prepared.description
             ptr = _native.pointer
             _native.check(lib.echo_b200_scene_set_qbvh(self._handle, ptr(prepared.nodes), len(prepared.nodes), prepared.max_depth))
-            _native.check(lib.echo_b200_scene_set_triangles(self._handle, ptr(d.triangles), len(d.triangles)))
-            _native.check(lib.echo_b200_scene_set_spheres(self._handle, ptr(d.spheres), len(d.spheres)))
-            _native.check(lib.echo_b200_scene_set_materials(self._handle, ptr(d.materials), len(d.materials)))
+            triangles, spheres, materials = prepared.triangles, prepared.spheres, prepared.materials
+            _native.check(lib.echo_b200_scene_set_triangles(self._handle, ptr(triangles), len(triangles)))
+            _native.check(lib.echo_b200_scene_set_spheres(self._handle, ptr(spheres), len(spheres)))
+            _native.check(lib.echo_b200_scene_set_materials(self._handle, ptr(materials), len(materials)))
+            if prepared.packs is not None:
+                _native.check(lib.echo_b200_scene_set_packs(self._handle, ptr(prepared.packs), len(prepared.packs), ptr(prepared.instances), len(prepared.instances)))
             _native.check(lib.echo_b200_scene_set_light_tree(self._handle, ptr(prepared.light_nodes), len(prepared.light_nodes),
                                                              ptr(prepared.emitter_tokens), ptr(prepared.emitter_bitpaths), len(prepared.emitter_tokens),
                                                              ptr(d.point_lights), len(d.point_lights)))
@@ -79,6 +82,25 @@ class PreparedScene:
         rays = np.ascontiguousarray(rays, dtype=structs.RAY)
         occluded = out if out is not None else np.empty(len(rays), dtype=np.uint8)
         _native.check(self._lib.echo_b200_occlude_batch(self._handle, _native.pointer(rays), len(rays), _native.pointer(occluded)))
+        return occluded
+
+    # ---- the same with full TokenHierarchy in and out, for instanced scenes (GeometryCollection.cs:123-131,160-168) ----
+    def trace_hierarchy(self, rays, ignore_layers=None):
+        """Returns (hits, layers): structs.HIT plus the structs.TOKEN_HIERARCHY instance layers of every hit."""
+        rays = np.ascontiguousarray(rays, dtype=structs.RAY)
+        ignore = None if ignore_layers is None else np.ascontiguousarray(ignore_layers, dtype=structs.TOKEN_HIERARCHY)
+        hits = np.empty(len(rays), dtype=structs.HIT)
+        layers = np.zeros(len(rays), dtype=structs.TOKEN_HIERARCHY)
+        _native.check(self._lib.echo_b200_trace_batch_hierarchy(self._handle, _native.pointer(rays), _native.pointer(ignore) if ignore is not None else None,
+                                                                len(rays), _native.pointer(hits), _native.pointer(layers)))
+        return hits, layers
+
+    def occlude_hierarchy(self, rays, ignore_layers=None):
+        rays = np.ascontiguousarray(rays, dtype=structs.RAY)
+        ignore = None if ignore_layers is None else np.ascontiguousarray(ignore_layers, dtype=structs.TOKEN_HIERARCHY)
+        occluded = np.empty(len(rays), dtype=np.uint8)
+        _native.check(self._lib.echo_b200_occlude_batch_hierarchy(self._handle, _native.pointer(rays), _native.pointer(ignore) if ignore is not None else None,
+                                                                  len(rays), _native.pointer(occluded)))
         return occluded
 
     # ---- raw-pointer variants for pinned host memory / device memory owned by the caller (torch tensors) ----

@@ -405,6 +405,46 @@ def mixed_material_scene(rings=128, segments=130):
                             camera=camera, name="mixed")
 
 
+def instanced_scene(grid=6, rings=24, segments=26, nested=True):
+    """a ground plane plus `grid` x `grid` placements of two packs with different rotations and uniform
+    scales. Pack 0 is a blob with two spheres; pack 1 ("cluster") holds a box and three placements of pack 0, so hits inside it
+    carry two instance layers. Every third placement overrides the pack's swatch (PackInstance materials)."""
+    from .host import InstanceDescription, PackDescription
+    blob_materials = np.concatenate([material(structs.MATERIAL_DIFFUSE, (0.8, 0.3, 0.25)), material(structs.MATERIAL_CONDUCTOR, (1, 1, 1), roughness=(0.1, 0.1),
+                                    param_a=(0.9, 0.8, 0.5), param_b=(1.0, 0.9, 0.7), flags=structs.MATERIAL_FLAG_ARTISTIC)])
+    blob_spheres = np.zeros(2, dtype=structs.SPHERE)
+    blob_spheres["position"], blob_spheres["radius"], blob_spheres["material"] = [(1.4, 0.3, 0.0), (-0.4, 1.5, 0.6)], [0.35, 0.25], [1, 1]
+    blob = PackDescription(triangles=blob_triangles((0, 0, 0), 1.0, 0, rings, segments, seed=5), spheres=blob_spheres, materials=blob_materials)
+
+    cluster_materials = material(structs.MATERIAL_DIFFUSE, (0.3, 0.6, 0.8), roughness=(0.5, 0.5))
+    cluster = PackDescription(triangles=box(0, (1.2, 0.4, 1.2), (0, -0.9, 0)), materials=cluster_materials,
+                              instances=[InstanceDescription(0, (-1.3, 0.4, 0.0), (0, 30, 0), 0.5), InstanceDescription(0, (1.3, 0.4, 0.2), (20, 0, 45), 0.45),
+                                         InstanceDescription(0, (0.0, 0.6, 1.4), (0, 200, 10), 0.4)])
+    override = np.concatenate([material(structs.MATERIAL_DIELECTRIC, (1, 1, 1), roughness=(0.05, 0.05), ior=1.5), material(structs.MATERIAL_DIFFUSE, (0.2, 0.8, 0.3))])
+
+    instances = []
+    k = 0
+    for ix in range(grid):
+        for iz in range(grid):
+            position = ((ix - (grid - 1) / 2) * 4.0, 1.4 + 0.3 * ((ix * 7 + iz * 3) % 5), (iz - (grid - 1) / 2) * 4.0)
+            rotation = ((ix * 37) % 360, (iz * 53 + ix * 11) % 360, (k * 29) % 360)
+            scale = 0.6 + 0.15 * ((ix + 2 * iz) % 5)
+            pack = 1 if nested and k % 2 == 1 else 0
+            instances.append(InstanceDescription(pack, position, rotation, scale, override if k % 3 == 0 and pack == 0 else None))
+            k += 1
+
+    materials = np.concatenate([material(structs.MATERIAL_DIFFUSE, (0.7, 0.7, 0.7)), material(structs.MATERIAL_EMISSIVE, (10.0, 9.0, 8.0))])
+    extent = grid * 4.0 + 8.0
+    triangles = np.concatenate([plane(0, (extent, extent)), plane(1, (extent / 3, extent / 3), (0, 9, 0), (180, 0, 0))])
+    spheres = np.zeros(1, dtype=structs.SPHERE)
+    spheres["position"], spheres["radius"], spheres["material"] = (0, 3.5, 0), 0.8, 0
+
+    position = (0.0, 9.0, -extent * 0.75)
+    camera = perspective_camera(position, look_rotation(position, (0, 1, 0)), field_of_view=50.0)
+    return SceneDescription(triangles=triangles, spheres=spheres, materials=materials, instances=instances, packs=[blob, cluster],
+                            infinite_lights=ambient_light((0.3, 0.35, 0.4)), camera=camera, name="instanced")
+
+
 def many_lights_scene(light_count=10000, rings=128, segments=130, seed=23):
     """C4: the C3 geometry, diffuse only, plus `light_count` small emissive triangles in a 60 x 20 x 60 volume."""
     base_materials = np.concatenate([

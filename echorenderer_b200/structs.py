@@ -61,6 +61,14 @@ RAY = np.dtype([("origin", "<f4", 3), ("direction", "<f4", 3), ("distance", "<f4
 
 HIT = np.dtype([("token", "<u4"), ("distance", "<f4"), ("uv", "<f4", 2)])
 
+MAX_INSTANCE_LAYERS = 5  # TokenHierarchy.MaxLayer
+PACK = np.dtype([("nodeOffset", "<u4"), ("nodeCount", "<u4"), ("maxDepth", "<u4"), ("triangleOffset", "<u4"), ("triangleCount", "<u4"),
+                 ("sphereOffset", "<u4"), ("sphereCount", "<u4"), ("instanceOffset", "<u4"), ("instanceCount", "<u4"), ("materialOffset", "<u4"),
+                 ("reserved", "<u4", 6)])
+INSTANCE = np.dtype([("forward", "<f4", 12), ("inverse", "<f4", 12), ("forwardScale", "<f4"), ("inverseScale", "<f4"), ("pack", "<u4"),
+                     ("materialOffset", "<u4"), ("reserved", "<u4", 4)])
+TOKEN_HIERARCHY = np.dtype([("instanceCount", "<u4"), ("instances", "<u4", MAX_INSTANCE_LAYERS)])
+
 MATERIAL = np.dtype([
     ("type", "<u4"), ("flags", "<u4"), ("albedo", "<f4", 4), ("roughness", "<f4", 2), ("ior", "<f4"),
     ("paramA", "<f4", 3), ("paramB", "<f4", 3), ("base", "<u4"),

@@ -154,6 +154,43 @@ typedef struct EchoInfiniteLight
 	uint32_t directlyVisible; /* InfiniteLight.DirectlyVisible */
 } EchoInfiniteLight;
 
+/* ---- instancing: PreparedPack / PreparedInstance / TokenHierarchy ----
+ * A scene with instances is a set of packs (PreparedPack.cs:13-24): pack 0 is the PreparedScene itself, the others are the
+ * packs its instances refer to (packs may be instanced many times and may hold instances themselves, at most
+ * ECHO_MAX_INSTANCE_LAYERS deep). The arrays handed to set_qbvh / set_triangles / set_spheres / set_materials hold all
+ * packs back to back; every token inside a pack (node children, triangle / sphere / instance indices) is relative to
+ * the pack's own offsets, exactly as each C# pack sees its own arrays. The root of a pack's accelerator is its node 0. */
+#define ECHO_MAX_INSTANCE_LAYERS 5u /* TokenHierarchy.MaxLayer, TokenHierarchy.cs:41 */
+
+typedef struct EchoPack
+{
+	uint32_t nodeOffset, nodeCount; /* into the node array; maxDepth as for set_qbvh */
+	uint32_t maxDepth;
+	uint32_t triangleOffset, triangleCount;
+	uint32_t sphereOffset, sphereCount;
+	uint32_t instanceOffset, instanceCount; /* into the instance array: GeometryCollection.instances of this pack */
+	uint32_t materialOffset;                /* the pack's own swatch (LightCollection reads it, LightCollection.cs:145,151) */
+	uint32_t reserved[6];
+} EchoPack; /* 64 bytes */
+
+typedef struct EchoInstance
+{
+	float forward[12];   /* rows 0..2 of PreparedInstance.forwardTransform (parent -> local), PreparedInstance.cs:22 */
+	float inverse[12];   /* rows 0..2 of PreparedInstance.inverseTransform (local -> parent), :23 */
+	float forwardScale;  /* parent -> local scale multiplier, :26 */
+	float inverseScale;  /* local -> parent scale multiplier, :27 */
+	uint32_t pack;       /* index of the instanced pack */
+	uint32_t materialOffset; /* PreparedInstance.swatch: material index of a hit = this + the geometry's own index */
+	uint32_t reserved[4];
+} EchoInstance; /* 128 bytes */
+
+/* the instance layers of a TokenHierarchy (TokenHierarchy.cs:19-60); its TopToken travels in EchoRay.ignore / EchoHit.token */
+typedef struct EchoTokenHierarchy
+{
+	uint32_t instanceCount;
+	uint32_t instances[ECHO_MAX_INSTANCE_LAYERS]; /* TokenType.Instance tokens, outermost first */
+} EchoTokenHierarchy; /* 24 bytes */
+
 /* ---- PerspectiveCamera + RaySpawner inputs (PerspectiveCamera.cs:41-98, RaySpawner.cs:11-64) ---- */
 typedef struct EchoCamera
 {
@@ -214,12 +251,22 @@ int32_t echo_b200_scene_set_light_tree(EchoScene*, const EchoLightNode* nodes, u
                                        const EchoPointLight* points, uint32_t point_count);
 int32_t echo_b200_scene_set_infinite(EchoScene*, const EchoInfiniteLight* lights, uint32_t count, float threshold, float pdf);
 int32_t echo_b200_scene_set_camera(EchoScene*, const EchoCamera* camera);
+/* optional: declares the scene instanced (see EchoPack). Without it the scene is the single pack the arrays describe. */
+int32_t echo_b200_scene_set_packs(EchoScene*, const EchoPack* packs, uint32_t pack_count, const EchoInstance* instances, uint32_t instance_count);
 int32_t echo_b200_scene_commit(EchoScene*);
 int32_t echo_b200_scene_destroy(EchoScene*);
 
 /* batched Accelerator.Trace / Accelerator.Occlude through PreparedScene's guards (PreparedScene.cs:66-86). Host buffers. */
 int32_t echo_b200_trace_batch(EchoScene*, const EchoRay* rays, uint64_t n, EchoHit* hits);
 int32_t echo_b200_occlude_batch(EchoScene*, const EchoRay* rays, uint64_t n, uint8_t* occluded);
+
+/* the same queries with full TokenHierarchy in and out, for instanced scenes (GeometryCollection.cs:123-131,160-168,
+ * PreparedInstance.cs:47-83). `ignore` (nullable) holds the instance layers of each query's ignore hierarchy;
+ * `hit_layers` (nullable) receives the instance layers of each hit. Plain trace_batch / occlude_batch on an instanced
+ * scene behave as if `ignore` held empty hierarchies and drop the hit layers. Host buffers. */
+int32_t echo_b200_trace_batch_hierarchy(EchoScene*, const EchoRay* rays, const EchoTokenHierarchy* ignore, uint64_t n,
+                                        EchoHit* hits, EchoTokenHierarchy* hit_layers);
+int32_t echo_b200_occlude_batch_hierarchy(EchoScene*, const EchoRay* rays, const EchoTokenHierarchy* ignore, uint64_t n, uint8_t* occluded);
 
 /* same, device-resident buffers on `stream` (a cudaStream_t passed as void*; NULL = default stream). Asynchronous. */
 int32_t echo_b200_trace_batch_device(EchoScene*, const EchoRay* d_rays, uint64_t n, EchoHit* d_hits, void* stream);

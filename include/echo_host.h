@@ -28,6 +28,13 @@ int32_t echo_host_build_qbvh(const EchoTriangle* triangles, uint32_t triangle_co
                              const EchoSphere* spheres, uint32_t sphere_count, int32_t threads,
                              EchoQbvhNode** out_nodes, uint32_t* out_node_count, uint32_t* out_max_depth);
 
+/* The same with the boxes of the pack's instances appended (PreparedInstance.BoxBound, PreparedInstance.cs:29):
+ * instance_bounds holds 6 floats per instance, min xyz then max xyz, in parent space. */
+int32_t echo_host_build_qbvh_instanced(const EchoTriangle* triangles, uint32_t triangle_count,
+                                       const EchoSphere* spheres, uint32_t sphere_count,
+                                       const float* instance_bounds, uint32_t instance_count, int32_t threads,
+                                       EchoQbvhNode** out_nodes, uint32_t* out_node_count, uint32_t* out_max_depth);
+
 /* Builds the light tree over point lights, emissive triangles, emissive spheres (LightCollection.CreateBounds order).
  * out_power receives the root LightBound power (0 when there is no light; then node_count == 0). */
 int32_t echo_host_build_light_tree(const EchoTriangle* triangles, uint32_t triangle_count,

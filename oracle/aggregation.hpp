@@ -47,7 +47,24 @@ struct Ray
 	Float3 get_point(float distance) const { return direction * distance + origin; } // Ray.cs:33
 };
 
-// ---- Aggregation/Primitives/TraceQuery.cs:16-70 (no instancing: a TokenHierarchy is its top token) ----
+// ---- Aggregation/Primitives/TokenHierarchy.cs:19-129: the instance layers; the TopToken is kept beside it ----
+struct Layers
+{
+	uint32_t count = 0;
+	uint32_t instances[ECHO_MAX_INSTANCE_LAYERS] = {};
+
+	void push(uint32_t token) { instances[count++] = token; } // :62-70
+	void pop() { --count; }                                   // :72-81
+
+	bool operator==(const Layers& other) const // :117-129 (the hash is only a shortcut there)
+	{
+		if (count != other.count) return false;
+		for (uint32_t i = 0; i < count; i++) if (instances[i] != other.instances[i]) return false;
+		return true;
+	}
+};
+
+// ---- Aggregation/Primitives/TraceQuery.cs:16-70; a TokenHierarchy is {layers, top token} ----
 struct TraceQuery
 {
 	Ray ray;
@@ -55,6 +72,7 @@ struct TraceQuery
 	uint32_t token = ECHO_TOKEN_EMPTY;
 	float distance = kInfinity;
 	Float2 uv = { 0.0f, 0.0f };
+	Layers ignoreLayers, tokenLayers, current;
 
 	Float3 position() const { return ray.get_point(math_max(distance, kEpsilon)); } // TraceQuery.cs:76-82
 };
@@ -65,6 +83,7 @@ struct OccludeQuery
 	Ray ray;
 	uint32_t ignore = ECHO_TOKEN_EMPTY;
 	float travel = kInfinity;
+	Layers ignoreLayers, current;
 };
 
 // per-query visit counters: the algorithmic-bytes inputs of SURVEY.md §8(d) (a node visit = one BoxBound4.Intersect,
@@ -289,67 +308,132 @@ struct Scene
 
 	EchoCamera camera = {};
 
-	// ---- Aggregation/Preparation/GeometryCollection.cs:85-134 ----
-	void geometry_trace(uint32_t token, TraceQuery& query, VisitCounters* counters) const
+	// instancing: the arrays above hold every pack back to back (include/echo_b200.h EchoPack); empty = one pack
+	std::vector<EchoPack> packs;
+	std::vector<EchoInstance> instances;
+
+	EchoPack pack_view(uint32_t pack) const
 	{
+		if (!packs.empty()) return packs[pack];
+		EchoPack view = {};
+		view.nodeCount = (uint32_t)nodes.size();
+		view.maxDepth = maxDepth;
+		view.triangleCount = (uint32_t)triangles.size();
+		view.sphereCount = (uint32_t)spheres.size();
+		return view;
+	}
+
+	// ---- Aggregation/Preparation/PreparedInstance.cs:105-111 ----
+	static void transform_forward(const EchoInstance& instance, Ray& ray)
+	{
+		Float3 origin = multiply_point(instance.forward, ray.origin);
+		Float3 direction = multiply_direction(instance.forward, ray.direction);
+		ray = Ray(origin, direction * instance.inverseScale);
+	}
+
+	// ---- Aggregation/Preparation/GeometryCollection.cs:85-134 ----
+	void geometry_trace(uint32_t token, TraceQuery& query, VisitCounters* counters, uint32_t pack = 0) const
+	{
+		EchoPack view = pack_view(pack);
+
 		switch (token_type(token))
 		{
 			case ECHO_TOKEN_TYPE_TRIANGLE:
 			{
-				if (query.ignore == token) return;
+				if (query.ignore == token && query.ignoreLayers == query.current) return; // query.ignore == query.current, :93
 				if (counters) ++counters->triangles;
 
 				Float2 uv = query.uv; // an unaccepted test leaves query.uv untouched (uv is a local there, :96-103)
-				float distance = triangle_intersect(triangles[token_index(token)], query.ray.origin, query.ray.direction, uv);
+				float distance = triangle_intersect(triangles[view.triangleOffset + token_index(token)], query.ray.origin, query.ray.direction, uv);
 				if (distance >= query.distance) return;
 
 				query.token = token;
+				query.tokenLayers = query.current;
 				query.distance = distance;
 				query.uv = uv;
 				break;
 			}
 			case ECHO_TOKEN_TYPE_SPHERE:
 			{
-				bool findFar = query.ignore == token;
+				bool findFar = query.ignore == token && query.ignoreLayers == query.current;
 				if (counters) ++counters->spheres;
 
 				Float2 uv = query.uv;
-				float distance = sphere_intersect(spheres[token_index(token)], query.ray, uv, findFar);
+				float distance = sphere_intersect(spheres[view.sphereOffset + token_index(token)], query.ray, uv, findFar);
 				if (distance >= query.distance) return;
 
 				query.token = token;
+				query.tokenLayers = query.current;
 				query.distance = distance;
 				query.uv = uv;
 				break;
 			}
-			default: break; // instances are outside the hot path
+			case ECHO_TOKEN_TYPE_INSTANCE: // :123-131 + PreparedInstance.Trace, PreparedInstance.cs:47-61
+			{
+				const EchoInstance& instance = instances[view.instanceOffset + token_index(token)];
+				query.current.push(token);
+
+				Ray oldRay = query.ray;
+				transform_forward(instance, query.ray);
+				query.distance *= instance.forwardScale;
+
+				accelerator_trace(query, counters, instance.pack);
+
+				query.ray = oldRay;
+				query.distance *= instance.inverseScale;
+				query.current.pop();
+				break;
+			}
+			default: break;
 		}
 	}
 
 	// ---- GeometryCollection.cs:140-171 ----
-	bool geometry_occlude(uint32_t token, const OccludeQuery& query, VisitCounters* counters) const
+	bool geometry_occlude(uint32_t token, OccludeQuery& query, VisitCounters* counters, uint32_t pack = 0) const
 	{
+		EchoPack view = pack_view(pack);
+
 		switch (token_type(token))
 		{
 			case ECHO_TOKEN_TYPE_TRIANGLE:
 			{
-				if (query.ignore == token) return false;
+				if (query.ignore == token && query.ignoreLayers == query.current) return false;
 				if (counters) ++counters->triangles;
-				return triangle_occlude(triangles[token_index(token)], query.ray.origin, query.ray.direction, query.travel);
+				return triangle_occlude(triangles[view.triangleOffset + token_index(token)], query.ray.origin, query.ray.direction, query.travel);
 			}
 			case ECHO_TOKEN_TYPE_SPHERE:
 			{
-				bool findFar = query.ignore == token;
+				bool findFar = query.ignore == token && query.ignoreLayers == query.current;
 				if (counters) ++counters->spheres;
-				return sphere_occlude(spheres[token_index(token)], query.ray, query.travel, findFar);
+				return sphere_occlude(spheres[view.sphereOffset + token_index(token)], query.ray, query.travel, findFar);
+			}
+			case ECHO_TOKEN_TYPE_INSTANCE: // :160-168 + PreparedInstance.Occlude, PreparedInstance.cs:63-83
+			{
+				const EchoInstance& instance = instances[view.instanceOffset + token_index(token)];
+				query.current.push(token);
+
+				Ray oldRay = query.ray;
+				float oldTravel = query.travel;
+				transform_forward(instance, query.ray);
+				query.travel *= instance.forwardScale;
+
+				if (accelerator_occlude(query, counters, instance.pack)) return true;
+
+				query.ray = oldRay;
+				query.travel = oldTravel;
+				query.current.pop();
+				return false;
 			}
 			default: return false;
 		}
 	}
 
 	// ---- Aggregation/Acceleration/QuadBoundingVolumeHierarchy.cs:123-219 ----
-	void accelerator_trace(TraceQuery& query, VisitCounters* counters) const
+	void accelerator_trace(TraceQuery& query, VisitCounters* counters, uint32_t pack = 0) const
 	{
+		EchoPack view = pack_view(pack);
+		const EchoQbvhNode* nodes = this->nodes.data() + view.nodeOffset;
+		uint32_t maxDepth = view.maxDepth;
 		int stackSize = (int)maxDepth * 3 + 1; // :34
 		uint32_t* stack = (uint32_t*)alloca(sizeof(uint32_t) * stackSize); // stackalloc, :125-126
 		float* hitsBase = (float*)alloca(sizeof(float) * stackSize);
@@ -373,7 +457,7 @@ struct Scene
 				*next++ = token;
 				*hits++ = hit;
 			}
-			else geometry_trace(token, query, counters);
+			else geometry_trace(token, query, counters, pack);
 		};
 
 		do
@@ -439,8 +523,11 @@ struct Scene
 	}
 
 	// ---- QuadBoundingVolumeHierarchy.cs:223-315 ----
-	bool accelerator_occlude(const OccludeQuery& query, VisitCounters* counters) const
+	bool accelerator_occlude(OccludeQuery& query, VisitCounters* counters, uint32_t pack = 0) const
 	{
+		EchoPack view = pack_view(pack);
+		const EchoQbvhNode* nodes = this->nodes.data() + view.nodeOffset;
+		uint32_t maxDepth = view.maxDepth;
 		int stackSize = (int)maxDepth * 3 + 1;
 		uint32_t* stack = (uint32_t*)alloca(sizeof(uint32_t) * stackSize); // stackalloc, :227
 
@@ -455,7 +542,7 @@ struct Scene
 			if (hit >= query.travel) return false;
 
 			uint32_t token = node.token4[offset];
-			if (token_is_geometry(token)) return geometry_occlude(token, query, counters);
+			if (token_is_geometry(token)) return geometry_occlude(token, query, counters, pack);
 
 			*next++ = token;
 			return false;
@@ -532,9 +619,10 @@ struct Scene
 		return query.distance < original;
 	}
 
-	bool occlude(const OccludeQuery& query, VisitCounters* counters = nullptr) const
+	bool occlude(const OccludeQuery& original, VisitCounters* counters = nullptr) const
 	{
-		if (!positive(query.travel)) return false;
+		if (!positive(original.travel)) return false;
+		OccludeQuery query = original; // instances rewrite ray and travel while they are entered
 		return accelerator_occlude(query, counters);
 	}
 
@@ -544,18 +632,24 @@ struct Scene
 	{
 		if (!positive(query.distance)) return false;
 		float original = query.distance;
-		for (uint32_t i = 0; i < triangles.size(); i++) geometry_trace(ECHO_TOKEN_MAKE(ECHO_TOKEN_TYPE_TRIANGLE, i), query, nullptr);
-		for (uint32_t i = 0; i < spheres.size(); i++) geometry_trace(ECHO_TOKEN_MAKE(ECHO_TOKEN_TYPE_SPHERE, i), query, nullptr);
+		EchoPack view = pack_view(0);
+		for (uint32_t i = 0; i < view.triangleCount; i++) geometry_trace(ECHO_TOKEN_MAKE(ECHO_TOKEN_TYPE_TRIANGLE, i), query, nullptr);
+		for (uint32_t i = 0; i < view.sphereCount; i++) geometry_trace(ECHO_TOKEN_MAKE(ECHO_TOKEN_TYPE_SPHERE, i), query, nullptr);
+		for (uint32_t i = 0; i < view.instanceCount; i++) geometry_trace(ECHO_TOKEN_MAKE(ECHO_TOKEN_TYPE_INSTANCE, i), query, nullptr);
 		return query.distance < original;
 	}
 
-	bool occlude_linear(const OccludeQuery& query) const
+	bool occlude_linear(const OccludeQuery& original) const
 	{
-		if (!positive(query.travel)) return false;
-		for (uint32_t i = 0; i < triangles.size(); i++)
+		if (!positive(original.travel)) return false;
+		OccludeQuery query = original;
+		EchoPack view = pack_view(0);
+		for (uint32_t i = 0; i < view.triangleCount; i++)
 			if (geometry_occlude(ECHO_TOKEN_MAKE(ECHO_TOKEN_TYPE_TRIANGLE, i), query, nullptr)) return true;
-		for (uint32_t i = 0; i < spheres.size(); i++)
+		for (uint32_t i = 0; i < view.sphereCount; i++)
 			if (geometry_occlude(ECHO_TOKEN_MAKE(ECHO_TOKEN_TYPE_SPHERE, i), query, nullptr)) return true;
+		for (uint32_t i = 0; i < view.instanceCount; i++)
+			if (geometry_occlude(ECHO_TOKEN_MAKE(ECHO_TOKEN_TYPE_INSTANCE, i), query, nullptr)) return true;
 		return false;
 	}
 

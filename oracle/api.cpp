@@ -151,6 +151,66 @@ void oracle_occlude_batch(const OracleScene* s, const EchoRay* rays, uint64_t n,
 	if (counters) for (int i = 0; i < 3; i++) counters[i] = totals[i];
 }
 
+void oracle_scene_set_packs(OracleScene* s, const EchoPack* packs, uint32_t packCount, const EchoInstance* instances, uint32_t instanceCount)
+{
+	s->scene.packs.assign(packs, packs + packCount);
+	s->scene.instances.assign(instances, instances + instanceCount);
+}
+
+static Layers make_layers(const EchoTokenHierarchy* in)
+{
+	Layers layers;
+	if (!in) return layers;
+	layers.count = in->instanceCount;
+	for (uint32_t k = 0; k < layers.count && k < ECHO_MAX_INSTANCE_LAYERS; k++) layers.instances[k] = in->instances[k];
+	return layers;
+}
+
+// the batch queries with full TokenHierarchy in and out (include/echo_b200.h echo_b200_trace_batch_hierarchy); linear != 0
+// replaces the root accelerator by the brute-force loop over the root pack's geometry
+void oracle_trace_batch_hierarchy(const OracleScene* s, const EchoRay* rays, const EchoTokenHierarchy* ignore, uint64_t n,
+                                  EchoHit* hits, EchoTokenHierarchy* hitLayers, int linear, int threads)
+{
+	parallel_chunks(n, linear ? 16 : 4096, threads, [&](int, uint64_t begin, uint64_t end)
+	{
+		for (uint64_t i = begin; i < end; i++)
+		{
+			TraceQuery query = make_trace_query(rays[i]);
+			query.ignoreLayers = make_layers(ignore ? ignore + i : nullptr);
+			bool hit = linear ? s->scene.trace_linear(query) : s->scene.trace(query, nullptr);
+			store_hit(query, hit, rays[i], hits[i]);
+
+			if (hitLayers)
+			{
+				EchoTokenHierarchy out = {};
+				if (hit)
+				{
+					out.instanceCount = query.tokenLayers.count;
+					for (uint32_t k = 0; k < out.instanceCount; k++) out.instances[k] = query.tokenLayers.instances[k];
+				}
+				hitLayers[i] = out;
+			}
+		}
+	});
+}
+
+void oracle_occlude_batch_hierarchy(const OracleScene* s, const EchoRay* rays, const EchoTokenHierarchy* ignore, uint64_t n,
+                                    uint8_t* occluded, int linear, int threads)
+{
+	parallel_chunks(n, linear ? 16 : 4096, threads, [&](int, uint64_t begin, uint64_t end)
+	{
+		for (uint64_t i = begin; i < end; i++)
+		{
+			OccludeQuery query;
+			query.ray = Ray(f3(rays[i].origin), f3(rays[i].direction));
+			query.ignore = rays[i].ignore;
+			query.travel = rays[i].distance;
+			query.ignoreLayers = make_layers(ignore ? ignore + i : nullptr);
+			occluded[i] = (linear ? s->scene.occlude_linear(query) : s->scene.occlude(query, nullptr)) ? 1 : 0;
+		}
+	});
+}
+
 void oracle_trace_linear_batch(const OracleScene* s, const EchoRay* rays, uint64_t n, EchoHit* hits, int threads)
 {
 	parallel_chunks(n, 16, threads, [&](int, uint64_t begin, uint64_t end)

@@ -188,6 +188,26 @@ inline Float3 identity_multiply_direction(Float3 d)
 	};
 }
 
+// Float4x4.MultiplyPoint / MultiplyDirection (Float4x4.cs:260-272) on rows 0..2 of an affine matrix, row-major m[12];
+// plain left-to-right products and sums, as the C# JIT emits them (no contraction)
+inline Float3 multiply_point(const float* m, Float3 p)
+{
+	return {
+		m[0] * p.x + m[1] * p.y + m[2] * p.z + m[3],
+		m[4] * p.x + m[5] * p.y + m[6] * p.z + m[7],
+		m[8] * p.x + m[9] * p.y + m[10] * p.z + m[11]
+	};
+}
+
+inline Float3 multiply_direction(const float* m, Float3 d)
+{
+	return {
+		m[0] * d.x + m[1] * d.y + m[2] * d.z,
+		m[4] * d.x + m[5] * d.y + m[6] * d.z,
+		m[8] * d.x + m[9] * d.y + m[10] * d.z
+	};
+}
+
 // Textures/Colors/RGB128.cs (a Float4 with W == 0)
 struct RGB
 {

@@ -42,6 +42,9 @@ def library():
     lib.oracle_scene_set_light_tree.argtypes = [p, p, u32, p, p, u32, p, u32]
     lib.oracle_scene_set_infinite.argtypes = [p, p, u32, f32, f32]
     lib.oracle_scene_set_camera.argtypes = [p, p]
+    lib.oracle_scene_set_packs.argtypes = [p, p, u32, p, u32]
+    lib.oracle_trace_batch_hierarchy.argtypes = [p, p, p, u64, p, p, i32, i32]
+    lib.oracle_occlude_batch_hierarchy.argtypes = [p, p, p, u64, p, i32, i32]
     lib.oracle_trace_batch.argtypes = [p, p, u64, p, p, i32]
     lib.oracle_occlude_batch.argtypes = [p, p, u64, p, p, i32]
     lib.oracle_trace_linear_batch.argtypes = [p, p, u64, p, i32]
@@ -97,9 +100,11 @@ class OracleScene:
         self.handle = ctypes.c_void_p(lib.oracle_scene_create())
         d = prepared.description
         lib.oracle_scene_set_qbvh(self.handle, ptr(prepared.nodes), len(prepared.nodes), prepared.max_depth)
-        lib.oracle_scene_set_triangles(self.handle, ptr(d.triangles), len(d.triangles))
-        lib.oracle_scene_set_spheres(self.handle, ptr(d.spheres), len(d.spheres))
-        lib.oracle_scene_set_materials(self.handle, ptr(d.materials), len(d.materials))
+        lib.oracle_scene_set_triangles(self.handle, ptr(prepared.triangles), len(prepared.triangles))
+        lib.oracle_scene_set_spheres(self.handle, ptr(prepared.spheres), len(prepared.spheres))
+        lib.oracle_scene_set_materials(self.handle, ptr(prepared.materials), len(prepared.materials))
+        if prepared.packs is not None:
+            lib.oracle_scene_set_packs(self.handle, ptr(prepared.packs), len(prepared.packs), ptr(prepared.instances), len(prepared.instances))
         lib.oracle_scene_set_light_tree(self.handle, ptr(prepared.light_nodes), len(prepared.light_nodes), ptr(prepared.emitter_tokens),
                                         ptr(prepared.emitter_bitpaths), len(prepared.emitter_tokens), ptr(d.point_lights), len(d.point_lights))
         lib.oracle_scene_set_infinite(self.handle, ptr(d.infinite_lights), len(d.infinite_lights), prepared.infinite_threshold, prepared.infinite_pdf)
@@ -123,6 +128,21 @@ class OracleScene:
         counters = np.zeros(3, dtype=np.uint64)
         self.lib.oracle_occlude_batch(self.handle, ptr(rays), len(rays), ptr(occluded), ptr(counters) if count_visits else None, threads)
         return (occluded, counters) if count_visits else occluded
+
+    def trace_hierarchy(self, rays, ignore_layers=None, linear=False, threads=0):
+        rays = np.ascontiguousarray(rays, dtype=structs.RAY)
+        ignore = None if ignore_layers is None else np.ascontiguousarray(ignore_layers, dtype=structs.TOKEN_HIERARCHY)
+        hits = np.zeros(len(rays), dtype=structs.HIT)
+        layers = np.zeros(len(rays), dtype=structs.TOKEN_HIERARCHY)
+        self.lib.oracle_trace_batch_hierarchy(self.handle, ptr(rays), ptr(ignore), len(rays), ptr(hits), ptr(layers), int(linear), threads)
+        return hits, layers
+
+    def occlude_hierarchy(self, rays, ignore_layers=None, linear=False, threads=0):
+        rays = np.ascontiguousarray(rays, dtype=structs.RAY)
+        ignore = None if ignore_layers is None else np.ascontiguousarray(ignore_layers, dtype=structs.TOKEN_HIERARCHY)
+        occluded = np.zeros(len(rays), dtype=np.uint8)
+        self.lib.oracle_occlude_batch_hierarchy(self.handle, ptr(rays), ptr(ignore), len(rays), ptr(occluded), int(linear), threads)
+        return occluded
 
     def trace_linear(self, rays, threads=0):
         rays = np.ascontiguousarray(rays, dtype=structs.RAY)

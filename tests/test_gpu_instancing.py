@@ -1,0 +1,117 @@
+"""Parity of the CUDA traversal through instanced packs with the oracle, through the C ABI:
+hit tokens, the instance layers of every hit, distances and barycentrics bit-exact, with and without ignore hierarchies."""
+import numpy as np
+import pytest
+
+from echorenderer_b200 import EchoNativeError, PreparedScene, host, scenes, structs
+from tests import oracle_lib
+from tests.test_gpu_trace import assert_hits_equal
+from tests.test_instancing import spawn_from_hits
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def instanced():
+    return host.prepare(scenes.instanced_scene())
+
+
+def test_trace_hierarchy_matches_oracle(instanced):
+    oracle = oracle_lib.OracleScene(instanced)
+    rays = scenes.random_rays(instanced.bounds, 300_000, seed=11)
+
+    with PreparedScene(instanced) as scene:
+        hits, layers = scene.trace_hierarchy(rays)
+        expected, expected_layers = oracle.trace_hierarchy(rays)
+        hit = expected["token"] != structs.TOKEN_EMPTY
+        assert hit.mean() > 0.1 and set(np.unique(expected_layers["instanceCount"][hit])) == {0, 1, 2}
+        assert_hits_equal(hits, expected)
+        assert np.array_equal(layers, expected_layers)
+
+        # the plain batch call on an instanced scene: same hits, layers dropped
+        assert_hits_equal(scene.trace(rays), expected)
+
+        # rays leaving the hit points, ignoring the full hierarchy they start on
+        spawned, ignore = spawn_from_hits(rays, expected, expected_layers)
+        again, again_layers = scene.trace_hierarchy(spawned, ignore)
+        expected_again, expected_again_layers = oracle.trace_hierarchy(spawned, ignore)
+        assert_hits_equal(again, expected_again)
+        assert np.array_equal(again_layers, expected_again_layers)
+
+        # and with the layers left out (a different ignore hierarchy for hits inside placements)
+        naive, naive_layers = scene.trace_hierarchy(spawned, None)
+        expected_naive, expected_naive_layers = oracle.trace_hierarchy(spawned, None)
+        assert_hits_equal(naive, expected_naive)
+        assert np.array_equal(naive_layers, expected_naive_layers)
+
+
+def test_occlude_hierarchy_matches_oracle(instanced):
+    oracle = oracle_lib.OracleScene(instanced)
+    rays = scenes.random_rays(instanced.bounds, 300_000, seed=13, occlusion=True)
+
+    with PreparedScene(instanced) as scene:
+        expected = oracle.occlude_hierarchy(rays)
+        assert 0.02 < expected.mean() < 0.98
+        assert np.array_equal(scene.occlude_hierarchy(rays), expected)
+        assert np.array_equal(scene.occlude(rays), expected)
+
+        primary = scenes.random_rays(instanced.bounds, 200_000, seed=17)
+        hits, layers = oracle.trace_hierarchy(primary)
+        spawned, ignore = spawn_from_hits(primary, hits, layers)
+        spawned["distance"] = 4.0
+        assert np.array_equal(scene.occlude_hierarchy(spawned, ignore), oracle.occlude_hierarchy(spawned, ignore))
+
+
+def test_edge_cases(instanced):
+    oracle = oracle_lib.OracleScene(instanced)
+
+    with PreparedScene(instanced) as scene:
+        empty = np.zeros(0, dtype=structs.RAY)
+        hits, layers = scene.trace_hierarchy(empty)
+        assert len(hits) == 0 and len(layers) == 0
+
+        rays = scenes.random_rays(instanced.bounds, 1001, seed=19)  # ragged size, zero / negative / tiny limits
+        rays["distance"][::5] = 0.0
+        rays["distance"][1::5] = -1.0
+        rays["distance"][2::5] = 3.0
+        hits, layers = scene.trace_hierarchy(rays)
+        expected, expected_layers = oracle.trace_hierarchy(rays)
+        assert_hits_equal(hits, expected)
+        assert np.array_equal(layers, expected_layers)
+        assert np.array_equal(scene.occlude_hierarchy(rays), oracle.occlude_hierarchy(rays))
+
+
+def test_commit_rejects_broken_packs(instanced):
+    import copy
+    broken = copy.copy(instanced)
+    broken.instances = instanced.instances.copy()
+    broken.instances["pack"][0] = 0  # a placement of the scene itself: cyclic
+    with pytest.raises(EchoNativeError):
+        PreparedScene(broken)
+
+    broken = copy.copy(instanced)
+    broken.packs = instanced.packs.copy()
+    broken.packs["instanceCount"][0] += 100
+    with pytest.raises(EchoNativeError):
+        PreparedScene(broken)
+
+
+def test_deep_nesting():
+    """Five instance layers (TokenHierarchy.MaxLayer): a chain of packs each holding one placement of the next."""
+    leaf = host.PackDescription(triangles=scenes.box(0, (1, 1, 1)), materials=scenes.material(structs.MATERIAL_DIFFUSE))
+    packs = [leaf]
+    for level in range(1, 5):
+        packs.append(host.PackDescription(triangles=scenes.box(0, (0.3, 0.3, 0.3), (2.0, 0, 0)), materials=scenes.material(structs.MATERIAL_DIFFUSE),
+                                          instances=[host.InstanceDescription(level - 1, (0.1 * level, 0.2, 0), (10 * level, 25, 0), 0.9)]))
+    description = host.SceneDescription(triangles=scenes.plane(0, (20, 20), (0, -3, 0)), materials=scenes.material(structs.MATERIAL_DIFFUSE),
+                                        instances=[host.InstanceDescription(4, (0, 0, 0), (0, 15, 0), 1.5)], packs=packs, camera=scenes.cornell_box().camera)
+    prepared = host.prepare(description)
+    oracle = oracle_lib.OracleScene(prepared)
+    rays = scenes.random_rays(prepared.bounds, 100_000, seed=23)
+
+    with PreparedScene(prepared) as scene:
+        hits, layers = scene.trace_hierarchy(rays)
+        expected, expected_layers = oracle.trace_hierarchy(rays)
+        assert expected_layers["instanceCount"].max() == 5
+        assert_hits_equal(hits, expected)
+        assert np.array_equal(layers, expected_layers)
