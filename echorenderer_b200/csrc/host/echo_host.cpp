@@ -711,6 +711,16 @@ int32_t echo_host_build_light_tree(const EchoTriangle* triangles, uint32_t trian
                                    EchoLightNode** outNodes, uint32_t* outNodeCount,
                                    uint32_t** outTokens, uint64_t** outPaths, uint32_t* outEmitterCount, float* outPower)
 {
+	return echo_host_build_light_tree_instanced(triangles, triangleCount, spheres, sphereCount, materials, materialCount, points, pointCount, nullptr, 0,
+	                                            outNodes, outNodeCount, outTokens, outPaths, outEmitterCount, outPower);
+}
+
+int32_t echo_host_build_light_tree_instanced(const EchoTriangle* triangles, uint32_t triangleCount, const EchoSphere* spheres, uint32_t sphereCount,
+                                             const EchoMaterial* materials, uint32_t materialCount, const EchoPointLight* points, uint32_t pointCount,
+                                             const float* instanceLights, uint32_t instanceCount,
+                                             EchoLightNode** outNodes, uint32_t* outNodeCount,
+                                             uint32_t** outTokens, uint64_t** outPaths, uint32_t* outEmitterCount, float* outPower)
+{
 	if (!outNodes || !outNodeCount || !outTokens || !outPaths || !outEmitterCount || !outPower) return ECHO_B200_ERR_INVALID;
 
 	auto geometry_power = [&](uint32_t material, float area) -> float // LightCollection.GetGeometryPower, LightCollection.cs:221-222
@@ -751,6 +761,14 @@ int32_t echo_host_build_light_tree(const EchoTriangle* triangles, uint32_t trian
 		if (!(kEpsilon <= power)) continue;
 
 		lights.push_back({ ECHO_TOKEN_MAKE(ECHO_TOKEN_TYPE_SPHERE, i), { sphere_box(s), fullSphere, power } });
+	}
+
+	for (uint32_t i = 0; i < instanceCount; i++) // AddInstances, LightCollection.cs:123-135: PreparedInstance.LightBound
+	{
+		const float* v = instanceLights + (size_t)i * 12; // box min xyz, max xyz, cone axis xyz, cosOffset, cosExtend, power
+		if (!(kEpsilon <= v[11])) continue;
+		LightBound bound = { { { v[0], v[1], v[2] }, { v[3], v[4], v[5] } }, { { v[6], v[7], v[8] }, v[9], v[10] }, v[11] };
+		lights.push_back({ ECHO_TOKEN_MAKE(ECHO_TOKEN_TYPE_INSTANCE, i), bound });
 	}
 
 	LightTreeBuilder builder;

@@ -32,6 +32,9 @@ def _library():
     lib.echo_host_build_qbvh.restype = ctypes.c_int32
     lib.echo_host_build_qbvh_instanced.argtypes = [p, u32, p, u32, p, u32, ctypes.c_int32, ctypes.POINTER(p), ctypes.POINTER(u32), ctypes.POINTER(u32)]
     lib.echo_host_build_qbvh_instanced.restype = ctypes.c_int32
+    lib.echo_host_build_light_tree_instanced.argtypes = [p, u32, p, u32, p, u32, p, u32, p, u32, ctypes.POINTER(p), ctypes.POINTER(u32),
+                                                         ctypes.POINTER(p), ctypes.POINTER(p), ctypes.POINTER(u32), ctypes.POINTER(ctypes.c_float)]
+    lib.echo_host_build_light_tree_instanced.restype = ctypes.c_int32
     lib.echo_host_build_light_tree.argtypes = [p, u32, p, u32, p, u32, p, u32, ctypes.POINTER(p), ctypes.POINTER(u32),
                                                ctypes.POINTER(p), ctypes.POINTER(p), ctypes.POINTER(u32), ctypes.POINTER(ctypes.c_float)]
     lib.echo_host_build_light_tree.restype = ctypes.c_int32
@@ -86,6 +89,7 @@ class PackDescription:
     spheres: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=structs.SPHERE))
     materials: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=structs.MATERIAL))
     instances: list = field(default_factory=list)
+    point_lights: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=structs.POINT_LIGHT))
 
 
 @dataclass
@@ -120,6 +124,11 @@ class PreparedArrays:
     all_triangles: np.ndarray = None
     all_spheres: np.ndarray = None
     all_materials: np.ndarray = None
+    all_point_lights: np.ndarray = None
+
+    @property
+    def point_lights(self):
+        return self.description.point_lights if self.all_point_lights is None else self.all_point_lights
 
     @property
     def triangles(self):
@@ -216,21 +225,28 @@ def instance_matrices(instance):
     inverse[:3, 3] = instance.position
     inverse = inverse.astype(np.float32)
     forward = np.linalg.inv(inverse.astype(np.float64)).astype(np.float32)
-    inverse_scale = np.float32(np.sqrt(np.sum(inverse[0, :3].astype(np.float64) ** 2)))
+    x, y, z = inverse[0, :3]
+    inverse_scale = np.sqrt((x * x + y * y) + (z * z + np.float32(0)), dtype=np.float32)  # GetRow(0).XYZ_.Magnitude, Float4.cs:51-61,73-81
     forward_scale = np.float32(1) / inverse_scale
     return forward[:3].reshape(-1), inverse[:3].reshape(-1), forward_scale, inverse_scale
 
 
-def build_light_tree(description):
-    """LightCollection.CreateBounds + LightTree constructor (LightCollection.cs:91-137, LightTree.cs:21-38)."""
+def build_light_tree(description, instance_lights=None):
+    """LightCollection.CreateBounds + LightTree constructor (LightCollection.cs:91-137, LightTree.cs:21-38).
+    instance_lights: [n, 12] float32 PreparedInstance.LightBound rows (box min, box max, cone axis, cosOffset, cosExtend, power)."""
     lib = _library()
     d = description
+    triangles = np.ascontiguousarray(d.triangles, dtype=structs.TRIANGLE)
+    spheres = np.ascontiguousarray(d.spheres, dtype=structs.SPHERE)
+    materials = np.ascontiguousarray(d.materials, dtype=structs.MATERIAL)
+    points = np.ascontiguousarray(d.point_lights, dtype=structs.POINT_LIGHT)
+    bounds = np.zeros((0, 12), dtype=np.float32) if instance_lights is None else np.ascontiguousarray(instance_lights, dtype=np.float32).reshape(-1, 12)
     nodes, tokens, paths = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
     node_count, emitter_count, power = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_float()
-    status = lib.echo_host_build_light_tree(_pointer(d.triangles), len(d.triangles), _pointer(d.spheres), len(d.spheres),
-                                            _pointer(d.materials), len(d.materials), _pointer(d.point_lights), len(d.point_lights),
-                                            ctypes.byref(nodes), ctypes.byref(node_count), ctypes.byref(tokens), ctypes.byref(paths),
-                                            ctypes.byref(emitter_count), ctypes.byref(power))
+    status = lib.echo_host_build_light_tree_instanced(_pointer(triangles), len(triangles), _pointer(spheres), len(spheres),
+                                                      _pointer(materials), len(materials), _pointer(points), len(points), _pointer(bounds), len(bounds),
+                                                      ctypes.byref(nodes), ctypes.byref(node_count), ctypes.byref(tokens), ctypes.byref(paths),
+                                                      ctypes.byref(emitter_count), ctypes.byref(power))
     if status != 0:
         raise ValueError(f"echo_host_build_light_tree failed with status {status}")
     return (_take(nodes, node_count.value, structs.LIGHT_NODE), _take(tokens, emitter_count.value, np.uint32),
@@ -249,15 +265,27 @@ def _prepare_packs(description, threads):
         if index in trail or len(trail) > structs.MAX_INSTANCE_LAYERS:
             raise ValueError("instancing is cyclic or deeper than TokenHierarchy.MaxLayer")
         source = sources[index]
-        boxes, records = [], []
+        boxes, records, lights = [], [], []
         for instance in source.instances:
             child = instance.pack + 1
-            child_nodes, _ = build(child, trail + (index,))
+            child_nodes, _, child_lights = build(child, trail + (index,))
             forward, inverse, forward_scale, inverse_scale = instance_matrices(instance)
             boxes.append(transformed_bound(fill_bounds(child_nodes), inverse))  # PreparedInstance.BoxBound
             records.append((forward, inverse, forward_scale, inverse_scale, child, instance))
+
+            # PreparedInstance.LightBound / Power (PreparedInstance.cs:31-40): the pack's light-tree root moved to parent space
+            light_nodes = child_lights[0]
+            if len(light_nodes):
+                root = light_nodes[0]
+                box = transformed_bound(np.concatenate([root["boxMin"], root["boxMax"]])[None, :], inverse)
+                axis = inverse.reshape(3, 4)[:, :3].astype(np.float64) @ root["coneAxis"].astype(np.float64)
+                axis = (axis / max(np.linalg.norm(axis), 1e-300)).astype(np.float32)  # ConeBound operator *, ConeBound.cs:68-72
+                power = np.float32(root["power"]) * inverse_scale * inverse_scale
+                lights.append(np.concatenate([box, axis, [root["cosOffset"], root["cosExtend"], power]]).astype(np.float32))
+            else:
+                lights.append(np.zeros(12, dtype=np.float32))
         nodes, depth = build_qbvh(source.triangles, source.spheres, threads, np.asarray(boxes, dtype=np.float32) if boxes else None)
-        built[index] = (nodes, depth)
+        built[index] = (nodes, depth, build_light_tree(source, np.asarray(lights, dtype=np.float32) if lights else None))
         source._records = records
         return built[index]
 
@@ -266,11 +294,13 @@ def _prepare_packs(description, threads):
     remap = {old: new for new, old in enumerate(used)}
     packs = np.zeros(len(used), dtype=structs.PACK)
     all_nodes, all_triangles, all_spheres, all_materials, all_instances = [], [], [], [], []
-    counts = dict(node=0, triangle=0, sphere=0, material=0, instance=0)
+    all_light_nodes, all_tokens, all_paths, all_points = [], [], [], []
+    counts = dict(node=0, triangle=0, sphere=0, material=0, instance=0, light=0, emitter=0, point=0)
     overrides = []
 
     for new, old in enumerate(used):
-        source, (nodes, depth) = sources[old], built[old]
+        source, (nodes, depth, (light_nodes, tokens, paths, _)) = sources[old], built[old]
+        points = np.ascontiguousarray(source.point_lights, dtype=structs.POINT_LIGHT)
         triangles = np.ascontiguousarray(source.triangles, dtype=structs.TRIANGLE)
         spheres = np.ascontiguousarray(source.spheres, dtype=structs.SPHERE)
         materials = np.ascontiguousarray(source.materials, dtype=structs.MATERIAL)
@@ -280,6 +310,13 @@ def _prepare_packs(description, threads):
         record["sphereOffset"], record["sphereCount"] = counts["sphere"], len(spheres)
         record["instanceOffset"], record["instanceCount"] = counts["instance"], len(source.instances)
         record["materialOffset"] = counts["material"]
+        record["lightNodeOffset"], record["lightNodeCount"] = counts["light"], len(light_nodes)
+        record["emitterOffset"], record["emitterCount"] = counts["emitter"], len(tokens)
+        record["pointLightOffset"], record["pointLightCount"] = counts["point"], len(points)
+        all_light_nodes.append(light_nodes), all_tokens.append(tokens), all_paths.append(paths), all_points.append(points)
+        counts["light"] += len(light_nodes)
+        counts["emitter"] += len(tokens)
+        counts["point"] += len(points)
         all_nodes.append(nodes), all_triangles.append(triangles), all_spheres.append(spheres), all_materials.append(materials)
         counts["node"] += len(nodes)
         counts["triangle"] += len(triangles)
@@ -312,8 +349,9 @@ def _prepare_packs(description, threads):
         view["base"][view["type"] == structs.MATERIAL_ONESIDED] += offset
         offset += len(block)
 
+    lights = (np.concatenate(all_light_nodes), np.concatenate(all_tokens), np.concatenate(all_paths), np.concatenate(all_points), float(built[0][2][3]))
     return (packs, instances, np.concatenate(all_nodes), np.concatenate(all_triangles), np.concatenate(all_spheres), materials,
-            max(int(p["maxDepth"]) for p in packs))
+            max(int(p["maxDepth"]) for p in packs), lights)
 
 
 def prepare(description, threads=0):
@@ -328,10 +366,11 @@ def prepare(description, threads=0):
 
     instanced = bool(d.instances)
     if instanced:
-        packs, instances, nodes, all_triangles, all_spheres, all_materials, max_depth = _prepare_packs(d, threads)
+        packs, instances, nodes, all_triangles, all_spheres, all_materials, max_depth, lights = _prepare_packs(d, threads)
+        light_nodes, tokens, paths, all_points, scene_power = lights
     else:
         nodes, max_depth = build_qbvh(d.triangles, d.spheres, threads)
-    light_nodes, tokens, paths, scene_power = build_light_tree(d)  # lights inside instanced packs: not sampled yet
+        light_nodes, tokens, paths, scene_power = build_light_tree(d)
 
     # FilterLights / SumInfiniteLightsPower / CalculateThreshold (PreparedScene.cs:279-325)
     infinite_power = np.float32(0)
@@ -359,4 +398,5 @@ def prepare(description, threads=0):
     if instanced:
         result.packs, result.instances = packs, instances
         result.all_triangles, result.all_spheres, result.all_materials = all_triangles, all_spheres, all_materials
+        result.all_point_lights = all_points
     return result

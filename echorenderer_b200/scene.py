@@ -41,7 +41,7 @@ class PreparedScene:
                 _native.check(lib.echo_b200_scene_set_packs(self._handle, ptr(prepared.packs), len(prepared.packs), ptr(prepared.instances), len(prepared.instances)))
             _native.check(lib.echo_b200_scene_set_light_tree(self._handle, ptr(prepared.light_nodes), len(prepared.light_nodes),
                                                              ptr(prepared.emitter_tokens), ptr(prepared.emitter_bitpaths), len(prepared.emitter_tokens),
-                                                             ptr(d.point_lights), len(d.point_lights)))
+                                                             ptr(prepared.point_lights), len(prepared.point_lights)))
             _native.check(lib.echo_b200_scene_set_infinite(self._handle, ptr(d.infinite_lights), len(d.infinite_lights),
                                                            prepared.infinite_threshold, prepared.infinite_pdf))
             _native.check(lib.echo_b200_scene_set_camera(self._handle, ptr(d.camera)))

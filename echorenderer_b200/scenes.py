@@ -411,16 +411,20 @@ def instanced_scene(grid=6, rings=24, segments=26, nested=True):
     carry two instance layers. Every third placement overrides the pack's swatch (PackInstance materials)."""
     from .host import InstanceDescription, PackDescription
     blob_materials = np.concatenate([material(structs.MATERIAL_DIFFUSE, (0.8, 0.3, 0.25)), material(structs.MATERIAL_CONDUCTOR, (1, 1, 1), roughness=(0.1, 0.1),
-                                    param_a=(0.9, 0.8, 0.5), param_b=(1.0, 0.9, 0.7), flags=structs.MATERIAL_FLAG_ARTISTIC)])
+                                    param_a=(0.9, 0.8, 0.5), param_b=(1.0, 0.9, 0.7), flags=structs.MATERIAL_FLAG_ARTISTIC),
+                                    material(structs.MATERIAL_EMISSIVE, (6.0, 4.0, 2.0))])
     blob_spheres = np.zeros(2, dtype=structs.SPHERE)
-    blob_spheres["position"], blob_spheres["radius"], blob_spheres["material"] = [(1.4, 0.3, 0.0), (-0.4, 1.5, 0.6)], [0.35, 0.25], [1, 1]
+    blob_spheres["position"], blob_spheres["radius"], blob_spheres["material"] = [(1.4, 0.3, 0.0), (-0.4, 1.5, 0.6)], [0.35, 0.25], [1, 2]  # the second one glows
     blob = PackDescription(triangles=blob_triangles((0, 0, 0), 1.0, 0, rings, segments, seed=5), spheres=blob_spheres, materials=blob_materials)
 
     cluster_materials = material(structs.MATERIAL_DIFFUSE, (0.3, 0.6, 0.8), roughness=(0.5, 0.5))
-    cluster = PackDescription(triangles=box(0, (1.2, 0.4, 1.2), (0, -0.9, 0)), materials=cluster_materials,
+    cluster_light = np.zeros(1, dtype=structs.POINT_LIGHT)
+    cluster_light["intensity"], cluster_light["position"] = (3.0, 3.0, 4.0), (0.0, 1.8, 0.0)
+    cluster = PackDescription(triangles=box(0, (1.2, 0.4, 1.2), (0, -0.9, 0)), materials=cluster_materials, point_lights=cluster_light,
                               instances=[InstanceDescription(0, (-1.3, 0.4, 0.0), (0, 30, 0), 0.5), InstanceDescription(0, (1.3, 0.4, 0.2), (20, 0, 45), 0.45),
                                          InstanceDescription(0, (0.0, 0.6, 1.4), (0, 200, 10), 0.4)])
-    override = np.concatenate([material(structs.MATERIAL_DIELECTRIC, (1, 1, 1), roughness=(0.05, 0.05), ior=1.5), material(structs.MATERIAL_DIFFUSE, (0.2, 0.8, 0.3))])
+    override = np.concatenate([material(structs.MATERIAL_DIELECTRIC, (1, 1, 1), roughness=(0.05, 0.05), ior=1.5), material(structs.MATERIAL_DIFFUSE, (0.2, 0.8, 0.3)),
+                               material(structs.MATERIAL_EMISSIVE, (6.0, 4.0, 2.0))])
 
     instances = []
     k = 0

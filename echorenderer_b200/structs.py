@@ -64,7 +64,8 @@ HIT = np.dtype([("token", "<u4"), ("distance", "<f4"), ("uv", "<f4", 2)])
 MAX_INSTANCE_LAYERS = 5  # TokenHierarchy.MaxLayer
 PACK = np.dtype([("nodeOffset", "<u4"), ("nodeCount", "<u4"), ("maxDepth", "<u4"), ("triangleOffset", "<u4"), ("triangleCount", "<u4"),
                  ("sphereOffset", "<u4"), ("sphereCount", "<u4"), ("instanceOffset", "<u4"), ("instanceCount", "<u4"), ("materialOffset", "<u4"),
-                 ("reserved", "<u4", 6)])
+                 ("lightNodeOffset", "<u4"), ("lightNodeCount", "<u4"), ("emitterOffset", "<u4"), ("emitterCount", "<u4"),
+                 ("pointLightOffset", "<u4"), ("pointLightCount", "<u4")])
 INSTANCE = np.dtype([("forward", "<f4", 12), ("inverse", "<f4", 12), ("forwardScale", "<f4"), ("inverseScale", "<f4"), ("pack", "<u4"),
                      ("materialOffset", "<u4"), ("reserved", "<u4", 4)])
 TOKEN_HIERARCHY = np.dtype([("instanceCount", "<u4"), ("instances", "<u4", MAX_INSTANCE_LAYERS)])

@@ -170,7 +170,12 @@ typedef struct EchoPack
 	uint32_t sphereOffset, sphereCount;
 	uint32_t instanceOffset, instanceCount; /* into the instance array: GeometryCollection.instances of this pack */
 	uint32_t materialOffset;                /* the pack's own swatch (LightCollection reads it, LightCollection.cs:145,151) */
-	uint32_t reserved[6];
+	/* the pack's LightTree / LightCollection (PreparedPack.cs:21-23): ranges of the arrays handed to set_light_tree, child
+	 * indices and emitter tokens pack-relative; a placement with light inside appears as a TokenType.Instance leaf of its
+	 * parent's light tree (LightCollection.cs:123-135) */
+	uint32_t lightNodeOffset, lightNodeCount;
+	uint32_t emitterOffset, emitterCount;
+	uint32_t pointLightOffset, pointLightCount;
 } EchoPack; /* 64 bytes */
 
 typedef struct EchoInstance

@@ -45,6 +45,18 @@ int32_t echo_host_build_light_tree(const EchoTriangle* triangles, uint32_t trian
                                    uint32_t** out_emitter_tokens, uint64_t** out_emitter_bitpaths, uint32_t* out_emitter_count,
                                    float* out_power);
 
+/* The same with the light bounds of the pack's instances appended (PreparedInstance.LightBound, PreparedInstance.cs:31-38;
+ * LightCollection.AddInstances, LightCollection.cs:123-135). instance_lights holds 12 floats per instance: box min xyz,
+ * box max xyz, cone axis xyz, cosOffset, cosExtend, power (parent space); instances without power are skipped. */
+int32_t echo_host_build_light_tree_instanced(const EchoTriangle* triangles, uint32_t triangle_count,
+                                             const EchoSphere* spheres, uint32_t sphere_count,
+                                             const EchoMaterial* materials, uint32_t material_count,
+                                             const EchoPointLight* points, uint32_t point_count,
+                                             const float* instance_lights, uint32_t instance_count,
+                                             EchoLightNode** out_nodes, uint32_t* out_node_count,
+                                             uint32_t** out_emitter_tokens, uint64_t** out_emitter_bitpaths, uint32_t* out_emitter_count,
+                                             float* out_power);
+
 /* PreparedScene.CalculateThreshold (PreparedScene.cs:317-325) and the ambient-light power of AmbientLight.Prepare
  * (AmbientLight.cs:42-51) with the scene radius taken as the half diagonal of the root bound. */
 float echo_host_infinite_threshold(float infinite_power, float scene_power);

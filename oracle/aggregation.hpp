@@ -299,7 +299,9 @@ struct Scene
 	std::vector<EchoMaterial> materials;
 
 	std::vector<EchoLightNode> lightNodes;
-	std::unordered_map<uint32_t, uint64_t> lightMap; // LightTree.map, LightTree.cs:41
+	std::vector<uint32_t> emitterTokens; // LightTree.map of every pack, back to back (EchoPack.emitterOffset / emitterCount)
+	std::vector<uint64_t> emitterPaths;
+	std::vector<std::unordered_map<uint32_t, uint64_t>> lightMaps; // LightTree.map per pack, LightTree.cs:41
 	std::vector<EchoPointLight> pointLights;
 
 	std::vector<EchoInfiniteLight> infiniteLights;
@@ -320,7 +322,69 @@ struct Scene
 		view.maxDepth = maxDepth;
 		view.triangleCount = (uint32_t)triangles.size();
 		view.sphereCount = (uint32_t)spheres.size();
+		view.lightNodeCount = (uint32_t)lightNodes.size();
+		view.emitterCount = (uint32_t)emitterTokens.size();
+		view.pointLightCount = (uint32_t)pointLights.size();
 		return view;
+	}
+
+	void rebuild_light_maps()
+	{
+		size_t count = packs.empty() ? 1 : packs.size();
+		lightMaps.assign(count, {});
+
+		for (size_t p = 0; p < count; p++)
+		{
+			EchoPack view = pack_view((uint32_t)p);
+			for (uint32_t i = 0; i < view.emitterCount && view.emitterOffset + i < emitterTokens.size(); i++)
+				lightMaps[p][emitterTokens[view.emitterOffset + i]] = emitterPaths[view.emitterOffset + i];
+		}
+	}
+
+	// ---- PreparedScene.FindLayer (PreparedScene.cs:255-277): walks the instance layers; forward / inverse are rows 0..2 of the
+	// composed Float4x4s (the bottom row stays 0 0 0 1). Both products put the new instance on the LEFT, as the reference
+	// does (:272-273) — for the inverse transform of nested placements that is not the geometric order, and it is kept.
+	struct Layer
+	{
+		float forward[12], inverse[12];
+		uint32_t pack;           // the pack the hierarchy ends in
+		uint32_t materialOffset; // its placement's swatch (PreparedInstance.swatch); the scene's own for no layers
+	};
+
+	static void multiply_rows(const float* a, const float* b, float* out) // Float4x4 operator *, Float4x4.cs:352-358, affine operands
+	{
+		float result[12];
+
+		for (int i = 0; i < 3; i++)
+		{
+			for (int j = 0; j < 4; j++)
+			{
+				float bottom = j == 3 ? 1.0f : 0.0f; // second.f3j
+				result[i * 4 + j] = a[i * 4 + 0] * b[0 * 4 + j] + a[i * 4 + 1] * b[1 * 4 + j] + a[i * 4 + 2] * b[2 * 4 + j] + a[i * 4 + 3] * bottom;
+			}
+		}
+
+		for (int k = 0; k < 12; k++) out[k] = result[k];
+	}
+
+	Layer find_layer(const Layers& layers) const
+	{
+		static const float identity[12] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0 };
+		Layer layer;
+		for (int k = 0; k < 12; k++) layer.forward[k] = layer.inverse[k] = identity[k];
+		layer.pack = 0;
+		layer.materialOffset = pack_view(0).materialOffset;
+
+		for (uint32_t k = 0; k < layers.count; k++)
+		{
+			const EchoInstance& instance = instances[pack_view(layer.pack).instanceOffset + token_index(layers.instances[k])];
+			multiply_rows(instance.forward, layer.forward, layer.forward);
+			multiply_rows(instance.inverse, layer.inverse, layer.inverse);
+			layer.pack = instance.pack;
+			layer.materialOffset = instance.materialOffset;
+		}
+
+		return layer;
 	}
 
 	// ---- Aggregation/Preparation/PreparedInstance.cs:105-111 ----
@@ -653,9 +717,11 @@ struct Scene
 		return false;
 	}
 
-	uint32_t geometry_material(uint32_t token) const // GeometryCollection.cs:236-246
+	uint32_t geometry_material(uint32_t token, uint32_t pack = 0) const // GeometryCollection.cs:236-246, index inside the swatch
 	{
-		return token_type(token) == ECHO_TOKEN_TYPE_TRIANGLE ? triangles[token_index(token)].material : spheres[token_index(token)].material;
+		EchoPack view = pack_view(pack);
+		return token_type(token) == ECHO_TOKEN_TYPE_TRIANGLE ? triangles[view.triangleOffset + token_index(token)].material
+		                                                     : spheres[view.sphereOffset + token_index(token)].material;
 	}
 
 	// ---- Aggregation/Bounds/LightBound.cs:30-80 ----
@@ -710,10 +776,12 @@ struct Scene
 
 	// ---- Aggregation/Selection/LightTree.cs:115-134 (recursion unrolled into a loop; same arithmetic order) ----
 	// returns the picked token and its probability mass; mass == 0 means Probable.Impossible
-	uint32_t light_tree_pick(const GeometryPoint& origin, float& sample, float& outPdf) const
+	uint32_t light_tree_pick(const GeometryPoint& origin, float& sample, float& outPdf, uint32_t pack = 0) const
 	{
 		outPdf = 0.0f;
-		if (lightNodes.empty()) return ECHO_TOKEN_EMPTY;
+		EchoPack view = pack_view(pack);
+		if (view.lightNodeCount == 0) return ECHO_TOKEN_EMPTY;
+		const EchoLightNode* lightNodes = this->lightNodes.data() + view.lightNodeOffset;
 
 		uint32_t index = 0;
 		float pdf = 1.0f;
@@ -751,14 +819,15 @@ struct Scene
 	}
 
 	// ---- LightTree.cs:53-57,136-154: split0 * (split1 * (... * 1)) — the recursion multiplies from the leaf upward ----
-	float light_tree_mass(uint32_t token, const GeometryPoint& origin) const
+	float light_tree_mass(uint32_t token, const GeometryPoint& origin, uint32_t pack = 0) const
 	{
-		auto found = lightMap.find(token);
-		if (found == lightMap.end()) return 0.0f;
-		return light_tree_mass_recursive(origin, 0, found->second);
+		if (pack >= lightMaps.size()) return 0.0f;
+		auto found = lightMaps[pack].find(token);
+		if (found == lightMaps[pack].end()) return 0.0f;
+		return light_tree_mass_recursive(origin, 0, found->second, this->lightNodes.data() + pack_view(pack).lightNodeOffset);
 	}
 
-	float light_tree_mass_recursive(const GeometryPoint& origin, uint32_t index, uint64_t branches) const
+	float light_tree_mass_recursive(const GeometryPoint& origin, uint32_t index, uint64_t branches, const EchoLightNode* lightNodes) const
 	{
 		const EchoLightNode& node = lightNodes[index];
 		if (node.child0 == ECHO_TOKEN_EMPTY) return 1.0f;
@@ -767,13 +836,16 @@ struct Scene
 		float importance1 = light_importance(lightNodes[node.child1], origin);
 		float split = importance0 / (importance0 + importance1);
 
-		if ((branches & 1) == 0) return split * light_tree_mass_recursive(origin, node.child0, branches >> 1);
-		return (1.0f - split) * light_tree_mass_recursive(origin, node.child1, branches >> 1);
+		if ((branches & 1) == 0) return split * light_tree_mass_recursive(origin, node.child0, branches >> 1, lightNodes);
+		return (1.0f - split) * light_tree_mass_recursive(origin, node.child1, branches >> 1, lightNodes);
 	}
 
 	// ---- PreparedScene.cs:113-150 ----
-	uint32_t pick(const GeometryPoint& origin, float sample, float& outPdf) const
+	uint32_t pick(const GeometryPoint& origin, float sample, float& outPdf, Layers* outLayers = nullptr) const
 	{
+		Layers layers;
+		if (outLayers) *outLayers = layers;
+
 		if (sample < infiniteLightsThreshold)
 		{
 			sample = sample_stretch(sample, 0.0f, infiniteLightsThreshold);
@@ -784,26 +856,49 @@ struct Scene
 
 		sample = sample_stretch(sample, infiniteLightsThreshold, 1.0f);
 		float pdf = 1.0f - infiniteLightsThreshold;
+		uint32_t pack = 0;
 
-		float tokenPdf;
-		uint32_t token = light_tree_pick(origin, sample, tokenPdf);
-
-		if (almost_zero(tokenPdf))
+		while (true) // :132-147: the same `origin` serves every layer (it is not moved into the placement's space)
 		{
-			outPdf = 0.0f;
-			return ECHO_TOKEN_EMPTY;
-		}
+			float tokenPdf;
+			uint32_t token = light_tree_pick(origin, sample, tokenPdf, pack);
 
-		outPdf = pdf * tokenPdf;
-		return token;
+			if (almost_zero(tokenPdf))
+			{
+				outPdf = 0.0f;
+				return ECHO_TOKEN_EMPTY;
+			}
+
+			pdf *= tokenPdf;
+
+			if (token_type(token) != ECHO_TOKEN_TYPE_INSTANCE || layers.count >= ECHO_MAX_INSTANCE_LAYERS)
+			{
+				outPdf = pdf;
+				if (outLayers) *outLayers = layers;
+				return token;
+			}
+
+			const EchoInstance& instance = instances[pack_view(pack).instanceOffset + token_index(token)];
+			layers.push(token);
+			pack = instance.pack;
+		}
 	}
 
 	// ---- PreparedScene.cs:158-179 ----
-	float probability_mass(uint32_t light, const GeometryPoint& origin) const
+	float probability_mass(uint32_t light, const GeometryPoint& origin, const Layers& layers = Layers()) const
 	{
 		if (token_is_infinite_light(light)) return infiniteLightsPdf;
 		float pdf = 1.0f - infiniteLightsThreshold;
-		return pdf * light_tree_mass(light, origin);
+		uint32_t pack = 0;
+
+		for (uint32_t k = 0; k < layers.count; k++)
+		{
+			pdf *= light_tree_mass(layers.instances[k], origin, pack);
+			pack = instances[pack_view(pack).instanceOffset + token_index(layers.instances[k])].pack;
+			if (almost_zero(pdf)) return 0.0f;
+		}
+
+		return pdf * light_tree_mass(light, origin, pack);
 	}
 };
 

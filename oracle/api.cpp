@@ -71,9 +71,10 @@ void oracle_scene_set_light_tree(OracleScene* s, const EchoLightNode* nodes, uin
                                  const EchoPointLight* points, uint32_t pointCount)
 {
 	s->scene.lightNodes.assign(nodes, nodes + nodeCount);
-	s->scene.lightMap.clear();
-	for (uint32_t i = 0; i < emitterCount; i++) s->scene.lightMap[tokens[i]] = bitpaths[i];
+	s->scene.emitterTokens.assign(tokens, tokens + emitterCount);
+	s->scene.emitterPaths.assign(bitpaths, bitpaths + emitterCount);
 	s->scene.pointLights.assign(points, points + pointCount);
+	s->scene.rebuild_light_maps();
 }
 
 void oracle_scene_set_infinite(OracleScene* s, const EchoInfiniteLight* lights, uint32_t count, float threshold, float pdf)
@@ -155,6 +156,7 @@ void oracle_scene_set_packs(OracleScene* s, const EchoPack* packs, uint32_t pack
 {
 	s->scene.packs.assign(packs, packs + packCount);
 	s->scene.instances.assign(instances, instances + instanceCount);
+	s->scene.rebuild_light_maps();
 }
 
 static Layers make_layers(const EchoTokenHierarchy* in)

@@ -23,36 +23,42 @@ inline void interact(const Scene& scene, const TraceQuery& query, Contact& conta
 	Float3 infoNormal, infoShading;
 	uint32_t material;
 
+	Scene::Layer layer = scene.find_layer(query.tokenLayers); // FindLayer, :97
+	EchoPack view = scene.pack_view(layer.pack);
+
 	if (token_type(query.token) == ECHO_TOKEN_TYPE_TRIANGLE)
 	{
-		const EchoTriangle& triangle = scene.triangles[token_index(query.token)];
+		const EchoTriangle& triangle = scene.triangles[view.triangleOffset + token_index(query.token)];
 		material = triangle.material;
 		infoNormal = triangle_normal(triangle);
 		infoShading = triangle_shading_normal(triangle, query.uv);
 	}
 	else
 	{
-		material = scene.spheres[token_index(query.token)].material;
+		material = scene.spheres[view.sphereOffset + token_index(query.token)].material;
 		infoNormal = infoShading = sphere_normal(query.uv);
 	}
 
-	// root instance: inverseTransform is the identity, but MultiplyDirection + Normalized still run (:100-101)
+	// without layers inverseTransform is the identity, but MultiplyDirection + Normalized still run (:100-101)
 	contact.token = query.token;
+	contact.layers = query.tokenLayers;
 	contact.outgoing = -query.ray.direction;                                    // Contact.cs:39
 	contact.point.position = query.position();                                  // Contact.cs:25
-	contact.point.normal = normalized(identity_multiply_direction(infoNormal));
-	contact.shadeNormal = normalized(identity_multiply_direction(infoShading)); // constant Pure.normal: no normal mapping (Material.cs:61,84-86)
-	contact.material = material;
+	contact.point.normal = normalized(multiply_direction(layer.inverse, infoNormal));
+	contact.shadeNormal = normalized(multiply_direction(layer.inverse, infoShading)); // constant Pure.normal: no normal mapping (Material.cs:61,84-86)
+	contact.material = layer.materialOffset + material;                        // instance.swatch[info.material], :102
 
-	scatter_material(scene, material, contact);
+	scatter_material(scene, contact.material, contact);
 }
 
 // ---- PreparedTriangle.Sample (TriangleEntity.cs:166-174) / PreparedSphere.Sample (SphereEntity.cs:151-191) ----
-inline bool geometry_sample(const Scene& scene, uint32_t token, Float3 origin, Float2 sample, GeometryPoint& point, float& pdf)
+inline bool geometry_sample(const Scene& scene, uint32_t token, Float3 origin, Float2 sample, GeometryPoint& point, float& pdf, uint32_t pack = 0)
 {
+	EchoPack view = scene.pack_view(pack);
+
 	if (token_type(token) == ECHO_TOKEN_TYPE_TRIANGLE)
 	{
-		const EchoTriangle& triangle = scene.triangles[token_index(token)];
+		const EchoTriangle& triangle = scene.triangles[view.triangleOffset + token_index(token)];
 		Float2 uv = uniform_triangle(sample);
 		point.position = triangle_point(triangle, uv);
 		point.normal = triangle_shading_normal(triangle, uv);
@@ -60,7 +66,7 @@ inline bool geometry_sample(const Scene& scene, uint32_t token, Float3 origin, F
 		return true;
 	}
 
-	const EchoSphere& sphere = scene.spheres[token_index(token)];
+	const EchoSphere& sphere = scene.spheres[view.sphereOffset + token_index(token)];
 	Float3 position = f3(sphere.position);
 	float radius = sphere.radius;
 
@@ -106,18 +112,20 @@ inline bool geometry_sample(const Scene& scene, uint32_t token, Float3 origin, F
 }
 
 // ---- PreparedTriangle.ProbabilityDensity (TriangleEntity.cs:177-185) / PreparedSphere.ProbabilityDensity (SphereEntity.cs:194-225) ----
-inline float geometry_pdf(const Scene& scene, uint32_t token, Float3 origin, Float3 incident)
+inline float geometry_pdf(const Scene& scene, uint32_t token, Float3 origin, Float3 incident, uint32_t pack = 0)
 {
+	EchoPack view = scene.pack_view(pack);
+
 	if (token_type(token) == ECHO_TOKEN_TYPE_TRIANGLE)
 	{
-		const EchoTriangle& triangle = scene.triangles[token_index(token)];
+		const EchoTriangle& triangle = scene.triangles[view.triangleOffset + token_index(token)];
 		Float2 uv = { 0.0f, 0.0f };
 		float distance = triangle_intersect(triangle, origin, incident, uv);
 		if (distance == kInfinity) return 0.0f;
 		return distance * distance / fabs_bits(dot(triangle_shading_normal(triangle, uv), incident) * triangle_area(triangle));
 	}
 
-	const EchoSphere& sphere = scene.spheres[token_index(token)];
+	const EchoSphere& sphere = scene.spheres[view.sphereOffset + token_index(token)];
 	float radius = sphere.radius;
 	Float3 offset = origin - f3(sphere.position);
 	float radius2 = radius * radius;
@@ -144,7 +152,7 @@ inline float geometry_pdf(const Scene& scene, uint32_t token, Float3 origin, Flo
 
 // ---- PreparedScene.Sample (PreparedScene.cs:182-204) -> LightCollection.Sample (LightCollection.cs:141-193),
 //      PreparedPointLight.Sample (Scenic/Lights/PointLight.cs:48-66), AmbientLight.Sample over a Pure texture ----
-inline ProbableRGB scene_sample_light(const Scene& scene, uint32_t light, const GeometryPoint& origin, Float2 sample, Float3& incident, float& travel)
+inline ProbableRGB scene_sample_light(const Scene& scene, uint32_t light, const Layers& layers, const GeometryPoint& origin, Float2 sample, Float3& incident, float& travel)
 {
 	incident = { 0.0f, 0.0f, 0.0f };
 	travel = 0.0f;
@@ -159,10 +167,17 @@ inline ProbableRGB scene_sample_light(const Scene& scene, uint32_t light, const 
 		return { RGB{ infinite.radiance[0], infinite.radiance[1], infinite.radiance[2] }, kUniformSpherePdf };
 	}
 
-	if (token_type(light) == ECHO_TOKEN_TYPE_LIGHT) // point light
+	// FindLayer + `forwardTransform * origin` (PreparedScene.cs:192-198, GeometryPoint.cs:41-45): the shading point in the
+	// space of the pack that owns the light
+	Scene::Layer layer = scene.find_layer(layers);
+	EchoPack view = scene.pack_view(layer.pack);
+	GeometryPoint local = { multiply_point(layer.forward, origin.position), normalized(multiply_direction(layer.forward, origin.normal)) };
+	ProbableRGB result = {};
+
+	if (token_type(light) == ECHO_TOKEN_TYPE_LIGHT) // point light, PointLight.cs:48-66
 	{
-		const EchoPointLight& point = scene.pointLights[token_light_index(light)];
-		Float3 offset = f3(point.position) - origin.position;
+		const EchoPointLight& point = scene.pointLights[view.pointLightOffset + token_light_index(light)];
+		Float3 offset = f3(point.position) - local.position;
 		float travel2 = squared_magnitude(offset);
 
 		if (!positive(travel2)) return {};
@@ -172,39 +187,50 @@ inline ProbableRGB scene_sample_light(const Scene& scene, uint32_t light, const 
 		incident = offset * travelR;
 
 		RGB intensity = { point.intensity[0], point.intensity[1], point.intensity[2] };
-		return { intensity * travelR * travelR, 1.0f };
+		result = { intensity * travelR * travelR, 1.0f };
+	}
+	else
+	{
+		// emissive geometry: LightCollection.HandleGeometry, LightCollection.cs:166-183; the material comes from the PACK's
+		// swatch (geometries.swatch, :145,151), not from the placement's
+		uint32_t materialIndex = view.materialOffset + scene.geometry_material(light, layer.pack);
+		const EchoMaterial& material = scene.materials[materialIndex];
+		if (material.type != ECHO_MATERIAL_EMISSIVE) return {};
+
+		GeometryPoint point;
+		float pdf;
+		if (!geometry_sample(scene, light, local.position, sample, point, pdf, layer.pack)) return {};
+		if (!positive(pdf)) return {};
+
+		Float3 delta = point.position - local.position;
+		float travel2 = squared_magnitude(delta);
+		if (!positive(travel2)) return {};
+
+		travel = sqrt0(travel2);
+		incident = delta * (1.0f / travel);
+
+		travel *= 1.0f - 2E-5f; // TravelMultiplier, LightCollection.cs:89
+		result = { emissive_emit(material, point, -incident), pdf };
 	}
 
-	// emissive geometry: LightCollection.HandleGeometry, LightCollection.cs:166-183
-	uint32_t materialIndex = scene.geometry_material(light);
-	const EchoMaterial& material = scene.materials[materialIndex];
-	if (material.type != ECHO_MATERIAL_EMISSIVE) return {};
-
-	GeometryPoint point;
-	float pdf;
-	if (!geometry_sample(scene, light, origin.position, sample, point, pdf)) return {};
-	if (!positive(pdf)) return {};
-
-	Float3 delta = point.position - origin.position;
-	float travel2 = squared_magnitude(delta);
-	if (!positive(travel2)) return {};
-
-	travel = sqrt0(travel2);
-	incident = delta * (1.0f / travel);
-
-	travel *= 1.0f - 2E-5f; // TravelMultiplier, LightCollection.cs:89
-	return { emissive_emit(material, point, -incident), pdf };
+	// back to world space, PreparedScene.cs:200-201
+	incident = normalized(multiply_direction(layer.inverse, incident));
+	travel *= get_scale(layer.inverse); // Utility.GetScale, Utility.cs:82
+	return result;
 }
 
 // ---- PreparedScene.ProbabilityDensity (PreparedScene.cs:207-225) -> LightCollection.ProbabilityDensity (:196-219) ----
-inline float scene_light_pdf(const Scene& scene, uint32_t light, const GeometryPoint& origin, Float3 incident)
+inline float scene_light_pdf(const Scene& scene, uint32_t light, const Layers& layers, const GeometryPoint& origin, Float3 incident)
 {
 	if (token_is_infinite_light(light)) return kUniformSpherePdf;
+
+	Scene::Layer layer = scene.find_layer(layers);
 	if (token_type(light) == ECHO_TOKEN_TYPE_LIGHT) return 1.0f; // LightCollection.cs:206 (point)
 
-	// identity forwardTransform: MultiplyDirection(incident).Normalized still runs (:221-224)
-	Float3 direction = normalized(identity_multiply_direction(incident));
-	return geometry_pdf(scene, light, origin.position, direction);
+	// forwardTransform * origin, forwardTransform.MultiplyDirection(incident).Normalized (:219-223)
+	Float3 position = multiply_point(layer.forward, origin.position);
+	Float3 direction = normalized(multiply_direction(layer.forward, incident));
+	return geometry_pdf(scene, light, position, direction, layer.pack);
 }
 
 // ---- PreparedScene.EvaluateInfinite (PreparedScene.cs:233-253) ----
@@ -313,6 +339,7 @@ struct PathTracedEvaluator
 				TraceQuery spawned;
 				spawned.ray = Ray(query.position(), incident);
 				spawned.ignore = query.token;
+				spawned.ignoreLayers = query.tokenLayers;
 				query = spawned;
 			}
 
@@ -324,7 +351,8 @@ struct PathTracedEvaluator
 	RGB importance_sample_radiant(const Scene& scene, const Contact& contact, EvaluatorStats& stats, float lightSample, Float2 radiantSample, bool& mis) const
 	{
 		float lightPdf;
-		uint32_t light = scene.pick(contact.point, lightSample, lightPdf);
+		Layers lightLayers;
+		uint32_t light = scene.pick(contact.point, lightSample, lightPdf, &lightLayers);
 
 		if (!positive(lightPdf))
 		{
@@ -334,7 +362,7 @@ struct PathTracedEvaluator
 
 		Float3 incident;
 		float travel;
-		ProbableRGB radiantSampled = scene_sample_light(scene, light, contact.point, radiantSample, incident, travel);
+		ProbableRGB radiantSampled = scene_sample_light(scene, light, lightLayers, contact.point, radiantSample, incident, travel);
 		RGB radiant = radiantSampled.content;
 
 		float pdf = lightPdf * radiantSampled.pdf;
@@ -353,6 +381,7 @@ struct PathTracedEvaluator
 		query.ray = Ray(contact.point.position, incident);
 		query.travel = travel;
 		query.ignore = contact.token;
+		query.ignoreLayers = contact.layers;
 		++stats.occludeQueries;
 		if (scene.occlude(query)) return kBlack;
 
@@ -413,10 +442,10 @@ struct PathTracedEvaluator
 					if (path.advance(scene, stats))
 					{
 						uint32_t light = path.contact.token;
-						float pmf = scene.probability_mass(light, oldPoint);
+						float pmf = scene.probability_mass(light, oldPoint, path.contact.layers);
 						if (!positive(pmf)) continue;
 
-						float pdf = scene_light_pdf(scene, light, oldPoint, path.current_direction());
+						float pdf = scene_light_pdf(scene, light, path.contact.layers, oldPoint, path.current_direction());
 						if (!positive(pdf)) continue;
 
 						path.contribute_emissive(scene, power_heuristic(bounceScatterPdf, pmf * pdf));
@@ -428,7 +457,7 @@ struct PathTracedEvaluator
 					for (size_t i = 0; i < scene.infiniteLights.size(); i++)
 					{
 						uint32_t token = ECHO_LIGHT_TOKEN_MAKE(ECHO_LIGHT_TYPE_INFINITE, (uint32_t)i);
-						float pdf = scene.probability_mass(token, oldPoint) * scene_light_pdf(scene, token, oldPoint, direction);
+						float pdf = scene.probability_mass(token, oldPoint) * scene_light_pdf(scene, token, Layers(), oldPoint, direction);
 						if (!positive(pdf)) continue;
 
 						float weight = power_heuristic(bounceScatterPdf, pdf);

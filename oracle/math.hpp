@@ -208,6 +208,9 @@ inline Float3 multiply_direction(const float* m, Float3 d)
 	};
 }
 
+// Utility.GetScale (Utility.cs:82): Float4 Magnitude of row 0 with W = 0 — SqrtScalar of (x*x + y*y) + (z*z + 0) (Float4.cs:51-61,73-81)
+inline float get_scale(const float* m) { return std::sqrt((m[0] * m[0] + m[1] * m[1]) + (m[2] * m[2] + 0.0f)); }
+
 // Textures/Colors/RGB128.cs (a Float4 with W == 0)
 struct RGB
 {

@@ -701,6 +701,7 @@ struct BSDF
 struct Contact
 {
 	uint32_t token = ECHO_TOKEN_EMPTY;
+	Layers layers; // the instance layers of the hit's TokenHierarchy
 	Float3 outgoing = {};
 	GeometryPoint point = {};
 	Float3 shadeNormal = {};

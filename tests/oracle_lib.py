@@ -106,7 +106,7 @@ class OracleScene:
         if prepared.packs is not None:
             lib.oracle_scene_set_packs(self.handle, ptr(prepared.packs), len(prepared.packs), ptr(prepared.instances), len(prepared.instances))
         lib.oracle_scene_set_light_tree(self.handle, ptr(prepared.light_nodes), len(prepared.light_nodes), ptr(prepared.emitter_tokens),
-                                        ptr(prepared.emitter_bitpaths), len(prepared.emitter_tokens), ptr(d.point_lights), len(d.point_lights))
+                                        ptr(prepared.emitter_bitpaths), len(prepared.emitter_tokens), ptr(prepared.point_lights), len(prepared.point_lights))
         lib.oracle_scene_set_infinite(self.handle, ptr(d.infinite_lights), len(d.infinite_lights), prepared.infinite_threshold, prepared.infinite_pdf)
         lib.oracle_scene_set_camera(self.handle, ptr(d.camera))
 

@@ -31,31 +31,41 @@ def spawn_from_hits(rays, hits, layers, seed=41):
 
 
 def bake(prepared):
-    """Every placement flattened into world-space triangles and spheres (float64 composition of the instance matrices)."""
-    triangles, spheres = [], []
+    """Every placement flattened into world-space triangles, spheres and point lights (float64 composition of the instance
+    matrices), with each placement's swatch resolved to absolute material indices."""
+    triangles, spheres, points = [], [], []
 
-    def visit(pack_index, matrix, scale):
+    def visit(pack_index, matrix, scale, material_offset):
         pack = prepared.packs[pack_index]
         t = prepared.triangles[pack["triangleOffset"]:pack["triangleOffset"] + pack["triangleCount"]]
         if len(t):
             v0 = t["vertex0"].astype(np.float64)
             v1, v2 = v0 + t["edge1"], v0 + t["edge2"]
             world = [v @ matrix[:3, :3].T + matrix[:3, 3] for v in (v0, v1, v2)]
-            triangles.append(scenes.make_triangles(*world, 0))
+            normals = [t[k].astype(np.float64) @ matrix[:3, :3].T for k in ("normal0", "normal1", "normal2")]
+            triangles.append(scenes.make_triangles(*world, t["material"] + material_offset, *normals))
         s = prepared.spheres[pack["sphereOffset"]:pack["sphereOffset"] + pack["sphereCount"]].copy()
         if len(s):
             s["position"] = s["position"].astype(np.float64) @ matrix[:3, :3].T + matrix[:3, 3]
             s["radius"] = s["radius"] * scale
+            s["material"] += material_offset
             spheres.append(s)
+        p = prepared.point_lights[pack["pointLightOffset"]:pack["pointLightOffset"] + pack["pointLightCount"]].copy()
+        if len(p):
+            p["position"] = p["position"].astype(np.float64) @ matrix[:3, :3].T + matrix[:3, 3]
+            p["intensity"] = p["intensity"] * np.float32(scale * scale)  # same radiance at the same world distance
+            points.append(p)
         for k in range(pack["instanceCount"]):
             instance = prepared.instances[pack["instanceOffset"] + k]
             local = np.eye(4)
             local[:3] = instance["inverse"].reshape(3, 4)
-            visit(int(instance["pack"]), matrix @ local, scale * float(instance["inverseScale"]))
+            visit(int(instance["pack"]), matrix @ local, scale * float(instance["inverseScale"]), int(instance["materialOffset"]))
 
-    visit(0, np.eye(4), 1.0)
-    description = host.SceneDescription(triangles=np.concatenate(triangles), spheres=np.concatenate(spheres),
-                                        materials=scenes.material(structs.MATERIAL_DIFFUSE), camera=prepared.description.camera)
+    visit(0, np.eye(4), 1.0, 0)
+    d = prepared.description
+    description = host.SceneDescription(triangles=np.concatenate(triangles), spheres=np.concatenate(spheres), materials=prepared.materials,
+                                        point_lights=np.concatenate(points) if points else np.zeros(0, dtype=structs.POINT_LIGHT),
+                                        infinite_lights=d.infinite_lights, camera=d.camera)
     return host.prepare(description)
 
 
@@ -134,3 +144,39 @@ def test_ignore_needs_the_whole_hierarchy(instanced):
     assert self_hits.sum() > 10
     outside = ~inside
     assert np.array_equal(naive[outside], again[outside])
+
+
+def test_light_hierarchy(instanced):
+    """Lights inside placements are leaves of type Instance in their parent's light tree (LightCollection.cs:123-135); Pick
+    descends through them (PreparedScene.cs:132-147) and ProbabilityMass multiplies the masses layer by layer (:166-176)."""
+    prepared, _ = instanced
+    packs = prepared.packs
+    assert packs["lightNodeCount"].tolist() == [75, 1, 7]  # 1 emissive quad + 36 lit placements (+1 sphere per blob; 3 blobs + 1 point light per cluster)
+    root_tokens = prepared.emitter_tokens[:packs[0]["emitterCount"]]
+    kinds = structs.token_type(root_tokens)
+    assert np.count_nonzero(kinds == structs.TOKEN_TYPE_INSTANCE) == 36 and np.count_nonzero(kinds == structs.TOKEN_TYPE_TRIANGLE) == 2
+    cluster_tokens = prepared.emitter_tokens[packs[2]["emitterOffset"]:packs[2]["emitterOffset"] + packs[2]["emitterCount"]]
+    assert sorted(structs.token_type(cluster_tokens).tolist()) == [structs.TOKEN_TYPE_INSTANCE] * 3 + [structs.TOKEN_TYPE_LIGHT]
+
+
+def test_render_matches_baked_scene():
+    """The integrator through placements (Interact with FindLayer, lights picked through the hierarchy, occlusion with full
+    ignore hierarchies) converges to the image of the same scene with every placement baked into world space. One instance
+    layer only: with nested placements the reference composes the inverse transforms in the order of PreparedScene.cs:273,
+    which does not commute with rotations, and the restatement keeps that."""
+    prepared = host.prepare(scenes.instanced_scene(grid=4, rings=12, segments=14, nested=False))
+    baked = bake(prepared)
+    width, height = 96, 54
+    tiles = scenes.tile_grid(width, height, 16)
+    params = structs.render_params(width, height, 16, extend=96, seed=3, bounce_limit=6)
+    image, stats = oracle_lib.OracleScene(prepared).render_tiles(params, tiles, threads=4)
+    flat, flat_stats = oracle_lib.OracleScene(baked).render_tiles(params, tiles, threads=4)
+    assert not np.isnan(image).any() and int(stats["lightOcclusionPassed"][0]) > 0
+
+    a = scenes.assemble_tiles(image, tiles, width, height, 16)[..., :3]
+    b = scenes.assemble_tiles(flat, tiles, width, height, 16)[..., :3]
+    assert np.all(np.abs(a.mean(axis=(0, 1)) - b.mean(axis=(0, 1))) <= 0.03 * b.mean(axis=(0, 1)))
+    # block means: the two images show the same picture, not just the same average
+    blocks_a = a[:48, :96].reshape(6, 8, 12, 8, 3).mean(axis=(1, 3))
+    blocks_b = b[:48, :96].reshape(6, 8, 12, 8, 3).mean(axis=(1, 3))
+    assert np.mean(np.abs(blocks_a - blocks_b)) <= 0.06 * blocks_b.mean()
