@@ -275,18 +275,9 @@ int32_t echo_b200_scene_set_light_tree(EchoScene* scene, const EchoLightNode* no
 	if (!scene || (!nodes && nodeCount) || ((!tokens || !paths) && emitterCount) || (!points && pointCount)) return fail(ECHO_B200_ERR_INVALID, "null argument");
 	scene->lightNodes.assign(nodes, nodes + nodeCount);
 
-	// LightTree.map as a sorted array (binary-searched on the device)
-	std::vector<uint32_t> order(emitterCount);
-	std::iota(order.begin(), order.end(), 0u);
-	std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return tokens[a] < tokens[b]; });
-	scene->emitterTokens.resize(emitterCount);
-	scene->emitterPaths.resize(emitterCount);
-
-	for (uint32_t i = 0; i < emitterCount; i++)
-	{
-		scene->emitterTokens[i] = tokens[order[i]];
-		scene->emitterPaths[i] = paths[order[i]];
-	}
+	// LightTree.map: kept as given here; commit sorts each pack's range for the device's binary search
+	scene->emitterTokens.assign(tokens, tokens + emitterCount);
+	scene->emitterPaths.assign(paths, paths + emitterCount);
 
 	scene->pointLights.assign(points, points + pointCount);
 	scene->committed = false;
@@ -400,6 +391,35 @@ int32_t echo_b200_scene_commit(EchoScene* scene)
 	for (const EchoSphere& s : scene->spheres)
 		if (s.material >= scene->materials.size() && !scene->materials.empty()) return fail(ECHO_B200_ERR_INVALID, "sphere material index out of range");
 
+	// LightTree.map of every pack as a sorted array (binary-searched on the device)
+	std::vector<uint32_t> emitterTokens(scene->emitterTokens.size());
+	std::vector<uint64_t> emitterPaths(scene->emitterPaths.size());
+
+	if (scene->packs.empty())
+	{
+		packs[0].lightNodeCount = (uint32_t)scene->lightNodes.size();
+		packs[0].emitterCount = (uint32_t)scene->emitterTokens.size();
+		packs[0].pointLightCount = (uint32_t)scene->pointLights.size();
+	}
+
+	for (const EchoPack& pack : packs)
+	{
+		if ((uint64_t)pack.lightNodeOffset + pack.lightNodeCount > scene->lightNodes.size() || (uint64_t)pack.emitterOffset + pack.emitterCount > scene->emitterTokens.size()
+			|| (uint64_t)pack.pointLightOffset + pack.pointLightCount > scene->pointLights.size())
+			return fail(ECHO_B200_ERR_INVALID, "pack light range out of bounds");
+
+		std::vector<uint32_t> order(pack.emitterCount);
+		std::iota(order.begin(), order.end(), 0u);
+		const uint32_t* tokens = scene->emitterTokens.data() + pack.emitterOffset;
+		std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return tokens[a] < tokens[b]; });
+
+		for (uint32_t i = 0; i < pack.emitterCount; i++)
+		{
+			emitterTokens[pack.emitterOffset + i] = tokens[order[i]];
+			emitterPaths[pack.emitterOffset + i] = scene->emitterPaths[pack.emitterOffset + order[i]];
+		}
+	}
+
 	DeviceGuard guard(scene->device);
 	if (!guard.ok) return ECHO_B200_ERR_NO_DEVICE;
 	free_device(scene);
@@ -462,8 +482,8 @@ int32_t echo_b200_scene_commit(EchoScene* scene)
 
 	bool ok = upload(scene, scene->packs, devicePacks) && upload(scene, scene->instances, deviceInstances) && upload(scene, scene->nodes, nodes) && upload(scene, triHot, d.triHot) && upload(scene, triShade, d.triShade)
 		&& upload(scene, spheres, d.spheres) && upload(scene, sphereMaterial, d.sphereMaterial) && upload(scene, scene->materials, materials)
-		&& upload(scene, scene->lightNodes, lightNodes) && upload(scene, scene->emitterTokens, d.emitterTokens)
-		&& upload(scene, scene->emitterPaths, d.emitterPaths) && upload(scene, pointLights, d.pointLights) && upload(scene, infiniteLights, d.infiniteLights);
+		&& upload(scene, scene->lightNodes, lightNodes) && upload(scene, emitterTokens, d.emitterTokens)
+		&& upload(scene, emitterPaths, d.emitterPaths) && upload(scene, pointLights, d.pointLights) && upload(scene, infiniteLights, d.infiniteLights);
 
 	if (!ok)
 	{

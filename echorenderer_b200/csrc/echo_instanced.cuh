@@ -32,6 +32,138 @@ struct PackView
 	uint32_t nodeOffset, triangleOffset, sphereOffset, instanceOffset;
 };
 
+// EchoInstance, 128 bytes = 8 float4: forward rows 0..2, inverse rows 3..5, {forwardScale, inverseScale, pack, materialOffset}, reserved
+ECHO_DEVICE const float4* instance_data(const DeviceScene& scene, uint32_t instance) { return scene.instances + (size_t)instance * 8; }
+
+// everything shading needs to know about a pack (EchoPack): geometry offsets, its own swatch, its light tree ranges
+struct PackInfo
+{
+	uint32_t triangleOffset, sphereOffset, instanceOffset, materialOffset;
+	uint32_t lightNodeOffset, lightNodeCount, emitterOffset, emitterCount, pointLightOffset;
+};
+
+ECHO_DEVICE PackInfo whole_scene_pack(const DeviceScene& scene) // a scene without packs is one pack
+{
+	return { 0u, 0u, 0u, 0u, 0u, scene.lightNodeCount, 0u, scene.emitterCount, 0u };
+}
+
+ECHO_DEVICE PackInfo load_pack_info(const DeviceScene& scene, uint32_t pack)
+{
+	if (scene.packCount == 0u) return whole_scene_pack(scene);
+	const uint4* data = scene.packs + (size_t)pack * 4;
+	uint4 a = __ldg(data), b = __ldg(data + 1), c = __ldg(data + 2), d = __ldg(data + 3);
+	// a = nodeOffset nodeCount maxDepth triangleOffset | b = triangleCount sphereOffset sphereCount instanceOffset
+	// c = instanceCount materialOffset lightNodeOffset lightNodeCount | d = emitterOffset emitterCount pointLightOffset pointLightCount
+	return { a.w, b.y, b.w, c.y, c.z, c.w, d.x, d.y, d.z };
+}
+
+// rows 0..2 of an affine Float4x4 (the bottom row is 0 0 0 1)
+struct Transform
+{
+	float m[12];
+};
+
+ECHO_DEVICE Transform identity_transform() { return { { 1.0f, 0.0f, 0.0f, 0.0f, 0.0f, 1.0f, 0.0f, 0.0f, 0.0f, 0.0f, 1.0f, 0.0f } }; }
+
+ECHO_DEVICE vec3 transform_point(const Transform& t, vec3 p) // Float4x4.MultiplyPoint, Float4x4.cs:260-265
+{
+	const float* m = t.m;
+	return { m[0] * p.x + m[1] * p.y + m[2] * p.z + m[3], m[4] * p.x + m[5] * p.y + m[6] * p.z + m[7], m[8] * p.x + m[9] * p.y + m[10] * p.z + m[11] };
+}
+
+ECHO_DEVICE vec3 transform_direction(const Transform& t, vec3 d) // Float4x4.MultiplyDirection, Float4x4.cs:267-272
+{
+	const float* m = t.m;
+	return { m[0] * d.x + m[1] * d.y + m[2] * d.z, m[4] * d.x + m[5] * d.y + m[6] * d.z, m[8] * d.x + m[9] * d.y + m[10] * d.z };
+}
+
+// Utility.GetScale (Utility.cs:82): Float4 Magnitude of row 0 with W = 0 = SqrtScalar((x*x + y*y) + (z*z + 0)), Float4.cs:51-61,73-81
+ECHO_DEVICE float transform_scale(const Transform& t) { return __fsqrt_rn((t.m[0] * t.m[0] + t.m[1] * t.m[1]) + (t.m[2] * t.m[2] + 0.0f)); }
+
+// Float4x4 operator * (Float4x4.cs:352-358) of two affine matrices: `first` straight from an EchoInstance's rows
+ECHO_DEVICE Transform multiply_rows(const float4* first, const Transform& second)
+{
+	Transform result;
+
+#pragma unroll
+	for (int i = 0; i < 3; i++)
+	{
+		float4 a = __ldg(first + i);
+
+#pragma unroll
+		for (int j = 0; j < 4; j++)
+		{
+			float bottom = j == 3 ? 1.0f : 0.0f; // second.f3j
+			result.m[i * 4 + j] = a.x * second.m[j] + a.y * second.m[4 + j] + a.z * second.m[8 + j] + a.w * bottom;
+		}
+	}
+
+	return result;
+}
+
+// the instance layers of a TokenHierarchy as the wavefront stores them: 8 words {count, 5 tokens, 2 pad}
+struct PathLayers
+{
+	uint32_t count;
+	uint32_t tokens[ECHO_MAX_INSTANCE_LAYERS];
+};
+
+ECHO_DEVICE PathLayers no_layers() { return { 0u, { 0u, 0u, 0u, 0u, 0u } }; }
+
+ECHO_DEVICE PathLayers load_layers(const uint4* buffer, uint32_t slot)
+{
+	uint4 a = buffer[(size_t)slot * 2], b = buffer[(size_t)slot * 2 + 1];
+	return { a.x, { a.y, a.z, a.w, b.x, b.y } };
+}
+
+ECHO_DEVICE void store_layers(uint4* buffer, uint32_t slot, const PathLayers& layers)
+{
+	buffer[(size_t)slot * 2] = make_uint4(layers.count, layers.tokens[0], layers.tokens[1], layers.tokens[2]);
+	buffer[(size_t)slot * 2 + 1] = make_uint4(layers.tokens[3], layers.tokens[4], 0u, 0u);
+}
+
+// PreparedScene.FindLayer (PreparedScene.cs:255-277). Both products put the new placement on the LEFT, as the reference
+// does (:272-273): for the inverse transform of nested placements that is not the geometric order, and it is kept.
+struct Layer
+{
+	Transform forward, inverse;
+	uint32_t pack;           // the pack the hierarchy ends in
+	uint32_t materialOffset; // its placement's swatch (PreparedInstance.swatch); the scene's own without layers
+	PackInfo info;
+};
+
+template<bool INST>
+ECHO_DEVICE Layer find_layer(const DeviceScene& scene, const PathLayers& layers)
+{
+	Layer layer;
+	layer.forward = identity_transform();
+	layer.inverse = identity_transform();
+	layer.pack = 0u;
+	layer.materialOffset = 0u;
+
+	if (!INST)
+	{
+		layer.info = whole_scene_pack(scene);
+		return layer;
+	}
+
+	layer.info = load_pack_info(scene, 0u);
+	layer.materialOffset = layer.info.materialOffset;
+
+	for (uint32_t k = 0; k < layers.count; k++)
+	{
+		const float4* data = instance_data(scene, layer.info.instanceOffset + token_index(layers.tokens[k]));
+		layer.forward = multiply_rows(data, layer.forward);
+		layer.inverse = multiply_rows(data + 3, layer.inverse);
+		float4 tail = __ldg(data + 6);
+		layer.pack = __float_as_uint(tail.z);
+		layer.materialOffset = __float_as_uint(tail.w);
+		layer.info = load_pack_info(scene, layer.pack);
+	}
+
+	return layer;
+}
+
 ECHO_DEVICE PackView load_pack(const DeviceScene& scene, uint32_t pack)
 {
 	const uint4* data = scene.packs + (size_t)pack * 4; // EchoPack, 64 bytes
@@ -53,8 +185,6 @@ ECHO_DEVICE vec3 multiply_direction(const float4* rows, vec3 d) // Float4x4.Mult
 	return { r0.x * d.x + r0.y * d.y + r0.z * d.z, r1.x * d.x + r1.y * d.y + r1.z * d.z, r2.x * d.x + r2.y * d.y + r2.z * d.z };
 }
 
-// EchoInstance, 128 bytes = 8 float4: forward rows 0..2, inverse rows 3..5, {forwardScale, inverseScale, pack, materialOffset}, reserved
-ECHO_DEVICE const float4* instance_data(const DeviceScene& scene, uint32_t instance) { return scene.instances + (size_t)instance * 8; }
 
 // TokenHierarchy equality of the query's `ignore` and `current` instance layers (TokenHierarchy.cs:117-129)
 ECHO_DEVICE bool layers_match(const uint32_t* ignoreLayers, uint32_t ignoreCount, const uint32_t* current, uint32_t level)

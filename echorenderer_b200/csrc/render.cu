@@ -17,6 +17,7 @@
 
 #include "echo_internal.h"
 #include "echo_shading.cuh"
+#include "echo_instanced.cuh"
 #include "echo_traverse.cuh"
 
 namespace echo
@@ -48,6 +49,12 @@ struct PathBuffers
 	// shadow rays of the current bounce, compacted: {origin.xyz, direction.x | direction.yz, travel, ignore} + pending value
 	float4* shadowQueue;
 	float4* shadowValue;  // pending energy * radiant, w = path id bits
+
+	// instanced scenes only (null otherwise): the instance layers of each ray's ignore hierarchy, of each hit and of each
+	// shadow ray's ignore hierarchy, 8 words per slot (echo_instanced.cuh PathLayers)
+	uint4* rayLayers[2];
+	uint4* hitLayers;
+	uint4* shadowLayers;
 
 	uint32_t* classQueue[CLASS_COUNT]; // ray slots sorted by the material class of what they hit
 	uint32_t* counters;
@@ -214,9 +221,9 @@ struct LightNode
 	uint32_t child0, child1;
 };
 
-ECHO_DEVICE LightNode load_light_node(const DeviceScene& scene, uint32_t index)
+ECHO_DEVICE LightNode load_light_node(const DeviceScene& scene, const PackInfo& info, uint32_t index)
 {
-	const float4* p = scene.lightNodes + (size_t)index * 4;
+	const float4* p = scene.lightNodes + ((size_t)info.lightNodeOffset + index) * 4;
 	float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
 	LightNode n;
 	n.boxMin = { a.x, a.y, a.z };
@@ -279,12 +286,12 @@ ECHO_DEVICE float light_importance(const LightNode& bound, const SurfacePoint& o
 }
 
 // LightTree.Pick, LightTree.cs:115-134 (tail recursion as a loop). Returns the token; pdf == 0 means impossible.
-ECHO_DEVICE uint32_t light_tree_pick(const DeviceScene& scene, const SurfacePoint& origin, float sample, float& outPdf)
+ECHO_DEVICE uint32_t light_tree_pick(const DeviceScene& scene, const PackInfo& info, const SurfacePoint& origin, float& sample, float& outPdf)
 {
 	outPdf = 0.0f;
-	if (scene.lightNodeCount == 0u) return ECHO_TOKEN_EMPTY;
+	if (info.lightNodeCount == 0u) return ECHO_TOKEN_EMPTY;
 
-	LightNode node = load_light_node(scene, 0u);
+	LightNode node = load_light_node(scene, info, 0u);
 	float pdf = 1.0f;
 
 	while (true)
@@ -295,8 +302,8 @@ ECHO_DEVICE uint32_t light_tree_pick(const DeviceScene& scene, const SurfacePoin
 			return node.child1;
 		}
 
-		LightNode left = load_light_node(scene, node.child0);
-		LightNode right = load_light_node(scene, node.child1);
+		LightNode left = load_light_node(scene, info, node.child0);
+		LightNode right = load_light_node(scene, info, node.child1);
 		float importance0 = light_importance(left, origin);
 		float importance1 = light_importance(right, origin);
 
@@ -321,10 +328,10 @@ ECHO_DEVICE uint32_t light_tree_pick(const DeviceScene& scene, const SurfacePoin
 
 // LightTree.ProbabilityMass, LightTree.cs:53-57,136-154: the recursion multiplies split factors from the leaf upward,
 // so the factors of the root-to-leaf walk are kept and folded right to left.
-ECHO_DEVICE float light_tree_mass(const DeviceScene& scene, uint32_t token, const SurfacePoint& origin)
+ECHO_DEVICE float light_tree_mass(const DeviceScene& scene, const PackInfo& info, uint32_t token, const SurfacePoint& origin)
 {
-	// map.TryGetValue: binary search over the sorted emitter tokens
-	int low = 0, high = (int)scene.emitterCount - 1, found = -1;
+	// map.TryGetValue: binary search over the pack's sorted emitter tokens
+	int low = (int)info.emitterOffset, high = (int)(info.emitterOffset + info.emitterCount) - 1, found = -1;
 
 	while (low <= high)
 	{
@@ -340,12 +347,12 @@ ECHO_DEVICE float light_tree_mass(const DeviceScene& scene, uint32_t token, cons
 
 	float factors[64];
 	int depth = 0;
-	LightNode node = load_light_node(scene, 0u);
+	LightNode node = load_light_node(scene, info, 0u);
 
 	while (node.child0 != ECHO_TOKEN_EMPTY && depth < 64)
 	{
-		LightNode left = load_light_node(scene, node.child0);
-		LightNode right = load_light_node(scene, node.child1);
+		LightNode left = load_light_node(scene, info, node.child0);
+		LightNode right = load_light_node(scene, info, node.child1);
 		float importance0 = light_importance(left, origin);
 		float importance1 = light_importance(right, origin);
 		float split = div(importance0, importance0 + importance1);
@@ -369,9 +376,12 @@ ECHO_DEVICE float light_tree_mass(const DeviceScene& scene, uint32_t token, cons
 	return mass;
 }
 
-// PreparedScene.Pick, PreparedScene.cs:113-150
-ECHO_DEVICE uint32_t scene_pick(const DeviceScene& scene, const SurfacePoint& origin, float sample, float& outPdf)
+// PreparedScene.Pick, PreparedScene.cs:113-150; outLayers receives the instance layers of the picked light's hierarchy
+template<bool INST>
+ECHO_DEVICE uint32_t scene_pick(const DeviceScene& scene, const SurfacePoint& origin, float sample, float& outPdf, PathLayers& outLayers)
 {
+	outLayers = no_layers();
+
 	if (sample < scene.infiniteThreshold)
 	{
 		sample = sample_stretch(sample, 0.0f, scene.infiniteThreshold);
@@ -382,43 +392,71 @@ ECHO_DEVICE uint32_t scene_pick(const DeviceScene& scene, const SurfacePoint& or
 
 	sample = sample_stretch(sample, scene.infiniteThreshold, 1.0f);
 	float pdf = 1.0f - scene.infiniteThreshold;
+	PackInfo info = INST ? load_pack_info(scene, 0u) : whole_scene_pack(scene);
 
-	float tokenPdf;
-	uint32_t token = light_tree_pick(scene, origin, sample, tokenPdf);
-
-	if (almost_zero(tokenPdf))
+	while (true) // :132-147: the same `origin` serves every layer (it is not moved into the placement's space)
 	{
-		outPdf = 0.0f;
-		return ECHO_TOKEN_EMPTY;
-	}
+		float tokenPdf;
+		uint32_t token = light_tree_pick(scene, info, origin, sample, tokenPdf);
 
-	outPdf = pdf * tokenPdf;
-	return token;
+		if (almost_zero(tokenPdf))
+		{
+			outPdf = 0.0f;
+			return ECHO_TOKEN_EMPTY;
+		}
+
+		pdf *= tokenPdf;
+
+		if (!INST || token_type(token) != ECHO_TOKEN_TYPE_INSTANCE || outLayers.count >= ECHO_MAX_INSTANCE_LAYERS)
+		{
+			outPdf = pdf;
+			return token;
+		}
+
+		float4 tail = __ldg(instance_data(scene, info.instanceOffset + token_index(token)) + 6);
+		outLayers.tokens[outLayers.count++] = token;
+		info = load_pack_info(scene, __float_as_uint(tail.z));
+	}
 }
 
 // PreparedScene.ProbabilityMass, PreparedScene.cs:158-179
-ECHO_DEVICE float scene_probability_mass(const DeviceScene& scene, uint32_t light, const SurfacePoint& origin)
+template<bool INST>
+ECHO_DEVICE float scene_probability_mass(const DeviceScene& scene, uint32_t light, const PathLayers& layers, const SurfacePoint& origin)
 {
 	if (token_is_infinite_light(light)) return scene.infinitePdf;
 	float pdf = 1.0f - scene.infiniteThreshold;
-	return pdf * light_tree_mass(scene, light, origin);
+	PackInfo info = INST ? load_pack_info(scene, 0u) : whole_scene_pack(scene);
+
+	if (INST)
+	{
+		for (uint32_t k = 0; k < layers.count; k++)
+		{
+			pdf *= light_tree_mass(scene, info, layers.tokens[k], origin);
+			float4 tail = __ldg(instance_data(scene, info.instanceOffset + token_index(layers.tokens[k])) + 6);
+			info = load_pack_info(scene, __float_as_uint(tail.z));
+			if (almost_zero(pdf)) return 0.0f;
+		}
+	}
+
+	return pdf * light_tree_mass(scene, info, light, origin);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // light sampling (Aggregation/Preparation/LightCollection.cs, TriangleEntity.cs:166-185, SphereEntity.cs:151-225)
 // ---------------------------------------------------------------------------------------------------------------------
 
-ECHO_DEVICE uint32_t geometry_material(const DeviceScene& scene, uint32_t token)
+// index inside the swatch the geometry's pack (or placement) uses
+ECHO_DEVICE uint32_t geometry_material(const DeviceScene& scene, const PackInfo& info, uint32_t token)
 {
-	if (token_type(token) == ECHO_TOKEN_TYPE_TRIANGLE) return __float_as_uint(__ldg(scene.triShade + (size_t)token_index(token) * 3).w);
-	return __ldg(scene.sphereMaterial + token_index(token));
+	if (token_type(token) == ECHO_TOKEN_TYPE_TRIANGLE) return __float_as_uint(__ldg(scene.triShade + ((size_t)info.triangleOffset + token_index(token)) * 3).w);
+	return __ldg(scene.sphereMaterial + info.sphereOffset + token_index(token));
 }
 
-ECHO_DEVICE bool geometry_sample(const DeviceScene& scene, uint32_t token, vec3 origin, vec2 sample, SurfacePoint& point, float& pdf)
+ECHO_DEVICE bool geometry_sample(const DeviceScene& scene, const PackInfo& info, uint32_t token, vec3 origin, vec2 sample, SurfacePoint& point, float& pdf)
 {
 	if (token_type(token) == ECHO_TOKEN_TYPE_TRIANGLE)
 	{
-		TriangleData triangle = load_triangle(scene, token_index(token));
+		TriangleData triangle = load_triangle(scene, info.triangleOffset + token_index(token));
 		vec2 uv = uniform_triangle(sample);
 		point.position = triangle_point(triangle, uv);
 		point.normal = triangle_shading_normal(triangle, uv);
@@ -426,7 +464,7 @@ ECHO_DEVICE bool geometry_sample(const DeviceScene& scene, uint32_t token, vec3 
 		return true;
 	}
 
-	float4 sphere = __ldg(scene.spheres + token_index(token));
+	float4 sphere = __ldg(scene.spheres + info.sphereOffset + token_index(token));
 	vec3 position = { sphere.x, sphere.y, sphere.z };
 	float radius = sphere.w;
 
@@ -471,18 +509,18 @@ ECHO_DEVICE bool geometry_sample(const DeviceScene& scene, uint32_t token, vec3 
 	return true;
 }
 
-ECHO_DEVICE float geometry_pdf(const DeviceScene& scene, uint32_t token, vec3 origin, vec3 incident)
+ECHO_DEVICE float geometry_pdf(const DeviceScene& scene, const PackInfo& info, uint32_t token, vec3 origin, vec3 incident)
 {
 	if (token_type(token) == ECHO_TOKEN_TYPE_TRIANGLE)
 	{
-		TriangleData triangle = load_triangle(scene, token_index(token));
+		TriangleData triangle = load_triangle(scene, info.triangleOffset + token_index(token));
 		vec2 uv = { 0.0f, 0.0f };
 		float distance = triangle_intersect(triangle.vertex0, triangle.edge1, triangle.edge2, origin, incident, uv);
 		if (distance == kInfinity) return 0.0f;
 		return div(distance * distance, abs_bits(dot(triangle_shading_normal(triangle, uv), incident) * triangle_area(triangle)));
 	}
 
-	float4 sphere = __ldg(scene.spheres + token_index(token));
+	float4 sphere = __ldg(scene.spheres + info.sphereOffset + token_index(token));
 	float radius = sphere.w;
 	vec3 offset = origin - vec3{ sphere.x, sphere.y, sphere.z };
 	float radius2 = radius * radius;
@@ -508,7 +546,8 @@ ECHO_DEVICE float geometry_pdf(const DeviceScene& scene, uint32_t token, vec3 or
 }
 
 // PreparedScene.Sample, PreparedScene.cs:182-204 -> LightCollection.Sample (:141-193) / PointLight.cs:48-66 / AmbientLight.cs:60-67
-ECHO_DEVICE Sampled scene_sample_light(const DeviceScene& scene, uint32_t light, const SurfacePoint& origin, vec2 sample, vec3& incident, float& travel)
+template<bool INST>
+ECHO_DEVICE Sampled scene_sample_light(const DeviceScene& scene, uint32_t light, const PathLayers& layers, const SurfacePoint& origin, vec2 sample, vec3& incident, float& travel)
 {
 	incident = { 0.0f, 0.0f, 0.0f };
 	travel = 0.0f;
@@ -521,11 +560,17 @@ ECHO_DEVICE Sampled scene_sample_light(const DeviceScene& scene, uint32_t light,
 		return { as_rgb(infinite), kUniformSpherePdf };
 	}
 
+	// FindLayer + `forwardTransform * origin` (:192-198, GeometryPoint.cs:41-45): the shading point in the space of the pack
+	// that owns the light (without layers: the identity, still multiplied through)
+	Layer layer = find_layer<INST>(scene, layers);
+	vec3 position = transform_point(layer.forward, origin.position);
+	Sampled result;
+
 	if (token_type(light) == ECHO_TOKEN_TYPE_LIGHT)
 	{
-		const float4* p = scene.pointLights + (size_t)token_light_index(light) * 2;
-		float4 intensity = __ldg(p), position = __ldg(p + 1);
-		vec3 offset = xyz(position) - origin.position;
+		const float4* p = scene.pointLights + ((size_t)layer.info.pointLightOffset + token_light_index(light)) * 2;
+		float4 intensity = __ldg(p), lightPosition = __ldg(p + 1);
+		vec3 offset = xyz(lightPosition) - position;
 		float travel2 = squared_magnitude(offset);
 
 		if (!positive(travel2)) return impossible();
@@ -533,36 +578,48 @@ ECHO_DEVICE Sampled scene_sample_light(const DeviceScene& scene, uint32_t light,
 		travel = sqrt0(travel2);
 		float travelR = rcp(travel);
 		incident = offset * travelR;
-		return { as_rgb(intensity) * travelR * travelR, 1.0f };
+		result = { as_rgb(intensity) * travelR * travelR, 1.0f };
+	}
+	else
+	{
+		// the material comes from the PACK's swatch (geometries.swatch, LightCollection.cs:145,151), not from the placement's
+		MaterialRecord material = load_material(scene, layer.info.materialOffset + geometry_material(scene, layer.info, light));
+		if (material.type != ECHO_MATERIAL_EMISSIVE) return impossible();
+
+		SurfacePoint point;
+		float pdf;
+		if (!geometry_sample(scene, layer.info, light, position, sample, point, pdf)) return impossible();
+		if (!positive(pdf)) return impossible();
+
+		vec3 delta = point.position - position;
+		float travel2 = squared_magnitude(delta);
+		if (!positive(travel2)) return impossible();
+
+		travel = sqrt0(travel2);
+		incident = delta * rcp(travel);
+		travel *= 1.0f - 2E-5f; // TravelMultiplier, LightCollection.cs:89
+
+		rgb emitted = dot(-incident, point.normal) > 0.0f ? material_emission(material) : make_rgb(0.0f); // Emissive.Emit, Emissive.cs:64
+		result = { emitted, pdf };
 	}
 
-	MaterialRecord material = load_material(scene, geometry_material(scene, light));
-	if (material.type != ECHO_MATERIAL_EMISSIVE) return impossible();
-
-	SurfacePoint point;
-	float pdf;
-	if (!geometry_sample(scene, light, origin.position, sample, point, pdf)) return impossible();
-	if (!positive(pdf)) return impossible();
-
-	vec3 delta = point.position - origin.position;
-	float travel2 = squared_magnitude(delta);
-	if (!positive(travel2)) return impossible();
-
-	travel = sqrt0(travel2);
-	incident = delta * rcp(travel);
-	travel *= 1.0f - 2E-5f; // TravelMultiplier, LightCollection.cs:89
-
-	rgb emitted = dot(-incident, point.normal) > 0.0f ? material_emission(material) : make_rgb(0.0f); // Emissive.Emit, Emissive.cs:64
-	return { emitted, pdf };
+	// back to world space, :200-201
+	incident = normalized(transform_direction(layer.inverse, incident));
+	travel *= transform_scale(layer.inverse);
+	return result;
 }
 
 // PreparedScene.ProbabilityDensity, PreparedScene.cs:207-225
-ECHO_DEVICE float scene_light_pdf(const DeviceScene& scene, uint32_t light, const SurfacePoint& origin, vec3 incident)
+template<bool INST>
+ECHO_DEVICE float scene_light_pdf(const DeviceScene& scene, uint32_t light, const PathLayers& layers, const SurfacePoint& origin, vec3 incident)
 {
 	if (token_is_infinite_light(light)) return kUniformSpherePdf;
 	if (token_type(light) == ECHO_TOKEN_TYPE_LIGHT) return 1.0f;
-	vec3 direction = normalized(identity_multiply_direction(incident));
-	return geometry_pdf(scene, light, origin.position, direction);
+
+	Layer layer = find_layer<INST>(scene, layers);
+	vec3 position = transform_point(layer.forward, origin.position);
+	vec3 direction = normalized(transform_direction(layer.forward, incident));
+	return geometry_pdf(scene, layer.info, light, position, direction);
 }
 
 ECHO_DEVICE rgb evaluate_infinite(const DeviceScene& scene, bool direct) // PreparedScene.cs:233-253
@@ -648,6 +705,7 @@ __global__ void __launch_bounds__(kBlock) raygen_kernel(DeviceScene scene, EchoR
 	paths.rayQueue[0][i * 2u] = make_float4(origin.x, origin.y, origin.z, direction.x);
 	paths.rayQueue[0][i * 2u + 1u] = make_float4(direction.y, direction.z, kInfinity, __uint_as_float(ECHO_TOKEN_EMPTY));
 	paths.rayPath[0][i] = i;
+	if (paths.rayLayers[0]) store_layers(paths.rayLayers[0], i, no_layers());
 	paths.energy[i] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
 	paths.result[i] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(MODE_FIRST << 16));
 	paths.key[i] = key;
@@ -715,7 +773,36 @@ __global__ void __launch_bounds__(kBlock) extend_narrow_kernel(DeviceScene scene
 	io.store_closest(i, hit, token, distance, uv, b.z);
 }
 
+// Instanced scenes: the same query through the packs (echo_instanced.cuh), one thread per ray, with the ignore hierarchy's
+// instance layers in and the hit's instance layers out.
+template<int STACK>
+__global__ void __launch_bounds__(kBlock) extend_instanced_kernel(DeviceScene scene, ExtendIO io, const uint4* __restrict__ rayLayers, uint4* __restrict__ hitLayers,
+                                                                  const uint32_t* __restrict__ queueCount)
+{
+	uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+	if (i >= *queueCount) return;
+
+	float4 a = io.rays[i * 2u], b = io.rays[i * 2u + 1u];
+	PathLayers ignore = load_layers(rayLayers, i);
+	PathLayers hitLayer = no_layers();
+	float distance = b.z;
+	uint32_t token = ECHO_TOKEN_EMPTY;
+	vec2 uv = { 0.0f, 0.0f };
+	bool hit = false;
+
+	if (positive(b.z)) // PreparedScene.Trace, PreparedScene.cs:69
+	{
+		traverse_instanced<STACK, false, false>(scene, { a.x, a.y, a.z }, { a.w, b.x, b.y }, __float_as_uint(b.w), ignore.tokens, ignore.count,
+		                                        distance, token, uv, hitLayer.tokens, hitLayer.count, nullptr);
+		hit = distance < b.z;
+	}
+
+	io.store_closest(i, hit, token, distance, uv, b.z);
+	store_layers(hitLayers, i, hit ? hitLayer : no_layers());
+}
+
 // the material-class sort: one thread per traced ray appends its slot to the queue of the class it hit
+template<bool INST>
 __global__ void __launch_bounds__(kBlock) classify_kernel(DeviceScene scene, const uint32_t* __restrict__ queueCount, PathBuffers paths)
 {
 	uint32_t i = blockIdx.x * kBlock + threadIdx.x;
@@ -725,7 +812,30 @@ __global__ void __launch_bounds__(kBlock) classify_kernel(DeviceScene scene, con
 	if (active)
 	{
 		uint32_t token = __float_as_uint(paths.hitQueue[i].x);
-		shadeClass = token != ECHO_TOKEN_EMPTY ? classify_material(scene, geometry_material(scene, token)) : CLASS_MISS;
+		shadeClass = CLASS_MISS;
+
+		if (token != ECHO_TOKEN_EMPTY)
+		{
+			// the hit's pack and the swatch of its placement (PreparedScene.Interact: instance.swatch[info.material])
+			PackInfo info = whole_scene_pack(scene);
+			uint32_t materialOffset = 0u;
+
+			if (INST)
+			{
+				PathLayers layers = load_layers(paths.hitLayers, i);
+				info = load_pack_info(scene, 0u);
+				materialOffset = info.materialOffset;
+
+				for (uint32_t k = 0; k < layers.count; k++)
+				{
+					float4 tail = __ldg(instance_data(scene, info.instanceOffset + token_index(layers.tokens[k])) + 6);
+					materialOffset = __float_as_uint(tail.w);
+					info = load_pack_info(scene, __float_as_uint(tail.z));
+				}
+			}
+
+			shadeClass = classify_material(scene, materialOffset + geometry_material(scene, info, token));
+		}
 	}
 
 	stat_add(paths.stats, STAT_TRACE_QUERIES, active);
@@ -740,7 +850,7 @@ __global__ void __launch_bounds__(kBlock) classify_kernel(DeviceScene scene, con
 }
 
 // One loop body of PathTracedEvaluator.Evaluate for every path in a material-class queue.
-template<int CLASS, uint32_t KINDS>
+template<int CLASS, uint32_t KINDS, bool INST>
 __global__ void __launch_bounds__(kBlock) shade_kernel(DeviceScene scene, EchoRenderParams params, const uint32_t* __restrict__ queue,
                                                       const uint32_t* __restrict__ queueCount, PathBuffers paths, int current)
 {
@@ -754,6 +864,7 @@ __global__ void __launch_bounds__(kBlock) shade_kernel(DeviceScene scene, EchoRe
 
 	float4 nextOrigin = make_float4(0, 0, 0, 0), nextDirection = make_float4(0, 0, 0, 0), nextEnergy = make_float4(0, 0, 0, 0);
 	float4 shadowOrigin = make_float4(0, 0, 0, 0), shadowDirection = make_float4(0, 0, 0, 0), shadowValue = make_float4(0, 0, 0, 0);
+	PathLayers hitLayers = no_layers(); // the instance layers of the hit: the ignore hierarchy of both spawned rays
 
 	if (active)
 	{
@@ -806,23 +917,26 @@ __global__ void __launch_bounds__(kBlock) shade_kernel(DeviceScene scene, EchoRe
 			vec3 infoNormal, infoShading;
 			uint32_t materialIndex;
 
+			if (INST) hitLayers = load_layers(paths.hitLayers, raySlot);
+			Layer layer = find_layer<INST>(scene, hitLayers); // FindLayer, :97
+
 			if (token_type(token) == ECHO_TOKEN_TYPE_TRIANGLE)
 			{
-				TriangleData triangle = load_triangle(scene, token_index(token));
-				materialIndex = triangle.material;
+				TriangleData triangle = load_triangle(scene, layer.info.triangleOffset + token_index(token));
+				materialIndex = layer.materialOffset + triangle.material; // instance.swatch[info.material], :102
 				infoNormal = triangle_normal(triangle);
 				infoShading = triangle_shading_normal(triangle, uv);
 			}
 			else
 			{
-				materialIndex = __ldg(scene.sphereMaterial + token_index(token));
+				materialIndex = layer.materialOffset + __ldg(scene.sphereMaterial + layer.info.sphereOffset + token_index(token));
 				infoNormal = infoShading = sphere_normal(uv);
 			}
 
 			SurfacePoint point;
 			point.position = direction * max_net(distance, kEpsilon) + rayOrigin; // TraceQuery.Position, TraceQuery.cs:76-82
-			point.normal = normalized(identity_multiply_direction(infoNormal));
-			vec3 shadeNormal = normalized(identity_multiply_direction(infoShading));
+			point.normal = normalized(transform_direction(layer.inverse, infoNormal)); // :100-101 (the identity without layers)
+			vec3 shadeNormal = normalized(transform_direction(layer.inverse, infoShading));
 			vec3 outgoing = -direction;
 
 			MaterialRecord material = load_material(scene, materialIndex);
@@ -838,12 +952,12 @@ __global__ void __launch_bounds__(kBlock) shade_kernel(DeviceScene scene, EchoRe
 				if (mode == MODE_MIS)
 				{
 					SurfacePoint oldPoint = { xyz(paths.oldPosition[id]), xyz(paths.oldNormal[id]) };
-					float pmf = scene_probability_mass(scene, token, oldPoint);
+					float pmf = scene_probability_mass<INST>(scene, token, hitLayers, oldPoint);
 					contribute = positive(pmf);
 
 					if (contribute)
 					{
-						float pdf = scene_light_pdf(scene, token, oldPoint, direction);
+						float pdf = scene_light_pdf<INST>(scene, token, hitLayers, oldPoint, direction);
 						contribute = positive(pdf);
 						if (contribute) weight = power_heuristic(scatterPdfPrevious, pmf * pdf);
 					}
@@ -881,13 +995,14 @@ __global__ void __launch_bounds__(kBlock) shade_kernel(DeviceScene scene, EchoRe
 				{
 					// ---- ImportanceSampleRadiant, :162-207 ----
 					float lightPdf;
-					uint32_t light = scene_pick(scene, point, lightSample, lightPdf);
+					PathLayers lightLayers;
+					uint32_t light = scene_pick<INST>(scene, point, lightSample, lightPdf, lightLayers);
 
 					if (positive(lightPdf))
 					{
 						vec3 lightIncident;
 						float travel;
-						Sampled radiantSampled = scene_sample_light(scene, light, point, radiantSample, lightIncident, travel);
+						Sampled radiantSampled = scene_sample_light<INST>(scene, light, lightLayers, point, radiantSample, lightIncident, travel);
 						rgb radiant = radiantSampled.content;
 
 						float pdf = lightPdf * radiantSampled.pdf;
@@ -956,6 +1071,7 @@ __global__ void __launch_bounds__(kBlock) shade_kernel(DeviceScene scene, EchoRe
 		paths.rayQueue[current ^ 1][nextSlot * 2u] = nextOrigin;
 		paths.rayQueue[current ^ 1][nextSlot * 2u + 1u] = nextDirection;
 		paths.rayPath[current ^ 1][nextSlot] = id;
+		if (INST) store_layers(paths.rayLayers[current ^ 1], nextSlot, hitLayers);
 	}
 
 	uint32_t shadowSlot = queue_slot(paths.counters + COUNTER_SHADOW, shadow);
@@ -965,6 +1081,7 @@ __global__ void __launch_bounds__(kBlock) shade_kernel(DeviceScene scene, EchoRe
 		paths.shadowQueue[shadowSlot * 2u] = shadowOrigin;
 		paths.shadowQueue[shadowSlot * 2u + 1u] = shadowDirection;
 		paths.shadowValue[shadowSlot] = shadowValue;
+		if (INST) store_layers(paths.shadowLayers, shadowSlot, hitLayers);
 	}
 
 	stat_add(paths.stats, STAT_LIGHT_EVALUATED_INFINITE, statInfinite);
@@ -1026,6 +1143,34 @@ __global__ void __launch_bounds__(kBlock) shadow_narrow_kernel(DeviceScene scene
 	{
 		float4 a = io.rays[i * 2u], b = io.rays[i * 2u + 1u];
 		bool occluded = scene_occlude<STACK, false>(scene, { a.x, a.y, a.z }, { a.w, b.x, b.y }, __float_as_uint(b.w), b.z, nullptr);
+		io.store_any(i, occluded);
+	}
+
+	stat_add(stats, STAT_OCCLUDE_QUERIES, active);
+	stat_add(stats, STAT_LIGHT_OCCLUSION_PASSED, io.passed != 0u);
+}
+
+template<int STACK>
+__global__ void __launch_bounds__(kBlock) shadow_instanced_kernel(DeviceScene scene, ShadowIO io, const uint4* __restrict__ shadowLayers,
+                                                                  const uint32_t* __restrict__ shadowCount, unsigned long long* __restrict__ stats)
+{
+	uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+	bool active = i < *shadowCount;
+	io.passed = 0u;
+
+	if (active)
+	{
+		float4 a = io.rays[i * 2u], b = io.rays[i * 2u + 1u];
+		PathLayers ignore = load_layers(shadowLayers, i);
+		PathLayers unusedLayers = no_layers();
+		float travel = b.z;
+		uint32_t unusedToken = ECHO_TOKEN_EMPTY;
+		vec2 unusedUV = { 0.0f, 0.0f };
+		bool occluded = false;
+
+		if (positive(b.z)) // PreparedScene.Occlude, PreparedScene.cs:84
+			occluded = traverse_instanced<STACK, true, false>(scene, { a.x, a.y, a.z }, { a.w, b.x, b.y }, __float_as_uint(b.w), ignore.tokens, ignore.count,
+			                                                  travel, unusedToken, unusedUV, unusedLayers.tokens, unusedLayers.count, nullptr);
 		io.store_any(i, occluded);
 	}
 
@@ -1235,6 +1380,7 @@ static void release(WorkerState* state)
 {
 	for (void* p : state->allocations) cudaFree(p);
 	state->allocations.clear();
+	state->paths.rayLayers[0] = state->paths.rayLayers[1] = state->paths.hitLayers = state->paths.shadowLayers = nullptr;
 	state->capacity = 0;
 	state->pixelCapacity = 0;
 	state->tileCapacity = 0;
@@ -1283,10 +1429,11 @@ static bool allocate(WorkerState* state, T*& pointer, uint64_t count)
 	return true;
 }
 
-static bool ensure_capacity(WorkerState* state, uint64_t paths, uint64_t pixels, uint64_t tiles)
+static bool ensure_capacity(WorkerState* state, uint64_t paths, uint64_t pixels, uint64_t tiles, bool instanced)
 {
 	if (!state->hostCounters && !check_cuda(cudaMallocHost((void**)&state->hostCounters, sizeof(uint32_t) * 64), "cudaMallocHost")) return false;
-	if (paths <= state->capacity && pixels <= state->pixelCapacity && tiles <= state->tileCapacity) return true;
+	bool layersReady = !instanced || state->paths.hitLayers != nullptr;
+	if (paths <= state->capacity && pixels <= state->pixelCapacity && tiles <= state->tileCapacity && layersReady) return true;
 
 	paths = std::max(paths, state->capacity);
 	pixels = std::max(pixels, state->pixelCapacity);
@@ -1305,6 +1452,11 @@ static bool ensure_capacity(WorkerState* state, uint64_t paths, uint64_t pixels,
 		&& allocate(state, state->batchPixelXY, pixels) && allocate(state, state->tileXYDevice, tiles * 2);
 
 	for (int c = 0; ok && c < CLASS_COUNT; c++) ok = allocate(state, b.classQueue[c], paths);
+
+	if (instanced)
+		ok = ok && allocate(state, b.rayLayers[0], paths * 2) && allocate(state, b.rayLayers[1], paths * 2) && allocate(state, b.hitLayers, paths * 2)
+			&& allocate(state, b.shadowLayers, paths * 2);
+
 	if (!ok) return false;
 
 	state->capacity = paths;
@@ -1364,7 +1516,7 @@ static KernelTimer gTimer;
 static unsigned int blocks_for(uint64_t count) { return (unsigned int)std::max<uint64_t>((count + kBlock - 1) / kBlock, 1); }
 
 // Evaluates `count` path slots already described in state->pixelXY / sampleIndex; radiance lands in state->sampleOut.
-template<int STACK>
+template<int STACK, bool INST>
 static bool evaluate_paths(WorkerState* state, const DeviceScene& scene, const EchoRenderParams& params, uint32_t count, uint64_t& launches, cudaStream_t stream)
 {
 	PathBuffers& paths = state->paths;
@@ -1400,34 +1552,36 @@ static bool evaluate_paths(WorkerState* state, const DeviceScene& scene, const E
 
 		gTimer.start(stream);
 		ExtendIO extendIO = { paths.rayQueue[current], paths.hitQueue };
-		if (active < narrowLimit) extend_narrow_kernel<STACK><<<blocks, kBlock, 0, stream>>>(scene, extendIO, activeCount);
+		if (INST) extend_instanced_kernel<STACK><<<blocks, kBlock, 0, stream>>>(scene, extendIO, paths.rayLayers[current], paths.hitLayers, activeCount);
+		else if (active < narrowLimit) extend_narrow_kernel<STACK><<<blocks, kBlock, 0, stream>>>(scene, extendIO, activeCount);
 		else extend_kernel<STACK><<<std::min<unsigned int>(blocks, (unsigned int)extendGrid), kTraverseBlock, 0, stream>>>(scene, extendIO, activeCount, extendCounter);
 		gTimer.stop(KernelTimer::EXTEND, stream);
 		float extendMs = gTimer.last;
 
 		gTimer.start(stream);
-		classify_kernel<<<blocks, kBlock, 0, stream>>>(scene, activeCount, paths);
+		classify_kernel<INST><<<blocks, kBlock, 0, stream>>>(scene, activeCount, paths);
 		gTimer.stop(KernelTimer::OTHER, stream);
 
 		gTimer.start(stream);
-		shade_kernel<CLASS_MISS, 0u><<<blocks, kBlock, 0, stream>>>(scene, params, paths.classQueue[CLASS_MISS], counters + COUNTER_CLASS + CLASS_MISS, paths, current);
+		shade_kernel<CLASS_MISS, 0u, INST><<<blocks, kBlock, 0, stream>>>(scene, params, paths.classQueue[CLASS_MISS], counters + COUNTER_CLASS + CLASS_MISS, paths, current);
 		gTimer.stop(KernelTimer::SHADE_MISS, stream);
 		gTimer.start(stream);
-		shade_kernel<CLASS_DIFFUSE, KINDS_DIFFUSE><<<blocks, kBlock, 0, stream>>>(scene, params, paths.classQueue[CLASS_DIFFUSE], counters + COUNTER_CLASS + CLASS_DIFFUSE, paths, current);
+		shade_kernel<CLASS_DIFFUSE, KINDS_DIFFUSE, INST><<<blocks, kBlock, 0, stream>>>(scene, params, paths.classQueue[CLASS_DIFFUSE], counters + COUNTER_CLASS + CLASS_DIFFUSE, paths, current);
 		gTimer.stop(KernelTimer::SHADE_DIFFUSE, stream);
 		gTimer.start(stream);
-		shade_kernel<CLASS_DIELECTRIC, KINDS_DIELECTRIC><<<blocks, kBlock, 0, stream>>>(scene, params, paths.classQueue[CLASS_DIELECTRIC], counters + COUNTER_CLASS + CLASS_DIELECTRIC, paths, current);
+		shade_kernel<CLASS_DIELECTRIC, KINDS_DIELECTRIC, INST><<<blocks, kBlock, 0, stream>>>(scene, params, paths.classQueue[CLASS_DIELECTRIC], counters + COUNTER_CLASS + CLASS_DIELECTRIC, paths, current);
 		gTimer.stop(KernelTimer::SHADE_DIELECTRIC, stream);
 		gTimer.start(stream);
-		shade_kernel<CLASS_CONDUCTOR, KINDS_CONDUCTOR><<<blocks, kBlock, 0, stream>>>(scene, params, paths.classQueue[CLASS_CONDUCTOR], counters + COUNTER_CLASS + CLASS_CONDUCTOR, paths, current);
+		shade_kernel<CLASS_CONDUCTOR, KINDS_CONDUCTOR, INST><<<blocks, kBlock, 0, stream>>>(scene, params, paths.classQueue[CLASS_CONDUCTOR], counters + COUNTER_CLASS + CLASS_CONDUCTOR, paths, current);
 		gTimer.stop(KernelTimer::SHADE_CONDUCTOR, stream);
 		gTimer.start(stream);
-		shade_kernel<CLASS_TERMINAL, KINDS_TERMINAL><<<blocks, kBlock, 0, stream>>>(scene, params, paths.classQueue[CLASS_TERMINAL], counters + COUNTER_CLASS + CLASS_TERMINAL, paths, current);
+		shade_kernel<CLASS_TERMINAL, KINDS_TERMINAL, INST><<<blocks, kBlock, 0, stream>>>(scene, params, paths.classQueue[CLASS_TERMINAL], counters + COUNTER_CLASS + CLASS_TERMINAL, paths, current);
 		gTimer.stop(KernelTimer::SHADE_TERMINAL, stream);
 
 		gTimer.start(stream);
 		ShadowIO shadowIO = { paths.shadowQueue, paths.shadowValue, paths.result, 0u };
-		if (active < narrowLimit) shadow_narrow_kernel<STACK><<<blocks, kBlock, 0, stream>>>(scene, shadowIO, counters + COUNTER_SHADOW, paths.stats);
+		if (INST) shadow_instanced_kernel<STACK><<<blocks, kBlock, 0, stream>>>(scene, shadowIO, paths.shadowLayers, counters + COUNTER_SHADOW, paths.stats);
+		else if (active < narrowLimit) shadow_narrow_kernel<STACK><<<blocks, kBlock, 0, stream>>>(scene, shadowIO, counters + COUNTER_SHADOW, paths.stats);
 		else shadow_kernel<STACK><<<std::min<unsigned int>(blocks, (unsigned int)shadowGrid), kTraverseBlock, 0, stream>>>(scene, shadowIO, counters + COUNTER_SHADOW, shadowCounter, paths.stats);
 		gTimer.stop(KernelTimer::SHADOW, stream);
 		if (gTimer.enabled && std::getenv("ECHO_B200_PROFILE_ITERATIONS"))
@@ -1458,11 +1612,13 @@ static bool evaluate_paths(WorkerState* state, const DeviceScene& scene, const E
 
 static bool evaluate_paths_dispatch(WorkerState* state, const DeviceScene& scene, const EchoRenderParams& params, uint32_t count, uint64_t& launches, cudaStream_t stream)
 {
+	bool instanced = scene.packCount != 0u;
+
 	switch (stack_class(scene.maxDepth))
 	{
-		case 0: return evaluate_paths<48>(state, scene, params, count, launches, stream);
-		case 1: return evaluate_paths<96>(state, scene, params, count, launches, stream);
-		case 2: return evaluate_paths<192>(state, scene, params, count, launches, stream);
+		case 0: return instanced ? evaluate_paths<48, true>(state, scene, params, count, launches, stream) : evaluate_paths<48, false>(state, scene, params, count, launches, stream);
+		case 1: return instanced ? evaluate_paths<96, true>(state, scene, params, count, launches, stream) : evaluate_paths<96, false>(state, scene, params, count, launches, stream);
+		case 2: return instanced ? evaluate_paths<192, true>(state, scene, params, count, launches, stream) : evaluate_paths<192, false>(state, scene, params, count, launches, stream);
 		default: set_error("QBVH deeper than 63 quad levels is not supported"); return false;
 	}
 }
@@ -1488,7 +1644,7 @@ static bool render_batch(WorkerState* state, const DeviceScene& scene, const Ech
 	uint64_t perTile = (uint64_t)params.tileSize * params.tileSize;
 	uint32_t pixelTotal = (uint32_t)(tiles * perTile);
 
-	if (!ensure_capacity(state, (uint64_t)pixelTotal * params.extend, pixelTotal, tiles)) return false;
+	if (!ensure_capacity(state, (uint64_t)pixelTotal * params.extend, pixelTotal, tiles, scene.packCount != 0u)) return false;
 	if (!check_cuda(cudaMemcpyAsync(state->tileXYDevice, tileXY, sizeof(int32_t) * 2 * tiles, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync(tiles)")) return false;
 	if (!check_cuda(cudaMemsetAsync(state->paths.counters, 0, sizeof(uint32_t) * 64, stream), "cudaMemsetAsync(counters)")) return false;
 
@@ -1579,7 +1735,7 @@ bool render_tiles(RenderState* state, const DeviceScene& scene, const EchoRender
 		bool ok = check_cuda(cudaSetDevice(device), "cudaSetDevice(render worker)");
 
 		// the statistics buffer is allocated with the wavefront state: size the worker for a full batch up front
-		ok = ok && ensure_capacity(worker, tilesPerBatch * perTile * params.extend, tilesPerBatch * perTile, tilesPerBatch);
+		ok = ok && ensure_capacity(worker, tilesPerBatch * perTile * params.extend, tilesPerBatch * perTile, tilesPerBatch, scene.packCount != 0u);
 		ok = ok && check_cuda(cudaMemsetAsync(worker->paths.stats, 0, sizeof(unsigned long long) * STAT_COUNT, worker->stream), "cudaMemsetAsync(stats)");
 
 		while (ok && !failed.load())
@@ -1633,7 +1789,7 @@ bool evaluate_sample_list(RenderState* renderState, const DeviceScene& scene, co
 	for (uint64_t first = 0; first < n; first += kPathsPerBatch)
 	{
 		uint32_t count = (uint32_t)std::min<uint64_t>(kPathsPerBatch, n - first);
-		if (!ensure_capacity(state, count, 1, 1)) return false;
+		if (!ensure_capacity(state, count, 1, 1, scene.packCount != 0u)) return false;
 
 		if (!check_cuda(cudaMemcpyAsync(state->pixelXY, pixelXYHost + first * 2, sizeof(int2) * count, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync(pixels)")) return false;
 		if (!check_cuda(cudaMemcpyAsync(state->sampleIndex, sampleIndexHost + first, sizeof(uint32_t) * count, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync(samples)")) return false;

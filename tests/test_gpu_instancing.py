@@ -115,3 +115,40 @@ def test_deep_nesting():
         assert expected_layers["instanceCount"].max() == 5
         assert_hits_equal(hits, expected)
         assert np.array_equal(layers, expected_layers)
+
+
+@pytest.mark.parametrize("nested", [False, True])
+def test_samples_match_oracle(nested):
+    """Per-sample radiance of the wavefront path tracer on an instanced scene: Interact through FindLayer, lights picked and
+    sampled through the instance layers, shadow rays with full ignore hierarchies — bit-identical to the oracle."""
+    from tests.test_gpu_render import relative_rmse, sample_grid
+    prepared = host.prepare(scenes.instanced_scene(grid=4, rings=12, segments=14, nested=nested))
+    oracle = oracle_lib.OracleScene(prepared)
+    width, height = 96, 64
+    params = structs.render_params(width, height, 16, extend=4, bounce_limit=16, seed=7)
+    pixel_xy, sample_index = sample_grid(width, height, 4)
+
+    with PreparedScene(prepared) as scene:
+        actual = scene.evaluate_samples(params, pixel_xy, sample_index)
+
+    expected = oracle.evaluate_samples(params, pixel_xy, sample_index)
+    assert np.isfinite(actual).all() and expected.max() > 0
+    different = np.any(actual.view(np.uint32) != expected.view(np.uint32), axis=1)
+    assert different.mean() <= 1e-4, f"{different.sum()} of {len(different)} samples are not bit-identical"
+    assert relative_rmse(actual, expected) <= 1e-4
+
+
+def test_render_tiles_match_oracle(instanced):
+    from tests.test_gpu_render import relative_rmse
+    oracle = oracle_lib.OracleScene(instanced)
+    width, height = 80, 48
+    params = structs.render_params(width, height, 32, extend=8, min_epoch=2, max_epoch=2, bounce_limit=16, seed=3)
+    tiles = scenes.tile_grid(width, height, 32)
+
+    with PreparedScene(instanced) as scene:
+        actual, stats = scene.render_tiles(params, tiles)
+
+    expected, expected_stats = oracle.render_tiles(params, tiles)
+    assert relative_rmse(actual, expected) <= 1e-4
+    for name in structs.STATS_FIELDS[:12]:
+        assert abs(int(stats[name][0]) - int(expected_stats[name][0])) <= 1e-4 * max(1, int(expected_stats[name][0])), name
