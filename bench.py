@@ -43,7 +43,9 @@ def parse():
     parser.add_argument("--width", type=int, default=1920)
     parser.add_argument("--height", type=int, default=1080)
     parser.add_argument("--spp", type=int, default=16, help="render workload: samples per pixel per step (one epoch)")
-    parser.add_argument("--scene", default="mixed", choices=["cornell", "mixed", "lights", "large"], help="render workload scene: C1 / C3 / C4 / C5")
+    parser.add_argument("--scene", default="mixed", choices=["cornell", "mixed", "lights", "large", "instanced"],
+                        help="render workload scene: C1 / C3 / C4 / C5 / 2 304 placements of two packs (SURVEY.md 8f rank 2)")
+    parser.add_argument("--instanced", action="store_true", help="trace workload: the instanced scene instead of the C2 terrain (same ray recipe)")
     parser.add_argument("--bounce-limit", type=int, default=8, help="render workload: PathTracedEvaluator.BounceLimit (C3: 8; reference default 128)")
     parser.add_argument("--no-cpu-baseline", action="store_true")
     parser.add_argument("--no-secondary", action="store_true", help="skip the secondary-ray batch reported beside the headline (SURVEY.md 8d)")
@@ -128,8 +130,12 @@ class ClockSampler:
                 "samples": len(inside), "scope": scope}
 
 
+def instanced_bench_scene():
+    return scenes.instanced_scene(grid=48, rings=128, segments=130)
+
+
 def build_trace_inputs(args, rank):
-    description = scenes.terrain_scene(args.quads[0], args.quads[1], 10000)
+    description = instanced_bench_scene() if getattr(args, "instanced", False) else scenes.terrain_scene(args.quads[0], args.quads[1], 10000)
     prepared = host.prepare(description)
     # every rank traces its own batch (distinct seeds per rank)
     rays = scenes.random_rays(prepared.bounds, args.rays, seed=11 + 1000 * rank)
@@ -262,6 +268,10 @@ def reference_arm(args):
 
 
 def trace_config(args, rays):
+    if getattr(args, "instanced", False):
+        return {"workload": "incoherent ray-batch intersection through instanced packs (48 x 48 placements of a 33 k-triangle pack and of a pack of three of those): closest-hit + occlusion",
+                "rays_per_pass_per_gpu": rays, "passes_per_step": 2, "parallelism": f"replicated scene x{args.gpus}",
+                "l2": "inputs larger than L2 (ray batch 512 MiB + hit buffer 256 MiB per pass vs 126 MB L2)"}
     return {"workload": "C2 incoherent ray-batch intersection: closest-hit + occlusion", "triangles": args.quads[0] * args.quads[1] * 2,
             "spheres": 10000, "rays_per_pass_per_gpu": rays, "passes_per_step": 2, "parallelism": f"replicated scene x{args.gpus}",
             "l2": "inputs larger than L2 (ray batch 512 MiB + hit buffer 256 MiB per pass vs 126 MB L2)"}
@@ -272,6 +282,7 @@ RENDER_SCENES = {
     "mixed": ("C3 mixed-material scene (Dielectric, Conductor GGX, Oren-Nayar)", scenes.mixed_material_scene),
     "lights": ("C4 many-lights scene (10 k emissive triangles, light-tree NEE)", scenes.many_lights_scene),
     "large": ("C5 ~10 M-triangle terrain with the C3 material mix", scenes.large_scene),
+    "instanced": ("2 304 placements of two packs (one nests three placements of the other), lights inside the packs", instanced_bench_scene),
 }
 
 
@@ -398,7 +409,7 @@ def main():
 
         line = base_line(args, "Mrays/s", value, total_ms / args.steps, trace_config(args, n), "f32")
         achieved = bytes_trace * n / (trace_ms * 1e-3) / 1e9
-        line["roofline"] = {"bound": "hbm", "kernel": "persistent_batch_kernel<48, false> (closest hit)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        line["roofline"] = {"bound": "hbm", "kernel": "instanced closest-hit kernel" if args.instanced else "persistent_batch_kernel<48, false> (closest hit)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                             "traffic": ncu_traffic("closest_hit_dram_bytes_per_launch"), "peak_source": peak_source, "algorithmic_bytes_per_query": bytes_trace, "ms_per_launch": trace_ms,
                             "mrays_per_s": n / (trace_ms * 1e-3) / MRAYS,
                             "visits_per_query": {"nodes": counts[0], "triangles": counts[1], "spheres": counts[2]},
@@ -409,7 +420,7 @@ def main():
         line["gpu_launches"] = 2 * args.steps
         line["clocks"] = clocks.summary()
 
-        if not args.no_secondary:
+        if not args.no_secondary and not args.instanced:
             line["secondary"] = secondary_batch(scene, prepared, rays, d_hits, device, stream, args, max_over_ranks)
 
         if rank == 0 and not args.no_cpu_baseline:

@@ -28,6 +28,10 @@ bool launch_trace_instanced(const DeviceScene& scene, const EchoRay* rays, const
 bool launch_occlude_instanced(const DeviceScene& scene, const EchoRay* rays, const EchoTokenHierarchy* ignore, uint64_t n, uint8_t* occluded,
                               unsigned long long* counts, cudaStream_t stream);
 
+// trace.cu: the persistent, work-replacing form of the two calls above; `launched` = false when ECHO_B200_SIMPLE_TRACE asks for the simple kernels
+bool launch_persistent_instanced(const DeviceScene& scene, const EchoRay* rays, const EchoTokenHierarchy* ignore, uint64_t n, EchoHit* hits,
+                                 EchoTokenHierarchy* hitLayers, uint8_t* occluded, cudaStream_t stream, bool& launched);
+
 unsigned long long* next_ray_counter(cudaStream_t stream); // zeroed work counter for one persistent launch
 int persistent_grid(const void* kernel);                  // resident CTAs of a persistent kernel on the current device
 

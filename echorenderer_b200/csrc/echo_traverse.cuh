@@ -11,6 +11,7 @@
 // GeometryCollection.cs:85-171): same visit order, same culling comparisons, leaves intersected in push order. Only the
 // interleaving ACROSS rays changes, so results stay bit-identical to the one-thread-per-ray kernels and to the oracle.
 #pragma once
+#include "echo_instanced.cuh"
 #include "echo_scene.cuh"
 
 namespace echo
@@ -76,7 +77,15 @@ ECHO_DEVICE bool finite_bits(float v) { return (__float_as_uint(v) & 0x7F800000u
 //   B  node visit      lanes whose current node has no slots left pop the next un-culled node and run the 4 slab tests
 //   C  slot scan       the Push calls of that node in reference order, up to the first primitive (which becomes pending)
 //   D  primitive test  only when enough lanes have a primitive pending (or nobody can do anything else), then C again
-template<int STACK, bool ANY, class IO>
+//
+// INST = true adds instanced packs (echo_instanced.cuh): a TokenType.Instance leaf is "tested" in stage D by saving a frame
+// (parent ray, node, slot position, stack base), moving the ray into the pack's space and making the pack's root the top of
+// the stack; when a lane's part of the stack above its base runs empty in stage B the frame is popped and the suspended node
+// visit is redone from the saved slot. The IO then also provides
+//   uint32_t load_ignore_layers(uint32_t index, uint32_t* tokens)             -> count of the ignore hierarchy's instance layers
+//   void store_hit_layers(uint32_t index, bool hit, const uint32_t* tokens, uint32_t count)
+// INST = false compiles to exactly the single-pack kernel.
+template<int STACK, bool ANY, bool INST = false, class IO>
 ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, uint32_t count, unsigned long long* __restrict__ nextRay, float4* stagedRays)
 {
 	const unsigned int lane = threadIdx.x & 31u;
@@ -115,6 +124,25 @@ ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, uint32_t 
 	uint2 top = make_uint2(0u, 0u);
 	bool haveTop = false;
 
+	// instancing state of the lane's ray (INST only)
+	const PackView rootPack = INST ? load_pack(scene, 0u) : PackView{ 0u, 0u, 0u, 0u };
+	PackView pack = rootPack;
+	uint32_t level = 0u, packIndex = 0u, currentNode = 0u, ignoreCount = 0u, hitCount = 0u;
+	int base = 0, resume = 0;   // stack base of the current layer; slot at which a resumed node visit continues
+	bool ignoreHere = true;     // query.ignore's instance layers == query.current's
+	InstanceFrame frames[INST ? ECHO_MAX_INSTANCE_LAYERS : 1];
+	uint32_t current[INST ? ECHO_MAX_INSTANCE_LAYERS : 1], ignoreLayers[INST ? ECHO_MAX_INSTANCE_LAYERS : 1], hitLayers[INST ? ECHO_MAX_INSTANCE_LAYERS : 1];
+
+	auto set_ray = [&](vec3 newOrigin, vec3 newDirection)
+	{
+		origin = newOrigin;
+		direction = newDirection;
+		directionR = { rcp(direction.x), rcp(direction.y), rcp(direction.z) }; // Ray.cs:23
+		orders = (directionR.x > 0.0f ? 1u : 0u) | (directionR.y > 0.0f ? 2u : 0u) | (directionR.z > 0.0f ? 4u : 0u) | 8u;
+		finite = finite_bits(directionR.x) && finite_bits(directionR.y) && finite_bits(directionR.z)
+			&& finite_bits(origin.x) && finite_bits(origin.y) && finite_bits(origin.z);
+	};
+
 	// The Push calls of the current node, in order, up to the first primitive (:200-216 / :296-312). `best` only changes in
 	// a primitive test, so the remaining slots are classified at once: bit k of `valid` = slot k passes the distance test,
 	// `nodes` = it is a branch, `leaves` = it is a primitive that is not the ignored triangle (GeometryCollection.cs:93-94).
@@ -125,6 +153,7 @@ ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, uint32_t 
 		uint32_t nodes = (token_type(child0) == 0u ? 1u : 0u) | (token_type(child1) == 0u ? 2u : 0u) | (token_type(child2) == 0u ? 4u : 0u) | (token_type(child3) == 0u ? 8u : 0u);
 		uint32_t ignored = (child0 == ignore && token_type(child0) == ECHO_TOKEN_TYPE_TRIANGLE ? 1u : 0u) | (child1 == ignore && token_type(child1) == ECHO_TOKEN_TYPE_TRIANGLE ? 2u : 0u)
 			| (child2 == ignore && token_type(child2) == ECHO_TOKEN_TYPE_TRIANGLE ? 4u : 0u) | (child3 == ignore && token_type(child3) == ECHO_TOKEN_TYPE_TRIANGLE ? 8u : 0u);
+		if (INST && !ignoreHere) ignored = 0u;
 
 		valid &= pending;
 		uint32_t leaves = valid & ~nodes & ~ignored;
@@ -154,10 +183,15 @@ ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, uint32_t 
 	while (true)
 	{
 		// ---- E: finish rays whose traversal ran out of work ----
-		if (haveRay && leaf == ECHO_TOKEN_EMPTY && position == 4 && next == 0 && !haveTop)
+		if (haveRay && leaf == ECHO_TOKEN_EMPTY && position == 4 && next == 0 && !haveTop && (!INST || level == 0u))
 		{
 			if (ANY) io.store_any(rayIndex, false);
-			else io.store_closest(rayIndex, best < limit, bestToken, best, bestUV, limit);
+			else
+			{
+				io.store_closest(rayIndex, best < limit, bestToken, best, bestUV, limit);
+				if constexpr (INST) io.store_hit_layers(rayIndex, best < limit, hitLayers, hitCount);
+			}
+
 			haveRay = false;
 		}
 
@@ -176,10 +210,26 @@ ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, uint32_t 
 			best = limit;
 			bestToken = ECHO_TOKEN_EMPTY;
 
+			if constexpr (INST)
+			{
+				ignoreCount = io.load_ignore_layers(rayIndex, ignoreLayers);
+				ignoreHere = ignoreCount == 0u;
+				level = 0u;
+				base = 0;
+				resume = 0;
+				packIndex = 0u;
+				pack = rootPack;
+				hitCount = 0u;
+			}
+
 			if (!positive(limit)) // PreparedScene.Trace / Occlude guard, PreparedScene.cs:69,84
 			{
 				if (ANY) io.store_any(rayIndex, false);
-				else io.store_closest(rayIndex, false, ECHO_TOKEN_EMPTY, limit, bestUV, limit);
+				else
+				{
+					io.store_closest(rayIndex, false, ECHO_TOKEN_EMPTY, limit, bestUV, limit);
+					if constexpr (INST) io.store_hit_layers(rayIndex, false, hitLayers, 0u);
+				}
 			}
 			else
 			{
@@ -249,7 +299,7 @@ ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, uint32_t 
 
 		if (haveRay && leaf == ECHO_TOKEN_EMPTY && position == 4)
 		{
-			while (haveTop || next > 0) // pop; skip entries the closest hit has already passed (:144-146)
+			while (haveTop || next > (INST ? base : 0)) // pop; skip entries the closest hit has already passed (:144-146)
 			{
 				uint2 entry = top;
 				if (haveTop) haveTop = false;
@@ -262,12 +312,29 @@ ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, uint32_t 
 					break;
 				}
 			}
+
+			if (INST && !visit && level > 0u)
+			{
+				// the instanced pack's accelerator returned: back to the parent's space (PreparedInstance.cs:58-60 / :78-80),
+				// then the rest of the parent's suspended node visit
+				const InstanceFrame& frame = frames[--level];
+				set_ray(frame.origin, frame.direction);
+				best = ANY ? frame.travel : best * __ldg(instance_data(scene, frame.instance) + 6).y;
+				packIndex = frame.pack;
+				pack = load_pack(scene, packIndex);
+				base = (int)frame.base;
+				nodeToken = frame.node;
+				resume = (int)frame.position;
+				ignoreHere = layers_match(ignoreLayers, ignoreCount, current, level);
+				visit = true;
+			}
 		}
 
 		if (visit)
 		{
-			const float4* base = scene.nodes + (size_t)token_index(nodeToken) * 8;
-			float8 q0 = ldg256(base + 0), q1 = ldg256(base + 2), q2 = ldg256(base + 4), q3 = ldg256(base + 6);
+			const float4* nodeData = scene.nodes + ((size_t)(INST ? pack.nodeOffset : 0u) + token_index(nodeToken)) * 8;
+			float8 q0 = ldg256(nodeData + 0), q1 = ldg256(nodeData + 2), q2 = ldg256(nodeData + 4), q3 = ldg256(nodeData + 6);
+			if (INST) currentNode = nodeToken;
 			// q0 = minX[4] minY[4], q1 = minZ[4] maxX[4], q2 = maxY[4] maxZ[4], q3 = axisMajor axisMinor0 axisMinor1 token4[4] pad
 
 			float t0, t1, t2, t3;
@@ -300,7 +367,8 @@ ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, uint32_t 
 
 			hit0 = swapPairs ? b0 : a0; hit1 = swapPairs ? b1 : a1; hit2 = swapPairs ? a0 : b0; hit3 = swapPairs ? a1 : b1;
 			child0 = swapPairs ? d0 : c0; child1 = swapPairs ? d1 : c1; child2 = swapPairs ? c0 : d0; child3 = swapPairs ? c1 : d1;
-			position = 0;
+			position = INST ? resume : 0;
+			resume = 0;
 		}
 
 		// ---- C: slot scan ----
@@ -320,9 +388,45 @@ ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, uint32_t 
 			{
 				bool occluded = false;
 
-				if (token_type(leaf) == ECHO_TOKEN_TYPE_TRIANGLE)
+				if (INST && token_type(leaf) == ECHO_TOKEN_TYPE_INSTANCE)
 				{
-					const float4* data = scene.triHot + (size_t)token_index(leaf) * 3;
+					if (level < ECHO_MAX_INSTANCE_LAYERS)
+					{
+						// query.current.Push(token); instances[token.Index].Trace / Occlude (GeometryCollection.cs:123-131,160-168)
+						uint32_t instance = pack.instanceOffset + token_index(leaf);
+						const float4* data = instance_data(scene, instance);
+						float4 scales = __ldg(data + 6);
+
+						InstanceFrame& frame = frames[level];
+						frame.origin = origin;
+						frame.direction = direction;
+						frame.travel = best;
+						frame.node = currentNode;
+						frame.position = (uint32_t)position;
+						frame.pack = packIndex;
+						frame.instance = instance;
+						current[level++] = leaf;
+
+						// TransformForward + the scaled distance, PreparedInstance.cs:51,105-111
+						vec3 localOrigin = multiply_point(data, origin);
+						vec3 localDirection = multiply_direction(data, direction) * scales.y;
+						set_ray(localOrigin, localDirection);
+						best *= scales.x;
+
+						packIndex = __float_as_uint(scales.z);
+						pack = load_pack(scene, packIndex);
+						if (haveTop) stack[next++] = top; // the parent's entries all live below the new base
+						frame.base = (uint32_t)base;
+						base = next;
+						top = make_uint2(0u, 0u); // the pack's NewNodeToken(0), entry distance 0
+						haveTop = true;
+						position = 4; // the rest of this node's slots wait in the frame
+						ignoreHere = layers_match(ignoreLayers, ignoreCount, current, level);
+					}
+				}
+				else if (token_type(leaf) == ECHO_TOKEN_TYPE_TRIANGLE)
+				{
+					const float4* data = scene.triHot + ((size_t)(INST ? pack.triangleOffset : 0u) + token_index(leaf)) * 3;
 					float4 a = __ldg(data), b = __ldg(data + 1), c = __ldg(data + 2);
 
 					if (ANY) occluded = triangle_occlude({ a.x, a.y, a.z }, { b.x, b.y, b.z }, { c.x, c.y, c.z }, origin, direction, best);
@@ -336,24 +440,37 @@ ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, uint32_t 
 							best = d;
 							bestToken = leaf;
 							bestUV = uv;
+
+							if (INST)
+							{
+								hitCount = level;
+								for (uint32_t k = 0; k < level; k++) hitLayers[k] = current[k];
+							}
 						}
 					}
 				}
 				else
 				{
-					float4 sphere = __ldg(scene.spheres + token_index(leaf));
+					float4 sphere = __ldg(scene.spheres + (INST ? pack.sphereOffset : 0u) + token_index(leaf));
+					bool findFar = leaf == ignore && (!INST || ignoreHere);
 
-					if (ANY) occluded = sphere_occlude(sphere, origin, direction, best, leaf == ignore);
+					if (ANY) occluded = sphere_occlude(sphere, origin, direction, best, findFar);
 					else
 					{
 						vec2 uv;
-						float d = sphere_intersect(sphere, origin, direction, uv, leaf == ignore);
+						float d = sphere_intersect(sphere, origin, direction, uv, findFar);
 
 						if (!(d >= best)) // GeometryCollection.cs:115
 						{
 							best = d;
 							bestToken = leaf;
 							bestUV = uv;
+
+							if (INST)
+							{
+								hitCount = level;
+								for (uint32_t k = 0; k < level; k++) hitLayers[k] = current[k];
+							}
 						}
 					}
 				}
@@ -367,6 +484,7 @@ ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, uint32_t 
 					haveTop = false;
 					position = 4;
 					next = 0;
+					if (INST) { level = 0u; base = 0; }
 				}
 				else if (position < 4) scan_slots(); // the rest of this node's Push calls
 			}

@@ -109,6 +109,15 @@ static bool launch_instanced(const DeviceScene& scene, const EchoRay* rays, cons
 bool launch_trace_instanced(const DeviceScene& scene, const EchoRay* rays, const EchoTokenHierarchy* ignore, uint64_t n, EchoHit* hits,
                             EchoTokenHierarchy* hitLayers, unsigned long long* counts, cudaStream_t stream)
 {
+	if (n == 0) return true;
+
+	if (!counts && scene.packCount != 0u)
+	{
+		bool launched = false;
+		bool ok = launch_persistent_instanced(scene, rays, ignore, n, hits, hitLayers, nullptr, stream, launched);
+		if (launched || !ok) return ok;
+	}
+
 	return counts ? launch_instanced<false, true>(scene, rays, ignore, n, hits, hitLayers, nullptr, counts, stream)
 	              : launch_instanced<false, false>(scene, rays, ignore, n, hits, hitLayers, nullptr, nullptr, stream);
 }
@@ -116,6 +125,15 @@ bool launch_trace_instanced(const DeviceScene& scene, const EchoRay* rays, const
 bool launch_occlude_instanced(const DeviceScene& scene, const EchoRay* rays, const EchoTokenHierarchy* ignore, uint64_t n, uint8_t* occluded,
                               unsigned long long* counts, cudaStream_t stream)
 {
+	if (n == 0) return true;
+
+	if (!counts && scene.packCount != 0u)
+	{
+		bool launched = false;
+		bool ok = launch_persistent_instanced(scene, rays, ignore, n, nullptr, nullptr, occluded, stream, launched);
+		if (launched || !ok) return ok;
+	}
+
 	return counts ? launch_instanced<true, true>(scene, rays, ignore, n, nullptr, nullptr, occluded, counts, stream)
 	              : launch_instanced<true, false>(scene, rays, ignore, n, nullptr, nullptr, occluded, nullptr, stream);
 }

@@ -749,6 +749,38 @@ struct ExtendIO
 	ECHO_DEVICE void store_any(uint32_t, bool) const {}
 };
 
+// the instance layers of the wavefront's queues, in the IO form the instanced traversal core asks for
+struct ExtendLayersIO : ExtendIO
+{
+	const uint4* __restrict__ rayLayers;
+	uint4* __restrict__ hitLayers;
+
+	ECHO_DEVICE uint32_t load_ignore_layers(uint32_t index, uint32_t* tokens) const
+	{
+		PathLayers layers = load_layers(rayLayers, index);
+		for (uint32_t k = 0; k < ECHO_MAX_INSTANCE_LAYERS; k++) tokens[k] = layers.tokens[k];
+		return min(layers.count, ECHO_MAX_INSTANCE_LAYERS);
+	}
+
+	ECHO_DEVICE void store_hit_layers(uint32_t index, bool hit, const uint32_t* tokens, uint32_t count) const
+	{
+		PathLayers layers = no_layers();
+		if (hit)
+		{
+			layers.count = count;
+			for (uint32_t k = 0; k < count; k++) layers.tokens[k] = tokens[k];
+		}
+		store_layers(hitLayers, index, layers);
+	}
+};
+
+template<int STACK>
+__global__ void __launch_bounds__(kTraverseBlock) extend_layers_kernel(DeviceScene scene, ExtendLayersIO io, const uint32_t* __restrict__ queueCount, unsigned long long* __restrict__ nextRay)
+{
+	__shared__ float4 stagedRays[kTraverseBlock * 2];
+	persistent_traverse<STACK, false, true>(scene, io, *queueCount, nextRay, stagedRays);
+}
+
 template<int STACK>
 __global__ void __launch_bounds__(kTraverseBlock, ECHO_MIN_BLOCKS) extend_kernel(DeviceScene scene, ExtendIO io, const uint32_t* __restrict__ queueCount, unsigned long long* __restrict__ nextRay)
 {
@@ -1117,6 +1149,34 @@ struct ShadowIO
 		++passed;
 	}
 };
+
+struct ShadowLayersIO : ShadowIO
+{
+	const uint4* __restrict__ shadowLayers;
+
+	ECHO_DEVICE uint32_t load_ignore_layers(uint32_t index, uint32_t* tokens) const
+	{
+		PathLayers layers = load_layers(shadowLayers, index);
+		for (uint32_t k = 0; k < ECHO_MAX_INSTANCE_LAYERS; k++) tokens[k] = layers.tokens[k];
+		return min(layers.count, ECHO_MAX_INSTANCE_LAYERS);
+	}
+
+	ECHO_DEVICE void store_hit_layers(uint32_t, bool, const uint32_t*, uint32_t) const {}
+};
+
+template<int STACK>
+__global__ void __launch_bounds__(kTraverseBlock) shadow_layers_kernel(DeviceScene scene, ShadowLayersIO io, const uint32_t* __restrict__ shadowCount, unsigned long long* __restrict__ nextRay,
+                                                                       unsigned long long* __restrict__ stats)
+{
+	__shared__ float4 stagedRays[kTraverseBlock * 2];
+	io.passed = 0u;
+	persistent_traverse<STACK, true, true>(scene, io, *shadowCount, nextRay, stagedRays);
+
+	uint32_t passed = io.passed;
+	for (int offset = 16; offset > 0; offset >>= 1) passed += __shfl_down_sync(0xFFFFFFFFu, passed, offset);
+	if ((threadIdx.x & 31u) == 0u && passed) atomicAdd(stats + STAT_LIGHT_OCCLUSION_PASSED, (unsigned long long)passed);
+	if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(stats + STAT_OCCLUDE_QUERIES, (unsigned long long)*shadowCount);
+}
 
 template<int STACK>
 __global__ void __launch_bounds__(kTraverseBlock, ECHO_MIN_BLOCKS) shadow_kernel(DeviceScene scene, ShadowIO io, const uint32_t* __restrict__ shadowCount, unsigned long long* __restrict__ nextRay,
@@ -1552,7 +1612,17 @@ static bool evaluate_paths(WorkerState* state, const DeviceScene& scene, const E
 
 		gTimer.start(stream);
 		ExtendIO extendIO = { paths.rayQueue[current], paths.hitQueue };
-		if (INST) extend_instanced_kernel<STACK><<<blocks, kBlock, 0, stream>>>(scene, extendIO, paths.rayLayers[current], paths.hitLayers, activeCount);
+		if (INST && active >= narrowLimit)
+		{
+			static int layersGrid = persistent_grid((const void*)extend_layers_kernel<STACK>);
+			ExtendLayersIO layersIO;
+			layersIO.rays = extendIO.rays;
+			layersIO.hits = extendIO.hits;
+			layersIO.rayLayers = paths.rayLayers[current];
+			layersIO.hitLayers = paths.hitLayers;
+			extend_layers_kernel<STACK><<<std::min<unsigned int>(blocks, (unsigned int)layersGrid), kTraverseBlock, 0, stream>>>(scene, layersIO, activeCount, extendCounter);
+		}
+		else if (INST) extend_instanced_kernel<STACK><<<blocks, kBlock, 0, stream>>>(scene, extendIO, paths.rayLayers[current], paths.hitLayers, activeCount);
 		else if (active < narrowLimit) extend_narrow_kernel<STACK><<<blocks, kBlock, 0, stream>>>(scene, extendIO, activeCount);
 		else extend_kernel<STACK><<<std::min<unsigned int>(blocks, (unsigned int)extendGrid), kTraverseBlock, 0, stream>>>(scene, extendIO, activeCount, extendCounter);
 		gTimer.stop(KernelTimer::EXTEND, stream);
@@ -1580,7 +1650,18 @@ static bool evaluate_paths(WorkerState* state, const DeviceScene& scene, const E
 
 		gTimer.start(stream);
 		ShadowIO shadowIO = { paths.shadowQueue, paths.shadowValue, paths.result, 0u };
-		if (INST) shadow_instanced_kernel<STACK><<<blocks, kBlock, 0, stream>>>(scene, shadowIO, paths.shadowLayers, counters + COUNTER_SHADOW, paths.stats);
+		if (INST && active >= narrowLimit)
+		{
+			static int layersGrid = persistent_grid((const void*)shadow_layers_kernel<STACK>);
+			ShadowLayersIO layersIO;
+			layersIO.rays = shadowIO.rays;
+			layersIO.values = shadowIO.values;
+			layersIO.result = shadowIO.result;
+			layersIO.passed = 0u;
+			layersIO.shadowLayers = paths.shadowLayers;
+			shadow_layers_kernel<STACK><<<std::min<unsigned int>(blocks, (unsigned int)layersGrid), kTraverseBlock, 0, stream>>>(scene, layersIO, counters + COUNTER_SHADOW, shadowCounter, paths.stats);
+		}
+		else if (INST) shadow_instanced_kernel<STACK><<<blocks, kBlock, 0, stream>>>(scene, shadowIO, paths.shadowLayers, counters + COUNTER_SHADOW, paths.stats);
 		else if (active < narrowLimit) shadow_narrow_kernel<STACK><<<blocks, kBlock, 0, stream>>>(scene, shadowIO, counters + COUNTER_SHADOW, paths.stats);
 		else shadow_kernel<STACK><<<std::min<unsigned int>(blocks, (unsigned int)shadowGrid), kTraverseBlock, 0, stream>>>(scene, shadowIO, counters + COUNTER_SHADOW, shadowCounter, paths.stats);
 		gTimer.stop(KernelTimer::SHADOW, stream);

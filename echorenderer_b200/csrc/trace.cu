@@ -106,6 +106,25 @@ struct BatchIO
 	const float4* __restrict__ rays;
 	float4* __restrict__ hits;
 	uint8_t* __restrict__ occluded;
+	const uint32_t* __restrict__ ignoreLayers; // instanced scenes: EchoTokenHierarchy per query (6 words), nullable
+	uint32_t* __restrict__ hitLayers;          // EchoTokenHierarchy per hit, nullable
+
+	ECHO_DEVICE uint32_t load_ignore_layers(uint32_t index, uint32_t* tokens) const
+	{
+		if (!ignoreLayers) return 0u;
+		const uint32_t* in = ignoreLayers + (size_t)index * 6;
+		uint32_t count = min(__ldg(in), ECHO_MAX_INSTANCE_LAYERS);
+		for (uint32_t k = 0; k < count; k++) tokens[k] = __ldg(in + 1 + k);
+		return count;
+	}
+
+	ECHO_DEVICE void store_hit_layers(uint32_t index, bool hit, const uint32_t* tokens, uint32_t count) const
+	{
+		if (!hitLayers) return;
+		uint32_t* out = hitLayers + (size_t)index * 6;
+		out[0] = hit ? count : 0u;
+		for (uint32_t k = 0; k < ECHO_MAX_INSTANCE_LAYERS; k++) out[1 + k] = hit && k < count ? tokens[k] : 0u;
+	}
 
 	ECHO_DEVICE const float4* ray_pointer(uint32_t index) const { return rays + (size_t)index * 2; }
 
@@ -122,6 +141,14 @@ __global__ void __launch_bounds__(kTraverseBlock, ECHO_MIN_BLOCKS) persistent_ba
 {
 	__shared__ float4 stagedRays[kTraverseBlock * 2];
 	persistent_traverse<STACK, ANY>(scene, io, n, nextRay, stagedRays);
+}
+
+// the same through instanced packs (echo_traverse.cuh INST); more per-lane state, so no occupancy target is forced
+template<int STACK, bool ANY>
+__global__ void __launch_bounds__(kTraverseBlock) persistent_instanced_kernel(DeviceScene scene, BatchIO io, uint32_t n, unsigned long long* __restrict__ nextRay)
+{
+	__shared__ float4 stagedRays[kTraverseBlock * 2];
+	persistent_traverse<STACK, ANY, true>(scene, io, n, nextRay, stagedRays);
 }
 
 // Every persistent launch needs its own zeroed ray counter (launches on different streams may overlap): a per-device ring.
@@ -166,7 +193,7 @@ static bool launch_persistent(const DeviceScene& scene, const EchoRay* rays, uin
 		unsigned long long* counter = next_ray_counter(stream);
 		if (!counter) return false;
 
-		BatchIO io = { reinterpret_cast<const float4*>(rays + first), hits ? reinterpret_cast<float4*>(hits + first) : nullptr, occluded ? occluded + first : nullptr };
+		BatchIO io = { reinterpret_cast<const float4*>(rays + first), hits ? reinterpret_cast<float4*>(hits + first) : nullptr, occluded ? occluded + first : nullptr, nullptr, nullptr };
 		uint64_t needed = (count + kTraverseBlock - 1) / kTraverseBlock;
 		unsigned int blocks = (unsigned int)(needed < (uint64_t)grid ? needed : (uint64_t)grid);
 		persistent_batch_kernel<STACK, ANY><<<blocks, kTraverseBlock, 0, stream>>>(scene, io, (uint32_t)count, counter);
@@ -174,6 +201,53 @@ static bool launch_persistent(const DeviceScene& scene, const EchoRay* rays, uin
 	}
 
 	return true;
+}
+
+template<int STACK, bool ANY>
+static bool launch_persistent_instanced_impl(const DeviceScene& scene, const EchoRay* rays, const EchoTokenHierarchy* ignore, uint64_t n, EchoHit* hits,
+                                             EchoTokenHierarchy* hitLayers, uint8_t* occluded, cudaStream_t stream)
+{
+	static int grid = persistent_grid((const void*)persistent_instanced_kernel<STACK, ANY>);
+	constexpr uint64_t kLaunchLimit = 1ull << 31;
+
+	for (uint64_t first = 0; first < n; first += kLaunchLimit)
+	{
+		uint64_t count = n - first < kLaunchLimit ? n - first : kLaunchLimit;
+		unsigned long long* counter = next_ray_counter(stream);
+		if (!counter) return false;
+
+		BatchIO io = { reinterpret_cast<const float4*>(rays + first), hits ? reinterpret_cast<float4*>(hits + first) : nullptr, occluded ? occluded + first : nullptr,
+		               ignore ? reinterpret_cast<const uint32_t*>(ignore + first) : nullptr, hitLayers ? reinterpret_cast<uint32_t*>(hitLayers + first) : nullptr };
+		uint64_t needed = (count + kTraverseBlock - 1) / kTraverseBlock;
+		unsigned int blocks = (unsigned int)(needed < (uint64_t)grid ? needed : (uint64_t)grid);
+		persistent_instanced_kernel<STACK, ANY><<<blocks, kTraverseBlock, 0, stream>>>(scene, io, (uint32_t)count, counter);
+		if (!check_cuda(cudaGetLastError(), "persistent_instanced_kernel launch")) return false;
+	}
+
+	return true;
+}
+
+static bool use_simple_kernels();
+
+// persistent, work-replacing kernels for instanced scenes; false + no error when the simple kernels should be used instead
+bool launch_persistent_instanced(const DeviceScene& scene, const EchoRay* rays, const EchoTokenHierarchy* ignore, uint64_t n, EchoHit* hits,
+                                 EchoTokenHierarchy* hitLayers, uint8_t* occluded, cudaStream_t stream, bool& launched)
+{
+	launched = false;
+	if (use_simple_kernels()) return true;
+	launched = true;
+	bool any = occluded != nullptr;
+
+	switch (stack_class(scene.maxDepth))
+	{
+		case 0: return any ? launch_persistent_instanced_impl<48, true>(scene, rays, ignore, n, hits, hitLayers, occluded, stream)
+		                   : launch_persistent_instanced_impl<48, false>(scene, rays, ignore, n, hits, hitLayers, occluded, stream);
+		case 1: return any ? launch_persistent_instanced_impl<96, true>(scene, rays, ignore, n, hits, hitLayers, occluded, stream)
+		                   : launch_persistent_instanced_impl<96, false>(scene, rays, ignore, n, hits, hitLayers, occluded, stream);
+		case 2: return any ? launch_persistent_instanced_impl<192, true>(scene, rays, ignore, n, hits, hitLayers, occluded, stream)
+		                   : launch_persistent_instanced_impl<192, false>(scene, rays, ignore, n, hits, hitLayers, occluded, stream);
+		default: set_error("the deepest chain of instanced packs needs more than 192 stack entries"); return false;
+	}
 }
 
 static bool use_simple_kernels()
