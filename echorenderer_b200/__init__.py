@@ -4,9 +4,9 @@ The package holds only what the hot path needs: csrc/ (hand-written CUDA for sm_
 scene preparation in C++), the ctypes binding, and the host-side mirror of the reference interface for this path.
 """
 from . import structs  # noqa: F401
-from .host import PreparedArrays, SceneDescription, prepare  # noqa: F401
-from .scene import (EvaluationOperation, EvaluationProfile, PathTracedEvaluator, PreparedScene, RenderTexture,  # noqa: F401
-                    shard_tiles)
+from .host import InstanceDescription, PackDescription, PreparedArrays, SceneDescription, prepare  # noqa: F401
+from .scene import (AlbedoEvaluator, EvaluationOperation, EvaluationProfile, NormalDepthEvaluator, PathTracedEvaluator,  # noqa: F401
+                    PreparedScene, RenderTexture, shard_tiles)
 from ._native import EchoNativeError  # noqa: F401
 
 __version__ = "0.1.0"

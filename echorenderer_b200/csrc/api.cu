@@ -25,7 +25,7 @@ bool check_cuda(cudaError_t status, const char* what)
 	return false;
 }
 
-bool evaluate_sample_list(RenderState* state, const DeviceScene& scene, const EchoRenderParams& params, const int32_t* pixelXYHost, const uint32_t* sampleIndexHost,
+bool evaluate_sample_list(RenderState* state, const DeviceScene& scene, const EchoRenderParams& params, int channels, const int32_t* pixelXYHost, const uint32_t* sampleIndexHost,
                           uint64_t n, float* outRGBHost, cudaStream_t stream);
 
 } // namespace echo
@@ -302,6 +302,14 @@ int32_t echo_b200_scene_set_camera(EchoScene* scene, const EchoCamera* camera)
 	return ECHO_B200_OK;
 }
 
+int32_t echo_b200_scene_set_bound_radius(EchoScene* scene, float radius)
+{
+	if (!scene) return fail(ECHO_B200_ERR_INVALID, "null argument");
+	scene->boundRadius = radius;
+	if (scene->committed) scene->d.boundRadius = radius; // travels by value with every launch, like the camera
+	return ECHO_B200_OK;
+}
+
 int32_t echo_b200_scene_set_packs(EchoScene* scene, const EchoPack* packs, uint32_t packCount, const EchoInstance* instances, uint32_t instanceCount)
 {
 	if (!scene || (!packs && packCount) || (!instances && instanceCount)) return fail(ECHO_B200_ERR_INVALID, "null argument");
@@ -510,6 +518,7 @@ int32_t echo_b200_scene_commit(EchoScene* scene)
 	d.infiniteThreshold = scene->infiniteThreshold;
 	d.infinitePdf = scene->infinitePdf;
 	d.camera = scene->camera;
+	d.boundRadius = scene->boundRadius;
 
 	scene->committed = true;
 	return ECHO_B200_OK;
@@ -670,7 +679,16 @@ int32_t echo_b200_debug_evaluate_samples(EchoScene* scene, const EchoRenderParam
 	if (!params || !pixelXY || !sampleIndex || !outRGB) return fail(ECHO_B200_ERR_INVALID, "null argument");
 	DeviceGuard guard(scene->device);
 	if (!guard.ok) return ECHO_B200_ERR_NO_DEVICE;
-	return evaluate_sample_list(scene->render, scene->d, *params, pixelXY, sampleIndex, n, outRGB, scene->stream) ? ECHO_B200_OK : ECHO_B200_ERR_CUDA;
+	return evaluate_sample_list(scene->render, scene->d, *params, 3, pixelXY, sampleIndex, n, outRGB, scene->stream) ? ECHO_B200_OK : ECHO_B200_ERR_CUDA;
+}
+
+int32_t echo_b200_debug_evaluate_samples4(EchoScene* scene, const EchoRenderParams* params, const int32_t* pixelXY, const uint32_t* sampleIndex, uint64_t n, float* outRGBA)
+{
+	if (!require_committed(scene)) return ECHO_B200_ERR_INVALID;
+	if (!params || !pixelXY || !sampleIndex || !outRGBA) return fail(ECHO_B200_ERR_INVALID, "null argument");
+	DeviceGuard guard(scene->device);
+	if (!guard.ok) return ECHO_B200_ERR_NO_DEVICE;
+	return evaluate_sample_list(scene->render, scene->d, *params, 4, pixelXY, sampleIndex, n, outRGBA, scene->stream) ? ECHO_B200_OK : ECHO_B200_ERR_CUDA;
 }
 
 static int32_t debug_device(int32_t device)

@@ -75,6 +75,7 @@ struct EchoScene
 	std::vector<EchoInfiniteLight> infiniteLights;
 	float infiniteThreshold = 0.0f, infinitePdf = 0.0f;
 	EchoCamera camera = {};
+	float boundRadius = 0.0f;
 	std::vector<EchoPack> packs; // empty: the arrays are one pack
 	std::vector<EchoInstance> instances;
 

@@ -37,6 +37,7 @@ struct DeviceScene
 	uint32_t maxDepth;             // quad depth whose 3 * maxDepth + 1 stack entries serve the deepest chain of packs
 	uint32_t packCount, instanceCount;
 	float infiniteThreshold, infinitePdf;
+	float boundRadius; // Accelerator.SphereBound.radius, read by the NormalDepth evaluator
 
 	EchoCamera camera;
 };

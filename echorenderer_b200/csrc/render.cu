@@ -1238,6 +1238,137 @@ __global__ void __launch_bounds__(kBlock) shadow_instanced_kernel(DeviceScene sc
 	stat_add(stats, STAT_LIGHT_OCCLUSION_PASSED, io.passed != 0u);
 }
 
+// ---- Scalars.AlmostEquals (Scalars.cs:153-168) and Float3.Equals (Float3.cs:369) ----
+ECHO_DEVICE bool almost_equals(float value, float other)
+{
+	if (value == other) return true;
+	const float epsilon = 1E-5f, normal = 1.17549435E-38f; // (1L << 23) * float.Epsilon
+
+	float difference = fabsf(value - other);
+	if (value == 0.0f || other == 0.0f || difference < normal) return difference < epsilon * normal;
+
+	float sum = fabsf(value) + fabsf(other);
+	float capped = sum != sum ? sum : (sum < 3.40282347E+38f ? sum : 3.40282347E+38f); // Math.Min(sum, float.MaxValue)
+	return difference < epsilon * capped;
+}
+
+ECHO_DEVICE bool float3_equals(vec3 a, vec3 b) { return almost_equals(a.x, b.x) && almost_equals(a.y, b.y) && almost_equals(a.z, b.z); }
+
+constexpr uint32_t KINDS_AUXILIARY = kind_bit(BSDF_EMPTY) | kind_bit(BSDF_DIELECTRIC_SPECULAR) | kind_bit(BSDF_CONDUCTOR_SPECULAR) | kind_bit(BSDF_INVISIBLE);
+constexpr int kAuxiliaryBounceCap = 1024; // both evaluators loop `while (scene.Trace(...))`; the cap only guards the GPU against a hall of mirrors (the oracle has the same one)
+
+// AlbedoEvaluator.Evaluate (AlbedoEvaluator.cs:18-55) / NormalDepthEvaluator.Evaluate (NormalDepthEvaluator.cs:20-60): one
+// thread per sample follows purely specular bounces from the camera ray raygen_kernel left in rayQueue[0] and reports the
+// first other surface. These passes run at a few samples per pixel for the denoiser: a plain loop, no wavefront.
+template<int STACK, bool INST>
+__global__ void __launch_bounds__(kBlock) auxiliary_kernel(DeviceScene scene, EchoRenderParams params, uint32_t count, PathBuffers paths, float4* __restrict__ out)
+{
+	uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+	if (i >= count) return;
+
+	float4 rayA = paths.rayQueue[0][i * 2u], rayB = paths.rayQueue[0][i * 2u + 1u];
+	vec3 origin = xyz(rayA), direction = { rayA.w, rayB.x, rayB.y };
+	const vec3 cameraDirection = direction;
+	const uint32_t key = paths.key[i];
+	const int kind = params.evaluator & ECHO_EVALUATOR_KIND_MASK;
+	const bool divergeOnce = (params.evaluator & ECHO_EVALUATOR_DIVERGE_ONCE) != 0;
+
+	uint32_t dimension = 4u; // after CameraSample's four (CameraSample.cs:19-23); one Next2D per specular bounce
+	uint32_t ignore = ECHO_TOKEN_EMPTY;
+	PathLayers ignoreLayers = no_layers();
+	bool direct = true; // whether the path is still going in its original direction
+	bool exited = false;
+	float depth = 0.0f;
+	float4 result = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+
+	for (int bounce = 0; bounce < kAuxiliaryBounceCap && !exited; bounce++)
+	{
+		float distance = kInfinity;
+		uint32_t token = ECHO_TOKEN_EMPTY;
+		vec2 uv = { 0.0f, 0.0f };
+		PathLayers hitLayers = no_layers();
+		bool hit;
+
+		if (INST)
+		{
+			traverse_instanced<STACK, false, false>(scene, origin, direction, ignore, ignoreLayers.tokens, ignoreLayers.count, distance, token, uv, hitLayers.tokens, hitLayers.count, nullptr);
+			hit = distance < kInfinity;
+		}
+		else hit = scene_trace<STACK, false>(scene, origin, direction, ignore, distance, token, uv, nullptr);
+
+		if (!hit) break;
+
+		// PreparedScene.Interact + material.Scatter, as in shade_kernel
+		Layer layer = find_layer<INST>(scene, hitLayers);
+		vec3 infoNormal, infoShading;
+		uint32_t materialIndex;
+
+		if (token_type(token) == ECHO_TOKEN_TYPE_TRIANGLE)
+		{
+			TriangleData triangle = load_triangle(scene, layer.info.triangleOffset + token_index(token));
+			materialIndex = layer.materialOffset + triangle.material;
+			infoNormal = triangle_normal(triangle);
+			infoShading = triangle_shading_normal(triangle, uv);
+		}
+		else
+		{
+			materialIndex = layer.materialOffset + __ldg(scene.sphereMaterial + layer.info.sphereOffset + token_index(token));
+			infoNormal = infoShading = sphere_normal(uv);
+		}
+
+		vec3 position = direction * max_net(distance, kEpsilon) + origin;
+		vec3 normal = normalized(transform_direction(layer.inverse, infoNormal));
+		vec3 shadeNormal = normalized(transform_direction(layer.inverse, infoShading));
+		vec3 outgoing = -direction;
+
+		MaterialRecord material = load_material(scene, materialIndex);
+		Bsdf bsdf;
+		material_scatter(scene, material, outgoing, normal, shadeNormal, bsdf);
+
+		// Exit(): (RGB128)material.SampleAlbedo(contact) / new NormalDepth128(contact.shade.Normal, depth).ToFloat4()
+		auto leave = [&]()
+		{
+			result = kind == ECHO_EVALUATOR_ALBEDO ? make_float4(material.albedo[0], material.albedo[1], material.albedo[2], 0.0f)
+			                                       : make_float4(shadeNormal.x, shadeNormal.y, shadeNormal.z, depth);
+			exited = true;
+		};
+
+		if (!direct) { leave(); continue; }
+		if (kind == ECHO_EVALUATOR_NORMAL_DEPTH) depth += distance;
+
+		if (((KINDS_AUXILIARY >> bsdf.kind) & 1u) == 0u) { leave(); continue; } // bsdf.Count != bsdf.CountSpecular: not fully specular
+
+		vec2 sample = { sample_value(key, dimension), sample_value(key, dimension + 1u) };
+		dimension += 2u;
+
+		vec3 incident;
+		int selectedType;
+		Sampled sampled = bsdf_sample<KINDS_AUXILIARY>(bsdf, outgoing, sample, incident, selectedType);
+		if (!positive(sampled.pdf)) { leave(); continue; } // sample.NotPossible
+
+		if (!float3_equals(incident, cameraDirection)) direct = false; // compared with the CAMERA ray's direction
+		if (!divergeOnce && !direct) { leave(); continue; }
+
+		// query.SpawnTrace(incident), TraceQuery.cs:88
+		origin = position;
+		direction = incident;
+		ignore = token;
+		ignoreLayers = hitLayers;
+	}
+
+	if (!exited)
+	{
+		if (kind == ECHO_EVALUATOR_ALBEDO) result = make4(evaluate_infinite(scene, direct), 0.0f); // scene.EvaluateInfinite(query.ray.direction, direct)
+		else
+		{
+			if (direct) depth = scene.boundRadius * 2.0f; // negative direction and scene diameter for escaped rays
+			result = make_float4(-cameraDirection.x, -cameraDirection.y, -cameraDirection.z, depth);
+		}
+	}
+
+	out[i] = result;
+}
+
 __global__ void __launch_bounds__(kBlock) finish_kernel(uint32_t count, PathBuffers paths, float4* __restrict__ out)
 {
 	uint32_t i = blockIdx.x * kBlock + threadIdx.x;
@@ -1591,6 +1722,13 @@ static bool evaluate_paths(WorkerState* state, const DeviceScene& scene, const E
 	if (!check_cuda(cudaMemcpyAsync(activeCount, &count, sizeof(uint32_t), cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync(count)")) return false;
 	++launches;
 
+	if ((params.evaluator & ECHO_EVALUATOR_KIND_MASK) != ECHO_EVALUATOR_PATH_TRACED)
+	{
+		auxiliary_kernel<STACK, INST><<<blocks_for(count), kBlock, 0, stream>>>(scene, params, count, paths, state->sampleOut);
+		++launches;
+		return check_cuda(cudaGetLastError(), "auxiliary_kernel launch");
+	}
+
 	uint32_t active = count;
 	int current = 0;
 
@@ -1859,7 +1997,7 @@ bool render_tiles(RenderState* state, const DeviceScene& scene, const EchoRender
 }
 
 // debug: explicit (pixel, sample) lists -> per-sample radiance (device pointers in, device pointer out)
-bool evaluate_sample_list(RenderState* renderState, const DeviceScene& scene, const EchoRenderParams& params, const int32_t* pixelXYHost, const uint32_t* sampleIndexHost,
+bool evaluate_sample_list(RenderState* renderState, const DeviceScene& scene, const EchoRenderParams& params, int channels, const int32_t* pixelXYHost, const uint32_t* sampleIndexHost,
                           uint64_t n, float* outRGBHost, cudaStream_t)
 {
 	WorkerState* state = get_worker(renderState, 0);
@@ -1885,9 +2023,8 @@ bool evaluate_sample_list(RenderState* renderState, const DeviceScene& scene, co
 
 		for (uint32_t i = 0; i < count; i++)
 		{
-			outRGBHost[(first + i) * 3 + 0] = staging[i].x;
-			outRGBHost[(first + i) * 3 + 1] = staging[i].y;
-			outRGBHost[(first + i) * 3 + 2] = staging[i].z;
+			const float lanes[4] = { staging[i].x, staging[i].y, staging[i].z, staging[i].w };
+			for (int c = 0; c < channels; c++) outRGBHost[(first + i) * channels + c] = lanes[c];
 		}
 	}
 

@@ -143,6 +143,13 @@ class PreparedArrays:
         return self.description.materials if self.all_materials is None else self.all_materials
 
     @property
+    def bound_radius(self):
+        """Stand-in for Accelerator.SphereBound.radius (Accelerator.cs:43-63): the half diagonal of the root bound, the same
+        stand-in the ambient-light power uses."""
+        low, high = self.bounds
+        return float(np.float32(np.linalg.norm((high.astype(np.float64) - low.astype(np.float64))) / 2))
+
+    @property
     def bounds(self):
         """BoxBound of the whole accelerator (Accelerator.BoxBound): min/max over the root node's children."""
         root = self.nodes[0]

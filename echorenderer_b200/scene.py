@@ -45,6 +45,7 @@ class PreparedScene:
             _native.check(lib.echo_b200_scene_set_infinite(self._handle, ptr(d.infinite_lights), len(d.infinite_lights),
                                                            prepared.infinite_threshold, prepared.infinite_pdf))
             _native.check(lib.echo_b200_scene_set_camera(self._handle, ptr(d.camera)))
+            _native.check(lib.echo_b200_scene_set_bound_radius(self._handle, prepared.bound_radius))
             _native.check(lib.echo_b200_scene_commit(self._handle))
         except Exception:
             self.close()
@@ -147,13 +148,14 @@ class PreparedScene:
     def frame_resolve_device(self, frame_pointer, width, height, stream=0):
         _native.check(self._lib.echo_b200_frame_resolve_device(self._handle, ctypes.c_void_p(frame_pointer), width, height, ctypes.c_void_p(stream)))
 
-    def evaluate_samples(self, params, pixel_xy, sample_index):
-        """Diagnostic: one Evaluator.Evaluate per (pixel, sample index) -> radiance[n, 3]."""
+    def evaluate_samples(self, params, pixel_xy, sample_index, channels=3):
+        """Diagnostic: one Evaluator.Evaluate per (pixel, sample index) -> radiance[n, 3] (channels=4 keeps the W lane the
+        auxiliary evaluators use, e.g. NormalDepth128's depth)."""
         pixel_xy = np.ascontiguousarray(pixel_xy, dtype=np.int32).reshape(-1, 2)
         sample_index = np.ascontiguousarray(sample_index, dtype=np.uint32)
-        out = np.zeros((len(sample_index), 3), dtype=np.float32)
-        _native.check(self._lib.echo_b200_debug_evaluate_samples(self._handle, _native.pointer(params), _native.pointer(pixel_xy),
-                                                                 _native.pointer(sample_index), len(sample_index), _native.pointer(out)))
+        out = np.zeros((len(sample_index), channels), dtype=np.float32)
+        entry = self._lib.echo_b200_debug_evaluate_samples if channels == 3 else self._lib.echo_b200_debug_evaluate_samples4
+        _native.check(entry(self._handle, _native.pointer(params), _native.pointer(pixel_xy), _native.pointer(sample_index), len(sample_index), _native.pointer(out)))
         return out
 
 
@@ -164,10 +166,39 @@ class PathTracedEvaluator:
     survivability: float = 2.5
 
 
+    @property
+    def code(self):
+        return structs.EVALUATOR_PATH_TRACED
+
+
+@dataclass(frozen=True)
+class AlbedoEvaluator:
+    """Evaluation/Evaluators/AlbedoEvaluator.cs:13-16: the first non-specular surface's albedo (Float4, W = 0)."""
+    diverge_once: bool = True
+    bounce_limit: int = 128      # unused by this evaluator; kept so every evaluator fills EchoRenderParams the same way
+    survivability: float = 2.5
+
+    @property
+    def code(self):
+        return structs.EVALUATOR_ALBEDO | (structs.EVALUATOR_DIVERGE_ONCE if self.diverge_once else 0)
+
+
+@dataclass(frozen=True)
+class NormalDepthEvaluator:
+    """Evaluation/Evaluators/NormalDepthEvaluator.cs:13-18: shading normal + depth (NormalDepth128.ToFloat4)."""
+    diverge_once: bool = False
+    bounce_limit: int = 128
+    survivability: float = 2.5
+
+    @property
+    def code(self):
+        return structs.EVALUATOR_NORMAL_DEPTH | (structs.EVALUATOR_DIVERGE_ONCE if self.diverge_once else 0)
+
+
 @dataclass(frozen=True)
 class EvaluationProfile:
     """Processes/Evaluation/EvaluationProfile.cs:13-75 (Distribution reduced to its Extend and seed)."""
-    evaluator: PathTracedEvaluator = field(default_factory=PathTracedEvaluator)
+    evaluator: object = field(default_factory=PathTracedEvaluator)
     extend: int = 16                # ContinuousDistribution.Extend, ContinuousDistribution.cs:25
     min_epoch: int = 1
     max_epoch: int = 20
@@ -232,7 +263,8 @@ class EvaluationOperation:
     def params(self):
         p = self.profile
         return structs.render_params(self.destination.width, self.destination.height, self.destination.tile_size, p.extend, p.min_epoch,
-                                     p.max_epoch, p.noise_threshold, p.evaluator.bounce_limit, p.evaluator.survivability, p.seed)
+                                     p.max_epoch, p.noise_threshold, p.evaluator.bounce_limit, p.evaluator.survivability, p.seed,
+                                     evaluator=p.evaluator.code)
 
     @property
     def total_samples(self):

@@ -89,8 +89,11 @@ CAMERA = np.dtype([("transform", "<f4", 12), ("forwardLength", "<f4"), ("lensRad
 RENDER_PARAMS = np.dtype([
     ("width", "<i4"), ("height", "<i4"), ("tileSize", "<i4"), ("extend", "<i4"), ("minEpoch", "<i4"), ("maxEpoch", "<i4"),
     ("noiseThreshold", "<f4"), ("bounceLimit", "<i4"), ("survivability", "<f4"), ("seed", "<u4"), ("epochOffset", "<i4"),
-    ("reserved", "<i4"),
+    ("evaluator", "<i4"),
 ])
+
+EVALUATOR_PATH_TRACED, EVALUATOR_ALBEDO, EVALUATOR_NORMAL_DEPTH = 0, 1, 2
+EVALUATOR_DIVERGE_ONCE = 0x100
 
 STATS_FIELDS = [
     "sampleEvaluated", "sampleRejected", "pixelEvaluated", "bounceCreated", "bounceSpecular", "bounceMis",
@@ -120,11 +123,12 @@ assert STATS.itemsize == 128
 
 
 def render_params(width, height, tile_size=16, extend=16, min_epoch=1, max_epoch=1, noise_threshold=0.045,
-                  bounce_limit=128, survivability=2.5, seed=1, epoch_offset=0):
-    """EvaluationProfile + PathTracedEvaluator defaults (EvaluationProfile.cs:42-60, PathTracedEvaluator.cs:33,40)."""
+                  bounce_limit=128, survivability=2.5, seed=1, epoch_offset=0, evaluator=EVALUATOR_PATH_TRACED):
+    """EvaluationProfile + PathTracedEvaluator defaults (EvaluationProfile.cs:42-60, PathTracedEvaluator.cs:33,40).
+    evaluator: EVALUATOR_* [| EVALUATOR_DIVERGE_ONCE] (AlbedoEvaluator.cs, NormalDepthEvaluator.cs)."""
     params = np.zeros(1, dtype=RENDER_PARAMS)
     params["width"], params["height"], params["tileSize"] = width, height, tile_size
     params["extend"], params["minEpoch"], params["maxEpoch"] = extend, min_epoch, max_epoch
     params["noiseThreshold"], params["bounceLimit"], params["survivability"] = noise_threshold, bounce_limit, survivability
-    params["seed"], params["epochOffset"] = seed, epoch_offset
+    params["seed"], params["epochOffset"], params["evaluator"] = seed, epoch_offset, evaluator
     return params

@@ -218,8 +218,19 @@ typedef struct EchoRenderParams
 	float survivability;    /* PathTracedEvaluator.Survivability */
 	uint32_t seed;          /* counter-based sample sequence seed */
 	int32_t epochOffset;    /* first epoch index this call renders (sample sharding across devices) */
-	int32_t reserved;
+	int32_t evaluator;      /* ECHO_EVALUATOR_* [| ECHO_EVALUATOR_DIVERGE_ONCE]; 0 = PathTracedEvaluator */
 } EchoRenderParams;
+
+/* EvaluationProfile.Evaluator (EvaluationProfile.cs:23): the path tracer, or one of the two auxiliary evaluators the
+ * StandardPathTracedProfile runs for its denoiser (Processes/StandardPathTracedProfile.cs:27-45). The auxiliary ones
+ * follow purely specular bounces from the camera and report the first other surface: its albedo, W = 0
+ * (Evaluation/Evaluators/AlbedoEvaluator.cs:18-55) or NormalDepth128.ToFloat4() = shading normal, W = depth travelled
+ * (Evaluation/Evaluators/NormalDepthEvaluator.cs:20-60). bounceLimit / survivability are not read by them. */
+#define ECHO_EVALUATOR_PATH_TRACED 0
+#define ECHO_EVALUATOR_ALBEDO 1
+#define ECHO_EVALUATOR_NORMAL_DEPTH 2
+#define ECHO_EVALUATOR_KIND_MASK 0xFF
+#define ECHO_EVALUATOR_DIVERGE_ONCE 0x100 /* the evaluator's DivergeOnce property (default: true for Albedo, false for NormalDepth) */
 
 /* ---- EvaluatorStatistics rows on the hot path, same labels/order as the reference reports them
  * (EvaluationOperation.cs:130-140; PathTracedEvaluator.cs:50-199) ---- */
@@ -256,6 +267,9 @@ int32_t echo_b200_scene_set_light_tree(EchoScene*, const EchoLightNode* nodes, u
                                        const EchoPointLight* points, uint32_t point_count);
 int32_t echo_b200_scene_set_infinite(EchoScene*, const EchoInfiniteLight* lights, uint32_t count, float threshold, float pdf);
 int32_t echo_b200_scene_set_camera(EchoScene*, const EchoCamera* camera);
+/* Accelerator.SphereBound.radius of the scene (Accelerator.cs:43-63): the NormalDepthEvaluator reports twice this as the
+ * depth of rays that escape (NormalDepthEvaluator.cs:57). Optional; 0 when never set. May be called after commit. */
+int32_t echo_b200_scene_set_bound_radius(EchoScene*, float radius);
 /* optional: declares the scene instanced (see EchoPack). Without it the scene is the single pack the arrays describe. */
 int32_t echo_b200_scene_set_packs(EchoScene*, const EchoPack* packs, uint32_t pack_count, const EchoInstance* instances, uint32_t instance_count);
 int32_t echo_b200_scene_commit(EchoScene*);

@@ -29,6 +29,10 @@ int32_t echo_b200_debug_math(int32_t device, int32_t op, const float* a, const f
 int32_t echo_b200_debug_evaluate_samples(EchoScene*, const EchoRenderParams*, const int32_t* pixel_xy, const uint32_t* sample_index,
                                          uint64_t n, float* out_rgb);
 
+/* The same with the W lane kept (n x 4 floats): the auxiliary evaluators use it (NormalDepth128's depth). */
+int32_t echo_b200_debug_evaluate_samples4(EchoScene*, const EchoRenderParams*, const int32_t* pixel_xy, const uint32_t* sample_index,
+                                          uint64_t n, float* out_rgba);
+
 #ifdef __cplusplus
 }
 #endif

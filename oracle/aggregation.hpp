@@ -309,6 +309,7 @@ struct Scene
 	float infiniteLightsPdf = 0.0f;       // PreparedScene.cs:39
 
 	EchoCamera camera = {};
+	float boundRadius = 0.0f; // Accelerator.SphereBound.radius (Accelerator.cs:43-63), read by NormalDepthEvaluator
 
 	// instancing: the arrays above hold every pack back to back (include/echo_b200.h EchoPack); empty = one pack
 	std::vector<EchoPack> packs;

@@ -77,6 +77,8 @@ void oracle_scene_set_light_tree(OracleScene* s, const EchoLightNode* nodes, uin
 	s->scene.rebuild_light_maps();
 }
 
+void oracle_scene_set_bound_radius(OracleScene* s, float radius) { s->scene.boundRadius = radius; }
+
 void oracle_scene_set_infinite(OracleScene* s, const EchoInfiniteLight* lights, uint32_t count, float threshold, float pdf)
 {
 	s->scene.infiniteLights.assign(lights, lights + count);
@@ -308,14 +310,21 @@ void oracle_render_tiles(const OracleScene* s, const EchoRenderParams* params, c
 }
 
 // one Evaluator.Evaluate per listed (pixel, sample index): the sample-exact view used to compare device paths
+void oracle_evaluate_samples4(const OracleScene* s, const EchoRenderParams* params, const int32_t* pixelXY, const uint32_t* sampleIndex,
+                              uint64_t n, float* out, int channels, int threads);
+
 void oracle_evaluate_samples(const OracleScene* s, const EchoRenderParams* params, const int32_t* pixelXY, const uint32_t* sampleIndex,
                              uint64_t n, float* outRGB, int threads)
 {
+	oracle_evaluate_samples4(s, params, pixelXY, sampleIndex, n, outRGB, 3, threads);
+}
+
+// the same with `channels` floats per sample (4: the W lane of the auxiliary evaluators, e.g. NormalDepth128's depth)
+void oracle_evaluate_samples4(const OracleScene* s, const EchoRenderParams* params, const int32_t* pixelXY, const uint32_t* sampleIndex,
+                              uint64_t n, float* out, int channels, int threads)
+{
 	parallel_chunks(n, 256, threads, [&](int, uint64_t begin, uint64_t end)
 	{
-		PathTracedEvaluator evaluator;
-		evaluator.bounceLimit = params->bounceLimit;
-		evaluator.survivability = params->survivability;
 		CameraSpawner spawner(params->width, params->height);
 		EvaluatorStats stats;
 
@@ -328,11 +337,8 @@ void oracle_evaluate_samples(const OracleScene* s, const EchoRenderParams* param
 			Float2 shift = distribution.next2d();
 			Float2 lens = distribution.next2d();
 			Ray ray = camera_spawn_ray(s->scene.camera, spawner, px, py, shift, lens);
-			RGB value = evaluator.evaluate(s->scene, ray, distribution, stats);
-
-			outRGB[i * 3 + 0] = value.r;
-			outRGB[i * 3 + 1] = value.g;
-			outRGB[i * 3 + 2] = value.b;
+			Float4 value = evaluate_sample(s->scene, *params, ray, distribution, stats);
+			for (int c = 0; c < channels; c++) out[i * channels + c] = value.v[c];
 		}
 	});
 }

@@ -484,6 +484,111 @@ struct PathTracedEvaluator
 	}
 };
 
+struct Float4 // Common/Packed/Float4.cs, as the evaluators return it and the Accumulator sums it
+{
+	float v[4];
+};
+
+// ---- Common/Mathematics/Scalars.cs:153-168 (float.AlmostEquals) and Float3.Equals (Common/Packed/Float3.cs:369) ----
+inline bool almost_equals(float value, float other, float epsilon = 1E-5f)
+{
+	if (value == other) return true;
+	const float normal = 1.17549435E-38f; // (1L << 23) * float.Epsilon
+
+	float difference = std::fabs(value - other);
+	if (value == 0.0f || other == 0.0f || difference < normal) return difference < epsilon * normal;
+
+	float sum = std::fabs(value) + std::fabs(other);
+	return difference < epsilon * math_min(sum, 3.40282347E+38f);
+}
+
+inline bool float3_equals(Float3 a, Float3 b) { return almost_equals(a.x, b.x) && almost_equals(a.y, b.y) && almost_equals(a.z, b.z); }
+
+// ---- Evaluation/Evaluators/AlbedoEvaluator.cs:18-55 and NormalDepthEvaluator.cs:20-60: follow purely specular bounces from
+// the camera, report the first other surface. They share everything but Exit() and the escaped-ray value. ----
+struct AuxiliaryEvaluator
+{
+	int kind = ECHO_EVALUATOR_ALBEDO;
+	bool divergeOnce = true;
+
+	Float4 evaluate(const Scene& scene, const Ray& ray, SampleStream& distribution) const
+	{
+		TraceQuery query;
+		query.ray = ray;
+		bool direct = true; // whether the path is still going in its original direction
+		float depth = 0.0f;
+		Contact contact;
+
+		auto exit = [&]() -> Float4
+		{
+			if (kind == ECHO_EVALUATOR_ALBEDO)
+			{
+				const EchoMaterial& material = scene.materials[contact.material]; // (RGB128)material.SampleAlbedo(contact), constant texture
+				return { { material.albedo[0], material.albedo[1], material.albedo[2], 0.0f } };
+			}
+
+			return { { contact.shadeNormal.x, contact.shadeNormal.y, contact.shadeNormal.z, depth } }; // NormalDepth128.ToFloat4
+		};
+
+		// `while (scene.Trace(ref query))`; the cap only guards against a hall of mirrors (the device has the same one)
+		for (int bounce = 0; bounce < 1024 && scene.trace(query); bounce++)
+		{
+			interact(scene, query, contact); // Interact + material.Scatter (Scatter has no effect on Exit())
+
+			if (!direct) return exit();
+			if (kind == ECHO_EVALUATOR_NORMAL_DEPTH) depth += query.distance;
+
+			int specular = 0;
+			for (int i = 0; i < contact.bsdf.count; i++) specular += type_any(contact.bsdf.functions[i]->type, Specular) ? 1 : 0;
+			if (contact.bsdf.count != specular) return exit(); // not fully specular
+
+			Float3 incident;
+			const BxDF* function;
+			ProbableRGB sample = contact.bsdf.sample(contact.outgoing, distribution.next2d(), incident, function);
+			if (sample.not_possible()) return exit();
+
+			if (!float3_equals(incident, ray.direction)) direct = false; // compared with the CAMERA ray's direction
+			if (!divergeOnce && !direct) return exit();
+
+			TraceQuery spawned; // query.SpawnTrace(incident), TraceQuery.cs:88
+			spawned.ray = Ray(query.position(), incident);
+			spawned.ignore = query.token;
+			spawned.ignoreLayers = query.tokenLayers;
+			query = spawned;
+		}
+
+		if (kind == ECHO_EVALUATOR_ALBEDO)
+		{
+			RGB infinite = evaluate_infinite(scene, query.ray.direction, direct);
+			return { { infinite.r, infinite.g, infinite.b, 0.0f } };
+		}
+
+		if (direct) depth = scene.boundRadius * 2.0f; // negative direction and scene diameter for escaped rays
+		Float3 outward = -ray.direction;
+		return { { outward.x, outward.y, outward.z, depth } };
+	}
+};
+
+// the evaluator EchoRenderParams selects, as Float4 (RGB128 radiance has W = 0)
+inline Float4 evaluate_sample(const Scene& scene, const EchoRenderParams& params, const Ray& ray, SampleStream& distribution, EvaluatorStats& stats)
+{
+	int kind = params.evaluator & ECHO_EVALUATOR_KIND_MASK;
+
+	if (kind == ECHO_EVALUATOR_PATH_TRACED)
+	{
+		PathTracedEvaluator evaluator;
+		evaluator.bounceLimit = params.bounceLimit;
+		evaluator.survivability = params.survivability;
+		RGB value = evaluator.evaluate(scene, ray, distribution, stats);
+		return { { value.r, value.g, value.b, 0.0f } };
+	}
+
+	AuxiliaryEvaluator evaluator;
+	evaluator.kind = kind;
+	evaluator.divergeOnce = (params.evaluator & ECHO_EVALUATOR_DIVERGE_ONCE) != 0;
+	return evaluator.evaluate(scene, ray, distribution);
+}
+
 // ---- Scenic/Cameras/RaySpawner.cs:19-46 + PerspectiveCamera.cs:51-98 ----
 struct CameraSpawner
 {
@@ -550,11 +655,6 @@ inline Ray camera_spawn_ray(const EchoCamera& camera, const CameraSpawner& spawn
 }
 
 // ---- Common/Mathematics/Primitives/Summation.cs (Kahan) on one Float4 lane-set; W lane carried like the reference ----
-struct Float4
-{
-	float v[4];
-};
-
 inline Float4 f4_op(Float4 a, Float4 b, char op)
 {
 	Float4 r;
@@ -647,10 +747,6 @@ struct Accumulator
 // ---- Processes/Evaluation/EvaluationOperation.cs:100-141, one pixel ----
 inline Float4 evaluate_pixel(const Scene& scene, const EchoRenderParams& params, int px, int py, EvaluatorStats& stats, uint64_t& samples, uint64_t& rejected)
 {
-	PathTracedEvaluator evaluator;
-	evaluator.bounceLimit = params.bounceLimit;
-	evaluator.survivability = params.survivability;
-
 	CameraSpawner spawner(params.width, params.height);
 	Accumulator accumulator;
 	uint32_t pixel = (uint32_t)py * (uint32_t)params.width + (uint32_t)px;
@@ -670,10 +766,10 @@ inline Float4 evaluate_pixel(const Scene& scene, const EchoRenderParams& params,
 			Float2 lens = distribution.next2d();
 			Ray ray = camera_spawn_ray(scene.camera, spawner, px, py, shift, lens);
 
-			RGB evaluated = evaluator.evaluate(scene, ray, distribution, stats);
+			Float4 evaluated = evaluate_sample(scene, params, ray, distribution, stats);
 			++samples;
 
-			if (!accumulator.add(Float4{ { evaluated.r, evaluated.g, evaluated.b, 0.0f } })) ++rejected;
+			if (!accumulator.add(evaluated)) ++rejected;
 		}
 	}
 	while (epoch < params.maxEpoch && (epoch < params.minEpoch || accumulator.noise_max() > params.noiseThreshold));

@@ -51,6 +51,8 @@ def library():
     lib.oracle_occlude_linear_batch.argtypes = [p, p, u64, p, i32]
     lib.oracle_render_tiles.argtypes = [p, p, p, u32, p, p, i32]
     lib.oracle_evaluate_samples.argtypes = [p, p, p, p, u64, p, i32]
+    lib.oracle_evaluate_samples4.argtypes = [p, p, p, p, u64, p, i32, i32]
+    lib.oracle_scene_set_bound_radius.argtypes = [p, f32]
     lib.oracle_spawn_rays.argtypes = [p, p, p, p, u64, p]
     lib.oracle_fastmath.argtypes = [i32, f32, f32, f32]
     lib.oracle_fastmath.restype = f32
@@ -109,6 +111,7 @@ class OracleScene:
                                         ptr(prepared.emitter_bitpaths), len(prepared.emitter_tokens), ptr(prepared.point_lights), len(prepared.point_lights))
         lib.oracle_scene_set_infinite(self.handle, ptr(d.infinite_lights), len(d.infinite_lights), prepared.infinite_threshold, prepared.infinite_pdf)
         lib.oracle_scene_set_camera(self.handle, ptr(d.camera))
+        lib.oracle_scene_set_bound_radius(self.handle, prepared.bound_radius)
 
     def __del__(self):
         if getattr(self, "handle", None):

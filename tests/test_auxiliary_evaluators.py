@@ -1,0 +1,115 @@
+"""AlbedoEvaluator / NormalDepthEvaluator (Evaluation/Evaluators/AlbedoEvaluator.cs:18-55,
+NormalDepthEvaluator.cs:20-60) on the oracle: the auxiliary passes StandardPathTracedProfile renders for its denoiser."""
+import numpy as np
+import pytest
+
+from echorenderer_b200 import scenes, structs
+
+from . import oracle_lib
+
+ALBEDO = structs.EVALUATOR_ALBEDO | structs.EVALUATOR_DIVERGE_ONCE        # AlbedoEvaluator default: DivergeOnce = true
+NORMAL_DEPTH = structs.EVALUATOR_NORMAL_DEPTH                             # NormalDepthEvaluator default: DivergeOnce = false
+
+
+def grid(width, height, stride=1):
+    ys, xs = np.meshgrid(np.arange(0, height, stride), np.arange(0, width, stride), indexing="ij")
+    pixels = np.stack([xs.reshape(-1), ys.reshape(-1)], axis=-1).astype(np.int32)
+    return pixels, np.zeros(len(pixels), dtype=np.uint32)
+
+
+def evaluate4(oracle, params, pixels, index):
+    out = np.zeros((len(index), 4), dtype=np.float32)
+    oracle.lib.oracle_evaluate_samples4(oracle.handle, oracle_lib.ptr(params), oracle_lib.ptr(pixels), oracle_lib.ptr(index), len(index), oracle_lib.ptr(out), 4, 0)
+    return out
+
+
+def first_hits(oracle, params, pixels, index):
+    rays = oracle.spawn_rays(params, pixels, index)
+    return rays, oracle.trace(rays)
+
+
+def test_albedo_of_directly_visible_surfaces(cornell):
+    """No specular surface in the Cornell box: the albedo pass is the albedo of the first hit (the emission colour on the light)."""
+    oracle = oracle_lib.OracleScene(cornell)
+    params = structs.render_params(64, 64, 16, extend=1, seed=2, evaluator=ALBEDO)
+    pixels, index = grid(64, 64)
+    value = evaluate4(oracle, params, pixels, index)
+    rays, hits = first_hits(oracle, params, pixels, index)
+
+    hit = hits["token"] != structs.TOKEN_EMPTY
+    assert hit.mean() > 0.9 and np.all(value[:, 3] == 0)
+    material = cornell.triangles["material"][structs.token_index(hits["token"][hit])]
+    expected = cornell.materials["albedo"][material][:, :3]
+    # the front wall is OneSided: seen from outside it is invisible and the pass reports what lies behind it
+    one_sided = cornell.materials["type"][material] == structs.MATERIAL_ONESIDED
+    assert np.array_equal(value[hit][~one_sided][:, :3], expected[~one_sided])
+    assert len(np.unique(value[:, :3], axis=0)) >= 4  # white, red, green, the light
+
+
+def test_normal_depth_of_directly_visible_surfaces(cornell):
+    oracle = oracle_lib.OracleScene(cornell)
+    params = structs.render_params(64, 64, 16, extend=1, seed=2, evaluator=NORMAL_DEPTH)
+    pixels, index = grid(64, 64)
+    value = evaluate4(oracle, params, pixels, index)
+    rays, hits = first_hits(oracle, params, pixels, index)
+
+    hit = hits["token"] != structs.TOKEN_EMPTY
+    material = cornell.triangles["material"][structs.token_index(hits["token"][hit])]
+    plain = cornell.materials["type"][material] != structs.MATERIAL_ONESIDED
+    assert np.array_equal(value[hit][plain][:, 3], hits["distance"][hit][plain])           # depth = distance of the first hit
+    assert np.allclose(np.linalg.norm(value[:, :3], axis=1), 1.0, atol=1e-5)               # unit normals (or -direction)
+    triangles = cornell.triangles[structs.token_index(hits["token"][hit])][plain]
+    assert np.allclose(value[hit][plain][:, :3], triangles["normal0"], atol=1e-6)          # flat shading normals
+
+    escaped = ~hit
+    if escaped.any():
+        assert np.allclose(value[escaped][:, :3], -rays["direction"][escaped], atol=0)
+        assert np.all(value[escaped][:, 3] == np.float32(cornell.bound_radius) * 2)
+
+
+def test_specular_surfaces_are_followed(mixed_small):
+    """Through the specular glass blob the passes report what is seen in or behind it; DivergeOnce decides how far they follow."""
+    oracle = oracle_lib.OracleScene(mixed_small)
+    width, height = 96, 54
+    pixels, index = grid(width, height)
+    _, hits = first_hits(oracle, structs.render_params(width, height, 16, extend=1, seed=2), pixels, index)
+    hit = hits["token"] != structs.TOKEN_EMPTY
+    first_material = np.full(len(hits), -1)
+    triangle = hit & (structs.token_type(hits["token"]) == structs.TOKEN_TYPE_TRIANGLE)
+    first_material[triangle] = mixed_small.triangles["material"][structs.token_index(hits["token"][triangle])]
+    glass = first_material == 2  # specular Dielectric (scenes.mixed_materials)
+    assert glass.sum() > 20
+
+    once = evaluate4(oracle, structs.render_params(width, height, 16, extend=1, seed=2, evaluator=ALBEDO), pixels, index)
+    never = evaluate4(oracle, structs.render_params(width, height, 16, extend=1, seed=2, evaluator=structs.EVALUATOR_ALBEDO), pixels, index)
+    swatch = mixed_small.materials["albedo"][:, :3]
+    ambient = mixed_small.description.infinite_lights["radiance"]
+    allowed = np.concatenate([swatch, ambient, np.zeros((1, 3), dtype=np.float32)])
+
+    for value in (once, never):
+        distance = np.abs(value[:, None, :3] - allowed[None]).max(axis=2).min(axis=1)
+        assert np.all(distance == 0)  # every value is a swatch albedo, or the ambient light of an escaped ray
+
+    # DivergeOnce = false stops at the glass itself once the bounce leaves the camera direction: white glass albedo
+    assert np.all(never[glass][:, :3] == 1.0)
+    # DivergeOnce = true follows one diverging bounce and reports the next surface: the far side of the same glass blob for
+    # refracted bounces (white again), something else for the reflected ones
+    assert np.mean(np.all(once[glass][:, :3] == 1.0, axis=1)) < 1.0
+    assert np.array_equal(once[~glass], never[~glass])
+
+    depth_once = evaluate4(oracle, structs.render_params(width, height, 16, extend=1, seed=2, evaluator=NORMAL_DEPTH | structs.EVALUATOR_DIVERGE_ONCE), pixels, index)
+    depth_never = evaluate4(oracle, structs.render_params(width, height, 16, extend=1, seed=2, evaluator=NORMAL_DEPTH), pixels, index)
+    assert np.array_equal(depth_never[glass][:, 3], hits["distance"][glass])
+    assert np.all(depth_once[glass][:, 3] >= hits["distance"][glass])
+
+
+def test_render_tiles_accumulates_all_four_lanes(cornell):
+    """EvaluationOperation accumulates the evaluator's Float4 whatever it means (EvaluationOperation.cs:124-131): the W lane of
+    the NormalDepth pass is the mean depth of the pixel's samples."""
+    oracle = oracle_lib.OracleScene(cornell)
+    tiles = np.array([[1, 1]], dtype=np.int32)
+    params = structs.render_params(48, 48, 16, extend=8, seed=4, evaluator=NORMAL_DEPTH)
+    image, stats = oracle.render_tiles(params, tiles)
+    assert int(stats["sampleEvaluated"][0]) == 16 * 16 * 8
+    assert image[..., 3].min() > 5.0 and image[..., 3].max() < 40.0
+    assert np.all(np.linalg.norm(image[..., :3], axis=-1) <= 1.0 + 1e-5)

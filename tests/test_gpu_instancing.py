@@ -152,3 +152,20 @@ def test_render_tiles_match_oracle(instanced):
     assert relative_rmse(actual, expected) <= 1e-4
     for name in structs.STATS_FIELDS[:12]:
         assert abs(int(stats[name][0]) - int(expected_stats[name][0])) <= 1e-4 * max(1, int(expected_stats[name][0])), name
+
+
+def test_auxiliary_evaluators_match_oracle(instanced):
+    from tests.test_gpu_render import sample_grid
+    oracle = oracle_lib.OracleScene(instanced)
+    width, height = 96, 64
+    pixel_xy, sample_index = sample_grid(width, height, 2)
+
+    with PreparedScene(instanced) as scene:
+        for evaluator in (structs.EVALUATOR_ALBEDO | structs.EVALUATOR_DIVERGE_ONCE, structs.EVALUATOR_NORMAL_DEPTH):
+            params = structs.render_params(width, height, 32, extend=2, seed=7, evaluator=evaluator)
+            expected = np.zeros((len(sample_index), 4), dtype=np.float32)
+            oracle.lib.oracle_evaluate_samples4(oracle.handle, oracle_lib.ptr(params), oracle_lib.ptr(pixel_xy), oracle_lib.ptr(sample_index), len(sample_index),
+                                                oracle_lib.ptr(expected), 4, 0)
+            actual = scene.evaluate_samples(params, pixel_xy, sample_index, channels=4)
+            assert np.array_equal(actual.view(np.uint32), expected.view(np.uint32))
+            assert len(np.unique(expected[:, :3], axis=0)) > 4

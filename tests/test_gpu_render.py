@@ -104,3 +104,29 @@ def test_evaluation_operation_interface(cornell):
         # the red wall is on the left, the green wall on the right (CornellBox.cs:44-45)
         assert image[24:40, 2:8, 0].mean() > 2 * image[24:40, 2:8, 1].mean()
         assert image[24:40, -8:-2, 1].mean() > 2 * image[24:40, -8:-2, 0].mean()
+
+
+@pytest.mark.parametrize("fixture", ["cornell", "mixed_small", "coated_small"])
+@pytest.mark.parametrize("evaluator", [structs.EVALUATOR_ALBEDO | structs.EVALUATOR_DIVERGE_ONCE, structs.EVALUATOR_ALBEDO,
+                                       structs.EVALUATOR_NORMAL_DEPTH, structs.EVALUATOR_NORMAL_DEPTH | structs.EVALUATOR_DIVERGE_ONCE])
+def test_auxiliary_evaluators_match_oracle(fixture, evaluator, request):
+    """AlbedoEvaluator / NormalDepthEvaluator (AlbedoEvaluator.cs:18-55, NormalDepthEvaluator.cs:20-60): all four lanes of every
+    sample bit-identical to the oracle, then the accumulated tiles."""
+    prepared = request.getfixturevalue(fixture)
+    oracle = oracle_lib.OracleScene(prepared)
+    width, height = 96, 64
+    params = structs.render_params(width, height, 32, extend=4, seed=7, evaluator=evaluator)
+    pixel_xy, sample_index = sample_grid(width, height, 4)
+    expected = np.zeros((len(sample_index), 4), dtype=np.float32)
+    oracle.lib.oracle_evaluate_samples4(oracle.handle, oracle_lib.ptr(params), oracle_lib.ptr(pixel_xy), oracle_lib.ptr(sample_index), len(sample_index),
+                                        oracle_lib.ptr(expected), 4, 0)
+    tiles = scenes.tile_grid(width, height, 32)
+    expected_tiles, expected_stats = oracle.render_tiles(params, tiles)
+
+    with PreparedScene(prepared) as scene:
+        actual = scene.evaluate_samples(params, pixel_xy, sample_index, channels=4)
+        actual_tiles, stats = scene.render_tiles(params, tiles)
+
+    assert np.array_equal(actual.view(np.uint32), expected.view(np.uint32))
+    assert np.array_equal(actual_tiles.view(np.uint32), expected_tiles.view(np.uint32))
+    assert int(stats["sampleEvaluated"][0]) == int(expected_stats["sampleEvaluated"][0]) == width * height * 4
