@@ -461,7 +461,7 @@ int32_t echo_b200_scene_commit(EchoScene* scene)
 		sphereMaterial[i] = s.material;
 	}
 
-	std::vector<float4> pointLights(scene->pointLights.size() * 2), infiniteLights(scene->infiniteLights.size());
+	std::vector<float4> pointLights(scene->pointLights.size() * 2), infiniteLights(scene->infiniteLights.size() * 7);
 
 	for (size_t i = 0; i < scene->pointLights.size(); i++)
 	{
@@ -470,13 +470,8 @@ int32_t echo_b200_scene_commit(EchoScene* scene)
 		pointLights[i * 2 + 1] = make_float4(p.position[0], p.position[1], p.position[2], 0.0f);
 	}
 
-	for (size_t i = 0; i < scene->infiniteLights.size(); i++)
-	{
-		const EchoInfiniteLight& l = scene->infiniteLights[i];
-		float visibleBits;
-		std::memcpy(&visibleBits, &l.directlyVisible, 4);
-		infiniteLights[i] = make_float4(l.radiance[0], l.radiance[1], l.radiance[2], visibleBits);
-	}
+	static_assert(sizeof(EchoInfiniteLight) == 112, "POD layout");
+	std::memcpy(infiniteLights.data(), scene->infiniteLights.data(), sizeof(EchoInfiniteLight) * scene->infiniteLights.size()); // 7 float4 each, verbatim
 
 	static_assert(sizeof(EchoQbvhNode) == 128 && sizeof(EchoMaterial) == 64 && sizeof(EchoLightNode) == 64, "POD layout");
 	static_assert(sizeof(EchoTriangle) == 100 && sizeof(EchoSphere) == 20 && sizeof(EchoRay) == 32 && sizeof(EchoHit) == 16, "POD layout");

@@ -225,6 +225,8 @@ ECHO_DEVICE vec3 project_sphere(float z, float u) // Sample2D.cs:153-158
 
 ECHO_DEVICE vec3 uniform_sphere(vec2 s) { return project_sphere(fma_f(s.x, -2.0f, 1.0f), s.y); } // Sample2D.cs:35
 
+ECHO_DEVICE vec3 uniform_cone(vec2 s, float cosMaxP) { return project_sphere(fma_f(cosMaxP - 1.0f, s.x, 1.0f), s.y); } // Sample2D.cs:123-127
+
 ECHO_DEVICE vec2 uniform_triangle(vec2 s) // Sample2D.cs:54-62
 {
 	float v = sqrt0(s.x);

@@ -376,6 +376,66 @@ ECHO_DEVICE float light_tree_mass(const DeviceScene& scene, const PackInfo& info
 	return mass;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// infinite lights: AmbientLight over a Pure texture (AmbientLight.cs:53-67) and DirectionalLight (DirectionalLight.cs:78-108).
+// EchoInfiniteLight = 7 float4: {radiance, directlyVisible} {type, isDelta, cosAngle, -} {intensity, -} {direction, -} rotation[9] + pad
+// ---------------------------------------------------------------------------------------------------------------------
+
+struct InfiniteLight
+{
+	rgb radiance;
+	bool directlyVisible, directional, delta;
+	float cosAngle;
+	const float4* data;
+};
+
+ECHO_DEVICE InfiniteLight load_infinite(const DeviceScene& scene, uint32_t index)
+{
+	const float4* p = scene.infiniteLights + (size_t)index * 7;
+	float4 a = __ldg(p), b = __ldg(p + 1);
+	return { as_rgb(a), __float_as_uint(a.w) != 0u, __float_as_uint(b.x) == ECHO_INFINITE_DIRECTIONAL, __float_as_uint(b.y) != 0u, b.z, p };
+}
+
+ECHO_DEVICE rgb infinite_evaluate(const InfiniteLight& light, vec3 incident)
+{
+	if (!light.directional) return light.radiance;
+	if (light.delta) return make_rgb(0.0f);
+
+	float cosIncident = dot(xyz(__ldg(light.data + 3)), incident);
+	if (cosIncident <= light.cosAngle) return make_rgb(0.0f);
+	return light.radiance; // scaledIntensity
+}
+
+ECHO_DEVICE float infinite_pdf(const InfiniteLight& light)
+{
+	if (!light.directional) return kUniformSpherePdf;
+	if (light.delta) return 0.0f;
+	return uniform_cone_pdf(light.cosAngle);
+}
+
+ECHO_DEVICE Sampled infinite_sample(const InfiniteLight& light, vec2 sample, vec3& incident, float& travel)
+{
+	travel = kInfinity;
+
+	if (!light.directional)
+	{
+		incident = uniform_sphere(sample); // IDirectionalTexture.Sample default, Textures/Directional/IDirectionalTexture.cs
+		return { light.radiance, kUniformSpherePdf };
+	}
+
+	if (light.delta)
+	{
+		incident = xyz(__ldg(light.data + 3));
+		return { as_rgb(__ldg(light.data + 2)), 1.0f };
+	}
+
+	vec3 local = uniform_cone(sample, light.cosAngle);
+	local.z = -local.z; // Utility.NegateZ
+	float4 r0 = __ldg(light.data + 4), r1 = __ldg(light.data + 5), r2 = __ldg(light.data + 6); // rotation[0..3], [4..7], [8] + pad
+	incident = { r0.x * local.x + r0.y * local.y + r0.z * local.z, r0.w * local.x + r1.x * local.y + r1.y * local.z, r1.z * local.x + r1.w * local.y + r2.x * local.z };
+	return { light.radiance, uniform_cone_pdf(light.cosAngle) };
+}
+
 // PreparedScene.Pick, PreparedScene.cs:113-150; outLayers receives the instance layers of the picked light's hierarchy
 template<bool INST>
 ECHO_DEVICE uint32_t scene_pick(const DeviceScene& scene, const SurfacePoint& origin, float sample, float& outPdf, PathLayers& outLayers)
@@ -387,7 +447,8 @@ ECHO_DEVICE uint32_t scene_pick(const DeviceScene& scene, const SurfacePoint& or
 		sample = sample_stretch(sample, 0.0f, scene.infiniteThreshold);
 		int index = sample_range(sample, (int)scene.infiniteLightCount);
 		outPdf = scene.infinitePdf;
-		return ECHO_LIGHT_TOKEN_MAKE(ECHO_LIGHT_TYPE_INFINITE, (uint32_t)index);
+		bool delta = __float_as_uint(__ldg(scene.infiniteLights + (size_t)index * 7 + 1).y) != 0u;
+		return ECHO_LIGHT_TOKEN_MAKE(delta ? ECHO_LIGHT_TYPE_INFINITE_DELTA : ECHO_LIGHT_TYPE_INFINITE, (uint32_t)index); // :120
 	}
 
 	sample = sample_stretch(sample, scene.infiniteThreshold, 1.0f);
@@ -554,10 +615,7 @@ ECHO_DEVICE Sampled scene_sample_light(const DeviceScene& scene, uint32_t light,
 
 	if (token_is_infinite_light(light))
 	{
-		float4 infinite = __ldg(scene.infiniteLights + token_light_index(light));
-		incident = uniform_sphere(sample); // IDirectionalTexture.Sample default, Textures/Directional/IDirectionalTexture.cs
-		travel = kInfinity;
-		return { as_rgb(infinite), kUniformSpherePdf };
+		return infinite_sample(load_infinite(scene, token_light_index(light)), sample, incident, travel);
 	}
 
 	// FindLayer + `forwardTransform * origin` (:192-198, GeometryPoint.cs:41-45): the shading point in the space of the pack
@@ -613,7 +671,7 @@ ECHO_DEVICE Sampled scene_sample_light(const DeviceScene& scene, uint32_t light,
 template<bool INST>
 ECHO_DEVICE float scene_light_pdf(const DeviceScene& scene, uint32_t light, const PathLayers& layers, const SurfacePoint& origin, vec3 incident)
 {
-	if (token_is_infinite_light(light)) return kUniformSpherePdf;
+	if (token_is_infinite_light(light)) return infinite_pdf(load_infinite(scene, token_light_index(light)));
 	if (token_type(light) == ECHO_TOKEN_TYPE_LIGHT) return 1.0f;
 
 	Layer layer = find_layer<INST>(scene, layers);
@@ -622,15 +680,15 @@ ECHO_DEVICE float scene_light_pdf(const DeviceScene& scene, uint32_t light, cons
 	return geometry_pdf(scene, layer.info, light, position, direction);
 }
 
-ECHO_DEVICE rgb evaluate_infinite(const DeviceScene& scene, bool direct) // PreparedScene.cs:233-253
+ECHO_DEVICE rgb evaluate_infinite(const DeviceScene& scene, vec3 direction, bool direct) // PreparedScene.cs:233-253
 {
 	rgb total = make_rgb(0.0f);
 
 	for (uint32_t i = 0; i < scene.infiniteLightCount; i++)
 	{
-		float4 light = __ldg(scene.infiniteLights + i);
-		if (direct && __float_as_uint(light.w) == 0u) continue;
-		total = total + as_rgb(light);
+		InfiniteLight light = load_infinite(scene, i);
+		if (direct && !light.directlyVisible) continue;
+		total = total + infinite_evaluate(light, direction);
 	}
 
 	return total;
@@ -919,19 +977,22 @@ __global__ void __launch_bounds__(kBlock) shade_kernel(DeviceScene scene, EchoRe
 			// no intersection: PathTracedEvaluator.cs:48-52 (first), :112-130 (MIS), :137-143 (fallback)
 			statInfinite = true;
 
-			if (mode == MODE_FIRST) result = evaluate_infinite(scene, true);
-			else if (mode == MODE_NO_MIS) result = result + energy * evaluate_infinite(scene, false);
+			if (mode == MODE_FIRST) result = evaluate_infinite(scene, direction, true);
+			else if (mode == MODE_NO_MIS) result = result + energy * evaluate_infinite(scene, direction, false);
 			else
 			{
 				SurfacePoint oldPoint = { xyz(paths.oldPosition[id]), xyz(paths.oldNormal[id]) };
 				(void)oldPoint;
 
-				for (uint32_t light = 0; light < scene.infiniteLightCount; light++)
+				for (uint32_t index = 0; index < scene.infiniteLightCount; index++)
 				{
-					float pdf = scene.infinitePdf * kUniformSpherePdf; // ProbabilityMass * light.ProbabilityDensity, :122-123
+					InfiniteLight light = load_infinite(scene, index);
+					if (light.delta) continue; // "Skip delta lights; they do not like MIS", :118
+
+					float pdf = scene.infinitePdf * infinite_pdf(light); // ProbabilityMass * light.ProbabilityDensity, :121-122
 					if (!positive(pdf)) continue;
 					float weight = power_heuristic(scatterPdfPrevious, pdf);
-					result = result + energy * (as_rgb(__ldg(scene.infiniteLights + light)) * weight);
+					result = result + energy * (infinite_evaluate(light, direction) * weight);
 				}
 			}
 
@@ -1358,7 +1419,7 @@ __global__ void __launch_bounds__(kBlock) auxiliary_kernel(DeviceScene scene, Ec
 
 	if (!exited)
 	{
-		if (kind == ECHO_EVALUATOR_ALBEDO) result = make4(evaluate_infinite(scene, direct), 0.0f); // scene.EvaluateInfinite(query.ray.direction, direct)
+		if (kind == ECHO_EVALUATOR_ALBEDO) result = make4(evaluate_infinite(scene, direction, direct), 0.0f); // scene.EvaluateInfinite(query.ray.direction, direct)
 		else
 		{
 			if (direct) depth = scene.boundRadius * 2.0f; // negative direction and scene diameter for escaped rays

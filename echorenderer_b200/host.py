@@ -5,6 +5,7 @@ build the SweepBuilder hierarchy, collapse it into the QuadBoundingVolumeHierarc
 compute the infinite-light threshold (PreparedScene.cs:34-39). The results are the arrays echo_b200.h takes.
 """
 import ctypes
+import math
 import os
 from dataclasses import dataclass, field
 
@@ -361,6 +362,14 @@ def _prepare_packs(description, threads):
             max(int(p["maxDepth"]) for p in packs), lights)
 
 
+def _root_bound_radius(root):
+    """Stand-in for Accelerator.SphereBound.radius: the half diagonal of the root node's bound (see PreparedArrays.bound_radius)."""
+    valid = root["token4"] != structs.TOKEN_EMPTY
+    low = np.array([root[k][valid].min() for k in ("minX", "minY", "minZ")], dtype=np.float64)
+    high = np.array([root[k][valid].max() for k in ("maxX", "maxY", "maxZ")], dtype=np.float64)
+    return np.float32(np.linalg.norm(high - low) / 2)
+
+
 def prepare(description, threads=0):
     """ScenePreparer.Prepare -> PreparedScene constructor (PreparedScene.cs:26-40)."""
     lib = _library()
@@ -383,8 +392,15 @@ def prepare(description, threads=0):
     infinite_power = np.float32(0)
     keep = []
     for i, light in enumerate(d.infinite_lights):
-        radiance = np.ascontiguousarray(light["radiance"], dtype=np.float32)
-        power = lib.echo_host_ambient_power(_pointer(radiance), _pointer(nodes[:1]))
+        if light["type"] == structs.INFINITE_DIRECTIONAL:
+            # DirectionalLight.Prepare (DirectionalLight.cs:71-74): half of the scene's bounding disk area
+            r, g, b = (np.float32(c) for c in light["intensity"])
+            luminance = (r * np.float32(0.212671) + g * np.float32(0.715160)) + (b * np.float32(0.072169) + np.float32(0))
+            radius = np.float32(_root_bound_radius(nodes[0]))
+            power = float(luminance * np.float32(math.pi * 0.5) * radius * radius)
+        else:
+            radiance = np.ascontiguousarray(light["radiance"], dtype=np.float32)
+            power = lib.echo_host_ambient_power(_pointer(radiance), _pointer(nodes[:1]))
         if power >= 8e-7:
             keep.append(i)
             infinite_power = np.float32(infinite_power + np.float32(power))

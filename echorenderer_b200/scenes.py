@@ -158,6 +158,30 @@ def ambient_light(radiance, directly_visible=True):
 
 
 # ---------------------------------------------------------------- C1
+def directional_light(intensity, rotation=(0, 0, 0), angle=0.6, directly_visible=False):
+    """DirectionalLight (Scenic/Lights/DirectionalLight.cs:12-75) with what its Prepare() computes: the light shines along its
+    local backward axis, `angle` (degrees, default 0.6) is the half opening of the cone it is visible in; 0 makes it a delta light."""
+    light = np.zeros(1, dtype=structs.INFINITE_LIGHT)
+    matrix = rotation_matrix(*rotation).astype(np.float32)
+    direction = matrix.astype(np.float64) @ np.array([0.0, 0.0, -1.0])  # Float3.Backward
+    direction = direction / np.linalg.norm(direction)
+    radians = np.float32(math.radians(angle))
+    cos_angle = np.float32(math.cos(radians))                           # MathF.Cos
+    is_delta = not (np.float32(1) - cos_angle >= np.float32(8e-7))      # !FastMath.Positive(1f - cosAngle)
+    intensity = np.asarray(intensity, dtype=np.float32)
+
+    if not is_delta:
+        scale = np.float32(0.5) - np.float32(0.5) * np.float32(math.cos(radians * np.float32(2)))
+        scaled = intensity / scale * np.float32(1 / math.pi)            # Intensity / scale * Scalars.PiR
+    else:
+        scaled = np.zeros(3, dtype=np.float32)
+
+    light["radiance"], light["directlyVisible"] = scaled, 1 if directly_visible else 0
+    light["type"], light["isDelta"], light["cosAngle"] = structs.INFINITE_DIRECTIONAL, 1 if is_delta else 0, cos_angle
+    light["intensity"], light["direction"], light["rotation"] = intensity, direction.astype(np.float32), matrix.reshape(-1)
+    return light
+
+
 def cornell_box():
     """Scenic/CornellBox.cs:18-60 with the camera of ext/Scenes/Simple/cornell.echo:43 (FOV 42 at z = -18.025444)."""
     green, red, blue, white = (hex_color(v) for v in (0x00CB21, 0xCB0021, 0x0021CB, 0xEEEEF2))

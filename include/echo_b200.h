@@ -147,12 +147,26 @@ typedef struct EchoPointLight
 	float position[3];
 } EchoPointLight;
 
-/* ---- infinite lights with constant textures: AmbientLight over a Pure texture (Scenic/Lights/AmbientLight.cs). ---- */
+/* ---- infinite lights (Scenic/Lights/InfiniteLight.cs): AmbientLight over a constant (Pure) texture (AmbientLight.cs) and
+ * DirectionalLight (DirectionalLight.cs:12-108), with everything DirectionalLight.Prepare computes on the host (:52-75). ---- */
+#define ECHO_INFINITE_AMBIENT 0u
+#define ECHO_INFINITE_DIRECTIONAL 1u
+
 typedef struct EchoInfiniteLight
 {
-	float radiance[3];        /* Intensity * Texture colour */
-	uint32_t directlyVisible; /* InfiniteLight.DirectlyVisible */
-} EchoInfiniteLight;
+	float radiance[3];        /* Ambient: Intensity * texture colour. Directional: scaledIntensity (black when delta), :63-69 */
+	uint32_t directlyVisible; /* InfiniteLight.DirectlyVisible (DirectionalLight defaults to false, :15) */
+	uint32_t type;            /* ECHO_INFINITE_* */
+	uint32_t isDelta;         /* DirectionalLight.IsDelta: !Positive(1 - cosAngle), :50 */
+	float cosAngle;           /* cos(Angle), :61 */
+	float pad0;
+	float intensity[3];       /* DirectionalLight.Intensity: what a delta light's Sample returns, :101 */
+	float pad1;
+	float direction[3];       /* incidentDirection = (LocalToWorldRotation * Float3.Backward).Normalized, :58 */
+	float pad2;
+	float rotation[9];        /* LocalToWorldRotation, row-major (InfiniteLight.cs:31-37): orients the sampled cone, :105 */
+	float pad3[3];
+} EchoInfiniteLight; /* 112 bytes; an ambient light only needs the first 16, the rest zero */
 
 /* ---- instancing: PreparedPack / PreparedInstance / TokenHierarchy ----
  * A scene with instances is a set of packs (PreparedPack.cs:13-24): pack 0 is the PreparedScene itself, the others are the

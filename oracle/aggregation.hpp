@@ -852,7 +852,7 @@ struct Scene
 			sample = sample_stretch(sample, 0.0f, infiniteLightsThreshold);
 			int index = sample_range(sample, (int)infiniteLights.size());
 			outPdf = infiniteLightsPdf;
-			return ECHO_LIGHT_TOKEN_MAKE(ECHO_LIGHT_TYPE_INFINITE, index); // in-scope infinite lights are never delta
+			return ECHO_LIGHT_TOKEN_MAKE(infiniteLights[index].isDelta ? ECHO_LIGHT_TYPE_INFINITE_DELTA : ECHO_LIGHT_TYPE_INFINITE, index); // :120
 		}
 
 		sample = sample_stretch(sample, infiniteLightsThreshold, 1.0f);

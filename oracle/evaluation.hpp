@@ -150,6 +150,52 @@ inline float geometry_pdf(const Scene& scene, uint32_t token, Float3 origin, Flo
 	return almost_zero(1.0f - cosMaxT) ? 0.0f : uniform_cone_pdf(cosMaxT);
 }
 
+// ---- Scenic/Lights: AmbientLight over a Pure texture (AmbientLight.cs:53-67 with IDirectionalTexture's defaults) and
+//      DirectionalLight (DirectionalLight.cs:78-108) ----
+inline RGB infinite_radiance(const EchoInfiniteLight& light) { return { light.radiance[0], light.radiance[1], light.radiance[2] }; }
+
+inline RGB infinite_evaluate(const EchoInfiniteLight& light, Float3 incident)
+{
+	if (light.type != ECHO_INFINITE_DIRECTIONAL) return infinite_radiance(light);
+	if (light.isDelta) return kBlack;
+
+	float cosIncident = dot(f3(light.direction), incident);
+	if (cosIncident <= light.cosAngle) return kBlack;
+	return infinite_radiance(light); // scaledIntensity
+}
+
+inline float infinite_pdf(const EchoInfiniteLight& light, Float3 /*incident*/)
+{
+	if (light.type != ECHO_INFINITE_DIRECTIONAL) return kUniformSpherePdf;
+	if (light.isDelta) return 0.0f;
+	return uniform_cone_pdf(light.cosAngle);
+}
+
+inline ProbableRGB infinite_sample(const EchoInfiniteLight& light, Float2 sample, Float3& incident, float& travel)
+{
+	travel = kInfinity;
+
+	if (light.type != ECHO_INFINITE_DIRECTIONAL)
+	{
+		// AmbientLight.cs:60-67 with Pure as IDirectionalTexture: the default interface Sample draws a uniform sphere
+		// direction with pdf 1/(4 pi) (Textures/Directional/IDirectionalTexture.cs); rotation is the identity in scope.
+		incident = uniform_sphere(sample);
+		return { infinite_radiance(light), kUniformSpherePdf };
+	}
+
+	if (light.isDelta)
+	{
+		incident = f3(light.direction);
+		return { RGB{ light.intensity[0], light.intensity[1], light.intensity[2] }, 1.0f };
+	}
+
+	Float3 local = uniform_cone(sample, light.cosAngle);
+	local = { local.x, local.y, -local.z }; // Utility.NegateZ
+	const float* m = light.rotation;        // Float3x3 * Float3, Float3x3.cs:264-269
+	incident = { m[0] * local.x + m[1] * local.y + m[2] * local.z, m[3] * local.x + m[4] * local.y + m[5] * local.z, m[6] * local.x + m[7] * local.y + m[8] * local.z };
+	return { infinite_radiance(light), uniform_cone_pdf(light.cosAngle) };
+}
+
 // ---- PreparedScene.Sample (PreparedScene.cs:182-204) -> LightCollection.Sample (LightCollection.cs:141-193),
 //      PreparedPointLight.Sample (Scenic/Lights/PointLight.cs:48-66), AmbientLight.Sample over a Pure texture ----
 inline ProbableRGB scene_sample_light(const Scene& scene, uint32_t light, const Layers& layers, const GeometryPoint& origin, Float2 sample, Float3& incident, float& travel)
@@ -159,12 +205,7 @@ inline ProbableRGB scene_sample_light(const Scene& scene, uint32_t light, const 
 
 	if (token_is_infinite_light(light))
 	{
-		// AmbientLight.cs:60-67 with Pure as IDirectionalTexture: the default interface Sample draws a uniform sphere
-		// direction with pdf 1/(4 pi) (Textures/Directional/IDirectionalTexture.cs); rotation is the identity in scope.
-		const EchoInfiniteLight& infinite = scene.infiniteLights[token_light_index(light)];
-		incident = uniform_sphere(sample);
-		travel = kInfinity;
-		return { RGB{ infinite.radiance[0], infinite.radiance[1], infinite.radiance[2] }, kUniformSpherePdf };
+		return infinite_sample(scene.infiniteLights[token_light_index(light)], sample, incident, travel);
 	}
 
 	// FindLayer + `forwardTransform * origin` (PreparedScene.cs:192-198, GeometryPoint.cs:41-45): the shading point in the
@@ -222,7 +263,7 @@ inline ProbableRGB scene_sample_light(const Scene& scene, uint32_t light, const 
 // ---- PreparedScene.ProbabilityDensity (PreparedScene.cs:207-225) -> LightCollection.ProbabilityDensity (:196-219) ----
 inline float scene_light_pdf(const Scene& scene, uint32_t light, const Layers& layers, const GeometryPoint& origin, Float3 incident)
 {
-	if (token_is_infinite_light(light)) return kUniformSpherePdf;
+	if (token_is_infinite_light(light)) return infinite_pdf(scene.infiniteLights[token_light_index(light)], incident);
 
 	Scene::Layer layer = scene.find_layer(layers);
 	if (token_type(light) == ECHO_TOKEN_TYPE_LIGHT) return 1.0f; // LightCollection.cs:206 (point)
@@ -234,14 +275,14 @@ inline float scene_light_pdf(const Scene& scene, uint32_t light, const Layers& l
 }
 
 // ---- PreparedScene.EvaluateInfinite (PreparedScene.cs:233-253) ----
-inline RGB evaluate_infinite(const Scene& scene, Float3 /*direction*/, bool direct)
+inline RGB evaluate_infinite(const Scene& scene, Float3 direction, bool direct)
 {
 	RGB total = kBlack;
 
 	for (const EchoInfiniteLight& light : scene.infiniteLights)
 	{
 		if (direct && !light.directlyVisible) continue;
-		total = total + RGB{ light.radiance[0], light.radiance[1], light.radiance[2] };
+		total = total + infinite_evaluate(light, direction);
 	}
 
 	return total;
@@ -456,13 +497,15 @@ struct PathTracedEvaluator
 
 					for (size_t i = 0; i < scene.infiniteLights.size(); i++)
 					{
+						const EchoInfiniteLight& light = scene.infiniteLights[i];
+						if (light.isDelta) continue; // "Skip delta lights; they do not like MIS", :118
+
 						uint32_t token = ECHO_LIGHT_TOKEN_MAKE(ECHO_LIGHT_TYPE_INFINITE, (uint32_t)i);
-						float pdf = scene.probability_mass(token, oldPoint) * scene_light_pdf(scene, token, Layers(), oldPoint, direction);
+						float pdf = scene.probability_mass(token, oldPoint) * infinite_pdf(light, direction);
 						if (!positive(pdf)) continue;
 
 						float weight = power_heuristic(bounceScatterPdf, pdf);
-						const EchoInfiniteLight& light = scene.infiniteLights[i];
-						path.contribute(RGB{ light.radiance[0], light.radiance[1], light.radiance[2] } * weight);
+						path.contribute(infinite_evaluate(light, direction) * weight);
 					}
 
 					++stats.lightEvaluatedInfinite;

@@ -313,6 +313,9 @@ inline Float3 project_sphere(float z, float u)
 // Sample2D.cs:35
 inline Float3 uniform_sphere(Float2 s) { return project_sphere(fma_f(s.x, -2.0f, 1.0f), s.y); }
 
+// Sample2D.cs:123-127
+inline Float3 uniform_cone(Float2 s, float cosMaxP) { return project_sphere(fma_f(cosMaxP - 1.0f, s.x, 1.0f), s.y); }
+
 // Sample2D.cs:54-62
 inline Float2 uniform_triangle(Float2 s)
 {

@@ -58,3 +58,15 @@ def coated_small():
     description.triangles["material"][description.triangles["material"] == 0] = first       # ground
     description.triangles["material"][description.triangles["material"] == 4] = first + 1   # the Lambertian blobs
     return host.prepare(description)
+
+
+@pytest.fixture(scope="session")
+def directional_small():
+    """The small mixed scene lit by an AmbientLight, a DirectionalLight with a 2 degree cone and a delta DirectionalLight
+    (Scenic/Lights/DirectionalLight.cs)."""
+    import numpy as np
+    from echorenderer_b200 import host, scenes
+    description = scenes.mixed_material_scene(rings=24, segments=24)
+    description.infinite_lights = np.concatenate([scenes.ambient_light((0.05, 0.05, 0.05)), scenes.directional_light((4.0, 3.6, 3.0), (50, 30, 0), angle=2.0, directly_visible=True),
+                                                  scenes.directional_light((1.5, 1.5, 2.0), (70, -120, 0), angle=0.0)])
+    return host.prepare(description)

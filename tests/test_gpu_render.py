@@ -25,7 +25,8 @@ def relative_rmse(actual, expected):
     return float(np.sqrt(np.mean((actual - expected) ** 2)) / max(np.sqrt(np.mean(expected ** 2)), 1e-12))
 
 
-@pytest.mark.parametrize("fixture,bounce_limit", [("cornell", 128), ("mixed_small", 8), ("lights_small", 128), ("terrain_small", 16), ("coated_small", 12)])
+@pytest.mark.parametrize("fixture,bounce_limit", [("cornell", 128), ("mixed_small", 8), ("lights_small", 128), ("terrain_small", 16), ("coated_small", 12),
+                                                  ("directional_small", 12)])
 def test_samples_match_oracle(fixture, bounce_limit, request):
     prepared = request.getfixturevalue(fixture)
     oracle = oracle_lib.OracleScene(prepared)
@@ -45,7 +46,7 @@ def test_samples_match_oracle(fixture, bounce_limit, request):
     assert relative_rmse(actual, expected) <= 1e-4
 
 
-@pytest.mark.parametrize("fixture", ["cornell", "mixed_small"])
+@pytest.mark.parametrize("fixture", ["cornell", "mixed_small", "directional_small"])
 def test_render_tiles_match_oracle(fixture, request):
     prepared = request.getfixturevalue(fixture)
     oracle = oracle_lib.OracleScene(prepared)

@@ -232,3 +232,28 @@ def test_golden_fixtures(cornell, terrain_small):
     index = np.tile(np.arange(2, dtype=np.uint32), len(pixels) // 2)
     radiance = oracle.evaluate_samples(params, pixels, index)
     assert np.array_equal(radiance.view(np.uint32), data["cornell_radiance_bits"])
+
+
+@pytest.mark.parametrize("angle", [0.0, 2.0])
+def test_directional_light_irradiance(angle):
+    """DirectionalLight (Scenic/Lights/DirectionalLight.cs:52-108): a lone Lambertian plane under a light tilted by 60 degrees
+    shows albedo / pi * Intensity * cos(60) whether the light is a delta light or a narrow cone (":66 Maintain consistent
+    intensity regardless of the angle"), and the light is picked, sampled and weighed as InfiniteDelta / Infinite."""
+    albedo, intensity = 0.6, 3.0
+    description = host.SceneDescription(triangles=scenes.plane(0, (200, 200)), materials=scenes.material(structs.MATERIAL_DIFFUSE, (albedo,) * 3),
+                                        infinite_lights=scenes.directional_light((intensity,) * 3, (90 - 60, 0, 0), angle=angle))
+    position = (0.0, 5.0, -3.0)
+    description.camera = scenes.perspective_camera(position, scenes.look_rotation(position, (0, 0, 0)), field_of_view=30.0)
+    prepared = host.prepare(description)
+    light = prepared.description.infinite_lights[0]
+    assert bool(light["isDelta"]) == (angle == 0.0) and prepared.infinite_threshold == 1.0  # no other light: always picked
+    assert np.allclose(light["direction"], [0, 0.5, -np.cos(np.radians(30))], atol=1e-6)  # incidentDirection points TOWARDS the light
+
+    oracle = ol.OracleScene(prepared)
+    params = structs.render_params(32, 32, 16, extend=256, seed=5, bounce_limit=4)
+    image, stats = oracle.render_tiles(params, scenes.tile_grid(32, 32, 16))
+    cosine = abs(float(light["direction"][1]))  # the plane's normal is +Y
+    expected = albedo / np.pi * intensity * cosine
+    assert image[..., :3].mean() == pytest.approx(expected, rel=0.02)
+    checked, passed = int(stats["lightOcclusionChecked"][0]), int(stats["lightOcclusionPassed"][0])
+    assert checked > 0 and passed >= 0.999 * checked  # nothing shadows the plane (but its own other triangle, along the diagonal seam)
