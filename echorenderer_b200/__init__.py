@@ -4,7 +4,7 @@ The package holds only what the hot path needs: csrc/ (hand-written CUDA for sm_
 scene preparation in C++), the ctypes binding, and the host-side mirror of the reference interface for this path.
 """
 from . import structs  # noqa: F401
-from .host import InstanceDescription, PackDescription, PreparedArrays, SceneDescription, prepare  # noqa: F401
+from .host import InstanceDescription, PackDescription, PreparedArrays, SceneDescription, TextureDescription, prepare  # noqa: F401
 from .scene import (AlbedoEvaluator, EvaluationOperation, EvaluationProfile, NormalDepthEvaluator, PathTracedEvaluator,  # noqa: F401
                     PreparedScene, RenderTexture, shard_tiles)
 from ._native import EchoNativeError  # noqa: F401

@@ -302,6 +302,32 @@ int32_t echo_b200_scene_set_camera(EchoScene* scene, const EchoCamera* camera)
 	return ECHO_B200_OK;
 }
 
+int32_t echo_b200_scene_set_textures(EchoScene* scene, const EchoTexture* textures, uint32_t textureCount, const float* texels, uint64_t texelCount,
+                                     const EchoMaterialTextures* materialTextures, uint32_t materialCount)
+{
+	if (!scene || (!textures && textureCount) || (!texels && texelCount) || (!materialTextures && textureCount)) return fail(ECHO_B200_ERR_INVALID, "null argument");
+
+	for (uint32_t i = 0; i < textureCount; i++)
+	{
+		const EchoTexture& t = textures[i];
+		if (t.width == 0 || t.height == 0 || (uint64_t)t.texelOffset + (uint64_t)t.width * t.height > texelCount) return fail(ECHO_B200_ERR_INVALID, "texture range out of bounds");
+		if (t.filter > ECHO_FILTER_BILINEAR || t.wrapper > ECHO_WRAPPER_MIRROR) return fail(ECHO_B200_ERR_UNSUPPORTED, "unknown texture filter or wrapper");
+	}
+
+	for (uint32_t i = 0; textureCount && i < materialCount; i++)
+	{
+		const EchoMaterialTextures& m = materialTextures[i];
+		for (uint32_t slot : { m.albedo, m.normal, m.roughness, m.paramA, m.paramB })
+			if (slot != ECHO_TEXTURE_NONE && slot >= textureCount) return fail(ECHO_B200_ERR_INVALID, "material texture slot out of range");
+	}
+
+	scene->textures.assign(textures, textures + textureCount);
+	scene->texels.assign(texels, texels + texelCount * 4);
+	scene->materialTextures.assign(materialTextures, materialTextures + (textureCount ? materialCount : 0));
+	scene->committed = false;
+	return ECHO_B200_OK;
+}
+
 int32_t echo_b200_scene_set_bound_radius(EchoScene* scene, float radius)
 {
 	if (!scene) return fail(ECHO_B200_ERR_INVALID, "null argument");
@@ -451,6 +477,19 @@ int32_t echo_b200_scene_commit(EchoScene* scene)
 		triShade[i * 3 + 2] = make_float4(t.normal2[0], t.normal2[1], t.normal2[2], 0.0f);
 	}
 
+	// texture coordinates are only read by textured scenes
+	if (!scene->textures.empty() && scene->materialTextures.size() != scene->materials.size())
+		return fail(ECHO_B200_ERR_INVALID, "set_textures needs one EchoMaterialTextures per material");
+
+	std::vector<float4> triTexcoord(scene->textures.empty() ? 0 : scene->triangles.size() * 2);
+
+	for (size_t i = 0; i < triTexcoord.size() / 2; i++)
+	{
+		const EchoTriangle& t = scene->triangles[i];
+		triTexcoord[i * 2 + 0] = make_float4(t.texcoord0[0], t.texcoord0[1], t.texcoord1[0], t.texcoord1[1]);
+		triTexcoord[i * 2 + 1] = make_float4(t.texcoord2[0], t.texcoord2[1], 0.0f, 0.0f);
+	}
+
 	std::vector<float4> spheres(scene->spheres.size());
 	std::vector<uint32_t> sphereMaterial(scene->spheres.size());
 
@@ -481,9 +520,15 @@ int32_t echo_b200_scene_commit(EchoScene* scene)
 	const EchoLightNode* lightNodes = nullptr;
 	const EchoPack* devicePacks = nullptr;
 	const EchoInstance* deviceInstances = nullptr;
+	const EchoTexture* deviceTextures = nullptr;
+	const EchoMaterialTextures* deviceMaterialTextures = nullptr;
+	const float* deviceTexels = nullptr;
+	static_assert(sizeof(EchoTexture) == 32 && sizeof(EchoMaterialTextures) == 32, "POD layout");
 	static_assert(sizeof(EchoPack) == 64 && sizeof(EchoInstance) == 128 && sizeof(EchoTokenHierarchy) == 24, "POD layout");
 
-	bool ok = upload(scene, scene->packs, devicePacks) && upload(scene, scene->instances, deviceInstances) && upload(scene, scene->nodes, nodes) && upload(scene, triHot, d.triHot) && upload(scene, triShade, d.triShade)
+	bool ok = upload(scene, scene->packs, devicePacks) && upload(scene, scene->instances, deviceInstances) && upload(scene, scene->textures, deviceTextures)
+		&& upload(scene, scene->materialTextures, deviceMaterialTextures) && upload(scene, scene->texels, deviceTexels) && upload(scene, triTexcoord, d.triTexcoord)
+		&& upload(scene, scene->nodes, nodes) && upload(scene, triHot, d.triHot) && upload(scene, triShade, d.triShade)
 		&& upload(scene, spheres, d.spheres) && upload(scene, sphereMaterial, d.sphereMaterial) && upload(scene, scene->materials, materials)
 		&& upload(scene, scene->lightNodes, lightNodes) && upload(scene, emitterTokens, d.emitterTokens)
 		&& upload(scene, emitterPaths, d.emitterPaths) && upload(scene, pointLights, d.pointLights) && upload(scene, infiniteLights, d.infiniteLights);
@@ -508,6 +553,10 @@ int32_t echo_b200_scene_commit(EchoScene* scene)
 	d.maxDepth = stackDepth;
 	d.packs = reinterpret_cast<const uint4*>(devicePacks);
 	d.instances = reinterpret_cast<const float4*>(deviceInstances);
+	d.textures = reinterpret_cast<const uint4*>(deviceTextures);
+	d.materialTextures = reinterpret_cast<const uint4*>(deviceMaterialTextures);
+	d.texels = reinterpret_cast<const float4*>(deviceTexels);
+	d.textureCount = (uint32_t)scene->textures.size();
 	d.packCount = (uint32_t)scene->packs.size();
 	d.instanceCount = (uint32_t)scene->instances.size();
 	d.infiniteThreshold = scene->infiniteThreshold;

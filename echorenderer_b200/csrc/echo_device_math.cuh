@@ -225,6 +225,80 @@ ECHO_DEVICE vec3 project_sphere(float z, float u) // Sample2D.cs:153-158
 
 ECHO_DEVICE vec3 uniform_sphere(vec2 s) { return project_sphere(fma_f(s.x, -2.0f, 1.0f), s.y); } // Sample2D.cs:35
 
+// MathF.Atan2 / Asin / Acos pinned to the Cephes single-precision algorithms, operation for operation as oracle/math.hpp
+// (atan_det, atan2_det, asin_det, acos_det): only reached through textures.
+ECHO_DEVICE float atan_det(float value)
+{
+	float sign = value < 0.0f ? -1.0f : 1.0f;
+	float x = value < 0.0f ? -value : value;
+	float y;
+
+	if (x > 2.414213562373095f)
+	{
+		y = 1.5707963267948966f;
+		x = -div(1.0f, x);
+	}
+	else if (x > 0.4142135623730950f)
+	{
+		y = 0.7853981633974483f;
+		x = div(x - 1.0f, x + 1.0f);
+	}
+	else y = 0.0f;
+
+	float z = x * x;
+	float p = 8.05374449538e-2f * z - 1.38776856032e-1f;
+	p = p * z + 1.99777106478e-1f;
+	p = p * z - 3.33329491539e-1f;
+	y = y + (p * z * x + x);
+	return sign * y;
+}
+
+ECHO_DEVICE float atan2_det(float y, float x)
+{
+	if (x == 0.0f)
+	{
+		if (y == 0.0f) return 0.0f;
+		return y > 0.0f ? 1.5707963267948966f : -1.5707963267948966f;
+	}
+
+	if (y == 0.0f) return x < 0.0f ? 3.14159265358979323846f : 0.0f;
+
+	float w = x > 0.0f ? 0.0f : (y < 0.0f ? -3.14159265358979323846f : 3.14159265358979323846f);
+	return w + atan_det(div(y, x));
+}
+
+ECHO_DEVICE float asin_det(float value)
+{
+	float sign = value < 0.0f ? -1.0f : 1.0f;
+	float a = value < 0.0f ? -value : value;
+	if (a < 1.0e-4f) return value;
+
+	bool large = a > 0.5f;
+	float z, x;
+
+	if (large)
+	{
+		z = 0.5f * (1.0f - a);
+		x = __fsqrt_rn(z);
+	}
+	else
+	{
+		x = a;
+		z = x * x;
+	}
+
+	float p = 4.2163199048e-2f * z + 2.4181311049e-2f;
+	p = p * z + 4.5470025998e-2f;
+	p = p * z + 7.4953002686e-2f;
+	p = p * z + 1.6666752422e-1f;
+	float result = p * z * x + x;
+
+	if (large) result = 1.5707963267948966f - (result + result);
+	return sign * result;
+}
+
+ECHO_DEVICE float acos_det(float value) { return 1.5707963267948966f - asin_det(value); }
+
 ECHO_DEVICE vec3 uniform_cone(vec2 s, float cosMaxP) { return project_sphere(fma_f(cosMaxP - 1.0f, s.x, 1.0f), s.y); } // Sample2D.cs:123-127
 
 ECHO_DEVICE vec2 uniform_triangle(vec2 s) // Sample2D.cs:54-62

@@ -76,6 +76,9 @@ struct EchoScene
 	float infiniteThreshold = 0.0f, infinitePdf = 0.0f;
 	EchoCamera camera = {};
 	float boundRadius = 0.0f;
+	std::vector<EchoTexture> textures;
+	std::vector<float> texels; // RGBA
+	std::vector<EchoMaterialTextures> materialTextures;
 	std::vector<EchoPack> packs; // empty: the arrays are one pack
 	std::vector<EchoInstance> instances;
 

@@ -29,13 +29,17 @@ struct DeviceScene
 	const uint64_t* emitterPaths;  // LightTree.map values, parallel to emitterTokens
 	const float4* pointLights;     // 2 x float4: {intensity, 0}, {position, 0}
 	const float4* infiniteLights;  // {radiance, directlyVisible bits}
+	const uint4* textures;         // 2 x uint4 per EchoTexture; null without image textures
+	const float4* texels;          // RGBA128 texels of every texture back to back
+	const uint4* materialTextures; // 2 x uint4 per EchoMaterialTextures, parallel to materials
+	const float4* triTexcoord;     // 2 x float4 per triangle: texcoord0.xy texcoord1.xy | texcoord2.xy - - (only with textures)
 	const uint4* packs;            // 4 x uint4 per EchoPack; null when the scene is a single pack
 	const float4* instances;       // 8 x float4 per EchoInstance
 
 	uint32_t nodeCount, triangleCount, sphereCount, materialCount;
 	uint32_t lightNodeCount, emitterCount, pointLightCount, infiniteLightCount;
 	uint32_t maxDepth;             // quad depth whose 3 * maxDepth + 1 stack entries serve the deepest chain of packs
-	uint32_t packCount, instanceCount;
+	uint32_t packCount, instanceCount, textureCount;
 	float infiniteThreshold, infinitePdf;
 	float boundRadius; // Accelerator.SphereBound.radius, read by the NormalDepth evaluator
 

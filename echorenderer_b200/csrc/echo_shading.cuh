@@ -716,9 +716,132 @@ ECHO_DEVICE void conductor_artistic(float mainColor, float edge, float& eta, flo
 	k = __fsqrt_rn(max_sse(div(value, 1.0f - mainColor), 0.0f));
 }
 
+// =====================================================================================================================
+// Image textures: TextureGrid.this[Float2] -> IFilter.Evaluate (Textures/Grids/IFilter.cs:17-68) with IWrapper (IWrapper.cs:18-96)
+// =====================================================================================================================
+
+ECHO_DEVICE int repeat_int(int value, int length) // Scalars.Repeat(int, int), Scalars.cs:205-210
+{
+	if ((0 <= value) & (value < length)) return value;
+	int mod = value % length;
+	return mod < 0 ? mod + length : mod;
+}
+
+ECHO_DEVICE void texture_wrap(uint32_t wrapper, int width, int height, int& x, int& y)
+{
+	if (wrapper == ECHO_WRAPPER_CLAMP)
+	{
+		x = x < 0 ? 0 : (x > width - 1 ? width - 1 : x);
+		y = y < 0 ? 0 : (y > height - 1 ? height - 1 : y);
+	}
+	else if (wrapper == ECHO_WRAPPER_REPEAT)
+	{
+		x = repeat_int(x, width);
+		y = repeat_int(y, height);
+	}
+	else
+	{
+		x = repeat_int(x, width * 2);
+		y = repeat_int(y, height * 2);
+		x = x < width * 2 - 1 - x ? x : width * 2 - 1 - x;
+		y = y < height * 2 - 1 - y ? y : height * 2 - 1 - y;
+	}
+}
+
+ECHO_DEVICE float lerp_fma(float first, float second, float value) { return __fmaf_rn(value, second, __fmaf_rn(-value, first, first)); } // Float4.Lerp, Float4.cs:396-406
+
+ECHO_DEVICE float4 texture_sample(const DeviceScene& scene, uint32_t index, vec2 uv)
+{
+	uint4 header = __ldg(scene.textures + (size_t)index * 2); // width height texelOffset filter
+	uint32_t wrapper = __ldg(scene.textures + (size_t)index * 2 + 1).x;
+	int width = (int)header.x, height = (int)header.y;
+	const float4* texels = scene.texels + header.z;
+	float sizeX = (float)width, sizeY = (float)height;
+
+	if (header.w == ECHO_FILTER_POINT)
+	{
+		int x = (int)floor((double)(uv.x * sizeX)), y = (int)floor((double)(uv.y * sizeY)); // ToPosition: (uv * size).Floored
+		texture_wrap(wrapper, width, height, x, y);
+		return __ldg(texels + (size_t)y * width + x);
+	}
+
+	float scaledX = uv.x * sizeX, scaledY = uv.y * sizeY;
+	int roundX = __float2int_rn(scaledX), roundY = __float2int_rn(scaledY); // cvtps2dq: round to nearest even
+	int x0 = roundX - 1, x1 = roundX, y0 = roundY - 1, y1 = roundY;
+	int minX = x0, minY = y0;
+
+	int ax = x0, ay = y0, bx = x1, by = y0, cx = x0, cy = y1, dx = x1, dy = y1;
+	texture_wrap(wrapper, width, height, ax, ay);
+	texture_wrap(wrapper, width, height, bx, by);
+	texture_wrap(wrapper, width, height, cx, cy);
+	texture_wrap(wrapper, width, height, dx, dy);
+
+	float4 y0x0 = __ldg(texels + (size_t)ay * width + ax), y0x1 = __ldg(texels + (size_t)by * width + bx);
+	float4 y1x0 = __ldg(texels + (size_t)cy * width + cx), y1x1 = __ldg(texels + (size_t)dy * width + dx);
+
+	float timeX = scaledX - 0.5f - (float)minX;
+	float timeY = scaledY - 0.5f - (float)minY;
+
+	return make_float4(lerp_fma(lerp_fma(y0x0.x, y0x1.x, timeX), lerp_fma(y1x0.x, y1x1.x, timeX), timeY),
+	                   lerp_fma(lerp_fma(y0x0.y, y0x1.y, timeX), lerp_fma(y1x0.y, y1x1.y, timeX), timeY),
+	                   lerp_fma(lerp_fma(y0x0.z, y0x1.z, timeX), lerp_fma(y1x0.z, y1x1.z, timeX), timeY),
+	                   lerp_fma(lerp_fma(y0x0.w, y0x1.w, timeX), lerp_fma(y1x0.w, y1x1.w, timeX), timeY));
+}
+
+// every textured slot of material `index` sampled at the contact's texture coordinate (Material.SampleAlbedo / Material.Sample)
+ECHO_DEVICE void resolve_material_textures(const DeviceScene& scene, uint32_t index, vec2 texcoord, MaterialRecord& m)
+{
+	uint4 slots = __ldg(scene.materialTextures + (size_t)index * 2);     // albedo normal roughness paramA
+	uint32_t paramB = __ldg(scene.materialTextures + (size_t)index * 2 + 1).x;
+
+	if (slots.x != ECHO_TEXTURE_NONE)
+	{
+		float4 value = texture_sample(scene, slots.x, texcoord);
+		m.albedo[0] = value.x; m.albedo[1] = value.y; m.albedo[2] = value.z; m.albedo[3] = value.w;
+	}
+
+	if (slots.z != ECHO_TEXTURE_NONE)
+	{
+		float4 value = texture_sample(scene, slots.z, texcoord);
+		m.roughness[0] = value.x; m.roughness[1] = value.y;
+	}
+
+	if (slots.w != ECHO_TEXTURE_NONE)
+	{
+		float4 value = texture_sample(scene, slots.w, texcoord);
+		m.paramA[0] = value.x; m.paramA[1] = value.y; m.paramA[2] = value.z;
+	}
+
+	if (paramB != ECHO_TEXTURE_NONE)
+	{
+		float4 value = texture_sample(scene, paramB, texcoord);
+		m.paramB[0] = value.x; m.paramB[1] = value.y; m.paramB[2] = value.z;
+	}
+}
+
+// Material.ApplyNormalMapping (Material.cs:77-98), run by GeometryShade's constructor on the hit's own material
+ECHO_DEVICE void apply_normal_mapping(const DeviceScene& scene, uint32_t index, vec2 texcoord, vec3& normal)
+{
+	uint32_t slot = __ldg(scene.materialTextures + (size_t)index * 2).y;
+	float intensity = __uint_as_float(__ldg(scene.materialTextures + (size_t)index * 2 + 1).y);
+	if (slot == ECHO_TEXTURE_NONE || almost_zero(intensity)) return; // zeroNormal, Material.cs:58
+
+	float4 value = texture_sample(scene, slot, texcoord);
+	float x = (max_sse(0.0f, min_sse(1.0f, value.x)) * -2.0f + 1.0f) * intensity; // Float4.Clamp: min.Max(max.Min(this)), Float4.cs:379
+	float y = (max_sse(0.0f, min_sse(1.0f, value.y)) * 2.0f + -1.0f) * intensity;
+	float z = (max_sse(0.0f, min_sse(1.0f, value.z)) * 2.0f + -2.0f) * intensity;
+
+	frame transform = make_frame(normal);
+	vec3 delta = apply_forward(transform, vec3{ x, y, z });
+	normal = normalized(normal - delta);
+}
+
 // Resolves OneSided (OneSided.cs:50-58) and the alpha test (Material.cs:63-75), then fills `b`.
 // `m` is the record of the hit's material; on return it still describes that top-level material (for emission tests).
-ECHO_DEVICE void material_scatter(const DeviceScene& scene, const MaterialRecord& top, vec3 outgoing, vec3 geometricNormal, vec3 shadingNormal, Bsdf& b)
+// TEX: the scene has image textures; `topIndex` / `texcoord` then select and place the samples of the textured slots.
+template<bool TEX = false>
+ECHO_DEVICE void material_scatter(const DeviceScene& scene, const MaterialRecord& top, vec3 outgoing, vec3 geometricNormal, vec3 shadingNormal, Bsdf& b,
+                                  uint32_t topIndex = 0u, vec2 texcoord = vec2{ 0.0f, 0.0f })
 {
 	b.transform = make_frame(shadingNormal); // BSDF.Reset, BSDF.cs:26-36
 	b.geometricNormal = geometricNormal;
@@ -729,6 +852,7 @@ ECHO_DEVICE void material_scatter(const DeviceScene& scene, const MaterialRecord
 	b.coatedMultiplier = make_rgb(0.0f);
 
 	MaterialRecord m = top;
+	uint32_t materialIndex = topIndex;
 	bool invisible = false;
 
 	for (int level = 0; level < 4 && !invisible && m.type == ECHO_MATERIAL_ONESIDED; level++)
@@ -736,8 +860,14 @@ ECHO_DEVICE void material_scatter(const DeviceScene& scene, const MaterialRecord
 		bool backface = (m.flags & ECHO_MATERIAL_FLAG_BACKFACE) != 0u;
 		bool cull = positive(dot(outgoing, geometricNormal)) != backface;
 		if (cull) invisible = true;
-		else m = load_material(scene, m.base);
+		else
+		{
+			materialIndex = m.base;
+			m = load_material(scene, materialIndex);
+		}
 	}
+
+	if (TEX && !invisible && scene.textureCount != 0u) resolve_material_textures(scene, materialIndex, texcoord, m);
 
 	if (!invisible && m.type == ECHO_MATERIAL_EMISSIVE)
 	{

@@ -192,6 +192,27 @@ ECHO_DEVICE vec3 sphere_normal(vec2 uv) // SphereEntity.cs:229-234,252-266
 	return normalized(vec3{ sinT * cosP, sinP, cosT * cosP });
 }
 
+ECHO_DEVICE vec2 triangle_texcoord(const DeviceScene& scene, uint32_t index, vec2 uv) // PreparedTriangle.GetTexcoord, TriangleEntity.cs:188
+{
+	float4 a = __ldg(scene.triTexcoord + (size_t)index * 2), b = __ldg(scene.triTexcoord + (size_t)index * 2 + 1);
+	float w = 1.0f - uv.x - uv.y;
+	return { w * a.x + uv.x * a.z + uv.y * b.x, w * a.y + uv.x * a.w + uv.y * b.y };
+}
+
+ECHO_DEVICE vec2 sphere_texcoord(vec2 uv) // PreparedSphere.GetTexcoord, SphereEntity.cs:236-245 (Atan2 / Asin pinned)
+{
+	float sinT = uv.x, sinP = uv.y, sign = 1.0f;
+
+	if (sinT > 1.5f)
+	{
+		sinT -= 3.0f;
+		sign = -1.0f;
+	}
+
+	float cosT = identity(sinT) * sign;
+	return { fma_f(atan2_det(sinT, cosT), kTauR, 0.5f), fma_f(asin_det(clamp11(sinP)), kPiR, 0.5f) };
+}
+
 ECHO_DEVICE float sphere_area(float radius) { return 4.0f * kPi * radius * radius; } // SphereEntity.cs:72
 
 struct SurfacePoint // GeometryPoint
@@ -1012,6 +1033,8 @@ __global__ void __launch_bounds__(kBlock) shade_kernel(DeviceScene scene, EchoRe
 
 			if (INST) hitLayers = load_layers(paths.hitLayers, raySlot);
 			Layer layer = find_layer<INST>(scene, hitLayers); // FindLayer, :97
+			const bool textured = INST && scene.textureCount != 0u;
+			vec2 texcoord = { 0.0f, 0.0f };
 
 			if (token_type(token) == ECHO_TOKEN_TYPE_TRIANGLE)
 			{
@@ -1019,11 +1042,13 @@ __global__ void __launch_bounds__(kBlock) shade_kernel(DeviceScene scene, EchoRe
 				materialIndex = layer.materialOffset + triangle.material; // instance.swatch[info.material], :102
 				infoNormal = triangle_normal(triangle);
 				infoShading = triangle_shading_normal(triangle, uv);
+				if (textured) texcoord = triangle_texcoord(scene, layer.info.triangleOffset + token_index(token), uv);
 			}
 			else
 			{
 				materialIndex = layer.materialOffset + __ldg(scene.sphereMaterial + layer.info.sphereOffset + token_index(token));
 				infoNormal = infoShading = sphere_normal(uv);
+				if (textured) texcoord = sphere_texcoord(uv);
 			}
 
 			SurfacePoint point;
@@ -1031,10 +1056,11 @@ __global__ void __launch_bounds__(kBlock) shade_kernel(DeviceScene scene, EchoRe
 			point.normal = normalized(transform_direction(layer.inverse, infoNormal)); // :100-101 (the identity without layers)
 			vec3 shadeNormal = normalized(transform_direction(layer.inverse, infoShading));
 			vec3 outgoing = -direction;
+			if (textured) apply_normal_mapping(scene, materialIndex, texcoord, shadeNormal); // GeometryShade's constructor, GeometryShade.cs:17
 
 			MaterialRecord material = load_material(scene, materialIndex);
 			Bsdf bsdf;
-			material_scatter(scene, material, outgoing, point.normal, shadeNormal, bsdf);
+			material_scatter<INST>(scene, material, outgoing, point.normal, shadeNormal, bsdf, materialIndex, texcoord);
 
 			// ---- emission of the new vertex: ContributeEmissive (:305-311), MIS-weighted after a MIS bounce (:96-109) ----
 			if (CLASS == CLASS_TERMINAL && material.type == ECHO_MATERIAL_EMISSIVE && positive(emissive_power(material)))
@@ -1361,7 +1387,9 @@ __global__ void __launch_bounds__(kBlock) auxiliary_kernel(DeviceScene scene, Ec
 
 		// PreparedScene.Interact + material.Scatter, as in shade_kernel
 		Layer layer = find_layer<INST>(scene, hitLayers);
+		const bool textured = INST && scene.textureCount != 0u;
 		vec3 infoNormal, infoShading;
+		vec2 texcoord = { 0.0f, 0.0f };
 		uint32_t materialIndex;
 
 		if (token_type(token) == ECHO_TOKEN_TYPE_TRIANGLE)
@@ -1370,21 +1398,25 @@ __global__ void __launch_bounds__(kBlock) auxiliary_kernel(DeviceScene scene, Ec
 			materialIndex = layer.materialOffset + triangle.material;
 			infoNormal = triangle_normal(triangle);
 			infoShading = triangle_shading_normal(triangle, uv);
+			if (textured) texcoord = triangle_texcoord(scene, layer.info.triangleOffset + token_index(token), uv);
 		}
 		else
 		{
 			materialIndex = layer.materialOffset + __ldg(scene.sphereMaterial + layer.info.sphereOffset + token_index(token));
 			infoNormal = infoShading = sphere_normal(uv);
+			if (textured) texcoord = sphere_texcoord(uv);
 		}
 
 		vec3 position = direction * max_net(distance, kEpsilon) + origin;
 		vec3 normal = normalized(transform_direction(layer.inverse, infoNormal));
 		vec3 shadeNormal = normalized(transform_direction(layer.inverse, infoShading));
 		vec3 outgoing = -direction;
+		if (textured) apply_normal_mapping(scene, materialIndex, texcoord, shadeNormal);
 
 		MaterialRecord material = load_material(scene, materialIndex);
 		Bsdf bsdf;
-		material_scatter(scene, material, outgoing, normal, shadeNormal, bsdf);
+		material_scatter<INST>(scene, material, outgoing, normal, shadeNormal, bsdf, materialIndex, texcoord);
+		if (textured) resolve_material_textures(scene, materialIndex, texcoord, material); // (RGB128)material.SampleAlbedo(contact)
 
 		// Exit(): (RGB128)material.SampleAlbedo(contact) / new NormalDepth128(contact.shade.Normal, depth).ToFloat4()
 		auto leave = [&]()
@@ -1707,7 +1739,8 @@ static bool ensure_capacity(WorkerState* state, uint64_t paths, uint64_t pixels,
 
 	if (instanced)
 		ok = ok && allocate(state, b.rayLayers[0], paths * 2) && allocate(state, b.rayLayers[1], paths * 2) && allocate(state, b.hitLayers, paths * 2)
-			&& allocate(state, b.shadowLayers, paths * 2);
+			&& allocate(state, b.shadowLayers, paths * 2)
+			&& check_cuda(cudaMemset(b.hitLayers, 0, sizeof(uint4) * paths * 2), "cudaMemset(hit layers)"); // only instanced traversal writes them
 
 	if (!ok) return false;
 
@@ -1811,7 +1844,9 @@ static bool evaluate_paths(WorkerState* state, const DeviceScene& scene, const E
 
 		gTimer.start(stream);
 		ExtendIO extendIO = { paths.rayQueue[current], paths.hitQueue };
-		if (INST && active >= narrowLimit)
+		const bool packs = INST && scene.packCount != 0u; // INST without packs: a textured scene, ordinary traversal, zeroed hit layers
+
+		if (packs && active >= narrowLimit)
 		{
 			static int layersGrid = persistent_grid((const void*)extend_layers_kernel<STACK>);
 			ExtendLayersIO layersIO;
@@ -1821,7 +1856,7 @@ static bool evaluate_paths(WorkerState* state, const DeviceScene& scene, const E
 			layersIO.hitLayers = paths.hitLayers;
 			extend_layers_kernel<STACK><<<std::min<unsigned int>(blocks, (unsigned int)layersGrid), kTraverseBlock, 0, stream>>>(scene, layersIO, activeCount, extendCounter);
 		}
-		else if (INST) extend_instanced_kernel<STACK><<<blocks, kBlock, 0, stream>>>(scene, extendIO, paths.rayLayers[current], paths.hitLayers, activeCount);
+		else if (packs) extend_instanced_kernel<STACK><<<blocks, kBlock, 0, stream>>>(scene, extendIO, paths.rayLayers[current], paths.hitLayers, activeCount);
 		else if (active < narrowLimit) extend_narrow_kernel<STACK><<<blocks, kBlock, 0, stream>>>(scene, extendIO, activeCount);
 		else extend_kernel<STACK><<<std::min<unsigned int>(blocks, (unsigned int)extendGrid), kTraverseBlock, 0, stream>>>(scene, extendIO, activeCount, extendCounter);
 		gTimer.stop(KernelTimer::EXTEND, stream);
@@ -1849,7 +1884,7 @@ static bool evaluate_paths(WorkerState* state, const DeviceScene& scene, const E
 
 		gTimer.start(stream);
 		ShadowIO shadowIO = { paths.shadowQueue, paths.shadowValue, paths.result, 0u };
-		if (INST && active >= narrowLimit)
+		if (packs && active >= narrowLimit)
 		{
 			static int layersGrid = persistent_grid((const void*)shadow_layers_kernel<STACK>);
 			ShadowLayersIO layersIO;
@@ -1860,7 +1895,7 @@ static bool evaluate_paths(WorkerState* state, const DeviceScene& scene, const E
 			layersIO.shadowLayers = paths.shadowLayers;
 			shadow_layers_kernel<STACK><<<std::min<unsigned int>(blocks, (unsigned int)layersGrid), kTraverseBlock, 0, stream>>>(scene, layersIO, counters + COUNTER_SHADOW, shadowCounter, paths.stats);
 		}
-		else if (INST) shadow_instanced_kernel<STACK><<<blocks, kBlock, 0, stream>>>(scene, shadowIO, paths.shadowLayers, counters + COUNTER_SHADOW, paths.stats);
+		else if (packs) shadow_instanced_kernel<STACK><<<blocks, kBlock, 0, stream>>>(scene, shadowIO, paths.shadowLayers, counters + COUNTER_SHADOW, paths.stats);
 		else if (active < narrowLimit) shadow_narrow_kernel<STACK><<<blocks, kBlock, 0, stream>>>(scene, shadowIO, counters + COUNTER_SHADOW, paths.stats);
 		else shadow_kernel<STACK><<<std::min<unsigned int>(blocks, (unsigned int)shadowGrid), kTraverseBlock, 0, stream>>>(scene, shadowIO, counters + COUNTER_SHADOW, shadowCounter, paths.stats);
 		gTimer.stop(KernelTimer::SHADOW, stream);
@@ -1892,7 +1927,7 @@ static bool evaluate_paths(WorkerState* state, const DeviceScene& scene, const E
 
 static bool evaluate_paths_dispatch(WorkerState* state, const DeviceScene& scene, const EchoRenderParams& params, uint32_t count, uint64_t& launches, cudaStream_t stream)
 {
-	bool instanced = scene.packCount != 0u;
+	bool instanced = scene.packCount != 0u || scene.textureCount != 0u; // the full-featured shading kernels
 
 	switch (stack_class(scene.maxDepth))
 	{
@@ -1924,7 +1959,7 @@ static bool render_batch(WorkerState* state, const DeviceScene& scene, const Ech
 	uint64_t perTile = (uint64_t)params.tileSize * params.tileSize;
 	uint32_t pixelTotal = (uint32_t)(tiles * perTile);
 
-	if (!ensure_capacity(state, (uint64_t)pixelTotal * params.extend, pixelTotal, tiles, scene.packCount != 0u)) return false;
+	if (!ensure_capacity(state, (uint64_t)pixelTotal * params.extend, pixelTotal, tiles, scene.packCount != 0u || scene.textureCount != 0u)) return false;
 	if (!check_cuda(cudaMemcpyAsync(state->tileXYDevice, tileXY, sizeof(int32_t) * 2 * tiles, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync(tiles)")) return false;
 	if (!check_cuda(cudaMemsetAsync(state->paths.counters, 0, sizeof(uint32_t) * 64, stream), "cudaMemsetAsync(counters)")) return false;
 
@@ -2015,7 +2050,7 @@ bool render_tiles(RenderState* state, const DeviceScene& scene, const EchoRender
 		bool ok = check_cuda(cudaSetDevice(device), "cudaSetDevice(render worker)");
 
 		// the statistics buffer is allocated with the wavefront state: size the worker for a full batch up front
-		ok = ok && ensure_capacity(worker, tilesPerBatch * perTile * params.extend, tilesPerBatch * perTile, tilesPerBatch, scene.packCount != 0u);
+		ok = ok && ensure_capacity(worker, tilesPerBatch * perTile * params.extend, tilesPerBatch * perTile, tilesPerBatch, scene.packCount != 0u || scene.textureCount != 0u);
 		ok = ok && check_cuda(cudaMemsetAsync(worker->paths.stats, 0, sizeof(unsigned long long) * STAT_COUNT, worker->stream), "cudaMemsetAsync(stats)");
 
 		while (ok && !failed.load())
@@ -2069,7 +2104,7 @@ bool evaluate_sample_list(RenderState* renderState, const DeviceScene& scene, co
 	for (uint64_t first = 0; first < n; first += kPathsPerBatch)
 	{
 		uint32_t count = (uint32_t)std::min<uint64_t>(kPathsPerBatch, n - first);
-		if (!ensure_capacity(state, count, 1, 1, scene.packCount != 0u)) return false;
+		if (!ensure_capacity(state, count, 1, 1, scene.packCount != 0u || scene.textureCount != 0u)) return false;
 
 		if (!check_cuda(cudaMemcpyAsync(state->pixelXY, pixelXYHost + first * 2, sizeof(int2) * count, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync(pixels)")) return false;
 		if (!check_cuda(cudaMemcpyAsync(state->sampleIndex, sampleIndexHost + first, sizeof(uint32_t) * count, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync(samples)")) return false;

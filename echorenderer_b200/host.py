@@ -81,6 +81,7 @@ class InstanceDescription:
     rotation: tuple = (0.0, 0.0, 0.0)
     scale: float = 1.0
     materials: np.ndarray = None
+    material_textures: np.ndarray = None  # texture slots of the replacement swatch
 
 
 @dataclass
@@ -91,6 +92,15 @@ class PackDescription:
     materials: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=structs.MATERIAL))
     instances: list = field(default_factory=list)
     point_lights: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=structs.POINT_LIGHT))
+    material_textures: np.ndarray = None
+
+
+@dataclass
+class TextureDescription:
+    """Textures/Grids/TextureGrid.cs: texels[height, width, 4] RGBA128 (row 0 at the bottom), IFilter and IWrapper."""
+    texels: np.ndarray
+    filter: int = structs.FILTER_BILINEAR   # TextureGrid.Filter defaults to bilinear (TextureGrid.cs:35)
+    wrapper: int = structs.WRAPPER_CLAMP    # TextureGrid.Wrapper defaults to clamp (TextureGrid.cs:34)
 
 
 @dataclass
@@ -101,6 +111,8 @@ class SceneDescription:
     materials: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=structs.MATERIAL))
     instances: list = field(default_factory=list)  # InstanceDescription placed directly in the scene
     packs: list = field(default_factory=list)      # PackDescription referred to by instances
+    textures: list = field(default_factory=list)   # TextureDescription, shared by every pack of the scene
+    material_textures: np.ndarray = None           # structs.MATERIAL_TEXTURES per material; None = constants only
     point_lights: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=structs.POINT_LIGHT))
     infinite_lights: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=structs.INFINITE_LIGHT))
     camera: np.ndarray = field(default_factory=lambda: np.zeros(1, dtype=structs.CAMERA))
@@ -126,6 +138,9 @@ class PreparedArrays:
     all_spheres: np.ndarray = None
     all_materials: np.ndarray = None
     all_point_lights: np.ndarray = None
+    textures: np.ndarray = None           # structs.TEXTURE records, None without image textures
+    texels: np.ndarray = None             # [n, 4] float32
+    material_textures: np.ndarray = None  # structs.MATERIAL_TEXTURES per entry of `materials`
 
     @property
     def point_lights(self):
@@ -303,6 +318,12 @@ def _prepare_packs(description, threads):
     packs = np.zeros(len(used), dtype=structs.PACK)
     all_nodes, all_triangles, all_spheres, all_materials, all_instances = [], [], [], [], []
     all_light_nodes, all_tokens, all_paths, all_points = [], [], [], []
+    slot_blocks, slot_overrides = [], []
+
+    def slots_of(source, count):
+        given = getattr(source, "material_textures", None)
+        return structs.material_textures(count) if given is None else np.ascontiguousarray(given, dtype=structs.MATERIAL_TEXTURES)
+
     counts = dict(node=0, triangle=0, sphere=0, material=0, instance=0, light=0, emitter=0, point=0)
     overrides = []
 
@@ -325,6 +346,7 @@ def _prepare_packs(description, threads):
         counts["light"] += len(light_nodes)
         counts["emitter"] += len(tokens)
         counts["point"] += len(points)
+        slot_blocks.append(slots_of(source, len(materials)))
         all_nodes.append(nodes), all_triangles.append(triangles), all_spheres.append(spheres), all_materials.append(materials)
         counts["node"] += len(nodes)
         counts["triangle"] += len(triangles)
@@ -346,6 +368,7 @@ def _prepare_packs(description, threads):
             record["materialOffset"] = counts["material"]
             override = np.ascontiguousarray(instance.materials, dtype=structs.MATERIAL)
             overrides.append(override)
+            slot_overrides.append(slots_of(instance, len(override)))
             counts["material"] += len(override)
 
     # OneSided.base indexes the swatch it lives in: make it absolute
@@ -358,8 +381,9 @@ def _prepare_packs(description, threads):
         offset += len(block)
 
     lights = (np.concatenate(all_light_nodes), np.concatenate(all_tokens), np.concatenate(all_paths), np.concatenate(all_points), float(built[0][2][3]))
+    slots = np.concatenate(slot_blocks + slot_overrides) if blocks else structs.material_textures(0)
     return (packs, instances, np.concatenate(all_nodes), np.concatenate(all_triangles), np.concatenate(all_spheres), materials,
-            max(int(p["maxDepth"]) for p in packs), lights)
+            max(int(p["maxDepth"]) for p in packs), lights, slots)
 
 
 def _root_bound_radius(root):
@@ -382,7 +406,7 @@ def prepare(description, threads=0):
 
     instanced = bool(d.instances)
     if instanced:
-        packs, instances, nodes, all_triangles, all_spheres, all_materials, max_depth, lights = _prepare_packs(d, threads)
+        packs, instances, nodes, all_triangles, all_spheres, all_materials, max_depth, lights, all_slots = _prepare_packs(d, threads)
         light_nodes, tokens, paths, all_points, scene_power = lights
     else:
         nodes, max_depth = build_qbvh(d.triangles, d.spheres, threads)
@@ -422,4 +446,21 @@ def prepare(description, threads=0):
         result.packs, result.instances = packs, instances
         result.all_triangles, result.all_spheres, result.all_materials = all_triangles, all_spheres, all_materials
         result.all_point_lights = all_points
+
+    if d.textures:
+        records = np.zeros(len(d.textures), dtype=structs.TEXTURE)
+        grids, offset = [], 0
+        for record, texture in zip(records, d.textures):
+            texels = np.ascontiguousarray(texture.texels, dtype=np.float32)
+            height, width = texels.shape[:2]
+            record["width"], record["height"], record["texelOffset"] = width, height, offset
+            record["filter"], record["wrapper"] = texture.filter, texture.wrapper
+            grids.append(texels.reshape(-1, 4))
+            offset += width * height
+        result.textures, result.texels = records, np.ascontiguousarray(np.concatenate(grids))
+        if instanced:
+            result.material_textures = all_slots
+        else:
+            given = d.material_textures
+            result.material_textures = structs.material_textures(len(d.materials)) if given is None else np.ascontiguousarray(given, dtype=structs.MATERIAL_TEXTURES)
     return result

@@ -37,6 +37,9 @@ class PreparedScene:
             _native.check(lib.echo_b200_scene_set_triangles(self._handle, ptr(triangles), len(triangles)))
             _native.check(lib.echo_b200_scene_set_spheres(self._handle, ptr(spheres), len(spheres)))
             _native.check(lib.echo_b200_scene_set_materials(self._handle, ptr(materials), len(materials)))
+            if prepared.textures is not None:
+                _native.check(lib.echo_b200_scene_set_textures(self._handle, ptr(prepared.textures), len(prepared.textures), ptr(prepared.texels), len(prepared.texels),
+                                                                  ptr(prepared.material_textures), len(prepared.material_textures)))
             if prepared.packs is not None:
                 _native.check(lib.echo_b200_scene_set_packs(self._handle, ptr(prepared.packs), len(prepared.packs), ptr(prepared.instances), len(prepared.instances)))
             _native.check(lib.echo_b200_scene_set_light_tree(self._handle, ptr(prepared.light_nodes), len(prepared.light_nodes),

@@ -473,6 +473,81 @@ def instanced_scene(grid=6, rings=24, segments=26, nested=True):
                             infinite_lights=ambient_light((0.3, 0.35, 0.4)), camera=camera, name="instanced")
 
 
+def _planar_texcoords(triangles, scale, axes=(0, 2)):
+    """Texture coordinates from two position axes (a planar projection), `scale` repeats per unit."""
+    v0 = triangles["vertex0"].astype(np.float64)
+    v1, v2 = v0 + triangles["edge1"], v0 + triangles["edge2"]
+    for key, v in (("texcoord0", v0), ("texcoord1", v1), ("texcoord2", v2)):
+        triangles[key] = (v[:, list(axes)] * scale).astype(np.float32)
+    return triangles
+
+
+def textured_scene(rings=24, segments=26):
+    """image textures in every material slot — a point-filtered repeating checker on the ground, bilinear
+    albedo + tangent-space normal map on a diffuse blob, roughness and main-colour maps on a conductor, a roughness map on
+    rough glass, a mirrored albedo map on a sphere (sphere texture coordinates) and an alpha cut-out quad."""
+    from .host import TextureDescription
+    rng = np.random.default_rng(17)
+
+    def grid(height, width):
+        y, x = np.meshgrid((np.arange(height) + 0.5) / height, (np.arange(width) + 0.5) / width, indexing="ij")
+        return x, y
+
+    x, y = grid(8, 8)
+    checker = np.where(((np.floor(x * 8) + np.floor(y * 8)) % 2 == 0)[..., None], [0.85, 0.85, 0.8, 1.0], [0.15, 0.2, 0.3, 1.0])
+    x, y = grid(48, 64)
+    marble = np.stack([0.5 + 0.4 * np.sin(9 * x + 4 * np.sin(7 * y)), 0.45 + 0.3 * np.cos(5 * y + 2 * x), 0.4 + 0.35 * np.sin(6 * (x + y)), np.ones_like(x)], axis=-1)
+    bumps = np.stack([0.5 + 0.35 * np.sin(25 * x), 0.5 + 0.35 * np.cos(19 * y), 0.9 + 0.1 * np.sin(7 * x * y), np.ones_like(x)], axis=-1)
+    x, y = grid(32, 32)
+    rough = np.stack([0.05 + 0.5 * x, 0.05 + 0.5 * y, np.zeros_like(x), np.ones_like(x)], axis=-1)
+    tint = np.stack([0.55 + 0.4 * x, 0.6 + 0.3 * y, 0.95 - 0.5 * x * y, np.ones_like(x)], axis=-1)
+    stripes = np.stack([0.9 * np.ones_like(x), 0.5 + 0.4 * np.sin(12 * y), 0.2 + 0.2 * x, np.ones_like(x)], axis=-1)
+    cutout = np.concatenate([rng.uniform(0.2, 0.9, (16, 16, 3)), (rng.uniform(0, 1, (16, 16, 1)) > 0.45).astype(np.float64)], axis=-1)
+
+    textures = [TextureDescription(checker, structs.FILTER_POINT, structs.WRAPPER_REPEAT),     # 0
+                TextureDescription(marble, structs.FILTER_BILINEAR, structs.WRAPPER_MIRROR),   # 1
+                TextureDescription(bumps, structs.FILTER_BILINEAR, structs.WRAPPER_REPEAT),    # 2
+                TextureDescription(rough, structs.FILTER_BILINEAR, structs.WRAPPER_CLAMP),     # 3
+                TextureDescription(tint, structs.FILTER_BILINEAR, structs.WRAPPER_REPEAT),     # 4
+                TextureDescription(stripes, structs.FILTER_BILINEAR, structs.WRAPPER_MIRROR),  # 5
+                TextureDescription(cutout, structs.FILTER_POINT, structs.WRAPPER_CLAMP)]       # 6
+
+    materials = np.concatenate([
+        material(structs.MATERIAL_DIFFUSE, (1, 1, 1), roughness=(0.4, 0.4)),                                  # 0 ground: checker albedo
+        material(structs.MATERIAL_DIFFUSE, (1, 1, 1)),                                                        # 1 marble albedo + normal map
+        material(structs.MATERIAL_CONDUCTOR, (1, 1, 1), roughness=(0.2, 0.2), param_a=(0.9, 0.8, 0.6), param_b=(1.0, 0.9, 0.8),
+                 flags=structs.MATERIAL_FLAG_ARTISTIC),                                                       # 2 roughness + main colour maps
+        material(structs.MATERIAL_DIELECTRIC, (1, 1, 1), roughness=(0.1, 0.1), ior=1.5),                      # 3 roughness map
+        material(structs.MATERIAL_DIFFUSE, (1, 1, 1)),                                                        # 4 sphere: striped albedo
+        material(structs.MATERIAL_DIFFUSE, (1, 1, 1)),                                                        # 5 alpha cut-out quad
+        material(structs.MATERIAL_EMISSIVE, (14.0, 13.0, 11.0)),                                              # 6 light
+        material(structs.MATERIAL_COATED_DIFFUSE, (1, 1, 1), roughness=(0.1, 0.3), ior=1.5,
+                 param_a=(coated_diffuse()["paramA"][0][0], 0, 0)),                                           # 7 coated: marble albedo + roughness map
+    ])
+    slots = structs.material_textures(len(materials))
+    slots["albedo"][[0, 1, 4, 5, 7]] = [0, 1, 5, 6, 1]
+    slots["normal"][1], slots["normalIntensity"][1] = 2, 0.6
+    slots["roughness"][[2, 3, 7]] = 3
+    slots["paramA"][2] = 4
+
+    parts = [_planar_texcoords(plane(0, (40, 40)), 0.5),
+             _planar_texcoords(blob_triangles((-4.5, 2.0, 0.0), 1.8, 1, rings, segments, seed=1), 0.3, (0, 1)),
+             _planar_texcoords(blob_triangles((0.0, 2.0, 2.0), 1.8, 2, rings, segments, seed=2), 0.25, (0, 1)),
+             _planar_texcoords(blob_triangles((4.5, 2.0, 0.0), 1.8, 3, rings, segments, seed=3), 0.25, (1, 2)),
+             _planar_texcoords(blob_triangles((0.0, 1.4, -4.0), 1.2, 7, rings, segments, seed=4), 0.4, (0, 1)),
+             _planar_texcoords(plane(5, (3, 3), (2.4, 1.6, -5.0), (90, 0, 0)), 0.33, (0, 1)),
+             plane(6, (5, 5), (0, 11, 0), (180, 0, 0))]
+    triangles = np.concatenate(parts)
+
+    spheres = np.zeros(2, dtype=structs.SPHERE)
+    spheres["position"], spheres["radius"], spheres["material"] = [(-2.4, 0.9, -5.5), (-6.0, 0.8, -4.5)], [0.9, 0.8], [4, 4]
+
+    position = (0.0, 6.5, -15.0)
+    camera = perspective_camera(position, look_rotation(position, (0, 1.5, 0)), field_of_view=50.0)
+    return SceneDescription(triangles=triangles, spheres=spheres, materials=materials, infinite_lights=ambient_light((0.25, 0.28, 0.35)),
+                            camera=camera, textures=textures, material_textures=slots, name="textured")
+
+
 def many_lights_scene(light_count=10000, rings=128, segments=130, seed=23):
     """C4: the C3 geometry, diffuse only, plus `light_count` small emissive triangles in a 60 x 20 x 60 volume."""
     base_materials = np.concatenate([

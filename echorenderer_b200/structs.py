@@ -75,6 +75,23 @@ MATERIAL = np.dtype([
     ("paramA", "<f4", 3), ("paramB", "<f4", 3), ("base", "<u4"),
 ])
 
+TEXTURE_NONE = 0xFFFFFFFF
+FILTER_POINT, FILTER_BILINEAR = 0, 1
+WRAPPER_CLAMP, WRAPPER_REPEAT, WRAPPER_MIRROR = 0, 1, 2
+TEXTURE = np.dtype([("width", "<u4"), ("height", "<u4"), ("texelOffset", "<u4"), ("filter", "<u4"), ("wrapper", "<u4"), ("reserved", "<u4", 3)])
+MATERIAL_TEXTURES = np.dtype([("albedo", "<u4"), ("normal", "<u4"), ("roughness", "<u4"), ("paramA", "<u4"), ("paramB", "<u4"), ("normalIntensity", "<f4"),
+                              ("reserved", "<u4", 2)])
+
+
+def material_textures(count, **slots):
+    """`count` EchoMaterialTextures records with every slot empty (NormalIntensity 0.25, Material.cs:54)."""
+    records = np.zeros(count, dtype=MATERIAL_TEXTURES)
+    for name in ("albedo", "normal", "roughness", "paramA", "paramB"):
+        records[name] = TEXTURE_NONE
+    records["normalIntensity"] = 0.25
+    return records
+
+
 LIGHT_NODE = np.dtype([
     ("boxMin", "<f4", 3), ("boxMax", "<f4", 3), ("coneAxis", "<f4", 3), ("cosOffset", "<f4"), ("cosExtend", "<f4"),
     ("power", "<f4"), ("child0", "<u4"), ("child1", "<u4"), ("pad", "<u4", 2),

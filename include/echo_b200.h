@@ -128,6 +128,38 @@ typedef struct EchoMaterial
 	uint32_t base;      /* OneSided.Base material index */
 } EchoMaterial; /* 64 B */
 
+/* ---- image textures: TextureGrid (Textures/Grids/TextureGrid.cs) flattened to RGBA128 texels, with its
+ * IFilter (Textures/Grids/IFilter.cs) and IWrapper (Textures/Grids/IWrapper.cs). Texel (x, y) of texture t is
+ * texels[t.texelOffset + y * t.width + x], rows growing upward like every Echo texture. ---- */
+#define ECHO_TEXTURE_NONE 0xFFFFFFFFu /* the slot keeps the constant of EchoMaterial (a Pure texture) */
+#define ECHO_FILTER_POINT 0u
+#define ECHO_FILTER_BILINEAR 1u
+#define ECHO_WRAPPER_CLAMP 0u
+#define ECHO_WRAPPER_REPEAT 1u
+#define ECHO_WRAPPER_MIRROR 2u
+
+typedef struct EchoTexture
+{
+	uint32_t width, height;
+	uint32_t texelOffset; /* in texels */
+	uint32_t filter;      /* ECHO_FILTER_* */
+	uint32_t wrapper;     /* ECHO_WRAPPER_* */
+	uint32_t reserved[3];
+} EchoTexture; /* 32 bytes */
+
+/* the texture slots of one material, parallel to the material array; a slot holding a texture index replaces the constant
+ * of the same name in EchoMaterial with `(RGB128)texture[contact.shade.Texcoord]` (Material.Sample, Material.cs:102) */
+typedef struct EchoMaterialTextures
+{
+	uint32_t albedo;       /* Material.Albedo, RGBA (Material.cs:63-75,100) */
+	uint32_t normal;       /* Material.Normal: tangent-space normal map (Material.ApplyNormalMapping, Material.cs:77-98) */
+	uint32_t roughness;    /* R and G of the Roughness texture */
+	uint32_t paramA;       /* Conductor.MainColor / RefractiveIndex */
+	uint32_t paramB;       /* Conductor.EdgeColor / Extinction */
+	float normalIntensity; /* Material.NormalIntensity (default 0.25); ~0 switches normal mapping off (Material.cs:58) */
+	uint32_t reserved[2];
+} EchoMaterialTextures; /* 32 bytes */
+
 /* ---- flattened LightTree node (LightTree.cs:156-171, LightBound.cs:10-20, ConeBound.cs:20-24). Node 0 = root.
  * Branch: child0/child1 are node indices. Leaf: child0 == ECHO_TOKEN_EMPTY and child1 holds the light's token. ---- */
 typedef struct EchoLightNode
@@ -276,6 +308,10 @@ int32_t echo_b200_scene_set_qbvh(EchoScene*, const EchoQbvhNode* nodes, uint32_t
 int32_t echo_b200_scene_set_triangles(EchoScene*, const EchoTriangle* triangles, uint32_t count);
 int32_t echo_b200_scene_set_spheres(EchoScene*, const EchoSphere* spheres, uint32_t count);
 int32_t echo_b200_scene_set_materials(EchoScene*, const EchoMaterial* materials, uint32_t count);
+/* optional: image textures and the texture slots of every material (material_textures: one record per material set with
+ * set_materials, or NULL when texture_count is 0). texels_rgba holds texel_count RGBA128 texels. */
+int32_t echo_b200_scene_set_textures(EchoScene*, const EchoTexture* textures, uint32_t texture_count, const float* texels_rgba, uint64_t texel_count,
+                                     const EchoMaterialTextures* material_textures, uint32_t material_count);
 int32_t echo_b200_scene_set_light_tree(EchoScene*, const EchoLightNode* nodes, uint32_t node_count,
                                        const uint32_t* emitter_tokens, const uint64_t* emitter_bitpaths, uint32_t emitter_count,
                                        const EchoPointLight* points, uint32_t point_count);

@@ -308,6 +308,103 @@ struct Scene
 	float infiniteLightsThreshold = 0.0f; // PreparedScene.cs:38
 	float infiniteLightsPdf = 0.0f;       // PreparedScene.cs:39
 
+	// image textures (include/echo_b200.h EchoTexture): RGBA128 texels of every grid back to back, and the texture slots of
+	// every material (empty: every slot is a constant)
+	std::vector<EchoTexture> textures;
+	std::vector<float> texels;
+	std::vector<EchoMaterialTextures> materialTextures;
+
+	struct Rgba
+	{
+		float v[4];
+	};
+
+	Rgba texel(const EchoTexture& texture, int x, int y) const // TextureGrid.this[Int2], ArrayGrid.cs
+	{
+		const float* p = texels.data() + ((size_t)texture.texelOffset + (size_t)y * texture.width + (size_t)x) * 4;
+		return { { p[0], p[1], p[2], p[3] } };
+	}
+
+	static int repeat_int(int value, int length) // Scalars.Repeat(int, int), Scalars.cs:205-210
+	{
+		if ((0 <= value) & (value < length)) return value;
+		int mod = value % length;
+		return mod < 0 ? mod + length : mod;
+	}
+
+	static void wrap(const EchoTexture& texture, int& x, int& y) // IWrapper.cs:18-96 (the SSE and the scalar forms agree)
+	{
+		int width = (int)texture.width, height = (int)texture.height;
+
+		if (texture.wrapper == ECHO_WRAPPER_CLAMP)
+		{
+			x = x < 0 ? 0 : (x > width - 1 ? width - 1 : x);
+			y = y < 0 ? 0 : (y > height - 1 ? height - 1 : y);
+		}
+		else if (texture.wrapper == ECHO_WRAPPER_REPEAT)
+		{
+			x = repeat_int(x, width);
+			y = repeat_int(y, height);
+		}
+		else
+		{
+			x = repeat_int(x, width * 2);
+			y = repeat_int(y, height * 2);
+			x = x < width * 2 - 1 - x ? x : width * 2 - 1 - x;
+			y = y < height * 2 - 1 - y ? y : height * 2 - 1 - y;
+		}
+	}
+
+	// TextureGrid.this[Float2] -> IFilter.Evaluate, IFilter.cs:17-68
+	Rgba texture_sample(uint32_t index, Float2 uv) const
+	{
+		const EchoTexture& texture = textures[index];
+		float sizeX = (float)texture.width, sizeY = (float)texture.height;
+
+		if (texture.filter == ECHO_FILTER_POINT)
+		{
+			int x = (int)std::floor((double)(uv.x * sizeX)), y = (int)std::floor((double)(uv.y * sizeY)); // ToPosition: (uv * size).Floored
+			wrap(texture, x, y);
+			return texel(texture, x, y);
+		}
+
+		float scaledX = uv.x * sizeX, scaledY = uv.y * sizeY;
+		int roundX = (int)std::nearbyint(scaledX), roundY = (int)std::nearbyint(scaledY); // cvtps2dq: round to nearest even
+		int x0 = roundX - 1, x1 = roundX, y0 = roundY - 1, y1 = roundY;
+		int minX = x0, minY = y0;
+
+		int ax = x0, ay = y0, bx = x1, by = y0, cx = x0, cy = y1, dx = x1, dy = y1;
+		wrap(texture, ax, ay);
+		wrap(texture, bx, by);
+		wrap(texture, cx, cy);
+		wrap(texture, dx, dy);
+
+		Rgba y0x0 = texel(texture, ax, ay), y0x1 = texel(texture, bx, by), y1x0 = texel(texture, cx, cy), y1x1 = texel(texture, dx, dy);
+
+		float timeX = scaledX - 0.5f - (float)minX;
+		float timeY = scaledY - 0.5f - (float)minY;
+
+		auto lerp = [](float first, float second, float value) { return std::fma(value, second, std::fma(-value, first, first)); }; // Float4.Lerp on an FMA host, Float4.cs:396-406
+		Rgba result;
+
+		for (int c = 0; c < 4; c++)
+		{
+			float low = lerp(y0x0.v[c], y0x1.v[c], timeX);
+			float high = lerp(y1x0.v[c], y1x1.v[c], timeX);
+			result.v[c] = lerp(low, high, timeY);
+		}
+
+		return result;
+	}
+
+	EchoMaterialTextures material_textures(uint32_t material) const
+	{
+		if (material < materialTextures.size()) return materialTextures[material];
+		EchoMaterialTextures none = {};
+		none.albedo = none.normal = none.roughness = none.paramA = none.paramB = ECHO_TEXTURE_NONE;
+		return none;
+	}
+
 	EchoCamera camera = {};
 	float boundRadius = 0.0f; // Accelerator.SphereBound.radius (Accelerator.cs:43-63), read by NormalDepthEvaluator
 

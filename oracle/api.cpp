@@ -77,6 +77,28 @@ void oracle_scene_set_light_tree(OracleScene* s, const EchoLightNode* nodes, uin
 	s->scene.rebuild_light_maps();
 }
 
+void oracle_scene_set_textures(OracleScene* s, const EchoTexture* textures, uint32_t textureCount, const float* texels, uint64_t texelCount,
+                               const EchoMaterialTextures* materialTextures, uint32_t materialCount)
+{
+	s->scene.textures.assign(textures, textures + textureCount);
+	s->scene.texels.assign(texels, texels + texelCount * 4);
+	s->scene.materialTextures.assign(materialTextures, materialTextures + (textureCount ? materialCount : 0));
+}
+
+// KAT hook: TextureGrid.this[Float2] for n texture coordinates
+void oracle_texture_sample(const OracleScene* s, uint32_t texture, const float* uv, uint64_t n, float* outRGBA)
+{
+	for (uint64_t i = 0; i < n; i++)
+	{
+		Scene::Rgba value = s->scene.texture_sample(texture, Float2{ uv[i * 2], uv[i * 2 + 1] });
+		for (int c = 0; c < 4; c++) outRGBA[i * 4 + c] = value.v[c];
+	}
+}
+
+float oracle_atan2(float y, float x) { return atan2_det(y, x); }
+float oracle_asin(float x) { return asin_det(x); }
+float oracle_acos(float x) { return acos_det(x); }
+
 void oracle_scene_set_bound_radius(OracleScene* s, float radius) { s->scene.boundRadius = radius; }
 
 void oracle_scene_set_infinite(OracleScene* s, const EchoInfiniteLight* lights, uint32_t count, float threshold, float pdf)

@@ -21,6 +21,7 @@ inline RGB emissive_emit(const EchoMaterial& m, const GeometryPoint& point, Floa
 inline void interact(const Scene& scene, const TraceQuery& query, Contact& contact)
 {
 	Float3 infoNormal, infoShading;
+	Float2 texcoord;
 	uint32_t material;
 
 	Scene::Layer layer = scene.find_layer(query.tokenLayers); // FindLayer, :97
@@ -32,11 +33,21 @@ inline void interact(const Scene& scene, const TraceQuery& query, Contact& conta
 		material = triangle.material;
 		infoNormal = triangle_normal(triangle);
 		infoShading = triangle_shading_normal(triangle, query.uv);
+
+		// PreparedTriangle.GetTexcoord, TriangleEntity.cs:188
+		float w = 1.0f - query.uv.x - query.uv.y;
+		texcoord = { w * triangle.texcoord0[0] + query.uv.x * triangle.texcoord1[0] + query.uv.y * triangle.texcoord2[0],
+		             w * triangle.texcoord0[1] + query.uv.x * triangle.texcoord1[1] + query.uv.y * triangle.texcoord2[1] };
 	}
 	else
 	{
 		material = scene.spheres[view.sphereOffset + token_index(query.token)].material;
 		infoNormal = infoShading = sphere_normal(query.uv);
+
+		// PreparedSphere.GetTexcoord, SphereEntity.cs:236-245 (Atan2 / Asin pinned, oracle/math.hpp)
+		float sinT, sinP, cosT;
+		sphere_theta_phi(query.uv, sinT, sinP, cosT);
+		texcoord = { fma_f(atan2_det(sinT, cosT), kTauR, 0.5f), fma_f(asin_det(clamp11(sinP)), kPiR, 0.5f) };
 	}
 
 	// without layers inverseTransform is the identity, but MultiplyDirection + Normalized still run (:100-101)
@@ -45,8 +56,10 @@ inline void interact(const Scene& scene, const TraceQuery& query, Contact& conta
 	contact.outgoing = -query.ray.direction;                                    // Contact.cs:39
 	contact.point.position = query.position();                                  // Contact.cs:25
 	contact.point.normal = normalized(multiply_direction(layer.inverse, infoNormal));
-	contact.shadeNormal = normalized(multiply_direction(layer.inverse, infoShading)); // constant Pure.normal: no normal mapping (Material.cs:61,84-86)
+	contact.shadeNormal = normalized(multiply_direction(layer.inverse, infoShading));
+	contact.texcoord = texcoord;
 	contact.material = layer.materialOffset + material;                        // instance.swatch[info.material], :102
+	apply_normal_mapping(scene, contact.material, texcoord, contact.shadeNormal); // GeometryShade's constructor, GeometryShade.cs:17
 
 	scatter_material(scene, contact.material, contact);
 }
@@ -566,7 +579,7 @@ struct AuxiliaryEvaluator
 		{
 			if (kind == ECHO_EVALUATOR_ALBEDO)
 			{
-				const EchoMaterial& material = scene.materials[contact.material]; // (RGB128)material.SampleAlbedo(contact), constant texture
+				EchoMaterial material = resolve_material(scene, contact.material, contact.texcoord); // (RGB128)material.SampleAlbedo(contact)
 				return { { material.albedo[0], material.albedo[1], material.albedo[2], 0.0f } };
 			}
 

@@ -116,6 +116,81 @@ inline void sincos_det(float radians, float& sin_out, float& cos_out)
 	cos_out = c;
 }
 
+// MathF.Atan2 / Asin / Acos are CRT functions like SinCos: pinned to the Cephes single-precision algorithms (atanf, asinf;
+// ~2e-7 relative error), every operation a separately rounded IEEE op so that oracle and device agree exactly. They are
+// only reached through textures (sphere texture coordinates, SphereEntity.cs:236-245; CylindricalTexture.ToUV).
+inline float atan_det(float value)
+{
+	float sign = value < 0.0f ? -1.0f : 1.0f;
+	float x = value < 0.0f ? -value : value;
+	float y;
+
+	if (x > 2.414213562373095f) // tan(3 pi / 8)
+	{
+		y = 1.5707963267948966f;
+		x = -(1.0f / x);
+	}
+	else if (x > 0.4142135623730950f) // tan(pi / 8)
+	{
+		y = 0.7853981633974483f;
+		x = (x - 1.0f) / (x + 1.0f);
+	}
+	else y = 0.0f;
+
+	float z = x * x;
+	float p = 8.05374449538e-2f * z - 1.38776856032e-1f;
+	p = p * z + 1.99777106478e-1f;
+	p = p * z - 3.33329491539e-1f;
+	y = y + (p * z * x + x);
+	return sign * y;
+}
+
+inline float atan2_det(float y, float x)
+{
+	if (x == 0.0f)
+	{
+		if (y == 0.0f) return 0.0f;
+		return y > 0.0f ? 1.5707963267948966f : -1.5707963267948966f;
+	}
+
+	if (y == 0.0f) return x < 0.0f ? 3.14159265358979323846f : 0.0f;
+
+	float w = x > 0.0f ? 0.0f : (y < 0.0f ? -3.14159265358979323846f : 3.14159265358979323846f);
+	return w + atan_det(y / x);
+}
+
+inline float asin_det(float value) // |value| <= 1 (callers clamp)
+{
+	float sign = value < 0.0f ? -1.0f : 1.0f;
+	float a = value < 0.0f ? -value : value;
+	if (a < 1.0e-4f) return value;
+
+	bool large = a > 0.5f;
+	float z, x;
+
+	if (large)
+	{
+		z = 0.5f * (1.0f - a);
+		x = std::sqrt(z);
+	}
+	else
+	{
+		x = a;
+		z = x * x;
+	}
+
+	float p = 4.2163199048e-2f * z + 2.4181311049e-2f;
+	p = p * z + 4.5470025998e-2f;
+	p = p * z + 7.4953002686e-2f;
+	p = p * z + 1.6666752422e-1f;
+	float result = p * z * x + x;
+
+	if (large) result = 1.5707963267948966f - (result + result);
+	return sign * result;
+}
+
+inline float acos_det(float value) { return 1.5707963267948966f - asin_det(value); } // |value| <= 1
+
 struct Float2
 {
 	float x, y;

@@ -705,6 +705,7 @@ struct Contact
 	Float3 outgoing = {};
 	GeometryPoint point = {};
 	Float3 shadeNormal = {};
+	Float2 texcoord = { 0.0f, 0.0f }; // GeometryShade.Texcoord
 	uint32_t material = 0;
 	BSDF bsdf;
 
@@ -719,9 +720,68 @@ inline void scatter_invisible(Contact& contact) // Invisible.cs:22-26
 	contact.bsdf.add(&contact.bsdf.specularTransmission);
 }
 
+// The material with every textured slot sampled at the contact's texture coordinate (Material.SampleAlbedo / Material.Sample,
+// Material.cs:100-102): the rest of Scatter then reads constants, as it does for Pure textures.
+inline EchoMaterial resolve_material(const Scene& scene, uint32_t materialIndex, Float2 texcoord)
+{
+	EchoMaterial material = scene.materials[materialIndex];
+	if (scene.materialTextures.empty()) return material;
+
+	EchoMaterialTextures slots = scene.material_textures(materialIndex);
+
+	if (slots.albedo != ECHO_TEXTURE_NONE)
+	{
+		Scene::Rgba value = scene.texture_sample(slots.albedo, texcoord);
+		for (int c = 0; c < 4; c++) material.albedo[c] = value.v[c];
+	}
+
+	if (slots.roughness != ECHO_TEXTURE_NONE)
+	{
+		Scene::Rgba value = scene.texture_sample(slots.roughness, texcoord);
+		material.roughness[0] = value.v[0];
+		material.roughness[1] = value.v[1];
+	}
+
+	if (slots.paramA != ECHO_TEXTURE_NONE)
+	{
+		Scene::Rgba value = scene.texture_sample(slots.paramA, texcoord);
+		for (int c = 0; c < 3; c++) material.paramA[c] = value.v[c];
+	}
+
+	if (slots.paramB != ECHO_TEXTURE_NONE)
+	{
+		Scene::Rgba value = scene.texture_sample(slots.paramB, texcoord);
+		for (int c = 0; c < 3; c++) material.paramB[c] = value.v[c];
+	}
+
+	return material;
+}
+
+// Material.ApplyNormalMapping (Material.cs:77-98), run by GeometryShade's constructor on the hit's own material
+inline void apply_normal_mapping(const Scene& scene, uint32_t materialIndex, Float2 texcoord, Float3& normal)
+{
+	if (scene.materialTextures.empty()) return;
+	EchoMaterialTextures slots = scene.material_textures(materialIndex);
+	if (slots.normal == ECHO_TEXTURE_NONE || almost_zero(slots.normalIntensity)) return; // zeroNormal, Material.cs:58
+
+	Scene::Rgba value = scene.texture_sample(slots.normal, texcoord);
+	float local[3];
+	const float scale[3] = { -2.0f, 2.0f, 2.0f }, offset[3] = { 1.0f, -1.0f, -2.0f };
+
+	for (int c = 0; c < 3; c++)
+	{
+		float clamped = sse_max(0.0f, sse_min(1.0f, value.v[c])); // Float4.Clamp: min.Max(max.Min(this)), Float4.cs:379
+		local[c] = (clamped * scale[c] + offset[c]) * slots.normalIntensity;
+	}
+
+	OrthonormalTransform transform(normal);
+	Float3 delta = transform.apply_forward(Float3{ local[0], local[1], local[2] });
+	normal = normalized(normal - delta);
+}
+
 inline void scatter_material(const Scene& scene, uint32_t materialIndex, Contact& contact)
 {
-	const EchoMaterial& material = scene.materials[materialIndex];
+	const EchoMaterial material = resolve_material(scene, materialIndex, contact.texcoord);
 	BSDF& bsdf = contact.bsdf;
 
 	switch (material.type)

@@ -70,3 +70,10 @@ def directional_small():
     description.infinite_lights = np.concatenate([scenes.ambient_light((0.05, 0.05, 0.05)), scenes.directional_light((4.0, 3.6, 3.0), (50, 30, 0), angle=2.0, directly_visible=True),
                                                   scenes.directional_light((1.5, 1.5, 2.0), (70, -120, 0), angle=0.0)])
     return host.prepare(description)
+
+
+@pytest.fixture(scope="session")
+def textured_small():
+    """Image textures in every material slot, normal mapping, sphere texture coordinates, an alpha cut-out (scenes.textured_scene)."""
+    from echorenderer_b200 import host, scenes
+    return host.prepare(scenes.textured_scene())

@@ -43,6 +43,14 @@ def library():
     lib.oracle_scene_set_infinite.argtypes = [p, p, u32, f32, f32]
     lib.oracle_scene_set_camera.argtypes = [p, p]
     lib.oracle_scene_set_packs.argtypes = [p, p, u32, p, u32]
+    lib.oracle_scene_set_textures.argtypes = [p, p, u32, p, u64, p, u32]
+    lib.oracle_texture_sample.argtypes = [p, u32, p, u64, p]
+    lib.oracle_atan2.argtypes = [f32, f32]
+    lib.oracle_atan2.restype = f32
+    lib.oracle_asin.argtypes = [f32]
+    lib.oracle_asin.restype = f32
+    lib.oracle_acos.argtypes = [f32]
+    lib.oracle_acos.restype = f32
     lib.oracle_trace_batch_hierarchy.argtypes = [p, p, p, u64, p, p, i32, i32]
     lib.oracle_occlude_batch_hierarchy.argtypes = [p, p, p, u64, p, i32, i32]
     lib.oracle_trace_batch.argtypes = [p, p, u64, p, p, i32]
@@ -105,6 +113,9 @@ class OracleScene:
         lib.oracle_scene_set_triangles(self.handle, ptr(prepared.triangles), len(prepared.triangles))
         lib.oracle_scene_set_spheres(self.handle, ptr(prepared.spheres), len(prepared.spheres))
         lib.oracle_scene_set_materials(self.handle, ptr(prepared.materials), len(prepared.materials))
+        if prepared.textures is not None:
+            lib.oracle_scene_set_textures(self.handle, ptr(prepared.textures), len(prepared.textures), ptr(prepared.texels), len(prepared.texels),
+                                          ptr(prepared.material_textures), len(prepared.material_textures))
         if prepared.packs is not None:
             lib.oracle_scene_set_packs(self.handle, ptr(prepared.packs), len(prepared.packs), ptr(prepared.instances), len(prepared.instances))
         lib.oracle_scene_set_light_tree(self.handle, ptr(prepared.light_nodes), len(prepared.light_nodes), ptr(prepared.emitter_tokens),
