@@ -328,6 +328,14 @@ int32_t echo_b200_scene_set_textures(EchoScene* scene, const EchoTexture* textur
 	return ECHO_B200_OK;
 }
 
+int32_t echo_b200_scene_set_distributions(EchoScene* scene, const float* values, uint64_t count)
+{
+	if (!scene || (!values && count)) return fail(ECHO_B200_ERR_INVALID, "null argument");
+	scene->distributions.assign(values, values + count);
+	scene->committed = false;
+	return ECHO_B200_OK;
+}
+
 int32_t echo_b200_scene_set_bound_radius(EchoScene* scene, float radius)
 {
 	if (!scene) return fail(ECHO_B200_ERR_INVALID, "null argument");
@@ -477,6 +485,15 @@ int32_t echo_b200_scene_commit(EchoScene* scene)
 		triShade[i * 3 + 2] = make_float4(t.normal2[0], t.normal2[1], t.normal2[2], 0.0f);
 	}
 
+	for (const EchoInfiniteLight& light : scene->infiniteLights)
+	{
+		if (light.type > ECHO_INFINITE_ENVIRONMENT) return fail(ECHO_B200_ERR_UNSUPPORTED, "unknown infinite light type");
+		if (light.type != ECHO_INFINITE_ENVIRONMENT) continue;
+		if (light.texture >= scene->textures.size()) return fail(ECHO_B200_ERR_INVALID, "environment light texture out of range");
+		const EchoTexture& t = scene->textures[light.texture];
+		if ((uint64_t)light.distribution + (uint64_t)t.height * (t.width + 1ull) > scene->distributions.size()) return fail(ECHO_B200_ERR_INVALID, "environment light distribution out of range");
+	}
+
 	// texture coordinates are only read by textured scenes
 	if (!scene->textures.empty() && scene->materialTextures.size() != scene->materials.size())
 		return fail(ECHO_B200_ERR_INVALID, "set_textures needs one EchoMaterialTextures per material");
@@ -500,7 +517,7 @@ int32_t echo_b200_scene_commit(EchoScene* scene)
 		sphereMaterial[i] = s.material;
 	}
 
-	std::vector<float4> pointLights(scene->pointLights.size() * 2), infiniteLights(scene->infiniteLights.size() * 7);
+	std::vector<float4> pointLights(scene->pointLights.size() * 2), infiniteLights(scene->infiniteLights.size() * 10);
 
 	for (size_t i = 0; i < scene->pointLights.size(); i++)
 	{
@@ -509,8 +526,8 @@ int32_t echo_b200_scene_commit(EchoScene* scene)
 		pointLights[i * 2 + 1] = make_float4(p.position[0], p.position[1], p.position[2], 0.0f);
 	}
 
-	static_assert(sizeof(EchoInfiniteLight) == 112, "POD layout");
-	std::memcpy(infiniteLights.data(), scene->infiniteLights.data(), sizeof(EchoInfiniteLight) * scene->infiniteLights.size()); // 7 float4 each, verbatim
+	static_assert(sizeof(EchoInfiniteLight) == 160, "POD layout");
+	std::memcpy(infiniteLights.data(), scene->infiniteLights.data(), sizeof(EchoInfiniteLight) * scene->infiniteLights.size()); // 10 float4 each, verbatim
 
 	static_assert(sizeof(EchoQbvhNode) == 128 && sizeof(EchoMaterial) == 64 && sizeof(EchoLightNode) == 64, "POD layout");
 	static_assert(sizeof(EchoTriangle) == 100 && sizeof(EchoSphere) == 20 && sizeof(EchoRay) == 32 && sizeof(EchoHit) == 16, "POD layout");
@@ -527,7 +544,7 @@ int32_t echo_b200_scene_commit(EchoScene* scene)
 	static_assert(sizeof(EchoPack) == 64 && sizeof(EchoInstance) == 128 && sizeof(EchoTokenHierarchy) == 24, "POD layout");
 
 	bool ok = upload(scene, scene->packs, devicePacks) && upload(scene, scene->instances, deviceInstances) && upload(scene, scene->textures, deviceTextures)
-		&& upload(scene, scene->materialTextures, deviceMaterialTextures) && upload(scene, scene->texels, deviceTexels) && upload(scene, triTexcoord, d.triTexcoord)
+		&& upload(scene, scene->materialTextures, deviceMaterialTextures) && upload(scene, scene->texels, deviceTexels) && upload(scene, triTexcoord, d.triTexcoord) && upload(scene, scene->distributions, d.distributions)
 		&& upload(scene, scene->nodes, nodes) && upload(scene, triHot, d.triHot) && upload(scene, triShade, d.triShade)
 		&& upload(scene, spheres, d.spheres) && upload(scene, sphereMaterial, d.sphereMaterial) && upload(scene, scene->materials, materials)
 		&& upload(scene, scene->lightNodes, lightNodes) && upload(scene, emitterTokens, d.emitterTokens)

@@ -76,6 +76,7 @@ struct EchoScene
 	float infiniteThreshold = 0.0f, infinitePdf = 0.0f;
 	EchoCamera camera = {};
 	float boundRadius = 0.0f;
+	std::vector<float> distributions;
 	std::vector<EchoTexture> textures;
 	std::vector<float> texels; // RGBA
 	std::vector<EchoMaterialTextures> materialTextures;

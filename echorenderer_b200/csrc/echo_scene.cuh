@@ -28,7 +28,8 @@ struct DeviceScene
 	const uint32_t* emitterTokens; // sorted ascending
 	const uint64_t* emitterPaths;  // LightTree.map values, parallel to emitterTokens
 	const float4* pointLights;     // 2 x float4: {intensity, 0}, {position, 0}
-	const float4* infiniteLights;  // {radiance, directlyVisible bits}
+	const float4* infiniteLights;  // 10 x float4 per EchoInfiniteLight
+	const float* distributions;    // DiscreteDistribution2D cdf values of the environment lights
 	const uint4* textures;         // 2 x uint4 per EchoTexture; null without image textures
 	const float4* texels;          // RGBA128 texels of every texture back to back
 	const uint4* materialTextures; // 2 x uint4 per EchoMaterialTextures, parallel to materials

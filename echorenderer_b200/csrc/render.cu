@@ -399,26 +399,173 @@ ECHO_DEVICE float light_tree_mass(const DeviceScene& scene, const PackInfo& info
 
 // ---------------------------------------------------------------------------------------------------------------------
 // infinite lights: AmbientLight over a Pure texture (AmbientLight.cs:53-67) and DirectionalLight (DirectionalLight.cs:78-108).
-// EchoInfiniteLight = 7 float4: {radiance, directlyVisible} {type, isDelta, cosAngle, -} {intensity, -} {direction, -} rotation[9] + pad
+// EchoInfiniteLight = 10 float4: {radiance, directlyVisible} {type, isDelta, cosAngle, -} {intensity, -} {direction, -}
+// rotation[9] texture distribution - | inverseRotation[9] + pad
 // ---------------------------------------------------------------------------------------------------------------------
+
+constexpr int kInfiniteStride = 10;
 
 struct InfiniteLight
 {
 	rgb radiance;
-	bool directlyVisible, directional, delta;
+	bool directlyVisible, directional, delta, environment;
 	float cosAngle;
 	const float4* data;
 };
 
 ECHO_DEVICE InfiniteLight load_infinite(const DeviceScene& scene, uint32_t index)
 {
-	const float4* p = scene.infiniteLights + (size_t)index * 7;
+	const float4* p = scene.infiniteLights + (size_t)index * kInfiniteStride;
 	float4 a = __ldg(p), b = __ldg(p + 1);
-	return { as_rgb(a), __float_as_uint(a.w) != 0u, __float_as_uint(b.x) == ECHO_INFINITE_DIRECTIONAL, __float_as_uint(b.y) != 0u, b.z, p };
+	uint32_t type = __float_as_uint(b.x);
+	return { as_rgb(a), __float_as_uint(a.w) != 0u, type == ECHO_INFINITE_DIRECTIONAL, __float_as_uint(b.y) != 0u, type == ECHO_INFINITE_ENVIRONMENT, b.z, p };
 }
 
-ECHO_DEVICE rgb infinite_evaluate(const InfiniteLight& light, vec3 incident)
+ECHO_DEVICE vec3 rotate3x3(float4 r0, float4 r1, float r8, vec3 v) // Float3x3 * Float3 (Float3x3.cs:264-269), nine row-major floats
 {
+	return { r0.x * v.x + r0.y * v.y + r0.z * v.z, r0.w * v.x + r1.x * v.y + r1.y * v.z, r1.z * v.x + r1.w * v.y + r8 * v.z };
+}
+
+ECHO_DEVICE vec3 infinite_to_world(const InfiniteLight& light, vec3 v) // LocalToWorldRotation: words 16..24
+{
+	return rotate3x3(__ldg(light.data + 4), __ldg(light.data + 5), __ldg(light.data + 6).x, v);
+}
+
+ECHO_DEVICE vec3 infinite_to_local(const InfiniteLight& light, vec3 v) // WorldToLocalRotation: words 28..36
+{
+	return rotate3x3(__ldg(light.data + 7), __ldg(light.data + 8), __ldg(light.data + 9).x, v);
+}
+
+// ---- Evaluation/Sampling/DiscreteDistribution1D.cs:58-166 over a stored cdf ----
+struct Distribution1D
+{
+	const float* cdf;
+	int count;
+
+	ECHO_DEVICE void bounds(int index, float& lower, float& upper) const
+	{
+		lower = index == 0 ? 0.0f : __ldg(cdf + index - 1);
+		upper = __ldg(cdf + index);
+	}
+
+	ECHO_DEVICE int find_index(float sample) const // FindIndex / FixIndex / BinarySearch
+	{
+		uint32_t head = 0u, tail = (uint32_t)count;
+		int index = -1;
+
+		while (head < tail)
+		{
+			uint32_t middle = (tail + head) >> 1;
+			float current = __ldg(cdf + middle);
+			if (current == sample) { index = (int)middle; break; }
+			if (current > sample) tail = middle;
+			else head = middle + 1u;
+		}
+
+		if (index < 0) return (int)head;
+
+		float lower, upper;
+		bounds(index, lower, upper);
+		if (upper - lower > 0.0f) return index + 1;
+
+		do
+		{
+			lower = upper;
+			upper = __ldg(cdf + ++index);
+		}
+		while (lower == upper);
+
+		return index;
+	}
+
+	ECHO_DEVICE float sample(float u, float& pdf) const
+	{
+		int index = find_index(u);
+		float lower, upper;
+		bounds(index, lower, upper);
+
+		float gap = upper - lower;
+		float countR = rcp((float)count);
+		float shift = div(u - lower, gap) + (float)index;
+		pdf = gap * (float)count;
+		return sample1d(shift * countR);
+	}
+
+	ECHO_DEVICE float probability_density(float result) const
+	{
+		float lower, upper;
+		bounds(sample_range(result, count), lower, upper);
+		return (upper - lower) * (float)count;
+	}
+};
+
+// ---- Textures/Directional/CylindricalTexture.cs:98-165 ----
+ECHO_DEVICE vec2 cylindrical_to_uv(vec3 direction) // ToUV, :142-151 (Atan2 / Acos pinned)
+{
+	return { fma_f(atan2_det(direction.x, direction.z), kTauR, 0.5f), fma_f(acos_det(clamp11(direction.y)), -kPiR, 1.0f) };
+}
+
+struct EnvironmentGrid
+{
+	uint32_t texture;
+	const float* values;
+	int width, height;
+};
+
+ECHO_DEVICE EnvironmentGrid environment_grid(const DeviceScene& scene, const InfiniteLight& light)
+{
+	float4 tail = __ldg(light.data + 6); // rotation[8], texture, distribution, pad
+	uint32_t texture = __float_as_uint(tail.y);
+	uint4 header = __ldg(scene.textures + (size_t)texture * 2);
+	return { texture, scene.distributions + __float_as_uint(tail.z), (int)header.x, (int)header.y };
+}
+
+ECHO_DEVICE float cylindrical_pdf(const DeviceScene& scene, const InfiniteLight& light, vec3 incident) // :100-110
+{
+	vec2 uv = cylindrical_to_uv(incident);
+	float cosP = -incident.y;
+	float sinP = identity(cosP);
+	if (!positive(sinP)) return 0.0f;
+
+	EnvironmentGrid grid = environment_grid(scene, light);
+	float x = sample1d(uv.x), y = sample1d(uv.y); // (Sample2D)uv
+
+	Distribution1D vertical{ grid.values, grid.height };
+	Distribution1D slice{ grid.values + grid.height + (size_t)sample_range(y, grid.height) * grid.width, grid.width };
+	float pdfX = slice.probability_density(x);
+	float pdfY = vertical.probability_density(y);
+	return div(pdfX * pdfY * (kTauR / kPi), sinP);
+}
+
+ECHO_DEVICE Sampled cylindrical_sample(const DeviceScene& scene, const InfiniteLight& light, vec2 sample, vec3& incident) // :112-140
+{
+	EnvironmentGrid grid = environment_grid(scene, light);
+
+	float pdfY, pdfX;
+	float y = Distribution1D{ grid.values, grid.height }.sample(sample.y, pdfY);
+	float x = Distribution1D{ grid.values + grid.height + (size_t)sample_range(y, grid.height) * grid.width, grid.width }.sample(sample.x, pdfX);
+	float pdf = pdfX * pdfY;
+
+	incident = { 0.0f, 0.0f, 0.0f };
+	if (!positive(pdf)) return impossible();
+
+	float sinT, cosT, sinP, cosP;
+	sincos_det(x * kTau, sinT, cosT);
+	sincos_det(y * kPi, sinP, cosP);
+	if (!positive(sinP)) return impossible();
+
+	incident = { -sinP * sinT, -cosP, -sinP * cosT };
+	return { as_rgb(texture_sample(scene, grid.texture, vec2{ x, y })), div(pdf * (kTauR / kPi), sinP) };
+}
+
+ECHO_DEVICE rgb infinite_evaluate(const DeviceScene& scene, const InfiniteLight& light, vec3 incident)
+{
+	if (light.environment) // AmbientLight.Evaluate, AmbientLight.cs:53-54
+	{
+		uint32_t texture = __float_as_uint(__ldg(light.data + 6).y);
+		return light.radiance * as_rgb(texture_sample(scene, texture, cylindrical_to_uv(infinite_to_local(light, incident))));
+	}
+
 	if (!light.directional) return light.radiance;
 	if (light.delta) return make_rgb(0.0f);
 
@@ -427,16 +574,24 @@ ECHO_DEVICE rgb infinite_evaluate(const InfiniteLight& light, vec3 incident)
 	return light.radiance; // scaledIntensity
 }
 
-ECHO_DEVICE float infinite_pdf(const InfiniteLight& light)
+ECHO_DEVICE float infinite_pdf(const DeviceScene& scene, const InfiniteLight& light, vec3 incident)
 {
+	if (light.environment) return cylindrical_pdf(scene, light, infinite_to_local(light, incident)); // AmbientLight.cs:56-57
 	if (!light.directional) return kUniformSpherePdf;
 	if (light.delta) return 0.0f;
 	return uniform_cone_pdf(light.cosAngle);
 }
 
-ECHO_DEVICE Sampled infinite_sample(const InfiniteLight& light, vec2 sample, vec3& incident, float& travel)
+ECHO_DEVICE Sampled infinite_sample(const DeviceScene& scene, const InfiniteLight& light, vec2 sample, vec3& incident, float& travel)
 {
 	travel = kInfinity;
+
+	if (light.environment) // AmbientLight.Sample, AmbientLight.cs:59-66
+	{
+		Sampled sampled = cylindrical_sample(scene, light, sample, incident);
+		incident = infinite_to_world(light, incident);
+		return { sampled.content * light.radiance, sampled.pdf };
+	}
 
 	if (!light.directional)
 	{
@@ -452,8 +607,7 @@ ECHO_DEVICE Sampled infinite_sample(const InfiniteLight& light, vec2 sample, vec
 
 	vec3 local = uniform_cone(sample, light.cosAngle);
 	local.z = -local.z; // Utility.NegateZ
-	float4 r0 = __ldg(light.data + 4), r1 = __ldg(light.data + 5), r2 = __ldg(light.data + 6); // rotation[0..3], [4..7], [8] + pad
-	incident = { r0.x * local.x + r0.y * local.y + r0.z * local.z, r0.w * local.x + r1.x * local.y + r1.y * local.z, r1.z * local.x + r1.w * local.y + r2.x * local.z };
+	incident = infinite_to_world(light, local);
 	return { light.radiance, uniform_cone_pdf(light.cosAngle) };
 }
 
@@ -468,7 +622,7 @@ ECHO_DEVICE uint32_t scene_pick(const DeviceScene& scene, const SurfacePoint& or
 		sample = sample_stretch(sample, 0.0f, scene.infiniteThreshold);
 		int index = sample_range(sample, (int)scene.infiniteLightCount);
 		outPdf = scene.infinitePdf;
-		bool delta = __float_as_uint(__ldg(scene.infiniteLights + (size_t)index * 7 + 1).y) != 0u;
+		bool delta = __float_as_uint(__ldg(scene.infiniteLights + (size_t)index * kInfiniteStride + 1).y) != 0u;
 		return ECHO_LIGHT_TOKEN_MAKE(delta ? ECHO_LIGHT_TYPE_INFINITE_DELTA : ECHO_LIGHT_TYPE_INFINITE, (uint32_t)index); // :120
 	}
 
@@ -636,7 +790,7 @@ ECHO_DEVICE Sampled scene_sample_light(const DeviceScene& scene, uint32_t light,
 
 	if (token_is_infinite_light(light))
 	{
-		return infinite_sample(load_infinite(scene, token_light_index(light)), sample, incident, travel);
+		return infinite_sample(scene, load_infinite(scene, token_light_index(light)), sample, incident, travel);
 	}
 
 	// FindLayer + `forwardTransform * origin` (:192-198, GeometryPoint.cs:41-45): the shading point in the space of the pack
@@ -692,7 +846,7 @@ ECHO_DEVICE Sampled scene_sample_light(const DeviceScene& scene, uint32_t light,
 template<bool INST>
 ECHO_DEVICE float scene_light_pdf(const DeviceScene& scene, uint32_t light, const PathLayers& layers, const SurfacePoint& origin, vec3 incident)
 {
-	if (token_is_infinite_light(light)) return infinite_pdf(load_infinite(scene, token_light_index(light)));
+	if (token_is_infinite_light(light)) return infinite_pdf(scene, load_infinite(scene, token_light_index(light)), incident);
 	if (token_type(light) == ECHO_TOKEN_TYPE_LIGHT) return 1.0f;
 
 	Layer layer = find_layer<INST>(scene, layers);
@@ -709,7 +863,7 @@ ECHO_DEVICE rgb evaluate_infinite(const DeviceScene& scene, vec3 direction, bool
 	{
 		InfiniteLight light = load_infinite(scene, i);
 		if (direct && !light.directlyVisible) continue;
-		total = total + infinite_evaluate(light, direction);
+		total = total + infinite_evaluate(scene, light, direction);
 	}
 
 	return total;
@@ -1010,10 +1164,10 @@ __global__ void __launch_bounds__(kBlock) shade_kernel(DeviceScene scene, EchoRe
 					InfiniteLight light = load_infinite(scene, index);
 					if (light.delta) continue; // "Skip delta lights; they do not like MIS", :118
 
-					float pdf = scene.infinitePdf * infinite_pdf(light); // ProbabilityMass * light.ProbabilityDensity, :121-122
+					float pdf = scene.infinitePdf * infinite_pdf(scene, light, direction); // ProbabilityMass * light.ProbabilityDensity, :121-122
 					if (!positive(pdf)) continue;
 					float weight = power_heuristic(scatterPdfPrevious, pdf);
-					result = result + energy * (infinite_evaluate(light, direction) * weight);
+					result = result + energy * (infinite_evaluate(scene, light, direction) * weight);
 				}
 			}
 

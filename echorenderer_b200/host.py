@@ -141,6 +141,7 @@ class PreparedArrays:
     textures: np.ndarray = None           # structs.TEXTURE records, None without image textures
     texels: np.ndarray = None             # [n, 4] float32
     material_textures: np.ndarray = None  # structs.MATERIAL_TEXTURES per entry of `materials`
+    distributions: np.ndarray = None      # DiscreteDistribution2D cdf values of the environment lights
 
     @property
     def point_lights(self):
@@ -386,6 +387,82 @@ def _prepare_packs(description, threads):
             max(int(p["maxDepth"]) for p in packs), lights, slots)
 
 
+def _wrap_index(index, size, wrapper):
+    if wrapper == structs.WRAPPER_CLAMP:
+        return np.clip(index, 0, size - 1)
+    if wrapper == structs.WRAPPER_REPEAT:
+        return np.mod(index, size)
+    folded = np.mod(index, 2 * size)
+    return np.minimum(folded, 2 * size - 1 - folded)
+
+
+def sample_texture(texture, uv):
+    """TextureGrid.this[Float2] (IFilter.cs:17-68) in float64 numpy: host-side preparation only (distributions, averages)."""
+    texels = np.asarray(texture.texels, dtype=np.float64)
+    height, width = texels.shape[:2]
+    scaled = np.asarray(uv, dtype=np.float64) * [width, height]
+    if texture.filter == structs.FILTER_POINT:
+        x = _wrap_index(np.floor(scaled[..., 0]).astype(int), width, texture.wrapper)
+        y = _wrap_index(np.floor(scaled[..., 1]).astype(int), height, texture.wrapper)
+        return texels[y, x]
+    base = np.floor(scaled - 0.5).astype(int)
+    time = scaled - 0.5 - base
+    x0, x1 = _wrap_index(base[..., 0], width, texture.wrapper), _wrap_index(base[..., 0] + 1, width, texture.wrapper)
+    y0, y1 = _wrap_index(base[..., 1], height, texture.wrapper), _wrap_index(base[..., 1] + 1, height, texture.wrapper)
+    tx, ty = time[..., :1], time[..., 1:]
+    low = texels[y0, x0] * (1 - tx) + texels[y0, x1] * tx
+    high = texels[y1, x0] * (1 - tx) + texels[y1, x1] * tx
+    return low * (1 - ty) + high * ty
+
+
+def _distribution_1d(values):
+    """DiscreteDistribution1D constructor (DiscreteDistribution1D.cs:12-56): returns (cdfValues float32, sum float32)."""
+    values = np.asarray(values, dtype=np.float32)
+    length = len(values)
+    count_r = np.float32(1) / np.float32(length)
+    cdf = np.cumsum(values.astype(np.float64)).astype(np.float32)
+    total = np.float32(np.sum(values.astype(np.float64)))
+
+    if not total >= np.float32(8e-7):  # FastMath.AlmostZero(sum)
+        cdf = (np.arange(length, dtype=np.float32) * count_r + count_r).astype(np.float32)
+        total = np.float32(0)
+    else:
+        cdf = (cdf * (np.float32(1) / total)).astype(np.float32)
+
+    index = length - 1
+    last = cdf[index]
+    while True:  # "Assign the last identical values to one to ensure no leaking when sampling"
+        cdf[index] = 1.0
+        index -= 1
+        if not (index > 0 and last == cdf[index]):
+            break
+    return cdf, total
+
+
+def build_environment(texture):
+    """CylindricalTexture.Prepare (CylindricalTexture.cs:33-96): the sin-weighted luminance of every cell of the grid, the
+    DiscreteDistribution2D over it (vertical cdf, then one cdf per row) and the texture's Average."""
+    texels = np.asarray(texture.texels, dtype=np.float64)
+    height, width = texels.shape[:2]
+    ys, xs = np.meshgrid(np.arange(height + 1), np.arange(width + 1), indexing="ij")
+    corners = sample_texture(texture, np.stack([xs / width, ys / height], axis=-1))[..., :3]  # texture[(x, y) * sizeR]
+    sines = np.clip(np.sin(np.pi * np.arange(height + 1) / height), 0.0, 1.0)
+    weighted = corners * sines[:, None, None]
+    grab = weighted[:-1] + weighted[1:]                 # Grab(x): lower * sin0 + upper * sin1, per row y
+    average = (grab[:, :-1] + grab[:, 1:]) / 4.0         # the four corners of every cell
+    weights = (average[..., 0] * 0.212671 + average[..., 1] * 0.715160 + average[..., 2] * 0.072169).astype(np.float32)
+
+    rows, sums = [], []
+    for y in range(height):
+        cdf, total = _distribution_1d(weights[y])
+        rows.append(cdf)
+        sums.append(total)
+    vertical, _ = _distribution_1d(np.asarray(sums, dtype=np.float32))
+    values = np.concatenate([vertical] + rows).astype(np.float32)
+    mean = (average.reshape(-1, 3).sum(axis=0) * np.pi / 2 / (width * height)).astype(np.float32)
+    return values, mean
+
+
 def _root_bound_radius(root):
     """Stand-in for Accelerator.SphereBound.radius: the half diagonal of the root node's bound (see PreparedArrays.bound_radius)."""
     valid = root["token4"] != structs.TOKEN_EMPTY
@@ -415,8 +492,17 @@ def prepare(description, threads=0):
     # FilterLights / SumInfiniteLightsPower / CalculateThreshold (PreparedScene.cs:279-325)
     infinite_power = np.float32(0)
     keep = []
+    distributions = []
     for i, light in enumerate(d.infinite_lights):
-        if light["type"] == structs.INFINITE_DIRECTIONAL:
+        if light["type"] == structs.INFINITE_ENVIRONMENT:
+            # AmbientLight.Prepare (AmbientLight.cs:36-46) over a CylindricalTexture: pi r^2 * Average.Luminance * Intensity.Luminance
+            values, mean = build_environment(d.textures[int(light["texture"])])
+            d.infinite_lights[i]["distribution"] = sum(len(v) for v in distributions)
+            distributions.append(values)
+            luminance = lambda c: (np.float32(c[0]) * np.float32(0.212671) + np.float32(c[1]) * np.float32(0.715160)) + (np.float32(c[2]) * np.float32(0.072169) + np.float32(0))
+            radius = max(np.float32(_root_bound_radius(nodes[0])), np.float32(1))
+            power = float(np.float32(math.pi) * radius * radius * (luminance(mean) * luminance(light["radiance"])))
+        elif light["type"] == structs.INFINITE_DIRECTIONAL:
             # DirectionalLight.Prepare (DirectionalLight.cs:71-74): half of the scene's bounding disk area
             r, g, b = (np.float32(c) for c in light["intensity"])
             luminance = (r * np.float32(0.212671) + g * np.float32(0.715160)) + (b * np.float32(0.072169) + np.float32(0))
@@ -446,6 +532,8 @@ def prepare(description, threads=0):
         result.packs, result.instances = packs, instances
         result.all_triangles, result.all_spheres, result.all_materials = all_triangles, all_spheres, all_materials
         result.all_point_lights = all_points
+
+    result.distributions = np.concatenate(distributions) if distributions else None
 
     if d.textures:
         records = np.zeros(len(d.textures), dtype=structs.TEXTURE)

@@ -40,6 +40,8 @@ class PreparedScene:
             if prepared.textures is not None:
                 _native.check(lib.echo_b200_scene_set_textures(self._handle, ptr(prepared.textures), len(prepared.textures), ptr(prepared.texels), len(prepared.texels),
                                                                   ptr(prepared.material_textures), len(prepared.material_textures)))
+            if prepared.distributions is not None:
+                _native.check(lib.echo_b200_scene_set_distributions(self._handle, ptr(prepared.distributions), len(prepared.distributions)))
             if prepared.packs is not None:
                 _native.check(lib.echo_b200_scene_set_packs(self._handle, ptr(prepared.packs), len(prepared.packs), ptr(prepared.instances), len(prepared.instances)))
             _native.check(lib.echo_b200_scene_set_light_tree(self._handle, ptr(prepared.light_nodes), len(prepared.light_nodes),

@@ -158,6 +158,18 @@ def ambient_light(radiance, directly_visible=True):
 
 
 # ---------------------------------------------------------------- C1
+def environment_light(texture, intensity=(1, 1, 1), rotation=(0, 0, 0), directly_visible=True):
+    """AmbientLight over a CylindricalTexture (Scenic/Lights/AmbientLight.cs, Textures/Directional/CylindricalTexture.cs):
+    `texture` indexes SceneDescription.textures (a latitude-longitude map, v = 0 at the bottom)."""
+    light = np.zeros(1, dtype=structs.INFINITE_LIGHT)
+    matrix = rotation_matrix(*rotation)
+    light["radiance"], light["directlyVisible"], light["type"] = intensity, 1 if directly_visible else 0, structs.INFINITE_ENVIRONMENT
+    light["texture"] = texture
+    light["rotation"] = matrix.astype(np.float32).reshape(-1)            # LocalToWorldRotation
+    light["inverseRotation"] = matrix.T.astype(np.float32).reshape(-1)   # WorldToLocalRotation = (Float3x3)RootedRotation.Inverse
+    return light
+
+
 def directional_light(intensity, rotation=(0, 0, 0), angle=0.6, directly_visible=False):
     """DirectionalLight (Scenic/Lights/DirectionalLight.cs:12-75) with what its Prepare() computes: the light shines along its
     local backward axis, `angle` (degrees, default 0.6) is the half opening of the cone it is visible in; 0 makes it a delta light."""

@@ -99,9 +99,10 @@ LIGHT_NODE = np.dtype([
 
 POINT_LIGHT = np.dtype([("intensity", "<f4", 3), ("position", "<f4", 3)])
 
-INFINITE_AMBIENT, INFINITE_DIRECTIONAL = 0, 1
+INFINITE_AMBIENT, INFINITE_DIRECTIONAL, INFINITE_ENVIRONMENT = 0, 1, 2
 INFINITE_LIGHT = np.dtype([("radiance", "<f4", 3), ("directlyVisible", "<u4"), ("type", "<u4"), ("isDelta", "<u4"), ("cosAngle", "<f4"), ("pad0", "<f4"),
-                           ("intensity", "<f4", 3), ("pad1", "<f4"), ("direction", "<f4", 3), ("pad2", "<f4"), ("rotation", "<f4", 9), ("pad3", "<f4", 3)])
+                           ("intensity", "<f4", 3), ("pad1", "<f4"), ("direction", "<f4", 3), ("pad2", "<f4"), ("rotation", "<f4", 9), ("texture", "<u4"), ("distribution", "<u4"), ("pad3", "<f4"),
+                           ("inverseRotation", "<f4", 9), ("pad4", "<f4", 3)])
 
 CAMERA = np.dtype([("transform", "<f4", 12), ("forwardLength", "<f4"), ("lensRadius", "<f4"), ("focalDistance", "<f4"), ("pad", "<f4")])
 
@@ -135,7 +136,7 @@ assert HIT.itemsize == 16
 assert MATERIAL.itemsize == 64
 assert LIGHT_NODE.itemsize == 64
 assert POINT_LIGHT.itemsize == 24
-assert INFINITE_LIGHT.itemsize == 112
+assert INFINITE_LIGHT.itemsize == 160
 assert CAMERA.itemsize == 64
 assert RENDER_PARAMS.itemsize == 48
 assert STATS.itemsize == 128

@@ -183,6 +183,7 @@ typedef struct EchoPointLight
  * DirectionalLight (DirectionalLight.cs:12-108), with everything DirectionalLight.Prepare computes on the host (:52-75). ---- */
 #define ECHO_INFINITE_AMBIENT 0u
 #define ECHO_INFINITE_DIRECTIONAL 1u
+#define ECHO_INFINITE_ENVIRONMENT 2u /* AmbientLight over a CylindricalTexture (Textures/Directional/CylindricalTexture.cs) */
 
 typedef struct EchoInfiniteLight
 {
@@ -196,9 +197,13 @@ typedef struct EchoInfiniteLight
 	float pad1;
 	float direction[3];       /* incidentDirection = (LocalToWorldRotation * Float3.Backward).Normalized, :58 */
 	float pad2;
-	float rotation[9];        /* LocalToWorldRotation, row-major (InfiniteLight.cs:31-37): orients the sampled cone, :105 */
-	float pad3[3];
-} EchoInfiniteLight; /* 112 bytes; an ambient light only needs the first 16, the rest zero */
+	float rotation[9];        /* LocalToWorldRotation, row-major (InfiniteLight.cs:31-37): orients the sampled cone / the environment */
+	uint32_t texture;         /* Environment: the CylindricalTexture's grid (EchoTexture index); radiance then holds Intensity */
+	uint32_t distribution;    /* Environment: offset of its DiscreteDistribution2D in the array of set_distributions */
+	float pad3;
+	float inverseRotation[9]; /* WorldToLocalRotation (InfiniteLight.cs:37), Environment only */
+	float pad4[3];
+} EchoInfiniteLight; /* 160 bytes; an ambient light only needs the first 16, the rest zero */
 
 /* ---- instancing: PreparedPack / PreparedInstance / TokenHierarchy ----
  * A scene with instances is a set of packs (PreparedPack.cs:13-24): pack 0 is the PreparedScene itself, the others are the
@@ -316,6 +321,10 @@ int32_t echo_b200_scene_set_light_tree(EchoScene*, const EchoLightNode* nodes, u
                                        const uint32_t* emitter_tokens, const uint64_t* emitter_bitpaths, uint32_t emitter_count,
                                        const EchoPointLight* points, uint32_t point_count);
 int32_t echo_b200_scene_set_infinite(EchoScene*, const EchoInfiniteLight* lights, uint32_t count, float threshold, float pdf);
+/* The DiscreteDistribution2D of every environment light (Evaluation/Sampling/DiscreteDistribution2D.cs, built by
+ * CylindricalTexture.Prepare, CylindricalTexture.cs:33-96): for a width x height grid, `height` cdfValues of the vertical
+ * DiscreteDistribution1D followed by height rows of `width` cdfValues of the slices (DiscreteDistribution1D.cs:12-56). */
+int32_t echo_b200_scene_set_distributions(EchoScene*, const float* values, uint64_t count);
 int32_t echo_b200_scene_set_camera(EchoScene*, const EchoCamera* camera);
 /* Accelerator.SphereBound.radius of the scene (Accelerator.cs:43-63): the NormalDepthEvaluator reports twice this as the
  * depth of rays that escape (NormalDepthEvaluator.cs:57). Optional; 0 when never set. May be called after commit. */

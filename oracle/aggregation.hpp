@@ -397,6 +397,8 @@ struct Scene
 		return result;
 	}
 
+	std::vector<float> distributions; // DiscreteDistribution2D cdf values of the environment lights (echo_b200_scene_set_distributions)
+
 	EchoMaterialTextures material_textures(uint32_t material) const
 	{
 		if (material < materialTextures.size()) return materialTextures[material];

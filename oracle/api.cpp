@@ -99,6 +99,23 @@ float oracle_atan2(float y, float x) { return atan2_det(y, x); }
 float oracle_asin(float x) { return asin_det(x); }
 float oracle_acos(float x) { return acos_det(x); }
 
+void oracle_scene_set_distributions(OracleScene* s, const float* values, uint64_t count) { s->scene.distributions.assign(values, values + count); }
+
+// KAT hook for infinite lights: Sample(sample2) -> out[0..2] radiance, out[3] pdf, out[4..6] incident; then Evaluate(direction3)
+// -> out[7..9] and ProbabilityDensity(direction3) -> out[10]
+void oracle_infinite_light(const OracleScene* s, uint32_t index, const float* sample2, const float* direction3, float* out11)
+{
+	const EchoInfiniteLight& light = s->scene.infiniteLights[index];
+	Float3 incident;
+	float travel;
+	ProbableRGB sampled = infinite_sample(s->scene, light, Float2{ sample1d(sample2[0]), sample1d(sample2[1]) }, incident, travel);
+	out11[0] = sampled.content.r; out11[1] = sampled.content.g; out11[2] = sampled.content.b; out11[3] = sampled.pdf;
+	out11[4] = incident.x; out11[5] = incident.y; out11[6] = incident.z;
+	RGB value = infinite_evaluate(s->scene, light, f3(direction3));
+	out11[7] = value.r; out11[8] = value.g; out11[9] = value.b;
+	out11[10] = infinite_pdf(s->scene, light, f3(direction3));
+}
+
 void oracle_scene_set_bound_radius(OracleScene* s, float radius) { s->scene.boundRadius = radius; }
 
 void oracle_scene_set_infinite(OracleScene* s, const EchoInfiniteLight* lights, uint32_t count, float threshold, float pdf)

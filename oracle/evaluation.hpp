@@ -163,12 +163,143 @@ inline float geometry_pdf(const Scene& scene, uint32_t token, Float3 origin, Flo
 	return almost_zero(1.0f - cosMaxT) ? 0.0f : uniform_cone_pdf(cosMaxT);
 }
 
+// ---- Evaluation/Sampling/DiscreteDistribution1D.cs:58-166 over a stored cdf ----
+struct Distribution1D
+{
+	const float* cdf;
+	int count;
+
+	void bounds(int index, float& lower, float& upper) const // GetBounds, :157-164
+	{
+		lower = index == 0 ? 0.0f : cdf[index - 1];
+		upper = cdf[index];
+	}
+
+	int find_index(float sample) const // FindIndex / FixIndex / BinarySearch, :111-155,166-190
+	{
+		uint32_t head = 0u, tail = (uint32_t)count;
+		int index = -1;
+
+		while (head < tail)
+		{
+			uint32_t middle = (tail + head) >> 1;
+			float current = cdf[middle];
+			if (current == sample) { index = (int)middle; break; }
+			if (current > sample) tail = middle;
+			else head = middle + 1u;
+		}
+
+		if (index < 0) return (int)head;
+
+		float lower, upper; // landed exactly on an anchor
+		bounds(index, lower, upper);
+		if (upper - lower > 0.0f) return index + 1;
+
+		do
+		{
+			lower = upper;
+			upper = cdf[++index];
+		}
+		while (lower == upper);
+
+		return index;
+	}
+
+	float sample(float u, float& pdf) const // Sample, :58-71
+	{
+		int index = find_index(u);
+		float lower, upper;
+		bounds(index, lower, upper);
+
+		float gap = upper - lower;
+		float countR = 1.0f / (float)count;
+		float shift = (u - lower) / gap + (float)index;
+		pdf = gap * (float)count;
+		return sample1d(shift * countR);
+	}
+
+	float probability_density(float result) const // :89-93
+	{
+		float lower, upper;
+		bounds(sample_range(result, count), lower, upper);
+		return (upper - lower) * (float)count;
+	}
+};
+
+// ---- Textures/Directional/CylindricalTexture.cs:98-165 ----
+constexpr float kCylindricalJacobian = kTauR / kPi; // :19
+
+inline Float2 cylindrical_to_uv(Float3 direction) // ToUV, :142-151 (Atan2 / Acos pinned, oracle/math.hpp)
+{
+	return { fma_f(atan2_det(direction.x, direction.z), kTauR, 0.5f), fma_f(acos_det(clamp11(direction.y)), -kPiR, 1.0f) };
+}
+
+inline RGB environment_texel(const Scene& scene, const EchoInfiniteLight& light, Float2 uv)
+{
+	Scene::Rgba value = scene.texture_sample(light.texture, uv);
+	return { value.v[0], value.v[1], value.v[2] };
+}
+
+inline float cylindrical_pdf(const Scene& scene, const EchoInfiniteLight& light, Float3 incident) // ProbabilityDensity, :100-110
+{
+	Float2 uv = cylindrical_to_uv(incident);
+	float cosP = -incident.y;
+	float sinP = identity(cosP);
+	if (!positive(sinP)) return 0.0f;
+
+	const EchoTexture& texture = scene.textures[light.texture];
+	const float* values = scene.distributions.data() + light.distribution;
+	int width = (int)texture.width, height = (int)texture.height;
+	float x = sample1d(uv.x), y = sample1d(uv.y); // (Sample2D)uv
+
+	Distribution1D vertical{ values, height };
+	Distribution1D slice{ values + height + (size_t)sample_range(y, height) * width, width }; // DiscreteDistribution2D.ProbabilityDensity, :69-77
+	float pdfX = slice.probability_density(x);
+	float pdfY = vertical.probability_density(y);
+	return pdfX * pdfY * kCylindricalJacobian / sinP;
+}
+
+inline ProbableRGB cylindrical_sample(const Scene& scene, const EchoInfiniteLight& light, Float2 sample, Float3& incident) // Sample, :112-140
+{
+	const EchoTexture& texture = scene.textures[light.texture];
+	const float* values = scene.distributions.data() + light.distribution;
+	int width = (int)texture.width, height = (int)texture.height;
+
+	// DiscreteDistribution2D.Sample, DiscreteDistribution2D.cs:40-46
+	float pdfY, pdfX;
+	float y = Distribution1D{ values, height }.sample(sample.y, pdfY);
+	float x = Distribution1D{ values + height + (size_t)sample_range(y, height) * width, width }.sample(sample.x, pdfX);
+	float pdf = pdfX * pdfY;
+
+	incident = { 0.0f, 0.0f, 0.0f };
+	if (!positive(pdf)) return {};
+
+	float theta = x * kTau;
+	float phi = y * kPi;
+
+	float sinT, cosT, sinP, cosP;
+	sincos_det(theta, sinT, cosT);
+	sincos_det(phi, sinP, cosP);
+	if (!positive(sinP)) return {};
+
+	incident = { -sinP * sinT, -cosP, -sinP * cosT };
+	return { environment_texel(scene, light, Float2{ x, y }), pdf * kCylindricalJacobian / sinP };
+}
+
+inline Float3 rotate3x3(const float* m, Float3 v) // Float3x3 * Float3, Float3x3.cs:264-269
+{
+	return { m[0] * v.x + m[1] * v.y + m[2] * v.z, m[3] * v.x + m[4] * v.y + m[5] * v.z, m[6] * v.x + m[7] * v.y + m[8] * v.z };
+}
+
 // ---- Scenic/Lights: AmbientLight over a Pure texture (AmbientLight.cs:53-67 with IDirectionalTexture's defaults) and
 //      DirectionalLight (DirectionalLight.cs:78-108) ----
 inline RGB infinite_radiance(const EchoInfiniteLight& light) { return { light.radiance[0], light.radiance[1], light.radiance[2] }; }
 
-inline RGB infinite_evaluate(const EchoInfiniteLight& light, Float3 incident)
+inline RGB infinite_evaluate(const Scene& scene, const EchoInfiniteLight& light, Float3 incident)
 {
+	if (light.type == ECHO_INFINITE_ENVIRONMENT) // AmbientLight.Evaluate, AmbientLight.cs:53-54
+		return infinite_radiance(light) * environment_texel(scene, light, cylindrical_to_uv(rotate3x3(light.inverseRotation, incident)));
+
 	if (light.type != ECHO_INFINITE_DIRECTIONAL) return infinite_radiance(light);
 	if (light.isDelta) return kBlack;
 
@@ -177,16 +308,24 @@ inline RGB infinite_evaluate(const EchoInfiniteLight& light, Float3 incident)
 	return infinite_radiance(light); // scaledIntensity
 }
 
-inline float infinite_pdf(const EchoInfiniteLight& light, Float3 /*incident*/)
+inline float infinite_pdf(const Scene& scene, const EchoInfiniteLight& light, Float3 incident)
 {
+	if (light.type == ECHO_INFINITE_ENVIRONMENT) return cylindrical_pdf(scene, light, rotate3x3(light.inverseRotation, incident)); // AmbientLight.cs:56-57
 	if (light.type != ECHO_INFINITE_DIRECTIONAL) return kUniformSpherePdf;
 	if (light.isDelta) return 0.0f;
 	return uniform_cone_pdf(light.cosAngle);
 }
 
-inline ProbableRGB infinite_sample(const EchoInfiniteLight& light, Float2 sample, Float3& incident, float& travel)
+inline ProbableRGB infinite_sample(const Scene& scene, const EchoInfiniteLight& light, Float2 sample, Float3& incident, float& travel)
 {
 	travel = kInfinity;
+
+	if (light.type == ECHO_INFINITE_ENVIRONMENT) // AmbientLight.Sample, AmbientLight.cs:59-66
+	{
+		ProbableRGB sampled = cylindrical_sample(scene, light, sample, incident);
+		incident = rotate3x3(light.rotation, incident);
+		return { sampled.content * infinite_radiance(light), sampled.pdf };
+	}
 
 	if (light.type != ECHO_INFINITE_DIRECTIONAL)
 	{
@@ -218,7 +357,7 @@ inline ProbableRGB scene_sample_light(const Scene& scene, uint32_t light, const 
 
 	if (token_is_infinite_light(light))
 	{
-		return infinite_sample(scene.infiniteLights[token_light_index(light)], sample, incident, travel);
+		return infinite_sample(scene, scene.infiniteLights[token_light_index(light)], sample, incident, travel);
 	}
 
 	// FindLayer + `forwardTransform * origin` (PreparedScene.cs:192-198, GeometryPoint.cs:41-45): the shading point in the
@@ -276,7 +415,7 @@ inline ProbableRGB scene_sample_light(const Scene& scene, uint32_t light, const 
 // ---- PreparedScene.ProbabilityDensity (PreparedScene.cs:207-225) -> LightCollection.ProbabilityDensity (:196-219) ----
 inline float scene_light_pdf(const Scene& scene, uint32_t light, const Layers& layers, const GeometryPoint& origin, Float3 incident)
 {
-	if (token_is_infinite_light(light)) return infinite_pdf(scene.infiniteLights[token_light_index(light)], incident);
+	if (token_is_infinite_light(light)) return infinite_pdf(scene, scene.infiniteLights[token_light_index(light)], incident);
 
 	Scene::Layer layer = scene.find_layer(layers);
 	if (token_type(light) == ECHO_TOKEN_TYPE_LIGHT) return 1.0f; // LightCollection.cs:206 (point)
@@ -295,7 +434,7 @@ inline RGB evaluate_infinite(const Scene& scene, Float3 direction, bool direct)
 	for (const EchoInfiniteLight& light : scene.infiniteLights)
 	{
 		if (direct && !light.directlyVisible) continue;
-		total = total + infinite_evaluate(light, direction);
+		total = total + infinite_evaluate(scene, light, direction);
 	}
 
 	return total;
@@ -514,11 +653,11 @@ struct PathTracedEvaluator
 						if (light.isDelta) continue; // "Skip delta lights; they do not like MIS", :118
 
 						uint32_t token = ECHO_LIGHT_TOKEN_MAKE(ECHO_LIGHT_TYPE_INFINITE, (uint32_t)i);
-						float pdf = scene.probability_mass(token, oldPoint) * infinite_pdf(light, direction);
+						float pdf = scene.probability_mass(token, oldPoint) * infinite_pdf(scene, light, direction);
 						if (!positive(pdf)) continue;
 
 						float weight = power_heuristic(bounceScatterPdf, pdf);
-						path.contribute(infinite_evaluate(light, direction) * weight);
+						path.contribute(infinite_evaluate(scene, light, direction) * weight);
 					}
 
 					++stats.lightEvaluatedInfinite;

@@ -77,3 +77,22 @@ def textured_small():
     """Image textures in every material slot, normal mapping, sphere texture coordinates, an alpha cut-out (scenes.textured_scene)."""
     from echorenderer_b200 import host, scenes
     return host.prepare(scenes.textured_scene())
+
+
+def sky_texture(height=32, width=64):
+    """A latitude-longitude sky: a vertical gradient plus a small, very bright sun (what importance sampling is for)."""
+    import numpy as np
+    y, x = np.meshgrid((np.arange(height) + 0.5) / height, (np.arange(width) + 0.5) / width, indexing="ij")
+    base = np.stack([0.3 + 0.5 * y, 0.4 + 0.5 * y, 0.6 + 0.4 * y], axis=-1)
+    sun = np.exp(-((x - 0.3) ** 2 / 0.002 + (y - 0.8) ** 2 / 0.004))[..., None] * np.array([60.0, 55.0, 40.0])
+    return np.concatenate([base + sun, np.ones((height, width, 1))], axis=-1)
+
+
+@pytest.fixture(scope="session")
+def environment_small():
+    """The small mixed scene under an AmbientLight with a CylindricalTexture (importance-sampled environment map), rotated."""
+    from echorenderer_b200 import host, scenes, structs
+    description = scenes.mixed_material_scene(rings=24, segments=24)
+    description.textures = [host.TextureDescription(sky_texture(), structs.FILTER_BILINEAR, structs.WRAPPER_REPEAT)]
+    description.infinite_lights = scenes.environment_light(0, (1.0, 0.9, 0.8), (10, 40, 0))
+    return host.prepare(description)

@@ -44,6 +44,8 @@ def library():
     lib.oracle_scene_set_camera.argtypes = [p, p]
     lib.oracle_scene_set_packs.argtypes = [p, p, u32, p, u32]
     lib.oracle_scene_set_textures.argtypes = [p, p, u32, p, u64, p, u32]
+    lib.oracle_scene_set_distributions.argtypes = [p, p, u64]
+    lib.oracle_infinite_light.argtypes = [p, u32, p, p, p]
     lib.oracle_texture_sample.argtypes = [p, u32, p, u64, p]
     lib.oracle_atan2.argtypes = [f32, f32]
     lib.oracle_atan2.restype = f32
@@ -116,6 +118,8 @@ class OracleScene:
         if prepared.textures is not None:
             lib.oracle_scene_set_textures(self.handle, ptr(prepared.textures), len(prepared.textures), ptr(prepared.texels), len(prepared.texels),
                                           ptr(prepared.material_textures), len(prepared.material_textures))
+        if prepared.distributions is not None:
+            lib.oracle_scene_set_distributions(self.handle, ptr(prepared.distributions), len(prepared.distributions))
         if prepared.packs is not None:
             lib.oracle_scene_set_packs(self.handle, ptr(prepared.packs), len(prepared.packs), ptr(prepared.instances), len(prepared.instances))
         lib.oracle_scene_set_light_tree(self.handle, ptr(prepared.light_nodes), len(prepared.light_nodes), ptr(prepared.emitter_tokens),

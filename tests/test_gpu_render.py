@@ -26,7 +26,7 @@ def relative_rmse(actual, expected):
 
 
 @pytest.mark.parametrize("fixture,bounce_limit", [("cornell", 128), ("mixed_small", 8), ("lights_small", 128), ("terrain_small", 16), ("coated_small", 12),
-                                                  ("directional_small", 12), ("textured_small", 12)])
+                                                  ("directional_small", 12), ("textured_small", 12), ("environment_small", 12)])
 def test_samples_match_oracle(fixture, bounce_limit, request):
     prepared = request.getfixturevalue(fixture)
     oracle = oracle_lib.OracleScene(prepared)
@@ -46,7 +46,7 @@ def test_samples_match_oracle(fixture, bounce_limit, request):
     assert relative_rmse(actual, expected) <= 1e-4
 
 
-@pytest.mark.parametrize("fixture", ["cornell", "mixed_small", "directional_small", "textured_small"])
+@pytest.mark.parametrize("fixture", ["cornell", "mixed_small", "directional_small", "textured_small", "environment_small"])
 def test_render_tiles_match_oracle(fixture, request):
     prepared = request.getfixturevalue(fixture)
     oracle = oracle_lib.OracleScene(prepared)
@@ -107,7 +107,7 @@ def test_evaluation_operation_interface(cornell):
         assert image[24:40, -8:-2, 1].mean() > 2 * image[24:40, -8:-2, 0].mean()
 
 
-@pytest.mark.parametrize("fixture", ["cornell", "mixed_small", "coated_small", "textured_small"])
+@pytest.mark.parametrize("fixture", ["cornell", "mixed_small", "coated_small", "textured_small", "environment_small"])
 @pytest.mark.parametrize("evaluator", [structs.EVALUATOR_ALBEDO | structs.EVALUATOR_DIVERGE_ONCE, structs.EVALUATOR_ALBEDO,
                                        structs.EVALUATOR_NORMAL_DEPTH, structs.EVALUATOR_NORMAL_DEPTH | structs.EVALUATOR_DIVERGE_ONCE])
 def test_auxiliary_evaluators_match_oracle(fixture, evaluator, request):

@@ -147,3 +147,54 @@ def test_normal_mapping(textured):
     assert np.abs(mapped[marble][:, :3] - flat[marble][:, :3]).max(axis=1).mean() > 0.02  # the map bends the normals
     assert np.array_equal(mapped[material == 0], flat[material == 0])                     # only where a normal map is bound
     assert np.array_equal(mapped[:, 3], flat[:, 3])                                       # depth is untouched
+
+
+def infinite_light(oracle, index, sample, direction):
+    out = np.zeros(11, dtype=np.float32)
+    sample, direction = np.ascontiguousarray(sample, dtype=np.float32), np.ascontiguousarray(direction, dtype=np.float32)
+    oracle.lib.oracle_infinite_light(oracle.handle, index, oracle_lib.ptr(sample), oracle_lib.ptr(direction), oracle_lib.ptr(out))
+    return out
+
+
+def test_environment_light_sampling_is_consistent(environment_small):
+    """CylindricalTexture (CylindricalTexture.cs:98-140): Sample, Evaluate and ProbabilityDensity agree on the same direction,
+    the density integrates to one over the sphere, and the sun texels are drawn far more often than their solid angle."""
+    oracle = oracle_lib.OracleScene(environment_small)
+    rng = np.random.default_rng(9)
+    inverse, ratios, bright = [], [], 0
+
+    for _ in range(3000):
+        out = infinite_light(oracle, 0, rng.uniform(0, 1, 2), (0, 1, 0))
+        radiance, pdf, incident = out[0:3], out[3], out[4:7]
+        assert pdf > 0 and np.linalg.norm(incident) == pytest.approx(1.0, abs=1e-5)
+        again = infinite_light(oracle, 0, (0.5, 0.5), incident)
+        assert again[10] == pytest.approx(pdf, rel=2e-3)           # ProbabilityDensity(Sample().incident) == Sample().pdf
+        assert np.allclose(again[7:10], radiance, rtol=2e-2, atol=1e-3)  # Evaluate(incident) == sampled radiance (bilinear, re-derived uv)
+        inverse.append(1.0 / pdf)
+        bright += radiance[0] > 5.0
+
+    assert np.mean(inverse) == pytest.approx(4 * np.pi, rel=0.05)  # E[1 / pdf] = the sphere's solid angle
+    assert bright / 3000 > 0.15                                       # the sun covers ~0.3 % of the map
+
+
+def test_environment_light_irradiance():
+    """A lone Lambertian plane under the sky: albedo / pi * the cosine-weighted integral of the map over the upper hemisphere,
+    computed by quadrature with the texture's own direction convention (CylindricalTexture.ToDirection, :153-164)."""
+    from tests.conftest import sky_texture
+    albedo = 0.7
+    texture = host.TextureDescription(sky_texture(), structs.FILTER_BILINEAR, structs.WRAPPER_REPEAT)
+    description = host.SceneDescription(triangles=scenes.plane(0, (400, 400)), materials=scenes.material(structs.MATERIAL_DIFFUSE, (albedo,) * 3),
+                                        textures=[texture], infinite_lights=scenes.environment_light(0, (1, 1, 1), directly_visible=False))
+    position = (0.0, 4.0, -2.0)
+    description.camera = scenes.perspective_camera(position, scenes.look_rotation(position, (0, 0, 0)), field_of_view=20.0)
+    prepared = host.prepare(description)
+    image, _ = oracle_lib.OracleScene(prepared).render_tiles(structs.render_params(32, 32, 16, extend=512, seed=3, bounce_limit=3), scenes.tile_grid(32, 32, 16))
+
+    n = 1024
+    v, u = np.meshgrid((np.arange(n // 2) + 0.5) / (n // 2), (np.arange(n) + 0.5) / n, indexing="ij")
+    radiance = host.sample_texture(texture, np.stack([u, v], axis=-1))[..., :3]
+    phi = v * np.pi
+    cosine = np.maximum(-np.cos(phi), 0.0)  # direction.y = -cos(phi): the upper hemisphere is v > 0.5
+    solid_angle = np.sin(phi) * (np.pi / (n // 2)) * (2 * np.pi / n)
+    expected = albedo / np.pi * (radiance * (cosine * solid_angle)[..., None]).sum(axis=(0, 1))
+    assert np.allclose(image[..., :3].mean(axis=(0, 1, 2)), expected, rtol=0.03)
