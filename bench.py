@@ -43,7 +43,7 @@ def parse():
     parser.add_argument("--width", type=int, default=1920)
     parser.add_argument("--height", type=int, default=1080)
     parser.add_argument("--spp", type=int, default=16, help="render workload: samples per pixel per step (one epoch)")
-    parser.add_argument("--scene", default="mixed", choices=["cornell", "mixed", "lights", "large", "instanced"],
+    parser.add_argument("--scene", default="mixed", choices=["cornell", "mixed", "lights", "large", "instanced", "textured"],
                         help="render workload scene: C1 / C3 / C4 / C5 / 2 304 placements of two packs (SURVEY.md 8f rank 2)")
     parser.add_argument("--instanced", action="store_true", help="trace workload: the instanced scene instead of the C2 terrain (same ray recipe)")
     parser.add_argument("--bounce-limit", type=int, default=8, help="render workload: PathTracedEvaluator.BounceLimit (C3: 8; reference default 128)")
@@ -282,6 +282,7 @@ RENDER_SCENES = {
     "mixed": ("C3 mixed-material scene (Dielectric, Conductor GGX, Oren-Nayar)", scenes.mixed_material_scene),
     "lights": ("C4 many-lights scene (10 k emissive triangles, light-tree NEE)", scenes.many_lights_scene),
     "large": ("C5 ~10 M-triangle terrain with the C3 material mix", scenes.large_scene),
+    "textured": ("image textures in every material slot, normal map, alpha cut-out (SURVEY.md 8f rank 3)", lambda: scenes.textured_scene(rings=128, segments=130)),
     "instanced": ("2 304 placements of two packs (one nests three placements of the other), lights inside the packs", instanced_bench_scene),
 }
 
