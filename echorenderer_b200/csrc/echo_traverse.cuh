@@ -25,6 +25,9 @@ constexpr unsigned long long kPool = 256;         // rays reserved per global at
 #ifndef ECHO_MIN_BLOCKS
 #define ECHO_MIN_BLOCKS 7
 #endif
+#ifndef ECHO_PREFETCH
+#define ECHO_PREFETCH 0 // A/B: 1 = prefetch the next node into L1 after the slot scan, 2 = the pending triangle, 3 = both
+#endif
 #ifndef ECHO_LEAF_MAX_WAIT
 #define ECHO_LEAF_MAX_WAIT 2 // a lane waits at most two iterations for its primitive test (A/B on C2/C3/C4: +1-2 %)
 #endif
@@ -176,6 +179,16 @@ ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, uint32_t 
 
 		if (first < 4u) leaf = first == 0u ? child0 : (first == 1u ? child1 : (first == 2u ? child2 : child3));
 		position = first < 4u ? (int)first + 1 : 4;
+
+#if ECHO_PREFETCH & 1
+		// the node this lane pops next is known now, a whole iteration before its 128-byte line is needed
+		if (pushes != 0u) asm volatile("prefetch.global.L1 [%0];" :: "l"(scene.nodes + ((size_t)(INST ? pack.nodeOffset : 0u) + token_index(top.x)) * 8));
+#endif
+#if ECHO_PREFETCH & 2
+		// so is the primitive it tests next (it waits for the vote)
+		if (first < 4u && token_type(leaf) == ECHO_TOKEN_TYPE_TRIANGLE)
+			asm volatile("prefetch.global.L1 [%0];" :: "l"(scene.triHot + ((size_t)(INST ? pack.triangleOffset : 0u) + token_index(leaf)) * 3));
+#endif
 	};
 
 	int waited = 0; // warp-uniform: iterations some lane has been waiting for its primitive test
