@@ -487,7 +487,8 @@ int32_t echo_b200_scene_commit(EchoScene* scene)
 
 	for (const EchoInfiniteLight& light : scene->infiniteLights)
 	{
-		if (light.type > ECHO_INFINITE_ENVIRONMENT) return fail(ECHO_B200_ERR_UNSUPPORTED, "unknown infinite light type");
+		if (light.type > ECHO_INFINITE_CUBEMAP) return fail(ECHO_B200_ERR_UNSUPPORTED, "unknown infinite light type");
+		if (light.type == ECHO_INFINITE_CUBEMAP && (uint64_t)light.texture + 6 > scene->textures.size()) return fail(ECHO_B200_ERR_INVALID, "cubemap needs six consecutive textures");
 		if (light.type != ECHO_INFINITE_ENVIRONMENT) continue;
 		if (light.texture >= scene->textures.size()) return fail(ECHO_B200_ERR_INVALID, "environment light texture out of range");
 		const EchoTexture& t = scene->textures[light.texture];

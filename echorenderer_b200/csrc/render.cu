@@ -408,7 +408,7 @@ constexpr int kInfiniteStride = 10;
 struct InfiniteLight
 {
 	rgb radiance;
-	bool directlyVisible, directional, delta, environment;
+	bool directlyVisible, directional, delta, environment, cubemap;
 	float cosAngle;
 	const float4* data;
 };
@@ -418,7 +418,8 @@ ECHO_DEVICE InfiniteLight load_infinite(const DeviceScene& scene, uint32_t index
 	const float4* p = scene.infiniteLights + (size_t)index * kInfiniteStride;
 	float4 a = __ldg(p), b = __ldg(p + 1);
 	uint32_t type = __float_as_uint(b.x);
-	return { as_rgb(a), __float_as_uint(a.w) != 0u, type == ECHO_INFINITE_DIRECTIONAL, __float_as_uint(b.y) != 0u, type == ECHO_INFINITE_ENVIRONMENT, b.z, p };
+	return { as_rgb(a), __float_as_uint(a.w) != 0u, type == ECHO_INFINITE_DIRECTIONAL, __float_as_uint(b.y) != 0u, type == ECHO_INFINITE_ENVIRONMENT,
+	         type == ECHO_INFINITE_CUBEMAP, b.z, p };
 }
 
 ECHO_DEVICE vec3 rotate3x3(float4 r0, float4 r1, float r8, vec3 v) // Float3x3 * Float3 (Float3x3.cs:264-269), nine row-major floats
@@ -558,8 +559,36 @@ ECHO_DEVICE Sampled cylindrical_sample(const DeviceScene& scene, const InfiniteL
 	return { as_rgb(texture_sample(scene, grid.texture, vec2{ x, y })), div(pdf * (kTauR / kPi), sinP) };
 }
 
+// Textures/Directional/Cubemap.cs:62-82 with (Direction)incident (Direction.cs:325-333)
+ECHO_DEVICE rgb cubemap_evaluate(const DeviceScene& scene, const InfiniteLight& light, vec3 incident)
+{
+	float ax = fabsf(incident.x), ay = fabsf(incident.y), az = fabsf(incident.z);
+	int axis = ax > ay ? (ax > az ? 0 : 2) : (ay > az ? 1 : 2);
+	float part = axis == 0 ? incident.x : (axis == 1 ? incident.y : incident.z);
+	bool negative = part < 0.0f;
+	int index = axis * 2 + (negative ? 1 : 0);
+
+	vec2 uv;
+	switch (index)
+	{
+		case 0: uv = { -incident.z, incident.y }; break;
+		case 1: uv = { incident.z, incident.y }; break;
+		case 2: uv = { incident.x, -incident.z }; break;
+		case 3: uv = { incident.x, incident.z }; break;
+		case 4: uv = { incident.x, incident.y }; break;
+		default: uv = { -incident.x, incident.y }; break;
+	}
+
+	float scale = div(0.5f, negative ? -part : part); // target.ExtractComponent(incident)
+	uv = { uv.x * scale + 0.5f, uv.y * scale + 0.5f };
+	uint32_t first = __float_as_uint(__ldg(light.data + 6).y);
+	return as_rgb(texture_sample(scene, first + (uint32_t)index, uv));
+}
+
 ECHO_DEVICE rgb infinite_evaluate(const DeviceScene& scene, const InfiniteLight& light, vec3 incident)
 {
+	if (light.cubemap) return light.radiance * cubemap_evaluate(scene, light, infinite_to_local(light, incident));
+
 	if (light.environment) // AmbientLight.Evaluate, AmbientLight.cs:53-54
 	{
 		uint32_t texture = __float_as_uint(__ldg(light.data + 6).y);
@@ -591,6 +620,13 @@ ECHO_DEVICE Sampled infinite_sample(const DeviceScene& scene, const InfiniteLigh
 		Sampled sampled = cylindrical_sample(scene, light, sample, incident);
 		incident = infinite_to_world(light, incident);
 		return { sampled.content * light.radiance, sampled.pdf };
+	}
+
+	if (light.cubemap) // IDirectionalTexture.Sample's default inside AmbientLight.Sample
+	{
+		vec3 local = uniform_sphere(sample);
+		incident = infinite_to_world(light, local);
+		return { cubemap_evaluate(scene, light, local) * light.radiance, kUniformSpherePdf };
 	}
 
 	if (!light.directional)
@@ -2162,6 +2198,12 @@ bool render_tiles(RenderState* state, const DeviceScene& scene, const EchoRender
 	if (params.width <= 0 || params.height <= 0 || params.tileSize <= 0 || params.extend <= 0 || params.maxEpoch < 1 || params.minEpoch > params.maxEpoch)
 	{
 		set_error("invalid EchoRenderParams");
+		return false;
+	}
+
+	if ((params.evaluator & ECHO_EVALUATOR_KIND_MASK) > ECHO_EVALUATOR_NORMAL_DEPTH || (params.evaluator & ~(ECHO_EVALUATOR_KIND_MASK | ECHO_EVALUATOR_DIVERGE_ONCE)) != 0)
+	{
+		set_error("unknown EchoRenderParams.evaluator");
 		return false;
 	}
 

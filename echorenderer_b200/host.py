@@ -463,6 +463,29 @@ def build_environment(texture):
     return values, mean
 
 
+def cubemap_average(faces, count=128):
+    """Stand-in for Cubemap.Prepare's AverageConverge (a seeded-by-time Monte Carlo, IDirectionalTexture.cs:28-63): the mean of
+    Cubemap.Evaluate over a stratified set of directions."""
+    v, u = np.meshgrid((np.arange(count) + 0.5) / count, (np.arange(2 * count) + 0.5) / (2 * count), indexing="ij")
+    z = 1 - 2 * v
+    r = np.sqrt(np.maximum(0, 1 - z * z))
+    d = np.stack([r * np.cos(2 * np.pi * u), r * np.sin(2 * np.pi * u), z], axis=-1).reshape(-1, 3)
+    axis = np.argmax(np.abs(d), axis=1)
+    part = d[np.arange(len(d)), axis]
+    index = axis * 2 + (part < 0)
+    uv = np.zeros((len(d), 2))
+    table = {0: (-d[:, 2], d[:, 1]), 1: (d[:, 2], d[:, 1]), 2: (d[:, 0], -d[:, 2]), 3: (d[:, 0], d[:, 2]), 4: (d[:, 0], d[:, 1]), 5: (-d[:, 0], d[:, 1])}
+    total = np.zeros(3)
+    for face in range(6):
+        mask = index == face
+        if not mask.any():
+            continue
+        a, b = table[face]
+        uv = np.stack([a[mask], b[mask]], axis=-1) * (0.5 / np.abs(part[mask]))[:, None] + 0.5
+        total += sample_texture(faces[face], uv)[..., :3].sum(axis=0)
+    return (total / len(d)).astype(np.float32)
+
+
 def _root_bound_radius(root):
     """Stand-in for Accelerator.SphereBound.radius: the half diagonal of the root node's bound (see PreparedArrays.bound_radius)."""
     valid = root["token4"] != structs.TOKEN_EMPTY
@@ -494,7 +517,13 @@ def prepare(description, threads=0):
     keep = []
     distributions = []
     for i, light in enumerate(d.infinite_lights):
-        if light["type"] == structs.INFINITE_ENVIRONMENT:
+        if light["type"] == structs.INFINITE_CUBEMAP:
+            first = int(light["texture"])
+            mean = cubemap_average(d.textures[first:first + 6])
+            luminance = lambda c: (np.float32(c[0]) * np.float32(0.212671) + np.float32(c[1]) * np.float32(0.715160)) + (np.float32(c[2]) * np.float32(0.072169) + np.float32(0))
+            radius = max(np.float32(_root_bound_radius(nodes[0])), np.float32(1))
+            power = float(np.float32(math.pi) * radius * radius * (luminance(mean) * luminance(light["radiance"])))
+        elif light["type"] == structs.INFINITE_ENVIRONMENT:
             # AmbientLight.Prepare (AmbientLight.cs:36-46) over a CylindricalTexture: pi r^2 * Average.Luminance * Intensity.Luminance
             values, mean = build_environment(d.textures[int(light["texture"])])
             d.infinite_lights[i]["distribution"] = sum(len(v) for v in distributions)

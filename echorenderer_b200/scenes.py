@@ -170,6 +170,14 @@ def environment_light(texture, intensity=(1, 1, 1), rotation=(0, 0, 0), directly
     return light
 
 
+def cubemap_light(first_texture, intensity=(1, 1, 1), rotation=(0, 0, 0), directly_visible=True):
+    """AmbientLight over a Cubemap (Textures/Directional/Cubemap.cs): SceneDescription.textures[first_texture : first_texture + 6]
+    are its px, nx, py, ny, pz, nz faces."""
+    light = environment_light(first_texture, intensity, rotation, directly_visible)
+    light["type"] = structs.INFINITE_CUBEMAP
+    return light
+
+
 def directional_light(intensity, rotation=(0, 0, 0), angle=0.6, directly_visible=False):
     """DirectionalLight (Scenic/Lights/DirectionalLight.cs:12-75) with what its Prepare() computes: the light shines along its
     local backward axis, `angle` (degrees, default 0.6) is the half opening of the cone it is visible in; 0 makes it a delta light."""

@@ -99,7 +99,7 @@ LIGHT_NODE = np.dtype([
 
 POINT_LIGHT = np.dtype([("intensity", "<f4", 3), ("position", "<f4", 3)])
 
-INFINITE_AMBIENT, INFINITE_DIRECTIONAL, INFINITE_ENVIRONMENT = 0, 1, 2
+INFINITE_AMBIENT, INFINITE_DIRECTIONAL, INFINITE_ENVIRONMENT, INFINITE_CUBEMAP = 0, 1, 2, 3
 INFINITE_LIGHT = np.dtype([("radiance", "<f4", 3), ("directlyVisible", "<u4"), ("type", "<u4"), ("isDelta", "<u4"), ("cosAngle", "<f4"), ("pad0", "<f4"),
                            ("intensity", "<f4", 3), ("pad1", "<f4"), ("direction", "<f4", 3), ("pad2", "<f4"), ("rotation", "<f4", 9), ("texture", "<u4"), ("distribution", "<u4"), ("pad3", "<f4"),
                            ("inverseRotation", "<f4", 9), ("pad4", "<f4", 3)])

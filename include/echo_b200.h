@@ -184,6 +184,9 @@ typedef struct EchoPointLight
 #define ECHO_INFINITE_AMBIENT 0u
 #define ECHO_INFINITE_DIRECTIONAL 1u
 #define ECHO_INFINITE_ENVIRONMENT 2u /* AmbientLight over a CylindricalTexture (Textures/Directional/CylindricalTexture.cs) */
+#define ECHO_INFINITE_CUBEMAP 3u     /* AmbientLight over a Cubemap (Textures/Directional/Cubemap.cs): `texture` is the first of six
+                                        consecutive EchoTexture records in px, nx, py, ny, pz, nz order (Cubemap.cs:49); sampled
+                                        uniformly over the sphere (IDirectionalTexture's defaults), no distribution */
 
 typedef struct EchoInfiniteLight
 {

@@ -291,6 +291,32 @@ inline Float3 rotate3x3(const float* m, Float3 v) // Float3x3 * Float3, Float3x3
 	return { m[0] * v.x + m[1] * v.y + m[2] * v.z, m[3] * v.x + m[4] * v.y + m[5] * v.z, m[6] * v.x + m[7] * v.y + m[8] * v.z };
 }
 
+// ---- Textures/Directional/Cubemap.cs:62-82 with (Direction)incident (Direction.cs:325-333, Float3.MaxIndex Float3.cs:130-138) ----
+inline RGB cubemap_evaluate(const Scene& scene, const EchoInfiniteLight& light, Float3 incident)
+{
+	float ax = std::fabs(incident.x), ay = std::fabs(incident.y), az = std::fabs(incident.z);
+	int axis = ax > ay ? (ax > az ? 0 : 2) : (ay > az ? 1 : 2);
+	float part = axis == 0 ? incident.x : (axis == 1 ? incident.y : incident.z);
+	bool negative = part < 0.0f;
+	int index = axis * 2 + (negative ? 1 : 0);
+
+	Float2 uv;
+	switch (index)
+	{
+		case 0: uv = { -incident.z, incident.y }; break;
+		case 1: uv = { incident.z, incident.y }; break;
+		case 2: uv = { incident.x, -incident.z }; break;
+		case 3: uv = { incident.x, incident.z }; break;
+		case 4: uv = { incident.x, incident.y }; break;
+		default: uv = { -incident.x, incident.y }; break;
+	}
+
+	float scale = 0.5f / (negative ? -part : part); // target.ExtractComponent(incident)
+	uv = { uv.x * scale + 0.5f, uv.y * scale + 0.5f };
+	Scene::Rgba value = scene.texture_sample(light.texture + (uint32_t)index, uv);
+	return { value.v[0], value.v[1], value.v[2] };
+}
+
 // ---- Scenic/Lights: AmbientLight over a Pure texture (AmbientLight.cs:53-67 with IDirectionalTexture's defaults) and
 //      DirectionalLight (DirectionalLight.cs:78-108) ----
 inline RGB infinite_radiance(const EchoInfiniteLight& light) { return { light.radiance[0], light.radiance[1], light.radiance[2] }; }
@@ -300,6 +326,7 @@ inline RGB infinite_evaluate(const Scene& scene, const EchoInfiniteLight& light,
 	if (light.type == ECHO_INFINITE_ENVIRONMENT) // AmbientLight.Evaluate, AmbientLight.cs:53-54
 		return infinite_radiance(light) * environment_texel(scene, light, cylindrical_to_uv(rotate3x3(light.inverseRotation, incident)));
 
+	if (light.type == ECHO_INFINITE_CUBEMAP) return infinite_radiance(light) * cubemap_evaluate(scene, light, rotate3x3(light.inverseRotation, incident));
 	if (light.type != ECHO_INFINITE_DIRECTIONAL) return infinite_radiance(light);
 	if (light.isDelta) return kBlack;
 
@@ -325,6 +352,13 @@ inline ProbableRGB infinite_sample(const Scene& scene, const EchoInfiniteLight& 
 		ProbableRGB sampled = cylindrical_sample(scene, light, sample, incident);
 		incident = rotate3x3(light.rotation, incident);
 		return { sampled.content * infinite_radiance(light), sampled.pdf };
+	}
+
+	if (light.type == ECHO_INFINITE_CUBEMAP) // IDirectionalTexture.Sample's default (IDirectionalTexture.cs:22-26) inside AmbientLight.Sample
+	{
+		Float3 local = uniform_sphere(sample);
+		incident = rotate3x3(light.rotation, local);
+		return { cubemap_evaluate(scene, light, local) * infinite_radiance(light), kUniformSpherePdf };
 	}
 
 	if (light.type != ECHO_INFINITE_DIRECTIONAL)

@@ -96,3 +96,19 @@ def environment_small():
     description.textures = [host.TextureDescription(sky_texture(), structs.FILTER_BILINEAR, structs.WRAPPER_REPEAT)]
     description.infinite_lights = scenes.environment_light(0, (1.0, 0.9, 0.8), (10, 40, 0))
     return host.prepare(description)
+
+
+@pytest.fixture(scope="session")
+def cubemap_small():
+    """The small mixed scene under an AmbientLight with a Cubemap of six differently coloured gradient faces, rotated."""
+    import numpy as np
+    from echorenderer_b200 import host, scenes, structs
+    description = scenes.mixed_material_scene(rings=24, segments=24)
+    faces = []
+    for k, colour in enumerate([(1.0, 0.3, 0.2), (0.2, 1.0, 0.3), (0.5, 0.7, 1.6), (0.4, 0.3, 0.2), (0.9, 0.9, 0.3), (0.8, 0.3, 0.9)]):
+        y, x = np.meshgrid((np.arange(8) + 0.5) / 8, (np.arange(8) + 0.5) / 8, indexing="ij")
+        shade = (0.4 + 0.6 * x * y + 0.2 * ((np.floor(x * 4) + np.floor(y * 4)) % 2))[..., None]
+        faces.append(host.TextureDescription(np.concatenate([shade * np.array(colour), np.ones((8, 8, 1))], axis=-1), structs.FILTER_BILINEAR, structs.WRAPPER_CLAMP))
+    description.textures = faces
+    description.infinite_lights = scenes.cubemap_light(0, (0.8, 0.8, 0.8), (20, -30, 10))
+    return host.prepare(description)

@@ -26,7 +26,7 @@ def relative_rmse(actual, expected):
 
 
 @pytest.mark.parametrize("fixture,bounce_limit", [("cornell", 128), ("mixed_small", 8), ("lights_small", 128), ("terrain_small", 16), ("coated_small", 12),
-                                                  ("directional_small", 12), ("textured_small", 12), ("environment_small", 12)])
+                                                  ("directional_small", 12), ("textured_small", 12), ("environment_small", 12), ("cubemap_small", 12)])
 def test_samples_match_oracle(fixture, bounce_limit, request):
     prepared = request.getfixturevalue(fixture)
     oracle = oracle_lib.OracleScene(prepared)
@@ -46,7 +46,7 @@ def test_samples_match_oracle(fixture, bounce_limit, request):
     assert relative_rmse(actual, expected) <= 1e-4
 
 
-@pytest.mark.parametrize("fixture", ["cornell", "mixed_small", "directional_small", "textured_small", "environment_small"])
+@pytest.mark.parametrize("fixture", ["cornell", "mixed_small", "directional_small", "textured_small", "environment_small", "cubemap_small"])
 def test_render_tiles_match_oracle(fixture, request):
     prepared = request.getfixturevalue(fixture)
     oracle = oracle_lib.OracleScene(prepared)
@@ -131,3 +131,10 @@ def test_auxiliary_evaluators_match_oracle(fixture, evaluator, request):
     assert np.array_equal(actual.view(np.uint32), expected.view(np.uint32))
     assert np.array_equal(actual_tiles.view(np.uint32), expected_tiles.view(np.uint32))
     assert int(stats["sampleEvaluated"][0]) == int(expected_stats["sampleEvaluated"][0]) == width * height * 4
+
+
+def test_unknown_evaluator_is_rejected(cornell):
+    from echorenderer_b200 import EchoNativeError
+    with PreparedScene(cornell) as scene:
+        with pytest.raises(EchoNativeError, match="evaluator"):
+            scene.render_tiles(structs.render_params(32, 32, 16, evaluator=7), scenes.tile_grid(32, 32, 16))

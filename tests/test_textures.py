@@ -198,3 +198,26 @@ def test_environment_light_irradiance():
     solid_angle = np.sin(phi) * (np.pi / (n // 2)) * (2 * np.pi / n)
     expected = albedo / np.pi * (radiance * (cosine * solid_angle)[..., None]).sum(axis=(0, 1))
     assert np.allclose(image[..., :3].mean(axis=(0, 1, 2)), expected, rtol=0.03)
+
+
+def test_cubemap_faces(cubemap_small):
+    """Cubemap.Evaluate (Cubemap.cs:62-82): the face is the major axis of the direction, px nx py ny pz nz; sampling is
+    uniform over the sphere (IDirectionalTexture's defaults)."""
+    oracle = oracle_lib.OracleScene(cubemap_small)
+    light = cubemap_small.description.infinite_lights[0]
+    to_world = light["rotation"].reshape(3, 3).astype(np.float64)
+    colours = np.array([(1.0, 0.3, 0.2), (0.2, 1.0, 0.3), (0.5, 0.7, 1.6), (0.4, 0.3, 0.2), (0.9, 0.9, 0.3), (0.8, 0.3, 0.9)])
+
+    for face, local in enumerate([(1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1)]):
+        world = to_world @ np.array(local, dtype=np.float64)
+        out = infinite_light(oracle, 0, (0.5, 0.5), world / np.linalg.norm(world))
+        ratio = out[7:10] / (colours[face] * 0.8)
+        assert np.allclose(ratio, ratio[0], rtol=1e-4) and 0.3 < ratio[0] < 1.3  # the face's colour, shaded by its pattern
+        assert out[10] == pytest.approx(1 / (4 * np.pi), rel=1e-6)
+
+    rng = np.random.default_rng(4)
+    for _ in range(200):
+        out = infinite_light(oracle, 0, rng.uniform(0, 1, 2), (0, 1, 0))
+        again = infinite_light(oracle, 0, (0.5, 0.5), out[4:7])
+        assert out[3] == pytest.approx(1 / (4 * np.pi), rel=1e-6)
+        assert np.allclose(again[7:10], out[0:3], rtol=5e-3, atol=1e-4)  # Evaluate(LocalToWorld * d) == the value sampled for d
