@@ -47,6 +47,8 @@ def parse():
                         help="render workload scene: C1 / C3 / C4 / C5 / 2 304 placements of two packs (SURVEY.md 8f rank 2)")
     parser.add_argument("--instanced", action="store_true", help="trace workload: the instanced scene instead of the C2 terrain (same ray recipe)")
     parser.add_argument("--bounce-limit", type=int, default=8, help="render workload: PathTracedEvaluator.BounceLimit (C3: 8; reference default 128)")
+    parser.add_argument("--shard", default="tiles", choices=["tiles", "samples"],
+                        help="render workload, N > 1: tile sharding (tile i -> rank i mod N) or sample sharding (every rank renders spp / N samples of every tile)")
     parser.add_argument("--no-cpu-baseline", action="store_true")
     parser.add_argument("--no-secondary", action="store_true", help="skip the secondary-ray batch reported beside the headline (SURVEY.md 8d)")
     return parser.parse_args()
@@ -289,7 +291,7 @@ RENDER_SCENES = {
 
 def render_config(args):
     return {"workload": f"{RENDER_SCENES[args.scene][0]}, path tracer bounce limit {args.bounce_limit}", "width": args.width,
-            "height": args.height, "spp_per_step": args.spp, "parallelism": f"tile-sharded x{args.gpus} + NCCL all-reduce of the frame",
+            "height": args.height, "spp_per_step": args.spp, "parallelism": f"{'sample' if args.shard == 'samples' else 'tile'}-sharded x{args.gpus} + NCCL all-reduce of the frame",
             "l2": "wavefront state (up to ~4 GB) larger than L2"}
 
 
@@ -433,7 +435,9 @@ def main():
         width, height, tile = args.width, args.height, 16
         all_tiles = scenes.tile_grid(width, height, tile)
         from echorenderer_b200 import shard_tiles
-        tiles = shard_tiles(all_tiles, rank, world)
+        by_samples = args.shard == "samples" and world > 1
+        tiles = all_tiles if by_samples else shard_tiles(all_tiles, rank, world)
+        extend = max(1, args.spp // world) if by_samples else args.spp
         frame = torch.zeros(height * width * 4, dtype=torch.float32, device=device)
         host_frame = torch.empty(height * width * 4, dtype=torch.float32).pin_memory()
         stream = torch.cuda.current_stream().cuda_stream
@@ -442,7 +446,9 @@ def main():
 
         def step(index):
             nonlocal launches, samples
-            params = structs.render_params(width, height, tile, extend=args.spp, min_epoch=1, max_epoch=1, bounce_limit=args.bounce_limit, seed=1, epoch_offset=index)
+            # sample sharding: rank r renders epoch index * world + r, spp / world samples per pixel; the summed weight is `world`
+            epoch = index * world + rank if by_samples else index
+            params = structs.render_params(width, height, tile, extend=extend, min_epoch=1, max_epoch=1, bounce_limit=args.bounce_limit, seed=1, epoch_offset=epoch)
             frame.zero_()
             stats = scene.render_frame_device(params, tiles, frame.data_ptr(), stream)
             if distributed:

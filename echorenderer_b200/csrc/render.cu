@@ -1820,8 +1820,8 @@ __global__ void __launch_bounds__(kBlock) batch_pixels_kernel(EchoRenderParams p
 }
 
 __global__ void __launch_bounds__(kBlock) resolve_tiles_kernel(EchoRenderParams params, uint32_t pixelTotal, const int2* __restrict__ batchPixelXY,
-                                                              const float4* __restrict__ accumulator, float4* __restrict__ tilesOut, float4* __restrict__ frame,
-                                                              unsigned long long* __restrict__ stats)
+                                                              const float4* __restrict__ accumulator, const uint32_t* __restrict__ sampleCount,
+                                                              float4* __restrict__ tilesOut, float4* __restrict__ frame, unsigned long long* __restrict__ stats)
 {
 	uint32_t i = blockIdx.x * kBlock + threadIdx.x;
 	if (i >= pixelTotal) return;
@@ -1831,7 +1831,14 @@ __global__ void __launch_bounds__(kBlock) resolve_tiles_kernel(EchoRenderParams 
 	float4 value = inside ? accumulator[i * 4u] : make_float4(0, 0, 0, 0); // Accumulator.Value = average.Result
 
 	if (tilesOut) tilesOut[i] = value;
-	if (frame && inside) frame[(size_t)pixel.y * params.width + pixel.x] = make_float4(value.x, value.y, value.z, 1.0f);
+	if (frame && inside)
+	{
+		// (mean * n, n) with n = samples accumulated, ADDED: frames of devices that rendered other tiles (zeros here) or other
+		// epochs of the same pixel (sample sharding) sum to (sum of samples, count); exact whenever n is a power of two
+		float weight = (float)sampleCount[i];
+		float4& target = frame[(size_t)pixel.y * params.width + pixel.x];
+		target = make_float4(target.x + value.x * weight, target.y + value.y * weight, target.z + value.z * weight, target.w + weight);
+	}
 	if (inside) atomicAdd(stats + STAT_PIXEL_EVALUATED, 1ull);
 }
 
@@ -2187,7 +2194,7 @@ static bool render_batch(WorkerState* state, const DeviceScene& scene, const Ech
 		list ^= 1;
 	}
 
-	resolve_tiles_kernel<<<blocks_for(pixelTotal), kBlock, 0, stream>>>(params, pixelTotal, state->batchPixelXY, state->accumulator, tilesOut, frame, state->paths.stats);
+	resolve_tiles_kernel<<<blocks_for(pixelTotal), kBlock, 0, stream>>>(params, pixelTotal, state->batchPixelXY, state->accumulator, state->sampleCount, tilesOut, frame, state->paths.stats);
 	++launches;
 	return check_cuda(cudaGetLastError(), "resolve_tiles_kernel launch");
 }

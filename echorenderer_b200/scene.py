@@ -252,6 +252,17 @@ def shard_tiles(tile_positions, rank, world_size):
     return np.ascontiguousarray(tile_positions[rank::world_size])
 
 
+def shard_epochs(max_epoch, rank, world_size):
+    """Sample sharding across devices (few tiles, many samples): rank r renders block r of
+    ceil(max_epoch / world_size) consecutive epochs of EVERY tile; returns (epoch_offset, epoch_count) for that rank's
+    EchoRenderParams (epochOffset, minEpoch = maxEpoch = epoch_count). The sample index of a path is epoch * extend + i, so the
+    blocks are disjoint sample sets. Each device accumulates (mean * epochs, epochs) per pixel (render_frame_device), the frames
+    are summed with one all-reduce and frame_resolve divides by the summed weight."""
+    per_rank = (max_epoch + world_size - 1) // world_size
+    first = min(rank * per_rank, max_epoch)
+    return first, max(0, min(per_rank, max_epoch - first))
+
+
 class EvaluationOperation:
     """Processes/Evaluation/EvaluationOperation.cs:21-177 on the GPU: same public surface (tile_positions, destination,
     profile, total_samples, statistics), Execute renders every tile through libecho_b200 and applies it to the destination."""

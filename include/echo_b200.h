@@ -359,9 +359,11 @@ int32_t echo_b200_occlude_batch_device(EchoScene*, const EchoRay* d_rays, uint64
 int32_t echo_b200_render_tiles(EchoScene*, const EchoRenderParams*, const int32_t* tile_xy, uint32_t tile_count,
                                float* out_rgba, EchoStats* stats);
 
-/* device-resident accumulation into a full-frame buffer (width*height Float4: RGB sum of sample means weight, W = epochs
- * rendered). Used for multi-GPU sharding: each device renders its tiles/epochs into its own frame, frames are summed
- * with one NCCL all-reduce, then echo_b200_frame_resolve divides by W. Asynchronous on `stream`. */
+/* device-resident accumulation into a full-frame buffer (width*height Float4): every rendered pixel ADDS (mean * n, n), n = the
+ * samples it accumulated. Used for multi-GPU sharding: each device renders its tiles (tile sharding) or its epochs of every
+ * tile (sample sharding, epochOffset) into its own zeroed frame, the frames are summed with one NCCL all-reduce, then
+ * echo_b200_frame_resolve_device divides RGB by W. Exact for a pixel rendered by one device whenever n is a power of two.
+ * Asynchronous on `stream`. */
 int32_t echo_b200_render_frame_device(EchoScene*, const EchoRenderParams*, const int32_t* tile_xy, uint32_t tile_count,
                                       float* d_frame_rgba, EchoStats* stats, void* stream);
 int32_t echo_b200_frame_resolve_device(EchoScene*, float* d_frame_rgba, int32_t width, int32_t height, void* stream);

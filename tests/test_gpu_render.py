@@ -138,3 +138,53 @@ def test_unknown_evaluator_is_rejected(cornell):
     with PreparedScene(cornell) as scene:
         with pytest.raises(EchoNativeError, match="evaluator"):
             scene.render_tiles(structs.render_params(32, 32, 16, evaluator=7), scenes.tile_grid(32, 32, 16))
+
+
+def test_frame_sharding_paths(cornell):
+    """The multi-device path of bench.py --workload render on one device: render_frame_device accumulates (mean * epochs,
+    epochs) per pixel, frames of different "ranks" are summed (the all-reduce), frame_resolve divides. Tile sharding is
+    bit-exact against a whole-frame render; sample sharding matches the all-epochs render to rounding."""
+    import torch
+    from echorenderer_b200 import shard_epochs, shard_tiles
+    oracle = oracle_lib.OracleScene(cornell)
+    width, height, tile = 80, 48, 16
+    tiles = scenes.tile_grid(width, height, tile)
+    world = 2
+
+    with PreparedScene(cornell) as scene:
+        stream = torch.cuda.current_stream().cuda_stream
+
+        # tile sharding: disjoint tiles, sum with zeros
+        params = structs.render_params(width, height, tile, extend=4, min_epoch=2, max_epoch=2, seed=6)
+        frames = []
+        for rank in range(world):
+            frame = torch.zeros(height * width * 4, dtype=torch.float32, device="cuda")
+            scene.render_frame_device(params, shard_tiles(tiles, rank, world), frame.data_ptr(), stream)
+            frames.append(frame)
+        total = frames[0] + frames[1]
+        scene.frame_resolve_device(total.data_ptr(), width, height, stream)
+        torch.cuda.synchronize()
+        reduced = total.cpu().numpy().reshape(height, width, 4)
+        expected, _ = oracle.render_tiles(params, tiles)
+        whole = scenes.assemble_tiles(expected, tiles, width, height, tile)
+        assert np.array_equal(reduced[..., :3].view(np.uint32), whole[..., :3].view(np.uint32))
+
+        # sample sharding: every rank renders its block of epochs of all tiles
+        epochs = 4
+        frames = []
+        for rank in range(world):
+            first, count = shard_epochs(epochs, rank, world)
+            block = structs.render_params(width, height, tile, extend=4, min_epoch=count, max_epoch=count, seed=6, epoch_offset=first)
+            frame = torch.zeros(height * width * 4, dtype=torch.float32, device="cuda")
+            scene.render_frame_device(block, tiles, frame.data_ptr(), stream)
+            frames.append(frame)
+        total = frames[0] + frames[1]
+        torch.cuda.synchronize()
+        assert np.all(total.cpu().numpy().reshape(height, width, 4)[..., 3] == epochs * 4)  # the weights add up to the sample count
+        scene.frame_resolve_device(total.data_ptr(), width, height, stream)
+        torch.cuda.synchronize()
+        reduced = total.cpu().numpy().reshape(height, width, 4)
+        everything = structs.render_params(width, height, tile, extend=4, min_epoch=epochs, max_epoch=epochs, seed=6)
+        expected, _ = oracle.render_tiles(everything, tiles)
+        whole = scenes.assemble_tiles(expected, tiles, width, height, tile)
+        assert np.allclose(reduced[..., :3], whole[..., :3], rtol=2e-6, atol=1e-7)
