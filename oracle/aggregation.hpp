@@ -616,6 +616,11 @@ struct Scene
 
 			uint32_t token = node.token4[offset];
 
+			// An empty child has bounds at +infinity and never passes the test above — unless query.distance has become NaN
+			// (a NaN hit distance is accepted, GeometryCollection.cs:99, e.g. after an overflow on absurdly large coordinates).
+			// The reference would then index nodes[] out of range (:211); here the slot is skipped, like on the device.
+			if (token == ECHO_TOKEN_EMPTY) return;
+
 			if (!token_is_geometry(token))
 			{
 				*next++ = token;
@@ -706,6 +711,7 @@ struct Scene
 			if (hit >= query.travel) return false;
 
 			uint32_t token = node.token4[offset];
+			if (token == ECHO_TOKEN_EMPTY) return false; // only reachable with a NaN travel, see accelerator_trace
 			if (token_is_geometry(token)) return geometry_occlude(token, query, counters, pack);
 
 			*next++ = token;

@@ -1,0 +1,106 @@
+"""Randomised parity: many small scenes with degenerate content (zero-area and duplicated triangles, zero-radius and nested
+spheres, coincident geometry, tiny and huge scales) queried with hostile rays (axis-aligned, starting on vertices and
+surfaces, zero / denormal / infinite / NaN components, all limits) — closest hit and occlusion must match the oracle bit
+for bit, through the persistent kernels and through the one-thread-per-ray kernels (visit counters)."""
+import numpy as np
+import pytest
+
+from echorenderer_b200 import PreparedScene, host, scenes, structs
+from tests import oracle_lib
+pytestmark = pytest.mark.gpu
+
+
+def assert_hits_equal(actual, expected):
+    """Bit-exact tokens and distances; barycentrics bit-exact too, except that two NaNs (an overflow on absurd coordinates)
+    count as equal whatever their payload."""
+    assert np.array_equal(actual["token"], expected["token"])
+    assert np.array_equal(actual["distance"].view(np.uint32), expected["distance"].view(np.uint32))
+    hit = expected["token"] != structs.TOKEN_EMPTY
+    a, e = actual["uv"][hit], expected["uv"][hit]
+    both_nan = np.isnan(a) & np.isnan(e)
+    assert np.array_equal(a.view(np.uint32)[~both_nan], e.view(np.uint32)[~both_nan])
+
+
+def random_scene(rng):
+    scale = float(10.0 ** rng.integers(-3, 4))
+    count = int(rng.integers(2, 400))
+    v0 = rng.normal(size=(count, 3)) * scale
+    v1 = v0 + rng.normal(size=(count, 3)) * scale * rng.choice([1e-4, 0.1, 1.0, 5.0], size=(count, 1))
+    v2 = v0 + rng.normal(size=(count, 3)) * scale * rng.choice([1e-4, 0.1, 1.0, 5.0], size=(count, 1))
+
+    degenerate = rng.random(count) < 0.05
+    v2[degenerate] = v1[degenerate]                        # zero area
+    copies = rng.random(count) < 0.05
+    source = rng.integers(0, count, size=count)
+    v0[copies], v1[copies], v2[copies] = v0[source[copies]], v1[source[copies]], v2[source[copies]]  # coincident triangles (exact ties)
+    snapped = rng.random(count) < 0.2
+    v0[snapped], v1[snapped], v2[snapped] = np.round(v0[snapped] / scale) * scale, np.round(v1[snapped] / scale) * scale, np.round(v2[snapped] / scale) * scale
+
+    triangles = scenes.make_triangles(v0, v1, v2, 0)
+    spheres = np.zeros(int(rng.integers(0, 40)), dtype=structs.SPHERE)
+    spheres["position"] = rng.normal(size=(len(spheres), 3)) * scale
+    spheres["radius"] = np.abs(rng.normal(size=len(spheres))) * scale * rng.choice([0.0, 0.01, 1.0, 3.0], size=len(spheres))
+    description = host.SceneDescription(triangles=triangles, spheres=spheres, materials=scenes.material(structs.MATERIAL_DIFFUSE), camera=scenes.cornell_box().camera)
+    return host.prepare(description), scale
+
+
+def hostile_rays(prepared, rng, scale, count=4000):
+    rays = scenes.random_rays(prepared.bounds, count, seed=int(rng.integers(1, 1 << 30)))
+    kind = rng.integers(0, 10, size=count)
+
+    axis = np.eye(3, dtype=np.float32)[rng.integers(0, 3, size=count)] * rng.choice([-1.0, 1.0], size=(count, 1)).astype(np.float32)
+    rays["direction"][kind == 0] = axis[kind == 0]                                         # axis-aligned: two reciprocals are +-inf
+    plane = rays["direction"].copy()
+    plane[:, 1] = 0
+    plane /= np.maximum(np.linalg.norm(plane, axis=1, keepdims=True), 1e-30)
+    rays["direction"][kind == 1] = plane[kind == 1]                                        # one zero component
+
+    triangles = prepared.triangles
+    pick = rng.integers(0, len(triangles), size=count)
+    on_vertex = triangles["vertex0"][pick]
+    on_surface = on_vertex + 0.3 * triangles["edge1"][pick] + 0.3 * triangles["edge2"][pick]
+    rays["origin"][kind == 2] = on_vertex[kind == 2]                                       # starting exactly on a vertex
+    rays["origin"][kind == 3] = on_surface[kind == 3]                                      # starting on a surface, ignoring it
+    rays["ignore"][kind == 3] = (structs.TOKEN_TYPE_TRIANGLE << structs.TOKEN_INDEX_BITS) | pick[kind == 3].astype(np.uint32)
+    toward = on_surface - rays["origin"]
+    toward /= np.maximum(np.linalg.norm(toward, axis=1, keepdims=True), 1e-30)
+    rays["direction"][kind == 4] = toward[kind == 4].astype(np.float32)                    # aimed at geometry
+
+    limits = np.array([0.0, -1.0, 1e-30, 8e-7, 7.9e-7, np.inf, scale, scale * 1e-3], dtype=np.float32)
+    rays["distance"][kind == 5] = limits[rng.integers(0, len(limits), size=int((kind == 5).sum()))]
+    rays["distance"][kind == 6] = (np.abs(rng.normal(size=int((kind == 6).sum()))) * scale * 3).astype(np.float32)
+
+    special = np.array([np.nan, np.inf, -np.inf, 0.0, -0.0, 1e-40, 3e38], dtype=np.float32)
+    rows = np.flatnonzero(kind == 7)
+    rays["origin"][rows, rng.integers(0, 3, size=len(rows))] = special[rng.integers(0, len(special), size=len(rows))]
+    rows = np.flatnonzero(kind == 8)
+    rays["direction"][rows, rng.integers(0, 3, size=len(rows))] = special[rng.integers(0, len(special), size=len(rows))]
+    return rays
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_scene_parity(seed):
+    rng = np.random.default_rng(1000 + seed)
+    prepared, scale = random_scene(rng)
+    oracle = oracle_lib.OracleScene(prepared)
+    rays = hostile_rays(prepared, rng, scale)
+
+    with PreparedScene(prepared) as scene:
+        expected = oracle.trace(rays)
+        assert_hits_equal(scene.trace(rays), expected)
+
+        shadow = rays.copy()
+        finite = np.isfinite(shadow["distance"]) & (shadow["distance"] > 0)
+        shadow["distance"][~finite & (rng.random(len(rays)) < 0.5)] = np.float32(scale)
+        assert np.array_equal(scene.occlude(shadow), oracle.occlude(shadow))
+
+        # the one-thread-per-ray kernels (the ones behind the visit counters) walk the same tree in the same order
+        import torch
+        d_rays = torch.from_numpy(rays.view(np.uint8).reshape(-1)).cuda()
+        d_hits = torch.empty(len(rays) * 16, dtype=torch.uint8, device="cuda")
+        d_counts = torch.zeros(3, dtype=torch.int64, device="cuda")
+        scene.trace_device(d_rays.data_ptr(), len(rays), d_hits.data_ptr(), 0, d_counts.data_ptr())
+        torch.cuda.synchronize()
+        assert_hits_equal(d_hits.cpu().numpy().view(structs.HIT), expected)
+        _, counters = oracle.trace(rays, count_visits=True)
+        assert np.array_equal(d_counts.cpu().numpy().astype(np.uint64), counters)

@@ -257,3 +257,27 @@ def test_directional_light_irradiance(angle):
     assert image[..., :3].mean() == pytest.approx(expected, rel=0.02)
     checked, passed = int(stats["lightOcclusionChecked"][0]), int(stats["lightOcclusionPassed"][0])
     assert checked > 0 and passed >= 0.999 * checked  # nothing shadows the plane (but its own other triangle, along the diagonal seam)
+
+
+@pytest.mark.parametrize("seed", [0, 7, 22])
+def test_hostile_rays_on_degenerate_scenes(seed):
+    """The oracle on the fuzz inputs of tests/test_gpu_fuzz.py: queries with infinite / NaN / overflowing components must not
+    walk off the node array (an accepted NaN hit distance lets empty children through the distance test; the reference would
+    index out of range there, QuadBoundingVolumeHierarchy.cs:211), and for well-formed rays the tree agrees with brute force."""
+    from tests.test_gpu_fuzz import hostile_rays, random_scene
+    rng = np.random.default_rng(1000 + seed)
+    prepared, scale = random_scene(rng)
+    oracle = ol.OracleScene(prepared)
+    rays = hostile_rays(prepared, rng, scale)
+    hits = oracle.trace(rays)
+    oracle.occlude(rays)
+
+    sane = np.isfinite(rays["origin"]).all(axis=1) & np.isfinite(rays["direction"]).all(axis=1) & (np.abs(rays["direction"]).max(axis=1) < 2) \
+        & (np.abs(rays["origin"]).max(axis=1) < 1e30)
+    linear = oracle.trace_linear(rays[sane])
+    same = hits["token"][sane] == linear["token"]
+    # exact ties between coincident triangles resolve by visit order, which differs between the tree and the brute-force loop
+    assert same.mean() > 0.97
+    assert np.array_equal(hits["distance"][sane][same].view(np.uint32), linear["distance"][same].view(np.uint32))
+    tied = ~same
+    assert np.array_equal(hits["distance"][sane][tied], linear["distance"][tied])
