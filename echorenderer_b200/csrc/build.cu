@@ -1,0 +1,393 @@
+// build.cu — optional device-side tree build: a linear BVH over 63-bit Morton codes (Karras 2012,
+// "Maximizing Parallelism in the Construction of BVHs, Octrees, and k-d Trees") collapsed into the reference's QBVH node
+// format (QuadBoundingVolumeHierarchy.cs:363-565: every other binary level becomes a quad node, children sorted by the
+// lower bound along the split axis, a leaf child becomes a [leaf, empty] pair with axis 3, empty slots at +infinity).
+//
+// This is NOT the reference's SweepBuilder tree (full-sweep SAH; echo_host_build_qbvh is its host-side mirror and the
+// default): it is a valid tree of lower quality that builds in milliseconds. Hit results do not depend on the tree except
+// for the order in which exact ties are found, and both the device and the oracle walk whichever tree they are given.
+// Sorting and the prefix sum are CUB (a CUDA toolkit library); the other passes are written here.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <vector>
+
+#include "echo_internal.h"
+
+namespace echo
+{
+
+namespace
+{
+
+constexpr int kBuildBlock = 256;
+constexpr uint32_t kLeafFlag = 0x80000000u; // child reference: leaf (sorted position) or internal node index
+
+struct BuildBox
+{
+	float minX, minY, minZ, maxX, maxY, maxZ;
+};
+
+__device__ __forceinline__ int float_to_ordered(float value)
+{
+	int bits = __float_as_int(value);
+	return bits >= 0 ? bits : bits ^ 0x7FFFFFFF;
+}
+
+__device__ __forceinline__ float ordered_to_float(int value) { return __int_as_float(value >= 0 ? value : value ^ 0x7FFFFFFF); }
+
+// PreparedTriangle.BoxBound (TriangleEntity.cs:142) / PreparedSphere.BoxBound (SphereEntity.cs:66) + the scene bound of the centres
+__global__ void primitive_bounds_kernel(const EchoTriangle* __restrict__ triangles, uint32_t triangleCount, const EchoSphere* __restrict__ spheres, uint32_t sphereCount,
+                                        BuildBox* __restrict__ boxes, uint32_t* __restrict__ tokens, int* __restrict__ sceneBound)
+{
+	uint32_t i = blockIdx.x * kBuildBlock + threadIdx.x;
+	uint32_t total = triangleCount + sphereCount;
+	if (i >= total) return;
+
+	BuildBox box;
+
+	if (i < triangleCount)
+	{
+		const EchoTriangle& t = triangles[i];
+		float v1x = t.vertex0[0] + t.edge1[0], v1y = t.vertex0[1] + t.edge1[1], v1z = t.vertex0[2] + t.edge1[2];
+		float v2x = t.vertex0[0] + t.edge2[0], v2y = t.vertex0[1] + t.edge2[1], v2z = t.vertex0[2] + t.edge2[2];
+		box = { fminf(t.vertex0[0], fminf(v1x, v2x)), fminf(t.vertex0[1], fminf(v1y, v2y)), fminf(t.vertex0[2], fminf(v1z, v2z)),
+		        fmaxf(t.vertex0[0], fmaxf(v1x, v2x)), fmaxf(t.vertex0[1], fmaxf(v1y, v2y)), fmaxf(t.vertex0[2], fmaxf(v1z, v2z)) };
+		tokens[i] = ECHO_TOKEN_MAKE(ECHO_TOKEN_TYPE_TRIANGLE, i);
+	}
+	else
+	{
+		const EchoSphere& s = spheres[i - triangleCount];
+		box = { s.position[0] - s.radius, s.position[1] - s.radius, s.position[2] - s.radius, s.position[0] + s.radius, s.position[1] + s.radius, s.position[2] + s.radius };
+		tokens[i] = ECHO_TOKEN_MAKE(ECHO_TOKEN_TYPE_SPHERE, i - triangleCount);
+	}
+
+	boxes[i] = box;
+
+	float cx = (box.minX + box.maxX) * 0.5f, cy = (box.minY + box.maxY) * 0.5f, cz = (box.minZ + box.maxZ) * 0.5f;
+	atomicMin(sceneBound + 0, float_to_ordered(cx));
+	atomicMin(sceneBound + 1, float_to_ordered(cy));
+	atomicMin(sceneBound + 2, float_to_ordered(cz));
+	atomicMax(sceneBound + 3, float_to_ordered(cx));
+	atomicMax(sceneBound + 4, float_to_ordered(cy));
+	atomicMax(sceneBound + 5, float_to_ordered(cz));
+}
+
+__device__ __forceinline__ unsigned long long spread21(unsigned long long v) // 21 bits -> every third bit
+{
+	v &= 0x1FFFFFull;
+	v = (v | v << 32) & 0x1F00000000FFFFull;
+	v = (v | v << 16) & 0x1F0000FF0000FFull;
+	v = (v | v << 8) & 0x100F00F00F00F00Full;
+	v = (v | v << 4) & 0x10C30C30C30C30C3ull;
+	v = (v | v << 2) & 0x1249249249249249ull;
+	return v;
+}
+
+__global__ void morton_kernel(const BuildBox* __restrict__ boxes, uint32_t total, const int* __restrict__ sceneBound, unsigned long long* __restrict__ keys, uint32_t* __restrict__ order)
+{
+	uint32_t i = blockIdx.x * kBuildBlock + threadIdx.x;
+	if (i >= total) return;
+
+	float lowX = ordered_to_float(sceneBound[0]), lowY = ordered_to_float(sceneBound[1]), lowZ = ordered_to_float(sceneBound[2]);
+	float highX = ordered_to_float(sceneBound[3]), highY = ordered_to_float(sceneBound[4]), highZ = ordered_to_float(sceneBound[5]);
+	BuildBox box = boxes[i];
+
+	auto quantise = [](float centre, float low, float high) -> unsigned long long
+	{
+		float extent = high - low;
+		float unit = extent > 0.0f ? (centre - low) / extent : 0.0f;
+		unit = fminf(fmaxf(unit, 0.0f), 1.0f);
+		return (unsigned long long)fminf(unit * 2097152.0f, 2097151.0f);
+	};
+
+	unsigned long long x = quantise((box.minX + box.maxX) * 0.5f, lowX, highX);
+	unsigned long long y = quantise((box.minY + box.maxY) * 0.5f, lowY, highY);
+	unsigned long long z = quantise((box.minZ + box.maxZ) * 0.5f, lowZ, highZ);
+	keys[i] = spread21(x) << 2 | spread21(y) << 1 | spread21(z);
+	order[i] = i;
+}
+
+// length of the common prefix of sorted keys i and j; equal keys fall back to the positions so that every pair differs
+__device__ __forceinline__ int common_prefix(const unsigned long long* __restrict__ keys, int total, int i, int j)
+{
+	if (j < 0 || j >= total) return -1;
+	unsigned long long a = keys[i], b = keys[j];
+	if (a != b) return __clzll((long long)(a ^ b));
+	return 64 + __clz(i ^ j);
+}
+
+// Karras 2012, section 4: internal node i of the binary radix tree over `total` sorted keys
+__global__ void radix_tree_kernel(const unsigned long long* __restrict__ keys, int total, uint32_t* __restrict__ left, uint32_t* __restrict__ right,
+                                  uint32_t* __restrict__ parentOfInternal, uint32_t* __restrict__ parentOfLeaf)
+{
+	int i = blockIdx.x * kBuildBlock + threadIdx.x;
+	if (i >= total - 1) return;
+
+	int direction = common_prefix(keys, total, i, i + 1) - common_prefix(keys, total, i, i - 1) >= 0 ? 1 : -1;
+	int minimum = common_prefix(keys, total, i, i - direction);
+
+	int limit = 2;
+	while (common_prefix(keys, total, i, i + limit * direction) > minimum) limit *= 2;
+
+	int length = 0;
+	for (int step = limit / 2; step >= 1; step /= 2)
+		if (common_prefix(keys, total, i, i + (length + step) * direction) > minimum) length += step;
+
+	int last = i + length * direction;
+	int node = common_prefix(keys, total, i, last);
+
+	int split = 0;
+	for (int divisor = 2, step = (length + 1) / 2;; divisor *= 2, step = (length + divisor - 1) / divisor)
+	{
+		if (common_prefix(keys, total, i, i + (split + step) * direction) > node) split += step;
+		if (step <= 1) break;
+	}
+
+	int gamma = i + split * direction + min(direction, 0);
+	int low = min(i, last), high = max(i, last);
+
+	uint32_t leftChild = low == gamma ? ((uint32_t)gamma | kLeafFlag) : (uint32_t)gamma;
+	uint32_t rightChild = high == gamma + 1 ? ((uint32_t)(gamma + 1) | kLeafFlag) : (uint32_t)(gamma + 1);
+	left[i] = leftChild;
+	right[i] = rightChild;
+
+	if (leftChild & kLeafFlag) parentOfLeaf[gamma] = (uint32_t)i;
+	else parentOfInternal[gamma] = (uint32_t)i;
+	if (rightChild & kLeafFlag) parentOfLeaf[gamma + 1] = (uint32_t)i;
+	else parentOfInternal[gamma + 1] = (uint32_t)i;
+	if (i == 0) parentOfInternal[0] = 0xFFFFFFFFu;
+}
+
+// bottom-up boxes: the second thread to reach a node merges its children (Karras 2012, section 5)
+__global__ void fit_kernel(const BuildBox* __restrict__ boxes, const uint32_t* __restrict__ order, int total, const uint32_t* __restrict__ left, const uint32_t* __restrict__ right,
+                           const uint32_t* __restrict__ parentOfInternal, const uint32_t* __restrict__ parentOfLeaf, BuildBox* __restrict__ nodeBoxes, uint32_t* __restrict__ visits)
+{
+	int i = blockIdx.x * kBuildBlock + threadIdx.x;
+	if (i >= total) return;
+
+	uint32_t node = parentOfLeaf[i];
+
+	while (node != 0xFFFFFFFFu)
+	{
+		if (atomicAdd(visits + node, 1u) == 0u) return; // the sibling subtree is not finished yet
+		__threadfence();
+
+		uint32_t a = left[node], b = right[node];
+		BuildBox boxA = (a & kLeafFlag) ? boxes[order[a & ~kLeafFlag]] : nodeBoxes[a];
+		BuildBox boxB = (b & kLeafFlag) ? boxes[order[b & ~kLeafFlag]] : nodeBoxes[b];
+		nodeBoxes[node] = { fminf(boxA.minX, boxB.minX), fminf(boxA.minY, boxB.minY), fminf(boxA.minZ, boxB.minZ),
+		                    fmaxf(boxA.maxX, boxB.maxX), fmaxf(boxA.maxY, boxB.maxY), fmaxf(boxA.maxZ, boxB.maxZ) };
+		__threadfence();
+		node = parentOfInternal[node];
+	}
+}
+
+// binary depth of every internal node; nodes at even depth become quad nodes (QuadBoundingVolumeHierarchy.cs:363-404)
+__global__ void depth_kernel(const uint32_t* __restrict__ parentOfInternal, int internalCount, uint32_t* __restrict__ isQuad)
+{
+	int i = blockIdx.x * kBuildBlock + threadIdx.x;
+	if (i >= internalCount) return;
+
+	uint32_t depth = 0u;
+	for (uint32_t node = parentOfInternal[i]; node != 0xFFFFFFFFu; node = parentOfInternal[node]) ++depth;
+	isQuad[i] = (depth & 1u) == 0u ? 1u : 0u;
+}
+
+struct ChildRef
+{
+	uint32_t reference; // kLeafFlag | sorted position, or internal node index; 0xFFFFFFFF = none
+};
+
+__device__ __forceinline__ BuildBox reference_box(uint32_t reference, const BuildBox* boxes, const uint32_t* order, const BuildBox* nodeBoxes)
+{
+	return (reference & kLeafFlag) ? boxes[order[reference & ~kLeafFlag]] : nodeBoxes[reference];
+}
+
+// GetChildrenSorted (:551-563): the split axis (here: the axis along which the two children's centres are furthest apart)
+// and the two children ordered by their lower bound on it
+__device__ int sorted_children(uint32_t node, const uint32_t* left, const uint32_t* right, const BuildBox* boxes, const uint32_t* order, const BuildBox* nodeBoxes,
+                               uint32_t& child0, uint32_t& child1)
+{
+	child0 = left[node];
+	child1 = right[node];
+	BuildBox a = reference_box(child0, boxes, order, nodeBoxes), b = reference_box(child1, boxes, order, nodeBoxes);
+
+	float dx = fabsf((a.minX + a.maxX) - (b.minX + b.maxX)), dy = fabsf((a.minY + a.maxY) - (b.minY + b.maxY)), dz = fabsf((a.minZ + a.maxZ) - (b.minZ + b.maxZ));
+	int axis = dx >= dy ? (dx >= dz ? 0 : 2) : (dy >= dz ? 1 : 2);
+	float lowA = axis == 0 ? a.minX : (axis == 1 ? a.minY : a.minZ), lowB = axis == 0 ? b.minX : (axis == 1 ? b.minY : b.minZ);
+
+	if (lowA > lowB)
+	{
+		uint32_t swap = child0;
+		child0 = child1;
+		child1 = swap;
+	}
+
+	return axis;
+}
+
+__global__ void emit_kernel(int internalCount, const uint32_t* __restrict__ isQuad, const uint32_t* __restrict__ quadIndex, const uint32_t* __restrict__ left,
+                            const uint32_t* __restrict__ right, const BuildBox* __restrict__ boxes, const uint32_t* __restrict__ order, const uint32_t* __restrict__ tokens,
+                            const BuildBox* __restrict__ nodeBoxes, EchoQbvhNode* __restrict__ out)
+{
+	int i = blockIdx.x * kBuildBlock + threadIdx.x;
+	if (i >= internalCount || isQuad[i] == 0u) return;
+
+	uint32_t child0, child1;
+	int axisMajor = sorted_children((uint32_t)i, left, right, boxes, order, nodeBoxes, child0, child1);
+
+	uint32_t slots[4];
+	int axisMinor[2];
+	const uint32_t children[2] = { child0, child1 };
+
+	for (int k = 0; k < 2; k++) // AddChildren (:517-543): a leaf becomes [leaf, empty] with axis 3
+	{
+		if (children[k] & kLeafFlag)
+		{
+			slots[k * 2] = children[k];
+			slots[k * 2 + 1] = 0xFFFFFFFFu;
+			axisMinor[k] = 3;
+		}
+		else axisMinor[k] = sorted_children(children[k], left, right, boxes, order, nodeBoxes, slots[k * 2], slots[k * 2 + 1]);
+	}
+
+	EchoQbvhNode node;
+	node.axisMajor = axisMajor;
+	node.axisMinor0 = axisMinor[0];
+	node.axisMinor1 = axisMinor[1];
+	node.pad = 0u;
+
+	const float infinity = __int_as_float(0x7F800000);
+
+	for (int k = 0; k < 4; k++)
+	{
+		BuildBox box = { infinity, infinity, infinity, infinity, infinity, infinity }; // BoxBound.None, BoxBound.cs:94
+		uint32_t token = ECHO_TOKEN_EMPTY;
+
+		if (slots[k] != 0xFFFFFFFFu)
+		{
+			box = reference_box(slots[k], boxes, order, nodeBoxes);
+			token = (slots[k] & kLeafFlag) ? tokens[order[slots[k] & ~kLeafFlag]] : ECHO_TOKEN_MAKE(ECHO_TOKEN_TYPE_NODE, quadIndex[slots[k]]);
+		}
+
+		node.minX[k] = box.minX; node.minY[k] = box.minY; node.minZ[k] = box.minZ;
+		node.maxX[k] = box.maxX; node.maxY[k] = box.maxY; node.maxZ[k] = box.maxZ;
+		node.token4[k] = token;
+	}
+
+	out[quadIndex[i]] = node;
+}
+
+unsigned int build_blocks(uint64_t count) { return (unsigned int)((count + kBuildBlock - 1) / kBuildBlock); }
+
+struct DeviceBuffers
+{
+	std::vector<void*> pointers;
+
+	template<class T>
+	bool allocate(T*& pointer, uint64_t count)
+	{
+		void* p = nullptr;
+		if (!check_cuda(cudaMalloc(&p, sizeof(T) * (count ? count : 1)), "cudaMalloc(build)")) return false;
+		pointers.push_back(p);
+		pointer = (T*)p;
+		return true;
+	}
+
+	~DeviceBuffers() { for (void* p : pointers) cudaFree(p); }
+};
+
+} // namespace
+
+bool build_qbvh_device(const EchoTriangle* triangles, uint32_t triangleCount, const EchoSphere* spheres, uint32_t sphereCount,
+                       EchoQbvhNode* outNodes, uint32_t* outNodeCount, uint32_t* outMaxDepth)
+{
+	uint64_t total64 = (uint64_t)triangleCount + sphereCount;
+	if (total64 < 2 || total64 >= (1ull << ECHO_TOKEN_INDEX_BITS)) { set_error("a tree needs 2..2^28-1 primitives"); return false; }
+	int total = (int)total64, internal = total - 1;
+
+	DeviceBuffers buffers;
+	EchoTriangle* dTriangles;
+	EchoSphere* dSpheres;
+	BuildBox *boxes, *nodeBoxes;
+	uint32_t *tokens, *order, *orderSorted, *left, *right, *parentOfInternal, *parentOfLeaf, *visits, *isQuad, *quadIndex;
+	unsigned long long *keys, *keysSorted;
+	int* sceneBound;
+	EchoQbvhNode* nodes;
+
+	bool ok = buffers.allocate(dTriangles, triangleCount) && buffers.allocate(dSpheres, sphereCount) && buffers.allocate(boxes, total) && buffers.allocate(nodeBoxes, internal)
+		&& buffers.allocate(tokens, total) && buffers.allocate(order, total) && buffers.allocate(orderSorted, total) && buffers.allocate(left, internal)
+		&& buffers.allocate(right, internal) && buffers.allocate(parentOfInternal, internal) && buffers.allocate(parentOfLeaf, total) && buffers.allocate(visits, internal)
+		&& buffers.allocate(isQuad, internal) && buffers.allocate(quadIndex, internal) && buffers.allocate(keys, total) && buffers.allocate(keysSorted, total)
+		&& buffers.allocate(sceneBound, 6) && buffers.allocate(nodes, internal);
+	if (!ok) return false;
+
+	cudaStream_t stream = nullptr;
+	ok = check_cuda(cudaMemcpyAsync(dTriangles, triangles, sizeof(EchoTriangle) * triangleCount, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync(triangles)")
+		&& check_cuda(cudaMemcpyAsync(dSpheres, spheres, sizeof(EchoSphere) * sphereCount, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync(spheres)");
+	if (!ok) return false;
+
+	const int initial[6] = { 0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF, (int)0x80000000, (int)0x80000000, (int)0x80000000 };
+	ok = check_cuda(cudaMemcpyAsync(sceneBound, initial, sizeof(initial), cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync(bound)")
+		&& check_cuda(cudaMemsetAsync(visits, 0, sizeof(uint32_t) * internal, stream), "cudaMemsetAsync(visits)");
+	if (!ok) return false;
+
+	primitive_bounds_kernel<<<build_blocks(total), kBuildBlock, 0, stream>>>(dTriangles, triangleCount, dSpheres, sphereCount, boxes, tokens, sceneBound);
+	morton_kernel<<<build_blocks(total), kBuildBlock, 0, stream>>>(boxes, (uint32_t)total, sceneBound, keys, order);
+
+	size_t sortBytes = 0, scanBytes = 0;
+	cub::DeviceRadixSort::SortPairs(nullptr, sortBytes, keys, keysSorted, order, orderSorted, total, 0, 63, stream);
+	cub::DeviceScan::ExclusiveSum(nullptr, scanBytes, isQuad, quadIndex, internal, stream);
+	char* scratch;
+	if (!buffers.allocate(scratch, std::max(sortBytes, scanBytes))) return false;
+
+	cub::DeviceRadixSort::SortPairs(scratch, sortBytes, keys, keysSorted, order, orderSorted, total, 0, 63, stream);
+	radix_tree_kernel<<<build_blocks(internal), kBuildBlock, 0, stream>>>(keysSorted, total, left, right, parentOfInternal, parentOfLeaf);
+	fit_kernel<<<build_blocks(total), kBuildBlock, 0, stream>>>(boxes, orderSorted, total, left, right, parentOfInternal, parentOfLeaf, nodeBoxes, visits);
+	depth_kernel<<<build_blocks(internal), kBuildBlock, 0, stream>>>(parentOfInternal, internal, isQuad);
+	cub::DeviceScan::ExclusiveSum(scratch, scanBytes, isQuad, quadIndex, internal, stream);
+	emit_kernel<<<build_blocks(internal), kBuildBlock, 0, stream>>>(internal, isQuad, quadIndex, left, right, boxes, orderSorted, tokens, nodeBoxes, nodes);
+	if (!check_cuda(cudaGetLastError(), "tree build launch")) return false;
+
+	uint32_t lastFlag = 0, lastIndex = 0;
+	ok = check_cuda(cudaMemcpyAsync(&lastFlag, isQuad + internal - 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream), "cudaMemcpyAsync(count)")
+		&& check_cuda(cudaMemcpyAsync(&lastIndex, quadIndex + internal - 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream), "cudaMemcpyAsync(count)")
+		&& check_cuda(cudaStreamSynchronize(stream), "tree build");
+	if (!ok) return false;
+
+	uint32_t nodeCount = lastIndex + lastFlag;
+	if (!check_cuda(cudaMemcpy(outNodes, nodes, sizeof(EchoQbvhNode) * nodeCount, cudaMemcpyDeviceToHost), "cudaMemcpy(nodes)")) return false;
+
+	// depth as CreateNode counts it (:375-414): an empty slot 0, a leaf 1, a node 1 + the deepest of its slots
+	std::vector<uint32_t> depth(nodeCount, 0u);
+	std::vector<std::pair<uint32_t, int>> stack = { { 0u, 0 } };
+
+	while (!stack.empty())
+	{
+		auto& [index, slot] = stack.back();
+
+		if (slot == 4)
+		{
+			uint32_t deepest = 0u;
+			for (uint32_t token : outNodes[index].token4)
+			{
+				if (token == ECHO_TOKEN_EMPTY) continue;
+				bool isNode = (token >> ECHO_TOKEN_INDEX_BITS) == ECHO_TOKEN_TYPE_NODE;
+				deepest = std::max(deepest, isNode ? depth[token & ((1u << ECHO_TOKEN_INDEX_BITS) - 1u)] : 1u);
+			}
+			depth[index] = deepest + 1u;
+			stack.pop_back();
+			continue;
+		}
+
+		uint32_t token = outNodes[index].token4[slot++];
+		if (token != ECHO_TOKEN_EMPTY && (token >> ECHO_TOKEN_INDEX_BITS) == ECHO_TOKEN_TYPE_NODE) stack.push_back({ token & ((1u << ECHO_TOKEN_INDEX_BITS) - 1u), 0 });
+	}
+
+	*outNodeCount = nodeCount;
+	*outMaxDepth = depth[0];
+	return true;
+}
+
+} // namespace echo

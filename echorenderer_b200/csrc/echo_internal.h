@@ -35,6 +35,10 @@ bool launch_persistent_instanced(const DeviceScene& scene, const EchoRay* rays, 
 unsigned long long* next_ray_counter(cudaStream_t stream); // zeroed work counter for one persistent launch
 int persistent_grid(const void* kernel);                  // resident CTAs of a persistent kernel on the current device
 
+// ---- build.cu: linear BVH on the device, collapsed to the QBVH node format (host buffers in and out) ----
+bool build_qbvh_device(const EchoTriangle* triangles, uint32_t triangleCount, const EchoSphere* spheres, uint32_t sphereCount,
+                       EchoQbvhNode* outNodes, uint32_t* outNodeCount, uint32_t* outMaxDepth);
+
 // ---- render.cu ----
 struct RenderState; // wavefront buffers, owned per scene
 

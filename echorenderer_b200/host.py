@@ -494,8 +494,9 @@ def _root_bound_radius(root):
     return np.float32(np.linalg.norm(high - low) / 2)
 
 
-def prepare(description, threads=0):
-    """ScenePreparer.Prepare -> PreparedScene constructor (PreparedScene.cs:26-40)."""
+def prepare(description, threads=0, tree=None):
+    """ScenePreparer.Prepare -> PreparedScene constructor (PreparedScene.cs:26-40). `tree` = (nodes, max_depth) replaces the
+    SweepBuilder mirror for a scene without instances (e.g. the device-side build, scene.build_qbvh_device)."""
     lib = _library()
     d = description
     d.triangles = np.ascontiguousarray(d.triangles, dtype=structs.TRIANGLE)
@@ -509,7 +510,7 @@ def prepare(description, threads=0):
         packs, instances, nodes, all_triangles, all_spheres, all_materials, max_depth, lights, all_slots = _prepare_packs(d, threads)
         light_nodes, tokens, paths, all_points, scene_power = lights
     else:
-        nodes, max_depth = build_qbvh(d.triangles, d.spheres, threads)
+        nodes, max_depth = tree if tree is not None else build_qbvh(d.triangles, d.spheres, threads)
         light_nodes, tokens, paths, scene_power = build_light_tree(d)
 
     # FilterLights / SumInfiniteLightsPower / CalculateThreshold (PreparedScene.cs:279-325)

@@ -252,6 +252,20 @@ def shard_tiles(tile_positions, rank, world_size):
     return np.ascontiguousarray(tile_positions[rank::world_size])
 
 
+def build_qbvh_device(triangles, spheres, device=0):
+    """The optional device-side tree build (echo_b200_build_qbvh): a linear BVH collapsed to the reference's QBVH node format.
+    Returns (nodes, max_depth) like host.build_qbvh — a valid tree, not the SweepBuilder's."""
+    lib = _native.library()
+    triangles = np.ascontiguousarray(triangles, dtype=structs.TRIANGLE)
+    spheres = np.ascontiguousarray(spheres, dtype=structs.SPHERE)
+    total = len(triangles) + len(spheres)
+    nodes = np.zeros(max(total - 1, 1), dtype=structs.QBVH_NODE)
+    count, depth = ctypes.c_uint32(), ctypes.c_uint32()
+    _native.check(lib.echo_b200_build_qbvh(device, _native.pointer(triangles), len(triangles), _native.pointer(spheres), len(spheres),
+                                           _native.pointer(nodes), ctypes.byref(count), ctypes.byref(depth)))
+    return nodes[:count.value].copy(), int(depth.value)
+
+
 def shard_epochs(max_epoch, rank, world_size):
     """Sample sharding across devices (few tiles, many samples): rank r renders block r of
     ceil(max_epoch / world_size) consecutive epochs of EVERY tile; returns (epoch_offset, epoch_count) for that rank's

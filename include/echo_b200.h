@@ -368,6 +368,14 @@ int32_t echo_b200_render_frame_device(EchoScene*, const EchoRenderParams*, const
                                       float* d_frame_rgba, EchoStats* stats, void* stream);
 int32_t echo_b200_frame_resolve_device(EchoScene*, float* d_frame_rgba, int32_t width, int32_t height, void* stream);
 
+/* Optional device-side tree build: a linear BVH over 63-bit Morton codes (Karras 2012) collapsed into the
+ * reference's QBVH node format (QuadBoundingVolumeHierarchy.cs:363-565). NOT the SweepBuilder's SAH tree (echo_host.h mirrors
+ * that one and stays the default): a valid tree of lower quality that builds in milliseconds, for previews and animated
+ * geometry. Tokens: triangles, then spheres, as GeometryCollection.CreateBounds numbers them. `out_nodes` (host) needs room for
+ * triangle_count + sphere_count - 1 nodes; out_max_depth is the depth CreateNode reports (what set_qbvh takes). */
+int32_t echo_b200_build_qbvh(int32_t device, const EchoTriangle* triangles, uint32_t triangle_count, const EchoSphere* spheres, uint32_t sphere_count,
+                             EchoQbvhNode* out_nodes, uint32_t* out_node_count, uint32_t* out_max_depth);
+
 const char* echo_b200_last_error(void);
 const char* echo_b200_version(void);
 
