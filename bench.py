@@ -47,6 +47,8 @@ def parse():
                         help="render workload scene: C1 / C3 / C4 / C5 / 2 304 placements of two packs (SURVEY.md 8f rank 2)")
     parser.add_argument("--instanced", action="store_true", help="trace workload: the instanced scene instead of the C2 terrain (same ray recipe)")
     parser.add_argument("--bounce-limit", type=int, default=8, help="render workload: PathTracedEvaluator.BounceLimit (C3: 8; reference default 128)")
+    parser.add_argument("--tree", default="sah", choices=["sah", "device"],
+                        help="trace workload: the SweepBuilder mirror's tree (default) or the device-built linear BVH (echo_b200_build_qbvh)")
     parser.add_argument("--shard", default="tiles", choices=["tiles", "samples"],
                         help="render workload, N > 1: tile sharding (tile i -> rank i mod N) or sample sharding (every rank renders spp / N samples of every tile)")
     parser.add_argument("--no-cpu-baseline", action="store_true")
@@ -138,7 +140,16 @@ def instanced_bench_scene():
 
 def build_trace_inputs(args, rank):
     description = instanced_bench_scene() if getattr(args, "instanced", False) else scenes.terrain_scene(args.quads[0], args.quads[1], 10000)
-    prepared = host.prepare(description)
+    tree = None
+    if getattr(args, "tree", "sah") == "device" and not getattr(args, "instanced", False):
+        from echorenderer_b200 import build_qbvh_device
+        build_qbvh_device(description.triangles[:64], description.spheres[:0], device=int(os.environ.get("LOCAL_RANK", "0")))  # context + module load
+        started = time.perf_counter()
+        tree = build_qbvh_device(description.triangles, description.spheres, device=int(os.environ.get("LOCAL_RANK", "0")))
+        args.tree_build_seconds = time.perf_counter() - started
+    started = time.perf_counter()
+    prepared = host.prepare(description, tree=tree)
+    args.prepare_seconds = time.perf_counter() - started
     # every rank traces its own batch (distinct seeds per rank)
     rays = scenes.random_rays(prepared.bounds, args.rays, seed=11 + 1000 * rank)
     shadow = rays.copy()
@@ -422,6 +433,8 @@ def main():
         line["e2e"] = {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 2 * n * 32, "d2h_bytes_per_step": n * 16 + n, "ms_per_step": e2e_ms / args.steps}
         line["gpu_launches"] = 2 * args.steps
         line["clocks"] = clocks.summary()
+        line["config"]["tree"] = {"builder": args.tree, "nodes": int(len(prepared.nodes)), "quad_depth": int(prepared.max_depth),
+                                  "device_build_seconds": getattr(args, "tree_build_seconds", None), "host_prepare_seconds": getattr(args, "prepare_seconds", None)}
 
         if not args.no_secondary and not args.instanced:
             line["secondary"] = secondary_batch(scene, prepared, rays, d_hits, device, stream, args, max_over_ranks)

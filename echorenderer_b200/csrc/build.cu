@@ -10,6 +10,9 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "echo_internal.h"
@@ -281,21 +284,28 @@ __global__ void emit_kernel(int internalCount, const uint32_t* __restrict__ isQu
 
 unsigned int build_blocks(uint64_t count) { return (unsigned int)((count + kBuildBlock - 1) / kBuildBlock); }
 
-struct DeviceBuffers
+// one cudaMalloc for every build buffer (eighteen separate ones cost ~60 ms, far more than the build itself)
+struct DeviceArena
 {
-	std::vector<void*> pointers;
+	char* base = nullptr;
+	size_t bytes = 0;
+	std::vector<std::pair<void**, size_t>> slots;
 
 	template<class T>
-	bool allocate(T*& pointer, uint64_t count)
+	void reserve(T*& pointer, uint64_t count)
 	{
-		void* p = nullptr;
-		if (!check_cuda(cudaMalloc(&p, sizeof(T) * (count ? count : 1)), "cudaMalloc(build)")) return false;
-		pointers.push_back(p);
-		pointer = (T*)p;
+		slots.push_back({ (void**)&pointer, bytes });
+		bytes += (sizeof(T) * (count ? count : 1) + 255) & ~size_t(255);
+	}
+
+	bool commit()
+	{
+		if (!check_cuda(cudaMalloc((void**)&base, bytes), "cudaMalloc(build)")) return false;
+		for (auto& [pointer, offset] : slots) *pointer = base + offset;
 		return true;
 	}
 
-	~DeviceBuffers() { for (void* p : pointers) cudaFree(p); }
+	~DeviceArena() { cudaFree(base); }
 };
 
 } // namespace
@@ -307,7 +317,12 @@ bool build_qbvh_device(const EchoTriangle* triangles, uint32_t triangleCount, co
 	if (total64 < 2 || total64 >= (1ull << ECHO_TOKEN_INDEX_BITS)) { set_error("a tree needs 2..2^28-1 primitives"); return false; }
 	int total = (int)total64, internal = total - 1;
 
-	DeviceBuffers buffers;
+	const bool profile = std::getenv("ECHO_B200_PROFILE") != nullptr;
+	auto clock = [] { return std::chrono::steady_clock::now(); };
+	auto since = [&](std::chrono::steady_clock::time_point from) { return std::chrono::duration<double, std::milli>(clock() - from).count(); };
+	auto started = clock();
+
+	DeviceArena arena;
 	EchoTriangle* dTriangles;
 	EchoSphere* dSpheres;
 	BuildBox *boxes, *nodeBoxes;
@@ -315,14 +330,22 @@ bool build_qbvh_device(const EchoTriangle* triangles, uint32_t triangleCount, co
 	unsigned long long *keys, *keysSorted;
 	int* sceneBound;
 	EchoQbvhNode* nodes;
+	char* scratch;
 
-	bool ok = buffers.allocate(dTriangles, triangleCount) && buffers.allocate(dSpheres, sphereCount) && buffers.allocate(boxes, total) && buffers.allocate(nodeBoxes, internal)
-		&& buffers.allocate(tokens, total) && buffers.allocate(order, total) && buffers.allocate(orderSorted, total) && buffers.allocate(left, internal)
-		&& buffers.allocate(right, internal) && buffers.allocate(parentOfInternal, internal) && buffers.allocate(parentOfLeaf, total) && buffers.allocate(visits, internal)
-		&& buffers.allocate(isQuad, internal) && buffers.allocate(quadIndex, internal) && buffers.allocate(keys, total) && buffers.allocate(keysSorted, total)
-		&& buffers.allocate(sceneBound, 6) && buffers.allocate(nodes, internal);
-	if (!ok) return false;
+	size_t sortBytes = 0, scanBytes = 0;
+	cub::DeviceRadixSort::SortPairs(nullptr, sortBytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, total, 0, 63);
+	cub::DeviceScan::ExclusiveSum(nullptr, scanBytes, (uint32_t*)nullptr, (uint32_t*)nullptr, internal);
 
+	arena.reserve(dTriangles, triangleCount); arena.reserve(dSpheres, sphereCount); arena.reserve(boxes, total); arena.reserve(nodeBoxes, internal);
+	arena.reserve(tokens, total); arena.reserve(order, total); arena.reserve(orderSorted, total); arena.reserve(left, internal); arena.reserve(right, internal);
+	arena.reserve(parentOfInternal, internal); arena.reserve(parentOfLeaf, total); arena.reserve(visits, internal); arena.reserve(isQuad, internal);
+	arena.reserve(quadIndex, internal); arena.reserve(keys, total); arena.reserve(keysSorted, total); arena.reserve(sceneBound, 6); arena.reserve(nodes, internal);
+	arena.reserve(scratch, std::max(sortBytes, scanBytes));
+	if (!arena.commit()) return false;
+	bool ok = true;
+
+	double allocateMs = since(started);
+	auto phase = clock();
 	cudaStream_t stream = nullptr;
 	ok = check_cuda(cudaMemcpyAsync(dTriangles, triangles, sizeof(EchoTriangle) * triangleCount, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync(triangles)")
 		&& check_cuda(cudaMemcpyAsync(dSpheres, spheres, sizeof(EchoSphere) * sphereCount, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync(spheres)");
@@ -333,14 +356,12 @@ bool build_qbvh_device(const EchoTriangle* triangles, uint32_t triangleCount, co
 		&& check_cuda(cudaMemsetAsync(visits, 0, sizeof(uint32_t) * internal, stream), "cudaMemsetAsync(visits)");
 	if (!ok) return false;
 
+	if (profile) cudaStreamSynchronize(stream);
+	double uploadMs = since(phase);
+	phase = clock();
+
 	primitive_bounds_kernel<<<build_blocks(total), kBuildBlock, 0, stream>>>(dTriangles, triangleCount, dSpheres, sphereCount, boxes, tokens, sceneBound);
 	morton_kernel<<<build_blocks(total), kBuildBlock, 0, stream>>>(boxes, (uint32_t)total, sceneBound, keys, order);
-
-	size_t sortBytes = 0, scanBytes = 0;
-	cub::DeviceRadixSort::SortPairs(nullptr, sortBytes, keys, keysSorted, order, orderSorted, total, 0, 63, stream);
-	cub::DeviceScan::ExclusiveSum(nullptr, scanBytes, isQuad, quadIndex, internal, stream);
-	char* scratch;
-	if (!buffers.allocate(scratch, std::max(sortBytes, scanBytes))) return false;
 
 	cub::DeviceRadixSort::SortPairs(scratch, sortBytes, keys, keysSorted, order, orderSorted, total, 0, 63, stream);
 	radix_tree_kernel<<<build_blocks(internal), kBuildBlock, 0, stream>>>(keysSorted, total, left, right, parentOfInternal, parentOfLeaf);
@@ -356,8 +377,13 @@ bool build_qbvh_device(const EchoTriangle* triangles, uint32_t triangleCount, co
 		&& check_cuda(cudaStreamSynchronize(stream), "tree build");
 	if (!ok) return false;
 
+	double kernelsMs = since(phase);
+	phase = clock();
 	uint32_t nodeCount = lastIndex + lastFlag;
 	if (!check_cuda(cudaMemcpy(outNodes, nodes, sizeof(EchoQbvhNode) * nodeCount, cudaMemcpyDeviceToHost), "cudaMemcpy(nodes)")) return false;
+
+	double downloadMs = since(phase);
+	phase = clock();
 
 	// depth as CreateNode counts it (:375-414): an empty slot 0, a leaf 1, a node 1 + the deepest of its slots
 	std::vector<uint32_t> depth(nodeCount, 0u);
@@ -384,6 +410,10 @@ bool build_qbvh_device(const EchoTriangle* triangles, uint32_t triangleCount, co
 		uint32_t token = outNodes[index].token4[slot++];
 		if (token != ECHO_TOKEN_EMPTY && (token >> ECHO_TOKEN_INDEX_BITS) == ECHO_TOKEN_TYPE_NODE) stack.push_back({ token & ((1u << ECHO_TOKEN_INDEX_BITS) - 1u), 0 });
 	}
+
+	if (profile)
+		std::fprintf(stderr, "[echo_b200 build] %d primitives -> %u nodes: allocate %.2f ms, upload %.2f ms, kernels + sort %.2f ms, download %.2f ms, depth pass %.2f ms\n",
+		             total, nodeCount, allocateMs, uploadMs, kernelsMs, downloadMs, since(phase));
 
 	*outNodeCount = nodeCount;
 	*outMaxDepth = depth[0];
