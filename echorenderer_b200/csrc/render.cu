@@ -82,6 +82,7 @@ struct WorkerState
 	uint64_t tileCapacity = 0;
 
 	uint32_t* hostCounters = nullptr; // pinned
+	cudaEvent_t iterationDone = nullptr; // blocking-sync event: the pipeline thread sleeps between wavefront iterations
 };
 
 // Tile batches are rendered by up to kWorkers concurrent pipelines (host thread + stream + wavefront buffers each): the
@@ -1875,6 +1876,7 @@ void render_state_destroy(RenderState* state)
 	{
 		release(worker);
 		if (worker->hostCounters) cudaFreeHost(worker->hostCounters);
+		if (worker->iterationDone) cudaEventDestroy(worker->iterationDone);
 		if (worker->stream) cudaStreamDestroy(worker->stream);
 		delete worker;
 	}
@@ -1995,6 +1997,26 @@ struct KernelTimer
 
 static KernelTimer gTimer;
 
+// Every pipeline thread waits once per wavefront iteration for the active-ray count. Spinning in cudaStreamSynchronize is the
+// fastest wake-up, but N ranks x 8 pipelines spin on N x 8 host cores: when the host has fewer cores than that the threads
+// preempt each other (8 GPUs on a 16-core host scaled 5.7x). A blocking-sync event lets them sleep instead.
+// ECHO_B200_BLOCKING_SYNC=0/1 overrides the choice (default: block when pipelines of all visible devices outnumber the cores).
+static bool wait_for_iteration(WorkerState* state, cudaStream_t stream)
+{
+	static const bool blocking = []
+	{
+		if (const char* value = std::getenv("ECHO_B200_BLOCKING_SYNC")) return value[0] != '0';
+		int devices = 1;
+		cudaGetDeviceCount(&devices);
+		return (unsigned int)(devices * kWorkers) > std::thread::hardware_concurrency();
+	}();
+
+	if (!blocking) return check_cuda(cudaStreamSynchronize(stream), "wavefront iteration");
+
+	if (!state->iterationDone && !check_cuda(cudaEventCreateWithFlags(&state->iterationDone, cudaEventBlockingSync | cudaEventDisableTiming), "cudaEventCreate")) return false;
+	return check_cuda(cudaEventRecord(state->iterationDone, stream), "cudaEventRecord") && check_cuda(cudaEventSynchronize(state->iterationDone), "wavefront iteration");
+}
+
 static unsigned int blocks_for(uint64_t count) { return (unsigned int)std::max<uint64_t>((count + kBlock - 1) / kBlock, 1); }
 
 // Evaluates `count` path slots already described in state->pixelXY / sampleIndex; radiance lands in state->sampleOut.
@@ -2109,7 +2131,7 @@ static bool evaluate_paths(WorkerState* state, const DeviceScene& scene, const E
 		launches += 9;
 
 		if (!check_cuda(cudaGetLastError(), "wavefront launch")) return false;
-		if (!check_cuda(cudaStreamSynchronize(stream), "wavefront iteration")) return false;
+		if (!wait_for_iteration(state, stream)) return false;
 
 		active = state->hostCounters[0];
 		current ^= 1;
