@@ -169,3 +169,45 @@ def test_auxiliary_evaluators_match_oracle(instanced):
             actual = scene.evaluate_samples(params, pixel_xy, sample_index, channels=4)
             assert np.array_equal(actual.view(np.uint32), expected.view(np.uint32))
             assert len(np.unique(expected[:, :3], axis=0)) > 4
+
+
+def test_textured_placements_match_oracle():
+    """Image textures inside instanced packs: the pack's own swatch and a placement's replacement swatch bind different
+    textures; the environment is an importance-sampled map. Per-sample radiance and the albedo pass against the oracle."""
+    from tests.conftest import sky_texture
+    from tests.test_gpu_render import sample_grid
+    description = scenes.instanced_scene(grid=3, rings=10, segments=12)
+    rng = np.random.default_rng(8)
+    noise = np.concatenate([rng.uniform(0.1, 0.9, (16, 16, 3)), np.ones((16, 16, 1))], axis=-1)
+    stripes = np.where((np.arange(16) % 2 == 0)[None, :, None], np.array([0.9, 0.2, 0.1]), np.array([0.1, 0.3, 0.9])) * np.ones((16, 1, 1))
+    stripes = np.concatenate([stripes, np.ones((16, 16, 1))], axis=-1)
+    description.textures = [host.TextureDescription(noise, structs.FILTER_BILINEAR, structs.WRAPPER_REPEAT),
+                            host.TextureDescription(stripes, structs.FILTER_POINT, structs.WRAPPER_MIRROR),
+                            host.TextureDescription(sky_texture(16, 32), structs.FILTER_BILINEAR, structs.WRAPPER_REPEAT)]
+    blob = description.packs[0]
+    blob.material_textures = structs.material_textures(len(blob.materials))
+    blob.material_textures["albedo"][0] = 0
+    for instance in description.instances:
+        if instance.materials is not None:
+            instance.material_textures = structs.material_textures(len(instance.materials))
+            instance.material_textures["albedo"][1] = 1
+            instance.material_textures["roughness"][0] = 0
+    description.material_textures = structs.material_textures(len(description.materials))
+    description.material_textures["albedo"][0] = 1
+    description.infinite_lights = scenes.environment_light(2, (0.6, 0.6, 0.7), (0, 25, 0))
+
+    prepared = host.prepare(description)
+    assert (prepared.material_textures["albedo"] != structs.TEXTURE_NONE).sum() >= 3
+    oracle = oracle_lib.OracleScene(prepared)
+    width, height = 96, 64
+    pixel_xy, sample_index = sample_grid(width, height, 2)
+
+    with PreparedScene(prepared) as scene:
+        for evaluator, channels in ((structs.EVALUATOR_PATH_TRACED, 3), (structs.EVALUATOR_ALBEDO | structs.EVALUATOR_DIVERGE_ONCE, 4)):
+            params = structs.render_params(width, height, 32, extend=2, bounce_limit=12, seed=5, evaluator=evaluator)
+            expected = np.zeros((len(sample_index), 4), dtype=np.float32)
+            oracle.lib.oracle_evaluate_samples4(oracle.handle, oracle_lib.ptr(params), oracle_lib.ptr(pixel_xy), oracle_lib.ptr(sample_index), len(sample_index),
+                                                oracle_lib.ptr(expected), 4, 0)
+            actual = scene.evaluate_samples(params, pixel_xy, sample_index, channels=4)
+            assert np.array_equal(actual.view(np.uint32), expected.view(np.uint32))
+            assert len(np.unique(expected[:, :3].round(3), axis=0)) > 50
