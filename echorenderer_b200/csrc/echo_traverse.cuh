@@ -28,6 +28,9 @@ constexpr unsigned long long kPool = 256;         // rays reserved per global at
 #ifndef ECHO_PREFETCH
 #define ECHO_PREFETCH 0 // A/B: 1 = prefetch the next node into L1 after the slot scan, 2 = the pending triangle, 3 = both
 #endif
+#ifndef ECHO_INST_MIN_BLOCKS
+#define ECHO_INST_MIN_BLOCKS 6 // resident CTAs per SM asked of the INST instantiations (80 registers), see trace.cu
+#endif
 #ifndef ECHO_LEAF_MAX_WAIT
 #define ECHO_LEAF_MAX_WAIT 2 // a lane waits at most two iterations for its primitive test (A/B on C2/C3/C4: +1-2 %)
 #endif

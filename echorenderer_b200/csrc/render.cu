@@ -1045,7 +1045,7 @@ struct ExtendLayersIO : ExtendIO
 };
 
 template<int STACK>
-__global__ void __launch_bounds__(kTraverseBlock) extend_layers_kernel(DeviceScene scene, ExtendLayersIO io, const uint32_t* __restrict__ queueCount, unsigned long long* __restrict__ nextRay)
+__global__ void __launch_bounds__(kTraverseBlock, ECHO_INST_MIN_BLOCKS) extend_layers_kernel(DeviceScene scene, ExtendLayersIO io, const uint32_t* __restrict__ queueCount, unsigned long long* __restrict__ nextRay)
 {
 	__shared__ float4 stagedRays[kTraverseBlock * 2];
 	persistent_traverse<STACK, false, true>(scene, io, *queueCount, nextRay, stagedRays);
@@ -1443,7 +1443,7 @@ struct ShadowLayersIO : ShadowIO
 };
 
 template<int STACK>
-__global__ void __launch_bounds__(kTraverseBlock) shadow_layers_kernel(DeviceScene scene, ShadowLayersIO io, const uint32_t* __restrict__ shadowCount, unsigned long long* __restrict__ nextRay,
+__global__ void __launch_bounds__(kTraverseBlock, ECHO_INST_MIN_BLOCKS) shadow_layers_kernel(DeviceScene scene, ShadowLayersIO io, const uint32_t* __restrict__ shadowCount, unsigned long long* __restrict__ nextRay,
                                                                        unsigned long long* __restrict__ stats)
 {
 	__shared__ float4 stagedRays[kTraverseBlock * 2];

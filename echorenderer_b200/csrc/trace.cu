@@ -143,9 +143,11 @@ __global__ void __launch_bounds__(kTraverseBlock, ECHO_MIN_BLOCKS) persistent_ba
 	persistent_traverse<STACK, ANY>(scene, io, n, nextRay, stagedRays);
 }
 
-// the same through instanced packs (echo_traverse.cuh INST); more per-lane state, so no occupancy target is forced
+// the same through instanced packs (echo_traverse.cuh INST); more per-lane state than the plain kernel: 95 registers when
+// left alone. A/B on the instanced bench scene (variants/ab6.sh): 6 CTAs per SM (80 registers) 3691 / 6692 Mrays/s closest
+// hit / occlusion, unconstrained 3507 / 6233, 7 CTAs (72 registers, spills) 3430 / 6773.
 template<int STACK, bool ANY>
-__global__ void __launch_bounds__(kTraverseBlock) persistent_instanced_kernel(DeviceScene scene, BatchIO io, uint32_t n, unsigned long long* __restrict__ nextRay)
+__global__ void __launch_bounds__(kTraverseBlock, ECHO_INST_MIN_BLOCKS) persistent_instanced_kernel(DeviceScene scene, BatchIO io, uint32_t n, unsigned long long* __restrict__ nextRay)
 {
 	__shared__ float4 stagedRays[kTraverseBlock * 2];
 	persistent_traverse<STACK, ANY, true>(scene, io, n, nextRay, stagedRays);
