@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <atomic>
 #include <string>
+#include <cstring>
 #include <thread>
 #include <cstdio>
 #include <cstdlib>
@@ -83,6 +84,11 @@ struct WorkerState
 
 	uint32_t* hostCounters = nullptr; // pinned
 	cudaEvent_t iterationDone = nullptr; // blocking-sync event: the pipeline thread sleeps between wavefront iterations
+
+	// one narrow wavefront iteration (9 kernels) as an instantiated CUDA graph per ping-pong side; `graphKey` is what the
+	// captured launches depend on (scene, parameters, buffers), anything else comes from device memory
+	cudaGraphExec_t narrowGraph[2] = { nullptr, nullptr };
+	std::vector<unsigned char> graphKey;
 };
 
 // Tile batches are rendered by up to kWorkers concurrent pipelines (host thread + stream + wavefront buffers each): the
@@ -1863,6 +1869,12 @@ static void release(WorkerState* state)
 	for (void* p : state->allocations) cudaFree(p);
 	state->allocations.clear();
 	state->paths.rayLayers[0] = state->paths.rayLayers[1] = state->paths.hitLayers = state->paths.shadowLayers = nullptr;
+	for (cudaGraphExec_t& graph : state->narrowGraph)
+	{
+		if (graph) cudaGraphExecDestroy(graph);
+		graph = nullptr;
+	}
+	state->graphKey.clear();
 	state->capacity = 0;
 	state->pixelCapacity = 0;
 	state->tileCapacity = 0;
@@ -2019,6 +2031,88 @@ static bool wait_for_iteration(WorkerState* state, cudaStream_t stream)
 
 static unsigned int blocks_for(uint64_t count) { return (unsigned int)std::max<uint64_t>((count + kBlock - 1) / kBlock, 1); }
 
+// One iteration of a NARROW wavefront (fewer rays than resident lanes: one-thread-per-ray traversal): extend, classify, the
+// five shading launches, shadow, counter rotation. Every kernel reads its count from device memory and exits early, so the
+// grid can be a fixed `blocks` — which makes the sequence a capturable, replayable CUDA graph.
+template<int STACK, bool INST>
+static void launch_narrow_iteration(WorkerState* state, const DeviceScene& scene, const EchoRenderParams& params, int current, unsigned int blocks, cudaStream_t stream)
+{
+	PathBuffers& paths = state->paths;
+	uint32_t* counters = paths.counters;
+	uint32_t* activeCount = counters + 32;
+	const bool packs = INST && scene.packCount != 0u;
+
+	ExtendIO extendIO = { paths.rayQueue[current], paths.hitQueue };
+	if (packs) extend_instanced_kernel<STACK><<<blocks, kBlock, 0, stream>>>(scene, extendIO, paths.rayLayers[current], paths.hitLayers, activeCount);
+	else extend_narrow_kernel<STACK><<<blocks, kBlock, 0, stream>>>(scene, extendIO, activeCount);
+
+	classify_kernel<INST><<<blocks, kBlock, 0, stream>>>(scene, activeCount, paths);
+	shade_kernel<CLASS_MISS, 0u, INST><<<blocks, kBlock, 0, stream>>>(scene, params, paths.classQueue[CLASS_MISS], counters + COUNTER_CLASS + CLASS_MISS, paths, current);
+	shade_kernel<CLASS_DIFFUSE, KINDS_DIFFUSE, INST><<<blocks, kBlock, 0, stream>>>(scene, params, paths.classQueue[CLASS_DIFFUSE], counters + COUNTER_CLASS + CLASS_DIFFUSE, paths, current);
+	shade_kernel<CLASS_DIELECTRIC, KINDS_DIELECTRIC, INST><<<blocks, kBlock, 0, stream>>>(scene, params, paths.classQueue[CLASS_DIELECTRIC], counters + COUNTER_CLASS + CLASS_DIELECTRIC, paths, current);
+	shade_kernel<CLASS_CONDUCTOR, KINDS_CONDUCTOR, INST><<<blocks, kBlock, 0, stream>>>(scene, params, paths.classQueue[CLASS_CONDUCTOR], counters + COUNTER_CLASS + CLASS_CONDUCTOR, paths, current);
+	shade_kernel<CLASS_TERMINAL, KINDS_TERMINAL, INST><<<blocks, kBlock, 0, stream>>>(scene, params, paths.classQueue[CLASS_TERMINAL], counters + COUNTER_CLASS + CLASS_TERMINAL, paths, current);
+
+	ShadowIO shadowIO = { paths.shadowQueue, paths.shadowValue, paths.result, 0u };
+	if (packs) shadow_instanced_kernel<STACK><<<blocks, kBlock, 0, stream>>>(scene, shadowIO, paths.shadowLayers, counters + COUNTER_SHADOW, paths.stats);
+	else shadow_narrow_kernel<STACK><<<blocks, kBlock, 0, stream>>>(scene, shadowIO, counters + COUNTER_SHADOW, paths.stats);
+
+	rotate_counters_kernel<<<1, 1, 0, stream>>>(counters, activeCount, state->hostCounters);
+}
+
+// The instantiated graph of launch_narrow_iteration for this ping-pong side, captured on first use and whenever what the
+// launches depend on changes. nullptr = graphs are off or capture failed: launch directly. OFF by default
+// (ECHO_B200_GRAPHS=1 switches them on): with eight pipelines in flight the host-side launch cost is already hidden and a
+// narrow iteration is bound by the dependent latencies of its kernels — A/B on C1 / C3 / C4 / C5: 257 / 438 / 304 / 314 M
+// samples/s with graphs vs 268 / 446 / 303 / 317 without (variants/ab7.sh); parity is identical either way.
+template<int STACK, bool INST>
+static cudaGraphExec_t narrow_graph(WorkerState* state, const DeviceScene& scene, const EchoRenderParams& params, int current, unsigned int blocks, cudaStream_t stream)
+{
+	static const bool enabled = []
+	{
+		const char* value = std::getenv("ECHO_B200_GRAPHS");
+		return value && value[0] == '1';
+	}();
+
+	if (!enabled) return nullptr;
+
+	std::vector<unsigned char> key(sizeof(DeviceScene) + sizeof(EchoRenderParams) + sizeof(PathBuffers) + 3 * sizeof(int));
+	unsigned char* cursor = key.data();
+	int tags[3] = { STACK, INST ? 1 : 0, (int)blocks };
+	std::memcpy(cursor, &scene, sizeof(DeviceScene)); cursor += sizeof(DeviceScene);
+	std::memcpy(cursor, &params, sizeof(EchoRenderParams)); cursor += sizeof(EchoRenderParams);
+	std::memcpy(cursor, &state->paths, sizeof(PathBuffers)); cursor += sizeof(PathBuffers);
+	std::memcpy(cursor, tags, sizeof(tags));
+
+	if (key != state->graphKey)
+	{
+		for (cudaGraphExec_t& graph : state->narrowGraph)
+		{
+			if (graph) cudaGraphExecDestroy(graph);
+			graph = nullptr;
+		}
+
+		state->graphKey = key;
+	}
+
+	if (state->narrowGraph[current]) return state->narrowGraph[current];
+
+	cudaGraph_t graph = nullptr;
+	if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+	launch_narrow_iteration<STACK, INST>(state, scene, params, current, blocks, stream);
+	bool captured = cudaStreamEndCapture(stream, &graph) == cudaSuccess && graph;
+	if (captured) captured = cudaGraphInstantiate(&state->narrowGraph[current], graph, 0) == cudaSuccess;
+	if (graph) cudaGraphDestroy(graph);
+
+	if (!captured)
+	{
+		cudaGetLastError();
+		state->narrowGraph[current] = nullptr;
+	}
+
+	return state->narrowGraph[current];
+}
+
 // Evaluates `count` path slots already described in state->pixelXY / sampleIndex; radiance lands in state->sampleOut.
 template<int STACK, bool INST>
 static bool evaluate_paths(WorkerState* state, const DeviceScene& scene, const EchoRenderParams& params, uint32_t count, uint64_t& launches, cudaStream_t stream)
@@ -2045,9 +2139,36 @@ static bool evaluate_paths(WorkerState* state, const DeviceScene& scene, const E
 	uint32_t active = count;
 	int current = 0;
 
+	// what the shading kernels read of the parameters does not include the epoch (it only numbers the samples, in raygen):
+	// keeping it out of the captured launches lets one graph serve every epoch
+	EchoRenderParams iterationParams = params;
+	iterationParams.epochOffset = 0;
+
+	static const uint32_t narrowLimitForGraphs = []
+	{
+		const char* value = std::getenv("ECHO_B200_NARROW_LIMIT");
+		return value ? (uint32_t)std::atoll(value) : kNarrowLimit;
+	}();
+
 	while (active > 0)
 	{
 		unsigned int blocks = blocks_for(active);
+
+		cudaGraphExec_t graph = nullptr;
+		if (!gTimer.enabled && active < narrowLimitForGraphs) graph = narrow_graph<STACK, INST>(state, scene, iterationParams, current, blocks_for(narrowLimitForGraphs), stream);
+
+		if (graph)
+		{
+			// replay the narrow iteration as one graph (fixed grid: the kernels exit early past their counts)
+			if (!check_cuda(cudaGraphLaunch(graph, stream), "cudaGraphLaunch")) return false;
+			launches += 9;
+			if (!check_cuda(cudaGetLastError(), "wavefront launch")) return false;
+			if (!wait_for_iteration(state, stream)) return false;
+
+			active = state->hostCounters[0];
+			current ^= 1;
+			continue;
+		}
 
 		static int extendGrid = persistent_grid((const void*)extend_kernel<STACK>);
 		static int shadowGrid = persistent_grid((const void*)shadow_kernel<STACK>);
