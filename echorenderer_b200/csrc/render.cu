@@ -94,6 +94,10 @@ struct WorkerState
 // Tile batches are rendered by up to kWorkers concurrent pipelines (host thread + stream + wavefront buffers each): the
 // long, narrow tail of one batch's late bounces overlaps the wide first bounces of another, keeping the SMs busy.
 constexpr uint32_t kNarrowLimit = 262144; // below this many rays a bounce uses the one-thread-per-ray kernels
+// below this many live paths one kernel finishes them (tail_kernel). A/B of the threshold on C1 / C4 / C5 (variants/ab8.sh):
+// 0 -> 260 / 302 / 314 M samples/s, 4096 -> 317 / 313 / 325, 16384 -> 314 / 314 / 323, 65536 -> 250 / 308 / 264 (the longest path
+// of a big tail then runs alone for milliseconds), 262144 -> 140 / 277 / 187
+constexpr uint32_t kTailLimit = 8192;
 constexpr int kWorkers = 8; // A/B on C3/C4/C5: 1 -> 134, 2 -> 207, 4 -> 280, 8 -> 329, 12 -> 330 M samples/s on C5 (profiles/README.md)
 
 struct RenderState
@@ -1157,6 +1161,235 @@ __global__ void __launch_bounds__(kBlock) classify_kernel(DeviceScene scene, con
 	}
 }
 
+// What one loop body of PathTracedEvaluator.Evaluate produces for a path: statistics, the next ray if the path goes on, the
+// shadow ray of its light sample if one is needed.
+struct ShadeOut
+{
+	bool statInfinite = false, statBounce = false, statSpecular = false, statMis = false, statSampled = false, statChecked = false;
+	bool survive = false, shadow = false;
+	uint32_t id = 0u;
+	float4 nextOrigin = make_float4(0, 0, 0, 0), nextDirection = make_float4(0, 0, 0, 0), nextEnergy = make_float4(0, 0, 0, 0);
+	float4 shadowOrigin = make_float4(0, 0, 0, 0), shadowDirection = make_float4(0, 0, 0, 0), shadowValue = make_float4(0, 0, 0, 0);
+	PathLayers hitLayers = no_layers(); // the instance layers of the hit: the ignore hierarchy of both spawned rays
+};
+
+// One loop body of PathTracedEvaluator.Evaluate for the path whose ray sits in slot `raySlot` of the current queue and whose hit
+// record is in hitQueue[raySlot]. CLASS / KINDS prune the code to what a material-class queue can contain; CLASS < 0 keeps
+// everything (the tail kernel), `missed` then says whether the ray hit anything.
+template<int CLASS, uint32_t KINDS, bool INST>
+ECHO_DEVICE void shade_body(const DeviceScene& scene, const EchoRenderParams& params, const PathBuffers& paths, int current, uint32_t raySlot, bool missed, ShadeOut& o)
+{
+	bool &statInfinite = o.statInfinite, &statBounce = o.statBounce, &statSpecular = o.statSpecular, &statMis = o.statMis;
+	bool &statSampled = o.statSampled, &statChecked = o.statChecked, &survive = o.survive, &shadow = o.shadow;
+	uint32_t& id = o.id;
+	float4 &nextOrigin = o.nextOrigin, &nextDirection = o.nextDirection, &nextEnergy = o.nextEnergy;
+	float4 &shadowOrigin = o.shadowOrigin, &shadowDirection = o.shadowDirection, &shadowValue = o.shadowValue;
+	PathLayers& hitLayers = o.hitLayers;
+	(void)missed;
+
+	id = paths.rayPath[current][raySlot];
+
+	float4 rayA = paths.rayQueue[current][raySlot * 2u], rayB = paths.rayQueue[current][raySlot * 2u + 1u];
+	float4 energy4 = paths.energy[id];
+	float4 result4 = paths.result[id];
+
+	vec3 direction = { rayA.w, rayB.x, rayB.y };
+	rgb energy = as_rgb(energy4);
+	rgb result = as_rgb(result4);
+	float scatterPdfPrevious = energy4.w;
+	uint32_t state = __float_as_uint(result4.w);
+	uint32_t bounces = state & 0xFFFFu, mode = state >> 16;
+
+	if (CLASS == CLASS_MISS || (CLASS < 0 && missed))
+	{
+		// no intersection: PathTracedEvaluator.cs:48-52 (first), :112-130 (MIS), :137-143 (fallback)
+		statInfinite = true;
+
+		if (mode == MODE_FIRST) result = evaluate_infinite(scene, direction, true);
+		else if (mode == MODE_NO_MIS) result = result + energy * evaluate_infinite(scene, direction, false);
+		else
+		{
+			SurfacePoint oldPoint = { xyz(paths.oldPosition[id]), xyz(paths.oldNormal[id]) };
+			(void)oldPoint;
+
+			for (uint32_t index = 0; index < scene.infiniteLightCount; index++)
+			{
+				InfiniteLight light = load_infinite(scene, index);
+				if (light.delta) continue; // "Skip delta lights; they do not like MIS", :118
+
+				float pdf = scene.infinitePdf * infinite_pdf(scene, light, direction); // ProbabilityMass * light.ProbabilityDensity, :121-122
+				if (!positive(pdf)) continue;
+				float weight = power_heuristic(scatterPdfPrevious, pdf);
+				result = result + energy * (infinite_evaluate(scene, light, direction) * weight);
+			}
+		}
+
+		paths.result[id] = make4(result, result4.w);
+	}
+	else
+	{
+		// ---- PreparedScene.Interact, PreparedScene.cs:95-105 + GeometryCollection.GetContactInfo (:200-232) ----
+		float4 hit4 = paths.hitQueue[raySlot];
+		uint32_t token = __float_as_uint(hit4.x);
+		float distance = hit4.y;
+		vec2 uv = { hit4.z, hit4.w };
+		vec3 rayOrigin = xyz(rayA);
+
+		vec3 infoNormal, infoShading;
+		uint32_t materialIndex;
+
+		if (INST) hitLayers = load_layers(paths.hitLayers, raySlot);
+		Layer layer = find_layer<INST>(scene, hitLayers); // FindLayer, :97
+		const bool textured = INST && scene.textureCount != 0u;
+		vec2 texcoord = { 0.0f, 0.0f };
+
+		if (token_type(token) == ECHO_TOKEN_TYPE_TRIANGLE)
+		{
+			TriangleData triangle = load_triangle(scene, layer.info.triangleOffset + token_index(token));
+			materialIndex = layer.materialOffset + triangle.material; // instance.swatch[info.material], :102
+			infoNormal = triangle_normal(triangle);
+			infoShading = triangle_shading_normal(triangle, uv);
+			if (textured) texcoord = triangle_texcoord(scene, layer.info.triangleOffset + token_index(token), uv);
+		}
+		else
+		{
+			materialIndex = layer.materialOffset + __ldg(scene.sphereMaterial + layer.info.sphereOffset + token_index(token));
+			infoNormal = infoShading = sphere_normal(uv);
+			if (textured) texcoord = sphere_texcoord(uv);
+		}
+
+		SurfacePoint point;
+		point.position = direction * max_net(distance, kEpsilon) + rayOrigin; // TraceQuery.Position, TraceQuery.cs:76-82
+		point.normal = normalized(transform_direction(layer.inverse, infoNormal)); // :100-101 (the identity without layers)
+		vec3 shadeNormal = normalized(transform_direction(layer.inverse, infoShading));
+		vec3 outgoing = -direction;
+		if (textured) apply_normal_mapping(scene, materialIndex, texcoord, shadeNormal); // GeometryShade's constructor, GeometryShade.cs:17
+
+		MaterialRecord material = load_material(scene, materialIndex);
+		Bsdf bsdf;
+		material_scatter<INST>(scene, material, outgoing, point.normal, shadeNormal, bsdf, materialIndex, texcoord);
+
+		// ---- emission of the new vertex: ContributeEmissive (:305-311), MIS-weighted after a MIS bounce (:96-109) ----
+		if ((CLASS == CLASS_TERMINAL || CLASS < 0) && material.type == ECHO_MATERIAL_EMISSIVE && positive(emissive_power(material)))
+		{
+			float weight = 1.0f;
+			bool contribute = true;
+
+			if (mode == MODE_MIS)
+			{
+				SurfacePoint oldPoint = { xyz(paths.oldPosition[id]), xyz(paths.oldNormal[id]) };
+				float pmf = scene_probability_mass<INST>(scene, token, hitLayers, oldPoint);
+				contribute = positive(pmf);
+
+				if (contribute)
+				{
+					float pdf = scene_light_pdf<INST>(scene, token, hitLayers, oldPoint, direction);
+					contribute = positive(pdf);
+					if (contribute) weight = power_heuristic(scatterPdfPrevious, pmf * pdf);
+				}
+			}
+
+			if (contribute)
+			{
+				rgb emitted = dot(outgoing, point.normal) > 0.0f ? material_emission(material) : make_rgb(0.0f);
+				result = result + energy * (emitted * weight);
+			}
+		}
+
+		// ---- the loop body: `for (int depth = 0; depth < BounceLimit; depth++)`, :57 ----
+		if (bounces < (uint32_t)params.bounceLimit)
+		{
+			uint32_t key = paths.key[id];
+			uint32_t dimension = 4u + 6u * bounces;
+			vec2 bounceSample = { sample_value(key, dimension), sample_value(key, dimension + 1u) };
+			float survivalSample = sample_value(key, dimension + 2u);
+			float lightSample = sample_value(key, dimension + 3u);
+			vec2 radiantSample = { sample_value(key, dimension + 4u), sample_value(key, dimension + 5u) };
+
+			// Bounce, :326-354
+			vec3 incident;
+			int selectedType;
+			Sampled bounced = bsdf_sample<KINDS>(bsdf, outgoing, bounceSample, incident, selectedType);
+			rgb scatter = bounced.content * abs_bits(dot(incident, shadeNormal));
+			float scatterPdf = bounced.pdf;
+			statBounce = true;
+
+			bool mis = false;
+
+			if (!positive(scatterPdf) || (selectedType & FT_SPECULAR)) statSpecular = true;
+			else
+			{
+				// ---- ImportanceSampleRadiant, :162-207 ----
+				float lightPdf;
+				PathLayers lightLayers;
+				uint32_t light = scene_pick<INST>(scene, point, lightSample, lightPdf, lightLayers);
+
+				if (positive(lightPdf))
+				{
+					vec3 lightIncident;
+					float travel;
+					Sampled radiantSampled = scene_sample_light<INST>(scene, light, lightLayers, point, radiantSample, lightIncident, travel);
+					rgb radiant = radiantSampled.content;
+
+					float pdf = lightPdf * radiantSampled.pdf;
+					mis = token_is_area_light(light);
+
+					if (positive(pdf) && !is_zero(radiant))
+					{
+						statSampled = true;
+
+						rgb lightScatter = bsdf_evaluate<KINDS>(bsdf, outgoing, lightIncident);
+						lightScatter = lightScatter * abs_bits(dot(lightIncident, shadeNormal));
+
+						if (!is_zero(lightScatter))
+						{
+							statChecked = true;
+
+							radiant = radiant * (lightScatter / pdf);
+							if (mis) radiant = radiant * power_heuristic(pdf, bsdf_pdf<KINDS>(bsdf, outgoing, lightIncident));
+
+							shadow = true;
+							shadowOrigin = make_float4(point.position.x, point.position.y, point.position.z, lightIncident.x);
+							shadowDirection = make_float4(lightIncident.y, lightIncident.z, travel, __uint_as_float(token)); // SpawnOcclude: ignore = hit token
+							shadowValue = make4(energy * radiant, __uint_as_float(id));
+						}
+					}
+				}
+			}
+
+			// ---- Path.Continue, :282-293 ----
+			if (positive(scatterPdf))
+			{
+				energy = energy * (scatter / scatterPdf);
+
+				float rate = clamp01(params.survivability * luminance(energy)); // RussianRoulette, :313-320
+
+				if (!(survivalSample >= rate))
+				{
+					energy = energy / rate;
+					survive = true;
+
+					if (mis && !statSpecular)
+					{
+						statMis = true;
+						paths.oldPosition[id] = make4(point.position, 0.0f);
+						paths.oldNormal[id] = make4(point.normal, 0.0f);
+					}
+
+					uint32_t nextMode = (mis && !statSpecular) ? MODE_MIS : MODE_NO_MIS;
+					nextOrigin = make_float4(point.position.x, point.position.y, point.position.z, incident.x);
+					nextDirection = make_float4(incident.y, incident.z, kInfinity, __uint_as_float(token)); // SpawnTrace: ignore = hit token, TraceQuery.cs:88
+					nextEnergy = make4(energy, scatterPdf);
+					result4.w = __uint_as_float((bounces + 1u) | (nextMode << 16));
+				}
+			}
+		}
+
+		paths.result[id] = make4(result, result4.w);
+		if (survive) paths.energy[id] = nextEnergy;
+	}
+}
+
 // One loop body of PathTracedEvaluator.Evaluate for every path in a material-class queue.
 template<int CLASS, uint32_t KINDS, bool INST>
 __global__ void __launch_bounds__(kBlock) shade_kernel(DeviceScene scene, EchoRenderParams params, const uint32_t* __restrict__ queue,
@@ -1165,220 +1398,14 @@ __global__ void __launch_bounds__(kBlock) shade_kernel(DeviceScene scene, EchoRe
 	uint32_t i = blockIdx.x * kBlock + threadIdx.x;
 	bool active = i < *queueCount;
 
-	bool statInfinite = false, statBounce = false, statSpecular = false, statMis = false;
-	bool statSampled = false, statChecked = false;
-	bool survive = false, shadow = false;
-	uint32_t id = 0u;
+	ShadeOut o;
+	if (active) shade_body<CLASS, KINDS, INST>(scene, params, paths, current, queue[i], false, o);
 
-	float4 nextOrigin = make_float4(0, 0, 0, 0), nextDirection = make_float4(0, 0, 0, 0), nextEnergy = make_float4(0, 0, 0, 0);
-	float4 shadowOrigin = make_float4(0, 0, 0, 0), shadowDirection = make_float4(0, 0, 0, 0), shadowValue = make_float4(0, 0, 0, 0);
-	PathLayers hitLayers = no_layers(); // the instance layers of the hit: the ignore hierarchy of both spawned rays
-
-	if (active)
-	{
-		uint32_t raySlot = queue[i];
-		id = paths.rayPath[current][raySlot];
-
-		float4 rayA = paths.rayQueue[current][raySlot * 2u], rayB = paths.rayQueue[current][raySlot * 2u + 1u];
-		float4 energy4 = paths.energy[id];
-		float4 result4 = paths.result[id];
-
-		vec3 direction = { rayA.w, rayB.x, rayB.y };
-		rgb energy = as_rgb(energy4);
-		rgb result = as_rgb(result4);
-		float scatterPdfPrevious = energy4.w;
-		uint32_t state = __float_as_uint(result4.w);
-		uint32_t bounces = state & 0xFFFFu, mode = state >> 16;
-
-		if (CLASS == CLASS_MISS)
-		{
-			// no intersection: PathTracedEvaluator.cs:48-52 (first), :112-130 (MIS), :137-143 (fallback)
-			statInfinite = true;
-
-			if (mode == MODE_FIRST) result = evaluate_infinite(scene, direction, true);
-			else if (mode == MODE_NO_MIS) result = result + energy * evaluate_infinite(scene, direction, false);
-			else
-			{
-				SurfacePoint oldPoint = { xyz(paths.oldPosition[id]), xyz(paths.oldNormal[id]) };
-				(void)oldPoint;
-
-				for (uint32_t index = 0; index < scene.infiniteLightCount; index++)
-				{
-					InfiniteLight light = load_infinite(scene, index);
-					if (light.delta) continue; // "Skip delta lights; they do not like MIS", :118
-
-					float pdf = scene.infinitePdf * infinite_pdf(scene, light, direction); // ProbabilityMass * light.ProbabilityDensity, :121-122
-					if (!positive(pdf)) continue;
-					float weight = power_heuristic(scatterPdfPrevious, pdf);
-					result = result + energy * (infinite_evaluate(scene, light, direction) * weight);
-				}
-			}
-
-			paths.result[id] = make4(result, result4.w);
-		}
-		else
-		{
-			// ---- PreparedScene.Interact, PreparedScene.cs:95-105 + GeometryCollection.GetContactInfo (:200-232) ----
-			float4 hit4 = paths.hitQueue[raySlot];
-			uint32_t token = __float_as_uint(hit4.x);
-			float distance = hit4.y;
-			vec2 uv = { hit4.z, hit4.w };
-			vec3 rayOrigin = xyz(rayA);
-
-			vec3 infoNormal, infoShading;
-			uint32_t materialIndex;
-
-			if (INST) hitLayers = load_layers(paths.hitLayers, raySlot);
-			Layer layer = find_layer<INST>(scene, hitLayers); // FindLayer, :97
-			const bool textured = INST && scene.textureCount != 0u;
-			vec2 texcoord = { 0.0f, 0.0f };
-
-			if (token_type(token) == ECHO_TOKEN_TYPE_TRIANGLE)
-			{
-				TriangleData triangle = load_triangle(scene, layer.info.triangleOffset + token_index(token));
-				materialIndex = layer.materialOffset + triangle.material; // instance.swatch[info.material], :102
-				infoNormal = triangle_normal(triangle);
-				infoShading = triangle_shading_normal(triangle, uv);
-				if (textured) texcoord = triangle_texcoord(scene, layer.info.triangleOffset + token_index(token), uv);
-			}
-			else
-			{
-				materialIndex = layer.materialOffset + __ldg(scene.sphereMaterial + layer.info.sphereOffset + token_index(token));
-				infoNormal = infoShading = sphere_normal(uv);
-				if (textured) texcoord = sphere_texcoord(uv);
-			}
-
-			SurfacePoint point;
-			point.position = direction * max_net(distance, kEpsilon) + rayOrigin; // TraceQuery.Position, TraceQuery.cs:76-82
-			point.normal = normalized(transform_direction(layer.inverse, infoNormal)); // :100-101 (the identity without layers)
-			vec3 shadeNormal = normalized(transform_direction(layer.inverse, infoShading));
-			vec3 outgoing = -direction;
-			if (textured) apply_normal_mapping(scene, materialIndex, texcoord, shadeNormal); // GeometryShade's constructor, GeometryShade.cs:17
-
-			MaterialRecord material = load_material(scene, materialIndex);
-			Bsdf bsdf;
-			material_scatter<INST>(scene, material, outgoing, point.normal, shadeNormal, bsdf, materialIndex, texcoord);
-
-			// ---- emission of the new vertex: ContributeEmissive (:305-311), MIS-weighted after a MIS bounce (:96-109) ----
-			if (CLASS == CLASS_TERMINAL && material.type == ECHO_MATERIAL_EMISSIVE && positive(emissive_power(material)))
-			{
-				float weight = 1.0f;
-				bool contribute = true;
-
-				if (mode == MODE_MIS)
-				{
-					SurfacePoint oldPoint = { xyz(paths.oldPosition[id]), xyz(paths.oldNormal[id]) };
-					float pmf = scene_probability_mass<INST>(scene, token, hitLayers, oldPoint);
-					contribute = positive(pmf);
-
-					if (contribute)
-					{
-						float pdf = scene_light_pdf<INST>(scene, token, hitLayers, oldPoint, direction);
-						contribute = positive(pdf);
-						if (contribute) weight = power_heuristic(scatterPdfPrevious, pmf * pdf);
-					}
-				}
-
-				if (contribute)
-				{
-					rgb emitted = dot(outgoing, point.normal) > 0.0f ? material_emission(material) : make_rgb(0.0f);
-					result = result + energy * (emitted * weight);
-				}
-			}
-
-			// ---- the loop body: `for (int depth = 0; depth < BounceLimit; depth++)`, :57 ----
-			if (bounces < (uint32_t)params.bounceLimit)
-			{
-				uint32_t key = paths.key[id];
-				uint32_t dimension = 4u + 6u * bounces;
-				vec2 bounceSample = { sample_value(key, dimension), sample_value(key, dimension + 1u) };
-				float survivalSample = sample_value(key, dimension + 2u);
-				float lightSample = sample_value(key, dimension + 3u);
-				vec2 radiantSample = { sample_value(key, dimension + 4u), sample_value(key, dimension + 5u) };
-
-				// Bounce, :326-354
-				vec3 incident;
-				int selectedType;
-				Sampled bounced = bsdf_sample<KINDS>(bsdf, outgoing, bounceSample, incident, selectedType);
-				rgb scatter = bounced.content * abs_bits(dot(incident, shadeNormal));
-				float scatterPdf = bounced.pdf;
-				statBounce = true;
-
-				bool mis = false;
-
-				if (!positive(scatterPdf) || (selectedType & FT_SPECULAR)) statSpecular = true;
-				else
-				{
-					// ---- ImportanceSampleRadiant, :162-207 ----
-					float lightPdf;
-					PathLayers lightLayers;
-					uint32_t light = scene_pick<INST>(scene, point, lightSample, lightPdf, lightLayers);
-
-					if (positive(lightPdf))
-					{
-						vec3 lightIncident;
-						float travel;
-						Sampled radiantSampled = scene_sample_light<INST>(scene, light, lightLayers, point, radiantSample, lightIncident, travel);
-						rgb radiant = radiantSampled.content;
-
-						float pdf = lightPdf * radiantSampled.pdf;
-						mis = token_is_area_light(light);
-
-						if (positive(pdf) && !is_zero(radiant))
-						{
-							statSampled = true;
-
-							rgb lightScatter = bsdf_evaluate<KINDS>(bsdf, outgoing, lightIncident);
-							lightScatter = lightScatter * abs_bits(dot(lightIncident, shadeNormal));
-
-							if (!is_zero(lightScatter))
-							{
-								statChecked = true;
-
-								radiant = radiant * (lightScatter / pdf);
-								if (mis) radiant = radiant * power_heuristic(pdf, bsdf_pdf<KINDS>(bsdf, outgoing, lightIncident));
-
-								shadow = true;
-								shadowOrigin = make_float4(point.position.x, point.position.y, point.position.z, lightIncident.x);
-								shadowDirection = make_float4(lightIncident.y, lightIncident.z, travel, __uint_as_float(token)); // SpawnOcclude: ignore = hit token
-								shadowValue = make4(energy * radiant, __uint_as_float(id));
-							}
-						}
-					}
-				}
-
-				// ---- Path.Continue, :282-293 ----
-				if (positive(scatterPdf))
-				{
-					energy = energy * (scatter / scatterPdf);
-
-					float rate = clamp01(params.survivability * luminance(energy)); // RussianRoulette, :313-320
-
-					if (!(survivalSample >= rate))
-					{
-						energy = energy / rate;
-						survive = true;
-
-						if (mis && !statSpecular)
-						{
-							statMis = true;
-							paths.oldPosition[id] = make4(point.position, 0.0f);
-							paths.oldNormal[id] = make4(point.normal, 0.0f);
-						}
-
-						uint32_t nextMode = (mis && !statSpecular) ? MODE_MIS : MODE_NO_MIS;
-						nextOrigin = make_float4(point.position.x, point.position.y, point.position.z, incident.x);
-						nextDirection = make_float4(incident.y, incident.z, kInfinity, __uint_as_float(token)); // SpawnTrace: ignore = hit token, TraceQuery.cs:88
-						nextEnergy = make4(energy, scatterPdf);
-						result4.w = __uint_as_float((bounces + 1u) | (nextMode << 16));
-					}
-				}
-			}
-
-			paths.result[id] = make4(result, result4.w);
-			if (survive) paths.energy[id] = nextEnergy;
-		}
-	}
+	const bool survive = o.survive, shadow = o.shadow;
+	const bool statInfinite = o.statInfinite, statBounce = o.statBounce, statSpecular = o.statSpecular, statMis = o.statMis, statSampled = o.statSampled, statChecked = o.statChecked;
+	const uint32_t id = o.id;
+	const float4 nextOrigin = o.nextOrigin, nextDirection = o.nextDirection, shadowOrigin = o.shadowOrigin, shadowDirection = o.shadowDirection, shadowValue = o.shadowValue;
+	const PathLayers& hitLayers = o.hitLayers;
 
 	uint32_t nextSlot = queue_slot(paths.counters + COUNTER_NEXT, survive);
 
@@ -1657,6 +1684,106 @@ __global__ void __launch_bounds__(kBlock) auxiliary_kernel(DeviceScene scene, Ec
 	}
 
 	out[i] = result;
+}
+
+// The tail of a wavefront: once only a few thousand paths are alive, every further bounce still costs nine dependent kernel
+// launches whose duration no longer depends on the ray count. This kernel finishes those paths instead: one thread per path
+// loops trace -> shade -> shadow -> next bounce until its path ends, with the same device functions as the wavefront
+// kernels (shade_body with every lobe compiled in) and the same per-path buffers, so every path sees the same sequence of
+// operations and its radiance keeps its bits.
+template<int STACK, bool INST>
+__global__ void __launch_bounds__(kBlock) tail_kernel(DeviceScene scene, EchoRenderParams params, const uint32_t* __restrict__ queueCount, PathBuffers paths, int current)
+{
+	uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+	bool active = i < *queueCount;
+	const bool packs = INST && scene.packCount != 0u;
+	uint32_t counted[9] = { 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u }; // trace, occlude, passed, infinite, bounce, specular, mis, sampled, checked
+
+	while (active)
+	{
+		// ---- Path.Advance: scene.Trace (PathTracedEvaluator.cs:261-271) ----
+		float4 a = paths.rayQueue[current][i * 2u], b = paths.rayQueue[current][i * 2u + 1u];
+		float distance = b.z;
+		uint32_t token = ECHO_TOKEN_EMPTY;
+		vec2 uv = { 0.0f, 0.0f };
+		bool hit = false;
+
+		if (packs)
+		{
+			PathLayers ignore = load_layers(paths.rayLayers[current], i);
+			PathLayers hitLayer = no_layers();
+
+			if (positive(b.z))
+			{
+				traverse_instanced<STACK, false, false>(scene, { a.x, a.y, a.z }, { a.w, b.x, b.y }, __float_as_uint(b.w), ignore.tokens, ignore.count,
+				                                        distance, token, uv, hitLayer.tokens, hitLayer.count, nullptr);
+				hit = distance < b.z;
+			}
+
+			store_layers(paths.hitLayers, i, hit ? hitLayer : no_layers());
+		}
+		else hit = scene_trace<STACK, false>(scene, { a.x, a.y, a.z }, { a.w, b.x, b.y }, __float_as_uint(b.w), distance, token, uv, nullptr);
+
+		paths.hitQueue[i] = make_float4(__uint_as_float(hit ? token : ECHO_TOKEN_EMPTY), hit ? distance : b.z, uv.x, uv.y);
+		++counted[0];
+
+		// ---- one loop body of Evaluate ----
+		ShadeOut o;
+		shade_body<-1, KINDS_ALL, INST>(scene, params, paths, current, i, !hit, o);
+		counted[3] += o.statInfinite; counted[4] += o.statBounce; counted[5] += o.statSpecular;
+		counted[6] += o.statMis; counted[7] += o.statSampled; counted[8] += o.statChecked;
+
+		// ---- scene.Occlude of ImportanceSampleRadiant (:196-197) ----
+		if (o.shadow)
+		{
+			vec3 origin = xyz(o.shadowOrigin), direction = { o.shadowOrigin.w, o.shadowDirection.x, o.shadowDirection.y };
+			float travel = o.shadowDirection.z;
+			uint32_t ignore = __float_as_uint(o.shadowDirection.w);
+			bool occluded = false;
+
+			if (packs)
+			{
+				PathLayers unusedLayers = no_layers();
+				uint32_t unusedToken = ECHO_TOKEN_EMPTY;
+				vec2 unusedUV = { 0.0f, 0.0f };
+				if (positive(travel))
+					occluded = traverse_instanced<STACK, true, false>(scene, origin, direction, ignore, o.hitLayers.tokens, o.hitLayers.count, travel, unusedToken, unusedUV,
+					                                                  unusedLayers.tokens, unusedLayers.count, nullptr);
+			}
+			else occluded = scene_occlude<STACK, false>(scene, origin, direction, ignore, travel, nullptr);
+
+			++counted[1];
+
+			if (!occluded)
+			{
+				uint32_t id = __float_as_uint(o.shadowValue.w);
+				float4 total = paths.result[id];
+				total.x += o.shadowValue.x;
+				total.y += o.shadowValue.y;
+				total.z += o.shadowValue.z;
+				paths.result[id] = total;
+				++counted[2];
+			}
+		}
+
+		if (!o.survive) break;
+
+		// query.SpawnTrace: the path keeps its slot of the current queue
+		paths.rayQueue[current][i * 2u] = o.nextOrigin;
+		paths.rayQueue[current][i * 2u + 1u] = o.nextDirection;
+		if (INST) store_layers(paths.rayLayers[current], i, o.hitLayers);
+	}
+
+	const int slots[9] = { STAT_TRACE_QUERIES, STAT_OCCLUDE_QUERIES, STAT_LIGHT_OCCLUSION_PASSED, STAT_LIGHT_EVALUATED_INFINITE, STAT_BOUNCE_CREATED,
+	                       STAT_BOUNCE_SPECULAR, STAT_BOUNCE_MIS, STAT_LIGHT_SAMPLED, STAT_LIGHT_OCCLUSION_CHECKED };
+
+#pragma unroll
+	for (int k = 0; k < 9; k++)
+	{
+		uint32_t value = counted[k];
+		for (int offset = 16; offset > 0; offset >>= 1) value += __shfl_down_sync(0xFFFFFFFFu, value, offset);
+		if ((threadIdx.x & 31u) == 0u && value) atomicAdd(paths.stats + slots[k], (unsigned long long)value);
+	}
 }
 
 __global__ void __launch_bounds__(kBlock) finish_kernel(uint32_t count, PathBuffers paths, float4* __restrict__ out)
@@ -2153,6 +2280,18 @@ static bool evaluate_paths(WorkerState* state, const DeviceScene& scene, const E
 	while (active > 0)
 	{
 		unsigned int blocks = blocks_for(active);
+
+		// the tail: finish the few paths that are left in one launch (ECHO_B200_TAIL_LIMIT, 0 = never)
+		const char* tailText = std::getenv("ECHO_B200_TAIL_LIMIT");
+		uint32_t tailLimit = tailText ? (uint32_t)std::atoll(tailText) : kTailLimit;
+
+		if (!gTimer.enabled && active < tailLimit)
+		{
+			tail_kernel<STACK, INST><<<blocks, kBlock, 0, stream>>>(scene, iterationParams, activeCount, paths, current);
+			if (!check_cuda(cudaGetLastError(), "tail_kernel launch")) return false;
+			++launches;
+			break;
+		}
 
 		cudaGraphExec_t graph = nullptr;
 		if (!gTimer.enabled && active < narrowLimitForGraphs) graph = narrow_graph<STACK, INST>(state, scene, iterationParams, current, blocks_for(narrowLimitForGraphs), stream);
