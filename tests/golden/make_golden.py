@@ -30,5 +30,24 @@ pixels = np.repeat(np.stack([xs.reshape(-1), ys.reshape(-1)], axis=-1), 2, axis=
 index = np.tile(np.arange(2, dtype=np.uint32), len(pixels) // 2)
 out["cornell_radiance_bits"] = oracle.evaluate_samples(params, pixels, index).view(np.uint32)
 
+# the rows added after the hot path: instanced packs, image textures + environment light, the auxiliary passes
+instanced = host.prepare(scenes.instanced_scene(grid=3, rings=8, segments=10))
+oracle = ol.OracleScene(instanced)
+hits, layers = oracle.trace_hierarchy(scenes.random_rays(instanced.bounds, 4096, seed=21))
+out["instanced_token"], out["instanced_distance_bits"] = hits["token"], hits["distance"].view(np.uint32)
+out["instanced_layers"] = np.concatenate([layers["instanceCount"][:, None], layers["instances"]], axis=1)
+params = structs.render_params(32, 32, 16, extend=2, seed=9, bounce_limit=12)
+half_pixels, half_index = np.ascontiguousarray(pixels[::2]), np.ascontiguousarray(index[::2])
+out["instanced_radiance_bits"] = oracle.evaluate_samples(params, half_pixels, half_index).view(np.uint32)
+
+textured = host.prepare(scenes.textured_scene(rings=8, segments=10))
+oracle = ol.OracleScene(textured)
+out["textured_radiance_bits"] = oracle.evaluate_samples(params, half_pixels, half_index).view(np.uint32)
+for name, code in (("albedo", structs.EVALUATOR_ALBEDO | structs.EVALUATOR_DIVERGE_ONCE), ("normal_depth", structs.EVALUATOR_NORMAL_DEPTH)):
+    aux = structs.render_params(32, 32, 16, extend=2, seed=9, evaluator=code)
+    value = np.zeros((len(half_index), 4), dtype=np.float32)
+    oracle.lib.oracle_evaluate_samples4(oracle.handle, ol.ptr(aux), ol.ptr(half_pixels), ol.ptr(half_index), len(value), ol.ptr(value), 4, 0)
+    out[f"textured_{name}_bits"] = value.view(np.uint32)
+
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "oracle_regression.npz"), **out)
 print({k: v.shape for k, v in out.items()})

@@ -233,6 +233,25 @@ def test_golden_fixtures(cornell, terrain_small):
     radiance = oracle.evaluate_samples(params, pixels, index)
     assert np.array_equal(radiance.view(np.uint32), data["cornell_radiance_bits"])
 
+    # the rows added after the hot path: instanced packs, image textures, the auxiliary passes
+    instanced = host.prepare(scenes.instanced_scene(grid=3, rings=8, segments=10))
+    oracle = ol.OracleScene(instanced)
+    hits, layers = oracle.trace_hierarchy(scenes.random_rays(instanced.bounds, 4096, seed=21))
+    assert np.array_equal(hits["token"], data["instanced_token"]) and np.array_equal(hits["distance"].view(np.uint32), data["instanced_distance_bits"])
+    assert np.array_equal(np.concatenate([layers["instanceCount"][:, None], layers["instances"]], axis=1), data["instanced_layers"])
+    params = structs.render_params(32, 32, 16, extend=2, seed=9, bounce_limit=12)
+    half_pixels, half_index = np.ascontiguousarray(pixels[::2]), np.ascontiguousarray(index[::2])
+    assert np.array_equal(oracle.evaluate_samples(params, half_pixels, half_index).view(np.uint32), data["instanced_radiance_bits"])
+
+    textured = host.prepare(scenes.textured_scene(rings=8, segments=10))
+    oracle = ol.OracleScene(textured)
+    assert np.array_equal(oracle.evaluate_samples(params, half_pixels, half_index).view(np.uint32), data["textured_radiance_bits"])
+    for name, code in (("albedo", structs.EVALUATOR_ALBEDO | structs.EVALUATOR_DIVERGE_ONCE), ("normal_depth", structs.EVALUATOR_NORMAL_DEPTH)):
+        aux = structs.render_params(32, 32, 16, extend=2, seed=9, evaluator=code)
+        value = np.zeros((len(half_index), 4), dtype=np.float32)
+        oracle.lib.oracle_evaluate_samples4(oracle.handle, ol.ptr(aux), ol.ptr(half_pixels), ol.ptr(half_index), len(value), ol.ptr(value), 4, 0)
+        assert np.array_equal(value.view(np.uint32), data[f"textured_{name}_bits"])
+
 
 @pytest.mark.parametrize("angle", [0.0, 2.0])
 def test_directional_light_irradiance(angle):
