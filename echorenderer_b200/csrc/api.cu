@@ -59,6 +59,7 @@ bool upload(EchoScene* scene, const std::vector<T>& host, const T*& device)
 	size_t bytes = sizeof(T) * std::max<size_t>(host.size(), 1);
 	if (!check_cuda(cudaMalloc(&p, bytes), "cudaMalloc(scene)")) return false;
 	scene->allocations.push_back(p);
+	if (host.empty() && !check_cuda(cudaMemset(p, 0, bytes), "cudaMemset(scene)")) return false; // the placeholder of an empty array
 	if (!host.empty() && !check_cuda(cudaMemcpy(p, host.data(), sizeof(T) * host.size(), cudaMemcpyHostToDevice), "cudaMemcpy(scene)")) return false;
 	device = (const T*)p;
 	return true;
@@ -588,6 +589,21 @@ int32_t echo_b200_scene_commit(EchoScene* scene)
 	d.materialTextures = reinterpret_cast<const uint4*>(deviceMaterialTextures);
 	d.texels = reinterpret_cast<const float4*>(deviceTexels);
 	d.textureCount = (uint32_t)scene->textures.size();
+	d.texelCount = (uint32_t)(scene->texels.size() / 4);
+	d.distributionCount = (uint32_t)scene->distributions.size();
+
+#ifdef ECHO_BOUNDS_CHECK
+	{
+		void* flag = nullptr;
+		if (!check_cuda(cudaMalloc(&flag, sizeof(unsigned int)), "cudaMalloc(violations)") || !check_cuda(cudaMemset(flag, 0, sizeof(unsigned int)), "cudaMemset(violations)"))
+		{
+			free_device(scene);
+			return ECHO_B200_ERR_CUDA;
+		}
+		scene->allocations.push_back(flag);
+		d.violations = (unsigned int*)flag;
+	}
+#endif
 	d.packCount = (uint32_t)scene->packs.size();
 	d.instanceCount = (uint32_t)scene->instances.size();
 	d.infiniteThreshold = scene->infiniteThreshold;
@@ -755,6 +771,22 @@ int32_t echo_b200_debug_evaluate_samples(EchoScene* scene, const EchoRenderParam
 	DeviceGuard guard(scene->device);
 	if (!guard.ok) return ECHO_B200_ERR_NO_DEVICE;
 	return evaluate_sample_list(scene->render, scene->d, *params, 3, pixelXY, sampleIndex, n, outRGB, scene->stream) ? ECHO_B200_OK : ECHO_B200_ERR_CUDA;
+}
+
+// Bounds-check builds (-DECHO_BOUNDS_CHECK): the bit set of failed checks since commit (echo_scene.cuh CHECK_*); release builds
+// report 0xFFFFFFFF = "not compiled in". Synchronises the device.
+int32_t echo_b200_debug_bounds_violations(EchoScene* scene, uint32_t* out)
+{
+	if (!scene || !out) return fail(ECHO_B200_ERR_INVALID, "null argument");
+	*out = 0xFFFFFFFFu;
+#ifdef ECHO_BOUNDS_CHECK
+	if (!scene->committed || !scene->d.violations) { *out = 0u; return ECHO_B200_OK; }
+	DeviceGuard guard(scene->device);
+	if (!guard.ok) return ECHO_B200_ERR_NO_DEVICE;
+	if (!check_cuda(cudaDeviceSynchronize(), "bounds violations") || !check_cuda(cudaMemcpy(out, scene->d.violations, sizeof(uint32_t), cudaMemcpyDeviceToHost), "cudaMemcpy(violations)"))
+		return ECHO_B200_ERR_CUDA;
+#endif
+	return ECHO_B200_OK;
 }
 
 int32_t echo_b200_debug_evaluate_samples4(EchoScene* scene, const EchoRenderParams* params, const int32_t* pixelXY, const uint32_t* sampleIndex, uint64_t n, float* outRGBA)

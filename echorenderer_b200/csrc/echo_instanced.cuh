@@ -50,6 +50,7 @@ ECHO_DEVICE PackInfo whole_scene_pack(const DeviceScene& scene) // a scene witho
 ECHO_DEVICE PackInfo load_pack_info(const DeviceScene& scene, uint32_t pack)
 {
 	if (scene.packCount == 0u) return whole_scene_pack(scene);
+	ECHO_CHECK(scene, pack < scene.packCount, CHECK_PACK);
 	const uint4* data = scene.packs + (size_t)pack * 4;
 	uint4 a = __ldg(data), b = __ldg(data + 1), c = __ldg(data + 2), d = __ldg(data + 3);
 	// a = nodeOffset nodeCount maxDepth triangleOffset | b = triangleCount sphereOffset sphereCount instanceOffset
@@ -152,6 +153,8 @@ ECHO_DEVICE Layer find_layer(const DeviceScene& scene, const PathLayers& layers)
 
 	for (uint32_t k = 0; k < layers.count; k++)
 	{
+		ECHO_CHECK(scene, layers.count <= ECHO_MAX_INSTANCE_LAYERS, CHECK_LAYER);
+		ECHO_CHECK(scene, layer.info.instanceOffset + token_index(layers.tokens[k]) < scene.instanceCount, CHECK_INSTANCE);
 		const float4* data = instance_data(scene, layer.info.instanceOffset + token_index(layers.tokens[k]));
 		layer.forward = multiply_rows(data, layer.forward);
 		layer.inverse = multiply_rows(data + 3, layer.inverse);
@@ -166,6 +169,7 @@ ECHO_DEVICE Layer find_layer(const DeviceScene& scene, const PathLayers& layers)
 
 ECHO_DEVICE PackView load_pack(const DeviceScene& scene, uint32_t pack)
 {
+	ECHO_CHECK(scene, pack < scene.packCount, CHECK_PACK);
 	const uint4* data = scene.packs + (size_t)pack * 4; // EchoPack, 64 bytes
 	uint4 a = __ldg(data), b = __ldg(data + 1), c = __ldg(data + 2);
 	// a = nodeOffset nodeCount maxDepth triangleOffset | b = triangleCount sphereOffset sphereCount instanceOffset | c = instanceCount materialOffset ..
@@ -248,8 +252,10 @@ ECHO_DEVICE bool traverse_instanced(const DeviceScene& scene, vec3 origin, vec3 
 
 		NodeData node;
 		{
+			ECHO_CHECK(scene, pack.nodeOffset + token_index(nodeToken) < scene.nodeCount, CHECK_NODE);
 			DeviceScene view = scene; // node array of the current pack
 			view.nodes = scene.nodes + (size_t)pack.nodeOffset * 8;
+			view.nodeCount = scene.nodeCount - pack.nodeOffset;
 			load_node(view, token_index(nodeToken), orders, node);
 		}
 
@@ -274,6 +280,7 @@ ECHO_DEVICE bool traverse_instanced(const DeviceScene& scene, vec3 origin, vec3 
 
 			if (type == ECHO_TOKEN_TYPE_NODE)
 			{
+				ECHO_CHECK(scene, next < (uint32_t)STACK, CHECK_STACK);
 				stack[next++] = make_uint2(child, __float_as_uint(hit));
 			}
 			else if (type == ECHO_TOKEN_TYPE_TRIANGLE)
@@ -281,6 +288,7 @@ ECHO_DEVICE bool traverse_instanced(const DeviceScene& scene, vec3 origin, vec3 
 				if (ignoreHere && child == ignore) continue; // query.ignore == query.current, GeometryCollection.cs:93-94
 				if (COUNT) ++counts->triangles;
 
+				ECHO_CHECK(scene, pack.triangleOffset + token_index(child) < scene.triangleCount, CHECK_TRIANGLE);
 				const float4* data = scene.triHot + ((size_t)pack.triangleOffset + token_index(child)) * 3;
 				float4 a = __ldg(data), b = __ldg(data + 1), c = __ldg(data + 2);
 
@@ -306,6 +314,7 @@ ECHO_DEVICE bool traverse_instanced(const DeviceScene& scene, vec3 origin, vec3 
 			else if (type == ECHO_TOKEN_TYPE_SPHERE)
 			{
 				if (COUNT) ++counts->spheres;
+				ECHO_CHECK(scene, pack.sphereOffset + token_index(child) < scene.sphereCount, CHECK_SPHERE);
 				float4 sphere = __ldg(scene.spheres + pack.sphereOffset + token_index(child));
 				bool findFar = ignoreHere && child == ignore;
 
@@ -332,6 +341,8 @@ ECHO_DEVICE bool traverse_instanced(const DeviceScene& scene, vec3 origin, vec3 
 			{
 				// query.current.Push(token); instances[token.Index].Trace(ref query)
 				uint32_t instance = pack.instanceOffset + token_index(child);
+				ECHO_CHECK(scene, instance < scene.instanceCount, CHECK_INSTANCE);
+				ECHO_CHECK(scene, next < (uint32_t)STACK, CHECK_STACK);
 				const float4* data = instance_data(scene, instance);
 				float4 scales = __ldg(data + 6);
 

@@ -37,15 +37,33 @@ struct DeviceScene
 	const uint4* packs;            // 4 x uint4 per EchoPack; null when the scene is a single pack
 	const float4* instances;       // 8 x float4 per EchoInstance
 
+	unsigned int* violations;      // ECHO_BOUNDS_CHECK builds: bit k set = check k failed somewhere (see ECHO_CHECK); null otherwise
+
 	uint32_t nodeCount, triangleCount, sphereCount, materialCount;
 	uint32_t lightNodeCount, emitterCount, pointLightCount, infiniteLightCount;
 	uint32_t maxDepth;             // quad depth whose 3 * maxDepth + 1 stack entries serve the deepest chain of packs
 	uint32_t packCount, instanceCount, textureCount;
+	uint32_t texelCount, distributionCount; // extents of `texels` and `distributions`, for the bounds-check build
 	float infiniteThreshold, infinitePdf;
 	float boundRadius; // Accelerator.SphereBound.radius, read by the NormalDepth evaluator
 
 	EchoCamera camera;
 };
+
+// compute-sanitizer is not available on the GPU pool, so the library can be built with -DECHO_BOUNDS_CHECK (variants/bounds.sh):
+// every index the kernels derive from scene data or from a stack pointer is then checked before use and a failure sets a bit
+// that tests read back through echo_b200_debug_bounds_violations. Release builds compile the checks out.
+enum : int
+{
+	CHECK_NODE = 0, CHECK_TRIANGLE, CHECK_SPHERE, CHECK_STACK, CHECK_INSTANCE, CHECK_PACK, CHECK_MATERIAL, CHECK_LIGHT_NODE, CHECK_EMITTER,
+	CHECK_POINT_LIGHT, CHECK_INFINITE_LIGHT, CHECK_TEXTURE, CHECK_TEXEL, CHECK_DISTRIBUTION, CHECK_LAYER
+};
+
+#ifdef ECHO_BOUNDS_CHECK
+#define ECHO_CHECK(scene, condition, code) do { if (!(condition) && (scene).violations) atomicOr((scene).violations, 1u << (code)); } while (0)
+#else
+#define ECHO_CHECK(scene, condition, code) do {} while (0)
+#endif
 
 struct VisitCounts
 {
@@ -210,6 +228,7 @@ struct NodeData
 
 ECHO_DEVICE void load_node(const DeviceScene& scene, uint32_t index, uint32_t orders, NodeData& node)
 {
+	ECHO_CHECK(scene, index < scene.nodeCount, CHECK_NODE);
 	const float4* base = scene.nodes + (size_t)index * 8;
 	node.minX = __ldg(base + 0);
 	node.minY = __ldg(base + 1);
@@ -267,12 +286,14 @@ ECHO_DEVICE void trace_closest(const DeviceScene& scene, vec3 origin, vec3 direc
 
 			if (type == ECHO_TOKEN_TYPE_NODE)
 			{
+				ECHO_CHECK(scene, next < STACK, CHECK_STACK);
 				stack[next++] = make_uint2(child, __float_as_uint(hit));
 			}
 			else if (type == ECHO_TOKEN_TYPE_TRIANGLE)
 			{
 				if (child == ignore) continue; // GeometryCollection.cs:93-94
 				if (COUNT) ++counts->triangles;
+				ECHO_CHECK(scene, token_index(child) < scene.triangleCount, CHECK_TRIANGLE);
 
 				const float4* data = scene.triHot + (size_t)token_index(child) * 3;
 				float4 a = __ldg(data), b = __ldg(data + 1), c = __ldg(data + 2);
@@ -290,6 +311,7 @@ ECHO_DEVICE void trace_closest(const DeviceScene& scene, vec3 origin, vec3 direc
 			else if (type == ECHO_TOKEN_TYPE_SPHERE)
 			{
 				if (COUNT) ++counts->spheres;
+				ECHO_CHECK(scene, token_index(child) < scene.sphereCount, CHECK_SPHERE);
 
 				vec2 hitUV;
 				float d = sphere_intersect(__ldg(scene.spheres + token_index(child)), origin, direction, hitUV, child == ignore);
@@ -342,12 +364,14 @@ ECHO_DEVICE bool trace_any(const DeviceScene& scene, vec3 origin, vec3 direction
 
 			if (type == ECHO_TOKEN_TYPE_NODE)
 			{
+				ECHO_CHECK(scene, next < STACK, CHECK_STACK);
 				stack[next++] = child;
 			}
 			else if (type == ECHO_TOKEN_TYPE_TRIANGLE)
 			{
 				if (child == ignore) continue;
 				if (COUNT) ++counts->triangles;
+				ECHO_CHECK(scene, token_index(child) < scene.triangleCount, CHECK_TRIANGLE);
 
 				const float4* data = scene.triHot + (size_t)token_index(child) * 3;
 				float4 a = __ldg(data), b = __ldg(data + 1), c = __ldg(data + 2);
@@ -356,6 +380,7 @@ ECHO_DEVICE bool trace_any(const DeviceScene& scene, vec3 origin, vec3 direction
 			else if (type == ECHO_TOKEN_TYPE_SPHERE)
 			{
 				if (COUNT) ++counts->spheres;
+				ECHO_CHECK(scene, token_index(child) < scene.sphereCount, CHECK_SPHERE);
 				if (sphere_occlude(__ldg(scene.spheres + token_index(child)), origin, direction, travel, child == ignore)) return true;
 			}
 		}

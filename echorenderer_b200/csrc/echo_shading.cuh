@@ -686,6 +686,7 @@ struct MaterialRecord
 
 ECHO_DEVICE MaterialRecord load_material(const DeviceScene& scene, uint32_t index)
 {
+	ECHO_CHECK(scene, index < scene.materialCount, CHECK_MATERIAL);
 	const float4* p = scene.materials + (size_t)index * 4;
 	float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
 	MaterialRecord m;
@@ -752,7 +753,9 @@ ECHO_DEVICE float lerp_fma(float first, float second, float value) { return __fm
 
 ECHO_DEVICE float4 texture_sample(const DeviceScene& scene, uint32_t index, vec2 uv)
 {
+	ECHO_CHECK(scene, index < scene.textureCount, CHECK_TEXTURE);
 	uint4 header = __ldg(scene.textures + (size_t)index * 2); // width height texelOffset filter
+	ECHO_CHECK(scene, (uint64_t)header.z + (uint64_t)header.x * header.y <= scene.texelCount, CHECK_TEXEL);
 	uint32_t wrapper = __ldg(scene.textures + (size_t)index * 2 + 1).x;
 	int width = (int)header.x, height = (int)header.y;
 	const float4* texels = scene.texels + header.z;
@@ -762,6 +765,7 @@ ECHO_DEVICE float4 texture_sample(const DeviceScene& scene, uint32_t index, vec2
 	{
 		int x = (int)floor((double)(uv.x * sizeX)), y = (int)floor((double)(uv.y * sizeY)); // ToPosition: (uv * size).Floored
 		texture_wrap(wrapper, width, height, x, y);
+		ECHO_CHECK(scene, x >= 0 && x < width && y >= 0 && y < height, CHECK_TEXEL);
 		return __ldg(texels + (size_t)y * width + x);
 	}
 
@@ -776,6 +780,8 @@ ECHO_DEVICE float4 texture_sample(const DeviceScene& scene, uint32_t index, vec2
 	texture_wrap(wrapper, width, height, cx, cy);
 	texture_wrap(wrapper, width, height, dx, dy);
 
+	ECHO_CHECK(scene, ax >= 0 && ax < width && bx >= 0 && bx < width && cx >= 0 && cx < width && dx >= 0 && dx < width, CHECK_TEXEL);
+	ECHO_CHECK(scene, ay >= 0 && ay < height && by >= 0 && by < height && cy >= 0 && cy < height && dy >= 0 && dy < height, CHECK_TEXEL);
 	float4 y0x0 = __ldg(texels + (size_t)ay * width + ax), y0x1 = __ldg(texels + (size_t)by * width + bx);
 	float4 y1x0 = __ldg(texels + (size_t)cy * width + cx), y1x1 = __ldg(texels + (size_t)dy * width + dx);
 
@@ -791,6 +797,7 @@ ECHO_DEVICE float4 texture_sample(const DeviceScene& scene, uint32_t index, vec2
 // every textured slot of material `index` sampled at the contact's texture coordinate (Material.SampleAlbedo / Material.Sample)
 ECHO_DEVICE void resolve_material_textures(const DeviceScene& scene, uint32_t index, vec2 texcoord, MaterialRecord& m)
 {
+	ECHO_CHECK(scene, index < scene.materialCount, CHECK_MATERIAL);
 	uint4 slots = __ldg(scene.materialTextures + (size_t)index * 2);     // albedo normal roughness paramA
 	uint32_t paramB = __ldg(scene.materialTextures + (size_t)index * 2 + 1).x;
 

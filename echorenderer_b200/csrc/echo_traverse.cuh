@@ -169,6 +169,7 @@ ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, uint32_t 
 #define ECHO_PUSH(bit, childK, hitK)                                   \
 		if (pushes & (bit))                                            \
 		{                                                              \
+			ECHO_CHECK(scene, next < STACK, CHECK_STACK);              \
 			if (haveTop) stack[next++] = top;                          \
 			top = make_uint2((childK), __float_as_uint(hitK));         \
 			haveTop = true;                                            \
@@ -348,6 +349,7 @@ ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, uint32_t 
 
 		if (visit)
 		{
+			ECHO_CHECK(scene, (INST ? pack.nodeOffset : 0u) + token_index(nodeToken) < scene.nodeCount, CHECK_NODE);
 			const float4* nodeData = scene.nodes + ((size_t)(INST ? pack.nodeOffset : 0u) + token_index(nodeToken)) * 8;
 			float8 q0 = ldg256(nodeData + 0), q1 = ldg256(nodeData + 2), q2 = ldg256(nodeData + 4), q3 = ldg256(nodeData + 6);
 			if (INST) currentNode = nodeToken;
@@ -410,6 +412,7 @@ ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, uint32_t 
 					{
 						// query.current.Push(token); instances[token.Index].Trace / Occlude (GeometryCollection.cs:123-131,160-168)
 						uint32_t instance = pack.instanceOffset + token_index(leaf);
+						ECHO_CHECK(scene, instance < scene.instanceCount, CHECK_INSTANCE);
 						const float4* data = instance_data(scene, instance);
 						float4 scales = __ldg(data + 6);
 
@@ -431,6 +434,7 @@ ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, uint32_t 
 
 						packIndex = __float_as_uint(scales.z);
 						pack = load_pack(scene, packIndex);
+						ECHO_CHECK(scene, next < STACK, CHECK_STACK);
 						if (haveTop) stack[next++] = top; // the parent's entries all live below the new base
 						frame.base = (uint32_t)base;
 						base = next;
@@ -442,6 +446,7 @@ ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, uint32_t 
 				}
 				else if (token_type(leaf) == ECHO_TOKEN_TYPE_TRIANGLE)
 				{
+					ECHO_CHECK(scene, (INST ? pack.triangleOffset : 0u) + token_index(leaf) < scene.triangleCount, CHECK_TRIANGLE);
 					const float4* data = scene.triHot + ((size_t)(INST ? pack.triangleOffset : 0u) + token_index(leaf)) * 3;
 					float4 a = __ldg(data), b = __ldg(data + 1), c = __ldg(data + 2);
 
@@ -467,6 +472,7 @@ ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, uint32_t 
 				}
 				else
 				{
+					ECHO_CHECK(scene, (INST ? pack.sphereOffset : 0u) + token_index(leaf) < scene.sphereCount, CHECK_SPHERE);
 					float4 sphere = __ldg(scene.spheres + (INST ? pack.sphereOffset : 0u) + token_index(leaf));
 					bool findFar = leaf == ignore && (!INST || ignoreHere);
 

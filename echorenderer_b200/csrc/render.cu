@@ -171,6 +171,7 @@ struct TriangleData
 
 ECHO_DEVICE TriangleData load_triangle(const DeviceScene& scene, uint32_t index)
 {
+	ECHO_CHECK(scene, index < scene.triangleCount, CHECK_TRIANGLE);
 	const float4* hot = scene.triHot + (size_t)index * 3;
 	const float4* shade = scene.triShade + (size_t)index * 3;
 	float4 a = __ldg(hot), b = __ldg(hot + 1), c = __ldg(hot + 2);
@@ -255,6 +256,7 @@ struct LightNode
 
 ECHO_DEVICE LightNode load_light_node(const DeviceScene& scene, const PackInfo& info, uint32_t index)
 {
+	ECHO_CHECK(scene, index < info.lightNodeCount && info.lightNodeOffset + index < scene.lightNodeCount, CHECK_LIGHT_NODE);
 	const float4* p = scene.lightNodes + ((size_t)info.lightNodeOffset + index) * 4;
 	float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
 	LightNode n;
@@ -363,6 +365,7 @@ ECHO_DEVICE uint32_t light_tree_pick(const DeviceScene& scene, const PackInfo& i
 ECHO_DEVICE float light_tree_mass(const DeviceScene& scene, const PackInfo& info, uint32_t token, const SurfacePoint& origin)
 {
 	// map.TryGetValue: binary search over the pack's sorted emitter tokens
+	ECHO_CHECK(scene, info.emitterOffset + info.emitterCount <= scene.emitterCount, CHECK_EMITTER);
 	int low = (int)info.emitterOffset, high = (int)(info.emitterOffset + info.emitterCount) - 1, found = -1;
 
 	while (low <= high)
@@ -426,6 +429,7 @@ struct InfiniteLight
 
 ECHO_DEVICE InfiniteLight load_infinite(const DeviceScene& scene, uint32_t index)
 {
+	ECHO_CHECK(scene, index < scene.infiniteLightCount, CHECK_INFINITE_LIGHT);
 	const float4* p = scene.infiniteLights + (size_t)index * kInfiniteStride;
 	float4 a = __ldg(p), b = __ldg(p + 1);
 	uint32_t type = __float_as_uint(b.x);
@@ -528,7 +532,9 @@ ECHO_DEVICE EnvironmentGrid environment_grid(const DeviceScene& scene, const Inf
 {
 	float4 tail = __ldg(light.data + 6); // rotation[8], texture, distribution, pad
 	uint32_t texture = __float_as_uint(tail.y);
+	ECHO_CHECK(scene, texture < scene.textureCount, CHECK_TEXTURE);
 	uint4 header = __ldg(scene.textures + (size_t)texture * 2);
+	ECHO_CHECK(scene, (uint64_t)__float_as_uint(tail.z) + (uint64_t)header.y * (header.x + 1ull) <= scene.distributionCount, CHECK_DISTRIBUTION);
 	return { texture, scene.distributions + __float_as_uint(tail.z), (int)header.x, (int)header.y };
 }
 
@@ -731,6 +737,8 @@ ECHO_DEVICE float scene_probability_mass(const DeviceScene& scene, uint32_t ligh
 // index inside the swatch the geometry's pack (or placement) uses
 ECHO_DEVICE uint32_t geometry_material(const DeviceScene& scene, const PackInfo& info, uint32_t token)
 {
+	ECHO_CHECK(scene, token_type(token) == ECHO_TOKEN_TYPE_TRIANGLE ? info.triangleOffset + token_index(token) < scene.triangleCount
+	                                                               : info.sphereOffset + token_index(token) < scene.sphereCount, CHECK_SPHERE);
 	if (token_type(token) == ECHO_TOKEN_TYPE_TRIANGLE) return __float_as_uint(__ldg(scene.triShade + ((size_t)info.triangleOffset + token_index(token)) * 3).w);
 	return __ldg(scene.sphereMaterial + info.sphereOffset + token_index(token));
 }
@@ -848,6 +856,7 @@ ECHO_DEVICE Sampled scene_sample_light(const DeviceScene& scene, uint32_t light,
 
 	if (token_type(light) == ECHO_TOKEN_TYPE_LIGHT)
 	{
+		ECHO_CHECK(scene, layer.info.pointLightOffset + token_light_index(light) < scene.pointLightCount, CHECK_POINT_LIGHT);
 		const float4* p = scene.pointLights + ((size_t)layer.info.pointLightOffset + token_light_index(light)) * 2;
 		float4 intensity = __ldg(p), lightPosition = __ldg(p + 1);
 		vec3 offset = xyz(lightPosition) - position;
@@ -1600,7 +1609,7 @@ __global__ void __launch_bounds__(kBlock) auxiliary_kernel(DeviceScene scene, Ec
 		PathLayers hitLayers = no_layers();
 		bool hit;
 
-		if (INST)
+		if (INST && scene.packCount != 0u) // INST without packs is a textured scene: one pack, ordinary traversal
 		{
 			traverse_instanced<STACK, false, false>(scene, origin, direction, ignore, ignoreLayers.tokens, ignoreLayers.count, distance, token, uv, hitLayers.tokens, hitLayers.count, nullptr);
 			hit = distance < kInfinity;

@@ -56,10 +56,24 @@ class PreparedScene:
             self.close()
             raise
 
+    def bounds_violations(self):
+        """Bit set of failed index checks since commit in a -DECHO_BOUNDS_CHECK build of the library (0 = clean); None for a
+        release build, which has no checks compiled in."""
+        bits = ctypes.c_uint32()
+        _native.check(self._lib.echo_b200_debug_bounds_violations(self._handle, ctypes.byref(bits)))
+        return None if bits.value == 0xFFFFFFFF else int(bits.value)
+
     def close(self):
         if getattr(self, "_handle", None) is not None and self._handle.value:
+            violations = None
+            try:
+                violations = self.bounds_violations()
+            except Exception:  # a failed context must not hide the error that led here
+                pass
             self._lib.echo_b200_scene_destroy(self._handle)
             self._handle = ctypes.c_void_p()
+            if violations:
+                raise _native.EchoNativeError(-2, f"out-of-bounds index in a kernel: failed checks 0x{violations:x} (echo_scene.cuh CHECK_*)")
 
     def __del__(self):
         self.close()

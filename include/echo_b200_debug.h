@@ -33,6 +33,10 @@ int32_t echo_b200_debug_evaluate_samples(EchoScene*, const EchoRenderParams*, co
 int32_t echo_b200_debug_evaluate_samples4(EchoScene*, const EchoRenderParams*, const int32_t* pixel_xy, const uint32_t* sample_index,
                                           uint64_t n, float* out_rgba);
 
+/* Libraries built with -DECHO_BOUNDS_CHECK check every index the kernels derive from scene data or stack pointers; this returns the
+ * bit set of checks that failed since commit (0 = clean). Release builds write 0xFFFFFFFF ("not compiled in"). */
+int32_t echo_b200_debug_bounds_violations(EchoScene*, uint32_t* out_bits);
+
 #ifdef __cplusplus
 }
 #endif
