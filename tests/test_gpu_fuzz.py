@@ -164,3 +164,52 @@ def test_random_materials_render_parity(seed):
     both_nan = np.isnan(actual) & np.isnan(expected)
     different = np.any((actual.view(np.uint32) != expected.view(np.uint32)) & ~both_nan, axis=1)
     assert different.mean() <= 1e-4, f"{different.sum()} of {len(different)} samples are not bit-identical"
+
+
+def random_instanced_scene(rng):
+    """Random packs placed with random rotations, uniform scales over six decades and random nesting (up to four layers)."""
+    def random_pack(instances):
+        count = int(rng.integers(2, 60))
+        v0 = rng.normal(size=(count, 3))
+        triangles = scenes.make_triangles(v0, v0 + rng.normal(size=(count, 3)) * 0.6, v0 + rng.normal(size=(count, 3)) * 0.6, 0)
+        spheres = np.zeros(int(rng.integers(0, 6)), dtype=structs.SPHERE)
+        spheres["position"], spheres["radius"] = rng.normal(size=(len(spheres), 3)), np.abs(rng.normal(size=len(spheres))) * 0.5
+        return host.PackDescription(triangles=triangles, spheres=spheres, materials=scenes.material(structs.MATERIAL_DIFFUSE), instances=instances)
+
+    def placement(pack):
+        scale = float(10.0 ** rng.uniform(-2, 2))
+        return host.InstanceDescription(pack, tuple(rng.normal(size=3) * 3), tuple(rng.uniform(0, 360, size=3)), scale)
+
+    packs = [random_pack([])]
+    for level in range(int(rng.integers(1, 4))):  # pack k + 1 places one to three copies of earlier packs
+        packs.append(random_pack([placement(int(rng.integers(0, len(packs)))) for _ in range(int(rng.integers(1, 4)))]))
+
+    root = random_pack([placement(int(rng.integers(0, len(packs)))) for _ in range(int(rng.integers(1, 12)))])
+    description = host.SceneDescription(triangles=root.triangles, spheres=root.spheres, materials=root.materials, instances=root.instances, packs=packs,
+                                        camera=scenes.cornell_box().camera)
+    return host.prepare(description)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_instanced_parity(seed):
+    from tests.test_instancing import spawn_from_hits
+    rng = np.random.default_rng(2000 + seed)
+    prepared = random_instanced_scene(rng)
+    oracle = oracle_lib.OracleScene(prepared)
+    rays = hostile_rays(prepared, rng, 1.0, count=6000)
+    rays["ignore"] = structs.TOKEN_EMPTY
+
+    with PreparedScene(prepared) as scene:
+        expected, expected_layers = oracle.trace_hierarchy(rays)
+        hits, layers = scene.trace_hierarchy(rays)
+        assert_hits_equal(hits, expected)
+        assert np.array_equal(layers, expected_layers)
+        assert np.array_equal(scene.occlude_hierarchy(rays), oracle.occlude_hierarchy(rays))
+
+        spawned, ignore = spawn_from_hits(rays, expected, expected_layers)
+        sane = np.isfinite(spawned["origin"]).all(axis=1)
+        spawned, ignore = spawned[sane], ignore[sane]
+        again, again_layers = scene.trace_hierarchy(spawned, ignore)
+        expected_again, expected_again_layers = oracle.trace_hierarchy(spawned, ignore)
+        assert_hits_equal(again, expected_again)
+        assert np.array_equal(again_layers, expected_again_layers)
