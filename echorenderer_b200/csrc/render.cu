@@ -954,6 +954,25 @@ ECHO_DEVICE void camera_spawn(const EchoCamera& camera, int width, int height, i
 	float sx = shift.x + (float)px, sy = shift.y + (float)py;
 	vec2 uv = { fma_f(sx, sizeRX, 1.0f / -2.0f), fma_f(sy, sizeRX, offsetY) }; // SpawnX, RaySpawner.cs:37-46
 
+	if (camera.type == ECHO_CAMERA_ORTHOGRAPHIC) // OrthographicCamera.cs:33-38
+	{
+		origin = camera_point(camera, vec3{ uv.x * camera.width, uv.y * camera.width, 0.0f });
+		direction = { camera.direction[0], camera.direction[1], camera.direction[2] };
+		return;
+	}
+
+	if (camera.type == ECHO_CAMERA_CYLINDRICAL) // CylindricalCamera.cs:27-33 + CylindricalTexture.ToDirection (CylindricalTexture.cs:153-164)
+	{
+		float sizeRY = rcp((float)height);
+		float sinT, cosT, sinP, cosP;
+		sincos_det(sx * sizeRX * kTau, sinT, cosT);
+		sincos_det(sy * sizeRY * kPi, sinP, cosP);
+		vec3 local = normalized(vec3{ -sinP * sinT, -cosP, -sinP * cosT });
+		origin = { camera.transform[3], camera.transform[7], camera.transform[11] };
+		direction = normalized(camera_direction(camera, local));
+		return;
+	}
+
 	bool hasDepthOfField = positive(camera.lensRadius) && positive(camera.focalDistance);
 
 	if (!hasDepthOfField)
@@ -1795,6 +1814,132 @@ __global__ void __launch_bounds__(kBlock) tail_kernel(DeviceScene scene, EchoRen
 	}
 }
 
+// StandardNaiveEvaluator.Evaluate (StandardNaiveEvaluator.cs:16-55): `scatter * Evaluate(depth + 1) + emission`, no light sampling,
+// no roulette. The recursion multiplies from the innermost bounce outwards, so the thread keeps every bounce's scatter and
+// emission (bounceLimit <= 128) and folds them backwards once the path has ended.
+constexpr int kNaiveBounceCap = 128;
+
+template<int STACK, bool INST>
+__global__ void __launch_bounds__(kBlock) naive_kernel(DeviceScene scene, EchoRenderParams params, uint32_t count, PathBuffers paths, float4* __restrict__ out)
+{
+	uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+	bool active = i < count;
+	uint32_t traced = 0u, bounced = 0u;
+
+	if (active)
+	{
+		float4 rayA = paths.rayQueue[0][i * 2u], rayB = paths.rayQueue[0][i * 2u + 1u];
+		vec3 origin = xyz(rayA), direction = { rayA.w, rayB.x, rayB.y };
+		const uint32_t key = paths.key[i];
+		const bool packs = INST && scene.packCount != 0u;
+		const bool textured = INST && scene.textureCount != 0u;
+		const int limit = params.bounceLimit < kNaiveBounceCap ? params.bounceLimit : kNaiveBounceCap;
+
+		rgb scatters[kNaiveBounceCap], emissions[kNaiveBounceCap];
+		int depth = 0;
+		uint32_t ignore = ECHO_TOKEN_EMPTY;
+		PathLayers ignoreLayers = no_layers();
+		rgb value = make_rgb(0.0f);
+
+		while (true)
+		{
+			bool hit = false;
+			float distance = kInfinity;
+			uint32_t token = ECHO_TOKEN_EMPTY;
+			vec2 uv = { 0.0f, 0.0f };
+			PathLayers hitLayers = no_layers();
+
+			if (depth != limit)
+			{
+				++traced;
+
+				if (packs)
+				{
+					traverse_instanced<STACK, false, false>(scene, origin, direction, ignore, ignoreLayers.tokens, ignoreLayers.count, distance, token, uv, hitLayers.tokens, hitLayers.count, nullptr);
+					hit = distance < kInfinity;
+				}
+				else hit = scene_trace<STACK, false>(scene, origin, direction, ignore, distance, token, uv, nullptr);
+			}
+
+			if (!hit) // depth exhausted or escaped: scene.EvaluateInfinite(query.ray.direction, direct), :27-31
+			{
+				value = evaluate_infinite(scene, direction, depth == 0);
+				break;
+			}
+
+			// scene.Interact + material.Scatter, as in shade_body
+			Layer layer = find_layer<INST>(scene, hitLayers);
+			vec3 infoNormal, infoShading;
+			vec2 texcoord = { 0.0f, 0.0f };
+			uint32_t materialIndex;
+
+			if (token_type(token) == ECHO_TOKEN_TYPE_TRIANGLE)
+			{
+				TriangleData triangle = load_triangle(scene, layer.info.triangleOffset + token_index(token));
+				materialIndex = layer.materialOffset + triangle.material;
+				infoNormal = triangle_normal(triangle);
+				infoShading = triangle_shading_normal(triangle, uv);
+				if (textured) texcoord = triangle_texcoord(scene, layer.info.triangleOffset + token_index(token), uv);
+			}
+			else
+			{
+				materialIndex = layer.materialOffset + __ldg(scene.sphereMaterial + layer.info.sphereOffset + token_index(token));
+				infoNormal = infoShading = sphere_normal(uv);
+				if (textured) texcoord = sphere_texcoord(uv);
+			}
+
+			vec3 position = direction * max_net(distance, kEpsilon) + origin;
+			vec3 normal = normalized(transform_direction(layer.inverse, infoNormal));
+			vec3 shadeNormal = normalized(transform_direction(layer.inverse, infoShading));
+			vec3 outgoing = -direction;
+			if (textured) apply_normal_mapping(scene, materialIndex, texcoord, shadeNormal);
+
+			MaterialRecord material = load_material(scene, materialIndex);
+			Bsdf bsdf;
+			material_scatter<INST>(scene, material, outgoing, normal, shadeNormal, bsdf, materialIndex, texcoord);
+
+			// `material is Emissive emissive ? emissive.Emit(contact.point, contact.outgoing) : RGB128.Black`, :42
+			rgb emission = material.type == ECHO_MATERIAL_EMISSIVE && dot(outgoing, normal) > 0.0f ? material_emission(material) : make_rgb(0.0f);
+
+			vec2 sample = { sample_value(key, 4u + 2u * (uint32_t)depth), sample_value(key, 5u + 2u * (uint32_t)depth) };
+			vec3 incident;
+			int selectedType;
+			Sampled sampled = bsdf_sample<KINDS_ALL>(bsdf, outgoing, sample, incident, selectedType);
+			++bounced;
+
+			if (!positive(sampled.pdf) || is_zero(sampled.content)) // "Exit if the BSDF sample is not promising", :46
+			{
+				value = emission;
+				break;
+			}
+
+			scatters[depth] = (sampled.content / sampled.pdf) * abs_bits(dot(incident, shadeNormal));
+			emissions[depth] = emission;
+			++depth;
+
+			origin = position; // query.SpawnTrace(incident)
+			direction = incident;
+			ignore = token;
+			ignoreLayers = hitLayers;
+		}
+
+		for (int d = depth - 1; d >= 0; d--) value = scatters[d] * value + emissions[d]; // :54, innermost first
+		out[i] = make4(value, 0.0f);
+	}
+
+	for (int offset = 16; offset > 0; offset >>= 1)
+	{
+		traced += __shfl_down_sync(0xFFFFFFFFu, traced, offset);
+		bounced += __shfl_down_sync(0xFFFFFFFFu, bounced, offset);
+	}
+
+	if ((threadIdx.x & 31u) == 0u)
+	{
+		if (traced) atomicAdd(paths.stats + STAT_TRACE_QUERIES, (unsigned long long)traced);
+		if (bounced) atomicAdd(paths.stats + STAT_BOUNCE_CREATED, (unsigned long long)bounced);
+	}
+}
+
 __global__ void __launch_bounds__(kBlock) finish_kernel(uint32_t count, PathBuffers paths, float4* __restrict__ out)
 {
 	uint32_t i = blockIdx.x * kBlock + threadIdx.x;
@@ -2265,6 +2410,13 @@ static bool evaluate_paths(WorkerState* state, const DeviceScene& scene, const E
 	if (!check_cuda(cudaMemcpyAsync(activeCount, &count, sizeof(uint32_t), cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync(count)")) return false;
 	++launches;
 
+	if ((params.evaluator & ECHO_EVALUATOR_KIND_MASK) == ECHO_EVALUATOR_NAIVE)
+	{
+		naive_kernel<STACK, INST><<<blocks_for(count), kBlock, 0, stream>>>(scene, params, count, paths, state->sampleOut);
+		++launches;
+		return check_cuda(cudaGetLastError(), "naive_kernel launch");
+	}
+
 	if ((params.evaluator & ECHO_EVALUATOR_KIND_MASK) != ECHO_EVALUATOR_PATH_TRACED)
 	{
 		auxiliary_kernel<STACK, INST><<<blocks_for(count), kBlock, 0, stream>>>(scene, params, count, paths, state->sampleOut);
@@ -2499,7 +2651,13 @@ bool render_tiles(RenderState* state, const DeviceScene& scene, const EchoRender
 		return false;
 	}
 
-	if ((params.evaluator & ECHO_EVALUATOR_KIND_MASK) > ECHO_EVALUATOR_NORMAL_DEPTH || (params.evaluator & ~(ECHO_EVALUATOR_KIND_MASK | ECHO_EVALUATOR_DIVERGE_ONCE)) != 0)
+	if ((params.evaluator & ECHO_EVALUATOR_KIND_MASK) == ECHO_EVALUATOR_NAIVE && (params.bounceLimit < 0 || params.bounceLimit > kNaiveBounceCap))
+	{
+		set_error("the naive evaluator supports bounce limits up to 128");
+		return false;
+	}
+
+	if ((params.evaluator & ECHO_EVALUATOR_KIND_MASK) > ECHO_EVALUATOR_NAIVE || (params.evaluator & ~(ECHO_EVALUATOR_KIND_MASK | ECHO_EVALUATOR_DIVERGE_ONCE)) != 0)
 	{
 		set_error("unknown EchoRenderParams.evaluator");
 		return false;

@@ -215,6 +215,18 @@ class NormalDepthEvaluator:
 
 
 @dataclass(frozen=True)
+class StandardNaiveEvaluator:
+    """Evaluation/Evaluators/StandardNaiveEvaluator.cs:13-14: brute-force path tracing (no light sampling, no roulette) — slow
+    to converge, but an independent estimator of the same image."""
+    bounce_limit: int = 128
+    survivability: float = 2.5  # unused
+
+    @property
+    def code(self):
+        return structs.EVALUATOR_NAIVE
+
+
+@dataclass(frozen=True)
 class EvaluationProfile:
     """Processes/Evaluation/EvaluationProfile.cs:13-75 (Distribution reduced to its Extend and seed)."""
     evaluator: object = field(default_factory=PathTracedEvaluator)

@@ -142,6 +142,23 @@ def perspective_camera(position, rotation=(0, 0, 0), field_of_view=65.0, lens_ra
     return camera
 
 
+def orthographic_camera(position, rotation=(0, 0, 0), width=8.0):
+    """OrthographicCamera (Scenic/Cameras/OrthographicCamera.cs:15-39): parallel rays along the camera's forward axis from a
+    `width`-wide window."""
+    camera = perspective_camera(position, rotation)
+    matrix = rotation_matrix(*rotation)
+    camera["type"], camera["width"] = structs.CAMERA_ORTHOGRAPHIC, width
+    camera["direction"] = (matrix @ np.array([0.0, 0.0, 1.0])).astype(np.float32)  # RootedRotation * Float3.Forward
+    return camera
+
+
+def cylindrical_camera(position, rotation=(0, 0, 0)):
+    """CylindricalCamera (Scenic/Cameras/CylindricalCamera.cs:12-34): a full latitude-longitude panorama around `position`."""
+    camera = perspective_camera(position, rotation)
+    camera["type"] = structs.CAMERA_CYLINDRICAL
+    return camera
+
+
 def look_rotation(position, target):
     """Euler angles (x, y) in degrees so the camera's +Z looks from position to target."""
     d = np.asarray(target, dtype=np.float64) - np.asarray(position, dtype=np.float64)

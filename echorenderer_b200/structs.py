@@ -104,7 +104,9 @@ INFINITE_LIGHT = np.dtype([("radiance", "<f4", 3), ("directlyVisible", "<u4"), (
                            ("intensity", "<f4", 3), ("pad1", "<f4"), ("direction", "<f4", 3), ("pad2", "<f4"), ("rotation", "<f4", 9), ("texture", "<u4"), ("distribution", "<u4"), ("pad3", "<f4"),
                            ("inverseRotation", "<f4", 9), ("pad4", "<f4", 3)])
 
-CAMERA = np.dtype([("transform", "<f4", 12), ("forwardLength", "<f4"), ("lensRadius", "<f4"), ("focalDistance", "<f4"), ("pad", "<f4")])
+CAMERA_PERSPECTIVE, CAMERA_ORTHOGRAPHIC, CAMERA_CYLINDRICAL = 0, 1, 2
+CAMERA = np.dtype([("transform", "<f4", 12), ("forwardLength", "<f4"), ("lensRadius", "<f4"), ("focalDistance", "<f4"), ("type", "<u4"),
+                   ("direction", "<f4", 3), ("width", "<f4")])
 
 RENDER_PARAMS = np.dtype([
     ("width", "<i4"), ("height", "<i4"), ("tileSize", "<i4"), ("extend", "<i4"), ("minEpoch", "<i4"), ("maxEpoch", "<i4"),
@@ -112,7 +114,7 @@ RENDER_PARAMS = np.dtype([
     ("evaluator", "<i4"),
 ])
 
-EVALUATOR_PATH_TRACED, EVALUATOR_ALBEDO, EVALUATOR_NORMAL_DEPTH = 0, 1, 2
+EVALUATOR_PATH_TRACED, EVALUATOR_ALBEDO, EVALUATOR_NORMAL_DEPTH, EVALUATOR_NAIVE = 0, 1, 2, 3
 EVALUATOR_DIVERGE_ONCE = 0x100
 
 STATS_FIELDS = [
@@ -137,7 +139,7 @@ assert MATERIAL.itemsize == 64
 assert LIGHT_NODE.itemsize == 64
 assert POINT_LIGHT.itemsize == 24
 assert INFINITE_LIGHT.itemsize == 160
-assert CAMERA.itemsize == 64
+assert CAMERA.itemsize == 80
 assert RENDER_PARAMS.itemsize == 48
 assert STATS.itemsize == 128
 

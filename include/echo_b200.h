@@ -250,15 +250,21 @@ typedef struct EchoTokenHierarchy
 	uint32_t instances[ECHO_MAX_INSTANCE_LAYERS]; /* TokenType.Instance tokens, outermost first */
 } EchoTokenHierarchy; /* 24 bytes */
 
-/* ---- PerspectiveCamera + RaySpawner inputs (PerspectiveCamera.cs:41-98, RaySpawner.cs:11-64) ---- */
+/* ---- Camera.SpawnRay inputs (Scenic/Cameras/{Perspective,Orthographic,Cylindrical}Camera.cs, RaySpawner.cs:11-64) ---- */
+#define ECHO_CAMERA_PERSPECTIVE 0u  /* PerspectiveCamera.cs:41-98 (thin lens when lensRadius and focalDistance are both >= 8e-7) */
+#define ECHO_CAMERA_ORTHOGRAPHIC 1u /* OrthographicCamera.cs:15-39: origin = InverseTransform * (SpawnX(shift) * Width, 0), fixed direction */
+#define ECHO_CAMERA_CYLINDRICAL 2u  /* CylindricalCamera.cs:12-34: direction = rotation * CylindricalTexture.ToDirection((pixel + shift) / size) */
+
 typedef struct EchoCamera
 {
 	float transform[12]; /* rows 0..2 of Entity.InverseTransform (entity -> world), row-major f00..f23 */
-	float forwardLength; /* 0.5 / tan(fov / 2) */
+	float forwardLength; /* Perspective: 0.5 / tan(fov / 2) */
 	float lensRadius;
 	float focalDistance; /* depth of field is on iff lensRadius and focalDistance are both >= 8e-7 */
-	float pad;
-} EchoCamera;
+	uint32_t type;       /* ECHO_CAMERA_* */
+	float direction[3];  /* Orthographic: RootedRotation * Float3.Forward (OrthographicCamera.cs:22-26) */
+	float width;         /* Orthographic: Width (:18) */
+} EchoCamera; /* 80 bytes */
 
 /* ---- EvaluationProfile + PathTracedEvaluator knobs (EvaluationProfile.cs:42-60, PathTracedEvaluator.cs:33,40) ---- */
 typedef struct EchoRenderParams
@@ -283,6 +289,8 @@ typedef struct EchoRenderParams
 #define ECHO_EVALUATOR_PATH_TRACED 0
 #define ECHO_EVALUATOR_ALBEDO 1
 #define ECHO_EVALUATOR_NORMAL_DEPTH 2
+#define ECHO_EVALUATOR_NAIVE 3 /* StandardNaiveEvaluator (Evaluation/Evaluators/StandardNaiveEvaluator.cs:16-55): no light sampling, no
+                                 roulette; reads bounceLimit (<= 128 here: the device unrolls the recursion into two arrays) */
 #define ECHO_EVALUATOR_KIND_MASK 0xFF
 #define ECHO_EVALUATOR_DIVERGE_ONCE 0x100 /* the evaluator's DivergeOnce property (default: true for Albedo, false for NormalDepth) */
 

@@ -798,6 +798,41 @@ struct AuxiliaryEvaluator
 	}
 };
 
+// ---- Evaluation/Evaluators/StandardNaiveEvaluator.cs:16-55: the recursion `scatter * Evaluate(depth + 1) + emission` ----
+struct NaiveEvaluator
+{
+	int bounceLimit = 128;
+
+	RGB evaluate(const Scene& scene, TraceQuery& query, SampleStream& distribution, EvaluatorStats& stats, int depth) const
+	{
+		if (depth == bounceLimit) return evaluate_infinite(scene, query.ray.direction, depth == 0);
+		++stats.traceQueries;
+		if (!scene.trace(query)) return evaluate_infinite(scene, query.ray.direction, depth == 0);
+
+		Contact contact;
+		interact(scene, query, contact);
+
+		const EchoMaterial& material = scene.materials[contact.material]; // `material is Emissive emissive ? emissive.Emit(...) : Black`
+		RGB emission = material.type == ECHO_MATERIAL_EMISSIVE ? emissive_emit(material, contact.point, contact.outgoing) : kBlack;
+
+		Float3 incident;
+		const BxDF* function;
+		ProbableRGB sample = contact.bsdf.sample(contact.outgoing, distribution.next2d(), incident, function);
+		++stats.bounceCreated;
+		if (sample.not_possible() || is_zero(sample.content)) return emission;
+
+		RGB scatter = sample.content / sample.pdf;
+		scatter = scatter * contact.normal_dot(incident);
+
+		TraceQuery spawned; // query.SpawnTrace(incident)
+		spawned.ray = Ray(query.position(), incident);
+		spawned.ignore = query.token;
+		spawned.ignoreLayers = query.tokenLayers;
+
+		return scatter * evaluate(scene, spawned, distribution, stats, depth + 1) + emission;
+	}
+};
+
 // the evaluator EchoRenderParams selects, as Float4 (RGB128 radiance has W = 0)
 inline Float4 evaluate_sample(const Scene& scene, const EchoRenderParams& params, const Ray& ray, SampleStream& distribution, EvaluatorStats& stats)
 {
@@ -812,6 +847,16 @@ inline Float4 evaluate_sample(const Scene& scene, const EchoRenderParams& params
 		return { { value.r, value.g, value.b, 0.0f } };
 	}
 
+	if (kind == ECHO_EVALUATOR_NAIVE)
+	{
+		NaiveEvaluator evaluator;
+		evaluator.bounceLimit = params.bounceLimit;
+		TraceQuery query;
+		query.ray = ray;
+		RGB value = evaluator.evaluate(scene, query, distribution, stats, 0);
+		return { { value.r, value.g, value.b, 0.0f } };
+	}
+
 	AuxiliaryEvaluator evaluator;
 	evaluator.kind = kind;
 	evaluator.divergeOnce = (params.evaluator & ECHO_EVALUATOR_DIVERGE_ONCE) != 0;
@@ -821,10 +866,11 @@ inline Float4 evaluate_sample(const Scene& scene, const EchoRenderParams& params
 // ---- Scenic/Cameras/RaySpawner.cs:19-46 + PerspectiveCamera.cs:51-98 ----
 struct CameraSpawner
 {
-	float sizeRX, offsetY;
+	float sizeRX, sizeRY, offsetY;
 
 	CameraSpawner(int width, int height)
 	{
+		sizeRY = 1.0f / (float)height;
 		sizeRX = 1.0f / (float)width;                        // TextureGrid.cs:22
 		float aspectY = (float)height / (float)width;        // TextureGrid.cs:25-29
 		offsetY = aspectY / -2.0f;                           // RaySpawner.cs:22
@@ -860,6 +906,24 @@ inline Float3 camera_multiply_point(const EchoCamera& c, Float3 p) // Float4x4.c
 
 inline Ray camera_spawn_ray(const EchoCamera& camera, const CameraSpawner& spawner, int px, int py, Float2 shift, Float2 lens)
 {
+	if (camera.type == ECHO_CAMERA_ORTHOGRAPHIC) // OrthographicCamera.cs:33-38
+	{
+		Float2 uv = spawner.spawn_x(px, py, shift);
+		Float3 origin = { uv.x * camera.width, uv.y * camera.width, 0.0f };
+		return Ray(camera_multiply_point(camera, origin), f3(camera.direction));
+	}
+
+	if (camera.type == ECHO_CAMERA_CYLINDRICAL) // CylindricalCamera.cs:27-33 + CylindricalTexture.ToDirection, CylindricalTexture.cs:153-164
+	{
+		Float2 uv = { (shift.x + (float)px) * spawner.sizeRX, (shift.y + (float)py) * spawner.sizeRY };
+		float sinT, cosT, sinP, cosP;
+		sincos_det(uv.x * kTau, sinT, cosT);
+		sincos_det(uv.y * kPi, sinP, cosP);
+		Float3 direction = normalized(Float3{ -sinP * sinT, -cosP, -sinP * cosT });
+		direction = normalized(camera_multiply_direction(camera, direction)); // (Float3x3)RootedRotation * direction
+		return Ray(Float3{ camera.transform[3], camera.transform[7], camera.transform[11] }, direction);
+	}
+
 	bool hasDepthOfField = positive(camera.lensRadius) && positive(camera.focalDistance); // PerspectiveCamera.cs:46
 
 	if (!hasDepthOfField) // :93-98

@@ -113,3 +113,44 @@ def test_render_tiles_accumulates_all_four_lanes(cornell):
     assert int(stats["sampleEvaluated"][0]) == 16 * 16 * 8
     assert image[..., 3].min() > 5.0 and image[..., 3].max() < 40.0
     assert np.all(np.linalg.norm(image[..., :3], axis=-1) <= 1.0 + 1e-5)
+
+
+def test_naive_evaluator_agrees_with_the_path_tracer(cornell):
+    """StandardNaiveEvaluator (StandardNaiveEvaluator.cs:16-55) has no light sampling, no MIS and no roulette: it is an independent
+    estimator of the image PathTracedEvaluator computes. Their block means agree within Monte-Carlo error."""
+    oracle = oracle_lib.OracleScene(cornell)
+    tiles = scenes.tile_grid(32, 32, 16)
+    naive, _ = oracle.render_tiles(structs.render_params(32, 32, 16, extend=2048, seed=11, bounce_limit=48, evaluator=structs.EVALUATOR_NAIVE), tiles)
+    traced, _ = oracle.render_tiles(structs.render_params(32, 32, 16, extend=256, seed=12, bounce_limit=128), tiles)
+    a = scenes.assemble_tiles(naive, tiles, 32, 32, 16)[..., :3]
+    b = scenes.assemble_tiles(traced, tiles, 32, 32, 16)[..., :3]
+    assert np.allclose(a.mean(axis=(0, 1)), b.mean(axis=(0, 1)), rtol=0.05)
+    blocks_a, blocks_b = a.reshape(4, 8, 4, 8, 3).mean(axis=(1, 3)), b.reshape(4, 8, 4, 8, 3).mean(axis=(1, 3))
+    assert np.mean(np.abs(blocks_a - blocks_b)) < 0.08 * blocks_b.mean()
+
+
+def test_orthographic_and_cylindrical_cameras(cornell):
+    """OrthographicCamera.SpawnRay (OrthographicCamera.cs:33-38) and CylindricalCamera.SpawnRay (CylindricalCamera.cs:27-33)."""
+    import copy
+    from echorenderer_b200 import host
+    ys, xs = np.meshgrid(np.arange(0, 16), np.arange(0, 32), indexing="ij")
+    pixels = np.stack([xs.reshape(-1), ys.reshape(-1)], axis=-1).astype(np.int32)
+    index = np.zeros(len(pixels), dtype=np.uint32)
+    params = structs.render_params(32, 16, 16, extend=1, seed=2)
+
+    description = scenes.cornell_box()
+    description.camera = scenes.orthographic_camera((0, 5, -18), (0, 0, 0), width=8.0)
+    rays = oracle_lib.OracleScene(host.prepare(description)).spawn_rays(params, pixels, index)
+    assert np.all(rays["direction"] == np.array([0, 0, 1], dtype=np.float32))
+    assert np.allclose(rays["origin"][:, 2], -18) and np.ptp(rays["origin"][:, 0]) == pytest.approx(8.0 * 31 / 32, rel=0.05)
+    assert np.ptp(rays["origin"][:, 1]) == pytest.approx(8.0 * 15 / 32, rel=0.1)  # SpawnX scales both axes by 1 / width
+
+    description = scenes.cornell_box()
+    description.camera = scenes.cylindrical_camera((0, 5, 0), (0, 0, 0))
+    rays = oracle_lib.OracleScene(host.prepare(description)).spawn_rays(params, pixels, index)
+    assert np.allclose(np.linalg.norm(rays["direction"], axis=1), 1.0, atol=1e-6) and np.all(rays["origin"] == np.array([0, 5, 0], dtype=np.float32))
+    bottom, top = rays["direction"][pixels[:, 1] == 0], rays["direction"][pixels[:, 1] == 15]
+    assert bottom[:, 1].max() < -0.9 and top[:, 1].min() > 0.9  # v = 0 looks down, v = 1 looks up
+    middle = rays["direction"][pixels[:, 1] == 8]
+    azimuth = np.unwrap(np.arctan2(middle[:, 0], middle[:, 2]))
+    assert abs(abs(azimuth[-1] - azimuth[0]) - 2 * np.pi * 31 / 32) < 0.05  # one full turn across the row

@@ -211,3 +211,14 @@ def test_textured_placements_match_oracle():
             actual = scene.evaluate_samples(params, pixel_xy, sample_index, channels=4)
             assert np.array_equal(actual.view(np.uint32), expected.view(np.uint32))
             assert len(np.unique(expected[:, :3].round(3), axis=0)) > 50
+
+
+def test_naive_evaluator_matches_oracle(instanced):
+    from tests.test_gpu_render import sample_grid
+    oracle = oracle_lib.OracleScene(instanced)
+    params = structs.render_params(64, 48, 16, extend=2, bounce_limit=24, seed=7, evaluator=structs.EVALUATOR_NAIVE)
+    pixel_xy, sample_index = sample_grid(64, 48, 2)
+    with PreparedScene(instanced) as scene:
+        actual = scene.evaluate_samples(params, pixel_xy, sample_index)
+    expected = oracle.evaluate_samples(params, pixel_xy, sample_index)
+    assert np.array_equal(actual.view(np.uint32), expected.view(np.uint32))

@@ -188,3 +188,47 @@ def test_frame_sharding_paths(cornell):
         expected, _ = oracle.render_tiles(everything, tiles)
         whole = scenes.assemble_tiles(expected, tiles, width, height, tile)
         assert np.allclose(reduced[..., :3], whole[..., :3], rtol=2e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("fixture", ["cornell", "mixed_small", "textured_small"])
+def test_naive_evaluator_matches_oracle(fixture, request):
+    """StandardNaiveEvaluator (StandardNaiveEvaluator.cs:16-55): the recursion folded innermost-first, bit-identical per sample."""
+    prepared = request.getfixturevalue(fixture)
+    oracle = oracle_lib.OracleScene(prepared)
+    width, height = 64, 48
+    params = structs.render_params(width, height, 16, extend=4, bounce_limit=40, seed=7, evaluator=structs.EVALUATOR_NAIVE)
+    pixel_xy, sample_index = sample_grid(width, height, 4)
+
+    with PreparedScene(prepared) as scene:
+        actual = scene.evaluate_samples(params, pixel_xy, sample_index)
+        with pytest.raises(Exception, match="bounce limits"):
+            scene.render_tiles(structs.render_params(32, 32, 16, bounce_limit=500, evaluator=structs.EVALUATOR_NAIVE), scenes.tile_grid(32, 32, 16))
+
+    expected = oracle.evaluate_samples(params, pixel_xy, sample_index)
+    assert expected.max() > 0
+    assert np.array_equal(actual.view(np.uint32), expected.view(np.uint32))
+
+
+@pytest.mark.parametrize("camera", ["orthographic", "cylindrical", "thin_lens"])
+def test_cameras_match_oracle(camera):
+    """OrthographicCamera, CylindricalCamera and the thin-lens PerspectiveCamera (Scenic/Cameras/*.cs) through the path tracer."""
+    from echorenderer_b200 import host
+    description = scenes.cornell_box()
+    if camera == "orthographic":
+        description.camera = scenes.orthographic_camera((0, 5, -4), (0, 0, 0), width=9.0)
+    elif camera == "cylindrical":
+        description.camera = scenes.cylindrical_camera((0, 5, 0), (10, 30, 0))
+    else:
+        description.camera = scenes.perspective_camera((0, 5, -18.025444), field_of_view=42.0, lens_radius=0.3, focal_distance=16.0)
+    prepared = host.prepare(description)
+    oracle = oracle_lib.OracleScene(prepared)
+    width, height = 64, 32
+    params = structs.render_params(width, height, 16, extend=4, bounce_limit=24, seed=9)
+    pixel_xy, sample_index = sample_grid(width, height, 4)
+
+    with PreparedScene(prepared) as scene:
+        actual = scene.evaluate_samples(params, pixel_xy, sample_index)
+
+    expected = oracle.evaluate_samples(params, pixel_xy, sample_index)
+    assert expected.max() > 0 and (expected.sum(axis=1) > 0).mean() > 0.5
+    assert np.array_equal(actual.view(np.uint32), expected.view(np.uint32))
