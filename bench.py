@@ -52,6 +52,8 @@ def parse():
                         help="trace workload: the SweepBuilder mirror's tree (default) or the device-built linear BVH (echo_b200_build_qbvh)")
     parser.add_argument("--shard", default="tiles", choices=["tiles", "samples"],
                         help="render workload, N > 1: tile sharding (tile i -> rank i mod N) or sample sharding (every rank renders spp / N samples of every tile)")
+    parser.add_argument("--pattern", default="hilbert", choices=["hilbert", "ordered"],
+                        help="render workload: tile sequence (EvaluationProfile.Pattern; the reference's default is HilbertCurvePattern)")
     parser.add_argument("--no-cpu-baseline", action="store_true")
     parser.add_argument("--no-secondary", action="store_true", help="skip the secondary-ray batch reported beside the headline (SURVEY.md 8d)")
     return parser.parse_args()
@@ -305,7 +307,7 @@ RENDER_SCENES = {
 def render_config(args):
     return {"workload": f"{RENDER_SCENES[args.scene][0]}, path tracer bounce limit {args.bounce_limit}", "width": args.width,
             "height": args.height, "spp_per_step": args.spp, "parallelism": f"{'sample' if args.shard == 'samples' else 'tile'}-sharded x{args.gpus} + NCCL all-reduce of the frame",
-            "l2": "wavefront state (up to ~4 GB) larger than L2"}
+            "tile_pattern": args.pattern, "l2": "wavefront state (up to ~4 GB) larger than L2"}
 
 
 def base_line(args, unit, value, ms_per_step, config, dtype):
@@ -448,8 +450,9 @@ def main():
         prepared = host.prepare(RENDER_SCENES[args.scene][1]())
         scene = PreparedScene(prepared, device=local_rank)
         width, height, tile = args.width, args.height, 16
-        all_tiles = scenes.tile_grid(width, height, tile)
-        from echorenderer_b200 import shard_tiles
+        from echorenderer_b200 import hilbert_curve_pattern, shard_tiles
+        tile_count = ((width + tile - 1) // tile, (height + tile - 1) // tile)
+        all_tiles = hilbert_curve_pattern(tile_count) if args.pattern == "hilbert" else scenes.tile_grid(width, height, tile)
         by_samples = args.shard == "samples" and world > 1
         tiles = all_tiles if by_samples else shard_tiles(all_tiles, rank, world)
         extend = max(1, args.spp // world) if by_samples else args.spp

@@ -424,7 +424,7 @@ def _distribution_1d(values):
     total = np.float32(np.sum(values.astype(np.float64)))
 
     if not total >= np.float32(8e-7):  # FastMath.AlmostZero(sum)
-        cdf = (np.arange(length, dtype=np.float32) * count_r + count_r).astype(np.float32)
+        cdf = (np.arange(length, dtype=np.float64) * np.float64(count_r) + np.float64(count_r)).astype(np.float32)  # FastMath.FMA(i, countR, countR)
         total = np.float32(0)
     else:
         cdf = (cdf * (np.float32(1) / total)).astype(np.float32)

@@ -258,17 +258,105 @@ class RenderTexture:
         self.pixels = np.zeros((height, width, 4), dtype=np.float32)
 
     @property
+    def tile_count(self):
+        return ((self.width + self.tile_size - 1) // self.tile_size, (self.height + self.tile_size - 1) // self.tile_size)
+
+    @property
     def tile_positions(self):
-        tiles_x = (self.width + self.tile_size - 1) // self.tile_size
-        tiles_y = (self.height + self.tile_size - 1) // self.tile_size
-        ty, tx = np.meshgrid(np.arange(tiles_y), np.arange(tiles_x), indexing="ij")
-        return np.stack([tx.reshape(-1), ty.reshape(-1)], axis=-1).astype(np.int32)
+        """profile.Pattern.CreateSequence(destination.size.CeiledDivide(tileSize)) with the default pattern
+        (EvaluationOperation.cs:157-160, EvaluationProfile.Pattern = new HilbertCurvePattern())."""
+        return hilbert_curve_pattern(self.tile_count)
 
     def apply(self, tile_position, tile):
         """IEvaluationLayer.Apply for one finished tile (EvaluationLayer.cs:111-121): tiles are immutable once applied."""
         x0, y0 = int(tile_position[0]) * self.tile_size, int(tile_position[1]) * self.tile_size
         w, h = min(self.tile_size, self.width - x0), min(self.tile_size, self.height - y0)
         self.pixels[y0:y0 + h, x0:x0 + w] = tile[:h, :w]
+
+
+def ordered_pattern(size, horizontal=True):
+    """OrderedPattern.CreateSequence (Processes/Evaluation/ITilePattern.cs:20-36): row-major (or column-major) tile positions."""
+    sx, sy = int(size[0]), int(size[1])
+    if horizontal:
+        return np.array([(x, y) for y in range(sy) for x in range(sx)], dtype=np.int32).reshape(-1, 2)
+    return np.array([(x, y) for x in range(sx) for y in range(sy)], dtype=np.int32).reshape(-1, 2)
+
+
+def _sign(v):
+    return (v > 0) - (v < 0)
+
+
+def _half(v):
+    return int(v / 2)  # C# integer division truncates toward zero, also for the negative rectangle sides
+
+
+def _hilbert_2d(position, rect_a, rect_b, out):
+    """The generalised Hilbert curve over an arbitrary rectangle (HilbertCurvePattern.Hilbert2D, ITilePattern.cs:143-202)."""
+    width, height = abs(rect_a[0] + rect_a[1]), abs(rect_b[0] + rect_b[1])
+    da = (_sign(rect_a[0]), _sign(rect_a[1]))  # unit major direction
+    db = (_sign(rect_b[0]), _sign(rect_b[1]))  # unit orthogonal direction
+    x, y = position
+
+    if height == 1:
+        for _ in range(width):
+            out.append((x, y))
+            x, y = x + da[0], y + da[1]
+    elif width == 1:
+        for _ in range(height):
+            out.append((x, y))
+            x, y = x + db[0], y + db[1]
+    else:
+        a2 = [_half(rect_a[0]), _half(rect_a[1])]
+        b2 = [_half(rect_b[0]), _half(rect_b[1])]
+        width2, height2 = abs(a2[0] + a2[1]), abs(b2[0] + b2[1])
+
+        if width * 2 > height * 3:
+            if width2 % 2 != 0 and width > 2:
+                a2 = [a2[0] + da[0], a2[1] + da[1]]
+            _hilbert_2d((x, y), a2, rect_b, out)
+            _hilbert_2d((x + a2[0], y + a2[1]), (rect_a[0] - a2[0], rect_a[1] - a2[1]), rect_b, out)
+        else:
+            if height2 % 2 != 0 and height > 2:
+                b2 = [b2[0] + db[0], b2[1] + db[1]]
+            _hilbert_2d((x, y), b2, a2, out)
+            _hilbert_2d((x + b2[0], y + b2[1]), rect_a, (rect_b[0] - b2[0], rect_b[1] - b2[1]), out)
+            _hilbert_2d((x + (rect_a[0] - da[0]) + (b2[0] - db[0]), y + (rect_a[1] - da[1]) + (b2[1] - db[1])),
+                        (-b2[0], -b2[1]), (-(rect_a[0] - a2[0]), -(rect_a[1] - a2[1])), out)
+
+
+def hilbert_curve_pattern(size):
+    """HilbertCurvePattern.CreateSequence (ITilePattern.cs:72-141), the default `EvaluationProfile.Pattern`
+    (EvaluationProfile.cs): one generalised Hilbert curve per quadrant, mirrored so that all four start at the centre of the
+    texture, interlaced one position at a time — tiles are handed out from the middle outwards, neighbours close in time."""
+    sx, sy = int(size[0]), int(size[1])
+    if (sx, sy) == (1, 1):
+        return np.zeros((1, 2), dtype=np.int32)
+
+    def corner(cx, cy):
+        out = []
+        if cx > cy:
+            _hilbert_2d((0, 0), (cx, 0), (0, cy), out)
+        else:
+            _hilbert_2d((0, 0), (0, cy), (cx, 0), out)
+        return out
+
+    floor_x, ceil_x, floor_y, ceil_y = sx // 2, (sx + 1) // 2, sy // 2, (sy + 1) // 2
+    top_right_size, top_left_size = (ceil_x, floor_y), (floor_x, floor_y)
+    bottom_right_size, bottom_left_size = (ceil_x, ceil_y), (floor_x, ceil_y)
+
+    top_left = [(top_left_size[0] - x - 1, top_left_size[1] - y - 1) for x, y in corner(*top_left_size)]
+    top_right = [(x + top_left_size[0], top_right_size[1] - y - 1) for x, y in corner(*top_right_size)]
+    bottom_left = [(bottom_left_size[0] - x - 1, y + top_left_size[1]) for x, y in corner(*bottom_left_size)]
+    bottom_right = [(x + top_left_size[0], y + top_left_size[1]) for x, y in corner(*bottom_right_size)]
+
+    result, cursors = [], [0, 0, 0, 0]
+    corners = [top_left, top_right, bottom_left, bottom_right]
+    while len(result) < sx * sy:
+        for k in range(4):
+            if cursors[k] < len(corners[k]):
+                result.append(corners[k][cursors[k]])
+                cursors[k] += 1
+    return np.array(result, dtype=np.int32).reshape(-1, 2)
 
 
 def shard_tiles(tile_positions, rank, world_size):

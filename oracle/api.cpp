@@ -116,6 +116,36 @@ void oracle_infinite_light(const OracleScene* s, uint32_t index, const float* sa
 	out11[10] = infinite_pdf(s->scene, light, f3(direction3));
 }
 
+// KAT hooks for src/Echo.UnitTests/Evaluation/DiscreteDistribution1Tests.cs over a cdf built by the host mirror of the
+// constructor: Sample -> out[0] value, out[1] pdf; ProbabilityDensity(out[0]) -> out[2]; Pick -> out[3] index, out[4] pdf
+// (Pick / ProbabilityMass are FindIndex + GetBounds, DiscreteDistribution1D.cs:79-101)
+void oracle_distribution1d(const float* cdf, int count, float sample, float* out5)
+{
+	Distribution1D distribution{ cdf, count };
+	float pdf;
+	out5[0] = distribution.sample(sample1d(sample), pdf);
+	out5[1] = pdf;
+	out5[2] = distribution.probability_density(out5[0]);
+	int index = distribution.find_index(sample1d(sample));
+	float lower, upper;
+	distribution.bounds(index, lower, upper);
+	out5[3] = (float)index;
+	out5[4] = upper - lower;
+}
+
+// KAT hooks for src/Echo.UnitTests/Textures/DirectionalTextureTests.cs:43-58 (CylindricalTexture.ToUV / ToDirection)
+void oracle_cylindrical_to_uv(const float* direction3, float* uv2)
+{
+	Float2 uv = cylindrical_to_uv(f3(direction3));
+	uv2[0] = uv.x; uv2[1] = uv.y;
+}
+
+void oracle_cylindrical_to_direction(const float* uv2, float* direction3)
+{
+	Float3 direction = cylindrical_to_direction(Float2{ uv2[0], uv2[1] });
+	direction3[0] = direction.x; direction3[1] = direction.y; direction3[2] = direction.z;
+}
+
 void oracle_scene_set_bound_radius(OracleScene* s, float radius) { s->scene.boundRadius = radius; }
 
 void oracle_scene_set_infinite(OracleScene* s, const EchoInfiniteLight* lights, uint32_t count, float threshold, float pdf)
@@ -488,6 +518,9 @@ float oracle_geometry_pdf(const OracleScene* s, uint32_t token, const float* ori
 {
 	return geometry_pdf(s->scene, token, f3(origin), f3(incident));
 }
+
+// test-only: see PathTracedEvaluator::failedPickKeepsMis (evaluation.hpp). Process-wide; tests reset it to 0.
+void oracle_set_failed_pick_keeps_mis(int enabled) { PathTracedEvaluator::failedPickKeepsMis = enabled != 0; }
 
 // light tree: pick (returns token, writes pdf) and probability mass
 uint32_t oracle_light_pick(const OracleScene* s, const float* position, const float* normal, float sample, float* pdf)

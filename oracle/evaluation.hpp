@@ -234,6 +234,14 @@ inline Float2 cylindrical_to_uv(Float3 direction) // ToUV, :142-151 (Atan2 / Aco
 	return { fma_f(atan2_det(direction.x, direction.z), kTauR, 0.5f), fma_f(acos_det(clamp11(direction.y)), -kPiR, 1.0f) };
 }
 
+inline Float3 cylindrical_to_direction(Float2 uv) // ToDirection, :153-164 (only the unit tests call it; Sample inlines the same lines)
+{
+	float sinT, cosT, sinP, cosP;
+	sincos_det(uv.x * kTau, sinT, cosT);
+	sincos_det(uv.y * kPi, sinP, cosP);
+	return normalized(Float3{ -sinP * sinT, -cosP, -sinP * cosT });
+}
+
 inline RGB environment_texel(const Scene& scene, const EchoInfiniteLight& light, Float2 uv)
 {
 	Scene::Rgba value = scene.texture_sample(light.texture, uv);
@@ -574,6 +582,13 @@ struct PathTracedEvaluator
 		}
 	};
 
+	// Test-only switch (oracle_set_failed_pick_keeps_mis, never set by parity tests): the reference turns MIS off when the
+	// light pick fails (:165-169 `mis = false`), so the BSDF-sampled ray then adds the emission it finds with full weight
+	// although the lights it can find were also reachable by Pick on other draws — an excess of P(pick fails) * w_light,
+	// 3-5 % on scenes with many oriented emitters. With the switch on, a failed pick keeps MIS and the estimator is unbiased,
+	// which is what lets StandardNaiveEvaluator validate everything else in this evaluator (tests/test_auxiliary_evaluators.py).
+	static inline bool failedPickKeepsMis = false;
+
 	// :162-207
 	RGB importance_sample_radiant(const Scene& scene, const Contact& contact, EvaluatorStats& stats, float lightSample, Float2 radiantSample, bool& mis) const
 	{
@@ -583,7 +598,7 @@ struct PathTracedEvaluator
 
 		if (!positive(lightPdf))
 		{
-			mis = false;
+			mis = failedPickKeepsMis;
 			return kBlack;
 		}
 

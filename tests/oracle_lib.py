@@ -82,6 +82,11 @@ def library():
     lib.oracle_geometry_sample.restype = i32
     lib.oracle_geometry_pdf.argtypes = [p, u32, p, p]
     lib.oracle_geometry_pdf.restype = f32
+    lib.oracle_distribution1d.argtypes = [p, i32, f32, p]
+    lib.oracle_cylindrical_to_uv.argtypes = [p, p]
+    lib.oracle_cylindrical_to_direction.argtypes = [p, p]
+    lib.oracle_set_failed_pick_keeps_mis.argtypes = [i32]
+    lib.oracle_set_failed_pick_keeps_mis.restype = None
     lib.oracle_light_pick.argtypes = [p, p, p, f32, p]
     lib.oracle_light_pick.restype = u32
     lib.oracle_light_mass.argtypes = [p, u32, p, p]
@@ -211,6 +216,26 @@ class OracleScene:
 
     def geometry_pdf(self, token, origin, incident):
         return float(self.lib.oracle_geometry_pdf(self.handle, int(token), ptr(f32(origin)), ptr(f32(incident))))
+
+
+def distribution1d(cdf, sample):
+    """(Sample value, Sample pdf, ProbabilityDensity(value), Pick index, Pick pdf) of a DiscreteDistribution1D given by its cdf."""
+    cdf = np.ascontiguousarray(cdf, dtype=np.float32)
+    out = np.zeros(5, dtype=np.float32)
+    library().oracle_distribution1d(ptr(cdf), len(cdf), float(sample), ptr(out))
+    return float(out[0]), float(out[1]), float(out[2]), int(out[3]), float(out[4])
+
+
+def cylindrical_to_uv(direction):
+    out = np.zeros(2, dtype=np.float32)
+    library().oracle_cylindrical_to_uv(ptr(f32(direction)), ptr(out))
+    return out
+
+
+def cylindrical_to_direction(uv):
+    out = np.zeros(3, dtype=np.float32)
+    library().oracle_cylindrical_to_direction(ptr(f32(uv)), ptr(out))
+    return out
 
 
 def fastmath(op, a, b=0.0, c=0.0):

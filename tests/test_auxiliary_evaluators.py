@@ -154,3 +154,82 @@ def test_orthographic_and_cylindrical_cameras(cornell):
     middle = rays["direction"][pixels[:, 1] == 8]
     azimuth = np.unwrap(np.arctan2(middle[:, 0], middle[:, 2]))
     assert abs(abs(azimuth[-1] - azimuth[0]) - 2 * np.pi * 31 / 32) < 0.05  # one full turn across the row
+
+
+def _scene_for(fixture, request):
+    if fixture == "directional_cone":
+        from echorenderer_b200 import host
+        description = scenes.mixed_material_scene(rings=12, segments=12)
+        description.infinite_lights = np.concatenate([scenes.ambient_light((0.05, 0.05, 0.05)), scenes.directional_light((3.0, 2.8, 2.5), (55, 20, 0), angle=12.0)])
+        return host.prepare(description)
+    return request.getfixturevalue(fixture)
+
+
+def _mean_radiance(oracle, evaluator, extend, seed, bounce_limit=12, **extra):
+    width, height = 32, 18
+    tiles = scenes.tile_grid(width, height, 16)
+    if evaluator is not None:
+        extra["evaluator"] = evaluator
+    image, _ = oracle.render_tiles(structs.render_params(width, height, 16, extend=extend, seed=seed, bounce_limit=bounce_limit, **extra), tiles, threads=8)
+    return scenes.assemble_tiles(image, tiles, width, height, 16)[..., :3].mean(axis=(0, 1)).astype(np.float64)
+
+
+@pytest.fixture
+def failed_pick_keeps_mis():
+    """Test-only oracle switch (oracle/evaluation.hpp `failedPickKeepsMis`): see test_failed_light_pick_excess_of_the_reference."""
+    lib = oracle_lib.library()
+    lib.oracle_set_failed_pick_keeps_mis(1)
+    yield
+    lib.oracle_set_failed_pick_keeps_mis(0)
+
+
+@pytest.mark.parametrize("fixture", ["mixed_small", "environment_small", "lights_small", "directional_cone"])
+def test_naive_evaluator_agrees_on_other_light_transport(fixture, request, failed_pick_keeps_mis):
+    """The same independent check on the other samplers of the unpinned integrator: rough / specular dielectrics and conductors
+    with area lights (mixed), the importance-sampled environment map, the light tree over hundreds of oriented emitters, and a
+    DirectionalLight cone. (A delta light cannot be found by brute force, so it is not in this list.) Run with the one
+    statistically visible quirk of the reference neutralised (next test), so the tolerance is Monte-Carlo error only."""
+    oracle = oracle_lib.OracleScene(_scene_for(fixture, request))
+    # the directly visible pin-point emitters of lights_small are what is noisy (in both estimators): more seeds there
+    seeds = 6 if fixture == "lights_small" else 2
+    naive = np.mean([_mean_radiance(oracle, structs.EVALUATOR_NAIVE, 4096, seed) for seed in range(1, 1 + seeds)], axis=0)
+    traced = np.mean([_mean_radiance(oracle, None, 512, seed, survivability=1e9) for seed in range(11, 11 + seeds)], axis=0)
+    assert np.allclose(naive, traced, rtol=0.04), (naive, traced)
+
+
+def _oriented_emitters(count, size, seed=23):
+    """A diffuse ground plane under `count` one-sided emissive triangles of random orientation: big enough for brute force to
+    converge, oriented so that light-tree branches whose two children both face away from a shading point are common."""
+    from echorenderer_b200 import host
+    from echorenderer_b200.scenes import F32, uniform, uniform_sphere_directions, make_triangles
+    j = np.arange(count, dtype=np.uint64)
+    centre = np.stack([(uniform(seed, j, 0) * 2 - 1) * F32(10.0), F32(1.0) + uniform(seed, j, 1) * F32(6.0), (uniform(seed, j, 2) * 2 - 1) * F32(10.0)], axis=-1).astype(np.float64)
+    axis_a = uniform_sphere_directions(uniform(seed, j, 3), uniform(seed, j, 4)).astype(np.float64)
+    axis_b = np.cross(axis_a, uniform_sphere_directions(uniform(seed, j, 5), uniform(seed, j, 6)).astype(np.float64))
+    axis_b /= np.linalg.norm(axis_b, axis=1, keepdims=True)
+    triangles = np.concatenate([scenes.plane(0, (60, 60)), make_triangles(centre, centre + axis_a * size, centre + axis_b * size, 1)])
+    materials = np.concatenate([scenes.material(structs.MATERIAL_DIFFUSE, (0.75, 0.75, 0.75)), scenes.material(structs.MATERIAL_EMISSIVE, (10.0, 10.0, 10.0))])
+    position = (0.0, 9.0, -22.0)
+    camera = scenes.perspective_camera(position, scenes.look_rotation(position, (0, 2, 0)), field_of_view=45.0)
+    return host.prepare(scenes.SceneDescription(triangles=triangles, materials=materials, camera=camera, name="oriented_emitters"))
+
+
+def test_failed_light_pick_excess_of_the_reference():
+    """A finding about the reference, kept on purpose. `ImportanceSampleRadiant` reports `mis = false` when `scene.Pick` fails
+    (PathTracedEvaluator.cs:165-169) — which happens whenever the descent reaches a light-tree branch whose two children both
+    have zero importance from the shading point (LightTree.cs:122). The loop then takes the no-MIS fallback (:138-149) and adds
+    the emission the BSDF-sampled ray finds with weight 1, although those emitters are also reached by Pick on other draws:
+    an excess of P(pick fails) x w_light. Direct light on a plane under 64 oriented emitters, against brute force
+    (StandardNaiveEvaluator, one bounce deeper because its depth counts the camera ray): the restated reference is 3-5 % high,
+    and exact within Monte-Carlo error once a failed pick keeps MIS. Oracle and device both keep the reference's behaviour."""
+    oracle = oracle_lib.OracleScene(_oriented_emitters(64, 1.0))
+    lib = oracle_lib.library()
+    naive = np.mean([_mean_radiance(oracle, structs.EVALUATOR_NAIVE, 4096, seed, bounce_limit=2)[0] for seed in (1, 2, 3)])
+    reference = np.mean([_mean_radiance(oracle, None, 256, seed, bounce_limit=1, survivability=1e9)[0] for seed in (11, 12, 13, 14)])
+    lib.oracle_set_failed_pick_keeps_mis(1)
+    try:
+        unbiased = np.mean([_mean_radiance(oracle, None, 256, seed, bounce_limit=1, survivability=1e9)[0] for seed in (11, 12, 13, 14)])
+    finally:
+        lib.oracle_set_failed_pick_keeps_mis(0)
+    assert 1.025 < reference / naive < 1.06, (reference, naive)   # measured 1.042 +- 0.004
+    assert abs(unbiased / naive - 1) < 0.012, (unbiased, naive)   # measured 1.006 +- 0.004

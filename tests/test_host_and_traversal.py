@@ -300,3 +300,32 @@ def test_hostile_rays_on_degenerate_scenes(seed):
     assert np.array_equal(hits["distance"][sane][same].view(np.uint32), linear["distance"][same].view(np.uint32))
     tied = ~same
     assert np.array_equal(hits["distance"][sane][tied], linear["distance"][tied])
+
+
+@pytest.mark.parametrize("size", [(10, 20), (31, 13), (1, 3), (1, 1), (123, 456)])
+@pytest.mark.parametrize("pattern", ["ordered", "ordered_vertical", "hilbert"])
+def test_tile_patterns(pattern, size):
+    """TilePatternTests.CreateSequence (src/Echo.UnitTests/Processes/TilePatternTests.cs:18-31, the reference's own sizes): every
+    position of the grid exactly once, all inside it. Plus what makes the Hilbert pattern the default of EvaluationProfile: the
+    sequence starts at the centre and the four interlaced quadrant curves each move one tile at a time."""
+    from echorenderer_b200 import hilbert_curve_pattern, ordered_pattern
+    positions = {"ordered": lambda s: ordered_pattern(s), "ordered_vertical": lambda s: ordered_pattern(s, False), "hilbert": hilbert_curve_pattern}[pattern](size)
+    assert positions.shape == (size[0] * size[1], 2)
+    assert np.all(positions >= 0) and np.all(positions < np.array(size))
+    assert len({(int(x), int(y)) for x, y in positions}) == len(positions)
+    if pattern == "hilbert" and min(size) >= 10:
+        centre = np.array(size) // 2
+        assert np.abs(positions[:4] - centre).max() <= 1
+        head = positions[: 4 * (min(size) // 2) ** 2 // 4 * 4].reshape(-1, 4, 2)  # while all four quadrant curves are still running
+        steps = np.abs(np.diff(head, axis=0)).sum(axis=2)
+        assert steps.max() <= 2 and (steps == 1).mean() > 0.95  # the generalised curve takes a diagonal step on odd sizes
+
+
+def test_render_texture_uses_the_default_pattern():
+    """EvaluationOperation.cs:174: `profile.Pattern.CreateSequence(size.CeiledDivide(tileSize))`, HilbertCurvePattern by default."""
+    from echorenderer_b200 import RenderTexture, hilbert_curve_pattern, shard_tiles
+    texture = RenderTexture(100, 50, 16)
+    assert texture.tile_count == (7, 4)
+    assert np.array_equal(texture.tile_positions, hilbert_curve_pattern((7, 4)))
+    shards = [shard_tiles(texture.tile_positions, rank, 4) for rank in range(4)]
+    assert sorted(map(tuple, np.concatenate(shards).tolist())) == sorted(map(tuple, texture.tile_positions.tolist()))

@@ -465,3 +465,77 @@ def test_accumulator_matches_welford():
     assert count == keep.sum() == 4094
     assert np.allclose(value, samples[keep].astype(np.float64).mean(axis=0), rtol=2e-6, atol=1e-7)
     assert 0 < noise < 0.1
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Evaluation/DiscreteDistribution1Tests.cs — the six literal distributions (:13-20), on the path through the environment
+# light's DiscreteDistribution2D. The cdf arrays are built by the host mirror of the constructor (host._distribution_1d).
+DISTRIBUTIONS = {
+    "constant": [1, 1, 1, 1, 1], "singular": [4], "sequence": [1, 2, 3],
+    "allZeros": [0, 0, 0], "zerosOne": [0, 0, 0, 1], "oneZeros": [1, 0, 0, 0],
+}
+
+
+def ulps(a, b):
+    a, b = np.float32(a).view(np.int32), np.float32(b).view(np.int32)
+    return abs(int(a) - int(b))
+
+
+def test_distribution1d_sum_integral_count():
+    """DiscreteDistribution1Tests.Sum / Integral / Count (:47-80), `Roughly()` = within 10 ulps (Utility.cs:18)."""
+    from echorenderer_b200 import host
+    expected = {"constant": (5, 1, 5), "singular": (4, 4, 1), "sequence": (6, 2, 3), "allZeros": (0, 0, 3), "zerosOne": (1, 0.25, 4), "oneZeros": (1, 0.25, 4)}
+    for name, values in DISTRIBUTIONS.items():
+        cdf, total = host._distribution_1d(values)
+        count = len(cdf)
+        integral = F32(total) * (F32(1) / F32(count))  # `integral = sum * countR`, DiscreteDistribution1D.cs:49
+        assert ulps(total, expected[name][0]) <= 10 and ulps(integral, expected[name][1]) <= 10 and count == expected[name][2]
+        assert cdf[-1] == 1.0 and np.all(np.diff(cdf) >= 0)
+
+
+@pytest.mark.parametrize("name", list(DISTRIBUTIONS))
+def test_distribution1d_probability(name):
+    """DiscreteDistribution1Tests.Probability / ProbabilityBoundaries (:82-110): for 1000 stratified samples (redrawn) and for the
+    `Count + 1` boundary samples i / Count, ProbabilityDensity(Sample(u)) == Sample(u).pdf and ProbabilityMass(Pick(u)) ==
+    Pick(u).pdf within 10 ulps, and neither pdf is zero — including the all-zero function, which the constructor turns
+    into a constant one (DiscreteDistribution1D.cs:34-43)."""
+    from echorenderer_b200 import host
+    cdf, _ = host._distribution_1d(DISTRIBUTIONS[name])
+    count = len(cdf)
+    rng = np.random.default_rng(1)
+    samples = list((np.arange(1000) + rng.random(1000)) / 1000) + [float(F32(i) * (F32(1) / F32(count))) for i in range(count + 1)]
+    for u in samples:
+        value, pdf, density, index, mass = ol.distribution1d(cdf, u)
+        assert pdf != 0 and mass != 0
+        assert ulps(density, pdf) <= 10
+        assert 0 <= index < count and DISTRIBUTIONS[name][index] > 0 or name == "allZeros"  # never picks a zero-probability cell
+        lower = 0.0 if index == 0 else float(cdf[index - 1])
+        assert ulps(mass, F32(cdf[index]) - F32(lower)) <= 10                                   # ProbabilityMass(index), :95-101
+        assert index == min(int(F32(value) * F32(count)), count - 1)                           # Sample lands inside the picked cell
+        assert ulps(pdf, F32(mass) * F32(count)) <= 10
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Textures/DirectionalTextureTests.cs:43-58 — CylindricalTexture.ToUV / ToDirection round trips. (Coherence :104-113, Sample vs
+# Evaluate / ProbabilityDensity on random textures, is restated in tests/test_textures.py on the environment-light fixtures.)
+def test_cylindrical_to_uv_round_trip():
+    """CylindricalTextureTests.ToUV: 100 uniform-sphere directions -> uv -> direction, squared distance AlmostZero."""
+    rng = np.random.default_rng(1)
+    for _ in range(100):
+        u, v = rng.random(2)
+        z = 1 - 2 * u
+        r = math.sqrt(max(0.0, 1 - z * z))
+        direction = np.array([r * math.cos(2 * math.pi * v), z, r * math.sin(2 * math.pi * v)], dtype=np.float32)
+        direction /= np.linalg.norm(direction)
+        check = ol.cylindrical_to_direction(ol.cylindrical_to_uv(direction))
+        assert float(((check - direction) ** 2).sum()) < float(EPSILON)
+
+
+def test_cylindrical_to_direction_round_trip():
+    """CylindricalTextureTests.ToDirection: 100 uvs -> direction -> uv; the reference asserts Float2 equality, which is
+    approximate (Float2 ==, Common/Packed/Float2.cs, FastMath.Epsilon per component like Float3's)."""
+    rng = np.random.default_rng(2)
+    for _ in range(100):
+        uv = rng.random(2).astype(np.float32)
+        check = ol.cylindrical_to_uv(ol.cylindrical_to_direction(uv))
+        assert np.all(np.abs(check - uv) < 1e-5), (uv, check)
