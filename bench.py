@@ -52,8 +52,8 @@ def parse():
                         help="trace workload: the SweepBuilder mirror's tree (default) or the device-built linear BVH (echo_b200_build_qbvh)")
     parser.add_argument("--shard", default="tiles", choices=["tiles", "samples"],
                         help="render workload, N > 1: tile sharding (tile i -> rank i mod N) or sample sharding (every rank renders spp / N samples of every tile)")
-    parser.add_argument("--pattern", default="hilbert", choices=["hilbert", "ordered"],
-                        help="render workload: tile sequence (EvaluationProfile.Pattern; the reference's default is HilbertCurvePattern)")
+    parser.add_argument("--pattern", default="ordered", choices=["hilbert", "ordered"],
+                        help="render workload: tile sequence, an OrderedPattern or the HilbertCurvePattern of EvaluationProfile.Pattern (A/B in profiles/README.md)")
     parser.add_argument("--no-cpu-baseline", action="store_true")
     parser.add_argument("--no-secondary", action="store_true", help="skip the secondary-ray batch reported beside the headline (SURVEY.md 8d)")
     return parser.parse_args()
