@@ -2589,7 +2589,10 @@ static void collect_stats(WorkerState* state, EchoStats* stats, uint64_t launche
 	stats->kernelLaunches += launches;
 }
 
-constexpr uint64_t kPathsPerBatch = 1ull << 22; // 4 Mi paths per batch and pipeline (about 1 GB of wavefront state each)
+// At most 16 Mi paths per batch and pipeline (250 B of wavefront state per path: about 4 GB each); render_tiles splits smaller
+// jobs so that every pipeline gets a share. A/B at 64 spp per step, 4 / 8 / 16 Mi: C3 439 / 459 / 456, C4 321 / 330 / 332, C5 (16 spp)
+// 337 / 350 / 368 M samples/s — wider launches per bounce and 2-4x fewer of them (variants/ab10.sh, ECHO_B200_BATCH_PATHS).
+constexpr uint64_t kPathsPerBatch = 1ull << 24;
 
 // one batch of tiles: pixel loop -> epoch loop -> sample loop of EvaluationOperation.Execute (EvaluationOperation.cs:100-141)
 static bool render_batch(WorkerState* state, const DeviceScene& scene, const EchoRenderParams& params, const int32_t* tileXY, uint32_t tiles,
@@ -2677,7 +2680,13 @@ bool render_tiles(RenderState* state, const DeviceScene& scene, const EchoRender
 	// (never below 256 Ki paths per batch: smaller wavefronts are launch- and latency-bound from the first bounce)
 	uint64_t perTile = (uint64_t)params.tileSize * params.tileSize;
 	uint64_t pathsPerTile = perTile * params.extend;
-	uint64_t maxTiles = std::max<uint64_t>(1, kPathsPerBatch / pathsPerTile);
+	static const uint64_t batchPaths = []
+	{
+		const char* value = std::getenv("ECHO_B200_BATCH_PATHS"); // A/B: paths per batch and pipeline
+		uint64_t paths = value ? (uint64_t)std::atoll(value) : kPathsPerBatch;
+		return std::min<uint64_t>(std::max<uint64_t>(paths, 1ull << 16), 1ull << 26);
+	}();
+	uint64_t maxTiles = std::max<uint64_t>(1, batchPaths / pathsPerTile);
 	uint64_t minTiles = std::max<uint64_t>(1, (1ull << 18) / pathsPerTile);
 	uint64_t share = (tileCount + configuredWorkers - 1) / configuredWorkers;
 	uint64_t tilesPerBatch = std::min<uint64_t>(std::max<uint64_t>(share, minTiles), maxTiles);
