@@ -281,7 +281,7 @@ def reference_arm(args):
     line["cpu_baseline"] = {"value": line["value"], "unit": line["unit"], "cores": cores, "kind": "port", "sample": sample}
     line["e2e"] = {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     line["gpu_launches"] = 0
-    print(json.dumps(line))
+    emit(line)
 
 
 def trace_config(args, rays):
@@ -317,10 +317,30 @@ def base_line(args, unit, value, ms_per_step, config, dtype):
             "dtype": dtype, "data": "synthetic", "config": config}
 
 
+_STDOUT = None
+
+
+def quiet_stdout():
+    """The contract is ONE JSON line on stdout. Libraries write there too (NCCL prints its version banner from C when the box
+    sets NCCL_DEBUG=VERSION), so file descriptor 1 points at stderr while the bench runs and emit() writes to the real one."""
+    global _STDOUT
+    if _STDOUT is None:
+        sys.stdout.flush()
+        _STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _STDOUT if _STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     args = parse()
     if args.warmup < 3:
         args.warmup = 3
+    quiet_stdout()
 
     if args.impl == "reference":
         reference_arm(args)
@@ -520,7 +540,7 @@ def main():
         line["stats_last_step"] = {label: int(stats[name][0]) for label, name in zip(structs.STATS_LABELS, structs.STATS_FIELDS)}
 
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
 
     scene.close()
     if distributed:
