@@ -14,6 +14,25 @@ namespace echo
 
 #define ECHO_DEVICE __device__ __forceinline__
 
+// The shading kernels are long straight-line code (the dielectric class: 15 k SASS instructions, 6 k of them executed by every
+// path) and stall on instruction fetch (ncu: stall_no_inst 49 % of samples, profiles/README.md). Helpers that are called from
+// many sites with scalar arguments only are therefore compiled ONCE per kernel (noinline), so that their call sites reuse the
+// same instruction-cache lines: level 1 = the microfacet helpers, level 2 = also Float3.Normalized and the glossy lobes'
+// evaluate / pdf. -DECHO_SHARE_LEVEL=0 restores full inlining (A/B: variants/ab13.sh). The arithmetic is the same either way.
+#ifndef ECHO_SHARE_LEVEL
+#define ECHO_SHARE_LEVEL 2
+#endif
+#if ECHO_SHARE_LEVEL >= 1
+#define ECHO_SHARED_CODE static __device__ __noinline__
+#else
+#define ECHO_SHARED_CODE ECHO_DEVICE
+#endif
+#if ECHO_SHARE_LEVEL >= 2
+#define ECHO_SHARED_CODE_2 static __device__ __noinline__
+#else
+#define ECHO_SHARED_CODE_2 ECHO_DEVICE
+#endif
+
 constexpr float kInfinity = __builtin_huge_valf();
 constexpr float kPi = 3.14159265358979323846f;     // Scalars.cs:15
 constexpr float kPiR = 0.31830988618379067154f;    // Scalars.cs:20
@@ -114,7 +133,7 @@ ECHO_DEVICE double squared_magnitude_double(vec3 a) // Float3.cs:48-52: ((x*x) +
 
 ECHO_DEVICE float magnitude(vec3 a) { return __double2float_rn(__dsqrt_rn(squared_magnitude_double(a))); } // Float3.cs:30-40
 
-ECHO_DEVICE vec3 normalized(vec3 a) // Float3.cs:171-181 + Scalars.cs:172-186
+ECHO_SHARED_CODE_2 vec3 normalized(vec3 a) // Float3.cs:171-181 + Scalars.cs:172-186
 {
 	double squared = squared_magnitude_double(a);
 	if (squared == 0.0 || fabs(squared) < 1E-10 * 2.2250738585072014e-308) return { 0.0f, 0.0f, 0.0f };

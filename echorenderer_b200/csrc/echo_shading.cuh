@@ -138,7 +138,7 @@ ECHO_DEVICE vec3 fresnel_refract(const FresnelPacket& p, vec3 outgoing, vec3 nor
 	return normalized(normal * (eta * p.cosOutgoing + p.cosIncident) - eta * outgoing);
 }
 
-ECHO_DEVICE float real_fresnel(float etaAbove, float etaBelow, float cosO) // :28-35
+ECHO_SHARED_CODE float real_fresnel(float etaAbove, float etaBelow, float cosO) // :28-35
 {
 	FresnelPacket p = fresnel_incomplete(etaAbove, etaBelow, cosO);
 	fresnel_complete(p);
@@ -193,7 +193,7 @@ ECHO_DEVICE float microfacet_alpha(float roughness, bool& specular) // :43-51
 	return specular ? Threshold : alpha;
 }
 
-ECHO_DEVICE float tr_projected_area(float alphaX, float alphaY, vec3 normal) // :101-120
+ECHO_SHARED_CODE float tr_projected_area(float alphaX, float alphaY, vec3 normal) // :101-120
 {
 	float cos2 = cosine_p2(normal);
 	if (!positive(cos2)) return 0.0f;
@@ -209,7 +209,7 @@ ECHO_DEVICE float tr_projected_area(float alphaX, float alphaY, vec3 normal) // 
 	return rcp(sum * sum * (alphaX * alphaY) * kPi);
 }
 
-ECHO_DEVICE float tr_shadowing_ratio(float alphaX, float alphaY, vec3 direction) // :123-132
+ECHO_SHARED_CODE float tr_shadowing_ratio(float alphaX, float alphaY, vec3 direction) // :123-132
 {
 	float cos2 = cosine_p2(direction);
 	if (!positive(cos2)) return 0.0f;
@@ -233,7 +233,7 @@ ECHO_DEVICE float tr_probability_density(float ax, float ay, vec3 outgoing, vec3
 	return fraction * abs_bits(div(dot(outgoing, normal), cosine_p(outgoing)));
 }
 
-ECHO_DEVICE vec3 tr_sample(float alphaX, float alphaY, vec3 outgoing, vec2 sample) // :137-173, Heitz 2017 VNDF
+ECHO_SHARED_CODE vec3 tr_sample(float alphaX, float alphaY, vec3 outgoing, vec2 sample) // :137-173, Heitz 2017 VNDF
 {
 	vec3 scaled = normalized(vec3{ outgoing.x * alphaX, outgoing.y * alphaY, outgoing.z });
 	if (scaled.z < 0.0f) scaled = -scaled;
@@ -257,7 +257,7 @@ ECHO_DEVICE vec3 tr_sample(float alphaX, float alphaY, vec3 outgoing, vec2 sampl
 	return normalized(vec3{ transformed.x * alphaX, transformed.y * alphaY, max_sse(transformed.z, kEpsilon) });
 }
 
-ECHO_DEVICE vec3 glossy_find_normal(vec3 outgoing, vec3 incident) // Scattering/Glossy.cs:61-71
+ECHO_SHARED_CODE vec3 glossy_find_normal(vec3 outgoing, vec3 incident) // Scattering/Glossy.cs:61-71
 {
 	vec3 normal = outgoing + incident;
 	float length2 = squared_magnitude(normal);
@@ -280,23 +280,45 @@ ECHO_DEVICE rgb lobe_fresnel(const Bsdf& b, float cosO)
 }
 
 // Glossy.cs:23-41
-template<bool REAL>
-ECHO_DEVICE rgb glossy_reflection_evaluate(const Bsdf& b, vec3 outgoing, vec3 incident)
+// shared-code forms of the two reflection lobes' Evaluate and of ProbabilityDensity: scalar arguments only (see ECHO_SHARED_CODE)
+ECHO_SHARED_CODE_2 float glossy_reflection_evaluate_real(float alphaX, float alphaY, float etaAbove, float etaBelow, vec3 outgoing, vec3 incident)
+{
+	if (flat_or_opposite_hemisphere(outgoing, incident)) return 0.0f;
+	vec3 normal = glossy_find_normal(outgoing, incident);
+
+	float ratio = tr_projected_area(alphaX, alphaY, normal) * tr_visibility(alphaX, alphaY, outgoing, incident) * 0.25f;
+	float evaluated = div(real_fresnel(etaAbove, etaBelow, dot(outgoing, normal)), cosine_p(outgoing) * cosine_p(incident));
+	return evaluated * ratio;
+}
+
+ECHO_SHARED_CODE_2 rgb glossy_reflection_evaluate_complex(float alphaX, float alphaY, rgb eta2, rgb etaK2, vec3 outgoing, vec3 incident)
 {
 	if (flat_or_opposite_hemisphere(outgoing, incident)) return make_rgb(0.0f);
 	vec3 normal = glossy_find_normal(outgoing, incident);
 
-	float ratio = tr_projected_area(b.alphaX, b.alphaY, normal) * tr_visibility(b.alphaX, b.alphaY, outgoing, incident) * 0.25f;
-	rgb evaluated = lobe_fresnel<REAL>(b, dot(outgoing, normal)) / (cosine_p(outgoing) * cosine_p(incident));
+	float ratio = tr_projected_area(alphaX, alphaY, normal) * tr_visibility(alphaX, alphaY, outgoing, incident) * 0.25f;
+	rgb evaluated = complex_fresnel(eta2, etaK2, dot(outgoing, normal)) / (cosine_p(outgoing) * cosine_p(incident));
 	return evaluated * ratio;
+}
+
+template<bool REAL>
+ECHO_DEVICE rgb glossy_reflection_evaluate(const Bsdf& b, vec3 outgoing, vec3 incident)
+{
+	if (REAL) return make_rgb(glossy_reflection_evaluate_real(b.alphaX, b.alphaY, b.etaAbove, b.etaBelow, outgoing, incident));
+	return glossy_reflection_evaluate_complex(b.alphaX, b.alphaY, b.eta2, b.etaK2, outgoing, incident);
+}
+
+ECHO_SHARED_CODE_2 float glossy_reflection_pdf_scalar(float alphaX, float alphaY, vec3 outgoing, vec3 incident)
+{
+	if (flat_or_opposite_hemisphere(outgoing, incident)) return 0.0f;
+	vec3 normal = glossy_find_normal(outgoing, incident);
+	return div(tr_probability_density(alphaX, alphaY, outgoing, normal), abs_bits(dot(outgoing, normal) * 4.0f));
 }
 
 template<bool REAL>
 ECHO_DEVICE float glossy_reflection_pdf(const Bsdf& b, vec3 outgoing, vec3 incident)
 {
-	if (flat_or_opposite_hemisphere(outgoing, incident)) return 0.0f;
-	vec3 normal = glossy_find_normal(outgoing, incident);
-	return div(tr_probability_density(b.alphaX, b.alphaY, outgoing, normal), abs_bits(dot(outgoing, normal) * 4.0f));
+	return glossy_reflection_pdf_scalar(b.alphaX, b.alphaY, outgoing, incident);
 }
 
 // Glossy.cs:43-59
@@ -316,20 +338,20 @@ ECHO_DEVICE Sampled glossy_reflection_sample(const Bsdf& b, vec2 sample, vec3 ou
 }
 
 // Glossy.cs:88-113
-ECHO_DEVICE rgb glossy_transmission_evaluate(const Bsdf& b, vec3 outgoing, vec3 incident)
+ECHO_SHARED_CODE_2 float glossy_transmission_evaluate_scalar(float alphaX, float alphaY, float etaAbove, float etaBelow, vec3 outgoing, vec3 incident)
 {
-	if (flat_or_same_hemisphere(outgoing, incident)) return make_rgb(0.0f);
+	if (flat_or_same_hemisphere(outgoing, incident)) return 0.0f;
 
-	FresnelPacket packet = fresnel_incomplete(b.etaAbove, b.etaBelow, cosine_p(outgoing));
+	FresnelPacket packet = fresnel_incomplete(etaAbove, etaBelow, cosine_p(outgoing));
 	float etaR = div(packet.etaIncident, packet.etaOutgoing);
 	vec3 normal = glossy_find_normal(outgoing, incident * etaR);
 
 	float dotO = dot(outgoing, normal);
 	float dotI = dot(incident, normal);
-	if (positive(dotO * dotI)) return make_rgb(0.0f);
+	if (positive(dotO * dotI)) return 0.0f;
 
-	float evaluated = 1.0f - real_fresnel(b.etaAbove, b.etaBelow, dotO);
-	if (!positive(evaluated)) return make_rgb(0.0f);
+	float evaluated = 1.0f - real_fresnel(etaAbove, etaBelow, dotO);
+	if (!positive(evaluated)) return 0.0f;
 
 	float numerator = etaR * etaR * dotO * dotI;
 	float denominator = fma_f(etaR, dotI, dotO);
@@ -338,16 +360,21 @@ ECHO_DEVICE rgb glossy_transmission_evaluate(const Bsdf& b, vec3 outgoing, vec3 
 	if (!positive(denominator)) denominator = 1.0f;
 	denominator *= cosine_p(outgoing) * cosine_p(incident);
 
-	float ratio = tr_projected_area(b.alphaX, b.alphaY, normal) * tr_visibility(b.alphaX, b.alphaY, outgoing, incident);
-	return make_rgb(evaluated * ratio * abs_bits(div(numerator, denominator)));
+	float ratio = tr_projected_area(alphaX, alphaY, normal) * tr_visibility(alphaX, alphaY, outgoing, incident);
+	return evaluated * ratio * abs_bits(div(numerator, denominator));
+}
+
+ECHO_DEVICE rgb glossy_transmission_evaluate(const Bsdf& b, vec3 outgoing, vec3 incident)
+{
+	return make_rgb(glossy_transmission_evaluate_scalar(b.alphaX, b.alphaY, b.etaAbove, b.etaBelow, outgoing, incident));
 }
 
 // Glossy.cs:115-133
-ECHO_DEVICE float glossy_transmission_pdf(const Bsdf& b, vec3 outgoing, vec3 incident)
+ECHO_SHARED_CODE_2 float glossy_transmission_pdf_scalar(float alphaX, float alphaY, float etaAbove, float etaBelow, vec3 outgoing, vec3 incident)
 {
 	if (flat_or_same_hemisphere(outgoing, incident)) return 0.0f;
 
-	FresnelPacket packet = fresnel_incomplete(b.etaAbove, b.etaBelow, cosine_p(outgoing));
+	FresnelPacket packet = fresnel_incomplete(etaAbove, etaBelow, cosine_p(outgoing));
 	float etaR = div(packet.etaIncident, packet.etaOutgoing);
 	vec3 normal = glossy_find_normal(outgoing, incident * etaR);
 
@@ -360,7 +387,12 @@ ECHO_DEVICE float glossy_transmission_pdf(const Bsdf& b, vec3 outgoing, vec3 inc
 	denominator *= denominator;
 
 	if (!positive(denominator)) denominator = 1.0f;
-	return tr_probability_density(b.alphaX, b.alphaY, outgoing, normal) * div(numerator, denominator);
+	return tr_probability_density(alphaX, alphaY, outgoing, normal) * div(numerator, denominator);
+}
+
+ECHO_DEVICE float glossy_transmission_pdf(const Bsdf& b, vec3 outgoing, vec3 incident)
+{
+	return glossy_transmission_pdf_scalar(b.alphaX, b.alphaY, b.etaAbove, b.etaBelow, outgoing, incident);
 }
 
 // Glossy.cs:135-160
