@@ -31,6 +31,9 @@ constexpr unsigned long long kPool = 256;         // rays reserved per global at
 #ifndef ECHO_INST_MIN_BLOCKS
 #define ECHO_INST_MIN_BLOCKS 6 // resident CTAs per SM asked of the INST instantiations (80 registers), see trace.cu
 #endif
+#ifndef ECHO_SHARED_STACK
+#define ECHO_SHARED_STACK 8 // traversal-stack entries per thread kept in shared memory (0 = all in local memory), see `stack` below
+#endif
 #ifndef ECHO_LEAF_MAX_WAIT
 #define ECHO_LEAF_MAX_WAIT 2 // a lane waits at most two iterations for its primitive test (A/B on C2/C3/C4: +1-2 %)
 #endif
@@ -126,9 +129,39 @@ ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, uint32_t 
 	// Traversal stack {token, entry distance bits}. The newest entry lives in registers (`top`): the nearest child pushed by
 	// a node visit is popped by the very next one, so most pushes and pops never touch local memory (per-thread local
 	// arrays are interleaved at 4-byte granularity: every 8-byte entry costs two 32-byte sectors in the L1 data pipe).
+	// The next ECHO_SHARED_STACK entries live in shared memory, only deeper ones in local memory: local memory is cached in L1,
+	// where the node stream keeps evicting it — the pop's wait for its local load was 14 % of all stall samples of the C2 kernel,
+	// as much as the wait for the node itself (SASS-level ncu, profiles/README.md). Column layout: entry k of thread t at
+	// [k * blockDim + t], consecutive lanes on consecutive 8-byte words.
 	uint2 stack[STACK];
 	uint2 top = make_uint2(0u, 0u);
 	bool haveTop = false;
+#if ECHO_SHARED_STACK > 0
+	__shared__ uint2 sharedStack[ECHO_SHARED_STACK * kTraverseBlock];
+	uint2* const sharedColumn = sharedStack + threadIdx.x;
+#endif
+
+	auto spill = [&](uint2 entry) // stack[next++] = entry
+	{
+#if ECHO_SHARED_STACK > 0
+		if (next < ECHO_SHARED_STACK) sharedColumn[next * kTraverseBlock] = entry;
+		else stack[next - ECHO_SHARED_STACK] = entry;
+#else
+		stack[next] = entry;
+#endif
+		++next;
+	};
+
+	auto unspill = [&]() -> uint2 // stack[--next]
+	{
+		--next;
+#if ECHO_SHARED_STACK > 0
+		if (next < ECHO_SHARED_STACK) return sharedColumn[next * kTraverseBlock];
+		return stack[next - ECHO_SHARED_STACK];
+#else
+		return stack[next];
+#endif
+	};
 
 	// instancing state of the lane's ray (INST only)
 	const PackView rootPack = INST ? load_pack(scene, 0u) : PackView{ 0u, 0u, 0u, 0u };
@@ -170,7 +203,7 @@ ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, uint32_t 
 		if (pushes & (bit))                                            \
 		{                                                              \
 			ECHO_CHECK(scene, next < STACK, CHECK_STACK);              \
-			if (haveTop) stack[next++] = top;                          \
+			if (haveTop) spill(top);                          \
 			top = make_uint2((childK), __float_as_uint(hitK));         \
 			haveTop = true;                                            \
 		}
@@ -320,7 +353,7 @@ ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, uint32_t 
 			{
 				uint2 entry = top;
 				if (haveTop) haveTop = false;
-				else entry = stack[--next];
+				else entry = unspill();
 
 				if (ANY || !(__uint_as_float(entry.y) >= best))
 				{
@@ -435,7 +468,7 @@ ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, uint32_t 
 						packIndex = __float_as_uint(scales.z);
 						pack = load_pack(scene, packIndex);
 						ECHO_CHECK(scene, next < STACK, CHECK_STACK);
-						if (haveTop) stack[next++] = top; // the parent's entries all live below the new base
+						if (haveTop) spill(top); // the parent's entries all live below the new base
 						frame.base = (uint32_t)base;
 						base = next;
 						top = make_uint2(0u, 0u); // the pack's NewNodeToken(0), entry distance 0
