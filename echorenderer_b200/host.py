@@ -142,6 +142,7 @@ class PreparedArrays:
     texels: np.ndarray = None             # [n, 4] float32
     material_textures: np.ndarray = None  # structs.MATERIAL_TEXTURES per entry of `materials`
     distributions: np.ndarray = None      # DiscreteDistribution2D cdf values of the environment lights
+    _bound_radius: float = None           # cache of bound_radius
 
     @property
     def point_lights(self):
@@ -161,10 +162,11 @@ class PreparedArrays:
 
     @property
     def bound_radius(self):
-        """Stand-in for Accelerator.SphereBound.radius (Accelerator.cs:43-63): the half diagonal of the root bound, the same
-        stand-in the ambient-light power uses."""
-        low, high = self.bounds
-        return float(np.float32(np.linalg.norm((high.astype(np.float64) - low.astype(np.float64))) / 2))
+        """Accelerator.SphereBound.radius (Accelerator.cs:43-63): the near-minimal sphere around the corners of the bounds two
+        quad levels below the root — what the auxiliary evaluators report for escaped rays and the infinite lights' power uses."""
+        if self._bound_radius is None:
+            self._bound_radius = float(accelerator_sphere_bound(self.nodes).radius)
+        return self._bound_radius
 
     @property
     def bounds(self):
@@ -486,12 +488,198 @@ def cubemap_average(faces, count=128):
     return (total / len(d)).astype(np.float32)
 
 
-def _root_bound_radius(root):
-    """Stand-in for Accelerator.SphereBound.radius: the half diagonal of the root node's bound (see PreparedArrays.bound_radius)."""
-    valid = root["token4"] != structs.TOKEN_EMPTY
-    low = np.array([root[k][valid].min() for k in ("minX", "minY", "minZ")], dtype=np.float64)
-    high = np.array([root[k][valid].max() for k in ("maxX", "maxY", "maxZ")], dtype=np.float64)
-    return np.float32(np.linalg.norm(high - low) / 2)
+# ---- Aggregation/Bounds/SphereBound.cs: near-minimal bounding sphere (extremal points + exact solver + grow), float32 like the reference ----
+_F = np.float32
+
+
+def _sq(v):  # Float3.SquaredMagnitude, X * X + Y * Y + Z * Z
+    return _F(_F(_F(v[0] * v[0]) + _F(v[1] * v[1])) + _F(v[2] * v[2]))
+
+
+def _cross(a, b):  # Float3.Cross rounds fp64 lanes once (Float3.cs:268-273)
+    a64, b64 = a.astype(np.float64), b.astype(np.float64)
+    return np.array([a64[1] * b64[2] - a64[2] * b64[1], a64[2] * b64[0] - a64[0] * b64[2], a64[0] * b64[1] - a64[1] * b64[0]]).astype(np.float32)
+
+
+def _determinant(m):  # Float4x4.Determinant, Float4x4.cs:95-121
+    (f00, f01, f02, f03), (f10, f11, f12, f13), (f20, f21, f22, f23), (f30, f31, f32, f33) = [[_F(x) for x in row] for row in m]
+    d21_32, d21_33, d22_33 = f21 * f32 - f22 * f31, f21 * f33 - f23 * f31, f22 * f33 - f23 * f32
+    d20_31, d20_32, d20_33 = f20 * f31 - f21 * f30, f20 * f32 - f22 * f30, f20 * f33 - f23 * f30
+    m00 = f11 * d22_33 - f12 * d21_33 + f13 * d21_32
+    m01 = f10 * d22_33 - f12 * d20_33 + f13 * d20_32
+    m02 = f10 * d21_33 - f11 * d20_33 + f13 * d20_31
+    m03 = f10 * d21_32 - f11 * d20_32 + f12 * d20_31
+    return _F(f00 * m00 - f01 * m01 + f02 * m02 - f03 * m03)
+
+
+def _sphere_normals():
+    """`new Versor(45f, 45f, 45f) * {Right, Up, Forward}` (SphereBound.cs:50-63, Versor.cs:21-35,223-240)."""
+    half = _F(45.0) * _F(_F(math.pi / 180.0) * _F(0.5))
+    s, c = _F(math.sin(half)), _F(math.cos(half))
+    d = np.array([s * c * c + c * s * s, c * s * c - s * c * s, c * c * s - s * s * c, c * c * c + s * s * s], dtype=np.float32)
+    dd = d * d
+    dw = (d[3] * _F(2)) * d[:3]
+    dz = (d[2] * _F(2)) * d[:2]
+    dy_x = d[1] * _F(2) * d[0]
+
+    def rotate(v):
+        x, y, z = (_F(k) for k in v)
+        return np.array([
+            dd[3] * x + dd[0] * x - dw[2] * y + dy_x * y + dw[1] * z + dz[0] * z - dd[2] * x - dd[1] * x,
+            dy_x * x + dw[2] * x + dd[1] * y - dd[2] * y + dz[1] * z - dw[0] * z + dd[3] * y - dd[0] * y,
+            dz[0] * x - dw[1] * x + dz[1] * y + dw[0] * y + dd[2] * z - dd[1] * z - dd[0] * z + dd[3] * z], dtype=np.float32)
+
+    return [rotate(axis) for axis in ((1, 0, 0), (0, 1, 0), (0, 0, 1))]
+
+
+_SPHERE_NORMALS = _sphere_normals()
+
+
+class SphereBound:
+    """Aggregation/Bounds/SphereBound.cs: `SphereBound(ReadOnlySpan<Float3> points)` -> center, radius."""
+
+    def __init__(self, points):
+        points = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 3)
+        assert len(points) > 0
+        if len(points) > len(_SPHERE_NORMALS) * 2:
+            center, radius2 = self._solve_exact(self._extremes(points))
+            center, radius2 = self._grow(points, center, radius2)
+        else:
+            center, radius2 = self._solve_exact(points)
+        self.center = center
+        radius = _F(np.sqrt(radius2)) if radius2 > 0 else _F(0)  # FastMath.Sqrt0
+        self.radius = _F(radius * _F(_F(1) + _F(8e-7)))          # "increase the radius of the sphere by an epsilon", :37-38
+
+    def contains(self, point):
+        return _sq(np.asarray(point, dtype=np.float32) - self.center) <= self.radius * self.radius
+
+    @staticmethod
+    def _contains(point, center, radius2):
+        return _sq(point - center) <= radius2
+
+    @staticmethod
+    def _extremes(points):  # FillExtremes, :75-107: first minimum / maximum along each normal
+        out = []
+        for normal in _SPHERE_NORMALS:
+            values = (points[:, 0] * normal[0] + points[:, 1] * normal[1]) + points[:, 2] * normal[2]  # Float3.Dot
+            out += [points[int(np.argmin(values))], points[int(np.argmax(values))]]
+        return np.array(out, dtype=np.float32)
+
+    @classmethod
+    def _grow(cls, points, center, radius2):  # GrowSphere, :109-125
+        for current in points:
+            if cls._contains(current, center, radius2):
+                continue
+            offset = center - current
+            length = _F(np.sqrt(_sq(offset)))
+            radius = _F(_F(_F(np.sqrt(radius2)) + length) / _F(2))
+            center = (current + (offset / length) * radius).astype(np.float32)
+            radius2 = _F(radius * radius)
+        return center, radius2
+
+    @staticmethod
+    def _diameter(a, b):  # SolveFromDiameterPoints, :273-277
+        return ((a + b) / _F(2)).astype(np.float32), _F(_sq(a - b) / _F(4))
+
+    @classmethod
+    def _triangle(cls, a, b, c):  # SolveFromTriangle, :201-224
+        pba, pca = b - a, c - a
+        normal = _cross(pba, pca)
+        magnitude2 = _sq(normal)
+        if magnitude2 > 0:
+            center = (_cross((_sq(pba) * pca - _sq(pca) * pba).astype(np.float32), normal) / magnitude2 / _F(2) + a).astype(np.float32)
+            return center, _sq(a - center)
+        if (pba[0] * pca[0] + pba[1] * pca[1]) + pba[2] * pca[2] > 0:
+            return cls._diameter(a, b)
+        return cls._diameter(b, c)
+
+    @staticmethod
+    def _circumsphere(a, b, c, d):  # SolveCircumSphereFromFourExtremes, :226-268
+        rows = [a, b, c, d]
+        squares = [_sq(p) for p in rows]
+        one = _F(1)
+        det_r = one / _determinant([[p[0], p[1], p[2], one] for p in rows])
+        center = (det_r / _F(2)) * np.array([
+            _determinant([[q, p[1], p[2], one] for p, q in zip(rows, squares)]),
+            _determinant([[p[0], q, p[2], one] for p, q in zip(rows, squares)]),
+            _determinant([[p[0], p[1], q, one] for p, q in zip(rows, squares)])], dtype=np.float32)
+        center = center.astype(np.float32)
+        return center, _sq(a - center)
+
+    @classmethod
+    def _solve_exact(cls, points):  # SolveExact, :130-149
+        if len(points) == 1:
+            return points[0].copy(), _F(0)
+        center, radius2 = cls._diameter(points[0], points[1])
+        for index in range(2, len(points)):
+            if cls._contains(points[index], center, radius2):
+                continue
+            center, radius2 = cls._solve_recursive(points, index, index)
+        return center, radius2
+
+    @classmethod
+    def _solve_recursive(cls, points, end, pin1, pin2=-1, pin3=-1):  # SolveExactRecursive, :154-197
+        index = 0
+        if pin2 < 0:
+            center, radius2 = cls._diameter(points[0], points[pin1])
+            index = 1
+        elif pin3 < 0:
+            center, radius2 = cls._diameter(points[pin1], points[pin2])
+        else:
+            center, radius2 = cls._triangle(points[pin1], points[pin2], points[pin3])
+
+        while index < end:
+            if not cls._contains(points[index], center, radius2):
+                if pin2 < 0:
+                    center, radius2 = cls._solve_recursive(points, index, pin1, index)
+                elif pin3 < 0:
+                    center, radius2 = cls._solve_recursive(points, index, pin1, pin2, index)
+                else:
+                    center, radius2 = cls._circumsphere(points[pin1], points[pin2], points[pin3], points[index])
+            index += 1
+        return center, radius2
+
+
+def box_vertices(low, high):
+    """BoxBound.FillVertices (BoxBound.cs:140-156), in the reference's order."""
+    (x0, y0, z0), (x1, y1, z1) = low, high
+    return np.array([(x0, y0, z0), (x1, y1, z1), (x0, y0, z1), (x0, y1, z0), (x1, y0, z0), (x1, y1, z0), (x1, y0, z1), (x0, y1, z1)], dtype=np.float32)
+
+
+def accelerator_sphere_bound(nodes):
+    """Accelerator.SphereBound (Accelerator.cs:43-63) over QuadBoundingVolumeHierarchy.FillBounds(6, ...) (:62-118): the child
+    bounds two quad levels below the root (leaf children met on the way are taken as they are), eight corners each."""
+    stack0, stack1, boxes = [0], [], []
+
+    def child_box(node, j):
+        return (node["minX"][j], node["minY"][j], node["minZ"][j]), (node["maxX"][j], node["maxY"][j], node["maxZ"][j])
+
+    for _ in range(6 // 2 - 1):
+        while stack0:
+            node = nodes[stack0.pop()]
+            for j in range(4):
+                child = int(node["token4"][j])
+                if child == structs.TOKEN_EMPTY:
+                    continue
+                if structs.token_type(child) == structs.TOKEN_TYPE_NODE:
+                    stack1.append(int(structs.token_index(child)))
+                else:
+                    boxes.append(child_box(node, j))
+        stack0, stack1 = stack1, stack0
+
+    while stack0:
+        node = nodes[stack0.pop()]
+        for j in range(4):
+            if int(node["token4"][j]) != structs.TOKEN_EMPTY:
+                boxes.append(child_box(node, j))
+
+    points = np.concatenate([box_vertices(low, high) for low, high in boxes])
+    return SphereBound(points)
+
+
+def _root_bound_radius(nodes):
+    """Accelerator.SphereBound.radius of the scene's accelerator (AmbientLight.cs:47, DirectionalLight.cs:72)."""
+    return accelerator_sphere_bound(nodes).radius
 
 
 def prepare(description, threads=0, tree=None):
@@ -522,7 +710,7 @@ def prepare(description, threads=0, tree=None):
             first = int(light["texture"])
             mean = cubemap_average(d.textures[first:first + 6])
             luminance = lambda c: (np.float32(c[0]) * np.float32(0.212671) + np.float32(c[1]) * np.float32(0.715160)) + (np.float32(c[2]) * np.float32(0.072169) + np.float32(0))
-            radius = max(np.float32(_root_bound_radius(nodes[0])), np.float32(1))
+            radius = max(np.float32(_root_bound_radius(nodes)), np.float32(1))
             power = float(np.float32(math.pi) * radius * radius * (luminance(mean) * luminance(light["radiance"])))
         elif light["type"] == structs.INFINITE_ENVIRONMENT:
             # AmbientLight.Prepare (AmbientLight.cs:36-46) over a CylindricalTexture: pi r^2 * Average.Luminance * Intensity.Luminance
@@ -530,17 +718,20 @@ def prepare(description, threads=0, tree=None):
             d.infinite_lights[i]["distribution"] = sum(len(v) for v in distributions)
             distributions.append(values)
             luminance = lambda c: (np.float32(c[0]) * np.float32(0.212671) + np.float32(c[1]) * np.float32(0.715160)) + (np.float32(c[2]) * np.float32(0.072169) + np.float32(0))
-            radius = max(np.float32(_root_bound_radius(nodes[0])), np.float32(1))
+            radius = max(np.float32(_root_bound_radius(nodes)), np.float32(1))
             power = float(np.float32(math.pi) * radius * radius * (luminance(mean) * luminance(light["radiance"])))
         elif light["type"] == structs.INFINITE_DIRECTIONAL:
             # DirectionalLight.Prepare (DirectionalLight.cs:71-74): half of the scene's bounding disk area
             r, g, b = (np.float32(c) for c in light["intensity"])
             luminance = (r * np.float32(0.212671) + g * np.float32(0.715160)) + (b * np.float32(0.072169) + np.float32(0))
-            radius = np.float32(_root_bound_radius(nodes[0]))
+            radius = np.float32(_root_bound_radius(nodes))
             power = float(luminance * np.float32(math.pi * 0.5) * radius * radius)
         else:
-            radiance = np.ascontiguousarray(light["radiance"], dtype=np.float32)
-            power = lib.echo_host_ambient_power(_pointer(radiance), _pointer(nodes[:1]))
+            # AmbientLight.Prepare (AmbientLight.cs:42-51) over a constant texture: pi * max(r, 1)^2 * luminance
+            r, g, b = (np.float32(c) for c in light["radiance"])
+            luminance = (r * np.float32(0.212671) + g * np.float32(0.715160)) + (b * np.float32(0.072169) + np.float32(0))
+            radius = max(np.float32(_root_bound_radius(nodes)), np.float32(1))
+            power = float(np.float32(math.pi) * radius * radius * luminance)
         if power >= 8e-7:
             keep.append(i)
             infinite_power = np.float32(infinite_power + np.float32(power))

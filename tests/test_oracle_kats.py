@@ -539,3 +539,47 @@ def test_cylindrical_to_direction_round_trip():
         uv = rng.random(2).astype(np.float32)
         check = ol.cylindrical_to_uv(ol.cylindrical_to_direction(uv))
         assert np.all(np.abs(check - uv) < 1e-5), (uv, check)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Aggregation/SphereBoundTests.cs — the host mirror of SphereBound (echorenderer_b200/host.py), whose radius is an INPUT of the C ABI
+# (echo_b200_scene_set_bound_radius; the infinite lights' power, AmbientLight.cs:47, DirectionalLight.cs:72)
+@pytest.mark.parametrize("count", [1, 2, 3, 4, 5, 6, 100, 1000])
+def test_sphere_bound_contains_all(count):
+    """SphereBoundTests.ContainsAll (:13-25): random points in a ball of radius in [count / 2, count)."""
+    from echorenderer_b200.host import SphereBound
+    rng = np.random.default_rng(42 + count)
+    radius = rng.uniform(count / 2, count)
+    points = (rng.normal(size=(count, 3)) / np.linalg.norm(rng.normal(size=(count, 3)), axis=1, keepdims=True) * radius * rng.random((count, 1))).astype(np.float32)
+    bound = SphereBound(points)
+    assert all(bound.contains(point) for point in points)
+
+
+@pytest.mark.parametrize("count", [64, 512])
+def test_sphere_bound_tightness(count):
+    """SphereBoundTests.Tightness (:27-52, 20 of its 1000 repeats): stratified points ON a sphere are all contained, and no
+    point of the sphere 3 % larger is."""
+    from echorenderer_b200.host import SphereBound
+    rng = np.random.default_rng(7 + count)
+    for _ in range(20):
+        radius = rng.uniform(count / 2, count)
+        side = int(math.isqrt(count))
+        cells = np.stack(np.meshgrid(np.arange(side), np.arange(count // side), indexing="ij"), axis=-1).reshape(-1, 2)
+        sample = (cells + rng.random(cells.shape)) / [side, count // side]
+        z = 1 - 2 * sample[:, 0]
+        r = np.sqrt(np.maximum(0, 1 - z * z))
+        points = (np.stack([r * np.cos(2 * np.pi * sample[:, 1]), z, r * np.sin(2 * np.pi * sample[:, 1])], axis=-1) * radius).astype(np.float32)
+        bound = SphereBound(points)
+        assert all(bound.contains(point) for point in points)
+        outside = rng.normal(size=(count, 3))
+        outside = outside / np.linalg.norm(outside, axis=1, keepdims=True) * radius * 1.03
+        assert not any(bound.contains(point) for point in outside.astype(np.float32))
+
+
+def test_sphere_bound_edge():
+    """SphereBoundTests.Edge (:54-64, "created from a bug"): the eight corners of the box [-3, 3]^3."""
+    from echorenderer_b200.host import SphereBound, box_vertices
+    points = box_vertices((-3, -3, -3), (3, 3, 3))
+    bound = SphereBound(points)
+    assert all(bound.contains(point) for point in points)
+    assert bound.radius == pytest.approx(3 * math.sqrt(3), rel=1e-5) and np.allclose(bound.center, 0, atol=1e-5)
