@@ -1419,8 +1419,11 @@ ECHO_DEVICE void shade_body(const DeviceScene& scene, const EchoRenderParams& pa
 }
 
 // One loop body of PathTracedEvaluator.Evaluate for every path in a material-class queue.
+#ifndef ECHO_SHADE_MIN_BLOCKS
+#define ECHO_SHADE_MIN_BLOCKS 6 // resident CTAs per SM asked of the shading kernels: 80 registers and a few hundred bytes of spills instead of 100-110 registers at 4 CTAs; no target / 5 / 6 / 7 / 8: C3 474 / 477 / 483 / 483 / 485, C4 329 / 338 / 342 / 345 / 347, textured 719 / 721 / 733 / 725 / 712 M samples/s (variants/ab15.sh)
+#endif
 template<int CLASS, uint32_t KINDS, bool INST>
-__global__ void __launch_bounds__(kBlock) shade_kernel(DeviceScene scene, EchoRenderParams params, const uint32_t* __restrict__ queue,
+__global__ void __launch_bounds__(kBlock, ECHO_SHADE_MIN_BLOCKS) shade_kernel(DeviceScene scene, EchoRenderParams params, const uint32_t* __restrict__ queue,
                                                       const uint32_t* __restrict__ queueCount, PathBuffers paths, int current)
 {
 	uint32_t i = blockIdx.x * kBlock + threadIdx.x;
