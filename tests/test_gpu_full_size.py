@@ -4,7 +4,8 @@ C2: the whole 1 000 000-triangle + 10 000-sphere scene and the whole 16 777 216-
 33.5 M queries in a few seconds on the box's host cores, so tokens, distances and barycentrics are compared bit for bit on
 every ray, followed by the size-independent properties of the domain (occlusion agrees with the closest hit on either side of
 the hit distance; a hit never lies beyond the ray's limit; re-tracing is idempotent under the persistent scheduler).
-C3 / C4: the full-resolution 1920 x 1080 frame of the full-size scenes, a spread of its tiles against the oracle."""
+C3 / C4: the full-resolution 1920 x 1080 frame of the full-size scenes, a spread of its tiles against the oracle.
+C5: the 9 998 246-triangle scene (4.9 M nodes, quad depth 16) at 3840 x 2160: a 2 Mi-ray incoherent batch and a spread of tiles."""
 import numpy as np
 import pytest
 
@@ -99,4 +100,35 @@ def test_full_resolution_tiles_match_oracle(name, bounce_limit):
     inside = (np.minimum(tiles[:, 0] * tile + tile, width) - tiles[:, 0] * tile) * (np.minimum(tiles[:, 1] * tile + tile, height) - tiles[:, 1] * tile)
     assert int(stats["sampleEvaluated"][0]) == int(expected_stats["sampleEvaluated"][0]) == int(inside.sum()) * 16  # the top row of tiles is half outside
     for field in ("bounceCreated", "lightSampled", "lightOcclusionChecked", "traceQueries", "occludeQueries"):
+        assert int(stats[field][0]) == int(expected_stats[field][0]) > 0, field
+
+
+def test_c5_ten_million_triangles():
+    """C5: 9 998 246 triangles, 4 948 274 QBVH nodes (633 MB), quad depth 16 — the largest scene of BASELINE.json. Closest hit and
+    occlusion of 2 Mi incoherent rays bit for bit, then 64 tiles spread over the 3840 x 2160 frame at bounce limit 128."""
+    prepared = host.prepare(scenes.large_scene())
+    assert len(prepared.triangles) > 9_900_000 and prepared.max_depth >= 14
+    oracle = oracle_lib.OracleScene(prepared)
+    rays = scenes.random_rays(prepared.bounds, 1 << 21, seed=11)
+    shadow = scenes.random_rays(prepared.bounds, 1 << 21, seed=11, occlusion=True)
+    width, height, tile = 3840, 2160, 16
+    tiles = np.ascontiguousarray(hilbert_curve_pattern((width // tile, height // tile))[::509][:64])
+    params = structs.render_params(width, height, tile, extend=4, min_epoch=1, max_epoch=1, bounce_limit=128, seed=1)
+
+    with PreparedScene(prepared) as scene:
+        hits, expected = scene.trace(rays), oracle.trace(rays)
+        assert np.array_equal(hits["token"], expected["token"])
+        assert np.array_equal(hits["distance"].view(np.uint32), expected["distance"].view(np.uint32))
+        hit = expected["token"] != structs.TOKEN_EMPTY
+        assert hit.mean() > 0.05 and np.array_equal(hits["uv"][hit].view(np.uint32), expected["uv"][hit].view(np.uint32))
+        assert np.array_equal(scene.occlude(shadow), oracle.occlude(shadow))
+        secondary = scenes.secondary_rays(prepared, rays, expected)
+        again, expected_again = scene.trace(secondary), oracle.trace(secondary)
+        assert np.array_equal(again.view(np.uint8), expected_again.view(np.uint8))
+        actual, stats = scene.render_tiles(params, tiles)
+
+    expected, expected_stats = oracle.render_tiles(params, tiles)
+    assert expected[..., :3].max() > 0 and relative_rmse(actual, expected) <= 1e-4
+    assert np.any(actual.view(np.uint32) != expected.view(np.uint32), axis=-1).mean() <= 1e-3
+    for field in ("sampleEvaluated", "bounceCreated", "lightSampled", "traceQueries", "occludeQueries"):
         assert int(stats[field][0]) == int(expected_stats[field][0]) > 0, field
