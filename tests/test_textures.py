@@ -221,3 +221,34 @@ def test_cubemap_faces(cubemap_small):
         again = infinite_light(oracle, 0, (0.5, 0.5), out[4:7])
         assert out[3] == pytest.approx(1 / (4 * np.pi), rel=1e-6)
         assert np.allclose(again[7:10], out[0:3], rtol=5e-3, atol=1e-4)  # Evaluate(LocalToWorld * d) == the value sampled for d
+
+
+@pytest.mark.parametrize("fixture", ["environment_small", "cubemap_small"])
+def test_directional_texture_average(fixture, request):
+    """DirectionalTextureBaseTests.Average (src/Echo.UnitTests/Textures/DirectionalTextureTests.cs:95-101): `AverageConverge` — the mean
+    of Evaluate over stratified uniform-sphere directions (IDirectionalTexture.cs:59-88) — equals the `Average` the texture's
+    Prepare computed, which is what the light's power is built from. Here: the oracle's Evaluate against the host mirror's
+    averages (CylindricalTexture.Prepare :93-95; the cubemap's stand-in), on a 160 x 160 stratification instead of 1000 x 1000,
+    so the tolerance is that sampling's error instead of the reference's AlmostZero."""
+    prepared = request.getfixturevalue(fixture)
+    oracle = oracle_lib.OracleScene(prepared)
+    light = prepared.description.infinite_lights[0]
+    textures = prepared.description.textures
+    if fixture == "environment_small":
+        _, expected = host.build_environment(textures[int(light["texture"])])
+    else:
+        first = int(light["texture"])
+        expected = host.cubemap_average(textures[first:first + 6])
+
+    size = 160
+    rng = np.random.default_rng(5)
+    total = np.zeros(3)
+    for y in range(size):
+        for x in range(size):
+            u, v = (x + rng.random()) / size, (y + rng.random()) / size
+            z = 1 - 2 * u  # Sample2D.UniformSphere, Sample2D.cs:35
+            r = np.sqrt(max(0.0, 1 - z * z))
+            direction = (r * np.cos(2 * np.pi * v), r * np.sin(2 * np.pi * v), z)
+            total += infinite_light(oracle, 0, (0.5, 0.5), direction)[7:10]
+    average = total / size ** 2 / np.asarray(light["radiance"], dtype=np.float64)
+    assert np.allclose(average, expected, rtol=0.01), (average, expected)
