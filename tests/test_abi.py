@@ -107,3 +107,36 @@ def test_null_scene_is_rejected():
     assert lib.echo_b200_trace_batch(None, None, 0, None) == _native.ERR_INVALID
     assert lib.echo_b200_render_tiles(None, None, None, 0, None, None) == _native.ERR_INVALID
     assert lib.echo_b200_scene_destroy(None) == _native.OK
+
+
+def _run_bench(arguments, environment=None):
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    result = subprocess.run([sys.executable, os.path.join(root, "bench.py")] + arguments, capture_output=True, text=True, timeout=600,
+                            env={**os.environ, **(environment or {})})
+    assert result.returncode == 0, result.stderr[-2000:]
+    lines = [line for line in result.stdout.splitlines() if line.strip()]
+    return [json.loads(line) for line in lines]
+
+
+@pytest.mark.parametrize("workload", ["trace", "render"])
+def test_bench_reference_arm_contract(workload):
+    """`bench.py --impl reference` (runs on the host cores, no GPU): ONE JSON line on stdout with the keys of the measurement
+    contract, `cpu_baseline` and `e2e` describing this very run; under torchrun every rank but 0 exits 0 without a line."""
+    arguments = ["--impl", "reference", "--steps", "1", "--warmup", "1"]
+    arguments += ["--quads", "64", "32", "--rays", "65536", "--cpu-sample", "65536"] if workload == "trace" else \
+        ["--workload", "render", "--scene", "cornell", "--width", "512", "--height", "512", "--spp", "2"]
+    lines = _run_bench(arguments)
+    assert len(lines) == 1
+    line = lines[0]
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config",
+                "impl", "cpu_baseline", "e2e", "gpu_launches"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["value"] > 0 and line["warmup"] >= 3 and line["vs_baseline"] is None and line["gpu_launches"] == 0
+    assert line["unit"] == ("Mrays/s" if workload == "trace" else "samples/s") and "workload" in line["config"]
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert _run_bench(arguments, {"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"}) == []
