@@ -34,6 +34,9 @@ constexpr unsigned long long kPool = 256;         // rays reserved per global at
 #ifndef ECHO_SHARED_STACK
 #define ECHO_SHARED_STACK 8 // traversal-stack entries per thread kept in shared memory (0 = all in local memory), see `stack` below
 #endif
+#ifndef ECHO_ANY_UNORDERED
+#define ECHO_ANY_UNORDERED 0
+#endif
 #ifndef ECHO_LEAF_MAX_WAIT
 #define ECHO_LEAF_MAX_WAIT 2 // a lane waits at most two iterations for its primitive test (A/B on C2/C3/C4: +1-2 %)
 #endif
@@ -412,6 +415,11 @@ ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, uint32_t 
 			bool swap0 = (orders >> __float_as_int(q3.v[1])) & 1u;
 			bool swap1 = (orders >> __float_as_int(q3.v[2])) & 1u;
 			bool swapPairs = (orders >> __float_as_int(q3.v[0])) & 1u;
+#if ECHO_ANY_UNORDERED
+			// A/B only (default off): an occlusion query's answer does not depend on the visit order, so the any-hit kernels
+			// could take the children as stored. Measured in profiles/README.md; the visit counters would no longer be the reference's.
+			if (ANY) swap0 = swap1 = swapPairs = false;
+#endif
 
 			float a0 = swap0 ? t1 : t0, a1 = swap0 ? t0 : t1, b0 = swap1 ? t3 : t2, b1 = swap1 ? t2 : t3;
 			uint32_t c0 = swap0 ? token1 : token0, c1 = swap0 ? token0 : token1, d0 = swap1 ? token3 : token2, d1 = swap1 ? token2 : token3;
