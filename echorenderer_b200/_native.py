@@ -33,6 +33,7 @@ EXPORTS = [
     "echo_b200_debug_evaluate_samples4", "echo_b200_debug_bounds_violations",
     "echo_b200_trace_batch_device_counted", "echo_b200_occlude_batch_device_counted", "echo_b200_debug_bxdf_batch", "echo_b200_debug_math",
     "echo_b200_debug_evaluate_samples",
+    "echo_b200_host_alloc", "echo_b200_host_free", "echo_b200_host_register", "echo_b200_host_unregister", "echo_b200_debug_set_option",
 ]
 
 
@@ -79,6 +80,11 @@ def library():
         "echo_b200_debug_bxdf_batch": [i32, i32, p, p, p, u64, p, p, p],
         "echo_b200_debug_math": [i32, i32, p, p, p, u64, p],
         "echo_b200_debug_evaluate_samples": [p, p, p, p, u64, p],
+        "echo_b200_host_alloc": [ctypes.POINTER(p), u64],
+        "echo_b200_host_free": [p],
+        "echo_b200_host_register": [p, u64],
+        "echo_b200_host_unregister": [p],
+        "echo_b200_debug_set_option": [ctypes.c_char_p, ctypes.c_int64],
     }
 
     for name, argtypes in signatures.items():
@@ -108,3 +114,47 @@ def device_count():
     count = ctypes.c_int32()
     check(library().echo_b200_device_count(ctypes.byref(count)))
     return count.value
+
+
+class HostBuffer:
+    """Page-locked host memory from echo_b200_host_alloc, viewed as a numpy array: what a host hands to the host-buffer entry
+    points so that their copies run asynchronously at the link's rate (a `fixed`-pinned managed array is pageable for CUDA)."""
+
+    def __init__(self, count, dtype):
+        import numpy as np
+        self.dtype = np.dtype(dtype)
+        self.count = int(count)
+        self._pointer = ctypes.c_void_p()
+        check(library().echo_b200_host_alloc(ctypes.byref(self._pointer), self.count * self.dtype.itemsize))
+        buffer = (ctypes.c_uint8 * max(self.count * self.dtype.itemsize, 1)).from_address(self._pointer.value)
+        self.array = np.frombuffer(buffer, dtype=self.dtype, count=self.count)
+
+    @property
+    def address(self):
+        return self._pointer.value
+
+    def free(self):
+        if self._pointer is not None and self._pointer.value:
+            self.array = None
+            library().echo_b200_host_free(self._pointer)
+            self._pointer = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def set_option(name, value):
+    """echo_b200_debug_set_option: one tuning switch of the wavefront (the ECHO_B200_<name> environment variables), at run time."""
+    check(library().echo_b200_debug_set_option(name.encode(), int(value)))
+
+
+def host_register(array):
+    """cudaHostRegister of a caller-owned numpy array (echo_b200_host_register); pair with host_unregister before it is freed."""
+    check(library().echo_b200_host_register(ctypes.c_void_p(array.ctypes.data), array.nbytes))
+
+
+def host_unregister(array):
+    check(library().echo_b200_host_unregister(ctypes.c_void_p(array.ctypes.data)))

@@ -85,6 +85,16 @@ bool require_committed(EchoScene* scene)
 	return true;
 }
 
+// Shading indexes the material array with what the geometry stores; commit only validates those indices against a non-empty
+// array (a scene without materials is fine for trace / occlude batches), so the render entry points must refuse such a scene
+// instead of reading the zeroed placeholder out of bounds.
+bool require_renderable(EchoScene* scene)
+{
+	if (!require_committed(scene)) return false;
+	if (scene->d.materialCount == 0u) { set_error("the scene has no materials: it can serve trace / occlude batches but cannot be rendered"); return false; }
+	return true;
+}
+
 // rays per pipelined chunk of the host-buffer batch (1 Mi: 32 MB in, 16 MB out); the last chunk's kernel and download are
 // the only work the PCIe upload cannot hide, so chunks are kept small, but large enough to fill one resident wave
 uint64_t chunk_rays()
@@ -140,21 +150,27 @@ int32_t batch_host(EchoScene* scene, const EchoRay* rays, uint64_t n, Out* out, 
 	if (!ensure_scratch(scene, chunk)) return ECHO_B200_ERR_CUDA;
 
 	int slot = 0;
+	bool ok = true;
 
-	for (uint64_t first = 0; first < n; first += chunk, slot = (slot + 1) % EchoScene::kSlots)
+	for (uint64_t first = 0; ok && first < n; first += chunk, slot = (slot + 1) % EchoScene::kSlots)
 	{
 		uint64_t count = std::min<uint64_t>(chunk, n - first);
 		cudaStream_t stream = scene->copyStreams[slot];
 
-		if (!check_cuda(cudaMemcpyAsync(scene->scratchRays[slot], rays + first, sizeof(EchoRay) * count, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync(rays)")) return ECHO_B200_ERR_CUDA;
-		if (!launch((const EchoRay*)scene->scratchRays[slot], count, (Out*)scene->scratchOut[slot], stream)) return ECHO_B200_ERR_CUDA;
-		if (!check_cuda(cudaMemcpyAsync(out + first, scene->scratchOut[slot], sizeof(Out) * count, cudaMemcpyDeviceToHost, stream), "cudaMemcpyAsync(out)")) return ECHO_B200_ERR_CUDA;
+		ok = check_cuda(cudaMemcpyAsync(scene->scratchRays[slot], rays + first, sizeof(EchoRay) * count, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync(rays)")
+			&& launch((const EchoRay*)scene->scratchRays[slot], count, (Out*)scene->scratchOut[slot], stream)
+			&& check_cuda(cudaMemcpyAsync(out + first, scene->scratchOut[slot], sizeof(Out) * count, cudaMemcpyDeviceToHost, stream), "cudaMemcpyAsync(out)");
 	}
 
-	for (int i = 0; i < EchoScene::kSlots; i++)
-		if (!check_cuda(cudaStreamSynchronize(scene->copyStreams[i]), "batch")) return ECHO_B200_ERR_CUDA;
+	// Also after a failed enqueue: downloads of earlier chunks may still be writing into the caller's buffer, which the caller
+	// is free to release as soon as this call returns. The first error is the one reported.
+	std::string firstError = ok ? std::string() : last_error_string();
 
-	return ECHO_B200_OK;
+	for (int i = 0; i < EchoScene::kSlots; i++)
+		if (!check_cuda(cudaStreamSynchronize(scene->copyStreams[i]), "batch") && ok) { ok = false; firstError = last_error_string(); }
+
+	if (!ok) set_error(firstError);
+	return ok ? ECHO_B200_OK : ECHO_B200_ERR_CUDA;
 }
 
 } // namespace
@@ -180,6 +196,38 @@ int32_t echo_b200_device_count(int32_t* out)
 
 	*out = count;
 	return ECHO_B200_OK;
+}
+
+int32_t echo_b200_host_alloc(void** out, uint64_t bytes)
+{
+	if (!out) return fail(ECHO_B200_ERR_INVALID, "out is null");
+	*out = nullptr;
+	int32_t count = 0;
+	int32_t status = echo_b200_device_count(&count);
+	if (status != ECHO_B200_OK) return status;
+	// portable: page-locked for every device of the process, not only the current one
+	return check_cuda(cudaHostAlloc(out, std::max<uint64_t>(bytes, 1), cudaHostAllocPortable), "cudaHostAlloc") ? ECHO_B200_OK : ECHO_B200_ERR_CUDA;
+}
+
+int32_t echo_b200_host_free(void* pointer)
+{
+	if (!pointer) return ECHO_B200_OK;
+	return check_cuda(cudaFreeHost(pointer), "cudaFreeHost") ? ECHO_B200_OK : ECHO_B200_ERR_CUDA;
+}
+
+int32_t echo_b200_host_register(void* pointer, uint64_t bytes)
+{
+	if (!pointer || bytes == 0) return fail(ECHO_B200_ERR_INVALID, "null or empty range");
+	int32_t count = 0;
+	int32_t status = echo_b200_device_count(&count);
+	if (status != ECHO_B200_OK) return status;
+	return check_cuda(cudaHostRegister(pointer, bytes, cudaHostRegisterPortable), "cudaHostRegister") ? ECHO_B200_OK : ECHO_B200_ERR_CUDA;
+}
+
+int32_t echo_b200_host_unregister(void* pointer)
+{
+	if (!pointer) return ECHO_B200_OK;
+	return check_cuda(cudaHostUnregister(pointer), "cudaHostUnregister") ? ECHO_B200_OK : ECHO_B200_ERR_CUDA;
 }
 
 int32_t echo_b200_scene_create(EchoScene** out, int32_t device)
@@ -370,22 +418,32 @@ int32_t echo_b200_scene_set_packs(EchoScene* scene, const EchoPack* packs, uint3
 namespace
 {
 
-// Traversal stack entries the deepest chain of packs needs below `pack`: the reference stackallocs maxDepth * 3 + 1 per
-// recursion (QuadBoundingVolumeHierarchy.cs:34,125); the device keeps all layers in one stack. 0 = invalid (cycle / too deep).
-uint32_t chain_stack(const EchoScene* scene, uint32_t pack, uint32_t layer)
+// Traversal stack entries the deepest chain of packs needs from `pack` down: the reference stackallocs maxDepth * 3 + 1 per
+// recursion (QuadBoundingVolumeHierarchy.cs:34,125); the device keeps all layers in one stack. Memoised per pack (a pack placed
+// 1e5 times is walked once): `need[p]` entries and `height[p]` layers below p, `mark` = 1 while p is on the walk (a cycle), 2 when done.
+// false = cyclic or deeper than TokenHierarchy.MaxLayer.
+bool chain_stack(const EchoScene* scene, uint32_t pack, std::vector<uint32_t>& need, std::vector<uint32_t>& height, std::vector<uint8_t>& mark)
 {
-	if (layer > ECHO_MAX_INSTANCE_LAYERS) return 0u;
+	if (mark[pack] == 2) return true;
+	if (mark[pack] == 1) return false; // the pack contains itself
+	mark[pack] = 1;
+
 	const EchoPack& p = scene->packs[pack];
-	uint32_t deepest = 0u;
+	uint32_t deepest = 0u, layers = 0u;
 
 	for (uint32_t i = 0; i < p.instanceCount; i++)
 	{
-		uint32_t below = chain_stack(scene, scene->instances[p.instanceOffset + i].pack, layer + 1u);
-		if (below == 0u) return 0u;
-		deepest = std::max(deepest, below);
+		uint32_t child = scene->instances[p.instanceOffset + i].pack;
+		if (!chain_stack(scene, child, need, height, mark)) return false;
+		deepest = std::max(deepest, need[child]);
+		layers = std::max(layers, height[child] + 1u);
 	}
 
-	return p.maxDepth * 3u + 1u + deepest;
+	if (layers > ECHO_MAX_INSTANCE_LAYERS) return false;
+	need[pack] = p.maxDepth * 3u + 1u + deepest;
+	height[pack] = layers;
+	mark[pack] = 2;
+	return true;
 }
 
 } // namespace
@@ -436,7 +494,9 @@ int32_t echo_b200_scene_commit(EchoScene* scene)
 
 	if (!scene->packs.empty())
 	{
-		uint32_t entries = chain_stack(scene, 0u, 0u);
+		std::vector<uint32_t> need(scene->packs.size(), 0u), height(scene->packs.size(), 0u);
+		std::vector<uint8_t> mark(scene->packs.size(), 0);
+		uint32_t entries = chain_stack(scene, 0u, need, height, mark) ? need[0] : 0u;
 		if (entries == 0u) return fail(ECHO_B200_ERR_INVALID, "instancing deeper than TokenHierarchy.MaxLayer (5) or cyclic");
 		stackDepth = (entries + 1u) / 3u; // smallest depth with depth * 3 + 1 >= entries
 		if (stack_class(stackDepth) < 0) return fail(ECHO_B200_ERR_UNSUPPORTED, "the deepest chain of instanced packs needs more than 192 stack entries");
@@ -722,7 +782,7 @@ int32_t echo_b200_occlude_batch_device_counted(EchoScene* scene, const EchoRay* 
 
 int32_t echo_b200_render_tiles(EchoScene* scene, const EchoRenderParams* params, const int32_t* tileXY, uint32_t tileCount, float* outRGBA, EchoStats* stats)
 {
-	if (!require_committed(scene)) return ECHO_B200_ERR_INVALID;
+	if (!require_renderable(scene)) return ECHO_B200_ERR_INVALID;
 	if (!params || (!tileXY && tileCount) || (!outRGBA && tileCount)) return fail(ECHO_B200_ERR_INVALID, "null argument");
 	if (stats) *stats = EchoStats{};
 	if (tileCount == 0) return ECHO_B200_OK;
@@ -743,7 +803,7 @@ int32_t echo_b200_render_tiles(EchoScene* scene, const EchoRenderParams* params,
 
 int32_t echo_b200_render_frame_device(EchoScene* scene, const EchoRenderParams* params, const int32_t* tileXY, uint32_t tileCount, float* frame, EchoStats* stats, void* stream)
 {
-	if (!require_committed(scene)) return ECHO_B200_ERR_INVALID;
+	if (!require_renderable(scene)) return ECHO_B200_ERR_INVALID;
 	if (!params || (!tileXY && tileCount) || !frame) return fail(ECHO_B200_ERR_INVALID, "null argument");
 	if (stats) *stats = EchoStats{};
 	if (tileCount == 0) return ECHO_B200_OK;
@@ -766,7 +826,7 @@ int32_t echo_b200_frame_resolve_device(EchoScene* scene, float* frame, int32_t w
 
 int32_t echo_b200_debug_evaluate_samples(EchoScene* scene, const EchoRenderParams* params, const int32_t* pixelXY, const uint32_t* sampleIndex, uint64_t n, float* outRGB)
 {
-	if (!require_committed(scene)) return ECHO_B200_ERR_INVALID;
+	if (!require_renderable(scene)) return ECHO_B200_ERR_INVALID;
 	if (!params || !pixelXY || !sampleIndex || !outRGB) return fail(ECHO_B200_ERR_INVALID, "null argument");
 	DeviceGuard guard(scene->device);
 	if (!guard.ok) return ECHO_B200_ERR_NO_DEVICE;
@@ -791,11 +851,17 @@ int32_t echo_b200_debug_bounds_violations(EchoScene* scene, uint32_t* out)
 
 int32_t echo_b200_debug_evaluate_samples4(EchoScene* scene, const EchoRenderParams* params, const int32_t* pixelXY, const uint32_t* sampleIndex, uint64_t n, float* outRGBA)
 {
-	if (!require_committed(scene)) return ECHO_B200_ERR_INVALID;
+	if (!require_renderable(scene)) return ECHO_B200_ERR_INVALID;
 	if (!params || !pixelXY || !sampleIndex || !outRGBA) return fail(ECHO_B200_ERR_INVALID, "null argument");
 	DeviceGuard guard(scene->device);
 	if (!guard.ok) return ECHO_B200_ERR_NO_DEVICE;
 	return evaluate_sample_list(scene->render, scene->d, *params, 4, pixelXY, sampleIndex, n, outRGBA, scene->stream) ? ECHO_B200_OK : ECHO_B200_ERR_CUDA;
+}
+
+int32_t echo_b200_debug_set_option(const char* name, int64_t value)
+{
+	if (!name) return fail(ECHO_B200_ERR_INVALID, "name is null");
+	return set_render_option(name, (long long)value) ? ECHO_B200_OK : fail(ECHO_B200_ERR_INVALID, "unknown option");
 }
 
 static int32_t debug_device(int32_t device)

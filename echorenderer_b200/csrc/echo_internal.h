@@ -32,8 +32,8 @@ bool launch_occlude_instanced(const DeviceScene& scene, const EchoRay* rays, con
 bool launch_persistent_instanced(const DeviceScene& scene, const EchoRay* rays, const EchoTokenHierarchy* ignore, uint64_t n, EchoHit* hits,
                                  EchoTokenHierarchy* hitLayers, uint8_t* occluded, cudaStream_t stream, bool& launched);
 
-unsigned long long* next_ray_counter(cudaStream_t stream); // zeroed work counter for one persistent launch
-int persistent_grid(const void* kernel);                  // resident CTAs of a persistent kernel on the current device
+unsigned long long* ray_counters(cudaStream_t stream); // the self-resetting work counter pair of persistent launches on this device and stream
+int persistent_grid(const void* kernel);              // resident CTAs of a persistent kernel on the current device (cached per device)
 
 // ---- build.cu: linear BVH on the device, collapsed to the QBVH node format (host buffers in and out) ----
 bool build_qbvh_device(const EchoTriangle* triangles, uint32_t triangleCount, const EchoSphere* spheres, uint32_t sphereCount,
@@ -52,6 +52,9 @@ bool render_tiles(RenderState* state, const DeviceScene& scene, const EchoRender
                   float4* tilesOut, float4* frame, EchoStats* stats, cudaStream_t stream);
 
 bool launch_frame_resolve(float4* frame, int32_t width, int32_t height, cudaStream_t stream);
+
+// tuning switches of the wavefront (the ECHO_B200_<NAME> environment variables), changeable at run time; false = unknown name
+bool set_render_option(const char* name, long long value);
 
 // ---- debug.cu: device mirrors of the oracle's known-answer hooks ----
 bool launch_debug_bxdf(int32_t kind, const float* params, const float* outgoing, const float* samples, uint64_t n,

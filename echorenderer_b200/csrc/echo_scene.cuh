@@ -38,6 +38,7 @@ struct DeviceScene
 	const float4* instances;       // 8 x float4 per EchoInstance
 
 	unsigned int* violations;      // ECHO_BOUNDS_CHECK builds: bit k set = check k failed somewhere (see ECHO_CHECK); null otherwise
+	unsigned long long* lightVisits; // counted passes only (ECHO_EVALUATOR_COUNT_VISITS): LightBound.Importance evaluations; null otherwise
 
 	uint32_t nodeCount, triangleCount, sphereCount, materialCount;
 	uint32_t lightNodeCount, emitterCount, pointLightCount, infiniteLightCount;

@@ -75,6 +75,27 @@ ECHO_DEVICE float8 ldg256(const void* pointer)
 
 ECHO_DEVICE bool finite_bits(float v) { return (__float_as_uint(v) & 0x7F800000u) != 0x7F800000u; }
 
+// The work counter of a persistent launch is a pair: [0] = the next unreserved ray, [1] = CTAs that have left. Every kernel
+// built on persistent_traverse ends with this call; the last CTA to leave puts both words back to zero, so the pair can serve
+// the next launch on the same stream with no memset in between and no host-side bookkeeping of which launch still owns it
+// (trace.cu ray_counters: one pair per device and stream, launches on one stream are ordered).
+ECHO_DEVICE void persistent_finish(unsigned long long* __restrict__ nextRay)
+{
+	__syncthreads();
+
+	if (threadIdx.x == 0)
+	{
+		__threadfence();
+
+		if (atomicAdd(nextRay + 1, 1ull) == (unsigned long long)gridDim.x - 1ull)
+		{
+			nextRay[0] = 0ull;
+			nextRay[1] = 0ull;
+			__threadfence();
+		}
+	}
+}
+
 // IO concept:
 //   const float4* ray_pointer(uint32_t index)   -> 32 contiguous bytes: origin.xyz direction.x | direction.yz limit ignore
 //   void store_closest(uint32_t index, bool hit, uint32_t token, float distance, vec2 uv, float limit)

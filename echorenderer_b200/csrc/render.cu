@@ -62,6 +62,62 @@ struct PathBuffers
 	unsigned long long* stats; // EchoStats layout
 };
 
+// ECHO_B200_PROFILE=1: per-kernel device time of the wavefront (CUDA events around every launch, synchronised; the
+// numbers printed by a run with this switch on are diagnostics, never bench values).
+struct KernelTimer
+{
+	enum { RAYGEN, EXTEND, SHADE_MISS, SHADE_DIFFUSE, SHADE_DIELECTRIC, SHADE_CONDUCTOR, SHADE_TERMINAL, SHADOW, ROTATE, FINISH, ACCUMULATE, OTHER, COUNT };
+	bool enabled = false;
+	double milliseconds[COUNT] = {};
+	uint64_t launches[COUNT] = {};
+	cudaEvent_t begin = nullptr, end = nullptr;
+
+	KernelTimer()
+	{
+		const char* value = std::getenv("ECHO_B200_PROFILE");
+		enabled = value && value[0] == '1';
+	}
+
+	~KernelTimer()
+	{
+		if (begin) cudaEventDestroy(begin);
+		if (end) cudaEventDestroy(end);
+	}
+
+	void start(cudaStream_t stream)
+	{
+		if (!enabled) return;
+		if (!begin) { cudaEventCreate(&begin); cudaEventCreate(&end); } // on the worker's own device
+		cudaEventRecord(begin, stream);
+	}
+
+	float last = 0.0f;
+
+	void stop(int slot, cudaStream_t stream)
+	{
+		if (!enabled) return;
+		cudaEventRecord(end, stream);
+		cudaEventSynchronize(end);
+		float ms = 0.0f;
+		cudaEventElapsedTime(&ms, begin, end);
+		milliseconds[slot] += ms;
+		++launches[slot];
+		last = ms;
+	}
+
+	void report()
+	{
+		if (!enabled) return;
+		static const char* names[COUNT] = { "raygen", "extend", "shade<miss>", "shade<diffuse>", "shade<dielectric>", "shade<conductor>", "shade<terminal>", "shadow", "rotate", "finish", "accumulate", "other" };
+		double total = 0.0;
+		for (double ms : milliseconds) total += ms;
+		for (int i = 0; i < COUNT; i++)
+			if (launches[i]) std::fprintf(stderr, "[echo_b200 profile] %-18s %8llu launches %10.3f ms %5.1f %%\n", names[i], (unsigned long long)launches[i], milliseconds[i], 100.0 * milliseconds[i] / total);
+		std::fprintf(stderr, "[echo_b200 profile] total %.3f ms\n", total);
+		for (int i = 0; i < COUNT; i++) { milliseconds[i] = 0.0; launches[i] = 0; }
+	}
+};
+
 struct WorkerState
 {
 	cudaStream_t stream = nullptr;
@@ -82,13 +138,16 @@ struct WorkerState
 	int32_t* tileXYDevice = nullptr;
 	uint64_t tileCapacity = 0;
 
-	uint32_t* hostCounters = nullptr; // pinned
-	cudaEvent_t iterationDone = nullptr; // blocking-sync event: the pipeline thread sleeps between wavefront iterations
+	uint32_t* hostCounters = nullptr; // pinned, mapped: [0..1] the 8-byte iteration mirror the device writes, [8] active pixels of an epoch
 
-	// one narrow wavefront iteration (9 kernels) as an instantiated CUDA graph per ping-pong side; `graphKey` is what the
-	// captured launches depend on (scene, parameters, buffers), anything else comes from device memory
-	cudaGraphExec_t narrowGraph[2] = { nullptr, nullptr };
-	std::vector<unsigned char> graphKey;
+	// Run-ahead launching (evaluate_paths): the pipeline thread queues wavefront iterations without waiting for their counts;
+	// `serial` numbers every iteration this worker ever launched, the rotate kernel publishes {serial, rays left} in the mirror
+	static constexpr int kEventRing = 8;
+	cudaEvent_t iterationDone[kEventRing] = {};
+	bool eventsBlocking = false;
+	uint32_t serial = 0;
+
+	KernelTimer timer; // ECHO_B200_PROFILE=1 diagnostics (one pipeline, lock step)
 };
 
 // Tile batches are rendered by up to kWorkers concurrent pipelines (host thread + stream + wavefront buffers each): the
@@ -99,6 +158,11 @@ constexpr uint32_t kNarrowLimit = 262144; // below this many rays a bounce uses 
 // of a big tail then runs alone for milliseconds), 262144 -> 140 / 277 / 187
 constexpr uint32_t kTailLimit = 8192;
 constexpr int kWorkers = 8; // A/B on C3/C4/C5: 1 -> 134, 2 -> 207, 4 -> 280, 8 -> 329, 12 -> 330 M samples/s on C5 (profiles/README.md)
+
+// At most 16 Mi paths per batch and pipeline (250 B of wavefront state per path: about 4 GB each); render_tiles splits smaller
+// jobs so that every pipeline gets a share. A/B at 64 spp per step, 4 / 8 / 16 Mi: C3 439 / 459 / 456, C4 321 / 330 / 332, C5 (16 spp)
+// 337 / 350 / 368 M samples/s — wider launches per bounce and 2-4x fewer of them (variants/ab10.sh, ECHO_B200_BATCH_PATHS).
+constexpr uint64_t kPathsPerBatch = 1ull << 24;
 
 struct RenderState
 {
@@ -134,8 +198,31 @@ enum : int
 {
 	STAT_SAMPLE_EVALUATED = 0, STAT_SAMPLE_REJECTED, STAT_PIXEL_EVALUATED, STAT_BOUNCE_CREATED, STAT_BOUNCE_SPECULAR, STAT_BOUNCE_MIS,
 	STAT_LIGHT_SAMPLED, STAT_LIGHT_OCCLUSION_CHECKED, STAT_LIGHT_OCCLUSION_PASSED, STAT_LIGHT_EVALUATED_INFINITE,
-	STAT_TRACE_QUERIES, STAT_OCCLUDE_QUERIES, STAT_KERNEL_LAUNCHES, STAT_COUNT = 16
+	STAT_TRACE_QUERIES, STAT_OCCLUDE_QUERIES, STAT_KERNEL_LAUNCHES,
+	STAT_NODE_VISITS, STAT_TRIANGLE_VISITS, STAT_SPHERE_VISITS, STAT_LIGHT_NODE_VISITS, // counted passes only
+	STAT_COUNT = 24
 };
+static_assert(sizeof(EchoStats) == sizeof(unsigned long long) * STAT_COUNT, "EchoStats layout");
+
+// counted passes (ECHO_EVALUATOR_COUNT_VISITS): the visit counters of one thread's query into the statistics, one atomic per warp
+// and counter; every lane of the warp must call it
+ECHO_DEVICE void visit_flush(unsigned long long* stats, int firstSlot, VisitCounts local)
+{
+	for (int offset = 16; offset > 0; offset >>= 1)
+	{
+		local.nodes += __shfl_down_sync(0xFFFFFFFFu, local.nodes, offset);
+		local.triangles += __shfl_down_sync(0xFFFFFFFFu, local.triangles, offset);
+		local.spheres += __shfl_down_sync(0xFFFFFFFFu, local.spheres, offset);
+	}
+
+	if ((threadIdx.x & 31u) == 0u)
+	{
+		if (local.nodes) atomicAdd(stats + firstSlot + 0, (unsigned long long)local.nodes);
+		if (local.triangles) atomicAdd(stats + firstSlot + 1, (unsigned long long)local.triangles);
+		if (local.spheres) atomicAdd(stats + firstSlot + 2, (unsigned long long)local.spheres);
+	}
+}
+
 
 ECHO_DEVICE vec3 xyz(float4 v) { return { v.x, v.y, v.z }; }
 ECHO_DEVICE rgb as_rgb(float4 v) { return { v.x, v.y, v.z }; }
@@ -340,6 +427,7 @@ ECHO_DEVICE uint32_t light_tree_pick(const DeviceScene& scene, const PackInfo& i
 		LightNode right = load_light_node(scene, info, node.child1);
 		float importance0 = light_importance(left, origin);
 		float importance1 = light_importance(right, origin);
+		if (scene.lightVisits) atomicAdd(scene.lightVisits, 2ull); // counted passes only
 
 		if (!positive(importance0) && !positive(importance1)) return ECHO_TOKEN_EMPTY;
 
@@ -390,6 +478,7 @@ ECHO_DEVICE float light_tree_mass(const DeviceScene& scene, const PackInfo& info
 		LightNode right = load_light_node(scene, info, node.child1);
 		float importance0 = light_importance(left, origin);
 		float importance1 = light_importance(right, origin);
+		if (scene.lightVisits) atomicAdd(scene.lightVisits, 2ull); // counted passes only
 		float split = div(importance0, importance0 + importance1);
 
 		if ((branches & 1ull) == 0ull)
@@ -1087,6 +1176,7 @@ __global__ void __launch_bounds__(kTraverseBlock, ECHO_INST_MIN_BLOCKS) extend_l
 {
 	__shared__ float4 stagedRays[kTraverseBlock * 2];
 	persistent_traverse<STACK, false, true>(scene, io, *queueCount, nextRay, stagedRays);
+	persistent_finish(nextRay);
 }
 
 template<int STACK>
@@ -1094,51 +1184,62 @@ __global__ void __launch_bounds__(kTraverseBlock, ECHO_MIN_BLOCKS) extend_kernel
 {
 	__shared__ float4 stagedRays[kTraverseBlock * 2];
 	persistent_traverse<STACK, false>(scene, io, *queueCount, nextRay, stagedRays);
+	persistent_finish(nextRay);
 }
 
 // Narrow wavefronts (late bounces) have fewer rays than resident lanes: work replacement has nothing to replace with and
 // the launch is bound by the latency of its longest ray, so the leaner one-thread-per-ray loop is used instead.
-template<int STACK>
-__global__ void __launch_bounds__(kBlock) extend_narrow_kernel(DeviceScene scene, ExtendIO io, const uint32_t* __restrict__ queueCount)
+template<int STACK, bool COUNT>
+__global__ void __launch_bounds__(kBlock) extend_narrow_kernel(DeviceScene scene, ExtendIO io, const uint32_t* __restrict__ queueCount, unsigned long long* __restrict__ stats)
 {
 	uint32_t i = blockIdx.x * kBlock + threadIdx.x;
-	if (i >= *queueCount) return;
+	VisitCounts local = { 0u, 0u, 0u };
 
-	float4 a = io.rays[i * 2u], b = io.rays[i * 2u + 1u];
-	float distance = b.z;
-	uint32_t token = ECHO_TOKEN_EMPTY;
-	vec2 uv = { 0.0f, 0.0f };
+	if (i < *queueCount)
+	{
+		float4 a = io.rays[i * 2u], b = io.rays[i * 2u + 1u];
+		float distance = b.z;
+		uint32_t token = ECHO_TOKEN_EMPTY;
+		vec2 uv = { 0.0f, 0.0f };
 
-	bool hit = scene_trace<STACK, false>(scene, { a.x, a.y, a.z }, { a.w, b.x, b.y }, __float_as_uint(b.w), distance, token, uv, nullptr);
-	io.store_closest(i, hit, token, distance, uv, b.z);
+		bool hit = scene_trace<STACK, COUNT>(scene, { a.x, a.y, a.z }, { a.w, b.x, b.y }, __float_as_uint(b.w), distance, token, uv, COUNT ? &local : nullptr);
+		io.store_closest(i, hit, token, distance, uv, b.z);
+	}
+
+	if (COUNT) visit_flush(stats, STAT_NODE_VISITS, local);
 }
 
 // Instanced scenes: the same query through the packs (echo_instanced.cuh), one thread per ray, with the ignore hierarchy's
 // instance layers in and the hit's instance layers out.
-template<int STACK>
+template<int STACK, bool COUNT>
 __global__ void __launch_bounds__(kBlock) extend_instanced_kernel(DeviceScene scene, ExtendIO io, const uint4* __restrict__ rayLayers, uint4* __restrict__ hitLayers,
-                                                                  const uint32_t* __restrict__ queueCount)
+                                                                  const uint32_t* __restrict__ queueCount, unsigned long long* __restrict__ stats)
 {
 	uint32_t i = blockIdx.x * kBlock + threadIdx.x;
-	if (i >= *queueCount) return;
+	VisitCounts local = { 0u, 0u, 0u };
 
-	float4 a = io.rays[i * 2u], b = io.rays[i * 2u + 1u];
-	PathLayers ignore = load_layers(rayLayers, i);
-	PathLayers hitLayer = no_layers();
-	float distance = b.z;
-	uint32_t token = ECHO_TOKEN_EMPTY;
-	vec2 uv = { 0.0f, 0.0f };
-	bool hit = false;
-
-	if (positive(b.z)) // PreparedScene.Trace, PreparedScene.cs:69
+	if (i < *queueCount)
 	{
-		traverse_instanced<STACK, false, false>(scene, { a.x, a.y, a.z }, { a.w, b.x, b.y }, __float_as_uint(b.w), ignore.tokens, ignore.count,
-		                                        distance, token, uv, hitLayer.tokens, hitLayer.count, nullptr);
-		hit = distance < b.z;
+		float4 a = io.rays[i * 2u], b = io.rays[i * 2u + 1u];
+		PathLayers ignore = load_layers(rayLayers, i);
+		PathLayers hitLayer = no_layers();
+		float distance = b.z;
+		uint32_t token = ECHO_TOKEN_EMPTY;
+		vec2 uv = { 0.0f, 0.0f };
+		bool hit = false;
+
+		if (positive(b.z)) // PreparedScene.Trace, PreparedScene.cs:69
+		{
+			traverse_instanced<STACK, false, COUNT>(scene, { a.x, a.y, a.z }, { a.w, b.x, b.y }, __float_as_uint(b.w), ignore.tokens, ignore.count,
+			                                        distance, token, uv, hitLayer.tokens, hitLayer.count, COUNT ? &local : nullptr);
+			hit = distance < b.z;
+		}
+
+		io.store_closest(i, hit, token, distance, uv, b.z);
+		store_layers(hitLayers, i, hit ? hitLayer : no_layers());
 	}
 
-	io.store_closest(i, hit, token, distance, uv, b.z);
-	store_layers(hitLayers, i, hit ? hitLayer : no_layers());
+	if (COUNT) visit_flush(stats, STAT_NODE_VISITS, local);
 }
 
 // the material-class sort: one thread per traced ray appends its slot to the queue of the class it hit
@@ -1513,6 +1614,7 @@ __global__ void __launch_bounds__(kTraverseBlock, ECHO_INST_MIN_BLOCKS) shadow_l
 	__shared__ float4 stagedRays[kTraverseBlock * 2];
 	io.passed = 0u;
 	persistent_traverse<STACK, true, true>(scene, io, *shadowCount, nextRay, stagedRays);
+	persistent_finish(nextRay);
 
 	uint32_t passed = io.passed;
 	for (int offset = 16; offset > 0; offset >>= 1) passed += __shfl_down_sync(0xFFFFFFFFu, passed, offset);
@@ -1527,6 +1629,7 @@ __global__ void __launch_bounds__(kTraverseBlock, ECHO_MIN_BLOCKS) shadow_kernel
 	__shared__ float4 stagedRays[kTraverseBlock * 2];
 	io.passed = 0u;
 	persistent_traverse<STACK, true>(scene, io, *shadowCount, nextRay, stagedRays);
+	persistent_finish(nextRay);
 
 	uint32_t passed = io.passed;
 	for (int offset = 16; offset > 0; offset >>= 1) passed += __shfl_down_sync(0xFFFFFFFFu, passed, offset);
@@ -1534,31 +1637,34 @@ __global__ void __launch_bounds__(kTraverseBlock, ECHO_MIN_BLOCKS) shadow_kernel
 	if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(stats + STAT_OCCLUDE_QUERIES, (unsigned long long)*shadowCount);
 }
 
-template<int STACK>
+template<int STACK, bool COUNT>
 __global__ void __launch_bounds__(kBlock) shadow_narrow_kernel(DeviceScene scene, ShadowIO io, const uint32_t* __restrict__ shadowCount, unsigned long long* __restrict__ stats)
 {
 	uint32_t i = blockIdx.x * kBlock + threadIdx.x;
 	bool active = i < *shadowCount;
 	io.passed = 0u;
+	VisitCounts local = { 0u, 0u, 0u };
 
 	if (active)
 	{
 		float4 a = io.rays[i * 2u], b = io.rays[i * 2u + 1u];
-		bool occluded = scene_occlude<STACK, false>(scene, { a.x, a.y, a.z }, { a.w, b.x, b.y }, __float_as_uint(b.w), b.z, nullptr);
+		bool occluded = scene_occlude<STACK, COUNT>(scene, { a.x, a.y, a.z }, { a.w, b.x, b.y }, __float_as_uint(b.w), b.z, COUNT ? &local : nullptr);
 		io.store_any(i, occluded);
 	}
 
 	stat_add(stats, STAT_OCCLUDE_QUERIES, active);
 	stat_add(stats, STAT_LIGHT_OCCLUSION_PASSED, io.passed != 0u);
+	if (COUNT) visit_flush(stats, STAT_NODE_VISITS, local);
 }
 
-template<int STACK>
+template<int STACK, bool COUNT>
 __global__ void __launch_bounds__(kBlock) shadow_instanced_kernel(DeviceScene scene, ShadowIO io, const uint4* __restrict__ shadowLayers,
                                                                   const uint32_t* __restrict__ shadowCount, unsigned long long* __restrict__ stats)
 {
 	uint32_t i = blockIdx.x * kBlock + threadIdx.x;
 	bool active = i < *shadowCount;
 	io.passed = 0u;
+	VisitCounts local = { 0u, 0u, 0u };
 
 	if (active)
 	{
@@ -1571,13 +1677,14 @@ __global__ void __launch_bounds__(kBlock) shadow_instanced_kernel(DeviceScene sc
 		bool occluded = false;
 
 		if (positive(b.z)) // PreparedScene.Occlude, PreparedScene.cs:84
-			occluded = traverse_instanced<STACK, true, false>(scene, { a.x, a.y, a.z }, { a.w, b.x, b.y }, __float_as_uint(b.w), ignore.tokens, ignore.count,
-			                                                  travel, unusedToken, unusedUV, unusedLayers.tokens, unusedLayers.count, nullptr);
+			occluded = traverse_instanced<STACK, true, COUNT>(scene, { a.x, a.y, a.z }, { a.w, b.x, b.y }, __float_as_uint(b.w), ignore.tokens, ignore.count,
+			                                                  travel, unusedToken, unusedUV, unusedLayers.tokens, unusedLayers.count, COUNT ? &local : nullptr);
 		io.store_any(i, occluded);
 	}
 
 	stat_add(stats, STAT_OCCLUDE_QUERIES, active);
 	stat_add(stats, STAT_LIGHT_OCCLUSION_PASSED, io.passed != 0u);
+	if (COUNT) visit_flush(stats, STAT_NODE_VISITS, local);
 }
 
 // ---- Scalars.AlmostEquals (Scalars.cs:153-168) and Float3.Equals (Float3.cs:369) ----
@@ -1952,10 +2059,11 @@ __global__ void __launch_bounds__(kBlock) finish_kernel(uint32_t count, PathBuff
 }
 
 // iteration bookkeeping: the next-queue count becomes the active count, per-iteration counters are cleared
-__global__ void rotate_counters_kernel(uint32_t* counters, uint32_t* activeCount, uint32_t* hostMirror)
+// and {serial of this iteration, rays left} goes to the pipeline thread as ONE 8-byte store into mapped pinned memory
+__global__ void rotate_counters_kernel(uint32_t* counters, uint32_t* activeCount, unsigned long long* hostMirror, uint32_t serial)
 {
 	*activeCount = counters[COUNTER_NEXT];
-	*hostMirror = counters[COUNTER_NEXT];
+	*hostMirror = ((unsigned long long)serial << 32) | (unsigned long long)counters[COUNTER_NEXT];
 	counters[COUNTER_NEXT] = 0u;
 	counters[COUNTER_SHADOW] = 0u;
 	for (int c = 0; c < CLASS_COUNT; c++) counters[COUNTER_CLASS + c] = 0u;
@@ -2153,12 +2261,6 @@ static void release(WorkerState* state)
 	for (void* p : state->allocations) cudaFree(p);
 	state->allocations.clear();
 	state->paths.rayLayers[0] = state->paths.rayLayers[1] = state->paths.hitLayers = state->paths.shadowLayers = nullptr;
-	for (cudaGraphExec_t& graph : state->narrowGraph)
-	{
-		if (graph) cudaGraphExecDestroy(graph);
-		graph = nullptr;
-	}
-	state->graphKey.clear();
 	state->capacity = 0;
 	state->pixelCapacity = 0;
 	state->tileCapacity = 0;
@@ -2172,7 +2274,8 @@ void render_state_destroy(RenderState* state)
 	{
 		release(worker);
 		if (worker->hostCounters) cudaFreeHost(worker->hostCounters);
-		if (worker->iterationDone) cudaEventDestroy(worker->iterationDone);
+		for (cudaEvent_t event : worker->iterationDone)
+			if (event) cudaEventDestroy(event);
 		if (worker->stream) cudaStreamDestroy(worker->stream);
 		delete worker;
 	}
@@ -2210,7 +2313,11 @@ static bool allocate(WorkerState* state, T*& pointer, uint64_t count)
 
 static bool ensure_capacity(WorkerState* state, uint64_t paths, uint64_t pixels, uint64_t tiles, bool instanced)
 {
-	if (!state->hostCounters && !check_cuda(cudaMallocHost((void**)&state->hostCounters, sizeof(uint32_t) * 64), "cudaMallocHost")) return false;
+	if (!state->hostCounters)
+	{
+		if (!check_cuda(cudaMallocHost((void**)&state->hostCounters, sizeof(uint32_t) * 64), "cudaMallocHost")) return false;
+		std::memset(state->hostCounters, 0, sizeof(uint32_t) * 64); // the iteration mirror starts at serial 0 = "nothing finished"
+	}
 	bool layersReady = !instanced || state->paths.hitLayers != nullptr;
 	if (paths <= state->capacity && pixels <= state->pixelCapacity && tiles <= state->tileCapacity && layersReady) return true;
 
@@ -2245,211 +2352,200 @@ static bool ensure_capacity(WorkerState* state, uint64_t paths, uint64_t pixels,
 	return true;
 }
 
-// ECHO_B200_PROFILE=1: per-kernel device time of the wavefront (CUDA events around every launch, synchronised; the
-// numbers printed by a run with this switch on are diagnostics, never bench values).
-struct KernelTimer
+static bool profiling()
 {
-	enum { RAYGEN, EXTEND, SHADE_MISS, SHADE_DIFFUSE, SHADE_DIELECTRIC, SHADE_CONDUCTOR, SHADE_TERMINAL, SHADOW, ROTATE, FINISH, ACCUMULATE, OTHER, COUNT };
-	bool enabled = false;
-	double milliseconds[COUNT] = {};
-	uint64_t launches[COUNT] = {};
-	cudaEvent_t begin = nullptr, end = nullptr;
-
-	KernelTimer()
+	static const bool enabled = []
 	{
 		const char* value = std::getenv("ECHO_B200_PROFILE");
-		enabled = value && value[0] == '1';
-		if (enabled) { cudaEventCreate(&begin); cudaEventCreate(&end); }
+		return value && value[0] == '1';
+	}();
+	return enabled;
+}
+
+// Tuning switches of the wavefront: read once from the environment (ECHO_B200_<NAME>), changeable at run time through
+// echo_b200_debug_set_option so that one process can A/B them without rebuilding its scene (variants/r2_sweep_c5.py).
+struct RenderOptions
+{
+	std::atomic<long long> renderWorkers, batchPaths, narrowLimit, tailLimit, runAhead, blockingSync;
+
+	RenderOptions()
+	{
+		renderWorkers = from_environment("ECHO_B200_RENDER_WORKERS", kWorkers);      // concurrent tile-batch pipelines
+		batchPaths = from_environment("ECHO_B200_BATCH_PATHS", (long long)kPathsPerBatch); // paths per batch and pipeline
+		narrowLimit = from_environment("ECHO_B200_NARROW_LIMIT", kNarrowLimit);      // rays below which a bounce uses the one-thread-per-ray kernels
+		tailLimit = from_environment("ECHO_B200_TAIL_LIMIT", kTailLimit);            // live paths below which tail_kernel finishes a batch (0 = never)
+		runAhead = from_environment("ECHO_B200_RUN_AHEAD", -1);                      // -1 = automatic, see run_ahead()
+		blockingSync = from_environment("ECHO_B200_BLOCKING_SYNC", -1);              // -1 = automatic, see blocking_waits()
 	}
 
-	void start(cudaStream_t stream) { if (enabled) cudaEventRecord(begin, stream); }
-
-	float last = 0.0f;
-
-	void stop(int slot, cudaStream_t stream)
+	static long long from_environment(const char* name, long long fallback)
 	{
-		if (!enabled) return;
-		cudaEventRecord(end, stream);
-		cudaEventSynchronize(end);
-		float ms = 0.0f;
-		cudaEventElapsedTime(&ms, begin, end);
-		milliseconds[slot] += ms;
-		++launches[slot];
-		last = ms;
-	}
-
-	void report()
-	{
-		if (!enabled) return;
-		static const char* names[COUNT] = { "raygen", "extend", "shade<miss>", "shade<diffuse>", "shade<dielectric>", "shade<conductor>", "shade<terminal>", "shadow", "rotate", "finish", "accumulate", "other" };
-		double total = 0.0;
-		for (double ms : milliseconds) total += ms;
-		for (int i = 0; i < COUNT; i++)
-			if (launches[i]) std::fprintf(stderr, "[echo_b200 profile] %-18s %8llu launches %10.3f ms %5.1f %%\n", names[i], (unsigned long long)launches[i], milliseconds[i], 100.0 * milliseconds[i] / total);
-		std::fprintf(stderr, "[echo_b200 profile] total %.3f ms\n", total);
-		for (int i = 0; i < COUNT; i++) { milliseconds[i] = 0.0; launches[i] = 0; }
+		const char* value = std::getenv(name);
+		return value ? std::atoll(value) : fallback;
 	}
 };
 
-static KernelTimer gTimer;
-
-// Every pipeline thread waits once per wavefront iteration for the active-ray count. Spinning in cudaStreamSynchronize is the
-// fastest wake-up, but N ranks x 8 pipelines spin on N x 8 host cores: when the host has fewer cores than that the threads
-// preempt each other (8 GPUs on a 16-core host scaled 5.7x). A blocking-sync event lets them sleep instead.
-// ECHO_B200_BLOCKING_SYNC=0/1 overrides the choice (default: block when pipelines of all visible devices outnumber the cores).
-static bool wait_for_iteration(WorkerState* state, cudaStream_t stream)
+static RenderOptions& options()
 {
-	static const bool blocking = []
+	static RenderOptions instance;
+	return instance;
+}
+
+bool set_render_option(const char* name, long long value)
+{
+	RenderOptions& o = options();
+	const std::string key = name ? name : "";
+	if (key == "RENDER_WORKERS") o.renderWorkers = value;
+	else if (key == "BATCH_PATHS") o.batchPaths = value;
+	else if (key == "NARROW_LIMIT") o.narrowLimit = value;
+	else if (key == "TAIL_LIMIT") o.tailLimit = value;
+	else if (key == "RUN_AHEAD") o.runAhead = value;
+	else if (key == "BLOCKING_SYNC") o.blockingSync = value;
+	else return false;
+	return true;
+}
+
+// When a pipeline thread waits (run-ahead window full, or a batch's end), spinning in cudaEventSynchronize is the fastest
+// wake-up, but N ranks x 8 pipelines spin on N x 8 host cores: when the host has fewer cores than that the threads preempt
+// each other. Blocking-sync events let them sleep instead. Automatic choice: block when the pipelines of all visible devices
+// outnumber the cores.
+static bool blocking_waits()
+{
+	long long configured = options().blockingSync;
+	if (configured >= 0) return configured != 0;
+
+	static const bool oversubscribed = []
 	{
-		if (const char* value = std::getenv("ECHO_B200_BLOCKING_SYNC")) return value[0] != '0';
 		int devices = 1;
 		cudaGetDeviceCount(&devices);
 		return (unsigned int)(devices * kWorkers) > std::thread::hardware_concurrency();
 	}();
+	return oversubscribed;
+}
 
-	if (!blocking) return check_cuda(cudaStreamSynchronize(stream), "wavefront iteration");
+static bool ensure_events(WorkerState* state)
+{
+	const bool blocking = blocking_waits();
+	if (state->iterationDone[0] && state->eventsBlocking == blocking) return true;
 
-	if (!state->iterationDone && !check_cuda(cudaEventCreateWithFlags(&state->iterationDone, cudaEventBlockingSync | cudaEventDisableTiming), "cudaEventCreate")) return false;
-	return check_cuda(cudaEventRecord(state->iterationDone, stream), "cudaEventRecord") && check_cuda(cudaEventSynchronize(state->iterationDone), "wavefront iteration");
+	for (cudaEvent_t& event : state->iterationDone)
+	{
+		if (event) cudaEventDestroy(event);
+		event = nullptr;
+	}
+
+	unsigned int flags = cudaEventDisableTiming | (blocking ? cudaEventBlockingSync : 0u);
+	for (cudaEvent_t& event : state->iterationDone)
+		if (!check_cuda(cudaEventCreateWithFlags(&event, flags), "cudaEventCreate(iteration)")) return false;
+	state->eventsBlocking = blocking;
+	return true;
 }
 
 static unsigned int blocks_for(uint64_t count) { return (unsigned int)std::max<uint64_t>((count + kBlock - 1) / kBlock, 1); }
 
-// One iteration of a NARROW wavefront (fewer rays than resident lanes: one-thread-per-ray traversal): extend, classify, the
-// five shading launches, shadow, counter rotation. Every kernel reads its count from device memory and exits early, so the
-// grid can be a fixed `blocks` — which makes the sequence a capturable, replayable CUDA graph.
-template<int STACK, bool INST>
-static void launch_narrow_iteration(WorkerState* state, const DeviceScene& scene, const EchoRenderParams& params, int current, unsigned int blocks, cudaStream_t stream)
+// How many wavefront iterations a pipeline may have queued beyond the newest one whose ray count the host has seen
+// (ECHO_B200_RUN_AHEAD; 0 = lock step: launch, wait, read the count, launch). Running ahead sizes grids with counts that are one
+// to three bounces old — more CTAs that find nothing to do — which on one GPU with spinning waits costs more than the wake-up
+// latency it hides (A/B r2a, run-ahead 0 / 1 / 3 / 6: C1 323 / 318 / 303 / 283, C3 455 / 448 / 435 / 421, C4 344 / 340 / 332 / 322,
+// C5 394 / 390 / 379 / 367 M samples/s). Automatic choice: lock step while the pipeline threads can spin on cores of their own,
+// kRunAhead when they sleep in blocking waits (8 ranks x 8 pipelines on one host), where a wake-up costs tens of microseconds.
+constexpr uint32_t kRunAhead = 2;
+
+static uint32_t run_ahead()
 {
-	PathBuffers& paths = state->paths;
-	uint32_t* counters = paths.counters;
-	uint32_t* activeCount = counters + 32;
-	const bool packs = INST && scene.packCount != 0u;
-
-	ExtendIO extendIO = { paths.rayQueue[current], paths.hitQueue };
-	if (packs) extend_instanced_kernel<STACK><<<blocks, kBlock, 0, stream>>>(scene, extendIO, paths.rayLayers[current], paths.hitLayers, activeCount);
-	else extend_narrow_kernel<STACK><<<blocks, kBlock, 0, stream>>>(scene, extendIO, activeCount);
-
-	classify_kernel<INST><<<blocks, kBlock, 0, stream>>>(scene, activeCount, paths);
-	shade_kernel<CLASS_MISS, 0u, INST><<<blocks, kBlock, 0, stream>>>(scene, params, paths.classQueue[CLASS_MISS], counters + COUNTER_CLASS + CLASS_MISS, paths, current);
-	shade_kernel<CLASS_DIFFUSE, KINDS_DIFFUSE, INST><<<blocks, kBlock, 0, stream>>>(scene, params, paths.classQueue[CLASS_DIFFUSE], counters + COUNTER_CLASS + CLASS_DIFFUSE, paths, current);
-	shade_kernel<CLASS_DIELECTRIC, KINDS_DIELECTRIC, INST><<<blocks, kBlock, 0, stream>>>(scene, params, paths.classQueue[CLASS_DIELECTRIC], counters + COUNTER_CLASS + CLASS_DIELECTRIC, paths, current);
-	shade_kernel<CLASS_CONDUCTOR, KINDS_CONDUCTOR, INST><<<blocks, kBlock, 0, stream>>>(scene, params, paths.classQueue[CLASS_CONDUCTOR], counters + COUNTER_CLASS + CLASS_CONDUCTOR, paths, current);
-	shade_kernel<CLASS_TERMINAL, KINDS_TERMINAL, INST><<<blocks, kBlock, 0, stream>>>(scene, params, paths.classQueue[CLASS_TERMINAL], counters + COUNTER_CLASS + CLASS_TERMINAL, paths, current);
-
-	ShadowIO shadowIO = { paths.shadowQueue, paths.shadowValue, paths.result, 0u };
-	if (packs) shadow_instanced_kernel<STACK><<<blocks, kBlock, 0, stream>>>(scene, shadowIO, paths.shadowLayers, counters + COUNTER_SHADOW, paths.stats);
-	else shadow_narrow_kernel<STACK><<<blocks, kBlock, 0, stream>>>(scene, shadowIO, counters + COUNTER_SHADOW, paths.stats);
-
-	rotate_counters_kernel<<<1, 1, 0, stream>>>(counters, activeCount, state->hostCounters);
-}
-
-// The instantiated graph of launch_narrow_iteration for this ping-pong side, captured on first use and whenever what the
-// launches depend on changes. nullptr = graphs are off or capture failed: launch directly. OFF by default
-// (ECHO_B200_GRAPHS=1 switches them on): with eight pipelines in flight the host-side launch cost is already hidden and a
-// narrow iteration is bound by the dependent latencies of its kernels — A/B on C1 / C3 / C4 / C5: 257 / 438 / 304 / 314 M
-// samples/s with graphs vs 268 / 446 / 303 / 317 without (variants/ab7.sh); parity is identical either way.
-template<int STACK, bool INST>
-static cudaGraphExec_t narrow_graph(WorkerState* state, const DeviceScene& scene, const EchoRenderParams& params, int current, unsigned int blocks, cudaStream_t stream)
-{
-	static const bool enabled = []
-	{
-		const char* value = std::getenv("ECHO_B200_GRAPHS");
-		return value && value[0] == '1';
-	}();
-
-	if (!enabled) return nullptr;
-
-	std::vector<unsigned char> key(sizeof(DeviceScene) + sizeof(EchoRenderParams) + sizeof(PathBuffers) + 3 * sizeof(int));
-	unsigned char* cursor = key.data();
-	int tags[3] = { STACK, INST ? 1 : 0, (int)blocks };
-	std::memcpy(cursor, &scene, sizeof(DeviceScene)); cursor += sizeof(DeviceScene);
-	std::memcpy(cursor, &params, sizeof(EchoRenderParams)); cursor += sizeof(EchoRenderParams);
-	std::memcpy(cursor, &state->paths, sizeof(PathBuffers)); cursor += sizeof(PathBuffers);
-	std::memcpy(cursor, tags, sizeof(tags));
-
-	if (key != state->graphKey)
-	{
-		for (cudaGraphExec_t& graph : state->narrowGraph)
-		{
-			if (graph) cudaGraphExecDestroy(graph);
-			graph = nullptr;
-		}
-
-		state->graphKey = key;
-	}
-
-	if (state->narrowGraph[current]) return state->narrowGraph[current];
-
-	cudaGraph_t graph = nullptr;
-	if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-	launch_narrow_iteration<STACK, INST>(state, scene, params, current, blocks, stream);
-	bool captured = cudaStreamEndCapture(stream, &graph) == cudaSuccess && graph;
-	if (captured) captured = cudaGraphInstantiate(&state->narrowGraph[current], graph, 0) == cudaSuccess;
-	if (graph) cudaGraphDestroy(graph);
-
-	if (!captured)
-	{
-		cudaGetLastError();
-		state->narrowGraph[current] = nullptr;
-	}
-
-	return state->narrowGraph[current];
+	long long configured = options().runAhead;
+	if (configured < 0) configured = blocking_waits() ? kRunAhead : 0;
+	return (uint32_t)std::min<long long>(configured, WorkerState::kEventRing - 2);
 }
 
 // Evaluates `count` path slots already described in state->pixelXY / sampleIndex; radiance lands in state->sampleOut.
+//
+// The bounce loop runs AHEAD of the device. Every kernel of an iteration reads its ray / class / shadow counts from device
+// memory and exits past them, so the host only needs an UPPER BOUND of the live rays to size the grids — and the live count
+// never grows from one bounce to the next (a path spawns at most one ray). The rotate kernel that closes iteration k publishes
+// {serial of k, rays left} as one 8-byte word in mapped pinned memory; the pipeline thread reads the newest word it can see,
+// sizes the next iteration with it and keeps launching, at most `runAhead` iterations beyond the last count it has seen. It
+// blocks only when that window is full. The device therefore never idles between bounces waiting for a host thread to wake
+// up and launch (8 ranks x 8 pipelines share the box's host cores), and when the wavefront empties at most `runAhead`
+// surplus iterations were queued, each nine launches of kernels that find zero counts.
 template<int STACK, bool INST>
-static bool evaluate_paths(WorkerState* state, const DeviceScene& scene, const EchoRenderParams& params, uint32_t count, uint64_t& launches, cudaStream_t stream)
+static bool evaluate_paths(WorkerState* state, const DeviceScene& sceneIn, const EchoRenderParams& params, uint32_t count, uint64_t& launches, cudaStream_t stream)
 {
 	PathBuffers& paths = state->paths;
 	uint32_t* counters = paths.counters;
 	uint32_t* activeCount = counters + 32; // separate slot read by the kernels of one iteration
+	KernelTimer& timer = state->timer;
 
+	if (count == 0u) return true;
 	if (!check_cuda(cudaMemsetAsync(counters, 0, sizeof(uint32_t) * 64, stream), "cudaMemsetAsync(counters)")) return false;
 
-	gTimer.start(stream);
-	raygen_kernel<<<blocks_for(count), kBlock, 0, stream>>>(scene, params, count, state->pixelXY, state->sampleIndex, paths);
-	gTimer.stop(KernelTimer::RAYGEN, stream);
+	timer.start(stream);
+	raygen_kernel<<<blocks_for(count), kBlock, 0, stream>>>(sceneIn, params, count, state->pixelXY, state->sampleIndex, paths);
+	timer.stop(KernelTimer::RAYGEN, stream);
 	if (!check_cuda(cudaMemcpyAsync(activeCount, &count, sizeof(uint32_t), cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync(count)")) return false;
 	++launches;
 
 	if ((params.evaluator & ECHO_EVALUATOR_KIND_MASK) == ECHO_EVALUATOR_NAIVE)
 	{
-		naive_kernel<STACK, INST><<<blocks_for(count), kBlock, 0, stream>>>(scene, params, count, paths, state->sampleOut);
+		naive_kernel<STACK, INST><<<blocks_for(count), kBlock, 0, stream>>>(sceneIn, params, count, paths, state->sampleOut);
 		++launches;
 		return check_cuda(cudaGetLastError(), "naive_kernel launch");
 	}
 
 	if ((params.evaluator & ECHO_EVALUATOR_KIND_MASK) != ECHO_EVALUATOR_PATH_TRACED)
 	{
-		auxiliary_kernel<STACK, INST><<<blocks_for(count), kBlock, 0, stream>>>(scene, params, count, paths, state->sampleOut);
+		auxiliary_kernel<STACK, INST><<<blocks_for(count), kBlock, 0, stream>>>(sceneIn, params, count, paths, state->sampleOut);
 		++launches;
 		return check_cuda(cudaGetLastError(), "auxiliary_kernel launch");
 	}
 
-	uint32_t active = count;
-	int current = 0;
+	// a counted pass (ECHO_EVALUATOR_COUNT_VISITS): the one-thread-per-query kernels with visit counters for every bounce, no
+	// tail kernel; same per-ray operations, so the same results and the visit counts of the persistent kernels
+	const bool counted = (params.evaluator & ECHO_EVALUATOR_COUNT_VISITS) != 0;
+	DeviceScene scene = sceneIn;
+	if (counted) scene.lightVisits = paths.stats + STAT_LIGHT_NODE_VISITS;
 
-	// what the shading kernels read of the parameters does not include the epoch (it only numbers the samples, in raygen):
-	// keeping it out of the captured launches lets one graph serve every epoch
+	// what the shading kernels read of the parameters does not include the epoch (it only numbers the samples, in raygen)
 	EchoRenderParams iterationParams = params;
 	iterationParams.epochOffset = 0;
 
-	static const uint32_t narrowLimitForGraphs = []
+	const uint32_t narrowLimit = (uint32_t)options().narrowLimit;
+	const uint32_t tailLimit = (uint32_t)options().tailLimit;
+	const uint32_t runAhead = timer.enabled ? 0u : run_ahead();
+
+	if (!ensure_events(state)) return false;
+
+	volatile unsigned long long* mirror = reinterpret_cast<volatile unsigned long long*>(state->hostCounters);
+	const uint32_t firstSerial = state->serial + 1u; // serial of this call's iteration 0
+	uint32_t launched = 0u;                          // iterations queued so far
+	uint32_t bound = count;                          // upper bound of the live rays of every iteration not yet queued
+	const bool packs = INST && scene.packCount != 0u; // INST without packs: a textured scene, ordinary traversal, zeroed hit layers
+
+	while (true)
 	{
-		const char* value = std::getenv("ECHO_B200_NARROW_LIMIT");
-		return value ? (uint32_t)std::atoll(value) : kNarrowLimit;
-	}();
+		// the newest finished iteration the host can see (a word left by an earlier call fails the range test)
+		unsigned long long seen = *mirror;
+		uint32_t finished = (uint32_t)(seen >> 32) - firstSerial + 1u; // iterations of this call known to be finished
+		if (finished > launched) finished = 0u;
 
-	while (active > 0)
-	{
-		unsigned int blocks = blocks_for(active);
+		if (finished > 0u)
+		{
+			bound = std::min(bound, (uint32_t)seen);
+			if ((uint32_t)seen == 0u) break; // the wavefront is empty; whatever was queued beyond finds zero counts
+		}
 
-		// the tail: finish the few paths that are left in one launch (ECHO_B200_TAIL_LIMIT, 0 = never)
-		const char* tailText = std::getenv("ECHO_B200_TAIL_LIMIT");
-		uint32_t tailLimit = tailText ? (uint32_t)std::atoll(tailText) : kTailLimit;
+		if (launched - finished > runAhead)
+		{
+			// window full: sleep until the oldest iteration the host has not seen yet is done, then look again
+			if (!check_cuda(cudaEventSynchronize(state->iterationDone[finished % WorkerState::kEventRing]), "wavefront iteration")) return false;
+			continue;
+		}
 
-		if (!gTimer.enabled && active < tailLimit)
+		const unsigned int blocks = blocks_for(bound);
+		const int current = (int)(launched & 1u);
+
+		// the tail: finish the few paths that are left in one launch
+		if (!timer.enabled && !counted && bound < tailLimit)
 		{
 			tail_kernel<STACK, INST><<<blocks, kBlock, 0, stream>>>(scene, iterationParams, activeCount, paths, current);
 			if (!check_cuda(cudaGetLastError(), "tail_kernel launch")) return false;
@@ -2457,113 +2553,105 @@ static bool evaluate_paths(WorkerState* state, const DeviceScene& scene, const E
 			break;
 		}
 
-		cudaGraphExec_t graph = nullptr;
-		if (!gTimer.enabled && active < narrowLimitForGraphs) graph = narrow_graph<STACK, INST>(state, scene, iterationParams, current, blocks_for(narrowLimitForGraphs), stream);
+		const bool narrow = counted || bound < narrowLimit;
+		unsigned long long* rayCounters = narrow ? nullptr : ray_counters(stream); // extend and shadow run one after the other: one pair serves both
+		if (!narrow && !rayCounters) return false;
 
-		if (graph)
-		{
-			// replay the narrow iteration as one graph (fixed grid: the kernels exit early past their counts)
-			if (!check_cuda(cudaGraphLaunch(graph, stream), "cudaGraphLaunch")) return false;
-			launches += 9;
-			if (!check_cuda(cudaGetLastError(), "wavefront launch")) return false;
-			if (!wait_for_iteration(state, stream)) return false;
-
-			active = state->hostCounters[0];
-			current ^= 1;
-			continue;
-		}
-
-		static int extendGrid = persistent_grid((const void*)extend_kernel<STACK>);
-		static int shadowGrid = persistent_grid((const void*)shadow_kernel<STACK>);
-		unsigned long long* extendCounter = next_ray_counter(stream);
-		unsigned long long* shadowCounter = next_ray_counter(stream);
-		if (!extendCounter || !shadowCounter) return false;
-
-		static const uint32_t narrowLimit = []
-		{
-			const char* value = std::getenv("ECHO_B200_NARROW_LIMIT");
-			return value ? (uint32_t)std::atoll(value) : kNarrowLimit;
-		}();
-
-		gTimer.start(stream);
+		timer.start(stream);
 		ExtendIO extendIO = { paths.rayQueue[current], paths.hitQueue };
-		const bool packs = INST && scene.packCount != 0u; // INST without packs: a textured scene, ordinary traversal, zeroed hit layers
 
-		if (packs && active >= narrowLimit)
+		if (packs && !narrow)
 		{
-			static int layersGrid = persistent_grid((const void*)extend_layers_kernel<STACK>);
+			const int layersGrid = persistent_grid((const void*)extend_layers_kernel<STACK>);
 			ExtendLayersIO layersIO;
 			layersIO.rays = extendIO.rays;
 			layersIO.hits = extendIO.hits;
 			layersIO.rayLayers = paths.rayLayers[current];
 			layersIO.hitLayers = paths.hitLayers;
-			extend_layers_kernel<STACK><<<std::min<unsigned int>(blocks, (unsigned int)layersGrid), kTraverseBlock, 0, stream>>>(scene, layersIO, activeCount, extendCounter);
+			extend_layers_kernel<STACK><<<std::min<unsigned int>(blocks, (unsigned int)layersGrid), kTraverseBlock, 0, stream>>>(scene, layersIO, activeCount, rayCounters);
 		}
-		else if (packs) extend_instanced_kernel<STACK><<<blocks, kBlock, 0, stream>>>(scene, extendIO, paths.rayLayers[current], paths.hitLayers, activeCount);
-		else if (active < narrowLimit) extend_narrow_kernel<STACK><<<blocks, kBlock, 0, stream>>>(scene, extendIO, activeCount);
-		else extend_kernel<STACK><<<std::min<unsigned int>(blocks, (unsigned int)extendGrid), kTraverseBlock, 0, stream>>>(scene, extendIO, activeCount, extendCounter);
-		gTimer.stop(KernelTimer::EXTEND, stream);
-		float extendMs = gTimer.last;
-
-		gTimer.start(stream);
-		classify_kernel<INST><<<blocks, kBlock, 0, stream>>>(scene, activeCount, paths);
-		gTimer.stop(KernelTimer::OTHER, stream);
-
-		gTimer.start(stream);
-		shade_kernel<CLASS_MISS, 0u, INST><<<blocks, kBlock, 0, stream>>>(scene, params, paths.classQueue[CLASS_MISS], counters + COUNTER_CLASS + CLASS_MISS, paths, current);
-		gTimer.stop(KernelTimer::SHADE_MISS, stream);
-		gTimer.start(stream);
-		shade_kernel<CLASS_DIFFUSE, KINDS_DIFFUSE, INST><<<blocks, kBlock, 0, stream>>>(scene, params, paths.classQueue[CLASS_DIFFUSE], counters + COUNTER_CLASS + CLASS_DIFFUSE, paths, current);
-		gTimer.stop(KernelTimer::SHADE_DIFFUSE, stream);
-		gTimer.start(stream);
-		shade_kernel<CLASS_DIELECTRIC, KINDS_DIELECTRIC, INST><<<blocks, kBlock, 0, stream>>>(scene, params, paths.classQueue[CLASS_DIELECTRIC], counters + COUNTER_CLASS + CLASS_DIELECTRIC, paths, current);
-		gTimer.stop(KernelTimer::SHADE_DIELECTRIC, stream);
-		gTimer.start(stream);
-		shade_kernel<CLASS_CONDUCTOR, KINDS_CONDUCTOR, INST><<<blocks, kBlock, 0, stream>>>(scene, params, paths.classQueue[CLASS_CONDUCTOR], counters + COUNTER_CLASS + CLASS_CONDUCTOR, paths, current);
-		gTimer.stop(KernelTimer::SHADE_CONDUCTOR, stream);
-		gTimer.start(stream);
-		shade_kernel<CLASS_TERMINAL, KINDS_TERMINAL, INST><<<blocks, kBlock, 0, stream>>>(scene, params, paths.classQueue[CLASS_TERMINAL], counters + COUNTER_CLASS + CLASS_TERMINAL, paths, current);
-		gTimer.stop(KernelTimer::SHADE_TERMINAL, stream);
-
-		gTimer.start(stream);
-		ShadowIO shadowIO = { paths.shadowQueue, paths.shadowValue, paths.result, 0u };
-		if (packs && active >= narrowLimit)
+		else if (packs && counted) extend_instanced_kernel<STACK, true><<<blocks, kBlock, 0, stream>>>(scene, extendIO, paths.rayLayers[current], paths.hitLayers, activeCount, paths.stats);
+		else if (packs) extend_instanced_kernel<STACK, false><<<blocks, kBlock, 0, stream>>>(scene, extendIO, paths.rayLayers[current], paths.hitLayers, activeCount, paths.stats);
+		else if (counted) extend_narrow_kernel<STACK, true><<<blocks, kBlock, 0, stream>>>(scene, extendIO, activeCount, paths.stats);
+		else if (narrow) extend_narrow_kernel<STACK, false><<<blocks, kBlock, 0, stream>>>(scene, extendIO, activeCount, paths.stats);
+		else
 		{
-			static int layersGrid = persistent_grid((const void*)shadow_layers_kernel<STACK>);
+			const int extendGrid = persistent_grid((const void*)extend_kernel<STACK>);
+			extend_kernel<STACK><<<std::min<unsigned int>(blocks, (unsigned int)extendGrid), kTraverseBlock, 0, stream>>>(scene, extendIO, activeCount, rayCounters);
+		}
+
+		timer.stop(KernelTimer::EXTEND, stream);
+		float extendMs = timer.last;
+
+		timer.start(stream);
+		classify_kernel<INST><<<blocks, kBlock, 0, stream>>>(scene, activeCount, paths);
+		timer.stop(KernelTimer::OTHER, stream);
+
+		timer.start(stream);
+		shade_kernel<CLASS_MISS, 0u, INST><<<blocks, kBlock, 0, stream>>>(scene, iterationParams, paths.classQueue[CLASS_MISS], counters + COUNTER_CLASS + CLASS_MISS, paths, current);
+		timer.stop(KernelTimer::SHADE_MISS, stream);
+		timer.start(stream);
+		shade_kernel<CLASS_DIFFUSE, KINDS_DIFFUSE, INST><<<blocks, kBlock, 0, stream>>>(scene, iterationParams, paths.classQueue[CLASS_DIFFUSE], counters + COUNTER_CLASS + CLASS_DIFFUSE, paths, current);
+		timer.stop(KernelTimer::SHADE_DIFFUSE, stream);
+		timer.start(stream);
+		shade_kernel<CLASS_DIELECTRIC, KINDS_DIELECTRIC, INST><<<blocks, kBlock, 0, stream>>>(scene, iterationParams, paths.classQueue[CLASS_DIELECTRIC], counters + COUNTER_CLASS + CLASS_DIELECTRIC, paths, current);
+		timer.stop(KernelTimer::SHADE_DIELECTRIC, stream);
+		timer.start(stream);
+		shade_kernel<CLASS_CONDUCTOR, KINDS_CONDUCTOR, INST><<<blocks, kBlock, 0, stream>>>(scene, iterationParams, paths.classQueue[CLASS_CONDUCTOR], counters + COUNTER_CLASS + CLASS_CONDUCTOR, paths, current);
+		timer.stop(KernelTimer::SHADE_CONDUCTOR, stream);
+		timer.start(stream);
+		shade_kernel<CLASS_TERMINAL, KINDS_TERMINAL, INST><<<blocks, kBlock, 0, stream>>>(scene, iterationParams, paths.classQueue[CLASS_TERMINAL], counters + COUNTER_CLASS + CLASS_TERMINAL, paths, current);
+		timer.stop(KernelTimer::SHADE_TERMINAL, stream);
+
+		timer.start(stream);
+		ShadowIO shadowIO = { paths.shadowQueue, paths.shadowValue, paths.result, 0u };
+
+		if (packs && !narrow)
+		{
+			const int layersGrid = persistent_grid((const void*)shadow_layers_kernel<STACK>);
 			ShadowLayersIO layersIO;
 			layersIO.rays = shadowIO.rays;
 			layersIO.values = shadowIO.values;
 			layersIO.result = shadowIO.result;
 			layersIO.passed = 0u;
 			layersIO.shadowLayers = paths.shadowLayers;
-			shadow_layers_kernel<STACK><<<std::min<unsigned int>(blocks, (unsigned int)layersGrid), kTraverseBlock, 0, stream>>>(scene, layersIO, counters + COUNTER_SHADOW, shadowCounter, paths.stats);
+			shadow_layers_kernel<STACK><<<std::min<unsigned int>(blocks, (unsigned int)layersGrid), kTraverseBlock, 0, stream>>>(scene, layersIO, counters + COUNTER_SHADOW, rayCounters, paths.stats);
 		}
-		else if (packs) shadow_instanced_kernel<STACK><<<blocks, kBlock, 0, stream>>>(scene, shadowIO, paths.shadowLayers, counters + COUNTER_SHADOW, paths.stats);
-		else if (active < narrowLimit) shadow_narrow_kernel<STACK><<<blocks, kBlock, 0, stream>>>(scene, shadowIO, counters + COUNTER_SHADOW, paths.stats);
-		else shadow_kernel<STACK><<<std::min<unsigned int>(blocks, (unsigned int)shadowGrid), kTraverseBlock, 0, stream>>>(scene, shadowIO, counters + COUNTER_SHADOW, shadowCounter, paths.stats);
-		gTimer.stop(KernelTimer::SHADOW, stream);
-		if (gTimer.enabled && std::getenv("ECHO_B200_PROFILE_ITERATIONS"))
+		else if (packs && counted) shadow_instanced_kernel<STACK, true><<<blocks, kBlock, 0, stream>>>(scene, shadowIO, paths.shadowLayers, counters + COUNTER_SHADOW, paths.stats);
+		else if (packs) shadow_instanced_kernel<STACK, false><<<blocks, kBlock, 0, stream>>>(scene, shadowIO, paths.shadowLayers, counters + COUNTER_SHADOW, paths.stats);
+		else if (counted) shadow_narrow_kernel<STACK, true><<<blocks, kBlock, 0, stream>>>(scene, shadowIO, counters + COUNTER_SHADOW, paths.stats);
+		else if (narrow) shadow_narrow_kernel<STACK, false><<<blocks, kBlock, 0, stream>>>(scene, shadowIO, counters + COUNTER_SHADOW, paths.stats);
+		else
+		{
+			const int shadowGrid = persistent_grid((const void*)shadow_kernel<STACK>);
+			shadow_kernel<STACK><<<std::min<unsigned int>(blocks, (unsigned int)shadowGrid), kTraverseBlock, 0, stream>>>(scene, shadowIO, counters + COUNTER_SHADOW, rayCounters, paths.stats);
+		}
+
+		timer.stop(KernelTimer::SHADOW, stream);
+
+		if (timer.enabled && std::getenv("ECHO_B200_PROFILE_ITERATIONS"))
 		{
 			uint32_t shadowRays = 0;
 			cudaMemcpy(&shadowRays, counters + COUNTER_SHADOW, sizeof(uint32_t), cudaMemcpyDeviceToHost);
-			std::fprintf(stderr, "[echo_b200 iteration] rays %9u extend %7.3f ms (%6.0f Mrays/s)  shadow rays %9u %7.3f ms (%6.0f Mrays/s)\n", active, extendMs,
-			             active / (extendMs * 1e3), shadowRays, gTimer.last, shadowRays / (gTimer.last * 1e3));
+			std::fprintf(stderr, "[echo_b200 iteration] rays <= %9u extend %7.3f ms  shadow rays %9u %7.3f ms (%6.0f Mrays/s)\n", bound, extendMs,
+			             shadowRays, timer.last, shadowRays / (timer.last * 1e3));
 		}
-		gTimer.start(stream);
-		rotate_counters_kernel<<<1, 1, 0, stream>>>(counters, activeCount, state->hostCounters);
-		gTimer.stop(KernelTimer::ROTATE, stream);
+
+		timer.start(stream);
+		rotate_counters_kernel<<<1, 1, 0, stream>>>(counters, activeCount, const_cast<unsigned long long*>(mirror), firstSerial + launched);
+		timer.stop(KernelTimer::ROTATE, stream);
 		launches += 9;
 
 		if (!check_cuda(cudaGetLastError(), "wavefront launch")) return false;
-		if (!wait_for_iteration(state, stream)) return false;
-
-		active = state->hostCounters[0];
-		current ^= 1;
+		if (!check_cuda(cudaEventRecord(state->iterationDone[launched % WorkerState::kEventRing], stream), "cudaEventRecord(iteration)")) return false;
+		++launched;
 	}
 
-	gTimer.start(stream);
+	state->serial += launched;
+
+	timer.start(stream);
 	finish_kernel<<<blocks_for(count), kBlock, 0, stream>>>(count, paths, state->sampleOut);
-	gTimer.stop(KernelTimer::FINISH, stream);
+	timer.stop(KernelTimer::FINISH, stream);
 	++launches;
 	return check_cuda(cudaGetLastError(), "finish_kernel launch");
 }
@@ -2591,11 +2679,6 @@ static void collect_stats(WorkerState* state, EchoStats* stats, uint64_t launche
 	for (int i = 0; i < STAT_COUNT; i++) out[i] += host[i];
 	stats->kernelLaunches += launches;
 }
-
-// At most 16 Mi paths per batch and pipeline (250 B of wavefront state per path: about 4 GB each); render_tiles splits smaller
-// jobs so that every pipeline gets a share. A/B at 64 spp per step, 4 / 8 / 16 Mi: C3 439 / 459 / 456, C4 321 / 330 / 332, C5 (16 spp)
-// 337 / 350 / 368 M samples/s — wider launches per bounce and 2-4x fewer of them (variants/ab10.sh, ECHO_B200_BATCH_PATHS).
-constexpr uint64_t kPathsPerBatch = 1ull << 24;
 
 // one batch of tiles: pixel loop -> epoch loop -> sample loop of EvaluationOperation.Execute (EvaluationOperation.cs:100-141)
 static bool render_batch(WorkerState* state, const DeviceScene& scene, const EchoRenderParams& params, const int32_t* tileXY, uint32_t tiles,
@@ -2630,10 +2713,10 @@ static bool render_batch(WorkerState* state, const DeviceScene& scene, const Ech
 
 		if (!check_cuda(cudaMemsetAsync(state->paths.counters + COUNTER_PIXELS, 0, sizeof(uint32_t), stream), "cudaMemsetAsync(pixel counter)")) return false;
 
-		gTimer.start(stream);
+		state->timer.start(stream);
 		accumulate_kernel<<<blocks_for(activePixels), kBlock, 0, stream>>>(params, activePixels, state->activePixels[list], state->sampleOut, state->accumulator,
 		                                                                 state->sampleCount, epoch, state->activePixels[list ^ 1], state->paths.counters, state->paths.stats);
-		gTimer.stop(KernelTimer::ACCUMULATE, stream);
+		state->timer.stop(KernelTimer::ACCUMULATE, stream);
 		++launches;
 
 		if (!check_cuda(cudaMemcpyAsync(state->hostCounters + 8, state->paths.counters + COUNTER_PIXELS, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream), "cudaMemcpyAsync(pixels)")) return false;
@@ -2663,32 +2746,28 @@ bool render_tiles(RenderState* state, const DeviceScene& scene, const EchoRender
 		return false;
 	}
 
-	if ((params.evaluator & ECHO_EVALUATOR_KIND_MASK) > ECHO_EVALUATOR_NAIVE || (params.evaluator & ~(ECHO_EVALUATOR_KIND_MASK | ECHO_EVALUATOR_DIVERGE_ONCE)) != 0)
+	if ((params.evaluator & ECHO_EVALUATOR_KIND_MASK) > ECHO_EVALUATOR_NAIVE || (params.evaluator & ~(ECHO_EVALUATOR_KIND_MASK | ECHO_EVALUATOR_DIVERGE_ONCE | ECHO_EVALUATOR_COUNT_VISITS)) != 0)
 	{
 		set_error("unknown EchoRenderParams.evaluator");
+		return false;
+	}
+
+	if ((params.evaluator & ECHO_EVALUATOR_COUNT_VISITS) != 0 && (params.evaluator & ECHO_EVALUATOR_KIND_MASK) != ECHO_EVALUATOR_PATH_TRACED)
+	{
+		set_error("ECHO_EVALUATOR_COUNT_VISITS is a switch of the path-traced evaluator");
 		return false;
 	}
 
 	// work submitted earlier on the caller's stream (e.g. clearing the frame) must be visible to the worker streams
 	if (!check_cuda(cudaStreamSynchronize(stream), "render_tiles entry")) return false;
 
-	static const int configuredWorkers = []
-	{
-		const char* value = std::getenv("ECHO_B200_RENDER_WORKERS");
-		int workers = value ? std::atoi(value) : kWorkers;
-		return workers < 1 ? 1 : (workers > 16 ? 16 : workers);
-	}();
+	const int configuredWorkers = (int)std::min<long long>(std::max<long long>(options().renderWorkers, 1), 16);
 
 	// batch size: at most kPathsPerBatch paths, but small jobs are still split so that every pipeline gets a share
 	// (never below 256 Ki paths per batch: smaller wavefronts are launch- and latency-bound from the first bounce)
 	uint64_t perTile = (uint64_t)params.tileSize * params.tileSize;
 	uint64_t pathsPerTile = perTile * params.extend;
-	static const uint64_t batchPaths = []
-	{
-		const char* value = std::getenv("ECHO_B200_BATCH_PATHS"); // A/B: paths per batch and pipeline
-		uint64_t paths = value ? (uint64_t)std::atoll(value) : kPathsPerBatch;
-		return std::min<uint64_t>(std::max<uint64_t>(paths, 1ull << 16), 1ull << 26);
-	}();
+	const uint64_t batchPaths = std::min<uint64_t>(std::max<uint64_t>((uint64_t)std::max<long long>(options().batchPaths, 1), 1ull << 16), 1ull << 26);
 	uint64_t maxTiles = std::max<uint64_t>(1, batchPaths / pathsPerTile);
 	uint64_t minTiles = std::max<uint64_t>(1, (1ull << 18) / pathsPerTile);
 	uint64_t share = (tileCount + configuredWorkers - 1) / configuredWorkers;
@@ -2696,7 +2775,7 @@ bool render_tiles(RenderState* state, const DeviceScene& scene, const EchoRender
 	tilesPerBatch = std::min<uint64_t>(tilesPerBatch, tileCount);
 	uint64_t batchCount = (tileCount + tilesPerBatch - 1) / tilesPerBatch;
 
-	int workerCount = (int)std::min<uint64_t>(gTimer.enabled ? 1 : configuredWorkers, batchCount);
+	int workerCount = (int)std::min<uint64_t>(profiling() ? 1 : configuredWorkers, batchCount);
 	for (int i = 0; i < workerCount; i++)
 		if (!get_worker(state, i)) return false;
 
@@ -2752,7 +2831,7 @@ bool render_tiles(RenderState* state, const DeviceScene& scene, const EchoRender
 	}
 
 	for (int i = 0; i < workerCount; i++) collect_stats(state->workers[i], stats, launches[i], state->workers[i]->stream);
-	gTimer.report();
+	if (profiling()) state->workers[0]->timer.report();
 	return true;
 }
 

@@ -2,8 +2,11 @@
 // two 128-bit loads, EchoHit output written with one 128-bit store. These are the kernels behind
 // echo_b200_trace_batch / echo_b200_occlude_batch (BASELINE config C2) and the batched analogue of the benchmark loops in
 // the reference's src/Echo.Experimental/Benchmarks/Accelerators.cs:131-157.
+#include <algorithm>
 #include <cstdlib>
+#include <map>
 #include <mutex>
+#include <utility>
 
 #include "echo_internal.h"
 #include "echo_traverse.cuh"
@@ -141,6 +144,7 @@ __global__ void __launch_bounds__(kTraverseBlock, ECHO_MIN_BLOCKS) persistent_ba
 {
 	__shared__ float4 stagedRays[kTraverseBlock * 2];
 	persistent_traverse<STACK, ANY>(scene, io, n, nextRay, stagedRays);
+	persistent_finish(nextRay);
 }
 
 // the same through instanced packs (echo_traverse.cuh INST); more per-lane state than the plain kernel: 95 registers when
@@ -151,48 +155,67 @@ __global__ void __launch_bounds__(kTraverseBlock, ECHO_INST_MIN_BLOCKS) persiste
 {
 	__shared__ float4 stagedRays[kTraverseBlock * 2];
 	persistent_traverse<STACK, ANY, true>(scene, io, n, nextRay, stagedRays);
+	persistent_finish(nextRay);
 }
 
-// Every persistent launch needs its own zeroed ray counter (launches on different streams may overlap): a per-device ring.
-constexpr unsigned int kCounterRing = 256;
-
-unsigned long long* next_ray_counter(cudaStream_t stream)
+// The work counter pair of persistent launches on `stream` of the current device (echo_traverse.cuh persistent_finish). Launches
+// on one stream run in order and every kernel leaves its pair zeroed, so one pair per (device, stream) is enough however
+// many launches are outstanding and whoever issued them — there is nothing to hand out, recycle or memset. The pairs of
+// destroyed streams stay allocated (16 bytes each); a recycled stream handle simply finds its old, zeroed pair.
+unsigned long long* ray_counters(cudaStream_t stream)
 {
 	static std::mutex guard;
-	static unsigned long long* rings[64] = {};
-	static unsigned int cursors[64] = {};
+	static std::map<std::pair<int, cudaStream_t>, unsigned long long*> pairs;
 
 	int device = 0;
 	cudaGetDevice(&device);
-	device &= 63;
 
 	std::lock_guard<std::mutex> lock(guard);
-	if (!rings[device] && !check_cuda(cudaMalloc((void**)&rings[device], sizeof(unsigned long long) * kCounterRing), "cudaMalloc(ray counters)")) return nullptr;
+	unsigned long long*& pair = pairs[{ device, stream }];
 
-	unsigned long long* counter = rings[device] + (cursors[device]++ % kCounterRing);
-	if (!check_cuda(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream), "cudaMemsetAsync(ray counter)")) return nullptr;
-	return counter;
+	if (!pair)
+	{
+		// synchronous on purpose: the pair is zero before any launch on any stream can see it
+		if (!check_cuda(cudaMalloc((void**)&pair, sizeof(unsigned long long) * 2), "cudaMalloc(ray counters)")) { pair = nullptr; return nullptr; }
+		if (!check_cuda(cudaMemset(pair, 0, sizeof(unsigned long long) * 2), "cudaMemset(ray counters)")) return nullptr;
+	}
+
+	return pair;
 }
 
+// one resident wave of a persistent kernel on the current device: 148 SMs x resident CTAs per SM; remembered per device and kernel
 int persistent_grid(const void* kernel)
 {
-	int device = 0, sms = 0, perSM = 0;
+	static std::mutex guard;
+	static std::map<std::pair<int, const void*>, int> grids;
+
+	int device = 0;
 	cudaGetDevice(&device);
-	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, kTraverseBlock, 0);
-	return sms * (perSM > 0 ? perSM : 1); // one resident wave: 148 SMs x resident CTAs per SM
+
+	std::lock_guard<std::mutex> lock(guard);
+	int& grid = grids[{ device, kernel }];
+
+	if (grid == 0)
+	{
+		int sms = 0, perSM = 0;
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, kTraverseBlock, 0);
+		grid = std::max(sms, 1) * (perSM > 0 ? perSM : 1);
+	}
+
+	return grid;
 }
 
 template<int STACK, bool ANY>
 static bool launch_persistent(const DeviceScene& scene, const EchoRay* rays, uint64_t n, EchoHit* hits, uint8_t* occluded, cudaStream_t stream)
 {
-	static int grid = persistent_grid((const void*)persistent_batch_kernel<STACK, ANY>);
+	const int grid = persistent_grid((const void*)persistent_batch_kernel<STACK, ANY>);
 	constexpr uint64_t kLaunchLimit = 1ull << 31; // ray indices are 32-bit inside the kernel
 
 	for (uint64_t first = 0; first < n; first += kLaunchLimit)
 	{
 		uint64_t count = n - first < kLaunchLimit ? n - first : kLaunchLimit;
-		unsigned long long* counter = next_ray_counter(stream);
+		unsigned long long* counter = ray_counters(stream);
 		if (!counter) return false;
 
 		BatchIO io = { reinterpret_cast<const float4*>(rays + first), hits ? reinterpret_cast<float4*>(hits + first) : nullptr, occluded ? occluded + first : nullptr, nullptr, nullptr };
@@ -209,13 +232,13 @@ template<int STACK, bool ANY>
 static bool launch_persistent_instanced_impl(const DeviceScene& scene, const EchoRay* rays, const EchoTokenHierarchy* ignore, uint64_t n, EchoHit* hits,
                                              EchoTokenHierarchy* hitLayers, uint8_t* occluded, cudaStream_t stream)
 {
-	static int grid = persistent_grid((const void*)persistent_instanced_kernel<STACK, ANY>);
+	const int grid = persistent_grid((const void*)persistent_instanced_kernel<STACK, ANY>);
 	constexpr uint64_t kLaunchLimit = 1ull << 31;
 
 	for (uint64_t first = 0; first < n; first += kLaunchLimit)
 	{
 		uint64_t count = n - first < kLaunchLimit ? n - first : kLaunchLimit;
-		unsigned long long* counter = next_ray_counter(stream);
+		unsigned long long* counter = ray_counters(stream);
 		if (!counter) return false;
 
 		BatchIO io = { reinterpret_cast<const float4*>(rays + first), hits ? reinterpret_cast<float4*>(hits + first) : nullptr, occluded ? occluded + first : nullptr,

@@ -63,7 +63,9 @@ class PreparedScene:
         _native.check(self._lib.echo_b200_debug_bounds_violations(self._handle, ctypes.byref(bits)))
         return None if bits.value == 0xFFFFFFFF else int(bits.value)
 
-    def close(self):
+    def close(self, quiet=False):
+        """Destroys the native scene. A bounds-check build reports failed index checks here by raising — except with
+        `quiet` (what __del__ and an __exit__ that is already unwinding an exception use: they must not raise or mask)."""
         if getattr(self, "_handle", None) is not None and self._handle.value:
             violations = None
             try:
@@ -72,17 +74,20 @@ class PreparedScene:
                 pass
             self._lib.echo_b200_scene_destroy(self._handle)
             self._handle = ctypes.c_void_p()
-            if violations:
+            if violations and not quiet:
                 raise _native.EchoNativeError(-2, f"out-of-bounds index in a kernel: failed checks 0x{violations:x} (echo_scene.cuh CHECK_*)")
 
     def __del__(self):
-        self.close()
+        try:
+            self.close(quiet=True)
+        except Exception:  # interpreter shutdown: the library may already be gone
+            pass
 
     def __enter__(self):
         return self
 
-    def __exit__(self, *_):
-        self.close()
+    def __exit__(self, exception_type, *_):
+        self.close(quiet=exception_type is not None)
 
     @property
     def handle(self):
@@ -155,6 +160,14 @@ class PreparedScene:
         _native.check(self._lib.echo_b200_render_tiles(self._handle, _native.pointer(params), _native.pointer(tile_xy), len(tile_xy),
                                                        _native.pointer(out), _native.pointer(stats)))
         return out, stats
+
+    def render_tiles_pointers(self, params, tile_xy, out_pointer):
+        """echo_b200_render_tiles into caller-owned host memory (e.g. a HostBuffer): tile-major Float4s. Returns the stats record."""
+        tile_xy = np.ascontiguousarray(tile_xy, dtype=np.int32).reshape(-1, 2)
+        stats = np.zeros(1, dtype=structs.STATS)
+        _native.check(self._lib.echo_b200_render_tiles(self._handle, _native.pointer(params), _native.pointer(tile_xy), len(tile_xy),
+                                                       ctypes.c_void_p(out_pointer), _native.pointer(stats)))
+        return stats
 
     def render_frame_device(self, params, tile_xy, frame_pointer, stream=0):
         """Renders tiles into a device-resident full frame (width*height Float4; xyz = mean, w = 1 where rendered)."""

@@ -116,6 +116,7 @@ RENDER_PARAMS = np.dtype([
 
 EVALUATOR_PATH_TRACED, EVALUATOR_ALBEDO, EVALUATOR_NORMAL_DEPTH, EVALUATOR_NAIVE = 0, 1, 2, 3
 EVALUATOR_DIVERGE_ONCE = 0x100
+EVALUATOR_COUNT_VISITS = 0x200  # counted pass: EchoStats reports node / triangle / sphere / light-node visits (bench roofline)
 
 STATS_FIELDS = [
     "sampleEvaluated", "sampleRejected", "pixelEvaluated", "bounceCreated", "bounceSpecular", "bounceMis",
@@ -128,7 +129,9 @@ STATS_LABELS = [
     "Bounce/Multiple Importance", "Light/Sampled", "Light/Occlusion Checked", "Light/Occlusion Passed",
     "Light/Evaluated Infinite",
 ]
-STATS = np.dtype([(name, "<u8") for name in STATS_FIELDS] + [("reserved", "<u8", 3)])
+# filled only by a counted pass (EVALUATOR_COUNT_VISITS): the inputs of the algorithmic bytes per sample
+STATS_VISIT_FIELDS = ["nodeVisits", "triangleVisits", "sphereVisits", "lightNodeVisits"]
+STATS = np.dtype([(name, "<u8") for name in STATS_FIELDS + STATS_VISIT_FIELDS] + [("reserved", "<u8", 7)])
 
 assert QBVH_NODE.itemsize == 128
 assert TRIANGLE.itemsize == 100
@@ -141,7 +144,7 @@ assert POINT_LIGHT.itemsize == 24
 assert INFINITE_LIGHT.itemsize == 160
 assert CAMERA.itemsize == 80
 assert RENDER_PARAMS.itemsize == 48
-assert STATS.itemsize == 128
+assert STATS.itemsize == 192
 
 
 def render_params(width, height, tile_size=16, extend=16, min_epoch=1, max_epoch=1, noise_threshold=0.045,

@@ -30,7 +30,12 @@
 
 #ifdef __cplusplus
 extern "C" {
+#define ECHO_B200_STATIC_ASSERT(condition, message) static_assert(condition, message)
+#else
+#define ECHO_B200_STATIC_ASSERT(condition, message) _Static_assert(condition, message)
 #endif
+/* every POD below is followed by its size: a binding (C#, ctypes ...) that disagrees with one of them corrupts memory silently */
+#define ECHO_B200_ASSERT_SIZE(type, bytes) ECHO_B200_STATIC_ASSERT(sizeof(type) == (bytes), #type " must be " #bytes " bytes")
 
 #define ECHO_B200_OK 0
 #define ECHO_B200_ERR_INVALID 1     /* bad argument / scene not committed */
@@ -66,6 +71,7 @@ typedef struct EchoQbvhNode
 	uint32_t token4[4]; /* @108 child tokens; ECHO_TOKEN_EMPTY for none */
 	uint32_t pad;       /* @124 */
 } EchoQbvhNode;
+ECHO_B200_ASSERT_SIZE(EchoQbvhNode, 128);
 
 /* ---- PreparedTriangle, 100 B sequential layout (TriangleEntity.cs:118-139) ---- */
 typedef struct EchoTriangle
@@ -75,6 +81,7 @@ typedef struct EchoTriangle
 	float texcoord0[2], texcoord1[2], texcoord2[2];
 	uint32_t material; /* MaterialIndex */
 } EchoTriangle;
+ECHO_B200_ASSERT_SIZE(EchoTriangle, 100);
 
 /* ---- PreparedSphere, 20 B (SphereEntity.cs:59-63) ---- */
 typedef struct EchoSphere
@@ -83,6 +90,7 @@ typedef struct EchoSphere
 	float radius;
 	uint32_t material;
 } EchoSphere;
+ECHO_B200_ASSERT_SIZE(EchoSphere, 20);
 
 /* ---- one query: Ray + TraceQuery/OccludeQuery inputs (Ray.cs:17-28, TraceQuery.cs:16-40, OccludeQuery.cs:10-30).
  * `direction` must be unit length; `distance` is TraceQuery.distance / OccludeQuery.travel (may be +inf);
@@ -94,6 +102,7 @@ typedef struct EchoRay
 	float distance;
 	uint32_t ignore;
 } EchoRay;
+ECHO_B200_ASSERT_SIZE(EchoRay, 32);
 
 /* ---- TraceQuery outputs (TraceQuery.cs:42-58). token == ECHO_TOKEN_EMPTY and distance == input distance on a miss. ---- */
 typedef struct EchoHit
@@ -102,6 +111,7 @@ typedef struct EchoHit
 	float distance;
 	float uv[2];
 } EchoHit;
+ECHO_B200_ASSERT_SIZE(EchoHit, 16);
 
 /* ---- materials with constant (Pure) textures flattened (Evaluation/Materials/) ---- */
 #define ECHO_MATERIAL_DIFFUSE 0u    /* Diffuse.cs:33-47 */
@@ -127,6 +137,7 @@ typedef struct EchoMaterial
 	float paramB[3];    /* Conductor: EdgeColor (artistic) or Extinction (physical) */
 	uint32_t base;      /* OneSided.Base material index */
 } EchoMaterial; /* 64 B */
+ECHO_B200_ASSERT_SIZE(EchoMaterial, 64);
 
 /* ---- image textures: TextureGrid (Textures/Grids/TextureGrid.cs) flattened to RGBA128 texels, with its
  * IFilter (Textures/Grids/IFilter.cs) and IWrapper (Textures/Grids/IWrapper.cs). Texel (x, y) of texture t is
@@ -146,6 +157,7 @@ typedef struct EchoTexture
 	uint32_t wrapper;     /* ECHO_WRAPPER_* */
 	uint32_t reserved[3];
 } EchoTexture; /* 32 bytes */
+ECHO_B200_ASSERT_SIZE(EchoTexture, 32);
 
 /* the texture slots of one material, parallel to the material array; a slot holding a texture index replaces the constant
  * of the same name in EchoMaterial with `(RGB128)texture[contact.shade.Texcoord]` (Material.Sample, Material.cs:102) */
@@ -159,6 +171,7 @@ typedef struct EchoMaterialTextures
 	float normalIntensity; /* Material.NormalIntensity (default 0.25); ~0 switches normal mapping off (Material.cs:58) */
 	uint32_t reserved[2];
 } EchoMaterialTextures; /* 32 bytes */
+ECHO_B200_ASSERT_SIZE(EchoMaterialTextures, 32);
 
 /* ---- flattened LightTree node (LightTree.cs:156-171, LightBound.cs:10-20, ConeBound.cs:20-24). Node 0 = root.
  * Branch: child0/child1 are node indices. Leaf: child0 == ECHO_TOKEN_EMPTY and child1 holds the light's token. ---- */
@@ -171,6 +184,7 @@ typedef struct EchoLightNode
 	uint32_t child0, child1;
 	uint32_t pad[2];
 } EchoLightNode; /* 64 B */
+ECHO_B200_ASSERT_SIZE(EchoLightNode, 64);
 
 /* ---- PreparedPointLight (Scenic/Lights/PointLight.cs:20-33) ---- */
 typedef struct EchoPointLight
@@ -178,6 +192,7 @@ typedef struct EchoPointLight
 	float intensity[3];
 	float position[3];
 } EchoPointLight;
+ECHO_B200_ASSERT_SIZE(EchoPointLight, 24);
 
 /* ---- infinite lights (Scenic/Lights/InfiniteLight.cs): AmbientLight over a constant (Pure) texture (AmbientLight.cs) and
  * DirectionalLight (DirectionalLight.cs:12-108), with everything DirectionalLight.Prepare computes on the host (:52-75). ---- */
@@ -207,6 +222,7 @@ typedef struct EchoInfiniteLight
 	float inverseRotation[9]; /* WorldToLocalRotation (InfiniteLight.cs:37), Environment only */
 	float pad4[3];
 } EchoInfiniteLight; /* 160 bytes; an ambient light only needs the first 16, the rest zero */
+ECHO_B200_ASSERT_SIZE(EchoInfiniteLight, 160);
 
 /* ---- instancing: PreparedPack / PreparedInstance / TokenHierarchy ----
  * A scene with instances is a set of packs (PreparedPack.cs:13-24): pack 0 is the PreparedScene itself, the others are the
@@ -231,6 +247,7 @@ typedef struct EchoPack
 	uint32_t emitterOffset, emitterCount;
 	uint32_t pointLightOffset, pointLightCount;
 } EchoPack; /* 64 bytes */
+ECHO_B200_ASSERT_SIZE(EchoPack, 64);
 
 typedef struct EchoInstance
 {
@@ -242,6 +259,7 @@ typedef struct EchoInstance
 	uint32_t materialOffset; /* PreparedInstance.swatch: material index of a hit = this + the geometry's own index */
 	uint32_t reserved[4];
 } EchoInstance; /* 128 bytes */
+ECHO_B200_ASSERT_SIZE(EchoInstance, 128);
 
 /* the instance layers of a TokenHierarchy (TokenHierarchy.cs:19-60); its TopToken travels in EchoRay.ignore / EchoHit.token */
 typedef struct EchoTokenHierarchy
@@ -249,6 +267,7 @@ typedef struct EchoTokenHierarchy
 	uint32_t instanceCount;
 	uint32_t instances[ECHO_MAX_INSTANCE_LAYERS]; /* TokenType.Instance tokens, outermost first */
 } EchoTokenHierarchy; /* 24 bytes */
+ECHO_B200_ASSERT_SIZE(EchoTokenHierarchy, 24);
 
 /* ---- Camera.SpawnRay inputs (Scenic/Cameras/{Perspective,Orthographic,Cylindrical}Camera.cs, RaySpawner.cs:11-64) ---- */
 #define ECHO_CAMERA_PERSPECTIVE 0u  /* PerspectiveCamera.cs:41-98 (thin lens when lensRadius and focalDistance are both >= 8e-7) */
@@ -265,6 +284,7 @@ typedef struct EchoCamera
 	float direction[3];  /* Orthographic: RootedRotation * Float3.Forward (OrthographicCamera.cs:22-26) */
 	float width;         /* Orthographic: Width (:18) */
 } EchoCamera; /* 80 bytes */
+ECHO_B200_ASSERT_SIZE(EchoCamera, 80);
 
 /* ---- EvaluationProfile + PathTracedEvaluator knobs (EvaluationProfile.cs:42-60, PathTracedEvaluator.cs:33,40) ---- */
 typedef struct EchoRenderParams
@@ -280,6 +300,7 @@ typedef struct EchoRenderParams
 	int32_t epochOffset;    /* first epoch index this call renders (sample sharding across devices) */
 	int32_t evaluator;      /* ECHO_EVALUATOR_* [| ECHO_EVALUATOR_DIVERGE_ONCE]; 0 = PathTracedEvaluator */
 } EchoRenderParams;
+ECHO_B200_ASSERT_SIZE(EchoRenderParams, 48);
 
 /* EvaluationProfile.Evaluator (EvaluationProfile.cs:23): the path tracer, or one of the two auxiliary evaluators the
  * StandardPathTracedProfile runs for its denoiser (Processes/StandardPathTracedProfile.cs:27-45). The auxiliary ones
@@ -293,6 +314,9 @@ typedef struct EchoRenderParams
                                  roulette; reads bounceLimit (<= 128 here: the device unrolls the recursion into two arrays) */
 #define ECHO_EVALUATOR_KIND_MASK 0xFF
 #define ECHO_EVALUATOR_DIVERGE_ONCE 0x100 /* the evaluator's DivergeOnce property (default: true for Albedo, false for NormalDepth) */
+#define ECHO_EVALUATOR_COUNT_VISITS 0x200 /* PathTracedEvaluator only: a counted pass. Same samples, same results, but the traversal runs
+                                             on the one-thread-per-query kernels with visit counters and EchoStats reports node / triangle /
+                                             sphere / light-node visits. A measurement aid (bench.py's roofline), several times slower. */
 
 /* ---- EvaluatorStatistics rows on the hot path, same labels/order as the reference reports them
  * (EvaluationOperation.cs:130-140; PathTracedEvaluator.cs:50-199) ---- */
@@ -311,8 +335,15 @@ typedef struct EchoStats
 	uint64_t traceQueries;           /* closest-hit queries issued */
 	uint64_t occludeQueries;         /* occlusion queries issued */
 	uint64_t kernelLaunches;         /* CUDA kernels launched by this call */
-	uint64_t reserved[3];
-} EchoStats;
+	/* visit counters, filled only by a call with ECHO_EVALUATOR_COUNT_VISITS (zero otherwise): the inputs of the algorithmic
+	 * bytes per sample of SURVEY.md 8(d), counted on the reference's own visit order */
+	uint64_t nodeVisits;             /* BoxBound4.Intersect calls of the closest-hit and occlusion queries (128 B each) */
+	uint64_t triangleVisits;         /* PreparedTriangle.Intersect calls (36 B each) */
+	uint64_t sphereVisits;           /* PreparedSphere.Intersect calls (16 B each) */
+	uint64_t lightNodeVisits;        /* LightBound.Importance evaluations of LightTree.Pick / ProbabilityMass (64 B each) */
+	uint64_t reserved[7];
+} EchoStats; /* 192 bytes */
+ECHO_B200_ASSERT_SIZE(EchoStats, 192);
 
 typedef struct EchoScene EchoScene;
 
@@ -383,6 +414,16 @@ int32_t echo_b200_frame_resolve_device(EchoScene*, float* d_frame_rgba, int32_t 
  * triangle_count + sphere_count - 1 nodes; out_max_depth is the depth CreateNode reports (what set_qbvh takes). */
 int32_t echo_b200_build_qbvh(int32_t device, const EchoTriangle* triangles, uint32_t triangle_count, const EchoSphere* spheres, uint32_t sphere_count,
                              EchoQbvhNode* out_nodes, uint32_t* out_node_count, uint32_t* out_max_depth);
+
+/* Page-locked host memory for the host-buffer entry points. A P/Invoke caller pins managed arrays with `fixed`
+ * (Processes/Composition/OidnDenoise.cs:109-110): that stops the GC from moving them but leaves them PAGEABLE for CUDA, so every
+ * copy is staged through the driver's bounce buffer and cannot overlap the kernels (measured: bench.py `e2e_pageable`). Either
+ * allocate the batch buffers here (use them as the backing store of the managed view) or register the caller's own memory once.
+ * Registered memory stays owned by the caller; it must be unregistered before it is released. */
+int32_t echo_b200_host_alloc(void** out, uint64_t bytes);
+int32_t echo_b200_host_free(void* pointer);
+int32_t echo_b200_host_register(void* pointer, uint64_t bytes);
+int32_t echo_b200_host_unregister(void* pointer);
 
 const char* echo_b200_last_error(void);
 const char* echo_b200_version(void);

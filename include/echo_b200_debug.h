@@ -37,6 +37,11 @@ int32_t echo_b200_debug_evaluate_samples4(EchoScene*, const EchoRenderParams*, c
  * bit set of checks that failed since commit (0 = clean). Release builds write 0xFFFFFFFF ("not compiled in"). */
 int32_t echo_b200_debug_bounds_violations(EchoScene*, uint32_t* out_bits);
 
+/* Changes one tuning switch of the wavefront at run time: `name` is the part after ECHO_B200_ of the environment variable that
+ * sets its initial value (RENDER_WORKERS, BATCH_PATHS, NARROW_LIMIT, TAIL_LIMIT, RUN_AHEAD, BLOCKING_SYNC; -1 = automatic for the
+ * last two). Process-wide; takes effect with the next render call. For A/B runs that keep one uploaded scene. */
+int32_t echo_b200_debug_set_option(const char* name, int64_t value);
+
 #ifdef __cplusplus
 }
 #endif

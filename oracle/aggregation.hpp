@@ -93,6 +93,10 @@ struct VisitCounters
 	uint64_t nodes = 0, triangles = 0, spheres = 0;
 };
 
+// LightBound.Importance evaluations of the calling thread (one 64-byte light-tree node each): the D_lt term of SURVEY.md §8(d).
+// The path tracer's statistics take the difference around a sample.
+inline thread_local uint64_t lightNodeVisits = 0;
+
 struct GeometryPoint
 {
 	Float3 position, normal;
@@ -836,6 +840,7 @@ struct Scene
 
 	static float light_importance(const EchoLightNode& bound, const GeometryPoint& origin)
 	{
+		++lightNodeVisits;
 		Float3 boxMin = f3(bound.boxMin), boxMax = f3(bound.boxMax);
 		Float3 center = (boxMax + boxMin) / 2.0f; // BoxBound.cs:69
 		Float3 incident = origin.position - center;

@@ -328,6 +328,10 @@ static void merge_stats(EchoStats* out, const EvaluatorStats& stats, uint64_t sa
 	out->lightEvaluatedInfinite = stats.lightEvaluatedInfinite;
 	out->traceQueries = stats.traceQueries;
 	out->occludeQueries = stats.occludeQueries;
+	out->nodeVisits = stats.visits.nodes;
+	out->triangleVisits = stats.visits.triangles;
+	out->sphereVisits = stats.visits.spheres;
+	out->lightNodeVisits = stats.lightNodeVisits;
 }
 
 // EvaluationOperation.Execute over a list of tiles (Processes/Evaluation/EvaluationOperation.cs:83-148); one tile per

@@ -503,9 +503,13 @@ struct EvaluatorStats // the labels of EvaluatorStatistics used on this path, ec
 	uint64_t bounceCreated = 0, bounceSpecular = 0, bounceMis = 0;
 	uint64_t lightSampled = 0, lightOcclusionChecked = 0, lightOcclusionPassed = 0, lightEvaluatedInfinite = 0;
 	uint64_t traceQueries = 0, occludeQueries = 0;
+	VisitCounters visits;         // node / triangle / sphere visits of those queries (echo_b200.h EchoStats nodeVisits ...)
+	uint64_t lightNodeVisits = 0; // LightBound.Importance evaluations of scene.pick / scene.probability_mass
 
 	void add(const EvaluatorStats& o)
 	{
+		visits.nodes += o.visits.nodes; visits.triangles += o.visits.triangles; visits.spheres += o.visits.spheres;
+		lightNodeVisits += o.lightNodeVisits;
 		bounceCreated += o.bounceCreated; bounceSpecular += o.bounceSpecular; bounceMis += o.bounceMis;
 		lightSampled += o.lightSampled; lightOcclusionChecked += o.lightOcclusionChecked;
 		lightOcclusionPassed += o.lightOcclusionPassed; lightEvaluatedInfinite += o.lightEvaluatedInfinite;
@@ -537,7 +541,7 @@ struct PathTracedEvaluator
 		bool advance(const Scene& scene, EvaluatorStats& stats)
 		{
 			++stats.traceQueries;
-			if (!scene.trace(query)) return false;
+			if (!scene.trace(query, &stats.visits)) return false;
 			interact(scene, query, contact);
 			return true;
 		}
@@ -625,7 +629,7 @@ struct PathTracedEvaluator
 		query.ignore = contact.token;
 		query.ignoreLayers = contact.layers;
 		++stats.occludeQueries;
-		if (scene.occlude(query)) return kBlack;
+		if (scene.occlude(query, &stats.visits)) return kBlack;
 
 		++stats.lightOcclusionPassed;
 
@@ -858,7 +862,9 @@ inline Float4 evaluate_sample(const Scene& scene, const EchoRenderParams& params
 		PathTracedEvaluator evaluator;
 		evaluator.bounceLimit = params.bounceLimit;
 		evaluator.survivability = params.survivability;
+		uint64_t lightVisitsBefore = lightNodeVisits;
 		RGB value = evaluator.evaluate(scene, ray, distribution, stats);
+		stats.lightNodeVisits += lightNodeVisits - lightVisitsBefore;
 		return { { value.r, value.g, value.b, 0.0f } };
 	}
 

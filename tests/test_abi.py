@@ -41,43 +41,81 @@ def test_host_library_exports_every_declared_symbol():
         assert hasattr(lib, name), name
 
 
+# every POD of include/echo_b200.h and its numpy mirror in echorenderer_b200/structs.py
+POD_MIRRORS = {
+    "EchoQbvhNode": "QBVH_NODE", "EchoTriangle": "TRIANGLE", "EchoSphere": "SPHERE", "EchoRay": "RAY", "EchoHit": "HIT", "EchoMaterial": "MATERIAL",
+    "EchoTexture": "TEXTURE", "EchoMaterialTextures": "MATERIAL_TEXTURES", "EchoLightNode": "LIGHT_NODE", "EchoPointLight": "POINT_LIGHT",
+    "EchoInfiniteLight": "INFINITE_LIGHT", "EchoPack": "PACK", "EchoInstance": "INSTANCE", "EchoTokenHierarchy": "TOKEN_HIERARCHY", "EchoCamera": "CAMERA",
+    "EchoRenderParams": "RENDER_PARAMS", "EchoStats": "STATS",
+}
+
+
+def header_structs():
+    text = open(os.path.join(ROOT, "include", "echo_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return set(re.findall(r"typedef struct (\w+)\s*\{", text))
+
+
 def test_pod_layouts_match_the_header():
-    """sizeof / offsetof of the C structs, recomputed by compiling the header (gcc), equal the numpy mirrors."""
+    """sizeof and the offsetof of EVERY member of EVERY struct of the header, recomputed by compiling it (gcc), equal the numpy
+    mirrors; no struct of the header is left without a mirror; every struct carries its size assertion in the header."""
     import subprocess
     import tempfile
-    fields = {
-        "EchoQbvhNode": ("QBVH_NODE", ["minX", "maxZ", "axisMajor", "axisMinor1", "token4", "pad"]),
-        "EchoTriangle": ("TRIANGLE", ["vertex0", "edge2", "normal0", "texcoord0", "material"]),
-        "EchoSphere": ("SPHERE", ["position", "radius", "material"]),
-        "EchoRay": ("RAY", ["origin", "direction", "distance", "ignore"]),
-        "EchoHit": ("HIT", ["token", "distance", "uv"]),
-        "EchoMaterial": ("MATERIAL", ["type", "albedo", "roughness", "ior", "paramA", "paramB", "base"]),
-        "EchoLightNode": ("LIGHT_NODE", ["boxMin", "coneAxis", "cosOffset", "power", "child0", "child1"]),
-        "EchoCamera": ("CAMERA", ["transform", "forwardLength", "focalDistance"]),
-        "EchoRenderParams": ("RENDER_PARAMS", ["width", "extend", "noiseThreshold", "seed", "epochOffset"]),
-        "EchoStats": ("STATS", ["sampleEvaluated", "lightEvaluatedInfinite", "kernelLaunches"]),
-    }
+    assert header_structs() == set(POD_MIRRORS), "a struct of echo_b200.h has no mirror in this test"
+    header = open(os.path.join(ROOT, "include", "echo_b200.h")).read()
+
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "echo_b200.h"', "int main(void) {"]
-    for c_name, (_, names) in fields.items():
+    for c_name, mirror in POD_MIRRORS.items():
+        assert f"ECHO_B200_ASSERT_SIZE({c_name}, {getattr(structs, mirror).itemsize});" in header, f"{c_name} has no size assertion in the header"
         lines.append(f'printf("{c_name} %zu\\n", sizeof({c_name}));')
-        for name in names:
-            lines.append(f'printf("{c_name}.{name} %zu\\n", offsetof({c_name}, {name}));')
+        for name in getattr(structs, mirror).names:
+            lines.append(f'printf("{c_name}.{name} %zu %zu\\n", offsetof({c_name}, {name}), sizeof((({c_name}*)0)->{name}));')
     lines.append("return 0; }")
 
     with tempfile.TemporaryDirectory() as directory:
         source, binary = os.path.join(directory, "layout.c"), os.path.join(directory, "layout")
         open(source, "w").write("\n".join(lines))
-        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), source, "-o", binary], check=True)
+        subprocess.run(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), source, "-o", binary], check=True)
         output = subprocess.run([binary], check=True, capture_output=True, text=True).stdout
 
+    checked = 0
     for line in output.splitlines():
-        key, value = line.split()
+        key, *values = line.split()
         c_name, _, member = key.partition(".")
-        dtype = getattr(structs, fields[c_name][0])
-        assert int(value) == (dtype.fields[member][1] if member else dtype.itemsize), line
+        dtype = getattr(structs, POD_MIRRORS[c_name])
+        if member:
+            assert int(values[0]) == dtype.fields[member][1] and int(values[1]) == dtype.fields[member][0].itemsize, line
+        else:
+            assert int(values[0]) == dtype.itemsize, line
+        checked += 1
+    assert checked == len(POD_MIRRORS) + sum(len(getattr(structs, m).names) for m in POD_MIRRORS.values())
+
+    # the members of every C struct are all mirrored (the mirrors tile their structs without gaps)
+    for mirror in POD_MIRRORS.values():
+        dtype = getattr(structs, mirror)
+        assert sum(dtype.fields[name][0].itemsize for name in dtype.names) == dtype.itemsize, mirror
 
     # the sizes the reference's structs have (SURVEY.md §8a: a1, a9, a10)
     assert structs.QBVH_NODE.itemsize == 128 and structs.TRIANGLE.itemsize == 100 and structs.SPHERE.itemsize == 20
+
+
+def test_integration_document_states_the_header_sizes():
+    """INTEGRATION.md's C# binding must declare every struct at the size the header asserts (a stale size there corrupts memory
+    in a host that follows the document)."""
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    for c_name, mirror in POD_MIRRORS.items():
+        size = getattr(structs, mirror).itemsize
+        assert re.search(rf"Size\s*=\s*{size}\)\]\s*(?:public\s+)?(?:unsafe\s+)?struct\s+{c_name[4:]}\b", text), f"{c_name}: INTEGRATION.md does not declare it with Size = {size}"
+
+
+def test_integration_structs_are_the_generated_block():
+    """The struct block of INTEGRATION.md is exactly what tools/gen_csharp_structs.py derives from the checked layouts."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_csharp_structs", os.path.join(ROOT, "tools", "gen_csharp_structs.py"))
+    module = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(module)
+    assert {pod[0] for pod in module.PODS} == set(POD_MIRRORS)
+    assert module.BEGIN + "\n" + module.block() + "\n" + module.END in open(os.path.join(ROOT, "INTEGRATION.md")).read()
 
 
 @pytest.mark.skipif(have_gpu(), reason="checks the no-device behaviour")

@@ -1,0 +1,181 @@
+"""The drop-in boundary exercised the way a foreign host would (round 2):
+
+* a plain-C client (tests/c_client/echo_client.c, gcc, no Python, no C++) dlopen()s libecho_b200.so, uploads the Cornell box
+  from raw arrays and calls trace_batch / occlude_batch / render_tiles — what a .NET host does through [DllImport];
+* counted passes (ECHO_EVALUATOR_COUNT_VISITS) return the oracle's visit counters and leave the results untouched;
+* a scene without materials serves trace batches but is refused by the render entry points (api.cu:446);
+* scenes on two devices driven from two threads of one process (needs two GPUs; skipped on a one-GPU box)."""
+import os
+import subprocess
+import threading
+
+import numpy as np
+import pytest
+
+from echorenderer_b200 import PreparedScene, _native, host, scenes, structs
+from tests import oracle_lib
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_plain_c_client_matches_the_python_binding_and_the_oracle(cornell, tmp_path):
+    binary = tmp_path / "echo_client"
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c_client", "echo_client.c"), "-o", str(binary), "-ldl"], check=True)
+
+    d = cornell.description
+    rays = scenes.random_rays(cornell.bounds, 50000, seed=5)
+    shadow = scenes.random_rays(cornell.bounds, 50000, seed=6, occlusion=True)
+    tiles = scenes.tile_grid(64, 48, 16)
+    params = structs.render_params(64, 48, 16, extend=4, min_epoch=2, max_epoch=2, bounce_limit=32, seed=9)
+    scalars = np.zeros(4, dtype=np.uint32)
+    scalars[0] = cornell.max_depth
+    scalars[1:].view(np.float32)[:] = [cornell.infinite_threshold, cornell.infinite_pdf, cornell.bound_radius]
+
+    for name, array in [("nodes", cornell.nodes), ("triangles", cornell.triangles), ("spheres", cornell.spheres), ("materials", cornell.materials),
+                        ("light_nodes", cornell.light_nodes), ("emitter_tokens", cornell.emitter_tokens), ("emitter_paths", cornell.emitter_bitpaths),
+                        ("point_lights", cornell.point_lights), ("infinite", d.infinite_lights), ("camera", d.camera), ("scalars", scalars),
+                        ("rays", rays), ("shadow", shadow), ("tiles", tiles.astype(np.int32)), ("params", params)]:
+        np.ascontiguousarray(array).tofile(tmp_path / f"{name}.bin")
+
+    library = os.environ.get("ECHO_B200_LIBRARY") or os.path.join(ROOT, "echorenderer_b200", "libecho_b200.so")
+    result = subprocess.run([str(binary), library, str(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert result.returncode == 0, result.stderr
+    assert "echo_client ok" in result.stdout
+
+    hits = np.fromfile(tmp_path / "hits.bin", dtype=structs.HIT)
+    occluded = np.fromfile(tmp_path / "occluded.bin", dtype=np.uint8)
+    image = np.fromfile(tmp_path / "image.bin", dtype=np.float32).reshape(len(tiles), 16, 16, 4)
+    stats = np.fromfile(tmp_path / "stats.bin", dtype=structs.STATS)
+
+    oracle = oracle_lib.OracleScene(cornell)
+    expected_hits = oracle.trace(rays)
+    assert np.array_equal(hits["token"], expected_hits["token"]) and np.array_equal(hits.view(np.uint32), expected_hits.view(np.uint32))
+    assert np.array_equal(occluded, oracle.occlude(shadow))
+
+    with PreparedScene(cornell) as scene:
+        through_ctypes, ctypes_stats = scene.render_tiles(params, tiles)
+    assert np.array_equal(image.view(np.uint32), through_ctypes.view(np.uint32))
+    expected_image, expected_stats = oracle.render_tiles(params, tiles)
+    assert np.sqrt(np.mean((image - expected_image) ** 2)) <= 1e-4 * np.sqrt(np.mean(expected_image ** 2))
+    for name in structs.STATS_FIELDS[:12]:
+        assert int(stats[name][0]) == int(ctypes_stats[name][0]) == int(expected_stats[name][0]), name
+
+
+@pytest.mark.parametrize("fixture,bounce_limit", [("cornell", 32), ("lights_small", 16), ("mixed_small", 8)])
+def test_counted_pass_reports_the_oracles_visit_counters(fixture, bounce_limit, request):
+    """ECHO_EVALUATOR_COUNT_VISITS: same tiles bit for bit, and node / triangle / sphere / light-node visit totals equal to the
+    counters instrumented into the oracle's traversal and light tree (the inputs of bench.py's algorithmic bytes per sample)."""
+    prepared = request.getfixturevalue(fixture)
+    width, height = 64, 48
+    tiles = scenes.tile_grid(width, height, 16)
+    plain = structs.render_params(width, height, 16, extend=4, bounce_limit=bounce_limit, seed=11)
+    counted = structs.render_params(width, height, 16, extend=4, bounce_limit=bounce_limit, seed=11, evaluator=structs.EVALUATOR_PATH_TRACED | structs.EVALUATOR_COUNT_VISITS)
+
+    with PreparedScene(prepared) as scene:
+        image, stats = scene.render_tiles(plain, tiles)
+        counted_image, counted_stats = scene.render_tiles(counted, tiles)
+
+    assert np.array_equal(image.view(np.uint32), counted_image.view(np.uint32))
+    assert all(int(stats[name][0]) == 0 for name in structs.STATS_VISIT_FIELDS)
+
+    _, expected = oracle_lib.OracleScene(prepared).render_tiles(plain, tiles)
+    for name in structs.STATS_FIELDS[:12]:
+        assert int(counted_stats[name][0]) == int(stats[name][0]), name
+    for name in structs.STATS_VISIT_FIELDS:
+        assert int(counted_stats[name][0]) == int(expected[name][0]), name
+    assert int(counted_stats["nodeVisits"][0]) > 0 and int(counted_stats["triangleVisits"][0]) > 0
+    if fixture == "lights_small":
+        assert int(counted_stats["lightNodeVisits"][0]) > int(counted_stats["lightSampled"][0])  # a 300-light tree is several levels deep
+
+
+def test_a_scene_without_materials_traces_but_does_not_render(terrain_small):
+    lib = _native.library()
+    import ctypes
+    handle = ctypes.c_void_p()
+    _native.check(lib.echo_b200_scene_create(ctypes.byref(handle), 0))
+    try:
+        ptr = _native.pointer
+        _native.check(lib.echo_b200_scene_set_qbvh(handle, ptr(terrain_small.nodes), len(terrain_small.nodes), terrain_small.max_depth))
+        _native.check(lib.echo_b200_scene_set_triangles(handle, ptr(terrain_small.triangles), len(terrain_small.triangles)))
+        _native.check(lib.echo_b200_scene_set_spheres(handle, ptr(terrain_small.spheres), len(terrain_small.spheres)))
+        _native.check(lib.echo_b200_scene_commit(handle))
+
+        rays = scenes.random_rays(terrain_small.bounds, 4096, seed=3)
+        hits = np.empty(len(rays), dtype=structs.HIT)
+        _native.check(lib.echo_b200_trace_batch(handle, ptr(rays), len(rays), ptr(hits)))
+        assert np.array_equal(hits.view(np.uint32), oracle_lib.OracleScene(terrain_small).trace(rays).view(np.uint32))
+
+        params = structs.render_params(32, 32, 16, extend=1)
+        tiles = scenes.tile_grid(32, 32, 16).astype(np.int32)
+        out = np.zeros((len(tiles), 16, 16, 4), dtype=np.float32)
+        stats = np.zeros(1, dtype=structs.STATS)
+        assert lib.echo_b200_render_tiles(handle, ptr(params), ptr(tiles), len(tiles), ptr(out), ptr(stats)) == _native.ERR_INVALID
+        assert b"no materials" in lib.echo_b200_last_error()
+        pixel = np.zeros((1, 2), dtype=np.int32)
+        index = np.zeros(1, dtype=np.uint32)
+        rgb = np.zeros(3, dtype=np.float32)
+        assert lib.echo_b200_debug_evaluate_samples(handle, ptr(params), ptr(pixel), ptr(index), 1, ptr(rgb)) == _native.ERR_INVALID
+    finally:
+        lib.echo_b200_scene_destroy(handle)
+
+
+def test_many_outstanding_launches_on_many_streams(terrain_small):
+    """ADVICE r1 (trace.cu:172): the work counters of persistent launches are per (device, stream) and reset by the kernels
+    themselves — 600 asynchronous launches over three caller streams (more than the old 256-slot ring) all answer like one."""
+    import torch
+    rays = scenes.random_rays(terrain_small.bounds, 1 << 16, seed=21)
+    expected = oracle_lib.OracleScene(terrain_small).trace(rays)
+    device = torch.device("cuda", 0)
+
+    with PreparedScene(terrain_small) as scene:
+        d_rays = torch.from_numpy(rays.view(np.uint8).reshape(-1)).to(device)
+        streams = [torch.cuda.Stream(device=device) for _ in range(3)]
+        outputs = [[torch.zeros(len(rays) * 16, dtype=torch.uint8, device=device) for _ in range(4)] for _ in streams]
+        torch.cuda.synchronize()
+        for round_index in range(200):
+            for stream, buffers in zip(streams, outputs):
+                scene.trace_device(d_rays.data_ptr(), len(rays), buffers[round_index % 4].data_ptr(), stream.cuda_stream)
+        torch.cuda.synchronize()
+        for buffers in outputs:
+            for buffer in buffers:
+                assert np.array_equal(buffer.cpu().numpy().view(np.uint32), expected.view(np.uint32).reshape(-1))
+
+
+def device_total():
+    try:
+        return _native.device_count()
+    except _native.EchoNativeError:
+        return 0
+
+
+@pytest.mark.skipif(device_total() < 2, reason="needs two GPUs")
+def test_two_devices_from_one_process(cornell, terrain_small):
+    """One process, two scenes on two devices, two host threads (the reference is one process with N workers,
+    Common/Compute/Device.cs:20-24): per-device launch state (resident grids, work counters) must not leak between devices."""
+    oracle = oracle_lib.OracleScene(terrain_small)
+    rays = scenes.random_rays(terrain_small.bounds, 1 << 18, seed=31)
+    expected = oracle.trace(rays)
+    params = structs.render_params(64, 64, 16, extend=4, bounce_limit=16, seed=2)
+    tiles = scenes.tile_grid(64, 64, 16)
+    expected_image, _ = oracle_lib.OracleScene(cornell).render_tiles(params, tiles)
+    results = {}
+
+    def work(device):
+        with PreparedScene(terrain_small, device=device) as scene, PreparedScene(cornell, device=device) as box:
+            for _ in range(8):
+                hits = scene.trace(rays)
+                image, _ = box.render_tiles(params, tiles)
+            results[device] = (hits, image)
+
+    threads = [threading.Thread(target=work, args=(device,)) for device in (0, 1)]
+    for thread in threads:
+        thread.start()
+    for thread in threads:
+        thread.join()
+
+    for device in (0, 1):
+        hits, image = results[device]
+        assert np.array_equal(hits.view(np.uint32), expected.view(np.uint32))
+        assert np.sqrt(np.mean((image - expected_image) ** 2)) <= 1e-4 * np.sqrt(np.mean(expected_image ** 2))
