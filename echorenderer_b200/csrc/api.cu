@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
+#include <thread>
 
 #include "../../include/echo_b200_debug.h"
 #include "echo_internal.h"
@@ -173,6 +174,44 @@ int32_t batch_host(EchoScene* scene, const EchoRay* rays, uint64_t n, Out* out, 
 	return ok ? ECHO_B200_OK : ECHO_B200_ERR_CUDA;
 }
 
+// Multi-device scenes (echo_b200_scene_create_multi): runs `work(scene of device g, g)` for the primary and every replica, one host
+// thread per device. Returns the first failing status with that thread's error text as the caller's last error.
+template<class Work>
+int32_t fan_out(EchoScene* scene, Work work)
+{
+	const size_t devices = 1 + scene->replicas.size();
+	std::vector<int32_t> status(devices, ECHO_B200_OK);
+	std::vector<std::string> errors(devices);
+
+	auto run = [&](size_t g)
+	{
+		status[g] = work(g == 0 ? scene : scene->replicas[g - 1], g);
+		if (status[g] != ECHO_B200_OK) errors[g] = last_error_string();
+	};
+
+	std::vector<std::thread> threads;
+	for (size_t g = 1; g < devices; g++) threads.emplace_back(run, g);
+	run(0);
+	for (std::thread& thread : threads) thread.join();
+
+	for (size_t g = 0; g < devices; g++)
+	{
+		if (status[g] == ECHO_B200_OK) continue;
+		set_error(errors[g]);
+		return status[g];
+	}
+
+	return ECHO_B200_OK;
+}
+
+bool single_device(EchoScene* scene)
+{
+	if (scene && !scene->replicas.empty()) { set_error("this entry point takes device memory of one device: it needs a single-device scene (echo_b200_scene_create)"); return false; }
+	return true;
+}
+
+constexpr uint32_t kDealBlock = 64; // consecutive tiles of the caller's sequence that stay on one device (echo_b200.h, scene_create_multi)
+
 } // namespace
 
 extern "C"
@@ -256,9 +295,53 @@ int32_t echo_b200_scene_create(EchoScene** out, int32_t device)
 	return ECHO_B200_OK;
 }
 
+int32_t echo_b200_scene_create_multi(EchoScene** out, uint64_t deviceMask)
+{
+	if (!out) return fail(ECHO_B200_ERR_INVALID, "out is null");
+	*out = nullptr;
+
+	int32_t count = 0;
+	int32_t status = echo_b200_device_count(&count);
+	if (status != ECHO_B200_OK) return status;
+	if (deviceMask == 0) return fail(ECHO_B200_ERR_INVALID, "device_mask is empty");
+	if (count < 64 && (deviceMask >> count) != 0) return fail(ECHO_B200_ERR_INVALID, "device_mask names a device that does not exist");
+
+	EchoScene* primary = nullptr;
+
+	for (int32_t device = 0; device < count && device < 64; device++)
+	{
+		if (((deviceMask >> device) & 1ull) == 0) continue;
+		EchoScene* scene = nullptr;
+		status = echo_b200_scene_create(&scene, device);
+
+		if (status != ECHO_B200_OK)
+		{
+			std::string error = last_error_string();
+			echo_b200_scene_destroy(primary);
+			set_error(error);
+			return status;
+		}
+
+		if (!primary) primary = scene;
+		else primary->replicas.push_back(scene);
+	}
+
+	*out = primary;
+	return ECHO_B200_OK;
+}
+
+int32_t echo_b200_scene_gpu_count(EchoScene* scene, int32_t* out)
+{
+	if (!scene || !out) return fail(ECHO_B200_ERR_INVALID, "null argument");
+	*out = 1 + (int32_t)scene->replicas.size();
+	return ECHO_B200_OK;
+}
+
 int32_t echo_b200_scene_destroy(EchoScene* scene)
 {
 	if (!scene) return ECHO_B200_OK;
+	for (EchoScene* replica : scene->replicas) echo_b200_scene_destroy(replica);
+	scene->replicas.clear();
 	DeviceGuard guard(scene->device);
 	free_device(scene);
 	render_state_destroy(scene->render);
@@ -348,6 +431,7 @@ int32_t echo_b200_scene_set_camera(EchoScene* scene, const EchoCamera* camera)
 	if (!scene || !camera) return fail(ECHO_B200_ERR_INVALID, "null argument");
 	scene->camera = *camera;
 	if (scene->committed) scene->d.camera = *camera; // the camera travels by value with every launch
+	for (EchoScene* replica : scene->replicas) echo_b200_scene_set_camera(replica, camera);
 	return ECHO_B200_OK;
 }
 
@@ -403,6 +487,7 @@ int32_t echo_b200_scene_set_bound_radius(EchoScene* scene, float radius)
 	if (!scene) return fail(ECHO_B200_ERR_INVALID, "null argument");
 	scene->boundRadius = radius;
 	if (scene->committed) scene->d.boundRadius = radius; // travels by value with every launch, like the camera
+	for (EchoScene* replica : scene->replicas) echo_b200_scene_set_bound_radius(replica, radius);
 	return ECHO_B200_OK;
 }
 
@@ -448,9 +533,51 @@ bool chain_stack(const EchoScene* scene, uint32_t pack, std::vector<uint32_t>& n
 
 } // namespace
 
+static int32_t commit_device(EchoScene* scene);
+
+// the host staging of a scene: what the set_* calls filled and commit reads
+static void swap_staging(EchoScene* a, EchoScene* b)
+{
+	std::swap(a->nodes, b->nodes);
+	std::swap(a->maxDepth, b->maxDepth);
+	std::swap(a->triangles, b->triangles);
+	std::swap(a->spheres, b->spheres);
+	std::swap(a->materials, b->materials);
+	std::swap(a->lightNodes, b->lightNodes);
+	std::swap(a->emitterTokens, b->emitterTokens);
+	std::swap(a->emitterPaths, b->emitterPaths);
+	std::swap(a->pointLights, b->pointLights);
+	std::swap(a->infiniteLights, b->infiniteLights);
+	std::swap(a->infiniteThreshold, b->infiniteThreshold);
+	std::swap(a->infinitePdf, b->infinitePdf);
+	std::swap(a->camera, b->camera);
+	std::swap(a->boundRadius, b->boundRadius);
+	std::swap(a->distributions, b->distributions);
+	std::swap(a->textures, b->textures);
+	std::swap(a->texels, b->texels);
+	std::swap(a->materialTextures, b->materialTextures);
+	std::swap(a->packs, b->packs);
+	std::swap(a->instances, b->instances);
+}
+
 int32_t echo_b200_scene_commit(EchoScene* scene)
 {
 	if (!scene) return fail(ECHO_B200_ERR_INVALID, "scene is null");
+	int32_t status = commit_device(scene);
+
+	// the same staging, uploaded to every other device of a multi-device scene (lent to the replica for the duration of its commit)
+	for (size_t i = 0; status == ECHO_B200_OK && i < scene->replicas.size(); i++)
+	{
+		swap_staging(scene, scene->replicas[i]);
+		status = commit_device(scene->replicas[i]);
+		swap_staging(scene, scene->replicas[i]);
+	}
+
+	return status;
+}
+
+static int32_t commit_device(EchoScene* scene)
+{
 	if (scene->nodes.empty()) return fail(ECHO_B200_ERR_INVALID, "no QBVH was set");
 
 	// the packs the arrays are divided into; a scene without set_packs is one pack
@@ -677,17 +804,41 @@ int32_t echo_b200_scene_commit(EchoScene* scene)
 
 int32_t echo_b200_trace_batch(EchoScene* scene, const EchoRay* rays, uint64_t n, EchoHit* hits)
 {
-	return batch_host<EchoHit>(scene, rays, n, hits, [&](const EchoRay* in, uint64_t count, EchoHit* out, cudaStream_t stream)
+	auto trace = [](EchoScene* target, const EchoRay* in, uint64_t count, EchoHit* out)
 	{
-		return launch_trace(scene->d, in, count, out, nullptr, stream);
+		return batch_host<EchoHit>(target, in, count, out, [target](const EchoRay* chunk, uint64_t c, EchoHit* chunkOut, cudaStream_t stream)
+		{
+			return launch_trace(target->d, chunk, c, chunkOut, nullptr, stream);
+		});
+	};
+
+	if (!scene || scene->replicas.empty() || !rays || !hits || n == 0) return trace(scene, rays, n, hits);
+
+	const uint64_t devices = 1 + scene->replicas.size(); // one contiguous range of the batch per device
+	return fan_out(scene, [&](EchoScene* target, size_t g)
+	{
+		uint64_t first = n * g / devices;
+		return trace(target, rays + first, n * (g + 1) / devices - first, hits + first);
 	});
 }
 
 int32_t echo_b200_occlude_batch(EchoScene* scene, const EchoRay* rays, uint64_t n, uint8_t* occluded)
 {
-	return batch_host<uint8_t>(scene, rays, n, occluded, [&](const EchoRay* in, uint64_t count, uint8_t* out, cudaStream_t stream)
+	auto occlude = [](EchoScene* target, const EchoRay* in, uint64_t count, uint8_t* out)
 	{
-		return launch_occlude(scene->d, in, count, out, nullptr, stream);
+		return batch_host<uint8_t>(target, in, count, out, [target](const EchoRay* chunk, uint64_t c, uint8_t* chunkOut, cudaStream_t stream)
+		{
+			return launch_occlude(target->d, chunk, c, chunkOut, nullptr, stream);
+		});
+	};
+
+	if (!scene || scene->replicas.empty() || !rays || !occluded || n == 0) return occlude(scene, rays, n, occluded);
+
+	const uint64_t devices = 1 + scene->replicas.size();
+	return fan_out(scene, [&](EchoScene* target, size_t g)
+	{
+		uint64_t first = n * g / devices;
+		return occlude(target, rays + first, n * (g + 1) / devices - first, occluded + first);
 	});
 }
 
@@ -737,18 +888,32 @@ int32_t hierarchy_host(EchoScene* scene, const EchoRay* rays, const EchoTokenHie
 int32_t echo_b200_trace_batch_hierarchy(EchoScene* scene, const EchoRay* rays, const EchoTokenHierarchy* ignore, uint64_t n, EchoHit* hits, EchoTokenHierarchy* hitLayers)
 {
 	if (!hits && n != 0) return fail(ECHO_B200_ERR_INVALID, "null buffer");
-	return hierarchy_host(scene, rays, ignore, n, hits, hitLayers, nullptr);
+	if (!scene || scene->replicas.empty() || !rays || n == 0) return hierarchy_host(scene, rays, ignore, n, hits, hitLayers, nullptr);
+
+	const uint64_t devices = 1 + scene->replicas.size();
+	return fan_out(scene, [&](EchoScene* target, size_t g)
+	{
+		uint64_t first = n * g / devices;
+		return hierarchy_host(target, rays + first, ignore ? ignore + first : nullptr, n * (g + 1) / devices - first, hits + first, hitLayers ? hitLayers + first : nullptr, nullptr);
+	});
 }
 
 int32_t echo_b200_occlude_batch_hierarchy(EchoScene* scene, const EchoRay* rays, const EchoTokenHierarchy* ignore, uint64_t n, uint8_t* occluded)
 {
 	if (!occluded && n != 0) return fail(ECHO_B200_ERR_INVALID, "null buffer");
-	return hierarchy_host(scene, rays, ignore, n, nullptr, nullptr, occluded);
+	if (!scene || scene->replicas.empty() || !rays || n == 0) return hierarchy_host(scene, rays, ignore, n, nullptr, nullptr, occluded);
+
+	const uint64_t devices = 1 + scene->replicas.size();
+	return fan_out(scene, [&](EchoScene* target, size_t g)
+	{
+		uint64_t first = n * g / devices;
+		return hierarchy_host(target, rays + first, ignore ? ignore + first : nullptr, n * (g + 1) / devices - first, nullptr, nullptr, occluded + first);
+	});
 }
 
 int32_t echo_b200_trace_batch_device(EchoScene* scene, const EchoRay* rays, uint64_t n, EchoHit* hits, void* stream)
 {
-	if (!require_committed(scene)) return ECHO_B200_ERR_INVALID;
+	if (!require_committed(scene) || !single_device(scene)) return ECHO_B200_ERR_INVALID;
 	DeviceGuard guard(scene->device);
 	if (!guard.ok) return ECHO_B200_ERR_NO_DEVICE;
 	return launch_trace(scene->d, rays, n, hits, nullptr, (cudaStream_t)stream) ? ECHO_B200_OK : ECHO_B200_ERR_CUDA;
@@ -756,7 +921,7 @@ int32_t echo_b200_trace_batch_device(EchoScene* scene, const EchoRay* rays, uint
 
 int32_t echo_b200_occlude_batch_device(EchoScene* scene, const EchoRay* rays, uint64_t n, uint8_t* occluded, void* stream)
 {
-	if (!require_committed(scene)) return ECHO_B200_ERR_INVALID;
+	if (!require_committed(scene) || !single_device(scene)) return ECHO_B200_ERR_INVALID;
 	DeviceGuard guard(scene->device);
 	if (!guard.ok) return ECHO_B200_ERR_NO_DEVICE;
 	return launch_occlude(scene->d, rays, n, occluded, nullptr, (cudaStream_t)stream) ? ECHO_B200_OK : ECHO_B200_ERR_CUDA;
@@ -764,7 +929,7 @@ int32_t echo_b200_occlude_batch_device(EchoScene* scene, const EchoRay* rays, ui
 
 int32_t echo_b200_trace_batch_device_counted(EchoScene* scene, const EchoRay* rays, uint64_t n, EchoHit* hits, uint64_t* counts, void* stream)
 {
-	if (!require_committed(scene)) return ECHO_B200_ERR_INVALID;
+	if (!require_committed(scene) || !single_device(scene)) return ECHO_B200_ERR_INVALID;
 	if (!counts) return fail(ECHO_B200_ERR_INVALID, "d_counts3 is null");
 	DeviceGuard guard(scene->device);
 	if (!guard.ok) return ECHO_B200_ERR_NO_DEVICE;
@@ -773,20 +938,16 @@ int32_t echo_b200_trace_batch_device_counted(EchoScene* scene, const EchoRay* ra
 
 int32_t echo_b200_occlude_batch_device_counted(EchoScene* scene, const EchoRay* rays, uint64_t n, uint8_t* occluded, uint64_t* counts, void* stream)
 {
-	if (!require_committed(scene)) return ECHO_B200_ERR_INVALID;
+	if (!require_committed(scene) || !single_device(scene)) return ECHO_B200_ERR_INVALID;
 	if (!counts) return fail(ECHO_B200_ERR_INVALID, "d_counts3 is null");
 	DeviceGuard guard(scene->device);
 	if (!guard.ok) return ECHO_B200_ERR_NO_DEVICE;
 	return launch_occlude(scene->d, rays, n, occluded, (unsigned long long*)counts, (cudaStream_t)stream) ? ECHO_B200_OK : ECHO_B200_ERR_CUDA;
 }
 
-int32_t echo_b200_render_tiles(EchoScene* scene, const EchoRenderParams* params, const int32_t* tileXY, uint32_t tileCount, float* outRGBA, EchoStats* stats)
+// the tiles [first, first + count) of the caller's sequence on one device: render, then download into the caller's tile-major buffer
+static int32_t render_tiles_device(EchoScene* scene, const EchoRenderParams* params, const int32_t* tileXY, uint32_t tileCount, float* outRGBA, EchoStats* stats)
 {
-	if (!require_renderable(scene)) return ECHO_B200_ERR_INVALID;
-	if (!params || (!tileXY && tileCount) || (!outRGBA && tileCount)) return fail(ECHO_B200_ERR_INVALID, "null argument");
-	if (stats) *stats = EchoStats{};
-	if (tileCount == 0) return ECHO_B200_OK;
-
 	DeviceGuard guard(scene->device);
 	if (!guard.ok) return ECHO_B200_ERR_NO_DEVICE;
 
@@ -801,9 +962,72 @@ int32_t echo_b200_render_tiles(EchoScene* scene, const EchoRenderParams* params,
 	return ok ? ECHO_B200_OK : ECHO_B200_ERR_CUDA;
 }
 
-int32_t echo_b200_render_frame_device(EchoScene* scene, const EchoRenderParams* params, const int32_t* tileXY, uint32_t tileCount, float* frame, EchoStats* stats, void* stream)
+int32_t echo_b200_render_tiles(EchoScene* scene, const EchoRenderParams* params, const int32_t* tileXY, uint32_t tileCount, float* outRGBA, EchoStats* stats)
 {
 	if (!require_renderable(scene)) return ECHO_B200_ERR_INVALID;
+	if (!params || (!tileXY && tileCount) || (!outRGBA && tileCount)) return fail(ECHO_B200_ERR_INVALID, "null argument");
+	if (params->tileSize <= 0) return fail(ECHO_B200_ERR_INVALID, "invalid EchoRenderParams");
+	if (stats) *stats = EchoStats{};
+	if (tileCount == 0) return ECHO_B200_OK;
+	if (scene->replicas.empty()) return render_tiles_device(scene, params, tileXY, tileCount, outRGBA, stats);
+
+	// Several devices: blocks of kDealBlock consecutive tiles dealt round-robin; device g renders its blocks as one tile list and
+	// its tiles go back block by block to their places in the caller's buffer. Disjoint tiles: nothing to reduce.
+	const size_t devices = 1 + scene->replicas.size();
+	const uint64_t tileFloats = (uint64_t)params->tileSize * params->tileSize * 4;
+	const uint32_t blocks = (tileCount + kDealBlock - 1) / kDealBlock;
+	std::vector<EchoStats> perDevice(devices, EchoStats{});
+
+	int32_t status = fan_out(scene, [&](EchoScene* target, size_t g)
+	{
+		std::vector<int32_t> local;
+		std::vector<uint32_t> blockOf; // the block each run of `local` came from
+
+		for (uint32_t b = (uint32_t)g; b < blocks; b += (uint32_t)devices)
+		{
+			uint32_t first = b * kDealBlock, count = std::min(kDealBlock, tileCount - first);
+			local.insert(local.end(), tileXY + (size_t)first * 2, tileXY + (size_t)(first + count) * 2);
+			blockOf.push_back(b);
+		}
+
+		if (local.empty()) return (int32_t)ECHO_B200_OK;
+		uint32_t localCount = (uint32_t)(local.size() / 2);
+
+		DeviceGuard guard(target->device);
+		if (!guard.ok) return (int32_t)ECHO_B200_ERR_NO_DEVICE;
+
+		float4* deviceOut = nullptr;
+		if (!check_cuda(cudaMalloc((void**)&deviceOut, sizeof(float) * tileFloats * localCount), "cudaMalloc(tiles)")) return (int32_t)ECHO_B200_ERR_CUDA;
+
+		bool ok = render_tiles(target->render, target->d, *params, local.data(), localCount, deviceOut, nullptr, &perDevice[g], target->stream);
+		uint32_t localFirst = 0;
+
+		for (size_t k = 0; ok && k < blockOf.size(); k++)
+		{
+			uint32_t first = blockOf[k] * kDealBlock, count = std::min(kDealBlock, tileCount - first);
+			ok = check_cuda(cudaMemcpyAsync(outRGBA + (uint64_t)first * tileFloats, reinterpret_cast<const float*>(deviceOut) + (uint64_t)localFirst * tileFloats,
+			                                sizeof(float) * tileFloats * count, cudaMemcpyDeviceToHost, target->stream), "cudaMemcpyAsync(tiles)");
+			localFirst += count;
+		}
+
+		ok = check_cuda(cudaStreamSynchronize(target->stream), "render_tiles") && ok;
+		cudaFree(deviceOut);
+		return (int32_t)(ok ? ECHO_B200_OK : ECHO_B200_ERR_CUDA);
+	});
+
+	if (stats)
+	{
+		uint64_t* total = reinterpret_cast<uint64_t*>(stats);
+		for (const EchoStats& part : perDevice)
+			for (size_t i = 0; i < sizeof(EchoStats) / sizeof(uint64_t); i++) total[i] += reinterpret_cast<const uint64_t*>(&part)[i];
+	}
+
+	return status;
+}
+
+int32_t echo_b200_render_frame_device(EchoScene* scene, const EchoRenderParams* params, const int32_t* tileXY, uint32_t tileCount, float* frame, EchoStats* stats, void* stream)
+{
+	if (!require_renderable(scene) || !single_device(scene)) return ECHO_B200_ERR_INVALID;
 	if (!params || (!tileXY && tileCount) || !frame) return fail(ECHO_B200_ERR_INVALID, "null argument");
 	if (stats) *stats = EchoStats{};
 	if (tileCount == 0) return ECHO_B200_OK;
@@ -871,6 +1095,16 @@ static int32_t debug_device(int32_t device)
 	if (status != ECHO_B200_OK) return status;
 	if (device < 0 || device >= count) return fail(ECHO_B200_ERR_INVALID, "device index out of range");
 	return ECHO_B200_OK;
+}
+
+int32_t echo_b200_debug_measure_peaks(int32_t device, float* out3)
+{
+	if (!out3) return fail(ECHO_B200_ERR_INVALID, "out3 is null");
+	int32_t status = debug_device(device);
+	if (status != ECHO_B200_OK) return status;
+	DeviceGuard guard(device);
+	if (!guard.ok) return ECHO_B200_ERR_NO_DEVICE;
+	return measure_peaks(out3) ? ECHO_B200_OK : ECHO_B200_ERR_CUDA;
 }
 
 int32_t echo_b200_debug_bxdf_batch(int32_t device, int32_t kind, const float* params, const float* outgoing, const float* samples, uint64_t n,

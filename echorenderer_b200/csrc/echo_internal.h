@@ -56,6 +56,9 @@ bool launch_frame_resolve(float4* frame, int32_t width, int32_t height, cudaStre
 // tuning switches of the wavefront (the ECHO_B200_<NAME> environment variables), changeable at run time; false = unknown name
 bool set_render_option(const char* name, long long value);
 
+// ---- peaks.cu: on-chip ceilings measured on the current device: {L2 coalesced read, L2 random 32-byte sectors, L1 random sectors} GB/s
+bool measure_peaks(float* out3);
+
 // ---- debug.cu: device mirrors of the oracle's known-answer hooks ----
 bool launch_debug_bxdf(int32_t kind, const float* params, const float* outgoing, const float* samples, uint64_t n,
                        float* sampled8, float* evaluated4, float* inverse4, cudaStream_t stream);
@@ -103,4 +106,8 @@ struct EchoScene
 	cudaEvent_t chunkDone[kSlots] = {};
 
 	echo::RenderState* render = nullptr;
+
+	// echo_b200_scene_create_multi: this handle is the scene of the first device of the mask, `replicas` are the scenes of the
+	// others. Uploads go to the primary's host staging; commit replicates to every device.
+	std::vector<EchoScene*> replicas;
 };

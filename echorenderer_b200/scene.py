@@ -21,13 +21,22 @@ from .host import PreparedArrays
 class PreparedScene:
     """The flattened scene resident on one B200; the device twin of Echo's PreparedScene."""
 
-    def __init__(self, prepared: PreparedArrays, device: int = 0):
+    def __init__(self, prepared: PreparedArrays, device: int = 0, devices=None):
+        """`device`: the CUDA device of a single-device scene. `devices` (a list of device indices) instead replicates the scene
+        on several devices of this process (echo_b200_scene_create_multi): trace / occlude split their batches over them and
+        render_tiles deals blocks of tiles to them; the *_device methods then do not apply."""
         lib = _native.library()
         self._lib = lib
         self.prepared = prepared
         self.device = device
         self._handle = ctypes.c_void_p()
-        _native.check(lib.echo_b200_scene_create(ctypes.byref(self._handle), device))
+        if devices is None:
+            _native.check(lib.echo_b200_scene_create(ctypes.byref(self._handle), device))
+        else:
+            mask = 0
+            for index in devices:
+                mask |= 1 << int(index)
+            _native.check(lib.echo_b200_scene_create_multi(ctypes.byref(self._handle), mask))
 
         try:
             d = prepared.description
@@ -92,6 +101,12 @@ class PreparedScene:
     @property
     def handle(self):
         return self._handle
+
+    @property
+    def gpu_count(self):
+        count = ctypes.c_int32()
+        _native.check(self._lib.echo_b200_scene_gpu_count(self._handle, ctypes.byref(count)))
+        return count.value
 
     # ---- PreparedScene.Trace / Occlude, batched (PreparedScene.cs:66-86); host numpy buffers ----
     def trace(self, rays, out=None):
@@ -372,11 +387,17 @@ def hilbert_curve_pattern(size):
     return np.array(result, dtype=np.int32).reshape(-1, 2)
 
 
-def shard_tiles(tile_positions, rank, world_size):
-    """Tile sharding across devices: tile i -> rank (i mod world_size), the static analogue of Operation.Execute's shared
-    procedure counter (Common/Compute/Operation.cs:164-177). Round-robin over the scan order balances load."""
+def shard_tiles(tile_positions, rank, world_size, block=1):
+    """Tile sharding across devices, the static analogue of Operation.Execute's shared procedure counter
+    (Common/Compute/Operation.cs:164-177): the tile sequence is cut into blocks of `block` consecutive tiles and block b goes
+    to rank (b mod world_size). block = 1 deals single tiles round-robin. Larger blocks keep what one device renders together
+    compact in the image — consecutive tiles of a HilbertCurvePattern are neighbours, every world_size-th tile of it is not,
+    and a wavefront batch over scattered tiles traverses less coherently (measured on C5, 8 shards: 754 ms per step dealt tile
+    by tile against 664 ms for an ordered sequence) — while hundreds of blocks per device still balance the load."""
     tile_positions = np.asarray(tile_positions, dtype=np.int32).reshape(-1, 2)
-    return np.ascontiguousarray(tile_positions[rank::world_size])
+    block = max(1, int(block))
+    owner = (np.arange(len(tile_positions)) // block) % world_size
+    return np.ascontiguousarray(tile_positions[owner == rank])
 
 
 def build_qbvh_device(triangles, spheres, device=0):

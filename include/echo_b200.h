@@ -350,6 +350,18 @@ typedef struct EchoScene EchoScene;
 int32_t echo_b200_device_count(int32_t* out);
 int32_t echo_b200_scene_create(EchoScene** out, int32_t device);
 
+/* One scene on SEVERAL devices of this process — the reference is one process whose Device drives N workers
+ * (Common/Compute/Device.cs:20-24), so its host makes one call and the library fans out. Bit d of device_mask = CUDA device d.
+ * The set_* calls stage on the host as usual; commit uploads a replica to every device of the mask (the scene is
+ * replicated). echo_b200_trace_batch / occlude_batch (and the _hierarchy forms) cut a batch into one contiguous range per device;
+ * echo_b200_render_tiles deals blocks of 64 consecutive tiles of the caller's sequence round-robin to the devices
+ * (Common/Compute/Operation.cs:164-177's procedure claiming, made static) and gathers the accumulated tiles into the caller's
+ * tile-major buffer — every tile is rendered by exactly one device, so results equal the single-device ones bit for bit and no
+ * reduction is needed. One host thread per device, inside the call. The *_device entry points (caller-owned device memory on
+ * one device) need a single-device scene and fail with ECHO_B200_ERR_INVALID on a multi-device one. */
+int32_t echo_b200_scene_create_multi(EchoScene** out, uint64_t device_mask);
+int32_t echo_b200_scene_gpu_count(EchoScene*, int32_t* out); /* devices the scene is replicated on (1 for echo_b200_scene_create) */
+
 /* scene upload; pointers are only read during the call */
 int32_t echo_b200_scene_set_qbvh(EchoScene*, const EchoQbvhNode* nodes, uint32_t node_count, uint32_t max_depth);
 int32_t echo_b200_scene_set_triangles(EchoScene*, const EchoTriangle* triangles, uint32_t count);

@@ -37,6 +37,12 @@ int32_t echo_b200_debug_evaluate_samples4(EchoScene*, const EchoRenderParams*, c
  * bit set of checks that failed since commit (0 = clean). Release builds write 0xFFFFFFFF ("not compiled in"). */
 int32_t echo_b200_debug_bounds_violations(EchoScene*, uint32_t* out_bits);
 
+/* Microbenchmarks of the on-chip memory system of `device` (csrc/peaks.cu), a few milliseconds each: out3[0] = L2 read bandwidth with
+ * coalesced 128-bit loads, out3[1] = L2 bandwidth with one random 32-byte sector per lane (the access shape of an incoherent QBVH
+ * node fetch), out3[2] = the same out of L1 (the LSU / L1 data-pipe ceiling), all in GB/s. bench.py sets the traversal kernel's
+ * algorithmic bytes against them (`roofline.frac_l2`, `frac_l1_sectors`) beside the HBM fraction. */
+int32_t echo_b200_debug_measure_peaks(int32_t device, float* out3);
+
 /* Changes one tuning switch of the wavefront at run time: `name` is the part after ECHO_B200_ of the environment variable that
  * sets its initial value (RENDER_WORKERS, BATCH_PATHS, NARROW_LIMIT, TAIL_LIMIT, RUN_AHEAD, BLOCKING_SYNC; -1 = automatic for the
  * last two). Process-wide; takes effect with the next render call. For A/B runs that keep one uploaded scene. */

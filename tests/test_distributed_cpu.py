@@ -52,6 +52,12 @@ def test_shard_tiles_partition():
         assert sorted(map(tuple, merged)) == sorted(map(tuple, tiles))          # a partition: no tile lost or duplicated
         assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1     # balanced round-robin
 
+        # block-cyclic dealing (what bench.py uses with the Hilbert sequence): still a partition, runs of `block` tiles stay together
+        blocks = [shard_tiles(tiles, rank, world, block=4) for rank in range(world)]
+        assert sorted(map(tuple, np.concatenate(blocks))) == sorted(map(tuple, tiles))
+        assert max(len(p) for p in blocks) - min(len(p) for p in blocks) <= 4
+        assert np.array_equal(blocks[0][:4], tiles[:4])
+
 
 def test_two_rank_tile_sharding_matches_single_process(tmp_path):
     result = str(tmp_path / "frame.npy")

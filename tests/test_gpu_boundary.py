@@ -179,3 +179,53 @@ def test_two_devices_from_one_process(cornell, terrain_small):
         hits, image = results[device]
         assert np.array_equal(hits.view(np.uint32), expected.view(np.uint32))
         assert np.sqrt(np.mean((image - expected_image) ** 2)) <= 1e-4 * np.sqrt(np.mean(expected_image ** 2))
+
+
+def test_multi_device_scene_with_one_device_is_a_single_device_scene(cornell):
+    """echo_b200_scene_create_multi with a one-bit mask behaves like echo_b200_scene_create; bad masks are refused."""
+    import ctypes
+    lib = _native.library()
+    handle = ctypes.c_void_p()
+    assert lib.echo_b200_scene_create_multi(ctypes.byref(handle), 0) == _native.ERR_INVALID
+    assert lib.echo_b200_scene_create_multi(ctypes.byref(handle), 1 << 40) == _native.ERR_INVALID and not handle.value
+
+    params = structs.render_params(48, 48, 16, extend=4, bounce_limit=16, seed=4)
+    tiles = scenes.tile_grid(48, 48, 16)
+    with PreparedScene(cornell, devices=[0]) as scene, PreparedScene(cornell) as single:
+        assert scene.gpu_count == 1 and single.gpu_count == 1
+        image, _ = scene.render_tiles(params, tiles)
+        expected, _ = single.render_tiles(params, tiles)
+    assert np.array_equal(image.view(np.uint32), expected.view(np.uint32))
+
+
+@pytest.mark.skipif(device_total() < 2, reason="needs two GPUs")
+def test_multi_device_scene_fans_out_and_matches_one_device(cornell, terrain_small):
+    """One handle, every device of the box (SURVEY.md 8b's device_mask): batches are cut into one range per device, tiles are
+    dealt in blocks of 64 — results equal the single-device ones bit for bit, the statistics add up, and the entry points that
+    take device memory refuse a multi-device scene."""
+    import torch
+    devices = list(range(min(device_total(), 8)))
+    rays = scenes.random_rays(terrain_small.bounds, (1 << 20) + 12345, seed=41)
+    shadow = scenes.random_rays(terrain_small.bounds, (1 << 20) + 12345, seed=42, occlusion=True)
+
+    with PreparedScene(terrain_small) as single, PreparedScene(terrain_small, devices=devices) as multi:
+        assert multi.gpu_count == len(devices)
+        assert np.array_equal(multi.trace(rays).view(np.uint32), single.trace(rays).view(np.uint32))
+        assert np.array_equal(multi.occlude(shadow), single.occlude(shadow))
+        d_rays = torch.from_numpy(rays.view(np.uint8).reshape(-1)).to("cuda:0")
+        d_hits = torch.empty(len(rays) * 16, dtype=torch.uint8, device="cuda:0")
+        with pytest.raises(_native.EchoNativeError) as error:
+            multi.trace_device(d_rays.data_ptr(), len(rays), d_hits.data_ptr())
+        assert error.value.status == _native.ERR_INVALID and "single-device" in str(error.value)
+
+    # 40 x 23 tiles = 920 tiles = 15 blocks of 64 (the last one short), a ragged frame, two epochs
+    width, height = 636, 360
+    params = structs.render_params(width, height, 16, extend=2, min_epoch=2, max_epoch=2, bounce_limit=16, seed=8)
+    from echorenderer_b200 import hilbert_curve_pattern
+    tiles = hilbert_curve_pattern(((width + 15) // 16, (height + 15) // 16))
+    with PreparedScene(cornell) as single, PreparedScene(cornell, devices=devices) as multi:
+        expected, expected_stats = single.render_tiles(params, tiles)
+        image, stats = multi.render_tiles(params, tiles)
+    assert np.array_equal(image.view(np.uint32), expected.view(np.uint32))
+    for name in structs.STATS_FIELDS[:12]:
+        assert int(stats[name][0]) == int(expected_stats[name][0]), name
