@@ -61,7 +61,9 @@ def parse():
                         help="trace workload: the SweepBuilder mirror's tree (default) or the device-built linear BVH (echo_b200_build_qbvh)")
     parser.add_argument("--shard", default="tiles", choices=["tiles", "samples"],
                         help="render, N > 1: tile sharding (blocks of the tile sequence dealt round-robin) or sample sharding (every rank renders spp / N samples of every tile)")
-    parser.add_argument("--shard-block", type=int, default=64, help="tile sharding: consecutive tiles of the sequence per block (block b -> rank b mod N)")
+    parser.add_argument("--shard-by", default="position", choices=["position", "sequence"],
+                        help="tile sharding: tile (x, y) -> rank (x + y) mod N (default: every rank samples the whole image, balanced shards) or blocks of the tile sequence")
+    parser.add_argument("--shard-block", type=int, default=64, help="--shard-by sequence: consecutive tiles of the sequence per block (block b -> rank b mod N)")
     parser.add_argument("--pattern", default="hilbert", choices=["hilbert", "ordered"],
                         help="render: tile sequence, the HilbertCurvePattern of EvaluationProfile.Pattern (reference default) or an OrderedPattern")
     parser.add_argument("--reduce-every", type=int, default=1, help="--workload render: steps (epochs) accumulated on the device between frame all-reduces")
@@ -405,7 +407,8 @@ RENDER_SCENES = {
 
 
 def render_config(args, scene_key, width, height, spp, bounce_limit, reduce_every=1):
-    sharding = f"every rank renders {spp} / {args.gpus} samples of every tile" if args.shard == "samples" else f"blocks of {args.shard_block} tiles of the sequence dealt round-robin"
+    sharding = f"every rank renders {spp} / {args.gpus} samples of every tile" if args.shard == "samples" else \
+        ("tile (x, y) -> rank (x + y) mod N, rendered in sequence order" if args.shard_by == "position" else f"blocks of {args.shard_block} tiles of the sequence dealt round-robin")
     return {"workload": f"{RENDER_SCENES[scene_key][0]}, path tracer bounce limit {bounce_limit}", "width": width, "height": height, "spp_per_step": spp,
             "parallelism": f"scene replicated x{args.gpus}, {sharding}, accumulation frames merged by one NCCL all-reduce every {reduce_every} step(s)",
             "tile_pattern": args.pattern, "l2": "wavefront state (up to ~4 GB per pipeline) larger than L2"}
@@ -615,7 +618,7 @@ def run_render(ctx, args, scene_key, width, height, spp, bounce_limit, steps, wa
     tile_count = ((width + tile - 1) // tile, (height + tile - 1) // tile)
     all_tiles = hilbert_curve_pattern(tile_count) if args.pattern == "hilbert" else scenes.tile_grid(width, height, tile)
     by_samples = args.shard == "samples" and world > 1
-    tiles = all_tiles if by_samples else shard_tiles(all_tiles, rank, world, block=args.shard_block)
+    tiles = all_tiles if by_samples else shard_tiles(all_tiles, rank, world, block=args.shard_block, by=args.shard_by)
     extend = max(1, spp // world) if by_samples else spp
     frame = torch.zeros(height * width * 4, dtype=torch.float32, device=device)
 

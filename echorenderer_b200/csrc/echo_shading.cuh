@@ -30,6 +30,7 @@ enum BsdfKind : int
 constexpr uint32_t KINDS_ALL = 0x3FFu;
 constexpr uint32_t KINDS_DIFFUSE = kind_bit(BSDF_LAMBERT_REFLECTION) | kind_bit(BSDF_LAMBERT_TWO_SIDED) | kind_bit(BSDF_OREN_NAYAR) | kind_bit(BSDF_INVISIBLE);
 constexpr uint32_t KINDS_DIELECTRIC = kind_bit(BSDF_DIELECTRIC_GLOSSY) | kind_bit(BSDF_DIELECTRIC_SPECULAR) | kind_bit(BSDF_COATED_DIFFUSE) | kind_bit(BSDF_INVISIBLE);
+constexpr uint32_t KINDS_SMOOTH = kind_bit(BSDF_DIELECTRIC_SPECULAR) | kind_bit(BSDF_INVISIBLE); // Dielectric with both alphas specular: SpecularFresnel only
 constexpr uint32_t KINDS_CONDUCTOR = kind_bit(BSDF_CONDUCTOR_GLOSSY) | kind_bit(BSDF_CONDUCTOR_SPECULAR) | kind_bit(BSDF_INVISIBLE);
 constexpr uint32_t KINDS_TERMINAL = kind_bit(BSDF_EMPTY) | kind_bit(BSDF_INVISIBLE);
 

@@ -27,10 +27,16 @@ namespace echo
 constexpr int kBlock = 128;
 
 enum PathMode : uint32_t { MODE_FIRST = 0, MODE_NO_MIS = 1, MODE_MIS = 2 };
-enum ShadeClass : int { CLASS_MISS = 0, CLASS_DIFFUSE = 1, CLASS_DIELECTRIC = 2, CLASS_CONDUCTOR = 3, CLASS_TERMINAL = 4, CLASS_COUNT = 5 };
+// material classes of the shading queues. CLASS_SMOOTH holds the dielectrics whose roughness makes them purely specular: their
+// kernel carries no microfacet code and its lanes do not wait for the glossy lanes of a mixed queue (C3: the dielectric kernel ran
+// at 14.6 active threads per warp with both kinds in one queue, ncu r1m)
+enum ShadeClass : int { CLASS_MISS = 0, CLASS_DIFFUSE = 1, CLASS_DIELECTRIC = 2, CLASS_CONDUCTOR = 3, CLASS_TERMINAL = 4, CLASS_SMOOTH = 5, CLASS_COUNT = 6 };
 
 // counter slots in RenderState::counters
-enum : int { COUNTER_NEXT = 0, COUNTER_SHADOW = 1, COUNTER_CLASS = 2, COUNTER_PIXELS = COUNTER_CLASS + CLASS_COUNT, COUNTER_TOTAL = COUNTER_PIXELS + 1 };
+// (the class counts are double-buffered by iteration parity: classify of iteration k + 1 fills one set while the other, consumed by
+// the shading kernels of iteration k, waits to be cleared by the rotate kernel)
+enum : int { COUNTER_NEXT = 0, COUNTER_SHADOW = 1, COUNTER_CLASS = 2, COUNTER_PIXELS = COUNTER_CLASS + 2 * CLASS_COUNT, COUNTER_TOTAL = COUNTER_PIXELS + 1 };
+static_assert(COUNTER_TOTAL <= 32, "counters[32] is the saved active count");
 
 struct PathBuffers
 {
@@ -66,7 +72,7 @@ struct PathBuffers
 // numbers printed by a run with this switch on are diagnostics, never bench values).
 struct KernelTimer
 {
-	enum { RAYGEN, EXTEND, SHADE_MISS, SHADE_DIFFUSE, SHADE_DIELECTRIC, SHADE_CONDUCTOR, SHADE_TERMINAL, SHADOW, ROTATE, FINISH, ACCUMULATE, OTHER, COUNT };
+	enum { RAYGEN, EXTEND, SHADE_MISS, SHADE_DIFFUSE, SHADE_DIELECTRIC, SHADE_CONDUCTOR, SHADE_TERMINAL, SHADE_SMOOTH, SHADOW, ROTATE, FINISH, ACCUMULATE, OTHER, COUNT };
 	bool enabled = false;
 	double milliseconds[COUNT] = {};
 	uint64_t launches[COUNT] = {};
@@ -108,7 +114,7 @@ struct KernelTimer
 	void report()
 	{
 		if (!enabled) return;
-		static const char* names[COUNT] = { "raygen", "extend", "shade<miss>", "shade<diffuse>", "shade<dielectric>", "shade<conductor>", "shade<terminal>", "shadow", "rotate", "finish", "accumulate", "other" };
+		static const char* names[COUNT] = { "raygen", "extend", "shade<miss>", "shade<diffuse>", "shade<dielectric>", "shade<conductor>", "shade<terminal>", "shade<smooth>", "shadow", "rotate", "finish", "accumulate", "classify" };
 		double total = 0.0;
 		for (double ms : milliseconds) total += ms;
 		for (int i = 0; i < COUNT; i++)
@@ -172,6 +178,33 @@ struct RenderState
 // ---------------------------------------------------------------------------------------------------------------------
 // helpers
 // ---------------------------------------------------------------------------------------------------------------------
+
+// Wavefront state (ray / hit / class / shadow queues, per-path records) is written by one kernel and read by the next, gigabytes
+// later: it cannot be reused out of L2 and only evicts the tree, which can (C5: 630 MB of nodes against 126 MB of L2). With
+// ECHO_STREAM_STATE these accesses carry the streaming hint (ld.global.cs / st.global.cs: evict first). A/B in profiles/README.md.
+#ifndef ECHO_STREAM_STATE
+#define ECHO_STREAM_STATE 0
+#endif
+
+template<class T>
+ECHO_DEVICE T stream_load(const T* pointer)
+{
+#if ECHO_STREAM_STATE
+	return __ldcs(pointer);
+#else
+	return *pointer;
+#endif
+}
+
+template<class T>
+ECHO_DEVICE void stream_store(T* pointer, T value)
+{
+#if ECHO_STREAM_STATE
+	__stcs(pointer, value);
+#else
+	*pointer = value;
+#endif
+}
 
 // warp-aggregated append: one atomic per warp (ballot + popc + shuffle)
 ECHO_DEVICE uint32_t queue_slot(uint32_t* counter, bool predicate)
@@ -407,6 +440,8 @@ ECHO_DEVICE float light_importance(const LightNode& bound, const SurfacePoint& o
 }
 
 // LightTree.Pick, LightTree.cs:115-134 (tail recursion as a loop). Returns the token; pdf == 0 means impossible.
+// COUNT (counted passes only, see shade_counted_kernel): LightBound.Importance evaluations go to scene.lightVisits
+template<bool COUNT = false>
 ECHO_DEVICE uint32_t light_tree_pick(const DeviceScene& scene, const PackInfo& info, const SurfacePoint& origin, float& sample, float& outPdf)
 {
 	outPdf = 0.0f;
@@ -427,7 +462,7 @@ ECHO_DEVICE uint32_t light_tree_pick(const DeviceScene& scene, const PackInfo& i
 		LightNode right = load_light_node(scene, info, node.child1);
 		float importance0 = light_importance(left, origin);
 		float importance1 = light_importance(right, origin);
-		if (scene.lightVisits) atomicAdd(scene.lightVisits, 2ull); // counted passes only
+		if (COUNT) atomicAdd(scene.lightVisits, 2ull);
 
 		if (!positive(importance0) && !positive(importance1)) return ECHO_TOKEN_EMPTY;
 
@@ -450,6 +485,7 @@ ECHO_DEVICE uint32_t light_tree_pick(const DeviceScene& scene, const PackInfo& i
 
 // LightTree.ProbabilityMass, LightTree.cs:53-57,136-154: the recursion multiplies split factors from the leaf upward,
 // so the factors of the root-to-leaf walk are kept and folded right to left.
+template<bool COUNT = false>
 ECHO_DEVICE float light_tree_mass(const DeviceScene& scene, const PackInfo& info, uint32_t token, const SurfacePoint& origin)
 {
 	// map.TryGetValue: binary search over the pack's sorted emitter tokens
@@ -478,7 +514,7 @@ ECHO_DEVICE float light_tree_mass(const DeviceScene& scene, const PackInfo& info
 		LightNode right = load_light_node(scene, info, node.child1);
 		float importance0 = light_importance(left, origin);
 		float importance1 = light_importance(right, origin);
-		if (scene.lightVisits) atomicAdd(scene.lightVisits, 2ull); // counted passes only
+		if (COUNT) atomicAdd(scene.lightVisits, 2ull);
 		float split = div(importance0, importance0 + importance1);
 
 		if ((branches & 1ull) == 0ull)
@@ -754,7 +790,7 @@ ECHO_DEVICE Sampled infinite_sample(const DeviceScene& scene, const InfiniteLigh
 }
 
 // PreparedScene.Pick, PreparedScene.cs:113-150; outLayers receives the instance layers of the picked light's hierarchy
-template<bool INST>
+template<bool INST, bool COUNT = false>
 ECHO_DEVICE uint32_t scene_pick(const DeviceScene& scene, const SurfacePoint& origin, float sample, float& outPdf, PathLayers& outLayers)
 {
 	outLayers = no_layers();
@@ -775,7 +811,7 @@ ECHO_DEVICE uint32_t scene_pick(const DeviceScene& scene, const SurfacePoint& or
 	while (true) // :132-147: the same `origin` serves every layer (it is not moved into the placement's space)
 	{
 		float tokenPdf;
-		uint32_t token = light_tree_pick(scene, info, origin, sample, tokenPdf);
+		uint32_t token = light_tree_pick<COUNT>(scene, info, origin, sample, tokenPdf);
 
 		if (almost_zero(tokenPdf))
 		{
@@ -798,7 +834,7 @@ ECHO_DEVICE uint32_t scene_pick(const DeviceScene& scene, const SurfacePoint& or
 }
 
 // PreparedScene.ProbabilityMass, PreparedScene.cs:158-179
-template<bool INST>
+template<bool INST, bool COUNT = false>
 ECHO_DEVICE float scene_probability_mass(const DeviceScene& scene, uint32_t light, const PathLayers& layers, const SurfacePoint& origin)
 {
 	if (token_is_infinite_light(light)) return scene.infinitePdf;
@@ -809,14 +845,14 @@ ECHO_DEVICE float scene_probability_mass(const DeviceScene& scene, uint32_t ligh
 	{
 		for (uint32_t k = 0; k < layers.count; k++)
 		{
-			pdf *= light_tree_mass(scene, info, layers.tokens[k], origin);
+			pdf *= light_tree_mass<COUNT>(scene, info, layers.tokens[k], origin);
 			float4 tail = __ldg(instance_data(scene, info.instanceOffset + token_index(layers.tokens[k])) + 6);
 			info = load_pack_info(scene, __float_as_uint(tail.z));
 			if (almost_zero(pdf)) return 0.0f;
 		}
 	}
 
-	return pdf * light_tree_mass(scene, info, light, origin);
+	return pdf * light_tree_mass<COUNT>(scene, info, light, origin);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1099,13 +1135,13 @@ __global__ void __launch_bounds__(kBlock) raygen_kernel(DeviceScene scene, EchoR
 	vec3 origin, direction;
 	camera_spawn(scene.camera, params.width, params.height, pixel.x, pixel.y, shift, lens, origin, direction);
 
-	paths.rayQueue[0][i * 2u] = make_float4(origin.x, origin.y, origin.z, direction.x);
-	paths.rayQueue[0][i * 2u + 1u] = make_float4(direction.y, direction.z, kInfinity, __uint_as_float(ECHO_TOKEN_EMPTY));
-	paths.rayPath[0][i] = i;
+	stream_store(paths.rayQueue[0] + i * 2u, make_float4(origin.x, origin.y, origin.z, direction.x));
+	stream_store(paths.rayQueue[0] + i * 2u + 1u, make_float4(direction.y, direction.z, kInfinity, __uint_as_float(ECHO_TOKEN_EMPTY)));
+	stream_store(paths.rayPath[0] + i, i);
 	if (paths.rayLayers[0]) store_layers(paths.rayLayers[0], i, no_layers());
-	paths.energy[i] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
-	paths.result[i] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(MODE_FIRST << 16));
-	paths.key[i] = key;
+	stream_store(paths.energy + i, make_float4(1.0f, 1.0f, 1.0f, 0.0f));
+	stream_store(paths.result + i, make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(MODE_FIRST << 16)));
+	stream_store(paths.key + i, key);
 }
 
 ECHO_DEVICE int classify_material(const DeviceScene& scene, uint32_t materialIndex)
@@ -1115,8 +1151,8 @@ ECHO_DEVICE int classify_material(const DeviceScene& scene, uint32_t materialInd
 
 	for (int level = 0; level < 4 && type == ECHO_MATERIAL_ONESIDED; level++)
 	{
-		uint32_t base = __float_as_uint(__ldg(p + 3).w);
-		p = scene.materials + (size_t)base * 4;
+		materialIndex = __float_as_uint(__ldg(p + 3).w);
+		p = scene.materials + (size_t)materialIndex * 4;
 		type = __float_as_uint(__ldg(p).x);
 	}
 
@@ -1124,6 +1160,16 @@ ECHO_DEVICE int classify_material(const DeviceScene& scene, uint32_t materialInd
 	{
 		case ECHO_MATERIAL_DIFFUSE: return CLASS_DIFFUSE;
 		case ECHO_MATERIAL_DIELECTRIC:
+		{
+			// Dielectric.Scatter builds SpecularFresnel iff both alphas are specular (Dielectric.cs:29-47, IMicrofacet.cs:43-51); a textured
+			// roughness is only known per hit, so such materials stay in the class that carries both kinds
+			if (scene.textureCount != 0u && __ldg(scene.materialTextures + (size_t)materialIndex * 2).z != ECHO_TEXTURE_NONE) return CLASS_DIELECTRIC;
+			float4 second = __ldg(p + 1); // albedo.zw, roughness.xy
+			bool specularX, specularY;
+			microfacet_alpha(second.z, specularX);
+			microfacet_alpha(second.w, specularY);
+			return specularX && specularY ? CLASS_SMOOTH : CLASS_DIELECTRIC;
+		}
 		case ECHO_MATERIAL_COATED_DIFFUSE: return CLASS_DIELECTRIC; // shares the GlossyReflection<TR, RealFresnel> code
 		case ECHO_MATERIAL_CONDUCTOR: return CLASS_CONDUCTOR;
 		default: return CLASS_TERMINAL;
@@ -1140,7 +1186,7 @@ struct ExtendIO
 
 	ECHO_DEVICE void store_closest(uint32_t index, bool hit, uint32_t token, float distance, vec2 uv, float limit) const
 	{
-		hits[index] = make_float4(__uint_as_float(hit ? token : ECHO_TOKEN_EMPTY), hit ? distance : limit, uv.x, uv.y);
+		stream_store(hits + index, make_float4(__uint_as_float(hit ? token : ECHO_TOKEN_EMPTY), hit ? distance : limit, uv.x, uv.y));
 	}
 
 	ECHO_DEVICE void store_any(uint32_t, bool) const {}
@@ -1242,17 +1288,25 @@ __global__ void __launch_bounds__(kBlock) extend_instanced_kernel(DeviceScene sc
 	if (COUNT) visit_flush(stats, STAT_NODE_VISITS, local);
 }
 
-// the material-class sort: one thread per traced ray appends its slot to the queue of the class it hit
+// The material-class sort: one thread per traced ray appends its slot to the queue of the class it hit. The appends of a whole CTA
+// are gathered in shared memory first and reach each global class counter as ONE atomic per CTA: with one atomic per warp the
+// kernel was bound by the serialisation of a quarter million same-address atomics per launch (IPC 0.37, 0.38 ms for 8.3 M rays).
+constexpr int kClassifyBlock = 512;
+
 template<bool INST>
-__global__ void __launch_bounds__(kBlock) classify_kernel(DeviceScene scene, const uint32_t* __restrict__ queueCount, PathBuffers paths)
+__global__ void __launch_bounds__(kClassifyBlock) classify_kernel(DeviceScene scene, const uint32_t* __restrict__ queueCount, uint32_t* __restrict__ classCounts, PathBuffers paths)
 {
-	uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+	__shared__ uint32_t blockCount[CLASS_COUNT], blockBase[CLASS_COUNT];
+	if (threadIdx.x < CLASS_COUNT) blockCount[threadIdx.x] = 0u;
+	__syncthreads();
+
+	uint32_t i = blockIdx.x * kClassifyBlock + threadIdx.x;
 	bool active = i < *queueCount;
 	int shadeClass = -1;
 
 	if (active)
 	{
-		uint32_t token = __float_as_uint(paths.hitQueue[i].x);
+		uint32_t token = __float_as_uint(stream_load(paths.hitQueue + i).x);
 		shadeClass = CLASS_MISS;
 
 		if (token != ECHO_TOKEN_EMPTY)
@@ -1281,13 +1335,27 @@ __global__ void __launch_bounds__(kBlock) classify_kernel(DeviceScene scene, con
 
 	stat_add(paths.stats, STAT_TRACE_QUERIES, active);
 
+	// position inside the CTA's share of each class queue: one shared-memory atomic per warp and class
+	const uint32_t lane = threadIdx.x & 31u;
+	uint32_t offset = 0u;
+
 #pragma unroll
 	for (int c = 0; c < CLASS_COUNT; c++)
 	{
-		bool mine = shadeClass == c;
-		uint32_t slot = queue_slot(paths.counters + COUNTER_CLASS + c, mine);
-		if (mine) paths.classQueue[c][slot] = i;
+		uint32_t mask = __ballot_sync(0xFFFFFFFFu, shadeClass == c);
+		if (mask == 0u) continue;
+		uint32_t warpBase = 0u;
+		int leader = __ffs(mask) - 1;
+		if ((int)lane == leader) warpBase = atomicAdd(&blockCount[c], (uint32_t)__popc(mask));
+		warpBase = __shfl_sync(0xFFFFFFFFu, warpBase, leader);
+		if (shadeClass == c) offset = warpBase + (uint32_t)__popc(mask & ((1u << lane) - 1u));
 	}
+
+	__syncthreads();
+	if (threadIdx.x < CLASS_COUNT && blockCount[threadIdx.x] != 0u) blockBase[threadIdx.x] = atomicAdd(classCounts + threadIdx.x, blockCount[threadIdx.x]);
+	__syncthreads();
+
+	if (shadeClass >= 0) stream_store(paths.classQueue[shadeClass] + blockBase[shadeClass] + offset, i);
 }
 
 // What one loop body of PathTracedEvaluator.Evaluate produces for a path: statistics, the next ray if the path goes on, the
@@ -1305,7 +1373,7 @@ struct ShadeOut
 // One loop body of PathTracedEvaluator.Evaluate for the path whose ray sits in slot `raySlot` of the current queue and whose hit
 // record is in hitQueue[raySlot]. CLASS / KINDS prune the code to what a material-class queue can contain; CLASS < 0 keeps
 // everything (the tail kernel), `missed` then says whether the ray hit anything.
-template<int CLASS, uint32_t KINDS, bool INST>
+template<int CLASS, uint32_t KINDS, bool INST, bool COUNT = false>
 ECHO_DEVICE void shade_body(const DeviceScene& scene, const EchoRenderParams& params, const PathBuffers& paths, int current, uint32_t raySlot, bool missed, ShadeOut& o)
 {
 	bool &statInfinite = o.statInfinite, &statBounce = o.statBounce, &statSpecular = o.statSpecular, &statMis = o.statMis;
@@ -1316,11 +1384,11 @@ ECHO_DEVICE void shade_body(const DeviceScene& scene, const EchoRenderParams& pa
 	PathLayers& hitLayers = o.hitLayers;
 	(void)missed;
 
-	id = paths.rayPath[current][raySlot];
+	id = stream_load(paths.rayPath[current] + raySlot);
 
-	float4 rayA = paths.rayQueue[current][raySlot * 2u], rayB = paths.rayQueue[current][raySlot * 2u + 1u];
-	float4 energy4 = paths.energy[id];
-	float4 result4 = paths.result[id];
+	float4 rayA = stream_load(paths.rayQueue[current] + raySlot * 2u), rayB = stream_load(paths.rayQueue[current] + raySlot * 2u + 1u);
+	float4 energy4 = stream_load(paths.energy + id);
+	float4 result4 = stream_load(paths.result + id);
 
 	vec3 direction = { rayA.w, rayB.x, rayB.y };
 	rgb energy = as_rgb(energy4);
@@ -1338,7 +1406,7 @@ ECHO_DEVICE void shade_body(const DeviceScene& scene, const EchoRenderParams& pa
 		else if (mode == MODE_NO_MIS) result = result + energy * evaluate_infinite(scene, direction, false);
 		else
 		{
-			SurfacePoint oldPoint = { xyz(paths.oldPosition[id]), xyz(paths.oldNormal[id]) };
+			SurfacePoint oldPoint = { xyz(stream_load(paths.oldPosition + id)), xyz(stream_load(paths.oldNormal + id)) };
 			(void)oldPoint;
 
 			for (uint32_t index = 0; index < scene.infiniteLightCount; index++)
@@ -1353,12 +1421,12 @@ ECHO_DEVICE void shade_body(const DeviceScene& scene, const EchoRenderParams& pa
 			}
 		}
 
-		paths.result[id] = make4(result, result4.w);
+		stream_store(paths.result + id, make4(result, result4.w));
 	}
 	else
 	{
 		// ---- PreparedScene.Interact, PreparedScene.cs:95-105 + GeometryCollection.GetContactInfo (:200-232) ----
-		float4 hit4 = paths.hitQueue[raySlot];
+		float4 hit4 = stream_load(paths.hitQueue + raySlot);
 		uint32_t token = __float_as_uint(hit4.x);
 		float distance = hit4.y;
 		vec2 uv = { hit4.z, hit4.w };
@@ -1406,8 +1474,8 @@ ECHO_DEVICE void shade_body(const DeviceScene& scene, const EchoRenderParams& pa
 
 			if (mode == MODE_MIS)
 			{
-				SurfacePoint oldPoint = { xyz(paths.oldPosition[id]), xyz(paths.oldNormal[id]) };
-				float pmf = scene_probability_mass<INST>(scene, token, hitLayers, oldPoint);
+				SurfacePoint oldPoint = { xyz(stream_load(paths.oldPosition + id)), xyz(stream_load(paths.oldNormal + id)) };
+				float pmf = scene_probability_mass<INST, COUNT>(scene, token, hitLayers, oldPoint);
 				contribute = positive(pmf);
 
 				if (contribute)
@@ -1428,7 +1496,7 @@ ECHO_DEVICE void shade_body(const DeviceScene& scene, const EchoRenderParams& pa
 		// ---- the loop body: `for (int depth = 0; depth < BounceLimit; depth++)`, :57 ----
 		if (bounces < (uint32_t)params.bounceLimit)
 		{
-			uint32_t key = paths.key[id];
+			uint32_t key = stream_load(paths.key + id);
 			uint32_t dimension = 4u + 6u * bounces;
 			vec2 bounceSample = { sample_value(key, dimension), sample_value(key, dimension + 1u) };
 			float survivalSample = sample_value(key, dimension + 2u);
@@ -1451,7 +1519,7 @@ ECHO_DEVICE void shade_body(const DeviceScene& scene, const EchoRenderParams& pa
 				// ---- ImportanceSampleRadiant, :162-207 ----
 				float lightPdf;
 				PathLayers lightLayers;
-				uint32_t light = scene_pick<INST>(scene, point, lightSample, lightPdf, lightLayers);
+				uint32_t light = scene_pick<INST, COUNT>(scene, point, lightSample, lightPdf, lightLayers);
 
 				if (positive(lightPdf))
 				{
@@ -1501,8 +1569,8 @@ ECHO_DEVICE void shade_body(const DeviceScene& scene, const EchoRenderParams& pa
 					if (mis && !statSpecular)
 					{
 						statMis = true;
-						paths.oldPosition[id] = make4(point.position, 0.0f);
-						paths.oldNormal[id] = make4(point.normal, 0.0f);
+						stream_store(paths.oldPosition + id, make4(point.position, 0.0f));
+						stream_store(paths.oldNormal + id, make4(point.normal, 0.0f));
 					}
 
 					uint32_t nextMode = (mis && !statSpecular) ? MODE_MIS : MODE_NO_MIS;
@@ -1514,8 +1582,8 @@ ECHO_DEVICE void shade_body(const DeviceScene& scene, const EchoRenderParams& pa
 			}
 		}
 
-		paths.result[id] = make4(result, result4.w);
-		if (survive) paths.energy[id] = nextEnergy;
+		stream_store(paths.result + id, make4(result, result4.w));
+		if (survive) stream_store(paths.energy + id, nextEnergy);
 	}
 }
 
@@ -1523,6 +1591,39 @@ ECHO_DEVICE void shade_body(const DeviceScene& scene, const EchoRenderParams& pa
 #ifndef ECHO_SHADE_MIN_BLOCKS
 #define ECHO_SHADE_MIN_BLOCKS 6 // resident CTAs per SM asked of the shading kernels: 80 registers and a few hundred bytes of spills instead of 100-110 registers at 4 CTAs; no target / 5 / 6 / 7 / 8: C3 474 / 477 / 483 / 483 / 485, C4 329 / 338 / 342 / 345 / 347, textured 719 / 721 / 733 / 725 / 712 M samples/s (variants/ab15.sh)
 #endif
+// what a shading thread leaves behind: its next ray and its shadow ray appended to their queues, its statistics (every lane of the warp calls)
+template<bool INST>
+ECHO_DEVICE void shade_emit(const PathBuffers& paths, int current, const ShadeOut& o)
+{
+	const bool survive = o.survive, shadow = o.shadow;
+	uint32_t nextSlot = queue_slot(paths.counters + COUNTER_NEXT, survive);
+
+	if (survive)
+	{
+		stream_store(paths.rayQueue[current ^ 1] + nextSlot * 2u, o.nextOrigin);
+		stream_store(paths.rayQueue[current ^ 1] + nextSlot * 2u + 1u, o.nextDirection);
+		stream_store(paths.rayPath[current ^ 1] + nextSlot, o.id);
+		if (INST) store_layers(paths.rayLayers[current ^ 1], nextSlot, o.hitLayers);
+	}
+
+	uint32_t shadowSlot = queue_slot(paths.counters + COUNTER_SHADOW, shadow);
+
+	if (shadow)
+	{
+		stream_store(paths.shadowQueue + shadowSlot * 2u, o.shadowOrigin);
+		stream_store(paths.shadowQueue + shadowSlot * 2u + 1u, o.shadowDirection);
+		stream_store(paths.shadowValue + shadowSlot, o.shadowValue);
+		if (INST) store_layers(paths.shadowLayers, shadowSlot, o.hitLayers);
+	}
+
+	stat_add(paths.stats, STAT_LIGHT_EVALUATED_INFINITE, o.statInfinite);
+	stat_add(paths.stats, STAT_BOUNCE_CREATED, o.statBounce);
+	stat_add(paths.stats, STAT_BOUNCE_SPECULAR, o.statSpecular);
+	stat_add(paths.stats, STAT_BOUNCE_MIS, o.statMis);
+	stat_add(paths.stats, STAT_LIGHT_SAMPLED, o.statSampled);
+	stat_add(paths.stats, STAT_LIGHT_OCCLUSION_CHECKED, o.statChecked);
+}
+
 template<int CLASS, uint32_t KINDS, bool INST>
 __global__ void __launch_bounds__(kBlock, ECHO_SHADE_MIN_BLOCKS) shade_kernel(DeviceScene scene, EchoRenderParams params, const uint32_t* __restrict__ queue,
                                                       const uint32_t* __restrict__ queueCount, PathBuffers paths, int current)
@@ -1531,40 +1632,23 @@ __global__ void __launch_bounds__(kBlock, ECHO_SHADE_MIN_BLOCKS) shade_kernel(De
 	bool active = i < *queueCount;
 
 	ShadeOut o;
-	if (active) shade_body<CLASS, KINDS, INST>(scene, params, paths, current, queue[i], false, o);
+	if (active) shade_body<CLASS, KINDS, INST>(scene, params, paths, current, stream_load(queue + i), false, o);
+	shade_emit<INST>(paths, current, o);
+}
 
-	const bool survive = o.survive, shadow = o.shadow;
-	const bool statInfinite = o.statInfinite, statBounce = o.statBounce, statSpecular = o.statSpecular, statMis = o.statMis, statSampled = o.statSampled, statChecked = o.statChecked;
-	const uint32_t id = o.id;
-	const float4 nextOrigin = o.nextOrigin, nextDirection = o.nextDirection, shadowOrigin = o.shadowOrigin, shadowDirection = o.shadowDirection, shadowValue = o.shadowValue;
-	const PathLayers& hitLayers = o.hitLayers;
+// Counted passes (ECHO_EVALUATOR_COUNT_VISITS) shade every ray of the queue with this one kernel instead of the six class kernels:
+// the all-lobes body the tail kernel uses (same operations per path, same bits), instantiated with the light-tree visit counter, so
+// the class kernels of ordinary renders carry no counting code at all (a never-taken branch in the light-tree descent cost the
+// diffuse class 2.4x on the instanced scene: registers at the 80-register cap).
+template<bool INST>
+__global__ void __launch_bounds__(kBlock) shade_counted_kernel(DeviceScene scene, EchoRenderParams params, const uint32_t* __restrict__ rayCount, PathBuffers paths, int current)
+{
+	uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+	bool active = i < *rayCount;
 
-	uint32_t nextSlot = queue_slot(paths.counters + COUNTER_NEXT, survive);
-
-	if (survive)
-	{
-		paths.rayQueue[current ^ 1][nextSlot * 2u] = nextOrigin;
-		paths.rayQueue[current ^ 1][nextSlot * 2u + 1u] = nextDirection;
-		paths.rayPath[current ^ 1][nextSlot] = id;
-		if (INST) store_layers(paths.rayLayers[current ^ 1], nextSlot, hitLayers);
-	}
-
-	uint32_t shadowSlot = queue_slot(paths.counters + COUNTER_SHADOW, shadow);
-
-	if (shadow)
-	{
-		paths.shadowQueue[shadowSlot * 2u] = shadowOrigin;
-		paths.shadowQueue[shadowSlot * 2u + 1u] = shadowDirection;
-		paths.shadowValue[shadowSlot] = shadowValue;
-		if (INST) store_layers(paths.shadowLayers, shadowSlot, hitLayers);
-	}
-
-	stat_add(paths.stats, STAT_LIGHT_EVALUATED_INFINITE, statInfinite);
-	stat_add(paths.stats, STAT_BOUNCE_CREATED, statBounce);
-	stat_add(paths.stats, STAT_BOUNCE_SPECULAR, statSpecular);
-	stat_add(paths.stats, STAT_BOUNCE_MIS, statMis);
-	stat_add(paths.stats, STAT_LIGHT_SAMPLED, statSampled);
-	stat_add(paths.stats, STAT_LIGHT_OCCLUSION_CHECKED, statChecked);
+	ShadeOut o;
+	if (active) shade_body<-1, KINDS_ALL, INST, true>(scene, params, paths, current, i, __float_as_uint(paths.hitQueue[i].x) == ECHO_TOKEN_EMPTY, o);
+	shade_emit<INST>(paths, current, o);
 }
 
 // scene.Occlude of ImportanceSampleRadiant (:196-197); unoccluded pending contributions go into Path.Result (:80-84).
@@ -1582,13 +1666,13 @@ struct ShadowIO
 	ECHO_DEVICE void store_any(uint32_t index, bool occluded)
 	{
 		if (occluded) return;
-		float4 value = values[index];
+		float4 value = stream_load(values + index);
 		uint32_t id = __float_as_uint(value.w);
-		float4 total = result[id];
+		float4 total = stream_load(result + id);
 		total.x += value.x;
 		total.y += value.y;
 		total.z += value.z;
-		result[id] = total;
+		stream_store(result + id, total);
 		++passed;
 	}
 };
@@ -1837,33 +1921,46 @@ __global__ void __launch_bounds__(kBlock) tail_kernel(DeviceScene scene, EchoRen
 	const bool packs = INST && scene.packCount != 0u;
 	uint32_t counted[9] = { 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u }; // trace, occlude, passed, infinite, bounce, specular, mis, sampled, checked
 
+	// The wavefront queued extend (and classify) of this iteration before it decided for the tail: the first hit of every path is
+	// already in hitQueue (and counted), only later bounces are traced here.
+	bool traced = true;
+
 	while (active)
 	{
-		// ---- Path.Advance: scene.Trace (PathTracedEvaluator.cs:261-271) ----
-		float4 a = paths.rayQueue[current][i * 2u], b = paths.rayQueue[current][i * 2u + 1u];
-		float distance = b.z;
-		uint32_t token = ECHO_TOKEN_EMPTY;
-		vec2 uv = { 0.0f, 0.0f };
 		bool hit = false;
 
-		if (packs)
+		if (traced)
 		{
-			PathLayers ignore = load_layers(paths.rayLayers[current], i);
-			PathLayers hitLayer = no_layers();
-
-			if (positive(b.z))
-			{
-				traverse_instanced<STACK, false, false>(scene, { a.x, a.y, a.z }, { a.w, b.x, b.y }, __float_as_uint(b.w), ignore.tokens, ignore.count,
-				                                        distance, token, uv, hitLayer.tokens, hitLayer.count, nullptr);
-				hit = distance < b.z;
-			}
-
-			store_layers(paths.hitLayers, i, hit ? hitLayer : no_layers());
+			hit = __float_as_uint(paths.hitQueue[i].x) != ECHO_TOKEN_EMPTY;
+			traced = false;
 		}
-		else hit = scene_trace<STACK, false>(scene, { a.x, a.y, a.z }, { a.w, b.x, b.y }, __float_as_uint(b.w), distance, token, uv, nullptr);
+		else
+		{
+			// ---- Path.Advance: scene.Trace (PathTracedEvaluator.cs:261-271) ----
+			float4 a = paths.rayQueue[current][i * 2u], b = paths.rayQueue[current][i * 2u + 1u];
+			float distance = b.z;
+			uint32_t token = ECHO_TOKEN_EMPTY;
+			vec2 uv = { 0.0f, 0.0f };
 
-		paths.hitQueue[i] = make_float4(__uint_as_float(hit ? token : ECHO_TOKEN_EMPTY), hit ? distance : b.z, uv.x, uv.y);
-		++counted[0];
+			if (packs)
+			{
+				PathLayers ignore = load_layers(paths.rayLayers[current], i);
+				PathLayers hitLayer = no_layers();
+
+				if (positive(b.z))
+				{
+					traverse_instanced<STACK, false, false>(scene, { a.x, a.y, a.z }, { a.w, b.x, b.y }, __float_as_uint(b.w), ignore.tokens, ignore.count,
+					                                        distance, token, uv, hitLayer.tokens, hitLayer.count, nullptr);
+					hit = distance < b.z;
+				}
+
+				store_layers(paths.hitLayers, i, hit ? hitLayer : no_layers());
+			}
+			else hit = scene_trace<STACK, false>(scene, { a.x, a.y, a.z }, { a.w, b.x, b.y }, __float_as_uint(b.w), distance, token, uv, nullptr);
+
+			paths.hitQueue[i] = make_float4(__uint_as_float(hit ? token : ECHO_TOKEN_EMPTY), hit ? distance : b.z, uv.x, uv.y);
+			++counted[0];
+		}
 
 		// ---- one loop body of Evaluate ----
 		ShadeOut o;
@@ -2058,15 +2155,23 @@ __global__ void __launch_bounds__(kBlock) finish_kernel(uint32_t count, PathBuff
 	out[i] = make_float4(result.x, result.y, result.z, 0.0f);
 }
 
-// iteration bookkeeping: the next-queue count becomes the active count, per-iteration counters are cleared
-// and {serial of this iteration, rays left} goes to the pipeline thread as ONE 8-byte store into mapped pinned memory
-__global__ void rotate_counters_kernel(uint32_t* counters, uint32_t* activeCount, unsigned long long* hostMirror, uint32_t serial)
+// Iteration bookkeeping, launched right after classify of iteration k: the count of the ray queue that extend and classify of k
+// just consumed (COUNTER_NEXT) is saved as the active count, and goes to the pipeline thread together with the class counts of k as
+// one record in mapped pinned memory — class counts first, then {serial of k, rays} as ONE 8-byte store. The per-iteration counters
+// are cleared for the shading kernels of k, and so is the other parity's set of class counts (consumed by the shading of k - 1).
+__global__ void rotate_counters_kernel(uint32_t* counters, uint32_t* activeCount, unsigned long long* hostMirror, uint32_t serial, int parity)
 {
-	*activeCount = counters[COUNTER_NEXT];
-	*hostMirror = ((unsigned long long)serial << 32) | (unsigned long long)counters[COUNTER_NEXT];
+	uint32_t rays = counters[COUNTER_NEXT];
+	*activeCount = rays;
+
+	volatile uint32_t* classMirror = reinterpret_cast<volatile uint32_t*>(hostMirror + 1);
+	for (int c = 0; c < CLASS_COUNT; c++) classMirror[c] = counters[COUNTER_CLASS + parity * CLASS_COUNT + c];
+	__threadfence_system();
+	*reinterpret_cast<volatile unsigned long long*>(hostMirror) = ((unsigned long long)serial << 32) | (unsigned long long)rays;
+
 	counters[COUNTER_NEXT] = 0u;
 	counters[COUNTER_SHADOW] = 0u;
-	for (int c = 0; c < CLASS_COUNT; c++) counters[COUNTER_CLASS + c] = 0u;
+	for (int c = 0; c < CLASS_COUNT; c++) counters[COUNTER_CLASS + (parity ^ 1) * CLASS_COUNT + c] = 0u;
 }
 
 // ---- Kahan summation + Welford accumulation, Summation.cs:8-58 + Accumulator.cs:11-71 ----
@@ -2482,7 +2587,6 @@ static bool evaluate_paths(WorkerState* state, const DeviceScene& sceneIn, const
 	timer.start(stream);
 	raygen_kernel<<<blocks_for(count), kBlock, 0, stream>>>(sceneIn, params, count, state->pixelXY, state->sampleIndex, paths);
 	timer.stop(KernelTimer::RAYGEN, stream);
-	if (!check_cuda(cudaMemcpyAsync(activeCount, &count, sizeof(uint32_t), cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync(count)")) return false;
 	++launches;
 
 	if ((params.evaluator & ECHO_EVALUATOR_KIND_MASK) == ECHO_EVALUATOR_NAIVE)
@@ -2516,45 +2620,21 @@ static bool evaluate_paths(WorkerState* state, const DeviceScene& sceneIn, const
 	if (!ensure_events(state)) return false;
 
 	volatile unsigned long long* mirror = reinterpret_cast<volatile unsigned long long*>(state->hostCounters);
-	const uint32_t firstSerial = state->serial + 1u; // serial of this call's iteration 0
-	uint32_t launched = 0u;                          // iterations queued so far
-	uint32_t bound = count;                          // upper bound of the live rays of every iteration not yet queued
+	volatile uint32_t* classMirror = reinterpret_cast<volatile uint32_t*>(state->hostCounters + 2);
+	const uint32_t firstSerial = state->serial + 1u;  // serial of this call's unit 0
+	uint32_t launched = 0u;                           // units queued so far
+	uint32_t bound = count;                           // upper bound of the rays of every iteration not yet known exactly
 	const bool packs = INST && scene.packCount != 0u; // INST without packs: a textured scene, ordinary traversal, zeroed hit layers
+	uint32_t* const rayCount = counters + COUNTER_NEXT; // rays in the queue extend / classify are about to consume
 
-	while (true)
+	// A UNIT of work is [shade x6, shadow] of iteration k - 1 followed by [extend, classify, rotate] of iteration k (unit 0 has only the
+	// second half): extend and classify of the NEXT bounce are queued before the host looks at any count, so that when it does
+	// look — rotate k published {rays, class counts of k} — it can size the six shading launches of k exactly (and skip the empty
+	// ones) instead of covering each class with a grid for all live rays.
+	auto launch_trace_half = [&](uint32_t k, unsigned int blocks, bool narrow) -> bool
 	{
-		// the newest finished iteration the host can see (a word left by an earlier call fails the range test)
-		unsigned long long seen = *mirror;
-		uint32_t finished = (uint32_t)(seen >> 32) - firstSerial + 1u; // iterations of this call known to be finished
-		if (finished > launched) finished = 0u;
-
-		if (finished > 0u)
-		{
-			bound = std::min(bound, (uint32_t)seen);
-			if ((uint32_t)seen == 0u) break; // the wavefront is empty; whatever was queued beyond finds zero counts
-		}
-
-		if (launched - finished > runAhead)
-		{
-			// window full: sleep until the oldest iteration the host has not seen yet is done, then look again
-			if (!check_cuda(cudaEventSynchronize(state->iterationDone[finished % WorkerState::kEventRing]), "wavefront iteration")) return false;
-			continue;
-		}
-
-		const unsigned int blocks = blocks_for(bound);
-		const int current = (int)(launched & 1u);
-
-		// the tail: finish the few paths that are left in one launch
-		if (!timer.enabled && !counted && bound < tailLimit)
-		{
-			tail_kernel<STACK, INST><<<blocks, kBlock, 0, stream>>>(scene, iterationParams, activeCount, paths, current);
-			if (!check_cuda(cudaGetLastError(), "tail_kernel launch")) return false;
-			++launches;
-			break;
-		}
-
-		const bool narrow = counted || bound < narrowLimit;
-		unsigned long long* rayCounters = narrow ? nullptr : ray_counters(stream); // extend and shadow run one after the other: one pair serves both
+		const int current = (int)(k & 1u);
+		unsigned long long* rayCounters = narrow ? nullptr : ray_counters(stream);
 		if (!narrow && !rayCounters) return false;
 
 		timer.start(stream);
@@ -2568,82 +2648,146 @@ static bool evaluate_paths(WorkerState* state, const DeviceScene& sceneIn, const
 			layersIO.hits = extendIO.hits;
 			layersIO.rayLayers = paths.rayLayers[current];
 			layersIO.hitLayers = paths.hitLayers;
-			extend_layers_kernel<STACK><<<std::min<unsigned int>(blocks, (unsigned int)layersGrid), kTraverseBlock, 0, stream>>>(scene, layersIO, activeCount, rayCounters);
+			extend_layers_kernel<STACK><<<std::min<unsigned int>(blocks, (unsigned int)layersGrid), kTraverseBlock, 0, stream>>>(scene, layersIO, rayCount, rayCounters);
 		}
-		else if (packs && counted) extend_instanced_kernel<STACK, true><<<blocks, kBlock, 0, stream>>>(scene, extendIO, paths.rayLayers[current], paths.hitLayers, activeCount, paths.stats);
-		else if (packs) extend_instanced_kernel<STACK, false><<<blocks, kBlock, 0, stream>>>(scene, extendIO, paths.rayLayers[current], paths.hitLayers, activeCount, paths.stats);
-		else if (counted) extend_narrow_kernel<STACK, true><<<blocks, kBlock, 0, stream>>>(scene, extendIO, activeCount, paths.stats);
-		else if (narrow) extend_narrow_kernel<STACK, false><<<blocks, kBlock, 0, stream>>>(scene, extendIO, activeCount, paths.stats);
+		else if (packs && counted) extend_instanced_kernel<STACK, true><<<blocks, kBlock, 0, stream>>>(scene, extendIO, paths.rayLayers[current], paths.hitLayers, rayCount, paths.stats);
+		else if (packs) extend_instanced_kernel<STACK, false><<<blocks, kBlock, 0, stream>>>(scene, extendIO, paths.rayLayers[current], paths.hitLayers, rayCount, paths.stats);
+		else if (counted) extend_narrow_kernel<STACK, true><<<blocks, kBlock, 0, stream>>>(scene, extendIO, rayCount, paths.stats);
+		else if (narrow) extend_narrow_kernel<STACK, false><<<blocks, kBlock, 0, stream>>>(scene, extendIO, rayCount, paths.stats);
 		else
 		{
 			const int extendGrid = persistent_grid((const void*)extend_kernel<STACK>);
-			extend_kernel<STACK><<<std::min<unsigned int>(blocks, (unsigned int)extendGrid), kTraverseBlock, 0, stream>>>(scene, extendIO, activeCount, rayCounters);
+			extend_kernel<STACK><<<std::min<unsigned int>(blocks, (unsigned int)extendGrid), kTraverseBlock, 0, stream>>>(scene, extendIO, rayCount, rayCounters);
 		}
 
 		timer.stop(KernelTimer::EXTEND, stream);
-		float extendMs = timer.last;
 
 		timer.start(stream);
-		classify_kernel<INST><<<blocks, kBlock, 0, stream>>>(scene, activeCount, paths);
+		unsigned int classifyBlocks = (blocks * (unsigned int)kBlock + kClassifyBlock - 1) / kClassifyBlock;
+		classify_kernel<INST><<<classifyBlocks, kClassifyBlock, 0, stream>>>(scene, rayCount, counters + COUNTER_CLASS + current * CLASS_COUNT, paths);
 		timer.stop(KernelTimer::OTHER, stream);
 
 		timer.start(stream);
-		shade_kernel<CLASS_MISS, 0u, INST><<<blocks, kBlock, 0, stream>>>(scene, iterationParams, paths.classQueue[CLASS_MISS], counters + COUNTER_CLASS + CLASS_MISS, paths, current);
-		timer.stop(KernelTimer::SHADE_MISS, stream);
-		timer.start(stream);
-		shade_kernel<CLASS_DIFFUSE, KINDS_DIFFUSE, INST><<<blocks, kBlock, 0, stream>>>(scene, iterationParams, paths.classQueue[CLASS_DIFFUSE], counters + COUNTER_CLASS + CLASS_DIFFUSE, paths, current);
-		timer.stop(KernelTimer::SHADE_DIFFUSE, stream);
-		timer.start(stream);
-		shade_kernel<CLASS_DIELECTRIC, KINDS_DIELECTRIC, INST><<<blocks, kBlock, 0, stream>>>(scene, iterationParams, paths.classQueue[CLASS_DIELECTRIC], counters + COUNTER_CLASS + CLASS_DIELECTRIC, paths, current);
-		timer.stop(KernelTimer::SHADE_DIELECTRIC, stream);
-		timer.start(stream);
-		shade_kernel<CLASS_CONDUCTOR, KINDS_CONDUCTOR, INST><<<blocks, kBlock, 0, stream>>>(scene, iterationParams, paths.classQueue[CLASS_CONDUCTOR], counters + COUNTER_CLASS + CLASS_CONDUCTOR, paths, current);
-		timer.stop(KernelTimer::SHADE_CONDUCTOR, stream);
-		timer.start(stream);
-		shade_kernel<CLASS_TERMINAL, KINDS_TERMINAL, INST><<<blocks, kBlock, 0, stream>>>(scene, iterationParams, paths.classQueue[CLASS_TERMINAL], counters + COUNTER_CLASS + CLASS_TERMINAL, paths, current);
-		timer.stop(KernelTimer::SHADE_TERMINAL, stream);
-
-		timer.start(stream);
-		ShadowIO shadowIO = { paths.shadowQueue, paths.shadowValue, paths.result, 0u };
-
-		if (packs && !narrow)
-		{
-			const int layersGrid = persistent_grid((const void*)shadow_layers_kernel<STACK>);
-			ShadowLayersIO layersIO;
-			layersIO.rays = shadowIO.rays;
-			layersIO.values = shadowIO.values;
-			layersIO.result = shadowIO.result;
-			layersIO.passed = 0u;
-			layersIO.shadowLayers = paths.shadowLayers;
-			shadow_layers_kernel<STACK><<<std::min<unsigned int>(blocks, (unsigned int)layersGrid), kTraverseBlock, 0, stream>>>(scene, layersIO, counters + COUNTER_SHADOW, rayCounters, paths.stats);
-		}
-		else if (packs && counted) shadow_instanced_kernel<STACK, true><<<blocks, kBlock, 0, stream>>>(scene, shadowIO, paths.shadowLayers, counters + COUNTER_SHADOW, paths.stats);
-		else if (packs) shadow_instanced_kernel<STACK, false><<<blocks, kBlock, 0, stream>>>(scene, shadowIO, paths.shadowLayers, counters + COUNTER_SHADOW, paths.stats);
-		else if (counted) shadow_narrow_kernel<STACK, true><<<blocks, kBlock, 0, stream>>>(scene, shadowIO, counters + COUNTER_SHADOW, paths.stats);
-		else if (narrow) shadow_narrow_kernel<STACK, false><<<blocks, kBlock, 0, stream>>>(scene, shadowIO, counters + COUNTER_SHADOW, paths.stats);
-		else
-		{
-			const int shadowGrid = persistent_grid((const void*)shadow_kernel<STACK>);
-			shadow_kernel<STACK><<<std::min<unsigned int>(blocks, (unsigned int)shadowGrid), kTraverseBlock, 0, stream>>>(scene, shadowIO, counters + COUNTER_SHADOW, rayCounters, paths.stats);
-		}
-
-		timer.stop(KernelTimer::SHADOW, stream);
-
-		if (timer.enabled && std::getenv("ECHO_B200_PROFILE_ITERATIONS"))
-		{
-			uint32_t shadowRays = 0;
-			cudaMemcpy(&shadowRays, counters + COUNTER_SHADOW, sizeof(uint32_t), cudaMemcpyDeviceToHost);
-			std::fprintf(stderr, "[echo_b200 iteration] rays <= %9u extend %7.3f ms  shadow rays %9u %7.3f ms (%6.0f Mrays/s)\n", bound, extendMs,
-			             shadowRays, timer.last, shadowRays / (timer.last * 1e3));
-		}
-
-		timer.start(stream);
-		rotate_counters_kernel<<<1, 1, 0, stream>>>(counters, activeCount, const_cast<unsigned long long*>(mirror), firstSerial + launched);
+		rotate_counters_kernel<<<1, 1, 0, stream>>>(counters, activeCount, const_cast<unsigned long long*>(mirror), firstSerial + k, current);
 		timer.stop(KernelTimer::ROTATE, stream);
-		launches += 9;
+		launches += 3;
 
 		if (!check_cuda(cudaGetLastError(), "wavefront launch")) return false;
-		if (!check_cuda(cudaEventRecord(state->iterationDone[launched % WorkerState::kEventRing], stream), "cudaEventRecord(iteration)")) return false;
+		return check_cuda(cudaEventRecord(state->iterationDone[k % WorkerState::kEventRing], stream), "cudaEventRecord(iteration)");
+	};
+
+	// unit 0: the camera rays
+	if (!check_cuda(cudaMemcpyAsync(rayCount, &count, sizeof(uint32_t), cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync(count)")) return false;
+	if (!launch_trace_half(0u, blocks_for(count), counted || count < narrowLimit)) return false;
+	launched = 1u;
+
+	while (true)
+	{
+		// the newest finished unit the host can see (a word left by an earlier call fails the range test)
+		unsigned long long seen = *mirror;
+		uint32_t finished = (uint32_t)(seen >> 32) - firstSerial + 1u; // units of this call known to be finished
+		if (finished > launched) finished = 0u;
+
+		if (finished > 0u)
+		{
+			bound = std::min(bound, (uint32_t)seen);
+			if ((uint32_t)seen == 0u) break; // the wavefront is empty; whatever was queued beyond finds zero counts
+		}
+
+		if (launched - finished > runAhead)
+		{
+			// window full: sleep until the oldest unit the host has not seen yet is done, then look again
+			if (!check_cuda(cudaEventSynchronize(state->iterationDone[finished % WorkerState::kEventRing]), "wavefront iteration")) return false;
+			continue;
+		}
+
+		const uint32_t k = launched - 1u;           // the iteration this unit shades; its rays sit in queue k & 1
+		const int current = (int)(k & 1u);
+		const bool exact = finished == launched;    // nothing in flight: `bound` IS the ray count of k and the class counts are k's
+		const unsigned int blocks = blocks_for(bound);
+
+		// the tail: finish the few paths that are left in one launch (it traces for itself: the hits of k are simply not used)
+		if (!timer.enabled && !counted && bound < tailLimit)
+		{
+			tail_kernel<STACK, INST><<<blocks, kBlock, 0, stream>>>(scene, iterationParams, activeCount, paths, current);
+			if (!check_cuda(cudaGetLastError(), "tail_kernel launch")) return false;
+			++launches;
+			break;
+		}
+
+		uint32_t classRays[CLASS_COUNT];
+		for (int c = 0; c < CLASS_COUNT; c++) classRays[c] = counted ? 0u : (exact ? classMirror[c] : bound);
+		const uint32_t missRays = exact ? classMirror[CLASS_MISS] : 0u;
+
+		if (counted)
+		{
+			shade_counted_kernel<INST><<<blocks, kBlock, 0, stream>>>(scene, iterationParams, activeCount, paths, current);
+			++launches;
+		}
+
+		const uint32_t* classCounts = counters + COUNTER_CLASS + current * CLASS_COUNT;
+
+#define ECHO_SHADE(CLASS_VALUE, KINDS_VALUE, SLOT)                                                                                                       \
+		if (classRays[CLASS_VALUE] != 0u)                                                                                                                \
+		{                                                                                                                                                \
+			timer.start(stream);                                                                                                                         \
+			shade_kernel<CLASS_VALUE, KINDS_VALUE, INST><<<blocks_for(classRays[CLASS_VALUE]), kBlock, 0, stream>>>(scene, iterationParams, paths.classQueue[CLASS_VALUE], \
+			                                                                                                        classCounts + CLASS_VALUE, paths, current);         \
+			timer.stop(SLOT, stream);                                                                                                                    \
+			++launches;                                                                                                                                  \
+		}
+
+		ECHO_SHADE(CLASS_MISS, 0u, KernelTimer::SHADE_MISS)
+		ECHO_SHADE(CLASS_DIFFUSE, KINDS_DIFFUSE, KernelTimer::SHADE_DIFFUSE)
+		ECHO_SHADE(CLASS_SMOOTH, KINDS_SMOOTH, KernelTimer::SHADE_SMOOTH)
+		ECHO_SHADE(CLASS_DIELECTRIC, KINDS_DIELECTRIC, KernelTimer::SHADE_DIELECTRIC)
+		ECHO_SHADE(CLASS_CONDUCTOR, KINDS_CONDUCTOR, KernelTimer::SHADE_CONDUCTOR)
+		ECHO_SHADE(CLASS_TERMINAL, KINDS_TERMINAL, KernelTimer::SHADE_TERMINAL)
+#undef ECHO_SHADE
+
+		// shadow rays of k: at most one per ray that hit something
+		const uint32_t shadowBound = exact ? bound - missRays : bound;
+		const bool narrow = counted || bound < narrowLimit;
+
+		if (shadowBound != 0u)
+		{
+			const unsigned int shadowBlocks = blocks_for(shadowBound);
+			unsigned long long* rayCounters = narrow ? nullptr : ray_counters(stream);
+			if (!narrow && !rayCounters) return false;
+
+			timer.start(stream);
+			ShadowIO shadowIO = { paths.shadowQueue, paths.shadowValue, paths.result, 0u };
+
+			if (packs && !narrow)
+			{
+				const int layersGrid = persistent_grid((const void*)shadow_layers_kernel<STACK>);
+				ShadowLayersIO layersIO;
+				layersIO.rays = shadowIO.rays;
+				layersIO.values = shadowIO.values;
+				layersIO.result = shadowIO.result;
+				layersIO.passed = 0u;
+				layersIO.shadowLayers = paths.shadowLayers;
+				shadow_layers_kernel<STACK><<<std::min<unsigned int>(shadowBlocks, (unsigned int)layersGrid), kTraverseBlock, 0, stream>>>(scene, layersIO, counters + COUNTER_SHADOW, rayCounters, paths.stats);
+			}
+			else if (packs && counted) shadow_instanced_kernel<STACK, true><<<shadowBlocks, kBlock, 0, stream>>>(scene, shadowIO, paths.shadowLayers, counters + COUNTER_SHADOW, paths.stats);
+			else if (packs) shadow_instanced_kernel<STACK, false><<<shadowBlocks, kBlock, 0, stream>>>(scene, shadowIO, paths.shadowLayers, counters + COUNTER_SHADOW, paths.stats);
+			else if (counted) shadow_narrow_kernel<STACK, true><<<shadowBlocks, kBlock, 0, stream>>>(scene, shadowIO, counters + COUNTER_SHADOW, paths.stats);
+			else if (narrow) shadow_narrow_kernel<STACK, false><<<shadowBlocks, kBlock, 0, stream>>>(scene, shadowIO, counters + COUNTER_SHADOW, paths.stats);
+			else
+			{
+				const int shadowGrid = persistent_grid((const void*)shadow_kernel<STACK>);
+				shadow_kernel<STACK><<<std::min<unsigned int>(shadowBlocks, (unsigned int)shadowGrid), kTraverseBlock, 0, stream>>>(scene, shadowIO, counters + COUNTER_SHADOW, rayCounters, paths.stats);
+			}
+
+			timer.stop(KernelTimer::SHADOW, stream);
+			++launches;
+		}
+
+		if (!check_cuda(cudaGetLastError(), "wavefront launch")) return false;
+
+		// extend + classify + rotate of iteration k + 1: at most the rays of k that hit something go on
+		const uint32_t nextBound = std::max(shadowBound, 1u);
+		if (!launch_trace_half(launched, blocks_for(nextBound), counted || nextBound < narrowLimit)) return false;
 		++launched;
 	}
 

@@ -58,6 +58,15 @@ def test_shard_tiles_partition():
         assert max(len(p) for p in blocks) - min(len(p) for p in blocks) <= 4
         assert np.array_equal(blocks[0][:4], tiles[:4])
 
+        # ownership by position (bench.py's default): a partition, every rank in every row of tiles, sequence order kept
+        owned = [shard_tiles(tiles, rank, world, by="position") for rank in range(world)]
+        assert sorted(map(tuple, np.concatenate(owned))) == sorted(map(tuple, tiles))
+        assert max(len(p) for p in owned) - min(len(p) for p in owned) <= 5
+        for rank, part in enumerate(owned):
+            assert np.all((part[:, 0] + part[:, 1]) % world == rank)
+            order = {tuple(t): i for i, t in enumerate(map(tuple, tiles))}
+            assert [order[tuple(t)] for t in part] == sorted(order[tuple(t)] for t in part)
+
 
 def test_two_rank_tile_sharding_matches_single_process(tmp_path):
     result = str(tmp_path / "frame.npy")

@@ -229,3 +229,23 @@ def test_multi_device_scene_fans_out_and_matches_one_device(cornell, terrain_sma
     assert np.array_equal(image.view(np.uint32), expected.view(np.uint32))
     for name in structs.STATS_FIELDS[:12]:
         assert int(stats[name][0]) == int(expected_stats[name][0]), name
+
+
+def test_hand_derived_known_answers():
+    """The pencil-and-paper known answers of tests/test_independent_kats.py (derived from the C# alone, not from the oracle) through
+    the C ABI on the device: triangle / sphere hits with exact distances and barycentrics, the ignore rule, the strict comparisons,
+    and BoxBound4.Intersect's asymmetric treatment of rays grazing a box face (SSE min / max return the second operand on NaN)."""
+    from tests import test_independent_kats as kats
+    prepared = kats.kat_scene()
+    with PreparedScene(prepared) as scene:
+        kats.check_trace(scene.trace(kats.trace_rays(kats.TRACE_CASES)))
+        kats.check_occlude(scene.occlude(kats.trace_rays(kats.OCCLUDE_CASES)))
+        # the same queries in a batch large enough for the persistent kernels' work replacement (every lane a different case)
+        rays = np.tile(kats.trace_rays(kats.TRACE_CASES), 3000)
+        hits = scene.trace(rays)
+        kats.check_trace(hits[len(kats.TRACE_CASES) * 1500:len(kats.TRACE_CASES) * 1501])
+        shadow = np.tile(kats.trace_rays(kats.OCCLUDE_CASES), 3000)
+        flags = scene.occlude(shadow).reshape(3000, len(kats.OCCLUDE_CASES))
+        assert np.all(flags == flags[0]) and kats.check_occlude(flags[0]) is None
+        tiled = hits.reshape(3000, len(kats.TRACE_CASES))
+        assert np.all(tiled.view(np.uint32) == tiled[0].view(np.uint32))

@@ -1,0 +1,279 @@
+"""Known answers derived BY HAND from the reference's source, independent of oracle/*.hpp and of the kernels (the
+oracle, the golden fixtures and the device code come from one reading of the C#; a shared misreading would pass every
+device-vs-oracle test).
+
+Every expected value below is worked out in the comments from the cited C# lines with inputs chosen so that all intermediate
+values are exactly representable in binary32 (small integers, halves, quarters, infinities), so the arithmetic can be
+checked with pencil and paper and no rounding is involved. They pin the parts of the hot path the reference's own unit tests
+leave unpinned: PreparedTriangle.IntersectImpl (both variants), BoxBound4.Intersect's SSE NaN behaviour as seen
+through a traversal, the closest-hit / ignore / strict-comparison rules of GeometryCollection + QuadBoundingVolumeHierarchy,
+PreparedSphere.Intersect and the Accumulator. `TRACE_CASES` / `OCCLUDE_CASES` are run against the oracle here and against the
+device through the C ABI in tests/test_gpu_boundary.py::test_hand_derived_known_answers.
+
+A second, weaker kind of independence: `numpy_accumulator` is a transcription of Summation.cs / Accumulator.cs into numpy
+float32 scalar operations, written from the C# alone; the oracle's Accumulator must agree with it bit for bit on random samples.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+from echorenderer_b200 import host, scenes, structs
+from tests import oracle_lib
+
+INF = float("inf")
+F32 = np.float32
+
+
+def f3(values):
+    return np.asarray(values, dtype=np.float32)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# PreparedTriangle.IntersectImpl(origin, direction, out uv) — TriangleEntity.cs:204-235
+#   cross2 = direction x edge2; det = edge1 . cross2; det == 0 -> miss; detR = 1 / det
+#   offset = origin - vertex0; u = (offset . cross2) detR; (u < 0) | (u > 1) -> miss
+#   cross1 = offset x edge1;   v = (direction . cross1) detR; (v < 0) | (u + v > 1) -> miss
+#   distance = (edge2 . cross1) detR; distance < 0 -> miss
+# with a x b = (ay bz - az by, az bx - ax bz, ax by - ay bx).
+# Triangle A: vertex0 (0,0,0), edge1 (1,0,0), edge2 (0,1,0)  [the unit right triangle in the plane z = 0]
+# ---------------------------------------------------------------------------------------------------------------------
+TRIANGLE_A = dict(vertex0=(0, 0, 0), edge1=(1, 0, 0), edge2=(0, 1, 0))
+
+TRIANGLE_CASES = [
+    # origin (1/4, 1/4, 1), direction (0,0,-1):
+    #   cross2 = (0*0 - (-1)*1, (-1)*0 - 0*0, 0*1 - 0*0) = (1, 0, 0); det = (1,0,0).(1,0,0) = 1; detR = 1
+    #   offset = (1/4, 1/4, 1); u = 1/4
+    #   cross1 = offset x (1,0,0) = (1/4*0 - 1*0, 1*1 - 1/4*0, 1/4*0 - 1/4*1) = (0, 1, -1/4); v = (0,0,-1).(0,1,-1/4) = 1/4
+    #   distance = (0,1,0).(0,1,-1/4) = 1
+    ("front face", TRIANGLE_A, (0.25, 0.25, 1), (0, 0, -1), 1.0, (0.25, 0.25)),
+    # the same from behind, origin (1/4, 1/4, -2), direction (0,0,1): no back-face culling
+    #   cross2 = (0*0 - 1*1, 1*0 - 0*0, 0) = (-1, 0, 0); det = -1; detR = -1; offset = (1/4, 1/4, -2); u = (-1/4)(-1) = 1/4
+    #   cross1 = (1/4*0 - (-2)*0, (-2)*1 - 1/4*0, 1/4*0 - 1/4*1) = (0, -2, -1/4); v = ((0,0,1).(0,-2,-1/4))(-1) = 1/4
+    #   distance = ((0,1,0).(0,-2,-1/4))(-1) = 2
+    ("back face", TRIANGLE_A, (0.25, 0.25, -2), (0, 0, 1), 2.0, (0.25, 0.25)),
+    # on the hypotenuse, u + v == 1 exactly: `u + v > 1` is false -> accepted
+    ("hypotenuse is inside", TRIANGLE_A, (0.5, 0.5, 1), (0, 0, -1), 1.0, (0.5, 0.5)),
+    # on the edge u == 0: `(u < 0) | (u > 1)` is false -> accepted by the triangle itself (the box in front of it is another matter, below)
+    ("edge u = 0 is inside", TRIANGLE_A, (0, 0.5, 1), (0, 0, -1), 1.0, (0.0, 0.5)),
+    # u = 3/4, v = 1/2: u + v = 5/4 > 1
+    ("outside", TRIANGLE_A, (0.75, 0.5, 1), (0, 0, -1), INF, None),
+    # in the triangle's plane, direction (1,0,0): cross2 = (0*0 - 0*1, 0*0 - 1*0, 1*1 - 0*0) = (0,0,1); det = (1,0,0).(0,0,1) = 0
+    ("parallel", TRIANGLE_A, (-1, 0.25, 0), (1, 0, 0), INF, None),
+    # pointing away: u = v = 1/4 as in the first case with detR = -1 ... distance = -1 < 0
+    #   cross2 = (0*0 - 1*1, ...) = (-1,0,0); det = -1; u = (1/4)(-1)(-1) = 1/4; cross1 = (0, 1, -1/4); v = ((0,0,1).(0,1,-1/4))(-1) = 1/4
+    #   distance = ((0,1,0).(0,1,-1/4))(-1) = -1
+    ("behind the origin", TRIANGLE_A, (0.25, 0.25, 1), (0, 0, 1), INF, None),
+    # a scaled, tilted triangle: vertex0 (2,0,0), edge1 (0,4,0), edge2 (0,0,4), origin (0,1,1), direction (1,0,0)
+    #   cross2 = (0*4 - 0*0, 0*0 - 1*4, 1*0 - 0*0) = (0,-4,0); det = (0,4,0).(0,-4,0) = -16; detR = -1/16
+    #   offset = (-2,1,1); u = (-4)(-1/16) = 1/4
+    #   cross1 = offset x (0,4,0) = (1*0 - 1*4, 1*0 - (-2)*0, (-2)*4 - 1*0) = (-4, 0, -8); v = ((1,0,0).(-4,0,-8))(-1/16) = 1/4
+    #   distance = ((0,0,4).(-4,0,-8))(-1/16) = (-32)(-1/16) = 2
+    ("scaled and tilted", dict(vertex0=(2, 0, 0), edge1=(0, 4, 0), edge2=(0, 0, 4)), (0, 1, 1), (1, 0, 0), 2.0, (0.25, 0.25)),
+]
+
+# PreparedTriangle.IntersectImpl(origin, direction, travel) — TriangleEntity.cs:237-263: the same products multiplied by sign(det) and
+# compared against |det|; the last line is (distance >= 0) & (distance < travel |det|): STRICT in travel
+TRIANGLE_OCCLUDE_CASES = [
+    ("nearer than travel", TRIANGLE_A, (0.25, 0.25, 1), (0, 0, -1), 1.5, True),
+    ("travel ends exactly on the surface", TRIANGLE_A, (0.25, 0.25, 1), (0, 0, -1), 1.0, False),  # 1 < 1 * 1 is false
+    ("travel ends before", TRIANGLE_A, (0.25, 0.25, 1), (0, 0, -1), 0.5, False),
+    ("scaled: distance 2 |det| 16, travel 2 is not beyond", dict(vertex0=(2, 0, 0), edge1=(0, 4, 0), edge2=(0, 0, 4)), (0, 1, 1), (1, 0, 0), 2.0, False),  # 32 < 2 * 16 false
+    ("scaled: travel 2.5", dict(vertex0=(2, 0, 0), edge1=(0, 4, 0), edge2=(0, 0, 4)), (0, 1, 1), (1, 0, 0), 2.5, True),  # 32 < 40
+    ("outside", TRIANGLE_A, (0.75, 0.5, 1), (0, 0, -1), 10.0, False),
+]
+
+
+def as_triangle(fields):
+    triangle = np.zeros(1, dtype=structs.TRIANGLE)
+    for key, value in fields.items():
+        triangle[key] = value
+    return triangle
+
+
+@pytest.mark.parametrize("name,fields,origin,direction,distance,uv", TRIANGLE_CASES, ids=[case[0] for case in TRIANGLE_CASES])
+def test_triangle_intersect_by_hand(name, fields, origin, direction, distance, uv):
+    lib = oracle_lib.library()
+    lib.oracle_triangle_intersect.restype = ctypes.c_float
+    out = np.zeros(2, dtype=np.float32)
+    triangle, origin, direction = as_triangle(fields), f3(origin), f3(direction)  # named: the pointers below must outlive the call
+    result = lib.oracle_triangle_intersect(oracle_lib.ptr(triangle), oracle_lib.ptr(origin), oracle_lib.ptr(direction), oracle_lib.ptr(out))
+    assert result == distance
+    if uv is not None:
+        assert tuple(out) == uv
+
+
+@pytest.mark.parametrize("name,fields,origin,direction,travel,expected", TRIANGLE_OCCLUDE_CASES, ids=[case[0] for case in TRIANGLE_OCCLUDE_CASES])
+def test_triangle_occlude_by_hand(name, fields, origin, direction, travel, expected):
+    lib = oracle_lib.library()
+    lib.oracle_triangle_occlude.restype = ctypes.c_int32
+    lib.oracle_triangle_occlude.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float]
+    triangle, origin, direction = as_triangle(fields), f3(origin), f3(direction)
+    assert bool(lib.oracle_triangle_occlude(oracle_lib.ptr(triangle), oracle_lib.ptr(origin), oracle_lib.ptr(direction), travel)) == expected
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Whole queries: PreparedScene.Trace / Occlude -> QuadBoundingVolumeHierarchy -> BoxBound4.Intersect -> GeometryCollection
+#
+# Scene: triangle 0 = A (z = 0), triangle 1 = A moved to z = -1, triangle 2 = B with vertices (4,0,0) (5,0,0) (5,1,0)
+# [vertex0 (4,0,0), edge1 (1,0,0), edge2 (1,1,0)], sphere 0 at (10,0,0) radius 1.
+# Tokens: TokenType.Triangle = 1, Sphere = 2 in the top 4 bits (EntityToken.cs:22-39), so triangle i = 0x10000000 + i.
+#
+# BoxBound4.Intersect (BoxBound4.cs:64-112), per axis: length0 = (min - o) dR, length1 = (max - o) dR,
+#   far = min(far, maxps(length0, length1)), near = max(near, minps(length0, length1)) — Float4.Max(a, b) is Sse.Max(a, b)
+#   (Float4.cs:376-377): maxps / minps return their SECOND operand when either is NaN. far *= 1.00000024; hit iff far >= near & far >= 0.
+# A ray with a zero direction component has dR = +inf on that axis (Ray.cs:23: 1 / 0). If its origin sits exactly ON the box's
+# MIN plane of that axis, length0 = 0 * inf = NaN and length1 = +inf: maxps(NaN, +inf) = +inf but minps(NaN, +inf) = +inf too, so
+# near becomes +inf and the box is MISSED. On the MAX plane, length0 = -inf and length1 = NaN: the first axis gives far = near = NaN,
+# and the next axis repairs both (minps(NaN, x) = x, maxps(NaN, x) = x): the box is HIT. Grazing rays are asymmetric in the reference.
+# ---------------------------------------------------------------------------------------------------------------------
+T0, T1, T2, S0 = 0x10000000, 0x10000001, 0x10000002, 0x20000000
+EMPTY = 0xFFFFFFFF
+
+
+def kat_scene():
+    triangles = np.concatenate([
+        scenes.make_triangles([(0, 0, 0)], [(1, 0, 0)], [(0, 1, 0)], 0),
+        scenes.make_triangles([(0, 0, -1)], [(1, 0, -1)], [(0, 1, -1)], 0),
+        scenes.make_triangles([(4, 0, 0)], [(5, 0, 0)], [(5, 1, 0)], 0),
+    ])
+    spheres = np.zeros(1, dtype=structs.SPHERE)
+    spheres["position"], spheres["radius"], spheres["material"] = (10, 0, 0), 1.0, 0
+    description = host.SceneDescription(triangles=triangles, spheres=spheres, materials=scenes.material(structs.MATERIAL_DIFFUSE, (0.5, 0.5, 0.5)),
+                                        camera=scenes.perspective_camera((0, 0, -5)))
+    return host.prepare(description)
+
+
+# (name, origin, direction, distance in, ignore, expected token, expected distance, expected uv or None)
+TRACE_CASES = [
+    ("closest of two stacked triangles", (0.25, 0.25, 1), (0, 0, -1), INF, EMPTY, T0, 1.0, (0.25, 0.25)),
+    # TraceQuery.ignore = the triangle the ray leaves (GeometryCollection.cs:93-94): the one behind it is found instead, at z = -1
+    ("ignore skips the first triangle", (0.25, 0.25, 1), (0, 0, -1), INF, T0, T1, 2.0, (0.25, 0.25)),
+    # TraceQuery.distance caps the search and acceptance is strict, `distance < query.distance` (GeometryCollection.cs:99): a cap
+    # exactly at the surface finds nothing, token stays empty and distance stays the input (PreparedScene.cs:66-75)
+    ("cap exactly on the surface", (0.25, 0.25, 1), (0, 0, -1), 1.0, EMPTY, EMPTY, 1.0, None),
+    ("cap just beyond the first surface", (0.25, 0.25, 1), (0, 0, -1), 1.5, EMPTY, T0, 1.0, (0.25, 0.25)),
+    ("between the two, looking away from both", (0.25, 0.25, 1), (0, 0, 1), INF, EMPTY, EMPTY, INF, None),
+    ("from between, downwards", (0.25, 0.25, -0.5), (0, 0, -1), INF, EMPTY, T1, 0.5, (0.25, 0.25)),
+    # grazing the MIN plane x = 0 of A's box with direction.x = 0: the triangle itself would accept u = 0 (above), its box does not
+    ("grazing a box's min plane misses", (0, 0.5, 1), (0, 0, -1), INF, EMPTY, EMPTY, INF, None),
+    # grazing the MAX plane x = 5 of B's box: the box is hit, and so is B:
+    #   cross2 = (0,0,-1) x (1,1,0) = (0*0 - (-1)*1, (-1)*1 - 0*0, 0) = (1,-1,0); det = (1,0,0).(1,-1,0) = 1
+    #   offset = (5,1/2,1) - (4,0,0) = (1,1/2,1); u = 1 - 1/2 = 1/2; cross1 = (1/2*0 - 1*0, 1*1 - 1*0, 1*0 - 1/2*1) = (0,1,-1/2)
+    #   v = (0,0,-1).(0,1,-1/2) = 1/2 (u + v = 1: accepted); distance = (1,1,0).(0,1,-1/2) = 1
+    ("grazing a box's max plane hits", (5, 0.5, 1), (0, 0, -1), INF, EMPTY, T2, 1.0, (0.5, 0.5)),
+    # PreparedSphere.Intersect (SphereEntity.cs:88-124): offset = o - c = (0,0,3); center = -offset . d = 3;
+    #   extend2 = fma(3, 3, 1 - 9) = 1; distance = 3 - 1 = 2
+    ("sphere from outside", (10, 0, 3), (0, 0, -1), INF, EMPTY, S0, 2.0, None),
+    # from the centre: offset = 0, center = 0, extend2 = fma(0, 0, 1 - 0) = 1; distance = 0 - 1 < 0 -> center + extend = 1
+    ("sphere from its centre", (10, 0, 0), (0, 0, -1), INF, EMPTY, S0, 1.0, None),
+    # PreparedScene.Trace's guard (PreparedScene.cs:69): distance must be positive in FastMath's sense (>= 8e-7)
+    ("non-positive distance is not traced", (0.25, 0.25, 1), (0, 0, -1), 0.0, EMPTY, EMPTY, 0.0, None),
+]
+
+# (name, origin, direction, travel, ignore, expected)
+OCCLUDE_CASES = [
+    ("occluder inside travel", (0.25, 0.25, 1), (0, 0, -1), 1.5, EMPTY, True),
+    ("travel ends exactly on the occluder", (0.25, 0.25, 1), (0, 0, -1), 1.0, EMPTY, False),  # strict, TriangleEntity.cs:262
+    ("ignored occluder, travel short of the next", (0.25, 0.25, 1), (0, 0, -1), 1.5, T0, False),
+    ("ignored occluder, travel reaches the next", (0.25, 0.25, 1), (0, 0, -1), 2.5, T0, True),
+    ("grazing a box's min plane is not occluded", (0, 0.5, 1), (0, 0, -1), 10.0, EMPTY, False),
+    ("grazing a box's max plane is occluded", (5, 0.5, 1), (0, 0, -1), 10.0, EMPTY, True),
+    # PreparedSphere.Intersect(ray, travel) (SphereEntity.cs:126-148): the near root 2 is inside travel 2.5
+    ("sphere inside travel", (10, 0, 3), (0, 0, -1), 2.5, EMPTY, True),
+    ("sphere beyond travel", (10, 0, 3), (0, 0, -1), 1.5, EMPTY, False),
+]
+
+
+def trace_rays(cases):
+    rays = np.zeros(len(cases), dtype=structs.RAY)
+    for index, case in enumerate(cases):
+        rays["origin"][index], rays["direction"][index], rays["distance"][index], rays["ignore"][index] = case[1], case[2], case[3], case[4]
+    return rays
+
+
+def check_trace(hits):
+    for case, hit in zip(TRACE_CASES, hits):
+        name, _, _, _, _, token, distance, uv = case
+        assert int(hit["token"]) == token, name
+        assert float(hit["distance"]) == distance, name
+        if uv is not None:
+            assert tuple(float(v) for v in hit["uv"]) == uv, name
+
+
+def check_occlude(flags):
+    for case, flag in zip(OCCLUDE_CASES, flags):
+        assert bool(flag) == case[5], case[0]
+
+
+def test_whole_queries_by_hand():
+    oracle = oracle_lib.OracleScene(kat_scene())
+    check_trace(oracle.trace(trace_rays(TRACE_CASES)))
+    check_occlude(oracle.occlude(trace_rays(OCCLUDE_CASES)))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Accumulator.Add / Value / Noise — Accumulator.cs:11-71 over Summation.cs:8-58
+#   ++count; delta = average - sample; average -= delta / count; squared += delta * (average - sample)
+# Samples 1, 2, 3, 4 in every lane (all exactly representable, Kahan errors stay zero):
+#   n=1: delta = -1;   average = 0 + 1 = 1;        squared = 0 + (-1)(1 - 1) = 0
+#   n=2: delta = -1;   average = 1 + 1/2 = 3/2;    squared = 0 + (-1)(3/2 - 2) = 1/2
+#   n=3: delta = -3/2; delta * (1f / 3f) = -1.5 * 0.333333343 = -0.50000001 -> rounds to -1/2; average = 2; squared = 1/2 + (-3/2)(2 - 3) = 2
+#   n=4: delta = -2;   average = 2 + 2/4 = 5/2;    squared = 2 + (-2)(5/2 - 4) = 5
+# Value = 5/2. Noise (count >= 2): oneLess = 3, cubed 27; numerator = Value^2 * 27 = 168.75; 1 / sqrt(168.75 * (1 / 5)) = 1 / sqrt(33.75)
+# = 0.17213259 (the library evaluates the reciprocal and the square root exactly, INTEGRATION.md "Where results can differ").
+# ---------------------------------------------------------------------------------------------------------------------
+def test_accumulator_by_hand():
+    samples = np.repeat(np.array([1, 2, 3, 4], dtype=np.float32)[:, None], 4, axis=1)
+    value, noise, count = oracle_lib.accumulate(samples)
+    assert count == 4
+    assert np.all(value == F32(2.5))
+    assert noise == pytest.approx(1.0 / np.sqrt(33.75), rel=2e-6)
+
+    # a non-finite sample is rejected whole (Accumulator.cs:62) and does not advance the count
+    samples = np.concatenate([samples, np.array([[INF, 0, 0, 0]], dtype=np.float32)])
+    value, _, count = oracle_lib.accumulate(samples)
+    assert count == 4 and np.all(value == F32(2.5))
+
+
+def numpy_accumulator(samples):
+    """Summation.cs + Accumulator.Add transcribed into numpy float32 arithmetic (every operation rounds to binary32 as the C# does)."""
+    zero = np.zeros(4, dtype=np.float32)
+
+    def add(total, error, value):  # Summation + Float4, Summation.cs:35-42
+        delta = value - error
+        new_total = total + delta
+        return new_total, (new_total - total) - delta
+
+    def add_summation(total, error, other_total, other_error):  # Summation + Summation, :46-55
+        combined = error + other_error
+        delta = other_total - combined
+        new_total = total + delta
+        return new_total, (new_total - total) - delta
+
+    average, average_error, squared, squared_error, count = zero.copy(), zero.copy(), zero.copy(), zero.copy(), 0
+
+    for sample in np.asarray(samples, dtype=np.float32):
+        if not np.isfinite(np.float32(np.float32(sample[0] + sample[1]) + np.float32(sample[2] + sample[3]))):  # Float4.Sum pairs lanes (Float4.cs:73-81)
+            continue
+        count += 1
+        delta_total, delta_error = add(average, average_error, -sample)               # average - sample
+        reciprocal = np.float32(1.0) / np.full(4, count, dtype=np.float32)            # Summation / Float4 = * (1f / value)
+        scaled_total, scaled_error = delta_total * reciprocal, delta_error * reciprocal
+        average, average_error = add_summation(average, average_error, -scaled_total, -scaled_error)  # average -= ...
+        difference, _ = add(average, average_error, -sample)                           # (average - sample).Result
+        product_total, product_error = delta_total * difference, delta_error * difference  # Summation * Float4
+        squared, squared_error = add_summation(squared, squared_error, product_total, product_error)
+
+    return average, count
+
+
+def test_accumulator_matches_an_independent_transcription():
+    random = np.random.default_rng(5)
+    for scale in (1.0, 1e-3, 1e4):
+        samples = (random.random((257, 4)).astype(np.float32) * np.float32(scale)).astype(np.float32)
+        samples[100, 2] = np.nan  # rejected
+        value, _, count = oracle_lib.accumulate(samples)
+        expected, expected_count = numpy_accumulator(samples)
+        assert count == expected_count == 256
+        assert np.array_equal(value.view(np.uint32), expected.view(np.uint32))

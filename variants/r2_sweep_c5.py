@@ -57,11 +57,11 @@ def main():
         dist.all_gather(out, tensor)
         return [round(float(t.item()), 2) for t in out]
 
-    def run(tag, pattern="hilbert", block=64, reduce_every=1, **switches):
+    def run(tag, pattern="hilbert", block=64, reduce_every=1, by="sequence", **switches):
         defaults = {"RUN_AHEAD": -1, "BLOCKING_SYNC": -1, "RENDER_WORKERS": 8, "BATCH_PATHS": 1 << 24}
         for name, value in {**defaults, **switches}.items():
             _native.set_option(name, value)
-        tiles = shard_tiles(sequences[pattern], rank, world, block=block)
+        tiles = shard_tiles(sequences[pattern], rank, world, block=block, by=by)
         render_ms, reduce_ms = [], []
         for index in range(args.steps + 1):
             if index == 1:
@@ -99,9 +99,10 @@ def main():
             samples = args.width * args.height * args.spp * args.steps
             print(json.dumps({"tag": tag, "world": world, "ms_per_step": round(float(total.item()) / args.steps, 2), "msamples_per_s": round(samples / (float(total.item()) * 1e-3) / 1e6, 1),
                               "rank_render_ms_mean": per_rank_mean, "rank_render_ms_max": per_rank_max, "all_reduce_ms": round(reduce_mean, 3), "launches_rank0": int(stats["kernelLaunches"][0]),
-                              "pattern": pattern, "block": block, "reduce_every": reduce_every, "switches": switches}), flush=True)
+                              "pattern": pattern, "block": block, "by": by, "reduce_every": reduce_every, "switches": switches}), flush=True)
 
     run("warm-up (discard)")
+    run("hilbert, tiles owned by position", by="position")
     run("default (automatic run-ahead / blocking)")
     run("lock step, blocking waits", RUN_AHEAD=0, BLOCKING_SYNC=1)
     run("lock step, spinning waits", RUN_AHEAD=0, BLOCKING_SYNC=0)
