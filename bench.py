@@ -525,6 +525,29 @@ def run_trace(ctx, args):
     pageable_hits, pageable_occluded = np.empty(n, dtype=structs.HIT), np.empty(n, dtype=np.uint8)
     pageable_value, pageable_ms = e2e_leg(rays.ctypes.data, shadow.ctypes.data, pageable_hits.ctypes.data, pageable_occluded.ctypes.data, min(args.steps, 3))
 
+    # The ceiling of that leg: the bare copies of one step (H2D of both ray batches, D2H of hits and flags, the two directions on
+    # two streams as in the library's pipeline) with no kernel at all, all ranks at the same time — what the host's memory system and
+    # the PCIe links deliver when N ranks move their batches at once. `e2e` is reported as a fraction of it.
+    pinned = [torch.from_numpy(buffer.array.view(np.uint8).reshape(-1)) for buffer in (host_rays, host_shadow, host_hits, host_occluded)]
+    up, down = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
+
+    def bare_copies():
+        with torch.cuda.stream(up):
+            d_rays.copy_(pinned[0], non_blocking=True)
+            d_shadow.copy_(pinned[1], non_blocking=True)
+        with torch.cuda.stream(down):
+            pinned[2].copy_(d_hits, non_blocking=True)
+            pinned[3].copy_(d_occluded, non_blocking=True)
+
+    bare_copies()
+    ctx.barrier()
+    wall = time.perf_counter()
+    for _ in range(args.steps):
+        bare_copies()
+    ctx.barrier()
+    copy_ms = ctx.max_over_ranks((time.perf_counter() - wall) * 1e3) / args.steps
+    del pinned
+
     line = base_line(args, "Mrays/s", value, total_ms / args.steps, trace_config(args, n), "f32")
     achieved = bytes_trace * n / (trace_ms * 1e-3) / 1e9
     line["roofline"] = {"bound": "hbm", "kernel": "instanced closest-hit kernel" if args.instanced else "persistent_batch_kernel<48, false> (closest hit)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -551,7 +574,10 @@ def run_trace(ctx, args):
             "on_chip_peaks": on_chip})
 
     line["e2e"] = {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 2 * n * 32, "d2h_bytes_per_step": n * 16 + n, "ms_per_step": e2e_ms,
-                   "host_memory": "page-locked (echo_b200_host_alloc)"}
+                   "host_memory": "page-locked (echo_b200_host_alloc)",
+                   "copy_ceiling": {"ms_per_step": copy_ms, "gbs_per_rank": (2 * n * 32 + n * 17) / (copy_ms * 1e-3) / 1e9, "gbs_all_ranks": ctx.world * (2 * n * 32 + n * 17) / (copy_ms * 1e-3) / 1e9,
+                                    "what": "the same host<->device copies with no kernels, up and down on two streams, all ranks at once"},
+                   "frac_of_copy_ceiling": copy_ms / e2e_ms}
     line["e2e_pageable"] = {"value": pageable_value, "unit": "Mrays/s", "ms_per_step": pageable_ms, "host_memory": "pageable (what a `fixed`-pinned managed array is to CUDA)"}
     line["gpu_launches"] = 2 * args.steps
     line["clocks"] = clocks.summary()
@@ -702,6 +728,7 @@ def run_render(ctx, args, scene_key, width, height, spp, bounce_limit, steps, wa
     host_tiles.free()
 
     achieved = per_sample_bytes * value / 1e9
+    traffic_per_sample = ncu_traffic(f"{scene_key}_dram_bytes_per_sample")  # DRAM bytes of a whole step / its samples, from the committed ncu capture
     record = {"metric": "samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": total_ms / steps,
               "higher_is_better": True, "scaling": "strong", "dtype": "f32", "data": "synthetic",
               "config": render_config(args, scene_key, width, height, spp, bounce_limit, reduce_every),
@@ -710,7 +737,8 @@ def run_render(ctx, args, scene_key, width, height, spp, bounce_limit, steps, wa
                                "what": "host wall time of echo_b200_render_frame_device per step, mean over the timed steps, per rank"},
               "all_reduce": {"count": len(reduce_ms), "ms_mean": float(np.mean(reduce_ms)) if reduce_ms else None, "bytes": int(frame.numel() * 4), "collective": "NCCL all-reduce (sum) of the fp32 accumulation frame" if ctx.distributed else "none (one GPU)"},
               "roofline": {"bound": "hbm", "kernel": "wavefront step (raygen, extend, classify, shade x5, shadow, accumulate)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                           "traffic": ncu_traffic(f"{scene_key}_dram_bytes_per_step"), "peak_source": peak_source, "algorithmic_bytes_per_sample": per_sample_bytes,
+                           "traffic": traffic_per_sample * (total_samples // steps) if traffic_per_sample else None, "traffic_bytes_per_sample": traffic_per_sample,
+                           "peak_source": peak_source, "algorithmic_bytes_per_sample": per_sample_bytes,
                            "bytes_per_sample_parts": per_sample_parts, "per_sample_counters": per_sample_counters, "path_state_bytes": PATH_STATE_BYTES,
                            "counted_pass": f"{len(spread)} tiles spread over rank 0's shard at {extend} spp, one-thread-per-query kernels with visit counters (ECHO_EVALUATOR_COUNT_VISITS)",
                            "bound_measured": "latency / L1 sector fetches in extend + shadow, instruction fetch in the shading kernels (ncu: profiles/README.md); DRAM is not the limiter"},

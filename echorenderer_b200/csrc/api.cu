@@ -1085,7 +1085,7 @@ int32_t echo_b200_debug_evaluate_samples4(EchoScene* scene, const EchoRenderPara
 int32_t echo_b200_debug_set_option(const char* name, int64_t value)
 {
 	if (!name) return fail(ECHO_B200_ERR_INVALID, "name is null");
-	return set_render_option(name, (long long)value) ? ECHO_B200_OK : fail(ECHO_B200_ERR_INVALID, "unknown option");
+	return set_render_option(name, (long long)value) || set_build_option(name, (long long)value) ? ECHO_B200_OK : fail(ECHO_B200_ERR_INVALID, "unknown option");
 }
 
 static int32_t debug_device(int32_t device)

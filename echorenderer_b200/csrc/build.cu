@@ -1,15 +1,23 @@
-// build.cu — optional device-side tree build: a linear BVH over 63-bit Morton codes (Karras 2012,
-// "Maximizing Parallelism in the Construction of BVHs, Octrees, and k-d Trees") collapsed into the reference's QBVH node
-// format (QuadBoundingVolumeHierarchy.cs:363-565: every other binary level becomes a quad node, children sorted by the
-// lower bound along the split axis, a leaf child becomes a [leaf, empty] pair with axis 3, empty slots at +infinity).
+// build.cu — optional device-side tree build: a binary BVH built on the device and collapsed into the
+// reference's QBVH node format (QuadBoundingVolumeHierarchy.cs:363-565: every other binary level becomes a quad node, children
+// sorted by the lower bound along the split axis, a leaf child becomes a [leaf, empty] pair with axis 3, empty slots at +infinity).
+// Two ways to get the binary tree, both over the primitives sorted by 63-bit Morton code:
+//   PLOC (default)  parallel locally-ordered clustering (Meister & Bittner 2018): bottom-up agglomeration — every cluster looks
+//                   for the neighbour within +-kPlocRadius positions whose union with it has the smallest surface area, mutual
+//                   nearest neighbours merge, the survivors are compacted, repeat until one cluster is left. The surface-area
+//                   criterion is the SAH's, applied locally; it closes most of the gap to the reference's full-sweep SAH tree.
+//   LBVH            the linear BVH of Karras 2012 ("Maximizing Parallelism in the Construction of BVHs, Octrees, and k-d Trees"):
+//                   splits at the highest differing Morton bit. Fastest to build, lowest quality (ECHO_B200_BUILD_ALGORITHM=0).
 //
-// This is NOT the reference's SweepBuilder tree (full-sweep SAH; echo_host_build_qbvh is its host-side mirror and the
-// default): it is a valid tree of lower quality that builds in milliseconds. Hit results do not depend on the tree except
-// for the order in which exact ties are found, and both the device and the oracle walk whichever tree they are given.
-// Sorting and the prefix sum are CUB (a CUDA toolkit library); the other passes are written here.
+// Neither is the reference's SweepBuilder tree (full-sweep SAH; echo_host_build_qbvh is its host-side mirror and the default of
+// the tests and the bench). Hit results do not depend on the tree except for the order in which exact ties are found, and both
+// the device and the oracle walk whichever tree they are given.
+// Sorting and the prefix sums are CUB (a CUDA toolkit library); the other passes are written here.
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -197,6 +205,97 @@ __global__ void depth_kernel(const uint32_t* __restrict__ parentOfInternal, int 
 	isQuad[i] = (depth & 1u) == 0u ? 1u : 0u;
 }
 
+// ---- PLOC ----
+constexpr int kPlocRadius = 8; // neighbours examined on each side by default (ECHO_B200_BUILD_PLOC_RADIUS / set_option("BUILD_PLOC_RADIUS"))
+
+std::atomic<int>& ploc_radius()
+{
+	static std::atomic<int> value{ [] { const char* text = std::getenv("ECHO_B200_BUILD_PLOC_RADIUS"); return text ? std::atoi(text) : kPlocRadius; }() };
+	return value;
+}
+
+__device__ __forceinline__ float union_half_area(const BuildBox& a, const BuildBox& b)
+{
+	float dx = fmaxf(a.maxX, b.maxX) - fminf(a.minX, b.minX), dy = fmaxf(a.maxY, b.maxY) - fminf(a.minY, b.minY), dz = fmaxf(a.maxZ, b.maxZ) - fminf(a.minZ, b.minZ);
+	return dx * dy + dy * dz + dz * dx;
+}
+
+__global__ void ploc_init_kernel(const BuildBox* __restrict__ boxes, const uint32_t* __restrict__ order, int total, uint32_t* __restrict__ clusterRef, BuildBox* __restrict__ clusterBox)
+{
+	int i = blockIdx.x * kBuildBlock + threadIdx.x;
+	if (i >= total) return;
+	clusterRef[i] = (uint32_t)i | kLeafFlag;
+	clusterBox[i] = boxes[order[i]];
+}
+
+// the neighbour within the window whose union with cluster i has the smallest surface area (ties: the lower position)
+__global__ void ploc_nearest_kernel(const BuildBox* __restrict__ clusterBox, int count, int radius, uint32_t* __restrict__ nearest)
+{
+	int i = blockIdx.x * kBuildBlock + threadIdx.x;
+	if (i >= count) return;
+
+	BuildBox box = clusterBox[i];
+	float best = __int_as_float(0x7F800000);
+	int bestIndex = i == 0 ? 1 : i - 1;
+	int first = max(i - radius, 0), last = min(i + radius, count - 1);
+
+	for (int j = first; j <= last; j++)
+	{
+		if (j == i) continue;
+		float area = union_half_area(box, clusterBox[j]);
+		if (area < best) { best = area; bestIndex = j; }
+	}
+
+	nearest[i] = (uint32_t)bestIndex;
+}
+
+// mutual nearest neighbours merge into a new internal node (the lower position keeps the merged cluster, the higher one is dropped).
+// Node ids are handed out downwards from total - 2, so the last merge — the root — is node 0, where the collapse expects it.
+__global__ void ploc_merge_kernel(uint32_t* __restrict__ clusterRef, BuildBox* __restrict__ clusterBox, const uint32_t* __restrict__ nearest, int count, int* __restrict__ nextNode,
+                                  uint32_t* __restrict__ left, uint32_t* __restrict__ right, uint32_t* __restrict__ parentOfInternal, uint32_t* __restrict__ parentOfLeaf,
+                                  BuildBox* __restrict__ nodeBoxes, uint32_t* __restrict__ keep)
+{
+	int i = blockIdx.x * kBuildBlock + threadIdx.x;
+	if (i >= count) return;
+
+	int j = (int)nearest[i];
+	bool mutual = (int)nearest[j] == i;
+
+	if (!mutual) { keep[i] = 1u; return; }
+	if (i > j) { keep[i] = 0u; return; }
+
+	uint32_t a = clusterRef[i], b = clusterRef[j];
+	BuildBox boxA = clusterBox[i], boxB = clusterBox[j];
+	BuildBox merged = { fminf(boxA.minX, boxB.minX), fminf(boxA.minY, boxB.minY), fminf(boxA.minZ, boxB.minZ),
+	                    fmaxf(boxA.maxX, boxB.maxX), fmaxf(boxA.maxY, boxB.maxY), fmaxf(boxA.maxZ, boxB.maxZ) };
+
+	uint32_t node = (uint32_t)(atomicSub(nextNode, 1) - 1);
+	left[node] = a;
+	right[node] = b;
+	nodeBoxes[node] = merged;
+	if (a & kLeafFlag) parentOfLeaf[a & ~kLeafFlag] = node; else parentOfInternal[a] = node;
+	if (b & kLeafFlag) parentOfLeaf[b & ~kLeafFlag] = node; else parentOfInternal[b] = node;
+
+	clusterRef[i] = node; // only this thread touches clusters i and j in this pass
+	clusterBox[i] = merged;
+	keep[i] = 1u;
+}
+
+__global__ void ploc_compact_kernel(const uint32_t* __restrict__ clusterRef, const BuildBox* __restrict__ clusterBox, const uint32_t* __restrict__ keep, const uint32_t* __restrict__ position,
+                                    int count, uint32_t* __restrict__ outRef, BuildBox* __restrict__ outBox, int* __restrict__ outCount)
+{
+	int i = blockIdx.x * kBuildBlock + threadIdx.x;
+	if (i >= count) return;
+
+	if (keep[i])
+	{
+		outRef[position[i]] = clusterRef[i];
+		outBox[position[i]] = clusterBox[i];
+	}
+
+	if (i == count - 1) *outCount = (int)(position[i] + keep[i]);
+}
+
 struct ChildRef
 {
 	uint32_t reference; // kLeafFlag | sorted position, or internal node index; 0xFFFFFFFF = none
@@ -282,6 +381,13 @@ __global__ void emit_kernel(int internalCount, const uint32_t* __restrict__ isQu
 	out[quadIndex[i]] = node;
 }
 
+// 1 = PLOC (default), 0 = LBVH; ECHO_B200_BUILD_ALGORITHM / echo_b200_debug_set_option("BUILD_ALGORITHM", ...)
+std::atomic<int>& build_algorithm()
+{
+	static std::atomic<int> value{ [] { const char* text = std::getenv("ECHO_B200_BUILD_ALGORITHM"); return text ? std::atoi(text) : 1; }() };
+	return value;
+}
+
 unsigned int build_blocks(uint64_t count) { return (unsigned int)((count + kBuildBlock - 1) / kBuildBlock); }
 
 // one cudaMalloc for every build buffer (eighteen separate ones cost ~60 ms, far more than the build itself)
@@ -310,9 +416,36 @@ struct DeviceArena
 
 } // namespace
 
+bool set_build_option(const char* name, long long value)
+{
+	const std::string key = name ? name : "";
+	if (key == "BUILD_ALGORITHM") build_algorithm() = (int)value;
+	else if (key == "BUILD_PLOC_RADIUS") ploc_radius() = (int)value;
+	else return false;
+	return true;
+}
+
+static bool build_qbvh_with(bool ploc, const EchoTriangle* triangles, uint32_t triangleCount, const EchoSphere* spheres, uint32_t sphereCount,
+                            EchoQbvhNode* outNodes, uint32_t* outNodeCount, uint32_t* outMaxDepth, bool* stalled);
+
 bool build_qbvh_device(const EchoTriangle* triangles, uint32_t triangleCount, const EchoSphere* spheres, uint32_t sphereCount,
                        EchoQbvhNode* outNodes, uint32_t* outNodeCount, uint32_t* outMaxDepth)
 {
+	const bool ploc = build_algorithm() != 0;
+	bool stalled = false;
+	if (!build_qbvh_with(ploc, triangles, triangleCount, spheres, sphereCount, outNodes, outNodeCount, outMaxDepth, &stalled)) return false;
+
+	// Agglomeration has neither a depth bound nor a bound on its passes: thousands of coincident primitives merge one pair per pass
+	// and chain. The Morton tree has both (63 key bits). Fall back to it when the clustering stalls or when the clustered tree would
+	// not fit the deepest compiled traversal stack (192 entries = 63 quad levels).
+	if (ploc && (stalled || stack_class(*outMaxDepth) < 0)) return build_qbvh_with(false, triangles, triangleCount, spheres, sphereCount, outNodes, outNodeCount, outMaxDepth, &stalled);
+	return true;
+}
+
+static bool build_qbvh_with(bool ploc, const EchoTriangle* triangles, uint32_t triangleCount, const EchoSphere* spheres, uint32_t sphereCount,
+                            EchoQbvhNode* outNodes, uint32_t* outNodeCount, uint32_t* outMaxDepth, bool* stalled)
+{
+	*stalled = false;
 	uint64_t total64 = (uint64_t)triangleCount + sphereCount;
 	if (total64 < 2 || total64 >= (1ull << ECHO_TOKEN_INDEX_BITS)) { set_error("a tree needs 2..2^28-1 primitives"); return false; }
 	int total = (int)total64, internal = total - 1;
@@ -331,6 +464,9 @@ bool build_qbvh_device(const EchoTriangle* triangles, uint32_t triangleCount, co
 	int* sceneBound;
 	EchoQbvhNode* nodes;
 	char* scratch;
+	uint32_t *clusterRef[2], *nearest, *keep, *keepPosition;
+	BuildBox* clusterBox[2];
+	int* plocCounters; // [0] the next node id + 1, [1] clusters left
 
 	size_t sortBytes = 0, scanBytes = 0;
 	cub::DeviceRadixSort::SortPairs(nullptr, sortBytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, total, 0, 63);
@@ -341,6 +477,11 @@ bool build_qbvh_device(const EchoTriangle* triangles, uint32_t triangleCount, co
 	arena.reserve(parentOfInternal, internal); arena.reserve(parentOfLeaf, total); arena.reserve(visits, internal); arena.reserve(isQuad, internal);
 	arena.reserve(quadIndex, internal); arena.reserve(keys, total); arena.reserve(keysSorted, total); arena.reserve(sceneBound, 6); arena.reserve(nodes, internal);
 	arena.reserve(scratch, std::max(sortBytes, scanBytes));
+	if (ploc)
+	{
+		for (int side = 0; side < 2; side++) { arena.reserve(clusterRef[side], total); arena.reserve(clusterBox[side], total); }
+		arena.reserve(nearest, total); arena.reserve(keep, total); arena.reserve(keepPosition, total); arena.reserve(plocCounters, 2);
+	}
 	if (!arena.commit()) return false;
 	bool ok = true;
 
@@ -364,8 +505,36 @@ bool build_qbvh_device(const EchoTriangle* triangles, uint32_t triangleCount, co
 	morton_kernel<<<build_blocks(total), kBuildBlock, 0, stream>>>(boxes, (uint32_t)total, sceneBound, keys, order);
 
 	cub::DeviceRadixSort::SortPairs(scratch, sortBytes, keys, keysSorted, order, orderSorted, total, 0, 63, stream);
-	radix_tree_kernel<<<build_blocks(internal), kBuildBlock, 0, stream>>>(keysSorted, total, left, right, parentOfInternal, parentOfLeaf);
-	fit_kernel<<<build_blocks(total), kBuildBlock, 0, stream>>>(boxes, orderSorted, total, left, right, parentOfInternal, parentOfLeaf, nodeBoxes, visits);
+
+	if (ploc)
+	{
+		ploc_init_kernel<<<build_blocks(total), kBuildBlock, 0, stream>>>(boxes, orderSorted, total, clusterRef[0], clusterBox[0]);
+		const int firstCounters[2] = { internal, total };
+		if (!check_cuda(cudaMemcpyAsync(plocCounters, firstCounters, sizeof(firstCounters), cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync(ploc)")) return false;
+		const uint32_t noParent = 0xFFFFFFFFu;
+		if (!check_cuda(cudaMemcpyAsync(parentOfInternal, &noParent, sizeof(uint32_t), cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync(root)")) return false; // node 0 is the root
+
+		int count = total, side = 0;
+		const int radius = std::min(std::max(ploc_radius().load(), 1), 256);
+
+		for (int iteration = 0; count > 1; iteration++)
+		{
+			if (iteration >= 384) { *stalled = true; return true; } // ordinary inputs need 25-40 passes
+			ploc_nearest_kernel<<<build_blocks(count), kBuildBlock, 0, stream>>>(clusterBox[side], count, radius, nearest);
+			ploc_merge_kernel<<<build_blocks(count), kBuildBlock, 0, stream>>>(clusterRef[side], clusterBox[side], nearest, count, plocCounters, left, right, parentOfInternal, parentOfLeaf, nodeBoxes, keep);
+			cub::DeviceScan::ExclusiveSum(scratch, scanBytes, keep, keepPosition, count, stream);
+			ploc_compact_kernel<<<build_blocks(count), kBuildBlock, 0, stream>>>(clusterRef[side], clusterBox[side], keep, keepPosition, count, clusterRef[side ^ 1], clusterBox[side ^ 1], plocCounters + 1);
+			if (!check_cuda(cudaMemcpyAsync(&count, plocCounters + 1, sizeof(int), cudaMemcpyDeviceToHost, stream), "cudaMemcpyAsync(ploc count)")
+				|| !check_cuda(cudaStreamSynchronize(stream), "ploc iteration")) return false;
+			side ^= 1;
+		}
+	}
+	else
+	{
+		radix_tree_kernel<<<build_blocks(internal), kBuildBlock, 0, stream>>>(keysSorted, total, left, right, parentOfInternal, parentOfLeaf);
+		fit_kernel<<<build_blocks(total), kBuildBlock, 0, stream>>>(boxes, orderSorted, total, left, right, parentOfInternal, parentOfLeaf, nodeBoxes, visits);
+	}
+
 	depth_kernel<<<build_blocks(internal), kBuildBlock, 0, stream>>>(parentOfInternal, internal, isQuad);
 	cub::DeviceScan::ExclusiveSum(scratch, scanBytes, isQuad, quadIndex, internal, stream);
 	emit_kernel<<<build_blocks(internal), kBuildBlock, 0, stream>>>(internal, isQuad, quadIndex, left, right, boxes, orderSorted, tokens, nodeBoxes, nodes);

@@ -35,10 +35,18 @@ constexpr unsigned long long kPool = 256;         // rays reserved per global at
 #define ECHO_SHARED_STACK 8 // traversal-stack entries per thread kept in shared memory (0 = all in local memory), see `stack` below
 #endif
 #ifndef ECHO_ANY_UNORDERED
-#define ECHO_ANY_UNORDERED 0
+#define ECHO_ANY_UNORDERED 1 // any-hit traversal takes a node's children as stored (see the visit-order swaps below); 0 = the reference's order
 #endif
 #ifndef ECHO_LEAF_MAX_WAIT
 #define ECHO_LEAF_MAX_WAIT 2 // a lane waits at most two iterations for its primitive test (A/B on C2/C3/C4: +1-2 %)
+#endif
+// L2 residency hints (A/B in profiles/README.md): the ray stream is read once — marking its cp.async evict-first keeps it from
+// pushing the tree out of L2 (C2: 1.9 GB of DRAM traffic per launch against 0.93 GB compulsory) — and node loads can ask to stay.
+#ifndef ECHO_RAY_POLICY
+#define ECHO_RAY_POLICY 0
+#endif
+#ifndef ECHO_NODE_POLICY
+#define ECHO_NODE_POLICY 0
 #endif
 constexpr int kLeafVote = ECHO_LEAF_VOTE;                      // run the primitive tests once this many lanes have one pending
 
@@ -70,6 +78,14 @@ ECHO_DEVICE float8 ldg256(const void* pointer)
 	float8 r;
 	asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
 		: "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7]) : "l"(pointer));
+	return r;
+}
+
+ECHO_DEVICE float8 ldg256_hint(const void* pointer, unsigned long long policy)
+{
+	float8 r;
+	asm volatile("ld.global.nc.L2::cache_hint.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+		: "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7]) : "l"(pointer), "l"(policy));
 	return r;
 }
 
@@ -123,6 +139,15 @@ ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, uint32_t 
 {
 	const unsigned int lane = threadIdx.x & 31u;
 	const unsigned int lanesBelow = (1u << lane) - 1u;
+
+#if ECHO_RAY_POLICY
+	unsigned long long rayPolicy;
+	asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(rayPolicy));
+#endif
+#if ECHO_NODE_POLICY
+	unsigned long long nodePolicy;
+	asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(nodePolicy));
+#endif
 
 	float4* stagedSlot = stagedRays + threadIdx.x * 2;
 	const uint32_t stagedAddress = (uint32_t)__cvta_generic_to_shared(stagedSlot);
@@ -357,8 +382,13 @@ ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, uint32_t 
 			if (got)
 			{
 				const float4* source = io.ray_pointer(index);
+#if ECHO_RAY_POLICY
+				asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" :: "r"(stagedAddress), "l"(source), "l"(rayPolicy) : "memory");
+				asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" :: "r"(stagedAddress + 16u), "l"(source + 1), "l"(rayPolicy) : "memory");
+#else
 				asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(stagedAddress), "l"(source) : "memory");
 				asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(stagedAddress + 16u), "l"(source + 1) : "memory");
+#endif
 				asm volatile("cp.async.commit_group;" ::: "memory");
 				stagedIndex = index;
 				staged = true;
@@ -408,7 +438,11 @@ ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, uint32_t 
 		{
 			ECHO_CHECK(scene, (INST ? pack.nodeOffset : 0u) + token_index(nodeToken) < scene.nodeCount, CHECK_NODE);
 			const float4* nodeData = scene.nodes + ((size_t)(INST ? pack.nodeOffset : 0u) + token_index(nodeToken)) * 8;
+#if ECHO_NODE_POLICY
+			float8 q0 = ldg256_hint(nodeData + 0, nodePolicy), q1 = ldg256_hint(nodeData + 2, nodePolicy), q2 = ldg256_hint(nodeData + 4, nodePolicy), q3 = ldg256_hint(nodeData + 6, nodePolicy);
+#else
 			float8 q0 = ldg256(nodeData + 0), q1 = ldg256(nodeData + 2), q2 = ldg256(nodeData + 4), q3 = ldg256(nodeData + 6);
+#endif
 			if (INST) currentNode = nodeToken;
 			// q0 = minX[4] minY[4], q1 = minZ[4] maxX[4], q2 = maxY[4] maxZ[4], q3 = axisMajor axisMinor0 axisMinor1 token4[4] pad
 
@@ -437,8 +471,10 @@ ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, uint32_t 
 			bool swap1 = (orders >> __float_as_int(q3.v[2])) & 1u;
 			bool swapPairs = (orders >> __float_as_int(q3.v[0])) & 1u;
 #if ECHO_ANY_UNORDERED
-			// A/B only (default off): an occlusion query's answer does not depend on the visit order, so the any-hit kernels
-			// could take the children as stored. Measured in profiles/README.md; the visit counters would no longer be the reference's.
+			// An occlusion query's answer does not depend on the visit order (OccludeImpl returns on ANY hit within travel), so the
+			// any-hit kernels take the children as stored and skip the three order swaps: the same flags bit for bit (the whole GPU
+			// suite runs on this build), +1.9 % on the C2 occlusion batch, +11 % on the secondary-ray one, +1.6 % on C3 (r2f A/B). The
+			// visit COUNTERS of the roofline come from the one-thread-per-query kernels, which keep the reference's order.
 			if (ANY) swap0 = swap1 = swapPairs = false;
 #endif
 

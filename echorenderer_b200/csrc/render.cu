@@ -158,7 +158,10 @@ struct WorkerState
 
 // Tile batches are rendered by up to kWorkers concurrent pipelines (host thread + stream + wavefront buffers each): the
 // long, narrow tail of one batch's late bounces overlaps the wide first bounces of another, keeping the SMs busy.
-constexpr uint32_t kNarrowLimit = 262144; // below this many rays a bounce uses the one-thread-per-ray kernels
+// below this many rays a bounce uses the one-thread-per-ray kernels: a persistent launch only pays off while every resident
+// thread (148 x 7 x 128) gets several rays to replace finished ones with. A/B r2g with the exact class grids in place,
+// 64 Ki / 256 Ki / 1 Mi: C1 340 / 355 / 407, C4 344 / 345 / 344, C5 458 / 460 / 460 M samples/s
+constexpr uint32_t kNarrowLimit = 1048576;
 // below this many live paths one kernel finishes them (tail_kernel). A/B of the threshold on C1 / C4 / C5 (variants/ab8.sh):
 // 0 -> 260 / 302 / 314 M samples/s, 4096 -> 317 / 313 / 325, 16384 -> 314 / 314 / 323, 65536 -> 250 / 308 / 264 (the longest path
 // of a big tail then runs alone for milliseconds), 262144 -> 140 / 277 / 187

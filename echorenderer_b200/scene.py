@@ -188,6 +188,8 @@ class PreparedScene:
         """Renders tiles into a device-resident full frame (width*height Float4; xyz = mean, w = 1 where rendered)."""
         tile_xy = np.ascontiguousarray(tile_xy, dtype=np.int32).reshape(-1, 2)
         stats = np.zeros(1, dtype=structs.STATS)
+        if int(params["maxEpoch"][0]) == 0:  # a rank whose share of the epochs is empty (shard_epochs): its frame stays zero
+            return stats
         _native.check(self._lib.echo_b200_render_frame_device(self._handle, _native.pointer(params), _native.pointer(tile_xy), len(tile_xy),
                                                               ctypes.c_void_p(frame_pointer), _native.pointer(stats), ctypes.c_void_p(stream)))
         return stats
@@ -428,7 +430,8 @@ def shard_epochs(max_epoch, rank, world_size):
     ceil(max_epoch / world_size) consecutive epochs of EVERY tile; returns (epoch_offset, epoch_count) for that rank's
     EchoRenderParams (epochOffset, minEpoch = maxEpoch = epoch_count). The sample index of a path is epoch * extend + i, so the
     blocks are disjoint sample sets. Each device accumulates (mean * epochs, epochs) per pixel (render_frame_device), the frames
-    are summed with one all-reduce and frame_resolve divides by the summed weight."""
+    are summed with one all-reduce and frame_resolve divides by the summed weight. A trailing rank can be left with epoch_count 0
+    (max_epoch 20 on 8 ranks: rank 7): render_frame_device / render_tiles treat maxEpoch == 0 as nothing to render."""
     per_rank = (max_epoch + world_size - 1) // world_size
     first = min(rank * per_rank, max_epoch)
     return first, max(0, min(per_rank, max_epoch - first))

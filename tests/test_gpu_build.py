@@ -1,14 +1,24 @@
-"""The optional device-side tree build (echo_b200_build_qbvh): a linear BVH collapsed to the reference's
-QBVH node format. Checked for structural validity, against brute force through the oracle, and for device / oracle parity on
-the tree it produces."""
+"""The optional device-side tree build (echo_b200_build_qbvh): a binary BVH built on the device — by
+parallel locally-ordered clustering (the default) or as a linear BVH — and collapsed to the reference's QBVH node format. Both
+are checked for structural validity, against brute force through the oracle, and for device / oracle parity on the tree they
+produce."""
 import numpy as np
 import pytest
 
-from echorenderer_b200 import PreparedScene, build_qbvh_device, host, scenes, structs
+from echorenderer_b200 import PreparedScene, _native, build_qbvh_device, host, scenes, structs
 from tests import oracle_lib
 from tests.test_gpu_trace import assert_hits_equal
 
 pytestmark = pytest.mark.gpu
+
+ALGORITHMS = {"ploc": 1, "lbvh": 0}
+
+
+@pytest.fixture(params=list(ALGORITHMS))
+def algorithm(request):
+    _native.set_option("BUILD_ALGORITHM", ALGORITHMS[request.param])
+    yield request.param
+    _native.set_option("BUILD_ALGORITHM", 1)
 
 
 def check_tree(nodes, max_depth, triangles, spheres):
@@ -69,7 +79,7 @@ def check_tree(nodes, max_depth, triangles, spheres):
 
 
 @pytest.mark.parametrize("fixture", ["cornell", "terrain_small", "mixed_small"])
-def test_device_tree_is_valid_and_traces_like_brute_force(fixture, request):
+def test_device_tree_is_valid_and_traces_like_brute_force(fixture, request, algorithm):
     sah = request.getfixturevalue(fixture)
     nodes, depth = build_qbvh_device(sah.triangles, sah.spheres)
     assert len(nodes) <= len(sah.triangles) + len(sah.spheres) - 1
@@ -95,7 +105,7 @@ def test_device_tree_is_valid_and_traces_like_brute_force(fixture, request):
         assert np.array_equal(scene.occlude(shadow), oracle.occlude(shadow))
 
 
-def test_tiny_and_degenerate_inputs():
+def test_tiny_and_degenerate_inputs(algorithm):
     two = scenes.plane(0, (2, 2))
     nodes, depth = build_qbvh_device(two, np.zeros(0, dtype=structs.SPHERE))
     assert len(nodes) == 1 and depth == 2
@@ -106,6 +116,29 @@ def test_tiny_and_degenerate_inputs():
     nodes, depth = build_qbvh_device(same, np.zeros(0, dtype=structs.SPHERE))
     check_tree(nodes, depth, same, np.zeros(0, dtype=structs.SPHERE))
 
+    # thousands of coincident primitives: the clustering merges one pair per pass, stalls, and the build falls back to the Morton tree
+    many = np.repeat(scenes.plane(0, (2, 2))[:1], 3000)
+    nodes, depth = build_qbvh_device(many, np.zeros(0, dtype=structs.SPHERE))
+    check_tree(nodes, depth, many, np.zeros(0, dtype=structs.SPHERE))
+
     from echorenderer_b200 import EchoNativeError
     with pytest.raises(EchoNativeError):
         build_qbvh_device(two[:1], np.zeros(0, dtype=structs.SPHERE))
+
+
+def test_clustered_tree_is_cheaper_to_traverse_than_the_morton_tree(terrain_small):
+    """PLOC's surface-area criterion buys tree quality: fewer node visits per query than the linear BVH on the same rays (oracle
+    visit counters), within reach of the full-sweep SAH tree of the host mirror."""
+    rays = scenes.random_rays(terrain_small.bounds, 100_000, seed=37)
+    visits = {}
+    for name, code in ALGORITHMS.items():
+        _native.set_option("BUILD_ALGORITHM", code)
+        nodes, depth = build_qbvh_device(terrain_small.triangles, terrain_small.spheres)
+        prepared = host.prepare(terrain_small.description, tree=(nodes, depth))
+        _, counters = oracle_lib.OracleScene(prepared).trace(rays, count_visits=True)
+        visits[name] = counters[0] / len(rays)
+    _native.set_option("BUILD_ALGORITHM", 1)
+    _, counters = oracle_lib.OracleScene(terrain_small).trace(rays, count_visits=True)
+    sah = counters[0] / len(rays)
+    assert visits["ploc"] < visits["lbvh"]
+    assert visits["ploc"] < 1.25 * sah

@@ -30,6 +30,7 @@ def main():
     parser.add_argument("--height", type=int, default=2160)
     parser.add_argument("--bounce-limit", type=int, default=128)
     parser.add_argument("--quick", action="store_true", help="fewer configurations")
+    parser.add_argument("--tail-sweep", action="store_true", help="sweep TAIL_LIMIT / NARROW_LIMIT instead of the host-side switches")
     args = parser.parse_args()
 
     import torch
@@ -40,7 +41,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
 
-    builders = {"large": scenes.large_scene, "mixed": scenes.mixed_material_scene, "lights": scenes.many_lights_scene}
+    builders = {"large": scenes.large_scene, "mixed": scenes.mixed_material_scene, "lights": scenes.many_lights_scene, "cornell": scenes.cornell_box}
     prepared = host.prepare(builders[args.scene]())
     scene = PreparedScene(prepared, device=local_rank)
     tile = 16
@@ -58,7 +59,7 @@ def main():
         return [round(float(t.item()), 2) for t in out]
 
     def run(tag, pattern="hilbert", block=64, reduce_every=1, by="sequence", **switches):
-        defaults = {"RUN_AHEAD": -1, "BLOCKING_SYNC": -1, "RENDER_WORKERS": 8, "BATCH_PATHS": 1 << 24}
+        defaults = {"RUN_AHEAD": -1, "BLOCKING_SYNC": -1, "RENDER_WORKERS": 8, "BATCH_PATHS": 1 << 24, "TAIL_LIMIT": 8192, "NARROW_LIMIT": 1048576}
         for name, value in {**defaults, **switches}.items():
             _native.set_option(name, value)
         tiles = shard_tiles(sequences[pattern], rank, world, block=block, by=by)
@@ -100,6 +101,18 @@ def main():
             print(json.dumps({"tag": tag, "world": world, "ms_per_step": round(float(total.item()) / args.steps, 2), "msamples_per_s": round(samples / (float(total.item()) * 1e-3) / 1e6, 1),
                               "rank_render_ms_mean": per_rank_mean, "rank_render_ms_max": per_rank_max, "all_reduce_ms": round(reduce_mean, 3), "launches_rank0": int(stats["kernelLaunches"][0]),
                               "pattern": pattern, "block": block, "by": by, "reduce_every": reduce_every, "switches": switches}), flush=True)
+
+    if args.tail_sweep:
+        run("warm-up (discard)", by="position")
+        for tail in (4096, 16384):
+            run(f"tail limit {tail}", by="position", TAIL_LIMIT=tail)
+        for narrow in (262144, 2097152, 4194304):
+            run(f"narrow limit {narrow}", by="position", NARROW_LIMIT=narrow)
+        run("default again", by="position")
+        scene.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     run("warm-up (discard)")
     run("hilbert, tiles owned by position", by="position")
