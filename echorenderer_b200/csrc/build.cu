@@ -3,7 +3,7 @@
 // sorted by the lower bound along the split axis, a leaf child becomes a [leaf, empty] pair with axis 3, empty slots at +infinity).
 // Two ways to get the binary tree, both over the primitives sorted by 63-bit Morton code:
 //   PLOC (default)  parallel locally-ordered clustering (Meister & Bittner 2018): bottom-up agglomeration — every cluster looks
-//                   for the neighbour within +-kPlocRadius positions whose union with it has the smallest surface area, mutual
+//                   for the neighbour within +-16 positions whose union with it has the smallest surface area, mutual
 //                   nearest neighbours merge, the survivors are compacted, repeat until one cluster is left. The surface-area
 //                   criterion is the SAH's, applied locally; it closes most of the gap to the reference's full-sweep SAH tree.
 //   LBVH            the linear BVH of Karras 2012 ("Maximizing Parallelism in the Construction of BVHs, Octrees, and k-d Trees"):
@@ -206,7 +206,8 @@ __global__ void depth_kernel(const uint32_t* __restrict__ parentOfInternal, int 
 }
 
 // ---- PLOC ----
-constexpr int kPlocRadius = 8; // neighbours examined on each side by default (ECHO_B200_BUILD_PLOC_RADIUS / set_option("BUILD_PLOC_RADIUS"))
+// A/B on the C2 geometry (r2i): radius 4 / 8 / 16 / 32 / 64 -> 8.01 / 8.13 / 7.71 / 7.75 / 7.84 node visits per query, 4562 / 4574 / 4670 / 4665 / 4657 Mrays/s
+constexpr int kPlocRadius = 16; // neighbours examined on each side by default (ECHO_B200_BUILD_PLOC_RADIUS / set_option("BUILD_PLOC_RADIUS"))
 
 std::atomic<int>& ploc_radius()
 {
