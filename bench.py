@@ -674,15 +674,18 @@ def run_render(ctx, args, scene_key, width, height, spp, bounce_limit, steps, wa
             launches += int(stats["kernelLaunches"][0])
             samples += int(stats["sampleEvaluated"][0])
         if (index + 1) % reduce_every == 0:
-            first, last = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            first, middle, last = (torch.cuda.Event(enable_timing=True) for _ in range(3))
             first.record()
+            if ctx.distributed:
+                dist.barrier()  # the collective waits for the slowest rank either way; a barrier in front of it separates that wait from the transfer
+            middle.record()
             if ctx.distributed:
                 dist.all_reduce(frame)  # the accumulation-buffer reduce over NVLink (tile sharding: disjoint pixels, sum with zeros)
             last.record()
             scene.frame_resolve_device(frame.data_ptr(), width, height, stream)
             frame.zero_()  # the next render starts from an empty accumulation frame
             if timed:
-                reduce_events.append((first, last))
+                reduce_events.append((first, middle, last))
                 launches += 2
         return stats
 
@@ -704,7 +707,8 @@ def run_render(ctx, args, scene_key, width, height, spp, bounce_limit, steps, wa
         clocks.mark(1)
         total_ms = ctx.max_over_ranks(start.elapsed_time(stop))
 
-    reduce_ms = [a.elapsed_time(b) for a, b in reduce_events]
+    reduce_ms = [b.elapsed_time(c) for _, b, c in reduce_events]
+    skew_ms = [a.elapsed_time(b) for a, b, _ in reduce_events]
     total_samples = int(ctx.sum_over_ranks(samples))
     total_launches = int(ctx.sum_over_ranks(launches))
     value = total_samples / (total_ms * 1e-3)
@@ -735,7 +739,8 @@ def run_render(ctx, args, scene_key, width, height, spp, bounce_limit, steps, wa
               "samples_per_step": total_samples // steps,
               "rank_step_ms": {"min": min(per_rank_ms), "max": max(per_rank_ms), "mean": float(np.mean(per_rank_ms)), "worst_single_step": max(per_rank_worst), "per_rank": per_rank_ms,
                                "what": "host wall time of echo_b200_render_frame_device per step, mean over the timed steps, per rank"},
-              "all_reduce": {"count": len(reduce_ms), "ms_mean": float(np.mean(reduce_ms)) if reduce_ms else None, "bytes": int(frame.numel() * 4), "collective": "NCCL all-reduce (sum) of the fp32 accumulation frame" if ctx.distributed else "none (one GPU)"},
+              "all_reduce": {"count": len(reduce_ms), "ms_mean": float(np.mean(reduce_ms)) if reduce_ms else None, "wait_for_slowest_rank_ms_mean": float(np.mean(skew_ms)) if skew_ms else None,
+                             "bytes": int(frame.numel() * 4), "collective": "NCCL all-reduce (sum) of the fp32 accumulation frame" if ctx.distributed else "none (one GPU)"},
               "roofline": {"bound": "hbm", "kernel": "wavefront step (raygen, extend, classify, shade x5, shadow, accumulate)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                            "traffic": traffic_per_sample * (total_samples // steps) if traffic_per_sample else None, "traffic_bytes_per_sample": traffic_per_sample,
                            "peak_source": peak_source, "algorithmic_bytes_per_sample": per_sample_bytes,

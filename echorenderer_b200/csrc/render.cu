@@ -13,6 +13,7 @@
 #include <string>
 #include <cstring>
 #include <thread>
+#include <sched.h>
 #include <cstdio>
 #include <cstdlib>
 
@@ -2513,14 +2514,20 @@ bool set_render_option(const char* name, long long value)
 	return true;
 }
 
-// When a pipeline thread waits (run-ahead window full, or a batch's end), spinning in cudaEventSynchronize is the fastest
-// wake-up, but N ranks x 8 pipelines spin on N x 8 host cores: when the host has fewer cores than that the threads preempt
-// each other. Blocking-sync events let them sleep instead. Automatic choice: block when the pipelines of all visible devices
-// outnumber the cores.
-static bool blocking_waits()
+// How a pipeline thread waits for the counts of a unit (ECHO_B200_BLOCKING_SYNC):
+//   0  cudaEventSynchronize on a spinning event: the fastest wake-up while every pipeline thread has a core of its own;
+//   1  a blocking-sync event: the thread sleeps in the driver; a wake-up costs tens of microseconds, once per bounce in lock step;
+//   2  poll the mirror record in pinned memory, yielding the core between polls (sched_yield): when N ranks x 8 pipelines outnumber the
+//      host's cores (8 ranks on a 32-core box) a waiting thread hands its core to a runnable one at once and is back within
+//      microseconds of its counts arriving, so the loop can stay in lock step with exactly sized launches.
+// Automatic choice: 0 when the pipelines of all visible devices fit the cores, else the measured best of 1 / 2 (kOversubscribedWait).
+enum WaitMode : int { WAIT_SPIN = 0, WAIT_BLOCK = 1, WAIT_YIELD = 2 };
+constexpr int kOversubscribedWait = WAIT_YIELD;
+
+static int wait_mode()
 {
 	long long configured = options().blockingSync;
-	if (configured >= 0) return configured != 0;
+	if (configured >= 0) return (int)std::min<long long>(configured, 2);
 
 	static const bool oversubscribed = []
 	{
@@ -2528,8 +2535,10 @@ static bool blocking_waits()
 		cudaGetDeviceCount(&devices);
 		return (unsigned int)(devices * kWorkers) > std::thread::hardware_concurrency();
 	}();
-	return oversubscribed;
+	return oversubscribed ? kOversubscribedWait : WAIT_SPIN;
 }
+
+static bool blocking_waits() { return wait_mode() == WAIT_BLOCK; }
 
 static bool ensure_events(WorkerState* state)
 {
@@ -2619,6 +2628,7 @@ static bool evaluate_paths(WorkerState* state, const DeviceScene& sceneIn, const
 	const uint32_t narrowLimit = (uint32_t)options().narrowLimit;
 	const uint32_t tailLimit = (uint32_t)options().tailLimit;
 	const uint32_t runAhead = timer.enabled ? 0u : run_ahead();
+	const int waitMode = wait_mode();
 
 	if (!ensure_events(state)) return false;
 
@@ -2699,8 +2709,20 @@ static bool evaluate_paths(WorkerState* state, const DeviceScene& sceneIn, const
 
 		if (launched - finished > runAhead)
 		{
-			// window full: sleep until the oldest unit the host has not seen yet is done, then look again
-			if (!check_cuda(cudaEventSynchronize(state->iterationDone[finished % WorkerState::kEventRing]), "wavefront iteration")) return false;
+			// window full: wait until the oldest unit the host has not seen yet is done, then look again
+			if (waitMode == WAIT_YIELD)
+			{
+				for (uint32_t polls = 0; (uint32_t)(*mirror >> 32) - firstSerial + 1u <= finished || (uint32_t)(*mirror >> 32) - firstSerial + 1u > launched; polls++)
+				{
+					sched_yield();
+					// a failed launch never publishes its record: look at the stream now and then instead of polling forever
+					if ((polls & 0xFFFu) == 0xFFFu && cudaStreamQuery(stream) != cudaErrorNotReady) break;
+				}
+
+				if (!check_cuda(cudaGetLastError(), "wavefront iteration")) return false;
+			}
+			else if (!check_cuda(cudaEventSynchronize(state->iterationDone[finished % WorkerState::kEventRing]), "wavefront iteration")) return false;
+
 			continue;
 		}
 

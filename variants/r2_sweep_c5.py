@@ -31,6 +31,7 @@ def main():
     parser.add_argument("--bounce-limit", type=int, default=128)
     parser.add_argument("--quick", action="store_true", help="fewer configurations")
     parser.add_argument("--tail-sweep", action="store_true", help="sweep TAIL_LIMIT / NARROW_LIMIT instead of the host-side switches")
+    parser.add_argument("--wait-sweep", action="store_true", help="sweep the wait mode (0 spin, 1 blocking event, 2 poll + yield) x run-ahead x pipelines, tiles owned by position")
     args = parser.parse_args()
 
     import torch
@@ -109,6 +110,22 @@ def main():
         for narrow in (262144, 2097152, 4194304):
             run(f"narrow limit {narrow}", by="position", NARROW_LIMIT=narrow)
         run("default again", by="position")
+        scene.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    if args.wait_sweep:
+        run("warm-up (discard)", by="position")
+        run("automatic", by="position")
+        for wait, name in ((1, "blocking event"), (2, "poll + yield"), (0, "spinning event")):
+            for ahead in (0, 1, 2):
+                run(f"{name}, run-ahead {ahead}", by="position", BLOCKING_SYNC=wait, RUN_AHEAD=ahead)
+        run("poll + yield, lock step, 4 pipelines", by="position", BLOCKING_SYNC=2, RUN_AHEAD=0, RENDER_WORKERS=4)
+        run("poll + yield, lock step, 6 pipelines", by="position", BLOCKING_SYNC=2, RUN_AHEAD=0, RENDER_WORKERS=6)
+        run("spinning event, lock step, 4 pipelines", by="position", BLOCKING_SYNC=0, RUN_AHEAD=0, RENDER_WORKERS=4)
+        run("poll + yield, lock step, 8 Mi-path batches", by="position", BLOCKING_SYNC=2, RUN_AHEAD=0, BATCH_PATHS=1 << 23)
+        run("automatic again", by="position")
         scene.close()
         if world > 1:
             dist.destroy_process_group()
