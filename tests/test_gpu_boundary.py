@@ -249,3 +249,63 @@ def test_hand_derived_known_answers():
         assert np.all(flags == flags[0]) and kats.check_occlude(flags[0]) is None
         tiled = hits.reshape(3000, len(kats.TRACE_CASES))
         assert np.all(tiled.view(np.uint32) == tiled[0].view(np.uint32))
+
+
+def test_host_memory_entry_points(terrain_small):
+    """echo_b200_host_alloc / _register: page-locked host memory for the host-buffer entry points (what a P/Invoke caller needs, since
+    a `fixed`-pinned managed array is pageable for CUDA). Results do not depend on where the buffers live."""
+    import ctypes
+    lib = _native.library()
+    rays = scenes.random_rays(terrain_small.bounds, 1 << 16, seed=51)
+    expected = oracle_lib.OracleScene(terrain_small).trace(rays)
+
+    with PreparedScene(terrain_small) as scene:
+        locked_rays, locked_hits = _native.HostBuffer(len(rays), structs.RAY), _native.HostBuffer(len(rays), structs.HIT)
+        locked_rays.array[:] = rays
+        scene.trace_pointers(locked_rays.address, len(rays), locked_hits.address)
+        assert np.array_equal(locked_hits.array.view(np.uint32), expected.view(np.uint32))
+        locked_rays.free()
+        locked_hits.free()
+        locked_hits.free()  # idempotent
+
+        own_rays, own_hits = rays.copy(), np.empty(len(rays), dtype=structs.HIT)
+        _native.host_register(own_rays)
+        _native.host_register(own_hits)
+        try:
+            scene.trace_pointers(own_rays.ctypes.data, len(rays), own_hits.ctypes.data)
+        finally:
+            _native.host_unregister(own_rays)
+            _native.host_unregister(own_hits)
+        assert np.array_equal(own_hits.view(np.uint32), expected.view(np.uint32))
+
+    pointer = ctypes.c_void_p()
+    assert lib.echo_b200_host_alloc(None, 16) == _native.ERR_INVALID
+    assert lib.echo_b200_host_register(None, 16) == _native.ERR_INVALID
+    assert lib.echo_b200_host_free(None) == _native.OK and lib.echo_b200_host_unregister(None) == _native.OK
+    assert lib.echo_b200_host_alloc(ctypes.byref(pointer), 0) == _native.OK and pointer.value  # an empty buffer is still a buffer
+    assert lib.echo_b200_host_free(pointer) == _native.OK
+
+
+def test_runtime_options(cornell):
+    """echo_b200_debug_set_option: unknown names are refused; the wavefront's switches change how a render is scheduled, never its result."""
+    lib = _native.library()
+    assert lib.echo_b200_debug_set_option(b"NO_SUCH_SWITCH", 1) == _native.ERR_INVALID
+    assert lib.echo_b200_debug_set_option(None, 1) == _native.ERR_INVALID
+    params = structs.render_params(64, 64, 16, extend=4, bounce_limit=24, seed=6)
+    tiles = scenes.tile_grid(64, 64, 16)
+    defaults = {"RUN_AHEAD": -1, "BLOCKING_SYNC": -1, "RENDER_WORKERS": 8, "BATCH_PATHS": 1 << 24, "TAIL_LIMIT": 8192, "NARROW_LIMIT": 1 << 20}
+
+    with PreparedScene(cornell) as scene:
+        reference, reference_stats = scene.render_tiles(params, tiles)
+        try:
+            for switches in ({"RUN_AHEAD": 3}, {"BLOCKING_SYNC": 1, "RUN_AHEAD": 2}, {"BLOCKING_SYNC": 2}, {"BLOCKING_SYNC": 2, "RUN_AHEAD": 1}, {"RENDER_WORKERS": 1},
+                             {"TAIL_LIMIT": 0}, {"TAIL_LIMIT": 1 << 30}, {"NARROW_LIMIT": 0}, {"NARROW_LIMIT": 1 << 30}, {"BATCH_PATHS": 1 << 16}):
+                for name, value in {**defaults, **switches}.items():
+                    _native.set_option(name, value)
+                image, stats = scene.render_tiles(params, tiles)
+                assert np.array_equal(image.view(np.uint32), reference.view(np.uint32)), switches
+                for name in structs.STATS_FIELDS[:12]:
+                    assert int(stats[name][0]) == int(reference_stats[name][0]), (switches, name)
+        finally:
+            for name, value in defaults.items():
+                _native.set_option(name, value)
