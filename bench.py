@@ -11,7 +11,9 @@ Default run (`python bench.py [--gpus N --steps K --warmup W]`, what the driver 
 * `render` = the path tracer, measured the way the reference reports it (samples/s = Evaluate calls / wall time of the
   evaluation operation, Processes/ScheduledRender.cs:226-234), each record with its own roofline (algorithmic bytes per sample
   from one counted pass), cpu_baseline (oracle on a crop) and plugin-call e2e (echo_b200_render_tiles into host memory):
+    - `c1` (N = 1 only): the Cornell box 512x512, 16 spp per step, bounce limit 128 (BASELINE configs[0], the reference's CPU-runnable case)
     - `c3` (N = 1 only): mixed materials 1920x1080, 64 spp per step (C3's own epoch), bounce limit 8
+    - `c4` (N = 1 only): 10 000 emissive triangles 1920x1080, 64 spp per step, bounce limit 128 (light-tree NEE)
     - `c5` (every N): ~10 M triangles 3840x2160, 256 spp per step (C5's own epoch), bounce limit 128, tiles sharded over the ranks
       (strong scaling), the accumulation frames merged by one NCCL all-reduce per 1024-spp render = every 4th step.
 
@@ -45,7 +47,7 @@ def parse():
     parser.add_argument("--warmup", type=int, default=3)
     parser.add_argument("--impl", default="b200", choices=["b200", "reference"])
     parser.add_argument("--workload", default="all", choices=["all", "trace", "render"],
-                        help="all (default): the C2 headline plus the `render` records (C3 at N = 1, C5 at every N); trace / render: one part alone")
+                        help="all (default): the C2 headline plus the `render` records (C1, C3, C4 at N = 1, C5 at every N); trace / render: one part alone")
     parser.add_argument("--rays", type=int, default=1 << 24, help="rays per pass per GPU (C2: 16 Mi)")
     parser.add_argument("--quads", type=int, nargs=2, default=[1000, 500], help="terrain quads (C2: 1000 x 500 = 1 M triangles)")
     parser.add_argument("--cpu-sample", type=int, default=1 << 24,
@@ -578,7 +580,7 @@ def run_trace(ctx, args):
                    "copy_ceiling": {"ms_per_step": copy_ms, "gbs_per_rank": (2 * n * 32 + n * 17) / (copy_ms * 1e-3) / 1e9, "gbs_all_ranks": ctx.world * (2 * n * 32 + n * 17) / (copy_ms * 1e-3) / 1e9,
                                     "what": "the same host<->device copies with no kernels, up and down on two streams, all ranks at once"},
                    "frac_of_copy_ceiling": copy_ms / e2e_ms}
-    line["e2e_pageable"] = {"value": pageable_value, "unit": "Mrays/s", "ms_per_step": pageable_ms, "host_memory": "pageable (what a `fixed`-pinned managed array is to CUDA)"}
+    line["e2e_pageable"] = {"value": pageable_value, "unit": "Mrays/s", "ms_per_step": pageable_ms, "host_memory": "pageable (what a `fixed`-pinned managed array is to CUDA); the library stages it through page-locked buffers, one host thread per pipeline slot"}
     line["gpu_launches"] = 2 * args.steps
     line["clocks"] = clocks.summary()
     line["config"]["tree"] = {"builder": args.tree, "nodes": int(len(prepared.nodes)), "quad_depth": int(prepared.max_depth),
@@ -792,11 +794,15 @@ def main():
             line["render"] = {"what": "the path tracer measured as the reference reports it (samples/s, ScheduledRender.cs:226-234); records have the shape of a bench line"}
             # ECHO_BENCH_SHRINK=1 (tests/test_gpu_bench.py only): the same code path on scenes and frames that take seconds
             shrink = os.environ.get("ECHO_BENCH_SHRINK") == "1"
-            c3 = ("mixed", 256, 144, 8, lambda: scenes.mixed_material_scene(rings=24, segments=24)) if shrink else ("mixed", 1920, 1080, 64, None)
-            c5 = ("large", 384, 208, 16, lambda: scenes.large_scene(160, 80)) if shrink else ("large", 3840, 2160, 256, None)
-            if ctx.world == 1:
-                line["render"]["c3"] = run_render(ctx, args, c3[0], c3[1], c3[2], c3[3], 8, steps, args.render_warmup, 4, builder=c3[4])
-            line["render"]["c5"] = run_render(ctx, args, c5[0], c5[1], c5[2], c5[3], 128, c5_steps, args.render_warmup, 4, builder=c5[4])
+            # (key, scene, width, height, spp per step, bounce limit, steps per finished render, builder override)
+            c1 = ("c1", "cornell", 128, 128, 4, 128, 1, None) if shrink else ("c1", "cornell", 512, 512, 16, 128, 1, None)
+            c3 = ("c3", "mixed", 256, 144, 8, 8, 4, lambda: scenes.mixed_material_scene(rings=24, segments=24)) if shrink else ("c3", "mixed", 1920, 1080, 64, 8, 4, None)
+            c4 = ("c4", "lights", 256, 144, 8, 128, 4, lambda: scenes.many_lights_scene(light_count=300, rings=16, segments=16)) if shrink else ("c4", "lights", 1920, 1080, 64, 128, 4, None)
+            c5 = ("c5", "large", 384, 208, 16, 128, 4, lambda: scenes.large_scene(160, 80)) if shrink else ("c5", "large", 3840, 2160, 256, 128, 4, None)
+            records = [c1, c3, c4, c5] if ctx.world == 1 else [c5]  # C1, C3 and C4 are one-GPU configurations (BASELINE.json); C5 is the sharded one
+            for key, scene_key, width, height, spp, bounce_limit, reduce_every, builder in records:
+                record_steps = c5_steps if reduce_every == 4 else steps
+                line["render"][key] = run_render(ctx, args, scene_key, width, height, spp, bounce_limit, record_steps, args.render_warmup, reduce_every, builder=builder)
             line["gpu_launches"] += sum(record["gpu_launches"] for key, record in line["render"].items() if isinstance(record, dict))
 
     if ctx.rank == 0:

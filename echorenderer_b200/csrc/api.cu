@@ -135,6 +135,90 @@ bool ensure_scratch(EchoScene* scene, uint64_t rays)
 	return true;
 }
 
+// ordinary (pageable) host memory, as opposed to cudaHostAlloc / cudaHostRegister memory? Unknown pointers count as pageable.
+bool is_pageable(const void* pointer)
+{
+	cudaPointerAttributes attributes;
+	if (cudaPointerGetAttributes(&attributes, pointer) != cudaSuccess) { cudaGetLastError(); return true; }
+	return attributes.type == cudaMemoryTypeUnregistered;
+}
+
+bool ensure_staging(EchoScene* scene, uint64_t rays)
+{
+	if (scene->stagingCapacity >= rays) return true;
+
+	for (int i = 0; i < EchoScene::kSlots; i++)
+	{
+		if (scene->stagingIn[i]) cudaFreeHost(scene->stagingIn[i]);
+		if (scene->stagingOut[i]) cudaFreeHost(scene->stagingOut[i]);
+		scene->stagingIn[i] = scene->stagingOut[i] = nullptr;
+	}
+
+	scene->stagingCapacity = 0;
+
+	for (int i = 0; i < EchoScene::kSlots; i++)
+		if (!check_cuda(cudaHostAlloc(&scene->stagingIn[i], sizeof(EchoRay) * rays, cudaHostAllocDefault), "cudaHostAlloc(staging)")
+			|| !check_cuda(cudaHostAlloc(&scene->stagingOut[i], sizeof(EchoHit) * rays, cudaHostAllocDefault), "cudaHostAlloc(staging)")) return false;
+
+	scene->stagingCapacity = rays;
+	return true;
+}
+
+// Host-buffer batch from PAGEABLE memory — what a P/Invoke caller hands over when it pins a managed array with `fixed`
+// (OidnDenoise.cs:109-110) instead of using echo_b200_host_alloc / _register. cudaMemcpyAsync from such memory is neither
+// asynchronous nor fast (the driver stages it through one bounce buffer on the calling thread: 255 Mrays/s end to end against 1 530
+// from page-locked memory). Here every slot of the pipeline gets a host thread of its own that copies its chunks into page-locked
+// staging, runs upload / kernel / download on its stream and copies the results out: kSlots concurrent memcpys feed the link, and the
+// chunks of different slots overlap on the device as in the page-locked path.
+template<class Out, class Launch>
+int32_t batch_host_staged(EchoScene* scene, const EchoRay* rays, uint64_t n, Out* out, uint64_t chunk, Launch launch)
+{
+	if (!ensure_staging(scene, chunk)) return ECHO_B200_ERR_CUDA;
+
+	const uint64_t chunks = (n + chunk - 1) / chunk;
+	std::vector<std::string> errors(EchoScene::kSlots);
+	std::vector<char> failed(EchoScene::kSlots, 0);
+
+	auto work = [&](int slot)
+	{
+		DeviceGuard guard(scene->device);
+		bool ok = guard.ok;
+		cudaStream_t stream = scene->copyStreams[slot];
+
+		for (uint64_t index = (uint64_t)slot; ok && index < chunks; index += EchoScene::kSlots)
+		{
+			uint64_t first = index * chunk, count = std::min<uint64_t>(chunk, n - first);
+			std::memcpy(scene->stagingIn[slot], rays + first, sizeof(EchoRay) * count);
+			ok = check_cuda(cudaMemcpyAsync(scene->scratchRays[slot], scene->stagingIn[slot], sizeof(EchoRay) * count, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync(rays)")
+				&& launch((const EchoRay*)scene->scratchRays[slot], count, (Out*)scene->scratchOut[slot], stream)
+				&& check_cuda(cudaMemcpyAsync(scene->stagingOut[slot], scene->scratchOut[slot], sizeof(Out) * count, cudaMemcpyDeviceToHost, stream), "cudaMemcpyAsync(out)")
+				&& check_cuda(cudaStreamSynchronize(stream), "batch");
+			if (ok) std::memcpy(out + first, scene->stagingOut[slot], sizeof(Out) * count);
+		}
+
+		if (!ok)
+		{
+			cudaStreamSynchronize(stream);
+			failed[slot] = 1;
+			errors[slot] = last_error_string();
+		}
+	};
+
+	std::vector<std::thread> threads;
+	for (int slot = 1; slot < EchoScene::kSlots; slot++) threads.emplace_back(work, slot);
+	work(0);
+	for (std::thread& thread : threads) thread.join();
+
+	for (int slot = 0; slot < EchoScene::kSlots; slot++)
+	{
+		if (!failed[slot]) continue;
+		set_error(errors[slot]);
+		return ECHO_B200_ERR_CUDA;
+	}
+
+	return ECHO_B200_OK;
+}
+
 // Host-buffer batch: chunks rotate over kSlots streams so that chunk k's upload overlaps the kernels and downloads of the
 // chunks before it (H2D, compute and D2H engines run concurrently). With pinned host buffers the copies are truly asynchronous.
 template<class Out, class Launch>
@@ -149,6 +233,10 @@ int32_t batch_host(EchoScene* scene, const EchoRay* rays, uint64_t n, Out* out, 
 
 	uint64_t chunk = std::min<uint64_t>(chunk_rays(), n);
 	if (!ensure_scratch(scene, chunk)) return ECHO_B200_ERR_CUDA;
+
+	// pageable caller memory: staged through page-locked buffers by one host thread per slot (small batches are not worth the threads)
+	static const bool staging = [] { const char* text = getenv("ECHO_B200_STAGE_PAGEABLE"); return !text || text[0] != '0'; }();
+	if (staging && n >= 4 * chunk && (is_pageable(rays) || is_pageable(out))) return batch_host_staged<Out>(scene, rays, n, out, chunk, launch);
 
 	int slot = 0;
 	bool ok = true;
@@ -352,6 +440,8 @@ int32_t echo_b200_scene_destroy(EchoScene* scene)
 		if (scene->scratchOut[i]) cudaFree(scene->scratchOut[i]);
 		if (scene->copyStreams[i]) cudaStreamDestroy(scene->copyStreams[i]);
 		if (scene->chunkDone[i]) cudaEventDestroy(scene->chunkDone[i]);
+		if (scene->stagingIn[i]) cudaFreeHost(scene->stagingIn[i]);
+		if (scene->stagingOut[i]) cudaFreeHost(scene->stagingOut[i]);
 	}
 
 	if (scene->stream) cudaStreamDestroy(scene->stream);

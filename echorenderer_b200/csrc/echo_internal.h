@@ -99,12 +99,18 @@ struct EchoScene
 	std::vector<void*> allocations;
 
 	// scratch for the host-buffer batch calls (grown on demand)
-	static constexpr int kSlots = 4; // chunk buffers of the host-buffer batch pipeline
+#ifndef ECHO_HOST_SLOTS
+#define ECHO_HOST_SLOTS 4
+#endif
+	static constexpr int kSlots = ECHO_HOST_SLOTS; // chunk buffers (and, for pageable callers, host threads) of the host-buffer batch pipeline
 	void* scratchRays[kSlots] = {};
 	void* scratchOut[kSlots] = {};
 	uint64_t scratchCapacity = 0; // rays per chunk buffer
 	cudaStream_t copyStreams[kSlots] = {};
 	cudaEvent_t chunkDone[kSlots] = {};
+	void* stagingIn[kSlots] = {};  // page-locked staging of the same chunk size, allocated the first time a caller hands pageable buffers
+	void* stagingOut[kSlots] = {};
+	uint64_t stagingCapacity = 0;
 
 	echo::RenderState* render = nullptr;
 

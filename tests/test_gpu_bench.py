@@ -75,7 +75,7 @@ def test_render_bench_line():
 
 
 def test_default_line_carries_the_render_records(monkeypatch):
-    """`python bench.py` (what the driver runs): the C2 headline plus `render.c3` and `render.c5` with roofline, cpu_baseline and the
+    """`python bench.py` (what the driver runs): the C2 headline plus `render.c1 / c3 / c4 / c5` with roofline, cpu_baseline and the
     plugin-call e2e. Shrunk through the environment so that the whole default path runs in seconds."""
     environment = {**os.environ, "ECHO_BENCH_SHRINK": "1"}
     result = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "4", "--quads", "128", "64", "--rays", str(1 << 18), "--cpu-sample", "65536", "--no-secondary"],
@@ -85,8 +85,8 @@ def test_default_line_carries_the_render_records(monkeypatch):
     assert len(lines) == 1
     line = json.loads(lines[0])
     check_common(line)
-    assert line["unit"] == "Mrays/s" and set(line["render"]) >= {"c3", "c5"}
-    for key in ("c3", "c5"):
+    assert line["unit"] == "Mrays/s" and set(line["render"]) >= {"c1", "c3", "c4", "c5"}
+    for key in ("c1", "c3", "c4", "c5"):
         record = line["render"][key]
         check_render_record(record, record["config"]["width"], record["config"]["height"], record["config"]["spp_per_step"])
     assert line["render"]["c5"]["steps"] % 4 == 0 and "all-reduce every 4" in line["render"]["c5"]["config"]["parallelism"]
