@@ -230,6 +230,7 @@ int32_t batch_host(EchoScene* scene, const EchoRay* rays, uint64_t n, Out* out, 
 
 	DeviceGuard guard(scene->device);
 	if (!guard.ok) return ECHO_B200_ERR_NO_DEVICE;
+	std::lock_guard<std::mutex> turn(scene->compute);
 
 	uint64_t chunk = std::min<uint64_t>(chunk_rays(), n);
 	if (!ensure_scratch(scene, chunk)) return ECHO_B200_ERR_CUDA;
@@ -444,6 +445,8 @@ int32_t echo_b200_scene_destroy(EchoScene* scene)
 		if (scene->stagingOut[i]) cudaFreeHost(scene->stagingOut[i]);
 	}
 
+	if (scene->tilesOut) cudaFree(scene->tilesOut);
+	for (void* pointer : scene->hierarchyScratch) if (pointer) cudaFree(pointer);
 	if (scene->stream) cudaStreamDestroy(scene->stream);
 	delete scene;
 	return ECHO_B200_OK;
@@ -945,14 +948,31 @@ int32_t hierarchy_host(EchoScene* scene, const EchoRay* rays, const EchoTokenHie
 
 	DeviceGuard guard(scene->device);
 	if (!guard.ok) return ECHO_B200_ERR_NO_DEVICE;
+	std::lock_guard<std::mutex> turn(scene->compute);
 
 	void *dRays = nullptr, *dIgnore = nullptr, *dOut = nullptr, *dLayers = nullptr;
 	size_t outBytes = hits ? sizeof(EchoHit) * n : n;
 	cudaStream_t stream = scene->stream;
 
-	bool ok = check_cuda(cudaMalloc(&dRays, sizeof(EchoRay) * n), "cudaMalloc(rays)") && check_cuda(cudaMalloc(&dOut, outBytes), "cudaMalloc(out)")
-		&& (!ignore || check_cuda(cudaMalloc(&dIgnore, sizeof(EchoTokenHierarchy) * n), "cudaMalloc(ignore)"))
-		&& (!hitLayers || check_cuda(cudaMalloc(&dLayers, sizeof(EchoTokenHierarchy) * n), "cudaMalloc(layers)"))
+	// grow-only device scratch, kept between calls
+	auto scratch = [scene](int slot, size_t bytes, void*& pointer)
+	{
+		if (scene->hierarchyBytes[slot] < bytes)
+		{
+			if (scene->hierarchyScratch[slot]) cudaFree(scene->hierarchyScratch[slot]);
+			scene->hierarchyScratch[slot] = nullptr;
+			scene->hierarchyBytes[slot] = 0;
+			if (!check_cuda(cudaMalloc(&scene->hierarchyScratch[slot], bytes), "cudaMalloc(hierarchy batch)")) return false;
+			scene->hierarchyBytes[slot] = bytes;
+		}
+
+		pointer = scene->hierarchyScratch[slot];
+		return true;
+	};
+
+	bool ok = scratch(0, sizeof(EchoRay) * n, dRays) && scratch(2, outBytes, dOut)
+		&& (!ignore || scratch(1, sizeof(EchoTokenHierarchy) * n, dIgnore))
+		&& (!hitLayers || scratch(3, sizeof(EchoTokenHierarchy) * n, dLayers))
 		&& check_cuda(cudaMemcpyAsync(dRays, rays, sizeof(EchoRay) * n, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync(rays)")
 		&& (!ignore || check_cuda(cudaMemcpyAsync(dIgnore, ignore, sizeof(EchoTokenHierarchy) * n, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync(ignore)"));
 
@@ -966,10 +986,7 @@ int32_t hierarchy_host(EchoScene* scene, const EchoRay* rays, const EchoTokenHie
 		&& (!hitLayers || check_cuda(cudaMemcpyAsync(hitLayers, dLayers, sizeof(EchoTokenHierarchy) * n, cudaMemcpyDeviceToHost, stream), "cudaMemcpyAsync(layers)"))
 		&& check_cuda(cudaStreamSynchronize(stream), "hierarchy batch");
 
-	cudaFree(dRays);
-	cudaFree(dIgnore);
-	cudaFree(dOut);
-	cudaFree(dLayers);
+	if (!ok) cudaStreamSynchronize(stream); // copies queued before the failure must not outlive the caller's buffers
 	return ok ? ECHO_B200_OK : ECHO_B200_ERR_CUDA;
 }
 
@@ -1035,20 +1052,32 @@ int32_t echo_b200_occlude_batch_device_counted(EchoScene* scene, const EchoRay* 
 	return launch_occlude(scene->d, rays, n, occluded, (unsigned long long*)counts, (cudaStream_t)stream) ? ECHO_B200_OK : ECHO_B200_ERR_CUDA;
 }
 
+// the scene's grow-only device buffer for tile-major output
+static float4* tiles_out(EchoScene* scene, uint64_t bytes)
+{
+	if (scene->tilesOutBytes >= bytes) return (float4*)scene->tilesOut;
+	if (scene->tilesOut) cudaFree(scene->tilesOut);
+	scene->tilesOut = nullptr;
+	scene->tilesOutBytes = 0;
+	if (!check_cuda(cudaMalloc(&scene->tilesOut, bytes), "cudaMalloc(tiles)")) return nullptr;
+	scene->tilesOutBytes = bytes;
+	return (float4*)scene->tilesOut;
+}
+
 // the tiles [first, first + count) of the caller's sequence on one device: render, then download into the caller's tile-major buffer
 static int32_t render_tiles_device(EchoScene* scene, const EchoRenderParams* params, const int32_t* tileXY, uint32_t tileCount, float* outRGBA, EchoStats* stats)
 {
 	DeviceGuard guard(scene->device);
 	if (!guard.ok) return ECHO_B200_ERR_NO_DEVICE;
+	std::lock_guard<std::mutex> turn(scene->compute);
 
 	uint64_t pixels = (uint64_t)tileCount * params->tileSize * params->tileSize;
-	float4* deviceOut = nullptr;
-	if (!check_cuda(cudaMalloc((void**)&deviceOut, sizeof(float4) * pixels), "cudaMalloc(tiles)")) return ECHO_B200_ERR_CUDA;
+	float4* deviceOut = tiles_out(scene, sizeof(float4) * pixels);
+	if (!deviceOut) return ECHO_B200_ERR_CUDA;
 
 	bool ok = render_tiles(scene->render, scene->d, *params, tileXY, tileCount, deviceOut, nullptr, stats, scene->stream);
 	ok = ok && check_cuda(cudaMemcpyAsync(outRGBA, deviceOut, sizeof(float4) * pixels, cudaMemcpyDeviceToHost, scene->stream), "cudaMemcpyAsync(tiles)");
-	ok = ok && check_cuda(cudaStreamSynchronize(scene->stream), "render_tiles");
-	cudaFree(deviceOut);
+	ok = check_cuda(cudaStreamSynchronize(scene->stream), "render_tiles") && ok;
 	return ok ? ECHO_B200_OK : ECHO_B200_ERR_CUDA;
 }
 
@@ -1085,9 +1114,10 @@ int32_t echo_b200_render_tiles(EchoScene* scene, const EchoRenderParams* params,
 
 		DeviceGuard guard(target->device);
 		if (!guard.ok) return (int32_t)ECHO_B200_ERR_NO_DEVICE;
+		std::lock_guard<std::mutex> turn(target->compute);
 
-		float4* deviceOut = nullptr;
-		if (!check_cuda(cudaMalloc((void**)&deviceOut, sizeof(float) * tileFloats * localCount), "cudaMalloc(tiles)")) return (int32_t)ECHO_B200_ERR_CUDA;
+		float4* deviceOut = tiles_out(target, sizeof(float) * tileFloats * localCount);
+		if (!deviceOut) return (int32_t)ECHO_B200_ERR_CUDA;
 
 		bool ok = render_tiles(target->render, target->d, *params, local.data(), localCount, deviceOut, nullptr, &perDevice[g], target->stream);
 		uint32_t localFirst = 0;
@@ -1101,7 +1131,6 @@ int32_t echo_b200_render_tiles(EchoScene* scene, const EchoRenderParams* params,
 		}
 
 		ok = check_cuda(cudaStreamSynchronize(target->stream), "render_tiles") && ok;
-		cudaFree(deviceOut);
 		return (int32_t)(ok ? ECHO_B200_OK : ECHO_B200_ERR_CUDA);
 	});
 
@@ -1126,6 +1155,7 @@ int32_t echo_b200_render_frame_device(EchoScene* scene, const EchoRenderParams* 
 	if (!guard.ok) return ECHO_B200_ERR_NO_DEVICE;
 
 	cudaStream_t s = stream ? (cudaStream_t)stream : scene->stream;
+	std::lock_guard<std::mutex> turn(scene->compute);
 	return render_tiles(scene->render, scene->d, *params, tileXY, tileCount, nullptr, (float4*)frame, stats, s) ? ECHO_B200_OK : ECHO_B200_ERR_CUDA;
 }
 
@@ -1144,6 +1174,7 @@ int32_t echo_b200_debug_evaluate_samples(EchoScene* scene, const EchoRenderParam
 	if (!params || !pixelXY || !sampleIndex || !outRGB) return fail(ECHO_B200_ERR_INVALID, "null argument");
 	DeviceGuard guard(scene->device);
 	if (!guard.ok) return ECHO_B200_ERR_NO_DEVICE;
+	std::lock_guard<std::mutex> turn(scene->compute);
 	return evaluate_sample_list(scene->render, scene->d, *params, 3, pixelXY, sampleIndex, n, outRGB, scene->stream) ? ECHO_B200_OK : ECHO_B200_ERR_CUDA;
 }
 
@@ -1169,6 +1200,7 @@ int32_t echo_b200_debug_evaluate_samples4(EchoScene* scene, const EchoRenderPara
 	if (!params || !pixelXY || !sampleIndex || !outRGBA) return fail(ECHO_B200_ERR_INVALID, "null argument");
 	DeviceGuard guard(scene->device);
 	if (!guard.ok) return ECHO_B200_ERR_NO_DEVICE;
+	std::lock_guard<std::mutex> turn(scene->compute);
 	return evaluate_sample_list(scene->render, scene->d, *params, 4, pixelXY, sampleIndex, n, outRGBA, scene->stream) ? ECHO_B200_OK : ECHO_B200_ERR_CUDA;
 }
 

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -100,7 +101,7 @@ struct EchoScene
 
 	// scratch for the host-buffer batch calls (grown on demand)
 #ifndef ECHO_HOST_SLOTS
-#define ECHO_HOST_SLOTS 4
+#define ECHO_HOST_SLOTS 8 // A/B r2p, 4 vs 8: page-locked callers 1 527 vs 1 531 Mrays/s, pageable callers (one staging thread per slot) 753 vs 969
 #endif
 	static constexpr int kSlots = ECHO_HOST_SLOTS; // chunk buffers (and, for pageable callers, host threads) of the host-buffer batch pipeline
 	void* scratchRays[kSlots] = {};
@@ -112,7 +113,19 @@ struct EchoScene
 	void* stagingOut[kSlots] = {};
 	uint64_t stagingCapacity = 0;
 
+	// device buffer of echo_b200_render_tiles' tile-major output, kept between calls (allocating and freeing it per call cost the first
+	// calls hundreds of milliseconds at random: cudaFree hands the memory back to the system, the next cudaMalloc maps it again)
+	void* tilesOut = nullptr;
+	uint64_t tilesOutBytes = 0;
+	void* hierarchyScratch[4] = {}; // rays, ignore layers, out, hit layers of the *_batch_hierarchy calls, for the same reason
+	uint64_t hierarchyBytes[4] = {};
+
 	echo::RenderState* render = nullptr;
+
+	// Entry points that use the scene's own scratch (the host-buffer batches, the renderer's wavefront state) hold this for the length of
+	// the call: concurrent calls on ONE handle — Echo's workers all enter Operation.Execute at once (Operation.cs:164-177) — are safe and
+	// take turns; the asynchronous *_device batch calls on caller buffers do not need it.
+	std::mutex compute;
 
 	// echo_b200_scene_create_multi: this handle is the scene of the first device of the mask, `replicas` are the scenes of the
 	// others. Uploads go to the primary's host staging; commit replicates to every device.

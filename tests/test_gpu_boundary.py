@@ -309,3 +309,36 @@ def test_runtime_options(cornell):
         finally:
             for name, value in defaults.items():
                 _native.set_option(name, value)
+
+
+def test_concurrent_calls_on_one_handle(cornell, terrain_small):
+    """Echo's workers all enter Operation.Execute at once (Operation.cs:164-177): concurrent render / batch calls on ONE scene handle take turns
+    on its scratch and every caller gets the single-threaded answer."""
+    params = structs.render_params(64, 64, 16, extend=4, bounce_limit=16, seed=12)
+    tiles = scenes.tile_grid(64, 64, 16)
+    rays = scenes.random_rays(cornell.bounds, 1 << 16, seed=61)
+
+    with PreparedScene(cornell) as scene:
+        expected_image, _ = scene.render_tiles(params, tiles)
+        expected_hits = scene.trace(rays)
+        results, errors = {}, []
+
+        def work(index):
+            try:
+                for _ in range(3):
+                    image, _ = scene.render_tiles(params, tiles)
+                    hits = scene.trace(rays)
+                results[index] = (image, hits)
+            except Exception as error:  # noqa: BLE001
+                errors.append(error)
+
+        threads = [threading.Thread(target=work, args=(index,)) for index in range(6)]
+        for thread in threads:
+            thread.start()
+        for thread in threads:
+            thread.join()
+
+    assert not errors, errors
+    for image, hits in results.values():
+        assert np.array_equal(image.view(np.uint32), expected_image.view(np.uint32))
+        assert np.array_equal(hits.view(np.uint32), expected_hits.view(np.uint32))
