@@ -108,6 +108,13 @@ def test_integration_document_states_the_header_sizes():
         assert re.search(rf"Size\s*=\s*{size}\)\]\s*(?:public\s+)?(?:unsafe\s+)?struct\s+{c_name[4:]}\b", text), f"{c_name}: INTEGRATION.md does not declare it with Size = {size}"
 
 
+def test_plain_c_client_compiles_without_warnings(tmp_path):
+    """tests/c_client/echo_client.c (the non-Python, non-C++ host of the GPU suite) builds as C11 without a warning against the header alone (dlsym results become function pointers, which -pedantic alone objects to)."""
+    import subprocess
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c_client", "echo_client.c"),
+                    "-o", str(tmp_path / "echo_client"), "-ldl"], check=True)
+
+
 def test_integration_structs_are_the_generated_block():
     """The struct block of INTEGRATION.md is exactly what tools/gen_csharp_structs.py derives from the checked layouts."""
     import importlib.util

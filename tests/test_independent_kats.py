@@ -277,3 +277,114 @@ def test_accumulator_matches_an_independent_transcription():
         expected, expected_count = numpy_accumulator(samples)
         assert count == expected_count == 256
         assert np.array_equal(value.view(np.uint32), expected.view(np.uint32))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# LightBound.Importance (LightBound.cs:30-80), LightTree.Pick / ProbabilityMass (LightTree.cs:53-57,115-154) transcribed into plain
+# Python double arithmetic from the C# alone — no oracle header open. The oracle computes the same in binary32 in the reference's
+# operation order, so it must agree to rounding (a few 1e-6 relative), on every emitter of a many-lights scene from many shading
+# points: split probabilities, the descent, and pick-pdf == probability-mass.
+# ---------------------------------------------------------------------------------------------------------------------
+def _identity(value):  # FastMath.Identity = Sqrt0(1 - value^2), FastMath.cs:157-172
+    return max(0.0, 1.0 - value * value) ** 0.5
+
+
+def _clamp_subtract_cos(sin0, cos0, sin1, cos1):  # LightBound.cs:79
+    return 1.0 if cos0 > cos1 else cos0 * cos1 + sin0 * sin1
+
+
+def _clamp_subtract_sin(sin0, cos0, sin1, cos1):  # LightBound.cs:80
+    return 0.0 if cos0 > cos1 else sin0 * cos1 - cos0 * sin1
+
+
+def python_importance(node, position, normal):
+    box_min, box_max = np.asarray(node["boxMin"], np.float64), np.asarray(node["boxMax"], np.float64)
+    incident = np.asarray(position, np.float64) - (box_max + box_min) / 2.0  # BoxBound.Center
+    length2 = float(incident @ incident)
+    incident = np.zeros(3) if abs(length2) < 8e-7 else incident / length2 ** 0.5  # FastMath.AlmostZero
+
+    cos_axis = float(np.asarray(node["coneAxis"], np.float64) @ incident)
+    sin_axis = _identity(cos_axis)
+    cos_offset = float(node["cosOffset"])
+    sin_offset = _identity(cos_offset)
+
+    extent = box_max - box_min  # FindSubtendedAngles, :63-77
+    radius2 = float(extent @ extent) / 4.0
+    if length2 < radius2:
+        sin_radius, cos_radius = 0.0, -1.0
+    else:
+        sin_radius = (radius2 / length2) ** 0.5
+        cos_radius = max(0.0, 1.0 - radius2 / length2) ** 0.5
+
+    cos_remain = _clamp_subtract_cos(sin_axis, cos_axis, sin_offset, cos_offset)
+    sin_remain = _clamp_subtract_sin(sin_axis, cos_axis, sin_offset, cos_offset)
+    cos_final = _clamp_subtract_cos(sin_remain, cos_remain, sin_radius, cos_radius)
+    if cos_final <= float(node["cosExtend"]):
+        return 0.0
+
+    cos_incident = abs(float(np.asarray(normal, np.float64) @ incident))
+    cos_reflect = _clamp_subtract_cos(_identity(cos_incident), cos_incident, sin_radius, cos_radius)
+    length2 = max(length2, float(extent @ extent) ** 0.5 / 2.0)
+    return max(0.0, float(node["power"]) / length2 * cos_final * cos_reflect)
+
+
+def python_pick(nodes, position, normal, sample):
+    """LightTree.Pick: returns (token, pdf); pdf 0 = Probable.Impossible."""
+    index, pdf = 0, 1.0
+    while True:
+        node = nodes[index]
+        if node["child0"] == EMPTY:
+            return int(node["child1"]), pdf
+        first, second = python_importance(nodes[node["child0"]], position, normal), python_importance(nodes[node["child1"]], position, normal)
+        if first < 8e-7 and second < 8e-7:  # !Positive && !Positive, LightTree.cs:122
+            return EMPTY, 0.0
+        split = first / (first + second)
+        if sample < split:
+            sample, index, pdf = sample / split, int(node["child0"]), pdf * split            # Sample1D.Stretch(0, split)
+        else:
+            sample, index, pdf = (sample - split) / (1.0 - split), int(node["child1"]), pdf * (1.0 - split)
+
+
+def python_mass(nodes, path, position, normal):
+    """LightTree.ProbabilityMass: the product of the split factors along the emitter's bit path (0 = first child)."""
+    index, mass = 0, 1.0
+    while nodes[index]["child0"] != EMPTY:
+        node = nodes[index]
+        first, second = python_importance(nodes[node["child0"]], position, normal), python_importance(nodes[node["child1"]], position, normal)
+        split = first / (first + second) if first + second > 0 else float("nan")
+        mass *= split if (path & 1) == 0 else 1.0 - split
+        index = int(node["child0"] if (path & 1) == 0 else node["child1"])
+        path >>= 1
+    return mass
+
+
+def test_light_tree_matches_an_independent_transcription():
+    prepared = host.prepare(scenes.many_lights_scene(light_count=200, rings=8, segments=8))
+    oracle = oracle_lib.OracleScene(prepared)
+    nodes = prepared.light_nodes
+    paths = dict(zip((int(t) for t in prepared.emitter_tokens), (int(p) for p in prepared.emitter_bitpaths)))
+    random = np.random.default_rng(11)
+    checked = impossible = 0
+
+    for _ in range(300):
+        position = random.uniform(-25, 25, 3).astype(np.float32)
+        position[1] = abs(position[1]) * 0.4
+        normal = random.normal(size=3)
+        normal = (normal / np.linalg.norm(normal)).astype(np.float32)
+        sample = float(np.float32(random.random()))
+
+        token, pdf = oracle.light_pick(position, normal, sample)
+        expected_token, expected_pdf = python_pick(nodes, position, normal, sample)
+
+        if expected_pdf == 0.0 or pdf == 0.0:
+            assert expected_pdf < 1e-6 and pdf < 1e-6
+            impossible += 1
+            continue
+        if token != expected_token:  # the sample sat within rounding of a split: the neighbouring branch is as right as this one
+            continue
+        assert pdf == pytest.approx(expected_pdf, rel=2e-4)
+        assert oracle.light_mass(token, position, normal) == pytest.approx(python_mass(nodes, paths[token], position, normal), rel=2e-4)
+        assert oracle.light_mass(token, position, normal) == pytest.approx(pdf, rel=2e-4)  # Pick's pdf IS the probability mass
+        checked += 1
+
+    assert checked > 200, (checked, impossible)
