@@ -721,7 +721,8 @@ def run_render(ctx, args, scene_key, width, height, spp, bounce_limit, steps, wa
     note(ctx, f"render {scene_key}: plugin-call leg")
     e2e_steps = max(1, min(steps, 4))
     host_tiles = _native.HostBuffer(len(tiles) * tile * tile * 4, np.float32)
-    scene.render_tiles_pointers(params_for(0), tiles[:max(1, len(tiles) // 8)], host_tiles.address)  # first-call allocations
+    warm = structs.render_params(width, height, tile, extend=1, min_epoch=1, max_epoch=1, bounce_limit=bounce_limit, seed=1)
+    scene.render_tiles_pointers(warm, tiles, host_tiles.address)  # first-call allocations (the library's tile buffer for this many tiles), one sample per pixel
     ctx.barrier()
     wall = time.perf_counter()
     e2e_samples = 0
