@@ -734,7 +734,7 @@ def run_render(ctx, args, scene_key, width, height, spp, bounce_limit, steps, wa
     e2e_total = ctx.sum_over_ranks(e2e_samples)
     host_tiles.free()
 
-    achieved = per_sample_bytes * value / 1e9
+    achieved = per_sample_bytes * value / world / 1e9  # per GPU: every rank runs the same kernels on its share of the samples
     traffic_per_sample = ncu_traffic(f"{scene_key}_dram_bytes_per_sample")  # DRAM bytes of a whole step / its samples, from the committed ncu capture
     record = {"metric": "samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": total_ms / steps,
               "higher_is_better": True, "scaling": "strong", "dtype": "f32", "data": "synthetic",
@@ -744,7 +744,7 @@ def run_render(ctx, args, scene_key, width, height, spp, bounce_limit, steps, wa
                                "what": "host wall time of echo_b200_render_frame_device per step, mean over the timed steps, per rank"},
               "all_reduce": {"count": len(reduce_ms), "ms_mean": float(np.mean(reduce_ms)) if reduce_ms else None, "wait_for_slowest_rank_ms_mean": float(np.mean(skew_ms)) if skew_ms else None,
                              "bytes": int(frame.numel() * 4), "collective": "NCCL all-reduce (sum) of the fp32 accumulation frame" if ctx.distributed else "none (one GPU)"},
-              "roofline": {"bound": "hbm", "kernel": "wavefront step (raygen, extend, classify, shade x5, shadow, accumulate)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+              "roofline": {"bound": "hbm", "kernel": "wavefront step (raygen, extend, classify, shade x6, shadow, accumulate), per GPU", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                            "traffic": traffic_per_sample * (total_samples // steps) if traffic_per_sample else None, "traffic_bytes_per_sample": traffic_per_sample,
                            "peak_source": peak_source, "algorithmic_bytes_per_sample": per_sample_bytes,
                            "bytes_per_sample_parts": per_sample_parts, "per_sample_counters": per_sample_counters, "path_state_bytes": PATH_STATE_BYTES,

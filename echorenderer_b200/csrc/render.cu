@@ -2475,7 +2475,7 @@ static bool profiling()
 // echo_b200_debug_set_option so that one process can A/B them without rebuilding its scene (variants/r2_sweep_c5.py).
 struct RenderOptions
 {
-	std::atomic<long long> renderWorkers, batchPaths, narrowLimit, tailLimit, runAhead, blockingSync;
+	std::atomic<long long> renderWorkers, batchPaths, narrowLimit, tailLimit, runAhead, blockingSync, guidedBatches;
 
 	RenderOptions()
 	{
@@ -2484,7 +2484,8 @@ struct RenderOptions
 		narrowLimit = from_environment("ECHO_B200_NARROW_LIMIT", kNarrowLimit);      // rays below which a bounce uses the one-thread-per-ray kernels
 		tailLimit = from_environment("ECHO_B200_TAIL_LIMIT", kTailLimit);            // live paths below which tail_kernel finishes a batch (0 = never)
 		runAhead = from_environment("ECHO_B200_RUN_AHEAD", -1);                      // -1 = automatic, see run_ahead()
-		blockingSync = from_environment("ECHO_B200_BLOCKING_SYNC", -1);              // -1 = automatic, see blocking_waits()
+		blockingSync = from_environment("ECHO_B200_BLOCKING_SYNC", -1);              // -1 = automatic, see wait_mode()
+		guidedBatches = from_environment("ECHO_B200_GUIDED_BATCHES", 1);             // batches shrink towards the end of a call, see render_tiles
 	}
 
 	static long long from_environment(const char* name, long long fallback)
@@ -2510,6 +2511,7 @@ bool set_render_option(const char* name, long long value)
 	else if (key == "TAIL_LIMIT") o.tailLimit = value;
 	else if (key == "RUN_AHEAD") o.runAhead = value;
 	else if (key == "BLOCKING_SYNC") o.blockingSync = value;
+	else if (key == "GUIDED_BATCHES") o.guidedBatches = value;
 	else return false;
 	return true;
 }
@@ -2951,7 +2953,29 @@ bool render_tiles(RenderState* state, const DeviceScene& scene, const EchoRender
 	int device = 0;
 	cudaGetDevice(&device);
 
-	std::atomic<uint64_t> nextBatch{ 0 };
+	// Batches are claimed by the pipelines as they finish. GUIDED (default): a claim takes remaining / (2 x pipelines) tiles, capped by the
+	// batch size and floored at the minimum, so batches are full-sized while there is plenty of work and shrink towards the end of
+	// the call: the pipelines then finish within one small batch of each other instead of one large one. What a call loses to its
+	// drain — the last pipelines running their narrow tails alone — does not shrink with the job, so it weighs eight times more on
+	// an eighth of a frame (C5 at 8 GPUs) than on the whole.
+	const bool guided = options().guidedBatches != 0;
+	std::mutex claimGuard;
+	uint64_t nextTile = 0;
+
+	auto claim = [&](uint64_t& first, uint32_t& tiles) -> bool
+	{
+		std::lock_guard<std::mutex> lock(claimGuard);
+		if (nextTile >= tileCount) return false;
+		uint64_t remaining = tileCount - nextTile;
+		uint64_t size = tilesPerBatch;
+		if (guided) size = std::min<uint64_t>(tilesPerBatch, std::max<uint64_t>(minTiles, (remaining + 2 * workerCount - 1) / (2 * workerCount)));
+		size = std::min<uint64_t>(size, remaining);
+		first = nextTile;
+		tiles = (uint32_t)size;
+		nextTile += size;
+		return true;
+	};
+
 	std::atomic<bool> failed{ false };
 	std::vector<uint64_t> launches(workerCount, 0);
 	std::vector<std::string> errors(workerCount);
@@ -2967,11 +2991,9 @@ bool render_tiles(RenderState* state, const DeviceScene& scene, const EchoRender
 
 		while (ok && !failed.load())
 		{
-			uint64_t batch = nextBatch.fetch_add(1);
-			if (batch >= batchCount) break;
-
-			uint64_t first = batch * tilesPerBatch;
-			uint32_t tiles = (uint32_t)std::min<uint64_t>(tilesPerBatch, tileCount - first);
+			uint64_t first = 0;
+			uint32_t tiles = 0;
+			if (!claim(first, tiles)) break;
 			ok = render_batch(worker, scene, params, tileXY + first * 2, tiles, tilesOut ? tilesOut + first * perTile : nullptr, frame, launches[index]);
 		}
 
