@@ -2485,7 +2485,7 @@ struct RenderOptions
 		tailLimit = from_environment("ECHO_B200_TAIL_LIMIT", kTailLimit);            // live paths below which tail_kernel finishes a batch (0 = never)
 		runAhead = from_environment("ECHO_B200_RUN_AHEAD", -1);                      // -1 = automatic, see run_ahead()
 		blockingSync = from_environment("ECHO_B200_BLOCKING_SYNC", -1);              // -1 = automatic, see wait_mode()
-		guidedBatches = from_environment("ECHO_B200_GUIDED_BATCHES", 1);             // batches shrink towards the end of a call, see render_tiles
+		guidedBatches = from_environment("ECHO_B200_GUIDED_BATCHES", 0);             // batches shrink towards the end of a call, see render_tiles
 	}
 
 	static long long from_environment(const char* name, long long fallback)
@@ -2953,11 +2953,10 @@ bool render_tiles(RenderState* state, const DeviceScene& scene, const EchoRender
 	int device = 0;
 	cudaGetDevice(&device);
 
-	// Batches are claimed by the pipelines as they finish. GUIDED (default): a claim takes remaining / (2 x pipelines) tiles, capped by the
-	// batch size and floored at the minimum, so batches are full-sized while there is plenty of work and shrink towards the end of
-	// the call: the pipelines then finish within one small batch of each other instead of one large one. What a call loses to its
-	// drain — the last pipelines running their narrow tails alone — does not shrink with the job, so it weighs eight times more on
-	// an eighth of a frame (C5 at 8 GPUs) than on the whole.
+	// Batches are claimed by the pipelines as they finish. GUIDED_BATCHES (off): a claim takes remaining / (2 x pipelines) tiles, capped by
+	// the batch size and floored at the minimum, so that batches shrink towards the end of the call and the pipelines finish within one
+	// small batch of each other. Measured (r2s, one GPU): worse everywhere — rank 0's eighth of C5 602 vs 567 ms, C3 253 vs 236 ms, C4 398 vs
+	// 374 ms, C1 11.4 vs 10.3 ms: small batches cost more in launch-bound narrow bounces than an even finish saves. Kept as a switch.
 	const bool guided = options().guidedBatches != 0;
 	std::mutex claimGuard;
 	uint64_t nextTile = 0;

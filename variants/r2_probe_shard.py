@@ -47,6 +47,7 @@ def main():
     parser.add_argument("--bounce-limit", type=int, default=128)
     parser.add_argument("--pattern", default="ordered")
     parser.add_argument("--tag", default="")
+    parser.add_argument("--by", default="sequence", choices=["sequence", "position"])
     args = parser.parse_args()
 
     import torch
@@ -58,7 +59,7 @@ def main():
     tile = 16
     count = ((args.width + tile - 1) // tile, (args.height + tile - 1) // tile)
     all_tiles = hilbert_curve_pattern(count) if args.pattern == "hilbert" else scenes.tile_grid(args.width, args.height, tile)
-    tiles = shard_tiles(all_tiles, args.rank, args.world)
+    tiles = shard_tiles(all_tiles, args.rank, args.world, by=args.by)
     frame = torch.zeros(args.height * args.width * 4, dtype=torch.float32, device=device)
     stream = torch.cuda.current_stream().cuda_stream
     times, samples, launches = [], 0, 0
