@@ -48,6 +48,26 @@ constexpr unsigned long long kPool = 256;         // rays reserved per global at
 #ifndef ECHO_NODE_POLICY
 #define ECHO_NODE_POLICY 0
 #endif
+// Taking a new ray costs ~35 warp instructions (three IEEE reciprocals, the order bits, the finiteness test) whatever the number of lanes
+// that take one, and rays end one or two lanes at a time: on C2 that block was 12 % of all issued instructions at 4.3 active lanes (ncu source
+// page, profiles/README.md). ECHO_FETCH_VOTE > 0 holds the idle lanes back until that many are waiting (or ECHO_FETCH_MAX_WAIT iterations passed,
+// or nobody in the warp has a ray): fewer, fuller executions of the block against lanes idling a little longer. A/B in profiles/README.md.
+#ifndef ECHO_FETCH_VOTE
+#define ECHO_FETCH_VOTE 0
+#endif
+#ifndef ECHO_FETCH_MAX_WAIT
+#define ECHO_FETCH_MAX_WAIT 1
+#endif
+// ECHO_PREPARE_RAYS: closest-hit kernels compute the per-ray constants (the three IEEE reciprocals of Ray.cs:23, the order bits, the
+// finiteness flag) for a whole pool of rays at once, 32 lanes at a time, when the warp reserves the pool — into the ray's slot of the HIT
+// buffer, which belongs to this launch and is not written until the ray ends — and a lane that takes a ray copies them in with the ray. Taking
+// a ray then costs a few loads instead of ~35 instructions issued for the one to four lanes that happen to need a ray in that iteration.
+// Measured (r2v): parity green, and NO gain — C2 closest hit 4815 vs 4812 Mrays/s, secondary +1.3 %, C3 equal, C5 -0.7 %, the instanced
+// batch -4 %: a tenth fewer issued instructions buys nothing, the kernel waits for sector fetches, not for issue slots. Off.
+#ifndef ECHO_PREPARE_RAYS
+#define ECHO_PREPARE_RAYS 0
+#endif
+constexpr int kStagedFloat4 = 3; // staging slot per thread: the 32-byte ray + its prepared constants
 constexpr int kLeafVote = ECHO_LEAF_VOTE;                      // run the primitive tests once this many lanes have one pending
 
 // BoxBound4.Intersect for one lane with hardware min/max. Bit-identical to slab() whenever no operand is NaN, which holds
@@ -116,6 +136,8 @@ ECHO_DEVICE void persistent_finish(unsigned long long* __restrict__ nextRay)
 //   const float4* ray_pointer(uint32_t index)   -> 32 contiguous bytes: origin.xyz direction.x | direction.yz limit ignore
 //   void store_closest(uint32_t index, bool hit, uint32_t token, float distance, vec2 uv, float limit)
 //   void store_any(uint32_t index, bool occluded)
+//   float4* prepared_pointer(uint32_t index)    -> 16 bytes of scratch owned by this launch until ray `index` stores its result (closest-hit
+//                                                  kernels: the ray's slot of the hit buffer); never called by any-hit kernels
 //
 // Control flow is "if-if": one warp-wide loop whose body is a fixed sequence of predicated stages, so all 32 lanes
 // reconverge at every stage (a per-lane while loop with continue/break leaves the lanes of a warp scattered over the
@@ -149,7 +171,8 @@ ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, uint32_t 
 	asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(nodePolicy));
 #endif
 
-	float4* stagedSlot = stagedRays + threadIdx.x * 2;
+	constexpr bool PREPARE = ECHO_PREPARE_RAYS != 0 && !ANY;
+	float4* stagedSlot = stagedRays + threadIdx.x * kStagedFloat4;
 	const uint32_t stagedAddress = (uint32_t)__cvta_generic_to_shared(stagedSlot);
 
 	// warp-uniform pool of reserved ray indices [poolNext, poolEnd). Pool size: kPool for big batches; for small ones (late
@@ -278,6 +301,9 @@ ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, uint32_t 
 	};
 
 	int waited = 0; // warp-uniform: iterations some lane has been waiting for its primitive test
+#if ECHO_FETCH_VOTE > 0
+	int fetchWaited = 0; // warp-uniform: iterations some idle lane has been waiting to take its staged ray
+#endif
 
 	while (true)
 	{
@@ -295,7 +321,16 @@ ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, uint32_t 
 		}
 
 		// ---- E: idle lanes take their staged ray (already in shared memory) ----
+#if ECHO_FETCH_VOTE > 0
+		const unsigned int fetchReady = __ballot_sync(0xFFFFFFFFu, !haveRay && staged);
+		const unsigned int stillWorking = __ballot_sync(0xFFFFFFFFu, haveRay);
+		fetchWaited = fetchReady != 0u ? fetchWaited + 1 : 0;
+		const bool fetchNow = __popc(fetchReady) >= ECHO_FETCH_VOTE || fetchWaited > ECHO_FETCH_MAX_WAIT || stillWorking == 0u;
+		if (fetchNow) fetchWaited = 0;
+		if (fetchNow && !haveRay && staged)
+#else
 		if (!haveRay && staged)
+#endif
 		{
 			asm volatile("cp.async.wait_all;" ::: "memory");
 			float4 a = stagedSlot[0], b = stagedSlot[1];
@@ -332,10 +367,20 @@ ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, uint32_t 
 			}
 			else
 			{
-				directionR = { rcp(direction.x), rcp(direction.y), rcp(direction.z) }; // Ray.cs:23
-				orders = (directionR.x > 0.0f ? 1u : 0u) | (directionR.y > 0.0f ? 2u : 0u) | (directionR.z > 0.0f ? 4u : 0u) | 8u;
-				finite = finite_bits(directionR.x) && finite_bits(directionR.y) && finite_bits(directionR.z)
-					&& finite_bits(origin.x) && finite_bits(origin.y) && finite_bits(origin.z);
+				if constexpr (PREPARE)
+				{
+					float4 prepared = stagedSlot[2]; // computed with the rest of the ray's pool, see the pool reservation below
+					directionR = { prepared.x, prepared.y, prepared.z };
+					orders = __float_as_uint(prepared.w) & 15u;
+					finite = (__float_as_uint(prepared.w) & 16u) != 0u;
+				}
+				else
+				{
+					directionR = { rcp(direction.x), rcp(direction.y), rcp(direction.z) }; // Ray.cs:23
+					orders = (directionR.x > 0.0f ? 1u : 0u) | (directionR.y > 0.0f ? 2u : 0u) | (directionR.z > 0.0f ? 4u : 0u) | 8u;
+					finite = finite_bits(directionR.x) && finite_bits(directionR.y) && finite_bits(directionR.z)
+						&& finite_bits(origin.x) && finite_bits(origin.y) && finite_bits(origin.z);
+				}
 
 				haveRay = true;
 				top = make_uint2(0u, 0u); // NewNodeToken(0), entry distance 0
@@ -376,6 +421,23 @@ ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, uint32_t 
 				poolNext = base + (wanted - available);
 				if (poolNext > end) poolNext = end;
 				poolEnd = end;
+
+				if constexpr (PREPARE)
+				{
+					// the whole new pool, every lane busy: ray k -> {1 / direction, order bits | finite << 4} in its hit slot
+					for (uint32_t k = base + lane; k < end; k += 32u)
+					{
+						const float4* source = io.ray_pointer(k);
+						float4 a = __ldcg(source), b = __ldcg(source + 1); // L1 bypassed: the rays themselves are staged through L2 later
+						vec3 r = { rcp(a.w), rcp(b.x), rcp(b.y) }; // Ray.cs:23
+						uint32_t flags = (r.x > 0.0f ? 1u : 0u) | (r.y > 0.0f ? 2u : 0u) | (r.z > 0.0f ? 4u : 0u) | 8u;
+						if (finite_bits(r.x) && finite_bits(r.y) && finite_bits(r.z) && finite_bits(a.x) && finite_bits(a.y) && finite_bits(a.z)) flags |= 16u;
+						__stcg(io.prepared_pointer(k), make_float4(r.x, r.y, r.z, __uint_as_float(flags)));
+					}
+
+					__threadfence(); // the cp.async of ANY lane of this warp may fetch what another lane just wrote
+					__syncwarp();
+				}
 			}
 			else poolNext += wanted < available ? wanted : available;
 
@@ -389,6 +451,7 @@ ECHO_DEVICE void persistent_traverse(const DeviceScene& scene, IO& io, uint32_t 
 				asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(stagedAddress), "l"(source) : "memory");
 				asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(stagedAddress + 16u), "l"(source + 1) : "memory");
 #endif
+				if constexpr (PREPARE) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(stagedAddress + 32u), "l"(io.prepared_pointer(index)) : "memory");
 				asm volatile("cp.async.commit_group;" ::: "memory");
 				stagedIndex = index;
 				staged = true;

@@ -1187,6 +1187,7 @@ struct ExtendIO
 	float4* __restrict__ hits;
 
 	ECHO_DEVICE const float4* ray_pointer(uint32_t index) const { return rays + (size_t)index * 2; }
+	ECHO_DEVICE float4* prepared_pointer(uint32_t index) const { return hits + index; }
 
 	ECHO_DEVICE void store_closest(uint32_t index, bool hit, uint32_t token, float distance, vec2 uv, float limit) const
 	{
@@ -1224,7 +1225,7 @@ struct ExtendLayersIO : ExtendIO
 template<int STACK>
 __global__ void __launch_bounds__(kTraverseBlock, ECHO_INST_MIN_BLOCKS) extend_layers_kernel(DeviceScene scene, ExtendLayersIO io, const uint32_t* __restrict__ queueCount, unsigned long long* __restrict__ nextRay)
 {
-	__shared__ float4 stagedRays[kTraverseBlock * 2];
+	__shared__ float4 stagedRays[kTraverseBlock * kStagedFloat4];
 	persistent_traverse<STACK, false, true>(scene, io, *queueCount, nextRay, stagedRays);
 	persistent_finish(nextRay);
 }
@@ -1232,7 +1233,7 @@ __global__ void __launch_bounds__(kTraverseBlock, ECHO_INST_MIN_BLOCKS) extend_l
 template<int STACK>
 __global__ void __launch_bounds__(kTraverseBlock, ECHO_MIN_BLOCKS) extend_kernel(DeviceScene scene, ExtendIO io, const uint32_t* __restrict__ queueCount, unsigned long long* __restrict__ nextRay)
 {
-	__shared__ float4 stagedRays[kTraverseBlock * 2];
+	__shared__ float4 stagedRays[kTraverseBlock * kStagedFloat4];
 	persistent_traverse<STACK, false>(scene, io, *queueCount, nextRay, stagedRays);
 	persistent_finish(nextRay);
 }
@@ -1665,6 +1666,7 @@ struct ShadowIO
 	uint32_t passed;
 
 	ECHO_DEVICE const float4* ray_pointer(uint32_t index) const { return rays + (size_t)index * 2; }
+	ECHO_DEVICE float4* prepared_pointer(uint32_t) const { return nullptr; }
 	ECHO_DEVICE void store_closest(uint32_t, bool, uint32_t, float, vec2, float) const {}
 
 	ECHO_DEVICE void store_any(uint32_t index, bool occluded)
@@ -1699,7 +1701,7 @@ template<int STACK>
 __global__ void __launch_bounds__(kTraverseBlock, ECHO_INST_MIN_BLOCKS) shadow_layers_kernel(DeviceScene scene, ShadowLayersIO io, const uint32_t* __restrict__ shadowCount, unsigned long long* __restrict__ nextRay,
                                                                        unsigned long long* __restrict__ stats)
 {
-	__shared__ float4 stagedRays[kTraverseBlock * 2];
+	__shared__ float4 stagedRays[kTraverseBlock * kStagedFloat4];
 	io.passed = 0u;
 	persistent_traverse<STACK, true, true>(scene, io, *shadowCount, nextRay, stagedRays);
 	persistent_finish(nextRay);
@@ -1714,7 +1716,7 @@ template<int STACK>
 __global__ void __launch_bounds__(kTraverseBlock, ECHO_MIN_BLOCKS) shadow_kernel(DeviceScene scene, ShadowIO io, const uint32_t* __restrict__ shadowCount, unsigned long long* __restrict__ nextRay,
                                                               unsigned long long* __restrict__ stats)
 {
-	__shared__ float4 stagedRays[kTraverseBlock * 2];
+	__shared__ float4 stagedRays[kTraverseBlock * kStagedFloat4];
 	io.passed = 0u;
 	persistent_traverse<STACK, true>(scene, io, *shadowCount, nextRay, stagedRays);
 	persistent_finish(nextRay);

@@ -130,6 +130,7 @@ struct BatchIO
 	}
 
 	ECHO_DEVICE const float4* ray_pointer(uint32_t index) const { return rays + (size_t)index * 2; }
+	ECHO_DEVICE float4* prepared_pointer(uint32_t index) const { return hits + index; }
 
 	ECHO_DEVICE void store_closest(uint32_t index, bool hit, uint32_t token, float distance, vec2 uv, float limit) const
 	{
@@ -142,7 +143,7 @@ struct BatchIO
 template<int STACK, bool ANY>
 __global__ void __launch_bounds__(kTraverseBlock, ECHO_MIN_BLOCKS) persistent_batch_kernel(DeviceScene scene, BatchIO io, uint32_t n, unsigned long long* __restrict__ nextRay)
 {
-	__shared__ float4 stagedRays[kTraverseBlock * 2];
+	__shared__ float4 stagedRays[kTraverseBlock * kStagedFloat4];
 	persistent_traverse<STACK, ANY>(scene, io, n, nextRay, stagedRays);
 	persistent_finish(nextRay);
 }
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(kTraverseBlock, ECHO_MIN_BLOCKS) persistent_ba
 template<int STACK, bool ANY>
 __global__ void __launch_bounds__(kTraverseBlock, ECHO_INST_MIN_BLOCKS) persistent_instanced_kernel(DeviceScene scene, BatchIO io, uint32_t n, unsigned long long* __restrict__ nextRay)
 {
-	__shared__ float4 stagedRays[kTraverseBlock * 2];
+	__shared__ float4 stagedRays[kTraverseBlock * kStagedFloat4];
 	persistent_traverse<STACK, ANY, true>(scene, io, n, nextRay, stagedRays);
 	persistent_finish(nextRay);
 }
