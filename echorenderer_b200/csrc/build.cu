@@ -382,10 +382,10 @@ __global__ void emit_kernel(int internalCount, const uint32_t* __restrict__ isQu
 	out[quadIndex[i]] = node;
 }
 
-// 1 = PLOC (default), 0 = LBVH; ECHO_B200_BUILD_ALGORITHM / echo_b200_debug_set_option("BUILD_ALGORITHM", ...)
+// 2 = the reference's SweepBuilder tree (sweep.cu, default), 1 = PLOC, 0 = LBVH; ECHO_B200_BUILD_ALGORITHM / echo_b200_debug_set_option("BUILD_ALGORITHM", ...)
 std::atomic<int>& build_algorithm()
 {
-	static std::atomic<int> value{ [] { const char* text = std::getenv("ECHO_B200_BUILD_ALGORITHM"); return text ? std::atoi(text) : 1; }() };
+	static std::atomic<int> value{ [] { const char* text = std::getenv("ECHO_B200_BUILD_ALGORITHM"); return text ? std::atoi(text) : 2; }() };
 	return value;
 }
 
@@ -432,7 +432,18 @@ static bool build_qbvh_with(bool ploc, const EchoTriangle* triangles, uint32_t t
 bool build_qbvh_device(const EchoTriangle* triangles, uint32_t triangleCount, const EchoSphere* spheres, uint32_t sphereCount,
                        EchoQbvhNode* outNodes, uint32_t* outNodeCount, uint32_t* outMaxDepth)
 {
-	const bool ploc = build_algorithm() != 0;
+	const int algorithm = build_algorithm();
+
+	if (algorithm >= 2)
+	{
+		// The reference's own tree. Its depth is unbounded for degenerate inputs (coincident primitives peel off one per level, in the
+		// recursive original as well); then, or when the tree would not fit the deepest compiled traversal stack, the clustering takes over.
+		bool gaveUp = false;
+		if (!build_qbvh_sweep(triangles, triangleCount, spheres, sphereCount, outNodes, outNodeCount, outMaxDepth, &gaveUp)) return false;
+		if (!gaveUp && stack_class(*outMaxDepth) >= 0) return true;
+	}
+
+	const bool ploc = algorithm != 0;
 	bool stalled = false;
 	if (!build_qbvh_with(ploc, triangles, triangleCount, spheres, sphereCount, outNodes, outNodeCount, outMaxDepth, &stalled)) return false;
 

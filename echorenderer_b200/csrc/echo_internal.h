@@ -36,7 +36,10 @@ bool launch_persistent_instanced(const DeviceScene& scene, const EchoRay* rays, 
 unsigned long long* ray_counters(cudaStream_t stream); // the self-resetting work counter pair of persistent launches on this device and stream
 int persistent_grid(const void* kernel);              // resident CTAs of a persistent kernel on the current device (cached per device)
 
-// ---- build.cu: linear BVH on the device, collapsed to the QBVH node format (host buffers in and out) ----
+// ---- build.cu / sweep.cu: device-side tree builds in the QBVH node format (host buffers in and out): the reference's SweepBuilder tree
+// itself (sweep.cu, echo_sweep.h), or a clustered / Morton-ordered binary tree collapsed the same way (build.cu) ----
+bool build_qbvh_sweep(const EchoTriangle* triangles, uint32_t triangleCount, const EchoSphere* spheres, uint32_t sphereCount,
+                      EchoQbvhNode* outNodes, uint32_t* outNodeCount, uint32_t* outMaxDepth, bool* gaveUp);
 bool build_qbvh_device(const EchoTriangle* triangles, uint32_t triangleCount, const EchoSphere* spheres, uint32_t sphereCount,
                        EchoQbvhNode* outNodes, uint32_t* outNodeCount, uint32_t* outMaxDepth);
 
@@ -56,7 +59,7 @@ bool launch_frame_resolve(float4* frame, int32_t width, int32_t height, cudaStre
 
 // tuning switches of the wavefront (the ECHO_B200_<NAME> environment variables), changeable at run time; false = unknown name
 bool set_render_option(const char* name, long long value);
-bool set_build_option(const char* name, long long value); // build.cu: BUILD_ALGORITHM (1 = PLOC, 0 = LBVH)
+bool set_build_option(const char* name, long long value); // build.cu: BUILD_ALGORITHM (2 = SweepBuilder, 1 = PLOC, 0 = LBVH)
 
 // ---- peaks.cu: on-chip ceilings measured on the current device: {L2 coalesced read, L2 random 32-byte sectors, L1 random sectors} GB/s
 bool measure_peaks(float* out3);

@@ -1,7 +1,9 @@
-"""The optional device-side tree build (echo_b200_build_qbvh): a binary BVH built on the device — by
-parallel locally-ordered clustering (the default) or as a linear BVH — and collapsed to the reference's QBVH node format. Both
-are checked for structural validity, against brute force through the oracle, and for device / oracle parity on the tree they
-produce."""
+"""The optional device-side tree build (echo_b200_build_qbvh). The default (sweep.cu) builds the reference's
+SweepBuilder tree itself, level by level: the emitted nodes must equal the host mirror's byte for byte. The two other algorithms —
+parallel locally-ordered clustering and a linear BVH, collapsed to the reference's QBVH node format — give other valid trees. All three
+are checked for structural validity, against brute force through the oracle, and for device / oracle parity on the tree they produce."""
+import time
+
 import numpy as np
 import pytest
 
@@ -11,14 +13,15 @@ from tests.test_gpu_trace import assert_hits_equal
 
 pytestmark = pytest.mark.gpu
 
-ALGORITHMS = {"ploc": 1, "lbvh": 0}
+ALGORITHMS = {"sweep": 2, "ploc": 1, "lbvh": 0}
+DEFAULT_ALGORITHM = 2
 
 
 @pytest.fixture(params=list(ALGORITHMS))
 def algorithm(request):
     _native.set_option("BUILD_ALGORITHM", ALGORITHMS[request.param])
     yield request.param
-    _native.set_option("BUILD_ALGORITHM", 1)
+    _native.set_option("BUILD_ALGORITHM", DEFAULT_ALGORITHM)
 
 
 def check_tree(nodes, max_depth, triangles, spheres):
@@ -137,8 +140,53 @@ def test_clustered_tree_is_cheaper_to_traverse_than_the_morton_tree(terrain_smal
         prepared = host.prepare(terrain_small.description, tree=(nodes, depth))
         _, counters = oracle_lib.OracleScene(prepared).trace(rays, count_visits=True)
         visits[name] = counters[0] / len(rays)
-    _native.set_option("BUILD_ALGORITHM", 1)
+    _native.set_option("BUILD_ALGORITHM", DEFAULT_ALGORITHM)
     _, counters = oracle_lib.OracleScene(terrain_small).trace(rays, count_visits=True)
     sah = counters[0] / len(rays)
     assert visits["ploc"] < visits["lbvh"]
     assert visits["ploc"] < 1.25 * sah
+    assert visits["sweep"] == sah  # the same tree
+
+
+def assert_device_tree_is_the_host_mirrors(triangles, spheres):
+    expected, expected_depth = host.build_qbvh(triangles, spheres)
+    nodes, depth = build_qbvh_device(triangles, spheres)
+    assert len(nodes) == len(expected) and depth == expected_depth
+    assert nodes.tobytes() == expected.tobytes()
+
+
+@pytest.mark.parametrize("fixture", ["cornell", "terrain_small", "mixed_small", "lights_small"])
+def test_device_sweep_tree_is_the_host_mirrors_byte_for_byte(fixture, request):
+    """BUILD_ALGORITHM 2 (the default): SweepBuilder.cs + the QuadBoundingVolumeHierarchy collapse, level-synchronous on the device —
+    the same nodes in the same pre-order as the recursive build (tests/test_sweep_build.py asks the same of the CPU emulation)."""
+    _native.set_option("BUILD_ALGORITHM", 2)
+    prepared = request.getfixturevalue(fixture)
+    assert_device_tree_is_the_host_mirrors(prepared.triangles, prepared.spheres)
+
+
+def test_device_sweep_tree_on_soups_ties_and_tiny_inputs():
+    from tests.test_sweep_build import NO_SPHERES, random_soup
+    _native.set_option("BUILD_ALGORITHM", 2)
+    for seed, triangle_count, sphere_count, scale in [(1, 2, 0, 1.0), (2, 1, 1, 1.0), (3, 3, 0, 5.0), (4, 33, 7, 1.0), (5, 1000, 100, 100.0), (6, 20000, 500, 1e-3),
+                                                       (7, 5000, 5000, 1e4), (8, 0, 300, 2.0), (9, 300_000, 3000, 10.0)]:
+        assert_device_tree_is_the_host_mirrors(*random_soup(seed, triangle_count, sphere_count, scale))
+    quad = scenes.plane(0, (2, 2))
+    assert_device_tree_is_the_host_mirrors(np.concatenate([quad] * 40), NO_SPHERES)                # equal keys: the stable order decides
+    assert_device_tree_is_the_host_mirrors(scenes.terrain_triangles(24, 24, height=0.0), NO_SPHERES)  # a regular flat grid: equal costs everywhere
+    assert_device_tree_is_the_host_mirrors(np.concatenate([scenes.plane(0, (1, 1), position=(2.0 * k, 0, 0)) for k in range(70)]), NO_SPHERES)
+
+
+def test_device_sweep_tree_at_full_size():
+    """C2's geometry (1 000 000 triangles + 10 000 spheres): the device-built tree is the host mirror's 565 329 nodes, byte for byte."""
+    _native.set_option("BUILD_ALGORITHM", 2)
+    description = scenes.terrain_scene()
+    build_qbvh_device(description.triangles[:64], description.spheres[:0])  # context + module load
+    started = time.perf_counter()
+    nodes, depth = build_qbvh_device(description.triangles, description.spheres)
+    device_seconds = time.perf_counter() - started
+    started = time.perf_counter()
+    expected, expected_depth = host.build_qbvh(description.triangles, description.spheres)
+    host_seconds = time.perf_counter() - started
+    print(f"sweep build of {len(description.triangles) + len(description.spheres)} primitives: device call {device_seconds * 1e3:.1f} ms, host mirror {host_seconds * 1e3:.1f} ms")
+    assert len(nodes) == len(expected) == 565_329 and depth == expected_depth == 13
+    assert nodes.tobytes() == expected.tobytes()
