@@ -73,6 +73,7 @@ def parse():
     parser.add_argument("--render-warmup", type=int, default=1, help="default run: warm-up steps of each `render` record (a C5 step is seconds long)")
     parser.add_argument("--no-render", action="store_true", help="default run: skip the `render` records")
     parser.add_argument("--no-cpu-baseline", action="store_true")
+    parser.add_argument("--no-tree-build", action="store_true", help="skip the device tree build record (device SweepBuilder beside the host mirror)")
     parser.add_argument("--no-secondary", action="store_true", help="skip the secondary-ray batch reported beside the headline (SURVEY.md 8d)")
     return parser.parse_args()
 
@@ -240,6 +241,26 @@ def build_trace_inputs(args, rank):
     diagonal = float(np.linalg.norm(np.asarray(high, np.float64) - np.asarray(low, np.float64)))
     shadow["distance"] = scenes.uniform(17 + 1000 * rank, np.arange(args.rays, dtype=np.uint64)) * np.float32(diagonal)
     return prepared, rays, shadow
+
+
+def tree_build_record(prepared, device):
+    """The device-side SweepBuilder (echo_b200_build_qbvh, csrc/sweep.cu) on the headline's geometry beside the host mirror of the reference's
+    recursive build: the whole call from host buffers, its phases, and whether the two node arrays are the same bytes. Not part of `value`."""
+    from echorenderer_b200 import _native, build_qbvh_device
+    triangles, spheres = prepared.triangles, prepared.spheres
+    build_qbvh_device(triangles[:64], spheres[:0], device=device)  # context + module load
+    calls = []
+    for _ in range(3):
+        started = time.perf_counter()
+        nodes, depth = build_qbvh_device(triangles, spheres, device=device)
+        calls.append(((time.perf_counter() - started) * 1e3, _native.last_build()))
+    call_ms, phases = min(calls, key=lambda pair: pair[0])
+    started = time.perf_counter()
+    expected, expected_depth = host.build_qbvh(triangles, spheres)
+    host_ms = (time.perf_counter() - started) * 1e3
+    return {"what": "the reference's SweepBuilder tree (SweepBuilder.cs + the QBVH collapse) built level-synchronously on the device: echo_b200_build_qbvh from host buffers, best of 3 calls",
+            "primitives": int(len(triangles) + len(spheres)), "nodes": int(len(nodes)), "quad_depth": int(depth), "call_ms": call_ms, **phases,
+            "host_mirror_ms": host_ms, "host_mirror_threads": os.cpu_count(), "identical_to_host_mirror": bool(depth == expected_depth and nodes.tobytes() == expected.tobytes())}
 
 
 def secondary_batch(scene, prepared, rays, d_hits, ctx, args):
@@ -588,6 +609,9 @@ def run_trace(ctx, args):
 
     if not args.no_secondary and not args.instanced:
         line["secondary"] = secondary_batch(scene, prepared, rays, d_hits, ctx, args)
+
+    if ctx.rank == 0 and not args.instanced and not args.no_tree_build:
+        line["tree_build"] = tree_build_record(prepared, ctx.local_rank)
 
     if ctx.rank == 0 and not args.no_cpu_baseline:
         cpu_value, cores, seconds, sample = cpu_baseline_trace(prepared, rays, shadow, args.cpu_sample)

@@ -33,7 +33,7 @@ EXPORTS = [
     "echo_b200_debug_evaluate_samples4", "echo_b200_debug_bounds_violations",
     "echo_b200_trace_batch_device_counted", "echo_b200_occlude_batch_device_counted", "echo_b200_debug_bxdf_batch", "echo_b200_debug_math",
     "echo_b200_debug_evaluate_samples",
-    "echo_b200_host_alloc", "echo_b200_host_free", "echo_b200_host_register", "echo_b200_host_unregister", "echo_b200_debug_set_option", "echo_b200_debug_measure_peaks",
+    "echo_b200_host_alloc", "echo_b200_host_free", "echo_b200_host_register", "echo_b200_host_unregister", "echo_b200_debug_set_option", "echo_b200_debug_measure_peaks", "echo_b200_debug_last_build",
     "echo_b200_scene_create_multi", "echo_b200_scene_gpu_count",
 ]
 
@@ -87,6 +87,7 @@ def library():
         "echo_b200_host_unregister": [p],
         "echo_b200_debug_set_option": [ctypes.c_char_p, ctypes.c_int64],
         "echo_b200_debug_measure_peaks": [i32, p],
+        "echo_b200_debug_last_build": [p],
         "echo_b200_scene_create_multi": [ctypes.POINTER(p), u64],
         "echo_b200_scene_gpu_count": [p, ctypes.POINTER(i32)],
     }
@@ -162,6 +163,14 @@ def measure_peaks(device=0):
     check(library().echo_b200_debug_measure_peaks(int(device), pointer(out)))
     return {"l2_read_gbs": float(out[0]), "l2_sector_gbs": float(out[1]), "l1_sector_gbs": float(out[2]),
             "how": "library microbenchmarks: coalesced ld.global.cg over 32 MB in L2; one random 32-byte sector per lane (ld.global.nc.v8.f32) over 64 MB in L2; the same over 8 KB per CTA in L1"}
+
+
+def last_build():
+    """echo_b200_debug_last_build: phases of this thread's last SweepBuilder device build (host wall time around synchronised phases)."""
+    import numpy as np
+    out = np.zeros(4, dtype=np.float32)
+    check(library().echo_b200_debug_last_build(pointer(out)))
+    return {"upload_ms": float(out[0]), "device_build_ms": float(out[1]), "download_ms": float(out[2]), "binary_levels": int(out[3])}
 
 
 def host_register(array):

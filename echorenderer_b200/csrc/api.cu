@@ -1210,6 +1210,13 @@ int32_t echo_b200_debug_set_option(const char* name, int64_t value)
 	return set_render_option(name, (long long)value) || set_build_option(name, (long long)value) ? ECHO_B200_OK : fail(ECHO_B200_ERR_INVALID, "unknown option");
 }
 
+int32_t echo_b200_debug_last_build(float* out4)
+{
+	if (!out4) return fail(ECHO_B200_ERR_INVALID, "out4 is null");
+	last_sweep_build(out4);
+	return ECHO_B200_OK;
+}
+
 static int32_t debug_device(int32_t device)
 {
 	int32_t count = 0;

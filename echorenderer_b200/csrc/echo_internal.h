@@ -40,6 +40,7 @@ int persistent_grid(const void* kernel);              // resident CTAs of a pers
 // itself (sweep.cu, echo_sweep.h), or a clustered / Morton-ordered binary tree collapsed the same way (build.cu) ----
 bool build_qbvh_sweep(const EchoTriangle* triangles, uint32_t triangleCount, const EchoSphere* spheres, uint32_t sphereCount,
                       EchoQbvhNode* outNodes, uint32_t* outNodeCount, uint32_t* outMaxDepth, bool* gaveUp);
+void last_sweep_build(float* out4); // the calling thread's last build_qbvh_sweep: {upload, device build, download} ms, binary levels
 bool build_qbvh_device(const EchoTriangle* triangles, uint32_t triangleCount, const EchoSphere* spheres, uint32_t sphereCount,
                        EchoQbvhNode* outNodes, uint32_t* outNodeCount, uint32_t* outMaxDepth);
 

@@ -474,11 +474,12 @@ SWEEP_HD uint32_t add_children(const BinNode* nodes, uint32_t node, uint32_t* ou
 	return children_sorted(nodes, node, out[0], out[1]);
 }
 
-struct QuadCountPass // quad nodes in the subtree of every internal binary node of one even level (the levels below are done)
-{
+struct QuadCountPass // quad nodes in the subtree of every internal binary node of one even level (the levels below are done), and the
+{                     // subtree's depth as CreateNode counts it (:375-414): an empty slot 0, a leaf 1, a node 1 + the deepest of its slots
 	uint32_t first;
 	const BinNode* nodes;
 	uint32_t* quadCount;
+	uint32_t* quadDepth;
 
 	SWEEP_HD void operator()(uint32_t i) const
 	{
@@ -490,10 +491,19 @@ struct QuadCountPass // quad nodes in the subtree of every internal binary node 
 		add_children(nodes, child0, slots);
 		add_children(nodes, child1, slots + 2);
 
-		uint32_t total = 1u;
+		uint32_t total = 1u, deepest = 0u;
+
 		for (int k = 0; k < 4; k++)
-			if (slots[k] != kNone && nodes[slots[k]].child0 != kNone) total += quadCount[slots[k]];
+		{
+			if (slots[k] == kNone) continue;
+			bool internal = nodes[slots[k]].child0 != kNone;
+			if (internal) total += quadCount[slots[k]];
+			uint32_t below = internal ? quadDepth[slots[k]] : 1u;
+			if (below > deepest) deepest = below;
+		}
+
 		quadCount[node] = total;
+		quadDepth[node] = deepest + 1u;
 	}
 };
 
@@ -554,7 +564,7 @@ struct QuadEmitPass // CreateNode, :363-404: pre-order indices for the internal 
 	}
 };
 
-// depth as CreateNode counts it (:375-414): an empty slot 0, a leaf 1, a node 1 + the deepest of its slots (host pass over the emitted array)
+// the same depth by a host pass over an emitted array (what the clustered builds use; the emulation checks QuadCountPass against it)
 inline uint32_t quad_depth(const EchoQbvhNode* nodes, uint32_t nodeCount)
 {
 	std::vector<uint32_t> depth(nodeCount, 0u);
@@ -608,7 +618,7 @@ struct Arena
 struct Buffers
 {
 	Box* boxes;
-	uint32_t *tokens, *perm[2], *segmentOf[2], *stay, *newPosition, *keep, *newSegment, *totals, *quadCount, *quadIndex;
+	uint32_t *tokens, *perm[2], *segmentOf[2], *stay, *newPosition, *keep, *newSegment, *totals, *quadCount, *quadDepth, *quadIndex;
 	unsigned long long *keys[2], *best[2];
 	ScanItem *forwards, *backwards, *heads, *tails;
 	Segment *segments[2], *slots;
@@ -639,6 +649,7 @@ struct Buffers
 		slots = arena.take<Segment>(total + 2);
 		nodes = arena.take<BinNode>(2 * total);
 		quadCount = arena.take<uint32_t>(2 * total);
+		quadDepth = arena.take<uint32_t>(2 * total);
 		quadIndex = arena.take<uint32_t>(2 * total);
 		quads = arena.take<EchoQbvhNode>(total);
 	}
@@ -648,7 +659,7 @@ struct Result
 {
 	bool ok = false;       // false: a backend call failed (its error is set) ...
 	bool gaveUp = false;   // ... or the tree chains deeper than kMaxLevels
-	uint32_t nodeCount = 0, levels = 0;
+	uint32_t nodeCount = 0, maxDepth = 0, levels = 0;
 	const EchoQbvhNode* quads = nullptr; // backend memory
 };
 
@@ -741,15 +752,16 @@ Result build(Backend& backend, const EchoTriangle* triangles, uint32_t triangleC
 	if (!backend.fill_zero(b.quadIndex, sizeof(uint32_t))) return result; // the root is quad node 0
 	int last = (int)levels.size() - 1;
 	for (int level = last - (last & 1); level >= 0; level -= 2)
-		if (!backend.for_each(levels[level].second, QuadCountPass{ levels[level].first, b.nodes, b.quadCount })) return result;
+		if (!backend.for_each(levels[level].second, QuadCountPass{ levels[level].first, b.nodes, b.quadCount, b.quadDepth })) return result;
 	for (int level = 0; level <= last; level += 2)
 		if (!backend.for_each(levels[level].second, QuadEmitPass{ levels[level].first, b.nodes, b.quadCount, b.quadIndex, b.quads })) return result;
 
-	uint32_t nodeCount = 0;
-	if (!backend.read(b.quadCount, &nodeCount, 1)) return result;
+	uint32_t nodeCount = 0, maxDepth = 0;
+	if (!backend.read(b.quadCount, &nodeCount, 1) || !backend.read(b.quadDepth, &maxDepth, 1)) return result;
 
 	result.ok = true;
 	result.nodeCount = nodeCount;
+	result.maxDepth = maxDepth;
 	result.levels = (uint32_t)levels.size();
 	result.quads = b.quads;
 	return result;

@@ -104,7 +104,16 @@ struct CudaBackend
 	bool fill_zero(void* pointer, size_t bytes) { return check_cuda(cudaMemsetAsync(pointer, 0, bytes, stream), "cudaMemsetAsync(sweep)"); }
 };
 
+struct LastBuild { float uploadMs, buildMs, downloadMs, levels; };
+thread_local LastBuild gLastBuild = { 0.0f, 0.0f, 0.0f, 0.0f };
+
 } // namespace
+
+// the calling thread's last build_qbvh_sweep: {upload, device build, download} in ms of host wall time around synchronised phases, binary levels
+void last_sweep_build(float* out4)
+{
+	out4[0] = gLastBuild.uploadMs; out4[1] = gLastBuild.buildMs; out4[2] = gLastBuild.downloadMs; out4[3] = gLastBuild.levels;
+}
 
 // false: a CUDA call failed. `gaveUp`: the tree chains deeper than sweep::kMaxLevels (thousands of coincident primitives), nothing was written.
 bool build_qbvh_sweep(const EchoTriangle* triangles, uint32_t triangleCount, const EchoSphere* spheres, uint32_t sphereCount,
@@ -135,7 +144,7 @@ bool build_qbvh_sweep(const EchoTriangle* triangles, uint32_t triangleCount, con
 
 	if (!check_cuda(cudaMemcpyAsync(dTriangles, triangles, sizeof(EchoTriangle) * triangleCount, cudaMemcpyHostToDevice, backend.stream), "cudaMemcpyAsync(triangles)")
 		|| !check_cuda(cudaMemcpyAsync(dSpheres, spheres, sphereBytes, cudaMemcpyHostToDevice, backend.stream), "cudaMemcpyAsync(spheres)")) return false;
-	if (profile) cudaStreamSynchronize(backend.stream);
+	if (!check_cuda(cudaStreamSynchronize(backend.stream), "sweep upload")) return false; // the phases are reported separately (last_sweep_build)
 	double uploadMs = since(started);
 	auto phase = clock();
 
@@ -148,14 +157,14 @@ bool build_qbvh_sweep(const EchoTriangle* triangles, uint32_t triangleCount, con
 
 	if (!check_cuda(cudaMemcpy(outNodes, result.quads, sizeof(EchoQbvhNode) * result.nodeCount, cudaMemcpyDeviceToHost), "cudaMemcpy(nodes)")) return false;
 	double downloadMs = since(phase);
-	phase = clock();
 
 	*outNodeCount = result.nodeCount;
-	*outMaxDepth = sweep::quad_depth(outNodes, result.nodeCount);
+	*outMaxDepth = result.maxDepth;
+	gLastBuild = { (float)uploadMs, (float)buildMs, (float)downloadMs, (float)result.levels };
 
 	if (profile)
-		std::fprintf(stderr, "[echo_b200 build] sweep: %llu primitives -> %u nodes, %u binary levels: upload %.2f ms, build %.2f ms (%u launches, %u syncs), download %.2f ms, depth pass %.2f ms\n",
-		             (unsigned long long)total64, result.nodeCount, result.levels, uploadMs, buildMs, backend.launches, backend.syncs, downloadMs, since(phase));
+		std::fprintf(stderr, "[echo_b200 build] sweep: %llu primitives -> %u nodes, quad depth %u, %u binary levels: upload %.2f ms, build %.2f ms (%u launches, %u syncs), download %.2f ms\n",
+		             (unsigned long long)total64, result.nodeCount, result.maxDepth, result.levels, uploadMs, buildMs, backend.launches, backend.syncs, downloadMs);
 	return true;
 }
 

@@ -412,8 +412,10 @@ def shard_tiles(tile_positions, rank, world_size, block=1, by="sequence"):
 
 
 def build_qbvh_device(triangles, spheres, device=0):
-    """The optional device-side tree build (echo_b200_build_qbvh): a linear BVH collapsed to the reference's QBVH node format.
-    Returns (nodes, max_depth) like host.build_qbvh — a valid tree, not the SweepBuilder's."""
+    """The optional device-side tree build (echo_b200_build_qbvh). Returns (nodes, max_depth) like host.build_qbvh. By default
+    (BUILD_ALGORITHM 2, csrc/sweep.cu) the tree IS the SweepBuilder's — the nodes equal host.build_qbvh's byte for byte; inputs that
+    chain deeper than the traversal stacks allow, and BUILD_ALGORITHM 1 / 0, give a clustered (PLOC) or Morton-ordered tree instead:
+    valid, but not the reference's."""
     lib = _native.library()
     triangles = np.ascontiguousarray(triangles, dtype=structs.TRIANGLE)
     spheres = np.ascontiguousarray(spheres, dtype=structs.SPHERE)

@@ -419,11 +419,16 @@ int32_t echo_b200_render_frame_device(EchoScene*, const EchoRenderParams*, const
                                       float* d_frame_rgba, EchoStats* stats, void* stream);
 int32_t echo_b200_frame_resolve_device(EchoScene*, float* d_frame_rgba, int32_t width, int32_t height, void* stream);
 
-/* Optional device-side tree build: a linear BVH over 63-bit Morton codes (Karras 2012) collapsed into the
- * reference's QBVH node format (QuadBoundingVolumeHierarchy.cs:363-565). NOT the SweepBuilder's SAH tree (echo_host.h mirrors
- * that one and stays the default): a valid tree of lower quality that builds in milliseconds, for previews and animated
- * geometry. Tokens: triangles, then spheres, as GeometryCollection.CreateBounds numbers them. `out_nodes` (host) needs room for
- * triangle_count + sphere_count - 1 nodes; out_max_depth is the depth CreateNode reports (what set_qbvh takes). */
+/* Optional device-side tree build in the reference's QBVH node format. By default the tree is the reference's
+ * own: SweepBuilder.Build (Aggregation/Acceleration/SweepBuilder.cs:24-160 — stable sort by min + max along the major axis of the
+ * node's volume, one-axis sweep for the first cut of lowest cost, larger-area child first) and the QuadBoundingVolumeHierarchy collapse
+ * (QuadBoundingVolumeHierarchy.cs:363-565, nodes in pre-order), run level by level on the device; the emitted array equals what the
+ * recursive build emits byte for byte (echo_host.h's mirror; tests/test_gpu_build.py, tests/test_sweep_build.py). 1 010 000 primitives:
+ * 15 ms of device work against 430 ms for the host mirror on 16 cores. Inputs whose tree chains deeper than the traversal stacks allow
+ * (thousands of coincident primitives) — and ECHO_B200_BUILD_ALGORITHM=1 / 0 — get a clustered (PLOC) or Morton-ordered (Karras 2012)
+ * binary tree collapsed the same way instead: valid, lower quality, not the reference's. Tokens: triangles, then spheres, as
+ * GeometryCollection.CreateBounds numbers them. `out_nodes` (host) needs room for triangle_count + sphere_count - 1 nodes;
+ * out_max_depth is the depth CreateNode reports (what set_qbvh takes). */
 int32_t echo_b200_build_qbvh(int32_t device, const EchoTriangle* triangles, uint32_t triangle_count, const EchoSphere* spheres, uint32_t sphere_count,
                              EchoQbvhNode* out_nodes, uint32_t* out_node_count, uint32_t* out_max_depth);
 

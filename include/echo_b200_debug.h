@@ -48,6 +48,10 @@ int32_t echo_b200_debug_measure_peaks(int32_t device, float* out3);
  * last two). Process-wide; takes effect with the next render call. For A/B runs that keep one uploaded scene. */
 int32_t echo_b200_debug_set_option(const char* name, int64_t value);
 
+/* Phases of the calling thread's last echo_b200_build_qbvh that ran the SweepBuilder build (csrc/sweep.cu): out4 = {upload ms, device
+ * build ms, download ms, binary levels}, host wall time around synchronised phases. Zeros if no such build ran on this thread. */
+int32_t echo_b200_debug_last_build(float* out4);
+
 #ifdef __cplusplus
 }
 #endif

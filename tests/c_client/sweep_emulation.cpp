@@ -74,7 +74,8 @@ extern "C" int32_t sweep_emulation_build(const EchoTriangle* triangles, uint32_t
 	if (result.gaveUp) return 2;
 	std::memcpy(out, result.quads, sizeof(EchoQbvhNode) * result.nodeCount);
 	*outNodeCount = result.nodeCount;
-	*outMaxDepth = quad_depth(out, result.nodeCount);
+	*outMaxDepth = result.maxDepth;
+	if (quad_depth(out, result.nodeCount) != result.maxDepth) return 3; // the depth the passes computed is not the emitted array's
 	*outLevels = result.levels;
 	return 0;
 }

@@ -51,6 +51,9 @@ def test_trace_bench_line():
     # the on-chip ceilings are measured live by the library and the same algorithmic bytes are set against them
     assert roofline["frac_l2"] == pytest.approx(roofline["achieved"] / roofline["l2_peak_gbs"], rel=1e-6) and roofline["l2_peak_gbs"] > 0
     assert roofline["l1_sector_peak_gbs"] > 0 and "L1" in roofline["bound_measured"]
+    # the device SweepBuilder beside the host mirror of the recursive build: the same bytes
+    build = line["tree_build"]
+    assert build["identical_to_host_mirror"] and build["nodes"] == line["config"]["tree"]["nodes"] and build["device_build_ms"] > 0 and build["host_mirror_ms"] > 0
 
 
 def check_render_record(record, width, height, spp):
