@@ -554,17 +554,23 @@ int32_t echo_b200_scene_set_textures(EchoScene* scene, const EchoTexture* textur
 	return ECHO_B200_OK;
 }
 
-int32_t echo_b200_build_qbvh(int32_t device, const EchoTriangle* triangles, uint32_t triangleCount, const EchoSphere* spheres, uint32_t sphereCount,
-                             EchoQbvhNode* outNodes, uint32_t* outNodeCount, uint32_t* outMaxDepth)
+int32_t echo_b200_build_qbvh_instanced(int32_t device, const EchoTriangle* triangles, uint32_t triangleCount, const EchoSphere* spheres, uint32_t sphereCount,
+                                       const float* instanceBounds, uint32_t instanceCount, EchoQbvhNode* outNodes, uint32_t* outNodeCount, uint32_t* outMaxDepth)
 {
-	if ((!triangles && triangleCount) || (!spheres && sphereCount) || !outNodes || !outNodeCount || !outMaxDepth) return fail(ECHO_B200_ERR_INVALID, "null argument");
+	if ((!triangles && triangleCount) || (!spheres && sphereCount) || (!instanceBounds && instanceCount) || !outNodes || !outNodeCount || !outMaxDepth) return fail(ECHO_B200_ERR_INVALID, "null argument");
 	int32_t count = 0;
 	int32_t status = echo_b200_device_count(&count);
 	if (status != ECHO_B200_OK) return status;
 	if (device < 0 || device >= count) return fail(ECHO_B200_ERR_INVALID, "device index out of range");
 	DeviceGuard guard(device);
 	if (!guard.ok) return ECHO_B200_ERR_NO_DEVICE;
-	return build_qbvh_device(triangles, triangleCount, spheres, sphereCount, outNodes, outNodeCount, outMaxDepth) ? ECHO_B200_OK : ECHO_B200_ERR_CUDA;
+	return build_qbvh_device(triangles, triangleCount, spheres, sphereCount, instanceBounds, instanceCount, outNodes, outNodeCount, outMaxDepth) ? ECHO_B200_OK : ECHO_B200_ERR_CUDA;
+}
+
+int32_t echo_b200_build_qbvh(int32_t device, const EchoTriangle* triangles, uint32_t triangleCount, const EchoSphere* spheres, uint32_t sphereCount,
+                             EchoQbvhNode* outNodes, uint32_t* outNodeCount, uint32_t* outMaxDepth)
+{
+	return echo_b200_build_qbvh_instanced(device, triangles, triangleCount, spheres, sphereCount, nullptr, 0u, outNodes, outNodeCount, outMaxDepth);
 }
 
 int32_t echo_b200_scene_set_distributions(EchoScene* scene, const float* values, uint64_t count)

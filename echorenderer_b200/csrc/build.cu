@@ -49,10 +49,10 @@ __device__ __forceinline__ float ordered_to_float(int value) { return __int_as_f
 
 // PreparedTriangle.BoxBound (TriangleEntity.cs:142) / PreparedSphere.BoxBound (SphereEntity.cs:66) + the scene bound of the centres
 __global__ void primitive_bounds_kernel(const EchoTriangle* __restrict__ triangles, uint32_t triangleCount, const EchoSphere* __restrict__ spheres, uint32_t sphereCount,
-                                        BuildBox* __restrict__ boxes, uint32_t* __restrict__ tokens, int* __restrict__ sceneBound)
+                                        const float* __restrict__ instanceBounds, uint32_t instanceCount, BuildBox* __restrict__ boxes, uint32_t* __restrict__ tokens, int* __restrict__ sceneBound)
 {
 	uint32_t i = blockIdx.x * kBuildBlock + threadIdx.x;
-	uint32_t total = triangleCount + sphereCount;
+	uint32_t total = triangleCount + sphereCount + instanceCount;
 	if (i >= total) return;
 
 	BuildBox box;
@@ -65,6 +65,12 @@ __global__ void primitive_bounds_kernel(const EchoTriangle* __restrict__ triangl
 		box = { fminf(t.vertex0[0], fminf(v1x, v2x)), fminf(t.vertex0[1], fminf(v1y, v2y)), fminf(t.vertex0[2], fminf(v1z, v2z)),
 		        fmaxf(t.vertex0[0], fmaxf(v1x, v2x)), fmaxf(t.vertex0[1], fmaxf(v1y, v2y)), fmaxf(t.vertex0[2], fmaxf(v1z, v2z)) };
 		tokens[i] = ECHO_TOKEN_MAKE(ECHO_TOKEN_TYPE_TRIANGLE, i);
+	}
+	else if (i >= triangleCount + sphereCount) // PreparedInstance.BoxBound of a placement: min xyz, max xyz
+	{
+		const float* b = instanceBounds + (size_t)(i - triangleCount - sphereCount) * 6;
+		box = { b[0], b[1], b[2], b[3], b[4], b[5] };
+		tokens[i] = ECHO_TOKEN_MAKE(ECHO_TOKEN_TYPE_INSTANCE, i - triangleCount - sphereCount);
 	}
 	else
 	{
@@ -427,10 +433,10 @@ bool set_build_option(const char* name, long long value)
 }
 
 static bool build_qbvh_with(bool ploc, const EchoTriangle* triangles, uint32_t triangleCount, const EchoSphere* spheres, uint32_t sphereCount,
-                            EchoQbvhNode* outNodes, uint32_t* outNodeCount, uint32_t* outMaxDepth, bool* stalled);
+                            const float* instanceBounds, uint32_t instanceCount, EchoQbvhNode* outNodes, uint32_t* outNodeCount, uint32_t* outMaxDepth, bool* stalled);
 
 bool build_qbvh_device(const EchoTriangle* triangles, uint32_t triangleCount, const EchoSphere* spheres, uint32_t sphereCount,
-                       EchoQbvhNode* outNodes, uint32_t* outNodeCount, uint32_t* outMaxDepth)
+                       const float* instanceBounds, uint32_t instanceCount, EchoQbvhNode* outNodes, uint32_t* outNodeCount, uint32_t* outMaxDepth)
 {
 	const int algorithm = build_algorithm();
 
@@ -439,26 +445,26 @@ bool build_qbvh_device(const EchoTriangle* triangles, uint32_t triangleCount, co
 		// The reference's own tree. Its depth is unbounded for degenerate inputs (coincident primitives peel off one per level, in the
 		// recursive original as well); then, or when the tree would not fit the deepest compiled traversal stack, the clustering takes over.
 		bool gaveUp = false;
-		if (!build_qbvh_sweep(triangles, triangleCount, spheres, sphereCount, outNodes, outNodeCount, outMaxDepth, &gaveUp)) return false;
+		if (!build_qbvh_sweep(triangles, triangleCount, spheres, sphereCount, instanceBounds, instanceCount, outNodes, outNodeCount, outMaxDepth, &gaveUp)) return false;
 		if (!gaveUp && stack_class(*outMaxDepth) >= 0) return true;
 	}
 
 	const bool ploc = algorithm != 0;
 	bool stalled = false;
-	if (!build_qbvh_with(ploc, triangles, triangleCount, spheres, sphereCount, outNodes, outNodeCount, outMaxDepth, &stalled)) return false;
+	if (!build_qbvh_with(ploc, triangles, triangleCount, spheres, sphereCount, instanceBounds, instanceCount, outNodes, outNodeCount, outMaxDepth, &stalled)) return false;
 
 	// Agglomeration has neither a depth bound nor a bound on its passes: thousands of coincident primitives merge one pair per pass
 	// and chain. The Morton tree has both (63 key bits). Fall back to it when the clustering stalls or when the clustered tree would
 	// not fit the deepest compiled traversal stack (192 entries = 63 quad levels).
-	if (ploc && (stalled || stack_class(*outMaxDepth) < 0)) return build_qbvh_with(false, triangles, triangleCount, spheres, sphereCount, outNodes, outNodeCount, outMaxDepth, &stalled);
+	if (ploc && (stalled || stack_class(*outMaxDepth) < 0)) return build_qbvh_with(false, triangles, triangleCount, spheres, sphereCount, instanceBounds, instanceCount, outNodes, outNodeCount, outMaxDepth, &stalled);
 	return true;
 }
 
 static bool build_qbvh_with(bool ploc, const EchoTriangle* triangles, uint32_t triangleCount, const EchoSphere* spheres, uint32_t sphereCount,
-                            EchoQbvhNode* outNodes, uint32_t* outNodeCount, uint32_t* outMaxDepth, bool* stalled)
+                            const float* instanceBounds, uint32_t instanceCount, EchoQbvhNode* outNodes, uint32_t* outNodeCount, uint32_t* outMaxDepth, bool* stalled)
 {
 	*stalled = false;
-	uint64_t total64 = (uint64_t)triangleCount + sphereCount;
+	uint64_t total64 = (uint64_t)triangleCount + sphereCount + instanceCount;
 	if (total64 < 2 || total64 >= (1ull << ECHO_TOKEN_INDEX_BITS)) { set_error("a tree needs 2..2^28-1 primitives"); return false; }
 	int total = (int)total64, internal = total - 1;
 
@@ -470,6 +476,7 @@ static bool build_qbvh_with(bool ploc, const EchoTriangle* triangles, uint32_t t
 	DeviceArena arena;
 	EchoTriangle* dTriangles;
 	EchoSphere* dSpheres;
+	float* dInstanceBounds;
 	BuildBox *boxes, *nodeBoxes;
 	uint32_t *tokens, *order, *orderSorted, *left, *right, *parentOfInternal, *parentOfLeaf, *visits, *isQuad, *quadIndex;
 	unsigned long long *keys, *keysSorted;
@@ -484,7 +491,7 @@ static bool build_qbvh_with(bool ploc, const EchoTriangle* triangles, uint32_t t
 	cub::DeviceRadixSort::SortPairs(nullptr, sortBytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, total, 0, 63);
 	cub::DeviceScan::ExclusiveSum(nullptr, scanBytes, (uint32_t*)nullptr, (uint32_t*)nullptr, internal);
 
-	arena.reserve(dTriangles, triangleCount); arena.reserve(dSpheres, sphereCount); arena.reserve(boxes, total); arena.reserve(nodeBoxes, internal);
+	arena.reserve(dTriangles, triangleCount); arena.reserve(dSpheres, sphereCount); arena.reserve(dInstanceBounds, (uint64_t)instanceCount * 6); arena.reserve(boxes, total); arena.reserve(nodeBoxes, internal);
 	arena.reserve(tokens, total); arena.reserve(order, total); arena.reserve(orderSorted, total); arena.reserve(left, internal); arena.reserve(right, internal);
 	arena.reserve(parentOfInternal, internal); arena.reserve(parentOfLeaf, total); arena.reserve(visits, internal); arena.reserve(isQuad, internal);
 	arena.reserve(quadIndex, internal); arena.reserve(keys, total); arena.reserve(keysSorted, total); arena.reserve(sceneBound, 6); arena.reserve(nodes, internal);
@@ -501,7 +508,8 @@ static bool build_qbvh_with(bool ploc, const EchoTriangle* triangles, uint32_t t
 	auto phase = clock();
 	cudaStream_t stream = nullptr;
 	ok = check_cuda(cudaMemcpyAsync(dTriangles, triangles, sizeof(EchoTriangle) * triangleCount, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync(triangles)")
-		&& check_cuda(cudaMemcpyAsync(dSpheres, spheres, sizeof(EchoSphere) * sphereCount, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync(spheres)");
+		&& check_cuda(cudaMemcpyAsync(dSpheres, spheres, sizeof(EchoSphere) * sphereCount, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync(spheres)")
+		&& (instanceCount == 0u || check_cuda(cudaMemcpyAsync(dInstanceBounds, instanceBounds, sizeof(float) * 6 * instanceCount, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync(instance bounds)"));
 	if (!ok) return false;
 
 	const int initial[6] = { 0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF, (int)0x80000000, (int)0x80000000, (int)0x80000000 };
@@ -513,7 +521,7 @@ static bool build_qbvh_with(bool ploc, const EchoTriangle* triangles, uint32_t t
 	double uploadMs = since(phase);
 	phase = clock();
 
-	primitive_bounds_kernel<<<build_blocks(total), kBuildBlock, 0, stream>>>(dTriangles, triangleCount, dSpheres, sphereCount, boxes, tokens, sceneBound);
+	primitive_bounds_kernel<<<build_blocks(total), kBuildBlock, 0, stream>>>(dTriangles, triangleCount, dSpheres, sphereCount, dInstanceBounds, instanceCount, boxes, tokens, sceneBound);
 	morton_kernel<<<build_blocks(total), kBuildBlock, 0, stream>>>(boxes, (uint32_t)total, sceneBound, keys, order);
 
 	cub::DeviceRadixSort::SortPairs(scratch, sortBytes, keys, keysSorted, order, orderSorted, total, 0, 63, stream);

@@ -205,11 +205,13 @@ SWEEP_HD void atomic_or_u32(uint32_t* address, uint32_t value)
 
 // ---- passes ----
 
-struct BoundsPass // GeometryCollection.CreateBounds (GeometryCollection.cs:52-81): triangles, then spheres; position i starts as primitive i
+struct BoundsPass // GeometryCollection.CreateBounds (GeometryCollection.cs:52-81): triangles, spheres, then instances; position i starts as primitive i
 {
 	const EchoTriangle* triangles;
 	uint32_t triangleCount;
 	const EchoSphere* spheres;
+	uint32_t sphereCount;
+	const float* instanceBounds; // PreparedInstance.BoxBound of the pack's placements: min xyz, max xyz
 	Box* boxes;
 	uint32_t* tokens;
 	uint32_t* perm;
@@ -229,6 +231,12 @@ struct BoundsPass // GeometryCollection.CreateBounds (GeometryCollection.cs:52-8
 				box.hi[k] = select_max(select_max(v0, v1), v2);
 			}
 			tokens[i] = ECHO_TOKEN_MAKE(ECHO_TOKEN_TYPE_TRIANGLE, i);
+		}
+		else if (i >= triangleCount + sphereCount)
+		{
+			const float* bound = instanceBounds + (size_t)(i - triangleCount - sphereCount) * 6;
+			for (int k = 0; k < 3; k++) { box.lo[k] = bound[k]; box.hi[k] = bound[3 + k]; }
+			tokens[i] = ECHO_TOKEN_MAKE(ECHO_TOKEN_TYPE_INSTANCE, i - triangleCount - sphereCount);
 		}
 		else // PreparedSphere.BoxBound, SphereEntity.cs:66
 		{
@@ -673,10 +681,11 @@ struct Result
 //   template<class T> bool write(T* destination, const T* source, uint32_t n)   host -> backend
 //   bool fill_zero(void* pointer, size_t bytes)
 template<class Backend>
-Result build(Backend& backend, const EchoTriangle* triangles, uint32_t triangleCount, const EchoSphere* spheres, uint32_t sphereCount)
+Result build(Backend& backend, const EchoTriangle* triangles, uint32_t triangleCount, const EchoSphere* spheres, uint32_t sphereCount,
+             const float* instanceBounds, uint32_t instanceCount)
 {
 	Result result;
-	const uint32_t total = triangleCount + sphereCount;
+	const uint32_t total = triangleCount + sphereCount + instanceCount;
 
 	Buffers b;
 	Arena measure;
@@ -686,7 +695,7 @@ Result build(Backend& backend, const EchoTriangle* triangles, uint32_t triangleC
 	if (!arena.base) return result;
 	b.carve(arena, total);
 
-	if (!backend.for_each(total, BoundsPass{ triangles, triangleCount, spheres, b.boxes, b.tokens, b.perm[0], b.segmentOf[0] })) return result;
+	if (!backend.for_each(total, BoundsPass{ triangles, triangleCount, spheres, sphereCount, instanceBounds, b.boxes, b.tokens, b.perm[0], b.segmentOf[0] })) return result;
 
 	// Build, SweepBuilder.cs:24-36: the root is sorted by the major axis of the bound of everything
 	Segment root = { 0u, total, 0u, 0u };

@@ -117,10 +117,10 @@ void last_sweep_build(float* out4)
 
 // false: a CUDA call failed. `gaveUp`: the tree chains deeper than sweep::kMaxLevels (thousands of coincident primitives), nothing was written.
 bool build_qbvh_sweep(const EchoTriangle* triangles, uint32_t triangleCount, const EchoSphere* spheres, uint32_t sphereCount,
-                      EchoQbvhNode* outNodes, uint32_t* outNodeCount, uint32_t* outMaxDepth, bool* gaveUp)
+                      const float* instanceBounds, uint32_t instanceCount, EchoQbvhNode* outNodes, uint32_t* outNodeCount, uint32_t* outMaxDepth, bool* gaveUp)
 {
 	*gaveUp = false;
-	uint64_t total64 = (uint64_t)triangleCount + sphereCount;
+	uint64_t total64 = (uint64_t)triangleCount + sphereCount + instanceCount;
 	if (total64 < 2 || total64 >= (1ull << ECHO_TOKEN_INDEX_BITS)) { set_error("a tree needs 2..2^28-1 primitives"); return false; }
 
 	const bool profile = std::getenv("ECHO_B200_PROFILE") != nullptr;
@@ -137,18 +137,21 @@ bool build_qbvh_sweep(const EchoTriangle* triangles, uint32_t triangleCount, con
 		~Inputs() { cudaFree(base); }
 	} inputs;
 
-	size_t triangleBytes = (sizeof(EchoTriangle) * triangleCount + 255) & ~size_t(255), sphereBytes = sizeof(EchoSphere) * sphereCount;
-	if (!check_cuda(cudaMalloc((void**)&inputs.base, triangleBytes + sphereBytes + 256), "cudaMalloc(sweep inputs)")) return false;
+	size_t triangleBytes = (sizeof(EchoTriangle) * triangleCount + 255) & ~size_t(255), sphereBytes = (sizeof(EchoSphere) * sphereCount + 255) & ~size_t(255);
+	size_t instanceBytes = sizeof(float) * 6 * instanceCount;
+	if (!check_cuda(cudaMalloc((void**)&inputs.base, triangleBytes + sphereBytes + instanceBytes + 256), "cudaMalloc(sweep inputs)")) return false;
 	EchoTriangle* dTriangles = (EchoTriangle*)inputs.base;
 	EchoSphere* dSpheres = (EchoSphere*)(inputs.base + triangleBytes);
+	float* dInstanceBounds = (float*)(inputs.base + triangleBytes + sphereBytes);
 
 	if (!check_cuda(cudaMemcpyAsync(dTriangles, triangles, sizeof(EchoTriangle) * triangleCount, cudaMemcpyHostToDevice, backend.stream), "cudaMemcpyAsync(triangles)")
-		|| !check_cuda(cudaMemcpyAsync(dSpheres, spheres, sphereBytes, cudaMemcpyHostToDevice, backend.stream), "cudaMemcpyAsync(spheres)")) return false;
+		|| !check_cuda(cudaMemcpyAsync(dSpheres, spheres, sizeof(EchoSphere) * sphereCount, cudaMemcpyHostToDevice, backend.stream), "cudaMemcpyAsync(spheres)")
+		|| (instanceCount != 0u && !check_cuda(cudaMemcpyAsync(dInstanceBounds, instanceBounds, instanceBytes, cudaMemcpyHostToDevice, backend.stream), "cudaMemcpyAsync(instance bounds)"))) return false;
 	if (!check_cuda(cudaStreamSynchronize(backend.stream), "sweep upload")) return false; // the phases are reported separately (last_sweep_build)
 	double uploadMs = since(started);
 	auto phase = clock();
 
-	sweep::Result result = sweep::build(backend, dTriangles, triangleCount, dSpheres, sphereCount);
+	sweep::Result result = sweep::build(backend, dTriangles, triangleCount, dSpheres, sphereCount, dInstanceBounds, instanceCount);
 	if (!result.ok) return false;
 	if (result.gaveUp) { *gaveUp = true; return true; }
 

@@ -279,7 +279,7 @@ def build_light_tree(description, instance_lights=None):
             _take(paths, emitter_count.value, np.uint64), float(power.value))
 
 
-def _prepare_packs(description, threads):
+def _prepare_packs(description, threads, tree_builder=None):
     """ScenePreparer: every EntityPack becomes one PreparedPack (children before parents), then all arrays are laid back to
     back with an EchoPack record per pack (pack 0 = the scene) and an EchoInstance record per placement."""
     sources = [description] + list(description.packs)  # pack k+1 = description.packs[k]
@@ -310,7 +310,11 @@ def _prepare_packs(description, threads):
                 lights.append(np.concatenate([box, axis, [root["cosOffset"], root["cosExtend"], power]]).astype(np.float32))
             else:
                 lights.append(np.zeros(12, dtype=np.float32))
-        nodes, depth = build_qbvh(source.triangles, source.spheres, threads, np.asarray(boxes, dtype=np.float32) if boxes else None)
+        pack_boxes = np.asarray(boxes, dtype=np.float32) if boxes else None
+        if tree_builder is not None and len(source.triangles) + len(source.spheres) + len(boxes) >= 2:
+            nodes, depth = tree_builder(source.triangles, source.spheres, pack_boxes)
+        else:
+            nodes, depth = build_qbvh(source.triangles, source.spheres, threads, pack_boxes)
         built[index] = (nodes, depth, build_light_tree(source, np.asarray(lights, dtype=np.float32) if lights else None))
         source._records = records
         return built[index]
@@ -682,9 +686,10 @@ def _root_bound_radius(nodes):
     return accelerator_sphere_bound(nodes).radius
 
 
-def prepare(description, threads=0, tree=None):
+def prepare(description, threads=0, tree=None, tree_builder=None):
     """ScenePreparer.Prepare -> PreparedScene constructor (PreparedScene.cs:26-40). `tree` = (nodes, max_depth) replaces the
-    SweepBuilder mirror for a scene without instances (e.g. the device-side build, scene.build_qbvh_device)."""
+    SweepBuilder mirror for a scene without instances; `tree_builder(triangles, spheres, instance_bounds) -> (nodes, max_depth)`
+    replaces it for every pack of any scene (e.g. the device-side build: lambda t, s, b: scene.build_qbvh_device(t, s, instance_bounds=b))."""
     lib = _library()
     d = description
     d.triangles = np.ascontiguousarray(d.triangles, dtype=structs.TRIANGLE)
@@ -695,10 +700,10 @@ def prepare(description, threads=0, tree=None):
 
     instanced = bool(d.instances)
     if instanced:
-        packs, instances, nodes, all_triangles, all_spheres, all_materials, max_depth, lights, all_slots = _prepare_packs(d, threads)
+        packs, instances, nodes, all_triangles, all_spheres, all_materials, max_depth, lights, all_slots = _prepare_packs(d, threads, tree_builder)
         light_nodes, tokens, paths, all_points, scene_power = lights
     else:
-        nodes, max_depth = tree if tree is not None else build_qbvh(d.triangles, d.spheres, threads)
+        nodes, max_depth = tree if tree is not None else (tree_builder(d.triangles, d.spheres, None) if tree_builder is not None else build_qbvh(d.triangles, d.spheres, threads))
         light_nodes, tokens, paths, scene_power = build_light_tree(d)
 
     # FilterLights / SumInfiniteLightsPower / CalculateThreshold (PreparedScene.cs:279-325)

@@ -411,19 +411,21 @@ def shard_tiles(tile_positions, rank, world_size, block=1, by="sequence"):
     return np.ascontiguousarray(tile_positions[owner == rank])
 
 
-def build_qbvh_device(triangles, spheres, device=0):
+def build_qbvh_device(triangles, spheres, device=0, instance_bounds=None):
     """The optional device-side tree build (echo_b200_build_qbvh). Returns (nodes, max_depth) like host.build_qbvh. By default
     (BUILD_ALGORITHM 2, csrc/sweep.cu) the tree IS the SweepBuilder's — the nodes equal host.build_qbvh's byte for byte; inputs that
     chain deeper than the traversal stacks allow, and BUILD_ALGORITHM 1 / 0, give a clustered (PLOC) or Morton-ordered tree instead:
-    valid, but not the reference's."""
+    valid, but not the reference's. instance_bounds: [n, 6] float32 boxes (min xyz, max xyz) of the pack's placements, tokenized
+    after the spheres (echo_b200_build_qbvh_instanced), as in host.build_qbvh."""
     lib = _native.library()
     triangles = np.ascontiguousarray(triangles, dtype=structs.TRIANGLE)
     spheres = np.ascontiguousarray(spheres, dtype=structs.SPHERE)
-    total = len(triangles) + len(spheres)
-    nodes = np.zeros(max(total - 1, 1), dtype=structs.QBVH_NODE)
+    boxes = np.zeros((0, 6), dtype=np.float32) if instance_bounds is None else np.ascontiguousarray(instance_bounds, dtype=np.float32).reshape(-1, 6)
+    total = len(triangles) + len(spheres) + len(boxes)
+    nodes = np.empty(max(total - 1, 1), dtype=structs.QBVH_NODE)
     count, depth = ctypes.c_uint32(), ctypes.c_uint32()
-    _native.check(lib.echo_b200_build_qbvh(device, _native.pointer(triangles), len(triangles), _native.pointer(spheres), len(spheres),
-                                           _native.pointer(nodes), ctypes.byref(count), ctypes.byref(depth)))
+    _native.check(lib.echo_b200_build_qbvh_instanced(device, _native.pointer(triangles), len(triangles), _native.pointer(spheres), len(spheres), _native.pointer(boxes), len(boxes),
+                                                     _native.pointer(nodes), ctypes.byref(count), ctypes.byref(depth)))
     return nodes[:count.value].copy(), int(depth.value)
 
 

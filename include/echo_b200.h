@@ -431,6 +431,11 @@ int32_t echo_b200_frame_resolve_device(EchoScene*, float* d_frame_rgba, int32_t 
  * out_max_depth is the depth CreateNode reports (what set_qbvh takes). */
 int32_t echo_b200_build_qbvh(int32_t device, const EchoTriangle* triangles, uint32_t triangle_count, const EchoSphere* spheres, uint32_t sphere_count,
                              EchoQbvhNode* out_nodes, uint32_t* out_node_count, uint32_t* out_max_depth);
+/* The same for a pack that holds placements (GeometryCollection.CreateBounds, GeometryCollection.cs:52-81: triangles, spheres, then
+ * instances): `instance_bounds` = 6 floats per placement, PreparedInstance.BoxBound as min xyz, max xyz; their tokens are
+ * TokenType.Instance in the order given. Mirrors echo_host_build_qbvh_instanced (echo_host.h). */
+int32_t echo_b200_build_qbvh_instanced(int32_t device, const EchoTriangle* triangles, uint32_t triangle_count, const EchoSphere* spheres, uint32_t sphere_count,
+                                       const float* instance_bounds, uint32_t instance_count, EchoQbvhNode* out_nodes, uint32_t* out_node_count, uint32_t* out_max_depth);
 
 /* Page-locked host memory for the host-buffer entry points. A P/Invoke caller pins managed arrays with `fixed`
  * (Processes/Composition/OidnDenoise.cs:109-110): that stops the GC from moving them but leaves them PAGEABLE for CUDA, so every

@@ -63,13 +63,14 @@ struct CpuBackend
 
 } // namespace
 
-// 0 = built; 1 = failed; 2 = gave up (deeper than kMaxLevels). `out` holds triangleCount + sphereCount - 1 nodes at most.
-extern "C" int32_t sweep_emulation_build(const EchoTriangle* triangles, uint32_t triangleCount, const EchoSphere* spheres, uint32_t sphereCount, int32_t reverse,
+// 0 = built; 1 = failed; 2 = gave up (deeper than kMaxLevels). `out` holds (primitives - 1) nodes at most.
+extern "C" int32_t sweep_emulation_build(const EchoTriangle* triangles, uint32_t triangleCount, const EchoSphere* spheres, uint32_t sphereCount,
+                                         const float* instanceBounds, uint32_t instanceCount, int32_t reverse,
                                          EchoQbvhNode* out, uint32_t* outNodeCount, uint32_t* outMaxDepth, uint32_t* outLevels)
 {
 	CpuBackend backend;
 	backend.reverse = reverse != 0;
-	Result result = build(backend, triangles, triangleCount, spheres, sphereCount);
+	Result result = build(backend, triangles, triangleCount, spheres, sphereCount, instanceBounds, instanceCount);
 	if (!result.ok) return 1;
 	if (result.gaveUp) return 2;
 	std::memcpy(out, result.quads, sizeof(EchoQbvhNode) * result.nodeCount);

@@ -148,9 +148,9 @@ def test_clustered_tree_is_cheaper_to_traverse_than_the_morton_tree(terrain_smal
     assert visits["sweep"] == sah  # the same tree
 
 
-def assert_device_tree_is_the_host_mirrors(triangles, spheres):
-    expected, expected_depth = host.build_qbvh(triangles, spheres)
-    nodes, depth = build_qbvh_device(triangles, spheres)
+def assert_device_tree_is_the_host_mirrors(triangles, spheres, instance_bounds=None):
+    expected, expected_depth = host.build_qbvh(triangles, spheres, instance_bounds=instance_bounds)
+    nodes, depth = build_qbvh_device(triangles, spheres, instance_bounds=instance_bounds)
     assert len(nodes) == len(expected) and depth == expected_depth
     assert nodes.tobytes() == expected.tobytes()
 
@@ -165,8 +165,11 @@ def test_device_sweep_tree_is_the_host_mirrors_byte_for_byte(fixture, request):
 
 
 def test_device_sweep_tree_on_soups_ties_and_tiny_inputs():
-    from tests.test_sweep_build import NO_SPHERES, random_soup
+    from tests.test_sweep_build import NO_SPHERES, random_instance_bounds, random_soup
     _native.set_option("BUILD_ALGORITHM", 2)
+    triangles, spheres = random_soup(21, 400, 30, 10.0)  # packs with placements: TokenType.Instance leaves after the spheres
+    assert_device_tree_is_the_host_mirrors(triangles, spheres, random_instance_bounds(22, 200, 10.0))
+    assert_device_tree_is_the_host_mirrors(triangles[:0], spheres[:0], random_instance_bounds(23, 2304, 50.0))
     for seed, triangle_count, sphere_count, scale in [(1, 2, 0, 1.0), (2, 1, 1, 1.0), (3, 3, 0, 5.0), (4, 33, 7, 1.0), (5, 1000, 100, 100.0), (6, 20000, 500, 1e-3),
                                                        (7, 5000, 5000, 1e4), (8, 0, 300, 2.0), (9, 300_000, 3000, 10.0)]:
         assert_device_tree_is_the_host_mirrors(*random_soup(seed, triangle_count, sphere_count, scale))
@@ -190,3 +193,14 @@ def test_device_sweep_tree_at_full_size():
     print(f"sweep build of {len(description.triangles) + len(description.spheres)} primitives: device call {device_seconds * 1e3:.1f} ms, host mirror {host_seconds * 1e3:.1f} ms")
     assert len(nodes) == len(expected) == 565_329 and depth == expected_depth == 13
     assert nodes.tobytes() == expected.tobytes()
+
+
+
+def test_instanced_scene_prepared_with_device_built_trees_is_the_same_scene():
+    """Every pack of a nested instanced scene (placements of placements) built on the device: host.prepare with the device builder gives
+    the very arrays the host mirror gives, so everything downstream — traversal, shading, light trees — is unchanged."""
+    _native.set_option("BUILD_ALGORITHM", 2)
+    expected = host.prepare(scenes.instanced_scene(grid=4, rings=12, segments=12))
+    built = host.prepare(scenes.instanced_scene(grid=4, rings=12, segments=12), tree_builder=lambda t, s, b: build_qbvh_device(t, s, instance_bounds=b))
+    assert built.max_depth == expected.max_depth and built.nodes.tobytes() == expected.nodes.tobytes()
+    assert np.any(structs.token_type(built.nodes["token4"].reshape(-1)) == structs.TOKEN_TYPE_INSTANCE)

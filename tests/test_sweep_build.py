@@ -21,24 +21,25 @@ def emulation(tmp_path_factory):
                     os.path.join(ROOT, "tests", "c_client", "sweep_emulation.cpp"), "-o", str(library)], check=True)
     lib = ctypes.CDLL(str(library))
     p, u32 = ctypes.c_void_p, ctypes.c_uint32
-    lib.sweep_emulation_build.argtypes = [p, u32, p, u32, ctypes.c_int32, p, ctypes.POINTER(u32), ctypes.POINTER(u32), ctypes.POINTER(u32)]
+    lib.sweep_emulation_build.argtypes = [p, u32, p, u32, p, u32, ctypes.c_int32, p, ctypes.POINTER(u32), ctypes.POINTER(u32), ctypes.POINTER(u32)]
     lib.sweep_emulation_build.restype = ctypes.c_int32
 
-    def build(triangles, spheres, reverse=False):
+    def build(triangles, spheres, reverse=False, instance_bounds=None):
         triangles = np.ascontiguousarray(triangles, dtype=structs.TRIANGLE)
         spheres = np.ascontiguousarray(spheres, dtype=structs.SPHERE)
-        nodes = np.zeros(max(len(triangles) + len(spheres) - 1, 1), dtype=structs.QBVH_NODE)
+        boxes = np.zeros((0, 6), dtype=np.float32) if instance_bounds is None else np.ascontiguousarray(instance_bounds, dtype=np.float32).reshape(-1, 6)
+        nodes = np.zeros(max(len(triangles) + len(spheres) + len(boxes) - 1, 1), dtype=structs.QBVH_NODE)
         count, depth, levels = u32(), u32(), u32()
-        status = lib.sweep_emulation_build(triangles.ctypes.data, len(triangles), spheres.ctypes.data, len(spheres), int(reverse), nodes.ctypes.data,
+        status = lib.sweep_emulation_build(triangles.ctypes.data, len(triangles), spheres.ctypes.data, len(spheres), boxes.ctypes.data, len(boxes), int(reverse), nodes.ctypes.data,
                                            ctypes.byref(count), ctypes.byref(depth), ctypes.byref(levels))
         return status, nodes[:count.value], depth.value, levels.value
 
     return build
 
 
-def assert_same_tree(emulation, triangles, spheres, reverse=False):
-    expected, expected_depth = host.build_qbvh(triangles, spheres)
-    status, nodes, depth, levels = emulation(triangles, spheres, reverse)
+def assert_same_tree(emulation, triangles, spheres, reverse=False, instance_bounds=None):
+    expected, expected_depth = host.build_qbvh(triangles, spheres, instance_bounds=instance_bounds)
+    status, nodes, depth, levels = emulation(triangles, spheres, reverse, instance_bounds)
     assert status == 0
     assert len(nodes) == len(expected) and depth == expected_depth
     assert nodes.tobytes() == expected.tobytes()
@@ -72,6 +73,21 @@ def random_soup(seed, triangle_count, sphere_count, scale):
 def test_random_soups(emulation, seed, triangle_count, sphere_count, scale):
     triangles, spheres = random_soup(seed, triangle_count, sphere_count, scale)
     assert_same_tree(emulation, triangles, spheres)
+
+
+def random_instance_bounds(seed, count, scale):
+    rng = np.random.default_rng(seed)
+    low = rng.uniform(-scale, scale, (count, 3))
+    return np.concatenate([low, low + rng.uniform(0.0, 0.3 * scale, (count, 3))], axis=1).astype(np.float32)
+
+
+def test_packs_with_placements(emulation):
+    """GeometryCollection.CreateBounds: triangles, spheres, then the boxes of the pack's instances (TokenType.Instance leaves)."""
+    triangles, spheres = random_soup(21, 400, 30, 10.0)
+    assert_same_tree(emulation, triangles, spheres, instance_bounds=random_instance_bounds(22, 200, 10.0))
+    assert_same_tree(emulation, triangles[:0], spheres[:0], instance_bounds=random_instance_bounds(23, 2304, 50.0))  # a pack of placements only
+    prepared = host.prepare(scenes.instanced_scene(grid=4, rings=8, segments=8))
+    assert np.any(structs.token_type(prepared.nodes["token4"].reshape(-1)) == structs.TOKEN_TYPE_INSTANCE)
 
 
 def test_ties_and_degenerate_boxes(emulation):
