@@ -29,7 +29,7 @@ EXPORTS = [
     "echo_b200_scene_set_camera", "echo_b200_scene_commit", "echo_b200_scene_destroy", "echo_b200_trace_batch", "echo_b200_occlude_batch",
     "echo_b200_trace_batch_device", "echo_b200_occlude_batch_device", "echo_b200_render_tiles", "echo_b200_render_frame_device",
     "echo_b200_frame_resolve_device", "echo_b200_last_error", "echo_b200_version",
-    "echo_b200_scene_set_packs", "echo_b200_trace_batch_hierarchy", "echo_b200_occlude_batch_hierarchy", "echo_b200_scene_set_bound_radius", "echo_b200_scene_set_textures", "echo_b200_scene_set_distributions", "echo_b200_build_qbvh", "echo_b200_build_qbvh_instanced",
+    "echo_b200_scene_set_packs", "echo_b200_trace_batch_hierarchy", "echo_b200_occlude_batch_hierarchy", "echo_b200_scene_set_bound_radius", "echo_b200_scene_set_textures", "echo_b200_scene_set_distributions", "echo_b200_build_qbvh", "echo_b200_build_qbvh_instanced", "echo_b200_scene_build_qbvh",
     "echo_b200_debug_evaluate_samples4", "echo_b200_debug_bounds_violations",
     "echo_b200_trace_batch_device_counted", "echo_b200_occlude_batch_device_counted", "echo_b200_debug_bxdf_batch", "echo_b200_debug_math",
     "echo_b200_debug_evaluate_samples",
@@ -65,6 +65,7 @@ def library():
         "echo_b200_scene_set_textures": [p, p, u32, p, u64, p, u32],
         "echo_b200_scene_set_distributions": [p, p, u64],
         "echo_b200_build_qbvh": [i32, p, u32, p, u32, p, ctypes.POINTER(u32), ctypes.POINTER(u32)],
+        "echo_b200_scene_build_qbvh": [p, ctypes.POINTER(u32), ctypes.POINTER(u32)],
         "echo_b200_build_qbvh_instanced": [i32, p, u32, p, u32, p, u32, p, ctypes.POINTER(u32), ctypes.POINTER(u32)],
         "echo_b200_debug_evaluate_samples4": [p, p, p, p, u64, p],
         "echo_b200_debug_bounds_violations": [p, ctypes.POINTER(u32)],

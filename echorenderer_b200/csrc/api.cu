@@ -463,6 +463,30 @@ int32_t echo_b200_scene_set_qbvh(EchoScene* scene, const EchoQbvhNode* nodes, ui
 	return ECHO_B200_OK;
 }
 
+int32_t echo_b200_scene_build_qbvh(EchoScene* scene, uint32_t* outNodeCount, uint32_t* outMaxDepth)
+{
+	if (!scene) return fail(ECHO_B200_ERR_INVALID, "null argument");
+	if (!scene->packs.empty()) return fail(ECHO_B200_ERR_UNSUPPORTED, "scene_build_qbvh builds the accelerator of a scene without packs; build each pack with echo_b200_build_qbvh_instanced");
+	uint64_t total = (uint64_t)scene->triangles.size() + scene->spheres.size();
+	if (total < 2) return fail(ECHO_B200_ERR_INVALID, "upload at least two primitives (set_triangles / set_spheres) before scene_build_qbvh");
+	DeviceGuard guard(scene->device);
+	if (!guard.ok) return ECHO_B200_ERR_NO_DEVICE;
+
+	std::vector<EchoQbvhNode> nodes(total - 1);
+	uint32_t count = 0, depth = 0;
+	if (!build_qbvh_device(scene->triangles.data(), (uint32_t)scene->triangles.size(), scene->spheres.data(), (uint32_t)scene->spheres.size(), nullptr, 0u, nodes.data(), &count, &depth))
+		return ECHO_B200_ERR_CUDA;
+	if (stack_class(depth) < 0) return fail(ECHO_B200_ERR_UNSUPPORTED, "QBVH deeper than 63 quad levels is not supported");
+
+	nodes.resize(count);
+	scene->nodes.swap(nodes);
+	scene->maxDepth = depth;
+	scene->committed = false;
+	if (outNodeCount) *outNodeCount = count;
+	if (outMaxDepth) *outMaxDepth = depth;
+	return ECHO_B200_OK;
+}
+
 int32_t echo_b200_scene_set_triangles(EchoScene* scene, const EchoTriangle* triangles, uint32_t count)
 {
 	if (!scene || (!triangles && count)) return fail(ECHO_B200_ERR_INVALID, "null argument");

@@ -21,8 +21,10 @@ from .host import PreparedArrays
 class PreparedScene:
     """The flattened scene resident on one B200; the device twin of Echo's PreparedScene."""
 
-    def __init__(self, prepared: PreparedArrays, device: int = 0, devices=None):
-        """`device`: the CUDA device of a single-device scene. `devices` (a list of device indices) instead replicates the scene
+    def __init__(self, prepared: PreparedArrays, device: int = 0, devices=None, build_tree_on_device: bool = False):
+        """`device`: the CUDA device of a single-device scene. `build_tree_on_device`: the library builds the accelerator itself from
+        the uploaded triangles and spheres (echo_b200_scene_build_qbvh: the SweepBuilder's tree, on the device) instead of taking
+        `prepared.nodes`; `self.built_tree` = (node count, max depth) then. `devices` (a list of device indices) instead replicates the scene
         on several devices of this process (echo_b200_scene_create_multi): trace / occlude split their batches over them and
         render_tiles deals blocks of tiles to them; the *_device methods then do not apply."""
         lib = _native.library()
@@ -41,10 +43,16 @@ class PreparedScene:
         try:
             d = prepared.description
             ptr = _native.pointer
-            _native.check(lib.echo_b200_scene_set_qbvh(self._handle, ptr(prepared.nodes), len(prepared.nodes), prepared.max_depth))
             triangles, spheres, materials = prepared.triangles, prepared.spheres, prepared.materials
             _native.check(lib.echo_b200_scene_set_triangles(self._handle, ptr(triangles), len(triangles)))
             _native.check(lib.echo_b200_scene_set_spheres(self._handle, ptr(spheres), len(spheres)))
+            self.built_tree = None
+            if build_tree_on_device:
+                count, depth = ctypes.c_uint32(), ctypes.c_uint32()
+                _native.check(lib.echo_b200_scene_build_qbvh(self._handle, ctypes.byref(count), ctypes.byref(depth)))
+                self.built_tree = (count.value, depth.value)
+            else:
+                _native.check(lib.echo_b200_scene_set_qbvh(self._handle, ptr(prepared.nodes), len(prepared.nodes), prepared.max_depth))
             _native.check(lib.echo_b200_scene_set_materials(self._handle, ptr(materials), len(materials)))
             if prepared.textures is not None:
                 _native.check(lib.echo_b200_scene_set_textures(self._handle, ptr(prepared.textures), len(prepared.textures), ptr(prepared.texels), len(prepared.texels),

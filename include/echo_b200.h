@@ -436,6 +436,11 @@ int32_t echo_b200_build_qbvh(int32_t device, const EchoTriangle* triangles, uint
  * TokenType.Instance in the order given. Mirrors echo_host_build_qbvh_instanced (echo_host.h). */
 int32_t echo_b200_build_qbvh_instanced(int32_t device, const EchoTriangle* triangles, uint32_t triangle_count, const EchoSphere* spheres, uint32_t sphere_count,
                                        const float* instance_bounds, uint32_t instance_count, EchoQbvhNode* out_nodes, uint32_t* out_node_count, uint32_t* out_max_depth);
+/* The same build for a scene handle: builds the accelerator of the triangles and spheres already uploaded with set_triangles /
+ * set_spheres on the scene's device and installs it as if set_qbvh had been called with the SweepBuilder's nodes — a host that
+ * does not want to run Accelerator construction (AcceleratorCreator.cs) on its CPU calls this instead of set_qbvh, before commit.
+ * out_node_count / out_max_depth are optional. Scenes with packs: ECHO_B200_ERR_UNSUPPORTED (build each pack, set_qbvh + set_packs). */
+int32_t echo_b200_scene_build_qbvh(EchoScene*, uint32_t* out_node_count, uint32_t* out_max_depth);
 
 /* Page-locked host memory for the host-buffer entry points. A P/Invoke caller pins managed arrays with `fixed`
  * (Processes/Composition/OidnDenoise.cs:109-110): that stops the GC from moving them but leaves them PAGEABLE for CUDA, so every

@@ -204,3 +204,16 @@ def test_instanced_scene_prepared_with_device_built_trees_is_the_same_scene():
     built = host.prepare(scenes.instanced_scene(grid=4, rings=12, segments=12), tree_builder=lambda t, s, b: build_qbvh_device(t, s, instance_bounds=b))
     assert built.max_depth == expected.max_depth and built.nodes.tobytes() == expected.nodes.tobytes()
     assert np.any(structs.token_type(built.nodes["token4"].reshape(-1)) == structs.TOKEN_TYPE_INSTANCE)
+
+
+def test_scene_builds_its_own_accelerator(terrain_small, cornell):
+    """echo_b200_scene_build_qbvh: a host that uploads only geometry gets the SweepBuilder's tree built on the device — the same node
+    count and depth as the host mirror's, and hits, distances and barycentrics bit for bit those of the scene given the mirror's nodes."""
+    _native.set_option("BUILD_ALGORITHM", 2)
+    for prepared in (terrain_small, cornell):
+        rays = scenes.random_rays(prepared.bounds, 50_000, seed=41)
+        shadow = scenes.random_rays(prepared.bounds, 50_000, seed=43, occlusion=True)
+        with PreparedScene(prepared) as given, PreparedScene(prepared, build_tree_on_device=True) as built:
+            assert built.built_tree == (len(prepared.nodes), prepared.max_depth)
+            assert_hits_equal(built.trace(rays), given.trace(rays))
+            assert np.array_equal(built.occlude(shadow), given.occlude(shadow))
