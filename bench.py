@@ -573,7 +573,7 @@ def run_trace(ctx, args):
 
     line = base_line(args, "Mrays/s", value, total_ms / args.steps, trace_config(args, n), "f32")
     achieved = bytes_trace * n / (trace_ms * 1e-3) / 1e9
-    line["roofline"] = {"bound": "hbm", "kernel": "instanced closest-hit kernel" if args.instanced else "persistent_batch_kernel<48, false> (closest hit)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    line["roofline"] = {"bound": "hbm", "kernel": "instanced closest-hit kernel" if args.instanced else "persistent_batch_kernel<48, false> (closest hit)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "frac_nominal_8tbs": achieved / 8000.0,
                         "traffic": ncu_traffic("closest_hit_dram_bytes_per_launch"), "peak_source": peak_source, "algorithmic_bytes_per_query": bytes_trace, "ms_per_launch": trace_ms,
                         "mrays_per_s": n / (trace_ms * 1e-3) / MRAYS,
                         "visits_per_query": {"nodes": counts[0], "triangles": counts[1], "spheres": counts[2]},
@@ -616,6 +616,9 @@ def run_trace(ctx, args):
     if ctx.rank == 0 and not args.no_cpu_baseline:
         cpu_value, cores, seconds, sample = cpu_baseline_trace(prepared, rays, shadow, args.cpu_sample)
         line["cpu_baseline"] = {"value": cpu_value, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample, "seconds": seconds}
+        # the single-thread rate too, to set beside the reference's published single-thread figures (1.68 / 2.06 Mrays/s in C#)
+        single_value, _, single_seconds, single_sample = cpu_baseline_trace(prepared, rays, shadow, max(4096, min(args.cpu_sample, len(rays)) // 16), threads=1)
+        line["cpu_baseline"]["single_thread"] = {"value": single_value, "unit": "Mrays/s", "cores": 1, "sample": single_sample, "seconds": single_seconds}
 
     for buffer in (host_rays, host_shadow, host_hits, host_occluded):
         buffer.free()
@@ -768,7 +771,7 @@ def run_render(ctx, args, scene_key, width, height, spp, bounce_limit, steps, wa
                                "what": "host wall time of echo_b200_render_frame_device per step, mean over the timed steps, per rank"},
               "all_reduce": {"count": len(reduce_ms), "ms_mean": float(np.mean(reduce_ms)) if reduce_ms else None, "wait_for_slowest_rank_ms_mean": float(np.mean(skew_ms)) if skew_ms else None,
                              "bytes": int(frame.numel() * 4), "collective": "NCCL all-reduce (sum) of the fp32 accumulation frame" if ctx.distributed else "none (one GPU)"},
-              "roofline": {"bound": "hbm", "kernel": "wavefront step (raygen, extend, classify, shade x6, shadow, accumulate), per GPU", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+              "roofline": {"bound": "hbm", "kernel": "wavefront step (raygen, extend, classify, shade x6, shadow, accumulate), per GPU", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "frac_nominal_8tbs": achieved / 8000.0,
                            "traffic": traffic_per_sample * (total_samples // steps) if traffic_per_sample else None, "traffic_bytes_per_sample": traffic_per_sample,
                            "peak_source": peak_source, "algorithmic_bytes_per_sample": per_sample_bytes,
                            "bytes_per_sample_parts": per_sample_parts, "per_sample_counters": per_sample_counters, "path_state_bytes": PATH_STATE_BYTES,

@@ -46,6 +46,8 @@ def test_trace_bench_line():
     assert line["gpu_launches"] == 2 * line["steps"]
     baseline = line["cpu_baseline"]
     assert baseline["kind"] == "port" and baseline["cores"] >= 1 and baseline["value"] > 0 and baseline["unit"] == "Mrays/s" and baseline["sample"]
+    assert baseline["single_thread"]["value"] > 0 and baseline["single_thread"]["cores"] == 1
+    assert roofline["frac_nominal_8tbs"] == pytest.approx(roofline["achieved"] / 8000.0, rel=1e-6)
     # the plugin-call leg from page-locked memory (echo_b200_host_alloc) and from pageable memory
     assert "page-locked" in line["e2e"]["host_memory"] and line["e2e_pageable"]["value"] > 0
     # the on-chip ceilings are measured live by the library and the same algorithmic bytes are set against them
