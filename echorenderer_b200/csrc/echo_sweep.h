@@ -306,16 +306,42 @@ struct CostPass // SearchSurfaceAreaHeuristics, SweepBuilder.cs:132-160
 
 	SWEEP_HD void operator()(uint32_t p) const
 	{
+#if defined(__CUDA_ARCH__)
+		const unsigned int active = __activemask(); // the lanes that run this pass (all 32 but in the last warp), taken before anything diverges
+#endif
 		uint32_t index = segmentOf[p];
 		Segment segment = segments[index];
 		uint32_t i = p - segment.begin;
-		if (i == 0u) return;
+		unsigned long long candidate = kNoCut;
 
-		float headArea = half_area(to_box(heads[p - 1u])), tailArea = half_area(to_box(tails[count - 1u - p]));
-		float cost = f_add(f_mul(headArea, (float)(int32_t)i), f_mul(tailArea, (float)(int32_t)(segment.length - i)));
-		if (cost == 0.0f) cost = 0.0f; // -0 and +0 are one cost
+		if (i != 0u)
+		{
+			float headArea = half_area(to_box(heads[p - 1u])), tailArea = half_area(to_box(tails[count - 1u - p]));
+			float cost = f_add(f_mul(headArea, (float)(int32_t)i), f_mul(tailArea, (float)(int32_t)(segment.length - i)));
+			if (cost == 0.0f) cost = 0.0f; // -0 and +0 are one cost
+			if (cost < 3.402823466e+38f) candidate = (unsigned long long)sort_key(cost) << 32 | i;
+		}
 
-		if (cost < 3.402823466e+38f) atomic_min_u64(best + index, (unsigned long long)sort_key(cost) << 32 | i);
+#if defined(__CUDA_ARCH__)
+		// Consecutive lanes hold consecutive positions, so the lanes of one segment are a contiguous run of the warp: a segmented
+		// shuffle reduction leaves the run's minimum in its first lane, and one atomic per (warp, segment) reaches memory. Per-lane
+		// atomics serialise on the segment's word — a million of them on ONE address at the root: 41 % of the whole build (r2y).
+		const unsigned int lane = threadIdx.x & 31u;
+
+		for (unsigned int offset = 1u; offset < 32u; offset <<= 1)
+		{
+			unsigned long long other = __shfl_down_sync(active, candidate, offset);
+			uint32_t otherIndex = __shfl_down_sync(active, index, offset);
+			bool valid = lane + offset < 32u && ((active >> (lane + offset)) & 1u) != 0u;
+			if (valid && otherIndex == index && other < candidate) candidate = other;
+		}
+
+		uint32_t before = __shfl_up_sync(active, index, 1u);
+		bool leader = lane == 0u || ((active >> (lane - 1u)) & 1u) == 0u || before != index;
+		if (leader && candidate != kNoCut) atomicMin(best + index, candidate);
+#else
+		if (candidate != kNoCut) atomic_min_u64(best + index, candidate);
+#endif
 	}
 };
 

@@ -434,7 +434,8 @@ def build_qbvh_device(triangles, spheres, device=0, instance_bounds=None):
     count, depth = ctypes.c_uint32(), ctypes.c_uint32()
     _native.check(lib.echo_b200_build_qbvh_instanced(device, _native.pointer(triangles), len(triangles), _native.pointer(spheres), len(spheres), _native.pointer(boxes), len(boxes),
                                                      _native.pointer(nodes), ctypes.byref(count), ctypes.byref(depth)))
-    return nodes[:count.value].copy(), int(depth.value)
+    nodes.resize(count.value, refcheck=False)  # shrinks in place (realloc): no second copy of a 600 MB array
+    return nodes, int(depth.value)
 
 
 def shard_epochs(max_epoch, rank, world_size):

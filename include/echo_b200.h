@@ -424,7 +424,7 @@ int32_t echo_b200_frame_resolve_device(EchoScene*, float* d_frame_rgba, int32_t 
  * node's volume, one-axis sweep for the first cut of lowest cost, larger-area child first) and the QuadBoundingVolumeHierarchy collapse
  * (QuadBoundingVolumeHierarchy.cs:363-565, nodes in pre-order), run level by level on the device; the emitted array equals what the
  * recursive build emits byte for byte (echo_host.h's mirror; tests/test_gpu_build.py, tests/test_sweep_build.py). 1 010 000 primitives:
- * 15 ms of device work against 430 ms for the host mirror on 16 cores. Inputs whose tree chains deeper than the traversal stacks allow
+ * 10-12 ms of device work against 430 ms for the host mirror on 16 cores. Inputs whose tree chains deeper than the traversal stacks allow
  * (thousands of coincident primitives) — and ECHO_B200_BUILD_ALGORITHM=1 / 0 — get a clustered (PLOC) or Morton-ordered (Karras 2012)
  * binary tree collapsed the same way instead: valid, lower quality, not the reference's. Tokens: triangles, then spheres, as
  * GeometryCollection.CreateBounds numbers them. `out_nodes` (host) needs room for triangle_count + sphere_count - 1 nodes;
