@@ -115,7 +115,8 @@ void last_sweep_build(float* out4)
 	out4[0] = gLastBuild.uploadMs; out4[1] = gLastBuild.buildMs; out4[2] = gLastBuild.downloadMs; out4[3] = gLastBuild.levels;
 }
 
-// false: a CUDA call failed. `gaveUp`: the tree chains deeper than sweep::kMaxLevels (thousands of coincident primitives), nothing was written.
+// false: a CUDA call failed. `gaveUp`: the tree chains deeper than sweep::kMaxLevels (thousands of coincident primitives) or the device
+// lacks the working memory; nothing was written.
 bool build_qbvh_sweep(const EchoTriangle* triangles, uint32_t triangleCount, const EchoSphere* spheres, uint32_t sphereCount,
                       const float* instanceBounds, uint32_t instanceCount, EchoQbvhNode* outNodes, uint32_t* outNodeCount, uint32_t* outMaxDepth, bool* gaveUp)
 {
@@ -130,6 +131,17 @@ bool build_qbvh_sweep(const EchoTriangle* triangles, uint32_t triangleCount, con
 
 	CudaBackend backend;
 	if (!backend.prepare((uint32_t)total64)) return false;
+
+	// ~450 bytes of working memory per primitive: when the device cannot spare them the caller's clustered build (~150) takes over
+	{
+		sweep::Buffers probe;
+		sweep::Arena measure;
+		probe.carve(measure, total64);
+		size_t freeBytes = 0, totalBytes = 0;
+		if (!check_cuda(cudaMemGetInfo(&freeBytes, &totalBytes), "cudaMemGetInfo")) return false;
+		size_t needed = measure.used + backend.scratchBytes + sizeof(EchoTriangle) * triangleCount + sizeof(EchoSphere) * sphereCount + sizeof(float) * 6 * instanceCount + (1u << 20);
+		if (needed > freeBytes - freeBytes / 16) { *gaveUp = true; return true; }
+	}
 
 	struct Inputs
 	{
