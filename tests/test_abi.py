@@ -185,3 +185,26 @@ def test_bench_reference_arm_contract(workload):
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert _run_bench(arguments, {"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"}) == []
+
+
+def test_cpp_host_mirror_compiles_without_warnings_and_its_host_logic_holds(tmp_path):
+    """include/echo_b200.hpp — the compiled-language host side above the C ABI (PreparedScene, EvaluationProfile, RenderTexture, tile
+    patterns, IWorker, EvaluationOperation + Factory): builds as C++17 with -Wall -Wextra -Werror, its tile patterns equal the Python
+    mirror's (which restates the reference's TilePatternTests), and the device-free logic checks of tests/c_client/echo_host_logic.cpp pass."""
+    import subprocess
+    import numpy as np
+    from echorenderer_b200 import hilbert_curve_pattern, ordered_pattern
+    package = os.path.join(ROOT, "echorenderer_b200")
+    flags = ["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include")]
+    link = ["-L", package, "-lecho_b200", f"-Wl,-rpath,{package}", "-pthread"]
+    logic, client = tmp_path / "echo_host_logic", tmp_path / "echo_host_client"
+    subprocess.run(flags + [os.path.join(ROOT, "tests", "c_client", "echo_host_logic.cpp"), "-o", str(logic)] + link, check=True)
+    subprocess.run(flags + [os.path.join(ROOT, "tests", "c_client", "echo_host_client.cpp"), "-o", str(client)] + link, check=True)
+
+    result = subprocess.run([str(logic), "checks"], capture_output=True, text=True, timeout=120)
+    assert result.returncode == 0 and "echo_host_logic ok" in result.stdout, result.stdout + result.stderr
+
+    for size in [(1, 1), (2, 1), (1, 9), (5, 3), (8, 8), (13, 7), (120, 68)]:
+        for hilbert, expected in ((1, hilbert_curve_pattern(size)), (0, ordered_pattern(size))):
+            printed = subprocess.run([str(logic), "pattern", str(hilbert), str(size[0]), str(size[1])], capture_output=True, text=True, check=True).stdout
+            assert np.array_equal(np.array(printed.split(), dtype=np.int32).reshape(-1, 2), expected), (size, hilbert)

@@ -63,6 +63,73 @@ def test_plain_c_client_matches_the_python_binding_and_the_oracle(cornell, tmp_p
         assert int(stats[name][0]) == int(ctypes_stats[name][0]) == int(expected_stats[name][0]), name
 
 
+def test_cpp_host_mirror_renders_what_the_python_mirror_renders(cornell, tmp_path):
+    """tests/c_client/echo_host_client.cpp, a host written against include/echo_b200.hpp: three worker threads enter
+    EvaluationOperation::Execute concurrently and claim procedures atomically (Operation.cs:164-177); the frame they assemble through
+    RenderTexture.Apply, the statistics rows and TotalSamples equal the Python mirror's EvaluationOperation bit for bit, with the tree
+    given or built by the library; an abort requested through IWorker.CheckSchedule stops the workers between tiles."""
+    from echorenderer_b200 import EvaluationOperation, EvaluationProfile, PathTracedEvaluator, RenderTexture
+    package = os.path.join(ROOT, "echorenderer_b200")
+    binary = tmp_path / "echo_host_client"
+    subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c_client", "echo_host_client.cpp"), "-o", str(binary),
+                    "-L", package, "-lecho_b200", f"-Wl,-rpath,{package}", "-pthread"], check=True)
+
+    d = cornell.description
+    rays = scenes.random_rays(cornell.bounds, 20000, seed=5)
+    shadow = scenes.random_rays(cornell.bounds, 20000, seed=6, occlusion=True)
+    width, height, tile = 200, 136, 8  # 25 x 17 = 425 tiles = 2 procedures, ragged on neither edge ... and 136 = 17 * 8
+    scalars = np.zeros(4, dtype=np.uint32)
+    scalars[0] = cornell.max_depth
+    scalars[1:].view(np.float32)[:] = [cornell.infinite_threshold, cornell.infinite_pdf, cornell.bound_radius]
+    profile = EvaluationProfile(PathTracedEvaluator(bounce_limit=16), extend=4, min_epoch=1, max_epoch=3, noise_threshold=0.3, seed=7)
+
+    def run(directory, workers, hilbert, build_on_device, abort_after=-1, size=(width, height, tile)):
+        directory.mkdir()
+        words = np.zeros(9, dtype=np.uint32)
+        words[[0, 1, 2, 3, 5, 7]] = [profile.evaluator.code, profile.extend, profile.min_epoch, profile.max_epoch, profile.evaluator.bounce_limit, profile.seed]
+        words[[4, 6]] = np.array([profile.noise_threshold, profile.evaluator.survivability], dtype=np.float32).view(np.uint32)
+        words[8:].view(np.int32)[:] = abort_after
+        for name, array in [("nodes", cornell.nodes), ("triangles", cornell.triangles), ("spheres", cornell.spheres), ("materials", cornell.materials),
+                            ("light_nodes", cornell.light_nodes), ("emitter_tokens", cornell.emitter_tokens), ("emitter_paths", cornell.emitter_bitpaths),
+                            ("point_lights", cornell.point_lights), ("infinite", d.infinite_lights), ("camera", d.camera), ("scalars", scalars),
+                            ("rays", rays), ("shadow", shadow), ("profile", words), ("size", np.array(size, dtype=np.int32))]:
+            np.ascontiguousarray(array).tofile(directory / f"{name}.bin")
+        result = subprocess.run([str(binary), str(directory), str(workers), str(int(hilbert)), str(int(build_on_device))], capture_output=True, text=True, timeout=300)
+        assert result.returncode == 0 and "echo_host_client ok" in result.stdout, result.stdout + result.stderr
+        summary = dict(line.split(" ", 1) for line in (directory / "summary.txt").read_text().splitlines())
+        frame = np.fromfile(directory / "frame.bin", dtype=np.float32).reshape(size[1], size[0], 4)
+        return frame, np.fromfile(directory / "stats.bin", dtype=structs.STATS), np.fromfile(directory / "sequence.bin", dtype=np.int32).reshape(-1, 2), summary, directory
+
+    with PreparedScene(cornell) as scene:
+        operation = EvaluationOperation(scene, profile, RenderTexture(width, height, tile))
+        expected = operation.execute().pixels.copy()
+        ragged = EvaluationOperation(scene, profile, RenderTexture(100, 70, 16))  # 7 x 5 tiles, the last column 4 wide, the top row 6 high
+        expected_ragged = ragged.execute().pixels.copy()
+
+    frame, stats, sequence, summary, directory = run(tmp_path / "given", 3, True, False)
+    assert np.array_equal(sequence, operation.tile_positions) and len(sequence) == 425
+    assert summary["procedures"] == "2 of 2" and summary["aborted_workers"] == "0" and summary["gpu_count"] == "1"
+    assert np.array_equal(frame.view(np.uint32), expected.view(np.uint32))
+    assert int(summary["total_samples"]) == operation.total_samples == int(stats["sampleEvaluated"][0])
+    for name in structs.STATS_FIELDS[:12]:
+        assert int(stats[name][0]) == int(operation.statistics[name][0]), name
+    oracle = oracle_lib.OracleScene(cornell)
+    assert np.array_equal(np.fromfile(directory / "hits.bin", dtype=structs.HIT).view(np.uint32), oracle.trace(rays).view(np.uint32))
+    assert np.array_equal(np.fromfile(directory / "occluded.bin", dtype=np.uint8), oracle.occlude(shadow))
+
+    built, _, _, _, _ = run(tmp_path / "built", 2, True, True)  # the library builds the SweepBuilder's tree itself: the same frame
+    assert np.array_equal(built.view(np.uint32), expected.view(np.uint32))
+
+    edge, _, _, _, _ = run(tmp_path / "ragged", 1, True, False, size=(100, 70, 16))
+    assert np.array_equal(edge.view(np.uint32), expected_ragged.view(np.uint32))
+
+    partial, _, _, summary, _ = run(tmp_path / "aborted", 2, False, False, abort_after=100)  # CheckSchedule throws after 100 tiles
+    assert int(summary["aborted_workers"]) >= 1 and summary["procedures"] != "2 of 2"
+    done = np.any(partial != 0, axis=-1)
+    assert 100 * tile * tile <= done.sum() < width * height
+    assert np.array_equal(partial[done].view(np.uint32), expected[done].view(np.uint32))
+
+
 @pytest.mark.parametrize("fixture,bounce_limit", [("cornell", 32), ("lights_small", 16), ("mixed_small", 8)])
 def test_counted_pass_reports_the_oracles_visit_counters(fixture, bounce_limit, request):
     """ECHO_EVALUATOR_COUNT_VISITS: same tiles bit for bit, and node / triangle / sphere / light-node visit totals equal to the
