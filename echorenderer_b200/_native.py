@@ -33,7 +33,7 @@ EXPORTS = [
     "echo_b200_debug_evaluate_samples4", "echo_b200_debug_bounds_violations",
     "echo_b200_trace_batch_device_counted", "echo_b200_occlude_batch_device_counted", "echo_b200_debug_bxdf_batch", "echo_b200_debug_math",
     "echo_b200_debug_evaluate_samples",
-    "echo_b200_host_alloc", "echo_b200_host_free", "echo_b200_host_register", "echo_b200_host_unregister", "echo_b200_debug_set_option", "echo_b200_debug_measure_peaks", "echo_b200_debug_last_build",
+    "echo_b200_host_alloc", "echo_b200_host_free", "echo_b200_host_register", "echo_b200_host_unregister", "echo_b200_debug_set_option", "echo_b200_debug_measure_peaks", "echo_b200_debug_last_build", "echo_b200_debug_last_light_build", "echo_b200_build_light_tree", "echo_b200_scene_build_light_tree",
     "echo_b200_scene_create_multi", "echo_b200_scene_gpu_count",
 ]
 
@@ -90,6 +90,9 @@ def library():
         "echo_b200_debug_set_option": [ctypes.c_char_p, ctypes.c_int64],
         "echo_b200_debug_measure_peaks": [i32, p],
         "echo_b200_debug_last_build": [p],
+        "echo_b200_debug_last_light_build": [p],
+        "echo_b200_build_light_tree": [i32, p, u32, p, u32, p, u32, p, u32, p, u32, p, u32, ctypes.POINTER(u32), p, p, u32, ctypes.POINTER(u32), ctypes.POINTER(f32)],
+        "echo_b200_scene_build_light_tree": [p, p, u32, ctypes.POINTER(u32), ctypes.POINTER(u32), ctypes.POINTER(f32)],
         "echo_b200_scene_create_multi": [ctypes.POINTER(p), u64],
         "echo_b200_scene_gpu_count": [p, ctypes.POINTER(i32)],
     }
@@ -173,6 +176,14 @@ def last_build():
     out = np.zeros(4, dtype=np.float32)
     check(library().echo_b200_debug_last_build(pointer(out)))
     return {"upload_ms": float(out[0]), "device_build_ms": float(out[1]), "download_ms": float(out[2]), "binary_levels": int(out[3])}
+
+
+def last_light_build():
+    """echo_b200_debug_last_light_build: phases of this thread's last device light-tree build (host wall time around synchronised phases)."""
+    import numpy as np
+    out = np.zeros(4, dtype=np.float32)
+    check(library().echo_b200_debug_last_light_build(pointer(out)))
+    return {"upload_ms": float(out[0]), "device_build_ms": float(out[1]), "download_ms": float(out[2]), "levels": int(out[3])}
 
 
 def host_register(array):

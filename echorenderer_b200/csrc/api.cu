@@ -10,6 +10,7 @@
 
 #include "../../include/echo_b200_debug.h"
 #include "echo_internal.h"
+#include "echo_light_build.h"
 
 namespace echo
 {
@@ -595,6 +596,68 @@ int32_t echo_b200_build_qbvh(int32_t device, const EchoTriangle* triangles, uint
                              EchoQbvhNode* outNodes, uint32_t* outNodeCount, uint32_t* outMaxDepth)
 {
 	return echo_b200_build_qbvh_instanced(device, triangles, triangleCount, spheres, sphereCount, nullptr, 0u, outNodes, outNodeCount, outMaxDepth);
+}
+
+int32_t echo_b200_build_light_tree(int32_t device, const EchoTriangle* triangles, uint32_t triangleCount, const EchoSphere* spheres, uint32_t sphereCount,
+                                   const EchoMaterial* materials, uint32_t materialCount, const EchoPointLight* points, uint32_t pointCount,
+                                   const float* instanceLights, uint32_t instanceCount,
+                                   EchoLightNode* outNodes, uint32_t nodeCapacity, uint32_t* outNodeCount,
+                                   uint32_t* outTokens, uint64_t* outPaths, uint32_t emitterCapacity, uint32_t* outEmitterCount, float* outPower)
+{
+	if ((!triangles && triangleCount) || (!spheres && sphereCount) || (!materials && materialCount) || (!points && pointCount) || (!instanceLights && instanceCount)
+		|| (!outNodes && nodeCapacity) || ((!outTokens || !outPaths) && emitterCapacity) || !outNodeCount || !outEmitterCount || !outPower) return fail(ECHO_B200_ERR_INVALID, "null argument");
+	int32_t count = 0;
+	int32_t status = echo_b200_device_count(&count);
+	if (status != ECHO_B200_OK) return status;
+	if (device < 0 || device >= count) return fail(ECHO_B200_ERR_INVALID, "device index out of range");
+	DeviceGuard guard(device);
+	if (!guard.ok) return ECHO_B200_ERR_NO_DEVICE;
+
+	const lightbuild::Sources sources = { triangles, triangleCount, spheres, sphereCount, materials, materialCount, points, pointCount, instanceLights, instanceCount };
+	std::vector<EchoLightNode> nodes;
+	std::vector<uint32_t> tokens;
+	std::vector<uint64_t> paths;
+	bool refused = false;
+	if (!build_light_tree_device(sources, nodes, tokens, paths, &refused)) return ECHO_B200_ERR_CUDA;
+	if (refused) return fail(ECHO_B200_ERR_UNSUPPORTED, "light tree deeper than 63 levels (LightTree.cs:29)");
+
+	*outNodeCount = (uint32_t)nodes.size();
+	*outEmitterCount = (uint32_t)tokens.size();
+	*outPower = nodes.empty() ? 0.0f : nodes[0].power;
+	if (nodes.size() > nodeCapacity || tokens.size() > emitterCapacity) return fail(ECHO_B200_ERR_INVALID, "light tree output buffers too small (needed counts returned)");
+
+	std::copy(nodes.begin(), nodes.end(), outNodes);
+	std::copy(tokens.begin(), tokens.end(), outTokens);
+	std::copy(paths.begin(), paths.end(), outPaths);
+	return ECHO_B200_OK;
+}
+
+int32_t echo_b200_scene_build_light_tree(EchoScene* scene, const EchoPointLight* points, uint32_t pointCount, uint32_t* outNodeCount, uint32_t* outEmitterCount, float* outPower)
+{
+	if (!scene || (!points && pointCount)) return fail(ECHO_B200_ERR_INVALID, "null argument");
+	if (!scene->packs.empty()) return fail(ECHO_B200_ERR_UNSUPPORTED, "scene_build_light_tree builds the light tree of a scene without packs; build each pack with echo_b200_build_light_tree");
+	DeviceGuard guard(scene->device);
+	if (!guard.ok) return ECHO_B200_ERR_NO_DEVICE;
+
+	const lightbuild::Sources sources = { scene->triangles.data(), (uint32_t)scene->triangles.size(), scene->spheres.data(), (uint32_t)scene->spheres.size(),
+	                                      scene->materials.data(), (uint32_t)scene->materials.size(), points, pointCount, nullptr, 0u };
+	std::vector<EchoLightNode> nodes;
+	std::vector<uint32_t> tokens;
+	std::vector<uint64_t> paths;
+	bool refused = false;
+	if (!build_light_tree_device(sources, nodes, tokens, paths, &refused)) return ECHO_B200_ERR_CUDA;
+	if (refused) return fail(ECHO_B200_ERR_UNSUPPORTED, "light tree deeper than 63 levels (LightTree.cs:29)");
+
+	if (outNodeCount) *outNodeCount = (uint32_t)nodes.size();
+	if (outEmitterCount) *outEmitterCount = (uint32_t)tokens.size();
+	if (outPower) *outPower = nodes.empty() ? 0.0f : nodes[0].power;
+
+	scene->lightNodes.swap(nodes);
+	scene->emitterTokens.swap(tokens);
+	scene->emitterPaths.swap(paths);
+	scene->pointLights.assign(points, points + pointCount);
+	scene->committed = false;
+	return ECHO_B200_OK;
 }
 
 int32_t echo_b200_scene_set_distributions(EchoScene* scene, const float* values, uint64_t count)
@@ -1244,6 +1307,13 @@ int32_t echo_b200_debug_last_build(float* out4)
 {
 	if (!out4) return fail(ECHO_B200_ERR_INVALID, "out4 is null");
 	last_sweep_build(out4);
+	return ECHO_B200_OK;
+}
+
+int32_t echo_b200_debug_last_light_build(float* out4)
+{
+	if (!out4) return fail(ECHO_B200_ERR_INVALID, "out4 is null");
+	last_light_build(out4);
 	return ECHO_B200_OK;
 }
 

@@ -44,6 +44,12 @@ void last_sweep_build(float* out4); // the calling thread's last build_qbvh_swee
 bool build_qbvh_device(const EchoTriangle* triangles, uint32_t triangleCount, const EchoSphere* spheres, uint32_t sphereCount,
                        const float* instanceBounds, uint32_t instanceCount, EchoQbvhNode* outNodes, uint32_t* outNodeCount, uint32_t* outMaxDepth);
 
+// ---- lightbuild.cu: the reference's light tree (LightCollection.CreateBounds + LightTree.Build + AddToMap) built on the device, byte for
+// byte the host mirror's (echo_light_build.h). Host buffers in, host vectors out; `refused` = deeper than a 64-bit path ----
+namespace lightbuild { struct Sources; }
+bool build_light_tree_device(const lightbuild::Sources& sources, std::vector<EchoLightNode>& nodes, std::vector<uint32_t>& tokens, std::vector<uint64_t>& paths, bool* refused);
+void last_light_build(float* out4); // the calling thread's last build_light_tree_device: {upload, device build, download} ms, levels
+
 // ---- render.cu ----
 struct RenderState; // wavefront buffers, owned per scene
 

@@ -17,9 +17,12 @@
 #include <vector>
 
 #include "../../../include/echo_host.h"
+#include "../echo_light_build.h"
 
 namespace
 {
+
+namespace lightbuild = echo::lightbuild;
 
 constexpr float kInf = std::numeric_limits<float>::infinity();
 constexpr float kPi = 3.14159265358979323846f;
@@ -418,92 +421,10 @@ struct QuadBuilder
 
 // ---------------- LightTree ----------------
 
-struct Cone // Aggregation/Bounds/ConeBound.cs
-{
-	Vec3 axis;
-	float cosOffset, cosExtend;
-};
-
-inline float sse_min(float a, float b) { return a < b ? a : b; }
-inline float sse_max(float a, float b) { return a > b ? a : b; }
-inline float clamp11(float v) { return sse_min(1.0f, sse_max(-1.0f, v)); }
-inline float identity(float v) { float s = std::fma(-v, v, 1.0f); return s <= 0.0f ? 0.0f : std::sqrt(s); }
-
-inline float angle_degrees(Vec3 a, Vec3 b) // Float3.Angle, Float3.cs:277-288 (returns DEGREES)
-{
-	double squared = squared_double(a) * squared_double(b);
-	if (squared == 0.0) return 0.0f;
-	double mag = std::sqrt(squared);
-	if (mag == 0.0) return 0.0f;
-	double d = (double)a.x * b.x + (double)a.y * b.y + (double)a.z * b.z;
-	return (float)std::acos(d / mag) * (float)(180.0 / 3.14159265358979323846);
-}
-
-inline Vec3 rotate_axis_angle(Vec3 axis, float angleDegrees, Vec3 v) // Versor(axis, angle) * v, Versor.cs:30-44,223-240
-{
-	float radians = (angleDegrees / 2.0f) * (float)(3.14159265358979323846 / 180.0);
-	float s = (float)std::sin(radians), c = (float)std::cos(radians);
-	float dx = axis.x * s, dy = axis.y * s, dz = axis.z * s, dw = c;
-
-	float ddx = dx * dx, ddy = dy * dy, ddz = dz * dz, ddw = dw * dw;
-	float dwx = dw * 2.0f * dx, dwy = dw * 2.0f * dy, dwz = dw * 2.0f * dz;
-	float dzx = dz * 2.0f * dx, dzy = dz * 2.0f * dy;
-	float dyx = dy * 2.0f * dx;
-
-	return {
-		ddw * v.x + ddx * v.x - dwz * v.y + dyx * v.y + dwy * v.z + dzx * v.z - ddz * v.x - ddy * v.x,
-		dyx * v.x + dwz * v.x + ddy * v.y - ddz * v.y + dzy * v.z - dwx * v.z + ddw * v.y - ddx * v.y,
-		dzx * v.x - dwy * v.x + dzy * v.y + dwx * v.y + ddz * v.z - ddy * v.z - ddx * v.z + ddw * v.z
-	};
-}
-
-inline Cone cone_union(const Cone& value0, const Cone& value1) // ConeBound.Union, ConeBound.cs:76-101 (quirks kept: degrees + radians)
-{
-	float offset0 = std::acos(clamp11(value0.cosOffset));
-	float offset1 = std::acos(clamp11(value1.cosOffset));
-	float cosExtend = sse_min(value0.cosExtend, value1.cosExtend);
-
-	Vec3 axis = value0.axis;
-	float max = angle_degrees(value0.axis, value1.axis) + offset1;
-
-	if (sse_min(max, kPi) <= offset0) return { axis, value0.cosOffset, cosExtend };
-
-	float offset = (offset0 + max) / 2.0f;
-	if (offset >= kPi) return { { 0.0f, 1.0f, 0.0f }, -1.0f, cosExtend }; // CreateFullSphere
-
-	Vec3 c = normalized(cross(axis, value1.axis));
-	float rotation = offset - offset0;
-	axis = rotate_axis_angle(c, rotation, axis);
-
-	return { axis, std::cos(offset), cosExtend };
-}
-
-inline Cone cone_encapsulate(const Cone& self, const Cone& other) // ConeBound.cs:50-56
-{
-	return other.cosOffset > self.cosOffset ? cone_union(self, other) : cone_union(other, self);
-}
-
-inline float cone_relative_area(const Cone& cone) // ConeBound.cs:28-46
-{
-	float offset = std::acos(clamp11(cone.cosOffset));
-	float extend = std::acos(clamp11(cone.cosExtend));
-
-	float angle = sse_min(offset + extend, kPi) * 2.0f;
-	float sinOffset = identity(cone.cosOffset);
-
-	return kTau * (1.0f - cone.cosOffset) + kPi / 2.0f * (angle * sinOffset - std::cos(offset - angle) - 2.0f * offset * sinOffset + cone.cosOffset);
-}
-
-struct LightBound // Aggregation/Bounds/LightBound.cs:10-28
-{
-	Box box;
-	Cone cone;
-	float power;
-
-	float relative_area() const { return box.half_area() * cone_relative_area(cone) * power; }
-
-	LightBound encapsulate(const LightBound& o) const { return { box.encapsulate(o.box), cone_encapsulate(cone, o.cone), power + o.power }; }
-};
+// LightBound / ConeBound arithmetic and LightCollection.CreateBounds live in echo_light_build.h, the one restatement this recursive build,
+// the device build (lightbuild.cu) and its CPU emulation share: MathF.Acos / Cos / SinCos and Math.Acos are pinned there, so all three
+// emit the same bits.
+using LightBound = lightbuild::Bound;
 
 struct TokenizedLight
 {
@@ -527,17 +448,17 @@ struct LightTreeBuilder
 			return index;
 		}
 
-		Box parentBound = data[0].bound.box;
-		for (int i = 0; i < length; i++) parentBound = parentBound.encapsulate(data[i].bound.box);
+		float lo[3], hi[3]; // parentBound = bounds[0].content.box, then Encapsulate over every emitter
+		for (int k = 0; k < 3; k++) { lo[k] = data[0].bound.lo[k]; hi[k] = data[0].bound.hi[k]; }
+		for (int i = 0; i < length; i++)
+			for (int k = 0; k < 3; k++) { lo[k] = lightbuild::math_min(lo[k], data[i].bound.lo[k]); hi[k] = lightbuild::math_max(hi[k], data[i].bound.hi[k]); }
 
-		int majorAxis = parentBound.major_axis();
+		uint32_t majorAxis = lightbuild::major_axis(lo, hi);
 
 		// the reference sorts with Span.Sort (unstable introsort); ties are broken stably here
 		std::stable_sort(data, data + length, [majorAxis](const TokenizedLight& a, const TokenizedLight& b)
 		{
-			float center0 = ((a.bound.box.max + a.bound.box.min) * 0.5f)[majorAxis]; // BoxBound.Center = (max + min) / 2
-			float center1 = ((b.bound.box.max + b.bound.box.min) * 0.5f)[majorAxis];
-			return center0 < center1;
+			return lightbuild::centre(a.bound, majorAxis) < lightbuild::centre(b.bound, majorAxis);
 		});
 
 		std::vector<float> costs(length);
@@ -545,8 +466,8 @@ struct LightTreeBuilder
 
 		for (int i = length - 2; i >= 0; i--)
 		{
-			costs[i + 1] = lightBound.relative_area();
-			lightBound = lightBound.encapsulate(data[i].bound);
+			costs[i + 1] = lightbuild::relative_area(lightBound);
+			lightBound = lightbuild::encapsulate(lightBound, data[i].bound);
 		}
 
 		float minCost = kInf;
@@ -556,7 +477,7 @@ struct LightTreeBuilder
 
 		for (int i = 1; i < length; i++)
 		{
-			float cost = costs[i] + lightBound.relative_area();
+			float cost = costs[i] + lightbuild::relative_area(lightBound);
 
 			if (cost < minCost)
 			{
@@ -564,7 +485,7 @@ struct LightTreeBuilder
 				minIndex = i;
 			}
 
-			lightBound = lightBound.encapsulate(data[i].bound);
+			lightBound = lightbuild::encapsulate(lightBound, data[i].bound);
 		}
 
 		if (minIndex < 0) minIndex = length / 2; // all costs NaN/inf: the reference would throw; split in the middle instead
@@ -574,7 +495,7 @@ struct LightTreeBuilder
 		uint32_t child0 = build(data + minIndex, length - minIndex);
 		uint32_t child1 = build(data, minIndex);
 
-		LightBound bound = bounds[child0].encapsulate(bounds[child1]);
+		LightBound bound = lightbuild::encapsulate(bounds[child0], bounds[child1]);
 		bounds[index] = bound;
 		fill(index, bound);
 		nodes[index].child0 = child0;
@@ -593,14 +514,8 @@ struct LightTreeBuilder
 
 	void fill(uint32_t index, const LightBound& bound)
 	{
-		EchoLightNode& node = nodes[index];
-		node.boxMin[0] = bound.box.min.x; node.boxMin[1] = bound.box.min.y; node.boxMin[2] = bound.box.min.z;
-		node.boxMax[0] = bound.box.max.x; node.boxMax[1] = bound.box.max.y; node.boxMax[2] = bound.box.max.z;
-		node.coneAxis[0] = bound.cone.axis.x; node.coneAxis[1] = bound.cone.axis.y; node.coneAxis[2] = bound.cone.axis.z;
-		node.cosOffset = bound.cone.cosOffset;
-		node.cosExtend = bound.cone.cosExtend;
-		node.power = bound.power;
-		node.pad[0] = node.pad[1] = 0;
+		lightbuild::fill_node(nodes[index], bound);
+		nodes[index].pad[0] = nodes[index].pad[1] = 0;
 	}
 
 	// LightTree ctor AddToMap, LightTree.cs:26-37
@@ -636,6 +551,9 @@ T* copy_out(const std::vector<T>& source)
 	if (result && !source.empty()) std::memcpy(result, source.data(), sizeof(T) * source.size());
 	return result;
 }
+
+inline float sse_min(float a, float b) { return a < b ? a : b; }
+inline float sse_max(float a, float b) { return a > b ? a : b; }
 
 Box triangle_box(const EchoTriangle& t) // PreparedTriangle.BoxBound, TriangleEntity.cs:142 (Float4 SSE min/max, no NaN in scope)
 {
@@ -704,7 +622,7 @@ int32_t echo_host_build_qbvh(const EchoTriangle* triangles, uint32_t triangleCou
 	return echo_host_build_qbvh_instanced(triangles, triangleCount, spheres, sphereCount, nullptr, 0, threads, outNodes, outNodeCount, outMaxDepth);
 }
 
-float echo_host_emissive_power(const float emission[3]) { return luminance(emission) * kPi; } // Emissive.cs:52-53
+float echo_host_emissive_power(const float emission[3]) { return lightbuild::luminance(emission) * kPi; } // Emissive.cs:52-53
 
 int32_t echo_host_build_light_tree(const EchoTriangle* triangles, uint32_t triangleCount, const EchoSphere* spheres, uint32_t sphereCount,
                                    const EchoMaterial* materials, uint32_t materialCount, const EchoPointLight* points, uint32_t pointCount,
@@ -723,52 +641,15 @@ int32_t echo_host_build_light_tree_instanced(const EchoTriangle* triangles, uint
 {
 	if (!outNodes || !outNodeCount || !outTokens || !outPaths || !outEmitterCount || !outPower) return ECHO_B200_ERR_INVALID;
 
-	auto geometry_power = [&](uint32_t material, float area) -> float // LightCollection.GetGeometryPower, LightCollection.cs:221-222
-	{
-		if (material >= materialCount || materials[material].type != ECHO_MATERIAL_EMISSIVE) return 0.0f;
-		return echo_host_emissive_power(materials[material].albedo) * area;
-	};
-
-	// LightCollection.CreateBounds, LightCollection.cs:91-137: point lights, emissive triangles, emissive spheres
+	// LightCollection.CreateBounds, LightCollection.cs:91-137: point lights, emissive triangles, emissive spheres, then the placements
+	// (AddInstances, :123-135: PreparedInstance.LightBound; those without power are skipped)
+	const lightbuild::Sources sources = { triangles, triangleCount, spheres, sphereCount, materials, materialCount, points, pointCount, instanceLights, instanceCount };
 	std::vector<TokenizedLight> lights;
-	const Cone fullSphere = { { 0.0f, 1.0f, 0.0f }, -1.0f, 0.0f };
 
-	for (uint32_t i = 0; i < pointCount; i++)
+	for (uint32_t c = 0; c < sources.candidates(); c++)
 	{
-		Vec3 p = v3(points[i].position);
-		float power = 4.0f * kPi * luminance(points[i].intensity); // PointLight.cs:31
-		lights.push_back({ ECHO_LIGHT_TOKEN_MAKE(ECHO_LIGHT_TYPE_POINT, i), { { p, p }, fullSphere, power } });
-	}
-
-	for (uint32_t i = 0; i < triangleCount; i++)
-	{
-		const EchoTriangle& t = triangles[i];
-		if (t.material >= materialCount || materials[t.material].type != ECHO_MATERIAL_EMISSIVE) continue;
-
-		Vec3 c = cross(v3(t.edge1), v3(t.edge2));
-		float area = magnitude(c) / 2.0f;
-		float power = geometry_power(t.material, area);
-		if (!(kEpsilon <= power)) continue;
-
-		lights.push_back({ ECHO_TOKEN_MAKE(ECHO_TOKEN_TYPE_TRIANGLE, i), { triangle_box(t), { normalized(c), 1.0f, 0.0f }, power } });
-	}
-
-	for (uint32_t i = 0; i < sphereCount; i++)
-	{
-		const EchoSphere& s = spheres[i];
-		float area = 4.0f * kPi * s.radius * s.radius;
-		float power = geometry_power(s.material, area);
-		if (!(kEpsilon <= power)) continue;
-
-		lights.push_back({ ECHO_TOKEN_MAKE(ECHO_TOKEN_TYPE_SPHERE, i), { sphere_box(s), fullSphere, power } });
-	}
-
-	for (uint32_t i = 0; i < instanceCount; i++) // AddInstances, LightCollection.cs:123-135: PreparedInstance.LightBound
-	{
-		const float* v = instanceLights + (size_t)i * 12; // box min xyz, max xyz, cone axis xyz, cosOffset, cosExtend, power
-		if (!(kEpsilon <= v[11])) continue;
-		LightBound bound = { { { v[0], v[1], v[2] }, { v[3], v[4], v[5] } }, { { v[6], v[7], v[8] }, v[9], v[10] }, v[11] };
-		lights.push_back({ ECHO_TOKEN_MAKE(ECHO_TOKEN_TYPE_INSTANCE, i), bound });
+		TokenizedLight light;
+		if (lightbuild::emitter(sources, c, light.bound, light.token)) lights.push_back(light);
 	}
 
 	LightTreeBuilder builder;

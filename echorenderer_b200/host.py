@@ -279,7 +279,7 @@ def build_light_tree(description, instance_lights=None):
             _take(paths, emitter_count.value, np.uint64), float(power.value))
 
 
-def _prepare_packs(description, threads, tree_builder=None):
+def _prepare_packs(description, threads, tree_builder=None, light_tree_builder=None):
     """ScenePreparer: every EntityPack becomes one PreparedPack (children before parents), then all arrays are laid back to
     back with an EchoPack record per pack (pack 0 = the scene) and an EchoInstance record per placement."""
     sources = [description] + list(description.packs)  # pack k+1 = description.packs[k]
@@ -315,7 +315,7 @@ def _prepare_packs(description, threads, tree_builder=None):
             nodes, depth = tree_builder(source.triangles, source.spheres, pack_boxes)
         else:
             nodes, depth = build_qbvh(source.triangles, source.spheres, threads, pack_boxes)
-        built[index] = (nodes, depth, build_light_tree(source, np.asarray(lights, dtype=np.float32) if lights else None))
+        built[index] = (nodes, depth, (light_tree_builder or build_light_tree)(source, np.asarray(lights, dtype=np.float32) if lights else None))
         source._records = records
         return built[index]
 
@@ -686,10 +686,12 @@ def _root_bound_radius(nodes):
     return accelerator_sphere_bound(nodes).radius
 
 
-def prepare(description, threads=0, tree=None, tree_builder=None):
+def prepare(description, threads=0, tree=None, tree_builder=None, light_tree_builder=None):
     """ScenePreparer.Prepare -> PreparedScene constructor (PreparedScene.cs:26-40). `tree` = (nodes, max_depth) replaces the
     SweepBuilder mirror for a scene without instances; `tree_builder(triangles, spheres, instance_bounds) -> (nodes, max_depth)`
-    replaces it for every pack of any scene (e.g. the device-side build: lambda t, s, b: scene.build_qbvh_device(t, s, instance_bounds=b))."""
+    replaces it for every pack of any scene (e.g. the device-side build: lambda t, s, b: scene.build_qbvh_device(t, s, instance_bounds=b));
+    `light_tree_builder(description, instance_lights) -> (nodes, tokens, paths, power)` replaces build_light_tree the same way
+    (the device-side build: scene.build_light_tree_device)."""
     lib = _library()
     d = description
     d.triangles = np.ascontiguousarray(d.triangles, dtype=structs.TRIANGLE)
@@ -700,11 +702,11 @@ def prepare(description, threads=0, tree=None, tree_builder=None):
 
     instanced = bool(d.instances)
     if instanced:
-        packs, instances, nodes, all_triangles, all_spheres, all_materials, max_depth, lights, all_slots = _prepare_packs(d, threads, tree_builder)
+        packs, instances, nodes, all_triangles, all_spheres, all_materials, max_depth, lights, all_slots = _prepare_packs(d, threads, tree_builder, light_tree_builder)
         light_nodes, tokens, paths, all_points, scene_power = lights
     else:
         nodes, max_depth = tree if tree is not None else (tree_builder(d.triangles, d.spheres, None) if tree_builder is not None else build_qbvh(d.triangles, d.spheres, threads))
-        light_nodes, tokens, paths, scene_power = build_light_tree(d)
+        light_nodes, tokens, paths, scene_power = (light_tree_builder or build_light_tree)(d)
 
     # FilterLights / SumInfiniteLightsPower / CalculateThreshold (PreparedScene.cs:279-325)
     infinite_power = np.float32(0)

@@ -21,10 +21,12 @@ from .host import PreparedArrays
 class PreparedScene:
     """The flattened scene resident on one B200; the device twin of Echo's PreparedScene."""
 
-    def __init__(self, prepared: PreparedArrays, device: int = 0, devices=None, build_tree_on_device: bool = False):
+    def __init__(self, prepared: PreparedArrays, device: int = 0, devices=None, build_tree_on_device: bool = False, build_light_tree_on_device: bool = False):
         """`device`: the CUDA device of a single-device scene. `build_tree_on_device`: the library builds the accelerator itself from
         the uploaded triangles and spheres (echo_b200_scene_build_qbvh: the SweepBuilder's tree, on the device) instead of taking
-        `prepared.nodes`; `self.built_tree` = (node count, max depth) then. `devices` (a list of device indices) instead replicates the scene
+        `prepared.nodes`; `self.built_tree` = (node count, max depth) then. `build_light_tree_on_device`: likewise the light tree
+        (echo_b200_scene_build_light_tree: LightTree.Build on the device) instead of `prepared.light_nodes` and the emitter map;
+        `self.built_light_tree` = (node count, emitter count, power) then. `devices` (a list of device indices) instead replicates the scene
         on several devices of this process (echo_b200_scene_create_multi): trace / occlude split their batches over them and
         render_tiles deals blocks of tiles to them; the *_device methods then do not apply."""
         lib = _native.library()
@@ -61,9 +63,16 @@ class PreparedScene:
                 _native.check(lib.echo_b200_scene_set_distributions(self._handle, ptr(prepared.distributions), len(prepared.distributions)))
             if prepared.packs is not None:
                 _native.check(lib.echo_b200_scene_set_packs(self._handle, ptr(prepared.packs), len(prepared.packs), ptr(prepared.instances), len(prepared.instances)))
-            _native.check(lib.echo_b200_scene_set_light_tree(self._handle, ptr(prepared.light_nodes), len(prepared.light_nodes),
-                                                             ptr(prepared.emitter_tokens), ptr(prepared.emitter_bitpaths), len(prepared.emitter_tokens),
-                                                             ptr(prepared.point_lights), len(prepared.point_lights)))
+            self.built_light_tree = None
+            if build_light_tree_on_device:
+                count, emitters, power = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_float()
+                _native.check(lib.echo_b200_scene_build_light_tree(self._handle, ptr(prepared.point_lights), len(prepared.point_lights),
+                                                                   ctypes.byref(count), ctypes.byref(emitters), ctypes.byref(power)))
+                self.built_light_tree = (count.value, emitters.value, power.value)
+            else:
+                _native.check(lib.echo_b200_scene_set_light_tree(self._handle, ptr(prepared.light_nodes), len(prepared.light_nodes),
+                                                                 ptr(prepared.emitter_tokens), ptr(prepared.emitter_bitpaths), len(prepared.emitter_tokens),
+                                                                 ptr(prepared.point_lights), len(prepared.point_lights)))
             _native.check(lib.echo_b200_scene_set_infinite(self._handle, ptr(d.infinite_lights), len(d.infinite_lights),
                                                            prepared.infinite_threshold, prepared.infinite_pdf))
             _native.check(lib.echo_b200_scene_set_camera(self._handle, ptr(d.camera)))
@@ -436,6 +445,33 @@ def build_qbvh_device(triangles, spheres, device=0, instance_bounds=None):
                                                      _native.pointer(nodes), ctypes.byref(count), ctypes.byref(depth)))
     nodes.resize(count.value, refcheck=False)  # shrinks in place (realloc): no second copy of a 600 MB array
     return nodes, int(depth.value)
+
+
+def build_light_tree_device(description, instance_lights=None, device=0):
+    """The optional device-side light-tree build (echo_b200_build_light_tree, csrc/lightbuild.cu). Takes and returns what
+    host.build_light_tree does — (nodes, emitter_tokens, emitter_bitpaths, power) — and the arrays equal that build's byte for byte:
+    LightCollection.CreateBounds + LightTree.Build + AddToMap, level by level on the device. `description` needs triangles, spheres,
+    materials and point_lights; instance_lights: [n, 12] float32 PreparedInstance.LightBound rows. Pass it to host.prepare as
+    `light_tree_builder=scene.build_light_tree_device`."""
+    lib = _native.library()
+    d = description
+    triangles = np.ascontiguousarray(d.triangles, dtype=structs.TRIANGLE)
+    spheres = np.ascontiguousarray(d.spheres, dtype=structs.SPHERE)
+    materials = np.ascontiguousarray(d.materials, dtype=structs.MATERIAL)
+    points = np.ascontiguousarray(d.point_lights, dtype=structs.POINT_LIGHT)
+    rows = np.zeros((0, 12), dtype=np.float32) if instance_lights is None else np.ascontiguousarray(instance_lights, dtype=np.float32).reshape(-1, 12)
+
+    # room: an emitter is a point light, a placement, or a primitive whose material is Emissive (LightCollection.cs:99-121)
+    emissive = materials["type"] == structs.MATERIAL_EMISSIVE
+    lit = lambda index: int(np.count_nonzero(emissive[index[index < len(materials)]])) if len(materials) else 0
+    capacity = len(points) + len(rows) + lit(triangles["material"]) + lit(spheres["material"])
+    nodes = np.empty(max(2 * capacity, 1), dtype=structs.LIGHT_NODE)
+    tokens, paths = np.empty(max(capacity, 1), dtype=np.uint32), np.empty(max(capacity, 1), dtype=np.uint64)
+    node_count, emitter_count, power = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_float()
+    _native.check(lib.echo_b200_build_light_tree(device, _native.pointer(triangles), len(triangles), _native.pointer(spheres), len(spheres), _native.pointer(materials), len(materials),
+                                                 _native.pointer(points), len(points), _native.pointer(rows), len(rows), _native.pointer(nodes), len(nodes), ctypes.byref(node_count),
+                                                 _native.pointer(tokens), _native.pointer(paths), len(tokens), ctypes.byref(emitter_count), ctypes.byref(power)))
+    return nodes[:node_count.value].copy(), tokens[:emitter_count.value].copy(), paths[:emitter_count.value].copy(), float(power.value)
 
 
 def shard_epochs(max_epoch, rank, world_size):

@@ -442,6 +442,33 @@ int32_t echo_b200_build_qbvh_instanced(int32_t device, const EchoTriangle* trian
  * out_node_count / out_max_depth are optional. Scenes with packs: ECHO_B200_ERR_UNSUPPORTED (build each pack, set_qbvh + set_packs). */
 int32_t echo_b200_scene_build_qbvh(EchoScene*, uint32_t* out_node_count, uint32_t* out_max_depth);
 
+/* Optional device-side LIGHT TREE build: LightCollection.CreateBounds (Aggregation/Preparation/LightCollection.cs:91-137
+ * — point lights, emissive triangles, emissive spheres, then the placements' PreparedInstance.LightBound rows, those below FastMath.Epsilon
+ * of power dropped), LightTree.Build (Aggregation/Selection/LightTree.cs:62-113 — sort by box centre along the major axis, one sweep from
+ * each end over LightBound.Encapsulate / RelativeArea, first cut of lowest cost, tail subtree first) and AddToMap (:26-37), run level by
+ * level on the device. The shape of this tree IS the light-sampling distribution (LightTree.Pick, :115-154), so the build emits the
+ * reference's own tree: nodes in pre-order, emitter tokens and bit paths equal to echo_host_build_light_tree's byte for byte
+ * (tests/test_light_build.py, tests/test_gpu_build.py). MathF.Acos / Cos / SinCos and Math.Acos are pinned (csrc/echo_light_build.h) so
+ * that host and device agree; the sort is stable (the reference's Span.Sort leaves the order of equal centres to the runtime).
+ * Mirrors echo_host_build_light_tree_instanced (echo_host.h), with caller-owned output: out_nodes needs room for node_capacity nodes,
+ * out_emitter_tokens / out_emitter_bitpaths for emitter_capacity entries; 2 e - 1 nodes for e emitters, and e <= point_count + the
+ * primitives with an Emissive material + instance_count. Too little room: ECHO_B200_ERR_INVALID with the needed counts in out_node_count /
+ * out_emitter_count. A tree deeper than 63 levels (LightTree.cs:29: a path is 64 bits): ECHO_B200_ERR_UNSUPPORTED. No emitters: both counts 0.
+ * out_power receives the root's LightBound.power (what PreparedScene.CalculateThreshold takes, echo_host_infinite_threshold).
+ * instance_lights: 12 floats per placement (box min xyz, max xyz, cone axis xyz, cosOffset, cosExtend, power), or NULL. */
+int32_t echo_b200_build_light_tree(int32_t device, const EchoTriangle* triangles, uint32_t triangle_count, const EchoSphere* spheres, uint32_t sphere_count,
+                                   const EchoMaterial* materials, uint32_t material_count, const EchoPointLight* points, uint32_t point_count,
+                                   const float* instance_lights, uint32_t instance_count,
+                                   EchoLightNode* out_nodes, uint32_t node_capacity, uint32_t* out_node_count,
+                                   uint32_t* out_emitter_tokens, uint64_t* out_emitter_bitpaths, uint32_t emitter_capacity, uint32_t* out_emitter_count,
+                                   float* out_power);
+/* The same build for a scene handle: the light tree of the triangles, spheres and materials already uploaded (set_triangles / set_spheres /
+ * set_materials) and of `points`, built on the scene's device and installed as if set_light_tree had been called with it — a host that
+ * does not want to run LightCollection / LightTree construction on its CPU calls this instead of set_light_tree, before commit.
+ * out_* are optional. Scenes with packs: ECHO_B200_ERR_UNSUPPORTED (build each pack's tree with echo_b200_build_light_tree). */
+int32_t echo_b200_scene_build_light_tree(EchoScene*, const EchoPointLight* points, uint32_t point_count,
+                                         uint32_t* out_node_count, uint32_t* out_emitter_count, float* out_power);
+
 /* Page-locked host memory for the host-buffer entry points. A P/Invoke caller pins managed arrays with `fixed`
  * (Processes/Composition/OidnDenoise.cs:109-110): that stops the GC from moving them but leaves them PAGEABLE for CUDA, so every
  * copy is staged through the driver's bounce buffer and cannot overlap the kernels (measured: bench.py `e2e_pageable`). Either

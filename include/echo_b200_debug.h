@@ -51,6 +51,8 @@ int32_t echo_b200_debug_set_option(const char* name, int64_t value);
 /* Phases of the calling thread's last echo_b200_build_qbvh that ran the SweepBuilder build (csrc/sweep.cu): out4 = {upload ms, device
  * build ms, download ms, binary levels}, host wall time around synchronised phases. Zeros if no such build ran on this thread. */
 int32_t echo_b200_debug_last_build(float* out4);
+/* The same for the calling thread's last echo_b200_build_light_tree / echo_b200_scene_build_light_tree (csrc/lightbuild.cu); out4[3] = levels. */
+int32_t echo_b200_debug_last_light_build(float* out4);
 
 #ifdef __cplusplus
 }

@@ -145,6 +145,13 @@ def test_no_cpu_fallback_without_a_device(cornell):
     zeros = np.zeros(8, dtype=np.float32)
     assert lib.echo_b200_debug_math(0, 0, _native.pointer(zeros), _native.pointer(zeros), _native.pointer(zeros), 8, _native.pointer(out)) == _native.ERR_NO_DEVICE
 
+    # the device-side builds have no host twin inside this library either (the host mirror is another library, libecho_host.so)
+    from echorenderer_b200 import build_light_tree_device, build_qbvh_device
+    for build in (lambda: build_qbvh_device(cornell.triangles, cornell.spheres), lambda: build_light_tree_device(cornell.description)):
+        with pytest.raises(_native.EchoNativeError) as error:
+            build()
+        assert error.value.status == _native.ERR_NO_DEVICE
+
 
 def test_null_scene_is_rejected():
     lib = _native.library()

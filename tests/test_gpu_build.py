@@ -217,3 +217,115 @@ def test_scene_builds_its_own_accelerator(terrain_small, cornell):
             assert built.built_tree == (len(prepared.nodes), prepared.max_depth)
             assert_hits_equal(built.trace(rays), given.trace(rays))
             assert np.array_equal(built.occlude(shadow), given.occlude(shadow))
+
+
+# ---- the light tree (echo_b200_build_light_tree, csrc/lightbuild.cu): LightTree.Build level by level on the device ----
+
+def assert_device_light_tree_is_the_host_mirrors(description, instance_lights=None):
+    from echorenderer_b200 import build_light_tree_device
+    expected_nodes, expected_tokens, expected_paths, expected_power = host.build_light_tree(description, instance_lights)
+    nodes, tokens, paths, power = build_light_tree_device(description, instance_lights)
+    assert len(nodes) == len(expected_nodes) and len(tokens) == len(expected_tokens)
+    assert nodes.tobytes() == expected_nodes.tobytes()
+    assert tokens.tobytes() == expected_tokens.tobytes() and paths.tobytes() == expected_paths.tobytes()
+    assert np.float32(power) == np.float32(expected_power)
+    return nodes, tokens
+
+
+@pytest.mark.parametrize("fixture", ["cornell", "lights_small", "mixed_small"])
+def test_device_light_tree_is_the_host_mirrors_byte_for_byte(fixture, request):
+    """The same nodes in the same pre-order, the same emitter tokens and bit paths as the recursive build (tests/test_light_build.py asks
+    the same of the CPU emulation of these passes) — and therefore what the scene was prepared with."""
+    from tests.test_light_build import describe
+    prepared = request.getfixturevalue(fixture)
+    nodes, tokens = assert_device_light_tree_is_the_host_mirrors(describe(prepared.triangles, prepared.spheres, prepared.materials, prepared.point_lights))
+    assert nodes.tobytes() == prepared.light_nodes.tobytes() and tokens.tobytes() == prepared.emitter_tokens.tobytes()
+
+
+def test_device_light_tree_on_random_emitters_ties_placements_and_tiny_inputs():
+    from echorenderer_b200 import build_light_tree_device
+    from tests.test_light_build import describe, random_emitters
+    for seed, triangle_count, sphere_count, point_count, scale in [(1, 2, 0, 0, 1.0), (2, 0, 0, 2, 1.0), (3, 1, 1, 1, 5.0), (4, 40, 9, 3, 1.0), (5, 1500, 100, 20, 100.0),
+                                                                   (6, 6000, 0, 0, 1e-2), (7, 500, 500, 500, 1e3), (8, 40_000, 2000, 100, 30.0)]:
+        assert_device_light_tree_is_the_host_mirrors(random_emitters(seed, triangle_count, sphere_count, point_count, scale, emissive_share=1.0 if triangle_count + sphere_count < 5 else 0.7))
+
+    rng = np.random.default_rng(11)
+    rows = np.zeros((9, 12), dtype=np.float32)  # PreparedInstance.LightBound rows: the placements join the list last
+    low = rng.uniform(-10, 10, (9, 3))
+    rows[:, 0:3], rows[:, 3:6] = low, low + rng.uniform(0.5, 3.0, (9, 3))
+    axis = rng.normal(size=(9, 3))
+    rows[:, 6:9] = axis / np.linalg.norm(axis, axis=1, keepdims=True)
+    rows[:, 9], rows[:, 10], rows[:, 11] = rng.uniform(-1, 1, 9), rng.uniform(0, 1, 9), rng.uniform(0.5, 80.0, 9)
+    rows[4, 11] = 0.0
+    assert_device_light_tree_is_the_host_mirrors(random_emitters(12, 60, 10, 4, 10.0), rows)
+
+    ix, iy = np.meshgrid(np.arange(-4, 4), np.arange(-2, 2), indexing="ij")  # a lattice of identical emitters, twice: every sort meets ties
+    v0 = np.stack([ix.reshape(-1), np.zeros(ix.size), iy.reshape(-1)], axis=-1).astype(np.float64)
+    v0 = np.concatenate([v0, v0, -v0 * 0.0])
+    lattice = describe(scenes.make_triangles(v0 - (0.25, 0, 0.25), v0 + (0.25, 0, -0.25), v0 + (-0.25, 0, 0.25), 0), materials=np.concatenate([scenes.material(structs.MATERIAL_EMISSIVE, (3.0, 2.0, 1.0))]))
+    assert_device_light_tree_is_the_host_mirrors(lattice)
+
+    dark = random_emitters(3, 50, 5, 0, 1.0, emissive_share=0.0)  # no emitter: an empty tree
+    nodes, tokens, paths, power = build_light_tree_device(dark)
+    assert len(nodes) == 0 and len(tokens) == 0 and len(paths) == 0 and power == 0.0
+    single = describe(point_lights=np.array([((1.0, 2.0, 3.0), (0.5, -1.0, 4.0))], dtype=structs.POINT_LIGHT))
+    nodes, _ = assert_device_light_tree_is_the_host_mirrors(single)  # one emitter: the root is its leaf
+    assert len(nodes) == 1
+
+    def chain(count):  # point lights on a line: every cut costs 0, the first wins, depth = count - 1 (LightTree.cs:29: at most 63)
+        points = np.zeros(count, dtype=structs.POINT_LIGHT)
+        points["position"][:, 0] = np.arange(count)
+        points["intensity"] = (10.0 ** (0.5 * np.arange(count) - 18.0))[:, None]
+        return describe(point_lights=points)
+
+    assert_device_light_tree_is_the_host_mirrors(chain(64))
+    with pytest.raises(_native.EchoNativeError) as refused:
+        build_light_tree_device(chain(65))
+    assert refused.value.status == _native.ERR_UNSUPPORTED
+
+
+def test_device_light_tree_at_full_size():
+    """C4's emitters (10 000 emissive triangles among 309 502): the device-built light tree is the host mirror's 19 999 nodes, byte for byte."""
+    from echorenderer_b200 import build_light_tree_device
+    from tests.test_light_build import describe
+    description = scenes.many_lights_scene()
+    build_light_tree_device(describe(description.triangles[:64], materials=description.materials))  # context + module load
+    started = time.perf_counter()
+    nodes, tokens, paths, power = build_light_tree_device(description)
+    device_seconds = time.perf_counter() - started
+    phases = _native.last_light_build()
+    started = time.perf_counter()
+    expected_nodes, expected_tokens, expected_paths, expected_power = host.build_light_tree(description)
+    host_seconds = time.perf_counter() - started
+    print(f"light tree over {len(tokens)} emitters of {len(description.triangles)} triangles: device call {device_seconds * 1e3:.1f} ms {phases}, host mirror {host_seconds * 1e3:.1f} ms")
+    assert len(nodes) == len(expected_nodes) == 19_999 and len(tokens) == 10_000
+    assert nodes.tobytes() == expected_nodes.tobytes() and tokens.tobytes() == expected_tokens.tobytes() and paths.tobytes() == expected_paths.tobytes()
+    assert np.float32(power) == np.float32(expected_power)
+
+
+def test_scene_builds_its_own_light_tree(lights_small, cornell):
+    """echo_b200_scene_build_light_tree: a host that uploads geometry and materials gets the reference's light tree built on the device —
+    and every rendered tile is, bit for bit, the tile of the scene given the host mirror's tree and emitter map."""
+    for prepared, size in ((lights_small, 64), (cornell, 32)):
+        params = structs.render_params(size, size, 16, extend=4, seed=5, bounce_limit=16)
+        tiles = scenes.tile_grid(size, size, 16)
+        with PreparedScene(prepared) as given, PreparedScene(prepared, build_light_tree_on_device=True) as built:
+            count, emitters, power = built.built_light_tree
+            assert count == len(prepared.light_nodes) and emitters == len(prepared.emitter_tokens) and np.float32(power) == prepared.light_nodes["power"][0]
+            expected, expected_stats = given.render_tiles(params, tiles)
+            actual, stats = built.render_tiles(params, tiles)
+            assert actual.tobytes() == expected.tobytes() and stats.tobytes() == expected_stats.tobytes()
+
+    with pytest.raises(_native.EchoNativeError):  # scenes with packs build each pack's tree with echo_b200_build_light_tree
+        PreparedScene(host.prepare(scenes.instanced_scene(grid=2, rings=6, segments=6)), build_light_tree_on_device=True)
+
+
+def test_instanced_scene_prepared_with_device_built_light_trees_is_the_same_scene():
+    """Every pack's light tree (placements included: PreparedInstance.LightBound rows) built on the device gives the arrays the host gives."""
+    from echorenderer_b200 import build_light_tree_device
+    expected = host.prepare(scenes.instanced_scene(grid=4, rings=12, segments=12))
+    built = host.prepare(scenes.instanced_scene(grid=4, rings=12, segments=12), light_tree_builder=build_light_tree_device)
+    assert len(expected.light_nodes) > 1
+    assert built.light_nodes.tobytes() == expected.light_nodes.tobytes()
+    assert built.emitter_tokens.tobytes() == expected.emitter_tokens.tobytes() and built.emitter_bitpaths.tobytes() == expected.emitter_bitpaths.tobytes()
+    assert built.infinite_threshold == expected.infinite_threshold

@@ -1,0 +1,205 @@
+"""The level-synchronous LightTree.Build (echorenderer_b200/csrc/echo_light_build.h: the passes and the driver of the device build,
+lightbuild.cu) on a sequential CPU backend (tests/c_client/light_emulation.cpp): the tree and the emitter map it emits must be the
+host mirror's — LightTree.cs:62-113 recursive, one node at a time — byte for byte: same nodes, same pre-order, same bit paths.
+The GPU suite (test_gpu_build.py) asks the same of the CUDA backend. Also here: the accuracy of the pinned transcendentals the
+builds share (the reference's come from the platform's C runtime), and the invariants of the emitted tree."""
+import ctypes
+import os
+import subprocess
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+
+from echorenderer_b200 import host, scenes, structs
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def library(tmp_path_factory):
+    path = tmp_path_factory.mktemp("light") / "liblight_emulation.so"
+    subprocess.run(["g++", "-std=c++17", "-O2", "-march=x86-64-v3", "-ffp-contract=off", "-Wall", "-Wextra", "-Werror", "-shared", "-fPIC",
+                    os.path.join(ROOT, "tests", "c_client", "light_emulation.cpp"), "-o", str(path)], check=True)
+    lib = ctypes.CDLL(str(path))
+    p, u32 = ctypes.c_void_p, ctypes.c_uint32
+    lib.light_emulation_build.argtypes = [p, u32, p, u32, p, u32, p, u32, p, u32, ctypes.c_int32, p, ctypes.POINTER(u32), p, p, ctypes.POINTER(u32), ctypes.POINTER(u32)]
+    lib.light_emulation_build.restype = ctypes.c_int32
+    lib.light_emulation_acos_double.argtypes, lib.light_emulation_acos_double.restype = [ctypes.c_double], ctypes.c_double
+    lib.light_emulation_acos.argtypes, lib.light_emulation_acos.restype = [ctypes.c_float], ctypes.c_float
+    lib.light_emulation_cos.argtypes, lib.light_emulation_cos.restype = [ctypes.c_float], ctypes.c_float
+    return lib
+
+
+def describe(triangles=None, spheres=None, materials=None, point_lights=None):
+    """what host.build_light_tree reads of a SceneDescription"""
+    return SimpleNamespace(triangles=np.zeros(0, dtype=structs.TRIANGLE) if triangles is None else triangles,
+                           spheres=np.zeros(0, dtype=structs.SPHERE) if spheres is None else spheres,
+                           materials=np.zeros(0, dtype=structs.MATERIAL) if materials is None else materials,
+                           point_lights=np.zeros(0, dtype=structs.POINT_LIGHT) if point_lights is None else point_lights)
+
+
+def emulate(lib, description, instance_lights=None, reverse=False):
+    d = description
+    triangles = np.ascontiguousarray(d.triangles, dtype=structs.TRIANGLE)
+    spheres = np.ascontiguousarray(d.spheres, dtype=structs.SPHERE)
+    materials = np.ascontiguousarray(d.materials, dtype=structs.MATERIAL)
+    points = np.ascontiguousarray(d.point_lights, dtype=structs.POINT_LIGHT)
+    bounds = np.zeros((0, 12), dtype=np.float32) if instance_lights is None else np.ascontiguousarray(instance_lights, dtype=np.float32).reshape(-1, 12)
+    candidates = len(triangles) + len(spheres) + len(points) + len(bounds)
+    nodes = np.zeros(max(2 * candidates, 1), dtype=structs.LIGHT_NODE)
+    tokens, paths = np.zeros(max(candidates, 1), dtype=np.uint32), np.zeros(max(candidates, 1), dtype=np.uint64)
+    node_count, emitter_count, levels = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
+    status = lib.light_emulation_build(triangles.ctypes.data, len(triangles), spheres.ctypes.data, len(spheres), materials.ctypes.data, len(materials),
+                                       points.ctypes.data, len(points), bounds.ctypes.data, len(bounds), int(reverse), nodes.ctypes.data, ctypes.byref(node_count),
+                                       tokens.ctypes.data, paths.ctypes.data, ctypes.byref(emitter_count), ctypes.byref(levels))
+    return status, nodes[:node_count.value], tokens[:emitter_count.value], paths[:emitter_count.value], levels.value
+
+
+def assert_same_tree(lib, description, instance_lights=None, reverse=False):
+    expected_nodes, expected_tokens, expected_paths, _ = host.build_light_tree(description, instance_lights)
+    status, nodes, tokens, paths, levels = emulate(lib, description, instance_lights, reverse)
+    assert status == 0
+    assert len(nodes) == len(expected_nodes) and len(tokens) == len(expected_tokens)
+    assert nodes.tobytes() == expected_nodes.tobytes()
+    assert tokens.tobytes() == expected_tokens.tobytes() and paths.tobytes() == expected_paths.tobytes()
+    return nodes, tokens, paths, levels
+
+
+def random_emitters(seed, triangle_count, sphere_count, point_count, scale, emissive_share=0.7):
+    """a soup of small triangles and spheres, a share of them emissive (several emission colours, one too dim to count), and point lights"""
+    rng = np.random.default_rng(seed)
+    materials = np.concatenate([scenes.material(structs.MATERIAL_DIFFUSE, (0.7, 0.7, 0.7))]
+                               + [scenes.material(structs.MATERIAL_EMISSIVE, tuple(rng.uniform(0.5, 40.0, 3))) for _ in range(5)]
+                               + [scenes.material(structs.MATERIAL_EMISSIVE, (1e-9, 1e-9, 1e-9))])
+    v0 = rng.uniform(-scale, scale, (triangle_count, 3))
+    e1, e2 = rng.normal(0, scale * 0.02, (triangle_count, 3)), rng.normal(0, scale * 0.02, (triangle_count, 3))
+    choice = np.where(rng.uniform(size=triangle_count) < emissive_share, rng.integers(1, 7, triangle_count), 0)
+    triangles = scenes.make_triangles(v0, v0 + e1, v0 + e2, choice.astype(np.uint32))
+    spheres = np.zeros(sphere_count, dtype=structs.SPHERE)
+    spheres["position"] = rng.uniform(-scale, scale, (sphere_count, 3))
+    spheres["radius"] = rng.uniform(0.01, 0.05, sphere_count) * scale
+    spheres["material"] = np.where(rng.uniform(size=sphere_count) < emissive_share, rng.integers(1, 7, sphere_count), 0)
+    points = np.zeros(point_count, dtype=structs.POINT_LIGHT)
+    points["position"] = rng.uniform(-scale, scale, (point_count, 3))
+    points["intensity"] = rng.uniform(0.1, 30.0, (point_count, 3))
+    return describe(triangles, spheres, materials, points)
+
+
+@pytest.mark.parametrize("fixture", ["cornell", "lights_small", "mixed_small"])
+def test_emitted_tree_is_the_host_mirrors_byte_for_byte(library, fixture, request):
+    prepared = request.getfixturevalue(fixture)
+    description = describe(prepared.triangles, prepared.spheres, prepared.materials, prepared.point_lights)
+    nodes, tokens, _, levels = assert_same_tree(library, description)
+    assert len(nodes) == 2 * len(tokens) - 1 and levels >= 1
+    assert nodes.tobytes() == prepared.light_nodes.tobytes()  # what the scene itself was prepared with
+    assert_same_tree(library, description, reverse=True)  # no pass depends on the order of its indices
+
+
+@pytest.mark.parametrize("seed,triangle_count,sphere_count,point_count,scale", [(1, 2, 0, 0, 1.0), (2, 0, 0, 2, 1.0), (3, 1, 1, 1, 5.0), (4, 40, 9, 3, 1.0),
+                                                                               (5, 1500, 100, 20, 100.0), (6, 6000, 0, 0, 1e-2), (7, 500, 500, 500, 1e3)])
+def test_random_emitters(library, seed, triangle_count, sphere_count, point_count, scale):
+    description = random_emitters(seed, triangle_count, sphere_count, point_count, scale, emissive_share=1.0 if triangle_count + sphere_count < 5 else 0.7)
+    nodes, tokens, paths, levels = assert_same_tree(library, description)
+    assert len(tokens) >= 2 and len(np.unique(tokens)) == len(tokens) and len(np.unique(paths)) == len(paths)
+    assert_same_tree(library, description, reverse=True)
+
+
+def test_placements_and_equal_centres(library):
+    """PreparedInstance.LightBound rows join the list last (AddInstances); emitters with EQUAL centres keep their order (the stable sort)."""
+    rng = np.random.default_rng(11)
+    description = random_emitters(12, 60, 10, 4, 10.0)
+    rows = np.zeros((9, 12), dtype=np.float32)
+    low = rng.uniform(-10, 10, (9, 3))
+    rows[:, 0:3], rows[:, 3:6] = low, low + rng.uniform(0.5, 3.0, (9, 3))
+    axis = rng.normal(size=(9, 3))
+    rows[:, 6:9] = axis / np.linalg.norm(axis, axis=1, keepdims=True)
+    rows[:, 9], rows[:, 10], rows[:, 11] = rng.uniform(-1, 1, 9), rng.uniform(0, 1, 9), rng.uniform(0.5, 80.0, 9)
+    rows[4, 11] = 0.0  # a placement without emitters is skipped
+    nodes, tokens, _, _ = assert_same_tree(library, description, rows)
+    assert np.count_nonzero(tokens >> 28 == 3) == 8
+
+    # a lattice of identical emissive triangles: every sort meets ties, on every axis (also: -0 and +0 centres are one key)
+    ix, iy = np.meshgrid(np.arange(-4, 4), np.arange(-2, 2), indexing="ij")
+    v0 = np.stack([ix.reshape(-1), np.zeros(ix.size), iy.reshape(-1)], axis=-1).astype(np.float64)
+    v0 = np.concatenate([v0, v0, -v0 * 0.0])
+    materials = np.concatenate([scenes.material(structs.MATERIAL_EMISSIVE, (3.0, 2.0, 1.0))])
+    lattice = describe(scenes.make_triangles(v0 - (0.25, 0, 0.25), v0 + (0.25, 0, -0.25), v0 + (-0.25, 0, 0.25), 0), materials=materials)
+    assert_same_tree(library, lattice)
+    assert_same_tree(library, lattice, reverse=True)
+
+
+def test_degenerate_counts(library):
+    """no emitter: an empty tree; one emitter: the root is its leaf (LightTree.cs:64-65)"""
+    status, nodes, tokens, _, _ = emulate(library, describe(materials=np.concatenate([scenes.material(structs.MATERIAL_DIFFUSE)])))
+    assert status == 0 and len(nodes) == 0 and len(tokens) == 0
+    dark = random_emitters(3, 50, 5, 0, 1.0, emissive_share=0.0)
+    status, nodes, tokens, _, _ = emulate(library, dark)
+    assert status == 0 and len(nodes) == 0 and len(tokens) == 0
+
+    single = describe(point_lights=np.array([((1.0, 2.0, 3.0), (0.5, -1.0, 4.0))], dtype=structs.POINT_LIGHT))
+    nodes, tokens, paths, levels = assert_same_tree(library, single)
+    assert len(nodes) == 1 and levels == 0 and nodes["child0"][0] == 0xFFFFFFFF and nodes["child1"][0] == tokens[0] and paths[0] == 0
+
+
+def test_chain_deeper_than_a_path_is_refused(library):
+    """LightTree.cs:29: 64 bits of path. Point lights on one line: every joint box has half area 0, every cut costs 0, the first one wins
+    (`cost < minCost`) and the emitters peel off one at a time: depth = count - 1."""
+    def chain(count):
+        points = np.zeros(count, dtype=structs.POINT_LIGHT)
+        points["position"][:, 0] = np.arange(count)
+        points["intensity"] = (10.0 ** (0.5 * np.arange(count) - 18.0))[:, None]
+        return describe(point_lights=points)
+
+    *_, levels = assert_same_tree(library, chain(40))
+    assert levels == 39
+    *_, levels = assert_same_tree(library, chain(64))
+    assert levels == 63  # the deepest tree a path can spell
+    status, *_ = emulate(library, chain(65))
+    assert status == 2
+    with pytest.raises(ValueError):
+        host.build_light_tree(chain(65))
+
+
+def test_tree_invariants(library, lights_small):
+    """structure of the emitted array: pre-order, tail subtree first, powers summed, boxes nested, paths spell the descent"""
+    description = describe(lights_small.triangles, lights_small.spheres, lights_small.materials, lights_small.point_lights)
+    _, nodes, tokens, paths, levels = emulate(library, description)
+    leaf = nodes["child0"] == 0xFFFFFFFF
+    assert np.count_nonzero(leaf) == len(tokens) == 300
+
+    def leaves_below(index):
+        return 1 if leaf[index] else leaves_below(nodes["child0"][index]) + leaves_below(nodes["child1"][index])
+
+    depth_seen = 0
+    for index in np.flatnonzero(~leaf):
+        child0, child1 = int(nodes["child0"][index]), int(nodes["child1"][index])
+        assert child0 == index + 1 and child1 == index + 2 * leaves_below(child0)
+        assert nodes["power"][index] == np.float32(nodes["power"][child0]) + np.float32(nodes["power"][child1])
+        for child in (child0, child1):
+            assert np.all(nodes["boxMin"][index] <= nodes["boxMin"][child]) and np.all(nodes["boxMax"][index] >= nodes["boxMax"][child])
+
+    for token, path in zip(tokens, paths):
+        index, depth = 0, 0
+        while not leaf[index]:
+            index = int(nodes["child1"][index] if (int(path) >> depth) & 1 else nodes["child0"][index])
+            depth += 1
+        assert nodes["child1"][index] == token and int(path) >> depth == 0
+        depth_seen = max(depth_seen, depth)
+    assert depth_seen == levels
+
+
+def test_pinned_transcendentals_are_the_runtime_functions_to_rounding(library):
+    """MathF.Acos / MathF.Cos / Math.Acos belong to the C runtime in the reference; the pinned versions must be them up to the last bits"""
+    rng = np.random.default_rng(5)
+    x = np.concatenate([rng.uniform(-1, 1, 20000), 1 - 2.0 ** -rng.uniform(1, 50, 5000), -1 + 2.0 ** -rng.uniform(1, 50, 5000), [0.0, 1.0, -1.0, 0.5, -0.5, 1e-300, 2.0 ** -60]])
+    mine = np.array([library.light_emulation_acos_double(float(v)) for v in x])
+    assert np.max(np.abs(mine - np.arccos(x)) / np.maximum(np.arccos(x), 1e-300)) < 4.5e-16  # within two units of the last place of binary64
+    assert np.array_equal(mine.astype(np.float32), np.arccos(x).astype(np.float32))        # Float3.Angle rounds it to binary32: the same float
+
+    xf = np.concatenate([rng.uniform(-1, 1, 20000), [0.0, 1.0, -1.0, 0.5, -0.5]]).astype(np.float32)
+    acos32 = np.array([library.light_emulation_acos(float(v)) for v in xf], dtype=np.float32)
+    assert np.max(np.abs(acos32.astype(np.float64) - np.arccos(xf.astype(np.float64)))) < 4e-7
+    angles = rng.uniform(-2 * np.pi, np.pi, 20000).astype(np.float32)  # ConeBound.RelativeArea's `offset - angle` and Union's `offset`
+    cos32 = np.array([library.light_emulation_cos(float(v)) for v in angles], dtype=np.float32)
+    assert np.max(np.abs(cos32.astype(np.float64) - np.cos(angles.astype(np.float64)))) < 2e-7
