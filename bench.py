@@ -263,6 +263,28 @@ def tree_build_record(prepared, device):
             "host_mirror_ms": host_ms, "host_mirror_threads": os.cpu_count(), "identical_to_host_mirror": bool(depth == expected_depth and nodes.tobytes() == expected.tobytes())}
 
 
+def light_tree_build_record(prepared, device):
+    """The device-side LightTree.Build (echo_b200_build_light_tree, csrc/lightbuild.cu) on a scene's emitters beside the host mirror of the
+    reference's recursive build: the whole call from host buffers, its phases, and whether nodes and emitter map are the same bytes."""
+    from echorenderer_b200 import _native, build_light_tree_device
+    description = prepared.description
+    build_light_tree_device(description, device=device)  # context + module load
+    calls = []
+    for _ in range(3):
+        started = time.perf_counter()
+        nodes, tokens, paths, power = build_light_tree_device(description, device=device)
+        calls.append(((time.perf_counter() - started) * 1e3, _native.last_light_build()))
+    call_ms, phases = min(calls, key=lambda pair: pair[0])
+    started = time.perf_counter()
+    expected_nodes, expected_tokens, expected_paths, _ = host.build_light_tree(description)
+    host_ms = (time.perf_counter() - started) * 1e3
+    identical = nodes.tobytes() == expected_nodes.tobytes() and tokens.tobytes() == expected_tokens.tobytes() and paths.tobytes() == expected_paths.tobytes()
+    return {"what": "the reference's light tree (LightCollection.CreateBounds + LightTree.Build + AddToMap) built level-synchronously on the device: echo_b200_build_light_tree from host buffers, best of 3 calls; "
+                    "a node's two sweeps are chains of non-associative cone unions, one thread each, so the time is a few chain lengths",
+            "candidates": int(len(description.triangles) + len(description.spheres) + len(description.point_lights)), "emitters": int(len(tokens)), "nodes": int(len(nodes)),
+            "call_ms": call_ms, **phases, "host_mirror_ms": host_ms, "host_mirror_threads": 1, "identical_to_host_mirror": bool(identical)}
+
+
 def secondary_batch(scene, prepared, rays, d_hits, ctx, args):
     """The second batch SURVEY.md §8(d) asks to report beside the headline: rays leaving the surfaces the first batch hit
     (cosine-hemisphere directions, ignore = hit token, as TraceQuery.SpawnTrace does), tiled up to the size of the first batch.
@@ -785,6 +807,9 @@ def run_render(ctx, args, scene_key, width, height, spp, bounce_limit, steps, wa
               "scene": {"triangles": int(len(prepared.triangles)), "spheres": int(len(prepared.spheres)), "nodes": int(len(prepared.nodes)), "quad_depth": int(prepared.max_depth),
                         "light_tree_nodes": int(len(prepared.light_nodes)), "host_prepare_seconds": prepare_seconds},
               "stats_last_step": {label: int(stats[name][0]) for label, name in zip(structs.STATS_LABELS, structs.STATS_FIELDS)}}
+
+    if rank == 0 and prepared.packs is None and len(prepared.light_nodes) > 1000 and not args.no_tree_build:
+        record["light_tree_build"] = light_tree_build_record(prepared, ctx.local_rank)
 
     if with_cpu_baseline and rank == 0 and not args.no_cpu_baseline:
         note(ctx, f"render {scene_key}: CPU baseline")

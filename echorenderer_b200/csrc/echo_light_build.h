@@ -10,11 +10,14 @@
 // the float power sum are not — a sweep is a chain that has to be walked in order to reproduce its bits. What IS free: the two sweeps of
 // a node do not depend on each other, and nothing couples two nodes of the same depth. So all nodes ("segments") of one depth are
 // processed together over one array of emitter positions in which every segment is a contiguous range:
-//   axis    per segment: the joint box of its emitters -> BoxBound.MajorAxis
+//   box     per position: six atomic min / max on the segment's joint box (integer images of the floats) -> BoxBound.MajorAxis
 //   keys    per position: (segment begin << 32) | order-preserving image of the centre along that axis; ONE stable radix sort of the
-//           whole level sorts every segment in place (finished positions keep theirs)
-//   sweeps  TWO threads per segment, one per direction, each walking its chain and storing the relative area before every cut
-//   split   per segment: the first minimum of `costs[i] + area` (`cost < minCost`, :98), the node's two children — the reference emits
+//           whole level sorts every segment in place (finished positions keep theirs); the bounds are gathered in that order
+//   sweeps  TWO threads per segment, one per direction, each walking its chain of Encapsulate and storing the bound before every cut
+//   cost    per position: the two relative areas of its cut (they depend on nothing but the stored bounds, so they leave the chains) and
+//           `costs[i] + area`; one 64-bit atomic min per cut over (image of the cost, cut index): the lowest cost, the FIRST cut among
+//           equals (`cost < minCost`, :98)
+//   split   per segment: the node's two children — the reference emits
 //           nodes in pre-order, tail subtree first (`new Node(Build(bounds[minIndex..]), Build(bounds[..minIndex]))`), and a subtree over
 //           L emitters holds 2 L - 1 nodes, so both child indices follow from the cut: parent + 1 and parent + 2 (L - minIndex)
 //   assign  positions move to their child segment; a range of one emitter becomes a leaf and drops out
@@ -59,7 +62,7 @@ struct Vec3
 	float x, y, z;
 };
 
-struct Bound // LightBound: BoxBound + ConeBound + power, 48 bytes
+struct alignas(16) Bound // LightBound: BoxBound + ConeBound + power, 48 bytes (three 16-byte loads / stores)
 {
 	float lo[3], hi[3];
 	float axis[3];
@@ -72,7 +75,11 @@ struct Segment // a branch under construction: positions [begin, begin + length)
 	uint32_t begin, length, node, axis;
 	uint32_t split, depth;
 	unsigned long long path; // AddToMap's `branches` on the way to this node
+	unsigned long long best; // (order-preserving image of the lowest cut cost << 32) | cut index; kNoCut until a cut has a finite cost
+	int32_t lo[3], hi[3];    // the joint box of the segment's emitters as order-preserving integers (int order == float order, -0 < +0)
 };
+
+constexpr unsigned long long kNoCut = ~0ull;
 
 // ---- bits ----
 
@@ -101,6 +108,52 @@ LIGHT_HD double clear_low_word(double value)
 }
 
 LIGHT_HD bool sign_bit(float value) { return (float_bits(value) >> 31) != 0u; }
+
+LIGHT_HD float bits_float(uint32_t bits)
+{
+#if defined(__CUDA_ARCH__)
+	return __uint_as_float(bits);
+#else
+	float value;
+	memcpy(&value, &bits, 4);
+	return value;
+#endif
+}
+
+LIGHT_HD int32_t to_ordered(float value)
+{
+	int32_t bits = (int32_t)float_bits(value);
+	return bits >= 0 ? bits : bits ^ 0x7FFFFFFF;
+}
+
+LIGHT_HD float from_ordered(int32_t value) { return bits_float((uint32_t)(value >= 0 ? value : value ^ 0x7FFFFFFF)); }
+
+LIGHT_HD void atomic_min_i32(int32_t* address, int32_t value)
+{
+#if defined(__CUDA_ARCH__)
+	atomicMin(address, value);
+#else
+	if (value < *address) *address = value;
+#endif
+}
+
+LIGHT_HD void atomic_max_i32(int32_t* address, int32_t value)
+{
+#if defined(__CUDA_ARCH__)
+	atomicMax(address, value);
+#else
+	if (value > *address) *address = value;
+#endif
+}
+
+LIGHT_HD void atomic_min_u64(unsigned long long* address, unsigned long long value)
+{
+#if defined(__CUDA_ARCH__)
+	atomicMin(address, value);
+#else
+	if (value < *address) *address = value;
+#endif
+}
 
 LIGHT_HD float round_even(float value)
 {
@@ -265,20 +318,20 @@ LIGHT_HD float identity(float v) // FastMath.Identity: sqrt(max(1 - v^2, 0)) wit
 	return s <= 0.0f ? 0.0f : sqrtf(s);
 }
 
-LIGHT_HD float math_min(float a, float b) // Math.Min: NaN-propagating, -0 < +0 (Float3.Min, Float3.cs:301)
+// Math.Min / Math.Max (Float3.Min / Max, Float3.cs:301-302): a NaN wins (the first one), and -0 < +0. Written as selects over the
+// order-preserving integer images — int order == float order with -0 below +0 — so that a chain step has no branches to resolve.
+LIGHT_HD float math_min(float a, float b)
 {
-	if (a != a) return a;
-	if (b != b) return b;
-	if (a == b) return sign_bit(a) ? a : b;
-	return a < b ? a : b;
+	float r = to_ordered(a) < to_ordered(b) ? a : b;
+	r = b != b ? b : r;
+	return a != a ? a : r;
 }
 
 LIGHT_HD float math_max(float a, float b)
 {
-	if (a != a) return a;
-	if (b != b) return b;
-	if (a == b) return sign_bit(a) ? b : a;
-	return a > b ? a : b;
+	float r = to_ordered(a) > to_ordered(b) ? a : b;
+	r = b != b ? b : r;
+	return a != a ? a : r;
 }
 
 LIGHT_HD float angle_degrees(Vec3 a, Vec3 b) // Float3.Angle, Float3.cs:277-288 (DEGREES)
@@ -320,11 +373,19 @@ struct Cone
 
 LIGHT_HD Cone cone_union(const Cone& value0, const Cone& value1) // ConeBound.Union, ConeBound.cs:76-101 (the degrees + radians sum is the reference's)
 {
+	float cosExtend = sse_min(value0.cosExtend, value1.cosExtend);
+	Vec3 axis = value0.axis;
+
+	// A cone that already is the whole sphere (offset0 == pi, the largest value acos gives) passes the early exit below whatever the angle
+	// between the axes is — Min(max, pi) <= pi, also for a NaN max (Sse.Min hands back its second operand) — so neither arc cosine nor the
+	// binary64 angle (a square root, a division, another arc cosine) is computed for it: the same result, and most of a long sweep over
+	// emitters facing all ways is such steps. offset0 == pi exactly when the clamped cosine is -1: acos_pin stays below pi for every
+	// other input (tests/test_light_build.py walks all of them next to -1).
+	if (value0.cosOffset <= -1.0f) return { axis, value0.cosOffset, cosExtend };
+
 	float offset0 = acos_pin(clamp11(value0.cosOffset));
 	float offset1 = acos_pin(clamp11(value1.cosOffset));
-	float cosExtend = sse_min(value0.cosExtend, value1.cosExtend);
 
-	Vec3 axis = value0.axis;
 	float max = angle_degrees(value0.axis, value1.axis) + offset1;
 
 	if (sse_min(max, kPi) <= offset0) return { axis, value0.cosOffset, cosExtend };
@@ -388,7 +449,7 @@ LIGHT_HD float centre(const Bound& b, uint32_t axis) { return (b.hi[axis] + b.lo
 
 // The comparison of LightTree.cs:76-81 (`center0.CompareTo(center1)`; the sort is made stable, like the host mirror's) as a radix key:
 // unsigned order == float order, and -0 == +0 as in the comparison.
-LIGHT_HD uint32_t centre_key(float value)
+LIGHT_HD uint32_t centre_key(float value) // also the image of a cut's cost
 {
 	if (value == 0.0f) value = 0.0f;
 	uint32_t bits = float_bits(value);
@@ -561,6 +622,17 @@ struct LeafWriter // `new Node(bounds[0].content, bounds[0].token)`, LightTree.c
 	}
 };
 
+LIGHT_HD Segment new_segment(uint32_t begin, uint32_t length, uint32_t node, uint32_t depth, unsigned long long path)
+{
+	Segment segment;
+	segment.begin = begin; segment.length = length; segment.node = node; segment.axis = 0u;
+	segment.split = 0u; segment.depth = depth;
+	segment.path = path;
+	segment.best = kNoCut;
+	for (int k = 0; k < 3; k++) { segment.lo[k] = 0x7FFFFFFF; segment.hi[k] = (int32_t)0x80000000; }
+	return segment;
+}
+
 struct RootPass // the whole emitter list as one segment — or as one leaf
 {
 	uint32_t count;
@@ -580,29 +652,40 @@ struct RootPass // the whole emitter list as one segment — or as one leaf
 			return;
 		}
 
-		segments[0] = { 0u, count, 0u, 0u, 0u, 0u, 0ull };
+		segments[0] = new_segment(0u, count, 0u, 0u, 0ull);
 		internalNodes[0] = 0u;
 	}
 };
 
-struct AxisPass // LightTree.cs:68-74: the joint box (unions are exact: their order is free), then its major axis
+// LightTree.cs:68-74: the joint box of a segment's emitters. BoxBound.Encapsulate is Math.Min / Math.Max per component — exact, and on the
+// integer images associative and commutative — so every position folds its emitter's box into its segment's with six atomics, in any order.
+struct BoxPass
 {
 	const uint32_t* order;
+	const uint32_t* segmentOf;
 	const Bound* bounds;
+	Segment* segments;
+
+	LIGHT_HD void operator()(uint32_t p) const
+	{
+		uint32_t s = segmentOf[p];
+		if (s == kNone) return;
+
+		const Bound& b = bounds[order[p]];
+		Segment& segment = segments[s];
+		for (int k = 0; k < 3; k++) { atomic_min_i32(&segment.lo[k], to_ordered(b.lo[k])); atomic_max_i32(&segment.hi[k], to_ordered(b.hi[k])); }
+	}
+};
+
+struct AxisPass // ... then its major axis
+{
 	Segment* segments;
 
 	LIGHT_HD void operator()(uint32_t s) const
 	{
 		Segment& segment = segments[s];
-		const Bound& first = bounds[order[segment.begin]];
-		float lo[3] = { first.lo[0], first.lo[1], first.lo[2] }, hi[3] = { first.hi[0], first.hi[1], first.hi[2] };
-
-		for (uint32_t i = 1u; i < segment.length; i++)
-		{
-			const Bound& b = bounds[order[segment.begin + i]];
-			for (int k = 0; k < 3; k++) { lo[k] = math_min(lo[k], b.lo[k]); hi[k] = math_max(hi[k], b.hi[k]); }
-		}
-
+		float lo[3], hi[3];
+		for (int k = 0; k < 3; k++) { lo[k] = from_ordered(segment.lo[k]); hi[k] = from_ordered(segment.hi[k]); }
 		segment.axis = major_axis(lo, hi);
 	}
 };
@@ -628,18 +711,37 @@ struct KeyPass
 	}
 };
 
-// LightTree.cs:83-104, one thread per (segment, direction). Direction 0: from the last emitter backwards, costs[i] = the relative area of
-// emitters [i, length) for i = length - 1 .. 1; direction 1: from the first one forwards, areas[i] = that of [0, i) for i = 1 .. length - 1.
-// Threads [0, stride) walk backwards, [stride, 2 stride) forwards, stride a multiple of the warp size: the two chains of a segment run in
-// different warps (at the root they ARE the level), each at the pace of its own branches.
+struct GatherPass // the bounds in position order: the sweeps read them front to back (and back to front) instead of through `order`
+{
+	const uint32_t* order;
+	const uint32_t* segmentOf;
+	const Bound* bounds;
+	Bound* sorted;
+
+	LIGHT_HD void operator()(uint32_t p) const
+	{
+		if (segmentOf[p] != kNone) sorted[p] = bounds[order[p]];
+	}
+};
+
+// LightTree.cs:83-104, the part that is a chain: one thread per (segment, direction) folds LightBound.Encapsulate over its segment and
+// stores the bound BEFORE every step. Direction 0: from the last emitter backwards, tails[i] = the bound of emitters [i, length) for
+// i = length - 1 .. 1; direction 1: from the first one forwards, heads[i] = that of [0, i) for i = 1 .. length - 1. What the reference
+// evaluates inside the same loops — LightBound.RelativeArea of every one of those bounds, four transcendentals each — depends on nothing but
+// its bound, so it leaves the chain for CostPass, one thread per cut. Threads [0, stride) walk backwards, [stride, 2 stride) forwards,
+// stride a multiple of the warp size: the two chains of a segment run in different warps (at the root they ARE the level), each at the pace
+// of its own branches. A chain is latency all the way — one thread, every step waiting for the last — and once the cone has grown to the
+// whole sphere a step is a few dozen instructions, far less than a trip to L2: the emitters of the next kAhead steps are kept in flight
+// in a ring of registers (the loop is unrolled over the ring, so its slots are registers, not local memory).
 struct SweepPass
 {
+	static constexpr uint32_t kAhead = 6u;
+
 	uint32_t live, stride;
-	const uint32_t* order;
-	const Bound* bounds;
-	const Segment* segments;
-	float* costs;
-	float* areas;
+	const Bound* __restrict__ sorted;
+	const Segment* __restrict__ segments;
+	Bound* __restrict__ tails;
+	Bound* __restrict__ heads;
 
 	LIGHT_HD void operator()(uint32_t t) const
 	{
@@ -647,27 +749,68 @@ struct SweepPass
 		const uint32_t s = forward ? t - stride : t;
 		if (s >= live) return;
 
-		const Segment& segment = segments[s];
-		const uint32_t begin = segment.begin, last = segment.length - 1u;
-		float* out = forward ? areas : costs;
+		const uint32_t begin = segments[s].begin, last = segments[s].length - 1u;
+		Bound* __restrict__ out = forward ? heads : tails;
 
-		Bound bound = bounds[order[begin + (forward ? 0u : last)]];
+		// step k (1 .. last) folds in the emitter at begin + k (forwards) or begin + last - k (backwards)
+		Bound bound = sorted[begin + (forward ? 0u : last)];
+		Bound ring[kAhead];
 
-		for (uint32_t k = 1u; k <= last; k++)
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+		for (uint32_t j = 0u; j < kAhead; j++)
+			if (1u + j <= last) ring[j] = sorted[begin + (forward ? 1u + j : last - 1u - j)];
+
+		for (uint32_t first = 1u; first <= last; first += kAhead)
 		{
-			out[begin + (forward ? k : last + 1u - k)] = relative_area(bound);
-			bound = encapsulate(bound, bounds[order[begin + (forward ? k : last - k)]]);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+			for (uint32_t j = 0u; j < kAhead; j++)
+			{
+				const uint32_t k = first + j;
+				if (k > last) break;
+
+				const Bound current = ring[j];
+				if (k + kAhead <= last) ring[j] = sorted[begin + (forward ? k + kAhead : last - k - kAhead)];
+
+				out[begin + (forward ? k : last + 1u - k)] = bound;
+				bound = encapsulate(bound, current);
+			}
 		}
 	}
 };
 
-struct SplitPass // LightTree.cs:93-112: the cut, the branch, its children (leaves are written, branches counted for the next level)
+// LightTree.cs:85-104, the part that is not: per cut i the cost `costs[i] + lightBound.RelativeArea` = RelativeArea(tails[i]) +
+// RelativeArea(heads[i]), and the first cut of lowest cost (`cost < minCost` from +inf: a NaN or infinite cost never wins) as one atomic
+// min over (image of the cost, cut index): the lowest cost, and among equal costs the lowest index.
+struct CostPass
+{
+	const uint32_t* segmentOf;
+	const Bound* tails;
+	const Bound* heads;
+	Segment* segments;
+
+	LIGHT_HD void operator()(uint32_t p) const
+	{
+		uint32_t s = segmentOf[p];
+		if (s == kNone) return;
+
+		Segment& segment = segments[s];
+		uint32_t i = p - segment.begin;
+		if (i == 0u) return;
+
+		float cost = relative_area(tails[p]) + relative_area(heads[p]);
+		if (cost < INFINITY) atomic_min_u64(&segment.best, (unsigned long long)centre_key(cost) << 32 | i);
+	}
+};
+
+struct SplitPass // LightTree.cs:106-112: the branch and its children at the cut CostPass found (leaves are written, branches counted for the next level)
 {
 	const uint32_t* order;
 	const Bound* bounds;
 	const uint32_t* tokens;
-	const float* costs;
-	const float* areas;
 	Segment* segments;
 	EchoLightNode* nodes;
 	uint32_t* counts; // [2 s] = the head half lives on, [2 s + 1] = the tail half does
@@ -678,20 +821,7 @@ struct SplitPass // LightTree.cs:93-112: the cut, the branch, its children (leav
 		Segment& segment = segments[s];
 		const uint32_t begin = segment.begin, length = segment.length;
 
-		float minCost = INFINITY;
-		uint32_t minIndex = kNone;
-
-		for (uint32_t i = 1u; i < length; i++)
-		{
-			float cost = costs[begin + i] + areas[begin + i];
-
-			if (cost < minCost)
-			{
-				minCost = cost;
-				minIndex = i;
-			}
-		}
-
+		uint32_t minIndex = segment.best == kNoCut ? kNone : (uint32_t)(segment.best & 0xFFFFFFFFull);
 		if (minIndex == kNone) minIndex = length / 2u; // every cost NaN / inf: the reference throws; the host mirror cuts in the middle
 		segment.split = minIndex;
 
@@ -724,14 +854,14 @@ struct ChildPass // the halves that live on become the next level's segments, in
 		if (segment.split > 1u)
 		{
 			uint32_t k = slots[2u * s];
-			next[k] = { segment.begin, segment.split, segment.node + 2u * tail, 0u, 0u, segment.depth + 1u, segment.path | 1ull << segment.depth };
+			next[k] = new_segment(segment.begin, segment.split, segment.node + 2u * tail, segment.depth + 1u, segment.path | 1ull << segment.depth);
 			internalNodes[k] = next[k].node;
 		}
 
 		if (tail > 1u)
 		{
 			uint32_t k = slots[2u * s + 1u];
-			next[k] = { segment.begin + segment.split, tail, segment.node + 1u, 0u, 0u, segment.depth + 1u, segment.path };
+			next[k] = new_segment(segment.begin + segment.split, tail, segment.node + 1u, segment.depth + 1u, segment.path);
 			internalNodes[k] = next[k].node;
 		}
 	}
@@ -814,13 +944,14 @@ struct Result
 struct Working // everything sized by the emitter count
 {
 	Bound* bounds;
+	Bound* sorted;
 	uint32_t* tokens;
 	uint32_t* order[2];
 	unsigned long long* keys[2];
 	uint32_t* segmentOf;
 	Segment* segments[2];
-	float* costs;
-	float* areas;
+	Bound* tails;
+	Bound* heads;
 	uint32_t* counts;
 	uint32_t* slots;
 	uint32_t* internalNodes;
@@ -835,11 +966,12 @@ struct Working // everything sized by the emitter count
 	{
 		size_t nodeCount = 2 * n;
 		bounds = arena.take<Bound>(n);
+		sorted = arena.take<Bound>(n);
 		tokens = arena.take<uint32_t>(n);
 		for (int k = 0; k < 2; k++) { order[k] = arena.take<uint32_t>(n); keys[k] = arena.take<unsigned long long>(n); segments[k] = arena.take<Segment>(n / 2 + 1); }
 		segmentOf = arena.take<uint32_t>(n);
-		costs = arena.take<float>(n);
-		areas = arena.take<float>(n);
+		tails = arena.take<Bound>(n);
+		heads = arena.take<Bound>(n);
 		counts = arena.take<uint32_t>(n + 2);
 		slots = arena.take<uint32_t>(n + 2);
 		internalNodes = arena.take<uint32_t>(n);
@@ -903,14 +1035,17 @@ Result build(Backend& backend, const Sources& sources)
 		uint32_t offset = levelOffsets.back();
 		levelOffsets.push_back(offset + live);
 
-		if (!backend.for_each(live, AxisPass{ w.order[side], w.bounds, segments })) return result;
+		if (!backend.for_each(count, BoxPass{ w.order[side], w.segmentOf, w.bounds, segments })) return result;
+		if (!backend.for_each(live, AxisPass{ segments })) return result;
 		if (!backend.for_each(count, KeyPass{ w.order[side], w.segmentOf, segments, w.bounds, w.keys[0] })) return result;
 		if (!backend.sort_pairs(w.keys[0], w.keys[1], w.order[side], w.order[side ^ 1], count, 64)) return result;
 		const uint32_t* order = w.order[side ^ 1];
 
 		const uint32_t stride = (live + 31u) & ~31u;
-		if (!backend.for_each(2u * stride, SweepPass{ live, stride, order, w.bounds, segments, w.costs, w.areas })) return result;
-		if (!backend.for_each(live, SplitPass{ order, w.bounds, w.tokens, w.costs, w.areas, segments, w.nodes, w.counts, leaves })) return result;
+		if (!backend.for_each(count, GatherPass{ order, w.segmentOf, w.bounds, w.sorted })) return result;
+		if (!backend.for_each(2u * stride, SweepPass{ live, stride, w.sorted, segments, w.tails, w.heads })) return result;
+		if (!backend.for_each(count, CostPass{ w.segmentOf, w.tails, w.heads, segments })) return result;
+		if (!backend.for_each(live, SplitPass{ order, w.bounds, w.tokens, segments, w.nodes, w.counts, leaves })) return result;
 		if (!backend.fill_zero(w.counts + 2u * live, sizeof(uint32_t))) return result;
 		if (!backend.exclusive_sum(w.counts, w.slots, 2u * live + 1u)) return result;
 		if (!backend.for_each(live, ChildPass{ segments, w.slots, w.segments[side ^ 1], w.internalNodes + offset + live })) return result;

@@ -86,3 +86,49 @@ extern "C" int32_t light_emulation_build(const EchoTriangle* triangles, uint32_t
 extern "C" double light_emulation_acos_double(double x) { return acos_double_pin(x); }
 extern "C" float light_emulation_acos(float x) { return acos_pin(x); }
 extern "C" float light_emulation_cos(float x) { return cos_pin(x); }
+
+// ConeBound.Union without the whole-sphere shortcut of echo_light_build.h's cone_union (ConeBound.cs:76-101 as written), to check that the
+// shortcut changes nothing: out5 = axis xyz, cosOffset, cosExtend of both forms for value0 = in[0..4], value1 = in[5..9]
+extern "C" void light_emulation_cone_unions(const float* in, float* abridged5, float* unabridged5)
+{
+	Cone value0 = { { in[0], in[1], in[2] }, in[3], in[4] }, value1 = { { in[5], in[6], in[7] }, in[8], in[9] };
+	Cone a = cone_union(value0, value1);
+
+	Cone b;
+	{
+		float offset0 = acos_pin(clamp11(value0.cosOffset));
+		float offset1 = acos_pin(clamp11(value1.cosOffset));
+		float cosExtend = sse_min(value0.cosExtend, value1.cosExtend);
+		Vec3 axis = value0.axis;
+		float max = angle_degrees(value0.axis, value1.axis) + offset1;
+
+		if (sse_min(max, kPi) <= offset0) b = { axis, value0.cosOffset, cosExtend };
+		else
+		{
+			float offset = (offset0 + max) / 2.0f;
+			if (offset >= kPi) b = { { 0.0f, 1.0f, 0.0f }, -1.0f, cosExtend };
+			else
+			{
+				Vec3 c = normalized(cross(axis, value1.axis));
+				axis = rotate_axis_angle(c, offset - offset0, axis);
+				b = { axis, cos_pin(offset), cosExtend };
+			}
+		}
+	}
+
+	float* outs[2] = { abridged5, unabridged5 };
+	const Cone* cones[2] = { &a, &b };
+	for (int k = 0; k < 2; k++) { outs[k][0] = cones[k]->axis.x; outs[k][1] = cones[k]->axis.y; outs[k][2] = cones[k]->axis.z; outs[k][3] = cones[k]->cosOffset; outs[k][4] = cones[k]->cosExtend; }
+}
+
+// cone_union tests `cosOffset <= -1` instead of `acos(clamp(cosOffset)) >= pi`: counts the floats in (-1, -0.5] — every one of them — and a
+// stride through (-0.5, 1] for which acos_pin reaches pi after all (expected: 0), and reports acos_pin(-1) == pi as bit 31
+extern "C" uint32_t light_emulation_acos_reaches_pi()
+{
+	uint32_t reached = 0u;
+	for (uint32_t bits = 0xBF000000u; bits < 0xBF800000u; bits++) if (acos_pin(bits_float(bits)) >= kPi) ++reached;     // -0.5 .. just above -1
+	for (uint32_t bits = 0x80000000u; bits < 0xBF000000u; bits += 97u) if (acos_pin(bits_float(bits)) >= kPi) ++reached;  // -0 .. -0.5
+	for (uint32_t bits = 0x00000000u; bits <= 0x3F800000u; bits += 97u) if (acos_pin(bits_float(bits)) >= kPi) ++reached; // +0 .. 1
+	if (acos_pin(-1.0f) >= kPi && acos_pin(clamp11(-1.5f)) >= kPi) reached |= 0x80000000u;
+	return reached;
+}

@@ -203,3 +203,34 @@ def test_pinned_transcendentals_are_the_runtime_functions_to_rounding(library):
     angles = rng.uniform(-2 * np.pi, np.pi, 20000).astype(np.float32)  # ConeBound.RelativeArea's `offset - angle` and Union's `offset`
     cos32 = np.array([library.light_emulation_cos(float(v)) for v in angles], dtype=np.float32)
     assert np.max(np.abs(cos32.astype(np.float64) - np.cos(angles.astype(np.float64)))) < 2e-7
+
+
+def test_whole_sphere_shortcut_of_the_cone_union_changes_nothing(library):
+    """cone_union skips Float3.Angle when value0 already is the whole sphere (offset0 == pi): ConeBound.Union as written gives the same bits —
+    for random cones, for cones at and next to cosOffset = -1, for parallel, opposite and zero axes (whose angle is 0 or NaN-free by the guards)."""
+    library.light_emulation_cone_unions.argtypes = [ctypes.c_void_p] * 3
+    library.light_emulation_acos_reaches_pi.restype = ctypes.c_uint32
+    assert library.light_emulation_acos_reaches_pi() == 0x80000000  # the arc cosine is pi at -1 (and below, clamped) and nowhere else
+    rng = np.random.default_rng(17)
+    count = 20000
+    cones = np.zeros((count, 10), dtype=np.float32)
+    for base in (0, 5):
+        axis = rng.normal(size=(count, 3))
+        cones[:, base:base + 3] = axis / np.linalg.norm(axis, axis=1, keepdims=True)
+        cones[:, base + 3] = rng.uniform(-1, 1, count)
+        cones[:, base + 4] = rng.uniform(0, 1, count)
+    cones[::3, 3] = -1.0                                             # value0 is the whole sphere
+    cones[1::9, 3] = np.nextafter(np.float32(-1), np.float32(0))     # ... and just not
+    cones[2::27, 3] = np.nextafter(np.float32(-1), np.float32(-2))   # below -1: the clamp makes it the whole sphere, the cosine is kept as it is
+    cones[::7, 5:8] = cones[::7, 0:3]                                # parallel axes
+    cones[::11, 5:8] = -cones[::11, 0:3]                             # opposite axes
+    cones[::13, 5:8] = 0.0                                           # a zero axis (Float3.Angle returns 0)
+    swap = cones[:, 8] < cones[:, 3]                                 # ConeBound.Encapsulate hands Union the wider cone (the lower cosOffset) first
+    cones[swap] = np.concatenate([cones[swap, 5:], cones[swap, :5]], axis=1)
+    a, b = np.zeros(5, dtype=np.float32), np.zeros(5, dtype=np.float32)
+    saturated = 0
+    for row in cones:
+        library.light_emulation_cone_unions(row.ctypes.data, a.ctypes.data, b.ctypes.data)
+        assert a.tobytes() == b.tobytes(), row
+        saturated += row[3] == -1.0
+    assert saturated > count // 4
