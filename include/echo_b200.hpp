@@ -74,6 +74,7 @@ struct SceneSource
 	EchoCamera camera = {};
 	float boundRadius = 0.0f;
 	bool buildAcceleratorOnDevice = false; // echo_b200_scene_build_qbvh instead of set_qbvh: the SweepBuilder's tree, built by the library
+	bool buildLightTreeOnDevice = false;   // echo_b200_scene_build_light_tree instead of set_light_tree: LightTree.Build, by the library (lightNodes / emitter* ignored)
 };
 
 // The prepared, flattened scene resident on the devices of `deviceMask` (bit d = CUDA device d): the device twin of Echo's PreparedScene.
@@ -91,8 +92,11 @@ public:
 			if (source.buildAcceleratorOnDevice) ThrowOnNativeError(echo_b200_scene_build_qbvh(handle, nullptr, nullptr), "echo_b200_scene_build_qbvh");
 			else ThrowOnNativeError(echo_b200_scene_set_qbvh(handle, source.nodes.data, (uint32_t)source.nodes.count, source.maxDepth), "echo_b200_scene_set_qbvh");
 			ThrowOnNativeError(echo_b200_scene_set_materials(handle, source.materials.data, (uint32_t)source.materials.count), "echo_b200_scene_set_materials");
-			ThrowOnNativeError(echo_b200_scene_set_light_tree(handle, source.lightNodes.data, (uint32_t)source.lightNodes.count, source.emitterTokens.data, source.emitterPaths.data,
-			                                                  (uint32_t)source.emitterTokens.count, source.pointLights.data, (uint32_t)source.pointLights.count), "echo_b200_scene_set_light_tree");
+			if (source.buildLightTreeOnDevice)
+				ThrowOnNativeError(echo_b200_scene_build_light_tree(handle, source.pointLights.data, (uint32_t)source.pointLights.count, nullptr, nullptr, nullptr), "echo_b200_scene_build_light_tree");
+			else
+				ThrowOnNativeError(echo_b200_scene_set_light_tree(handle, source.lightNodes.data, (uint32_t)source.lightNodes.count, source.emitterTokens.data, source.emitterPaths.data,
+				                                                  (uint32_t)source.emitterTokens.count, source.pointLights.data, (uint32_t)source.pointLights.count), "echo_b200_scene_set_light_tree");
 			ThrowOnNativeError(echo_b200_scene_set_infinite(handle, source.infiniteLights.data, (uint32_t)source.infiniteLights.count, source.infiniteThreshold, source.infinitePdf), "echo_b200_scene_set_infinite");
 			ThrowOnNativeError(echo_b200_scene_set_camera(handle, &source.camera), "echo_b200_scene_set_camera");
 			ThrowOnNativeError(echo_b200_scene_set_bound_radius(handle, source.boundRadius), "echo_b200_scene_set_bound_radius");

@@ -99,6 +99,7 @@ int main(int argc, char** argv)
 		source.boundRadius = as_float(scalars[3]);
 		source.camera = camera[0];
 		source.buildAcceleratorOnDevice = buildOnDevice;
+		source.buildLightTreeOnDevice = buildOnDevice; // both trees by the library: the frame must not change by a bit
 
 		PreparedScene scene(source);
 
