@@ -265,6 +265,10 @@ def test_device_light_tree_on_random_emitters_ties_placements_and_tiny_inputs():
     lattice = describe(scenes.make_triangles(v0 - (0.25, 0, 0.25), v0 + (0.25, 0, -0.25), v0 + (-0.25, 0, 0.25), 0), materials=np.concatenate([scenes.material(structs.MATERIAL_EMISSIVE, (3.0, 2.0, 1.0))]))
     assert_device_light_tree_is_the_host_mirrors(lattice)
 
+    from tests.test_independent_kats import _tilted_ceiling  # emitters facing almost the same way: proper cones, every step runs the whole union
+    nodes, _ = assert_device_light_tree_is_the_host_mirrors(_tilted_ceiling(scenes.many_lights_scene(light_count=3000, rings=8, segments=8), 1.5))
+    assert np.count_nonzero((nodes["child0"] != 0xFFFFFFFF) & (nodes["cosOffset"] > -1) & (nodes["cosOffset"] < 1)) > 2000
+
     dark = random_emitters(3, 50, 5, 0, 1.0, emissive_share=0.0)  # no emitter: an empty tree
     nodes, tokens, paths, power = build_light_tree_device(dark)
     assert len(nodes) == 0 and len(tokens) == 0 and len(paths) == 0 and power == 0.0

@@ -388,3 +388,160 @@ def test_light_tree_matches_an_independent_transcription():
         checked += 1
 
     assert checked > 200, (checked, impossible)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# LightTree.Build (LightTree.cs:62-113) over LightBound.Encapsulate / RelativeArea (LightBound.cs:22-28), ConeBound.Union /
+# Encapsulate / RelativeArea (ConeBound.cs:28-101), BoxBound.HalfArea / MajorAxis / Center / Encapsulate (BoxBound.cs:80-132),
+# Float3.Angle (Float3.cs:277-288, DEGREES), Versor(axis, angle) * v (Versor.cs, angle in DEGREES) and LightCollection.CreateBounds
+# (LightCollection.cs:91-137) with PreparedTriangle.BoxBound / ConeBound / Area (TriangleEntity.cs:142-148) and Emissive.Power
+# (Emissive.cs:53), transcribed into plain Python double arithmetic from the C# alone. The host mirror's recursive build and the
+# device build share ONE binary32 restatement (csrc/echo_light_build.h): a misreading there would pass every byte comparison between
+# them. This transcription shares nothing with it; the two must produce the same tree — the same cuts, hence the same emitter order and
+# bit paths — and the same bounds to rounding. Ties are avoided by the scene (random positions), not by the code.
+# ---------------------------------------------------------------------------------------------------------------------
+import math  # noqa: E402
+
+
+def _py_cone_union(value0, value1):  # ConeBound.Union, ConeBound.cs:76-101; a cone = (axis, cosOffset, cosExtend)
+    clamp = lambda v: min(1.0, max(-1.0, v))
+    offset0, offset1 = math.acos(clamp(value0[1])), math.acos(clamp(value1[1]))
+    cos_extend = min(value0[2], value1[2])
+    axis = value0[0]
+
+    squared = float(np.dot(value0[0], value0[0]) * np.dot(value1[0], value1[0]))  # Float3.Angle: degrees
+    angle = 0.0 if squared == 0.0 else math.degrees(math.acos(clamp(float(np.dot(value0[0], value1[0])) / math.sqrt(squared))))
+    maximum = angle + offset1  # degrees + radians, as written in the reference
+
+    if min(maximum, math.pi) <= offset0:
+        return axis, value0[1], cos_extend
+    offset = (offset0 + maximum) / 2.0
+    if offset >= math.pi:
+        return np.array([0.0, 1.0, 0.0]), -1.0, cos_extend  # CreateFullSphere
+
+    cross = np.cross(axis, value1[0])
+    cross = cross / np.linalg.norm(cross)
+    half = math.radians(offset - offset0) / 2.0  # new Versor(cross, rotation): rotation is taken as DEGREES
+    q = np.concatenate([cross * math.sin(half), [math.cos(half)]])  # a unit quaternion; rotate v by it: v + 2 w (u x v) + 2 u x (u x v)
+    u, w = q[:3], q[3]
+    rotated = axis + 2.0 * w * np.cross(u, axis) + 2.0 * np.cross(u, np.cross(u, axis))
+    return rotated, math.cos(offset), cos_extend
+
+
+def _py_encapsulate(a, b):  # LightBound.Encapsulate; a bound = (lo, hi, cone, power)
+    cone = _py_cone_union(a[2], b[2]) if b[2][1] > a[2][1] else _py_cone_union(b[2], a[2])  # ConeBound.Encapsulate, :50-56
+    return np.minimum(a[0], b[0]), np.maximum(a[1], b[1]), cone, a[3] + b[3]
+
+
+def _py_relative_area(bound):  # LightBound.RelativeArea = box.HalfArea * cone.RelativeArea * power
+    size = bound[1] - bound[0]
+    half_area = size[0] * (size[1] + size[2]) + size[1] * size[2]
+    cos_offset, cos_extend = bound[2][1], bound[2][2]
+    offset, extend = math.acos(min(1.0, max(-1.0, cos_offset))), math.acos(min(1.0, max(-1.0, cos_extend)))
+    angle = min(offset + extend, math.pi) * 2.0
+    sin_offset = math.sqrt(max(0.0, 1.0 - cos_offset * cos_offset))
+    cone_area = 2.0 * math.pi * (1.0 - cos_offset) + math.pi / 2.0 * (angle * sin_offset - math.cos(offset - angle) - 2.0 * offset * sin_offset + cos_offset)
+    return half_area * cone_area * bound[3]
+
+
+def _py_build(items, emitted, depth=0, path=0):
+    """items: [(token, bound)]. Appends (token or None, bound, child0, child1) rows to `emitted` in the reference's construction order
+    (`new Node(Build(tail), Build(head))`: the parent, then the tail subtree, then the head subtree) and yields the leaves' bit paths."""
+    if len(items) == 1:
+        emitted.append([items[0][0], items[0][1], None, None, path])
+        return len(emitted) - 1
+
+    lo, hi = items[0][1][0], items[0][1][1]
+    for _, bound in items:
+        lo, hi = np.minimum(lo, bound[0]), np.maximum(hi, bound[1])
+    size = hi - lo
+    major = (0 if size[0] > size[2] else 2) if size[0] > size[1] else (1 if size[1] > size[2] else 2)  # Float3.MaxIndex, Float3.cs:130-138
+    items = sorted(items, key=lambda item: (item[1][1][major] + item[1][0][major]) / 2.0)  # by box centre (stable, like the mirror)
+
+    count = len(items)
+    costs = [0.0] * count
+    bound = items[-1][1]
+    for i in range(count - 2, -1, -1):
+        costs[i + 1] = _py_relative_area(bound)
+        bound = _py_encapsulate(bound, items[i][1])
+
+    best, cut = math.inf, -1
+    bound = items[0][1]
+    for i in range(1, count):
+        cost = costs[i] + _py_relative_area(bound)
+        if cost < best:
+            best, cut = cost, i
+        bound = _py_encapsulate(bound, items[i][1])
+
+    emitted.append(None)
+    index = len(emitted) - 1
+    child0 = _py_build(items[cut:], emitted, depth + 1, path)
+    child1 = _py_build(items[:cut], emitted, depth + 1, path | 1 << depth)
+    emitted[index] = [None, _py_encapsulate(emitted[child0][1], emitted[child1][1]), child0, child1, None]
+    return index
+
+
+def _py_emitters(description):  # LightCollection.CreateBounds: emissive triangles only (no point lights, spheres or placements in this scene)
+    items = []
+    for i, t in enumerate(description.triangles):
+        m = description.materials[t["material"]]
+        if m["type"] != structs.MATERIAL_EMISSIVE:
+            continue
+        e1, e2, v0 = t["edge1"].astype(np.float64), t["edge2"].astype(np.float64), t["vertex0"].astype(np.float64)
+        normal = np.cross(e1, e2)
+        area = np.linalg.norm(normal) / 2.0
+        r, g, b = (float(c) for c in m["albedo"][:3])
+        power = (r * 0.212671 + g * 0.715160 + b * 0.072169) * math.pi * area  # Emissive.Power = emission.Luminance * pi (RGB128.cs), times Area
+        if not power > 0.0:
+            continue
+        points = np.stack([v0, v0 + e1, v0 + e2])
+        items.append(((structs.TOKEN_TYPE_TRIANGLE << 28) | i, (points.min(axis=0), points.max(axis=0), (normal / np.linalg.norm(normal), 1.0, 0.0), power)))
+    return items
+
+
+def _tilted_ceiling(description, degrees, seed=3):
+    """every emissive triangle of the scene turned to face down, tilted by at most `degrees`: unions of such cones stay proper cones
+    (ConeBound.Union's rotation path) instead of jumping to the whole sphere, which any two axes more than 2 pi DEGREES apart do"""
+    rng = np.random.default_rng(seed)
+    lit = np.flatnonzero(description.materials["type"][description.triangles["material"]] == structs.MATERIAL_EMISSIVE)
+    side = np.linalg.norm(description.triangles["edge1"][lit], axis=1, keepdims=True).astype(np.float64)
+    tilt, spin = np.radians(rng.uniform(0, degrees, len(lit))), rng.uniform(0, 2 * np.pi, len(lit))
+    normal = np.stack([np.sin(tilt) * np.cos(spin), -np.cos(tilt), np.sin(tilt) * np.sin(spin)], axis=-1)
+    e1 = np.cross(normal, [0.0, 0.0, 1.0])
+    e1 /= np.linalg.norm(e1, axis=1, keepdims=True)
+    e2 = np.cross(e1, normal)  # e1 x e2 = normal
+    description.triangles["edge1"][lit] = (e1 * side).astype(np.float32)
+    description.triangles["edge2"][lit] = (e2 * side).astype(np.float32)
+    return description
+
+
+@pytest.mark.parametrize("tilt", [None, 1.5])
+def test_light_tree_build_matches_an_independent_transcription(tilt):
+    description = scenes.many_lights_scene(light_count=400, rings=8, segments=8)
+    if tilt is not None:
+        description = _tilted_ceiling(description, tilt)
+    nodes, tokens, paths, power = host.build_light_tree(description)
+    emitted = []
+    assert _py_build(_py_emitters(description), emitted) == 0
+    assert len(emitted) == len(nodes) == 799
+
+    leaves = [(row[0], row[4]) for row in emitted if row[2] is None]
+    assert [int(t) for t in tokens] == [t for t, _ in leaves]  # the same cuts everywhere: the same pre-order of emitters ...
+    assert [int(p) for p in paths] == [p for _, p in leaves]   # ... reached by the same branches
+
+    proper = 0
+    for row, node in zip(emitted, nodes):
+        lo, hi, cone, node_power = row[1]
+        if row[2] is None:
+            assert node["child0"] == 0xFFFFFFFF and node["child1"] == row[0]
+        else:
+            assert (int(node["child0"]), int(node["child1"])) == (row[2], row[3])
+            proper += -1.0 < cone[1] < 1.0
+        assert np.allclose(node["boxMin"], lo, rtol=1e-6, atol=1e-6) and np.allclose(node["boxMax"], hi, rtol=1e-6, atol=1e-6)
+        assert node["power"] == pytest.approx(node_power, rel=1e-4)
+        assert node["cosOffset"] == pytest.approx(cone[1], abs=2e-5) and node["cosExtend"] == pytest.approx(cone[2], abs=1e-6)
+        if cone[1] > -1.0:  # the whole sphere's axis is a convention (Float3.Up), a proper cone's is geometry
+            assert np.allclose(node["coneAxis"], cone[0], atol=2e-4)
+    assert power == pytest.approx(emitted[0][1][3], rel=1e-4)
+    if tilt is not None:
+        assert proper > 300  # branches whose cone is neither a direction nor the whole sphere: the rotation path of ConeBound.Union was taken

@@ -105,6 +105,17 @@ def test_random_emitters(library, seed, triangle_count, sphere_count, point_coun
     assert_same_tree(library, description, reverse=True)
 
 
+def test_proper_cones(library):
+    """Emitters facing almost the same way (a ceiling of lights, tilted by up to 1.5 degrees): their unions stay proper cones, so every sweep
+    step runs all of ConeBound.Union — the binary64 angle, the rotation of the axis, the cosine — instead of the whole-sphere shortcut."""
+    from tests.test_independent_kats import _tilted_ceiling
+    description = _tilted_ceiling(scenes.many_lights_scene(light_count=700, rings=8, segments=8), 1.5)
+    nodes, tokens, _, _ = assert_same_tree(library, description)
+    branch = nodes["child0"] != 0xFFFFFFFF
+    assert np.count_nonzero(branch & (nodes["cosOffset"] > -1) & (nodes["cosOffset"] < 1)) > 500
+    assert_same_tree(library, description, reverse=True)
+
+
 def test_placements_and_equal_centres(library):
     """PreparedInstance.LightBound rows join the list last (AddInstances); emitters with EQUAL centres keep their order (the stable sort)."""
     rng = np.random.default_rng(11)
