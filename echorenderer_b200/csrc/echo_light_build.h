@@ -730,12 +730,11 @@ struct GatherPass // the bounds in position order: the sweeps read them front to
 // evaluates inside the same loops — LightBound.RelativeArea of every one of those bounds, four transcendentals each — depends on nothing but
 // its bound, so it leaves the chain for CostPass, one thread per cut. Threads [0, stride) walk backwards, [stride, 2 stride) forwards,
 // stride a multiple of the warp size: the two chains of a segment run in different warps (at the root they ARE the level), each at the pace
-// of its own branches. A chain is latency all the way — one thread, every step waiting for the last — and once the cone has grown to the
-// whole sphere a step is a few dozen instructions, far less than a trip to L2: the emitters of the next kAhead steps are kept in flight
-// in a ring of registers (the loop is unrolled over the ring, so its slots are registers, not local memory).
+// of its own branches. A chain is latency all the way — one thread, every step waiting for the last — so the emitter of the NEXT step is
+// loaded before this step's arithmetic starts (keeping six in flight in a ring of registers, or asking lines into L1 a dozen steps ahead,
+// changed nothing: the chain waits for its own arithmetic, not for memory).
 struct SweepPass
 {
-	static constexpr uint32_t kAhead = 6u;
 
 	uint32_t live, stride;
 	const Bound* __restrict__ sorted;
@@ -754,30 +753,15 @@ struct SweepPass
 
 		// step k (1 .. last) folds in the emitter at begin + k (forwards) or begin + last - k (backwards)
 		Bound bound = sorted[begin + (forward ? 0u : last)];
-		Bound ring[kAhead];
+		Bound next = sorted[begin + (forward ? 1u : last - 1u)];
 
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-		for (uint32_t j = 0u; j < kAhead; j++)
-			if (1u + j <= last) ring[j] = sorted[begin + (forward ? 1u + j : last - 1u - j)];
-
-		for (uint32_t first = 1u; first <= last; first += kAhead)
+		for (uint32_t k = 1u; k <= last; k++)
 		{
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-			for (uint32_t j = 0u; j < kAhead; j++)
-			{
-				const uint32_t k = first + j;
-				if (k > last) break;
+			const Bound current = next;
+			if (k < last) next = sorted[begin + (forward ? k + 1u : last - k - 1u)];
 
-				const Bound current = ring[j];
-				if (k + kAhead <= last) ring[j] = sorted[begin + (forward ? k + kAhead : last - k - kAhead)];
-
-				out[begin + (forward ? k : last + 1u - k)] = bound;
-				bound = encapsulate(bound, current);
-			}
+			out[begin + (forward ? k : last + 1u - k)] = bound;
+			bound = encapsulate(bound, current);
 		}
 	}
 };
