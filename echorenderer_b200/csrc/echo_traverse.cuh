@@ -17,8 +17,14 @@
 namespace echo
 {
 
-constexpr int kTraverseBlock = 128;              // 4 warps per CTA
-constexpr unsigned long long kPool = 256;         // rays reserved per global atomic
+#ifndef ECHO_TRAVERSE_BLOCK
+#define ECHO_TRAVERSE_BLOCK 128 // A/B r2af on C2, ECHO_MIN_BLOCKS scaled with it: 64 threads x 14 CTAs equal, 256 x 3 (768 threads per SM) -4 %
+#endif
+#ifndef ECHO_POOL
+#define ECHO_POOL 128 // A/B r2af / r2ag, two runs each: 512 -2 %, 256 (until r2ae) 5 374, 128 5 430 (+1.0 % on C2 and on the secondary batch, C3 +0.5 %), 64 5 423, 32 5 380 Mrays/s
+#endif
+constexpr int kTraverseBlock = ECHO_TRAVERSE_BLOCK;  // 4 warps per CTA
+constexpr unsigned long long kPool = ECHO_POOL;       // rays reserved per global atomic
 #ifndef ECHO_LEAF_VOTE
 #define ECHO_LEAF_VOTE 8
 #endif
