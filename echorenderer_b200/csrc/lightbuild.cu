@@ -5,9 +5,10 @@
 // the generic kernel, the CUB sort / sums, memory and the copies.
 //
 // What the device can and cannot buy here: the two sweeps of a node are chains of non-associative cone unions (echo_light_build.h), one
-// thread each; the root's two chains ARE the first level, so the build time is a few chain lengths, not a few launches. The point of this
-// build is not speed over the host's but that a scene whose geometry already lives on the device gets the reference's own light tree
-// without the emitter scan and the tree crossing the host.
+// thread each; the root's two chains ARE the first level, so the build time is a few chain lengths however wide the machine is — but only
+// the longest chain of every level is waited for (2-3 n steps in all against the recursion's n log n) and everything around the chains is
+// parallel: 3-5x the host recursion on 10 k - 100 k emitters (profiles/README.md), and a scene whose geometry already lives on the device gets
+// the reference's own light tree without the emitter scan crossing the host.
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -47,13 +48,14 @@ struct CudaBackend
 		cudaFree(scratch);
 	}
 
-	bool prepare(uint32_t most) // the largest temporary storage any CUB call of the build can ask for
+	// CUB's temporary storage, grown to what the call at hand asks for: the sums over the candidates come first (10 M triangles of which three
+	// emit light must not reserve the sort's storage for 10 M keys), the sorts over the emitters after; cudaFree orders itself behind the stream
+	bool ensure(size_t bytes)
 	{
-		size_t sortBytes = 0, sumBytes = 0;
-		if (!check_cuda(cub::DeviceRadixSort::SortPairs(nullptr, sortBytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, (const uint32_t*)nullptr, (uint32_t*)nullptr,
-		                                                 (int)most, 0, 64, stream), "cub sort (size)")) return false;
-		if (!check_cuda(cub::DeviceScan::ExclusiveSum(nullptr, sumBytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)most, stream), "cub sum (size)")) return false;
-		scratchBytes = (std::max(sortBytes, sumBytes) + 255) & ~size_t(255);
+		if (bytes <= scratchBytes) return true;
+		if (scratch && !check_cuda(cudaFree(scratch), "cudaFree(light build scratch)")) return false;
+		scratch = nullptr;
+		scratchBytes = (bytes + 255) & ~size_t(255);
 		return check_cuda(cudaMalloc(&scratch, scratchBytes), "cudaMalloc(light build scratch)");
 	}
 
@@ -76,14 +78,16 @@ struct CudaBackend
 
 	bool sort_pairs(const unsigned long long* keysIn, unsigned long long* keysOut, const uint32_t* valuesIn, uint32_t* valuesOut, uint32_t n, int endBit)
 	{
-		size_t bytes = scratchBytes; // cub's radix sort is stable
+		size_t bytes = 0; // cub's radix sort is stable
+		if (!check_cuda(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keysIn, keysOut, valuesIn, valuesOut, (int)n, 0, endBit, stream), "cub sort (size)") || !ensure(bytes)) return false;
 		++launches;
 		return check_cuda(cub::DeviceRadixSort::SortPairs(scratch, bytes, keysIn, keysOut, valuesIn, valuesOut, (int)n, 0, endBit, stream), "cub sort");
 	}
 
 	bool exclusive_sum(const uint32_t* in, uint32_t* out, uint32_t n)
 	{
-		size_t bytes = scratchBytes;
+		size_t bytes = 0;
+		if (!check_cuda(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, (int)n, stream), "cub sum (size)") || !ensure(bytes)) return false;
 		++launches;
 		return check_cuda(cub::DeviceScan::ExclusiveSum(scratch, bytes, in, out, (int)n, stream), "cub sum");
 	}
@@ -139,7 +143,6 @@ bool build_light_tree_device(const lightbuild::Sources& host, std::vector<EchoLi
 	auto started = clock();
 
 	CudaBackend backend;
-	if (!backend.prepare(2u * candidates + 2u)) return false;
 
 	lightbuild::Sources device = host;
 	if (!upload(host.triangles, host.triangleCount, device.triangles, backend) || !upload(host.spheres, host.sphereCount, device.spheres, backend)
