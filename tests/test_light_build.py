@@ -245,3 +245,25 @@ def test_whole_sphere_shortcut_of_the_cone_union_changes_nothing(library):
         assert a.tobytes() == b.tobytes(), row
         saturated += row[3] == -1.0
     assert saturated > count // 4
+
+
+def test_prepare_takes_a_light_tree_builder_for_every_pack(library):
+    """host.prepare(light_tree_builder=...) — the hook the device build plugs into — hands every pack's emitters and its placements'
+    PreparedInstance.LightBound rows to the builder: with the emulated level-synchronous build the prepared scene is the same scene."""
+    calls = []
+
+    def builder(description, instance_lights=None):
+        status, nodes, tokens, paths, _ = emulate(library, description, instance_lights)
+        assert status == 0
+        calls.append(0 if instance_lights is None else len(instance_lights))
+        return nodes.copy(), tokens.copy(), paths.copy(), float(nodes["power"][0]) if len(nodes) else 0.0
+
+    expected = host.prepare(scenes.instanced_scene(grid=3, rings=8, segments=10))
+    built = host.prepare(scenes.instanced_scene(grid=3, rings=8, segments=10), light_tree_builder=builder)
+    assert len(calls) >= 2 and max(calls) > 0  # several packs, at least one with placements
+    assert built.light_nodes.tobytes() == expected.light_nodes.tobytes()
+    assert built.emitter_tokens.tobytes() == expected.emitter_tokens.tobytes() and built.emitter_bitpaths.tobytes() == expected.emitter_bitpaths.tobytes()
+    assert built.infinite_threshold == expected.infinite_threshold and built.packs.tobytes() == expected.packs.tobytes()
+
+    plain = host.prepare(scenes.many_lights_scene(light_count=64, rings=6, segments=6), light_tree_builder=builder)  # a scene without packs takes the hook too
+    assert plain.light_nodes.tobytes() == host.prepare(scenes.many_lights_scene(light_count=64, rings=6, segments=6)).light_nodes.tobytes()
