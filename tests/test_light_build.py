@@ -4,6 +4,7 @@ host mirror's — LightTree.cs:62-113 recursive, one node at a time — byte for
 The GPU suite (test_gpu_build.py) asks the same of the CUDA backend. Also here: the accuracy of the pinned transcendentals the
 builds share (the reference's come from the platform's C runtime), and the invariants of the emitted tree."""
 import ctypes
+import math
 import os
 import subprocess
 from types import SimpleNamespace
@@ -267,3 +268,40 @@ def test_prepare_takes_a_light_tree_builder_for_every_pack(library):
 
     plain = host.prepare(scenes.many_lights_scene(light_count=64, rings=6, segments=6), light_tree_builder=builder)  # a scene without packs takes the hook too
     assert plain.light_nodes.tobytes() == host.prepare(scenes.many_lights_scene(light_count=64, rings=6, segments=6)).light_nodes.tobytes()
+
+
+def test_cone_union_by_hand(library):
+    """ConeBound.Union (ConeBound.cs:76-101) on cases worked out by hand from the C#, quirk included: `value0.axis.Angle(value1.axis)` is in
+    DEGREES (Float3.cs:277-288) and is added to an offset in radians, and the rotation handed to `new Versor(cross, rotation)` is read as degrees.
+      A  two direction cones (offset 0) whose axes are 4 degrees apart: max = 4 + 0; Min(4, pi) = pi > 0, no early exit; offset = (0 + 4) / 2 = 2
+         < pi: a cone of 2 RADIANS half-angle, cosOffset = cos(2) = -0.41614684, its axis value0's turned by 2 DEGREES towards value1's
+      B  the same, 8 degrees apart: offset = 4 >= pi: the whole sphere (axis Float3.Up, cosOffset -1)
+      C  value0 with offset 1 rad (cosOffset cos 1), value1 a direction cone 0.5 degrees off: max = 0.5 <= 1: value0 unchanged
+      D  the same axes: Angle = 0, max = offset1 = 0 <= offset0: value0 unchanged, whatever its offset
+    cosExtend is the smaller of the two in every case."""
+    library.light_emulation_cone_unions.argtypes = [ctypes.c_void_p] * 3
+
+    def union(axis0, cos_offset0, cos_extend0, axis1, cos_offset1, cos_extend1):
+        row = np.array([*axis0, cos_offset0, cos_extend0, *axis1, cos_offset1, cos_extend1], dtype=np.float32)
+        a, b = np.zeros(5, dtype=np.float32), np.zeros(5, dtype=np.float32)
+        library.light_emulation_cone_unions(row.ctypes.data, a.ctypes.data, b.ctypes.data)
+        assert a.tobytes() == b.tobytes()
+        return a
+
+    def tilted(degrees):  # +Y turned towards +X
+        return (math.sin(math.radians(degrees)), math.cos(math.radians(degrees)), 0.0)
+
+    up = (0.0, 1.0, 0.0)
+    a = union(up, 1.0, 0.25, tilted(4.0), 1.0, 0.5)
+    assert a[3] == pytest.approx(math.cos(2.0), abs=1e-6) and a[4] == 0.25
+    assert np.allclose(a[:3], tilted(2.0), atol=1e-6)
+
+    b = union(up, 1.0, 0.25, tilted(8.0), 1.0, 0.5)
+    assert b.tolist() == [0.0, 1.0, 0.0, -1.0, 0.25]
+
+    c = union(up, math.cos(1.0), 0.75, tilted(0.5), 1.0, 0.5)
+    assert c[:3].tolist() == [0.0, 1.0, 0.0] and c[3] == np.float32(math.cos(1.0)) and c[4] == 0.5
+
+    for cos_offset in (1.0, 0.3, -0.9, -1.0):
+        d = union(up, cos_offset, 0.1, up, 1.0, 0.2)
+        assert d[:3].tolist() == [0.0, 1.0, 0.0] and d[3] == np.float32(cos_offset) and d[4] == np.float32(0.1)
