@@ -36,7 +36,9 @@ int32_t echo_host_build_qbvh_instanced(const EchoTriangle* triangles, uint32_t t
                                        EchoQbvhNode** out_nodes, uint32_t* out_node_count, uint32_t* out_max_depth);
 
 /* Builds the light tree over point lights, emissive triangles, emissive spheres (LightCollection.CreateBounds order).
- * out_power receives the root LightBound power (0 when there is no light; then node_count == 0). */
+ * out_power receives the root LightBound power (0 when there is no light; then node_count == 0). The recursion is the reference's
+ * (LightTree.cs:62-113); the LightBound / ConeBound arithmetic is the one restatement it shares with the device build
+ * (echo_b200_build_light_tree, csrc/echo_light_build.h: stable sort, MathF.Acos / Cos / SinCos and Math.Acos pinned), so both emit the same bytes. */
 int32_t echo_host_build_light_tree(const EchoTriangle* triangles, uint32_t triangle_count,
                                    const EchoSphere* spheres, uint32_t sphere_count,
                                    const EchoMaterial* materials, uint32_t material_count,
