@@ -545,3 +545,184 @@ def test_light_tree_build_matches_an_independent_transcription(tilt):
     assert power == pytest.approx(emitted[0][1][3], rel=1e-4)
     if tilt is not None:
         assert proper > 300  # branches whose cone is neither a direction nor the whole sphere: the rotation path of ConeBound.Union was taken
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# QuadBoundingVolumeHierarchy.TraceImpl (QuadBoundingVolumeHierarchy.cs:123-216) over BoxBound4.Intersect (BoxBound4.cs:64-112),
+# GeometryCollection.Trace (GeometryCollection.cs:85-104) and PreparedTriangle.IntersectImpl (TriangleEntity.cs:204-235), transcribed
+# into Python binary32 scalar arithmetic from the C# alone: a stack of (node, entry distance) pairs popped last-in first-out,
+# entries at or beyond the closest hit dropped at the pop; per node one four-box slab test, then the four `Push` calls in the order
+# the ray's direction signs select (the second pair first when orders[axisMajor]), a Push dropping children at or beyond the
+# closest hit, stacking branches and testing leaves ON THE SPOT. Hits do not depend on that order (up to ties) — the brute-force test
+# of test_host_and_traversal.py pins them — but the number of node visits and primitive tests does, and those counts are what
+# bench.py's roofline multiplies by 128 and 36 bytes. This pins the oracle's visit order: per ray the same hit bits,
+# over the batch the same number of slab tests and triangle tests.
+# ---------------------------------------------------------------------------------------------------------------------
+F = np.float32
+
+
+def _py_slab4(node, origin, direction_r):  # BoxBound4.Intersect; Float4.Max / Min = maxps / minps: the SECOND operand unless the first wins
+    def axis(lo, hi, o, r):
+        length0, length1 = (lo - o) * r, (hi - o) * r
+        return np.where(length0 > length1, length0, length1), np.where(length0 < length1, length0, length1)
+
+    with np.errstate(invalid="ignore", over="ignore"):
+        far, near = axis(node["minX"], node["maxX"], origin[0], direction_r[0])
+        for lo, hi, k in ((node["minY"], node["maxY"], 1), (node["minZ"], node["maxZ"], 2)):
+            high, low = axis(lo, hi, origin[k], direction_r[k])
+            far = np.where(far < high, far, high)
+            near = np.where(near > low, near, low)
+        far = far * F(1.00000024)  # BoxBound.FarMultiplier
+        return np.where((far >= near) & (far >= F(0)), near, F(np.inf))
+
+
+def _py_cross(a, b):  # Float3.Cross: products and difference in binary64, one rounding to binary32
+    a, b = a.astype(np.float64), b.astype(np.float64)
+    return np.array([a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]]).astype(np.float32)
+
+
+def _py_dot(a, b):  # Float3.Dot: (x x' + y y') + z z' in binary32
+    return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]
+
+
+def _py_triangle(triangle, origin, direction):  # PreparedTriangle.IntersectImpl; returns (distance, u, v)
+    edge1, edge2, vertex0 = triangle["edge1"], triangle["edge2"], triangle["vertex0"]
+    cross2 = _py_cross(direction, edge2)
+    determinant = _py_dot(edge1, cross2)
+    if determinant == 0:
+        return F(np.inf), F(0), F(0)
+    determinant_r = F(1) / determinant
+    offset = origin - vertex0
+    u = _py_dot(offset, cross2) * determinant_r
+    if (u < 0) | (u > 1):
+        return F(np.inf), u, F(0)
+    cross1 = _py_cross(offset, edge1)
+    v = _py_dot(direction, cross1) * determinant_r
+    if (v < 0) | (u + v > 1):
+        return F(np.inf), u, v
+    distance = _py_dot(edge2, cross1) * determinant_r
+    return (F(np.inf) if distance < 0 else distance), u, v
+
+
+def _py_trace(nodes, triangles, ray, counts):
+    origin, direction = ray["origin"], ray["direction"]
+    with np.errstate(divide="ignore"):
+        direction_r = F(1) / direction  # Ray.cs:23
+    orders = [bool(direction_r[0] > 0), bool(direction_r[1] > 0), bool(direction_r[2] > 0), True]
+    best, best_token, best_uv = ray["distance"], structs.TOKEN_EMPTY, (F(0), F(0))
+    stack = [(0, F(0))]
+
+    while stack:
+        index, entry = stack.pop()
+        if entry >= best:
+            continue
+        node = nodes[index]
+        counts[0] += 1
+        intersections = _py_slab4(node, origin, direction_r)
+
+        first = (1, 0) if orders[node["axisMinor0"]] else (0, 1)
+        second = (3, 2) if orders[node["axisMinor1"]] else (2, 3)
+        for slot in (second + first if orders[node["axisMajor"]] else first + second):
+            hit = intersections[slot]
+            if hit >= best:
+                continue
+            token = int(node["token4"][slot])
+            if structs.token_type(token) == structs.TOKEN_TYPE_NODE:
+                stack.append((structs.token_index(token), hit))
+                continue
+            if token == int(ray["ignore"]):  # GeometryCollection.Trace: the ignored triangle is skipped before its test
+                continue
+            counts[1] += 1
+            distance, u, v = _py_triangle(triangles[structs.token_index(token)], origin, direction)
+            if distance >= best:
+                continue
+            best, best_token, best_uv = distance, token, (u, v)
+
+    return best_token, best, best_uv
+
+
+def test_trace_impl_matches_an_independent_transcription():
+    prepared = host.prepare(scenes.terrain_scene(48, 24, 0))  # 2 304 triangles, no spheres: 1 109 quad nodes, depth 7
+    oracle = oracle_lib.OracleScene(prepared)
+    rays = scenes.random_rays(prepared.bounds, 1500, seed=31)
+    hits = oracle.trace(rays)
+    rays["ignore"][::3] = hits["token"][::3]  # a third of the rays ignore what they would hit: the ignore rule takes part too
+    rays["distance"][1::5] = np.where(np.isfinite(hits["distance"][1::5]), hits["distance"][1::5] * F(1.5), F(30.0))  # and a fifth start with a finite limit
+    hits, counters = oracle.trace(rays, count_visits=True)
+
+    counts = [0, 0]
+    for ray, hit in zip(rays, hits):
+        token, distance, uv = _py_trace(prepared.nodes, prepared.triangles, ray, counts)
+        found = token != structs.TOKEN_EMPTY
+        assert int(hit["token"]) == token
+        if found:
+            assert hit["distance"].view(np.uint32) == np.float32(distance).view(np.uint32)
+            assert hit["uv"][0].view(np.uint32) == np.float32(uv[0]).view(np.uint32) and hit["uv"][1].view(np.uint32) == np.float32(uv[1]).view(np.uint32)
+
+    assert np.count_nonzero(hits["token"] != structs.TOKEN_EMPTY) > 150
+    assert [int(counters[0]), int(counters[1]), int(counters[2])] == [counts[0], counts[1], 0]  # the same slab tests, the same triangle tests
+
+
+# OccludeImpl (QuadBoundingVolumeHierarchy.cs:223-315): the same walk with no entry distances on the stack (nothing is dropped at the pop),
+# children dropped at or beyond `travel`, the first occluding primitive ends the query; GeometryCollection.Occlude (GeometryCollection.cs:134-172)
+# and PreparedTriangle.IntersectImpl(origin, direction, travel) (TriangleEntity.cs:237-263: sign(det) instead of 1 / det, STRICT in travel).
+def _py_triangle_occludes(triangle, origin, direction, travel):
+    edge1, edge2, vertex0 = triangle["edge1"], triangle["edge2"], triangle["vertex0"]
+    cross2 = _py_cross(direction, edge2)
+    determinant = _py_dot(edge1, cross2)
+    if determinant == 0:
+        return False
+    sign = F(1) if determinant > 0 else F(-1)
+    determinant = determinant * sign
+    offset = origin - vertex0
+    u = _py_dot(offset, cross2) * sign
+    if (u < 0) | (u > determinant):
+        return False
+    cross1 = _py_cross(offset, edge1)
+    v = _py_dot(direction, cross1) * sign
+    if (v < 0) | (u + v > determinant):
+        return False
+    distance = _py_dot(edge2, cross1) * sign
+    return bool((distance >= 0) & (distance < travel * determinant))
+
+
+def _py_occlude(nodes, triangles, ray, counts):
+    origin, direction, travel = ray["origin"], ray["direction"], ray["distance"]
+    with np.errstate(divide="ignore"):
+        direction_r = F(1) / direction
+    orders = [bool(direction_r[0] > 0), bool(direction_r[1] > 0), bool(direction_r[2] > 0), True]
+    stack = [0]
+
+    while stack:
+        node = nodes[stack.pop()]
+        counts[0] += 1
+        intersections = _py_slab4(node, origin, direction_r)
+        first = (1, 0) if orders[node["axisMinor0"]] else (0, 1)
+        second = (3, 2) if orders[node["axisMinor1"]] else (2, 3)
+        for slot in (second + first if orders[node["axisMajor"]] else first + second):
+            if intersections[slot] >= travel:
+                continue
+            token = int(node["token4"][slot])
+            if structs.token_type(token) == structs.TOKEN_TYPE_NODE:
+                stack.append(structs.token_index(token))
+                continue
+            if token == int(ray["ignore"]):
+                continue
+            counts[1] += 1
+            if _py_triangle_occludes(triangles[structs.token_index(token)], origin, direction, travel):
+                return True
+    return False
+
+
+def test_occlude_impl_matches_an_independent_transcription():
+    prepared = host.prepare(scenes.terrain_scene(48, 24, 0))
+    oracle = oracle_lib.OracleScene(prepared)
+    rays = scenes.random_rays(prepared.bounds, 1500, seed=37, occlusion=True)
+    rays["ignore"][::3] = oracle.trace(rays)["token"][::3]
+    occluded, counters = oracle.occlude(rays, count_visits=True)
+
+    counts = [0, 0]
+    for ray, expected in zip(rays, occluded):
+        assert _py_occlude(prepared.nodes, prepared.triangles, ray, counts) == bool(expected)
+    assert 100 < np.count_nonzero(occluded) < 1400
+    assert [int(counters[0]), int(counters[1]), int(counters[2])] == [counts[0], counts[1], 0]
