@@ -726,3 +726,164 @@ def test_occlude_impl_matches_an_independent_transcription():
         assert _py_occlude(prepared.nodes, prepared.triangles, ray, counts) == bool(expected)
     assert 100 < np.count_nonzero(occluded) < 1400
     assert [int(counters[0]), int(counters[1]), int(counters[2])] == [counts[0], counts[1], 0]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# SweepBuilder.Build / BuildLayer / BuildChild / Sorter (SweepBuilder.cs:24-251) and the binary -> quad collapse of
+# QuadBoundingVolumeHierarchy (constructor :24-36, CreateNode :363-404, Node :409-430, BuildNode :470-565), transcribed into Python from
+# the C# alone: box arithmetic in binary32, the sort a stable sort on Sorter.Transform's key, the children of a quad node a linked list
+# built back to front. The repository already holds two restatements that agree byte for byte — the host mirror's recursion
+# (csrc/host/echo_host.cpp) and the level-synchronous device build (csrc/echo_sweep.h) — but both come from one reading of the source.
+# This third one shares nothing with them and must emit the same 128-byte nodes: boxes, axes, tokens, pre-order indices, depth.
+# ---------------------------------------------------------------------------------------------------------------------
+class _Bin:  # HierarchyBuilder.Node
+    def __init__(self, lo, hi, child0=None, child1=None, axis=0, token=None):
+        self.lo, self.hi, self.child0, self.child1, self.axis, self.token = lo, hi, child0, child1, axis, token
+
+    @property
+    def leaf(self):
+        return self.child0 is None
+
+
+def _half_area(lo, hi):  # BoxBound.HalfArea
+    size = hi - lo
+    return size[0] * (size[1] + size[2]) + size[1] * size[2]
+
+
+def _max_index(v):  # Float3.MaxIndex
+    if v[0] > v[1]:
+        return 0 if v[0] > v[2] else 2
+    return 1 if v[1] > v[2] else 2
+
+
+def _transform(value):  # Sorter.Transform: flip the sign bit of a positive value, all bits of a negative one
+    bits = int(np.float32(value).view(np.uint32))
+    return bits ^ (0xFFFFFFFF if bits >> 31 else 0x80000000)
+
+
+def _sort_by_axis(data, axis):  # Sorter.Sort: insertion sort / LSD radix sort on the keys, both stable
+    return sorted(data, key=lambda item: _transform(item[1][axis] + item[2][axis]))
+
+
+def _build_layer(data):
+    length = len(data)
+    tails = [None] * length
+    lo, hi = data[-1][1], data[-1][2]
+    for i in range(length - 2, -1, -1):  # PrepareCutTailVolumes
+        tails[i + 1] = (lo, hi)
+        lo, hi = np.minimum(lo, data[i][1]), np.maximum(hi, data[i][2])
+
+    head_lo, head_hi = data[0][1], data[0][2]
+    min_cost, min_index, head, tail = F(np.finfo(np.float32).max), -1, None, None
+    for i in range(1, length):  # SearchSurfaceAreaHeuristics
+        cost = _half_area(head_lo, head_hi) * F(i) + _half_area(*tails[i]) * F(length - i)
+        if cost < min_cost:
+            min_cost, min_index, head, tail = cost, i, (head_lo, head_hi), tails[i]
+        head_lo, head_hi = np.minimum(head_lo, data[i][1]), np.maximum(head_hi, data[i][2])
+
+    lo, hi = np.minimum(head[0], tail[0]), np.maximum(head[1], tail[1])
+    axis = _max_index(hi - lo)
+    if min_index > length // 2:  # headData is always the larger half
+        head_data, tail_data = data[:min_index], data[min_index:]
+    else:
+        head_data, tail_data = data[min_index:], data[:min_index]
+        head, tail = tail, head
+
+    child0, child1 = _build_child(head_data, head, axis), _build_child(tail_data, tail, axis)
+    if _half_area(*head) < _half_area(*tail):  # the child with the larger surface area first
+        child0, child1 = child1, child0
+    return _Bin(lo, hi, child0, child1, axis)
+
+
+def _build_child(data, parent, parent_axis):
+    if len(data) == 1:
+        return _Bin(data[0][1], data[0][2], token=data[0][0])
+    axis = _max_index(parent[1] - parent[0])
+    if axis != parent_axis:
+        data = _sort_by_axis(data, axis)
+    return _build_layer(data)
+
+
+def _sweep_build(items):  # SweepBuilder.Build
+    if len(items) == 1:
+        return _Bin(items[0][1], items[0][2], token=items[0][0])
+    lo, hi = items[0][1], items[0][2]
+    for _, item_lo, item_hi in items:
+        lo, hi = np.minimum(lo, item_lo), np.maximum(hi, item_hi)
+    return _build_layer(_sort_by_axis(items, _max_index(hi - lo)))
+
+
+def _children_sorted(node):  # BuildNode.GetChildrenSorted: the child with the smaller min along the node's axis first
+    child0, child1 = node.child0, node.child1
+    if child0.lo[node.axis] > child1.lo[node.axis]:
+        child0, child1 = child1, child0
+    return node.axis, child0, child1
+
+
+def _quad_children(node):  # BuildNode's constructor: four children (None = empty) and the three axes
+    def pair(child):  # AddChildren
+        if child.leaf:
+            return 3, [child, None]
+        axis, first, second = _children_sorted(child)
+        return axis, [first, second]
+
+    axis_major, child0, child1 = _children_sorted(node)
+    axis_minor0, first = pair(child0)
+    axis_minor1, second = pair(child1)
+    return (axis_major, axis_minor0, axis_minor1), first + second
+
+
+def _quad_nodes(root):
+    """CreateNode: a child that is a branch claims the next index BEFORE its own subtree is emitted (pre-order); depth as CreateNode counts it"""
+    nodes = [None]
+
+    def create(node, index):
+        axes, children = _quad_children(node)
+        record = np.zeros(1, dtype=structs.QBVH_NODE)[0]
+        record["axisMajor"], record["axisMinor0"], record["axisMinor1"] = axes
+        depth = 0
+        for i, child in enumerate(children):
+            lo, hi = (np.full(3, np.inf, dtype=np.float32),) * 2 if child is None else (child.lo, child.hi)  # BoxBound.None
+            record["minX"][i], record["minY"][i], record["minZ"][i] = lo
+            record["maxX"][i], record["maxY"][i], record["maxZ"][i] = hi
+            if child is None:
+                record["token4"][i], child_depth = structs.TOKEN_EMPTY, 0
+            elif child.leaf:
+                record["token4"][i], child_depth = child.token, 1
+            else:
+                child_index = len(nodes)
+                nodes.append(None)
+                child_depth = create(child, child_index)
+                record["token4"][i] = child_index  # NewNodeToken: TokenType.Node = 0
+            depth = max(depth, child_depth)
+        nodes[index] = record
+        return depth + 1
+
+    depth = create(root, 0)
+    return np.array(nodes, dtype=structs.QBVH_NODE), depth
+
+
+@pytest.mark.parametrize("scene", ["terrain", "soup", "cornell"])
+def test_sweep_builder_and_quad_collapse_match_an_independent_transcription(scene):
+    if scene == "terrain":
+        description = scenes.terrain_scene(24, 12, 60)  # 576 triangles + 60 spheres
+        triangles, spheres = description.triangles, description.spheres
+    elif scene == "cornell":
+        description = scenes.cornell_box()
+        triangles, spheres = description.triangles, description.spheres
+    else:
+        from tests.test_sweep_build import random_soup
+        triangles, spheres = random_soup(14, 700, 90, 25.0)
+
+    items = []  # GeometryCollection.CreateBounds: triangles, then spheres
+    for i, t in enumerate(triangles):
+        points = np.stack([t["vertex0"], t["vertex0"] + t["edge1"], t["vertex0"] + t["edge2"]])  # PreparedTriangle.BoxBound over vertex0, Vertex1, Vertex2
+        items.append(((structs.TOKEN_TYPE_TRIANGLE << 28) | i, points.min(axis=0), points.max(axis=0)))
+    for i, s in enumerate(spheres):
+        items.append(((structs.TOKEN_TYPE_SPHERE << 28) | i, s["position"] - s["radius"], s["position"] + s["radius"]))
+
+    expected, expected_depth = host.build_qbvh(triangles, spheres)
+    nodes, depth = _quad_nodes(_sweep_build(items))
+    assert len(nodes) == len(expected) and depth == expected_depth
+    for field in ("token4", "axisMajor", "axisMinor0", "axisMinor1", "minX", "minY", "minZ", "maxX", "maxY", "maxZ"):
+        assert nodes[field].tobytes() == expected[field].tobytes(), field
