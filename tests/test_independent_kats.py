@@ -887,3 +887,39 @@ def test_sweep_builder_and_quad_collapse_match_an_independent_transcription(scen
     assert len(nodes) == len(expected) and depth == expected_depth
     for field in ("token4", "axisMajor", "axisMinor0", "axisMinor1", "minX", "minY", "minZ", "maxX", "maxY", "maxZ"):
         assert nodes[field].tobytes() == expected[field].tobytes(), field
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# PerspectiveCamera.SpawnRay without depth of field (PerspectiveCamera.cs:93-98) over RaySpawner.SpawnX (RaySpawner.cs:37-46): the ray leaves
+# the camera's position along InverseTransform * (uv.x, uv.y, forwardLength), normalised, with uv = ((x + jx) / W - 1/2, (y + jy) / W - (H / W) / 2)
+# for a jitter (jx, jy) in [0, 1)^2 — both coordinates scaled by the WIDTH, rows growing upward. Worked out from the C#; the jitter comes from
+# the library's own sample sequence, so the statement checked is the one that holds for any jitter: every ray of pixel (x, y), taken back into
+# camera space with the transposed rotation, crosses the plane z = forwardLength inside that pixel's cell, and the cells of a frame tile the
+# window [-1/2, 1/2] x [-(H / W) / 2, (H / W) / 2] — a wide frame (W > H), a rotated camera, several samples per pixel.
+# ---------------------------------------------------------------------------------------------------------------------
+def test_perspective_camera_rays_cross_their_pixel_cell():
+    width, height, field_of_view = 48, 20, 50.0
+    position, rotation = (3.0, 6.0, -14.0), (12.0, -25.0, 0.0)
+    description = scenes.cornell_box()
+    description.camera = scenes.perspective_camera(position, rotation, field_of_view=field_of_view, lens_radius=0.0)
+    oracle = oracle_lib.OracleScene(host.prepare(description))
+
+    ys, xs = np.meshgrid(np.arange(height), np.arange(width), indexing="ij")
+    pixels = np.repeat(np.stack([xs.reshape(-1), ys.reshape(-1)], axis=-1), 3, axis=0).astype(np.int32)
+    index = np.tile(np.arange(3, dtype=np.uint32), width * height)
+    rays = oracle.spawn_rays(structs.render_params(width, height, 16, extend=3, seed=4), pixels, index)
+
+    assert np.all(rays["origin"] == np.array(position, dtype=np.float32))
+    assert np.allclose(np.linalg.norm(rays["direction"].astype(np.float64), axis=1), 1.0, atol=1e-6)
+
+    to_camera = scenes.rotation_matrix(*rotation).T  # a rotation: its inverse is its transpose
+    local = rays["direction"].astype(np.float64) @ to_camera.T
+    forward_length = 0.5 / math.tan(math.radians(field_of_view) / 2.0)
+    assert np.all(local[:, 2] > 0)
+    u, v = local[:, 0] / local[:, 2] * forward_length, local[:, 1] / local[:, 2] * forward_length
+
+    slack = 1e-6
+    assert np.all(u >= pixels[:, 0] / width - 0.5 - slack) and np.all(u <= (pixels[:, 0] + 1) / width - 0.5 + slack)
+    assert np.all(v >= pixels[:, 1] / width - height / width / 2 - slack) and np.all(v <= (pixels[:, 1] + 1) / width - height / width / 2 + slack)
+    jitter_x, jitter_y = (u + 0.5) * width - pixels[:, 0], (v + height / width / 2) * width - pixels[:, 1]
+    assert 0.35 < jitter_x.mean() < 0.65 and 0.35 < jitter_y.mean() < 0.65 and jitter_x.std() > 0.2 and jitter_y.std() > 0.2  # the whole cell is used
