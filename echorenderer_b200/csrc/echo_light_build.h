@@ -24,9 +24,9 @@
 // then the branch bounds bottom-up (`bounds[child0].Encapsulate(bounds[child1])`, one pass per depth) and the emitter map
 // (LightTree.AddToMap, :26-37: leaves in pre-order, bit `depth` of the path set on every child1 step).
 //
-// Transcendentals: the reference calls MathF.Acos / MathF.Cos / Math.Acos / MathF.SinCos, whose bits belong to the platform's C runtime.
-// They are pinned here (acos_pin / sincos_pin: the algorithms of oracle/math.hpp's acos_det / sincos_det; acos_double_pin: the fdlibm
-// rational approximation, < 1 ulp of binary64) so that g++ and nvcc produce the same bits: the host mirror (libecho_host.so), the CUDA
+// Transcendentals: the reference calls MathF.Acos / MathF.Cos (ConeBound), Math.Acos (Float3.Angle) and Math.Sin / Math.Cos cast to float
+// (Versor(axis, angle)), whose bits belong to the platform's C runtime. They are pinned here (acos_pin / sincos_pin: the algorithms of
+// oracle/math.hpp's acos_det / sincos_det, also for the Versor; acos_double_pin: the fdlibm rational approximation, < 1 ulp of binary64) so that g++ and nvcc produce the same bits: the host mirror (libecho_host.so), the CUDA
 // backend (lightbuild.cu) and the CPU emulation the -m "not gpu" suite runs (tests/c_client/light_emulation.cpp) all compile THIS file.
 // Byte identity is claimed for inputs on which the reference produces no NaN (x86 and the GPU encode a NaN's sign / payload differently).
 //
@@ -344,7 +344,7 @@ LIGHT_HD float angle_degrees(Vec3 a, Vec3 b) // Float3.Angle, Float3.cs:277-288 
 	return (float)acos_double_pin(d / mag) * (float)(180.0 / 3.14159265358979323846);
 }
 
-LIGHT_HD Vec3 rotate_axis_angle(Vec3 axis, float angleDegrees, Vec3 v) // new Versor(axis, angle) * v, Versor.cs:30-44,223-240
+LIGHT_HD Vec3 rotate_axis_angle(Vec3 axis, float angleDegrees, Vec3 v) // new Versor(axis, angle) * v, Versor.cs:37-55,173,223-240 ((float)Math.Sin / Cos there: pinned)
 {
 	float radians = (angleDegrees / 2.0f) * (float)(3.14159265358979323846 / 180.0);
 	float s, c;

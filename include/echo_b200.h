@@ -448,7 +448,7 @@ int32_t echo_b200_scene_build_qbvh(EchoScene*, uint32_t* out_node_count, uint32_
  * each end over LightBound.Encapsulate / RelativeArea, first cut of lowest cost, tail subtree first) and AddToMap (:26-37), run level by
  * level on the device. The shape of this tree IS the light-sampling distribution (LightTree.Pick, :115-154), so the build emits the
  * reference's own tree: nodes in pre-order, emitter tokens and bit paths equal to echo_host_build_light_tree's byte for byte
- * (tests/test_light_build.py, tests/test_gpu_build.py). MathF.Acos / Cos / SinCos and Math.Acos are pinned (csrc/echo_light_build.h) so
+ * (tests/test_light_build.py, tests/test_gpu_build.py). MathF.Acos / Cos, Math.Acos and the Versor's Math.Sin / Cos are pinned (csrc/echo_light_build.h) so
  * that host and device agree; the sort is stable (the reference's Span.Sort leaves the order of equal centres to the runtime).
  * Mirrors echo_host_build_light_tree_instanced (echo_host.h), with caller-owned output: out_nodes needs room for node_capacity nodes,
  * out_emitter_tokens / out_emitter_bitpaths for emitter_capacity entries; 2 e - 1 nodes for e emitters, and e <= point_count + the

@@ -38,7 +38,7 @@ int32_t echo_host_build_qbvh_instanced(const EchoTriangle* triangles, uint32_t t
 /* Builds the light tree over point lights, emissive triangles, emissive spheres (LightCollection.CreateBounds order).
  * out_power receives the root LightBound power (0 when there is no light; then node_count == 0). The recursion is the reference's
  * (LightTree.cs:62-113); the LightBound / ConeBound arithmetic is the one restatement it shares with the device build
- * (echo_b200_build_light_tree, csrc/echo_light_build.h: stable sort, MathF.Acos / Cos / SinCos and Math.Acos pinned), so both emit the same bytes. */
+ * (echo_b200_build_light_tree, csrc/echo_light_build.h: stable sort, MathF.Acos / Cos, Math.Acos and the Versor's Math.Sin / Cos pinned), so both emit the same bytes. */
 int32_t echo_host_build_light_tree(const EchoTriangle* triangles, uint32_t triangle_count,
                                    const EchoSphere* spheres, uint32_t sphere_count,
                                    const EchoMaterial* materials, uint32_t material_count,
