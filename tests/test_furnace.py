@@ -69,3 +69,94 @@ def test_lossless_surfaces_in_a_uniform_environment(kind, label):
     assert hit.sum() > 1000
     assert np.allclose(radiance[hit], np.array(RADIANCE), rtol=2e-5, atol=0), label
     assert np.allclose(radiance[~hit], np.array(RADIANCE), rtol=1e-7, atol=0)
+
+
+def lit_plane(lights):
+    """a Lambertian plane (it cannot see itself: no indirect light), point lights above it, nothing else"""
+    points = np.zeros(len(lights), dtype=structs.POINT_LIGHT)
+    for k, (intensity, where) in enumerate(lights):
+        points["intensity"][k], points["position"][k] = intensity, where
+    position = (0.0, 6.0, -7.0)
+    camera = scenes.perspective_camera(position, scenes.look_rotation(position, (0, 0, 0)), field_of_view=50.0, lens_radius=0.0)
+    return SceneDescription(triangles=scenes.plane(0, (20, 20)), materials=np.concatenate([scenes.material(structs.MATERIAL_DIFFUSE, RHO)]), point_lights=points, camera=camera)
+
+
+def plane_samples(description, size, extend, seed):
+    oracle = oracle_lib.OracleScene(host.prepare(description))
+    params = structs.render_params(size, size, 8, extend=extend, seed=seed, bounce_limit=16)
+    ys, xs = np.meshgrid(np.arange(size), np.arange(size), indexing="ij")
+    pixels = np.repeat(np.stack([xs.reshape(-1), ys.reshape(-1)], axis=-1), extend, axis=0).astype(np.int32)
+    index = np.tile(np.arange(extend, dtype=np.uint32), size * size)
+    radiance = oracle.evaluate_samples(params, pixels, index).astype(np.float64)
+    rays = oracle.spawn_rays(params, pixels, index)
+    hits = oracle.trace(rays)
+    hit = hits["token"] != structs.TOKEN_EMPTY
+    points = rays["origin"].astype(np.float64) + rays["direction"].astype(np.float64) * np.where(hit, hits["distance"], 0.0).astype(np.float64)[:, None]
+    return radiance, hit, points
+
+
+def point_light_radiance(points, intensity, position):
+    """rho / pi * I cos(theta) / r^2 on the plane y = 0 with normal +Y: PreparedPointLight.Sample hands back intensity / distance^2 (PointLight.cs),
+    the evaluator multiplies by the Lambertian BSDF rho / pi and |cos| and divides by the pick probability"""
+    offset = np.asarray(position) - points
+    squared = (offset ** 2).sum(axis=1)
+    return np.array(RHO) / np.pi * np.asarray(intensity) * (offset[:, 1] / np.sqrt(squared) / squared)[:, None]
+
+
+def test_one_point_light_over_a_plane_is_exact_per_sample():
+    """One delta light: the light tree is its leaf (pick probability 1), no MIS partner, the bounce off the plane escapes into black — so every
+    sample IS the closed form at its own hit point, to rounding."""
+    light = ((30.0, 20.0, 10.0), (1.0, 3.0, -0.5))
+    radiance, hit, points = plane_samples(lit_plane([light]), 16, 2, seed=8)
+    assert hit.mean() > 0.8 and np.all(radiance[~hit] == 0)
+    assert np.allclose(radiance[hit], point_light_radiance(points[hit], *light), rtol=5e-6, atol=0)
+
+
+def test_two_point_lights_over_a_plane_converge_to_their_sum():
+    """Two lights of different power: LightTree.Pick chooses one per sample by LightBound.Importance and divides by that probability — each sample is
+    one light's share scaled up, the mean over many samples of a pixel neighbourhood the sum of both closed forms."""
+    lights = [((30.0, 20.0, 10.0), (1.5, 3.0, -0.5)), ((4.0, 8.0, 16.0), (-3.0, 1.5, 1.0))]
+    radiance, hit, points = plane_samples(lit_plane(lights), 12, 256, seed=9)
+    expected = sum(point_light_radiance(points[hit], *light) for light in lights)
+    mean, truth = radiance[hit].mean(axis=0), expected.mean(axis=0)
+    error = radiance[hit].std(axis=0) / np.sqrt(hit.sum())
+    assert np.all(np.abs(mean - truth) < 4 * error), (mean, truth, error)
+    assert np.all(error / truth < 0.01)
+    only_first = point_light_radiance(points[hit], *lights[0]).mean(axis=0)
+    assert np.all(np.abs(mean - only_first) > 10 * error)  # and the second light is in there
+
+
+def polygon_irradiance(points, vertices):
+    """Lambert's formula: the irradiance on a surface with normal +Y at `points` from a polygon of unit radiance, sum over the edges of the angle an
+    edge subtends times the cosine between the surface normal and the normal of the plane through the point and the edge, halved"""
+    total = np.zeros(len(points))
+    for a, b in zip(vertices, np.roll(vertices, -1, axis=0)):
+        va, vb = a - points, b - points
+        va, vb = va / np.linalg.norm(va, axis=1, keepdims=True), vb / np.linalg.norm(vb, axis=1, keepdims=True)
+        gamma = np.arccos(np.clip((va * vb).sum(axis=1), -1.0, 1.0))
+        normal = np.cross(va, vb)
+        total += gamma * normal[:, 1] / np.linalg.norm(normal, axis=1)
+    return np.abs(total) / 2.0
+
+
+def test_emissive_triangle_over_a_plane_converges_to_lamberts_formula():
+    """An area light: a one-sided Emissive triangle (Emissive.Emit: the side its normal faces, Emissive.cs:63) facing a Lambertian plane. The plane's
+    radiance is rho / pi times the irradiance Lambert's polygon formula gives in closed form; the evaluator gets there by sampling the triangle's
+    area (PreparedTriangle.Sample / ProbabilityDensity), by BSDF samples that happen to reach it, and by the power heuristic between the two."""
+    emission = np.array((10.0, 8.0, 6.0))
+    corner, side = np.array((-1.0, 3.0, -1.0)), 2.0
+    vertices = np.stack([corner, corner + (side, 0, 0), corner + (0, 0, side)])  # edge1 x edge2 = -Y: it faces the plane
+    materials = np.concatenate([scenes.material(structs.MATERIAL_DIFFUSE, RHO), scenes.material(structs.MATERIAL_EMISSIVE, tuple(emission))])
+    triangles = np.concatenate([scenes.plane(0, (20, 20)), scenes.make_triangles(vertices[0:1], vertices[1:2], vertices[2:3], 1)])
+    description = lit_plane([])
+    description.triangles, description.materials = triangles, materials
+
+    radiance, hit, points = plane_samples(description, 12, 256, seed=10)
+    on_plane = hit & (points[:, 1] < 1e-3)  # the samples that met the plane first (not the light, not the void)
+    assert on_plane.mean() > 0.7
+
+    expected = np.array(RHO) / np.pi * emission * polygon_irradiance(points[on_plane], vertices)[:, None]
+    mean, truth = radiance[on_plane].mean(axis=0), expected.mean(axis=0)
+    error = radiance[on_plane].std(axis=0) / np.sqrt(on_plane.sum())
+    assert np.all(np.abs(mean - truth) < 4 * error), (mean, truth, error)
+    assert np.all(error / truth < 0.01)
