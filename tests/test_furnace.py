@@ -160,3 +160,26 @@ def test_emissive_triangle_over_a_plane_converges_to_lamberts_formula():
     error = radiance[on_plane].std(axis=0) / np.sqrt(on_plane.sum())
     assert np.all(np.abs(mean - truth) < 4 * error), (mean, truth, error)
     assert np.all(error / truth < 0.01)
+
+
+def test_emissive_sphere_over_a_plane_converges_to_its_closed_form():
+    """A sphere of radiance Le and radius R whose centre is at distance d, wholly above the horizon of the lit point, gives the irradiance
+    pi Le (R / d)^2 cos(theta): PreparedSphere.Sample's cone sampling and its pdf (SphereEntity.cs), MIS against the BSDF samples that reach it."""
+    emission, centre, radius = np.array((12.0, 9.0, 5.0)), np.array((0.5, 3.0, 0.0)), 0.75
+    description = lit_plane([])
+    description.materials = np.concatenate([scenes.material(structs.MATERIAL_DIFFUSE, RHO), scenes.material(structs.MATERIAL_EMISSIVE, tuple(emission))])
+    description.spheres = np.zeros(1, dtype=structs.SPHERE)
+    description.spheres["position"], description.spheres["radius"], description.spheres["material"] = centre, radius, 1
+
+    radiance, hit, points = plane_samples(description, 12, 256, seed=11)
+    on_plane = hit & (np.abs(points[:, 1]) < 1e-3)
+    assert on_plane.mean() > 0.7
+
+    offset = centre - points[on_plane]
+    squared = (offset ** 2).sum(axis=1)
+    irradiance = np.pi * radius * radius / squared * offset[:, 1] / np.sqrt(squared)
+    expected = np.array(RHO) / np.pi * emission * irradiance[:, None]
+    mean, truth = radiance[on_plane].mean(axis=0), expected.mean(axis=0)
+    error = radiance[on_plane].std(axis=0) / np.sqrt(on_plane.sum())
+    assert np.all(np.abs(mean - truth) < 4 * error), (mean, truth, error)
+    assert np.all(error / truth < 0.01)
