@@ -183,3 +183,101 @@ def test_emissive_sphere_over_a_plane_converges_to_its_closed_form():
     error = radiance[on_plane].std(axis=0) / np.sqrt(on_plane.sum())
     assert np.all(np.abs(mean - truth) < 4 * error), (mean, truth, error)
     assert np.all(error / truth < 0.01)
+
+
+# ---- absolute BSDF values through the whole pipeline: with ONE delta light and a flat surface a sample's radiance is tint * f(outgoing, incident) *
+# I cos(theta) / r^2, nothing else — so radiance / (I cos / r^2) IS Material.Scatter + BSDF.Evaluate at that pair of directions, and can be set
+# beside the formula written down from the C# (BxDFTests.cs pins the lobes' sample / evaluate / pdf CONSISTENCY, not their absolute values) ----
+
+def bsdf_through_the_pipeline(plane_material, seed):
+    light = ((30.0, 20.0, 10.0), (1.0, 3.0, -0.5))
+    description = lit_plane([light])
+    description.materials = plane_material
+    radiance, hit, points = plane_samples(description, 16, 2, seed=seed)
+    offset = np.asarray(light[1]) - points[hit]
+    squared = (offset ** 2).sum(axis=1)
+    incident = offset / np.sqrt(squared)[:, None]
+    received = np.asarray(light[0]) * (incident[:, 1] / squared)[:, None]  # I cos(theta) / r^2 on the plane y = 0
+    camera = np.array((0.0, 6.0, -7.0))
+    outgoing = camera - points[hit]
+    outgoing /= np.linalg.norm(outgoing, axis=1, keepdims=True)
+    return radiance[hit] / received, outgoing, incident
+
+
+def test_oren_nayar_value_through_the_pipeline():
+    """Diffuse with a Roughness texture value above zero scatters as OrenNayar (Diffuse.cs): a = 1 / (pi + (pi / 2 - 2 / 3) sigma), b = a sigma,
+    f = a + b s with s = o . i - cos_o cos_i, divided by max(cos_o, cos_i) when positive (Lambertian.cs, OrenNayar.Evaluate)."""
+    sigma = 0.7
+    value, outgoing, incident = bsdf_through_the_pipeline(np.concatenate([scenes.material(structs.MATERIAL_DIFFUSE, RHO, roughness=(sigma, sigma))]), seed=12)
+    a = 1.0 / (np.pi + (np.pi / 2.0 - 2.0 / 3.0) * sigma)
+    b = a * sigma
+    cos_o, cos_i = outgoing[:, 1], incident[:, 1]
+    s = (outgoing * incident).sum(axis=1) - cos_o * cos_i
+    s = np.where(s > 8e-7, s / np.maximum(cos_o, cos_i), s)
+    expected = np.array(RHO) * (a + b * s)[:, None]
+    assert len(value) > 300 and np.ptp(s) > 0.3  # both signs of s, a real range of angles
+    assert np.allclose(value, expected, rtol=3e-5, atol=0)
+
+
+def test_rough_dielectric_reflection_value_through_the_pipeline():
+    """Dielectric with roughness scatters as GlossyReflection + GlossyTransmission over a TrowbridgeReitzMicrofacet and RealFresnel(1, eta)
+    (Dielectric.cs); light from the camera's side meets the reflection lobe only: f = F(o . h) D(h) G(o, i) / (4 cos_o cos_i) with alpha =
+    clamp01(0.75 roughness)^2 (IMicrofacet.GetAlpha), D = 1 / (pi alpha^2 (cos^2 + sin^2 / alpha^2)^2), G = 1 / (1 + Lambda(o) + Lambda(i)),
+    Lambda = sqrt(1 + alpha^2 tan^2) / 2 - 1 / 2 (IMicrofacet.cs), F the unpolarised Fresnel reflectance with Snell's law (Fresnel.cs)."""
+    roughness, eta, tint = 0.6, 1.5, (0.9, 0.8, 0.7)
+    value, outgoing, incident = bsdf_through_the_pipeline(np.concatenate([scenes.material(structs.MATERIAL_DIELECTRIC, tint, roughness=(roughness, roughness), ior=eta)]), seed=13)
+    alpha = min(1.0, max(0.0, roughness * 0.75)) ** 2
+    half = outgoing + incident
+    half /= np.linalg.norm(half, axis=1, keepdims=True)
+    cos_o, cos_i, cos_h = outgoing[:, 1], incident[:, 1], half[:, 1]
+
+    d = 1.0 / (np.pi * alpha * alpha * (cos_h ** 2 + (1.0 - cos_h ** 2) / (alpha * alpha)) ** 2)
+    shadow = lambda c: np.sqrt(1.0 + alpha * alpha * (1.0 - c * c) / (c * c)) / 2.0 - 0.5
+    g = 1.0 / (1.0 + shadow(cos_o) + shadow(cos_i))
+    cos_oh = (outgoing * half).sum(axis=1)
+    cos_t = np.sqrt(1.0 - (1.0 / eta) ** 2 * (1.0 - cos_oh ** 2))
+    parallel = (eta * cos_oh - cos_t) / (eta * cos_oh + cos_t)
+    perpendicular = (cos_oh - eta * cos_t) / (cos_oh + eta * cos_t)
+    fresnel = (parallel ** 2 + perpendicular ** 2) / 2.0
+
+    expected = np.array(tint) * (fresnel * d * g / (4.0 * cos_o * cos_i))[:, None]
+    assert len(value) > 300 and expected.max() / expected.min() > 5  # on and off the highlight
+
+    # PathTracedEvaluator draws the bounce FIRST and skips light sampling altogether when that sample is impossible (`!Positive(bounce.scatterPdf)`,
+    # PathTracedEvaluator.cs:68): a microfacet normal whose reflection or refraction leaves on the wrong side. Those samples are black in the
+    # reference too; every other one carries the closed form.
+    lit = value.max(axis=1) > 0
+    assert 0.8 < lit.mean() < 1.0
+    assert np.allclose(value[lit], expected[lit], rtol=2e-5, atol=0)
+
+
+def test_rough_conductor_value_through_the_pipeline():
+    """Conductor with physical parameters (Artistic off: RefractiveIndex n and Extinction k per channel) and roughness scatters as GlossyReflection over
+    the same microfacet with ComplexFresnel(1, n, k) (Conductor.cs): with t = n^2 - k^2 - sin^2, a2b2 = sqrt(t^2 + 4 n^2 k^2), Rs = (a2b2 + cos^2 -
+    cos sqrt(2 (a2b2 + t))) / (a2b2 + cos^2 + cos sqrt(2 (a2b2 + t))), Rp = Rs (cos^2 a2b2 + sin^4 - cos sqrt(2 (a2b2 + t)) sin^2) / (... + ...),
+    F = (Rs + Rp) / 2 (Fresnel.cs, ComplexFresnel.Evaluate)."""
+    roughness, n, k = 0.5, np.array((0.18, 0.42, 1.37)), np.array((3.42, 2.35, 1.77))
+    material = scenes.material(structs.MATERIAL_CONDUCTOR, (1.0, 1.0, 1.0), roughness=(roughness, roughness), param_a=tuple(n), param_b=tuple(k), flags=0)
+    value, outgoing, incident = bsdf_through_the_pipeline(np.concatenate([material]), seed=14)
+    alpha = min(1.0, max(0.0, roughness * 0.75)) ** 2
+    half = outgoing + incident
+    half /= np.linalg.norm(half, axis=1, keepdims=True)
+    cos_o, cos_i, cos_h = outgoing[:, 1], incident[:, 1], half[:, 1]
+
+    d = 1.0 / (np.pi * alpha * alpha * (cos_h ** 2 + (1.0 - cos_h ** 2) / (alpha * alpha)) ** 2)
+    shadow = lambda c: np.sqrt(1.0 + alpha * alpha * (1.0 - c * c) / (c * c)) / 2.0 - 0.5
+    g = 1.0 / (1.0 + shadow(cos_o) + shadow(cos_i))
+
+    cos = np.clip(np.abs((outgoing * half).sum(axis=1)), 0.0, 1.0)[:, None]
+    cos2, sin2 = cos * cos, 1.0 - cos * cos
+    term = n * n - k * k - sin2
+    a2b2 = np.sqrt(term * term + 4.0 * n * n * k * k)
+    para0, para1 = a2b2 + cos2, cos * np.sqrt(2.0) * np.sqrt(a2b2 + term)
+    perp0, perp1 = cos2 * a2b2 + sin2 * sin2, para1 * sin2
+    para, perp = (para0 - para1) / (para0 + para1), (perp0 - perp1) / (perp0 + perp1)
+    fresnel = (para * perp + para) / 2.0
+
+    expected = fresnel * (d * g / (4.0 * cos_o * cos_i))[:, None]
+    lit = value.max(axis=1) > 0  # see the dielectric: an impossible bounce sample switches light sampling off for that sample
+    assert len(value) > 300 and 0.8 < lit.mean() <= 1.0
+    assert np.allclose(value[lit], expected[lit], rtol=3e-5, atol=0)
