@@ -281,3 +281,48 @@ def test_rough_conductor_value_through_the_pipeline():
     lit = value.max(axis=1) > 0  # see the dielectric: an impossible bounce sample switches light sampling off for that sample
     assert len(value) > 300 and 0.8 < lit.mean() <= 1.0
     assert np.allclose(value[lit], expected[lit], rtol=3e-5, atol=0)
+
+
+def test_rough_dielectric_transmission_value_through_the_pipeline():
+    """The light BELOW the glass sheet, the camera above: only the GlossyTransmission lobe answers (Glossy.cs, GlossyTransmission.Evaluate). With
+    etaR = eta_incident / eta_outgoing = eta for a camera on the outside, h = normalize(o + etaR i) turned to the upper side, f = (1 - F(o . h)) D(h)
+    G(o, i) |etaR^2 (o . h)(i . h)| / ((etaR (i . h) + o . h)^2 |cos_o cos_i|), black when o . h and i . h have the same sign."""
+    roughness, eta, tint = 0.6, 1.5, (0.9, 0.8, 0.7)
+    light = ((30.0, 20.0, 10.0), (0.5, -2.5, 0.5))
+    description = lit_plane([light])
+    description.materials = np.concatenate([scenes.material(structs.MATERIAL_DIELECTRIC, tint, roughness=(roughness, roughness), ior=eta)])
+    radiance, hit, points = plane_samples(description, 16, 2, seed=15)
+
+    offset = np.asarray(light[1]) - points[hit]
+    squared = (offset ** 2).sum(axis=1)
+    incident = offset / np.sqrt(squared)[:, None]
+    received = np.asarray(light[0]) * (np.abs(incident[:, 1]) / squared)[:, None]
+    outgoing = np.array((0.0, 6.0, -7.0)) - points[hit]
+    outgoing /= np.linalg.norm(outgoing, axis=1, keepdims=True)
+    value = radiance[hit] / received
+
+    alpha = min(1.0, max(0.0, roughness * 0.75)) ** 2
+    half = outgoing + eta * incident
+    half /= np.linalg.norm(half, axis=1, keepdims=True)
+    half *= np.sign(half[:, 1])[:, None]
+    cos_o, cos_i, cos_h = outgoing[:, 1], incident[:, 1], half[:, 1]
+    dot_o, dot_i = (outgoing * half).sum(axis=1), (incident * half).sum(axis=1)
+
+    d = 1.0 / (np.pi * alpha * alpha * (cos_h ** 2 + (1.0 - cos_h ** 2) / (alpha * alpha)) ** 2)
+    shadow = lambda c: np.sqrt(1.0 + alpha * alpha * (1.0 - c * c) / (c * c)) / 2.0 - 0.5
+    g = 1.0 / (1.0 + shadow(cos_o) + shadow(cos_i))
+    cos_t = np.sqrt(np.maximum(0.0, 1.0 - (1.0 / eta) ** 2 * (1.0 - dot_o ** 2)))
+    parallel = (eta * dot_o - cos_t) / (eta * dot_o + cos_t)
+    perpendicular = (dot_o - eta * cos_t) / (dot_o + eta * cos_t)
+    fresnel = (parallel ** 2 + perpendicular ** 2) / 2.0
+
+    f = (1.0 - fresnel) * d * g * np.abs(eta * eta * dot_o * dot_i / ((eta * dot_i + dot_o) ** 2 * cos_o * cos_i))
+    f = np.where(dot_o * dot_i > 0, 0.0, f)
+    expected = np.array(tint) * f[:, None]
+    lit = value.max(axis=1) > 0
+    # black where the formula is black (o . h and i . h on the same side: no refraction connects the two directions through that microfacet),
+    # and on the few samples whose bounce was impossible (see the reflection lobe above)
+    assert len(value) > 300 and lit.sum() > 60 and np.all(expected[lit].min(axis=1) > 0)
+    dark_where_the_formula_is_lit = (~lit) & (expected.max(axis=1) > 0)
+    assert dark_where_the_formula_is_lit.sum() < 0.25 * (expected.max(axis=1) > 0).sum()
+    assert np.allclose(value[lit], expected[lit], rtol=5e-5, atol=0)
