@@ -326,3 +326,43 @@ def test_rough_dielectric_transmission_value_through_the_pipeline():
     dark_where_the_formula_is_lit = (~lit) & (expected.max(axis=1) > 0)
     assert dark_where_the_formula_is_lit.sum() < 0.25 * (expected.max(axis=1) > 0).sum()
     assert np.allclose(value[lit], expected[lit], rtol=5e-5, atol=0)
+
+
+def test_coated_diffuse_value_through_the_pipeline():
+    """CoatedDiffuse (CoatedDiffuse.cs:37-55) = CoatedLambertianReflection + GlossyReflection over RealFresnel(1, eta), both under the BSDF's albedo tint:
+    the coated lobe is eta_r^2 / pi / (1 - albedo R) (1 - F(cos_o)) (1 - F(cos_i)) with eta_r = 1 / eta and R = FresnelDiffuseReflectance(1 / eta)
+    (Lambertian.cs:131-199: 1 - eta_r^2 (1 - E(eta)), E the closed form with the two logarithms), the coat the GGX reflection checked above."""
+    roughness, eta, albedo = 0.5, 1.5, np.array((0.8, 0.5, 0.3))
+    value, outgoing, incident = bsdf_through_the_pipeline(scenes.coated_diffuse(tuple(albedo), roughness=(roughness, roughness), ior=eta), seed=16)
+
+    def fresnel(cos):  # RealFresnel(1, eta).Evaluate from the outside
+        cos_t = np.sqrt(1.0 - (1.0 / eta) ** 2 * (1.0 - cos ** 2))
+        parallel = (eta * cos - cos_t) / (eta * cos + cos_t)
+        perpendicular = (cos - eta * cos_t) / (cos + eta * cos_t)
+        return (parallel ** 2 + perpendicular ** 2) / 2.0
+
+    def entrance(e):  # CoatedLambertianReflection.FresnelDiffuseReflectance's EntranceReflectance, e >= 1
+        e2, e4 = e * e, e ** 4
+        q0 = (e - 1) * (3 * e + 1) / (6 * (e + 1) ** 2)
+        q1 = e2 * (e2 - 1) ** 2 / (e2 + 1) ** 3
+        q2 = -2 * e2 * e * (e2 + e + e - 1) / ((e2 + 1) * (e4 - 1))
+        q3 = 8 * e4 * (e4 + 1) / ((e2 + 1) * (e4 - 1) ** 2)
+        return 0.5 + (np.log((e - 1) / (e + 1)) * q1 + q0) + (np.log(e) * q3 + q2)
+
+    eta_r = 1.0 / eta
+    reflectance = 1.0 - eta_r * eta_r * (1.0 - entrance(eta))
+    cos_o, cos_i = outgoing[:, 1], incident[:, 1]
+    coated = (eta_r * eta_r / np.pi / (1.0 - albedo * reflectance)) * ((1.0 - fresnel(cos_o)) * (1.0 - fresnel(cos_i)))[:, None]
+
+    alpha = min(1.0, max(0.0, roughness * 0.75)) ** 2
+    half = outgoing + incident
+    half /= np.linalg.norm(half, axis=1, keepdims=True)
+    cos_h = half[:, 1]
+    d = 1.0 / (np.pi * alpha * alpha * (cos_h ** 2 + (1.0 - cos_h ** 2) / (alpha * alpha)) ** 2)
+    shadow = lambda c: np.sqrt(1.0 + alpha * alpha * (1.0 - c * c) / (c * c)) / 2.0 - 0.5
+    coat = fresnel((outgoing * half).sum(axis=1)) * d / (1.0 + shadow(cos_o) + shadow(cos_i)) / (4.0 * cos_o * cos_i)
+
+    expected = albedo * (coated + coat[:, None])
+    lit = value.max(axis=1) > 0
+    assert len(value) > 300 and 0.8 < lit.mean() <= 1.0 and 0.3 < reflectance < 0.7
+    assert np.allclose(value[lit], expected[lit], rtol=5e-5, atol=0)
