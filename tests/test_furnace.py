@@ -366,3 +366,29 @@ def test_coated_diffuse_value_through_the_pipeline():
     lit = value.max(axis=1) > 0
     assert len(value) > 300 and 0.8 < lit.mean() <= 1.0 and 0.3 < reflectance < 0.7
     assert np.allclose(value[lit], expected[lit], rtol=5e-5, atol=0)
+
+
+def test_ambient_and_point_light_together_carry_the_references_excess():
+    """PreparedScene.Pick first chooses between the infinite lights and the light tree by the power threshold t (PreparedScene.cs:279-325), then within;
+    on a plane (no interreflection) an unbiased estimator would return the sum of both closed forms, rho L + rho / pi I cos / r^2. The reference
+    returns MORE, and exactly how much follows from its code: when the picked light is a delta light, `mis = light.TopToken.IsAreaLight()` is false and
+    the bounce that escapes adds the WHOLE environment (PathTracedEvaluator.cs:136-143, "Fallback with no MIS") — although the environment's light-sampling
+    share is also collected, MIS-weighted, in the samples that picked the environment. Per sample the environment part is therefore counted
+    (1 - t) times too often by its light-sampling share: with the environment sampled uniformly over the sphere (pdf 1 / 4 pi, IDirectionalTexture.cs)
+    against the cosine lobe (cos / pi) under the power heuristic, that share of rho L is 2 * Integral_0^1 c a^2 / (a^2 + c^2 / pi^2) dc = (a pi)^2 ln(1 +
+    1 / (a pi)^2) with a = t / (4 pi). The oracle keeps the reference's behaviour, and must land on the sum PLUS that excess."""
+    light = ((30.0, 20.0, 10.0), (1.0, 3.0, -0.5))
+    description = lit_plane([light])
+    description.infinite_lights = scenes.ambient_light(RADIANCE)
+    prepared = host.prepare(description)
+    radiance, hit, points = plane_samples(description, 12, 256, seed=17)
+
+    threshold = float(prepared.infinite_threshold)
+    a_pi = threshold / 4.0
+    excess = (1.0 - threshold) * a_pi * a_pi * np.log(1.0 + 1.0 / (a_pi * a_pi)) * np.array(RHO) * np.array(RADIANCE)
+    unbiased = (point_light_radiance(points[hit], *light) + np.array(RHO) * np.array(RADIANCE)).mean(axis=0)
+    mean = radiance[hit].mean(axis=0)
+    error = radiance[hit].std(axis=0) / np.sqrt(hit.sum())
+    assert 0.3 < threshold < 0.7 and np.all(excess > 10 * error)             # the excess is far outside the noise ...
+    assert np.all(np.abs(mean - (unbiased + excess)) < 4 * error), (mean, unbiased, excess, error)  # ... and it is the one the code implies
+    assert np.all(mean - unbiased > 10 * error)
