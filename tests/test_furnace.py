@@ -392,3 +392,25 @@ def test_ambient_and_point_light_together_carry_the_references_excess():
     assert 0.3 < threshold < 0.7 and np.all(excess > 10 * error)             # the excess is far outside the noise ...
     assert np.all(np.abs(mean - (unbiased + excess)) < 4 * error), (mean, unbiased, excess, error)  # ... and it is the one the code implies
     assert np.all(mean - unbiased > 10 * error)
+
+
+def test_sky_and_an_area_light_together_converge_to_their_sum():
+    """Two non-delta lights, so every pick keeps MIS and nothing is counted twice: a plane under a uniform sky L and a one-sided emissive triangle Le
+    facing it. The triangle also hides its part of the sky, and that part is the same projected solid angle Lambert's formula gives:
+    radiance = rho / pi (L (pi - E) + Le E) with E the polygon irradiance for unit radiance."""
+    emission = np.array((10.0, 8.0, 6.0))
+    corner, side = np.array((-1.0, 3.0, -1.0)), 2.0
+    vertices = np.stack([corner, corner + (side, 0, 0), corner + (0, 0, side)])
+    description = lit_plane([])
+    description.materials = np.concatenate([scenes.material(structs.MATERIAL_DIFFUSE, RHO), scenes.material(structs.MATERIAL_EMISSIVE, tuple(emission))])
+    description.triangles = np.concatenate([scenes.plane(0, (20, 20)), scenes.make_triangles(vertices[0:1], vertices[1:2], vertices[2:3], 1)])
+    description.infinite_lights = scenes.ambient_light(RADIANCE)
+
+    radiance, hit, points = plane_samples(description, 12, 256, seed=18)
+    on_plane = hit & (points[:, 1] < 1e-3)
+    covered = polygon_irradiance(points[on_plane], vertices)[:, None]
+    expected = np.array(RHO) / np.pi * (np.array(RADIANCE) * (np.pi - covered) + emission * covered)
+    mean, truth = radiance[on_plane].mean(axis=0), expected.mean(axis=0)
+    error = radiance[on_plane].std(axis=0) / np.sqrt(on_plane.sum())
+    assert np.all(np.abs(mean - truth) < 4 * error), (mean, truth, error)
+    assert np.all(error / truth < 0.01)
