@@ -414,3 +414,68 @@ def test_sky_and_an_area_light_together_converge_to_their_sum():
     error = radiance[on_plane].std(axis=0) / np.sqrt(on_plane.sum())
     assert np.all(np.abs(mean - truth) < 4 * error), (mean, truth, error)
     assert np.all(error / truth < 0.01)
+
+
+# ---- specular surfaces: a flat sheet under a sky that is bright above the horizon and black below it. A ray reflected off the sheet sees the
+# sky, a refracted one the black below: the mean radiance of the samples of a view direction is the Fresnel reflectance times the sky — the
+# probability SpecularFresnel picks reflection with (Specular.cs), or the weight SpecularReflection<ComplexFresnel> carries. ----
+
+def half_sky(material):
+    from echorenderer_b200 import TextureDescription
+    texels = np.zeros((32, 64, 4), dtype=np.float32)
+    texels[16:, :, :3] = 1.0  # rows grow upward (v = 0 looks down): the upper hemisphere is white
+    texels[..., 3] = 1.0
+    description = lit_plane([])
+    description.materials = material
+    description.textures = [TextureDescription(texels)]
+    description.infinite_lights = scenes.environment_light(0, intensity=RADIANCE)
+    return description
+
+
+def view_directions(points, hit):
+    outgoing = np.array((0.0, 6.0, -7.0)) - points[hit]
+    return outgoing / np.linalg.norm(outgoing, axis=1, keepdims=True)
+
+
+def test_smooth_dielectric_sheet_reflects_the_fresnel_share_of_the_sky():
+    eta = 1.5
+    radiance, hit, points = plane_samples(half_sky(np.concatenate([scenes.material(structs.MATERIAL_DIELECTRIC, (1.0, 1.0, 1.0), ior=eta)])), 12, 256, seed=19)
+    cos = view_directions(points, hit)[:, 1]
+    cos_t = np.sqrt(1.0 - (1.0 / eta) ** 2 * (1.0 - cos ** 2))
+    fresnel = (((eta * cos - cos_t) / (eta * cos + cos_t)) ** 2 + ((cos - eta * cos_t) / (cos + eta * cos_t)) ** 2) / 2.0
+
+    values = radiance[hit] / np.array(RADIANCE)
+    assert np.all((np.abs(values - 1.0) < 1e-5) | (values == 0.0))  # every sample is the sky or the dark: the choice is the whole estimator
+    mean, truth = values[:, 0].mean(), fresnel.mean()
+    error = values[:, 0].std() / np.sqrt(hit.sum())
+    assert abs(mean - truth) < 4 * error and error / truth < 0.02 and 0.03 < truth < 0.2, (mean, truth, error)
+
+
+def test_smooth_conductor_sheet_reflects_its_complex_fresnel_reflectance():
+    """Physical parameters (n, k) and the artistic ones (Conductor.cs:66-96, after Gulbrandsen 2014: main colour r clamped below 1, edge colour g;
+    n = g (1 - r) / (1 + r) + (1 - g) (1 + sqrt r) / (1 - sqrt r), k = sqrt(max(0, (r (n + 1)^2 - (n - 1)^2) / (1 - r)))) through the same mirror:
+    every sample carries ComplexFresnel(1, n, k) at the view angle."""
+    def reflectance(n, k, cos):
+        cos = cos[:, None]
+        cos2, sin2 = cos * cos, 1.0 - cos * cos
+        term = n * n - k * k - sin2
+        a2b2 = np.sqrt(term * term + 4.0 * n * n * k * k)
+        para0, para1 = a2b2 + cos2, cos * np.sqrt(2.0) * np.sqrt(a2b2 + term)
+        perp0, perp1 = cos2 * a2b2 + sin2 * sin2, para1 * sin2
+        para, perp = (para0 - para1) / (para0 + para1), (perp0 - perp1) / (perp0 + perp1)
+        return (para * perp + para) / 2.0
+
+    n, k = np.array((0.18, 0.42, 1.37)), np.array((3.42, 2.35, 1.77))
+    physical = scenes.material(structs.MATERIAL_CONDUCTOR, (1.0, 1.0, 1.0), param_a=tuple(n), param_b=tuple(k), flags=0)
+    radiance, hit, points = plane_samples(half_sky(np.concatenate([physical])), 12, 4, seed=20)
+    expected = reflectance(n, k, view_directions(points, hit)[:, 1]) * np.array(RADIANCE)
+    assert hit.sum() > 400 and np.allclose(radiance[hit], expected, rtol=3e-5, atol=0)
+
+    main, edge = np.array((0.6, 0.7, 0.9)), np.array((0.0, 1.0, 0.5))  # the C3 conductor (bunny.echo)
+    artistic = scenes.material(structs.MATERIAL_CONDUCTOR, (1.0, 1.0, 1.0), param_a=tuple(main), param_b=tuple(edge), flags=structs.MATERIAL_FLAG_ARTISTIC)
+    radiance, hit, points = plane_samples(half_sky(np.concatenate([artistic])), 12, 4, seed=21)
+    root = np.sqrt(main)
+    n = edge * (1.0 - main) / (1.0 + main) + (1.0 - edge) * (1.0 + root) / (1.0 - root)
+    k = np.sqrt(np.maximum(0.0, (main * (n + 1.0) ** 2 - (n - 1.0) ** 2) / (1.0 - main)))
+    expected = reflectance(n, k, view_directions(points, hit)[:, 1]) * np.array(RADIANCE)
+    assert hit.sum() > 400 and np.allclose(radiance[hit], expected, rtol=5e-5, atol=0)
