@@ -479,3 +479,28 @@ def test_smooth_conductor_sheet_reflects_its_complex_fresnel_reflectance():
     k = np.sqrt(np.maximum(0.0, (main * (n + 1.0) ** 2 - (n - 1.0) ** 2) / (1.0 - main)))
     expected = reflectance(n, k, view_directions(points, hit)[:, 1]) * np.array(RADIANCE)
     assert hit.sum() > 400 and np.allclose(radiance[hit], expected, rtol=5e-5, atol=0)
+
+
+@pytest.mark.parametrize("backface", [True, False])
+def test_one_sided_sheet_under_a_uniform_sky(backface):
+    """OneSided (OneSided.cs): `Cull = Positive(outgoing . normal) != Backface` — with Backface (the default) the sheet scatters as its Base when seen
+    from the side its normal points to and is Invisible from behind; without it the other way round. Under a uniform sky L a Lambertian base
+    makes the scattering side rho L (the furnace again: a plane is convex) and the culled side L, sample for sample."""
+    description = lit_plane([])
+    description.materials = np.concatenate([scenes.material(structs.MATERIAL_DIFFUSE, RHO),
+                                            scenes.material(structs.MATERIAL_ONESIDED, flags=structs.MATERIAL_FLAG_BACKFACE if backface else 0, base=0)])
+    description.triangles["material"] = 1
+    description.infinite_lights = scenes.ambient_light(RADIANCE)
+
+    for camera_height in (6.0, -6.0):  # above the sheet (its normal is +Y), then below it
+        position = (0.0, camera_height, -7.0)
+        description.camera = scenes.perspective_camera(position, scenes.look_rotation(position, (0, 0, 0)), field_of_view=50.0, lens_radius=0.0)
+        radiance, hit, _ = plane_samples(description, 12, 64, seed=22)
+        scatters = (camera_height > 0) == backface
+        assert hit.mean() > 0.8
+        if scatters:
+            mean = radiance[hit].mean(axis=0)
+            error = radiance[hit].std(axis=0) / np.sqrt(hit.sum())
+            assert np.all(np.abs(mean - np.array(RHO) * np.array(RADIANCE)) < 4 * error + 1e-4) and np.all(error < 0.01)
+        else:
+            assert np.allclose(radiance[hit], np.array(RADIANCE), rtol=1e-6, atol=0)
