@@ -504,3 +504,27 @@ def test_one_sided_sheet_under_a_uniform_sky(backface):
             assert np.all(np.abs(mean - np.array(RHO) * np.array(RADIANCE)) < 4 * error + 1e-4) and np.all(error < 0.01)
         else:
             assert np.allclose(radiance[hit], np.array(RADIANCE), rtol=1e-6, atol=0)
+
+
+def test_transmissive_diffuse_sheet_and_a_visible_emitter():
+    """Diffuse with Transmissive scatters as the two-sided Lambertian (Diffuse.cs, Lambertian.cs: f = 1 / 2 pi into both hemispheres): under a uniform
+    sky the sheet returns rho L seen from either side. And an Emissive surface shows its emission to the side its normal faces and nothing of its
+    own to the other (Emissive.Emit): there the path goes on with the black BSDF and ends — the sample is black even under a sky."""
+    description = lit_plane([])
+    description.materials = np.concatenate([scenes.material(structs.MATERIAL_DIFFUSE, RHO, flags=structs.MATERIAL_FLAG_TRANSMISSIVE)])
+    description.infinite_lights = scenes.ambient_light(RADIANCE)
+    for camera_height in (6.0, -6.0):
+        position = (0.0, camera_height, -7.0)
+        description.camera = scenes.perspective_camera(position, scenes.look_rotation(position, (0, 0, 0)), field_of_view=50.0, lens_radius=0.0)
+        radiance, hit, _ = plane_samples(description, 12, 128, seed=23)
+        mean = radiance[hit].mean(axis=0)
+        error = radiance[hit].std(axis=0) / np.sqrt(hit.sum())
+        assert np.all(np.abs(mean - np.array(RHO) * np.array(RADIANCE)) < 4 * error) and np.all(error / mean < 0.01), (mean, error)
+
+    emission = (7.0, 5.0, 3.0)
+    description.materials = np.concatenate([scenes.material(structs.MATERIAL_EMISSIVE, emission)])
+    for camera_height, expected in ((6.0, emission), (-6.0, (0.0, 0.0, 0.0))):
+        position = (0.0, camera_height, -7.0)
+        description.camera = scenes.perspective_camera(position, scenes.look_rotation(position, (0, 0, 0)), field_of_view=50.0, lens_radius=0.0)
+        radiance, hit, _ = plane_samples(description, 12, 4, seed=24)
+        assert hit.sum() > 400 and np.allclose(radiance[hit], np.array(expected, dtype=np.float32).astype(np.float64), rtol=1e-6, atol=0)
