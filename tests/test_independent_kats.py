@@ -923,3 +923,32 @@ def test_perspective_camera_rays_cross_their_pixel_cell():
     assert np.all(v >= pixels[:, 1] / width - height / width / 2 - slack) and np.all(v <= (pixels[:, 1] + 1) / width - height / width / 2 + slack)
     jitter_x, jitter_y = (u + 0.5) * width - pixels[:, 0], (v + height / width / 2) * width - pixels[:, 1]
     assert 0.35 < jitter_x.mean() < 0.65 and 0.35 < jitter_y.mean() < 0.65 and jitter_x.std() > 0.2 and jitter_y.std() > 0.2  # the whole cell is used
+
+
+def test_thin_lens_rays_leave_the_lens_and_cross_their_pixel_cell_on_the_focal_plane():
+    """PerspectiveCamera.SpawnRay with depth of field (PerspectiveCamera.cs:61-77): the origin is a point of the lens disk (radius LensRadius, in the
+    camera's z = 0 plane), the ray aims at uv * focusScale on the plane z = FocalDistance, focusScale = FocalDistance / forwardLength — so whatever the
+    lens sample, a pixel's rays meet the focal plane inside that pixel's cell, magnified by focusScale."""
+    width, height, field_of_view, lens_radius, focal_distance = 40, 24, 55.0, 0.35, 9.0
+    position, rotation = (1.0, 2.0, -11.0), (-8.0, 15.0, 0.0)
+    description = scenes.cornell_box()
+    description.camera = scenes.perspective_camera(position, rotation, field_of_view=field_of_view, lens_radius=lens_radius, focal_distance=focal_distance)
+    oracle = oracle_lib.OracleScene(host.prepare(description))
+
+    ys, xs = np.meshgrid(np.arange(height), np.arange(width), indexing="ij")
+    pixels = np.repeat(np.stack([xs.reshape(-1), ys.reshape(-1)], axis=-1), 4, axis=0).astype(np.int32)
+    index = np.tile(np.arange(4, dtype=np.uint32), width * height)
+    rays = oracle.spawn_rays(structs.render_params(width, height, 16, extend=4, seed=5), pixels, index)
+
+    to_camera = scenes.rotation_matrix(*rotation).T
+    origin = (rays["origin"].astype(np.float64) - np.array(position)) @ to_camera.T
+    direction = rays["direction"].astype(np.float64) @ to_camera.T
+    assert np.allclose(origin[:, 2], 0.0, atol=1e-5) and np.all(np.hypot(origin[:, 0], origin[:, 1]) <= lens_radius * (1 + 1e-5))
+    assert np.hypot(origin[:, 0], origin[:, 1]).max() > 0.9 * lens_radius and np.abs(origin[:, :2].mean(axis=0)).max() < 0.05 * lens_radius  # the whole disk
+
+    focus = origin + direction * ((focal_distance - origin[:, 2]) / direction[:, 2])[:, None]
+    forward_length = 0.5 / math.tan(math.radians(field_of_view) / 2.0)
+    u, v = focus[:, 0] / focal_distance * forward_length, focus[:, 1] / focal_distance * forward_length
+    slack = 2e-6
+    assert np.all(u >= pixels[:, 0] / width - 0.5 - slack) and np.all(u <= (pixels[:, 0] + 1) / width - 0.5 + slack)
+    assert np.all(v >= pixels[:, 1] / width - height / width / 2 - slack) and np.all(v <= (pixels[:, 1] + 1) / width - height / width / 2 + slack)
