@@ -305,3 +305,28 @@ def test_cone_union_by_hand(library):
     for cos_offset in (1.0, 0.3, -0.9, -1.0):
         d = union(up, cos_offset, 0.1, up, 1.0, 0.2)
         assert d[:3].tolist() == [0.0, 1.0, 0.0] and d[3] == np.float32(cos_offset) and d[4] == np.float32(0.1)
+
+
+def test_many_small_random_emitter_sets(library):
+    """Two hundred small sets, built to make ties: few distinct positions (equal centres on every axis), repeated emitters, point lights among area
+    lights (zero-size boxes: zero costs), emitters facing all ways or all one way, powers from 1e-3 to 1e3 — the level-synchronous passes must follow
+    the recursion through every one of them."""
+    rng = np.random.default_rng(2026)
+    materials = np.concatenate([scenes.material(structs.MATERIAL_EMISSIVE, tuple(10.0 ** rng.uniform(-3, 3, 3))) for _ in range(6)])
+    for trial in range(200):
+        triangle_count, sphere_count, point_count = rng.integers(0, 14), rng.integers(0, 6), rng.integers(0, 6)
+        if triangle_count + sphere_count + point_count < 2:
+            triangle_count = 2
+        lattice = rng.integers(1, 4)  # positions snapped to a lattice this coarse: 1 = everything in one spot
+        snap = lambda count: np.round(rng.uniform(-2, 2, (count, 3)) * lattice) / lattice
+        v0 = snap(triangle_count)
+        if trial % 3 == 0:  # all facing one way: proper cones all the way up
+            e1, e2 = np.tile((0.3, 0.0, 0.0), (triangle_count, 1)), np.tile((0.0, 0.0, 0.3), (triangle_count, 1))
+        else:
+            e1, e2 = rng.normal(0, 0.3, (triangle_count, 3)), rng.normal(0, 0.3, (triangle_count, 3))
+        triangles = scenes.make_triangles(v0, v0 + e1, v0 + e2, rng.integers(0, 6, triangle_count).astype(np.uint32))
+        spheres = np.zeros(sphere_count, dtype=structs.SPHERE)
+        spheres["position"], spheres["radius"], spheres["material"] = snap(sphere_count), rng.choice([0.1, 0.25], sphere_count), rng.integers(0, 6, sphere_count)
+        points = np.zeros(point_count, dtype=structs.POINT_LIGHT)
+        points["position"], points["intensity"] = snap(point_count), 10.0 ** rng.uniform(-2, 2, (point_count, 3))
+        assert_same_tree(library, describe(triangles, spheres, materials, points), reverse=bool(trial & 1))
